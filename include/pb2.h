@@ -1,0 +1,261 @@
+/*
+ * pb2.h — C ABI of the B200-native pbrt-v3 path-tracing hot path.
+ *
+ * pbrt-v3 has no dlopen plugin ABI: its "plugins" are C++ classes selected by name in
+ * src/core/api.cpp.  The hot path sits behind these reference interfaces:
+ *
+ *   Integrator::Render(const Scene&)                      src/core/integrator.h:53-58
+ *   SamplerIntegrator::Render / PathIntegrator::Li        src/core/integrator.cpp:228-339, src/integrators/path.cpp:64-188
+ *   Aggregate / BVHAccel::Intersect / IntersectP          src/core/primitive.h:119-127, src/accelerators/bvh.cpp:662-738
+ *   Shape / Triangle::Intersect / IntersectP              src/core/shape.h:51-89, src/shapes/triangle.cpp:188-572
+ *   Scene::Intersect / IntersectP                         src/core/scene.cpp:45-55
+ *   FilmTile::AddSample / Film::MergeFilmTile             src/core/film.h:121-161, src/core/film.cpp:117-130
+ *
+ * The host C++ classes in pbrt_v3_b200/csrc/host (same names, same virtual signatures) flatten a
+ * scene into a pb2_scene_desc and call the entry points below; INTEGRATION.md shows the binding a
+ * reference maintainer would add.  Plain pointers and sizes only; every function returns 0 on
+ * success and a non-zero pb2_status otherwise (never throws); pb2_last_error() describes the
+ * failure.  Calls are blocking.  The caller keeps ownership of every host pointer; device copies
+ * are made inside.  There is NO CPU fallback: without a CUDA device every compute entry point
+ * returns PB2_ERR_NO_DEVICE.
+ */
+#ifndef PB2_H
+#define PB2_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB2_ABI_VERSION 1
+
+typedef enum pb2_status {
+    PB2_OK = 0,
+    PB2_ERR_NO_DEVICE = 1,   /* no CUDA device / driver: the product path fails loudly */
+    PB2_ERR_CUDA = 2,        /* a CUDA runtime call failed */
+    PB2_ERR_INVALID = 3,     /* bad argument / inconsistent scene description */
+    PB2_ERR_UNSUPPORTED = 4, /* feature of the reference outside this path's scope */
+    PB2_ERR_NCCL = 5
+} pb2_status;
+
+/* ---- scene description (host memory, flattened by the host-side Scene) ------------------- */
+
+/* Exactly the reference's LinearBVHNode, src/accelerators/bvh.cpp:95-104 (32 bytes,
+ * depth-first order: the first child of interior node i is i+1). */
+typedef struct pb2_bvh_node {
+    float bmin[3];
+    float bmax[3];
+    int32_t offset;   /* leaf: primitivesOffset into bvh_prims; interior: secondChildOffset */
+    uint16_t n_prims; /* 0 -> interior */
+    uint8_t axis;
+    uint8_t pad;
+} pb2_bvh_node;
+
+enum { PB2_PRIM_TRIANGLE = 0, PB2_PRIM_SPHERE = 1 };
+enum { PB2_MAT_NONE = 0, PB2_MAT_MATTE = 1, PB2_MAT_PLASTIC = 2 };
+enum { PB2_LIGHTDIST_UNIFORM = 0, PB2_LIGHTDIST_POWER = 1, PB2_LIGHTDIST_SPATIAL = 2 };
+
+/* One TriangleMesh (src/shapes/triangle.h:46-68).  Vertices are already in world space
+ * (src/shapes/triangle.cpp:73-74); normals already transformed (triangle.cpp:83). */
+typedef struct pb2_mesh {
+    int32_t first_tri, n_tris;        /* range in tri_index[] */
+    int32_t first_vertex, n_vertices; /* range in P/N/UV/S */
+    int32_t has_n, has_uv, has_s;
+    int32_t reverse_orientation;
+    int32_t transform_swaps_handedness;
+    int32_t pad;
+} pb2_mesh;
+
+/* Sphere (src/shapes/sphere.h:47-77). Matrices are row-major 4x4 (Matrix4x4::m). */
+typedef struct pb2_sphere {
+    float object_to_world[16];
+    float world_to_object[16];
+    float radius, z_min, z_max, theta_min, theta_max, phi_max;
+    int32_t reverse_orientation;
+    int32_t transform_swaps_handedness;
+} pb2_sphere;
+
+/* MatteMaterial (src/materials/matte.cpp:45-62) / PlasticMaterial (src/materials/plastic.cpp:45-70)
+ * with constant textures (src/textures/constant.h:54). */
+typedef struct pb2_material {
+    int32_t type;
+    float kd[3];
+    float sigma;
+    float ks[3];
+    float roughness;
+    int32_t remap_roughness;
+    int32_t pad[2];
+} pb2_material;
+
+/* DiffuseAreaLight (src/lights/diffuse.h:49-79) attached to one primitive. */
+typedef struct pb2_light {
+    int32_t prim;       /* index into prim_type[]/prim_index[] */
+    float L[3];         /* Lemit = L * scale */
+    int32_t two_sided;
+    float area;         /* Shape::Area() of that primitive (DiffuseAreaLight::area, diffuse.cpp:52) */
+    int32_t pad[2];
+} pb2_light;
+
+typedef struct pb2_scene_desc {
+    /* geometry */
+    int64_t n_vertices;
+    const float *P;        /* 3*n_vertices, world space */
+    const float *N;        /* 3*n_vertices or NULL (only read for meshes with has_n) */
+    const float *UV;       /* 2*n_vertices or NULL */
+    const float *S;        /* 3*n_vertices or NULL */
+    int64_t n_tris;
+    const int32_t *tri_index; /* 3*n_tris, indices into the GLOBAL vertex arrays */
+    const int32_t *tri_mesh;  /* n_tris, mesh of each triangle */
+    int32_t n_meshes;
+    const pb2_mesh *meshes;
+    int32_t n_spheres;
+    const pb2_sphere *spheres;
+
+    /* primitives in scene order (GeometricPrimitive, src/core/primitive.cpp:98-130) */
+    int64_t n_prims;
+    const uint8_t *prim_type;     /* PB2_PRIM_* */
+    const int32_t *prim_index;    /* triangle id or sphere id */
+    const int32_t *prim_material; /* index into materials[], -1 = no material (null BSDF) */
+    const int32_t *prim_light;    /* index into lights[], -1 = not emissive */
+
+    /* BVHAccel (src/accelerators/bvh.cpp:183-225) built on the host */
+    int64_t n_nodes;
+    const pb2_bvh_node *nodes;
+    const int32_t *bvh_prims;     /* n_prims: ordered primitive numbers (BVHAccel::primitives) */
+
+    int32_t n_materials;
+    const pb2_material *materials;
+    int32_t n_lights;
+    const pb2_light *lights;      /* Scene::lights order (src/core/api.cpp:1394-1400) */
+
+    int32_t light_strategy;       /* PB2_LIGHTDIST_*; src/core/lightdistrib.cpp:48-66 */
+    int32_t spatial_max_voxels;   /* 64, src/core/lightdistrib.h:104 */
+} pb2_scene_desc;
+
+/* PerspectiveCamera (src/cameras/perspective.cpp:45-67, 95-144). */
+typedef struct pb2_camera {
+    /* high-level parameters (what CreatePerspectiveCamera sees) */
+    float camera_to_world[16];   /* row-major */
+    float world_to_camera[16];
+    float screen_window[4];      /* xmin xmax ymin ymax */
+    float fov;
+    float lens_radius, focal_distance;
+    float shutter_open, shutter_close;
+    /* derived by the host exactly as ProjectiveCamera does (src/core/camera.h:84-115) */
+    float raster_to_camera[16];
+    float dx_camera[3], dy_camera[3];
+} pb2_camera;
+
+/* Film (src/core/film.cpp:45-78) with a box filter (src/filters/box.cpp). */
+typedef struct pb2_film_desc {
+    int32_t full_resolution[2];
+    int32_t cropped_pixel_bounds[4]; /* x0 y0 x1 y1 (Film::croppedPixelBounds) */
+    float filter_radius[2];          /* box filter only in this scope */
+    float max_sample_luminance;
+    float scale;
+} pb2_film_desc;
+
+/* HaltonSampler (src/samplers/halton.cpp:65-131) + PathIntegrator parameters
+ * (src/integrators/path.cpp:190-213). */
+typedef struct pb2_path_params {
+    int32_t samples_per_pixel;
+    int32_t sample_at_pixel_center;
+    int32_t max_depth;
+    float rr_threshold;
+    int32_t pixel_bounds[4];  /* x0 y0 x1 y1: PathIntegrator::pixelBounds */
+    /* work partition for multi-GPU: this call renders only the 16x16 sample
+     * tiles t of SamplerIntegrator::Render (integrator.cpp:235-240) with t % tile_count == tile_rank */
+    int32_t tile_rank, tile_count;
+    int32_t pad[2];
+} pb2_path_params;
+
+typedef struct pb2_ray {
+    float o[3];
+    float d[3];
+    float t_max;
+} pb2_ray;
+
+typedef struct pb2_hit {
+    int32_t prim;      /* scene-order primitive number, -1 = miss */
+    float t;           /* ray.tMax after Intersect (primitive.cpp:120) */
+    float b[3];        /* triangle barycentrics b0,b1,b2 (triangle.cpp:263-268); sphere: phi,0,0 */
+    float p[3];        /* SurfaceInteraction::p */
+    float p_error[3];
+    float n[3];        /* geometric normal after orientation/face-forward */
+    float ns[3];       /* shading.n */
+    float dpdu[3];     /* shading.dpdu */
+    float uv[2];
+} pb2_hit;
+
+typedef struct pb2_stats {
+    uint64_t camera_rays;     /* integrator.cpp:287 nCameraRays */
+    uint64_t regular_rays;    /* scene.cpp:46 nIntersectionTests */
+    uint64_t shadow_rays;     /* scene.cpp:52 nShadowTests */
+    uint64_t node_visits;     /* LinearBVHNode records fetched (0 unless built with PB2_COUNTERS) */
+    uint64_t prim_tests;      /* leaf primitive tests (0 unless built with PB2_COUNTERS) */
+    uint64_t kernel_launches; /* number of our kernels launched by the call */
+    double render_ms;         /* device time of the render kernels (CUDA events) */
+    double h2d_ms, d2h_ms;
+} pb2_stats;
+
+typedef struct pb2_scene pb2_scene; /* opaque: device-resident scene */
+
+/* ---- entry points ----------------------------------------------------------------------- */
+
+int pb2_abi_version(void);
+const char *pb2_last_error(void);
+
+/* Binds the calling process to one CUDA device (one process per GPU).  Replaces the reference's
+ * ParallelInit() (src/core/parallel.cpp:301-336) as "bring up the execution resource". */
+int pb2_init(int device_id);
+int pb2_shutdown(void);
+
+/* Uploads a flattened Scene (src/core/scene.h:50-80).  Builds the spatial light-distribution
+ * tables (src/core/lightdistrib.cpp:232-300) on the device. */
+int pb2_scene_create(const pb2_scene_desc *desc, pb2_scene **out);
+int pb2_scene_destroy(pb2_scene *scene);
+
+/* Scene::Intersect for a batch of rays (src/core/scene.cpp:45-49). rays/hits are HOST pointers. */
+int pb2_intersect(pb2_scene *scene, const pb2_ray *rays, int64_t n, pb2_hit *hits);
+/* Scene::IntersectP for a batch (src/core/scene.cpp:51-55). */
+int pb2_intersect_p(pb2_scene *scene, const pb2_ray *rays, int64_t n, uint8_t *occluded);
+
+/* SamplerIntegrator::Render with PathIntegrator::Li (src/core/integrator.cpp:228-339,
+ * src/integrators/path.cpp:64-188).  film_rgbw (HOST, 4 floats per pixel of croppedPixelBounds,
+ * row-major) receives what the reference's FilmTile pixels hold after all tiles were merged:
+ * contribSum RGB and filterWeightSum (src/core/film.h:109-113); the host Film applies
+ * MergeFilmTile's RGB->XYZ and WriteImage (src/core/film.cpp:117-130,169-211).
+ * Host buffers in, host buffer out: copies are inside the call. */
+int pb2_render_path(pb2_scene *scene, const pb2_camera *camera, const pb2_film_desc *film,
+                    const pb2_path_params *params, float *film_rgbw, pb2_stats *stats);
+
+/* Same computation with the film left resident in device memory (used by bench.py's device-timed
+ * `value` and by the multi-GPU reduce).  film_rgbw_device is a DEVICE pointer to
+ * 4*width*height floats, zeroed by the call when `clear` is non-zero.  `stream` is a cudaStream_t
+ * (0 = default stream). Does not synchronise unless stats != NULL. */
+int pb2_render_path_device(pb2_scene *scene, const pb2_camera *camera, const pb2_film_desc *film,
+                           const pb2_path_params *params, float *film_rgbw_device, int clear,
+                           void *stream, pb2_stats *stats);
+
+/* PathIntegrator::Li for explicit (pixel, sample number) pairs, after the NaN/negative/infinite
+ * guard of integrator.cpp:294-315: out_rgb gets 3 floats per sample, out_pfilm 2 floats
+ * (CameraSample::pFilm).  Parity/debug entry point; HOST pointers. */
+int pb2_li_samples(pb2_scene *scene, const pb2_camera *camera, const pb2_film_desc *film,
+                   const pb2_path_params *params, const int32_t *pixel_xy, const int64_t *sample_num,
+                   int64_t n, float *out_rgb, float *out_pfilm);
+
+/* HaltonSampler::SampleDimension(GetIndexForSample(sample_num), dim) for a batch, evaluated on the
+ * device (src/samplers/halton.cpp:96-127).  HOST pointers. */
+int pb2_halton_samples(const pb2_film_desc *film, const pb2_path_params *params,
+                       const int32_t *pixel_xy, const int64_t *sample_num, const int32_t *dim,
+                       int64_t n, float *out);
+
+/* Distribution1D of SpatialLightDistribution::Lookup(p) (src/core/lightdistrib.cpp:141-230):
+ * for each point writes n_lights func values followed by n_lights+1 cdf values. HOST pointers. */
+int pb2_light_distribution(pb2_scene *scene, const float *points_xyz, int64_t n, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PB2_H */

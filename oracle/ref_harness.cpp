@@ -1,0 +1,512 @@
+// TEST INFRASTRUCTURE ONLY — never linked into or called by the product (pbrt_v3_b200/).
+//
+// C-ABI harness around the UNMODIFIED reference sources, compiled where they lie under
+// /root/reference by oracle/Makefile.ref into oracle/_ref/libpbrt_ref.so.  It rebuilds a reference
+// Scene (TriangleMesh/Sphere shapes, GeometricPrimitives, matte/plastic materials, DiffuseAreaLights,
+// BVHAccel) from the same flattened pb2_scene_desc the CUDA library receives, and exposes the
+// reference's own Scene::Intersect/IntersectP, HaltonSampler, SpatialLightDistribution,
+// PathIntegrator::Li and SamplerIntegrator::Render on it.  Used (a) by tests as the parity oracle,
+// (b) to pin the restatement in oracle/pb2_oracle.cpp, (c) by bench.py's `--impl reference` arm and
+// `cpu_baseline` leg as the reference's CPU implementation of the path.
+//
+// The three symbols the reference's build would take from files we do not compile are defined
+// here: PbrtOptions (src/core/api.cpp:141), parserLoc (src/core/parser.cpp:57) and WriteImage
+// (src/core/imageio.cpp:81) — the last one captures the final RGB buffer instead of encoding a file.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include <atomic>
+#include <thread>
+#include <condition_variable>
+#include <functional>
+#include <set>
+#include <algorithm>
+#include <cmath>
+
+// The reference keeps the linear BVH, the sphere's derived angles and the camera matrices private;
+// a checker is allowed to look (and, for two const members that the flattened description stores
+// already evaluated, to overwrite them so both sides see identical inputs).
+#define private public
+#define protected public
+#include "pbrt.h"
+#include "accelerators/bvh.h"
+#include "cameras/perspective.h"
+#include "core/api.h"
+#include "core/film.h"
+#include "core/imageio.h"
+#include "core/light.h"
+#include "core/lightdistrib.h"
+#include "core/parallel.h"
+#include "core/paramset.h"
+#include "core/parser.h"
+#include "core/primitive.h"
+#include "core/sampling.h"
+#include "core/scene.h"
+#include "core/stats.h"
+#include "filters/box.h"
+#include "integrators/path.h"
+#include "lights/diffuse.h"
+#include "materials/matte.h"
+#include "materials/plastic.h"
+#include "samplers/halton.h"
+#include "shapes/loopsubdiv.h"
+#include "shapes/sphere.h"
+#include "shapes/triangle.h"
+#include "textures/constant.h"
+#undef private
+#undef protected
+
+#include "pb2.h"
+
+namespace pbrt {
+Options PbrtOptions;
+Loc *parserLoc = nullptr;
+
+static std::mutex g_imageMutex;
+static std::vector<Float> g_lastImage;
+static Bounds2i g_lastBounds;
+void WriteImage(const std::string &, const Float *rgb, const Bounds2i &outputBounds, const Point2i &) {
+    std::lock_guard<std::mutex> lock(g_imageMutex);
+    g_lastBounds = outputBounds;
+    g_lastImage.assign(rgb, rgb + 3 * (size_t)outputBounds.Area());
+}
+
+// Layout-identical restatement of the struct that exists only inside src/accelerators/bvh.cpp:95-104,
+// so that BVHAccel::nodes can be read.
+struct LinearBVHNode {
+    Bounds3f bounds;
+    union {
+        int primitivesOffset;
+        int secondChildOffset;
+    };
+    uint16_t nPrimitives;
+    uint8_t axis;
+    uint8_t pad[1];
+};
+}  // namespace pbrt
+
+using namespace pbrt;
+
+namespace {
+
+struct RefScene {
+    std::vector<std::unique_ptr<Transform>> transforms;
+    std::vector<std::shared_ptr<Primitive>> prims;  // scene order
+    std::unordered_map<const Primitive *, int> primNumber;
+    std::vector<std::shared_ptr<Light>> lights;
+    std::shared_ptr<BVHAccel> bvh;
+    std::unique_ptr<Scene> scene;
+    int lightStrategy = PB2_LIGHTDIST_SPATIAL;
+    std::unique_ptr<LightDistribution> distrib;  // for ref_light_distribution
+};
+
+Transform fromMatrices(const float m[16], const float mi[16]) {
+    Matrix4x4 a, b;
+    std::memcpy(a.m, m, sizeof(a.m));
+    std::memcpy(b.m, mi, sizeof(b.m));
+    return Transform(a, b);
+}
+
+const char *strategyName(int s) {
+    return s == PB2_LIGHTDIST_UNIFORM ? "uniform" : (s == PB2_LIGHTDIST_POWER ? "power" : "spatial");
+}
+
+struct RenderObjects {
+    Film *film = nullptr;  // owned by the camera (Camera::~Camera deletes it, camera.cpp:42)
+    std::shared_ptr<const Camera> camera;
+    std::shared_ptr<Sampler> sampler;
+    std::unique_ptr<PathIntegrator> integrator;
+    std::unique_ptr<Transform> c2w;
+};
+
+RenderObjects makeRenderObjects(const RefScene &rs, const pb2_camera *cam, const pb2_film_desc *fd,
+                                const pb2_path_params *pp) {
+    RenderObjects ro;
+    Point2i res(fd->full_resolution[0], fd->full_resolution[1]);
+    // Film takes a fractional crop window and ceil()s it (film.cpp:55-60); aim half a pixel low so
+    // that the ceil lands exactly on the integer bounds of the description.
+    Bounds2f crop(Point2f((fd->cropped_pixel_bounds[0] - 0.5f) / res.x, (fd->cropped_pixel_bounds[1] - 0.5f) / res.y),
+                  Point2f((fd->cropped_pixel_bounds[2] - 0.5f) / res.x, (fd->cropped_pixel_bounds[3] - 0.5f) / res.y));
+    crop.pMin.x = std::max(crop.pMin.x, 0.f);
+    crop.pMin.y = std::max(crop.pMin.y, 0.f);
+    std::unique_ptr<Filter> filter(new BoxFilter(Vector2f(fd->filter_radius[0], fd->filter_radius[1])));
+    ro.film = new Film(res, crop, std::move(filter), 35.f, "ref.pfm", fd->scale, fd->max_sample_luminance);
+    CHECK_EQ(ro.film->croppedPixelBounds.pMin.x, fd->cropped_pixel_bounds[0]);
+    CHECK_EQ(ro.film->croppedPixelBounds.pMin.y, fd->cropped_pixel_bounds[1]);
+    CHECK_EQ(ro.film->croppedPixelBounds.pMax.x, fd->cropped_pixel_bounds[2]);
+    CHECK_EQ(ro.film->croppedPixelBounds.pMax.y, fd->cropped_pixel_bounds[3]);
+    ro.c2w.reset(new Transform(fromMatrices(cam->camera_to_world, cam->world_to_camera)));
+    AnimatedTransform ac2w(ro.c2w.get(), 0.f, ro.c2w.get(), 1.f);
+    Bounds2f screen(Point2f(cam->screen_window[0], cam->screen_window[2]), Point2f(cam->screen_window[1], cam->screen_window[3]));
+    ro.camera.reset(new PerspectiveCamera(ac2w, screen, cam->shutter_open, cam->shutter_close, cam->lens_radius,
+                                          cam->focal_distance, cam->fov, ro.film, nullptr));
+    ro.sampler.reset(new HaltonSampler(pp->samples_per_pixel, ro.film->GetSampleBounds(), pp->sample_at_pixel_center != 0));
+    Bounds2i pb(Point2i(pp->pixel_bounds[0], pp->pixel_bounds[1]), Point2i(pp->pixel_bounds[2], pp->pixel_bounds[3]));
+    ro.integrator.reset(new PathIntegrator(pp->max_depth, ro.camera, ro.sampler, pb, pp->rr_threshold,
+                                           strategyName(rs.lightStrategy)));
+    return ro;
+}
+
+void setThreads(int n) {
+    static int current = -1;
+    if (n <= 0) n = (int)std::max(1u, std::thread::hardware_concurrency());
+    if (n == current) return;
+    if (current != -1) ParallelCleanup();
+    else std::atexit([] { ParallelCleanup(); });  // worker threads must be joined before static destructors run
+    PbrtOptions.nThreads = n;
+    PbrtOptions.quiet = true;
+    ParallelInit();
+    current = n;
+}
+
+uint64_t parseStat(const std::string &text, const char *label) {
+    size_t p = text.find(label);
+    if (p == std::string::npos) return 0;
+    p += std::strlen(label);
+    while (p < text.size() && (text[p] == ' ' || text[p] == '\t')) ++p;
+    return std::strtoull(text.c_str() + p, nullptr, 10);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *ref_kind(void) { return "reference"; }
+
+void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split_method) {
+    std::unique_ptr<RefScene> rs(new RefScene);
+    rs->transforms.emplace_back(new Transform());
+    const Transform *identity = rs->transforms.back().get();
+    rs->lightStrategy = d->light_strategy;
+
+    // shapes
+    std::vector<std::vector<std::shared_ptr<Shape>>> meshShapes(d->n_meshes);
+    for (int m = 0; m < d->n_meshes; ++m) {
+        const pb2_mesh &pm = d->meshes[m];
+        std::vector<int> local(3 * (size_t)pm.n_tris);
+        for (size_t i = 0; i < local.size(); ++i) local[i] = d->tri_index[3 * (size_t)pm.first_tri + i] - pm.first_vertex;
+        const Point3f *P = reinterpret_cast<const Point3f *>(d->P) + pm.first_vertex;
+        const Normal3f *N = (pm.has_n && d->N) ? reinterpret_cast<const Normal3f *>(d->N) + pm.first_vertex : nullptr;
+        const Point2f *UV = (pm.has_uv && d->UV) ? reinterpret_cast<const Point2f *>(d->UV) + pm.first_vertex : nullptr;
+        const Vector3f *S = (pm.has_s && d->S) ? reinterpret_cast<const Vector3f *>(d->S) + pm.first_vertex : nullptr;
+        // Vertices/normals in the description are already in world space, so the mesh is rebuilt
+        // under the identity transform (which maps every finite float to itself).
+        meshShapes[m] = CreateTriangleMesh(identity, identity, pm.reverse_orientation != 0, pm.n_tris, local.data(),
+                                           pm.n_vertices, P, S, N, UV, nullptr, nullptr, nullptr);
+        for (auto &s : meshShapes[m])
+            const_cast<bool &>(s->transformSwapsHandedness) = pm.transform_swaps_handedness != 0;
+    }
+    std::vector<std::shared_ptr<Shape>> sphereShapes(d->n_spheres);
+    for (int s = 0; s < d->n_spheres; ++s) {
+        const pb2_sphere &ps = d->spheres[s];
+        rs->transforms.emplace_back(new Transform(fromMatrices(ps.object_to_world, ps.world_to_object)));
+        const Transform *o2w = rs->transforms.back().get();
+        rs->transforms.emplace_back(new Transform(fromMatrices(ps.world_to_object, ps.object_to_world)));
+        const Transform *w2o = rs->transforms.back().get();
+        auto sp = std::make_shared<Sphere>(o2w, w2o, ps.reverse_orientation != 0, ps.radius, ps.z_min, ps.z_max, 360.f);
+        const_cast<Float &>(sp->thetaMin) = ps.theta_min;
+        const_cast<Float &>(sp->thetaMax) = ps.theta_max;
+        const_cast<Float &>(sp->phiMax) = ps.phi_max;
+        const_cast<bool &>(sp->transformSwapsHandedness) = ps.transform_swaps_handedness != 0;
+        sphereShapes[s] = sp;
+    }
+    // materials
+    std::vector<std::shared_ptr<Material>> materials(d->n_materials);
+    for (int i = 0; i < d->n_materials; ++i) {
+        const pb2_material &pm = d->materials[i];
+        auto kd = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kd));
+        if (pm.type == PB2_MAT_MATTE) {
+            auto sigma = std::make_shared<ConstantTexture<Float>>(pm.sigma);
+            materials[i] = std::make_shared<MatteMaterial>(kd, sigma, nullptr);
+        } else if (pm.type == PB2_MAT_PLASTIC) {
+            auto ks = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.ks));
+            auto rough = std::make_shared<ConstantTexture<Float>>(pm.roughness);
+            materials[i] = std::make_shared<PlasticMaterial>(kd, ks, rough, nullptr, pm.remap_roughness != 0);
+        }
+    }
+    // primitives + lights (lights indexed as in the description = Scene::lights order)
+    rs->lights.resize(d->n_lights);
+    rs->prims.resize(d->n_prims);
+    for (int64_t i = 0; i < d->n_prims; ++i) {
+        std::shared_ptr<Shape> shape;
+        if (d->prim_type[i] == PB2_PRIM_TRIANGLE) {
+            int tri = d->prim_index[i];
+            int m = d->tri_mesh[tri];
+            shape = meshShapes[m][tri - d->meshes[m].first_tri];
+        } else
+            shape = sphereShapes[d->prim_index[i]];
+        std::shared_ptr<Material> mtl = d->prim_material[i] >= 0 ? materials[d->prim_material[i]] : nullptr;
+        std::shared_ptr<AreaLight> area;
+        if (d->prim_light[i] >= 0) {
+            const pb2_light &pl = d->lights[d->prim_light[i]];
+            area = std::make_shared<DiffuseAreaLight>(*identity, MediumInterface(), Spectrum::FromRGB(pl.L), 1, shape,
+                                                      pl.two_sided != 0);
+            rs->lights[d->prim_light[i]] = area;
+        }
+        rs->prims[i] = std::make_shared<GeometricPrimitive>(shape, mtl, area, MediumInterface());
+        rs->primNumber[rs->prims[i].get()] = (int)i;
+    }
+    BVHAccel::SplitMethod sm = split_method == 1 ? BVHAccel::SplitMethod::HLBVH
+                             : split_method == 2 ? BVHAccel::SplitMethod::Middle
+                             : split_method == 3 ? BVHAccel::SplitMethod::EqualCounts
+                                                 : BVHAccel::SplitMethod::SAH;
+    rs->bvh = std::make_shared<BVHAccel>(rs->prims, max_prims_in_node > 0 ? max_prims_in_node : 4, sm);
+    rs->scene.reset(new Scene(rs->bvh, rs->lights));
+    return rs.release();
+}
+
+void ref_scene_destroy(void *h) { delete static_cast<RefScene *>(h); }
+
+// Copies the reference's own LinearBVHNode array and ordered primitive numbers.
+int64_t ref_bvh_dump(void *h, pb2_bvh_node *out_nodes, int64_t max_nodes, int32_t *out_prims) {
+    RefScene *rs = static_cast<RefScene *>(h);
+    // node count: walk depth first
+    const LinearBVHNode *nodes = reinterpret_cast<const LinearBVHNode *>(rs->bvh->nodes);
+    if (!nodes) return 0;
+    int64_t count = 0;
+    {
+        std::vector<int> stack{0};
+        while (!stack.empty()) {
+            int i = stack.back();
+            stack.pop_back();
+            count = std::max<int64_t>(count, i + 1);
+            if (nodes[i].nPrimitives == 0) {
+                stack.push_back(i + 1);
+                stack.push_back(nodes[i].secondChildOffset);
+            }
+        }
+    }
+    static_assert(sizeof(LinearBVHNode) == sizeof(pb2_bvh_node), "node layouts differ");
+    if (out_nodes) std::memcpy(out_nodes, nodes, sizeof(pb2_bvh_node) * (size_t)std::min(count, max_nodes));
+    if (out_prims)
+        for (size_t j = 0; j < rs->bvh->primitives.size(); ++j) out_prims[j] = rs->primNumber[rs->bvh->primitives[j].get()];
+    return count;
+}
+
+int ref_intersect(void *h, const pb2_ray *rays, int64_t n, pb2_hit *hits) {
+    RefScene *rs = static_cast<RefScene *>(h);
+    for (int64_t i = 0; i < n; ++i) {
+        Ray ray(Point3f(rays[i].o[0], rays[i].o[1], rays[i].o[2]), Vector3f(rays[i].d[0], rays[i].d[1], rays[i].d[2]),
+                rays[i].t_max);
+        SurfaceInteraction isect;
+        pb2_hit &o = hits[i];
+        std::memset(&o, 0, sizeof(o));
+        if (!rs->scene->Intersect(ray, &isect)) {
+            o.prim = -1;
+            o.t = ray.tMax;
+            continue;
+        }
+        o.prim = rs->primNumber[isect.primitive];
+        o.t = ray.tMax;
+        for (int k = 0; k < 3; ++k) {
+            o.p[k] = isect.p[k];
+            o.p_error[k] = isect.pError[k];
+            o.n[k] = isect.n[k];
+            o.ns[k] = isect.shading.n[k];
+            o.dpdu[k] = isect.shading.dpdu[k];
+        }
+        o.uv[0] = isect.uv[0];
+        o.uv[1] = isect.uv[1];
+        // barycentrics are not part of SurfaceInteraction; with the default (0,0),(1,0),(1,1)
+        // parameterisation (triangle.h:98-108) uv = (b1+b2, b2), which tests use instead.
+    }
+    return 0;
+}
+
+int ref_intersect_p(void *h, const pb2_ray *rays, int64_t n, uint8_t *occluded) {
+    RefScene *rs = static_cast<RefScene *>(h);
+    for (int64_t i = 0; i < n; ++i) {
+        Ray ray(Point3f(rays[i].o[0], rays[i].o[1], rays[i].o[2]), Vector3f(rays[i].d[0], rays[i].d[1], rays[i].d[2]),
+                rays[i].t_max);
+        occluded[i] = rs->scene->IntersectP(ray) ? 1 : 0;
+    }
+    return 0;
+}
+
+// SamplerIntegrator::Render with the reference's thread pool.  out_rgb: 3 floats per cropped pixel
+// (what Film::WriteImage hands to the image encoder).  seconds: wall time of Render().
+int ref_render(void *h, const pb2_camera *cam, const pb2_film_desc *fd, const pb2_path_params *pp, int n_threads,
+               float *out_rgb, double *seconds, pb2_stats *stats) {
+    RefScene *rs = static_cast<RefScene *>(h);
+    setThreads(n_threads);
+    RenderObjects ro = makeRenderObjects(*rs, cam, fd, pp);
+    ReportThreadStats();  // flush this thread's counters from earlier calls, then start from zero
+    ClearStats();
+    auto t0 = std::chrono::steady_clock::now();
+    ro.integrator->Render(*rs->scene);
+    auto t1 = std::chrono::steady_clock::now();
+    if (seconds) *seconds = std::chrono::duration<double>(t1 - t0).count();
+    {
+        std::lock_guard<std::mutex> lock(g_imageMutex);
+        if (out_rgb) std::memcpy(out_rgb, g_lastImage.data(), g_lastImage.size() * sizeof(float));
+    }
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        MergeWorkerThreadStats();
+        ReportThreadStats();
+        char *buf = nullptr;
+        size_t len = 0;
+        FILE *f = open_memstream(&buf, &len);
+        PrintStats(f);
+        std::fclose(f);
+        std::string text(buf, len);
+        free(buf);
+        stats->camera_rays = parseStat(text, "Camera rays traced");
+        stats->regular_rays = parseStat(text, "Regular ray intersection tests");
+        stats->shadow_rays = parseStat(text, "Shadow ray intersection tests");
+        stats->render_ms = seconds ? *seconds * 1e3 : 0;
+        ClearStats();
+    }
+    return 0;
+}
+
+int ref_li_samples(void *h, const pb2_camera *cam, const pb2_film_desc *fd, const pb2_path_params *pp,
+                   const int32_t *pixel_xy, const int64_t *sample_num, int64_t n, float *out_rgb, float *out_pfilm) {
+    RefScene *rs = static_cast<RefScene *>(h);
+    setThreads(1);
+    RenderObjects ro = makeRenderObjects(*rs, cam, fd, pp);
+    ro.integrator->Preprocess(*rs->scene, *ro.sampler);
+    MemoryArena arena;
+    std::unique_ptr<Sampler> sampler = ro.sampler->Clone(0);
+    for (int64_t i = 0; i < n; ++i) {
+        Point2i pixel(pixel_xy[2 * i], pixel_xy[2 * i + 1]);
+        sampler->StartPixel(pixel);
+        sampler->SetSampleNumber(sample_num[i]);
+        CameraSample cs = sampler->GetCameraSample(pixel);
+        RayDifferential ray;
+        Float rayWeight = ro.camera->GenerateRayDifferential(cs, &ray);
+        ray.ScaleDifferentials(1 / std::sqrt((Float)sampler->samplesPerPixel));
+        Spectrum L(0.f);
+        if (rayWeight > 0) L = ro.integrator->Li(ray, *rs->scene, *sampler, arena, 0);
+        // integrator.cpp:294-315
+        if (L.HasNaNs()) L = Spectrum(0.f);
+        else if (L.y() < -1e-5) L = Spectrum(0.f);
+        else if (std::isinf(L.y())) L = Spectrum(0.f);
+        Float rgb[3];
+        L.ToRGB(rgb);
+        for (int k = 0; k < 3; ++k) out_rgb[3 * i + k] = rgb[k];
+        if (out_pfilm) {
+            out_pfilm[2 * i] = cs.pFilm.x;
+            out_pfilm[2 * i + 1] = cs.pFilm.y;
+        }
+        arena.Reset();
+    }
+    return 0;
+}
+
+int ref_halton_samples(const pb2_film_desc *fd, const pb2_path_params *pp, const int32_t *pixel_xy,
+                       const int64_t *sample_num, const int32_t *dim, int64_t n, float *out) {
+    // sample bounds as Film::GetSampleBounds() computes them (film.cpp:80-86)
+    Bounds2i sb(Point2i((int)std::floor(fd->cropped_pixel_bounds[0] + 0.5f - fd->filter_radius[0]),
+                        (int)std::floor(fd->cropped_pixel_bounds[1] + 0.5f - fd->filter_radius[1])),
+                Point2i((int)std::ceil(fd->cropped_pixel_bounds[2] - 0.5f + fd->filter_radius[0]),
+                        (int)std::ceil(fd->cropped_pixel_bounds[3] - 0.5f + fd->filter_radius[1])));
+    HaltonSampler hs(pp->samples_per_pixel, sb, pp->sample_at_pixel_center != 0);
+    for (int64_t i = 0; i < n; ++i) {
+        hs.StartPixel(Point2i(pixel_xy[2 * i], pixel_xy[2 * i + 1]));
+        int64_t index = hs.GetIndexForSample(sample_num[i]);
+        out[i] = hs.SampleDimension(index, dim[i]);
+    }
+    return 0;
+}
+
+// RadicalInverse / ScrambledRadicalInverse (src/core/lowdiscrepancy.cpp:427, 2506) with the
+// sampler's permutation table; scrambled=0 -> RadicalInverse.
+int ref_radical_inverse(int base_index, const uint64_t *a, int64_t n, int scrambled, float *out) {
+    if (HaltonSampler::radicalInversePermutations.empty()) {
+        RNG rng;
+        HaltonSampler::radicalInversePermutations = ComputeRadicalInversePermutations(rng);
+    }
+    for (int64_t i = 0; i < n; ++i)
+        out[i] = scrambled ? ScrambledRadicalInverse(base_index, a[i], &HaltonSampler::radicalInversePermutations[PrimeSums[base_index]])
+                           : RadicalInverse(base_index, a[i]);
+    return 0;
+}
+
+// For each point: n_lights func values then n_lights+1 cdf values of LightDistribution::Lookup(p).
+int ref_light_distribution(void *h, const float *points, int64_t n, float *out) {
+    RefScene *rs = static_cast<RefScene *>(h);
+    if (!rs->distrib) rs->distrib = CreateLightSampleDistribution(strategyName(rs->lightStrategy), *rs->scene);
+    size_t nl = rs->lights.size(), stride = 2 * nl + 1;
+    for (int64_t i = 0; i < n; ++i) {
+        const Distribution1D *d = rs->distrib->Lookup(Point3f(points[3 * i], points[3 * i + 1], points[3 * i + 2]));
+        for (size_t k = 0; k < nl; ++k) out[i * stride + k] = d->func[k];
+        for (size_t k = 0; k <= nl; ++k) out[i * stride + nl + k] = d->cdf[k];
+    }
+    return 0;
+}
+
+// CreateLoopSubdiv (src/shapes/loopsubdiv.cpp:389-410) under the identity transform.
+int ref_loop_subdivide(int n_levels, int n_indices, const int *indices, int n_vertices, const float *P,
+                       int *out_n_vertices, int *out_n_indices, float *out_P, float *out_N, int *out_indices) {
+    ParamSet ps;
+    std::unique_ptr<int[]> idx(new int[n_indices]);
+    std::memcpy(idx.get(), indices, n_indices * sizeof(int));
+    ps.AddInt("indices", std::move(idx), n_indices);
+    std::unique_ptr<Point3f[]> pts(new Point3f[n_vertices]);
+    for (int i = 0; i < n_vertices; ++i) pts[i] = Point3f(P[3 * i], P[3 * i + 1], P[3 * i + 2]);
+    ps.AddPoint3f("P", std::move(pts), n_vertices);
+    std::unique_ptr<int[]> lv(new int[1]);
+    lv[0] = n_levels;
+    ps.AddInt("levels", std::move(lv), 1);
+    Transform identity;
+    std::vector<std::shared_ptr<Shape>> shapes = CreateLoopSubdiv(&identity, &identity, false, ps);
+    if (shapes.empty()) return 1;
+    const Triangle *t0 = static_cast<const Triangle *>(shapes[0].get());
+    const TriangleMesh *mesh = t0->mesh.get();
+    *out_n_vertices = mesh->nVertices;
+    *out_n_indices = 3 * mesh->nTriangles;
+    if (out_P)
+        for (int i = 0; i < mesh->nVertices; ++i)
+            for (int k = 0; k < 3; ++k) out_P[3 * i + k] = mesh->p[i][k];
+    if (out_N)
+        for (int i = 0; i < mesh->nVertices; ++i)
+            for (int k = 0; k < 3; ++k) out_N[3 * i + k] = mesh->n[i][k];
+    if (out_indices) std::memcpy(out_indices, mesh->vertexIndices.data(), sizeof(int) * 3 * mesh->nTriangles);
+    return 0;
+}
+
+// PerspectiveCamera's derived matrices for a description (tests compare with the host's).
+int ref_camera_derived(const pb2_camera *cam, const pb2_film_desc *fd, float *raster_to_camera16, float *dx3, float *dy3) {
+    RefScene dummy;
+    pb2_path_params pp;
+    std::memset(&pp, 0, sizeof(pp));
+    pp.samples_per_pixel = 1;
+    pp.max_depth = 1;
+    pp.pixel_bounds[2] = fd->full_resolution[0];
+    pp.pixel_bounds[3] = fd->full_resolution[1];
+    RenderObjects ro = makeRenderObjects(dummy, cam, fd, &pp);
+    const PerspectiveCamera *pc = static_cast<const PerspectiveCamera *>(ro.camera.get());
+    std::memcpy(raster_to_camera16, pc->RasterToCamera.m.m, 16 * sizeof(float));
+    for (int k = 0; k < 3; ++k) {
+        dx3[k] = pc->dxCamera[k];
+        dy3[k] = pc->dyCamera[k];
+    }
+    return 0;
+}
+
+// Transform helpers of src/core/transform.cpp for host-math tests: kind 0 LookAt(9 args),
+// 1 Rotate(angle, axis), 2 Perspective(fov, n, f), 3 Translate, 4 Scale. Returns m and mInv.
+int ref_transform(int kind, const float *args, float *m16, float *minv16) {
+    Transform t;
+    switch (kind) {
+    case 0: t = LookAt(Point3f(args[0], args[1], args[2]), Point3f(args[3], args[4], args[5]), Vector3f(args[6], args[7], args[8])); break;
+    case 1: t = Rotate(args[0], Vector3f(args[1], args[2], args[3])); break;
+    case 2: t = Perspective(args[0], args[1], args[2]); break;
+    case 3: t = Translate(Vector3f(args[0], args[1], args[2])); break;
+    case 4: t = Scale(args[0], args[1], args[2]); break;
+    default: return 1;
+    }
+    std::memcpy(m16, t.GetMatrix().m, 16 * sizeof(float));
+    std::memcpy(minv16, t.GetInverseMatrix().m, 16 * sizeof(float));
+    return 0;
+}
+
+}  // extern "C"

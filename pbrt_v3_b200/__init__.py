@@ -1,0 +1,347 @@
+"""pbrt_v3_b200 — B200-native path-tracing hot path behind pbrt-v3's plugin API.
+
+Python is only the driver here (tests, bench.py, multi-GPU launch through torch.distributed):
+everything below is a thin ctypes view of
+
+* ``lib/libpb2.so`` — the C ABI of ``include/pb2.h`` (CUDA kernels, sm_100a) plus the C++ host-side
+  scene front end (``csrc/host``: .pbrt parser, pbrt's Shape/Primitive/BVHAccel/Film/... classes,
+  SAH BVH build), exported for scripting through the ``pb2h_*`` helpers of ``csrc/host/capi.cpp``.
+
+There is no CPU implementation of the path in this package: without a CUDA device every compute
+entry point fails with ``Pb2Error`` (``PB2_ERR_NO_DEVICE``).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libpb2.so")
+
+c_float_p = C.POINTER(C.c_float)
+c_int32_p = C.POINTER(C.c_int32)
+c_int64_p = C.POINTER(C.c_int64)
+c_uint8_p = C.POINTER(C.c_uint8)
+
+PB2_OK, PB2_ERR_NO_DEVICE, PB2_ERR_CUDA, PB2_ERR_INVALID, PB2_ERR_UNSUPPORTED, PB2_ERR_NCCL = range(6)
+PB2_PRIM_TRIANGLE, PB2_PRIM_SPHERE = 0, 1
+PB2_LIGHTDIST_UNIFORM, PB2_LIGHTDIST_POWER, PB2_LIGHTDIST_SPATIAL = 0, 1, 2
+
+
+class BvhNode(C.Structure):
+    _fields_ = [("bmin", C.c_float * 3), ("bmax", C.c_float * 3), ("offset", C.c_int32),
+                ("n_prims", C.c_uint16), ("axis", C.c_uint8), ("pad", C.c_uint8)]
+
+
+class Mesh(C.Structure):
+    _fields_ = [("first_tri", C.c_int32), ("n_tris", C.c_int32), ("first_vertex", C.c_int32),
+                ("n_vertices", C.c_int32), ("has_n", C.c_int32), ("has_uv", C.c_int32), ("has_s", C.c_int32),
+                ("reverse_orientation", C.c_int32), ("transform_swaps_handedness", C.c_int32), ("pad", C.c_int32)]
+
+
+class Sphere(C.Structure):
+    _fields_ = [("object_to_world", C.c_float * 16), ("world_to_object", C.c_float * 16),
+                ("radius", C.c_float), ("z_min", C.c_float), ("z_max", C.c_float), ("theta_min", C.c_float),
+                ("theta_max", C.c_float), ("phi_max", C.c_float), ("reverse_orientation", C.c_int32),
+                ("transform_swaps_handedness", C.c_int32)]
+
+
+class Material(C.Structure):
+    _fields_ = [("type", C.c_int32), ("kd", C.c_float * 3), ("sigma", C.c_float), ("ks", C.c_float * 3),
+                ("roughness", C.c_float), ("remap_roughness", C.c_int32), ("pad", C.c_int32 * 2)]
+
+
+class Light(C.Structure):
+    _fields_ = [("prim", C.c_int32), ("L", C.c_float * 3), ("two_sided", C.c_int32), ("area", C.c_float),
+                ("pad", C.c_int32 * 2)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("n_vertices", C.c_int64), ("P", c_float_p), ("N", c_float_p), ("UV", c_float_p), ("S", c_float_p),
+                ("n_tris", C.c_int64), ("tri_index", c_int32_p), ("tri_mesh", c_int32_p),
+                ("n_meshes", C.c_int32), ("meshes", C.POINTER(Mesh)),
+                ("n_spheres", C.c_int32), ("spheres", C.POINTER(Sphere)),
+                ("n_prims", C.c_int64), ("prim_type", c_uint8_p), ("prim_index", c_int32_p),
+                ("prim_material", c_int32_p), ("prim_light", c_int32_p),
+                ("n_nodes", C.c_int64), ("nodes", C.POINTER(BvhNode)), ("bvh_prims", c_int32_p),
+                ("n_materials", C.c_int32), ("materials", C.POINTER(Material)),
+                ("n_lights", C.c_int32), ("lights", C.POINTER(Light)),
+                ("light_strategy", C.c_int32), ("spatial_max_voxels", C.c_int32)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("camera_to_world", C.c_float * 16), ("world_to_camera", C.c_float * 16),
+                ("screen_window", C.c_float * 4), ("fov", C.c_float), ("lens_radius", C.c_float),
+                ("focal_distance", C.c_float), ("shutter_open", C.c_float), ("shutter_close", C.c_float),
+                ("raster_to_camera", C.c_float * 16), ("dx_camera", C.c_float * 3), ("dy_camera", C.c_float * 3)]
+
+
+class FilmDesc(C.Structure):
+    _fields_ = [("full_resolution", C.c_int32 * 2), ("cropped_pixel_bounds", C.c_int32 * 4),
+                ("filter_radius", C.c_float * 2), ("max_sample_luminance", C.c_float), ("scale", C.c_float)]
+
+
+class PathParams(C.Structure):
+    _fields_ = [("samples_per_pixel", C.c_int32), ("sample_at_pixel_center", C.c_int32), ("max_depth", C.c_int32),
+                ("rr_threshold", C.c_float), ("pixel_bounds", C.c_int32 * 4), ("tile_rank", C.c_int32),
+                ("tile_count", C.c_int32), ("pad", C.c_int32 * 2)]
+
+
+class Ray(C.Structure):
+    _fields_ = [("o", C.c_float * 3), ("d", C.c_float * 3), ("t_max", C.c_float)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("prim", C.c_int32), ("t", C.c_float), ("b", C.c_float * 3), ("p", C.c_float * 3),
+                ("p_error", C.c_float * 3), ("n", C.c_float * 3), ("ns", C.c_float * 3), ("dpdu", C.c_float * 3),
+                ("uv", C.c_float * 2)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("camera_rays", C.c_uint64), ("regular_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
+                ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("render_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)]
+
+
+RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("t_max", np.float32)])
+HIT_DTYPE = np.dtype([("prim", np.int32), ("t", np.float32), ("b", np.float32, 3), ("p", np.float32, 3),
+                      ("p_error", np.float32, 3), ("n", np.float32, 3), ("ns", np.float32, 3),
+                      ("dpdu", np.float32, 3), ("uv", np.float32, 2)])
+NODE_DTYPE = np.dtype([("bmin", np.float32, 3), ("bmax", np.float32, 3), ("offset", np.int32),
+                       ("n_prims", np.uint16), ("axis", np.uint8), ("pad", np.uint8)])
+assert RAY_DTYPE.itemsize == C.sizeof(Ray) and HIT_DTYPE.itemsize == C.sizeof(Hit) and NODE_DTYPE.itemsize == 32
+
+
+class Pb2Error(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("pb2 status %d: %s" % (code, message))
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Loads lib/libpb2.so (built in-tree by __graft_entry__.build()); fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the CUDA extension is required; there is no fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.pb2_last_error.restype = C.c_char_p
+    L.pb2_scene_create.argtypes = [C.POINTER(SceneDesc), C.POINTER(vp)]
+    L.pb2_scene_destroy.argtypes = [vp]
+    L.pb2_intersect.argtypes = [vp, vp, C.c_int64, vp]
+    L.pb2_intersect_p.argtypes = [vp, vp, C.c_int64, vp]
+    L.pb2_render_path.argtypes = [vp, C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), vp, C.POINTER(Stats)]
+    L.pb2_render_path_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), vp,
+                                         C.c_int, vp, C.POINTER(Stats)]
+    L.pb2_li_samples.argtypes = [vp, C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), vp, vp, C.c_int64, vp, vp]
+    L.pb2_halton_samples.argtypes = [C.POINTER(FilmDesc), C.POINTER(PathParams), vp, vp, vp, C.c_int64, vp]
+    L.pb2_light_distribution.argtypes = [vp, vp, C.c_int64, vp]
+    L.pb2h_parse_file.argtypes = [C.c_char_p, C.c_char_p]
+    L.pb2h_parse_string.argtypes = [C.c_char_p]
+    L.pb2h_synth_soup.argtypes = [C.c_int64, C.c_uint64, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
+    L.pb2h_scene_desc.restype = C.POINTER(SceneDesc)
+    L.pb2h_camera.restype = C.POINTER(Camera)
+    L.pb2h_film.restype = C.POINTER(FilmDesc)
+    L.pb2h_path_params.restype = C.POINTER(PathParams)
+    L.pb2h_render.argtypes = [C.c_int, C.POINTER(Stats)]
+    L.pb2h_image.restype = c_float_p
+    L.pb2h_image.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pb2h_resolve_film.argtypes = [vp, vp]
+    L.pb2h_device_scene.restype = vp
+    L.pb2h_write_pfm.argtypes = [C.c_char_p, vp, C.c_int, C.c_int]
+    L.pb2h_loop_subdivide.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, vp]
+    L.pb2h_set_light_strategy.argtypes = [C.c_int]
+    _lib = L
+    return L
+
+
+def check(code):
+    if code != PB2_OK:
+        raise Pb2Error(code, lib().pb2_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+_initialised_device = None
+
+
+def init(device=None):
+    """pb2_init on this process's GPU (LOCAL_RANK under torchrun). Raises Pb2Error without a device."""
+    global _initialised_device
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", os.environ.get("PB2_DEVICE", "0")))
+    if _initialised_device == device:
+        return
+    check(lib().pb2_init(device))
+    _initialised_device = device
+
+
+class HostScene:
+    """A scene held by the C++ host front end (one at a time: it mirrors pbrt's global API state)."""
+
+    def __init__(self):
+        self.L = lib()
+
+    @classmethod
+    def from_file(cls, path, outfile=None):
+        s = cls()
+        if s.L.pb2h_parse_file(path.encode(), outfile.encode() if outfile else None) != 0:
+            raise RuntimeError("could not parse %s" % path)
+        return s
+
+    @classmethod
+    def from_string(cls, text):
+        s = cls()
+        if s.L.pb2h_parse_string(text.encode()) != 0:
+            raise RuntimeError("could not parse scene text")
+        return s
+
+    @classmethod
+    def soup(cls, n_tris, seed=1234, jitter=0.02, xres=1920, yres=1080, spp=64, maxdepth=8, light_strategy=None):
+        """SURVEY.md §8d synthetic triangle soup (config 2 with the defaults and n_tris=1_000_000)."""
+        s = cls()
+        if s.L.pb2h_synth_soup(n_tris, seed, jitter, xres, yres, spp, maxdepth,
+                               light_strategy.encode() if light_strategy else None) != 0:
+            raise RuntimeError("could not build the synthetic scene")
+        return s
+
+    # flattened descriptions (host memory owned by the C++ side)
+    @property
+    def desc(self):
+        p = self.L.pb2h_scene_desc()
+        if not p:
+            raise RuntimeError("scene could not be flattened (see stderr)")
+        return p
+
+    @property
+    def camera(self):
+        return self.L.pb2h_camera()
+
+    @property
+    def film(self):
+        return self.L.pb2h_film()
+
+    @property
+    def params(self):
+        return self.L.pb2h_path_params()
+
+    def params_copy(self, **overrides):
+        p = PathParams()
+        C.memmove(C.byref(p), self.params, C.sizeof(PathParams))
+        for k, v in overrides.items():
+            setattr(p, k, v)
+        return p
+
+    def film_shape(self):
+        b = self.film.contents.cropped_pixel_bounds
+        return (b[3] - b[1], b[2] - b[0])
+
+    def nodes(self):
+        d = self.desc.contents
+        return np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_uint8)), shape=(d.n_nodes * 32,)).view(NODE_DTYPE).copy()
+
+    def bvh_prims(self):
+        d = self.desc.contents
+        return np.ctypeslib.as_array(d.bvh_prims, shape=(d.n_prims,)).copy()
+
+    # device side
+    def device_scene(self):
+        init()
+        h = self.L.pb2h_device_scene()
+        if not h:
+            raise Pb2Error(PB2_ERR_CUDA, "device scene could not be created: " + self.L.pb2_last_error().decode())
+        return h
+
+    def render(self, write_image=False):
+        """Integrator::Render through the reference-shaped host API. Returns (rgb[h,w,3], Stats)."""
+        init()
+        st = Stats()
+        rc = self.L.pb2h_render(1 if write_image else 0, C.byref(st))
+        if rc != 0:
+            raise Pb2Error(rc, "render failed: " + self.L.pb2_last_error().decode())
+        w, h = C.c_int(), C.c_int()
+        p = self.L.pb2h_image(C.byref(w), C.byref(h))
+        img = np.ctypeslib.as_array(p, shape=(h.value, w.value, 3)).copy()
+        return img, st
+
+    def render_rgbw(self, params=None):
+        """pb2_render_path with host buffers: returns (rgbw[h,w,4], Stats)."""
+        dev = self.device_scene()
+        h, w = self.film_shape()
+        out = np.zeros((h, w, 4), np.float32)
+        st = Stats()
+        check(self.L.pb2_render_path(dev, self.camera, self.film, params if params is not None else self.params,
+                                     ptr(out), C.byref(st)))
+        return out, st
+
+    def resolve(self, rgbw):
+        """Film::MergeFilmTile + WriteImage arithmetic on an rgbw film. Returns rgb[h,w,3]."""
+        h, w = self.film_shape()
+        rgbw = np.ascontiguousarray(rgbw, np.float32)
+        out = np.zeros((h, w, 3), np.float32)
+        if self.L.pb2h_resolve_film(ptr(rgbw), ptr(out)) != 0:
+            raise RuntimeError("resolve failed")
+        return out
+
+    def intersect(self, rays):
+        dev = self.device_scene()
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        hits = np.zeros(len(rays), HIT_DTYPE)
+        check(self.L.pb2_intersect(dev, ptr(rays), len(rays), ptr(hits)))
+        return hits
+
+    def intersect_p(self, rays):
+        dev = self.device_scene()
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        occ = np.zeros(len(rays), np.uint8)
+        check(self.L.pb2_intersect_p(dev, ptr(rays), len(rays), ptr(occ)))
+        return occ
+
+    def li_samples(self, pixel_xy, sample_num, params=None):
+        dev = self.device_scene()
+        pixel_xy = np.ascontiguousarray(pixel_xy, np.int32)
+        sample_num = np.ascontiguousarray(sample_num, np.int64)
+        n = len(sample_num)
+        rgb = np.zeros((n, 3), np.float32)
+        pfilm = np.zeros((n, 2), np.float32)
+        check(self.L.pb2_li_samples(dev, self.camera, self.film, params if params is not None else self.params,
+                                    ptr(pixel_xy), ptr(sample_num), n, ptr(rgb), ptr(pfilm)))
+        return rgb, pfilm
+
+    def halton(self, pixel_xy, sample_num, dim):
+        init()
+        pixel_xy = np.ascontiguousarray(pixel_xy, np.int32)
+        sample_num = np.ascontiguousarray(sample_num, np.int64)
+        dim = np.ascontiguousarray(dim, np.int32)
+        out = np.zeros(len(dim), np.float32)
+        check(self.L.pb2_halton_samples(self.film, self.params, ptr(pixel_xy), ptr(sample_num), ptr(dim), len(dim), ptr(out)))
+        return out
+
+    def light_distribution(self, points):
+        dev = self.device_scene()
+        points = np.ascontiguousarray(points, np.float32)
+        nl = self.desc.contents.n_lights
+        out = np.zeros((len(points), 2 * nl + 1), np.float32)
+        check(self.L.pb2_light_distribution(dev, ptr(points), len(points), ptr(out)))
+        return out
+
+
+def loop_subdivide(n_levels, indices, P):
+    L = lib()
+    indices = np.ascontiguousarray(indices, np.int32)
+    P = np.ascontiguousarray(P, np.float32)
+    nv, ni = C.c_int(), C.c_int()
+    L.pb2h_loop_subdivide(n_levels, len(indices), ptr(indices), len(P), ptr(P), C.byref(nv), C.byref(ni), None, None, None)
+    oP = np.zeros((nv.value, 3), np.float32)
+    oN = np.zeros((nv.value, 3), np.float32)
+    oI = np.zeros(ni.value, np.int32)
+    L.pb2h_loop_subdivide(n_levels, len(indices), ptr(indices), len(P), ptr(P), C.byref(nv), C.byref(ni), ptr(oP), ptr(oN), ptr(oI))
+    return oP, oN, oI

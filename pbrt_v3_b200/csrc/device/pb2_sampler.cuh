@@ -1,0 +1,189 @@
+// Halton sampler and sampling routines, evaluated per (pixel, sample number, dimension) in
+// registers: the reference's GlobalSampler is stateless apart from its dimension counter
+// (src/core/sampler.cpp:136-195), which makes it a pure function a GPU thread can call.
+//
+//   RadicalInverse / ScrambledRadicalInverse   src/core/lowdiscrepancy.cpp:389-427, 2506
+//   InverseRadicalInverse                      src/core/lowdiscrepancy.h:83-91
+//   HaltonSampler index / SampleDimension      src/samplers/halton.cpp:96-127
+//   ConcentricSampleDisk, UniformSampleTriangle, CosineSampleHemisphere, PowerHeuristic,
+//   Distribution1D::SampleDiscrete             src/core/sampling.{h,cpp}
+#ifndef PB2_SAMPLER_CUH
+#define PB2_SAMPLER_CUH
+
+#include "pb2_math.cuh"
+
+namespace pb2 {
+
+constexpr int kMaxHaltonDims = 1000;   // PrimeTableSize (lowdiscrepancy.h:52)
+constexpr int kMaxResolution = 128;    // halton.cpp:41
+
+struct DHalton {
+    int baseScales[2], baseExponents[2];
+    int sampleStride;
+    int multInverse[2];
+    int sampleAtPixelCenter;
+    int samplesPerPixel;
+    const uint16_t *perms;      // radicalInversePermutations
+    const int32_t *primes;      // Primes[kMaxHaltonDims]
+    const int32_t *primeSums;   // PrimeSums[kMaxHaltonDims]
+};
+
+PB2_HD uint64_t reverseBits64(uint64_t n) {
+#if defined(__CUDA_ARCH__)
+    return __brevll(n);
+#else
+    uint64_t r = 0;
+    for (int i = 0; i < 64; ++i) { r = (r << 1) | (n & 1); n >>= 1; }
+    return r;
+#endif
+}
+
+// RadicalInverseSpecialized<base> / ScrambledRadicalInverseSpecialized<base> with a run-time base.
+// The digit loop divides a 32-bit value whenever the index fits (it does for every film size and
+// sample count in scope); the accumulators keep the reference's types (uint64 digits, float scale).
+PB2_HD float radicalInverseBase(uint32_t base, uint64_t a, const uint16_t *perm) {
+    const float invBase = 1.f / (float)base;
+    uint64_t reversedDigits = 0;
+    float invBaseN = 1;
+    if (a >> 32) {
+        while (a >> 32) {
+            uint64_t next = a / base;
+            uint64_t digit = a - next * base;
+            reversedDigits = reversedDigits * base + (perm ? (uint64_t)perm[digit] : digit);
+            invBaseN *= invBase;
+            a = next;
+        }
+    }
+    uint32_t a32 = (uint32_t)a;
+    while (a32) {
+        uint32_t next = a32 / base;
+        uint32_t digit = a32 - next * base;
+        reversedDigits = reversedDigits * base + (perm ? (uint32_t)perm[digit] : digit);
+        invBaseN *= invBase;
+        a32 = next;
+    }
+    if (perm) {
+        // lowdiscrepancy.cpp:420-423: closed form for the infinite tail of permuted zero digits
+        return pmin(invBaseN * ((float)reversedDigits + invBase * perm[0] / (1 - invBase)), kOneMinusEpsilon);
+    }
+    return pmin((float)reversedDigits * invBaseN, kOneMinusEpsilon);
+}
+
+// RadicalInverse(baseIndex, a), lowdiscrepancy.cpp:427-
+PB2_HD float radicalInverse(const DHalton &h, int baseIndex, uint64_t a) {
+    if (baseIndex == 0) return (float)((double)reverseBits64(a) * 0x1p-64);
+    return radicalInverseBase((uint32_t)h.primes[baseIndex], a, nullptr);
+}
+
+template <int base>
+PB2_HD uint64_t inverseRadicalInverse(uint64_t inverse, int nDigits) {
+    uint64_t index = 0;
+    for (int i = 0; i < nDigits; ++i) {
+        uint64_t digit = inverse % base;
+        inverse /= base;
+        index = index * base + digit;
+    }
+    return index;
+}
+
+PB2_HD int modPos(int a, int b) {
+    int r = a - (a / b) * b;
+    return (r < 0) ? r + b : r;
+}
+
+// HaltonSampler::GetIndexForSample (halton.cpp:96-116)
+PB2_HD int64_t haltonIndex(const DHalton &h, int px, int py, int64_t sampleNum) {
+    int64_t offset = 0;
+    if (h.sampleStride > 1) {
+        int pm0 = modPos(px, kMaxResolution), pm1 = modPos(py, kMaxResolution);
+        uint64_t d0 = inverseRadicalInverse<2>((uint64_t)pm0, h.baseExponents[0]);
+        uint64_t d1 = inverseRadicalInverse<3>((uint64_t)pm1, h.baseExponents[1]);
+        offset += (int64_t)(d0 * (uint64_t)(h.sampleStride / h.baseScales[0]) * (uint64_t)h.multInverse[0]);
+        offset += (int64_t)(d1 * (uint64_t)(h.sampleStride / h.baseScales[1]) * (uint64_t)h.multInverse[1]);
+        offset %= h.sampleStride;
+    }
+    return offset + sampleNum * h.sampleStride;
+}
+
+// HaltonSampler::SampleDimension (halton.cpp:118-127)
+PB2_HD float haltonSample(const DHalton &h, int64_t index, int dim) {
+    if (h.sampleAtPixelCenter && (dim == 0 || dim == 1)) return 0.5f;
+    if (dim == 0) return (float)((double)reverseBits64((uint64_t)(index >> h.baseExponents[0])) * 0x1p-64);
+    if (dim == 1) return radicalInverseBase(3u, (uint64_t)(index / h.baseScales[1]), nullptr);
+    return radicalInverseBase((uint32_t)h.primes[dim], (uint64_t)index, h.perms + h.primeSums[dim]);
+}
+
+// The GlobalSampler's dimension counter (sampler.cpp:178-195; PathIntegrator requests no sample
+// arrays, so arrayStartDim == arrayEndDim and no dimension is ever skipped).
+struct DSampler {
+    int64_t index;
+    int dim;
+};
+PB2_HD float get1D(const DHalton &h, DSampler &s) { return haltonSample(h, s.index, s.dim++); }
+PB2_HD V2 get2D(const DHalton &h, DSampler &s) {
+    V2 p = mk2(haltonSample(h, s.index, s.dim), haltonSample(h, s.index, s.dim + 1));
+    s.dim += 2;
+    return p;
+}
+
+// sampling.cpp:113-130
+PB2_HD V2 concentricSampleDisk(V2 u) {
+    float ox = 2.f * u.x - 1, oy = 2.f * u.y - 1;
+    if (ox == 0 && oy == 0) return mk2(0, 0);
+    float theta, r;
+    if (fabsf(ox) > fabsf(oy)) {
+        r = ox;
+        theta = kPiOver4 * (oy / ox);
+    } else {
+        r = oy;
+        theta = kPiOver2 - kPiOver4 * (ox / oy);
+    }
+    return mk2(r * cosf(theta), r * sinf(theta));
+}
+// sampling.h:159-163
+PB2_HD V3 cosineSampleHemisphere(V2 u) {
+    V2 d = concentricSampleDisk(u);
+    float z = sqrtf(pmax(0.f, 1 - d.x * d.x - d.y * d.y));
+    return mk3(d.x, d.y, z);
+}
+// sampling.cpp:154-157
+PB2_HD V2 uniformSampleTriangle(V2 u) {
+    float su0 = sqrtf(u.x);
+    return mk2(1 - su0, u.y * su0);
+}
+// sampling.cpp:93-98
+PB2_HD V3 uniformSampleSphere(V2 u) {
+    float z = 1 - 2 * u.x;
+    float r = sqrtf(pmax(0.f, 1.f - z * z));
+    float phi = 2 * kPi * u.y;
+    return mk3(r * cosf(phi), r * sinf(phi), z);
+}
+// sampling.h:171-174 with nf = ng = 1
+PB2_HD float powerHeuristic(float fPdf, float gPdf) {
+    float f = 1 * fPdf, g = 1 * gPdf;
+    return (f * f) / (f * f + g * g);
+}
+
+// Distribution1D::SampleDiscrete (sampling.h:90-100) over a record [func(n) | cdf(n+1) | funcInt]
+PB2_HD int sampleDiscrete(const float *rec, int n, float u, float *pdf) {
+    const float *func = rec, *cdf = rec + n;
+    float funcInt = rec[2 * n + 1];
+    // FindInterval(size = n+1, cdf[i] <= u), pbrt.h:403-415
+    int first = 0, len = n + 1;
+    while (len > 0) {
+        int half = len >> 1, middle = first + half;
+        if (cdf[middle] <= u) {
+            first = middle + 1;
+            len -= half + 1;
+        } else
+            len = half;
+    }
+    int offset = first - 1;
+    if (offset < 0) offset = 0;
+    if (offset > n - 1) offset = n - 1;
+    *pdf = (funcInt > 0) ? func[offset] / (funcInt * n) : 0;
+    return offset;
+}
+
+}  // namespace pb2
+#endif

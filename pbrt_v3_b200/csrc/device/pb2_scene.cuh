@@ -1,0 +1,274 @@
+// Device-resident scene layout and the ray/box, ray/triangle and BVH traversal code.
+//
+// HBM layout (all arrays are uploaded once per scene and read-only during rendering):
+//   nodes      pb2_bvh_node[n_nodes], 32 B each, byte-for-byte the reference's LinearBVHNode
+//              (src/accelerators/bvh.cpp:95-104); a node is fetched as two 16-B vector loads.
+//   leafPrims  one 48-B record per primitive IN BVH ORDER (= BVHAccel::primitives order):
+//              float4 a = (p0.xyz, primNumber), b = (p1.xyz, flags), c = (p2.xyz, sphereIndex);
+//              triangle vertices are pre-gathered through the index buffer so a leaf test is three
+//              16-B loads from consecutive addresses instead of the reference's
+//              primitive -> shape -> mesh -> index -> vertex pointer chase.
+//   everything else (P/N/UV/indices, per-primitive material and light ids, materials, lights,
+//   light-distribution tables, Halton permutations) is only touched at shading time.
+#ifndef PB2_SCENE_CUH
+#define PB2_SCENE_CUH
+
+#include "pb2.h"
+#include "pb2_math.cuh"
+
+namespace pb2 {
+
+enum : uint32_t {
+    LEAF_SPHERE = 1u,         // record describes a sphere, not a triangle
+    LEAF_DEGENERATE = 2u,     // Triangle::Intersect rejects every hit (triangle.cpp:308-314); IntersectP does not
+};
+
+struct DLightDist {
+    int strategy;             // PB2_LIGHTDIST_*
+    int nVoxels[3];
+    V3 boundsMin, boundsMax;  // Scene::WorldBound()
+    const float *table;       // uniform/power: one record; spatial: one record per voxel
+    int stride;               // floats per record: nLights func, nLights+1 cdf, 1 funcInt
+};
+
+struct DScene {
+    const float4 *nodes;
+    const float4 *leafPrims;
+    int64_t nNodes, nPrims, nTris;
+    const float *P, *N, *UV, *S;
+    const int32_t *triIndex, *triMesh;
+    const pb2_mesh *meshes;
+    const pb2_sphere *spheres;
+    const uint8_t *primType;
+    const int32_t *primIndex, *primMaterial, *primLight;
+    const pb2_material *materials;
+    const pb2_light *lights;
+    int nLights;
+    DLightDist lightDist;
+};
+
+struct DRay {
+    V3 o, d;
+    float tMax;
+};
+
+// Result of a closest-hit query: enough to rebuild the reference's SurfaceInteraction lazily.
+struct DHit {
+    int leaf;       // index into leafPrims (BVH order), -1 = miss
+    float b0, b1, b2;
+};
+
+#ifdef PB2_COUNTERS
+struct DCounters { unsigned long long nodes, prims; };
+#define PB2_COUNT_NODE(c) ((c)->nodes++)
+#define PB2_COUNT_PRIM(c) ((c)->prims++)
+#else
+struct DCounters { };
+#define PB2_COUNT_NODE(c) ((void)0)
+#define PB2_COUNT_PRIM(c) ((void)0)
+#endif
+
+// Per-ray constants of the watertight test (triangle.cpp:206-222) and of the slab test
+// (bvh.cpp:666-667), computed once per ray instead of once per primitive.
+struct DRaySetup {
+    V3 o;
+    V3 invDir;
+    int neg0, neg1, neg2;
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+};
+
+PB2_HD float permuted(V3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+
+PB2_HD DRaySetup setupRay(V3 o, V3 d) {
+    DRaySetup s;
+    s.o = o;
+    s.invDir = mk3(1 / d.x, 1 / d.y, 1 / d.z);
+    s.neg0 = s.invDir.x < 0;
+    s.neg1 = s.invDir.y < 0;
+    s.neg2 = s.invDir.z < 0;
+    V3 ad = vabs(d);
+    // MaxDimension (geometry.h:998-1001)
+    s.kz = (ad.x > ad.y) ? ((ad.x > ad.z) ? 0 : 2) : ((ad.y > ad.z) ? 1 : 2);
+    s.kx = s.kz + 1;
+    if (s.kx == 3) s.kx = 0;
+    s.ky = s.kx + 1;
+    if (s.ky == 3) s.ky = 0;
+    float dx = permuted(d, s.kx), dy = permuted(d, s.ky), dz = permuted(d, s.kz);
+    s.Sx = -dx / dz;
+    s.Sy = -dy / dz;
+    s.Sz = 1.f / dz;
+    return s;
+}
+
+// Bounds3::IntersectP(ray, invDir, dirIsNeg), geometry.h:1412-1438.
+PB2_HD bool slabTest(float4 n0, float4 n1, const DRaySetup &r, float rayTMax) {
+    // n0 = (min.x, min.y, min.z, max.x), n1 = (max.y, max.z, offset, meta)
+    float bx0 = r.neg0 ? n0.w : n0.x, bx1 = r.neg0 ? n0.x : n0.w;
+    float by0 = r.neg1 ? n1.x : n0.y, by1 = r.neg1 ? n0.y : n1.x;
+    float bz0 = r.neg2 ? n1.y : n0.z, bz1 = r.neg2 ? n0.z : n1.y;
+    float tMin = (bx0 - r.o.x) * r.invDir.x;
+    float tMax = (bx1 - r.o.x) * r.invDir.x;
+    float tyMin = (by0 - r.o.y) * r.invDir.y;
+    float tyMax = (by1 - r.o.y) * r.invDir.y;
+    tMax *= kSlabScale;
+    tyMax *= kSlabScale;
+    if (tMin > tyMax || tyMin > tMax) return false;
+    if (tyMin > tMin) tMin = tyMin;
+    if (tyMax < tMax) tMax = tyMax;
+    float tzMin = (bz0 - r.o.z) * r.invDir.z;
+    float tzMax = (bz1 - r.o.z) * r.invDir.z;
+    tzMax *= kSlabScale;
+    if (tMin > tzMax || tzMin > tMax) return false;
+    if (tzMin > tMin) tMin = tzMin;
+    if (tzMax < tMax) tMax = tzMax;
+    return (tMin < rayTMax) && (tMax > 0);
+}
+
+// The geometric part shared by Triangle::Intersect and IntersectP (triangle.cpp:197-291 / 435-527):
+// translate, permute, shear, edge functions (double fallback on exact zeros), scaled-t range test,
+// conservative t > deltaT test.  Returns true and t,b0,b1,b2 when the ray hits within (0, rayTMax).
+PB2_HD bool triangleTest(V3 p0, V3 p1, V3 p2, const DRaySetup &r, float rayTMax, float *tOut, float *b0Out,
+                         float *b1Out, float *b2Out) {
+    V3 q0 = p0 - r.o, q1 = p1 - r.o, q2 = p2 - r.o;
+    float p0x = permuted(q0, r.kx), p0y = permuted(q0, r.ky), p0z = permuted(q0, r.kz);
+    float p1x = permuted(q1, r.kx), p1y = permuted(q1, r.ky), p1z = permuted(q1, r.kz);
+    float p2x = permuted(q2, r.kx), p2y = permuted(q2, r.ky), p2z = permuted(q2, r.kz);
+    p0x += r.Sx * p0z;
+    p0y += r.Sy * p0z;
+    p1x += r.Sx * p1z;
+    p1y += r.Sy * p1z;
+    p2x += r.Sx * p2z;
+    p2y += r.Sy * p2z;
+    float e0 = p1x * p2y - p1y * p2x;
+    float e1 = p2x * p0y - p2y * p0x;
+    float e2 = p0x * p1y - p0y * p1x;
+    if (e0 == 0.0f || e1 == 0.0f || e2 == 0.0f) {
+        double p2txp1ty = (double)p2x * (double)p1y;
+        double p2typ1tx = (double)p2y * (double)p1x;
+        e0 = (float)(p2typ1tx - p2txp1ty);
+        double p0txp2ty = (double)p0x * (double)p2y;
+        double p0typ2tx = (double)p0y * (double)p2x;
+        e1 = (float)(p0typ2tx - p0txp2ty);
+        double p1txp0ty = (double)p1x * (double)p0y;
+        double p1typ0tx = (double)p1y * (double)p0x;
+        e2 = (float)(p1typ0tx - p1txp0ty);
+    }
+    if ((e0 < 0 || e1 < 0 || e2 < 0) && (e0 > 0 || e1 > 0 || e2 > 0)) return false;
+    float det = e0 + e1 + e2;
+    if (det == 0) return false;
+    p0z *= r.Sz;
+    p1z *= r.Sz;
+    p2z *= r.Sz;
+    float tScaled = e0 * p0z + e1 * p1z + e2 * p2z;
+    if (det < 0 && (tScaled >= 0 || tScaled < rayTMax * det)) return false;
+    else if (det > 0 && (tScaled <= 0 || tScaled > rayTMax * det)) return false;
+    float invDet = 1 / det;
+    float b0 = e0 * invDet, b1 = e1 * invDet, b2 = e2 * invDet;
+    float t = tScaled * invDet;
+    float maxZt = maxComponent(vabs(mk3(p0z, p1z, p2z)));
+    float deltaZ = kGamma3 * maxZt;
+    float maxXt = maxComponent(vabs(mk3(p0x, p1x, p2x)));
+    float maxYt = maxComponent(vabs(mk3(p0y, p1y, p2y)));
+    float deltaX = kGamma5 * (maxXt + maxZt);
+    float deltaY = kGamma5 * (maxYt + maxZt);
+    float deltaE = 2 * (kGamma2 * maxXt * maxYt + deltaY * maxXt + deltaX * maxYt);
+    float maxE = maxComponent(vabs(mk3(e0, e1, e2)));
+    float deltaT = 3 * (kGamma3 * maxE * maxZt + deltaE * maxZt + deltaZ * maxE) * fabsf(invDet);
+    if (t <= deltaT) return false;
+    *tOut = t;
+    *b0Out = b0;
+    *b1Out = b1;
+    *b2Out = b2;
+    return true;
+}
+
+PB2_HD float4 ldg4(const float4 *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+PB2_HD int asInt(float f) { return (int)floatBits(f); }
+
+struct SphereHit;  // pb2_sphere.cuh
+PB2_HD bool sphereLeafTest(const DScene &sc, int sphereIndex, const DRay &ray, float rayTMax, float *tHit, float *phi);
+
+// BVHAccel::Intersect (ANY=false, bvh.cpp:662-700) and IntersectP (ANY=true, bvh.cpp:702-738):
+// depth-first, near child first by dirIsNeg[axis], explicit stack of far children, every primitive
+// of a reached leaf tested, closest hit shrinks tMax.  Node visit order and the set of primitive
+// tests are exactly the reference's, so device counters equal the instrumented reference's.
+template <bool ANY>
+PB2_HD bool traverse(const DScene &sc, const DRay &ray, float *tMaxInOut, DHit *hit, DCounters *ctr) {
+    (void)ctr;
+    if (sc.nNodes == 0) return false;
+    DRaySetup rs = setupRay(ray.o, ray.d);
+    float tMax = *tMaxInOut;
+    bool found = false;
+    int stack[64];
+    int sp = 0, cur = 0;
+    while (true) {
+        float4 n0 = ldg4(&sc.nodes[2 * (size_t)cur]);
+        float4 n1 = ldg4(&sc.nodes[2 * (size_t)cur + 1]);
+        PB2_COUNT_NODE(ctr);
+        bool descend = false;
+        if (slabTest(n0, n1, rs, tMax)) {
+            uint32_t meta = floatBits(n1.w);
+            int nPrims = (int)(meta & 0xffffu);
+            if (nPrims > 0) {
+                int first = asInt(n1.z);
+                for (int i = 0; i < nPrims; ++i) {
+                    const float4 *rec = &sc.leafPrims[3 * (size_t)(first + i)];
+                    float4 a = ldg4(rec), b = ldg4(rec + 1), c = ldg4(rec + 2);
+                    PB2_COUNT_PRIM(ctr);
+                    uint32_t flags = floatBits(b.w);
+                    if (flags & LEAF_SPHERE) {
+                        float t, phi;
+                        if (sphereLeafTest(sc, asInt(c.w), ray, tMax, &t, &phi)) {
+                            if (ANY) return true;
+                            tMax = t;
+                            found = true;
+                            hit->leaf = first + i;
+                            hit->b0 = phi;
+                            hit->b1 = hit->b2 = 0;
+                        }
+                        continue;
+                    }
+                    float t, b0, b1, b2;
+                    if (triangleTest(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), rs, tMax, &t, &b0, &b1, &b2)) {
+                        if (ANY) return true;
+                        if (flags & LEAF_DEGENERATE) continue;
+                        tMax = t;
+                        found = true;
+                        hit->leaf = first + i;
+                        hit->b0 = b0;
+                        hit->b1 = b1;
+                        hit->b2 = b2;
+                    }
+                }
+            } else {
+                int axis = (int)((meta >> 16) & 0xffu);
+                int isNeg = axis == 0 ? rs.neg0 : (axis == 1 ? rs.neg1 : rs.neg2);
+                int second = asInt(n1.z);
+                if (isNeg) {
+                    stack[sp++] = cur + 1;
+                    cur = second;
+                } else {
+                    stack[sp++] = second;
+                    cur = cur + 1;
+                }
+                descend = true;
+            }
+        }
+        if (!descend) {
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+    *tMaxInOut = tMax;
+    return found;
+}
+
+}  // namespace pb2
+#endif

@@ -1,0 +1,922 @@
+// Everything that happens at a path vertex, per lane, in registers: rebuilding the
+// SurfaceInteraction of the hit, the matte/plastic BSDFs, diffuse area lights, the light-sampling
+// distributions, one-light next-event estimation with MIS, BSDF sampling, Russian roulette — and the
+// perspective camera that starts a path.  Restates, on flat POD records instead of arena-allocated
+// polymorphic objects:
+//
+//   Triangle::Intersect (post-hit part) / Sample / Area   src/shapes/triangle.cpp:293-424, 574-607
+//   Shape::Sample(ref) / Pdf(ref,wi)                       src/core/shape.cpp:61-95
+//   SurfaceInteraction, SetShadingGeometry, SpawnRay[To]   src/core/interaction.{h,cpp}
+//   BSDF, LambertianReflection, OrenNayar, MicrofacetReflection, FrDielectric
+//                                                          src/core/reflection.{h,cpp}
+//   TrowbridgeReitzDistribution                            src/core/microfacet.{h,cpp}
+//   MatteMaterial / PlasticMaterial                        src/materials/matte.cpp:45-62, plastic.cpp:45-70
+//   DiffuseAreaLight                                       src/lights/diffuse.{h,cpp}
+//   Uniform/Power/SpatialLightDistribution                 src/core/lightdistrib.cpp
+//   UniformSampleOneLight / EstimateDirect                 src/core/integrator.cpp:85-215
+//   PathIntegrator::Li                                     src/integrators/path.cpp:64-188
+//   PerspectiveCamera::GenerateRayDifferential             src/cameras/perspective.cpp:95-144
+#ifndef PB2_SHADE_CUH
+#define PB2_SHADE_CUH
+
+#include "pb2_sampler.cuh"
+#include "pb2_scene.cuh"
+
+namespace pb2 {
+
+// ---------------------------------------------------------------- interactions
+struct DInteraction {   // the part of (Surface)Interaction that Li and EstimateDirect read
+    V3 p, pError, n;    // n == 0 marks a non-surface point (Interaction::IsSurfaceInteraction)
+    V3 wo;              // Normalize(-ray.d) (interaction.h:61)
+    V3 ns;              // shading.n
+    V3 dpdus;           // shading.dpdu
+    V2 uv;
+    int prim;           // scene-order primitive number
+};
+
+struct TriVerts { V3 p0, p1, p2; };
+
+PB2_HD V3 ld3(const float *a, int64_t i) { return mk3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+
+PB2_HD TriVerts triVerts(const DScene &sc, int tri) {
+    TriVerts t;
+    t.p0 = ld3(sc.P, sc.triIndex[3 * (int64_t)tri]);
+    t.p1 = ld3(sc.P, sc.triIndex[3 * (int64_t)tri + 1]);
+    t.p2 = ld3(sc.P, sc.triIndex[3 * (int64_t)tri + 2]);
+    return t;
+}
+
+// Triangle::GetUVs (triangle.h:98-108)
+PB2_HD void triUVs(const DScene &sc, int tri, const pb2_mesh &mesh, V2 uv[3]) {
+    if (mesh.has_uv) {
+        for (int k = 0; k < 3; ++k) {
+            int64_t v = sc.triIndex[3 * (int64_t)tri + k];
+            uv[k] = mk2(sc.UV[2 * v], sc.UV[2 * v + 1]);
+        }
+    } else {
+        uv[0] = mk2(0, 0);
+        uv[1] = mk2(1, 0);
+        uv[2] = mk2(1, 1);
+    }
+}
+
+// dpdu/dpdv of a triangle (triangle.cpp:293-317).  Returns false when the triangle is degenerate
+// (the reference then rejects the hit).
+PB2_HD bool triPartials(V3 p0, V3 p1, V3 p2, const V2 uv[3], V3 *dpdu, V3 *dpdv) {
+    float duv02x = uv[0].x - uv[2].x, duv02y = uv[0].y - uv[2].y;
+    float duv12x = uv[1].x - uv[2].x, duv12y = uv[1].y - uv[2].y;
+    V3 dp02 = p0 - p2, dp12 = p1 - p2;
+    float determinant = duv02x * duv12y - duv02y * duv12x;
+    bool degenerateUV = (double)fabsf(determinant) < 1e-8;
+    *dpdu = mk3(0, 0, 0);
+    *dpdv = mk3(0, 0, 0);
+    if (!degenerateUV) {
+        float invdet = 1 / determinant;
+        *dpdu = (duv12y * dp02 - duv02y * dp12) * invdet;
+        *dpdv = (-duv12x * dp02 + duv02x * dp12) * invdet;
+    }
+    if (degenerateUV || lengthSquared(cross(*dpdu, *dpdv)) == 0) {
+        V3 ng = cross(p2 - p0, p1 - p0);
+        if (lengthSquared(ng) == 0) return false;
+        coordinateSystem(normalize(ng), dpdu, dpdv);
+    }
+    return true;
+}
+
+// The SurfaceInteraction Triangle::Intersect fills in for a hit with barycentrics (b0,b1,b2)
+// (triangle.cpp:319-419).
+PB2_HD DInteraction triangleInteraction(const DScene &sc, int prim, float b0, float b1, float b2, V3 rayD) {
+    DInteraction it;
+    int tri = sc.primIndex[prim];
+    const pb2_mesh mesh = sc.meshes[sc.triMesh[tri]];
+    TriVerts tv = triVerts(sc, tri);
+    V2 uv[3];
+    triUVs(sc, tri, mesh, uv);
+    V3 dpdu, dpdv;
+    triPartials(tv.p0, tv.p1, tv.p2, uv, &dpdu, &dpdv);
+    float xAbsSum = (fabsf(b0 * tv.p0.x) + fabsf(b1 * tv.p1.x) + fabsf(b2 * tv.p2.x));
+    float yAbsSum = (fabsf(b0 * tv.p0.y) + fabsf(b1 * tv.p1.y) + fabsf(b2 * tv.p2.y));
+    float zAbsSum = (fabsf(b0 * tv.p0.z) + fabsf(b1 * tv.p1.z) + fabsf(b2 * tv.p2.z));
+    it.pError = kGamma7 * mk3(xAbsSum, yAbsSum, zAbsSum);
+    it.p = b0 * tv.p0 + b1 * tv.p1 + b2 * tv.p2;
+    it.uv = mk2(b0 * uv[0].x + b1 * uv[1].x + b2 * uv[2].x, b0 * uv[0].y + b1 * uv[1].y + b2 * uv[2].y);
+    it.wo = normalize(-rayD);
+    it.prim = prim;
+    V3 dp02 = tv.p0 - tv.p2, dp12 = tv.p1 - tv.p2;
+    it.n = it.ns = normalize(cross(dp02, dp12));
+    if ((mesh.reverse_orientation != 0) ^ (mesh.transform_swaps_handedness != 0)) it.n = it.ns = -it.n;
+    it.dpdus = dpdu;
+    if (mesh.has_n || mesh.has_s) {
+        int64_t v0 = sc.triIndex[3 * (int64_t)tri], v1 = sc.triIndex[3 * (int64_t)tri + 1], v2 = sc.triIndex[3 * (int64_t)tri + 2];
+        V3 ns;
+        if (mesh.has_n) {
+            ns = (b0 * ld3(sc.N, v0) + b1 * ld3(sc.N, v1) + b2 * ld3(sc.N, v2));
+            if (lengthSquared(ns) > 0) ns = normalize(ns);
+            else ns = it.n;
+        } else
+            ns = it.n;
+        V3 ss;
+        if (mesh.has_s) {
+            ss = (b0 * ld3(sc.S, v0) + b1 * ld3(sc.S, v1) + b2 * ld3(sc.S, v2));
+            if (lengthSquared(ss) > 0) ss = normalize(ss);
+            else ss = normalize(dpdu);
+        } else
+            ss = normalize(dpdu);
+        V3 ts = cross(ss, ns);
+        if (lengthSquared(ts) > 0.f) {
+            ts = normalize(ts);
+            ss = cross(ts, ns);
+        } else
+            coordinateSystem(ns, &ss, &ts);
+        if (mesh.reverse_orientation) ts = -ts;
+        // SetShadingGeometry(ss, ts, dndu, dndv, orientationIsAuthoritative = true), interaction.cpp:73-90
+        it.ns = normalize(cross(ss, ts));
+        it.n = faceforward(it.n, it.ns);
+        it.dpdus = ss;
+    }
+    return it;
+}
+
+}  // namespace pb2
+
+#include "pb2_sphere.cuh"
+
+namespace pb2 {
+
+PB2_HD DInteraction hitInteraction(const DScene &sc, const DHit &hit, const DRay &ray, float tHit) {
+    float4 a = ldg4(&sc.leafPrims[3 * (size_t)hit.leaf]);
+    float4 b = ldg4(&sc.leafPrims[3 * (size_t)hit.leaf + 1]);
+    int prim = asInt(a.w);
+    if (floatBits(b.w) & LEAF_SPHERE) return sphereInteraction(sc, prim, ray, tHit, hit.b0);
+    return triangleInteraction(sc, prim, hit.b0, hit.b1, hit.b2, ray.d);
+}
+
+// Interaction::SpawnRay (interaction.h:64-67)
+PB2_HD DRay spawnRay(const DInteraction &it, V3 d) {
+    DRay r;
+    r.o = offsetRayOrigin(it.p, it.pError, it.n, d);
+    r.d = d;
+    r.tMax = PB2_INFINITY;
+    return r;
+}
+// Interaction::SpawnRayTo(const Interaction&) (interaction.h:73-78)
+PB2_HD DRay spawnRayTo(const DInteraction &from, V3 toP, V3 toPError, V3 toN) {
+    DRay r;
+    r.o = offsetRayOrigin(from.p, from.pError, from.n, toP - from.p);
+    V3 target = offsetRayOrigin(toP, toPError, toN, r.o - toP);
+    r.d = target - r.o;
+    r.tMax = 1 - kShadowEpsilon;
+    return r;
+}
+
+// ---------------------------------------------------------------- BSDF
+struct DBsdf {
+    V3 ns, ng, ss, ts;     // reflection.h:167-172
+    int nLobes;            // 0, 1 or 2
+    int diffuseKind;       // 0 none, 1 Lambertian, 2 Oren-Nayar
+    V3 R;                  // diffuse reflectance
+    float A, B;            // Oren-Nayar terms
+    int hasMicrofacet;
+    V3 Ks;
+    float alpha;           // TrowbridgeReitz alphax == alphay
+};
+
+PB2_HD V3 clampSpectrum(const float c[3]) {  // Spectrum::Clamp(0, Infinity), spectrum.h:126-132
+    return mk3(clampf(c[0], 0.f, PB2_INFINITY), clampf(c[1], 0.f, PB2_INFINITY), clampf(c[2], 0.f, PB2_INFINITY));
+}
+
+// TrowbridgeReitzDistribution::RoughnessToAlpha (microfacet.h:127-132)
+PB2_HD float roughnessToAlpha(float roughness) {
+    roughness = pmax(roughness, (float)1e-3);
+    float x = logf(roughness);
+    return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
+}
+
+// Material::ComputeScatteringFunctions for matte (matte.cpp:45-62) and plastic (plastic.cpp:45-70).
+// Returns false when the primitive has no material (null BSDF: the path skips the surface).
+PB2_HD bool makeBsdf(const DScene &sc, const DInteraction &it, DBsdf *bsdf) {
+    int m = sc.primMaterial[it.prim];
+    if (m < 0) return false;
+    const pb2_material mat = sc.materials[m];
+    if (mat.type == PB2_MAT_NONE) return false;
+    bsdf->ns = it.ns;
+    bsdf->ng = it.n;
+    bsdf->ss = normalize(it.dpdus);
+    bsdf->ts = cross(bsdf->ns, bsdf->ss);
+    bsdf->nLobes = 0;
+    bsdf->diffuseKind = 0;
+    bsdf->hasMicrofacet = 0;
+    bsdf->R = mk3(0, 0, 0);
+    bsdf->Ks = mk3(0, 0, 0);
+    bsdf->A = bsdf->B = 0;
+    bsdf->alpha = 0;
+    V3 kd = clampSpectrum(mat.kd);
+    if (mat.type == PB2_MAT_MATTE) {
+        float sig = clampf(mat.sigma, 0.f, 90.f);
+        if (!isBlack(kd)) {
+            bsdf->R = kd;
+            if (sig == 0)
+                bsdf->diffuseKind = 1;
+            else {
+                bsdf->diffuseKind = 2;
+                float sigma = (kPi / 180) * sig;  // Radians()
+                float sigma2 = sigma * sigma;
+                bsdf->A = 1.f - (sigma2 / (2.f * (sigma2 + 0.33f)));
+                bsdf->B = 0.45f * sigma2 / (sigma2 + 0.09f);
+            }
+            bsdf->nLobes = 1;
+        }
+    } else {
+        if (!isBlack(kd)) {
+            bsdf->R = kd;
+            bsdf->diffuseKind = 1;
+            bsdf->nLobes++;
+        }
+        V3 ks = clampSpectrum(mat.ks);
+        if (!isBlack(ks)) {
+            float rough = mat.roughness;
+            if (mat.remap_roughness) rough = roughnessToAlpha(rough);
+            bsdf->Ks = ks;
+            bsdf->alpha = pmax(0.001f, rough);  // microfacet.h:109-113
+            bsdf->hasMicrofacet = 1;
+            bsdf->nLobes++;
+        }
+    }
+    return true;
+}
+
+PB2_HD V3 worldToLocal(const DBsdf &b, V3 v) { return mk3(dot(v, b.ss), dot(v, b.ts), dot(v, b.ns)); }
+PB2_HD V3 localToWorld(const DBsdf &b, V3 v) {
+    return mk3(b.ss.x * v.x + b.ts.x * v.y + b.ns.x * v.z, b.ss.y * v.x + b.ts.y * v.y + b.ns.y * v.z,
+               b.ss.z * v.x + b.ts.z * v.y + b.ns.z * v.z);
+}
+
+// reflection.h:55-86
+PB2_HD float cosTheta(V3 w) { return w.z; }
+PB2_HD float cos2Theta(V3 w) { return w.z * w.z; }
+PB2_HD float absCosTheta(V3 w) { return fabsf(w.z); }
+PB2_HD float sin2Theta(V3 w) { return pmax(0.f, 1.f - cos2Theta(w)); }
+PB2_HD float sinTheta(V3 w) { return sqrtf(sin2Theta(w)); }
+PB2_HD float tanTheta(V3 w) { return sinTheta(w) / cosTheta(w); }
+PB2_HD float tan2Theta(V3 w) { return sin2Theta(w) / cos2Theta(w); }
+PB2_HD float cosPhi(V3 w) { float s = sinTheta(w); return (s == 0) ? 1 : clampf(w.x / s, -1.f, 1.f); }
+PB2_HD float sinPhi(V3 w) { float s = sinTheta(w); return (s == 0) ? 0 : clampf(w.y / s, -1.f, 1.f); }
+PB2_HD float cos2Phi(V3 w) { return cosPhi(w) * cosPhi(w); }
+PB2_HD float sin2Phi(V3 w) { return sinPhi(w) * sinPhi(w); }
+PB2_HD bool sameHemisphere(V3 w, V3 wp) { return w.z * wp.z > 0; }
+
+// FrDielectric(cosThetaI, 1.5, 1) (reflection.cpp:47-68)
+PB2_HD float frDielectric(float cosThetaI, float etaI, float etaT) {
+    cosThetaI = clampf(cosThetaI, -1.f, 1.f);
+    bool entering = cosThetaI > 0.f;
+    if (!entering) {
+        float t = etaI; etaI = etaT; etaT = t;
+        cosThetaI = fabsf(cosThetaI);
+    }
+    float sinThetaI = sqrtf(pmax(0.f, 1 - cosThetaI * cosThetaI));
+    float sinThetaT = etaI / etaT * sinThetaI;
+    if (sinThetaT >= 1) return 1;
+    float cosThetaT = sqrtf(pmax(0.f, 1 - sinThetaT * sinThetaT));
+    float Rparl = ((etaT * cosThetaI) - (etaI * cosThetaT)) / ((etaT * cosThetaI) + (etaI * cosThetaT));
+    float Rperp = ((etaI * cosThetaI) - (etaT * cosThetaT)) / ((etaI * cosThetaI) + (etaT * cosThetaT));
+    return (Rparl * Rparl + Rperp * Rperp) / 2;
+}
+
+// TrowbridgeReitzDistribution (microfacet.cpp:155-184, 338-344)
+PB2_HD float trD(float alpha, V3 wh) {
+    float t2 = tan2Theta(wh);
+    if (isinf(t2)) return 0.;
+    const float cos4Theta = cos2Theta(wh) * cos2Theta(wh);
+    float e = (cos2Phi(wh) / (alpha * alpha) + sin2Phi(wh) / (alpha * alpha)) * t2;
+    return 1 / (kPi * alpha * alpha * cos4Theta * (1 + e) * (1 + e));
+}
+PB2_HD float trLambda(float alpha, V3 w) {
+    float absTanTheta = fabsf(tanTheta(w));
+    if (isinf(absTanTheta)) return 0.;
+    float a = sqrtf(cos2Phi(w) * alpha * alpha + sin2Phi(w) * alpha * alpha);
+    float alpha2Tan2Theta = (a * absTanTheta) * (a * absTanTheta);
+    return (-1 + sqrtf(1.f + alpha2Tan2Theta)) / 2;
+}
+PB2_HD float trG1(float alpha, V3 w) { return 1 / (1 + trLambda(alpha, w)); }
+PB2_HD float trG(float alpha, V3 wo, V3 wi) { return 1 / (1 + trLambda(alpha, wo) + trLambda(alpha, wi)); }
+PB2_HD float trPdf(float alpha, V3 wo, V3 wh) {  // sampleVisibleArea == true
+    return trD(alpha, wh) * trG1(alpha, wo) * absDot(wo, wh) / absCosTheta(wo);
+}
+
+// TrowbridgeReitzSample11 (microfacet.cpp:238-282).  The normal-incidence branch runs in double,
+// as the reference's unqualified sqrt/cos/sin do.
+PB2_HD void trSample11(float cosThetaV, float U1, float U2, float *slope_x, float *slope_y) {
+    if ((double)cosThetaV > .9999) {
+        float r = (float)sqrt((double)(U1 / (1 - U1)));
+        float phi = (float)(6.28318530718 * (double)U2);
+        *slope_x = (float)((double)r * cos((double)phi));
+        *slope_y = (float)((double)r * sin((double)phi));
+        return;
+    }
+    float sinThetaV = sqrtf(pmax(0.f, 1.f - cosThetaV * cosThetaV));
+    float tanThetaV = sinThetaV / cosThetaV;
+    float a = 1 / tanThetaV;
+    float G1 = 2 / (1 + sqrtf(1.f + 1.f / (a * a)));
+    float A = 2 * U1 / G1 - 1;
+    float tmp = 1.f / (A * A - 1.f);
+    if (tmp > 1e10) tmp = 1e10;
+    float B = tanThetaV;
+    float D = sqrtf(pmax((float)(B * B * tmp * tmp - (A * A - B * B) * tmp), 0.f));
+    float slope_x_1 = B * tmp - D;
+    float slope_x_2 = B * tmp + D;
+    *slope_x = (A < 0 || slope_x_2 > 1.f / tanThetaV) ? slope_x_1 : slope_x_2;
+    float S;
+    if (U2 > 0.5f) {
+        S = 1.f;
+        U2 = 2.f * (U2 - .5f);
+    } else {
+        S = -1.f;
+        U2 = 2.f * (.5f - U2);
+    }
+    float z = (U2 * (U2 * (U2 * 0.27385f - 0.73369f) + 0.46341f)) /
+              (U2 * (U2 * (U2 * 0.093073f + 0.309420f) - 1.000000f) + 0.597999f);
+    *slope_y = S * z * sqrtf(1.f + *slope_x * *slope_x);
+}
+// TrowbridgeReitzSample + Sample_wh, visible-area branch (microfacet.cpp:284-336)
+PB2_HD V3 trSampleWh(float alpha, V3 wo, V2 u) {
+    bool flip = wo.z < 0;
+    V3 wi = flip ? -wo : wo;
+    V3 wiStretched = normalize(mk3(alpha * wi.x, alpha * wi.y, wi.z));
+    float slope_x, slope_y;
+    trSample11(cosTheta(wiStretched), u.x, u.y, &slope_x, &slope_y);
+    float tmp = cosPhi(wiStretched) * slope_x - sinPhi(wiStretched) * slope_y;
+    slope_y = sinPhi(wiStretched) * slope_x + cosPhi(wiStretched) * slope_y;
+    slope_x = tmp;
+    slope_x = alpha * slope_x;
+    slope_y = alpha * slope_y;
+    V3 wh = normalize(mk3(-slope_x, -slope_y, 1.f));
+    if (flip) wh = -wh;
+    return wh;
+}
+
+// individual BxDFs (local frame)
+PB2_HD V3 diffuseF(const DBsdf &b, V3 wo, V3 wi) {
+    if (b.diffuseKind == 1) return b.R * kInvPi;
+    // OrenNayar::f (reflection.cpp:197-219)
+    float sinThetaI = sinTheta(wi), sinThetaO = sinTheta(wo);
+    float maxCos = 0;
+    if ((double)sinThetaI > 1e-4 && (double)sinThetaO > 1e-4) {
+        float sinPhiI = sinPhi(wi), cosPhiI = cosPhi(wi);
+        float sinPhiO = sinPhi(wo), cosPhiO = cosPhi(wo);
+        float dCos = cosPhiI * cosPhiO + sinPhiI * sinPhiO;
+        maxCos = pmax(0.f, dCos);
+    }
+    float sinAlpha, tanBeta;
+    if (absCosTheta(wi) > absCosTheta(wo)) {
+        sinAlpha = sinThetaO;
+        tanBeta = sinThetaI / absCosTheta(wi);
+    } else {
+        sinAlpha = sinThetaI;
+        tanBeta = sinThetaO / absCosTheta(wo);
+    }
+    return b.R * kInvPi * (b.A + b.B * maxCos * sinAlpha * tanBeta);
+}
+PB2_HD float diffusePdf(V3 wo, V3 wi) { return sameHemisphere(wo, wi) ? absCosTheta(wi) * kInvPi : 0; }
+
+// MicrofacetReflection::f (reflection.cpp:226-238) with FresnelDielectric(1.5, 1)
+PB2_HD V3 microfacetF(const DBsdf &b, V3 wo, V3 wi) {
+    float cosThetaO = absCosTheta(wo), cosThetaI = absCosTheta(wi);
+    V3 wh = wi + wo;
+    if (cosThetaI == 0 || cosThetaO == 0) return mk3(0, 0, 0);
+    if (wh.x == 0 && wh.y == 0 && wh.z == 0) return mk3(0, 0, 0);
+    wh = normalize(wh);
+    float F = frDielectric(dot(wi, faceforward(wh, mk3(0, 0, 1))), 1.5f, 1.f);
+    // R * D * G * F / (4 cosI cosO): Spectrum*float products left to right, then one division
+    V3 num = b.Ks * trD(b.alpha, wh) * trG(b.alpha, wo, wi) * mk3(F, F, F);
+    float den = (4 * cosThetaI * cosThetaO);
+    return mk3(num.x / den, num.y / den, num.z / den);
+}
+PB2_HD float microfacetPdf(const DBsdf &b, V3 wo, V3 wi) {
+    if (!sameHemisphere(wo, wi)) return 0;
+    V3 wh = normalize(wo + wi);
+    return trPdf(b.alpha, wo, wh) / (4 * dot(wo, wh));
+}
+
+// BSDF::f (reflection.cpp:680-693).  All lobes in scope are reflective and non-specular, so they
+// match both BSDF_ALL and BSDF_ALL & ~BSDF_SPECULAR.
+PB2_HD V3 bsdfF(const DBsdf &b, V3 woW, V3 wiW) {
+    V3 wi = worldToLocal(b, wiW), wo = worldToLocal(b, woW);
+    if (wo.z == 0) return mk3(0, 0, 0);
+    bool reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
+    V3 f = mk3(0, 0, 0);
+    if (reflect) {
+        if (b.diffuseKind) f = f + diffuseF(b, wo, wi);
+        if (b.hasMicrofacet) f = f + microfacetF(b, wo, wi);
+    }
+    return f;
+}
+// BSDF::Pdf (reflection.cpp:781-796)
+PB2_HD float bsdfPdf(const DBsdf &b, V3 woW, V3 wiW) {
+    if (b.nLobes == 0) return 0.f;
+    V3 wo = worldToLocal(b, woW), wi = worldToLocal(b, wiW);
+    if (wo.z == 0) return 0.;
+    float pdf = 0.f;
+    if (b.diffuseKind) pdf += diffusePdf(wo, wi);
+    if (b.hasMicrofacet) pdf += microfacetPdf(b, wo, wi);
+    return pdf / b.nLobes;
+}
+// BSDF::Sample_f (reflection.cpp:714-779).  Returns f; *pdf == 0 means no sample.
+PB2_HD V3 bsdfSampleF(const DBsdf &b, V3 woW, V3 *wiW, V2 u, float *pdf) {
+    *pdf = 0;
+    int matching = b.nLobes;
+    if (matching == 0) return mk3(0, 0, 0);
+    int comp = (int)floorf(u.x * matching);
+    if (comp > matching - 1) comp = matching - 1;
+    // lobe order: diffuse first, then microfacet (plastic.cpp:53-68)
+    bool sampleMicro = b.hasMicrofacet && (comp == matching - 1) && !(b.diffuseKind && comp == 0);
+    V2 uRemapped = mk2(pmin(u.x * matching - comp, kOneMinusEpsilon), u.y);
+    V3 wo = worldToLocal(b, woW), wi;
+    if (wo.z == 0) return mk3(0, 0, 0);
+    V3 f;
+    if (!sampleMicro) {
+        // BxDF::Sample_f (reflection.cpp:383-390)
+        wi = cosineSampleHemisphere(uRemapped);
+        if (wo.z < 0) wi.z *= -1;
+        *pdf = diffusePdf(wo, wi);
+        f = diffuseF(b, wo, wi);
+    } else {
+        // MicrofacetReflection::Sample_f (reflection.cpp:410-423); wo.z == 0 handled above
+        V3 wh = trSampleWh(b.alpha, wo, uRemapped);
+        if (dot(wo, wh) < 0) return mk3(0, 0, 0);
+        wi = -wo + 2 * dot(wo, wh) * wh;  // Reflect
+        if (!sameHemisphere(wo, wi)) return mk3(0, 0, 0);
+        *pdf = trPdf(b.alpha, wo, wh) / (4 * dot(wo, wh));
+        f = microfacetF(b, wo, wi);
+    }
+    if (*pdf == 0) return mk3(0, 0, 0);
+    *wiW = localToWorld(b, wi);
+    if (matching > 1) {
+        if (sampleMicro) *pdf += diffusePdf(wo, wi);
+        else *pdf += microfacetPdf(b, wo, wi);
+        *pdf /= matching;
+    }
+    // non-specular lobes: f is re-evaluated over all matching lobes (reflection.cpp:767-775)
+    bool reflect = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
+    f = mk3(0, 0, 0);
+    if (reflect) {
+        if (b.diffuseKind) f = f + diffuseF(b, wo, wi);
+        if (b.hasMicrofacet) f = f + microfacetF(b, wo, wi);
+    }
+    return f;
+}
+
+// ---------------------------------------------------------------- area lights
+struct DLightSample {
+    V3 p, pError, n;   // pShape
+    V3 wi;
+    V3 Li;
+    float pdf;
+};
+
+// Triangle::Area (triangle.cpp:574-580)
+PB2_HD float triangleArea(const TriVerts &t) { return (float)(0.5 * (double)length(cross(t.p1 - t.p0, t.p2 - t.p0))); }
+
+// DiffuseAreaLight::L (diffuse.h:56-58)
+PB2_HD V3 lightL(const pb2_light &l, V3 n, V3 w) {
+    return (l.two_sided || dot(n, w) > 0) ? mk3(l.L[0], l.L[1], l.L[2]) : mk3(0, 0, 0);
+}
+
+// Sphere::Sample(u, pdf) (sphere.cpp:219-230): uniform over the whole sphere, area measure.
+PB2_HD void sphereSampleArea(const pb2_sphere &s, V2 u, V3 *p, V3 *pError, V3 *n, float *pdf) {
+    M44 o2w = loadM44(s.object_to_world), w2o = loadM44(s.world_to_object);
+    V3 pObj = mk3(0, 0, 0) + s.radius * uniformSampleSphere(u);
+    *n = normalize(xfNormalInv(w2o, pObj));
+    if (s.reverse_orientation) *n = *n * -1.f;
+    pObj = pObj * (s.radius / length(pObj));
+    V3 pObjError = kGamma5 * vabs(pObj);
+    *p = xfPointErrIn(o2w, pObj, pObjError, pError);
+    *pdf = 1 / (s.phi_max * s.radius * (s.z_max - s.z_min));
+}
+
+// DiffuseAreaLight::Sample_Li over Sphere::Sample(ref, u, pdf) (sphere.cpp:232-301)
+PB2_HD DLightSample sampleSphereLight(const DScene &sc, const pb2_light &l, const DInteraction &ref, V2 u) {
+    DLightSample ls;
+    const pb2_sphere s = sc.spheres[sc.primIndex[l.prim]];
+    M44 o2w = loadM44(s.object_to_world);
+    V3 pCenter = xfPoint(o2w, mk3(0, 0, 0));
+    V3 pOrigin = offsetRayOrigin(ref.p, ref.pError, ref.n, pCenter - ref.p);
+    if (lengthSquared(pOrigin - pCenter) <= s.radius * s.radius) {
+        sphereSampleArea(s, u, &ls.p, &ls.pError, &ls.n, &ls.pdf);
+        V3 wi = ls.p - ref.p;
+        if (lengthSquared(wi) == 0)
+            ls.pdf = 0;
+        else {
+            wi = normalize(wi);
+            ls.pdf *= lengthSquared(ref.p - ls.p) / absDot(ls.n, -wi);
+        }
+        if (isinf(ls.pdf)) ls.pdf = 0.f;
+    } else {
+        float dc = length(ref.p - pCenter);
+        float invDc = 1 / dc;
+        V3 wc = (pCenter - ref.p) * invDc;
+        V3 wcX, wcY;
+        coordinateSystem(wc, &wcX, &wcY);
+        float sinThetaMax = s.radius * invDc;
+        float sinThetaMax2 = sinThetaMax * sinThetaMax;
+        float invSinThetaMax = 1 / sinThetaMax;
+        float cosThetaMax = sqrtf(pmax(0.f, 1 - sinThetaMax2));
+        float cosThetaV = (cosThetaMax - 1) * u.x + 1;
+        float sinTheta2 = 1 - cosThetaV * cosThetaV;
+        if (sinThetaMax2 < 0.00068523f) {
+            sinTheta2 = sinThetaMax2 * u.x;
+            cosThetaV = sqrtf(1 - sinTheta2);
+        }
+        float cosAlpha = sinTheta2 * invSinThetaMax +
+                         cosThetaV * sqrtf(pmax(0.f, 1.f - sinTheta2 * invSinThetaMax * invSinThetaMax));
+        float sinAlpha = sqrtf(pmax(0.f, 1.f - cosAlpha * cosAlpha));
+        float phi = u.y * 2 * kPi;
+        // SphericalDirection(sinAlpha, cosAlpha, phi, -wcX, -wcY, -wc) (geometry.h:1461-1466)
+        V3 nWorld = sinAlpha * cosf(phi) * (-wcX) + sinAlpha * sinf(phi) * (-wcY) + cosAlpha * (-wc);
+        V3 pWorld = pCenter + s.radius * nWorld;
+        ls.p = pWorld;
+        ls.pError = kGamma5 * vabs(pWorld);
+        ls.n = nWorld;
+        if (s.reverse_orientation) ls.n = ls.n * -1.f;
+        ls.pdf = 1 / (2 * kPi * (1 - cosThetaMax));
+    }
+    if (ls.pdf == 0 || lengthSquared(ls.p - ref.p) == 0) {
+        ls.pdf = 0;
+        ls.Li = mk3(0, 0, 0);
+        ls.wi = mk3(0, 0, 0);
+        return ls;
+    }
+    ls.wi = normalize(ls.p - ref.p);
+    ls.Li = lightL(l, ls.n, -ls.wi);
+    return ls;
+}
+
+// Sphere::Pdf(ref, wi) (sphere.cpp:303-315); the inside case falls back to Shape::Pdf (shape.cpp:78-95)
+PB2_HD float sphereLightPdf(const DScene &sc, const pb2_light &l, const DInteraction &ref, V3 wi) {
+    const pb2_sphere s = sc.spheres[sc.primIndex[l.prim]];
+    M44 o2w = loadM44(s.object_to_world);
+    V3 pCenter = xfPoint(o2w, mk3(0, 0, 0));
+    V3 pOrigin = offsetRayOrigin(ref.p, ref.pError, ref.n, pCenter - ref.p);
+    if (lengthSquared(pOrigin - pCenter) <= s.radius * s.radius) {
+        DRay ray;
+        ray.o = offsetRayOrigin(ref.p, ref.pError, ref.n, wi);
+        ray.d = wi;
+        ray.tMax = PB2_INFINITY;
+        SphereRayHit h;
+        if (!sphereTest(s, ray, ray.tMax, &h)) return 0;
+        DInteraction li = sphereInteraction(sc, l.prim, ray, h.tHit, h.phi);
+        float pdf = lengthSquared(ref.p - li.p) / (absDot(li.n, -wi) * (s.phi_max * s.radius * (s.z_max - s.z_min)));
+        if (isinf(pdf)) pdf = 0.f;
+        return pdf;
+    }
+    float sinThetaMax2 = s.radius * s.radius / lengthSquared(ref.p - pCenter);
+    float cosThetaMax = sqrtf(pmax(0.f, 1 - sinThetaMax2));
+    return 1 / (2 * kPi * (1 - cosThetaMax));
+}
+
+// DiffuseAreaLight::Sample_Li (diffuse.cpp:68-81) for a triangle shape: Triangle::Sample(u)
+// (triangle.cpp:582-607) + Shape::Sample(ref,u,pdf) (shape.cpp:61-76).
+PB2_HD DLightSample sampleTriangleLight(const DScene &sc, const pb2_light &l, V3 refP, V2 u) {
+    DLightSample s;
+    int tri = sc.primIndex[l.prim];
+    const pb2_mesh mesh = sc.meshes[sc.triMesh[tri]];
+    TriVerts t = triVerts(sc, tri);
+    V2 b = uniformSampleTriangle(u);
+    float b2 = (1 - b.x - b.y);
+    s.p = b.x * t.p0 + b.y * t.p1 + b2 * t.p2;
+    s.n = normalize(cross(t.p1 - t.p0, t.p2 - t.p0));
+    if (mesh.has_n) {
+        int64_t v0 = sc.triIndex[3 * (int64_t)tri], v1 = sc.triIndex[3 * (int64_t)tri + 1], v2 = sc.triIndex[3 * (int64_t)tri + 2];
+        V3 ns = b.x * ld3(sc.N, v0) + b.y * ld3(sc.N, v1) + b2 * ld3(sc.N, v2);
+        s.n = faceforward(s.n, ns);
+    } else if ((mesh.reverse_orientation != 0) ^ (mesh.transform_swaps_handedness != 0))
+        s.n = s.n * -1.f;
+    V3 pAbsSum = vabs(b.x * t.p0) + vabs(b.y * t.p1) + vabs(b2 * t.p2);
+    s.pError = kGamma6 * pAbsSum;
+    s.pdf = 1 / triangleArea(t);
+    // Shape::Sample(ref, u, pdf)
+    V3 wi = s.p - refP;
+    if (lengthSquared(wi) == 0)
+        s.pdf = 0;
+    else {
+        wi = normalize(wi);
+        s.pdf *= lengthSquared(refP - s.p) / absDot(s.n, -wi);
+        if (isinf(s.pdf)) s.pdf = 0.f;
+    }
+    // DiffuseAreaLight::Sample_Li
+    if (s.pdf == 0 || lengthSquared(s.p - refP) == 0) {
+        s.pdf = 0;
+        s.Li = mk3(0, 0, 0);
+        s.wi = mk3(0, 0, 0);
+        return s;
+    }
+    s.wi = normalize(s.p - refP);
+    s.Li = lightL(l, s.n, -s.wi);
+    return s;
+}
+
+PB2_HD DLightSample sampleLight(const DScene &sc, const pb2_light &l, const DInteraction &ref, V2 u) {
+    if (sc.primType[l.prim] == PB2_PRIM_SPHERE) return sampleSphereLight(sc, l, ref, u);
+    return sampleTriangleLight(sc, l, ref.p, u);
+}
+
+// DiffuseAreaLight::Pdf_Li -> Shape::Pdf(ref, wi) (shape.cpp:78-95): re-intersect the light's own
+// shape with the spawned ray and convert the area density to solid angle.
+PB2_HD float lightPdfLi(const DScene &sc, const pb2_light &l, const DInteraction &ref, V3 wi) {
+    if (sc.primType[l.prim] == PB2_PRIM_SPHERE) return sphereLightPdf(sc, l, ref, wi);
+    DRay ray = spawnRay(ref, wi);
+    int tri = sc.primIndex[l.prim];
+    const pb2_mesh mesh = sc.meshes[sc.triMesh[tri]];
+    TriVerts t = triVerts(sc, tri);
+    DRaySetup rs = setupRay(ray.o, ray.d);
+    float tHit, b0, b1, b2;
+    if (!triangleTest(t.p0, t.p1, t.p2, rs, ray.tMax, &tHit, &b0, &b1, &b2)) return 0;
+    V2 uv[3];
+    triUVs(sc, tri, mesh, uv);
+    V3 dpdu, dpdv;
+    if (!triPartials(t.p0, t.p1, t.p2, uv, &dpdu, &dpdv)) return 0;
+    DInteraction li = triangleInteraction(sc, l.prim, b0, b1, b2, ray.d);
+    float pdf = lengthSquared(ref.p - li.p) / (absDot(li.n, -wi) * triangleArea(t));
+    if (isinf(pdf)) pdf = 0.f;
+    return pdf;
+}
+
+// ---------------------------------------------------------------- light distributions
+// LightDistribution::Lookup(p): returns the Distribution1D record for p.
+PB2_HD const float *lightDistLookup(const DLightDist &ld, V3 p) {
+    if (ld.strategy != PB2_LIGHTDIST_SPATIAL) return ld.table;
+    // SpatialLightDistribution::Lookup (lightdistrib.cpp:141-147): Bounds3::Offset, then clamp(int(o*n))
+    V3 o = p - ld.boundsMin;
+    if (ld.boundsMax.x > ld.boundsMin.x) o.x /= ld.boundsMax.x - ld.boundsMin.x;
+    if (ld.boundsMax.y > ld.boundsMin.y) o.y /= ld.boundsMax.y - ld.boundsMin.y;
+    if (ld.boundsMax.z > ld.boundsMin.z) o.z /= ld.boundsMax.z - ld.boundsMin.z;
+    int pi[3];
+    float of[3] = {o.x, o.y, o.z};
+    for (int i = 0; i < 3; ++i) {
+        float v = of[i] * ld.nVoxels[i];
+        int iv = (v != v) ? 0 : (v >= 2147483648.f ? ld.nVoxels[i] - 1 : (v <= -2147483648.f ? 0 : (int)v));
+        pi[i] = iv < 0 ? 0 : (iv > ld.nVoxels[i] - 1 ? ld.nVoxels[i] - 1 : iv);
+    }
+    int64_t voxel = ((int64_t)pi[0] * ld.nVoxels[1] + pi[1]) * ld.nVoxels[2] + pi[2];
+    return ld.table + voxel * ld.stride;
+}
+
+// SpatialLightDistribution::ComputeDistribution (lightdistrib.cpp:232-300) for one voxel, written
+// into rec = [func(n) | cdf(n+1) | funcInt] (Distribution1D ctor, sampling.h:57-70).
+PB2_HD void computeVoxelDistribution(const DScene &sc, const DHalton &h, const DLightDist &ld, int px, int py, int pz,
+                                     float *rec) {
+    int n = sc.nLights;
+    V3 p0 = mk3((float)px / (float)ld.nVoxels[0], (float)py / (float)ld.nVoxels[1], (float)pz / (float)ld.nVoxels[2]);
+    V3 p1 = mk3((float)(px + 1) / (float)ld.nVoxels[0], (float)(py + 1) / (float)ld.nVoxels[1], (float)(pz + 1) / (float)ld.nVoxels[2]);
+    // Bounds3f(WorldBound().Lerp(p0), WorldBound().Lerp(p1)): the two-point ctor takes min/max
+    V3 a = mk3(lerpf(p0.x, ld.boundsMin.x, ld.boundsMax.x), lerpf(p0.y, ld.boundsMin.y, ld.boundsMax.y), lerpf(p0.z, ld.boundsMin.z, ld.boundsMax.z));
+    V3 b = mk3(lerpf(p1.x, ld.boundsMin.x, ld.boundsMax.x), lerpf(p1.y, ld.boundsMin.y, ld.boundsMax.y), lerpf(p1.z, ld.boundsMin.z, ld.boundsMax.z));
+    V3 vMin = mk3(pmin(a.x, b.x), pmin(a.y, b.y), pmin(a.z, b.z));
+    V3 vMax = mk3(pmax(a.x, b.x), pmax(a.y, b.y), pmax(a.z, b.z));
+    for (int j = 0; j < n; ++j) rec[j] = 0;
+    const int nSamples = 128;
+    for (int i = 0; i < nSamples; ++i) {
+        V3 t = mk3(radicalInverse(h, 0, i), radicalInverse(h, 1, i), radicalInverse(h, 2, i));
+        DInteraction intr;
+        intr.p = mk3(lerpf(t.x, vMin.x, vMax.x), lerpf(t.y, vMin.y, vMax.y), lerpf(t.z, vMin.z, vMax.z));
+        intr.pError = mk3(0, 0, 0);
+        intr.n = mk3(0, 0, 0);
+        intr.wo = mk3(1, 0, 0);
+        intr.ns = mk3(0, 0, 0);
+        intr.dpdus = mk3(0, 0, 0);
+        intr.uv = mk2(0, 0);
+        intr.prim = -1;
+        V2 u = mk2(radicalInverse(h, 3, i), radicalInverse(h, 4, i));
+        for (int j = 0; j < n; ++j) {
+            DLightSample ls = sampleLight(sc, sc.lights[j], intr, u);
+            if (ls.pdf > 0) rec[j] += luminance(ls.Li) / ls.pdf;
+        }
+    }
+    float sumContrib = 0;
+    for (int j = 0; j < n; ++j) sumContrib += rec[j];
+    float avgContrib = sumContrib / (nSamples * n);
+    float minContrib = (avgContrib > 0) ? (float)(.001 * (double)avgContrib) : 1;
+    for (int j = 0; j < n; ++j) rec[j] = pmax(rec[j], minContrib);
+    // Distribution1D
+    float *cdf = rec + n;
+    cdf[0] = 0;
+    for (int i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + rec[i - 1] / n;
+    float funcInt = cdf[n];
+    if (funcInt == 0) {
+        for (int i = 1; i < n + 1; ++i) cdf[i] = (float)i / (float)n;
+    } else {
+        for (int i = 1; i < n + 1; ++i) cdf[i] /= funcInt;
+    }
+    rec[2 * n + 1] = funcInt;
+}
+
+// ---------------------------------------------------------------- camera
+struct DCamera {
+    M44 rasterToCamera, cameraToWorld;
+    float lensRadius, focalDistance;
+};
+
+// Sampler::GetCameraSample (sampler.cpp:46-52) + PerspectiveCamera::GenerateRayDifferential
+// (perspective.cpp:95-144) + Transform::operator()(Ray) (transform.h:251-264).  Differentials are
+// not carried: nothing on this path reads them (constant textures only).
+PB2_HD DRay generateCameraRay(const DCamera &cam, const DHalton &h, DSampler &smp, int px, int py, V2 *pFilmOut) {
+    V2 uf = get2D(h, smp);
+    V2 pFilm = mk2((float)px + uf.x, (float)py + uf.y);
+    get1D(h, smp);             // time
+    V2 uLens = get2D(h, smp);  // pLens
+    *pFilmOut = pFilm;
+    V3 pCamera = xfPoint(cam.rasterToCamera, mk3(pFilm.x, pFilm.y, 0));
+    DRay ray;
+    ray.o = mk3(0, 0, 0);
+    ray.d = normalize(pCamera);
+    ray.tMax = PB2_INFINITY;
+    if (cam.lensRadius > 0) {
+        V2 d = concentricSampleDisk(uLens);
+        V2 pLens = mk2(cam.lensRadius * d.x, cam.lensRadius * d.y);
+        float ft = cam.focalDistance / ray.d.z;
+        V3 pFocus = ray.o + ray.d * ft;
+        ray.o = mk3(pLens.x, pLens.y, 0);
+        ray.d = normalize(pFocus - ray.o);
+    }
+    V3 oError;
+    V3 o = xfPointErr(cam.cameraToWorld, ray.o, &oError);
+    V3 d = xfVector(cam.cameraToWorld, ray.d);
+    float l2 = lengthSquared(d);
+    float tMax = ray.tMax;
+    if (l2 > 0) {
+        float dt = dot(vabs(d), oError) / l2;
+        o = o + d * dt;
+        tMax -= dt;
+    }
+    ray.o = o;
+    ray.d = d;
+    ray.tMax = tMax;
+    return ray;
+}
+
+// ---------------------------------------------------------------- PathIntegrator::Li
+struct DPathParams {
+    int maxDepth;
+    float rrThreshold;
+};
+
+struct DPathState {
+    V3 L, beta;
+    DRay ray;
+    DSampler smp;
+    int bounces;
+    float etaScale;
+    bool specularBounce;
+};
+
+struct DRayStats {
+    unsigned int regular, shadow;
+};
+
+PB2_HD void initPath(DPathState &ps, const DRay &ray, const DSampler &smp) {
+    ps.L = mk3(0, 0, 0);
+    ps.beta = mk3(1, 1, 1);
+    ps.ray = ray;
+    ps.smp = smp;
+    ps.bounces = 0;
+    ps.etaScale = 1;
+    ps.specularBounce = false;
+}
+
+// One iteration of the bounce loop of PathIntegrator::Li (path.cpp:81-185).  Returns true when the
+// path continues with ps.ray; false when it ended (ps.L then holds the sample's radiance).
+PB2_HD bool pathVertex(const DScene &sc, const DHalton &h, const DPathParams &pp, DPathState &ps, DRayStats &st,
+                       DCounters *ctr) {
+    // scene.Intersect(ray, &isect)
+    DHit hit;
+    hit.leaf = -1;
+    hit.b0 = hit.b1 = hit.b2 = 0;
+    float tMax = ps.ray.tMax;
+    st.regular++;
+    bool found = traverse<false>(sc, ps.ray, &tMax, &hit, ctr);
+    DInteraction isect;
+    if (found) isect = hitInteraction(sc, hit, ps.ray, tMax);
+    // emitted light at the first vertex / after specular bounces (path.cpp:91-101)
+    if (ps.bounces == 0 || ps.specularBounce) {
+        if (found) {
+            int li = sc.primLight[isect.prim];
+            if (li >= 0) ps.L = ps.L + ps.beta * lightL(sc.lights[li], isect.n, -ps.ray.d);
+        }
+        // no infinite lights in scope
+    }
+    if (!found || ps.bounces >= pp.maxDepth) return false;
+
+    DBsdf bsdf;
+    if (!makeBsdf(sc, isect, &bsdf)) {
+        // null BSDF: skip the surface (path.cpp:108-113)
+        ps.ray = spawnRay(isect, ps.ray.d);
+        return true;  // bounces-- then ++bounces
+    }
+    const float *distrib = lightDistLookup(sc.lightDist, isect.p);
+
+    // direct lighting (path.cpp:119-128); NumComponents(~SPECULAR) == nLobes here
+    if (bsdf.nLobes > 0) {
+        V3 Ld = mk3(0, 0, 0);
+        // UniformSampleOneLight (integrator.cpp:85-106)
+        int nLights = sc.nLights;
+        if (nLights > 0) {
+            float lightPickPdf;
+            int lightNum = sampleDiscrete(distrib, nLights, get1D(h, ps.smp), &lightPickPdf);
+            if (lightPickPdf != 0) {
+                const pb2_light light = sc.lights[lightNum];
+                V2 uLight = get2D(h, ps.smp);
+                V2 uScattering = get2D(h, ps.smp);
+                // EstimateDirect (integrator.cpp:108-215), handleMedia = false, specular = false
+                V3 ld = mk3(0, 0, 0);
+                DLightSample ls = sampleLight(sc, light, isect, uLight);
+                float lightPdf = ls.pdf, scatteringPdf = 0;
+                bool returned = false;
+                if (lightPdf > 0 && !isBlack(ls.Li)) {
+                    V3 f = bsdfF(bsdf, isect.wo, ls.wi) * absDot(ls.wi, isect.ns);
+                    scatteringPdf = bsdfPdf(bsdf, isect.wo, ls.wi);
+                    if (!isBlack(f)) {
+                        DRay shadow = spawnRayTo(isect, ls.p, ls.pError, ls.n);
+                        float stMax = shadow.tMax;
+                        DHit dummy;
+                        st.shadow++;
+                        bool occluded = traverse<true>(sc, shadow, &stMax, &dummy, ctr);
+                        V3 Li = occluded ? mk3(0, 0, 0) : ls.Li;
+                        if (!isBlack(Li)) {
+                            float weight = powerHeuristic(lightPdf, scatteringPdf);
+                            V3 fl = f * Li * weight;
+                            ld = ld + mk3(fl.x / lightPdf, fl.y / lightPdf, fl.z / lightPdf);
+                        }
+                    }
+                }
+                // BSDF-sampled direction with MIS (area lights are never delta lights)
+                {
+                    V3 wi;
+                    V3 f = bsdfSampleF(bsdf, isect.wo, &wi, uScattering, &scatteringPdf);
+                    if (scatteringPdf != 0) f = f * absDot(wi, isect.ns);
+                    else f = mk3(0, 0, 0);
+                    if (!isBlack(f) && scatteringPdf > 0) {
+                        float weight = 1;
+                        lightPdf = lightPdfLi(sc, light, isect, wi);
+                        if (lightPdf == 0) returned = true;
+                        if (!returned) {
+                            weight = powerHeuristic(scatteringPdf, lightPdf);
+                            DRay ray = spawnRay(isect, wi);
+                            DHit lh;
+                            lh.leaf = -1;
+                            lh.b0 = lh.b1 = lh.b2 = 0;
+                            float ltMax = ray.tMax;
+                            st.regular++;
+                            bool foundLight = traverse<false>(sc, ray, &ltMax, &lh, ctr);
+                            V3 Li = mk3(0, 0, 0);
+                            if (foundLight) {
+                                int hitPrim = asInt(ldg4(&sc.leafPrims[3 * (size_t)lh.leaf]).w);
+                                if (sc.primLight[hitPrim] == lightNum) {
+                                    DInteraction lightIsect = hitInteraction(sc, lh, ray, ltMax);
+                                    Li = lightL(light, lightIsect.n, -wi);
+                                }
+                            }
+                            if (!isBlack(Li)) {
+                                V3 fl = f * Li * weight;  // Tr == 1
+                                ld = ld + mk3(fl.x / scatteringPdf, fl.y / scatteringPdf, fl.z / scatteringPdf);
+                            }
+                        }
+                    }
+                }
+                Ld = mk3(ld.x / lightPickPdf, ld.y / lightPickPdf, ld.z / lightPickPdf);
+            }
+        }
+        ps.L = ps.L + ps.beta * Ld;
+    }
+
+    // sample the BSDF for the next direction (path.cpp:130-150)
+    V3 wo = -ps.ray.d, wi;
+    float pdf;
+    V3 f = bsdfSampleF(bsdf, wo, &wi, get2D(h, ps.smp), &pdf);
+    if (isBlack(f) || pdf == 0.f) return false;
+    V3 s = f * absDot(wi, isect.ns);
+    ps.beta = ps.beta * mk3(s.x / pdf, s.y / pdf, s.z / pdf);
+    ps.specularBounce = false;  // no specular lobes in scope
+    ps.ray = spawnRay(isect, wi);
+
+    // Russian roulette (path.cpp:176-184)
+    V3 rrBeta = ps.beta * ps.etaScale;
+    if (maxComponentValue(rrBeta) < pp.rrThreshold && ps.bounces > 3) {
+        float q = pmax(.05f, 1 - maxComponentValue(rrBeta));
+        if (get1D(h, ps.smp) < q) return false;
+        float d = 1 - q;
+        ps.beta = mk3(ps.beta.x / d, ps.beta.y / d, ps.beta.z / d);
+    }
+    ps.bounces++;
+    return true;
+}
+
+// The per-sample guard of SamplerIntegrator::Render (integrator.cpp:294-315)
+PB2_HD V3 guardRadiance(V3 L) {
+    if (L.x != L.x || L.y != L.y || L.z != L.z) return mk3(0, 0, 0);
+    float y = luminance(L);
+    if ((double)y < -1e-5) return mk3(0, 0, 0);
+    if (isinf(y)) return mk3(0, 0, 0);
+    return L;
+}
+
+}  // namespace pb2
+#endif

@@ -1,0 +1,368 @@
+// Host BVH construction (the traversal lives on the GPU: ../device/traverse.cuh).
+//
+// Produces the reference's 32-byte depth-first LinearBVHNode array (src/accelerators/bvh.cpp:95-104,
+// 640-658) with the same split decisions as BVHAccel::recursiveBuild (bvh.cpp:236-402): 12-bucket
+// SAH, leaf when cheaper and <= maxPrimsInNode, middle / equal-count alternatives.  The tree is
+// built directly into a flat pool of build records instead of arena-allocated pointer nodes, and
+// the primitive order is produced as an index permutation.
+#include <unordered_map>
+
+#include "scene.h"
+
+namespace pbrt {
+
+namespace {
+struct PrimInfo {
+    size_t number;
+    Bounds3f bounds;
+    Point3f centroid;
+};
+struct BuildNode {
+    Bounds3f bounds;
+    int child[2] = {-1, -1};
+    int splitAxis = 0, firstPrimOffset = 0, nPrimitives = 0;
+};
+struct Builder {
+    std::vector<PrimInfo> info;
+    std::vector<BuildNode> pool;
+    std::vector<int32_t> ordered;
+    int maxPrimsInNode;
+    BVHAccel::SplitMethod method;
+
+    int makeLeaf(int node, int start, int end, const Bounds3f &bounds) {
+        pool[node].firstPrimOffset = (int)ordered.size();
+        for (int i = start; i < end; ++i) ordered.push_back((int32_t)info[i].number);
+        pool[node].nPrimitives = end - start;
+        pool[node].bounds = bounds;
+        return node;
+    }
+
+    int build(int start, int end) {
+        int node = (int)pool.size();
+        pool.push_back(BuildNode());
+        Bounds3f bounds;
+        for (int i = start; i < end; ++i) bounds = Union(bounds, info[i].bounds);
+        int nPrims = end - start;
+        if (nPrims == 1) return makeLeaf(node, start, end, bounds);
+        Bounds3f cb;
+        for (int i = start; i < end; ++i) cb = Union(cb, info[i].centroid);
+        int dim = cb.MaximumExtent();
+        if (cb.pMax[dim] == cb.pMin[dim]) return makeLeaf(node, start, end, bounds);
+
+        int mid = (start + end) / 2;
+        auto equalCounts = [&]() {
+            mid = (start + end) / 2;
+            std::nth_element(&info[start], &info[mid], &info[end - 1] + 1,
+                             [dim](const PrimInfo &a, const PrimInfo &b) { return a.centroid[dim] < b.centroid[dim]; });
+        };
+        bool done = false;
+        if (method == BVHAccel::SplitMethod::Middle) {
+            Float pmid = (cb.pMin[dim] + cb.pMax[dim]) / 2;
+            PrimInfo *m = std::partition(&info[start], &info[end - 1] + 1,
+                                         [dim, pmid](const PrimInfo &pi) { return pi.centroid[dim] < pmid; });
+            mid = (int)(m - &info[0]);
+            done = (mid != start && mid != end);
+            if (!done) equalCounts();  // bvh.cpp:286-290 falls through to EqualCounts
+        } else if (method == BVHAccel::SplitMethod::EqualCounts) {
+            equalCounts();
+        } else {
+            if (nPrims <= 2) {
+                equalCounts();
+            } else {
+                constexpr int nBuckets = 12;
+                struct Bucket { int count = 0; Bounds3f bounds; } buckets[nBuckets];
+                auto bucketOf = [&](const PrimInfo &pi) {
+                    int b = nBuckets * cb.Offset(pi.centroid)[dim];
+                    if (b == nBuckets) b = nBuckets - 1;
+                    return b;
+                };
+                for (int i = start; i < end; ++i) {
+                    int b = bucketOf(info[i]);
+                    buckets[b].count++;
+                    buckets[b].bounds = Union(buckets[b].bounds, info[i].bounds);
+                }
+                Float cost[nBuckets - 1];
+                for (int i = 0; i < nBuckets - 1; ++i) {
+                    Bounds3f b0, b1;
+                    int c0 = 0, c1 = 0;
+                    for (int j = 0; j <= i; ++j) { b0 = Union(b0, buckets[j].bounds); c0 += buckets[j].count; }
+                    for (int j = i + 1; j < nBuckets; ++j) { b1 = Union(b1, buckets[j].bounds); c1 += buckets[j].count; }
+                    cost[i] = 1 + (c0 * b0.SurfaceArea() + c1 * b1.SurfaceArea()) / bounds.SurfaceArea();
+                }
+                Float minCost = cost[0];
+                int minBucket = 0;
+                for (int i = 1; i < nBuckets - 1; ++i)
+                    if (cost[i] < minCost) { minCost = cost[i]; minBucket = i; }
+                Float leafCost = nPrims;
+                if (nPrims > maxPrimsInNode || minCost < leafCost) {
+                    PrimInfo *m = std::partition(&info[start], &info[end - 1] + 1,
+                                                 [&](const PrimInfo &pi) { return bucketOf(pi) <= minBucket; });
+                    mid = (int)(m - &info[0]);
+                } else
+                    return makeLeaf(node, start, end, bounds);
+            }
+        }
+        // The reference passes both recursive calls as arguments of InitInterior (bvh.cpp:394-398);
+        // its compiler (gcc, x86-64) evaluates them right to left, so the second child's primitives
+        // are appended to the ordered list first.  Keep that order: it fixes primitivesOffset values.
+        int c1 = build(mid, end);
+        int c0 = build(start, mid);
+        pool[node].child[0] = c0;
+        pool[node].child[1] = c1;
+        pool[node].bounds = Union(pool[c0].bounds, pool[c1].bounds);
+        pool[node].splitAxis = dim;
+        pool[node].nPrimitives = 0;
+        return node;
+    }
+
+    int flatten(int bn, std::vector<pb2_bvh_node> &out) {
+        int my = (int)out.size();
+        out.push_back(pb2_bvh_node());
+        const BuildNode &n = pool[bn];
+        pb2_bvh_node rec;
+        std::memset(&rec, 0, sizeof(rec));
+        for (int k = 0; k < 3; ++k) { rec.bmin[k] = n.bounds.pMin[k]; rec.bmax[k] = n.bounds.pMax[k]; }
+        if (n.nPrimitives > 0) {
+            rec.offset = n.firstPrimOffset;
+            rec.n_prims = (uint16_t)n.nPrimitives;
+            out[my] = rec;
+        } else {
+            rec.axis = (uint8_t)n.splitAxis;
+            rec.n_prims = 0;
+            out[my] = rec;
+            flatten(n.child[0], out);
+            int second = flatten(n.child[1], out);
+            out[my].offset = second;
+        }
+        return my;
+    }
+};
+}  // namespace
+
+BVHAccel::BVHAccel(std::vector<std::shared_ptr<Primitive>> p, int maxPrims, SplitMethod sm)
+    : sceneOrderPrims(std::move(p)), maxPrimsInNode(std::min(255, maxPrims)), splitMethod(sm) {
+    if (sceneOrderPrims.empty()) return;
+    if (splitMethod == SplitMethod::HLBVH) {
+        Warning("BVH split method \"hlbvh\" is built with \"sah\" here (SURVEY.md §8f.3)");
+    }
+    Builder b;
+    b.maxPrimsInNode = maxPrimsInNode;
+    b.method = splitMethod == SplitMethod::HLBVH ? SplitMethod::SAH : splitMethod;
+    b.info.resize(sceneOrderPrims.size());
+    for (size_t i = 0; i < sceneOrderPrims.size(); ++i) {
+        Bounds3f wb = sceneOrderPrims[i]->WorldBound();
+        b.info[i] = PrimInfo{i, wb, .5f * wb.pMin + .5f * wb.pMax};
+    }
+    b.pool.reserve(2 * sceneOrderPrims.size());
+    b.ordered.reserve(sceneOrderPrims.size());
+    int root = b.build(0, (int)sceneOrderPrims.size());
+    nodes.reserve(b.pool.size());
+    b.flatten(root, nodes);
+    orderedPrimNumbers = std::move(b.ordered);
+    primitives.reserve(orderedPrimNumbers.size());
+    for (int32_t n : orderedPrimNumbers) primitives.push_back(sceneOrderPrims[n]);
+}
+
+BVHAccel::~BVHAccel() {}
+
+Bounds3f BVHAccel::WorldBound() const {
+    if (nodes.empty()) return Bounds3f();
+    Bounds3f b;
+    b.pMin = Point3f(nodes[0].bmin[0], nodes[0].bmin[1], nodes[0].bmin[2]);
+    b.pMax = Point3f(nodes[0].bmax[0], nodes[0].bmax[1], nodes[0].bmax[2]);
+    return b;
+}
+
+std::shared_ptr<BVHAccel> CreateBVHAccelerator(std::vector<std::shared_ptr<Primitive>> prims, const ParamSet &ps) {
+    std::string name = ps.FindOneString("splitmethod", "sah");
+    BVHAccel::SplitMethod sm;
+    if (name == "sah") sm = BVHAccel::SplitMethod::SAH;
+    else if (name == "hlbvh") sm = BVHAccel::SplitMethod::HLBVH;
+    else if (name == "middle") sm = BVHAccel::SplitMethod::Middle;
+    else if (name == "equal") sm = BVHAccel::SplitMethod::EqualCounts;
+    else {
+        Warning("BVH split method \"%s\" unknown.  Using \"sah\".", name.c_str());
+        sm = BVHAccel::SplitMethod::SAH;
+    }
+    int maxPrimsInNode = ps.FindOneInt("maxnodeprims", 4);
+    return std::make_shared<BVHAccel>(std::move(prims), maxPrimsInNode, sm);
+}
+
+const AreaLight *Aggregate::GetAreaLight() const {
+    Error("Aggregate::GetAreaLight() method called; should have gone to GeometricPrimitive");
+    return nullptr;
+}
+const Material *Aggregate::GetMaterial() const {
+    Error("Aggregate::GetMaterial() method called; should have gone to GeometricPrimitive");
+    return nullptr;
+}
+
+// ---------------------------------------------------------------- flatten: object graph -> pb2_scene_desc
+static void copyMatrix(const Matrix4x4 &m, float out[16]) { std::memcpy(out, m.m, 16 * sizeof(float)); }
+
+std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<std::shared_ptr<Light>> &lights,
+                                        const std::string &lightStrategy) {
+    std::unique_ptr<FlatScene> fs(new FlatScene());
+    std::unordered_map<const TriangleMesh *, int> meshIds;
+    std::unordered_map<const Material *, int> materialIds;
+    std::unordered_map<const AreaLight *, int> lightIds;
+    // Scene::lights order is the order of creation in the scene file (api.cpp:1413-1416)
+    for (size_t i = 0; i < lights.size(); ++i) {
+        const AreaLight *al = dynamic_cast<const AreaLight *>(lights[i].get());
+        if (!al) {
+            Error("Only diffuse area lights are inside the GPU path's scope (SURVEY.md §2 rows 14-15)");
+            return nullptr;
+        }
+        lightIds[al] = (int)i;
+    }
+    fs->lights.resize(lights.size());
+    std::vector<char> lightSeen(lights.size(), 0);
+    bool anyN = false, anyUV = false, anyS = false;
+
+    size_t nPrims = bvh.sceneOrderPrims.size();
+    fs->primType.resize(nPrims);
+    fs->primIndex.resize(nPrims);
+    fs->primMaterial.resize(nPrims);
+    fs->primLight.resize(nPrims);
+    for (size_t i = 0; i < nPrims; ++i) {
+        const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>(bvh.sceneOrderPrims[i].get());
+        if (!gp) {
+            Error("Only GeometricPrimitives are supported below the top-level BVH (object instancing: SURVEY.md §8 a19)");
+            return nullptr;
+        }
+        // material
+        int mid = -1;
+        if (gp->material) {
+            auto it = materialIds.find(gp->material.get());
+            if (it == materialIds.end()) {
+                mid = (int)fs->materials.size();
+                fs->materials.push_back(gp->material->Record());
+                materialIds[gp->material.get()] = mid;
+            } else
+                mid = it->second;
+        }
+        fs->primMaterial[i] = mid;
+        // light
+        int lid = -1;
+        if (gp->areaLight) {
+            auto it = lightIds.find(gp->areaLight.get());
+            if (it == lightIds.end()) {
+                Error("Primitive's area light is not in the scene's light list");
+                return nullptr;
+            }
+            lid = it->second;
+            const DiffuseAreaLight *dl = dynamic_cast<const DiffuseAreaLight *>(gp->areaLight.get());
+            pb2_light rec;
+            std::memset(&rec, 0, sizeof(rec));
+            rec.prim = (int32_t)i;
+            rec.L[0] = dl->Lemit.c[0]; rec.L[1] = dl->Lemit.c[1]; rec.L[2] = dl->Lemit.c[2];
+            rec.two_sided = dl->twoSided ? 1 : 0;
+            rec.area = dl->area;
+            fs->lights[lid] = rec;
+            lightSeen[lid] = 1;
+        }
+        fs->primLight[i] = lid;
+        // shape
+        if (const Triangle *tri = dynamic_cast<const Triangle *>(gp->shape.get())) {
+            const TriangleMesh *mesh = tri->mesh.get();
+            auto it = meshIds.find(mesh);
+            int meshId;
+            if (it == meshIds.end()) {
+                meshId = (int)fs->meshes.size();
+                meshIds[mesh] = meshId;
+                pb2_mesh m;
+                std::memset(&m, 0, sizeof(m));
+                m.first_tri = (int32_t)(fs->triIndex.size() / 3);
+                m.n_tris = mesh->nTriangles;
+                m.first_vertex = (int32_t)(fs->P.size() / 3);
+                m.n_vertices = mesh->nVertices;
+                m.has_n = !mesh->n.empty();
+                m.has_uv = !mesh->uv.empty();
+                m.has_s = !mesh->s.empty();
+                m.reverse_orientation = tri->reverseOrientation;
+                m.transform_swaps_handedness = tri->transformSwapsHandedness;
+                anyN |= m.has_n != 0; anyUV |= m.has_uv != 0; anyS |= m.has_s != 0;
+                for (int v = 0; v < mesh->nVertices; ++v) {
+                    fs->P.insert(fs->P.end(), {mesh->p[v].x, mesh->p[v].y, mesh->p[v].z});
+                    if (m.has_n) fs->N.insert(fs->N.end(), {mesh->n[v].x, mesh->n[v].y, mesh->n[v].z});
+                    else fs->N.insert(fs->N.end(), {0.f, 0.f, 0.f});
+                    if (m.has_uv) fs->UV.insert(fs->UV.end(), {mesh->uv[v].x, mesh->uv[v].y});
+                    else fs->UV.insert(fs->UV.end(), {0.f, 0.f});
+                    if (m.has_s) fs->S.insert(fs->S.end(), {mesh->s[v].x, mesh->s[v].y, mesh->s[v].z});
+                    else fs->S.insert(fs->S.end(), {0.f, 0.f, 0.f});
+                }
+                for (int t = 0; t < mesh->nTriangles; ++t) {
+                    for (int k = 0; k < 3; ++k) fs->triIndex.push_back(m.first_vertex + mesh->vertexIndices[3 * t + k]);
+                    fs->triMesh.push_back(meshId);
+                }
+                fs->meshes.push_back(m);
+            } else
+                meshId = it->second;
+            if (fs->meshes[meshId].reverse_orientation != (int)tri->reverseOrientation) {
+                Error("Triangles of one mesh disagree on orientation");
+                return nullptr;
+            }
+            fs->primType[i] = PB2_PRIM_TRIANGLE;
+            fs->primIndex[i] = fs->meshes[meshId].first_tri + tri->triNumber;
+        } else if (const Sphere *sp = dynamic_cast<const Sphere *>(gp->shape.get())) {
+            pb2_sphere s;
+            std::memset(&s, 0, sizeof(s));
+            copyMatrix(sp->ObjectToWorld->GetMatrix(), s.object_to_world);
+            copyMatrix(sp->WorldToObject->GetMatrix(), s.world_to_object);
+            s.radius = sp->radius; s.z_min = sp->zMin; s.z_max = sp->zMax;
+            s.theta_min = sp->thetaMin; s.theta_max = sp->thetaMax; s.phi_max = sp->phiMax;
+            s.reverse_orientation = sp->reverseOrientation;
+            s.transform_swaps_handedness = sp->transformSwapsHandedness;
+            fs->primType[i] = PB2_PRIM_SPHERE;
+            fs->primIndex[i] = (int32_t)fs->spheres.size();
+            fs->spheres.push_back(s);
+        } else {
+            Error("Shape type outside the GPU path's scope (only triangles and spheres; SURVEY.md §2 row 27)");
+            return nullptr;
+        }
+    }
+    for (size_t i = 0; i < lights.size(); ++i)
+        if (!lightSeen[i]) {
+            Error("Area light %d is not attached to a primitive of the aggregate", (int)i);
+            return nullptr;
+        }
+
+    pb2_scene_desc &d = fs->desc;
+    std::memset(&d, 0, sizeof(d));
+    d.n_vertices = (int64_t)(fs->P.size() / 3);
+    d.P = fs->P.data();
+    d.N = anyN ? fs->N.data() : nullptr;
+    d.UV = anyUV ? fs->UV.data() : nullptr;
+    d.S = anyS ? fs->S.data() : nullptr;
+    d.n_tris = (int64_t)(fs->triIndex.size() / 3);
+    d.tri_index = fs->triIndex.data();
+    d.tri_mesh = fs->triMesh.data();
+    d.n_meshes = (int32_t)fs->meshes.size();
+    d.meshes = fs->meshes.data();
+    d.n_spheres = (int32_t)fs->spheres.size();
+    d.spheres = fs->spheres.data();
+    d.n_prims = (int64_t)nPrims;
+    d.prim_type = fs->primType.data();
+    d.prim_index = fs->primIndex.data();
+    d.prim_material = fs->primMaterial.data();
+    d.prim_light = fs->primLight.data();
+    d.n_nodes = (int64_t)bvh.nodes.size();
+    d.nodes = bvh.nodes.data();
+    d.bvh_prims = bvh.orderedPrimNumbers.data();
+    d.n_materials = (int32_t)fs->materials.size();
+    d.materials = fs->materials.data();
+    d.n_lights = (int32_t)fs->lights.size();
+    d.lights = fs->lights.data();
+    // lightdistrib.cpp:48-66: a single light always gets the uniform distribution
+    if (lightStrategy == "uniform" || lights.size() == 1) d.light_strategy = PB2_LIGHTDIST_UNIFORM;
+    else if (lightStrategy == "power") d.light_strategy = PB2_LIGHTDIST_POWER;
+    else {
+        if (lightStrategy != "spatial")
+            Error("Light sample distribution type \"%s\" unknown. Using \"spatial\".", lightStrategy.c_str());
+        d.light_strategy = PB2_LIGHTDIST_SPATIAL;
+    }
+    d.spatial_max_voxels = 64;
+    return fs;
+}
+
+}  // namespace pbrt

@@ -1,0 +1,138 @@
+// Typed name/value lists attached to every scene-file directive.
+// Interface mirrors the reference's ParamSet (src/core/paramset.h:57-140: AddXxx / FindXxx /
+// FindOneXxx / ReportUnused); the storage is a single tagged vector instead of one vector per type.
+#ifndef PB2_HOST_PARAMSET_H
+#define PB2_HOST_PARAMSET_H
+
+#include <map>
+#include "core.h"
+
+namespace pbrt {
+
+struct Spectrum {  // RGBSpectrum (src/core/spectrum.h:430-470); the only build configuration in scope
+    Float c[3];
+    Spectrum(Float v = 0.f) { c[0] = c[1] = c[2] = v; }
+    Spectrum(Float r, Float g, Float b) { c[0] = r; c[1] = g; c[2] = b; }
+    Spectrum operator*(const Spectrum &s) const { return Spectrum(c[0] * s.c[0], c[1] * s.c[1], c[2] * s.c[2]); }
+    bool IsBlack() const { return c[0] == 0 && c[1] == 0 && c[2] == 0; }
+};
+
+class ParamSet {
+  public:
+    enum class Type { Bool, Int, Float, Point2, Vector2, Point3, Vector3, Normal, Rgb, String, Texture };
+    struct Item {
+        Type type;
+        std::string name;
+        std::vector<double> nums;  // Bool/Int/Float/Point*/Vector*/Normal/Rgb, flattened
+        std::vector<std::string> strs;
+        mutable bool lookedUp = false;
+    };
+
+    void Add(Type t, const std::string &name, std::vector<double> nums, std::vector<std::string> strs = {}) {
+        for (auto &it : items)
+            if (it.type == t && it.name == name) {
+                it.nums = std::move(nums);
+                it.strs = std::move(strs);
+                return;
+            }
+        items.push_back(Item{t, name, std::move(nums), std::move(strs), false});
+    }
+    void AddInt(const std::string &n, const std::vector<int> &v) { Add(Type::Int, n, std::vector<double>(v.begin(), v.end())); }
+    void AddFloat(const std::string &n, const std::vector<Float> &v) { Add(Type::Float, n, std::vector<double>(v.begin(), v.end())); }
+    void AddPoint3f(const std::string &n, const std::vector<Float> &v) { Add(Type::Point3, n, std::vector<double>(v.begin(), v.end())); }
+    void AddNormal3f(const std::string &n, const std::vector<Float> &v) { Add(Type::Normal, n, std::vector<double>(v.begin(), v.end())); }
+    void AddRGBSpectrum(const std::string &n, const std::vector<Float> &v) { Add(Type::Rgb, n, std::vector<double>(v.begin(), v.end())); }
+    void AddString(const std::string &n, const std::string &v) { Add(Type::String, n, {}, {v}); }
+    void AddBool(const std::string &n, bool v) { Add(Type::Bool, n, {v ? 1.0 : 0.0}); }
+
+    const Item *Find(Type t, const std::string &name) const {
+        for (const auto &it : items)
+            if (it.type == t && it.name == name) {
+                it.lookedUp = true;
+                return &it;
+            }
+        return nullptr;
+    }
+    Float FindOneFloat(const std::string &n, Float d) const {
+        const Item *it = Find(Type::Float, n);
+        return (it && it->nums.size() == 1) ? (Float)it->nums[0] : d;
+    }
+    int FindOneInt(const std::string &n, int d) const {
+        const Item *it = Find(Type::Int, n);
+        return (it && it->nums.size() == 1) ? (int)it->nums[0] : d;
+    }
+    bool FindOneBool(const std::string &n, bool d) const {
+        const Item *it = Find(Type::Bool, n);
+        return (it && it->nums.size() == 1) ? it->nums[0] != 0 : d;
+    }
+    std::string FindOneString(const std::string &n, const std::string &d) const {
+        const Item *it = Find(Type::String, n);
+        return (it && it->strs.size() == 1) ? it->strs[0] : d;
+    }
+    Spectrum FindOneSpectrum(const std::string &n, const Spectrum &d) const {
+        const Item *it = Find(Type::Rgb, n);
+        if (it && it->nums.size() == 3) return Spectrum((Float)it->nums[0], (Float)it->nums[1], (Float)it->nums[2]);
+        return d;
+    }
+    std::string FindTexture(const std::string &n) const {
+        const Item *it = Find(Type::Texture, n);
+        return (it && it->strs.size() == 1) ? it->strs[0] : std::string();
+    }
+    // Array lookups return flattened floats / ints (count = number of scalars).
+    std::vector<Float> FindFloats(Type t, const std::string &n, bool *found = nullptr) const {
+        const Item *it = Find(t, n);
+        if (found) *found = it != nullptr;
+        std::vector<Float> r;
+        if (it) r.assign(it->nums.begin(), it->nums.end());
+        return r;
+    }
+    std::vector<int> FindInts(const std::string &n, bool *found = nullptr) const {
+        const Item *it = Find(Type::Int, n);
+        if (found) *found = it != nullptr;
+        std::vector<int> r;
+        if (it) {
+            r.reserve(it->nums.size());
+            for (double d : it->nums) r.push_back((int)d);
+        }
+        return r;
+    }
+    void ReportUnused() const {
+        for (const auto &it : items)
+            if (!it.lookedUp) Warning("Parameter \"%s\" not used", it.name.c_str());
+    }
+    void Clear() { items.clear(); }
+    std::vector<Item> items;
+};
+
+// TextureParams (src/core/paramset.h:142-190) restricted to constant textures: a material
+// parameter is looked up in the shape's parameters first, then in the material's.
+class TextureParams {
+  public:
+    TextureParams(const ParamSet &geom, const ParamSet &mat) : geomParams(geom), materialParams(mat) {}
+    Spectrum GetSpectrumTexture(const std::string &n, const Spectrum &def, bool *isTexture = nullptr) const {
+        if (isTexture) *isTexture = false;
+        if (geomParams.FindTexture(n) != "" || materialParams.FindTexture(n) != "") {
+            if (isTexture) *isTexture = true;
+            return def;
+        }
+        Spectrum s = materialParams.FindOneSpectrum(n, def);
+        return geomParams.FindOneSpectrum(n, s);
+    }
+    Float GetFloatTexture(const std::string &n, Float def, bool *isTexture = nullptr) const {
+        if (isTexture) *isTexture = false;
+        if (geomParams.FindTexture(n) != "" || materialParams.FindTexture(n) != "") {
+            if (isTexture) *isTexture = true;
+            return def;
+        }
+        return geomParams.FindOneFloat(n, materialParams.FindOneFloat(n, def));
+    }
+    bool FindBool(const std::string &n, bool d) const { return geomParams.FindOneBool(n, materialParams.FindOneBool(n, d)); }
+    std::string FindString(const std::string &n, const std::string &d = "") const {
+        return geomParams.FindOneString(n, materialParams.FindOneString(n, d));
+    }
+    void ReportUnused() const { materialParams.ReportUnused(); }
+    const ParamSet &geomParams, &materialParams;
+};
+
+}  // namespace pbrt
+#endif

@@ -1,0 +1,489 @@
+// Host-side render plumbing around the GPU hot path: materials/lights as parameter records,
+// film (merge + XYZ round trip + PFM), perspective camera matrices, sampler/integrator factories,
+// and the adapters that turn Shape/Primitive/Aggregate/Integrator calls into C-ABI calls.
+//
+//   Film ctor / GetSampleBounds / MergeFilmTile / WriteImage   src/core/film.cpp:45-211
+//   PerspectiveCamera / ProjectiveCamera                       src/cameras/perspective.cpp:45-67,227-273, src/core/camera.h:84-115
+//   CreateHaltonSampler / CreatePathIntegrator                 src/samplers/halton.cpp:133-139, src/integrators/path.cpp:190-213
+//   Matte / Plastic / DiffuseAreaLight factories               src/materials/matte.cpp:64-71, plastic.cpp:72-83, src/lights/diffuse.cpp:135-148
+#include <mutex>
+
+#include "scene.h"
+
+namespace pbrt {
+
+// ---------------------------------------------------------------- materials / lights
+static void clampSpectrum(const Spectrum &s, float out[3]) {
+    for (int i = 0; i < 3; ++i) out[i] = s.c[i];
+}
+pb2_material MatteMaterial::Record() const {
+    pb2_material m;
+    std::memset(&m, 0, sizeof(m));
+    m.type = PB2_MAT_MATTE;
+    clampSpectrum(Kd, m.kd);
+    m.sigma = sigma;
+    return m;
+}
+pb2_material PlasticMaterial::Record() const {
+    pb2_material m;
+    std::memset(&m, 0, sizeof(m));
+    m.type = PB2_MAT_PLASTIC;
+    clampSpectrum(Kd, m.kd);
+    clampSpectrum(Ks, m.ks);
+    m.roughness = roughness;
+    m.remap_roughness = remapRoughness ? 1 : 0;
+    return m;
+}
+static void rejectTextures(const TextureParams &mp, const char *what, std::initializer_list<const char *> names) {
+    for (const char *n : names)
+        if (mp.geomParams.FindTexture(n) != "" || mp.materialParams.FindTexture(n) != "")
+            Error("%s: textured parameter \"%s\" is outside the GPU path's scope (constant textures only, SURVEY.md §2 row 33); "
+                  "using the default value", what, n);
+}
+MatteMaterial *CreateMatteMaterial(const TextureParams &mp) {
+    rejectTextures(mp, "matte", {"Kd", "sigma", "bumpmap"});
+    Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(0.5f));
+    Float sigma = mp.GetFloatTexture("sigma", 0.f);
+    return new MatteMaterial(Kd, sigma);
+}
+PlasticMaterial *CreatePlasticMaterial(const TextureParams &mp) {
+    rejectTextures(mp, "plastic", {"Kd", "Ks", "roughness", "bumpmap"});
+    Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(0.25f));
+    Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(0.25f));
+    Float roughness = mp.GetFloatTexture("roughness", .1f);
+    bool remap = mp.FindBool("remaproughness", true);
+    return new PlasticMaterial(Kd, Ks, roughness, remap);
+}
+
+DiffuseAreaLight::DiffuseAreaLight(const Transform &LightToWorld, const Spectrum &Lemit, int nSamples,
+                                   const std::shared_ptr<Shape> &shape, bool twoSided)
+    : Lemit(Lemit), shape(shape), twoSided(twoSided), area(shape->Area()) {
+    if (Inverse(LightToWorld).HasScale() && dynamic_cast<const Triangle *>(shape.get()) == nullptr)
+        Warning("Scaling detected in world to light transformation! The system has numerous assumptions, implicit and "
+                "explicit, that this transform will have no scale factors in it. Proceed at your own risk; your image "
+                "may have errors.");
+}
+std::shared_ptr<AreaLight> CreateDiffuseAreaLight(const Transform &light2world, const ParamSet &paramSet,
+                                                  const std::shared_ptr<Shape> &shape) {
+    Spectrum L = paramSet.FindOneSpectrum("L", Spectrum(1.0));
+    Spectrum sc = paramSet.FindOneSpectrum("scale", Spectrum(1.0));
+    int nSamples = paramSet.FindOneInt("samples", paramSet.FindOneInt("nsamples", 1));
+    bool twoSided = paramSet.FindOneBool("twosided", false);
+    return std::make_shared<DiffuseAreaLight>(light2world, L * sc, nSamples, shape, twoSided);
+}
+
+// ---------------------------------------------------------------- film
+BoxFilter *CreateBoxFilter(const ParamSet &ps) {
+    Float xw = ps.FindOneFloat("xwidth", 0.5f);
+    Float yw = ps.FindOneFloat("ywidth", 0.5f);
+    return new BoxFilter(xw, yw);
+}
+
+Film::Film(const Point2i &resolution, const Bounds2f &cropWindow, std::unique_ptr<Filter> filt, Float diagonal,
+           const std::string &filename, Float scale, Float maxSampleLuminance)
+    : fullResolution(resolution), diagonal(diagonal * .001), filter(std::move(filt)), filename(filename), scale(scale),
+      maxSampleLuminance(maxSampleLuminance) {
+    croppedPixelBounds = Bounds2i(Point2i((int)std::ceil(fullResolution.x * cropWindow.pMin.x),
+                                          (int)std::ceil(fullResolution.y * cropWindow.pMin.y)),
+                                  Point2i((int)std::ceil(fullResolution.x * cropWindow.pMax.x),
+                                          (int)std::ceil(fullResolution.y * cropWindow.pMax.y)));
+    pixels.resize(std::max(0, croppedPixelBounds.Area()));
+}
+
+Bounds2i Film::GetSampleBounds() const {
+    Float x0 = std::floor(Float(croppedPixelBounds.pMin.x) + 0.5f - filter->radius[0]);
+    Float y0 = std::floor(Float(croppedPixelBounds.pMin.y) + 0.5f - filter->radius[1]);
+    Float x1 = std::ceil(Float(croppedPixelBounds.pMax.x) - 0.5f + filter->radius[0]);
+    Float y1 = std::ceil(Float(croppedPixelBounds.pMax.y) - 0.5f + filter->radius[1]);
+    return Bounds2i(Point2i((int)x0, (int)y0), Point2i((int)x1, (int)y1));
+}
+
+static inline void RGBToXYZ(const Float rgb[3], Float xyz[3]) {
+    xyz[0] = 0.412453f * rgb[0] + 0.357580f * rgb[1] + 0.180423f * rgb[2];
+    xyz[1] = 0.212671f * rgb[0] + 0.715160f * rgb[1] + 0.072169f * rgb[2];
+    xyz[2] = 0.019334f * rgb[0] + 0.119193f * rgb[1] + 0.950227f * rgb[2];
+}
+static inline void XYZToRGB(const Float xyz[3], Float rgb[3]) {
+    rgb[0] = 3.240479f * xyz[0] - 1.537150f * xyz[1] - 0.498535f * xyz[2];
+    rgb[1] = -0.969256f * xyz[0] + 1.875991f * xyz[1] + 0.041556f * xyz[2];
+    rgb[2] = 0.055648f * xyz[0] - 0.204043f * xyz[1] + 1.057311f * xyz[2];
+}
+
+void Film::MergeDeviceFilm(const float *rgbw) {
+    size_t n = pixels.size();
+    for (size_t i = 0; i < n; ++i) {
+        Float xyz[3];
+        RGBToXYZ(&rgbw[4 * i], xyz);
+        for (int c = 0; c < 3; ++c) pixels[i].xyz[c] += xyz[c];
+        pixels[i].filterWeightSum += rgbw[4 * i + 3];
+    }
+}
+
+std::vector<Float> Film::ResolveRGB() const {
+    std::vector<Float> rgb(3 * pixels.size());
+    for (size_t i = 0; i < pixels.size(); ++i) {
+        const Pixel &px = pixels[i];
+        XYZToRGB(px.xyz, &rgb[3 * i]);
+        Float w = px.filterWeightSum;
+        if (w != 0) {
+            Float invWt = (Float)1 / w;
+            for (int c = 0; c < 3; ++c) rgb[3 * i + c] = std::max((Float)0, rgb[3 * i + c] * invWt);
+        }
+        // splats are BDPT/MLT only (film.cpp:142-167): always zero on this path, but the
+        // reference still adds XYZToRGB(0) = 0 here, which cannot change a value.
+        for (int c = 0; c < 3; ++c) rgb[3 * i + c] *= scale;
+    }
+    return rgb;
+}
+
+bool WriteImagePFM(const std::string &filename, const Float *rgb, int width, int height) {
+    FILE *fp = std::fopen(filename.c_str(), "wb");
+    if (!fp) {
+        Error("Unable to open output PFM file \"%s\"", filename.c_str());
+        return false;
+    }
+    std::fprintf(fp, "PF\n%d %d\n%f\n", width, height, -1.f);
+    for (int y = height - 1; y >= 0; --y) std::fwrite(&rgb[(size_t)y * width * 3], sizeof(float), (size_t)width * 3, fp);
+    std::fclose(fp);
+    return true;
+}
+
+bool ReadImagePFM(const std::string &filename, std::vector<Float> *rgb, int *width, int *height) {
+    FILE *fp = std::fopen(filename.c_str(), "rb");
+    if (!fp) return false;
+    char magic[8];
+    float scale;
+    if (std::fscanf(fp, "%7s %d %d %f", magic, width, height, &scale) != 4 || std::string(magic) != "PF" || scale > 0) {
+        std::fclose(fp);
+        return false;
+    }
+    std::fgetc(fp);
+    rgb->resize((size_t)3 * *width * *height);
+    bool ok = true;
+    for (int y = *height - 1; y >= 0 && ok; --y)
+        ok = std::fread(&(*rgb)[(size_t)y * *width * 3], sizeof(float), (size_t)*width * 3, fp) == (size_t)*width * 3;
+    std::fclose(fp);
+    return ok;
+}
+
+void Film::WriteImage(Float splatScale) {
+    std::vector<Float> rgb = ResolveRGB();
+    int w = croppedPixelBounds.pMax.x - croppedPixelBounds.pMin.x;
+    int h = croppedPixelBounds.pMax.y - croppedPixelBounds.pMin.y;
+    std::string out = filename;
+    size_t dot = out.rfind('.');
+    std::string ext = dot == std::string::npos ? "" : out.substr(dot);
+    if (ext != ".pfm") {
+        // EXR/PNG/TGA encoders are file-format code outside the path; the
+        // float32 PFM carries strictly more precision than the reference's half-float EXR.
+        out = (dot == std::string::npos ? out : out.substr(0, dot)) + ".pfm";
+        Warning("Image format \"%s\" is not written by this build; writing float32 PFM \"%s\" instead", ext.c_str(), out.c_str());
+    }
+    WriteImagePFM(out, rgb.data(), w, h);
+}
+
+pb2_film_desc Film::Desc() const {
+    pb2_film_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.full_resolution[0] = fullResolution.x;
+    d.full_resolution[1] = fullResolution.y;
+    d.cropped_pixel_bounds[0] = croppedPixelBounds.pMin.x;
+    d.cropped_pixel_bounds[1] = croppedPixelBounds.pMin.y;
+    d.cropped_pixel_bounds[2] = croppedPixelBounds.pMax.x;
+    d.cropped_pixel_bounds[3] = croppedPixelBounds.pMax.y;
+    d.filter_radius[0] = filter->radius[0];
+    d.filter_radius[1] = filter->radius[1];
+    d.max_sample_luminance = maxSampleLuminance;
+    d.scale = scale;
+    return d;
+}
+
+extern std::string g_imageFileOverride;  // api.cpp (--outfile)
+extern Float g_cropWindow[2][2];
+Film *CreateFilm(const ParamSet &params, std::unique_ptr<Filter> filter) {
+    std::string filename;
+    if (g_imageFileOverride != "") {
+        filename = g_imageFileOverride;
+        std::string paramsFilename = params.FindOneString("filename", "");
+        if (paramsFilename != "")
+            Warning("Output filename supplied on command line, \"%s\" is overriding filename provided in scene "
+                    "description file, \"%s\".", g_imageFileOverride.c_str(), paramsFilename.c_str());
+    } else
+        filename = params.FindOneString("filename", "pbrt.exr");
+    int xres = params.FindOneInt("xresolution", 1280);
+    int yres = params.FindOneInt("yresolution", 720);
+    Bounds2f crop;
+    bool haveCrop = false;
+    std::vector<Float> cr = params.FindFloats(ParamSet::Type::Float, "cropwindow", &haveCrop);
+    if (haveCrop && cr.size() == 4) {
+        crop.pMin.x = Clamp(std::min(cr[0], cr[1]), 0.f, 1.f);
+        crop.pMax.x = Clamp(std::max(cr[0], cr[1]), 0.f, 1.f);
+        crop.pMin.y = Clamp(std::min(cr[2], cr[3]), 0.f, 1.f);
+        crop.pMax.y = Clamp(std::max(cr[2], cr[3]), 0.f, 1.f);
+    } else {
+        if (haveCrop) Error("%d values supplied for \"cropwindow\". Expected 4.", (int)cr.size());
+        crop.pMin = Point2f(Clamp(g_cropWindow[0][0], 0, 1), Clamp(g_cropWindow[1][0], 0, 1));
+        crop.pMax = Point2f(Clamp(g_cropWindow[0][1], 0, 1), Clamp(g_cropWindow[1][1], 0, 1));
+    }
+    Float scale = params.FindOneFloat("scale", 1.);
+    Float diagonal = params.FindOneFloat("diagonal", 35.);
+    Float maxSampleLuminance = params.FindOneFloat("maxsampleluminance", Infinity);
+    return new Film(Point2i(xres, yres), crop, std::move(filter), diagonal, filename, scale, maxSampleLuminance);
+}
+
+// ---------------------------------------------------------------- camera
+PerspectiveCamera::PerspectiveCamera(const Transform &c2w, const Bounds2f &screenWindow, Float shutterOpen,
+                                     Float shutterClose, Float lensr, Float focald, Float fov, Film *film)
+    : Camera(c2w, shutterOpen, shutterClose, film), CameraToScreen(Perspective(fov, 1e-2f, 1000.f)),
+      screenWindow(screenWindow), lensRadius(lensr), focalDistance(focald), fov(fov) {
+    ScreenToRaster = Scale(film->fullResolution.x, film->fullResolution.y, 1) *
+                     Scale(1 / (screenWindow.pMax.x - screenWindow.pMin.x), 1 / (screenWindow.pMin.y - screenWindow.pMax.y), 1) *
+                     Translate(Vector3f(-screenWindow.pMin.x, -screenWindow.pMax.y, 0));
+    RasterToScreen = Inverse(ScreenToRaster);
+    RasterToCamera = Inverse(CameraToScreen) * RasterToScreen;
+    dxCamera = RasterToCamera(Point3f(1, 0, 0)) - RasterToCamera(Point3f(0, 0, 0));
+    dyCamera = RasterToCamera(Point3f(0, 1, 0)) - RasterToCamera(Point3f(0, 0, 0));
+}
+
+pb2_camera PerspectiveCamera::Desc() const {
+    pb2_camera c;
+    std::memset(&c, 0, sizeof(c));
+    std::memcpy(c.camera_to_world, CameraToWorld.GetMatrix().m, sizeof(c.camera_to_world));
+    std::memcpy(c.world_to_camera, CameraToWorld.GetInverseMatrix().m, sizeof(c.world_to_camera));
+    c.screen_window[0] = screenWindow.pMin.x; c.screen_window[1] = screenWindow.pMax.x;
+    c.screen_window[2] = screenWindow.pMin.y; c.screen_window[3] = screenWindow.pMax.y;
+    c.fov = fov;
+    c.lens_radius = lensRadius;
+    c.focal_distance = focalDistance;
+    c.shutter_open = shutterOpen;
+    c.shutter_close = shutterClose;
+    std::memcpy(c.raster_to_camera, RasterToCamera.GetMatrix().m, sizeof(c.raster_to_camera));
+    for (int k = 0; k < 3; ++k) { c.dx_camera[k] = dxCamera[k]; c.dy_camera[k] = dyCamera[k]; }
+    return c;
+}
+
+PerspectiveCamera *CreatePerspectiveCamera(const ParamSet &params, const Transform &cam2world, Film *film) {
+    Float shutteropen = params.FindOneFloat("shutteropen", 0.f);
+    Float shutterclose = params.FindOneFloat("shutterclose", 1.f);
+    if (shutterclose < shutteropen) {
+        Warning("Shutter close time [%f] < shutter open [%f].  Swapping them.", shutterclose, shutteropen);
+        std::swap(shutterclose, shutteropen);
+    }
+    Float lensradius = params.FindOneFloat("lensradius", 0.f);
+    Float focaldistance = params.FindOneFloat("focaldistance", 1e6);
+    Float frame = params.FindOneFloat("frameaspectratio", Float(film->fullResolution.x) / Float(film->fullResolution.y));
+    Bounds2f screen;
+    if (frame > 1.f) {
+        screen.pMin.x = -frame; screen.pMax.x = frame; screen.pMin.y = -1.f; screen.pMax.y = 1.f;
+    } else {
+        screen.pMin.x = -1.f; screen.pMax.x = 1.f; screen.pMin.y = -1.f / frame; screen.pMax.y = 1.f / frame;
+    }
+    bool haveSw = false;
+    std::vector<Float> sw = params.FindFloats(ParamSet::Type::Float, "screenwindow", &haveSw);
+    if (haveSw) {
+        if (sw.size() == 4) {
+            screen.pMin.x = sw[0]; screen.pMax.x = sw[1]; screen.pMin.y = sw[2]; screen.pMax.y = sw[3];
+        } else
+            Error("\"screenwindow\" should have four values");
+    }
+    Float fov = params.FindOneFloat("fov", 90.);
+    Float halffov = params.FindOneFloat("halffov", -1.f);
+    if (halffov > 0.f) fov = 2.f * halffov;
+    return new PerspectiveCamera(cam2world, screen, shutteropen, shutterclose, lensradius, focaldistance, fov, film);
+}
+
+// ---------------------------------------------------------------- sampler / integrator factories
+HaltonSampler *CreateHaltonSampler(const ParamSet &params, const Bounds2i &sampleBounds) {
+    int nsamp = params.FindOneInt("pixelsamples", 16);
+    bool sampleAtCenter = params.FindOneBool("samplepixelcenter", false);
+    return new HaltonSampler(nsamp, sampleBounds, sampleAtCenter);
+}
+
+PathIntegrator *CreatePathIntegrator(const ParamSet &params, std::shared_ptr<Sampler> sampler,
+                                     std::shared_ptr<const Camera> camera) {
+    int maxDepth = params.FindOneInt("maxdepth", 5);
+    Bounds2i pixelBounds = camera->film->GetSampleBounds();
+    bool havePb = false;
+    std::vector<int> pb = params.FindInts("pixelbounds", &havePb);
+    if (havePb) {
+        if (pb.size() != 4)
+            Error("Expected four values for \"pixelbounds\" parameter. Got %d.", (int)pb.size());
+        else {
+            Bounds2i b(Point2i(std::max(pixelBounds.pMin.x, pb[0]), std::max(pixelBounds.pMin.y, pb[2])),
+                       Point2i(std::min(pixelBounds.pMax.x, pb[1]), std::min(pixelBounds.pMax.y, pb[3])));
+            pixelBounds = b;
+            if (pixelBounds.Area() == 0) Error("Degenerate \"pixelbounds\" specified.");
+        }
+    }
+    Float rrThreshold = params.FindOneFloat("rrthreshold", 1.);
+    std::string lightStrategy = params.FindOneString("lightsamplestrategy", "spatial");
+    return new PathIntegrator(maxDepth, camera, sampler, pixelBounds, rrThreshold, lightStrategy);
+}
+
+// ---------------------------------------------------------------- device adapters
+struct DeviceScene {
+    pb2_scene *handle = nullptr;
+    std::unique_ptr<FlatScene> flat;
+    ~DeviceScene() {
+        if (handle) pb2_scene_destroy(handle);
+    }
+};
+pb2_scene *DeviceSceneHandle(const DeviceScene &d) { return d.handle; }
+
+static bool ensureDevice() {
+    static std::once_flag once;
+    static int status = PB2_OK;
+    std::call_once(once, [] {
+        const char *dev = std::getenv("PB2_DEVICE");
+        if (!dev) dev = std::getenv("LOCAL_RANK");
+        status = pb2_init(dev ? std::atoi(dev) : 0);
+    });
+    if (status != PB2_OK) Error("pb2_init failed: %s (there is no CPU fallback for the path-tracing hot path)", pb2_last_error());
+    return status == PB2_OK;
+}
+
+std::shared_ptr<DeviceScene> GetDeviceScene(const BVHAccel &bvh, const std::vector<std::shared_ptr<Light>> &lights,
+                                            const std::string &lightStrategy) {
+    if (bvh.device) return bvh.device;
+    if (!ensureDevice()) return nullptr;
+    auto ds = std::make_shared<DeviceScene>();
+    ds->flat = FlattenScene(bvh, lights, lightStrategy);
+    if (!ds->flat) return nullptr;
+    if (pb2_scene_create(&ds->flat->desc, &ds->handle) != PB2_OK) {
+        Error("pb2_scene_create failed: %s", pb2_last_error());
+        return nullptr;
+    }
+    bvh.device = ds;
+    return ds;
+}
+
+static void fillInteraction(const pb2_hit &h, const BVHAccel &bvh, const Ray &ray, SurfaceInteraction *isect) {
+    isect->p = Point3f(h.p[0], h.p[1], h.p[2]);
+    isect->pError = Vector3f(h.p_error[0], h.p_error[1], h.p_error[2]);
+    isect->n = Normal3f(h.n[0], h.n[1], h.n[2]);
+    isect->shading.n = Normal3f(h.ns[0], h.ns[1], h.ns[2]);
+    isect->shading.dpdu = Vector3f(h.dpdu[0], h.dpdu[1], h.dpdu[2]);
+    isect->uv = Point2f(h.uv[0], h.uv[1]);
+    isect->wo = Normalize(-ray.d);
+    for (int k = 0; k < 3; ++k) isect->b[k] = h.b[k];
+    isect->primitive = bvh.sceneOrderPrims[h.prim].get();
+}
+
+bool BVHAccel::Intersect(const Ray &ray, SurfaceInteraction *isect) const {
+    if (nodes.empty()) return false;
+    std::vector<std::shared_ptr<Light>> noLights;
+    std::shared_ptr<DeviceScene> ds = device ? device : GetDeviceScene(*this, noLights, "uniform");
+    if (!ds) return false;
+    pb2_ray r = {{ray.o.x, ray.o.y, ray.o.z}, {ray.d.x, ray.d.y, ray.d.z}, ray.tMax};
+    pb2_hit h;
+    if (pb2_intersect(ds->handle, &r, 1, &h) != PB2_OK) {
+        Error("pb2_intersect failed: %s", pb2_last_error());
+        return false;
+    }
+    if (h.prim < 0) return false;
+    ray.tMax = h.t;
+    fillInteraction(h, *this, ray, isect);
+    return true;
+}
+
+bool BVHAccel::IntersectP(const Ray &ray) const {
+    if (nodes.empty()) return false;
+    std::vector<std::shared_ptr<Light>> noLights;
+    std::shared_ptr<DeviceScene> ds = device ? device : GetDeviceScene(*this, noLights, "uniform");
+    if (!ds) return false;
+    pb2_ray r = {{ray.o.x, ray.o.y, ray.o.z}, {ray.d.x, ray.d.y, ray.d.z}, ray.tMax};
+    uint8_t occ = 0;
+    if (pb2_intersect_p(ds->handle, &r, 1, &occ) != PB2_OK) {
+        Error("pb2_intersect_p failed: %s", pb2_last_error());
+        return false;
+    }
+    return occ != 0;
+}
+
+// A Shape (or GeometricPrimitive) asked to intersect on its own is wrapped in a one-primitive
+// aggregate so that the same device kernels answer (no host intersection code exists).
+namespace {
+struct ShapeProxy : public Shape {
+    // Non-owning view used only to build a shared_ptr<Shape> aliasing an existing shape.
+    using Shape::Shape;
+};
+std::mutex g_singleMutex;
+std::map<const Shape *, std::shared_ptr<BVHAccel>> g_singleShapeAccels;
+std::shared_ptr<BVHAccel> singleShapeAccel(const Shape *shape) {
+    std::lock_guard<std::mutex> lock(g_singleMutex);
+    auto it = g_singleShapeAccels.find(shape);
+    if (it != g_singleShapeAccels.end()) return it->second;
+    std::shared_ptr<Shape> alias(std::shared_ptr<Shape>(), const_cast<Shape *>(shape));
+    std::vector<std::shared_ptr<Primitive>> prims{std::make_shared<GeometricPrimitive>(alias, nullptr, nullptr)};
+    auto accel = std::make_shared<BVHAccel>(std::move(prims), 1);
+    g_singleShapeAccels[shape] = accel;
+    return accel;
+}
+}  // namespace
+
+bool Shape::Intersect(const Ray &ray, Float *tHit, SurfaceInteraction *isect, bool) const {
+    Ray r = ray;
+    if (!singleShapeAccel(this)->Intersect(r, isect)) return false;
+    *tHit = r.tMax;
+    return true;
+}
+bool Shape::IntersectP(const Ray &ray, bool) const { return singleShapeAccel(this)->IntersectP(ray); }
+
+bool GeometricPrimitive::Intersect(const Ray &r, SurfaceInteraction *isect) const {
+    Float tHit;
+    if (!shape->Intersect(r, &tHit, isect)) return false;
+    r.tMax = tHit;
+    isect->primitive = this;
+    return true;
+}
+bool GeometricPrimitive::IntersectP(const Ray &r) const { return shape->IntersectP(r); }
+
+// ---------------------------------------------------------------- PathIntegrator
+void PathIntegrator::Preprocess(const Scene &, Sampler &) {}
+
+pb2_path_params PathIntegrator::Params() const {
+    pb2_path_params p;
+    std::memset(&p, 0, sizeof(p));
+    const HaltonSampler *hs = dynamic_cast<const HaltonSampler *>(sampler.get());
+    p.samples_per_pixel = (int32_t)sampler->samplesPerPixel;
+    p.sample_at_pixel_center = hs && hs->sampleAtPixelCenter;
+    p.max_depth = maxDepth;
+    p.rr_threshold = rrThreshold;
+    p.pixel_bounds[0] = pixelBounds.pMin.x; p.pixel_bounds[1] = pixelBounds.pMin.y;
+    p.pixel_bounds[2] = pixelBounds.pMax.x; p.pixel_bounds[3] = pixelBounds.pMax.y;
+    p.tile_rank = tileRank;
+    p.tile_count = tileCount;
+    return p;
+}
+
+void PathIntegrator::Render(const Scene &scene) {
+    Preprocess(scene, *sampler);
+    const BVHAccel *bvh = dynamic_cast<const BVHAccel *>(scene.aggregate.get());
+    if (!bvh) {
+        Error("PathIntegrator::Render: the GPU path needs Accelerator \"bvh\" (kd-tree is out of scope, SURVEY.md §2 row 41)");
+        return;
+    }
+    if (!dynamic_cast<const HaltonSampler *>(sampler.get())) {
+        Error("PathIntegrator::Render: only Sampler \"halton\" is inside the GPU path's scope (SURVEY.md §2 rows 19-20)");
+        return;
+    }
+    if (bvh->nodes.empty()) {
+        if (writeImage) camera->film->WriteImage();
+        return;
+    }
+    std::shared_ptr<DeviceScene> ds = GetDeviceScene(*bvh, scene.lights, lightSampleStrategy);
+    if (!ds) return;
+    Film *film = camera->film;
+    pb2_camera cam = camera->Desc();
+    pb2_film_desc fd = film->Desc();
+    pb2_path_params pp = Params();
+    std::vector<float> rgbw((size_t)4 * film->pixels.size());
+    if (pb2_render_path(ds->handle, &cam, &fd, &pp, rgbw.data(), &lastStats) != PB2_OK) {
+        Error("pb2_render_path failed: %s", pb2_last_error());
+        return;
+    }
+    film->MergeDeviceFilm(rgbw.data());
+    if (writeImage) film->WriteImage();
+}
+
+}  // namespace pbrt

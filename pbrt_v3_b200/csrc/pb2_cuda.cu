@@ -1,0 +1,889 @@
+// CUDA kernels and the C ABI (include/pb2.h) of the path-tracing hot path, sm_100a only.
+//
+// Kernels
+//   k_build_leaf_records     scene upload: gather triangle vertices into BVH-ordered 48-B leaf records
+//   k_spatial_light_dist     scene upload: SpatialLightDistribution::ComputeDistribution for every voxel
+//   k_intersect / k_intersect_p   Scene::Intersect / IntersectP for a batch of rays (1 thread = 1 ray)
+//   k_render_path            SamplerIntegrator::Render + PathIntegrator::Li: persistent warps; every lane
+//                            owns one camera sample at a time and walks its path vertex by vertex, all
+//                            lanes of a warp entering the BVH traversal of the same ray class together;
+//                            a lane whose path ended deposits the sample in the film and takes the next
+//                            work item from a global counter (one warp-aggregated atomic per refill)
+//   k_li_samples, k_halton_samples, k_light_distribution   parity/debug entry points
+//
+// Compile flags that matter for parity: -fmad=false (the reference has no FMA contraction),
+// default IEEE division and square root, no fast-math.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "device/pb2_shade.cuh"
+#include "host/core.h"  // pbrt::RNG for the Halton permutation table
+#include "pb2.h"
+
+using namespace pb2;
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_lastError;
+static int setError(int code, const std::string &msg) {
+    g_lastError = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return setError(PB2_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+    } while (0)
+
+static bool g_initialised = false;
+static int g_device = -1;
+static int g_numSMs = 0;
+
+// ---------------------------------------------------------------------------------------------
+// Halton tables (lowdiscrepancy.cpp:40,124,2490-2504; halton.cpp:65-93)
+// ---------------------------------------------------------------------------------------------
+struct HaltonTables {
+    int32_t *primes = nullptr, *primeSums = nullptr;
+    uint16_t *perms = nullptr;
+    std::vector<int32_t> hPrimes, hPrimeSums;
+    std::vector<uint16_t> hPerms;
+};
+static HaltonTables g_halton;
+
+static void buildHaltonHostTables() {
+    if (!g_halton.hPrimes.empty()) return;
+    std::vector<int32_t> &primes = g_halton.hPrimes;
+    for (int n = 2; (int)primes.size() < kMaxHaltonDims; ++n) {
+        bool isPrime = true;
+        for (int p : primes) {
+            if (p * p > n) break;
+            if (n % p == 0) { isPrime = false; break; }
+        }
+        if (isPrime) primes.push_back(n);
+    }
+    g_halton.hPrimeSums.resize(kMaxHaltonDims);
+    int sum = 0;
+    for (int i = 0; i < kMaxHaltonDims; ++i) {
+        g_halton.hPrimeSums[i] = sum;
+        sum += primes[i];
+    }
+    // ComputeRadicalInversePermutations with a default-constructed RNG; Shuffle() from sampling.h:150-157
+    g_halton.hPerms.resize(sum);
+    pbrt::RNG rng;
+    uint16_t *p = g_halton.hPerms.data();
+    for (int i = 0; i < kMaxHaltonDims; ++i) {
+        int count = primes[i];
+        for (int j = 0; j < count; ++j) p[j] = (uint16_t)j;
+        for (int j = 0; j < count; ++j) {
+            int other = j + (int)rng.UniformUInt32((uint32_t)(count - j));
+            std::swap(p[j], p[other]);
+        }
+        p += count;
+    }
+}
+
+static void extendedGCD(uint64_t a, uint64_t b, int64_t *x, int64_t *y) {
+    if (b == 0) {
+        *x = 1;
+        *y = 0;
+        return;
+    }
+    int64_t d = a / b, xp, yp;
+    extendedGCD(b, a % b, &xp, &yp);
+    *x = yp;
+    *y = xp - (d * yp);
+}
+static uint64_t multiplicativeInverse(int64_t a, int64_t n) {
+    int64_t x, y;
+    extendedGCD(a, n, &x, &y);
+    int64_t r = x - (x / n) * n;
+    return (uint64_t)(r < 0 ? r + n : r);
+}
+
+struct SampleBounds { int x0, y0, x1, y1; };
+static SampleBounds filmSampleBounds(const pb2_film_desc *f) {  // Film::GetSampleBounds (film.cpp:80-86)
+    SampleBounds b;
+    b.x0 = (int)std::floor((float)f->cropped_pixel_bounds[0] + 0.5f - f->filter_radius[0]);
+    b.y0 = (int)std::floor((float)f->cropped_pixel_bounds[1] + 0.5f - f->filter_radius[1]);
+    b.x1 = (int)std::ceil((float)f->cropped_pixel_bounds[2] - 0.5f + f->filter_radius[0]);
+    b.y1 = (int)std::ceil((float)f->cropped_pixel_bounds[3] - 0.5f + f->filter_radius[1]);
+    return b;
+}
+
+static DHalton makeHalton(const pb2_film_desc *film, const pb2_path_params *pp) {
+    DHalton h;
+    SampleBounds sb = filmSampleBounds(film);
+    int res[2] = {sb.x1 - sb.x0, sb.y1 - sb.y0};
+    for (int i = 0; i < 2; ++i) {
+        int base = (i == 0) ? 2 : 3;
+        int scale = 1, exp = 0;
+        while (scale < std::min(res[i], kMaxResolution)) {
+            scale *= base;
+            ++exp;
+        }
+        h.baseScales[i] = scale;
+        h.baseExponents[i] = exp;
+    }
+    h.sampleStride = h.baseScales[0] * h.baseScales[1];
+    h.multInverse[0] = (int)multiplicativeInverse(h.baseScales[1], h.baseScales[0]);
+    h.multInverse[1] = (int)multiplicativeInverse(h.baseScales[0], h.baseScales[1]);
+    h.sampleAtPixelCenter = pp->sample_at_pixel_center;
+    h.samplesPerPixel = pp->samples_per_pixel;
+    h.perms = g_halton.perms;
+    h.primes = g_halton.primes;
+    h.primeSums = g_halton.primeSums;
+    return h;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scene
+// ---------------------------------------------------------------------------------------------
+struct pb2_scene {
+    DScene d;
+    std::vector<void *> allocations;
+    float *film = nullptr;  // cached device film for pb2_render_path
+    size_t filmFloats = 0;
+    unsigned long long *counters = nullptr;  // [0] work counter, [1..] stats
+    int64_t nPrims = 0;
+    int nLights = 0;
+};
+
+template <typename T>
+static int upload(pb2_scene *s, const T *host, size_t count, const T **dev) {
+    *dev = nullptr;
+    if (count == 0 || host == nullptr) return PB2_OK;
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, count * sizeof(T)));
+    s->allocations.push_back(p);
+    CUDA_TRY(cudaMemcpy(p, host, count * sizeof(T), cudaMemcpyHostToDevice));
+    *dev = (const T *)p;
+    return PB2_OK;
+}
+template <typename T>
+static int allocate(pb2_scene *s, size_t count, T **dev) {
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+    s->allocations.push_back(p);
+    *dev = (T *)p;
+    return PB2_OK;
+}
+
+__global__ void k_build_leaf_records(DScene sc, const int32_t *bvhPrims, float4 *out) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= sc.nPrims) return;
+    int prim = bvhPrims[j];
+    float4 a, b, c;
+    if (sc.primType[prim] == PB2_PRIM_SPHERE) {
+        a = make_float4(0, 0, 0, __int_as_float(prim));
+        b = make_float4(0, 0, 0, __uint_as_float(LEAF_SPHERE));
+        c = make_float4(0, 0, 0, __int_as_float(sc.primIndex[prim]));
+    } else {
+        int tri = sc.primIndex[prim];
+        TriVerts t = triVerts(sc, tri);
+        uint32_t flags = 0;
+        V2 uv[3];
+        triUVs(sc, tri, sc.meshes[sc.triMesh[tri]], uv);
+        V3 dpdu, dpdv;
+        if (!triPartials(t.p0, t.p1, t.p2, uv, &dpdu, &dpdv)) flags |= LEAF_DEGENERATE;
+        a = make_float4(t.p0.x, t.p0.y, t.p0.z, __int_as_float(prim));
+        b = make_float4(t.p1.x, t.p1.y, t.p1.z, __uint_as_float(flags));
+        c = make_float4(t.p2.x, t.p2.y, t.p2.z, 0.f);
+    }
+    out[3 * j] = a;
+    out[3 * j + 1] = b;
+    out[3 * j + 2] = c;
+}
+
+__global__ void k_spatial_light_dist(DScene sc, DHalton h, float *table) {
+    int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const DLightDist &ld = sc.lightDist;
+    int64_t total = (int64_t)ld.nVoxels[0] * ld.nVoxels[1] * ld.nVoxels[2];
+    if (v >= total) return;
+    int pz = (int)(v % ld.nVoxels[2]);
+    int py = (int)((v / ld.nVoxels[2]) % ld.nVoxels[1]);
+    int px = (int)(v / ((int64_t)ld.nVoxels[2] * ld.nVoxels[1]));
+    computeVoxelDistribution(sc, h, ld, px, py, pz, table + v * ld.stride);
+}
+
+// ---------------------------------------------------------------------------------------------
+// intersection kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_intersect(DScene sc, const pb2_ray *rays, int64_t n, pb2_hit *hits) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DRay r;
+    r.o = mk3(rays[i].o[0], rays[i].o[1], rays[i].o[2]);
+    r.d = mk3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+    r.tMax = rays[i].t_max;
+    DHit h;
+    h.leaf = -1;
+    h.b0 = h.b1 = h.b2 = 0;
+    float tMax = r.tMax;
+    DCounters ctr{};
+    bool found = traverse<false>(sc, r, &tMax, &h, &ctr);
+    pb2_hit out;
+    memset(&out, 0, sizeof(out));
+    out.prim = -1;
+    out.t = tMax;
+    if (found) {
+        DInteraction it = hitInteraction(sc, h, r, tMax);
+        out.prim = it.prim;
+        out.b[0] = h.b0; out.b[1] = h.b1; out.b[2] = h.b2;
+        out.p[0] = it.p.x; out.p[1] = it.p.y; out.p[2] = it.p.z;
+        out.p_error[0] = it.pError.x; out.p_error[1] = it.pError.y; out.p_error[2] = it.pError.z;
+        out.n[0] = it.n.x; out.n[1] = it.n.y; out.n[2] = it.n.z;
+        out.ns[0] = it.ns.x; out.ns[1] = it.ns.y; out.ns[2] = it.ns.z;
+        out.dpdu[0] = it.dpdus.x; out.dpdu[1] = it.dpdus.y; out.dpdu[2] = it.dpdus.z;
+        out.uv[0] = it.uv.x; out.uv[1] = it.uv.y;
+    }
+    hits[i] = out;
+}
+
+__global__ void k_intersect_p(DScene sc, const pb2_ray *rays, int64_t n, uint8_t *occluded) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    DRay r;
+    r.o = mk3(rays[i].o[0], rays[i].o[1], rays[i].o[2]);
+    r.d = mk3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+    r.tMax = rays[i].t_max;
+    DHit h;
+    float tMax = r.tMax;
+    DCounters ctr{};
+    occluded[i] = traverse<true>(sc, r, &tMax, &h, &ctr) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// render kernel
+// ---------------------------------------------------------------------------------------------
+struct DRenderParams {
+    DCamera cam;
+    DHalton halton;
+    DPathParams path;
+    int sbx0, sby0, sbx1, sby1;  // sample bounds (Film::GetSampleBounds)
+    int pbx0, pby0, pbx1, pby1;  // PathIntegrator::pixelBounds
+    int cx0, cy0, cx1, cy1;      // Film::croppedPixelBounds
+    float filterRadiusX, filterRadiusY;
+    float maxSampleLuminance;
+    int nTilesX, nTilesY;
+    int tileRank, tileCount;
+    long long nOwnedTiles;
+    long long nWorkItems;        // nOwnedTiles * 256 * spp
+    int spp;
+};
+
+enum { CTR_WORK = 0, CTR_CAMERA = 1, CTR_REGULAR = 2, CTR_SHADOW = 3, CTR_NODES = 4, CTR_PRIMS = 5, CTR_COUNT = 8 };
+
+__device__ __forceinline__ int compact1by1(unsigned x) {
+    x &= 0x55555555u;
+    x = (x ^ (x >> 1)) & 0x33333333u;
+    x = (x ^ (x >> 2)) & 0x0f0f0f0fu;
+    x = (x ^ (x >> 4)) & 0x00ff00ffu;
+    return (int)x;
+}
+
+// Work item -> (pixel, sample number).  Items are ordered tile by tile (the reference's 16x16 tiles,
+// integrator.cpp:235-240), then by sample number, then in Morton order inside the tile, so 32
+// consecutive items are one sample number of an 8x4 pixel block: coherent camera rays for a warp
+// that refills all its lanes at once.
+__device__ __forceinline__ bool decodeWork(const DRenderParams &rp, long long item, int *px, int *py, int *sample) {
+    long long perTile = 256LL * rp.spp;
+    long long owned = item / perTile;
+    int r = (int)(item - owned * perTile);
+    long long tile = (long long)rp.tileRank + owned * rp.tileCount;
+    int ty = (int)(tile / rp.nTilesX), tx = (int)(tile - (long long)ty * rp.nTilesX);
+    int s = r >> 8, m = r & 255;
+    int x = rp.sbx0 + tx * 16 + compact1by1((unsigned)m);
+    int y = rp.sby0 + ty * 16 + compact1by1((unsigned)m >> 1);
+    *px = x;
+    *py = y;
+    *sample = s;
+    if (x >= rp.sbx1 || y >= rp.sby1) return false;
+    // integrator.cpp:274: pixels outside pixelBounds are skipped
+    return x >= rp.pbx0 && x < rp.pbx1 && y >= rp.pby0 && y < rp.pby1;
+}
+
+// FilmTile::AddSample (film.h:121-161) with a box filter, accumulated straight into the merged film
+// (MergeFilmTile's sum, film.cpp:117-130).  For every tile the tile's pixel bounds contain the
+// support of each of its samples, so the clamp to the tile bounds is the clamp to the cropped bounds.
+__device__ __forceinline__ void addSample(const DRenderParams &rp, float4 *film, V2 pFilm, V3 L) {
+    float y = luminance(L);
+    if (y > rp.maxSampleLuminance) L = L * (rp.maxSampleLuminance / y);
+    float dx = pFilm.x - 0.5f, dy = pFilm.y - 0.5f;
+    int p0x = (int)ceilf(dx - rp.filterRadiusX), p0y = (int)ceilf(dy - rp.filterRadiusY);
+    int p1x = (int)floorf(dx + rp.filterRadiusX) + 1, p1y = (int)floorf(dy + rp.filterRadiusY) + 1;
+    p0x = max(p0x, rp.cx0);
+    p0y = max(p0y, rp.cy0);
+    p1x = min(p1x, rp.cx1);
+    p1y = min(p1y, rp.cy1);
+    int width = rp.cx1 - rp.cx0;
+    for (int yy = p0y; yy < p1y; ++yy)
+        for (int xx = p0x; xx < p1x; ++xx) {
+            // box filter: filterTable[...] == 1 everywhere; L * sampleWeight(1) * filterWeight(1)
+            float4 *px = film + ((size_t)(yy - rp.cy0) * width + (xx - rp.cx0));
+            atomicAdd(px, make_float4(L.x, L.y, L.z, 1.f));
+        }
+}
+
+__global__ void __launch_bounds__(128) k_render_path(DScene sc, DRenderParams rp, float4 *film, unsigned long long *counters) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    DPathState ps;
+    DRayStats st;
+    st.regular = st.shadow = 0;
+    unsigned cameraRays = 0;
+    DCounters ctr{};
+    bool active = false, exhausted = false;
+    int px = 0, py = 0;
+    V2 pFilm = mk2(0, 0);
+    ps.L = mk3(0, 0, 0);
+    while (true) {
+        // refill idle lanes: one atomic per warp
+        bool want = !active && !exhausted;
+        unsigned wantMask = __ballot_sync(FULL, want);
+        if (wantMask) {
+            int leader = __ffs(wantMask) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&counters[CTR_WORK], (unsigned long long)__popc(wantMask));
+            base = __shfl_sync(FULL, base, leader);
+            if (want) {
+                long long item = (long long)base + __popc(wantMask & ((1u << lane) - 1u));
+                if (item >= rp.nWorkItems)
+                    exhausted = true;
+                else {
+                    int sample;
+                    if (decodeWork(rp, item, &px, &py, &sample)) {
+                        DSampler smp;
+                        smp.index = haltonIndex(rp.halton, px, py, sample);
+                        smp.dim = 0;
+                        DRay ray = generateCameraRay(rp.cam, rp.halton, smp, px, py, &pFilm);
+                        initPath(ps, ray, smp);
+                        cameraRays++;
+                        active = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(FULL, active)) {
+            if (__all_sync(FULL, exhausted)) break;
+            continue;
+        }
+        if (active) {
+            bool cont = pathVertex(sc, rp.halton, rp.path, ps, st, &ctr);
+            if (!cont) {
+                addSample(rp, film, pFilm, guardRadiance(ps.L));
+                active = false;
+            }
+        }
+    }
+    // statistics: warp reduce, one atomic per warp and counter
+    unsigned long long c0 = cameraRays, c1 = st.regular, c2 = st.shadow;
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_down_sync(FULL, c0, o);
+        c1 += __shfl_down_sync(FULL, c1, o);
+        c2 += __shfl_down_sync(FULL, c2, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&counters[CTR_CAMERA], c0);
+        atomicAdd(&counters[CTR_REGULAR], c1);
+        atomicAdd(&counters[CTR_SHADOW], c2);
+    }
+#ifdef PB2_COUNTERS
+    unsigned long long n0 = ctr.nodes, n1 = ctr.prims;
+    for (int o = 16; o > 0; o >>= 1) {
+        n0 += __shfl_down_sync(FULL, n0, o);
+        n1 += __shfl_down_sync(FULL, n1, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&counters[CTR_NODES], n0);
+        atomicAdd(&counters[CTR_PRIMS], n1);
+    }
+#endif
+}
+
+__global__ void k_li_samples(DScene sc, DRenderParams rp, const int32_t *pixelXY, const int64_t *sampleNum, int64_t n,
+                             float *outRGB, float *outPFilm) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int px = pixelXY[2 * i], py = pixelXY[2 * i + 1];
+    DSampler smp;
+    smp.index = haltonIndex(rp.halton, px, py, sampleNum[i]);
+    smp.dim = 0;
+    V2 pFilm;
+    DRay ray = generateCameraRay(rp.cam, rp.halton, smp, px, py, &pFilm);
+    DPathState ps;
+    initPath(ps, ray, smp);
+    DRayStats st;
+    st.regular = st.shadow = 0;
+    DCounters ctr{};
+    while (pathVertex(sc, rp.halton, rp.path, ps, st, &ctr)) {
+    }
+    V3 L = guardRadiance(ps.L);
+    outRGB[3 * i] = L.x;
+    outRGB[3 * i + 1] = L.y;
+    outRGB[3 * i + 2] = L.z;
+    if (outPFilm) {
+        outPFilm[2 * i] = pFilm.x;
+        outPFilm[2 * i + 1] = pFilm.y;
+    }
+}
+
+__global__ void k_halton_samples(DHalton h, const int32_t *pixelXY, const int64_t *sampleNum, const int32_t *dim, int64_t n,
+                                 float *out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int64_t index = haltonIndex(h, pixelXY[2 * i], pixelXY[2 * i + 1], sampleNum[i]);
+    out[i] = haltonSample(h, index, dim[i]);
+}
+
+__global__ void k_light_distribution(DScene sc, const float *points, int64_t n, float *out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *rec = lightDistLookup(sc.lightDist, mk3(points[3 * i], points[3 * i + 1], points[3 * i + 2]));
+    int stride = 2 * sc.nLights + 1;
+    for (int k = 0; k < stride; ++k) out[i * stride + k] = rec[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side of the ABI
+// ---------------------------------------------------------------------------------------------
+static int requireDevice() {
+    if (!g_initialised) return setError(PB2_ERR_NO_DEVICE, "pb2_init() has not succeeded: no CUDA device is bound (there is no CPU fallback)");
+    return PB2_OK;
+}
+
+static DRenderParams makeRenderParams(const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp) {
+    DRenderParams rp;
+    memset(&rp, 0, sizeof(rp));
+    memcpy(rp.cam.rasterToCamera.m, cam->raster_to_camera, sizeof(float) * 16);
+    memcpy(rp.cam.cameraToWorld.m, cam->camera_to_world, sizeof(float) * 16);
+    rp.cam.lensRadius = cam->lens_radius;
+    rp.cam.focalDistance = cam->focal_distance;
+    rp.halton = makeHalton(film, pp);
+    rp.path.maxDepth = pp->max_depth;
+    rp.path.rrThreshold = pp->rr_threshold;
+    SampleBounds sb = filmSampleBounds(film);
+    rp.sbx0 = sb.x0; rp.sby0 = sb.y0; rp.sbx1 = sb.x1; rp.sby1 = sb.y1;
+    rp.pbx0 = pp->pixel_bounds[0]; rp.pby0 = pp->pixel_bounds[1]; rp.pbx1 = pp->pixel_bounds[2]; rp.pby1 = pp->pixel_bounds[3];
+    rp.cx0 = film->cropped_pixel_bounds[0]; rp.cy0 = film->cropped_pixel_bounds[1];
+    rp.cx1 = film->cropped_pixel_bounds[2]; rp.cy1 = film->cropped_pixel_bounds[3];
+    rp.filterRadiusX = film->filter_radius[0];
+    rp.filterRadiusY = film->filter_radius[1];
+    rp.maxSampleLuminance = film->max_sample_luminance;
+    rp.nTilesX = (sb.x1 - sb.x0 + 15) / 16;
+    rp.nTilesY = (sb.y1 - sb.y0 + 15) / 16;
+    rp.tileCount = std::max(1, pp->tile_count);
+    rp.tileRank = pp->tile_rank;
+    long long nTiles = (long long)std::max(0, rp.nTilesX) * std::max(0, rp.nTilesY);
+    rp.nOwnedTiles = nTiles > rp.tileRank ? (nTiles - rp.tileRank + rp.tileCount - 1) / rp.tileCount : 0;
+    rp.spp = pp->samples_per_pixel;
+    rp.nWorkItems = rp.nOwnedTiles * 256LL * rp.spp;
+    return rp;
+}
+
+static int validateRenderArgs(const pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp) {
+    if (!scene || !cam || !film || !pp) return setError(PB2_ERR_INVALID, "null argument");
+    if (pp->samples_per_pixel <= 0 || pp->max_depth < 0) return setError(PB2_ERR_INVALID, "bad samples_per_pixel / max_depth");
+    if (pp->tile_count < 0 || pp->tile_rank < 0 || (pp->tile_count > 0 && pp->tile_rank >= pp->tile_count))
+        return setError(PB2_ERR_INVALID, "bad tile_rank / tile_count");
+    if (film->cropped_pixel_bounds[2] < film->cropped_pixel_bounds[0] || film->cropped_pixel_bounds[3] < film->cropped_pixel_bounds[1])
+        return setError(PB2_ERR_INVALID, "bad cropped pixel bounds");
+    return PB2_OK;
+}
+
+extern "C" {
+
+int pb2_abi_version(void) { return PB2_ABI_VERSION; }
+const char *pb2_last_error(void) { return g_lastError.c_str(); }
+
+int pb2_init(int device_id) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return setError(PB2_ERR_NO_DEVICE, std::string("no CUDA device available (") +
+                                               (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                               "); the path-tracing hot path has no CPU fallback");
+    }
+    if (device_id < 0 || device_id >= count) return setError(PB2_ERR_INVALID, "device id out of range");
+    if (g_initialised && g_device == device_id) return PB2_OK;
+    CUDA_TRY(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major < 10)
+        return setError(PB2_ERR_NO_DEVICE, std::string("device \"") + prop.name + "\" is not sm_100-class; this library is built for sm_100a only");
+    g_numSMs = prop.multiProcessorCount;
+    buildHaltonHostTables();
+    CUDA_TRY(cudaMalloc((void **)&g_halton.primes, g_halton.hPrimes.size() * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc((void **)&g_halton.primeSums, g_halton.hPrimeSums.size() * sizeof(int32_t)));
+    CUDA_TRY(cudaMalloc((void **)&g_halton.perms, g_halton.hPerms.size() * sizeof(uint16_t)));
+    CUDA_TRY(cudaMemcpy(g_halton.primes, g_halton.hPrimes.data(), g_halton.hPrimes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(g_halton.primeSums, g_halton.hPrimeSums.data(), g_halton.hPrimeSums.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(g_halton.perms, g_halton.hPerms.data(), g_halton.hPerms.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    // the traversal stack lives in local memory: 64 ints per thread
+    g_device = device_id;
+    g_initialised = true;
+    return PB2_OK;
+}
+
+int pb2_shutdown(void) {
+    if (!g_initialised) return PB2_OK;
+    cudaFree(g_halton.primes);
+    cudaFree(g_halton.primeSums);
+    cudaFree(g_halton.perms);
+    g_halton.primes = g_halton.primeSums = nullptr;
+    g_halton.perms = nullptr;
+    g_initialised = false;
+    return PB2_OK;
+}
+
+int pb2_scene_destroy(pb2_scene *s) {
+    if (!s) return PB2_OK;
+    for (void *p : s->allocations) cudaFree(p);
+    if (s->film) cudaFree(s->film);
+    delete s;
+    return PB2_OK;
+}
+
+int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
+    if (!d || !out) return setError(PB2_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int rc = requireDevice();
+    if (rc) return rc;
+    if (d->n_prims <= 0 || d->n_nodes <= 0 || !d->nodes || !d->bvh_prims || !d->prim_type || !d->prim_index)
+        return setError(PB2_ERR_INVALID, "scene has no primitives / BVH");
+    if (d->n_prims > 0x7fffffffLL || d->n_nodes > 0x7fffffffLL) return setError(PB2_ERR_UNSUPPORTED, "more than 2^31 primitives/nodes");
+    for (int i = 0; i < d->n_materials; ++i)
+        if (d->materials[i].type != PB2_MAT_NONE && d->materials[i].type != PB2_MAT_MATTE && d->materials[i].type != PB2_MAT_PLASTIC)
+            return setError(PB2_ERR_UNSUPPORTED, "material type outside the path's scope (matte, plastic)");
+    struct Guard {
+        pb2_scene *s;
+        ~Guard() { if (s) pb2_scene_destroy(s); }
+    } guard{new pb2_scene()};
+    pb2_scene *s = guard.s;
+    DScene &sc = s->d;
+    memset(&sc, 0, sizeof(sc));
+    sc.nNodes = d->n_nodes;
+    sc.nPrims = d->n_prims;
+    sc.nTris = d->n_tris;
+    sc.nLights = d->n_lights;
+    s->nPrims = d->n_prims;
+    s->nLights = d->n_lights;
+    const pb2_bvh_node *nodes;
+    if ((rc = upload(s, d->nodes, (size_t)d->n_nodes, &nodes))) return rc;
+    sc.nodes = reinterpret_cast<const float4 *>(nodes);
+    if ((rc = upload(s, d->P, 3 * (size_t)d->n_vertices, &sc.P))) return rc;
+    if ((rc = upload(s, d->N, d->N ? 3 * (size_t)d->n_vertices : 0, &sc.N))) return rc;
+    if ((rc = upload(s, d->UV, d->UV ? 2 * (size_t)d->n_vertices : 0, &sc.UV))) return rc;
+    if ((rc = upload(s, d->S, d->S ? 3 * (size_t)d->n_vertices : 0, &sc.S))) return rc;
+    if ((rc = upload(s, d->tri_index, 3 * (size_t)d->n_tris, &sc.triIndex))) return rc;
+    if ((rc = upload(s, d->tri_mesh, (size_t)d->n_tris, &sc.triMesh))) return rc;
+    if ((rc = upload(s, d->meshes, (size_t)d->n_meshes, &sc.meshes))) return rc;
+    if ((rc = upload(s, d->spheres, (size_t)d->n_spheres, &sc.spheres))) return rc;
+    if ((rc = upload(s, d->prim_type, (size_t)d->n_prims, &sc.primType))) return rc;
+    if ((rc = upload(s, d->prim_index, (size_t)d->n_prims, &sc.primIndex))) return rc;
+    if ((rc = upload(s, d->prim_material, (size_t)d->n_prims, &sc.primMaterial))) return rc;
+    if ((rc = upload(s, d->prim_light, (size_t)d->n_prims, &sc.primLight))) return rc;
+    if ((rc = upload(s, d->materials, (size_t)d->n_materials, &sc.materials))) return rc;
+    if ((rc = upload(s, d->lights, (size_t)d->n_lights, &sc.lights))) return rc;
+    for (int m = 0; m < d->n_meshes; ++m) {
+        if (d->meshes[m].has_n && !d->N) return setError(PB2_ERR_INVALID, "mesh has_n but N is null");
+        if (d->meshes[m].has_uv && !d->UV) return setError(PB2_ERR_INVALID, "mesh has_uv but UV is null");
+        if (d->meshes[m].has_s && !d->S) return setError(PB2_ERR_INVALID, "mesh has_s but S is null");
+    }
+    // leaf records in BVH order
+    const int32_t *bvhPrims;
+    if ((rc = upload(s, d->bvh_prims, (size_t)d->n_prims, &bvhPrims))) return rc;
+    float4 *leaf;
+    if ((rc = allocate(s, 3 * (size_t)d->n_prims, &leaf))) return rc;
+    {
+        int threads = 256;
+        int64_t blocks = (d->n_prims + threads - 1) / threads;
+        k_build_leaf_records<<<(unsigned)blocks, threads>>>(sc, bvhPrims, leaf);
+        CUDA_TRY(cudaGetLastError());
+    }
+    sc.leafPrims = leaf;
+
+    // light-sampling distribution (lightdistrib.cpp:48-66)
+    DLightDist &ld = sc.lightDist;
+    memset(&ld, 0, sizeof(ld));
+    int nl = d->n_lights;
+    ld.stride = 2 * nl + 2;
+    ld.strategy = (nl <= 1) ? PB2_LIGHTDIST_UNIFORM : d->light_strategy;
+    ld.boundsMin = mk3(d->nodes[0].bmin[0], d->nodes[0].bmin[1], d->nodes[0].bmin[2]);
+    ld.boundsMax = mk3(d->nodes[0].bmax[0], d->nodes[0].bmax[1], d->nodes[0].bmax[2]);
+    if (nl > 0 && ld.strategy != PB2_LIGHTDIST_SPATIAL) {
+        // Distribution1D over constant 1 (uniform) or over Light::Power().y() (power)
+        std::vector<float> rec(ld.stride);
+        for (int i = 0; i < nl; ++i) {
+            if (ld.strategy == PB2_LIGHTDIST_UNIFORM)
+                rec[i] = 1.f;
+            else {
+                // DiffuseAreaLight::Power (diffuse.cpp:64-66): (twoSided ? 2 : 1) * Lemit * area * Pi, then y()
+                const pb2_light &l = d->lights[i];
+                float s2 = l.two_sided ? 2.f : 1.f;
+                float p[3];
+                for (int c = 0; c < 3; ++c) p[c] = ((s2 * l.L[c]) * l.area) * 3.14159265358979323846f;
+                rec[i] = 0.212671f * p[0] + 0.715160f * p[1] + 0.072169f * p[2];
+            }
+        }
+        float *cdf = rec.data() + nl;
+        cdf[0] = 0;
+        for (int i = 1; i < nl + 1; ++i) cdf[i] = cdf[i - 1] + rec[i - 1] / nl;
+        float funcInt = cdf[nl];
+        if (funcInt == 0) {
+            for (int i = 1; i < nl + 1; ++i) cdf[i] = float(i) / float(nl);
+        } else {
+            for (int i = 1; i < nl + 1; ++i) cdf[i] /= funcInt;
+        }
+        rec[2 * nl + 1] = funcInt;
+        if ((rc = upload(s, rec.data(), rec.size(), &ld.table))) return rc;
+    } else if (nl > 0) {
+        // SpatialLightDistribution ctor (lightdistrib.cpp:96-122)
+        float diag[3] = {ld.boundsMax.x - ld.boundsMin.x, ld.boundsMax.y - ld.boundsMin.y, ld.boundsMax.z - ld.boundsMin.z};
+        int maxExtent = (diag[0] > diag[1] && diag[0] > diag[2]) ? 0 : (diag[1] > diag[2] ? 1 : 2);
+        float bmax = diag[maxExtent];
+        int maxVoxels = d->spatial_max_voxels > 0 ? d->spatial_max_voxels : 64;
+        for (int i = 0; i < 3; ++i) ld.nVoxels[i] = std::max(1, int(std::round(diag[i] / bmax * maxVoxels)));
+        size_t nVox = (size_t)ld.nVoxels[0] * ld.nVoxels[1] * ld.nVoxels[2];
+        if (nVox * ld.stride * sizeof(float) > (size_t)8 << 30)
+            return setError(PB2_ERR_UNSUPPORTED, "spatial light distribution table would exceed 8 GiB (too many lights); use lightsamplestrategy \"uniform\" or \"power\"");
+        float *table;
+        if ((rc = allocate(s, nVox * ld.stride, &table))) return rc;
+        ld.table = table;
+        DHalton h;
+        memset(&h, 0, sizeof(h));
+        h.primes = g_halton.primes;
+        h.primeSums = g_halton.primeSums;
+        h.perms = g_halton.perms;
+        int threads = 128;
+        k_spatial_light_dist<<<(unsigned)((nVox + threads - 1) / threads), threads>>>(sc, h, table);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if ((rc = allocate(s, (size_t)CTR_COUNT, &s->counters))) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());
+    guard.s = nullptr;
+    *out = s;
+    return PB2_OK;
+}
+
+int pb2_intersect(pb2_scene *scene, const pb2_ray *rays, int64_t n, pb2_hit *hits) {
+    int rc = requireDevice();
+    if (rc) return rc;
+    if (!scene || (n > 0 && (!rays || !hits))) return setError(PB2_ERR_INVALID, "null argument");
+    if (n <= 0) return PB2_OK;
+    pb2_ray *dRays = nullptr;
+    pb2_hit *dHits = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&dRays, n * sizeof(pb2_ray)));
+    cudaError_t e = cudaMalloc((void **)&dHits, n * sizeof(pb2_hit));
+    if (e != cudaSuccess) { cudaFree(dRays); return setError(PB2_ERR_CUDA, cudaGetErrorString(e)); }
+    e = cudaMemcpy(dRays, rays, n * sizeof(pb2_ray), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_intersect<<<(unsigned)((n + 127) / 128), 128>>>(scene->d, dRays, n, dHits);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(hits, dHits, n * sizeof(pb2_hit), cudaMemcpyDeviceToHost);
+    cudaFree(dRays);
+    cudaFree(dHits);
+    if (e != cudaSuccess) return setError(PB2_ERR_CUDA, std::string("pb2_intersect: ") + cudaGetErrorString(e));
+    return PB2_OK;
+}
+
+int pb2_intersect_p(pb2_scene *scene, const pb2_ray *rays, int64_t n, uint8_t *occluded) {
+    int rc = requireDevice();
+    if (rc) return rc;
+    if (!scene || (n > 0 && (!rays || !occluded))) return setError(PB2_ERR_INVALID, "null argument");
+    if (n <= 0) return PB2_OK;
+    pb2_ray *dRays = nullptr;
+    uint8_t *dOcc = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&dRays, n * sizeof(pb2_ray)));
+    cudaError_t e = cudaMalloc((void **)&dOcc, n);
+    if (e != cudaSuccess) { cudaFree(dRays); return setError(PB2_ERR_CUDA, cudaGetErrorString(e)); }
+    e = cudaMemcpy(dRays, rays, n * sizeof(pb2_ray), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_intersect_p<<<(unsigned)((n + 127) / 128), 128>>>(scene->d, dRays, n, dOcc);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(occluded, dOcc, n, cudaMemcpyDeviceToHost);
+    cudaFree(dRays);
+    cudaFree(dOcc);
+    if (e != cudaSuccess) return setError(PB2_ERR_CUDA, std::string("pb2_intersect_p: ") + cudaGetErrorString(e));
+    return PB2_OK;
+}
+
+int pb2_render_path_device(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp,
+                           float *film_rgbw_device, int clear, void *stream_, pb2_stats *stats) {
+    int rc = requireDevice();
+    if (rc) return rc;
+    if ((rc = validateRenderArgs(scene, cam, film, pp))) return rc;
+    if (!film_rgbw_device) return setError(PB2_ERR_INVALID, "null film pointer");
+    if (film->filter_radius[0] <= 0 || film->filter_radius[1] <= 0) return setError(PB2_ERR_INVALID, "bad filter radius");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DRenderParams rp = makeRenderParams(cam, film, pp);
+    size_t nPixels = (size_t)(rp.cx1 - rp.cx0) * (size_t)(rp.cy1 - rp.cy0);
+    if (clear) CUDA_TRY(cudaMemsetAsync(film_rgbw_device, 0, nPixels * 4 * sizeof(float), stream));
+    CUDA_TRY(cudaMemsetAsync(scene->counters, 0, CTR_COUNT * sizeof(unsigned long long), stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (stats) {
+        CUDA_TRY(cudaEventCreate(&e0));
+        CUDA_TRY(cudaEventCreate(&e1));
+        CUDA_TRY(cudaEventRecord(e0, stream));
+    }
+    if (rp.nWorkItems > 0) {
+        int threads = 128, blocksPerSM = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_render_path, threads, 0));
+        blocksPerSM = std::max(1, blocksPerSM);
+        long long warpsNeeded = (rp.nWorkItems + 31) / 32;
+        long long blocks = std::min<long long>((long long)g_numSMs * blocksPerSM, (warpsNeeded + 3) / 4);
+        k_render_path<<<(unsigned)std::max<long long>(1, blocks), threads, 0, stream>>>(scene->d, rp, (float4 *)film_rgbw_device, scene->counters);
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (stats) {
+        CUDA_TRY(cudaEventRecord(e1, stream));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        unsigned long long c[CTR_COUNT];
+        CUDA_TRY(cudaMemcpyAsync(c, scene->counters, sizeof(c), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        memset(stats, 0, sizeof(*stats));
+        stats->camera_rays = c[CTR_CAMERA];
+        stats->regular_rays = c[CTR_REGULAR];
+        stats->shadow_rays = c[CTR_SHADOW];
+        stats->node_visits = c[CTR_NODES];
+        stats->prim_tests = c[CTR_PRIMS];
+        stats->kernel_launches = rp.nWorkItems > 0 ? 1 : 0;
+        stats->render_ms = ms;
+    }
+    return PB2_OK;
+}
+
+int pb2_render_path(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp,
+                    float *film_rgbw, pb2_stats *stats) {
+    int rc = requireDevice();
+    if (rc) return rc;
+    if ((rc = validateRenderArgs(scene, cam, film, pp))) return rc;
+    if (!film_rgbw) return setError(PB2_ERR_INVALID, "null film pointer");
+    size_t nFloats = 4 * (size_t)(film->cropped_pixel_bounds[2] - film->cropped_pixel_bounds[0]) *
+                     (size_t)(film->cropped_pixel_bounds[3] - film->cropped_pixel_bounds[1]);
+    if (nFloats == 0) return PB2_OK;
+    if (scene->filmFloats < nFloats) {
+        if (scene->film) cudaFree(scene->film);
+        scene->film = nullptr;
+        scene->filmFloats = 0;
+        CUDA_TRY(cudaMalloc((void **)&scene->film, nFloats * sizeof(float)));
+        scene->filmFloats = nFloats;
+    }
+    pb2_stats local;
+    rc = pb2_render_path_device(scene, cam, film, pp, scene->film, 1, nullptr, &local);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    CUDA_TRY(cudaEventRecord(e0));
+    CUDA_TRY(cudaMemcpy(film_rgbw, scene->film, nFloats * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaEventRecord(e1));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    local.d2h_ms = ms;
+    if (stats) *stats = local;
+    return PB2_OK;
+}
+
+int pb2_li_samples(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp,
+                   const int32_t *pixel_xy, const int64_t *sample_num, int64_t n, float *out_rgb, float *out_pfilm) {
+    int rc = requireDevice();
+    if (rc) return rc;
+    if ((rc = validateRenderArgs(scene, cam, film, pp))) return rc;
+    if (n <= 0) return PB2_OK;
+    if (!pixel_xy || !sample_num || !out_rgb) return setError(PB2_ERR_INVALID, "null argument");
+    DRenderParams rp = makeRenderParams(cam, film, pp);
+    int32_t *dXY = nullptr;
+    int64_t *dS = nullptr;
+    float *dRGB = nullptr, *dPF = nullptr;
+    cudaError_t e = cudaMalloc((void **)&dXY, n * 2 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dS, n * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dRGB, n * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dPF, n * 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(dXY, pixel_xy, n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dS, sample_num, n * sizeof(int64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_li_samples<<<(unsigned)((n + 63) / 64), 64>>>(scene->d, rp, dXY, dS, n, dRGB, dPF);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out_rgb, dRGB, n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && out_pfilm) e = cudaMemcpy(out_pfilm, dPF, n * 2 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(dXY);
+    cudaFree(dS);
+    cudaFree(dRGB);
+    cudaFree(dPF);
+    if (e != cudaSuccess) return setError(PB2_ERR_CUDA, std::string("pb2_li_samples: ") + cudaGetErrorString(e));
+    return PB2_OK;
+}
+
+int pb2_halton_samples(const pb2_film_desc *film, const pb2_path_params *pp, const int32_t *pixel_xy,
+                       const int64_t *sample_num, const int32_t *dim, int64_t n, float *out) {
+    int rc = requireDevice();
+    if (rc) return rc;
+    if (!film || !pp || (n > 0 && (!pixel_xy || !sample_num || !dim || !out))) return setError(PB2_ERR_INVALID, "null argument");
+    if (n <= 0) return PB2_OK;
+    for (int64_t i = 0; i < n; ++i)
+        if (dim[i] < 0 || dim[i] >= kMaxHaltonDims) return setError(PB2_ERR_INVALID, "HaltonSampler can only sample 1000 dimensions");
+    DHalton h = makeHalton(film, pp);
+    int32_t *dXY = nullptr, *dDim = nullptr;
+    int64_t *dS = nullptr;
+    float *dOut = nullptr;
+    cudaError_t e = cudaMalloc((void **)&dXY, n * 2 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dS, n * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dDim, n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dOut, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(dXY, pixel_xy, n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dS, sample_num, n * sizeof(int64_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dDim, dim, n * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_halton_samples<<<(unsigned)((n + 127) / 128), 128>>>(h, dXY, dS, dDim, n, dOut);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dOut, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(dXY);
+    cudaFree(dS);
+    cudaFree(dDim);
+    cudaFree(dOut);
+    if (e != cudaSuccess) return setError(PB2_ERR_CUDA, std::string("pb2_halton_samples: ") + cudaGetErrorString(e));
+    return PB2_OK;
+}
+
+int pb2_light_distribution(pb2_scene *scene, const float *points_xyz, int64_t n, float *out) {
+    int rc = requireDevice();
+    if (rc) return rc;
+    if (!scene || (n > 0 && (!points_xyz || !out))) return setError(PB2_ERR_INVALID, "null argument");
+    if (n <= 0 || scene->nLights == 0) return PB2_OK;
+    size_t stride = 2 * (size_t)scene->nLights + 1;
+    float *dP = nullptr, *dOut = nullptr;
+    cudaError_t e = cudaMalloc((void **)&dP, n * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dOut, n * stride * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(dP, points_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_light_distribution<<<(unsigned)((n + 127) / 128), 128>>>(scene->d, dP, n, dOut);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dOut, n * stride * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(dP);
+    cudaFree(dOut);
+    if (e != cudaSuccess) return setError(PB2_ERR_CUDA, std::string("pb2_light_distribution: ") + cudaGetErrorString(e));
+    return PB2_OK;
+}
+
+}  // extern "C"
