@@ -20,9 +20,11 @@
 #if defined(__CUDACC__)
 #define PB2_HD __host__ __device__ __forceinline__
 #define PB2_D __device__ __forceinline__
+#define PB2_HDN __host__ __device__ __noinline__
 #else
 #define PB2_HD inline
 #define PB2_D inline
+#define PB2_HDN inline
 #endif
 
 namespace pb2 {

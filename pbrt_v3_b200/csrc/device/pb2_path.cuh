@@ -1,0 +1,229 @@
+// PathIntegrator::Li as a per-lane state machine with ONE ray-tracing site.
+//
+// The reference's bounce loop (src/integrators/path.cpp:81-185) traces up to three rays per path
+// vertex, at three different places: the path ray (closest hit), the next-event-estimation shadow
+// ray (any hit, src/core/integrator.cpp:146) and the MIS ray of the BSDF sample (closest hit,
+// integrator.cpp:202).  None of the sampler dimensions, BSDF values or ray origins of a vertex
+// depends on the RESULT of the shadow or MIS ray, so a lane evaluates everything of the vertex up
+// front (shadeVertex), queues the rays, and then only adds `ldLight` if the shadow ray was
+// unoccluded and `misTerm` if the MIS ray reached the sampled light.  A warp therefore runs
+//     refill idle lanes -> every lane traces its current ray -> every lane advances its state
+// with all lanes inside the same traversal code at the same time, whatever class of ray they hold.
+// Sampler dimensions are consumed in the reference's order and the radiance is accumulated with
+// the reference's operation order (Ld = (light + mis) / pickPdf; L += beta * Ld).
+#ifndef PB2_PATH_CUH
+#define PB2_PATH_CUH
+
+#include "pb2_shade.cuh"
+
+namespace pb2 {
+
+enum { LS_IDLE = 0, LS_PATH = 1, LS_SHADOW = 2, LS_MIS = 3 };
+
+struct DLane {
+    int state;
+    DRay ray;            // ray to trace next (class given by state)
+    // path
+    V3 L, beta;
+    DSampler smp;
+    int bounces;
+    bool specularBounce;
+    float etaScale;
+    // pending at the current vertex
+    bool doNEE, hasMis, hasNext;
+    int lightNum;
+    float pick;          // light-pick pdf; 0 = UniformSampleOneLight returned black
+    V3 ldSum, ldLight, misTerm;
+    V3 misO, misD;       // MIS ray (tMax = inf)
+    V3 nextO, nextD;     // continuation ray
+    V3 betaNext;
+};
+
+PB2_HD void laneStartPath(DLane &ln, const DRay &ray, const DSampler &smp) {
+    ln.state = LS_PATH;
+    ln.ray = ray;
+    ln.L = mk3(0, 0, 0);
+    ln.beta = mk3(1, 1, 1);
+    ln.smp = smp;
+    ln.bounces = 0;
+    ln.specularBounce = false;
+    ln.etaScale = 1;
+    ln.doNEE = ln.hasMis = ln.hasNext = false;
+}
+
+// End of a vertex: fold the direct lighting in, then continue or stop (path.cpp:119-150,176-185).
+PB2_HD void finishVertex(DLane &ln) {
+    if (ln.doNEE) {
+        V3 Ld = mk3(0, 0, 0);
+        if (ln.pick != 0) Ld = mk3(ln.ldSum.x / ln.pick, ln.ldSum.y / ln.pick, ln.ldSum.z / ln.pick);
+        ln.L = ln.L + ln.beta * Ld;
+    }
+    if (ln.hasNext) {
+        ln.beta = ln.betaNext;
+        ln.ray.o = ln.nextO;
+        ln.ray.d = ln.nextD;
+        ln.ray.tMax = PB2_INFINITY;
+        ln.bounces++;
+        ln.state = LS_PATH;
+    } else
+        ln.state = LS_IDLE;
+}
+
+PB2_HD void startMisOrFinish(DLane &ln) {
+    if (ln.hasMis) {
+        ln.ray.o = ln.misO;
+        ln.ray.d = ln.misD;
+        ln.ray.tMax = PB2_INFINITY;
+        ln.state = LS_MIS;
+    } else
+        finishVertex(ln);
+}
+
+// The path ray has been traced: one iteration of the bounce loop up to (not including) the results
+// of the two direct-lighting rays.
+PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &pp, DLane &ln, bool found, const DHit &hit,
+                        float tMax) {
+    DInteraction isect;
+    if (found) isect = hitInteraction(sc, hit, ln.ray, tMax);
+    if (ln.bounces == 0 || ln.specularBounce) {
+        if (found) {
+            int li = sc.primLight[isect.prim];
+            if (li >= 0) ln.L = ln.L + ln.beta * lightL(sc.lights[li], isect.n, -ln.ray.d);
+        }
+    }
+    if (!found || ln.bounces >= pp.maxDepth) {
+        ln.state = LS_IDLE;
+        return;
+    }
+    DBsdf bsdf;
+    if (!makeBsdf(sc, isect, &bsdf)) {
+        ln.ray = spawnRay(isect, ln.ray.d);  // null BSDF: skip the surface, same bounce count
+        return;
+    }
+    const float *distrib = lightDistLookup(sc.lightDist, isect.p);
+
+    ln.doNEE = bsdf.nLobes > 0;
+    ln.hasMis = false;
+    ln.pick = 0;
+    ln.ldSum = mk3(0, 0, 0);
+    bool hasShadow = false;
+    DRay shadow;
+    shadow.o = shadow.d = mk3(0, 0, 0);
+    shadow.tMax = 0;
+    if (ln.doNEE && sc.nLights > 0) {
+        // UniformSampleOneLight (integrator.cpp:85-106)
+        float lightPickPdf;
+        int lightNum = sampleDiscrete(distrib, sc.nLights, get1D(h, ln.smp), &lightPickPdf);
+        if (lightPickPdf != 0) {
+            ln.pick = lightPickPdf;
+            ln.lightNum = lightNum;
+            const pb2_light light = sc.lights[lightNum];
+            V2 uLight = get2D(h, ln.smp);
+            V2 uScattering = get2D(h, ln.smp);
+            // EstimateDirect, light-sampling half (integrator.cpp:116-160)
+            DLightSample ls = sampleLight(sc, light, isect, uLight);
+            float lightPdf = ls.pdf, scatteringPdf = 0;
+            if (lightPdf > 0 && !isBlack(ls.Li)) {
+                V3 f = bsdfF(bsdf, isect.wo, ls.wi) * absDot(ls.wi, isect.ns);
+                scatteringPdf = bsdfPdf(bsdf, isect.wo, ls.wi);
+                if (!isBlack(f)) {
+                    shadow = spawnRayTo(isect, ls.p, ls.pError, ls.n);
+                    hasShadow = true;
+                    float weight = powerHeuristic(lightPdf, scatteringPdf);
+                    V3 fl = f * ls.Li * weight;
+                    ln.ldLight = mk3(fl.x / lightPdf, fl.y / lightPdf, fl.z / lightPdf);
+                }
+            }
+            // BSDF-sampling half (integrator.cpp:162-213); area lights are not delta lights
+            V3 wi;
+            V3 f = bsdfSampleF(bsdf, isect.wo, &wi, uScattering, &scatteringPdf);
+            if (scatteringPdf != 0) f = f * absDot(wi, isect.ns);
+            else f = mk3(0, 0, 0);
+            if (!isBlack(f) && scatteringPdf > 0) {
+                lightPdf = lightPdfLi(sc, light, isect, wi);
+                if (lightPdf != 0) {
+                    float weight = powerHeuristic(scatteringPdf, lightPdf);
+                    // Li is the light's Lemit when the MIS ray reaches its emitting side (checked after
+                    // the trace); f * Li * Tr(=1) * weight / scatteringPdf
+                    V3 fl = f * mk3(light.L[0], light.L[1], light.L[2]) * weight;
+                    ln.misTerm = mk3(fl.x / scatteringPdf, fl.y / scatteringPdf, fl.z / scatteringPdf);
+                    DRay mr = spawnRay(isect, wi);
+                    ln.misO = mr.o;
+                    ln.misD = mr.d;
+                    ln.hasMis = true;
+                }
+            }
+        }
+    }
+
+    // continuation (path.cpp:130-150, 176-184)
+    ln.hasNext = false;
+    {
+        V3 wo = -ln.ray.d, wi;
+        float pdf;
+        V3 f = bsdfSampleF(bsdf, wo, &wi, get2D(h, ln.smp), &pdf);
+        if (!(isBlack(f) || pdf == 0.f)) {
+            V3 s = f * absDot(wi, isect.ns);
+            V3 beta = ln.beta * mk3(s.x / pdf, s.y / pdf, s.z / pdf);
+            ln.specularBounce = false;
+            DRay nr = spawnRay(isect, wi);
+            bool survive = true;
+            V3 rrBeta = beta * ln.etaScale;
+            if (maxComponentValue(rrBeta) < pp.rrThreshold && ln.bounces > 3) {
+                float q = pmax(.05f, 1 - maxComponentValue(rrBeta));
+                if (get1D(h, ln.smp) < q) survive = false;
+                else {
+                    float d = 1 - q;
+                    beta = mk3(beta.x / d, beta.y / d, beta.z / d);
+                }
+            }
+            if (survive) {
+                ln.hasNext = true;
+                ln.nextO = nr.o;
+                ln.nextD = nr.d;
+                ln.betaNext = beta;
+            }
+        }
+    }
+
+    if (hasShadow) {
+        ln.ray = shadow;
+        ln.state = LS_SHADOW;
+    } else
+        startMisOrFinish(ln);
+}
+
+// Advance a lane after its current ray was traced.  Returns true when the path ended in this call
+// (ln.L is then final and ln.state == LS_IDLE).
+PB2_HD bool laneAdvance(const DScene &sc, const DHalton &h, const DPathParams &pp, DLane &ln, bool found, const DHit &hit,
+                        float tMax) {
+    if (ln.state == LS_PATH) {
+        shadeVertex(sc, h, pp, ln, found, hit, tMax);
+    } else if (ln.state == LS_SHADOW) {
+        if (!found) ln.ldSum = ln.ldSum + ln.ldLight;  // VisibilityTester::Unoccluded
+        startMisOrFinish(ln);
+    } else if (ln.state == LS_MIS) {
+        if (found) {
+            int hitPrim = asInt(ldg4(&sc.leafPrims[3 * (size_t)hit.leaf]).w);
+            if (sc.primLight[hitPrim] == ln.lightNum) {
+                // lightIsect.Le(-wi): DiffuseAreaLight::L with the hit's (face-forwarded) normal
+                DInteraction lightIsect = hitInteraction(sc, hit, ln.ray, tMax);
+                const pb2_light light = sc.lights[ln.lightNum];
+                if (light.two_sided || dot(lightIsect.n, -ln.ray.d) > 0) ln.ldSum = ln.ldSum + ln.misTerm;
+            }
+        }
+        finishVertex(ln);
+    }
+    return ln.state == LS_IDLE;
+}
+
+// Runtime-flag version of traverse<ANY> so that a kernel holds a single traversal instance.
+PB2_HD bool traceLane(const DScene &sc, const DLane &ln, float *tMax, DHit *hit, DCounters *ctr) {
+    *tMax = ln.ray.tMax;
+    hit->leaf = -1;
+    hit->b0 = hit->b1 = hit->b2 = 0;
+    return traverseAnyOrClosest(sc, ln.ray, ln.state == LS_SHADOW, tMax, hit, ctr);
+}
+
+}  // namespace pb2
+#endif

@@ -193,14 +193,14 @@ PB2_HD float4 ldg4(const float4 *p) {
 PB2_HD int asInt(float f) { return (int)floatBits(f); }
 
 struct SphereHit;  // pb2_sphere.cuh
-PB2_HD bool sphereLeafTest(const DScene &sc, int sphereIndex, const DRay &ray, float rayTMax, float *tHit, float *phi);
+PB2_HDN bool sphereLeafTest(const DScene &sc, int sphereIndex, const DRay &ray, float rayTMax, float *tHit, float *phi);
 
 // BVHAccel::Intersect (ANY=false, bvh.cpp:662-700) and IntersectP (ANY=true, bvh.cpp:702-738):
 // depth-first, near child first by dirIsNeg[axis], explicit stack of far children, every primitive
 // of a reached leaf tested, closest hit shrinks tMax.  Node visit order and the set of primitive
 // tests are exactly the reference's, so device counters equal the instrumented reference's.
-template <bool ANY>
-PB2_HD bool traverse(const DScene &sc, const DRay &ray, float *tMaxInOut, DHit *hit, DCounters *ctr) {
+PB2_HD bool traverseAnyOrClosest(const DScene &sc, const DRay &ray, const bool ANY, float *tMaxInOut, DHit *hit,
+                                 DCounters *ctr) {
     (void)ctr;
     if (sc.nNodes == 0) return false;
     DRaySetup rs = setupRay(ray.o, ray.d);
@@ -268,6 +268,11 @@ PB2_HD bool traverse(const DScene &sc, const DRay &ray, float *tMaxInOut, DHit *
     }
     *tMaxInOut = tMax;
     return found;
+}
+
+template <bool ANY>
+PB2_HD bool traverse(const DScene &sc, const DRay &ray, float *tMaxInOut, DHit *hit, DCounters *ctr) {
+    return traverseAnyOrClosest(sc, ray, ANY, tMaxInOut, hit, ctr);
 }
 
 }  // namespace pb2

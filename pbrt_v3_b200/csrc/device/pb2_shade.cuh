@@ -305,7 +305,7 @@ PB2_HD float trPdf(float alpha, V3 wo, V3 wh) {  // sampleVisibleArea == true
 
 // TrowbridgeReitzSample11 (microfacet.cpp:238-282).  The normal-incidence branch runs in double,
 // as the reference's unqualified sqrt/cos/sin do.
-PB2_HD void trSample11(float cosThetaV, float U1, float U2, float *slope_x, float *slope_y) {
+PB2_HDN void trSample11(float cosThetaV, float U1, float U2, float *slope_x, float *slope_y) {
     if ((double)cosThetaV > .9999) {
         float r = (float)sqrt((double)(U1 / (1 - U1)));
         float phi = (float)(6.28318530718 * (double)U2);
@@ -494,7 +494,7 @@ PB2_HD void sphereSampleArea(const pb2_sphere &s, V2 u, V3 *p, V3 *pError, V3 *n
 }
 
 // DiffuseAreaLight::Sample_Li over Sphere::Sample(ref, u, pdf) (sphere.cpp:232-301)
-PB2_HD DLightSample sampleSphereLight(const DScene &sc, const pb2_light &l, const DInteraction &ref, V2 u) {
+PB2_HDN DLightSample sampleSphereLight(const DScene &sc, const pb2_light &l, const DInteraction &ref, V2 u) {
     DLightSample ls;
     const pb2_sphere s = sc.spheres[sc.primIndex[l.prim]];
     M44 o2w = loadM44(s.object_to_world);
@@ -551,7 +551,7 @@ PB2_HD DLightSample sampleSphereLight(const DScene &sc, const pb2_light &l, cons
 }
 
 // Sphere::Pdf(ref, wi) (sphere.cpp:303-315); the inside case falls back to Shape::Pdf (shape.cpp:78-95)
-PB2_HD float sphereLightPdf(const DScene &sc, const pb2_light &l, const DInteraction &ref, V3 wi) {
+PB2_HDN float sphereLightPdf(const DScene &sc, const pb2_light &l, const DInteraction &ref, V3 wi) {
     const pb2_sphere s = sc.spheres[sc.primIndex[l.prim]];
     M44 o2w = loadM44(s.object_to_world);
     V3 pCenter = xfPoint(o2w, mk3(0, 0, 0));

@@ -121,7 +121,7 @@ struct SphereRayHit {
 };
 
 // The geometric part shared by Sphere::Intersect and IntersectP (sphere.cpp:49-103 / 158-214).
-PB2_HD bool sphereTest(const pb2_sphere &s, const DRay &r, float rayTMax, SphereRayHit *out) {
+PB2_HDN bool sphereTest(const pb2_sphere &s, const DRay &r, float rayTMax, SphereRayHit *out) {
     M44 w2o = loadM44(s.world_to_object);
     // Transform::operator()(Ray, &oErr, &dErr) (transform.h:382-394): tMax is NOT reduced
     V3 oErr, dErr;
@@ -169,7 +169,7 @@ PB2_HD bool sphereTest(const pb2_sphere &s, const DRay &r, float rayTMax, Sphere
     return true;
 }
 
-PB2_HD bool sphereLeafTest(const DScene &sc, int sphereIndex, const DRay &ray, float rayTMax, float *tHit, float *phi) {
+PB2_HDN bool sphereLeafTest(const DScene &sc, int sphereIndex, const DRay &ray, float rayTMax, float *tHit, float *phi) {
     SphereRayHit h;
     if (!sphereTest(sc.spheres[sphereIndex], ray, rayTMax, &h)) return false;
     *tHit = h.tHit;
@@ -180,7 +180,7 @@ PB2_HD bool sphereLeafTest(const DScene &sc, int sphereIndex, const DRay &ray, f
 // SurfaceInteraction of a sphere hit (sphere.cpp:105-155) mapped to world space
 // (transform.cpp:262-297).  The hit is recomputed from the ray with the tMax the traversal saw just
 // before accepting it: any tMax >= tHit accepts the same root, so +inf is used.
-PB2_HD DInteraction sphereInteraction(const DScene &sc, int prim, const DRay &ray, float tHit, float) {
+PB2_HDN DInteraction sphereInteraction(const DScene &sc, int prim, const DRay &ray, float tHit, float) {
     (void)tHit;
     DInteraction it;
     const pb2_sphere s = sc.spheres[sc.primIndex[prim]];
@@ -222,7 +222,7 @@ PB2_HD DInteraction sphereInteraction(const DScene &sc, int prim, const DRay &ra
 namespace pb2 {
 struct DLightSample;
 PB2_HD V3 lightL(const pb2_light &l, V3 n, V3 w);
-PB2_HD DLightSample sampleSphereLight(const DScene &sc, const pb2_light &l, const DInteraction &ref, V2 u);
-PB2_HD float sphereLightPdf(const DScene &sc, const pb2_light &l, const DInteraction &ref, V3 wi);
+PB2_HDN DLightSample sampleSphereLight(const DScene &sc, const pb2_light &l, const DInteraction &ref, V2 u);
+PB2_HDN float sphereLightPdf(const DScene &sc, const pb2_light &l, const DInteraction &ref, V3 wi);
 }  // namespace pb2
 #endif

@@ -22,7 +22,7 @@
 #include <string>
 #include <vector>
 
-#include "device/pb2_shade.cuh"
+#include "device/pb2_path.cuh"
 #include "host/core.h"  // pbrt::RNG for the Halton permutation table
 #include "pb2.h"
 
@@ -154,6 +154,12 @@ struct pb2_scene {
     unsigned long long *counters = nullptr;  // [0] work counter, [1..] stats
     int64_t nPrims = 0;
     int nLights = 0;
+    // wavefront pool (allocated on first render)
+    void *wfCtx = nullptr;
+    int *wfQueues = nullptr;
+    unsigned *wfCounts = nullptr;
+    unsigned *wfHostCounts = nullptr;  // pinned
+    int wfCapacity = 0;
 };
 
 template <typename T>
@@ -332,20 +338,25 @@ __device__ __forceinline__ void addSample(const DRenderParams &rp, float4 *film,
         }
 }
 
-__global__ void __launch_bounds__(128) k_render_path(DScene sc, DRenderParams rp, float4 *film, unsigned long long *counters) {
+#include "pb2_wavefront.cuh"
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_render_path(DScene sc, DRenderParams rp, float4 *film, unsigned long long *counters) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    DPathState ps;
+    DLane ln;
+    ln.state = LS_IDLE;
+    ln.L = mk3(0, 0, 0);
     DRayStats st;
     st.regular = st.shadow = 0;
     unsigned cameraRays = 0;
     DCounters ctr{};
-    bool active = false, exhausted = false;
+    bool exhausted = false;
     int px = 0, py = 0;
     V2 pFilm = mk2(0, 0);
-    ps.L = mk3(0, 0, 0);
     while (true) {
         // refill idle lanes: one atomic per warp
+        bool active = ln.state != LS_IDLE;
         bool want = !active && !exhausted;
         unsigned wantMask = __ballot_sync(FULL, want);
         if (wantMask) {
@@ -364,7 +375,7 @@ __global__ void __launch_bounds__(128) k_render_path(DScene sc, DRenderParams rp
                         smp.index = haltonIndex(rp.halton, px, py, sample);
                         smp.dim = 0;
                         DRay ray = generateCameraRay(rp.cam, rp.halton, smp, px, py, &pFilm);
-                        initPath(ps, ray, smp);
+                        laneStartPath(ln, ray, smp);
                         cameraRays++;
                         active = true;
                     }
@@ -375,12 +386,17 @@ __global__ void __launch_bounds__(128) k_render_path(DScene sc, DRenderParams rp
             if (__all_sync(FULL, exhausted)) break;
             continue;
         }
+        // every lane that holds a ray traces it (closest hit for path/MIS rays, any hit for shadow rays)
+        bool found = false;
+        DHit hit;
+        float tMax = 0;
         if (active) {
-            bool cont = pathVertex(sc, rp.halton, rp.path, ps, st, &ctr);
-            if (!cont) {
-                addSample(rp, film, pFilm, guardRadiance(ps.L));
-                active = false;
-            }
+            if (ln.state == LS_SHADOW) st.shadow++;
+            else st.regular++;
+            found = traceLane(sc, ln, &tMax, &hit, &ctr);
+        }
+        if (active) {
+            if (laneAdvance(sc, rp.halton, rp.path, ln, found, hit, tMax)) addSample(rp, film, pFilm, guardRadiance(ln.L));
         }
     }
     // statistics: warp reduce, one atomic per warp and counter
@@ -418,14 +434,16 @@ __global__ void k_li_samples(DScene sc, DRenderParams rp, const int32_t *pixelXY
     smp.dim = 0;
     V2 pFilm;
     DRay ray = generateCameraRay(rp.cam, rp.halton, smp, px, py, &pFilm);
-    DPathState ps;
-    initPath(ps, ray, smp);
-    DRayStats st;
-    st.regular = st.shadow = 0;
+    DLane ln;
+    laneStartPath(ln, ray, smp);
     DCounters ctr{};
-    while (pathVertex(sc, rp.halton, rp.path, ps, st, &ctr)) {
+    while (ln.state != LS_IDLE) {
+        DHit hit;
+        float tMax;
+        bool found = traceLane(sc, ln, &tMax, &hit, &ctr);
+        laneAdvance(sc, rp.halton, rp.path, ln, found, hit, tMax);
     }
-    V3 L = guardRadiance(ps.L);
+    V3 L = guardRadiance(ln.L);
     outRGB[3 * i] = L.x;
     outRGB[3 * i + 1] = L.y;
     outRGB[3 * i + 2] = L.z;
@@ -498,6 +516,67 @@ static int validateRenderArgs(const pb2_scene *scene, const pb2_camera *cam, con
     return PB2_OK;
 }
 
+// Host driver of the wavefront rounds (see pb2_wavefront.cuh).
+static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *film, cudaStream_t stream, unsigned long long *launches) {
+    static const int maxCapacity = std::getenv("PB2_POOL") ? std::atoi(std::getenv("PB2_POOL")) : (1 << 20);
+    long long want = std::min<long long>(maxCapacity, std::max<long long>(rp.nWorkItems, 1024));
+    int capacity = (int)((want + 255) / 256 * 256);
+    if (scene->wfCapacity < capacity) {
+        if (scene->wfCtx) cudaFree(scene->wfCtx);
+        if (scene->wfQueues) cudaFree(scene->wfQueues);
+        scene->wfCtx = nullptr;
+        scene->wfQueues = nullptr;
+        scene->wfCapacity = 0;
+        CUDA_TRY(cudaMalloc(&scene->wfCtx, (size_t)capacity * sizeof(WfCtx)));
+        CUDA_TRY(cudaMalloc((void **)&scene->wfQueues, (size_t)capacity * 6 * sizeof(int)));
+        if (!scene->wfCounts) CUDA_TRY(cudaMalloc((void **)&scene->wfCounts, WQ_COUNT * sizeof(unsigned)));
+        if (!scene->wfHostCounts) CUDA_TRY(cudaMallocHost((void **)&scene->wfHostCounts, (WQ_COUNT + 2) * sizeof(unsigned long long)));
+        scene->wfCapacity = capacity;
+    }
+    WfPool pool;
+    pool.capacity = capacity;
+    pool.ctx = (WfCtx *)scene->wfCtx;
+    for (int q = 0; q < 6; ++q) pool.queue[q] = scene->wfQueues + (size_t)q * scene->wfCapacity;
+    pool.counts = scene->wfCounts;
+    const int blocks256 = std::min((capacity + 255) / 256, g_numSMs * 16);
+    const int blocks128 = std::min((capacity + 127) / 128, g_numSMs * 32);
+    // trace kernel variant: 1 = one thread per ray, grid-stride; 2.. = persistent warps with ballot-scheduled steps
+    static const int traceVariant = std::getenv("PB2_TRACE") ? std::atoi(std::getenv("PB2_TRACE")) : 2;
+    void (*traceKernel)(DScene, WfPool, int, unsigned long long *) =
+        traceVariant == 3 ? k_wf_trace2<4, 4> : traceVariant == 4 ? k_wf_trace2<12, 12> : traceVariant == 5 ? k_wf_trace2<16, 8> : k_wf_trace2<8, 8>;
+    int traceBlocksPerSM = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&traceBlocksPerSM, traceKernel, 128, 0));
+    const int persistentBlocks = g_numSMs * std::max(1, traceBlocksPerSM);
+    k_wf_init<<<(capacity + 255) / 256, 256, 0, stream>>>(pool);
+    unsigned long long nLaunch = 1;
+    int cur = 0;
+    volatile unsigned *hc = scene->wfHostCounts;
+    unsigned long long *hWork = reinterpret_cast<unsigned long long *>(scene->wfHostCounts + WQ_COUNT);
+    for (long long round = 0;; ++round) {
+        int next = 1 - cur;
+        k_wf_gen<<<blocks256, 256, 0, stream>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur, scene->counters);
+        if (traceVariant == 1)
+            k_wf_trace<<<blocks128, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
+        else
+            traceKernel<<<persistentBlocks, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
+        k_wf_advance<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film);
+        k_wf_advance<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_SHADE, WQ_TRACE0 + next, WQ_FREE0 + next, film);
+        k_wf_reset<<<1, 32, 0, stream>>>(pool, WQ_FREE0 + cur, WQ_TRACE0 + cur, WQ_SHADE, WQ_LIGHT);
+        nLaunch += 5;
+        CUDA_TRY(cudaMemcpyAsync((void *)scene->wfHostCounts, pool.counts, WQ_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaMemcpyAsync(hWork, &scene->counters[CTR_WORK], sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        unsigned traceNext = hc[WQ_TRACE0 + next], freeNext = hc[WQ_FREE0 + next];
+        bool workLeft = (long long)*hWork < rp.nWorkItems;
+        if (traceNext == 0 && !(workLeft && freeNext > 0)) break;
+        cur = next;
+        if (round > 100000000LL) return setError(PB2_ERR_CUDA, "wavefront did not terminate");
+    }
+    CUDA_TRY(cudaGetLastError());
+    *launches = nLaunch;
+    return PB2_OK;
+}
+
 extern "C" {
 
 int pb2_abi_version(void) { return PB2_ABI_VERSION; }
@@ -548,6 +627,10 @@ int pb2_scene_destroy(pb2_scene *s) {
     if (!s) return PB2_OK;
     for (void *p : s->allocations) cudaFree(p);
     if (s->film) cudaFree(s->film);
+    if (s->wfCtx) cudaFree(s->wfCtx);
+    if (s->wfQueues) cudaFree(s->wfQueues);
+    if (s->wfCounts) cudaFree(s->wfCounts);
+    if (s->wfHostCounts) cudaFreeHost(s->wfHostCounts);
     delete s;
     return PB2_OK;
 }
@@ -736,13 +819,22 @@ int pb2_render_path_device(pb2_scene *scene, const pb2_camera *cam, const pb2_fi
         CUDA_TRY(cudaEventCreate(&e1));
         CUDA_TRY(cudaEventRecord(e0, stream));
     }
-    if (rp.nWorkItems > 0) {
+    static const bool megakernel = std::getenv("PB2_MODE") && std::string(std::getenv("PB2_MODE")) == "mega";
+    unsigned long long launches = 0;
+    if (rp.nWorkItems > 0 && !megakernel) {
+        int rc2 = renderWavefront(scene, rp, (float4 *)film_rgbw_device, stream, &launches);
+        if (rc2) return rc2;
+    } else if (rp.nWorkItems > 0) {
+        launches = 1;
         int threads = 128, blocksPerSM = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, k_render_path, threads, 0));
+        static int minb = std::getenv("PB2_MINBLOCKS") ? std::atoi(std::getenv("PB2_MINBLOCKS")) : 2;
+        void (*kernel)(DScene, DRenderParams, float4 *, unsigned long long *) =
+            minb >= 8 ? k_render_path<8> : minb >= 6 ? k_render_path<6> : minb >= 4 ? k_render_path<4> : minb >= 3 ? k_render_path<3> : k_render_path<2>;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kernel, threads, 0));
         blocksPerSM = std::max(1, blocksPerSM);
         long long warpsNeeded = (rp.nWorkItems + 31) / 32;
         long long blocks = std::min<long long>((long long)g_numSMs * blocksPerSM, (warpsNeeded + 3) / 4);
-        k_render_path<<<(unsigned)std::max<long long>(1, blocks), threads, 0, stream>>>(scene->d, rp, (float4 *)film_rgbw_device, scene->counters);
+        kernel<<<(unsigned)std::max<long long>(1, blocks), threads, 0, stream>>>(scene->d, rp, (float4 *)film_rgbw_device, scene->counters);
         CUDA_TRY(cudaGetLastError());
     }
     if (stats) {
@@ -761,7 +853,7 @@ int pb2_render_path_device(pb2_scene *scene, const pb2_camera *cam, const pb2_fi
         stats->shadow_rays = c[CTR_SHADOW];
         stats->node_visits = c[CTR_NODES];
         stats->prim_tests = c[CTR_PRIMS];
-        stats->kernel_launches = rp.nWorkItems > 0 ? 1 : 0;
+        stats->kernel_launches = launches;
         stats->render_ms = ms;
     }
     return PB2_OK;

@@ -1,0 +1,382 @@
+// Wavefront organisation of SamplerIntegrator::Render + PathIntegrator::Li (included by pb2_cuda.cu).
+//
+// A pool of N path contexts (one camera sample in flight each) lives in HBM.  Every context holds
+// the per-lane state machine of device/pb2_path.cuh: at any time it owns exactly one ray of one of
+// three classes (path ray, shadow ray, MIS ray).  One ROUND is
+//
+//   k_wf_gen      contexts on the free list take the next work item (pixel, sample number), generate
+//                 the camera ray (Halton dims 0-4, perspective camera) and join the trace list
+//   k_wf_trace    every listed context's ray is traced through the BVH (closest hit or any hit);
+//                 the context is appended to the shade list (path ray) or the light list (shadow /
+//                 MIS ray)                                           <- the dominant kernel
+//   k_wf_advance  (light list) adds ldLight / misTerm, then starts the next ray of the vertex or
+//                 finishes the vertex: next path ray, or the sample is deposited in the film and the
+//                 context goes to the free list
+//   k_wf_advance  (shade list) evaluates the whole path vertex (SurfaceInteraction, BSDF, light pick,
+//                 light sample + MIS sample, continuation + Russian roulette) and queues its rays
+//
+// so every kernel runs with all lanes of a warp in the same code, the trace kernel keeps only ray
+// state in registers, and a finished sample is replaced immediately (the pool stays full until the
+// work counter runs out).  Lists are plain index arrays with device-side counters; the host only
+// reads two counters per round to detect the end.
+#ifndef PB2_WAVEFRONT_CUH
+#define PB2_WAVEFRONT_CUH
+
+struct alignas(32) WfCtx {
+    DLane ln;       // starts with {int state; DRay ray;} = 32 bytes: what k_wf_trace reads
+    alignas(16) DHit hit;  // written by k_wf_trace as one 16-byte store
+    float tHit;
+    int found;
+    V2 pFilm;
+};
+static_assert(offsetof(WfCtx, ln) == 0 && offsetof(DLane, state) == 0 && offsetof(DLane, ray) == 4 && sizeof(DRay) == 28,
+              "k_wf_trace reads the first 32 bytes of a context as {state, o, d, tMax}");
+
+enum { WQ_TRACE0 = 0, WQ_TRACE1 = 1, WQ_SHADE = 2, WQ_LIGHT = 3, WQ_FREE0 = 4, WQ_FREE1 = 5, WQ_CURSOR = 6, WQ_RETIRED = 7, WQ_COUNT = 8 };
+
+struct WfPool {
+    int capacity;
+    WfCtx *ctx;
+    int *queue[6];            // WQ_TRACE0..WQ_FREE1, capacity entries each
+    unsigned *counts;         // WQ_COUNT counters
+};
+
+// warp-aggregated append of one index per participating lane
+__device__ __forceinline__ void wfPush(int *queue, unsigned *counter, int value, bool participate) {
+    unsigned mask = __ballot_sync(0xffffffffu, participate);
+    if (!mask) return;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (participate) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+__global__ void __launch_bounds__(256) k_wf_gen(DRenderParams rp, WfPool pool, int freeQ, int traceQ, unsigned long long *counters) {
+    unsigned n = pool.counts[freeQ];
+    unsigned stride = gridDim.x * blockDim.x;
+    unsigned cameraRays = 0;
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += stride) {
+        unsigned i = base + threadIdx.x;
+        bool have = i < n;
+        int c = have ? pool.queue[freeQ][i] : -1;
+        bool started = false;
+        // draw work items until one maps to a pixel inside the sample bounds / pixel bounds
+        while (__any_sync(0xffffffffu, have && !started)) {
+            bool want = have && !started;
+            unsigned mask = __ballot_sync(0xffffffffu, want);
+            int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+            unsigned long long w0 = 0;
+            if (lane == leader) w0 = atomicAdd(&counters[CTR_WORK], (unsigned long long)__popc(mask));
+            w0 = __shfl_sync(0xffffffffu, w0, leader);
+            if (want) {
+                long long item = (long long)w0 + __popc(mask & ((1u << lane) - 1u));
+                if (item >= rp.nWorkItems) {
+                    have = false;  // no work left: the context retires
+                } else {
+                    int px, py, sample;
+                    if (decodeWork(rp, item, &px, &py, &sample)) {
+                        WfCtx &cx = pool.ctx[c];
+                        DSampler smp;
+                        smp.index = haltonIndex(rp.halton, px, py, sample);
+                        smp.dim = 0;
+                        V2 pFilm;
+                        DRay ray = generateCameraRay(rp.cam, rp.halton, smp, px, py, &pFilm);
+                        laneStartPath(cx.ln, ray, smp);
+                        cx.pFilm = pFilm;
+                        cameraRays++;
+                        started = true;
+                    }
+                }
+            }
+        }
+        wfPush(pool.queue[traceQ], &pool.counts[traceQ], c, started);
+    }
+    for (int o = 16; o > 0; o >>= 1) cameraRays += __shfl_down_sync(0xffffffffu, cameraRays, o);
+    if ((threadIdx.x & 31) == 0 && cameraRays) atomicAdd(&counters[CTR_CAMERA], (unsigned long long)cameraRays);
+}
+
+// One thread per listed ray.  Reads 32 bytes of the context, writes 24.
+__global__ void __launch_bounds__(128) k_wf_trace(DScene sc, WfPool pool, int traceQ, unsigned long long *counters) {
+    unsigned n = pool.counts[traceQ];
+    unsigned stride = gridDim.x * blockDim.x;
+    unsigned regular = 0, shadow = 0;
+    DCounters ctr{};
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += stride) {
+        unsigned i = base + threadIdx.x;
+        bool have = i < n;
+        int c = have ? pool.queue[traceQ][i] : 0;
+        int state = LS_IDLE;
+        if (have) {
+            const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
+            float4 a = p[0], b = p[1];
+            state = __float_as_int(a.x);
+            DRay ray;
+            ray.o = mk3(a.y, a.z, a.w);
+            ray.d = mk3(b.x, b.y, b.z);
+            ray.tMax = b.w;
+            float tMax = ray.tMax;
+            DHit hit;
+            hit.leaf = -1;
+            hit.b0 = hit.b1 = hit.b2 = 0;
+            bool any = state == LS_SHADOW;
+            if (any) shadow++; else regular++;
+            bool found = traverseAnyOrClosest(sc, ray, any, &tMax, &hit, &ctr);
+            WfCtx &cx = pool.ctx[c];
+            *reinterpret_cast<float4 *>(&cx.hit) = make_float4(__int_as_float(hit.leaf), hit.b0, hit.b1, hit.b2);
+            cx.tHit = tMax;
+            cx.found = found ? 1 : 0;
+        }
+        wfPush(pool.queue[WQ_SHADE], &pool.counts[WQ_SHADE], c, have && state == LS_PATH);
+        wfPush(pool.queue[WQ_LIGHT], &pool.counts[WQ_LIGHT], c, have && state != LS_PATH);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        regular += __shfl_down_sync(0xffffffffu, regular, o);
+        shadow += __shfl_down_sync(0xffffffffu, shadow, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (regular) atomicAdd(&counters[CTR_REGULAR], (unsigned long long)regular);
+        if (shadow) atomicAdd(&counters[CTR_SHADOW], (unsigned long long)shadow);
+    }
+#ifdef PB2_COUNTERS
+    unsigned long long n0 = ctr.nodes, n1 = ctr.prims;
+    for (int o = 16; o > 0; o >>= 1) {
+        n0 += __shfl_down_sync(0xffffffffu, n0, o);
+        n1 += __shfl_down_sync(0xffffffffu, n1, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&counters[CTR_NODES], n0);
+        atomicAdd(&counters[CTR_PRIMS], n1);
+    }
+#endif
+}
+
+// Persistent-warp version of the trace kernel.  Each lane walks its own ray through the BVH with the
+// reference's visiting order (near child first, explicit stack, every primitive of a reached leaf),
+// but the WARP decides by ballot which of three steps to run next, so that the lanes inside a step
+// are (mostly) all busy:
+//   node step   lanes that stand at a node: fetch the 32-byte node, slab test, descend / pop
+//   leaf step   lanes that reached a leaf wait until LEAF_T lanes did (or nobody can walk any more),
+//               then test their leaf's primitives together
+//   fetch step  lanes whose ray is finished wait until FETCH_T lanes are (or nothing else is left),
+//               then store their results, append their context to the shade / light list, and take
+//               the next rays of the trace list (one warp-aggregated atomic)
+// Node-visit and primitive-test counts per ray are unchanged; only the interleaving across lanes is.
+template <int LEAF_T, int FETCH_T>
+__global__ void __launch_bounds__(128, 6) k_wf_trace2(DScene sc, WfPool pool, int traceQ, unsigned long long *counters) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned n = pool.counts[traceQ];
+    enum { M_FETCH = 0, M_NODE = 1, M_LEAF = 2 };
+    int mode = M_FETCH;
+    int c = -1;            // context of the ray in flight (>= 0 also while its result waits to be flushed)
+    bool exhausted = false;
+    DRaySetup rs;
+    rs.o = rs.invDir = mk3(0, 0, 0);
+    rs.neg0 = rs.neg1 = rs.neg2 = 0;
+    rs.kx = rs.ky = rs.kz = 0;
+    rs.Sx = rs.Sy = rs.Sz = 0;
+    float tMax = 0;
+    bool any = false, found = false;
+    int cur = 0, sp = 0, leafFirst = 0, leafN = 0;
+    DHit hit;
+    hit.leaf = -1;
+    hit.b0 = hit.b1 = hit.b2 = 0;
+    int stack[64];
+    unsigned regular = 0, shadow = 0;
+    DCounters ctr{};
+    while (true) {
+        unsigned mNode = __ballot_sync(FULL, mode == M_NODE);
+        unsigned mLeaf = __ballot_sync(FULL, mode == M_LEAF);
+        unsigned mFetch = __ballot_sync(FULL, mode == M_FETCH && !(exhausted && c < 0));
+        int nNode = __popc(mNode), nLeaf = __popc(mLeaf), nFetch = __popc(mFetch);
+        int step;
+        if (nFetch >= FETCH_T || (nFetch > 0 && nNode == 0 && nLeaf == 0)) step = M_FETCH;
+        else if (nLeaf >= LEAF_T || (nLeaf > 0 && nNode == 0)) step = M_LEAF;
+        else if (nNode > 0) step = M_NODE;
+        else break;
+
+        if (step == M_NODE) {
+            if (mode == M_NODE) {
+                float4 n0 = ldg4(&sc.nodes[2 * (size_t)cur]);
+                float4 n1 = ldg4(&sc.nodes[2 * (size_t)cur + 1]);
+                PB2_COUNT_NODE(&ctr);
+                bool popNext = true;
+                if (slabTest(n0, n1, rs, tMax)) {
+                    uint32_t meta = floatBits(n1.w);
+                    int nPrims = (int)(meta & 0xffffu);
+                    if (nPrims > 0) {
+                        leafFirst = asInt(n1.z);
+                        leafN = nPrims;
+                        mode = M_LEAF;
+                        popNext = false;
+                    } else {
+                        int axis = (int)((meta >> 16) & 0xffu);
+                        int isNeg = axis == 0 ? rs.neg0 : (axis == 1 ? rs.neg1 : rs.neg2);
+                        int second = asInt(n1.z);
+                        if (isNeg) {
+                            stack[sp++] = cur + 1;
+                            cur = second;
+                        } else {
+                            stack[sp++] = second;
+                            cur = cur + 1;
+                        }
+                        popNext = false;
+                    }
+                }
+                if (popNext) {
+                    if (sp == 0) mode = M_FETCH;
+                    else cur = stack[--sp];
+                }
+            }
+        } else if (step == M_LEAF) {
+            if (mode == M_LEAF) {
+                bool finished = false;
+                for (int i = 0; i < leafN; ++i) {
+                    const float4 *rec = &sc.leafPrims[3 * (size_t)(leafFirst + i)];
+                    float4 a = ldg4(rec), b = ldg4(rec + 1), c4 = ldg4(rec + 2);
+                    PB2_COUNT_PRIM(&ctr);
+                    uint32_t flags = floatBits(b.w);
+                    if (flags & LEAF_SPHERE) {
+                        const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
+                        float4 ra = p[0], rb = p[1];
+                        DRay ray;
+                        ray.o = mk3(ra.y, ra.z, ra.w);
+                        ray.d = mk3(rb.x, rb.y, rb.z);
+                        ray.tMax = rb.w;
+                        float t, phi;
+                        if (sphereLeafTest(sc, asInt(c4.w), ray, tMax, &t, &phi)) {
+                            found = true;
+                            if (any) { finished = true; break; }
+                            tMax = t;
+                            hit.leaf = leafFirst + i;
+                            hit.b0 = phi;
+                            hit.b1 = hit.b2 = 0;
+                        }
+                        continue;
+                    }
+                    float t, b0, b1, b2;
+                    if (triangleTest(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c4.x, c4.y, c4.z), rs, tMax, &t, &b0, &b1, &b2)) {
+                        if (any) { found = true; finished = true; break; }
+                        if (flags & LEAF_DEGENERATE) continue;
+                        found = true;
+                        tMax = t;
+                        hit.leaf = leafFirst + i;
+                        hit.b0 = b0;
+                        hit.b1 = b1;
+                        hit.b2 = b2;
+                    }
+                }
+                leafN = 0;
+                if (finished || sp == 0) mode = M_FETCH;
+                else {
+                    cur = stack[--sp];
+                    mode = M_NODE;
+                }
+            }
+        } else {  // M_FETCH
+            bool flush = mode == M_FETCH && c >= 0;
+            int state = LS_IDLE;
+            if (flush) {
+                WfCtx &cx = pool.ctx[c];
+                state = any ? LS_SHADOW : cx.ln.state;
+                *reinterpret_cast<float4 *>(&cx.hit) = make_float4(__int_as_float(hit.leaf), hit.b0, hit.b1, hit.b2);
+                cx.tHit = tMax;
+                cx.found = found ? 1 : 0;
+            }
+            wfPush(pool.queue[WQ_SHADE], &pool.counts[WQ_SHADE], c, flush && state == LS_PATH);
+            wfPush(pool.queue[WQ_LIGHT], &pool.counts[WQ_LIGHT], c, flush && state != LS_PATH);
+            if (flush) c = -1;
+            bool want = mode == M_FETCH && !exhausted;
+            unsigned wantMask = __ballot_sync(FULL, want);
+            if (wantMask) {
+                int leader = __ffs(wantMask) - 1;
+                unsigned base = 0;
+                if (lane == leader) base = atomicAdd(&pool.counts[WQ_CURSOR], (unsigned)__popc(wantMask));
+                base = __shfl_sync(FULL, base, leader);
+                if (want) {
+                    unsigned i = base + __popc(wantMask & ((1u << lane) - 1u));
+                    if (i >= n)
+                        exhausted = true;
+                    else {
+                        c = pool.queue[traceQ][i];
+                        const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
+                        float4 ra = p[0], rb = p[1];
+                        any = __float_as_int(ra.x) == LS_SHADOW;
+                        if (any) shadow++; else regular++;
+                        rs = setupRay(mk3(ra.y, ra.z, ra.w), mk3(rb.x, rb.y, rb.z));
+                        tMax = rb.w;
+                        found = false;
+                        hit.leaf = -1;
+                        hit.b0 = hit.b1 = hit.b2 = 0;
+                        cur = 0;
+                        sp = 0;
+                        leafN = 0;
+                        mode = M_NODE;
+                    }
+                }
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        regular += __shfl_down_sync(FULL, regular, o);
+        shadow += __shfl_down_sync(FULL, shadow, o);
+    }
+    if (lane == 0) {
+        if (regular) atomicAdd(&counters[CTR_REGULAR], (unsigned long long)regular);
+        if (shadow) atomicAdd(&counters[CTR_SHADOW], (unsigned long long)shadow);
+    }
+#ifdef PB2_COUNTERS
+    unsigned long long n0 = ctr.nodes, n1 = ctr.prims;
+    for (int o = 16; o > 0; o >>= 1) {
+        n0 += __shfl_down_sync(FULL, n0, o);
+        n1 += __shfl_down_sync(FULL, n1, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&counters[CTR_NODES], n0);
+        atomicAdd(&counters[CTR_PRIMS], n1);
+    }
+#endif
+}
+
+// laneAdvance for every context of one list (all in the same class of state, so warps stay converged).
+__global__ void __launch_bounds__(128) k_wf_advance(DScene sc, DRenderParams rp, WfPool pool, int srcQ, int traceQ, int freeQ,
+                                                    float4 *film) {
+    unsigned n = pool.counts[srcQ];
+    unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned base = blockIdx.x * blockDim.x; base < n; base += stride) {
+        unsigned i = base + threadIdx.x;
+        bool have = i < n;
+        int c = have ? pool.queue[srcQ][i] : 0;
+        bool ended = false;
+        if (have) {
+            WfCtx &cx = pool.ctx[c];
+            DLane ln = cx.ln;
+            DHit hit = cx.hit;
+            ended = laneAdvance(sc, rp.halton, rp.path, ln, cx.found != 0, hit, cx.tHit);
+            cx.ln = ln;
+            if (ended) addSample(rp, film, cx.pFilm, guardRadiance(ln.L));
+        }
+        wfPush(pool.queue[traceQ], &pool.counts[traceQ], c, have && !ended);
+        wfPush(pool.queue[freeQ], &pool.counts[freeQ], c, have && ended);
+    }
+}
+
+__global__ void k_wf_init(WfPool pool) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (unsigned)pool.capacity) pool.queue[WQ_FREE0][i] = (int)i;
+    if (i < WQ_COUNT) pool.counts[i] = (i == WQ_FREE0) ? (unsigned)pool.capacity : 0u;
+}
+
+__global__ void k_wf_reset(WfPool pool, int a, int b, int c2, int d) {
+    if (threadIdx.x == 0) {
+        pool.counts[WQ_CURSOR] = 0;
+        if (a >= 0) pool.counts[a] = 0;
+        if (b >= 0) pool.counts[b] = 0;
+        if (c2 >= 0) pool.counts[c2] = 0;
+        if (d >= 0) pool.counts[d] = 0;
+    }
+}
+
+#endif
