@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Benchmark of the path-tracing hot path (BASELINE.json metric: Msamples/sec at 1920x1080x64spp).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle/_ref)
+
+A "step" is one pass of the hot path over the whole workload: SamplerIntegrator::Render with
+PathIntegrator::Li for every pixel sample of BASELINE.json's configs[1] — synthetic 1 M random
+triangles, 1920x1080, 64 spp (Halton), maxdepth 8, 1 B200 per rank.  The scene (BVH, triangles,
+materials, lights, light-distribution tables, Halton tables) is resident in HBM before the timed
+region; with N ranks the film's 16x16 tiles are dealt round-robin to the ranks, every rank renders
+its tiles into its own film and one NCCL reduce(sum) to rank 0 merges them.
+
+One JSON line is printed by rank 0:
+  value        whole-job Msamples/s from the device-timed steps (inputs resident, film left on device)
+  e2e          the same metric through the public host-buffer call pb2_render_path: camera/film/params
+               structs go in, the merged film comes back to host memory inside the timed region
+  roofline     the BVH traversal kernel (k_wf_trace3): algorithmic bytes (32 B x node visits + 36 B x
+               primitive tests, counted on the device in the reference's traversal order) / its summed
+               launch time, against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline the reference's own CPU implementation (oracle/_ref, all host cores) on a bounded
+               sample of the same workload (centred crop at full spp)
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(tris=1000000, seed=1234, jitter=0.02, xres=1920, yres=1080, spp=64, maxdepth=8)
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason sampling during the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) >= 7:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = []
+        for name, col in (("hw_slowdown", 3), ("hw_thermal_slowdown", 4), ("sw_thermal_slowdown", 5), ("sw_power_cap", 6)):
+            if any(s[col].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def build_scene(args):
+    import pbrt_v3_b200 as pb
+    return pb.HostScene.soup(args.tris, seed=WORKLOAD["seed"], jitter=WORKLOAD["jitter"], xres=args.xres, yres=args.yres,
+                             spp=args.spp, maxdepth=args.maxdepth)
+
+
+def crop_params(hs, frac):
+    """PathIntegrator pixelbounds = centred crop holding `frac` of the pixels (full spp)."""
+    import math
+    xres, yres = hs.film.contents.full_resolution[0], hs.film.contents.full_resolution[1]
+    s = math.sqrt(min(1.0, max(frac, 1e-6)))
+    w, h = max(16, int(xres * s) // 16 * 16), max(16, int(yres * s) // 16 * 16)
+    x0, y0 = (xres - w) // 2 // 16 * 16, (yres - h) // 2 // 16 * 16
+    p = hs.params_copy()
+    p.pixel_bounds[0], p.pixel_bounds[1], p.pixel_bounds[2], p.pixel_bounds[3] = x0, y0, x0 + w, y0 + h
+    return p, w * h
+
+
+def time_reference(hs, args, target_seconds, threads=0):
+    """Times the reference CPU path (oracle/_ref; the C++ port if _ref was not built) on a centred crop."""
+    from oracle import pyoracle
+    checker = pyoracle.reference() or pyoracle.port()
+    if checker is None:
+        return None
+    scene = checker.scene(hs)
+    spp = hs.params.contents.samples_per_pixel
+    probe_params, probe_px = crop_params(hs, 64 * 32 / (args.xres * args.yres))
+    _, secs, _ = scene.render(n_threads=threads, params=probe_params)
+    rate = probe_px * spp / max(secs, 1e-6)
+    frac = min(1.0, rate * target_seconds / (args.xres * args.yres * spp))
+    params, px = crop_params(hs, frac)
+    _, secs, st = scene.render(n_threads=threads, params=params)
+    nsamp = px * spp
+    return {"value": nsamp / secs / 1e6, "unit": "Msamples/s", "cores": threads if threads > 0 else (os.cpu_count() or 1),
+            "kind": checker.kind, "seconds": secs, "mrays_per_s": (st.regular_rays + st.shadow_rays) / secs / 1e6,
+            "sample": "centred %d-pixel crop of the %dx%d frame at the full %d spp (%d camera samples), all host threads"
+                      % (px, args.xres, args.yres, spp, nsamp)}, scene
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    hs = build_scene(args)
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info, _ = time_reference(hs, args, target_seconds=args.ref_seconds)
+        if info is None:
+            print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref nor the oracle port is built"}))
+            return 0
+        if i >= args.warmup:
+            vals.append(info)
+    best = max(vals, key=lambda v: v["value"])
+    ms = 1e3 * sum(v["seconds"] for v in vals) / len(vals)
+    line = {"metric": "Msamples/sec", "value": best["value"], "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": workload_config(args, "cpu"),
+            "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": best["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "mrays_per_s": best["mrays_per_s"], "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, parallelism):
+    return {"workload": "synthetic %d random triangles (soup, SURVEY.md §8d C2), %dx%dx%dspp Halton, PathIntegrator maxdepth %d, "
+                        "matte Kd .6, 2-triangle area light" % (args.tris, args.xres, args.yres, args.spp, args.maxdepth),
+            "triangles": args.tris, "resolution": [args.xres, args.yres], "spp": args.spp, "maxdepth": args.maxdepth,
+            "parallelism": parallelism,
+            "l2_note": "scene (BVH 61 MB + leaf records 48 MB) plus 0.5 GB of path contexts exceed the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tris", type=int, default=WORKLOAD["tris"])
+    ap.add_argument("--xres", type=int, default=WORKLOAD["xres"])
+    ap.add_argument("--yres", type=int, default=WORKLOAD["yres"])
+    ap.add_argument("--spp", type=int, default=WORKLOAD["spp"])
+    ap.add_argument("--maxdepth", type=int, default=WORKLOAD["maxdepth"])
+    ap.add_argument("--ref-seconds", type=float, default=15.0, help="CPU seconds per reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import pbrt_v3_b200 as pb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    pb.init(local_rank)
+    L = pb.lib()
+
+    hs = build_scene(args)
+    dev = hs.device_scene()  # BVH + triangles + tables resident in HBM from here on
+    h, w = hs.film_shape()
+    film = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
+    params = hs.params_copy(tile_rank=rank, tile_count=world)
+    stream = torch.cuda.current_stream().cuda_stream
+    n_samples = w * h * args.spp
+
+    def step(stats=None):
+        pb.check(L.pb2_render_path_device(dev, hs.camera, hs.film, params, C.c_void_p(film.data_ptr()), 1, C.c_void_p(stream), stats))
+        if world > 1:
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # algorithmic bytes of one frame: one untimed frame with the counting traversal kernel
+    st = pb.Stats()
+    count_params = hs.params_copy(tile_rank=rank, tile_count=world, flags=1)
+    pb.check(L.pb2_render_path_device(dev, hs.camera, hs.film, count_params, C.c_void_p(film.data_ptr()), 1, C.c_void_p(stream), C.byref(st)))
+    node_visits, prim_tests = int(st.node_visits), int(st.prim_tests)
+    rays_frame = int(st.regular_rays + st.shadow_rays)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    trace_ms = 0.0
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        s = pb.Stats()
+        step(s)
+        launches += int(s.kernel_launches)
+        trace_ms += float(s.trace_ms)
+    e1.record()
+    sync()
+    ms_total = e0.elapsed_time(e1)
+    clock_info = clocks.stop()
+    t = torch.tensor([ms_total, trace_ms], dtype=torch.float64, device="cuda")
+    counts = torch.tensor([float(node_visits), float(prim_tests), float(rays_frame), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    ms_total, trace_ms = float(t[0]), float(t[1])
+    node_visits, prim_tests, rays_frame, launches = (int(x) for x in counts.tolist())
+    ms_per_step = ms_total / args.steps
+    value = n_samples / ms_per_step / 1e3
+
+    # end to end through the host-buffer ABI call (rank-local tiles; N>1: plus the NCCL reduce and the D2H of rank 0)
+    host_film = np.zeros((h, w, 4), np.float32)
+    e2e_ms = []
+    for i in range(2 + args.steps):
+        sync()
+        t0 = time.perf_counter()
+        if world == 1:
+            pb.check(L.pb2_render_path(dev, hs.camera, hs.film, params, pb.ptr(host_film), None))
+        else:
+            step()
+            if rank == 0:
+                host_film = film.cpu().numpy()
+        sync()
+        if i >= 2:
+            e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    e2e_t = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_ms_step = float(e2e_t[0])
+    in_bytes = C.sizeof(pb.Camera) + C.sizeof(pb.FilmDesc) + C.sizeof(pb.PathParams)
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        alg_bytes = 32 * node_visits + 36 * prim_tests  # SURVEY.md §8d, whole frame, all ranks
+        trace_s = trace_ms / args.steps / 1e3           # max over ranks of the summed trace-kernel time per frame
+        achieved = (alg_bytes / world) / trace_s / 1e9 if trace_s > 0 else None
+        line = {
+            "metric": "Msamples/sec", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, "tiles-dp%d" % world),
+            "mrays_per_s": rays_frame / ms_per_step / 1e3, "rays_per_sample": rays_frame / n_samples,
+            "e2e": {"value": n_samples / e2e_ms_step / 1e3, "unit": "Msamples/s", "ms_per_step": e2e_ms_step,
+                    "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": int(host_film.nbytes),
+                    "note": "scene upload happens once at pb2_scene_create (outside, like the reference's scene construction); "
+                            "per step the camera/film/integrator structs go in and the merged rgbw film comes back"},
+            "gpu_launches": launches, "clocks": clock_info,
+            "roofline": {"kernel": "k_wf_trace3 (BVH traversal + ray/triangle tests)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_frame": alg_bytes, "node_visits": node_visits, "prim_tests": prim_tests,
+                         "bytes_per_ray": alg_bytes / max(rays_frame, 1), "trace_ms_per_frame": trace_ms / args.steps,
+                         "trace_share_of_step": (trace_ms / args.steps) / ms_per_step},
+        }
+        if not args.no_cpu_baseline:
+            try:
+                cb, _ = time_reference(hs, args, target_seconds=args.ref_seconds)
+                if cb:
+                    line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                    line["cpu_baseline"]["mrays_per_s"] = cb["mrays_per_s"]
+            except Exception as e:  # the baseline is reporting only; never lose the GPU line
+                line["cpu_baseline"] = {"error": repr(e)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -167,8 +167,14 @@ typedef struct pb2_path_params {
     /* work partition for multi-GPU: this call renders only the 16x16 sample
      * tiles t of SamplerIntegrator::Render (integrator.cpp:235-240) with t % tile_count == tile_rank */
     int32_t tile_rank, tile_count;
-    int32_t pad[2];
+    int32_t flags;            /* PB2_FLAG_* */
+    int32_t pad;
 } pb2_path_params;
+
+/* Count LinearBVHNode fetches and primitive tests (pb2_stats.node_visits / prim_tests) with the
+ * one-thread-per-ray traversal kernel instead of the tuned one: the device analogue of the
+ * reference's STAT_COUNTERs, used to obtain the algorithmic bytes of a frame. */
+#define PB2_FLAG_COUNT_TRAVERSAL 1
 
 typedef struct pb2_ray {
     float o[3];
@@ -192,11 +198,12 @@ typedef struct pb2_stats {
     uint64_t camera_rays;     /* integrator.cpp:287 nCameraRays */
     uint64_t regular_rays;    /* scene.cpp:46 nIntersectionTests */
     uint64_t shadow_rays;     /* scene.cpp:52 nShadowTests */
-    uint64_t node_visits;     /* LinearBVHNode records fetched (0 unless built with PB2_COUNTERS) */
-    uint64_t prim_tests;      /* leaf primitive tests (0 unless built with PB2_COUNTERS) */
+    uint64_t node_visits;     /* LinearBVHNode records fetched (only with PB2_FLAG_COUNT_TRAVERSAL) */
+    uint64_t prim_tests;      /* leaf primitive tests (only with PB2_FLAG_COUNT_TRAVERSAL) */
     uint64_t kernel_launches; /* number of our kernels launched by the call */
-    double render_ms;         /* device time of the render kernels (CUDA events) */
+    double render_ms;         /* device time of the whole render (CUDA events on the launching stream) */
     double h2d_ms, d2h_ms;
+    double trace_ms;          /* summed device time of the BVH traversal kernel launches */
 } pb2_stats;
 
 typedef struct pb2_scene pb2_scene; /* opaque: device-resident scene */

@@ -84,7 +84,7 @@ class FilmDesc(C.Structure):
 class PathParams(C.Structure):
     _fields_ = [("samples_per_pixel", C.c_int32), ("sample_at_pixel_center", C.c_int32), ("max_depth", C.c_int32),
                 ("rr_threshold", C.c_float), ("pixel_bounds", C.c_int32 * 4), ("tile_rank", C.c_int32),
-                ("tile_count", C.c_int32), ("pad", C.c_int32 * 2)]
+                ("tile_count", C.c_int32), ("flags", C.c_int32), ("pad", C.c_int32)]
 
 
 class Ray(C.Structure):
@@ -100,7 +100,7 @@ class Hit(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("camera_rays", C.c_uint64), ("regular_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("render_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double)]
+                ("render_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("trace_ms", C.c_double)]
 
 
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("t_max", np.float32)])

@@ -6,9 +6,9 @@
 // integrator.cpp:202).  None of the sampler dimensions, BSDF values or ray origins of a vertex
 // depends on the RESULT of the shadow or MIS ray, so a lane evaluates everything of the vertex up
 // front (shadeVertex), queues the rays, and then only adds `ldLight` if the shadow ray was
-// unoccluded and `misTerm` if the MIS ray reached the sampled light.  A warp therefore runs
-//     refill idle lanes -> every lane traces its current ray -> every lane advances its state
-// with all lanes inside the same traversal code at the same time, whatever class of ray they hold.
+// unoccluded and `misTerm` if the MIS ray reached the sampled light (lightAdvance).  Every ray of
+// every class therefore goes through the same traversal kernel, and the heavy vertex code runs
+// in its own kernel with all lanes doing the same thing.
 // Sampler dimensions are consumed in the reference's order and the radiance is accumulated with
 // the reference's operation order (Ld = (light + mis) / pickPdf; L += beta * Ld).
 #ifndef PB2_PATH_CUH
@@ -81,10 +81,11 @@ PB2_HD void startMisOrFinish(DLane &ln) {
 
 // The path ray has been traced: one iteration of the bounce loop up to (not including) the results
 // of the two direct-lighting rays.
+template <bool SPH>
 PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &pp, DLane &ln, bool found, const DHit &hit,
                         float tMax) {
     DInteraction isect;
-    if (found) isect = hitInteraction(sc, hit, ln.ray, tMax);
+    if (found) isect = hitInteraction<SPH>(sc, hit, ln.ray, tMax);
     if (ln.bounces == 0 || ln.specularBounce) {
         if (found) {
             int li = sc.primLight[isect.prim];
@@ -121,7 +122,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
             V2 uLight = get2D(h, ln.smp);
             V2 uScattering = get2D(h, ln.smp);
             // EstimateDirect, light-sampling half (integrator.cpp:116-160)
-            DLightSample ls = sampleLight(sc, light, isect, uLight);
+            DLightSample ls = sampleLight<SPH>(sc, light, isect, uLight);
             float lightPdf = ls.pdf, scatteringPdf = 0;
             if (lightPdf > 0 && !isBlack(ls.Li)) {
                 V3 f = bsdfF(bsdf, isect.wo, ls.wi) * absDot(ls.wi, isect.ns);
@@ -140,7 +141,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
             if (scatteringPdf != 0) f = f * absDot(wi, isect.ns);
             else f = mk3(0, 0, 0);
             if (!isBlack(f) && scatteringPdf > 0) {
-                lightPdf = lightPdfLi(sc, light, isect, wi);
+                lightPdf = lightPdfLi<SPH>(sc, light, isect, wi);
                 if (lightPdf != 0) {
                     float weight = powerHeuristic(scatteringPdf, lightPdf);
                     // Li is the light's Lemit when the MIS ray reaches its emitting side (checked after
@@ -193,31 +194,37 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
         startMisOrFinish(ln);
 }
 
-// Advance a lane after its current ray was traced.  Returns true when the path ended in this call
-// (ln.L is then final and ln.state == LS_IDLE).
-PB2_HD bool laneAdvance(const DScene &sc, const DHalton &h, const DPathParams &pp, DLane &ln, bool found, const DHit &hit,
-                        float tMax) {
-    if (ln.state == LS_PATH) {
-        shadeVertex(sc, h, pp, ln, found, hit, tMax);
-    } else if (ln.state == LS_SHADOW) {
+// A shadow or MIS ray has been traced: add its term, then start the vertex's next ray or finish it.
+template <bool SPH>
+PB2_HD void lightAdvance(const DScene &sc, DLane &ln, bool found, const DHit &hit, float tMax) {
+    if (ln.state == LS_SHADOW) {
         if (!found) ln.ldSum = ln.ldSum + ln.ldLight;  // VisibilityTester::Unoccluded
         startMisOrFinish(ln);
-    } else if (ln.state == LS_MIS) {
+    } else {
         if (found) {
             int hitPrim = asInt(ldg4(&sc.leafPrims[3 * (size_t)hit.leaf]).w);
             if (sc.primLight[hitPrim] == ln.lightNum) {
                 // lightIsect.Le(-wi): DiffuseAreaLight::L with the hit's (face-forwarded) normal
-                DInteraction lightIsect = hitInteraction(sc, hit, ln.ray, tMax);
+                DInteraction lightIsect = hitInteraction<SPH>(sc, hit, ln.ray, tMax);
                 const pb2_light light = sc.lights[ln.lightNum];
                 if (light.two_sided || dot(lightIsect.n, -ln.ray.d) > 0) ln.ldSum = ln.ldSum + ln.misTerm;
             }
         }
         finishVertex(ln);
     }
+}
+
+// Advance a lane after its current ray was traced.  Returns true when the path ended in this call
+// (ln.L is then final and ln.state == LS_IDLE).
+template <bool SPH>
+PB2_HD bool laneAdvance(const DScene &sc, const DHalton &h, const DPathParams &pp, DLane &ln, bool found, const DHit &hit,
+                        float tMax) {
+    if (ln.state == LS_PATH) shadeVertex<SPH>(sc, h, pp, ln, found, hit, tMax);
+    else lightAdvance<SPH>(sc, ln, found, hit, tMax);
     return ln.state == LS_IDLE;
 }
 
-// Runtime-flag version of traverse<ANY> so that a kernel holds a single traversal instance.
+// Traces the lane's current ray with the one-thread-per-ray traversal.
 PB2_HD bool traceLane(const DScene &sc, const DLane &ln, float *tMax, DHit *hit, DCounters *ctr) {
     *tMax = ln.ray.tMax;
     hit->leaf = -1;

@@ -58,15 +58,11 @@ struct DHit {
     float b0, b1, b2;
 };
 
-#ifdef PB2_COUNTERS
+// Device analogue of the reference's STAT_COUNTERs around bvh.cpp:672/677/710/714: nodes fetched and
+// primitives tested.  Pass nullptr to traverse without counting (the branch folds away after inlining).
 struct DCounters { unsigned long long nodes, prims; };
-#define PB2_COUNT_NODE(c) ((c)->nodes++)
-#define PB2_COUNT_PRIM(c) ((c)->prims++)
-#else
-struct DCounters { };
-#define PB2_COUNT_NODE(c) ((void)0)
-#define PB2_COUNT_PRIM(c) ((void)0)
-#endif
+#define PB2_COUNT_NODE(c) do { if (c) (c)->nodes++; } while (0)
+#define PB2_COUNT_PRIM(c) do { if (c) (c)->prims++; } while (0)
 
 // Per-ray constants of the watertight test (triangle.cpp:206-222) and of the slab test
 // (bvh.cpp:666-667), computed once per ray instead of once per primitive.

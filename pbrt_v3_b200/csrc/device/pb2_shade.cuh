@@ -143,11 +143,14 @@ PB2_HD DInteraction triangleInteraction(const DScene &sc, int prim, float b0, fl
 
 namespace pb2 {
 
+// SPH = false compiles the sphere branches away (scenes without spheres get kernels without the
+// interval-arithmetic code and its call frames).
+template <bool SPH = true>
 PB2_HD DInteraction hitInteraction(const DScene &sc, const DHit &hit, const DRay &ray, float tHit) {
     float4 a = ldg4(&sc.leafPrims[3 * (size_t)hit.leaf]);
     float4 b = ldg4(&sc.leafPrims[3 * (size_t)hit.leaf + 1]);
     int prim = asInt(a.w);
-    if (floatBits(b.w) & LEAF_SPHERE) return sphereInteraction(sc, prim, ray, tHit, hit.b0);
+    if (SPH && (floatBits(b.w) & LEAF_SPHERE)) return sphereInteraction(sc, prim, ray, tHit, hit.b0);
     return triangleInteraction(sc, prim, hit.b0, hit.b1, hit.b2, ray.d);
 }
 
@@ -614,15 +617,17 @@ PB2_HD DLightSample sampleTriangleLight(const DScene &sc, const pb2_light &l, V3
     return s;
 }
 
+template <bool SPH = true>
 PB2_HD DLightSample sampleLight(const DScene &sc, const pb2_light &l, const DInteraction &ref, V2 u) {
-    if (sc.primType[l.prim] == PB2_PRIM_SPHERE) return sampleSphereLight(sc, l, ref, u);
+    if (SPH && sc.primType[l.prim] == PB2_PRIM_SPHERE) return sampleSphereLight(sc, l, ref, u);
     return sampleTriangleLight(sc, l, ref.p, u);
 }
 
 // DiffuseAreaLight::Pdf_Li -> Shape::Pdf(ref, wi) (shape.cpp:78-95): re-intersect the light's own
 // shape with the spawned ray and convert the area density to solid angle.
+template <bool SPH = true>
 PB2_HD float lightPdfLi(const DScene &sc, const pb2_light &l, const DInteraction &ref, V3 wi) {
-    if (sc.primType[l.prim] == PB2_PRIM_SPHERE) return sphereLightPdf(sc, l, ref, wi);
+    if (SPH && sc.primType[l.prim] == PB2_PRIM_SPHERE) return sphereLightPdf(sc, l, ref, wi);
     DRay ray = spawnRay(ref, wi);
     int tri = sc.primIndex[l.prim];
     const pb2_mesh mesh = sc.meshes[sc.triMesh[tri]];
@@ -759,6 +764,7 @@ struct DPathParams {
     float rrThreshold;
 };
 
+#if 0  // first, monolithic statement of the bounce loop; superseded by the lane state machine in pb2_path.cuh
 struct DPathState {
     V3 L, beta;
     DRay ray;
@@ -908,6 +914,8 @@ PB2_HD bool pathVertex(const DScene &sc, const DHalton &h, const DPathParams &pp
     ps.bounces++;
     return true;
 }
+
+#endif
 
 // The per-sample guard of SamplerIntegrator::Render (integrator.cpp:294-315)
 PB2_HD V3 guardRadiance(V3 L) {

@@ -1,24 +1,22 @@
 // CUDA kernels and the C ABI (include/pb2.h) of the path-tracing hot path, sm_100a only.
 //
 // Kernels
-//   k_build_leaf_records     scene upload: gather triangle vertices into BVH-ordered 48-B leaf records
-//   k_spatial_light_dist     scene upload: SpatialLightDistribution::ComputeDistribution for every voxel
+//   k_build_leaf_records      scene upload: gather triangle vertices into BVH-ordered 48-B leaf records
+//   k_spatial_light_dist      scene upload: SpatialLightDistribution::ComputeDistribution for every voxel
 //   k_intersect / k_intersect_p   Scene::Intersect / IntersectP for a batch of rays (1 thread = 1 ray)
-//   k_render_path            SamplerIntegrator::Render + PathIntegrator::Li: persistent warps; every lane
-//                            owns one camera sample at a time and walks its path vertex by vertex, all
-//                            lanes of a warp entering the BVH traversal of the same ray class together;
-//                            a lane whose path ended deposits the sample in the film and takes the next
-//                            work item from a global counter (one warp-aggregated atomic per refill)
-//   k_li_samples, k_halton_samples, k_light_distribution   parity/debug entry points
+//   k_wf_gen / k_wf_trace* / k_wf_advance<>   the wavefront renderer (pb2_wavefront.cuh):
+//                             SamplerIntegrator::Render + PathIntegrator::Li + FilmTile::AddSample
+//   k_li_samples, k_halton_samples, k_light_distribution   parity / debug entry points
 //
 // Compile flags that matter for parity: -fmad=false (the reference has no FMA contraction),
 // default IEEE division and square root, no fast-math.
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <vector>
 
@@ -46,6 +44,11 @@ static int setError(int code, const std::string &msg) {
 static bool g_initialised = false;
 static int g_device = -1;
 static int g_numSMs = 0;
+
+static int envInt(const char *name, int def) {
+    const char *v = std::getenv(name);
+    return v ? std::atoi(v) : def;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Halton tables (lowdiscrepancy.cpp:40,124,2490-2504; halton.cpp:65-93)
@@ -151,15 +154,17 @@ struct pb2_scene {
     std::vector<void *> allocations;
     float *film = nullptr;  // cached device film for pb2_render_path
     size_t filmFloats = 0;
-    unsigned long long *counters = nullptr;  // [0] work counter, [1..] stats
+    unsigned long long *counters = nullptr;  // CTR_*
     int64_t nPrims = 0;
     int nLights = 0;
+    int bvhDepth = 0;  // maximum number of simultaneously pending far children = tree depth
     // wavefront pool (allocated on first render)
     void *wfCtx = nullptr;
     int *wfQueues = nullptr;
     unsigned *wfCounts = nullptr;
     unsigned *wfHostCounts = nullptr;  // pinned
     int wfCapacity = 0;
+    std::vector<cudaEvent_t> traceEvents;
 };
 
 template <typename T>
@@ -233,14 +238,13 @@ __global__ void k_intersect(DScene sc, const pb2_ray *rays, int64_t n, pb2_hit *
     h.leaf = -1;
     h.b0 = h.b1 = h.b2 = 0;
     float tMax = r.tMax;
-    DCounters ctr{};
-    bool found = traverse<false>(sc, r, &tMax, &h, &ctr);
+    bool found = traverse<false>(sc, r, &tMax, &h, nullptr);
     pb2_hit out;
     memset(&out, 0, sizeof(out));
     out.prim = -1;
     out.t = tMax;
     if (found) {
-        DInteraction it = hitInteraction(sc, h, r, tMax);
+        DInteraction it = hitInteraction<true>(sc, h, r, tMax);
         out.prim = it.prim;
         out.b[0] = h.b0; out.b[1] = h.b1; out.b[2] = h.b2;
         out.p[0] = it.p.x; out.p[1] = it.p.y; out.p[2] = it.p.z;
@@ -262,12 +266,11 @@ __global__ void k_intersect_p(DScene sc, const pb2_ray *rays, int64_t n, uint8_t
     r.tMax = rays[i].t_max;
     DHit h;
     float tMax = r.tMax;
-    DCounters ctr{};
-    occluded[i] = traverse<true>(sc, r, &tMax, &h, &ctr) ? 1 : 0;
+    occluded[i] = traverse<true>(sc, r, &tMax, &h, nullptr) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// render kernel
+// render
 // ---------------------------------------------------------------------------------------------
 struct DRenderParams {
     DCamera cam;
@@ -297,8 +300,8 @@ __device__ __forceinline__ int compact1by1(unsigned x) {
 
 // Work item -> (pixel, sample number).  Items are ordered tile by tile (the reference's 16x16 tiles,
 // integrator.cpp:235-240), then by sample number, then in Morton order inside the tile, so 32
-// consecutive items are one sample number of an 8x4 pixel block: coherent camera rays for a warp
-// that refills all its lanes at once.
+// consecutive items are one sample number of an 8x4 pixel block: coherent camera rays for a warp.
+// Tile t belongs to this call when t % tileCount == tileRank (multi-GPU partition).
 __device__ __forceinline__ bool decodeWork(const DRenderParams &rp, long long item, int *px, int *py, int *sample) {
     long long perTile = 256LL * rp.spp;
     long long owned = item / perTile;
@@ -340,90 +343,7 @@ __device__ __forceinline__ void addSample(const DRenderParams &rp, float4 *film,
 
 #include "pb2_wavefront.cuh"
 
-template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_render_path(DScene sc, DRenderParams rp, float4 *film, unsigned long long *counters) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    DLane ln;
-    ln.state = LS_IDLE;
-    ln.L = mk3(0, 0, 0);
-    DRayStats st;
-    st.regular = st.shadow = 0;
-    unsigned cameraRays = 0;
-    DCounters ctr{};
-    bool exhausted = false;
-    int px = 0, py = 0;
-    V2 pFilm = mk2(0, 0);
-    while (true) {
-        // refill idle lanes: one atomic per warp
-        bool active = ln.state != LS_IDLE;
-        bool want = !active && !exhausted;
-        unsigned wantMask = __ballot_sync(FULL, want);
-        if (wantMask) {
-            int leader = __ffs(wantMask) - 1;
-            unsigned long long base = 0;
-            if (lane == leader) base = atomicAdd(&counters[CTR_WORK], (unsigned long long)__popc(wantMask));
-            base = __shfl_sync(FULL, base, leader);
-            if (want) {
-                long long item = (long long)base + __popc(wantMask & ((1u << lane) - 1u));
-                if (item >= rp.nWorkItems)
-                    exhausted = true;
-                else {
-                    int sample;
-                    if (decodeWork(rp, item, &px, &py, &sample)) {
-                        DSampler smp;
-                        smp.index = haltonIndex(rp.halton, px, py, sample);
-                        smp.dim = 0;
-                        DRay ray = generateCameraRay(rp.cam, rp.halton, smp, px, py, &pFilm);
-                        laneStartPath(ln, ray, smp);
-                        cameraRays++;
-                        active = true;
-                    }
-                }
-            }
-        }
-        if (!__any_sync(FULL, active)) {
-            if (__all_sync(FULL, exhausted)) break;
-            continue;
-        }
-        // every lane that holds a ray traces it (closest hit for path/MIS rays, any hit for shadow rays)
-        bool found = false;
-        DHit hit;
-        float tMax = 0;
-        if (active) {
-            if (ln.state == LS_SHADOW) st.shadow++;
-            else st.regular++;
-            found = traceLane(sc, ln, &tMax, &hit, &ctr);
-        }
-        if (active) {
-            if (laneAdvance(sc, rp.halton, rp.path, ln, found, hit, tMax)) addSample(rp, film, pFilm, guardRadiance(ln.L));
-        }
-    }
-    // statistics: warp reduce, one atomic per warp and counter
-    unsigned long long c0 = cameraRays, c1 = st.regular, c2 = st.shadow;
-    for (int o = 16; o > 0; o >>= 1) {
-        c0 += __shfl_down_sync(FULL, c0, o);
-        c1 += __shfl_down_sync(FULL, c1, o);
-        c2 += __shfl_down_sync(FULL, c2, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&counters[CTR_CAMERA], c0);
-        atomicAdd(&counters[CTR_REGULAR], c1);
-        atomicAdd(&counters[CTR_SHADOW], c2);
-    }
-#ifdef PB2_COUNTERS
-    unsigned long long n0 = ctr.nodes, n1 = ctr.prims;
-    for (int o = 16; o > 0; o >>= 1) {
-        n0 += __shfl_down_sync(FULL, n0, o);
-        n1 += __shfl_down_sync(FULL, n1, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&counters[CTR_NODES], n0);
-        atomicAdd(&counters[CTR_PRIMS], n1);
-    }
-#endif
-}
-
+// PathIntegrator::Li for explicit (pixel, sample) pairs: the same lane functions, one thread per sample.
 __global__ void k_li_samples(DScene sc, DRenderParams rp, const int32_t *pixelXY, const int64_t *sampleNum, int64_t n,
                              float *outRGB, float *outPFilm) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -436,12 +356,11 @@ __global__ void k_li_samples(DScene sc, DRenderParams rp, const int32_t *pixelXY
     DRay ray = generateCameraRay(rp.cam, rp.halton, smp, px, py, &pFilm);
     DLane ln;
     laneStartPath(ln, ray, smp);
-    DCounters ctr{};
     while (ln.state != LS_IDLE) {
         DHit hit;
         float tMax;
-        bool found = traceLane(sc, ln, &tMax, &hit, &ctr);
-        laneAdvance(sc, rp.halton, rp.path, ln, found, hit, tMax);
+        bool found = traceLane(sc, ln, &tMax, &hit, nullptr);
+        laneAdvance<true>(sc, rp.halton, rp.path, ln, found, hit, tMax);
     }
     V3 L = guardRadiance(ln.L);
     outRGB[3 * i] = L.x;
@@ -513,12 +432,17 @@ static int validateRenderArgs(const pb2_scene *scene, const pb2_camera *cam, con
         return setError(PB2_ERR_INVALID, "bad tile_rank / tile_count");
     if (film->cropped_pixel_bounds[2] < film->cropped_pixel_bounds[0] || film->cropped_pixel_bounds[3] < film->cropped_pixel_bounds[1])
         return setError(PB2_ERR_INVALID, "bad cropped pixel bounds");
+    if (!(film->filter_radius[0] > 0) || !(film->filter_radius[1] > 0)) return setError(PB2_ERR_INVALID, "bad filter radius");
     return PB2_OK;
 }
 
+typedef void (*TraceKernel)(DScene, WfPool, int);
+typedef void (*AdvanceKernel)(DScene, DRenderParams, WfPool, int, int, int, float4 *, unsigned long long *);
+
 // Host driver of the wavefront rounds (see pb2_wavefront.cuh).
-static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *film, cudaStream_t stream, unsigned long long *launches) {
-    static const int maxCapacity = std::getenv("PB2_POOL") ? std::atoi(std::getenv("PB2_POOL")) : (1 << 20);
+static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *film, cudaStream_t stream, bool countTraversal,
+                           bool timeTrace, unsigned long long *launches, double *traceMs) {
+    static const int maxCapacity = envInt("PB2_POOL", 1 << 21);
     long long want = std::min<long long>(maxCapacity, std::max<long long>(rp.nWorkItems, 1024));
     int capacity = (int)((want + 255) / 256 * 256);
     if (scene->wfCapacity < capacity) {
@@ -538,30 +462,55 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     pool.ctx = (WfCtx *)scene->wfCtx;
     for (int q = 0; q < 6; ++q) pool.queue[q] = scene->wfQueues + (size_t)q * scene->wfCapacity;
     pool.counts = scene->wfCounts;
+
+    // kernel selection: scenes without spheres whose BVH depth fits the shared-memory stack get the
+    // leanest traversal kernel; PB2_TRACE selects tuning variants for experiments
+    const bool spheres = scene->d.spheres != nullptr;
+    static const int variant = envInt("PB2_TRACE", 0);
+    TraceKernel trace;
+    if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
+    else if (scene->bvhDepth > 32) trace = k_wf_trace<12, 8, 4, 32, true, false, 8>;
+    else if (variant == 1) trace = k_wf_trace<12, 8, 8, 32, false, false, 8>;
+    else if (variant == 2) trace = k_wf_trace<16, 8, 4, 32, false, false, 8>;
+    else if (variant == 3) trace = k_wf_trace<12, 8, 4, 32, false, false, 10>;
+    else if (variant == 4) trace = k_wf_trace<12, 12, 6, 32, false, false, 8>;
+    else trace = k_wf_trace<12, 8, 4, 32, false, false, 8>;
+    AdvanceKernel advLight = spheres ? k_wf_advance<false, true> : k_wf_advance<false, false>;
+    AdvanceKernel advShade = spheres ? k_wf_advance<true, true> : k_wf_advance<true, false>;
+    int traceBlocksPerSM = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&traceBlocksPerSM, trace, 128, 0));
+    const int persistentBlocks = g_numSMs * std::max(1, traceBlocksPerSM);
     const int blocks256 = std::min((capacity + 255) / 256, g_numSMs * 16);
     const int blocks128 = std::min((capacity + 127) / 128, g_numSMs * 32);
-    // trace kernel variant: 1 = one thread per ray, grid-stride; 2.. = persistent warps with ballot-scheduled steps
-    static const int traceVariant = std::getenv("PB2_TRACE") ? std::atoi(std::getenv("PB2_TRACE")) : 2;
-    void (*traceKernel)(DScene, WfPool, int, unsigned long long *) =
-        traceVariant == 3 ? k_wf_trace2<4, 4> : traceVariant == 4 ? k_wf_trace2<12, 12> : traceVariant == 5 ? k_wf_trace2<16, 8> : k_wf_trace2<8, 8>;
-    int traceBlocksPerSM = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&traceBlocksPerSM, traceKernel, 128, 0));
-    const int persistentBlocks = g_numSMs * std::max(1, traceBlocksPerSM);
+
     k_wf_init<<<(capacity + 255) / 256, 256, 0, stream>>>(pool);
     unsigned long long nLaunch = 1;
+    size_t nEvents = 0;
     int cur = 0;
     volatile unsigned *hc = scene->wfHostCounts;
     unsigned long long *hWork = reinterpret_cast<unsigned long long *>(scene->wfHostCounts + WQ_COUNT);
     for (long long round = 0;; ++round) {
         int next = 1 - cur;
         k_wf_gen<<<blocks256, 256, 0, stream>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur, scene->counters);
-        if (traceVariant == 1)
-            k_wf_trace<<<blocks128, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
-        else
-            traceKernel<<<persistentBlocks, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
-        k_wf_advance<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film);
-        k_wf_advance<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_SHADE, WQ_TRACE0 + next, WQ_FREE0 + next, film);
-        k_wf_reset<<<1, 32, 0, stream>>>(pool, WQ_FREE0 + cur, WQ_TRACE0 + cur, WQ_SHADE, WQ_LIGHT);
+        if (timeTrace) {
+            if (scene->traceEvents.size() < nEvents + 2) {
+                cudaEvent_t e0, e1;
+                CUDA_TRY(cudaEventCreate(&e0));
+                CUDA_TRY(cudaEventCreate(&e1));
+                scene->traceEvents.push_back(e0);
+                scene->traceEvents.push_back(e1);
+            }
+            CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents], stream));
+        }
+        if (countTraversal) k_wf_trace_plain<true><<<blocks128, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
+        else trace<<<persistentBlocks, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur);
+        if (timeTrace) {
+            CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents + 1], stream));
+            nEvents += 2;
+        }
+        advLight<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
+        advShade<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_SHADE, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
+        k_wf_reset<<<1, 32, 0, stream>>>(pool, WQ_FREE0 + cur, WQ_TRACE0 + cur);
         nLaunch += 5;
         CUDA_TRY(cudaMemcpyAsync((void *)scene->wfHostCounts, pool.counts, WQ_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(hWork, &scene->counters[CTR_WORK], sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
@@ -574,6 +523,12 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     }
     CUDA_TRY(cudaGetLastError());
     *launches = nLaunch;
+    *traceMs = 0;
+    for (size_t e = 0; e + 1 < nEvents; e += 2) {
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, scene->traceEvents[e], scene->traceEvents[e + 1]));
+        *traceMs += ms;
+    }
     return PB2_OK;
 }
 
@@ -606,7 +561,6 @@ int pb2_init(int device_id) {
     CUDA_TRY(cudaMemcpy(g_halton.primes, g_halton.hPrimes.data(), g_halton.hPrimes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(g_halton.primeSums, g_halton.hPrimeSums.data(), g_halton.hPrimeSums.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(g_halton.perms, g_halton.hPerms.data(), g_halton.hPerms.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    // the traversal stack lives in local memory: 64 ints per thread
     g_device = device_id;
     g_initialised = true;
     return PB2_OK;
@@ -631,6 +585,7 @@ int pb2_scene_destroy(pb2_scene *s) {
     if (s->wfQueues) cudaFree(s->wfQueues);
     if (s->wfCounts) cudaFree(s->wfCounts);
     if (s->wfHostCounts) cudaFreeHost(s->wfHostCounts);
+    for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     delete s;
     return PB2_OK;
 }
@@ -659,6 +614,26 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
     sc.nLights = d->n_lights;
     s->nPrims = d->n_prims;
     s->nLights = d->n_lights;
+    {
+        // depth of the tree = deepest traversal stack any ray can need (selects the shared-memory-stack kernel)
+        std::vector<std::pair<int, int>> todo{{0, 0}};
+        int depth = 0;
+        while (!todo.empty()) {
+            std::pair<int, int> nd = todo.back();
+            todo.pop_back();
+            if (nd.first < 0 || nd.first >= d->n_nodes) return setError(PB2_ERR_INVALID, "BVH child index out of range");
+            depth = std::max(depth, nd.second);
+            const pb2_bvh_node &node = d->nodes[nd.first];
+            if (node.n_prims == 0) {
+                if (nd.second > 4096) return setError(PB2_ERR_INVALID, "BVH is not a tree");
+                todo.push_back({nd.first + 1, nd.second + 1});
+                todo.push_back({node.offset, nd.second + 1});
+            } else if ((int64_t)node.offset + node.n_prims > d->n_prims || node.offset < 0)
+                return setError(PB2_ERR_INVALID, "BVH leaf range out of bounds");
+        }
+        s->bvhDepth = depth;
+        if (depth > 64) return setError(PB2_ERR_UNSUPPORTED, "BVH deeper than the reference's 64-entry traversal stack (bvh.cpp:671)");
+    }
     const pb2_bvh_node *nodes;
     if ((rc = upload(s, d->nodes, (size_t)d->n_nodes, &nodes))) return rc;
     sc.nodes = reinterpret_cast<const float4 *>(nodes);
@@ -807,7 +782,6 @@ int pb2_render_path_device(pb2_scene *scene, const pb2_camera *cam, const pb2_fi
     if (rc) return rc;
     if ((rc = validateRenderArgs(scene, cam, film, pp))) return rc;
     if (!film_rgbw_device) return setError(PB2_ERR_INVALID, "null film pointer");
-    if (film->filter_radius[0] <= 0 || film->filter_radius[1] <= 0) return setError(PB2_ERR_INVALID, "bad filter radius");
     cudaStream_t stream = (cudaStream_t)stream_;
     DRenderParams rp = makeRenderParams(cam, film, pp);
     size_t nPixels = (size_t)(rp.cx1 - rp.cx0) * (size_t)(rp.cy1 - rp.cy0);
@@ -819,23 +793,12 @@ int pb2_render_path_device(pb2_scene *scene, const pb2_camera *cam, const pb2_fi
         CUDA_TRY(cudaEventCreate(&e1));
         CUDA_TRY(cudaEventRecord(e0, stream));
     }
-    static const bool megakernel = std::getenv("PB2_MODE") && std::string(std::getenv("PB2_MODE")) == "mega";
     unsigned long long launches = 0;
-    if (rp.nWorkItems > 0 && !megakernel) {
-        int rc2 = renderWavefront(scene, rp, (float4 *)film_rgbw_device, stream, &launches);
-        if (rc2) return rc2;
-    } else if (rp.nWorkItems > 0) {
-        launches = 1;
-        int threads = 128, blocksPerSM = 0;
-        static int minb = std::getenv("PB2_MINBLOCKS") ? std::atoi(std::getenv("PB2_MINBLOCKS")) : 2;
-        void (*kernel)(DScene, DRenderParams, float4 *, unsigned long long *) =
-            minb >= 8 ? k_render_path<8> : minb >= 6 ? k_render_path<6> : minb >= 4 ? k_render_path<4> : minb >= 3 ? k_render_path<3> : k_render_path<2>;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, kernel, threads, 0));
-        blocksPerSM = std::max(1, blocksPerSM);
-        long long warpsNeeded = (rp.nWorkItems + 31) / 32;
-        long long blocks = std::min<long long>((long long)g_numSMs * blocksPerSM, (warpsNeeded + 3) / 4);
-        kernel<<<(unsigned)std::max<long long>(1, blocks), threads, 0, stream>>>(scene->d, rp, (float4 *)film_rgbw_device, scene->counters);
-        CUDA_TRY(cudaGetLastError());
+    double traceMs = 0;
+    if (rp.nWorkItems > 0) {
+        rc = renderWavefront(scene, rp, (float4 *)film_rgbw_device, stream, (pp->flags & PB2_FLAG_COUNT_TRAVERSAL) != 0, stats != nullptr,
+                             &launches, &traceMs);
+        if (rc) return rc;
     }
     if (stats) {
         CUDA_TRY(cudaEventRecord(e1, stream));
@@ -855,6 +818,7 @@ int pb2_render_path_device(pb2_scene *scene, const pb2_camera *cam, const pb2_fi
         stats->prim_tests = c[CTR_PRIMS];
         stats->kernel_launches = launches;
         stats->render_ms = ms;
+        stats->trace_ms = traceMs;
     }
     return PB2_OK;
 }
@@ -876,7 +840,8 @@ int pb2_render_path(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc
         scene->filmFloats = nFloats;
     }
     pb2_stats local;
-    rc = pb2_render_path_device(scene, cam, film, pp, scene->film, 1, nullptr, &local);
+    memset(&local, 0, sizeof(local));
+    rc = pb2_render_path_device(scene, cam, film, pp, scene->film, 1, nullptr, stats ? &local : nullptr);
     if (rc) return rc;
     cudaEvent_t e0, e1;
     CUDA_TRY(cudaEventCreate(&e0));

@@ -4,16 +4,17 @@
 // the per-lane state machine of device/pb2_path.cuh: at any time it owns exactly one ray of one of
 // three classes (path ray, shadow ray, MIS ray).  One ROUND is
 //
-//   k_wf_gen      contexts on the free list take the next work item (pixel, sample number), generate
-//                 the camera ray (Halton dims 0-4, perspective camera) and join the trace list
-//   k_wf_trace    every listed context's ray is traced through the BVH (closest hit or any hit);
-//                 the context is appended to the shade list (path ray) or the light list (shadow /
-//                 MIS ray)                                           <- the dominant kernel
-//   k_wf_advance  (light list) adds ldLight / misTerm, then starts the next ray of the vertex or
-//                 finishes the vertex: next path ray, or the sample is deposited in the film and the
-//                 context goes to the free list
-//   k_wf_advance  (shade list) evaluates the whole path vertex (SurfaceInteraction, BSDF, light pick,
-//                 light sample + MIS sample, continuation + Russian roulette) and queues its rays
+//   k_wf_gen            contexts on the free list take the next work item (pixel, sample number),
+//                       generate the camera ray (Halton dims 0-4, perspective camera) and join the
+//                       trace list
+//   k_wf_trace*         every listed context's ray is traced through the BVH (closest hit or any
+//                       hit); the context is appended to the shade list (path ray) or the light list
+//                       (shadow / MIS ray)                                  <- the dominant kernel
+//   k_wf_advance<false> (light list) adds ldLight / misTerm, then starts the next ray of the vertex
+//                       or finishes the vertex: next path ray, or the sample is deposited in the film
+//                       and the context goes to the free list
+//   k_wf_advance<true>  (shade list) evaluates the whole path vertex (SurfaceInteraction, BSDF, light
+//                       pick, light sample + MIS sample, continuation + Russian roulette), queues its rays
 //
 // so every kernel runs with all lanes of a warp in the same code, the trace kernel keeps only ray
 // state in registers, and a finished sample is replaced immediately (the pool stays full until the
@@ -23,16 +24,17 @@
 #define PB2_WAVEFRONT_CUH
 
 struct alignas(32) WfCtx {
-    DLane ln;       // starts with {int state; DRay ray;} = 32 bytes: what k_wf_trace reads
-    alignas(16) DHit hit;  // written by k_wf_trace as one 16-byte store
+    DLane ln;              // starts with {int state; DRay ray;} = 32 bytes: what the trace kernels read
+    alignas(16) DHit hit;  // written by the trace kernels as one 16-byte store
     float tHit;
     int found;
     V2 pFilm;
 };
 static_assert(offsetof(WfCtx, ln) == 0 && offsetof(DLane, state) == 0 && offsetof(DLane, ray) == 4 && sizeof(DRay) == 28,
-              "k_wf_trace reads the first 32 bytes of a context as {state, o, d, tMax}");
+              "the trace kernels read the first 32 bytes of a context as {state, o, d, tMax}");
+static_assert(offsetof(WfCtx, tHit) % 8 == 0 && offsetof(WfCtx, found) == offsetof(WfCtx, tHit) + 4, "tHit/found are stored as one float2");
 
-enum { WQ_TRACE0 = 0, WQ_TRACE1 = 1, WQ_SHADE = 2, WQ_LIGHT = 3, WQ_FREE0 = 4, WQ_FREE1 = 5, WQ_CURSOR = 6, WQ_RETIRED = 7, WQ_COUNT = 8 };
+enum { WQ_TRACE0 = 0, WQ_TRACE1 = 1, WQ_SHADE = 2, WQ_LIGHT = 3, WQ_FREE0 = 4, WQ_FREE1 = 5, WQ_CURSOR = 6, WQ_COUNT = 8 };
 
 struct WfPool {
     int capacity;
@@ -51,6 +53,17 @@ __device__ __forceinline__ void wfPush(int *queue, unsigned *counter, int value,
     if (lane == leader) base = atomicAdd(counter, (unsigned)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, leader);
     if (participate) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
+}
+
+__device__ __forceinline__ void wfCountRays(unsigned long long *counters, unsigned regular, unsigned shadow) {
+    for (int o = 16; o > 0; o >>= 1) {
+        regular += __shfl_down_sync(0xffffffffu, regular, o);
+        shadow += __shfl_down_sync(0xffffffffu, shadow, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (regular) atomicAdd(&counters[CTR_REGULAR], (unsigned long long)regular);
+        if (shadow) atomicAdd(&counters[CTR_SHADOW], (unsigned long long)shadow);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_wf_gen(DRenderParams rp, WfPool pool, int freeQ, int traceQ, unsigned long long *counters) {
@@ -94,15 +107,23 @@ __global__ void __launch_bounds__(256) k_wf_gen(DRenderParams rp, WfPool pool, i
         wfPush(pool.queue[traceQ], &pool.counts[traceQ], c, started);
     }
     for (int o = 16; o > 0; o >>= 1) cameraRays += __shfl_down_sync(0xffffffffu, cameraRays, o);
-    if ((threadIdx.x & 31) == 0 && cameraRays) atomicAdd(&counters[CTR_CAMERA], (unsigned long long)cameraRays);
+    if ((threadIdx.x & 31) == 0 && cameraRays) {
+        atomicAdd(&counters[CTR_CAMERA], (unsigned long long)cameraRays);
+        atomicAdd(&counters[CTR_REGULAR], (unsigned long long)cameraRays);  // every camera ray is a Scene::Intersect call
+    }
 }
 
-// One thread per listed ray.  Reads 32 bytes of the context, writes 24.
-__global__ void __launch_bounds__(128) k_wf_trace(DScene sc, WfPool pool, int traceQ, unsigned long long *counters) {
+// ---------------------------------------------------------------------------------------------
+// Trace kernel, plain form: one thread per listed ray, BVHAccel::Intersect[P] exactly as written in
+// device/pb2_scene.cuh.  Used when PB2_FLAG_COUNT_TRAVERSAL asks for node / primitive counters
+// (COUNT) and as the simplest statement of what the tuned kernels below compute.
+// ---------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(128) k_wf_trace_plain(DScene sc, WfPool pool, int traceQ, unsigned long long *counters) {
     unsigned n = pool.counts[traceQ];
     unsigned stride = gridDim.x * blockDim.x;
-    unsigned regular = 0, shadow = 0;
-    DCounters ctr{};
+    DCounters ctr;
+    ctr.nodes = ctr.prims = 0;
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += stride) {
         unsigned i = base + threadIdx.x;
         bool have = i < n;
@@ -120,9 +141,7 @@ __global__ void __launch_bounds__(128) k_wf_trace(DScene sc, WfPool pool, int tr
             DHit hit;
             hit.leaf = -1;
             hit.b0 = hit.b1 = hit.b2 = 0;
-            bool any = state == LS_SHADOW;
-            if (any) shadow++; else regular++;
-            bool found = traverseAnyOrClosest(sc, ray, any, &tMax, &hit, &ctr);
+            bool found = traverseAnyOrClosest(sc, ray, state == LS_SHADOW, &tMax, &hit, COUNT ? &ctr : nullptr);
             WfCtx &cx = pool.ctx[c];
             *reinterpret_cast<float4 *>(&cx.hit) = make_float4(__int_as_float(hit.leaf), hit.b0, hit.b1, hit.b2);
             cx.tHit = tMax;
@@ -131,65 +150,71 @@ __global__ void __launch_bounds__(128) k_wf_trace(DScene sc, WfPool pool, int tr
         wfPush(pool.queue[WQ_SHADE], &pool.counts[WQ_SHADE], c, have && state == LS_PATH);
         wfPush(pool.queue[WQ_LIGHT], &pool.counts[WQ_LIGHT], c, have && state != LS_PATH);
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        regular += __shfl_down_sync(0xffffffffu, regular, o);
-        shadow += __shfl_down_sync(0xffffffffu, shadow, o);
+    if (COUNT) {
+        unsigned long long n0 = ctr.nodes, n1 = ctr.prims;
+        for (int o = 16; o > 0; o >>= 1) {
+            n0 += __shfl_down_sync(0xffffffffu, n0, o);
+            n1 += __shfl_down_sync(0xffffffffu, n1, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&counters[CTR_NODES], n0);
+            atomicAdd(&counters[CTR_PRIMS], n1);
+        }
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (regular) atomicAdd(&counters[CTR_REGULAR], (unsigned long long)regular);
-        if (shadow) atomicAdd(&counters[CTR_SHADOW], (unsigned long long)shadow);
-    }
-#ifdef PB2_COUNTERS
-    unsigned long long n0 = ctr.nodes, n1 = ctr.prims;
-    for (int o = 16; o > 0; o >>= 1) {
-        n0 += __shfl_down_sync(0xffffffffu, n0, o);
-        n1 += __shfl_down_sync(0xffffffffu, n1, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&counters[CTR_NODES], n0);
-        atomicAdd(&counters[CTR_PRIMS], n1);
-    }
-#endif
 }
 
-// Persistent-warp version of the trace kernel.  Each lane walks its own ray through the BVH with the
-// reference's visiting order (near child first, explicit stack, every primitive of a reached leaf),
-// but the WARP decides by ballot which of three steps to run next, so that the lanes inside a step
-// are (mostly) all busy:
-//   node step   lanes that stand at a node: fetch the 32-byte node, slab test, descend / pop
-//   leaf step   lanes that reached a leaf wait until LEAF_T lanes did (or nobody can walk any more),
-//               then test their leaf's primitives together
-//   fetch step  lanes whose ray is finished wait until FETCH_T lanes are (or nothing else is left),
-//               then store their results, append their context to the shade / light list, and take
-//               the next rays of the trace list (one warp-aggregated atomic)
-// Node-visit and primitive-test counts per ray are unchanged; only the interleaving across lanes is.
-template <int LEAF_T, int FETCH_T>
-__global__ void __launch_bounds__(128, 6) k_wf_trace2(DScene sc, WfPool pool, int traceQ, unsigned long long *counters) {
+// ---------------------------------------------------------------------------------------------
+// Trace kernel, tuned form: persistent warps.  Each lane walks its own ray through the BVH with
+// the reference's visiting order (near child first, explicit stack, every primitive of a reached
+// leaf), but the WARP decides by ballot which of three steps to run next, so that the lanes inside
+// a step are mostly all busy:
+//   node step   lanes that stand at a node: fetch the 32-byte node (two 16-byte loads), slab test,
+//               descend / pop; NSUB visits per scheduling round
+//   leaf step   lanes that reached a leaf wait until LEAF_T lanes did (or nobody can walk any
+//               more), then test their leaf's primitives together (three 16-byte loads each)
+//   fetch step  lanes whose ray is finished wait until FETCH_T lanes are (or nothing else is
+//               left), then store their results, append their context to the shade / light list,
+//               and take the next rays of the trace list (one warp-aggregated atomic)
+// Node-visit and primitive-test counts per ray are the reference's; only the interleaving across
+// lanes differs.  Details that came out of ncu (profiles/):
+//   * the traversal stack lives in shared memory, [depth][thread] (conflict-free): a local-memory
+//     stack missed L1 40 % of the time; entries beyond SDEPTH spill to a small local array (DEEP),
+//     or the host picks this kernel only when the BVH depth fits (DEEP = false);
+//   * the closest hit so far is written straight into the context (it changes ~1.5 times per ray);
+//     only tMax stays in a register -> 59 registers, 8 blocks of 128 threads per SM;
+//   * the descend / pop tail of the node step touches one stack slot with selects instead of
+//     diverging into push and pop branches;
+//   * context words are read / written with streaming hints so nodes + leaf records stay in L2.
+// ---------------------------------------------------------------------------------------------
+template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, bool DEEP, bool SPHERES, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, int traceQ) {
+    __shared__ int sstack[SDEPTH][128];
+    int lstack[DEEP ? 64 - SDEPTH : 1];
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
     const unsigned n = pool.counts[traceQ];
     enum { M_FETCH = 0, M_NODE = 1, M_LEAF = 2 };
+    enum { F_ANY = 1, F_FOUND = 2, F_EXHAUSTED = 4 };
     int mode = M_FETCH;
-    int c = -1;            // context of the ray in flight (>= 0 also while its result waits to be flushed)
-    bool exhausted = false;
+    int c = -1;
+    int flags = 0;
     DRaySetup rs;
     rs.o = rs.invDir = mk3(0, 0, 0);
     rs.neg0 = rs.neg1 = rs.neg2 = 0;
     rs.kx = rs.ky = rs.kz = 0;
     rs.Sx = rs.Sy = rs.Sz = 0;
     float tMax = 0;
-    bool any = false, found = false;
     int cur = 0, sp = 0, leafFirst = 0, leafN = 0;
-    DHit hit;
-    hit.leaf = -1;
-    hit.b0 = hit.b1 = hit.b2 = 0;
-    int stack[64];
-    unsigned regular = 0, shadow = 0;
-    DCounters ctr{};
+    auto stackGet = [&](int slot) -> int { return (!DEEP || slot < SDEPTH) ? sstack[slot][tid] : lstack[DEEP ? slot - SDEPTH : 0]; };
+    auto stackPut = [&](int slot, int v) {
+        if (!DEEP || slot < SDEPTH) sstack[slot][tid] = v;
+        else lstack[DEEP ? slot - SDEPTH : 0] = v;
+    };
     while (true) {
         unsigned mNode = __ballot_sync(FULL, mode == M_NODE);
         unsigned mLeaf = __ballot_sync(FULL, mode == M_LEAF);
-        unsigned mFetch = __ballot_sync(FULL, mode == M_FETCH && !(exhausted && c < 0));
+        unsigned mFetch = __ballot_sync(FULL, mode == M_FETCH && !((flags & F_EXHAUSTED) && c < 0));
         int nNode = __popc(mNode), nLeaf = __popc(mLeaf), nFetch = __popc(mFetch);
         int step;
         if (nFetch >= FETCH_T || (nFetch > 0 && nNode == 0 && nLeaf == 0)) step = M_FETCH;
@@ -198,47 +223,50 @@ __global__ void __launch_bounds__(128, 6) k_wf_trace2(DScene sc, WfPool pool, in
         else break;
 
         if (step == M_NODE) {
-            if (mode == M_NODE) {
-                float4 n0 = ldg4(&sc.nodes[2 * (size_t)cur]);
-                float4 n1 = ldg4(&sc.nodes[2 * (size_t)cur + 1]);
-                PB2_COUNT_NODE(&ctr);
-                bool popNext = true;
-                if (slabTest(n0, n1, rs, tMax)) {
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+                if (mode == M_NODE) {
+                    float4 n0 = ldg4(&sc.nodes[2 * (size_t)cur]);
+                    float4 n1 = ldg4(&sc.nodes[2 * (size_t)cur + 1]);
+                    bool pass = slabTest(n0, n1, rs, tMax);
                     uint32_t meta = floatBits(n1.w);
                     int nPrims = (int)(meta & 0xffffu);
-                    if (nPrims > 0) {
-                        leafFirst = asInt(n1.z);
+                    int axis = (int)((meta >> 16) & 0xffu);
+                    int isNeg = axis == 0 ? rs.neg0 : (axis == 1 ? rs.neg1 : rs.neg2);
+                    int second = asInt(n1.z);
+                    bool interior = pass && nPrims == 0;
+                    bool leaf = pass && nPrims > 0;
+                    int far = isNeg ? cur + 1 : second;
+                    int near = isNeg ? second : cur + 1;
+                    // one stack slot per visit: interior nodes store the far child at sp, every
+                    // other outcome reads the slot below (the node it would pop)
+                    int slot = interior ? sp : (sp > 0 ? sp - 1 : 0);
+                    int top = stackGet(slot);
+                    if (interior) stackPut(slot, far);
+                    if (interior) {
+                        cur = near;
+                        ++sp;
+                    } else if (leaf) {
+                        leafFirst = second;
                         leafN = nPrims;
                         mode = M_LEAF;
-                        popNext = false;
+                    } else if (sp == 0) {
+                        mode = M_FETCH;
                     } else {
-                        int axis = (int)((meta >> 16) & 0xffu);
-                        int isNeg = axis == 0 ? rs.neg0 : (axis == 1 ? rs.neg1 : rs.neg2);
-                        int second = asInt(n1.z);
-                        if (isNeg) {
-                            stack[sp++] = cur + 1;
-                            cur = second;
-                        } else {
-                            stack[sp++] = second;
-                            cur = cur + 1;
-                        }
-                        popNext = false;
+                        cur = top;
+                        --sp;
                     }
-                }
-                if (popNext) {
-                    if (sp == 0) mode = M_FETCH;
-                    else cur = stack[--sp];
                 }
             }
         } else if (step == M_LEAF) {
             if (mode == M_LEAF) {
                 bool finished = false;
+                const bool any = (flags & F_ANY) != 0;
                 for (int i = 0; i < leafN; ++i) {
                     const float4 *rec = &sc.leafPrims[3 * (size_t)(leafFirst + i)];
                     float4 a = ldg4(rec), b = ldg4(rec + 1), c4 = ldg4(rec + 2);
-                    PB2_COUNT_PRIM(&ctr);
-                    uint32_t flags = floatBits(b.w);
-                    if (flags & LEAF_SPHERE) {
+                    uint32_t pf = floatBits(b.w);
+                    if (SPHERES && (pf & LEAF_SPHERE)) {
                         const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
                         float4 ra = p[0], rb = p[1];
                         DRay ray;
@@ -247,48 +275,42 @@ __global__ void __launch_bounds__(128, 6) k_wf_trace2(DScene sc, WfPool pool, in
                         ray.tMax = rb.w;
                         float t, phi;
                         if (sphereLeafTest(sc, asInt(c4.w), ray, tMax, &t, &phi)) {
-                            found = true;
+                            flags |= F_FOUND;
                             if (any) { finished = true; break; }
                             tMax = t;
-                            hit.leaf = leafFirst + i;
-                            hit.b0 = phi;
-                            hit.b1 = hit.b2 = 0;
+                            __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(leafFirst + i), phi, 0.f, 0.f));
                         }
                         continue;
                     }
                     float t, b0, b1, b2;
                     if (triangleTest(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c4.x, c4.y, c4.z), rs, tMax, &t, &b0, &b1, &b2)) {
-                        if (any) { found = true; finished = true; break; }
-                        if (flags & LEAF_DEGENERATE) continue;
-                        found = true;
+                        if (any) { flags |= F_FOUND; finished = true; break; }
+                        if (pf & LEAF_DEGENERATE) continue;
+                        flags |= F_FOUND;
                         tMax = t;
-                        hit.leaf = leafFirst + i;
-                        hit.b0 = b0;
-                        hit.b1 = b1;
-                        hit.b2 = b2;
+                        __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(leafFirst + i), b0, b1, b2));
                     }
                 }
                 leafN = 0;
                 if (finished || sp == 0) mode = M_FETCH;
                 else {
-                    cur = stack[--sp];
+                    --sp;
+                    cur = stackGet(sp);
                     mode = M_NODE;
                 }
             }
-        } else {  // M_FETCH
+        } else {  // M_FETCH: flush finished rays, then take new ones
             bool flush = mode == M_FETCH && c >= 0;
             int state = LS_IDLE;
             if (flush) {
                 WfCtx &cx = pool.ctx[c];
-                state = any ? LS_SHADOW : cx.ln.state;
-                *reinterpret_cast<float4 *>(&cx.hit) = make_float4(__int_as_float(hit.leaf), hit.b0, hit.b1, hit.b2);
-                cx.tHit = tMax;
-                cx.found = found ? 1 : 0;
+                state = (flags & F_ANY) ? LS_SHADOW : __ldcs(&cx.ln.state);
+                __stcs(reinterpret_cast<float2 *>(&cx.tHit), make_float2(tMax, __int_as_float((flags & F_FOUND) ? 1 : 0)));
             }
             wfPush(pool.queue[WQ_SHADE], &pool.counts[WQ_SHADE], c, flush && state == LS_PATH);
             wfPush(pool.queue[WQ_LIGHT], &pool.counts[WQ_LIGHT], c, flush && state != LS_PATH);
             if (flush) c = -1;
-            bool want = mode == M_FETCH && !exhausted;
+            bool want = mode == M_FETCH && !(flags & F_EXHAUSTED);
             unsigned wantMask = __ballot_sync(FULL, want);
             if (wantMask) {
                 int leader = __ffs(wantMask) - 1;
@@ -298,18 +320,14 @@ __global__ void __launch_bounds__(128, 6) k_wf_trace2(DScene sc, WfPool pool, in
                 if (want) {
                     unsigned i = base + __popc(wantMask & ((1u << lane) - 1u));
                     if (i >= n)
-                        exhausted = true;
+                        flags |= F_EXHAUSTED;
                     else {
                         c = pool.queue[traceQ][i];
                         const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
-                        float4 ra = p[0], rb = p[1];
-                        any = __float_as_int(ra.x) == LS_SHADOW;
-                        if (any) shadow++; else regular++;
+                        float4 ra = __ldcs(p), rb = __ldcs(p + 1);
+                        flags = (__float_as_int(ra.x) == LS_SHADOW) ? F_ANY : 0;
                         rs = setupRay(mk3(ra.y, ra.z, ra.w), mk3(rb.x, rb.y, rb.z));
                         tMax = rb.w;
-                        found = false;
-                        hit.leaf = -1;
-                        hit.b0 = hit.b1 = hit.b2 = 0;
                         cur = 0;
                         sp = 0;
                         leafN = 0;
@@ -319,32 +337,19 @@ __global__ void __launch_bounds__(128, 6) k_wf_trace2(DScene sc, WfPool pool, in
             }
         }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        regular += __shfl_down_sync(FULL, regular, o);
-        shadow += __shfl_down_sync(FULL, shadow, o);
-    }
-    if (lane == 0) {
-        if (regular) atomicAdd(&counters[CTR_REGULAR], (unsigned long long)regular);
-        if (shadow) atomicAdd(&counters[CTR_SHADOW], (unsigned long long)shadow);
-    }
-#ifdef PB2_COUNTERS
-    unsigned long long n0 = ctr.nodes, n1 = ctr.prims;
-    for (int o = 16; o > 0; o >>= 1) {
-        n0 += __shfl_down_sync(FULL, n0, o);
-        n1 += __shfl_down_sync(FULL, n1, o);
-    }
-    if (lane == 0) {
-        atomicAdd(&counters[CTR_NODES], n0);
-        atomicAdd(&counters[CTR_PRIMS], n1);
-    }
-#endif
 }
 
-// laneAdvance for every context of one list (all in the same class of state, so warps stay converged).
-__global__ void __launch_bounds__(128) k_wf_advance(DScene sc, DRenderParams rp, WfPool pool, int srcQ, int traceQ, int freeQ,
-                                                    float4 *film) {
+// ---------------------------------------------------------------------------------------------
+// laneAdvance for every context of one list.  SHADE = true: the shade list (path rays: the whole
+// vertex is evaluated); SHADE = false: the light list (shadow / MIS rays: a few adds and the next
+// ray).  Two instantiations so that the light kernel is small and the warps of each stay converged.
+// ---------------------------------------------------------------------------------------------
+template <bool SHADE, bool SPH>
+__global__ void __launch_bounds__(128, SHADE ? 4 : 8) k_wf_advance(DScene sc, DRenderParams rp, WfPool pool, int srcQ, int traceQ,
+                                                                   int freeQ, float4 *film, unsigned long long *counters) {
     unsigned n = pool.counts[srcQ];
     unsigned stride = gridDim.x * blockDim.x;
+    unsigned regular = 0, shadow = 0;
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += stride) {
         unsigned i = base + threadIdx.x;
         bool have = i < n;
@@ -352,15 +357,21 @@ __global__ void __launch_bounds__(128) k_wf_advance(DScene sc, DRenderParams rp,
         bool ended = false;
         if (have) {
             WfCtx &cx = pool.ctx[c];
-            DLane ln = cx.ln;
+            DLane &ln = cx.ln;  // updated in place: each kernel touches only the fields its state needs
             DHit hit = cx.hit;
-            ended = laneAdvance(sc, rp.halton, rp.path, ln, cx.found != 0, hit, cx.tHit);
-            cx.ln = ln;
+            bool found = cx.found != 0;
+            float tHit = cx.tHit;
+            if (SHADE) shadeVertex<SPH>(sc, rp.halton, rp.path, ln, found, hit, tHit);
+            else lightAdvance<SPH>(sc, ln, found, hit, tHit);
+            ended = ln.state == LS_IDLE;
             if (ended) addSample(rp, film, cx.pFilm, guardRadiance(ln.L));
+            else if (ln.state == LS_SHADOW) shadow++;   // Scene::IntersectP call (scene.cpp:51-55)
+            else regular++;                             // Scene::Intersect call (scene.cpp:45-49)
         }
         wfPush(pool.queue[traceQ], &pool.counts[traceQ], c, have && !ended);
         wfPush(pool.queue[freeQ], &pool.counts[freeQ], c, have && ended);
     }
+    wfCountRays(counters, regular, shadow);
 }
 
 __global__ void k_wf_init(WfPool pool) {
@@ -369,13 +380,14 @@ __global__ void k_wf_init(WfPool pool) {
     if (i < WQ_COUNT) pool.counts[i] = (i == WQ_FREE0) ? (unsigned)pool.capacity : 0u;
 }
 
-__global__ void k_wf_reset(WfPool pool, int a, int b, int c2, int d) {
+// end of a round: the lists consumed in it are emptied
+__global__ void k_wf_reset(WfPool pool, int a, int b) {
     if (threadIdx.x == 0) {
         pool.counts[WQ_CURSOR] = 0;
-        if (a >= 0) pool.counts[a] = 0;
-        if (b >= 0) pool.counts[b] = 0;
-        if (c2 >= 0) pool.counts[c2] = 0;
-        if (d >= 0) pool.counts[d] = 0;
+        pool.counts[WQ_SHADE] = 0;
+        pool.counts[WQ_LIGHT] = 0;
+        pool.counts[a] = 0;
+        pool.counts[b] = 0;
     }
 }
 
