@@ -84,6 +84,25 @@ PB2_HD void coordinateSystem(V3 v1, V3 *v2, V3 *v3) {
         *v2 = divf(mk3(0, v1.z, -v1.y), sqrtf(v1.y * v1.y + v1.z * v1.z));
     *v3 = cross(v1, *v2);
 }
+// Transcendentals.  The reference calls glibc's float functions, which are (almost always) the
+// correctly rounded result; libdevice's sinf/cosf/logf/atan2f/acosf are allowed 1-2 ulp.  On the
+// device the double-precision routine rounded to float gives the correctly rounded value in all but
+// vanishingly rare cases, which removes nearly all last-bit differences from sampled directions (they
+// matter: a 1-ulp change of a direction moves a roughness-0.025 microfacet lobe's value by percents).
+// These run a few times per path vertex, never inside the traversal loop.
+#if defined(__CUDA_ARCH__)
+PB2_HD float psinf(float x) { return (float)sin((double)x); }
+PB2_HD float pcosf(float x) { return (float)cos((double)x); }
+PB2_HD float plogf(float x) { return (float)log((double)x); }
+PB2_HD float patan2f(float y, float x) { return (float)atan2((double)y, (double)x); }
+PB2_HD float pacosf(float x) { return (float)acos((double)x); }
+#else
+PB2_HD float psinf(float x) { return sinf(x); }
+PB2_HD float pcosf(float x) { return cosf(x); }
+PB2_HD float plogf(float x) { return logf(x); }
+PB2_HD float patan2f(float y, float x) { return atan2f(y, x); }
+PB2_HD float pacosf(float x) { return acosf(x); }
+#endif
 PB2_HD float clampf(float v, float lo, float hi) { return v < lo ? lo : (v > hi ? hi : v); }
 PB2_HD float lerpf(float t, float a, float b) { return (1 - t) * a + t * b; }
 

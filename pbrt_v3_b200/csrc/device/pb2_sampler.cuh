@@ -138,7 +138,7 @@ PB2_HD V2 concentricSampleDisk(V2 u) {
         r = oy;
         theta = kPiOver2 - kPiOver4 * (ox / oy);
     }
-    return mk2(r * cosf(theta), r * sinf(theta));
+    return mk2(r * pcosf(theta), r * psinf(theta));
 }
 // sampling.h:159-163
 PB2_HD V3 cosineSampleHemisphere(V2 u) {
@@ -156,7 +156,7 @@ PB2_HD V3 uniformSampleSphere(V2 u) {
     float z = 1 - 2 * u.x;
     float r = sqrtf(pmax(0.f, 1.f - z * z));
     float phi = 2 * kPi * u.y;
-    return mk3(r * cosf(phi), r * sinf(phi), z);
+    return mk3(r * pcosf(phi), r * psinf(phi), z);
 }
 // sampling.h:171-174 with nf = ng = 1
 PB2_HD float powerHeuristic(float fPdf, float gPdf) {

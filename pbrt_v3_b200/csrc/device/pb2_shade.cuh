@@ -191,7 +191,7 @@ PB2_HD V3 clampSpectrum(const float c[3]) {  // Spectrum::Clamp(0, Infinity), sp
 // TrowbridgeReitzDistribution::RoughnessToAlpha (microfacet.h:127-132)
 PB2_HD float roughnessToAlpha(float roughness) {
     roughness = pmax(roughness, (float)1e-3);
-    float x = logf(roughness);
+    float x = plogf(roughness);
     return 1.62142f + 0.819955f * x + 0.1734f * x * x + 0.0171201f * x * x * x + 0.000640711f * x * x * x * x;
 }
 
@@ -534,7 +534,7 @@ PB2_HDN DLightSample sampleSphereLight(const DScene &sc, const pb2_light &l, con
         float sinAlpha = sqrtf(pmax(0.f, 1.f - cosAlpha * cosAlpha));
         float phi = u.y * 2 * kPi;
         // SphericalDirection(sinAlpha, cosAlpha, phi, -wcX, -wcY, -wc) (geometry.h:1461-1466)
-        V3 nWorld = sinAlpha * cosf(phi) * (-wcX) + sinAlpha * sinf(phi) * (-wcY) + cosAlpha * (-wc);
+        V3 nWorld = sinAlpha * pcosf(phi) * (-wcX) + sinAlpha * psinf(phi) * (-wcY) + cosAlpha * (-wc);
         V3 pWorld = pCenter + s.radius * nWorld;
         ls.p = pWorld;
         ls.pError = kGamma5 * vabs(pWorld);

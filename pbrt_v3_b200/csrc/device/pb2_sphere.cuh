@@ -148,7 +148,7 @@ PB2_HDN bool sphereTest(const pb2_sphere &s, const DRay &r, float rayTMax, Spher
     V3 pHit = o + d * tShapeHit.v;
     pHit = pHit * (s.radius / length(pHit));  // Distance(pHit, origin)
     if (pHit.x == 0 && pHit.y == 0) pHit.x = 1e-5f * s.radius;
-    float phi = atan2f(pHit.y, pHit.x);
+    float phi = patan2f(pHit.y, pHit.x);
     if (phi < 0) phi += 2 * kPi;
     if ((s.z_min > -s.radius && pHit.z < s.z_min) || (s.z_max < s.radius && pHit.z > s.z_max) || phi > s.phi_max) {
         if (tShapeHit.v == t1.v) return false;
@@ -157,7 +157,7 @@ PB2_HDN bool sphereTest(const pb2_sphere &s, const DRay &r, float rayTMax, Spher
         pHit = o + d * tShapeHit.v;
         pHit = pHit * (s.radius / length(pHit));
         if (pHit.x == 0 && pHit.y == 0) pHit.x = 1e-5f * s.radius;
-        phi = atan2f(pHit.y, pHit.x);
+        phi = patan2f(pHit.y, pHit.x);
         if (phi < 0) phi += 2 * kPi;
         if ((s.z_min > -s.radius && pHit.z < s.z_min) || (s.z_max < s.radius && pHit.z > s.z_max) || phi > s.phi_max)
             return false;
@@ -189,14 +189,14 @@ PB2_HDN DInteraction sphereInteraction(const DScene &sc, int prim, const DRay &r
     sphereTest(s, ray, PB2_INFINITY, &h);
     V3 pHit = h.pHit;
     float u = h.phi / s.phi_max;
-    float theta = acosf(clampf(pHit.z / s.radius, -1.f, 1.f));
+    float theta = pacosf(clampf(pHit.z / s.radius, -1.f, 1.f));
     float v = (theta - s.theta_min) / (s.theta_max - s.theta_min);
     float zRadius = sqrtf(pHit.x * pHit.x + pHit.y * pHit.y);
     float invZRadius = 1 / zRadius;
     float cosPhiV = pHit.x * invZRadius;
     float sinPhiV = pHit.y * invZRadius;
     V3 dpdu = mk3(-s.phi_max * pHit.y, s.phi_max * pHit.x, 0);
-    V3 dpdv = (s.theta_max - s.theta_min) * mk3(pHit.z * cosPhiV, pHit.z * sinPhiV, -s.radius * sinf(theta));
+    V3 dpdv = (s.theta_max - s.theta_min) * mk3(pHit.z * cosPhiV, pHit.z * sinPhiV, -s.radius * psinf(theta));
     V3 pError = kGamma5 * vabs(pHit);
     // object-space SurfaceInteraction ctor (interaction.cpp:44-71)
     V3 n = normalize(cross(dpdu, dpdv));

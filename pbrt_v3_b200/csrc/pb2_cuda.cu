@@ -475,8 +475,14 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     else if (variant == 3) trace = k_wf_trace<12, 8, 4, 32, false, false, 10>;
     else if (variant == 4) trace = k_wf_trace<12, 12, 6, 32, false, false, 8>;
     else trace = k_wf_trace<12, 8, 4, 32, false, false, 8>;
-    AdvanceKernel advLight = spheres ? k_wf_advance<false, true> : k_wf_advance<false, false>;
-    AdvanceKernel advShade = spheres ? k_wf_advance<true, true> : k_wf_advance<true, false>;
+    static const int shadeMinB = envInt("PB2_SHADE_MINB", 4);
+    AdvanceKernel advLight = spheres ? k_wf_advance<false, true, 8> : k_wf_advance<false, false, 8>;
+    AdvanceKernel advShade = spheres ? k_wf_advance<true, true, 4>
+                             : shadeMinB == 3 ? k_wf_advance<true, false, 3>
+                             : shadeMinB == 5 ? k_wf_advance<true, false, 5>
+                             : shadeMinB == 6 ? k_wf_advance<true, false, 6>
+                             : shadeMinB == 8 ? k_wf_advance<true, false, 8>
+                                              : k_wf_advance<true, false, 4>;
     int traceBlocksPerSM = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&traceBlocksPerSM, trace, 128, 0));
     const int persistentBlocks = g_numSMs * std::max(1, traceBlocksPerSM);

@@ -344,8 +344,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
 // vertex is evaluated); SHADE = false: the light list (shadow / MIS rays: a few adds and the next
 // ray).  Two instantiations so that the light kernel is small and the warps of each stay converged.
 // ---------------------------------------------------------------------------------------------
-template <bool SHADE, bool SPH>
-__global__ void __launch_bounds__(128, SHADE ? 4 : 8) k_wf_advance(DScene sc, DRenderParams rp, WfPool pool, int srcQ, int traceQ,
+template <bool SHADE, bool SPH, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_wf_advance(DScene sc, DRenderParams rp, WfPool pool, int srcQ, int traceQ,
                                                                    int freeQ, float4 *film, unsigned long long *counters) {
     unsigned n = pool.counts[srcQ];
     unsigned stride = gridDim.x * blockDim.x;

@@ -1,0 +1,84 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (oracle/_ref, built from /root/reference by
+oracle/Makefile.ref) on the seeded inputs of tests/golden_cases.py.  Run in the build container:
+
+    python tests/make_golden.py
+
+The fixtures travel with the repo; the tests compare the oracle port (everywhere) and the CUDA path (on the GPU box)
+against them, so that parity is pinned to the reference even where /root/reference does not exist.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import golden_cases as gc  # noqa: E402
+import pbrt_v3_b200 as pb  # noqa: E402
+from oracle import pyoracle  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def record_scene(ref, hs, name, n_rays=1500, n_samples=3000, n_points=400):
+    rs = ref.scene(hs)
+    nodes = hs.nodes()
+    xres, yres = hs.film.contents.full_resolution[0], hs.film.contents.full_resolution[1]
+    spp = hs.params.contents.samples_per_pixel
+    rays = gc.rays_for(pb, nodes, n_rays, 11)
+    srays = gc.rays_for(pb, nodes, n_rays, 12, shadow=True)
+    pix, sn = gc.sample_ids(xres, yres, spp, n_samples, 13)
+    hpix, hsn, hdim = gc.sample_ids(xres, yres, spp, 4000, 14, max_dim=200)
+    pts = gc.points_for(nodes, n_points, 15)
+    li, pfilm = rs.li_samples(pix, sn)
+    img, _, st = rs.render(n_threads=0)
+    ref_nodes, ref_prims = rs.bvh()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"),
+                        hits=rs.intersect(rays), occluded=rs.intersect_p(srays),
+                        halton=ref.halton(hs.film, hs.params, hpix, hsn, hdim),
+                        light_distribution=rs.light_distribution(pts), li=li, pfilm=pfilm, image=img,
+                        rays=np.array([st.camera_rays, st.regular_rays, st.shadow_rays], np.int64),
+                        bvh_nodes=ref_nodes, bvh_prims=ref_prims)
+    print(name, "image mean", img.mean(), "rays", st.camera_rays, st.regular_rays, st.shadow_rays)
+
+
+def main():
+    ref = pyoracle.reference()
+    if ref is None:
+        raise SystemExit("oracle/_ref is not built: run `make -C oracle -f Makefile.ref` where /root/reference exists")
+    os.makedirs(OUT, exist_ok=True)
+    record_scene(ref, gc.soup_scene(pb), "soup")
+    record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "killeroo_like.pbrt")), "killeroo_like")
+    record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "materials.pbrt")), "materials")
+    # low-discrepancy known answers (src/tests/sampling.cpp:15-74 checks the same functions against naive versions)
+    a = np.concatenate([np.arange(0, 64), np.array([1023, 65535, 1234567, 2 ** 31 + 12345, 2 ** 40 + 7, 2 ** 62 + 99])]).astype(np.uint64)
+    np.savez_compressed(os.path.join(OUT, "lowdiscrepancy.npz"), a=a,
+                        **{"ri_%d" % b: ref.radical_inverse(b, a) for b in (0, 1, 2, 3, 10, 50, 127, 500, 999)},
+                        **{"sri_%d" % b: ref.radical_inverse(b, a, scrambled=True) for b in (0, 1, 2, 3, 10, 50, 127, 500, 999)})
+    # host math: transforms, camera matrices, loop subdivision
+    tr = {}
+    for i, (kind, args) in enumerate([(0, [400, 20, 30, 0, 63, -110, 0, 0, 1]), (0, [0, -4.2, .6, 0, 0, 0, 0, 0, 1]), (1, [-5, 0, 0, 1]),
+                                      (1, [-60, 0, 0, 1]), (1, [33, .3, -2, .7]), (2, [39, .01, 1000]), (2, [35, .01, 1000]),
+                                      (3, [150, 0, 20]), (4, [.5, .5, .5])]):
+        m, mi = ref.transform(kind, args)
+        tr["kind_%d" % i], tr["args_%d" % i], tr["m_%d" % i], tr["minv_%d" % i] = np.int32(kind), np.array(args, np.float32), m, mi
+    np.savez_compressed(os.path.join(OUT, "transforms.npz"), n=np.int32(9), **tr)
+    P = np.array([[0, 0, 160], [120, 0, 40], [0, 120, 40], [-120, 0, 40], [0, -120, 40], [0, 0, -80]], np.float32)
+    I = np.array([0, 1, 2, 0, 2, 3, 0, 3, 4, 0, 4, 1, 5, 2, 1, 5, 3, 2, 5, 4, 3, 5, 1, 4], np.int32)
+    P2 = np.array([[-90, -90, 0], [0, -90, 30], [90, -90, 0], [-90, 0, 40], [0, 0, 110], [90, 0, 40], [-90, 90, 0], [0, 90, 30], [90, 90, 0]], np.float32)
+    I2 = np.array([0, 1, 4, 0, 4, 3, 1, 2, 5, 1, 5, 4, 3, 4, 7, 3, 7, 6, 4, 5, 8, 4, 8, 7], np.int32)
+    sub = {"closed_P": P, "closed_I": I, "open_P": P2, "open_I": I2}
+    for tag, (pp, ii) in (("closed", (P, I)), ("open", (P2, I2))):
+        for lv in (1, 2, 3):
+            oP, oN, oI = ref.loop_subdivide(lv, ii, pp)
+            sub["%s_%d_P" % (tag, lv)], sub["%s_%d_N" % (tag, lv)], sub["%s_%d_I" % (tag, lv)] = oP, oN, oI
+    np.savez_compressed(os.path.join(OUT, "loopsubdiv.npz"), **sub)
+    hs = gc.soup_scene(pb, xres=1920, yres=1080)
+    r2c, dx, dy = ref.camera_derived(hs.camera, hs.film)
+    np.savez_compressed(os.path.join(OUT, "camera.npz"), raster_to_camera=r2c, dx=dx, dy=dy)
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

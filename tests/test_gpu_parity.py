@@ -1,0 +1,196 @@
+"""CUDA path (through the C ABI) against the CPU checker and the golden vectors of the reference.
+
+Tolerances (also stated in DESIGN.md):
+  * Scene::Intersect / IntersectP, Halton samples, light-sampling distributions, CameraSample::pFilm:
+    BIT-EXACT (integer / IEEE +-*/ sqrt arithmetic only, compiled with -fmad=false).
+  * PathIntegrator::Li per sample: |dL| <= 1e-4 * max(1, |L|) for >= 99.9 % of the samples (transcendentals are
+    evaluated in double and rounded, which almost always equals glibc's float result; a one-ulp difference in a
+    sampled direction can flip an edge decision or move a sharp microfacet lobe).
+  * images: >= 99.9 % of the pixels within 1 % relative, mean relative error <= 1e-4, image mean within 1e-4.
+  * Scene::Intersect / IntersectP call counters: equal to the reference's within 0.1 % (edge flips).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as gc
+from conftest import GOLDEN, SCENES
+from test_oracle import load_scene, tessellated_sphere_scene
+
+pytestmark = pytest.mark.gpu
+
+SCENE_CASES = ["soup", "killeroo_like", "materials"]
+
+
+def li_ok(got, want):
+    err = np.abs(got - want).max(axis=1) / np.maximum(1, np.abs(want).max(axis=1))
+    return float((err <= 1e-4).mean())
+
+
+def image_metrics(got, want):
+    rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-3)
+    return float((rel.max(axis=2) <= 0.01).mean()), float(rel.mean())
+
+
+@pytest.mark.parametrize("name", SCENE_CASES)
+def test_gpu_matches_reference_golden(pb, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    hs = load_scene(pb, name)
+    nodes = hs.nodes()
+    xres, yres = hs.film.contents.full_resolution[0], hs.film.contents.full_resolution[1]
+    spp = hs.params.contents.samples_per_pixel
+    hits = hs.intersect(gc.rays_for(pb, nodes, 1500, 11))
+    gh = g["hits"]
+    assert np.array_equal(hits["prim"], gh["prim"])
+    for f in ("t", "p", "p_error", "n", "ns", "dpdu", "uv"):
+        assert np.array_equal(gc.bits(hits[f]), gc.bits(gh[f])), "hit field %s must be bit-identical to the reference" % f
+    assert np.array_equal(hs.intersect_p(gc.rays_for(pb, nodes, 1500, 12, shadow=True)), g["occluded"])
+    hpix, hsn, hdim = gc.sample_ids(xres, yres, spp, 4000, 14, max_dim=200)
+    assert np.array_equal(gc.bits(hs.halton(hpix, hsn, hdim)), gc.bits(g["halton"]))
+    assert np.array_equal(gc.bits(hs.light_distribution(gc.points_for(nodes, 400, 15))), gc.bits(g["light_distribution"]))
+    pix, sn = gc.sample_ids(xres, yres, spp, 3000, 13)
+    li, pfilm = hs.li_samples(pix, sn)
+    assert np.array_equal(gc.bits(pfilm), gc.bits(g["pfilm"]))
+    assert li_ok(li, g["li"]) >= 0.999
+    img, st = hs.render()
+    frac, mean_rel = image_metrics(img, g["image"])
+    assert frac >= 0.999 and mean_rel <= 1e-4, (frac, mean_rel)
+    assert abs(float(img.mean()) - float(g["image"].mean())) <= 1e-4 * float(g["image"].mean())
+    cam, reg, sh = (int(x) for x in g["rays"])
+    assert st.camera_rays == cam
+    assert abs(int(st.regular_rays) - reg) <= max(2, reg // 1000) and abs(int(st.shadow_rays) - sh) <= max(2, sh // 1000)
+    assert st.kernel_launches > 0
+
+
+def test_gpu_matches_checker_on_a_larger_scene(pb, checker):
+    """20 000 random triangles at 96x54x8: sizes the CPU checker finishes in seconds."""
+    hs = pb.HostScene.soup(20000, xres=96, yres=54, spp=8)
+    sc = checker.scene(hs)
+    nodes = hs.nodes()
+    rays = gc.rays_for(pb, nodes, 20000, 21)
+    assert hs.intersect(rays).tobytes() == _without_b(sc.intersect(rays), hs.intersect(rays))
+    srays = gc.rays_for(pb, nodes, 20000, 22, shadow=True)
+    assert np.array_equal(hs.intersect_p(srays), sc.intersect_p(srays))
+    pix, sn = gc.sample_ids(96, 54, 8, 20000, 23)
+    li, _ = hs.li_samples(pix, sn)
+    ref_li, _ = sc.li_samples(pix, sn)
+    assert li_ok(li, ref_li) >= 0.999
+    img, st = hs.render()
+    ref_img, _, ref_st = sc.render(n_threads=0)
+    frac, mean_rel = image_metrics(img, ref_img)
+    assert frac >= 0.999 and mean_rel <= 1e-4
+    assert st.camera_rays == ref_st.camera_rays == 96 * 54 * 8
+    assert abs(int(st.regular_rays) - int(ref_st.regular_rays)) <= ref_st.regular_rays // 1000 + 2
+
+
+def _without_b(ref_hits, gpu_hits):
+    """The checker's SurfaceInteraction has no barycentrics; take the GPU's so that every other byte is compared."""
+    h = ref_hits.copy()
+    h["b"] = gpu_hits["b"]
+    return h.tobytes()
+
+
+def test_traversal_counters_equal_the_reference_order(pb, port):
+    """PB2_FLAG_COUNT_TRAVERSAL counts LinearBVHNode fetches / primitive tests like STAT_COUNTERs around bvh.cpp:672/677/710/714
+    would; the port counts the same events on the CPU: identical traversal order => identical counts."""
+    hs = pb.HostScene.soup(5000, xres=48, yres=27, spp=4)
+    dev = hs.device_scene()
+    film = np.zeros((27, 48, 4), np.float32)
+    st = pb.Stats()
+    pb.check(pb.lib().pb2_render_path(dev, hs.camera, hs.film, hs.params_copy(flags=1), pb.ptr(film), C.byref(st)))
+    _, _, pst = port.scene(hs).render(n_threads=1)
+    assert st.node_visits > 0 and st.prim_tests > 0
+    assert abs(int(st.node_visits) - int(pst.node_visits)) <= pst.node_visits // 1000 + 10
+    assert abs(int(st.prim_tests) - int(pst.prim_tests)) <= pst.prim_tests // 1000 + 10
+    # the counting kernel and the tuned kernel produce the same film
+    film2, st2 = hs.render_rgbw()
+    assert np.allclose(film, film2, rtol=1e-5, atol=1e-5)
+    assert st2.regular_rays == st.regular_rays and st2.shadow_rays == st.shadow_rays
+
+
+def test_watertight_on_gpu(pb):
+    hs, verts = tessellated_sphere_scene(pb)
+    rng = np.random.RandomState(1)
+    n = 50000
+    rays = np.zeros(n, pb.RAY_DTYPE)
+    rays["o"] = rng.uniform(-0.5, 0.5, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["d"][: n // 2] = verts[rng.randint(0, len(verts), n // 2)] - rays["o"][: n // 2]
+    rays["t_max"] = np.inf
+    assert (hs.intersect(rays)["prim"] >= 0).all()
+    assert hs.intersect_p(rays).all()
+
+
+def test_edge_cases(pb):
+    hs = gc.soup_scene(pb)
+    assert len(hs.intersect(np.zeros(0, pb.RAY_DTYPE))) == 0            # empty batch
+    rays = np.zeros(4, pb.RAY_DTYPE)
+    rays["o"] = (0, 0, 50)
+    rays["d"] = [(0, 0, -1), (0, 0, 1), (0, 0, -1), (0, 0, 0)]
+    rays["t_max"] = [np.inf, np.inf, 0.0, np.inf]                         # tMax 0 and a zero direction (NaN slabs) must miss
+    h = hs.intersect(rays)
+    assert h["prim"][0] >= 0 and (h["prim"][1:] == -1).all()
+    # maxdepth 0: only emitted light seen directly; spp 1; pixel bounds smaller than the film
+    p = hs.params_copy(max_depth=0, samples_per_pixel=1)
+    p.pixel_bounds[0], p.pixel_bounds[1], p.pixel_bounds[2], p.pixel_bounds[3] = 4, 2, 20, 10
+    film, st = hs.render_rgbw(p)
+    assert st.camera_rays == 16 * 8 and st.shadow_rays == 0 and st.regular_rays == st.camera_rays
+    w = film[..., 3]
+    assert w[2:10, 4:20].sum() >= 16 * 8 - 1e-3 and w[12:, :].sum() == 0
+    # invalid arguments are refused with PB2_ERR_INVALID, not crashes
+    bad = hs.params_copy(samples_per_pixel=0)
+    with pytest.raises(pb.Pb2Error):
+        hs.render_rgbw(bad)
+    bad = hs.params_copy(tile_rank=3, tile_count=2)
+    with pytest.raises(pb.Pb2Error):
+        hs.render_rgbw(bad)
+
+
+def test_tile_partition_sums_to_the_full_film(pb):
+    """Multi-GPU contract: the films of the tile subsets t % n == r add up to the single-GPU film."""
+    hs = pb.HostScene.soup(3000, xres=80, yres=45, spp=4)   # ragged 16x16 tiling
+    full, st = hs.render_rgbw()
+    for n in (2, 3):
+        parts, rays = [], 0
+        for r in range(n):
+            f, s = hs.render_rgbw(hs.params_copy(tile_rank=r, tile_count=n))
+            parts.append(f)
+            rays += int(s.camera_rays)
+        assert rays == st.camera_rays == 80 * 45 * 4
+        assert np.allclose(sum(parts), full, rtol=1e-5, atol=1e-5)
+        assert np.array_equal(sum(p[..., 3] for p in parts), full[..., 3])
+
+
+def test_reference_shaped_api_and_cli(pb, tmp_path):
+    """Integrator::Render through the host C++ classes writes the image the ABI call produced; the CLI runs a scene file."""
+    import subprocess
+    hs = pb.HostScene.from_file(os.path.join(SCENES, "materials.pbrt"))
+    img, st = hs.render()
+    film, _ = hs.render_rgbw()
+    assert np.allclose(hs.resolve(film), img, rtol=1e-5, atol=1e-6)
+    out = tmp_path / "out.pfm"
+    exe = os.path.join(os.path.dirname(pb.LIB_PATH), "pb2_pbrt")
+    res = subprocess.run([exe, "--outfile", str(out), os.path.join(SCENES, "materials.pbrt")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout
+    data = open(out, "rb").read()
+    assert data.startswith(b"PF\n48 32\n-1.000000\n")
+    cli = np.frombuffer(data[len(b"PF\n48 32\n-1.000000\n"):], "<f4").reshape(32, 48, 3)[::-1]
+    assert np.allclose(cli, img, rtol=1e-5, atol=1e-6)
+
+
+def test_single_shape_intersect_goes_to_the_device(pb):
+    """Shape::Intersect on the host classes is answered by the same kernels through a one-primitive aggregate:
+    exercised here through a scene with a single triangle (BVH of one leaf)."""
+    text = 'Camera "perspective"\nFilm "image" "integer xresolution" [4] "integer yresolution" [4]\nWorldBegin\n' \
+           'Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0  1 0 0  0 1 0]\nWorldEnd\n'
+    hs = pb.HostScene.from_string(text)
+    rays = np.zeros(2, pb.RAY_DTYPE)
+    rays["o"] = [(0.25, 0.25, 1), (2, 2, 1)]
+    rays["d"] = (0, 0, -1)
+    rays["t_max"] = np.inf
+    h = hs.intersect(rays)
+    assert h["prim"][0] == 0 and h["prim"][1] == -1 and h["t"][0] == 1.0
+    assert np.allclose(h["b"][0], (0.5, 0.25, 0.25)) and np.allclose(h["p"][0], (0.25, 0.25, 0))

@@ -1,0 +1,218 @@
+"""The CPU oracle (oracle/pb2_oracle.cpp) against (a) golden vectors recorded from the unmodified reference
+(tests/make_golden.py), (b) the reference's own known-answer tests for this path (src/tests/shapes.cpp,
+src/tests/sampling.cpp), and (c) where it exists, the compiled reference itself (oracle/_ref), live.
+Everything here runs on the CPU; bit-exact unless said otherwise.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import golden_cases as gc
+from conftest import GOLDEN, SCENES
+
+SCENE_CASES = ["soup", "killeroo_like", "materials"]
+
+
+def load_scene(pb, name):
+    if name == "soup":
+        return gc.soup_scene(pb)
+    return pb.HostScene.from_file(os.path.join(SCENES, name + ".pbrt"))
+
+
+def same_bvh(a, b):
+    """LinearBVHNode arrays are equal where the reference defines them: `axis` of a leaf and the pad byte are
+    uninitialised memory in the reference (bvh.cpp:640-658 never writes them)."""
+    if len(a) != len(b):
+        return False
+    interior = a["n_prims"] == 0
+    return (a["bmin"].tobytes() == b["bmin"].tobytes() and a["bmax"].tobytes() == b["bmax"].tobytes()
+            and np.array_equal(a["offset"], b["offset"]) and np.array_equal(a["n_prims"], b["n_prims"])
+            and np.array_equal(a["axis"][interior], b["axis"][interior]))
+
+
+def recompute(pb, oracle, hs):
+    """Everything tests/make_golden.py records, from `oracle`."""
+    sc = oracle.scene(hs)
+    nodes = hs.nodes()
+    xres, yres = hs.film.contents.full_resolution[0], hs.film.contents.full_resolution[1]
+    spp = hs.params.contents.samples_per_pixel
+    pix, sn = gc.sample_ids(xres, yres, spp, 3000, 13)
+    hpix, hsn, hdim = gc.sample_ids(xres, yres, spp, 4000, 14, max_dim=200)
+    li, pfilm = sc.li_samples(pix, sn)
+    img, _, st = sc.render(n_threads=2)
+    return dict(hits=sc.intersect(gc.rays_for(pb, nodes, 1500, 11)), occluded=sc.intersect_p(gc.rays_for(pb, nodes, 1500, 12, shadow=True)),
+                halton=oracle.halton(hs.film, hs.params, hpix, hsn, hdim), light_distribution=sc.light_distribution(gc.points_for(nodes, 400, 15)),
+                li=li, pfilm=pfilm, image=img, rays=np.array([st.camera_rays, st.regular_rays, st.shadow_rays], np.int64), bvh=sc.bvh())
+
+
+@pytest.mark.parametrize("name", SCENE_CASES)
+def test_port_matches_reference_golden(pb, port, name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    hs = load_scene(pb, name)
+    r = recompute(pb, port, hs)
+    assert r["hits"].tobytes() == g["hits"].tobytes(), "Scene::Intersect: every field of every hit must be bit-identical"
+    assert np.array_equal(r["occluded"], g["occluded"])
+    assert np.array_equal(gc.bits(r["halton"]), gc.bits(g["halton"]))
+    assert np.array_equal(gc.bits(r["light_distribution"]), gc.bits(g["light_distribution"]))
+    assert np.array_equal(gc.bits(r["pfilm"]), gc.bits(g["pfilm"]))
+    assert np.array_equal(gc.bits(r["li"]), gc.bits(g["li"])), "PathIntegrator::Li per sample must be bit-identical"
+    assert np.array_equal(gc.bits(r["image"]), gc.bits(g["image"])), "whole image (after the XYZ round trip) must be bit-identical"
+    assert np.array_equal(r["rays"], g["rays"]), "camera / regular / shadow ray counters"
+    nodes, prims = r["bvh"]
+    assert same_bvh(nodes, g["bvh_nodes"]) and np.array_equal(prims, g["bvh_prims"]), "BVHAccel linear nodes + primitive order"
+
+
+@pytest.mark.parametrize("name", SCENE_CASES)
+def test_port_matches_compiled_reference_live(pb, port, reference, name):
+    hs = load_scene(pb, name)
+    a, b = recompute(pb, reference, hs), recompute(pb, port, hs)
+    for k in ("hits", "occluded", "halton", "light_distribution", "li", "pfilm", "image", "rays"):
+        assert a[k].tobytes() == b[k].tobytes(), k
+
+
+def test_low_discrepancy_golden(port):
+    g = np.load(os.path.join(GOLDEN, "lowdiscrepancy.npz"))
+    for b in (0, 1, 2, 3, 10, 50, 127, 500, 999):
+        assert np.array_equal(gc.bits(port.radical_inverse(b, g["a"])), gc.bits(g["ri_%d" % b]))
+        assert np.array_equal(gc.bits(port.radical_inverse(b, g["a"], scrambled=True)), gc.bits(g["sri_%d" % b]))
+
+
+def test_radical_inverse_base2_is_bit_reversal(port):
+    """src/tests/sampling.cpp:15-20 (LowDiscrepancy.RadicalInverse)."""
+    a = np.arange(0, 1024, dtype=np.uint64)
+    got = port.radical_inverse(0, a)
+
+    def rev32(n):
+        return int("{:032b}".format(n)[::-1], 2)
+    want = np.array([rev32(int(x)) * 2.0 ** -32 for x in a], np.float32)
+    assert np.array_equal(got, want)
+
+
+def test_radical_inverse_against_naive_digits(port):
+    """src/tests/sampling.cpp:22-74: compare with a straightforward double-precision digit reversal (1e-5)."""
+    primes = [2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37, 41, 43, 47, 53]
+    a = np.array([0, 1, 2, 1151, 32351, 4363211, 681122], np.uint64)
+    for bi in range(1, 16):
+        base = primes[bi]
+        got = port.radical_inverse(bi, a)
+        for x, v in zip(a, got):
+            n, inv, val, scale = int(x), 1.0 / base, 0.0, 1.0 / base
+            while n:
+                val += (n % base) * scale
+                n //= base
+                scale *= inv
+            assert abs(val - float(v)) < 1e-5
+
+
+def test_triangle_bad_case_misses(pb, port):
+    """src/tests/shapes.cpp:544-559 (Triangle.BadCases): this exact ray must miss this exact triangle."""
+    text = """
+Camera "perspective"
+Film "image" "integer xresolution" [4] "integer yresolution" [4]
+WorldBegin
+Shape "trianglemesh" "integer indices" [0 1 2]
+  "point P" [-1113.45459 -79.049614 -56.2431908  -1113.45459 -87.0922699 -56.2431908  -1113.45459 -79.2490845 -56.2431908]
+WorldEnd
+"""
+    hs = pb.HostScene.from_string(text)
+    rays = np.zeros(1, pb.RAY_DTYPE)
+    rays["o"] = (-1081.47925, 99.9999542, 87.7701111)
+    rays["d"] = (-32.1072998, -183.355865, -144.607635)
+    rays["t_max"] = 0.9999
+    sc = port.scene(hs)
+    # the triangle is degenerate (collinear vertices): Triangle::Intersect rejects it at triangle.cpp:308-314.
+    # IntersectP has no such check without an alpha mask (triangle.cpp:531), so only Intersect is pinned.
+    assert sc.intersect(rays)["prim"][0] == -1
+
+
+def tessellated_sphere_scene(pb, n_theta=16, n_phi=16, seed=12111):
+    """The jittered unit-sphere mesh of src/tests/shapes.cpp:28-129 (Triangle.Watertight)."""
+    rng = np.random.RandomState(seed)
+    verts = []
+    for t in range(n_theta):
+        for p in range(n_phi):
+            theta = np.pi * t / (n_theta - 1)
+            phi = 2 * np.pi * p / n_phi
+            v = np.array([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)])
+            verts.append(v * (1 + 0.05 * rng.uniform(-1, 1)) if 0 < t < n_theta - 1 else v)
+    idx = []
+    for t in range(n_theta - 1):
+        for p in range(n_phi):
+            p1 = (p + 1) % n_phi
+            a, b, c, d = t * n_phi + p, t * n_phi + p1, (t + 1) * n_phi + p, (t + 1) * n_phi + p1
+            idx += [a, c, b, b, c, d]
+    P = " ".join("%.9g" % x for v in verts for x in v)
+    I = " ".join(str(i) for i in idx)
+    text = 'Camera "perspective"\nFilm "image" "integer xresolution" [4] "integer yresolution" [4]\nWorldBegin\n' \
+           'Shape "trianglemesh" "integer indices" [%s] "point P" [%s]\nWorldEnd\n' % (I, P)
+    return pb.HostScene.from_string(text), np.array(verts, np.float32)
+
+
+def test_triangle_mesh_is_watertight(pb, port):
+    """src/tests/shapes.cpp:94-129: rays from inside a closed tessellated sphere always hit, also through vertices."""
+    hs, verts = tessellated_sphere_scene(pb)
+    sc = port.scene(hs)
+    rng = np.random.RandomState(1)
+    n = 20000
+    rays = np.zeros(n, pb.RAY_DTYPE)
+    rays["o"] = rng.uniform(-0.5, 0.5, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays["d"] = d.astype(np.float32)
+    # half of the rays are aimed exactly at mesh vertices (the hard case of the reference test)
+    tgt = verts[rng.randint(0, len(verts), n // 2)]
+    rays["d"][: n // 2] = tgt - rays["o"][: n // 2]
+    rays["t_max"] = np.inf
+    assert (sc.intersect(rays)["prim"] >= 0).all()
+    assert sc.intersect_p(rays).all()
+
+
+def test_spawned_rays_do_not_reintersect(pb, port):
+    """src/tests/shapes.cpp:154-205 (Triangle.Reintersect): rays leaving a hit point, offset by the hit's error
+    bounds (OffsetRayOrigin), must not hit the same triangle again, for coordinates spanning many magnitudes."""
+    rng = np.random.RandomState(7)
+    for scale in (1e-3, 1.0, 1e4):
+        tri = (rng.uniform(-1, 1, (3, 3)) * scale).astype(np.float32)
+        text = 'Camera "perspective"\nFilm "image" "integer xresolution" [4] "integer yresolution" [4]\nWorldBegin\n' \
+               'Shape "trianglemesh" "integer indices" [0 1 2] "point P" [%s]\nWorldEnd\n' % " ".join("%.9g" % x for x in tri.ravel())
+        hs = pb.HostScene.from_string(text)
+        sc = port.scene(hs)
+        n = 2000
+        b = rng.dirichlet([1, 1, 1], n).astype(np.float32)
+        target = (b[:, :, None] * tri[None]).sum(axis=1)
+        rays = np.zeros(n, pb.RAY_DTYPE)
+        rays["o"] = (target + rng.normal(size=(n, 3)) * 3 * scale).astype(np.float32)
+        rays["d"] = target - rays["o"]
+        rays["t_max"] = np.inf
+        h = sc.intersect(rays)
+        ok = h["prim"] >= 0
+        assert ok.mean() > 0.9
+        # spawn in random directions from the reported hit point, origin offset exactly as Interaction::SpawnRay does
+        w = rng.normal(size=(n, 3)).astype(np.float32)
+        p, pe, nrm = h["p"], h["p_error"], h["n"]
+        d = (np.abs(nrm) * pe).sum(axis=1, keepdims=True)
+        off = d * nrm
+        off[(w * nrm).sum(axis=1) < 0] *= -1
+        po = (p + off).astype(np.float32)
+        up = off > 0
+        dn = off < 0
+        po[up] = np.nextafter(po[up], np.float32(np.inf))
+        po[dn] = np.nextafter(po[dn], np.float32(-np.inf))
+        rays2 = np.zeros(n, pb.RAY_DTYPE)
+        rays2["o"] = po
+        rays2["d"] = w
+        rays2["t_max"] = np.inf
+        assert (sc.intersect(rays2[ok])["prim"] == -1).all()
+
+
+def test_empty_and_degenerate_inputs(pb, port):
+    hs = gc.soup_scene(pb)
+    sc = port.scene(hs)
+    assert len(sc.intersect(np.zeros(0, pb.RAY_DTYPE))) == 0
+    rays = np.zeros(3, pb.RAY_DTYPE)
+    rays["o"] = (0, 0, 50)
+    rays["d"] = [(0, 0, -1), (0, 0, 1), (0, 0, -1)]
+    rays["t_max"] = [np.inf, np.inf, 0.0]
+    h = sc.intersect(rays)
+    assert h["prim"][0] >= 0 and h["prim"][1] == -1 and h["prim"][2] == -1
