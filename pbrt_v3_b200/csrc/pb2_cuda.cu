@@ -489,6 +489,25 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     const int blocks256 = std::min((capacity + 255) / 256, g_numSMs * 16);
     const int blocks128 = std::min((capacity + 127) / 128, g_numSMs * 32);
 
+    static const int syncEvery = std::max(1, envInt("PB2_SYNC_EVERY", 8));
+    static const int l2Persist = envInt("PB2_L2_PERSIST", 0);
+    if (l2Persist) {
+        // experiment: pin the node array in L2 (persisting access-policy window on the launching stream)
+        int maxWin = 0, maxPersist = 0;
+        cudaDeviceGetAttribute(&maxWin, cudaDevAttrMaxAccessPolicyWindowSize, g_device);
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, g_device);
+        size_t bytes = std::min<size_t>((size_t)scene->d.nNodes * 32, (size_t)maxWin);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, std::min<size_t>(bytes, (size_t)maxPersist));
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = (void *)scene->d.nodes;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = std::min(1.0f, (float)maxPersist / (float)std::max<size_t>(bytes, 1));
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError();
+    }
     k_wf_init<<<(capacity + 255) / 256, 256, 0, stream>>>(pool);
     unsigned long long nLaunch = 1;
     size_t nEvents = 0;
@@ -518,13 +537,16 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         advShade<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_SHADE, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
         k_wf_reset<<<1, 32, 0, stream>>>(pool, WQ_FREE0 + cur, WQ_TRACE0 + cur);
         nLaunch += 5;
+        cur = next;
+        // The host looks at the counters only every `syncEvery` rounds; rounds enqueued after the frame
+        // has drained find empty lists and cost a few microseconds each.
+        if ((round + 1) % syncEvery != 0) continue;
         CUDA_TRY(cudaMemcpyAsync((void *)scene->wfHostCounts, pool.counts, WQ_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(hWork, &scene->counters[CTR_WORK], sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
-        unsigned traceNext = hc[WQ_TRACE0 + next], freeNext = hc[WQ_FREE0 + next];
+        unsigned traceNext = hc[WQ_TRACE0 + cur], freeNext = hc[WQ_FREE0 + cur];
         bool workLeft = (long long)*hWork < rp.nWorkItems;
         if (traceNext == 0 && !(workLeft && freeNext > 0)) break;
-        cur = next;
         if (round > 100000000LL) return setError(PB2_ERR_CUDA, "wavefront did not terminate");
     }
     CUDA_TRY(cudaGetLastError());

@@ -23,11 +23,13 @@ def test_every_sample_is_deposited_once(pb, big):
     assert st.camera_rays == n
     w = film[..., 3]
     # box filter, radius 0.5: a sample weighs 1 in its own pixel, and additionally in a neighbour only when it falls
-    # exactly on a pixel boundary (film.h:128-131) -> total weight = n + (few), every pixel holds >= spp
-    assert n <= w.sum() <= n * 1.002
-    assert (w >= 2).all() and w.max() <= 2 + 4
+    # exactly on a pixel boundary (film.h:128-131; the first Halton samples of a pixel have u = 0 exactly, so this
+    # is common at low sample numbers) -> total weight = n + (boundary samples), every pixel holds >= spp
+    assert n <= w.sum() <= n * 1.02
+    assert (w >= 2).all() and w.max() <= 2 + 8
     assert np.isfinite(film).all() and (film[..., :3] >= 0).all()
-    assert 3.0 < st.regular_rays / n < 4.5 and 0.5 < st.shadow_rays / n < 1.5   # ~4 rays per sample on this scene
+    # ~4.0 Scene::Intersect + IntersectP calls per camera sample on this scene
+    assert 3.5 < (st.regular_rays + st.shadow_rays) / n < 4.5 and st.shadow_rays < st.regular_rays
 
 
 def test_ray_counters_are_deterministic_and_films_agree(pb, big):
