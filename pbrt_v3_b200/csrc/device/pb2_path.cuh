@@ -85,10 +85,10 @@ template <bool SPH>
 PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &pp, DLane &ln, bool found, const DHit &hit,
                         float tMax) {
     DInteraction isect;
-    if (found) isect = hitInteraction<SPH>(sc, hit, ln.ray, tMax);
+    int li = -1;
+    if (found) isect = hitInteraction<SPH>(sc, hit, ln.ray, tMax, &li);
     if (ln.bounces == 0 || ln.specularBounce) {
         if (found) {
-            int li = sc.primLight[isect.prim];
             if (li >= 0) ln.L = ln.L + ln.beta * lightL(sc.lights[li], isect.n, -ln.ray.d);
         }
     }
@@ -119,10 +119,11 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
             ln.pick = lightPickPdf;
             ln.lightNum = lightNum;
             const pb2_light light = sc.lights[lightNum];
+            const TriRec lightRec = loadTriRec(sc.lightRecs, (size_t)lightNum);
             V2 uLight = get2D(h, ln.smp);
             V2 uScattering = get2D(h, ln.smp);
             // EstimateDirect, light-sampling half (integrator.cpp:116-160)
-            DLightSample ls = sampleLight<SPH>(sc, light, isect, uLight);
+            DLightSample ls = sampleLight<SPH>(sc, light, lightRec, isect, uLight);
             float lightPdf = ls.pdf, scatteringPdf = 0;
             if (lightPdf > 0 && !isBlack(ls.Li)) {
                 V3 f = bsdfF(bsdf, isect.wo, ls.wi) * absDot(ls.wi, isect.ns);
@@ -141,7 +142,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
             if (scatteringPdf != 0) f = f * absDot(wi, isect.ns);
             else f = mk3(0, 0, 0);
             if (!isBlack(f) && scatteringPdf > 0) {
-                lightPdf = lightPdfLi<SPH>(sc, light, isect, wi);
+                lightPdf = lightPdfLi<SPH>(sc, light, lightRec, isect, wi);
                 if (lightPdf != 0) {
                     float weight = powerHeuristic(scatteringPdf, lightPdf);
                     // Li is the light's Lemit when the MIS ray reaches its emitting side (checked after
@@ -202,12 +203,18 @@ PB2_HD void lightAdvance(const DScene &sc, DLane &ln, bool found, const DHit &hi
         startMisOrFinish(ln);
     } else {
         if (found) {
-            int hitPrim = asInt(ldg4(&sc.leafPrims[3 * (size_t)hit.leaf]).w);
-            if (sc.primLight[hitPrim] == ln.lightNum) {
-                // lightIsect.Le(-wi): DiffuseAreaLight::L with the hit's (face-forwarded) normal
-                DInteraction lightIsect = hitInteraction<SPH>(sc, hit, ln.ray, tMax);
+            // the hit primitive's light number rides in its leaf record (spheres: via primLight)
+            float4 b = ldg4(&sc.leafPrims[3 * (size_t)hit.leaf + 1]), c = ldg4(&sc.leafPrims[3 * (size_t)hit.leaf + 2]);
+            int hitLight = asInt(c.w);
+            if (SPH && (floatBits(b.w) & LEAF_SPHERE)) hitLight = sc.primLight[asInt(ldg4(&sc.leafPrims[3 * (size_t)hit.leaf]).w)];
+            if (hitLight == ln.lightNum) {
                 const pb2_light light = sc.lights[ln.lightNum];
-                if (light.two_sided || dot(lightIsect.n, -ln.ray.d) > 0) ln.ldSum = ln.ldSum + ln.misTerm;
+                // lightIsect.Le(-wi): DiffuseAreaLight::L with the hit's (face-forwarded) normal
+                if (light.two_sided) ln.ldSum = ln.ldSum + ln.misTerm;
+                else {
+                    DInteraction lightIsect = hitInteraction<SPH>(sc, hit, ln.ray, tMax);
+                    if (dot(lightIsect.n, -ln.ray.d) > 0) ln.ldSum = ln.ldSum + ln.misTerm;
+                }
             }
         }
         finishVertex(ln);

@@ -26,6 +26,11 @@ struct DHalton {
     const uint16_t *perms;      // radicalInversePermutations
     const int32_t *primes;      // Primes[kMaxHaltonDims]
     const int32_t *primeSums;   // PrimeSums[kMaxHaltonDims]
+#if defined(__CUDACC__)
+    const ulonglong2 *dimRecs;  // per dimension {ceil(2^64 / prime), prime | primeSum << 32}
+#else
+    const void *dimRecs;
+#endif
 };
 
 PB2_HD uint64_t reverseBits64(uint64_t n) {
@@ -41,7 +46,20 @@ PB2_HD uint64_t reverseBits64(uint64_t n) {
 // RadicalInverseSpecialized<base> / ScrambledRadicalInverseSpecialized<base> with a run-time base.
 // The digit loop divides a 32-bit value whenever the index fits (it does for every film size and
 // sample count in scope); the accumulators keep the reference's types (uint64 digits, float scale).
-PB2_HD float radicalInverseBase(uint32_t base, uint64_t a, const uint16_t *perm) {
+// floor(a / d) for a < 2^32 through magic = ceil(2^64 / d): the error of the product is below
+// a / 2^64 < 2^-32 <= 1/d - so the high word is the exact quotient.  This takes the integer division
+// (a ~20-instruction, high-latency sequence for a run-time divisor) out of the digit loop's
+// loop-carried dependency.
+PB2_HD uint32_t divMagic(uint32_t a, uint64_t magic) {
+#if defined(__CUDA_ARCH__)
+    return (uint32_t)__umul64hi((uint64_t)a, magic);
+#else
+    return (uint32_t)(((unsigned __int128)a * magic) >> 64);
+#endif
+}
+
+// `magic` = ceil(2^64 / base), or 0 to divide.
+PB2_HD float radicalInverseBase(uint32_t base, uint64_t a, const uint16_t *perm, uint64_t magic = 0) {
     const float invBase = 1.f / (float)base;
     uint64_t reversedDigits = 0;
     float invBaseN = 1;
@@ -56,7 +74,7 @@ PB2_HD float radicalInverseBase(uint32_t base, uint64_t a, const uint16_t *perm)
     }
     uint32_t a32 = (uint32_t)a;
     while (a32) {
-        uint32_t next = a32 / base;
+        uint32_t next = magic ? divMagic(a32, magic) : a32 / base;
         uint32_t digit = a32 - next * base;
         reversedDigits = reversedDigits * base + (perm ? (uint32_t)perm[digit] : digit);
         invBaseN *= invBase;
@@ -110,7 +128,12 @@ PB2_HD float haltonSample(const DHalton &h, int64_t index, int dim) {
     if (h.sampleAtPixelCenter && (dim == 0 || dim == 1)) return 0.5f;
     if (dim == 0) return (float)((double)reverseBits64((uint64_t)(index >> h.baseExponents[0])) * 0x1p-64);
     if (dim == 1) return radicalInverseBase(3u, (uint64_t)(index / h.baseScales[1]), nullptr);
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 rec = __ldg(&h.dimRecs[dim]);   // {magic, prime | primeSum << 32}: one 16-B load per dimension
+    return radicalInverseBase((uint32_t)rec.y, (uint64_t)index, h.perms + (uint32_t)(rec.y >> 32), rec.x);
+#else
     return radicalInverseBase((uint32_t)h.primes[dim], (uint64_t)index, h.perms + h.primeSums[dim]);
+#endif
 }
 
 // The GlobalSampler's dimension counter (sampler.cpp:178-195; PathIntegrator requests no sample

@@ -4,11 +4,14 @@
 //   nodes      pb2_bvh_node[n_nodes], 32 B each, byte-for-byte the reference's LinearBVHNode
 //              (src/accelerators/bvh.cpp:95-104); a node is fetched as two 16-B vector loads.
 //   leafPrims  one 48-B record per primitive IN BVH ORDER (= BVHAccel::primitives order):
-//              float4 a = (p0.xyz, primNumber), b = (p1.xyz, flags), c = (p2.xyz, sphereIndex);
+//              float4 a = (p0.xyz, primNumber), b = (p1.xyz, flags),
+//              c = (p2.xyz, area-light number or -1 | sphereIndex for a sphere);
 //              triangle vertices are pre-gathered through the index buffer so a leaf test is three
 //              16-B loads from consecutive addresses instead of the reference's
-//              primitive -> shape -> mesh -> index -> vertex pointer chase.
-//   everything else (P/N/UV/indices, per-primitive material and light ids, materials, lights,
+//              primitive -> shape -> mesh -> index -> vertex pointer chase.  Shading rebuilds the
+//              SurfaceInteraction of a plain triangle (no per-vertex N/S/UV) from the same record.
+//   lightRecs  the same 48-B record for the shape of every area light, in light order (light sampling).
+//   everything else (P/N/UV/indices, per-primitive material ids, materials, lights,
 //   light-distribution tables, Halton permutations) is only touched at shading time.
 #ifndef PB2_SCENE_CUH
 #define PB2_SCENE_CUH
@@ -21,6 +24,8 @@ namespace pb2 {
 enum : uint32_t {
     LEAF_SPHERE = 1u,         // record describes a sphere, not a triangle
     LEAF_DEGENERATE = 2u,     // Triangle::Intersect rejects every hit (triangle.cpp:308-314); IntersectP does not
+    LEAF_FLIP = 4u,           // reverseOrientation ^ transformSwapsHandedness of the triangle's mesh
+    LEAF_ATTR = 8u,           // the mesh has per-vertex N, S or UV: shading must go through the index buffer
 };
 
 struct DLightDist {
@@ -34,6 +39,7 @@ struct DLightDist {
 struct DScene {
     const float4 *nodes;
     const float4 *leafPrims;
+    const float4 *lightRecs;
     int64_t nNodes, nPrims, nTris;
     const float *P, *N, *UV, *S;
     const int32_t *triIndex, *triMesh;

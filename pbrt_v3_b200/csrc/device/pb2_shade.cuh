@@ -85,11 +85,40 @@ PB2_HD bool triPartials(V3 p0, V3 p1, V3 p2, const V2 uv[3], V3 *dpdu, V3 *dpdv)
 
 // The SurfaceInteraction Triangle::Intersect fills in for a hit with barycentrics (b0,b1,b2)
 // (triangle.cpp:319-419).
-PB2_HD DInteraction triangleInteraction(const DScene &sc, int prim, float b0, float b1, float b2, V3 rayD) {
+// A 48-B leaf / light record (pb2_scene.cuh) unpacked: the triangle's world-space vertices, its
+// LEAF_* flags, the scene-order primitive number and the area-light number (-1: not emissive).
+struct TriRec {
+    TriVerts tv;
+    uint32_t flags;
+    int prim, light;
+};
+
+PB2_HD TriRec loadTriRec(const float4 *recs, size_t i) {
+    float4 a = ldg4(&recs[3 * i]), b = ldg4(&recs[3 * i + 1]), c = ldg4(&recs[3 * i + 2]);
+    TriRec r;
+    r.tv.p0 = mk3(a.x, a.y, a.z);
+    r.tv.p1 = mk3(b.x, b.y, b.z);
+    r.tv.p2 = mk3(c.x, c.y, c.z);
+    r.prim = asInt(a.w);
+    r.flags = floatBits(b.w);
+    r.light = asInt(c.w);
+    return r;
+}
+
+PB2_HD DInteraction triangleInteraction(const DScene &sc, const TriRec &rec, float b0, float b1, float b2, V3 rayD) {
     DInteraction it;
-    int tri = sc.primIndex[prim];
-    const pb2_mesh mesh = sc.meshes[sc.triMesh[tri]];
-    TriVerts tv = triVerts(sc, tri);
+    const int prim = rec.prim;
+    const TriVerts tv = rec.tv;   // bitwise the vertices the index buffer leads to
+    // meshes without per-vertex attributes never leave the record
+    int tri = 0;
+    pb2_mesh mesh;
+    mesh.has_n = mesh.has_s = mesh.has_uv = 0;
+    mesh.reverse_orientation = 0;
+    mesh.transform_swaps_handedness = (rec.flags & LEAF_FLIP) ? 1 : 0;
+    if (rec.flags & LEAF_ATTR) {
+        tri = sc.primIndex[prim];
+        mesh = sc.meshes[sc.triMesh[tri]];
+    }
     V2 uv[3];
     triUVs(sc, tri, mesh, uv);
     V3 dpdu, dpdv;
@@ -145,13 +174,16 @@ namespace pb2 {
 
 // SPH = false compiles the sphere branches away (scenes without spheres get kernels without the
 // interval-arithmetic code and its call frames).
+// *light receives the area-light number of the primitive that was hit (-1: not emissive).
 template <bool SPH = true>
-PB2_HD DInteraction hitInteraction(const DScene &sc, const DHit &hit, const DRay &ray, float tHit) {
-    float4 a = ldg4(&sc.leafPrims[3 * (size_t)hit.leaf]);
-    float4 b = ldg4(&sc.leafPrims[3 * (size_t)hit.leaf + 1]);
-    int prim = asInt(a.w);
-    if (SPH && (floatBits(b.w) & LEAF_SPHERE)) return sphereInteraction(sc, prim, ray, tHit, hit.b0);
-    return triangleInteraction(sc, prim, hit.b0, hit.b1, hit.b2, ray.d);
+PB2_HD DInteraction hitInteraction(const DScene &sc, const DHit &hit, const DRay &ray, float tHit, int *light = nullptr) {
+    TriRec rec = loadTriRec(sc.leafPrims, (size_t)hit.leaf);
+    if (SPH && (rec.flags & LEAF_SPHERE)) {
+        if (light) *light = sc.primLight[rec.prim];
+        return sphereInteraction(sc, rec.prim, ray, tHit, hit.b0);
+    }
+    if (light) *light = rec.light;
+    return triangleInteraction(sc, rec, hit.b0, hit.b1, hit.b2, ray.d);
 }
 
 // Interaction::SpawnRay (interaction.h:64-67)
@@ -578,21 +610,24 @@ PB2_HDN float sphereLightPdf(const DScene &sc, const pb2_light &l, const DIntera
 
 // DiffuseAreaLight::Sample_Li (diffuse.cpp:68-81) for a triangle shape: Triangle::Sample(u)
 // (triangle.cpp:582-607) + Shape::Sample(ref,u,pdf) (shape.cpp:61-76).
-PB2_HD DLightSample sampleTriangleLight(const DScene &sc, const pb2_light &l, V3 refP, V2 u) {
+PB2_HD DLightSample sampleTriangleLight(const DScene &sc, const pb2_light &l, const TriRec &rec, V3 refP, V2 u) {
     DLightSample s;
-    int tri = sc.primIndex[l.prim];
-    const pb2_mesh mesh = sc.meshes[sc.triMesh[tri]];
-    TriVerts t = triVerts(sc, tri);
+    const TriVerts t = rec.tv;
     V2 b = uniformSampleTriangle(u);
     float b2 = (1 - b.x - b.y);
     s.p = b.x * t.p0 + b.y * t.p1 + b2 * t.p2;
     s.n = normalize(cross(t.p1 - t.p0, t.p2 - t.p0));
-    if (mesh.has_n) {
-        int64_t v0 = sc.triIndex[3 * (int64_t)tri], v1 = sc.triIndex[3 * (int64_t)tri + 1], v2 = sc.triIndex[3 * (int64_t)tri + 2];
-        V3 ns = b.x * ld3(sc.N, v0) + b.y * ld3(sc.N, v1) + b2 * ld3(sc.N, v2);
-        s.n = faceforward(s.n, ns);
-    } else if ((mesh.reverse_orientation != 0) ^ (mesh.transform_swaps_handedness != 0))
-        s.n = s.n * -1.f;
+    bool hasN = false;
+    if (rec.flags & LEAF_ATTR) {
+        int tri = sc.primIndex[rec.prim];
+        if (sc.meshes[sc.triMesh[tri]].has_n) {
+            hasN = true;
+            int64_t v0 = sc.triIndex[3 * (int64_t)tri], v1 = sc.triIndex[3 * (int64_t)tri + 1], v2 = sc.triIndex[3 * (int64_t)tri + 2];
+            V3 ns = b.x * ld3(sc.N, v0) + b.y * ld3(sc.N, v1) + b2 * ld3(sc.N, v2);
+            s.n = faceforward(s.n, ns);
+        }
+    }
+    if (!hasN && (rec.flags & LEAF_FLIP)) s.n = s.n * -1.f;
     V3 pAbsSum = vabs(b.x * t.p0) + vabs(b.y * t.p1) + vabs(b2 * t.p2);
     s.pError = kGamma6 * pAbsSum;
     s.pdf = 1 / triangleArea(t);
@@ -617,29 +652,25 @@ PB2_HD DLightSample sampleTriangleLight(const DScene &sc, const pb2_light &l, V3
     return s;
 }
 
+// `rec` is the light's record out of DScene::lightRecs.
 template <bool SPH = true>
-PB2_HD DLightSample sampleLight(const DScene &sc, const pb2_light &l, const DInteraction &ref, V2 u) {
-    if (SPH && sc.primType[l.prim] == PB2_PRIM_SPHERE) return sampleSphereLight(sc, l, ref, u);
-    return sampleTriangleLight(sc, l, ref.p, u);
+PB2_HD DLightSample sampleLight(const DScene &sc, const pb2_light &l, const TriRec &rec, const DInteraction &ref, V2 u) {
+    if (SPH && (rec.flags & LEAF_SPHERE)) return sampleSphereLight(sc, l, ref, u);
+    return sampleTriangleLight(sc, l, rec, ref.p, u);
 }
 
 // DiffuseAreaLight::Pdf_Li -> Shape::Pdf(ref, wi) (shape.cpp:78-95): re-intersect the light's own
 // shape with the spawned ray and convert the area density to solid angle.
 template <bool SPH = true>
-PB2_HD float lightPdfLi(const DScene &sc, const pb2_light &l, const DInteraction &ref, V3 wi) {
-    if (SPH && sc.primType[l.prim] == PB2_PRIM_SPHERE) return sphereLightPdf(sc, l, ref, wi);
+PB2_HD float lightPdfLi(const DScene &sc, const pb2_light &l, const TriRec &rec, const DInteraction &ref, V3 wi) {
+    if (SPH && (rec.flags & LEAF_SPHERE)) return sphereLightPdf(sc, l, ref, wi);
     DRay ray = spawnRay(ref, wi);
-    int tri = sc.primIndex[l.prim];
-    const pb2_mesh mesh = sc.meshes[sc.triMesh[tri]];
-    TriVerts t = triVerts(sc, tri);
+    const TriVerts t = rec.tv;
     DRaySetup rs = setupRay(ray.o, ray.d);
     float tHit, b0, b1, b2;
     if (!triangleTest(t.p0, t.p1, t.p2, rs, ray.tMax, &tHit, &b0, &b1, &b2)) return 0;
-    V2 uv[3];
-    triUVs(sc, tri, mesh, uv);
-    V3 dpdu, dpdv;
-    if (!triPartials(t.p0, t.p1, t.p2, uv, &dpdu, &dpdv)) return 0;
-    DInteraction li = triangleInteraction(sc, l.prim, b0, b1, b2, ray.d);
+    if (rec.flags & LEAF_DEGENERATE) return 0;   // triPartials failed at upload (triangle.cpp:308-314)
+    DInteraction li = triangleInteraction(sc, rec, b0, b1, b2, ray.d);
     float pdf = lengthSquared(ref.p - li.p) / (absDot(li.n, -wi) * triangleArea(t));
     if (isinf(pdf)) pdf = 0.f;
     return pdf;
@@ -692,7 +723,7 @@ PB2_HD void computeVoxelDistribution(const DScene &sc, const DHalton &h, const D
         intr.prim = -1;
         V2 u = mk2(radicalInverse(h, 3, i), radicalInverse(h, 4, i));
         for (int j = 0; j < n; ++j) {
-            DLightSample ls = sampleLight(sc, sc.lights[j], intr, u);
+            DLightSample ls = sampleLight(sc, sc.lights[j], loadTriRec(sc.lightRecs, (size_t)j), intr, u);
             if (ls.pdf > 0) rec[j] += luminance(ls.Li) / ls.pdf;
         }
     }
@@ -763,159 +794,6 @@ struct DPathParams {
     int maxDepth;
     float rrThreshold;
 };
-
-#if 0  // first, monolithic statement of the bounce loop; superseded by the lane state machine in pb2_path.cuh
-struct DPathState {
-    V3 L, beta;
-    DRay ray;
-    DSampler smp;
-    int bounces;
-    float etaScale;
-    bool specularBounce;
-};
-
-struct DRayStats {
-    unsigned int regular, shadow;
-};
-
-PB2_HD void initPath(DPathState &ps, const DRay &ray, const DSampler &smp) {
-    ps.L = mk3(0, 0, 0);
-    ps.beta = mk3(1, 1, 1);
-    ps.ray = ray;
-    ps.smp = smp;
-    ps.bounces = 0;
-    ps.etaScale = 1;
-    ps.specularBounce = false;
-}
-
-// One iteration of the bounce loop of PathIntegrator::Li (path.cpp:81-185).  Returns true when the
-// path continues with ps.ray; false when it ended (ps.L then holds the sample's radiance).
-PB2_HD bool pathVertex(const DScene &sc, const DHalton &h, const DPathParams &pp, DPathState &ps, DRayStats &st,
-                       DCounters *ctr) {
-    // scene.Intersect(ray, &isect)
-    DHit hit;
-    hit.leaf = -1;
-    hit.b0 = hit.b1 = hit.b2 = 0;
-    float tMax = ps.ray.tMax;
-    st.regular++;
-    bool found = traverse<false>(sc, ps.ray, &tMax, &hit, ctr);
-    DInteraction isect;
-    if (found) isect = hitInteraction(sc, hit, ps.ray, tMax);
-    // emitted light at the first vertex / after specular bounces (path.cpp:91-101)
-    if (ps.bounces == 0 || ps.specularBounce) {
-        if (found) {
-            int li = sc.primLight[isect.prim];
-            if (li >= 0) ps.L = ps.L + ps.beta * lightL(sc.lights[li], isect.n, -ps.ray.d);
-        }
-        // no infinite lights in scope
-    }
-    if (!found || ps.bounces >= pp.maxDepth) return false;
-
-    DBsdf bsdf;
-    if (!makeBsdf(sc, isect, &bsdf)) {
-        // null BSDF: skip the surface (path.cpp:108-113)
-        ps.ray = spawnRay(isect, ps.ray.d);
-        return true;  // bounces-- then ++bounces
-    }
-    const float *distrib = lightDistLookup(sc.lightDist, isect.p);
-
-    // direct lighting (path.cpp:119-128); NumComponents(~SPECULAR) == nLobes here
-    if (bsdf.nLobes > 0) {
-        V3 Ld = mk3(0, 0, 0);
-        // UniformSampleOneLight (integrator.cpp:85-106)
-        int nLights = sc.nLights;
-        if (nLights > 0) {
-            float lightPickPdf;
-            int lightNum = sampleDiscrete(distrib, nLights, get1D(h, ps.smp), &lightPickPdf);
-            if (lightPickPdf != 0) {
-                const pb2_light light = sc.lights[lightNum];
-                V2 uLight = get2D(h, ps.smp);
-                V2 uScattering = get2D(h, ps.smp);
-                // EstimateDirect (integrator.cpp:108-215), handleMedia = false, specular = false
-                V3 ld = mk3(0, 0, 0);
-                DLightSample ls = sampleLight(sc, light, isect, uLight);
-                float lightPdf = ls.pdf, scatteringPdf = 0;
-                bool returned = false;
-                if (lightPdf > 0 && !isBlack(ls.Li)) {
-                    V3 f = bsdfF(bsdf, isect.wo, ls.wi) * absDot(ls.wi, isect.ns);
-                    scatteringPdf = bsdfPdf(bsdf, isect.wo, ls.wi);
-                    if (!isBlack(f)) {
-                        DRay shadow = spawnRayTo(isect, ls.p, ls.pError, ls.n);
-                        float stMax = shadow.tMax;
-                        DHit dummy;
-                        st.shadow++;
-                        bool occluded = traverse<true>(sc, shadow, &stMax, &dummy, ctr);
-                        V3 Li = occluded ? mk3(0, 0, 0) : ls.Li;
-                        if (!isBlack(Li)) {
-                            float weight = powerHeuristic(lightPdf, scatteringPdf);
-                            V3 fl = f * Li * weight;
-                            ld = ld + mk3(fl.x / lightPdf, fl.y / lightPdf, fl.z / lightPdf);
-                        }
-                    }
-                }
-                // BSDF-sampled direction with MIS (area lights are never delta lights)
-                {
-                    V3 wi;
-                    V3 f = bsdfSampleF(bsdf, isect.wo, &wi, uScattering, &scatteringPdf);
-                    if (scatteringPdf != 0) f = f * absDot(wi, isect.ns);
-                    else f = mk3(0, 0, 0);
-                    if (!isBlack(f) && scatteringPdf > 0) {
-                        float weight = 1;
-                        lightPdf = lightPdfLi(sc, light, isect, wi);
-                        if (lightPdf == 0) returned = true;
-                        if (!returned) {
-                            weight = powerHeuristic(scatteringPdf, lightPdf);
-                            DRay ray = spawnRay(isect, wi);
-                            DHit lh;
-                            lh.leaf = -1;
-                            lh.b0 = lh.b1 = lh.b2 = 0;
-                            float ltMax = ray.tMax;
-                            st.regular++;
-                            bool foundLight = traverse<false>(sc, ray, &ltMax, &lh, ctr);
-                            V3 Li = mk3(0, 0, 0);
-                            if (foundLight) {
-                                int hitPrim = asInt(ldg4(&sc.leafPrims[3 * (size_t)lh.leaf]).w);
-                                if (sc.primLight[hitPrim] == lightNum) {
-                                    DInteraction lightIsect = hitInteraction(sc, lh, ray, ltMax);
-                                    Li = lightL(light, lightIsect.n, -wi);
-                                }
-                            }
-                            if (!isBlack(Li)) {
-                                V3 fl = f * Li * weight;  // Tr == 1
-                                ld = ld + mk3(fl.x / scatteringPdf, fl.y / scatteringPdf, fl.z / scatteringPdf);
-                            }
-                        }
-                    }
-                }
-                Ld = mk3(ld.x / lightPickPdf, ld.y / lightPickPdf, ld.z / lightPickPdf);
-            }
-        }
-        ps.L = ps.L + ps.beta * Ld;
-    }
-
-    // sample the BSDF for the next direction (path.cpp:130-150)
-    V3 wo = -ps.ray.d, wi;
-    float pdf;
-    V3 f = bsdfSampleF(bsdf, wo, &wi, get2D(h, ps.smp), &pdf);
-    if (isBlack(f) || pdf == 0.f) return false;
-    V3 s = f * absDot(wi, isect.ns);
-    ps.beta = ps.beta * mk3(s.x / pdf, s.y / pdf, s.z / pdf);
-    ps.specularBounce = false;  // no specular lobes in scope
-    ps.ray = spawnRay(isect, wi);
-
-    // Russian roulette (path.cpp:176-184)
-    V3 rrBeta = ps.beta * ps.etaScale;
-    if (maxComponentValue(rrBeta) < pp.rrThreshold && ps.bounces > 3) {
-        float q = pmax(.05f, 1 - maxComponentValue(rrBeta));
-        if (get1D(h, ps.smp) < q) return false;
-        float d = 1 - q;
-        ps.beta = mk3(ps.beta.x / d, ps.beta.y / d, ps.beta.z / d);
-    }
-    ps.bounces++;
-    return true;
-}
-
-#endif
 
 // The per-sample guard of SamplerIntegrator::Render (integrator.cpp:294-315)
 PB2_HD V3 guardRadiance(V3 L) {
