@@ -15,7 +15,7 @@ One JSON line is printed by rank 0:
   value        whole-job Msamples/s from the device-timed steps (inputs resident, film left on device)
   e2e          the same metric through the public host-buffer call pb2_render_path: camera/film/params
                structs go in, the merged film comes back to host memory inside the timed region
-  roofline     the BVH traversal kernel (k_wf_trace3): algorithmic bytes (32 B x node visits + 36 B x
+  roofline     the BVH traversal kernel (k_wf_trace_w): algorithmic bytes (32 B x node visits + 36 B x
                primitive tests, counted on the device in the reference's traversal order) / its summed
                launch time, against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline the reference's own CPU implementation (oracle/_ref, all host cores) on a bounded
@@ -34,6 +34,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(tris=1000000, seed=1234, jitter=0.02, xres=1920, yres=1080, spp=64, maxdepth=8)
+# DRAM bytes of one full-pool k_wf_trace_w launch on this workload, from the committed `ncu --set full` capture
+NCU_TRACE_DRAM_BYTES_PER_LAUNCH = 937208832 + 162006784
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 
 
@@ -172,6 +174,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=15.0, help="CPU seconds per reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    default_workload = all(getattr(args, k) == WORKLOAD[k] for k in ("tris", "xres", "yres", "spp", "maxdepth"))
     args.warmup = max(args.warmup, 0)
 
     if args.impl == "reference":
@@ -282,8 +285,11 @@ def main():
                     "note": "scene upload happens once at pb2_scene_create (outside, like the reference's scene construction); "
                             "per step the camera/film/integrator structs go in and the merged rgbw film comes back"},
             "gpu_launches": launches, "clocks": clock_info,
-            "roofline": {"kernel": "k_wf_trace3 (BVH traversal + ray/triangle tests)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "peak_source": peak_src, "traffic": None,
+            "roofline": {"kernel": "k_wf_trace_w (BVH traversal + ray/triangle tests)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
+                         "traffic": NCU_TRACE_DRAM_BYTES_PER_LAUNCH if default_workload else None,
+                         "traffic_source": "profiles/r01_trace_w_ncu_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                           "full-pool launch (4.19 M rays, 11.8 GB algorithmic): the 124 MB of nodes + leaf records live in L2",
                          "algorithmic_bytes_per_frame": alg_bytes, "node_visits": node_visits, "prim_tests": prim_tests,
                          "bytes_per_ray": alg_bytes / max(rays_frame, 1), "trace_ms_per_frame": trace_ms / args.steps,
                          "trace_share_of_step": (trace_ms / args.steps) / ms_per_step},

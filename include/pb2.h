@@ -175,6 +175,9 @@ typedef struct pb2_path_params {
  * one-thread-per-ray traversal kernel instead of the tuned one: the device analogue of the
  * reference's STAT_COUNTERs, used to obtain the algorithmic bytes of a frame. */
 #define PB2_FLAG_COUNT_TRAVERSAL 1
+/* Trace with the kernel that reads the 32-byte LinearBVHNode array directly instead of the derived
+ * two-child records (same results; kept selectable so both kernels stay under test). */
+#define PB2_FLAG_LINEAR_NODES 2
 
 typedef struct pb2_ray {
     float o[3];

@@ -3,6 +3,14 @@
 // HBM layout (all arrays are uploaded once per scene and read-only during rendering):
 //   nodes      pb2_bvh_node[n_nodes], 32 B each, byte-for-byte the reference's LinearBVHNode
 //              (src/accelerators/bvh.cpp:95-104); a node is fetched as two 16-B vector loads.
+//   wide       the same tree with the boxes moved up one level: one 64-B record per INTERIOR node,
+//              float4 q0 = (c0.min.xyz, c0.max.x), q1 = (c0.max.yz, c1.min.xy), q2 = (c1.min.z, c1.max.xyz),
+//              q3 = (ref0, ref1, meta, -) with c0 = the node's first child (index + 1), c1 = its second;
+//              ref = index of the child's wide record, or WIDE_LEAF | nPrims << 24 | primitivesOffset;
+//              meta = the node's split axis (bits 0-1) | WIDE_SINGLE.  Record 0 is a pseudo node whose
+//              only child is the root.  One fetch tests both children's boxes, so the render kernel
+//              makes half the dependent memory round trips of the 32-B layout; every box is still
+//              tested exactly once per ray, with the verdict the reference reaches (see k_wf_trace_w).
 //   leafPrims  one 48-B record per primitive IN BVH ORDER (= BVHAccel::primitives order):
 //              float4 a = (p0.xyz, primNumber), b = (p1.xyz, flags),
 //              c = (p2.xyz, area-light number or -1 | sphereIndex for a sphere);
@@ -27,6 +35,12 @@ enum : uint32_t {
     LEAF_FLIP = 4u,           // reverseOrientation ^ transformSwapsHandedness of the triangle's mesh
     LEAF_ATTR = 8u,           // the mesh has per-vertex N, S or UV: shading must go through the index buffer
 };
+enum : uint32_t {
+    WIDE_LEAF = 0x80000000u,  // child reference: bits 0-23 primitivesOffset, bits 24-30 nPrimitives
+    WIDE_SINGLE = 4u,         // meta: the record has only child 0 (the pseudo node above the root)
+    WIDE_MAX_PRIMS = 1u << 24,
+    WIDE_MAX_LEAF = 127u,
+};
 
 struct DLightDist {
     int strategy;             // PB2_LIGHTDIST_*
@@ -38,6 +52,7 @@ struct DLightDist {
 
 struct DScene {
     const float4 *nodes;
+    const float4 *wide;       // two-child nodes (below), nullptr when the scene exceeds their limits
     const float4 *leafPrims;
     const float4 *lightRecs;
     int64_t nNodes, nPrims, nTris;
@@ -104,6 +119,34 @@ PB2_HD DRaySetup setupRay(V3 o, V3 d) {
 }
 
 // Bounds3::IntersectP(ray, invDir, dirIsNeg), geometry.h:1412-1438.
+// The same test with the box given as six floats; also returns the entry parameter tMin, the only
+// quantity the verdict compares with ray.tMax - a caller that keeps tMin can re-evaluate the test
+// for a smaller ray.tMax later without the box (`pass && tMin < newTMax`).
+PB2_HD bool slabTestT(float minx, float miny, float minz, float maxx, float maxy, float maxz, const DRaySetup &r,
+                      float rayTMax, float *tMinOut) {
+    float bx0 = r.neg0 ? maxx : minx, bx1 = r.neg0 ? minx : maxx;
+    float by0 = r.neg1 ? maxy : miny, by1 = r.neg1 ? miny : maxy;
+    float bz0 = r.neg2 ? maxz : minz, bz1 = r.neg2 ? minz : maxz;
+    float tMin = (bx0 - r.o.x) * r.invDir.x;
+    float tMax = (bx1 - r.o.x) * r.invDir.x;
+    float tyMin = (by0 - r.o.y) * r.invDir.y;
+    float tyMax = (by1 - r.o.y) * r.invDir.y;
+    tMax *= kSlabScale;
+    tyMax *= kSlabScale;
+    *tMinOut = tMin;
+    if (tMin > tyMax || tyMin > tMax) return false;
+    if (tyMin > tMin) tMin = tyMin;
+    if (tyMax < tMax) tMax = tyMax;
+    float tzMin = (bz0 - r.o.z) * r.invDir.z;
+    float tzMax = (bz1 - r.o.z) * r.invDir.z;
+    tzMax *= kSlabScale;
+    if (tMin > tzMax || tzMin > tMax) return false;
+    if (tzMin > tMin) tMin = tzMin;
+    if (tzMax < tMax) tMax = tzMax;
+    *tMinOut = tMin;
+    return (tMin < rayTMax) && (tMax > 0);
+}
+
 PB2_HD bool slabTest(float4 n0, float4 n1, const DRaySetup &r, float rayTMax) {
     // n0 = (min.x, min.y, min.z, max.x), n1 = (max.y, max.z, offset, meta)
     float bx0 = r.neg0 ? n0.w : n0.x, bx1 = r.neg0 ? n0.x : n0.w;

@@ -453,8 +453,10 @@ typedef void (*TraceKernel)(DScene, WfPool, int);
 typedef void (*AdvanceKernel)(DScene, DRenderParams, WfPool, int, int, int, float4 *, unsigned long long *);
 
 // Host driver of the wavefront rounds (see pb2_wavefront.cuh).
-static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *film, cudaStream_t stream, bool countTraversal,
+static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *film, cudaStream_t stream, int flags,
                            bool timeTrace, unsigned long long *launches, double *traceMs) {
+    const bool countTraversal = (flags & PB2_FLAG_COUNT_TRAVERSAL) != 0;
+    const bool wideNodes = scene->d.wide != nullptr && !(flags & PB2_FLAG_LINEAR_NODES);
     // 4 M contexts (1 GiB) measured best on 1920x1080: 1 M -> 160, 2 M -> 174, 4 M -> 180 Msamples/s
     static const int maxCapacity = envInt("PB2_POOL", 1 << 22);
     long long want = std::min<long long>(maxCapacity, std::max<long long>(rp.nWorkItems, 1024));
@@ -477,18 +479,23 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     for (int q = 0; q < 6; ++q) pool.queue[q] = scene->wfQueues + (size_t)q * scene->wfCapacity;
     pool.counts = scene->wfCounts;
 
-    // kernel selection: scenes without spheres whose BVH depth fits the shared-memory stack get the
-    // leanest traversal kernel; PB2_TRACE selects tuning variants for experiments
+    // kernel selection: triangle scenes take the two-child-record kernel (any BVH depth); scenes with
+    // spheres, or beyond the record limits, the 32-B-node kernel (shared-memory stack of 32, local
+    // spill beyond).  PB2_TRACE selects tuning variants for experiments.
     const bool spheres = scene->d.spheres != nullptr;
     static const int variant = envInt("PB2_TRACE", 0);
     TraceKernel trace;
     if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
+    else if (wideNodes && variant == 0) trace = k_wf_trace_w<8, 8, 2, 16, 8>;
+    else if (wideNodes && variant == 5) trace = k_wf_trace_w<12, 8, 4, 16, 8>;
+    else if (wideNodes && variant == 6) trace = k_wf_trace_w<12, 8, 2, 16, 8>;
+    else if (wideNodes && variant == 8) trace = k_wf_trace_w<8, 8, 2, 4, 8>;   // tests: forces the local-memory stack spill
     else if (scene->bvhDepth > 32) trace = k_wf_trace<12, 8, 4, 32, true, false, 8>;
     else if (variant == 1) trace = k_wf_trace<12, 8, 8, 32, false, false, 8>;
     else if (variant == 2) trace = k_wf_trace<16, 8, 4, 32, false, false, 8>;
     else if (variant == 3) trace = k_wf_trace<12, 8, 4, 32, false, false, 10>;
     else if (variant == 4) trace = k_wf_trace<12, 12, 6, 32, false, false, 8>;
-    else trace = k_wf_trace<12, 8, 4, 32, false, false, 8>;
+    else trace = k_wf_trace<12, 8, 4, 32, false, false, 8>;   // also PB2_TRACE=7: the 32-B-node kernel on a triangle scene
     static const int shadeMinB = envInt("PB2_SHADE_MINB", 4);
     AdvanceKernel advLight = spheres ? k_wf_advance<false, true, 8> : k_wf_advance<false, false, 8>;
     AdvanceKernel advShade = spheres ? k_wf_advance<true, true, 4>
@@ -499,6 +506,18 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
                                               : k_wf_advance<true, false, 4>;
     int traceBlocksPerSM = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&traceBlocksPerSM, trace, 128, 0));
+    {
+        // ask for exactly the shared-memory carve-out the resident blocks need; the rest stays L1
+        cudaFuncAttributes fa;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, trace));
+        size_t need = (size_t)traceBlocksPerSM * (fa.sharedSizeBytes + 1024);
+        int pct = (int)std::min<size_t>(100, (need * 100 + 233471) / 233472);
+        CUDA_TRY(cudaFuncSetAttribute(trace, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        static const int verbose = envInt("PB2_VERBOSE", 0);
+        if (verbose)
+            fprintf(stderr, "pb2: trace kernel %d regs, %zu B smem, %d blocks/SM, carve-out %d %%, BVH depth %d, wide %d\n", fa.numRegs,
+                    fa.sharedSizeBytes, traceBlocksPerSM, pct, scene->bvhDepth, scene->d.wide ? 1 : 0);
+    }
     const int persistentBlocks = g_numSMs * std::max(1, traceBlocksPerSM);
     const int blocks256 = std::min((capacity + 255) / 256, g_numSMs * 16);
     const int blocks128 = std::min((capacity + 127) / 128, g_numSMs * 32);
@@ -668,6 +687,48 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
     const pb2_bvh_node *nodes;
     if ((rc = upload(s, d->nodes, (size_t)d->n_nodes, &nodes))) return rc;
     sc.nodes = reinterpret_cast<const float4 *>(nodes);
+    sc.wide = nullptr;
+    if (d->n_nodes > 0 && d->n_prims < (int64_t)WIDE_MAX_PRIMS) {
+        // two-child records (pb2_scene.cuh): interior nodes keep their depth-first order
+        std::vector<int32_t> wideOf((size_t)d->n_nodes, -1);
+        int32_t nWide = 1;
+        bool fits = true;
+        for (int64_t i = 0; i < d->n_nodes; ++i) {
+            if (d->nodes[i].n_prims == 0) wideOf[i] = nWide++;
+            else if (d->nodes[i].n_prims > WIDE_MAX_LEAF) fits = false;
+        }
+        if (fits) {
+            struct WideRec { float b[12]; uint32_t ref0, ref1, meta, pad; };
+            static_assert(sizeof(WideRec) == 64, "wide record is 64 bytes");
+            std::vector<WideRec> wide((size_t)nWide);
+            auto childRef = [&](int64_t i) -> uint32_t {
+                const pb2_bvh_node &n = d->nodes[i];
+                return n.n_prims == 0 ? (uint32_t)wideOf[i] : (WIDE_LEAF | ((uint32_t)n.n_prims << 24) | (uint32_t)n.offset);
+            };
+            auto putBox = [&](float *dst, const pb2_bvh_node &n) {
+                dst[0] = n.bmin[0]; dst[1] = n.bmin[1]; dst[2] = n.bmin[2];
+                dst[3] = n.bmax[0]; dst[4] = n.bmax[1]; dst[5] = n.bmax[2];
+            };
+            memset(wide.data(), 0, wide.size() * sizeof(WideRec));
+            putBox(wide[0].b, d->nodes[0]);
+            putBox(wide[0].b + 6, d->nodes[0]);
+            wide[0].ref0 = wide[0].ref1 = childRef(0);
+            wide[0].meta = WIDE_SINGLE;
+            for (int64_t i = 0; i < d->n_nodes; ++i) {
+                const pb2_bvh_node &n = d->nodes[i];
+                if (n.n_prims != 0) continue;
+                WideRec &w = wide[(size_t)wideOf[i]];
+                putBox(w.b, d->nodes[i + 1]);
+                putBox(w.b + 6, d->nodes[n.offset]);
+                w.ref0 = childRef(i + 1);
+                w.ref1 = childRef(n.offset);
+                w.meta = (uint32_t)n.axis & 3u;
+            }
+            const WideRec *dWide;
+            if ((rc = upload(s, wide.data(), wide.size(), &dWide))) return rc;
+            sc.wide = reinterpret_cast<const float4 *>(dWide);
+        }
+    }
     if ((rc = upload(s, d->P, 3 * (size_t)d->n_vertices, &sc.P))) return rc;
     if ((rc = upload(s, d->N, d->N ? 3 * (size_t)d->n_vertices : 0, &sc.N))) return rc;
     if ((rc = upload(s, d->UV, d->UV ? 2 * (size_t)d->n_vertices : 0, &sc.UV))) return rc;
@@ -844,8 +905,7 @@ int pb2_render_path_device(pb2_scene *scene, const pb2_camera *cam, const pb2_fi
     unsigned long long launches = 0;
     double traceMs = 0;
     if (rp.nWorkItems > 0) {
-        rc = renderWavefront(scene, rp, (float4 *)film_rgbw_device, stream, (pp->flags & PB2_FLAG_COUNT_TRAVERSAL) != 0, stats != nullptr,
-                             &launches, &traceMs);
+        rc = renderWavefront(scene, rp, (float4 *)film_rgbw_device, stream, pp->flags, stats != nullptr, &launches, &traceMs);
         if (rc) return rc;
     }
     if (stats) {

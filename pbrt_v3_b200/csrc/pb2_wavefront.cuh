@@ -243,6 +243,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
                     int slot = interior ? sp : (sp > 0 ? sp - 1 : 0);
                     int top = stackGet(slot);
                     if (interior) stackPut(slot, far);
+                    // (prefetching the far child here - prefetch.global.L1 / .L2, CCTL.PF1/PF2 - was
+                    // measured: -3.5 % on the bench scene, the extra L1 traffic costs more than it hides)
                     if (interior) {
                         cur = near;
                         ++sp;
@@ -339,6 +341,173 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Trace kernel over the two-child records (DScene::wide, triangle scenes).  Same persistent-warp
+// scheduling as k_wf_trace; what changes is the node step.  A lane stands at an INTERIOR node whose
+// own box it has already passed, fetches that node's 64-B record and tests BOTH children's boxes:
+//   * the near child (by the node's split axis and the ray's direction sign, bvh.cpp:684-690) is
+//     entered at once when its box passes - the reference tests that box next, with the same tMax;
+//   * the far child is pushed only if its box passes, together with its entry parameter tMin.  The
+//     reference tests the far box when it pops it, possibly against a smaller tMax; the only term of
+//     Bounds3::IntersectP that depends on ray.tMax is `tMin < ray.tMax` (geometry.h:1437), so a pop
+//     re-evaluates exactly that with the stored tMin and skips the entry otherwise.
+// Every box is therefore tested once per ray with the reference's verdict, leaves are reached in
+// the reference's order, and the primitive tests are the reference's - but a ray makes one
+// dependent fetch per interior node it descends into instead of one per node it touches
+// (82 -> ~41 on the bench scene), and the two slab tests of a step are independent instructions.
+// ---------------------------------------------------------------------------------------------
+template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
+    __shared__ int2 sstack[SDEPTH][128];   // (child reference, tMin bits)
+    int2 lstack[64 - SDEPTH];              // entries beyond SDEPTH (rare: only passing far children are pushed)
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const unsigned n = pool.counts[traceQ];
+    enum { M_FETCH = 0, M_NODE = 1, M_LEAF = 2 };
+    enum { F_ANY = 1, F_FOUND = 2, F_EXHAUSTED = 4 };
+    int mode = M_FETCH;
+    int c = -1;
+    int flags = 0;
+    DRaySetup rs;
+    rs.o = rs.invDir = mk3(0, 0, 0);
+    rs.neg0 = rs.neg1 = rs.neg2 = 0;
+    rs.kx = rs.ky = rs.kz = 0;
+    rs.Sx = rs.Sy = rs.Sz = 0;
+    float tMax = 0;
+    int cur = 0, sp = 0, leafFirst = 0, leafN = 0;
+    // continue with child reference `ref`
+    auto enter = [&](int ref) {
+        if (ref < 0) {
+            leafFirst = ref & 0xffffff;
+            leafN = (ref >> 24) & 0x7f;
+            mode = M_LEAF;
+        } else {
+            cur = ref;
+            mode = M_NODE;
+        }
+    };
+    // pop far children until one still passes `tMin < tMax`; the ray is finished when none is left
+    auto popNext = [&]() {
+        mode = M_FETCH;
+        while (sp > 0) {
+            --sp;
+            int2 e = sp < SDEPTH ? sstack[sp][tid] : lstack[sp - SDEPTH];
+            if (__int_as_float(e.y) < tMax) {
+                enter(e.x);
+                break;
+            }
+        }
+    };
+    while (true) {
+        unsigned mNode = __ballot_sync(FULL, mode == M_NODE);
+        unsigned mLeaf = __ballot_sync(FULL, mode == M_LEAF);
+        unsigned mFetch = __ballot_sync(FULL, mode == M_FETCH && !((flags & F_EXHAUSTED) && c < 0));
+        int nNode = __popc(mNode), nLeaf = __popc(mLeaf), nFetch = __popc(mFetch);
+        int step;
+        if (nFetch >= FETCH_T || (nFetch > 0 && nNode == 0 && nLeaf == 0)) step = M_FETCH;
+        else if (nLeaf >= LEAF_T || (nLeaf > 0 && nNode == 0)) step = M_LEAF;
+        else if (nNode > 0) step = M_NODE;
+        else break;
+
+        if (step == M_NODE) {
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+                if (mode == M_NODE) {
+                    const float4 *w = &sc.wide[4 * (size_t)cur];
+                    float4 q0 = ldg4(w), q1 = ldg4(w + 1), q2 = ldg4(w + 2), q3 = ldg4(w + 3);
+                    float t0, t1;
+                    bool p0 = slabTestT(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, rs, tMax, &t0);
+                    bool p1 = slabTestT(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, rs, tMax, &t1);
+                    uint32_t meta = floatBits(q3.z);
+                    if (meta & WIDE_SINGLE) p1 = false;
+                    int axis = (int)(meta & 3u);
+                    int isNeg = axis == 0 ? rs.neg0 : (axis == 1 ? rs.neg1 : rs.neg2);
+                    int ref0 = asInt(q3.x), ref1 = asInt(q3.y);
+                    bool pn = isNeg ? p1 : p0, pf = isNeg ? p0 : p1;
+                    int rn = isNeg ? ref1 : ref0, rf = isNeg ? ref0 : ref1;
+                    float tf = isNeg ? t0 : t1;
+                    if (pn) {
+                        if (pf) {
+                            int2 e = make_int2(rf, __float_as_int(tf));
+                            if (sp < SDEPTH) sstack[sp][tid] = e;
+                            else lstack[sp - SDEPTH] = e;
+                            ++sp;
+                        }
+                        enter(rn);
+                    } else if (pf)
+                        enter(rf);
+                    else
+                        popNext();
+                }
+            }
+        } else if (step == M_LEAF) {
+            if (mode == M_LEAF) {
+                bool finished = false;
+                const bool any = (flags & F_ANY) != 0;
+                for (int i = 0; i < leafN; ++i) {
+                    const float4 *rec = &sc.leafPrims[3 * (size_t)(leafFirst + i)];
+                    float4 a = ldg4(rec), b = ldg4(rec + 1), c4 = ldg4(rec + 2);
+                    uint32_t pf = floatBits(b.w);
+                    float t, b0, b1, b2;
+                    if (triangleTest(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c4.x, c4.y, c4.z), rs, tMax, &t, &b0, &b1, &b2)) {
+                        if (any) { flags |= F_FOUND; finished = true; break; }
+                        if (pf & LEAF_DEGENERATE) continue;
+                        flags |= F_FOUND;
+                        tMax = t;
+                        __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(leafFirst + i), b0, b1, b2));
+                    }
+                }
+                leafN = 0;
+                if (finished) mode = M_FETCH;
+                else popNext();
+            }
+        } else {  // M_FETCH: flush finished rays, then take new ones
+            bool flush = mode == M_FETCH && c >= 0;
+            int state = LS_IDLE;
+            if (flush) {
+                WfCtx &cx = pool.ctx[c];
+                state = (flags & F_ANY) ? LS_SHADOW : __ldcs(&cx.ln.state);
+                __stcs(reinterpret_cast<float2 *>(&cx.tHit), make_float2(tMax, __int_as_float((flags & F_FOUND) ? 1 : 0)));
+            }
+            wfPush(pool.queue[WQ_SHADE], &pool.counts[WQ_SHADE], c, flush && state == LS_PATH);
+            wfPush(pool.queue[WQ_LIGHT], &pool.counts[WQ_LIGHT], c, flush && state != LS_PATH);
+            if (flush) c = -1;
+            bool want = mode == M_FETCH && !(flags & F_EXHAUSTED);
+            unsigned wantMask = __ballot_sync(FULL, want);
+            if (wantMask) {
+                int leader = __ffs(wantMask) - 1;
+                unsigned base = 0;
+                if (lane == leader) base = atomicAdd(&pool.counts[WQ_CURSOR], (unsigned)__popc(wantMask));
+                base = __shfl_sync(FULL, base, leader);
+                if (want) {
+                    unsigned i = base + __popc(wantMask & ((1u << lane) - 1u));
+                    if (i >= n)
+                        flags |= F_EXHAUSTED;
+                    else {
+                        c = pool.queue[traceQ][i];
+                        const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
+                        float4 ra = __ldcs(p), rb = __ldcs(p + 1);
+                        flags = (__float_as_int(ra.x) == LS_SHADOW) ? F_ANY : 0;
+                        rs = setupRay(mk3(ra.y, ra.z, ra.w), mk3(rb.x, rb.y, rb.z));
+                        tMax = rb.w;
+                        cur = 0;   // the pseudo node above the root
+                        sp = 0;
+                        leafN = 0;
+                        mode = M_NODE;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (Measured and dropped, round 1: a variant of k_wf_trace with TWO rays per lane - the active ray in
+// registers, a parked one in shared memory, swapped in whenever the active ray had to wait for a
+// leaf / fetch step.  It raised the node step from 17.5 to ~20 active lanes but paid 9 % of its
+// instructions for the swaps at 5 active lanes and squeezed L1 with the second stack: -9 % overall.)
+// ---------------------------------------------------------------------------------------------
 // ---------------------------------------------------------------------------------------------
 // laneAdvance for every context of one list.  SHADE = true: the shade list (path rays: the whole
 // vertex is evaluated); SHADE = false: the light list (shadow / MIS rays: a few adds and the next

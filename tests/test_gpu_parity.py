@@ -115,6 +115,38 @@ def test_traversal_counters_equal_the_reference_order(pb, port):
     film2, st2 = hs.render_rgbw()
     assert np.allclose(film, film2, rtol=1e-5, atol=1e-5)
     assert st2.regular_rays == st.regular_rays and st2.shadow_rays == st.shadow_rays
+    # ... and so does the tuned kernel over the 32-byte LinearBVHNode array (PB2_FLAG_LINEAR_NODES)
+    film3 = np.zeros((27, 48, 4), np.float32)
+    st3 = pb.Stats()
+    pb.check(pb.lib().pb2_render_path(dev, hs.camera, hs.film, hs.params_copy(flags=2), pb.ptr(film3), C.byref(st3)))
+    assert np.allclose(film, film3, rtol=1e-5, atol=1e-5)
+    assert st3.regular_rays == st.regular_rays and st3.shadow_rays == st.shadow_rays
+
+
+def test_stack_spill_of_the_two_child_kernel():
+    """PB2_TRACE=8 builds the two-child-record kernel with a 4-entry shared-memory stack, so nearly every ray
+    uses the local-memory spill; the film must equal the 32-byte-node kernel's (own process: the variant is read once)."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import ctypes as C, numpy as np, pbrt_v3_b200 as pb\n"
+        "pb.init()\n"
+        "hs = pb.HostScene.soup(20000, xres=64, yres=36, spp=4)\n"
+        "dev = hs.device_scene()\n"
+        "films = []\n"
+        "for flags in (0, 2):\n"
+        "    film = np.zeros((36, 64, 4), np.float32); st = pb.Stats()\n"
+        "    pb.check(pb.lib().pb2_render_path(dev, hs.camera, hs.film, hs.params_copy(flags=flags), pb.ptr(film), C.byref(st)))\n"
+        "    films.append(film)\n"
+        "assert films[0][..., 3].sum() > 0\n"
+        "assert np.allclose(films[0], films[1], rtol=1e-5, atol=1e-5), float(np.abs(films[0] - films[1]).max())\n"
+        "print('spill ok')\n"
+    )
+    env = dict(os.environ, PB2_TRACE="8")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "spill ok" in out.stdout, out.stdout + out.stderr
 
 
 def test_watertight_on_gpu(pb):
