@@ -157,7 +157,8 @@ def workload_config(args, parallelism):
                         "matte Kd .6, 2-triangle area light" % (args.tris, args.xres, args.yres, args.spp, args.maxdepth),
             "triangles": args.tris, "resolution": [args.xres, args.yres], "spp": args.spp, "maxdepth": args.maxdepth,
             "parallelism": parallelism,
-            "l2_note": "scene (BVH 61 MB + leaf records 48 MB) plus 0.5 GB of path contexts exceed the 126 MB L2; no explicit flush"}
+            "l2_note": "inputs larger than L2: every step streams the 1 GiB path-context pool and the 33 MB film through the 126 MB L2 "
+                       "next to the scene (BVH records 61 MB + leaf records 48 MB); no explicit flush"}
 
 
 def main():
