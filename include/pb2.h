@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 1
+#define PB2_ABI_VERSION 2   /* 2: pb2_scene_desc grew the object-instancing block at its end */
 
 typedef enum pb2_status {
     PB2_OK = 0,
@@ -52,7 +52,7 @@ typedef struct pb2_bvh_node {
     uint8_t pad;
 } pb2_bvh_node;
 
-enum { PB2_PRIM_TRIANGLE = 0, PB2_PRIM_SPHERE = 1 };
+enum { PB2_PRIM_TRIANGLE = 0, PB2_PRIM_SPHERE = 1, PB2_PRIM_INSTANCE = 2 };
 enum { PB2_MAT_NONE = 0, PB2_MAT_MATTE = 1, PB2_MAT_PLASTIC = 2 };
 enum { PB2_LIGHTDIST_UNIFORM = 0, PB2_LIGHTDIST_POWER = 1, PB2_LIGHTDIST_SPATIAL = 2 };
 
@@ -97,6 +97,24 @@ typedef struct pb2_light {
     int32_t pad[2];
 } pb2_light;
 
+/* One BVHAccel of the scene: bvhs[0] is Scene::aggregate, bvhs[k > 0] the accelerator that
+ * pbrtObjectInstance builds over the primitives of an instanced object (src/core/api.cpp:1565-1573).
+ * Node indices (secondChildOffset) and primitivesOffset values inside a BVH are LOCAL to it. */
+typedef struct pb2_bvh {
+    int64_t node_offset, n_nodes;   /* range in nodes[] */
+    int64_t prim_offset, n_prims;   /* range in bvh_prims[] */
+} pb2_bvh;
+
+/* TransformedPrimitive (src/core/primitive.cpp:69-96) with a static transform: an instance of an
+ * object.  Matrices are row-major 4x4: InstanceToWorld = the CTM at pbrtObjectInstance. */
+typedef struct pb2_instance {
+    float instance_to_world[16];
+    float world_to_instance[16];
+    int32_t bvh;        /* >= 1: bvhs[] entry of the object's accelerator; -1: the object is ONE primitive */
+    int32_t lone_prim;  /* bvh == -1: position in bvh_prims[] (past every BVH's range) of that primitive */
+    int32_t pad[2];
+} pb2_instance;
+
 typedef struct pb2_scene_desc {
     /* geometry */
     int64_t n_vertices;
@@ -131,6 +149,19 @@ typedef struct pb2_scene_desc {
 
     int32_t light_strategy;       /* PB2_LIGHTDIST_*; src/core/lightdistrib.cpp:48-66 */
     int32_t spatial_max_voxels;   /* 64, src/core/lightdistrib.h:104 */
+
+    /* Object instancing (optional; all zero / NULL for a scene without ObjectInstance).
+     * prim_type[i] == PB2_PRIM_INSTANCE: prim_index[i] = entry of instances[]; such primitives
+     * appear only in bvhs[0].  The scene-level primitives are numbered 0 .. bvhs[0].n_prims-1 in
+     * scene order; the GeometricPrimitives inside objects are ordinary entries of the prim_* arrays
+     * after them (object by object, creation order) and appear only in their object's BVH, or - for a
+     * one-primitive object - past all BVH ranges of bvh_prims.  With n_bvhs == 0 the arrays
+     * nodes[n_nodes] / bvh_prims[n_prims] are the one scene BVH as before. */
+    int32_t n_instances;
+    int32_t n_bvhs;
+    const pb2_instance *instances;
+    const pb2_bvh *bvhs;
+    int64_t n_bvh_prims;          /* length of bvh_prims when n_bvhs > 0 */
 } pb2_scene_desc;
 
 /* PerspectiveCamera (src/cameras/perspective.cpp:45-67, 95-144). */

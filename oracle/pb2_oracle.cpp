@@ -282,6 +282,30 @@ struct Xform {
         }
         return Ray(o, d, tMax);
     }
+    Bounds BoundsOp(const Bounds &b) const {  // transform.cpp:238-249
+        Bounds ret;
+        ret.pMin = ret.pMax = Point(Vec(b.pMin.x, b.pMin.y, b.pMin.z));
+        ret = Union(ret, Point(Vec(b.pMax.x, b.pMin.y, b.pMin.z)));
+        ret = Union(ret, Point(Vec(b.pMin.x, b.pMax.y, b.pMin.z)));
+        ret = Union(ret, Point(Vec(b.pMin.x, b.pMin.y, b.pMax.z)));
+        ret = Union(ret, Point(Vec(b.pMin.x, b.pMax.y, b.pMax.z)));
+        ret = Union(ret, Point(Vec(b.pMax.x, b.pMax.y, b.pMin.z)));
+        ret = Union(ret, Point(Vec(b.pMax.x, b.pMin.y, b.pMax.z)));
+        ret = Union(ret, Point(Vec(b.pMax.x, b.pMax.y, b.pMax.z)));
+        return ret;
+    }
+    bool IsIdentity() const {  // transform.h:137-143
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j)
+                if (m[i][j] != ((i == j) ? 1.f : 0.f)) return false;
+        return true;
+    }
+    Xform Inverse() const {
+        Xform t;
+        std::memcpy(t.m, mInv, sizeof(m));
+        std::memcpy(t.mInv, m, sizeof(m));
+        return t;
+    }
 };
 
 // ------------------------------------------------------------------ spectrum (src/core/spectrum.h, RGB)

@@ -99,7 +99,7 @@ class OracleScene:
         if not self.h:
             raise RuntimeError("oracle could not build the scene")
         self.n_lights = host_scene.desc.contents.n_lights
-        self.n_prims = host_scene.desc.contents.n_prims
+        self.n_prims = host_scene.bvh_range(0)[3]   # primitives of the scene-level BVH
 
     def __del__(self):
         try:

@@ -235,6 +235,7 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
     rs->lights.resize(d->n_lights);
     rs->prims.resize(d->n_prims);
     for (int64_t i = 0; i < d->n_prims; ++i) {
+        if (d->prim_type[i] == PB2_PRIM_INSTANCE) continue;   // TransformedPrimitives are made below
         std::shared_ptr<Shape> shape;
         if (d->prim_type[i] == PB2_PRIM_TRIANGLE) {
             int tri = d->prim_index[i];
@@ -257,7 +258,34 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
                              : split_method == 2 ? BVHAccel::SplitMethod::Middle
                              : split_method == 3 ? BVHAccel::SplitMethod::EqualCounts
                                                  : BVHAccel::SplitMethod::SAH;
-    rs->bvh = std::make_shared<BVHAccel>(rs->prims, max_prims_in_node > 0 ? max_prims_in_node : 4, sm);
+    const int maxPrims = max_prims_in_node > 0 ? max_prims_in_node : 4;
+    if (d->n_instances > 0) {
+        // Object instancing as pbrtObjectInstance does it (api.cpp:1547-1588): one accelerator per
+        // instanced object over its GeometricPrimitives in creation order (= ascending primitive
+        // number), or the lone primitive itself; one TransformedPrimitive per instance.
+        std::vector<std::shared_ptr<Primitive>> objectAccel(d->n_bvhs > 0 ? d->n_bvhs : 1);
+        for (int k = 1; k < d->n_bvhs; ++k) {
+            std::vector<int32_t> numbers(d->bvh_prims + d->bvhs[k].prim_offset, d->bvh_prims + d->bvhs[k].prim_offset + d->bvhs[k].n_prims);
+            std::sort(numbers.begin(), numbers.end());
+            std::vector<std::shared_ptr<Primitive>> objPrims;
+            for (int32_t n : numbers) objPrims.push_back(rs->prims[n]);
+            objectAccel[k] = std::make_shared<BVHAccel>(objPrims, maxPrims, sm);
+        }
+        for (int64_t i = 0; i < d->n_prims; ++i) {
+            if (d->prim_type[i] != PB2_PRIM_INSTANCE) continue;
+            const pb2_instance &pi = d->instances[d->prim_index[i]];
+            rs->transforms.emplace_back(new Transform(fromMatrices(pi.instance_to_world, pi.world_to_instance)));
+            const Transform *i2w = rs->transforms.back().get();
+            std::shared_ptr<Primitive> inner = pi.bvh >= 1 ? objectAccel[pi.bvh] : rs->prims[d->bvh_prims[pi.lone_prim]];
+            AnimatedTransform anim(i2w, 0, i2w, 1);
+            rs->prims[i] = std::make_shared<TransformedPrimitive>(inner, anim);
+            rs->primNumber[rs->prims[i].get()] = (int)i;
+        }
+        // Scene::aggregate is built over the scene-level primitives only: the first bvhs[0].n_prims numbers
+        std::vector<std::shared_ptr<Primitive>> top(rs->prims.begin(), rs->prims.begin() + d->bvhs[0].n_prims);
+        rs->bvh = std::make_shared<BVHAccel>(top, maxPrims, sm);
+    } else
+        rs->bvh = std::make_shared<BVHAccel>(rs->prims, maxPrims, sm);
     rs->scene.reset(new Scene(rs->bvh, rs->lights));
     return rs.release();
 }

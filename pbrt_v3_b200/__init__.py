@@ -24,7 +24,7 @@ c_int64_p = C.POINTER(C.c_int64)
 c_uint8_p = C.POINTER(C.c_uint8)
 
 PB2_OK, PB2_ERR_NO_DEVICE, PB2_ERR_CUDA, PB2_ERR_INVALID, PB2_ERR_UNSUPPORTED, PB2_ERR_NCCL = range(6)
-PB2_PRIM_TRIANGLE, PB2_PRIM_SPHERE = 0, 1
+PB2_PRIM_TRIANGLE, PB2_PRIM_SPHERE, PB2_PRIM_INSTANCE = 0, 1, 2
 PB2_LIGHTDIST_UNIFORM, PB2_LIGHTDIST_POWER, PB2_LIGHTDIST_SPATIAL = 0, 1, 2
 
 
@@ -56,6 +56,15 @@ class Light(C.Structure):
                 ("pad", C.c_int32 * 2)]
 
 
+class Bvh(C.Structure):
+    _fields_ = [("node_offset", C.c_int64), ("n_nodes", C.c_int64), ("prim_offset", C.c_int64), ("n_prims", C.c_int64)]
+
+
+class Instance(C.Structure):
+    _fields_ = [("instance_to_world", C.c_float * 16), ("world_to_instance", C.c_float * 16), ("bvh", C.c_int32),
+                ("lone_prim", C.c_int32), ("pad", C.c_int32 * 2)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [("n_vertices", C.c_int64), ("P", c_float_p), ("N", c_float_p), ("UV", c_float_p), ("S", c_float_p),
                 ("n_tris", C.c_int64), ("tri_index", c_int32_p), ("tri_mesh", c_int32_p),
@@ -66,7 +75,9 @@ class SceneDesc(C.Structure):
                 ("n_nodes", C.c_int64), ("nodes", C.POINTER(BvhNode)), ("bvh_prims", c_int32_p),
                 ("n_materials", C.c_int32), ("materials", C.POINTER(Material)),
                 ("n_lights", C.c_int32), ("lights", C.POINTER(Light)),
-                ("light_strategy", C.c_int32), ("spatial_max_voxels", C.c_int32)]
+                ("light_strategy", C.c_int32), ("spatial_max_voxels", C.c_int32),
+                ("n_instances", C.c_int32), ("n_bvhs", C.c_int32), ("instances", C.POINTER(Instance)),
+                ("bvhs", C.POINTER(Bvh)), ("n_bvh_prims", C.c_int64)]
 
 
 class Camera(C.Structure):
@@ -244,13 +255,24 @@ class HostScene:
         b = self.film.contents.cropped_pixel_bounds
         return (b[3] - b[1], b[2] - b[0])
 
-    def nodes(self):
+    def bvh_range(self, k=0):
+        """(node_offset, n_nodes, prim_offset, n_prims) of BVH k: 0 = the scene BVH, k >= 1 = an instanced object's."""
         d = self.desc.contents
-        return np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_uint8)), shape=(d.n_nodes * 32,)).view(NODE_DTYPE).copy()
+        if d.n_bvhs == 0:
+            return 0, d.n_nodes, 0, d.n_prims
+        b = d.bvhs[k]
+        return b.node_offset, b.n_nodes, b.prim_offset, b.n_prims
 
-    def bvh_prims(self):
+    def nodes(self, k=0):
         d = self.desc.contents
-        return np.ctypeslib.as_array(d.bvh_prims, shape=(d.n_prims,)).copy()
+        no, nn, _, _ = self.bvh_range(k)
+        return np.ctypeslib.as_array(C.cast(d.nodes, C.POINTER(C.c_uint8)), shape=(d.n_nodes * 32,)).view(NODE_DTYPE)[no:no + nn].copy()
+
+    def bvh_prims(self, k=0):
+        d = self.desc.contents
+        _, _, po, pn = self.bvh_range(k)
+        total = d.n_bvh_prims if d.n_bvhs > 0 else d.n_prims
+        return np.ctypeslib.as_array(d.bvh_prims, shape=(total,))[po:po + pn].copy()
 
     # device side
     def device_scene(self):

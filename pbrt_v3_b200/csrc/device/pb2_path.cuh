@@ -236,6 +236,7 @@ PB2_HD bool traceLane(const DScene &sc, const DLane &ln, float *tMax, DHit *hit,
     *tMax = ln.ray.tMax;
     hit->leaf = -1;
     hit->b0 = hit->b1 = hit->b2 = 0;
+    hit->inst = -1;
     return traverseAnyOrClosest(sc, ln.ray, ln.state == LS_SHADOW, tMax, hit, ctr);
 }
 

@@ -34,6 +34,7 @@ enum : uint32_t {
     LEAF_DEGENERATE = 2u,     // Triangle::Intersect rejects every hit (triangle.cpp:308-314); IntersectP does not
     LEAF_FLIP = 4u,           // reverseOrientation ^ transformSwapsHandedness of the triangle's mesh
     LEAF_ATTR = 8u,           // the mesh has per-vertex N, S or UV: shading must go through the index buffer
+    LEAF_INSTANCE = 16u,      // record describes a TransformedPrimitive: c.w = instance number
 };
 enum : uint32_t {
     WIDE_LEAF = 0x80000000u,  // child reference: bits 0-23 primitivesOffset, bits 24-30 nPrimitives
@@ -48,6 +49,15 @@ struct DLightDist {
     V3 boundsMin, boundsMax;  // Scene::WorldBound()
     const float *table;       // uniform/power: one record; spatial: one record per voxel
     int stride;               // floats per record: nLights func, nLights+1 cdf, 1 funcInt
+};
+
+// TransformedPrimitive with a static transform (pb2_instance).
+struct DInstance {
+    M44 i2w, w2i;
+    int root;       // global index of the object BVH's root node, or -1
+    int lone;       // root < 0: leaf record of the object's only primitive
+    int identity;   // Transform::IsIdentity(): the interaction is then not transformed (primitive.cpp:85-86)
+    int pad;
 };
 
 struct DScene {
@@ -65,6 +75,8 @@ struct DScene {
     const pb2_material *materials;
     const pb2_light *lights;
     int nLights;
+    const DInstance *instances;   // nullptr: no object instancing in this scene
+    int nInstances;
     DLightDist lightDist;
 };
 
@@ -77,6 +89,7 @@ struct DRay {
 struct DHit {
     int leaf;       // index into leafPrims (BVH order), -1 = miss
     float b0, b1, b2;
+    int inst;       // instance the hit primitive was reached through, -1 = none
 };
 
 // Device analogue of the reference's STAT_COUNTERs around bvh.cpp:672/677/710/714: nodes fetched and
@@ -240,19 +253,88 @@ PB2_HD int asInt(float f) { return (int)floatBits(f); }
 struct SphereHit;  // pb2_sphere.cuh
 PB2_HDN bool sphereLeafTest(const DScene &sc, int sphereIndex, const DRay &ray, float rayTMax, float *tHit, float *phi);
 
+// Transform::operator()(const Ray &) (transform.h:251-264): the ray in the space of `t`, its origin
+// moved along d to the edge of the transformed origin's error box and tMax shortened by the same dt.
+PB2_HD DRay xfRay(const M44 &t, const DRay &r, float tMax) {
+    V3 oError;
+    V3 o = xfPointErr(t, r.o, &oError);
+    V3 d = xfVector(t, r.d);
+    float lengthSq = lengthSquared(d);
+    if (lengthSq > 0) {
+        float dt = dot(vabs(d), oError) / lengthSq;
+        o = o + d * dt;
+        tMax -= dt;
+    }
+    DRay out;
+    out.o = o;
+    out.d = d;
+    out.tMax = tMax;
+    return out;
+}
+
+template <int LEVEL>
+PB2_HD bool traverseLevel(const DScene &sc, int root, const DRay &ray, const DRaySetup &rs, const bool ANY, float *tMaxInOut,
+                          DHit *hit, DCounters *ctr, int instId);
+
+// One primitive of a leaf (GeometricPrimitive::Intersect[P], primitive.cpp:112-130; LEVEL 0 also
+// TransformedPrimitive::Intersect[P], primitive.cpp:76-96).  Returns true when the primitive was
+// hit within tMax: for ANY the caller stops, otherwise *tMax and *hit are the new closest hit.
+template <int LEVEL>
+PB2_HD bool testLeafRecord(const DScene &sc, int recIndex, const DRay &ray, const DRaySetup &rs, const bool ANY, float *tMax,
+                           DHit *hit, DCounters *ctr, int instId) {
+    const float4 *rec = &sc.leafPrims[3 * (size_t)recIndex];
+    float4 a = ldg4(rec), b = ldg4(rec + 1), c = ldg4(rec + 2);
+    PB2_COUNT_PRIM(ctr);
+    uint32_t flags = floatBits(b.w);
+    if (flags & LEAF_SPHERE) {
+        float t, phi;
+        if (!sphereLeafTest(sc, asInt(c.w), ray, *tMax, &t, &phi)) return false;
+        if (ANY) return true;
+        *tMax = t;
+        hit->leaf = recIndex;
+        hit->b0 = phi;
+        hit->b1 = hit->b2 = 0;
+        hit->inst = instId;
+        return true;
+    }
+    if (flags & LEAF_INSTANCE) {
+        if (LEVEL != 0) return false;   // pbrtObjectInstance inside an object definition is an error (api.cpp:1554-1557)
+        const int id = asInt(c.w);
+        const DInstance &inst = sc.instances[id];
+        DRay r2 = xfRay(inst.w2i, ray, *tMax);
+        DRaySetup rs2 = setupRay(r2.o, r2.d);
+        float t2 = r2.tMax;
+        bool f = inst.root >= 0 ? traverseLevel<1>(sc, inst.root, r2, rs2, ANY, &t2, hit, ctr, id)
+                                : testLeafRecord<1>(sc, inst.lone, r2, rs2, ANY, &t2, hit, nullptr, id);   // counted once, above
+        if (!f) return false;
+        *tMax = t2;                      // r.tMax = ray.tMax (primitive.cpp:83)
+        return true;
+    }
+    float t, b0, b1, b2;
+    if (!triangleTest(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), rs, *tMax, &t, &b0, &b1, &b2)) return false;
+    if (ANY) return true;
+    if (flags & LEAF_DEGENERATE) return false;
+    *tMax = t;
+    hit->leaf = recIndex;
+    hit->b0 = b0;
+    hit->b1 = b1;
+    hit->b2 = b2;
+    hit->inst = instId;
+    return true;
+}
+
 // BVHAccel::Intersect (ANY=false, bvh.cpp:662-700) and IntersectP (ANY=true, bvh.cpp:702-738):
 // depth-first, near child first by dirIsNeg[axis], explicit stack of far children, every primitive
 // of a reached leaf tested, closest hit shrinks tMax.  Node visit order and the set of primitive
 // tests are exactly the reference's, so device counters equal the instrumented reference's.
-PB2_HD bool traverseAnyOrClosest(const DScene &sc, const DRay &ray, const bool ANY, float *tMaxInOut, DHit *hit,
-                                 DCounters *ctr) {
+template <int LEVEL>
+PB2_HD bool traverseLevel(const DScene &sc, int root, const DRay &ray, const DRaySetup &rs, const bool ANY, float *tMaxInOut,
+                          DHit *hit, DCounters *ctr, int instId) {
     (void)ctr;
-    if (sc.nNodes == 0) return false;
-    DRaySetup rs = setupRay(ray.o, ray.d);
     float tMax = *tMaxInOut;
     bool found = false;
     int stack[64];
-    int sp = 0, cur = 0;
+    int sp = 0, cur = root;
     while (true) {
         float4 n0 = ldg4(&sc.nodes[2 * (size_t)cur]);
         float4 n1 = ldg4(&sc.nodes[2 * (size_t)cur + 1]);
@@ -264,32 +346,9 @@ PB2_HD bool traverseAnyOrClosest(const DScene &sc, const DRay &ray, const bool A
             if (nPrims > 0) {
                 int first = asInt(n1.z);
                 for (int i = 0; i < nPrims; ++i) {
-                    const float4 *rec = &sc.leafPrims[3 * (size_t)(first + i)];
-                    float4 a = ldg4(rec), b = ldg4(rec + 1), c = ldg4(rec + 2);
-                    PB2_COUNT_PRIM(ctr);
-                    uint32_t flags = floatBits(b.w);
-                    if (flags & LEAF_SPHERE) {
-                        float t, phi;
-                        if (sphereLeafTest(sc, asInt(c.w), ray, tMax, &t, &phi)) {
-                            if (ANY) return true;
-                            tMax = t;
-                            found = true;
-                            hit->leaf = first + i;
-                            hit->b0 = phi;
-                            hit->b1 = hit->b2 = 0;
-                        }
-                        continue;
-                    }
-                    float t, b0, b1, b2;
-                    if (triangleTest(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), rs, tMax, &t, &b0, &b1, &b2)) {
+                    if (testLeafRecord<LEVEL>(sc, first + i, ray, rs, ANY, &tMax, hit, ctr, instId)) {
                         if (ANY) return true;
-                        if (flags & LEAF_DEGENERATE) continue;
-                        tMax = t;
                         found = true;
-                        hit->leaf = first + i;
-                        hit->b0 = b0;
-                        hit->b1 = b1;
-                        hit->b2 = b2;
                     }
                 }
             } else {
@@ -313,6 +372,14 @@ PB2_HD bool traverseAnyOrClosest(const DScene &sc, const DRay &ray, const bool A
     }
     *tMaxInOut = tMax;
     return found;
+}
+
+// Scene::Intersect / IntersectP (scene.cpp:45-55)
+PB2_HD bool traverseAnyOrClosest(const DScene &sc, const DRay &ray, const bool ANY, float *tMaxInOut, DHit *hit,
+                                 DCounters *ctr) {
+    if (sc.nNodes == 0) return false;
+    DRaySetup rs = setupRay(ray.o, ray.d);
+    return traverseLevel<0>(sc, 0, ray, rs, ANY, tMaxInOut, hit, ctr, -1);
 }
 
 template <bool ANY>

@@ -175,15 +175,37 @@ namespace pb2 {
 // SPH = false compiles the sphere branches away (scenes without spheres get kernels without the
 // interval-arithmetic code and its call frames).
 // *light receives the area-light number of the primitive that was hit (-1: not emissive).
+// A hit inside an instanced object was found with the ray in instance space (hit.inst >= 0): the
+// interaction is built there and then taken to world space as TransformedPrimitive::Intersect does
+// with Transform::operator()(const SurfaceInteraction &) (primitive.cpp:85-86, transform.cpp:262-297).
 template <bool SPH = true>
 PB2_HD DInteraction hitInteraction(const DScene &sc, const DHit &hit, const DRay &ray, float tHit, int *light = nullptr) {
     TriRec rec = loadTriRec(sc.leafPrims, (size_t)hit.leaf);
+    const DInstance *inst = nullptr;
+    DRay r = ray;
+    if (hit.inst >= 0 && sc.instances) {
+        inst = &sc.instances[hit.inst];
+        r = xfRay(inst->w2i, ray, ray.tMax);
+    }
+    DInteraction it;
     if (SPH && (rec.flags & LEAF_SPHERE)) {
         if (light) *light = sc.primLight[rec.prim];
-        return sphereInteraction(sc, rec.prim, ray, tHit, hit.b0);
+        it = sphereInteraction(sc, rec.prim, r, tHit, hit.b0);
+    } else {
+        if (light) *light = rec.light;
+        it = triangleInteraction(sc, rec, hit.b0, hit.b1, hit.b2, r.d);
     }
-    if (light) *light = rec.light;
-    return triangleInteraction(sc, rec, hit.b0, hit.b1, hit.b2, ray.d);
+    if (inst && !inst->identity) {
+        V3 pError;
+        it.p = xfPointErrIn(inst->i2w, it.p, it.pError, &pError);
+        it.pError = pError;
+        it.n = normalize(xfNormalInv(inst->w2i, it.n));
+        it.wo = normalize(xfVector(inst->i2w, it.wo));
+        it.ns = normalize(xfNormalInv(inst->w2i, it.ns));
+        it.dpdus = xfVector(inst->i2w, it.dpdus);
+        it.ns = faceforward(it.ns, it.n);
+    }
+    return it;
 }
 
 // Interaction::SpawnRay (interaction.h:64-67)

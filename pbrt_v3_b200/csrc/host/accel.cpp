@@ -219,17 +219,64 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
     std::vector<char> lightSeen(lights.size(), 0);
     bool anyN = false, anyUV = false, anyS = false;
 
-    size_t nPrims = bvh.sceneOrderPrims.size();
+    // Primitive numbering: the scene-level primitives in scene order (GeometricPrimitives and
+    // TransformedPrimitives), then the GeometricPrimitives of every distinct instanced object.
+    std::vector<const Primitive *> &objs = fs->primObjects;
+    for (const auto &p : bvh.sceneOrderPrims) objs.push_back(p.get());
+    const size_t nTop = objs.size();
+    struct ObjectInfo { int bvh; int32_t loneNumber; };
+    std::unordered_map<const Primitive *, ObjectInfo> objects;
+    std::vector<const BVHAccel *> objectBvhs;
+    std::vector<size_t> objectBase;
+    for (size_t i = 0; i < nTop; ++i) {
+        const TransformedPrimitive *tp = dynamic_cast<const TransformedPrimitive *>(objs[i]);
+        if (!tp) continue;
+        const Primitive *inner = tp->primitive.get();
+        if (objects.count(inner)) continue;
+        if (const BVHAccel *ob = dynamic_cast<const BVHAccel *>(inner)) {
+            objects[inner] = ObjectInfo{(int)objectBvhs.size() + 1, -1};
+            objectBvhs.push_back(ob);
+            objectBase.push_back(objs.size());
+            for (const auto &p : ob->sceneOrderPrims) objs.push_back(p.get());
+        } else if (dynamic_cast<const GeometricPrimitive *>(inner)) {
+            objects[inner] = ObjectInfo{-1, (int32_t)objs.size()};
+            objs.push_back(inner);
+        } else {
+            Error("An instanced object must be a GeometricPrimitive or a BVHAccel over GeometricPrimitives");
+            return nullptr;
+        }
+    }
+    size_t nPrims = objs.size();
     fs->primType.resize(nPrims);
     fs->primIndex.resize(nPrims);
     fs->primMaterial.resize(nPrims);
     fs->primLight.resize(nPrims);
     for (size_t i = 0; i < nPrims; ++i) {
-        const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>(bvh.sceneOrderPrims[i].get());
+        if (const TransformedPrimitive *tp = dynamic_cast<const TransformedPrimitive *>(objs[i])) {
+            if (i >= nTop) {
+                Error("Instances inside an instanced object are not allowed (api.cpp:1554-1557)");
+                return nullptr;
+            }
+            pb2_instance inst;
+            std::memset(&inst, 0, sizeof(inst));
+            copyMatrix(tp->PrimitiveToWorld.GetMatrix(), inst.instance_to_world);
+            copyMatrix(tp->PrimitiveToWorld.GetInverseMatrix(), inst.world_to_instance);
+            const ObjectInfo &oi = objects[tp->primitive.get()];
+            inst.bvh = oi.bvh;
+            inst.lone_prim = oi.loneNumber;   // primitive number for now; becomes its bvh_prims position below
+            fs->primType[i] = PB2_PRIM_INSTANCE;
+            fs->primIndex[i] = (int32_t)fs->instances.size();
+            fs->primMaterial[i] = -1;
+            fs->primLight[i] = -1;
+            fs->instances.push_back(inst);
+            continue;
+        }
+        const GeometricPrimitive *gp = dynamic_cast<const GeometricPrimitive *>(objs[i]);
         if (!gp) {
-            Error("Only GeometricPrimitives are supported below the top-level BVH (object instancing: SURVEY.md §8 a19)");
+            Error("Only GeometricPrimitives and TransformedPrimitives are supported below the scene BVH");
             return nullptr;
         }
+        const bool insideObject = i >= nTop;
         // material
         int mid = -1;
         if (gp->material) {
@@ -244,7 +291,12 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
         fs->primMaterial[i] = mid;
         // light
         int lid = -1;
-        if (gp->areaLight) {
+        if (gp->areaLight && insideObject) {
+            // The reference warns "Area lights not supported with object instancing" (api.cpp:1408-1409) and
+            // leaves the light out of Scene::lights; the primitive would still emit when seen directly.  That
+            // unsampled emission is not carried to the device.
+            Warning("Emission of an area light inside an instanced object is ignored on the GPU path");
+        } else if (gp->areaLight) {
             auto it = lightIds.find(gp->areaLight.get());
             if (it == lightIds.end()) {
                 Error("Primitive's area light is not in the scene's light list");
@@ -349,6 +401,37 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
     d.n_nodes = (int64_t)bvh.nodes.size();
     d.nodes = bvh.nodes.data();
     d.bvh_prims = bvh.orderedPrimNumbers.data();
+    if (!fs->instances.empty()) {
+        // every BVH's nodes / ordered primitive numbers, scene BVH first; indices stay local to each BVH
+        fs->nodes = bvh.nodes;
+        fs->bvhPrims = bvh.orderedPrimNumbers;
+        fs->bvhs.push_back(pb2_bvh{0, (int64_t)bvh.nodes.size(), 0, (int64_t)bvh.orderedPrimNumbers.size()});
+        for (size_t k = 0; k < objectBvhs.size(); ++k) {
+            const BVHAccel *ob = objectBvhs[k];
+            fs->bvhs.push_back(pb2_bvh{(int64_t)fs->nodes.size(), (int64_t)ob->nodes.size(), (int64_t)fs->bvhPrims.size(),
+                                       (int64_t)ob->orderedPrimNumbers.size()});
+            fs->nodes.insert(fs->nodes.end(), ob->nodes.begin(), ob->nodes.end());
+            for (int32_t n : ob->orderedPrimNumbers) fs->bvhPrims.push_back((int32_t)(objectBase[k] + n));
+        }
+        std::unordered_map<int32_t, int32_t> lonePosition;   // primitive number -> position in bvh_prims
+        for (pb2_instance &inst : fs->instances) {
+            if (inst.bvh >= 0) continue;
+            auto it = lonePosition.find(inst.lone_prim);
+            if (it == lonePosition.end()) {
+                it = lonePosition.emplace(inst.lone_prim, (int32_t)fs->bvhPrims.size()).first;
+                fs->bvhPrims.push_back(inst.lone_prim);
+            }
+            inst.lone_prim = it->second;
+        }
+        d.n_nodes = (int64_t)fs->nodes.size();
+        d.nodes = fs->nodes.data();
+        d.bvh_prims = fs->bvhPrims.data();
+        d.n_bvh_prims = (int64_t)fs->bvhPrims.size();
+        d.n_bvhs = (int32_t)fs->bvhs.size();
+        d.bvhs = fs->bvhs.data();
+        d.n_instances = (int32_t)fs->instances.size();
+        d.instances = fs->instances.data();
+    }
     d.n_materials = (int32_t)fs->materials.size();
     d.materials = fs->materials.data();
     d.n_lights = (int32_t)fs->lights.size();

@@ -54,7 +54,9 @@ struct RenderOptions {
     Transform CameraToWorld;
     std::vector<std::shared_ptr<Light>> lights;
     std::vector<std::shared_ptr<Primitive>> primitives;
-    bool inInstance = false;
+    // object instancing (api.cpp:181-183)
+    std::map<std::string, std::vector<std::shared_ptr<Primitive>>> instances;
+    std::vector<std::shared_ptr<Primitive>> *currentInstance = nullptr;
 };
 
 Transform curTransform;
@@ -355,8 +357,56 @@ void pbrtShape(const std::string &name, const ParamSet &params) {
         prims.push_back(std::make_shared<GeometricPrimitive>(s, mtl, area));
     }
     graphicsState.areaLightParams.ReportUnused();
-    renderOptions->primitives.insert(renderOptions->primitives.end(), prims.begin(), prims.end());
-    renderOptions->lights.insert(renderOptions->lights.end(), areaLights.begin(), areaLights.end());
+    // Add prims and areaLights to scene or current instance (api.cpp:1406-1419)
+    if (renderOptions->currentInstance) {
+        if (areaLights.size()) Warning("Area lights not supported with object instancing");
+        renderOptions->currentInstance->insert(renderOptions->currentInstance->end(), prims.begin(), prims.end());
+    } else {
+        renderOptions->primitives.insert(renderOptions->primitives.end(), prims.begin(), prims.end());
+        renderOptions->lights.insert(renderOptions->lights.end(), areaLights.begin(), areaLights.end());
+    }
+}
+
+// api.cpp:1520-1543
+void pbrtObjectBegin(const std::string &name) {
+    if (!verifyWorld("ObjectBegin")) return;
+    pbrtAttributeBegin();
+    if (renderOptions->currentInstance) Error("ObjectBegin called inside of instance definition");
+    renderOptions->instances[name] = std::vector<std::shared_ptr<Primitive>>();
+    renderOptions->currentInstance = &renderOptions->instances[name];
+}
+void pbrtObjectEnd() {
+    if (!verifyWorld("ObjectEnd")) return;
+    if (!renderOptions->currentInstance) Error("ObjectEnd called outside of instance definition");
+    renderOptions->currentInstance = nullptr;
+    pbrtAttributeEnd();
+}
+// api.cpp:1547-1588.  The instance transform is static here (no ActiveTransform / TransformTimes on this path).
+void pbrtObjectInstance(const std::string &name) {
+    if (!verifyWorld("ObjectInstance")) return;
+    if (renderOptions->currentInstance) {
+        Error("ObjectInstance can't be called inside instance definition");
+        return;
+    }
+    if (renderOptions->instances.find(name) == renderOptions->instances.end()) {
+        Error("Unable to find instance named \"%s\"", name.c_str());
+        return;
+    }
+    std::vector<std::shared_ptr<Primitive>> &in = renderOptions->instances[name];
+    if (in.empty()) return;
+    if (in.size() > 1) {
+        // Create aggregate for instance Primitives
+        std::shared_ptr<Primitive> accel;
+        if (renderOptions->AcceleratorName == "bvh")
+            accel = CreateBVHAccelerator(std::move(in), renderOptions->AcceleratorParams);
+        else {
+            Error("Accelerator \"%s\" is outside the GPU path's scope (bvh). Using \"bvh\".", renderOptions->AcceleratorName.c_str());
+            accel = std::make_shared<BVHAccel>(std::move(in));
+        }
+        in.clear();
+        in.push_back(accel);
+    }
+    renderOptions->primitives.push_back(std::make_shared<TransformedPrimitive>(in[0], *internTransform(curTransform)));
 }
 
 RenderSetup *pbrtLastSetup() { return lastSetup.get(); }
@@ -701,12 +751,14 @@ struct Parser {
                 if (!fn.empty() && fn[0] != '/' && !g_sceneDirectory.empty()) fn = g_sceneDirectory + "/" + fn;
                 pushFile(fn);
             }
-            else if (tok == "LightSource" || tok == "Texture" || tok == "ObjectBegin" || tok == "ObjectInstance" ||
-                     tok == "MakeNamedMedium" || tok == "MediumInterface") {
+            else if (tok == "ObjectBegin") pbrtObjectBegin(requireString());
+            else if (tok == "ObjectEnd") pbrtObjectEnd();
+            else if (tok == "ObjectInstance") pbrtObjectInstance(requireString());
+            else if (tok == "LightSource" || tok == "Texture" || tok == "MakeNamedMedium" || tok == "MediumInterface") {
                 // directives of the reference that lead outside this path (SURVEY.md §2 rows 15,33,42; §8 a19)
                 Error("%s:%d: directive \"%s\" is outside the GPU path's scope; skipped", cur().filename.c_str(), cur().line, tok.c_str());
                 std::string n;
-                if (tok != "ObjectInstance" && tok != "ObjectBegin" && tok != "MediumInterface") {
+                if (tok != "MediumInterface") {
                     requireString();
                     if (tok == "Texture") { requireString(); requireString(); }
                     parseParams();
@@ -717,7 +769,7 @@ struct Parser {
                     }
                 }
             }
-            else if (tok == "ObjectEnd" || tok == "ActiveTransform" || tok == "TransformTimes") {
+            else if (tok == "ActiveTransform" || tok == "TransformTimes") {
                 Error("%s:%d: directive \"%s\" is outside the GPU path's scope; skipped", cur().filename.c_str(), cur().line, tok.c_str());
                 if (tok == "ActiveTransform") nextToken(&tok);
                 if (tok == "TransformTimes") { requireNumber(); requireNumber(); }

@@ -43,6 +43,9 @@ void pbrtMakeNamedMaterial(const std::string &name, const ParamSet &params);
 void pbrtNamedMaterial(const std::string &name);
 void pbrtAreaLightSource(const std::string &name, const ParamSet &params);
 void pbrtShape(const std::string &name, const ParamSet &params);
+void pbrtObjectBegin(const std::string &name);
+void pbrtObjectEnd();
+void pbrtObjectInstance(const std::string &name);
 void pbrtReverseOrientation();
 void pbrtWorldEnd();
 

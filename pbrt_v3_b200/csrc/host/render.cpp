@@ -357,7 +357,7 @@ std::shared_ptr<DeviceScene> GetDeviceScene(const BVHAccel &bvh, const std::vect
     return ds;
 }
 
-static void fillInteraction(const pb2_hit &h, const BVHAccel &bvh, const Ray &ray, SurfaceInteraction *isect) {
+static void fillInteraction(const pb2_hit &h, const FlatScene &flat, const Ray &ray, SurfaceInteraction *isect) {
     isect->p = Point3f(h.p[0], h.p[1], h.p[2]);
     isect->pError = Vector3f(h.p_error[0], h.p_error[1], h.p_error[2]);
     isect->n = Normal3f(h.n[0], h.n[1], h.n[2]);
@@ -366,7 +366,7 @@ static void fillInteraction(const pb2_hit &h, const BVHAccel &bvh, const Ray &ra
     isect->uv = Point2f(h.uv[0], h.uv[1]);
     isect->wo = Normalize(-ray.d);
     for (int k = 0; k < 3; ++k) isect->b[k] = h.b[k];
-    isect->primitive = bvh.sceneOrderPrims[h.prim].get();
+    isect->primitive = flat.primObjects[h.prim];   // the GeometricPrimitive, also for a hit inside an instance
 }
 
 bool BVHAccel::Intersect(const Ray &ray, SurfaceInteraction *isect) const {
@@ -382,7 +382,7 @@ bool BVHAccel::Intersect(const Ray &ray, SurfaceInteraction *isect) const {
     }
     if (h.prim < 0) return false;
     ray.tMax = h.t;
-    fillInteraction(h, *this, ray, isect);
+    fillInteraction(h, *ds->flat, ray, isect);
     return true;
 }
 
@@ -437,6 +437,19 @@ bool GeometricPrimitive::Intersect(const Ray &r, SurfaceInteraction *isect) cons
     return true;
 }
 bool GeometricPrimitive::IntersectP(const Ray &r) const { return shape->IntersectP(r); }
+
+// TransformedPrimitive::Intersect[P] (primitive.cpp:76-96) run on the device like everything else:
+// a one-primitive aggregate holding a copy of this instance.
+bool TransformedPrimitive::Intersect(const Ray &r, SurfaceInteraction *isect) const {
+    if (!single)
+        single = std::make_shared<BVHAccel>(std::vector<std::shared_ptr<Primitive>>{std::make_shared<TransformedPrimitive>(primitive, PrimitiveToWorld)});
+    return single->Intersect(r, isect);
+}
+bool TransformedPrimitive::IntersectP(const Ray &r) const {
+    if (!single)
+        single = std::make_shared<BVHAccel>(std::vector<std::shared_ptr<Primitive>>{std::make_shared<TransformedPrimitive>(primitive, PrimitiveToWorld)});
+    return single->IntersectP(r);
+}
 
 // ---------------------------------------------------------------- PathIntegrator
 void PathIntegrator::Preprocess(const Scene &, Sampler &) {}

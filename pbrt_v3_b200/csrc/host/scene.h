@@ -185,6 +185,24 @@ class GeometricPrimitive : public Primitive {
     std::shared_ptr<AreaLight> areaLight;
 };
 
+// primitive.h:93-116 with a static transform (the reference holds an AnimatedTransform; animated
+// instance transforms are outside this path and refused by pbrtObjectInstance).
+class BVHAccel;
+class TransformedPrimitive : public Primitive {
+  public:
+    TransformedPrimitive(std::shared_ptr<Primitive> primitive, const Transform &PrimitiveToWorld)
+        : primitive(std::move(primitive)), PrimitiveToWorld(PrimitiveToWorld) {}
+    Bounds3f WorldBound() const override { return PrimitiveToWorld(primitive->WorldBound()); }  // MotionBounds, not animated
+    bool Intersect(const Ray &r, SurfaceInteraction *isect) const override;
+    bool IntersectP(const Ray &r) const override;
+    const AreaLight *GetAreaLight() const override { return nullptr; }
+    const Material *GetMaterial() const override { return nullptr; }
+    std::shared_ptr<Primitive> primitive;
+    const Transform PrimitiveToWorld;
+  private:
+    mutable std::shared_ptr<BVHAccel> single;  // one-primitive aggregate behind the direct Intersect calls
+};
+
 class Aggregate : public Primitive {
   public:
     const AreaLight *GetAreaLight() const override;
@@ -237,6 +255,12 @@ struct FlatScene {
     std::vector<int32_t> primIndex, primMaterial, primLight;
     std::vector<pb2_material> materials;
     std::vector<pb2_light> lights;
+    // object instancing: every BVH's nodes / ordered primitive numbers concatenated (scene BVH first)
+    std::vector<pb2_bvh_node> nodes;
+    std::vector<int32_t> bvhPrims;
+    std::vector<pb2_bvh> bvhs;
+    std::vector<pb2_instance> instances;
+    std::vector<const Primitive *> primObjects;   // primitive number -> object (GeometricPrimitive or TransformedPrimitive)
 };
 std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<std::shared_ptr<Light>> &lights,
                                         const std::string &lightStrategy);

@@ -206,6 +206,10 @@ __global__ void k_build_leaf_records(DScene sc, const int32_t *prims, int64_t n,
         a = make_float4(0, 0, 0, __int_as_float(prim));
         b = make_float4(0, 0, 0, __uint_as_float(LEAF_SPHERE));
         c = make_float4(0, 0, 0, __int_as_float(sc.primIndex[prim]));
+    } else if (sc.primType[prim] == PB2_PRIM_INSTANCE) {
+        a = make_float4(0, 0, 0, __int_as_float(prim));
+        b = make_float4(0, 0, 0, __uint_as_float(LEAF_INSTANCE));
+        c = make_float4(0, 0, 0, __int_as_float(sc.primIndex[prim]));
     } else {
         int tri = sc.primIndex[prim];
         TriVerts t = triVerts(sc, tri);
@@ -250,6 +254,7 @@ __global__ void k_intersect(DScene sc, const pb2_ray *rays, int64_t n, pb2_hit *
     DHit h;
     h.leaf = -1;
     h.b0 = h.b1 = h.b2 = 0;
+    h.inst = -1;
     float tMax = r.tMax;
     bool found = traverse<false>(sc, r, &tMax, &h, nullptr);
     pb2_hit out;
@@ -278,6 +283,8 @@ __global__ void k_intersect_p(DScene sc, const pb2_ray *rays, int64_t n, uint8_t
     r.d = mk3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
     r.tMax = rays[i].t_max;
     DHit h;
+    h.leaf = -1;
+    h.inst = -1;
     float tMax = r.tMax;
     occluded[i] = traverse<true>(sc, r, &tMax, &h, nullptr) ? 1 : 0;
 }
@@ -483,6 +490,9 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     // spheres, or beyond the record limits, the 32-B-node kernel (shared-memory stack of 32, local
     // spill beyond).  PB2_TRACE selects tuning variants for experiments.
     const bool spheres = scene->d.spheres != nullptr;
+    // scenes with object instances (TransformedPrimitive, two BVH levels) are traced by the plain
+    // one-thread-per-ray kernel for now; the tuned kernels know triangles and spheres only
+    const bool instanced = scene->d.instances != nullptr;
     static const int variant = envInt("PB2_TRACE", 0);
     TraceKernel trace;
     if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
@@ -546,6 +556,7 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
             CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents], stream));
         }
         if (countTraversal) k_wf_trace_plain<true><<<blocks128, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
+        else if (instanced) k_wf_trace_plain<false><<<blocks128, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
         else trace<<<persistentBlocks, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur);
         if (timeTrace) {
             CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents + 1], stream));
@@ -664,31 +675,94 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
     sc.nLights = d->n_lights;
     s->nPrims = d->n_prims;
     s->nLights = d->n_lights;
-    {
+    // the scene's BVHs: one, or the scene BVH followed by one per instanced object
+    std::vector<pb2_bvh> bvhs;
+    int64_t nBvhPrims = d->n_prims;
+    if (d->n_bvhs >= 1) {
+        if (!d->bvhs) return setError(PB2_ERR_INVALID, "n_bvhs > 0 but bvhs is null");
+        bvhs.assign(d->bvhs, d->bvhs + d->n_bvhs);
+        nBvhPrims = d->n_bvh_prims;
+        if (nBvhPrims <= 0 || nBvhPrims > d->n_prims) return setError(PB2_ERR_INVALID, "bad n_bvh_prims");
+    } else
+        bvhs.push_back(pb2_bvh{0, d->n_nodes, 0, d->n_prims});
+    if (d->n_instances < 0 || (d->n_instances > 0 && !d->instances)) return setError(PB2_ERR_INVALID, "bad instances");
+    for (const pb2_bvh &b : bvhs)
+        if (b.node_offset < 0 || b.n_nodes <= 0 || b.node_offset + b.n_nodes > d->n_nodes || b.prim_offset < 0 || b.n_prims <= 0 ||
+            b.prim_offset + b.n_prims > nBvhPrims)
+            return setError(PB2_ERR_INVALID, "BVH range out of bounds");
+    // device copy of the nodes with every index made global (secondChildOffset += node_offset,
+    // primitivesOffset += prim_offset); bvhs[0] starts at 0, so a scene without instances is uploaded verbatim
+    std::vector<pb2_bvh_node> rebased;
+    if (bvhs.size() > 1) rebased.assign(d->nodes, d->nodes + d->n_nodes);
+    s->bvhDepth = 0;
+    for (size_t k = 0; k < bvhs.size(); ++k) {
         // depth of the tree = deepest traversal stack any ray can need (selects the shared-memory-stack kernel)
-        std::vector<std::pair<int, int>> todo{{0, 0}};
+        const pb2_bvh &b = bvhs[k];
+        std::vector<std::pair<int64_t, int>> todo{{0, 0}};
         int depth = 0;
         while (!todo.empty()) {
-            std::pair<int, int> nd = todo.back();
+            std::pair<int64_t, int> nd = todo.back();
             todo.pop_back();
-            if (nd.first < 0 || nd.first >= d->n_nodes) return setError(PB2_ERR_INVALID, "BVH child index out of range");
+            if (nd.first < 0 || nd.first >= b.n_nodes) return setError(PB2_ERR_INVALID, "BVH child index out of range");
             depth = std::max(depth, nd.second);
-            const pb2_bvh_node &node = d->nodes[nd.first];
+            const pb2_bvh_node &node = d->nodes[b.node_offset + nd.first];
             if (node.n_prims == 0) {
                 if (nd.second > 4096) return setError(PB2_ERR_INVALID, "BVH is not a tree");
                 todo.push_back({nd.first + 1, nd.second + 1});
-                todo.push_back({node.offset, nd.second + 1});
-            } else if ((int64_t)node.offset + node.n_prims > d->n_prims || node.offset < 0)
-                return setError(PB2_ERR_INVALID, "BVH leaf range out of bounds");
+                todo.push_back({(int64_t)node.offset, nd.second + 1});
+                if (!rebased.empty()) rebased[b.node_offset + nd.first].offset = (int32_t)(node.offset + b.node_offset);
+            } else {
+                if ((int64_t)node.offset + node.n_prims > b.n_prims || node.offset < 0)
+                    return setError(PB2_ERR_INVALID, "BVH leaf range out of bounds");
+                if (!rebased.empty()) rebased[b.node_offset + nd.first].offset = (int32_t)(node.offset + b.prim_offset);
+            }
         }
-        s->bvhDepth = depth;
         if (depth > 64) return setError(PB2_ERR_UNSUPPORTED, "BVH deeper than the reference's 64-entry traversal stack (bvh.cpp:671)");
+        if (k == 0) s->bvhDepth = depth;
+    }
+    for (int64_t j = 0; j < nBvhPrims; ++j)
+        if (d->bvh_prims[j] < 0 || d->bvh_prims[j] >= d->n_prims) return setError(PB2_ERR_INVALID, "bvh_prims entry out of range");
+    for (int64_t i = 0; i < d->n_prims; ++i) {
+        if (d->prim_type[i] == PB2_PRIM_INSTANCE) {
+            if (d->prim_index[i] < 0 || d->prim_index[i] >= d->n_instances) return setError(PB2_ERR_INVALID, "instance index out of range");
+        } else if (d->prim_type[i] != PB2_PRIM_TRIANGLE && d->prim_type[i] != PB2_PRIM_SPHERE)
+            return setError(PB2_ERR_UNSUPPORTED, "primitive type outside the path's scope");
     }
     const pb2_bvh_node *nodes;
-    if ((rc = upload(s, d->nodes, (size_t)d->n_nodes, &nodes))) return rc;
+    if ((rc = upload(s, rebased.empty() ? d->nodes : rebased.data(), (size_t)d->n_nodes, &nodes))) return rc;
+    sc.instances = nullptr;
+    sc.nInstances = d->n_instances;
+    if (d->n_instances > 0) {
+        std::vector<DInstance> inst((size_t)d->n_instances);
+        const float identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        for (int i = 0; i < d->n_instances; ++i) {
+            const pb2_instance &pi = d->instances[i];
+            memcpy(inst[i].i2w.m, pi.instance_to_world, sizeof(float) * 16);
+            memcpy(inst[i].w2i.m, pi.world_to_instance, sizeof(float) * 16);
+            inst[i].identity = memcmp(pi.instance_to_world, identity, sizeof(identity)) == 0;   // Transform::IsIdentity (transform.h:137-143)
+            inst[i].pad = 0;
+            if (pi.bvh >= 0) {
+                if (pi.bvh == 0 || pi.bvh >= (int)bvhs.size()) return setError(PB2_ERR_INVALID, "instance BVH out of range");
+                inst[i].root = (int)bvhs[pi.bvh].node_offset;
+                inst[i].lone = -1;
+            } else {
+                if (pi.lone_prim < 0 || pi.lone_prim >= nBvhPrims) return setError(PB2_ERR_INVALID, "instance primitive out of range");
+                if (d->prim_type[d->bvh_prims[pi.lone_prim]] == PB2_PRIM_INSTANCE) return setError(PB2_ERR_INVALID, "instance of an instance");
+                inst[i].root = -1;
+                inst[i].lone = pi.lone_prim;
+            }
+        }
+        for (size_t k = 1; k < bvhs.size(); ++k)
+            for (int64_t j = 0; j < bvhs[k].n_prims; ++j)
+                if (d->prim_type[d->bvh_prims[bvhs[k].prim_offset + j]] == PB2_PRIM_INSTANCE)
+                    return setError(PB2_ERR_INVALID, "instance inside an object BVH (api.cpp:1554-1557 forbids it)");
+        const DInstance *dInst;
+        if ((rc = upload(s, inst.data(), inst.size(), &dInst))) return rc;
+        sc.instances = dInst;
+    }
     sc.nodes = reinterpret_cast<const float4 *>(nodes);
     sc.wide = nullptr;
-    if (d->n_nodes > 0 && d->n_prims < (int64_t)WIDE_MAX_PRIMS) {
+    if (d->n_nodes > 0 && d->n_prims < (int64_t)WIDE_MAX_PRIMS && bvhs.size() == 1 && d->n_instances == 0) {
         // two-child records (pb2_scene.cuh): interior nodes keep their depth-first order
         std::vector<int32_t> wideOf((size_t)d->n_nodes, -1);
         int32_t nWide = 1;
@@ -750,13 +824,13 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
     }
     // leaf records in BVH order
     const int32_t *bvhPrims;
-    if ((rc = upload(s, d->bvh_prims, (size_t)d->n_prims, &bvhPrims))) return rc;
+    if ((rc = upload(s, d->bvh_prims, (size_t)nBvhPrims, &bvhPrims))) return rc;
     float4 *leaf;
-    if ((rc = allocate(s, 3 * (size_t)d->n_prims, &leaf))) return rc;
+    if ((rc = allocate(s, 3 * (size_t)nBvhPrims, &leaf))) return rc;
     {
         int threads = 256;
-        int64_t blocks = (d->n_prims + threads - 1) / threads;
-        k_build_leaf_records<<<(unsigned)blocks, threads>>>(sc, bvhPrims, d->n_prims, leaf);
+        int64_t blocks = (nBvhPrims + threads - 1) / threads;
+        k_build_leaf_records<<<(unsigned)blocks, threads>>>(sc, bvhPrims, nBvhPrims, leaf);
         CUDA_TRY(cudaGetLastError());
     }
     sc.leafPrims = leaf;

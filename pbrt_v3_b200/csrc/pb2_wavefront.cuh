@@ -25,9 +25,9 @@
 
 struct alignas(32) WfCtx {
     DLane ln;              // starts with {int state; DRay ray;} = 32 bytes: what the trace kernels read
-    alignas(16) DHit hit;  // written by the trace kernels as one 16-byte store
+    alignas(16) float4 hit;  // (leaf record, b0, b1, b2): written by the trace kernels as one 16-byte store
     float tHit;
-    int found;
+    int found;               // 0 = miss, 1 = hit, 2 + i = hit inside instance i
     V2 pFilm;
 };
 static_assert(offsetof(WfCtx, ln) == 0 && offsetof(DLane, state) == 0 && offsetof(DLane, ray) == 4 && sizeof(DRay) == 28,
@@ -141,11 +141,12 @@ __global__ void __launch_bounds__(128) k_wf_trace_plain(DScene sc, WfPool pool, 
             DHit hit;
             hit.leaf = -1;
             hit.b0 = hit.b1 = hit.b2 = 0;
+            hit.inst = -1;
             bool found = traverseAnyOrClosest(sc, ray, state == LS_SHADOW, &tMax, &hit, COUNT ? &ctr : nullptr);
             WfCtx &cx = pool.ctx[c];
-            *reinterpret_cast<float4 *>(&cx.hit) = make_float4(__int_as_float(hit.leaf), hit.b0, hit.b1, hit.b2);
+            cx.hit = make_float4(__int_as_float(hit.leaf), hit.b0, hit.b1, hit.b2);
             cx.tHit = tMax;
-            cx.found = found ? 1 : 0;
+            cx.found = found ? (state != LS_SHADOW && hit.inst >= 0 ? 2 + hit.inst : 1) : 0;
         }
         wfPush(pool.queue[WQ_SHADE], &pool.counts[WQ_SHADE], c, have && state == LS_PATH);
         wfPush(pool.queue[WQ_LIGHT], &pool.counts[WQ_LIGHT], c, have && state != LS_PATH);
@@ -527,8 +528,15 @@ __global__ void __launch_bounds__(128, MINB) k_wf_advance(DScene sc, DRenderPara
         if (have) {
             WfCtx &cx = pool.ctx[c];
             DLane &ln = cx.ln;  // updated in place: each kernel touches only the fields its state needs
-            DHit hit = cx.hit;
-            bool found = cx.found != 0;
+            const float4 h4 = cx.hit;
+            const int foundCode = cx.found;
+            DHit hit;
+            hit.leaf = __float_as_int(h4.x);
+            hit.b0 = h4.y;
+            hit.b1 = h4.z;
+            hit.b2 = h4.w;
+            hit.inst = foundCode >= 2 ? foundCode - 2 : -1;
+            bool found = foundCode != 0;
             float tHit = cx.tHit;
             if (SHADE) shadeVertex<SPH>(sc, rp.halton, rp.path, ln, found, hit, tHit);
             else lightAdvance<SPH>(sc, ln, found, hit, tHit);

@@ -12,7 +12,7 @@ from test_oracle import same_bvh
 
 def test_host_bvh_equals_reference_bvh(pb):
     """The host SAH builder reproduces BVHAccel's LinearBVHNode array and primitive order (src/accelerators/bvh.cpp:183-402)."""
-    for name in ("soup", "killeroo_like", "materials"):
+    for name in ("soup", "killeroo_like", "materials", "instances"):
         g = np.load(os.path.join(GOLDEN, name + ".npz"))
         hs = gc.soup_scene(pb) if name == "soup" else pb.HostScene.from_file(os.path.join(SCENES, name + ".pbrt"))
         assert same_bvh(hs.nodes(), g["bvh_nodes"]), name
@@ -134,3 +134,32 @@ def test_film_resolve_is_the_xyz_round_trip(pb):
     want = np.where(w != 0, np.maximum(0, want * (f32(1) / np.where(w != 0, w, 1))), want).astype(f32)
     assert np.allclose(out, want, rtol=0, atol=1e-6)
     assert (out[0, 0] == 0).all()
+
+
+def test_object_instancing_directives(pb):
+    """pbrtObjectBegin/End/Instance (src/core/api.cpp:1520-1588): an object with several primitives gets its own
+    accelerator, a one-primitive object is instanced directly, every ObjectInstance becomes a TransformedPrimitive
+    carrying the CTM, and the scene BVH is built over the scene-level primitives only."""
+    hs = pb.HostScene.from_file(os.path.join(SCENES, "instances.pbrt"))
+    d = hs.desc.contents
+    assert d.n_instances == 5 and d.n_bvhs == 2
+    prim_type = np.ctypeslib.as_array(d.prim_type, shape=(d.n_prims,))
+    n_top = hs.bvh_range(0)[3]
+    assert n_top == 9 and (prim_type[:n_top] == pb.PB2_PRIM_INSTANCE).sum() == 5 and (prim_type[n_top:] == pb.PB2_PRIM_INSTANCE).sum() == 0
+    assert sorted(hs.bvh_prims(0)) == list(range(9))
+    assert sorted(hs.bvh_prims(1)) == list(range(9, 16))            # the pyramid's 6 triangles + its sphere
+    inst = [d.instances[i] for i in range(5)]
+    assert [i.bvh for i in inst] == [1, 1, 1, -1, -1]
+    assert inst[3].lone_prim == inst[4].lone_prim == d.n_bvh_prims - 1  # the flag's triangle, once, past every BVH range
+    eye = np.eye(4, dtype=np.float32).ravel()
+    assert np.array_equal(np.array(inst[0].instance_to_world), eye)    # ObjectInstance under the identity CTM
+    m = np.array(inst[1].instance_to_world).reshape(4, 4)
+    w = np.array(inst[1].world_to_instance).reshape(4, 4)
+    assert np.allclose(m @ w, np.eye(4), atol=1e-6) and np.allclose(m[:3, 3], [-2, .5, 0])
+    assert np.linalg.det(np.array(inst[2].instance_to_world).reshape(4, 4)[:3, :3]) < 0   # the mirrored instance
+    # the errors the reference reports
+    before = pb.lib().pb2h_error_count()
+    pb.HostScene.from_string('WorldBegin\nShape "sphere"\nObjectInstance "nope"\nWorldEnd\n')
+    assert pb.lib().pb2h_error_count() == before + 1
+    pb.HostScene.from_string('WorldBegin\nShape "sphere"\nObjectBegin "a"\nObjectBegin "b"\nObjectEnd\nObjectEnd\nWorldEnd\n')
+    assert pb.lib().pb2h_error_count() > before + 1
