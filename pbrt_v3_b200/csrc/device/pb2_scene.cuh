@@ -146,18 +146,20 @@ PB2_HD bool slabTestT(float minx, float miny, float minz, float maxx, float maxy
     float tyMax = (by1 - r.o.y) * r.invDir.y;
     tMax *= kSlabScale;
     tyMax *= kSlabScale;
-    *tMinOut = tMin;
-    if (tMin > tyMax || tyMin > tMax) return false;
-    if (tyMin > tMin) tMin = tyMin;
-    if (tyMax < tMax) tMax = tyMax;
+    // The reference's early returns, evaluated without branches (lanes of a warp test different
+    // boxes; diverging here costs more than the few instructions an early exit would skip).  Each
+    // comparison and update is the reference's, so every value that reaches the verdict is too.
+    const bool miss1 = (tMin > tyMax) | (tyMin > tMax);
+    tMin = (tyMin > tMin) ? tyMin : tMin;
+    tMax = (tyMax < tMax) ? tyMax : tMax;
     float tzMin = (bz0 - r.o.z) * r.invDir.z;
     float tzMax = (bz1 - r.o.z) * r.invDir.z;
     tzMax *= kSlabScale;
-    if (tMin > tzMax || tzMin > tMax) return false;
-    if (tzMin > tMin) tMin = tzMin;
-    if (tzMax < tMax) tMax = tzMax;
+    const bool miss2 = (tMin > tzMax) | (tzMin > tMax);
+    tMin = (tzMin > tMin) ? tzMin : tMin;
+    tMax = (tzMax < tMax) ? tzMax : tMax;
     *tMinOut = tMin;
-    return (tMin < rayTMax) && (tMax > 0);
+    return !miss1 & !miss2 & (tMin < rayTMax) & (tMax > 0);
 }
 
 PB2_HD bool slabTest(float4 n0, float4 n1, const DRaySetup &r, float rayTMax) {

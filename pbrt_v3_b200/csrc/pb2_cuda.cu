@@ -496,9 +496,14 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     static const int variant = envInt("PB2_TRACE", 0);
     TraceKernel trace;
     if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
-    else if (wideNodes && variant == 0) trace = k_wf_trace_w<8, 8, 2, 16, 8>;
+    else if (wideNodes && variant == 0) trace = k_wf_trace_w<8, 8, 3, 16, 8, 1>;
+    else if (wideNodes && variant == 13) trace = k_wf_trace_w<8, 8, 2, 16, 8>;
     else if (wideNodes && variant == 5) trace = k_wf_trace_w<12, 8, 4, 16, 8>;
     else if (wideNodes && variant == 6) trace = k_wf_trace_w<12, 8, 2, 16, 8>;
+    else if (wideNodes && variant == 9) trace = k_wf_trace_w<8, 8, 2, 16, 8, 1>;
+    else if (wideNodes && variant == 10) trace = k_wf_trace_w<12, 8, 4, 16, 8, 1>;
+    else if (wideNodes && variant == 11) trace = k_wf_trace_w<8, 8, 3, 16, 8, 1>;
+    else if (wideNodes && variant == 12) trace = k_wf_trace_w<16, 8, 4, 16, 8, 1>;
     else if (wideNodes && variant == 8) trace = k_wf_trace_w<8, 8, 2, 4, 8>;   // tests: forces the local-memory stack spill
     else if (scene->bvhDepth > 32) trace = k_wf_trace<12, 8, 4, 32, true, false, 8>;
     else if (variant == 1) trace = k_wf_trace<12, 8, 8, 32, false, false, 8>;

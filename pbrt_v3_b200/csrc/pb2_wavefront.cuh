@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
 // dependent fetch per interior node it descends into instead of one per node it touches
 // (82 -> ~41 on the bench scene), and the two slab tests of a step are independent instructions.
 // ---------------------------------------------------------------------------------------------
-template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB>
+template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, int TAIL = 0>
 __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
     __shared__ int2 sstack[SDEPTH][128];   // (child reference, tMin bits)
     int2 lstack[64 - SDEPTH];              // entries beyond SDEPTH (rare: only passing far children are pushed)
@@ -414,7 +414,22 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
         if (step == M_NODE) {
 #pragma unroll
             for (int sub = 0; sub < NSUB; ++sub) {
-                if (mode == M_NODE) {
+                if (TAIL && mode == M_NODE && cur < 0) {
+                    // the last visit (or leaf) left nothing to descend into: take pending far children,
+                    // at most two per visit (a culled one costs a load and a compare)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (mode == M_NODE && cur < 0) {
+                            if (sp == 0) mode = M_FETCH;
+                            else {
+                                --sp;
+                                int2 e = sp < SDEPTH ? sstack[sp][tid] : lstack[sp - SDEPTH];
+                                if (__int_as_float(e.y) < tMax) enter(e.x);
+                            }
+                        }
+                    }
+                }
+                if (mode == M_NODE && (!TAIL || cur >= 0)) {
                     const float4 *w = &sc.wide[4 * (size_t)cur];
                     float4 q0 = ldg4(w), q1 = ldg4(w + 1), q2 = ldg4(w + 2), q3 = ldg4(w + 3);
                     float t0, t1;
@@ -428,7 +443,23 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                     bool pn = isNeg ? p1 : p0, pf = isNeg ? p0 : p1;
                     int rn = isNeg ? ref1 : ref0, rf = isNeg ? ref0 : ref1;
                     float tf = isNeg ? t0 : t1;
-                    if (pn) {
+                    if (TAIL) {
+                        // straight-line tail: push the far child if both pass, continue with whichever
+                        // passed, otherwise leave the pop to the next visit
+                        if (pn & pf) {
+                            int2 e = make_int2(rf, __float_as_int(tf));
+                            if (sp < SDEPTH) sstack[sp][tid] = e;
+                            else lstack[sp - SDEPTH] = e;
+                            ++sp;
+                        }
+                        const int ref = pn ? rn : rf;
+                        const bool have = pn | pf;
+                        const bool isLeaf = have & (ref < 0);
+                        leafFirst = isLeaf ? (ref & 0xffffff) : leafFirst;
+                        leafN = isLeaf ? ((ref >> 24) & 0x7f) : leafN;
+                        mode = isLeaf ? (int)M_LEAF : (int)M_NODE;
+                        cur = (have & !isLeaf) ? ref : -1;
+                    } else if (pn) {
                         if (pf) {
                             int2 e = make_int2(rf, __float_as_int(tf));
                             if (sp < SDEPTH) sstack[sp][tid] = e;
@@ -461,7 +492,12 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                 }
                 leafN = 0;
                 if (finished) mode = M_FETCH;
-                else popNext();
+                else if (!TAIL) popNext();
+                else if (sp == 0) mode = M_FETCH;
+                else {
+                    mode = M_NODE;   // the next node visit pops
+                    cur = -1;
+                }
             }
         } else {  // M_FETCH: flush finished rays, then take new ones
             bool flush = mode == M_FETCH && c >= 0;
