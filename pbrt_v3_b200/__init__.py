@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpb2.so")
+LIB_PATH = os.environ.get("PB2_LIB") or os.path.join(_HERE, "lib", "libpb2.so")   # PB2_LIB: A/B builds during tuning
 
 c_float_p = C.POINTER(C.c_float)
 c_int32_p = C.POINTER(C.c_int32)

@@ -87,6 +87,22 @@ PB2_HD float radicalInverseBase(uint32_t base, uint64_t a, const uint16_t *perm,
     return pmin((float)reversedDigits * invBaseN, kOneMinusEpsilon);
 }
 
+// The hot case of the above - ScrambledRadicalInverse of an index below 2^32 - as its own tight
+// loop (same operations, same results; no 64-bit path, no per-digit "magic or divide" decision).
+PB2_HD float scrambledRadicalInverse32(uint32_t base, uint64_t magic, uint32_t a, const uint16_t *perm) {
+    const float invBase = 1.f / (float)base;
+    uint64_t reversedDigits = 0;
+    float invBaseN = 1;
+    while (a) {
+        uint32_t next = divMagic(a, magic);
+        uint32_t digit = a - next * base;
+        reversedDigits = reversedDigits * base + (uint32_t)perm[digit];
+        invBaseN *= invBase;
+        a = next;
+    }
+    return pmin(invBaseN * ((float)reversedDigits + invBase * perm[0] / (1 - invBase)), kOneMinusEpsilon);
+}
+
 // RadicalInverse(baseIndex, a), lowdiscrepancy.cpp:427-
 PB2_HD float radicalInverse(const DHalton &h, int baseIndex, uint64_t a) {
     if (baseIndex == 0) return (float)((double)reverseBits64(a) * 0x1p-64);
@@ -130,6 +146,7 @@ PB2_HD float haltonSample(const DHalton &h, int64_t index, int dim) {
     if (dim == 1) return radicalInverseBase(3u, (uint64_t)(index / h.baseScales[1]), nullptr);
 #if defined(__CUDA_ARCH__)
     const ulonglong2 rec = __ldg(&h.dimRecs[dim]);   // {magic, prime | primeSum << 32}: one 16-B load per dimension
+    if (((uint64_t)index >> 32) == 0) return scrambledRadicalInverse32((uint32_t)rec.y, rec.x, (uint32_t)index, h.perms + (uint32_t)(rec.y >> 32));
     return radicalInverseBase((uint32_t)rec.y, (uint64_t)index, h.perms + (uint32_t)(rec.y >> 32), rec.x);
 #else
     return radicalInverseBase((uint32_t)h.primes[dim], (uint64_t)index, h.perms + h.primeSums[dim]);

@@ -39,6 +39,7 @@ enum : uint32_t {
 enum : uint32_t {
     WIDE_LEAF = 0x80000000u,  // child reference: bits 0-23 primitivesOffset, bits 24-30 nPrimitives
     WIDE_SINGLE = 4u,         // meta: the record has only child 0 (the pseudo node above the root)
+    WIDE_TOP = 0x40000000u,   // child reference inside wideTop: bits 0-23 index into wideTop
     WIDE_MAX_PRIMS = 1u << 24,
     WIDE_MAX_LEAF = 127u,
 };
@@ -63,6 +64,8 @@ struct DInstance {
 struct DScene {
     const float4 *nodes;
     const float4 *wide;       // two-child nodes (below), nullptr when the scene exceeds their limits
+    const float4 *wideTop;    // the first nTop of them in breadth-first order, child references into this table
+    int nTop;                 //   carry WIDE_TOP; a trace kernel may keep the table in shared memory
     const float4 *leafPrims;
     const float4 *lightRecs;
     int64_t nNodes, nPrims, nTris;

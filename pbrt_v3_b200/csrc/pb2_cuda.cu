@@ -495,16 +495,23 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     const bool instanced = scene->d.instances != nullptr;
     static const int variant = envInt("PB2_TRACE", 0);
     TraceKernel trace;
+    int traceBlock = 128, traceDynStack = 0;
+    bool traceTop = false;
+    size_t traceSmem = 0;
+    auto wideKernel = [&](TraceKernel k, int block, int sdepth, bool top) {
+        trace = k;
+        traceBlock = block;
+        traceDynStack = sdepth;
+        traceTop = top;
+    };
     if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
-    else if (wideNodes && variant == 0) trace = k_wf_trace_w<8, 8, 3, 16, 8, 1>;
-    else if (wideNodes && variant == 13) trace = k_wf_trace_w<8, 8, 2, 16, 8>;
-    else if (wideNodes && variant == 5) trace = k_wf_trace_w<12, 8, 4, 16, 8>;
-    else if (wideNodes && variant == 6) trace = k_wf_trace_w<12, 8, 2, 16, 8>;
-    else if (wideNodes && variant == 9) trace = k_wf_trace_w<8, 8, 2, 16, 8, 1>;
-    else if (wideNodes && variant == 10) trace = k_wf_trace_w<12, 8, 4, 16, 8, 1>;
-    else if (wideNodes && variant == 11) trace = k_wf_trace_w<8, 8, 3, 16, 8, 1>;
-    else if (wideNodes && variant == 12) trace = k_wf_trace_w<16, 8, 4, 16, 8, 1>;
-    else if (wideNodes && variant == 8) trace = k_wf_trace_w<8, 8, 2, 4, 8>;   // tests: forces the local-memory stack spill
+    else if (wideNodes && variant == 0) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1>, 128, 16, false);
+    else if (wideNodes && variant == 5) wideKernel(k_wf_trace_w<12, 8, 4, 16, 8>, 128, 16, false);
+    else if (wideNodes && variant == 8) wideKernel(k_wf_trace_w<8, 8, 2, 4, 8>, 128, 4, false);   // tests: forces the local-memory stack spill
+    else if (wideNodes && variant == 9) wideKernel(k_wf_trace_w<8, 8, 3, 16, 1, 1, 1024, true>, 1024, 16, true);
+    else if (wideNodes && variant == 10) wideKernel(k_wf_trace_w<8, 8, 3, 12, 1, 1, 1024, true>, 1024, 12, true);
+    else if (wideNodes && variant == 11) wideKernel(k_wf_trace_w<8, 8, 3, 16, 1, 1, 1024, false>, 1024, 16, false);
+    else if (wideNodes && variant == 12) wideKernel(k_wf_trace_w<8, 8, 3, 16, 2, 1, 512, true>, 512, 16, true);
     else if (scene->bvhDepth > 32) trace = k_wf_trace<12, 8, 4, 32, true, false, 8>;
     else if (variant == 1) trace = k_wf_trace<12, 8, 8, 32, false, false, 8>;
     else if (variant == 2) trace = k_wf_trace<16, 8, 4, 32, false, false, 8>;
@@ -519,13 +526,18 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
                              : shadeMinB == 6 ? k_wf_advance<true, false, 6>
                              : shadeMinB == 8 ? k_wf_advance<true, false, 8>
                                               : k_wf_advance<true, false, 4>;
+    // the two-child kernels take their stack (and the optional top-of-tree table) as dynamic shared memory
+    if (traceDynStack > 0) {
+        traceSmem = (size_t)traceDynStack * traceBlock * sizeof(int2) + (traceTop ? (size_t)scene->d.nTop * 64 : 0);
+        CUDA_TRY(cudaFuncSetAttribute(trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceSmem));
+    }
     int traceBlocksPerSM = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&traceBlocksPerSM, trace, 128, 0));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&traceBlocksPerSM, trace, traceBlock, traceSmem));
     {
         // ask for exactly the shared-memory carve-out the resident blocks need; the rest stays L1
         cudaFuncAttributes fa;
         CUDA_TRY(cudaFuncGetAttributes(&fa, trace));
-        size_t need = (size_t)traceBlocksPerSM * (fa.sharedSizeBytes + 1024);
+        size_t need = (size_t)traceBlocksPerSM * (fa.sharedSizeBytes + traceSmem + 1024);
         int pct = (int)std::min<size_t>(100, (need * 100 + 233471) / 233472);
         CUDA_TRY(cudaFuncSetAttribute(trace, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
         static const int verbose = envInt("PB2_VERBOSE", 0);
@@ -562,7 +574,7 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         }
         if (countTraversal) k_wf_trace_plain<true><<<blocks128, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
         else if (instanced) k_wf_trace_plain<false><<<blocks128, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
-        else trace<<<persistentBlocks, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur);
+        else trace<<<persistentBlocks, traceBlock, traceSmem, stream>>>(scene->d, pool, WQ_TRACE0 + cur);
         if (timeTrace) {
             CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents + 1], stream));
             nEvents += 2;
@@ -806,6 +818,30 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
             const WideRec *dWide;
             if ((rc = upload(s, wide.data(), wide.size(), &dWide))) return rc;
             sc.wide = reinterpret_cast<const float4 *>(dWide);
+            // the top of the tree in breadth-first order (any prefix of that order is closed under "parent of")
+            static const int topMax = std::max(1, std::min(envInt("PB2_TOP", 1024), 3072));
+            std::vector<int32_t> bfs{0};
+            std::vector<int32_t> topOf((size_t)nWide, -1);
+            topOf[0] = 0;
+            for (size_t qi = 0; qi < bfs.size() && (int)bfs.size() < topMax; ++qi) {
+                const WideRec &w = wide[(size_t)bfs[qi]];
+                const uint32_t refs[2] = {w.ref0, w.ref1};
+                for (int k = 0; k < ((w.meta & WIDE_SINGLE) ? 1 : 2); ++k)
+                    if (!(refs[k] & WIDE_LEAF) && (int)bfs.size() < topMax && topOf[refs[k]] < 0) {
+                        topOf[refs[k]] = (int32_t)bfs.size();
+                        bfs.push_back((int32_t)refs[k]);
+                    }
+            }
+            std::vector<WideRec> top(bfs.size());
+            for (size_t i = 0; i < bfs.size(); ++i) {
+                top[i] = wide[(size_t)bfs[i]];
+                if (!(top[i].ref0 & WIDE_LEAF) && topOf[top[i].ref0] >= 0) top[i].ref0 = WIDE_TOP | (uint32_t)topOf[top[i].ref0];
+                if (!(top[i].ref1 & WIDE_LEAF) && topOf[top[i].ref1] >= 0) top[i].ref1 = WIDE_TOP | (uint32_t)topOf[top[i].ref1];
+            }
+            const WideRec *dTop;
+            if ((rc = upload(s, top.data(), top.size(), &dTop))) return rc;
+            sc.wideTop = reinterpret_cast<const float4 *>(dTop);
+            sc.nTop = (int)top.size();
         }
     }
     if ((rc = upload(s, d->P, 3 * (size_t)d->n_vertices, &sc.P))) return rc;

@@ -357,12 +357,22 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
 // dependent fetch per interior node it descends into instead of one per node it touches
 // (82 -> ~41 on the bench scene), and the two slab tests of a step are independent instructions.
 // ---------------------------------------------------------------------------------------------
-template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, int TAIL = 0>
-__global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
-    __shared__ int2 sstack[SDEPTH][128];   // (child reference, tMin bits)
+// TOP: the first sc.nTop records in breadth-first order (the levels every ray walks through) are
+// copied into shared memory at kernel start and read from there: the kernel is bound by the number
+// of L1 tag look-ups (4 scattered 16-byte requests per record), not by bytes, and shared-memory
+// reads need none.  BLOCK = 1024 gives one resident block per SM, so that copy exists once per SM.
+template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, int TAIL = 0, int BLOCK = 128, bool TOP = false>
+__global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
+    extern __shared__ int2 dynSmem[];
+    int2 *sstack = dynSmem;                // [SDEPTH][BLOCK] of (child reference, tMin bits)
+    float4 *stop = reinterpret_cast<float4 *>(dynSmem + SDEPTH * BLOCK);   // [4 * sc.nTop]
     int2 lstack[64 - SDEPTH];              // entries beyond SDEPTH (rare: only passing far children are pushed)
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
+    if (TOP) {
+        for (int i = tid; i < 4 * sc.nTop; i += BLOCK) stop[i] = sc.wideTop[i];
+        __syncthreads();
+    }
     const int lane = tid & 31;
     const unsigned n = pool.counts[traceQ];
     enum { M_FETCH = 0, M_NODE = 1, M_LEAF = 2 };
@@ -393,7 +403,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
         mode = M_FETCH;
         while (sp > 0) {
             --sp;
-            int2 e = sp < SDEPTH ? sstack[sp][tid] : lstack[sp - SDEPTH];
+            int2 e = sp < SDEPTH ? sstack[sp * BLOCK + tid] : lstack[sp - SDEPTH];
             if (__int_as_float(e.y) < tMax) {
                 enter(e.x);
                 break;
@@ -423,15 +433,21 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                             if (sp == 0) mode = M_FETCH;
                             else {
                                 --sp;
-                                int2 e = sp < SDEPTH ? sstack[sp][tid] : lstack[sp - SDEPTH];
+                                int2 e = sp < SDEPTH ? sstack[sp * BLOCK + tid] : lstack[sp - SDEPTH];
                                 if (__int_as_float(e.y) < tMax) enter(e.x);
                             }
                         }
                     }
                 }
                 if (mode == M_NODE && (!TAIL || cur >= 0)) {
-                    const float4 *w = &sc.wide[4 * (size_t)cur];
-                    float4 q0 = ldg4(w), q1 = ldg4(w + 1), q2 = ldg4(w + 2), q3 = ldg4(w + 3);
+                    float4 q0, q1, q2, q3;
+                    if (TOP && (cur & (int)WIDE_TOP)) {
+                        const float4 *w = &stop[4 * (cur & 0xffffff)];
+                        q0 = w[0]; q1 = w[1]; q2 = w[2]; q3 = w[3];
+                    } else {
+                        const float4 *w = &sc.wide[4 * (size_t)cur];
+                        q0 = ldg4(w); q1 = ldg4(w + 1); q2 = ldg4(w + 2); q3 = ldg4(w + 3);
+                    }
                     float t0, t1;
                     bool p0 = slabTestT(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, rs, tMax, &t0);
                     bool p1 = slabTestT(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, rs, tMax, &t1);
@@ -448,7 +464,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                         // passed, otherwise leave the pop to the next visit
                         if (pn & pf) {
                             int2 e = make_int2(rf, __float_as_int(tf));
-                            if (sp < SDEPTH) sstack[sp][tid] = e;
+                            if (sp < SDEPTH) sstack[sp * BLOCK + tid] = e;
                             else lstack[sp - SDEPTH] = e;
                             ++sp;
                         }
@@ -462,7 +478,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                     } else if (pn) {
                         if (pf) {
                             int2 e = make_int2(rf, __float_as_int(tf));
-                            if (sp < SDEPTH) sstack[sp][tid] = e;
+                            if (sp < SDEPTH) sstack[sp * BLOCK + tid] = e;
                             else lstack[sp - SDEPTH] = e;
                             ++sp;
                         }
@@ -528,7 +544,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                         flags = (__float_as_int(ra.x) == LS_SHADOW) ? F_ANY : 0;
                         rs = setupRay(mk3(ra.y, ra.z, ra.w), mk3(rb.x, rb.y, rb.z));
                         tMax = rb.w;
-                        cur = 0;   // the pseudo node above the root
+                        cur = TOP ? (int)WIDE_TOP : 0;   // the pseudo node above the root
                         sp = 0;
                         leafN = 0;
                         mode = M_NODE;
