@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(tris=1000000, seed=1234, jitter=0.02, xres=1920, yres=1080, spp=64, maxdepth=8)
 # DRAM bytes of one full-pool k_wf_trace_w launch on this workload, from the committed `ncu --set full` capture
-NCU_TRACE_DRAM_BYTES_PER_LAUNCH = 937208832 + 162006784
+NCU_TRACE_DRAM_BYTES_PER_LAUNCH = 938578432 + 161948416
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 
 
