@@ -21,7 +21,8 @@ def test_library_exports_every_declared_symbol(pb):
     assert len(syms) >= 12
     for s in syms:
         assert hasattr(L, s), "libpb2.so does not export %s declared in include/pb2.h" % s
-    assert L.pb2_abi_version() == 2
+    declared = int(re.search(r"#define\s+PB2_ABI_VERSION\s+(\d+)", open(os.path.join(ROOT, "include", "pb2.h")).read()).group(1))
+    assert L.pb2_abi_version() == declared == pb.PB2_ABI_VERSION
 
 
 def test_struct_layouts_match_header(pb):
