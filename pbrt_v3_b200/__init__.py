@@ -157,6 +157,7 @@ def lib():
     L.pb2h_parse_file.argtypes = [C.c_char_p, C.c_char_p]
     L.pb2h_parse_string.argtypes = [C.c_char_p]
     L.pb2h_synth_soup.argtypes = [C.c_int64, C.c_uint64, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
+    L.pb2h_synth_instanced.argtypes = [C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int]
     L.pb2h_scene_desc.restype = C.POINTER(SceneDesc)
     L.pb2h_camera.restype = C.POINTER(Camera)
     L.pb2h_film.restype = C.POINTER(FilmDesc)
@@ -223,6 +224,14 @@ class HostScene:
         if s.L.pb2h_synth_soup(n_tris, seed, jitter, xres, yres, spp, maxdepth,
                                light_strategy.encode() if light_strategy else None) != 0:
             raise RuntimeError("could not build the synthetic scene")
+        return s
+
+    @classmethod
+    def instanced_soup(cls, n_object_tris, grid=10, seed=4321, seed_instances=99, jitter=0.05, xres=1920, yres=1080, spp=128, maxdepth=5):
+        """one soup object instanced grid x grid times (100 000 triangles x 100 with the defaults)."""
+        s = cls()
+        if s.L.pb2h_synth_instanced(n_object_tris, grid, seed, seed_instances, jitter, xres, yres, spp, maxdepth) != 0:
+            raise RuntimeError("could not build the synthetic instanced scene")
         return s
 
     # flattened descriptions (host memory owned by the C++ side)

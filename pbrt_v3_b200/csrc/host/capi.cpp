@@ -122,6 +122,92 @@ int pb2h_synth_soup(int64_t n_tris, uint64_t seed, float jitter, int xres, int y
     return pbrtLastSetup() && pbrtLastSetup()->integrator ? 0 : 1;
 }
 
+// Synthetic instanced workload: ONE object - a soup of `n_object_tris` random
+// triangles in the unit cube (centre U[-.5,.5]^3, vertices centre + U[-jitter,jitter]^3, RNG(seed)) -
+// instanced grid x grid times on a regular grid with a random rotation about z and a small random
+// offset per instance (RNG(seed_instances)); matte Kd .6, a floor quad and a 2-triangle area light
+// above the grid; perspective camera looking down at the field.
+int pb2h_synth_instanced(int64_t n_object_tris, int grid, uint64_t seed, uint64_t seed_instances, float jitter, int xres,
+                         int yres, int spp, int maxdepth) {
+    Options opt;
+    g_flat.reset();
+    if (pbrtIsInitialized()) pbrtCleanup();
+    pbrtInit(opt);
+    pbrtSetRenderAtWorldEnd(false);
+    const Float spacing = 1.4f, half = spacing * grid / 2;
+    pbrtLookAt(0, -2.2f * half - 2.f, 1.3f * half + 1.5f, 0, 0, 0, 0, 0, 1);
+    ParamSet cam;
+    cam.AddFloat("fov", {40.f});
+    pbrtCamera("perspective", cam);
+    ParamSet film;
+    film.AddInt("xresolution", {xres});
+    film.AddInt("yresolution", {yres});
+    film.AddString("filename", "instanced.pfm");
+    pbrtFilm("image", film);
+    ParamSet samp;
+    samp.AddInt("pixelsamples", {spp});
+    pbrtSampler("halton", samp);
+    ParamSet integ;
+    integ.AddInt("maxdepth", {maxdepth});
+    pbrtIntegrator("path", integ);
+    pbrtWorldBegin();
+    ParamSet mat;
+    mat.AddRGBSpectrum("Kd", {.6f, .6f, .6f});
+    pbrtMaterial("matte", mat);
+    pbrtObjectBegin("soup");
+    {
+        RNG rng(seed);
+        std::vector<Float> P((size_t)9 * n_object_tris);
+        std::vector<int> idx((size_t)3 * n_object_tris);
+        for (int64_t t = 0; t < n_object_tris; ++t) {
+            Float c[3];
+            for (int k = 0; k < 3; ++k) c[k] = rng.UniformFloat() - .5f;
+            for (int v = 0; v < 3; ++v)
+                for (int k = 0; k < 3; ++k) P[9 * t + 3 * v + k] = c[k] + jitter * (2.f * rng.UniformFloat() - 1.f);
+            for (int v = 0; v < 3; ++v) idx[3 * t + v] = (int)(3 * t + v);
+        }
+        ParamSet ps;
+        ps.AddPoint3f("P", P);
+        ps.AddInt("indices", idx);
+        if (n_object_tris > 0) pbrtShape("trianglemesh", ps);
+    }
+    pbrtObjectEnd();
+    {
+        RNG rng(seed_instances);
+        for (int gy = 0; gy < grid; ++gy)
+            for (int gx = 0; gx < grid; ++gx) {
+                pbrtAttributeBegin();
+                Float tx = (gx + .5f) * spacing - half + .2f * (rng.UniformFloat() - .5f);
+                Float ty = (gy + .5f) * spacing - half + .2f * (rng.UniformFloat() - .5f);
+                pbrtTranslate(tx, ty, .55f);
+                pbrtRotate(360.f * rng.UniformFloat(), 0, 0, 1);
+                pbrtObjectInstance("soup");
+                pbrtAttributeEnd();
+            }
+    }
+    {
+        ParamSet ps;
+        Float e = half + 2.f;
+        ps.AddPoint3f("P", {-e, -e, 0, e, -e, 0, e, e, 0, -e, e, 0});
+        ps.AddInt("indices", {0, 1, 2, 0, 2, 3});
+        pbrtShape("trianglemesh", ps);
+    }
+    pbrtAttributeBegin();
+    {
+        ParamSet al;
+        al.AddRGBSpectrum("L", {30.f, 30.f, 30.f});
+        pbrtAreaLightSource("diffuse", al);
+        ParamSet ps;
+        Float e = .6f * half + .5f, z = half + 3.f;
+        ps.AddPoint3f("P", {-e, -e, z, -e, e, z, e, e, z, e, -e, z});
+        ps.AddInt("indices", {0, 1, 2, 0, 2, 3});
+        pbrtShape("trianglemesh", ps);
+    }
+    pbrtAttributeEnd();
+    pbrtWorldEnd();
+    return pbrtLastSetup() && pbrtLastSetup()->integrator ? 0 : 1;
+}
+
 // Flattened description of the last parsed scene (host memory, valid until the next parse/cleanup).
 const pb2_scene_desc *pb2h_scene_desc(void) {
     if (g_flat) return &g_flat->desc;

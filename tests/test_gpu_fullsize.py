@@ -77,3 +77,44 @@ def test_per_sample_parity_on_the_full_size_scene(pb, big, port):
     g, r = big.intersect(rays), sc.intersect(rays)
     assert np.array_equal(g["prim"], r["prim"]) and np.array_equal(gc.bits(g["t"]), gc.bits(r["t"]))
     assert np.array_equal(gc.bits(g["p"]), gc.bits(r["p"])) and np.array_equal(gc.bits(g["n"]), gc.bits(r["n"]))
+
+
+# ---------------------------------------------------------------- BASELINE.json configs[3]: 10 M instanced triangles
+@pytest.fixture(scope="module")
+def instanced(pb):
+    """One 100 000-triangle object instanced 10 x 10 times, 1920x1080, 1 spp for the tests."""
+    return pb.HostScene.instanced_soup(100000, grid=10, xres=XRES, yres=YRES, spp=1, maxdepth=5)
+
+
+def test_instanced_scene_properties_at_full_size(pb, instanced):
+    d = instanced.desc.contents
+    assert d.n_instances == 100 and d.n_bvhs == 2 and instanced.bvh_range(1)[3] == 100000
+    film, st = instanced.render_rgbw()
+    n = XRES * YRES
+    assert st.camera_rays == n
+    w = film[..., 3]
+    assert n <= w.sum() <= n * 1.02 and (w >= 1).all()
+    assert np.isfinite(film).all() and (film[..., :3] >= 0).all() and film[..., :3].sum() > 0
+    # the two-GPU tile partition adds up to the same film
+    parts = [instanced.render_rgbw(instanced.params_copy(tile_rank=r, tile_count=2)) for r in range(2)]
+    assert sum(int(s.camera_rays) for _, s in parts) == st.camera_rays
+    assert np.array_equal(parts[0][0][..., 3] + parts[1][0][..., 3], w)
+    assert np.allclose(parts[0][0] + parts[1][0], film, rtol=1e-4, atol=1e-4)
+    assert sum(int(s.regular_rays) for _, s in parts) == st.regular_rays and sum(int(s.shadow_rays) for _, s in parts) == st.shadow_rays
+
+
+def test_instanced_scene_per_sample_parity_at_full_size(pb, instanced, port):
+    sc = port.scene(instanced)
+    pix, sn = gc.sample_ids(XRES, YRES, 1, 3000, 41)
+    li, pfilm = instanced.li_samples(pix, sn)
+    ref_li, ref_pfilm = sc.li_samples(pix, sn)
+    assert np.array_equal(gc.bits(pfilm), gc.bits(ref_pfilm))
+    err = np.abs(li - ref_li).max(axis=1) / np.maximum(1, np.abs(ref_li).max(axis=1))
+    assert (err <= 1e-4).mean() >= 0.999
+    rays = gc.rays_for(pb, instanced.nodes(), 20000, 42)
+    g, r = instanced.intersect(rays), sc.intersect(rays)
+    assert (g["prim"] >= 0).mean() > 0.05
+    assert np.array_equal(g["prim"], r["prim"]) and np.array_equal(gc.bits(g["t"]), gc.bits(r["t"]))
+    assert np.array_equal(gc.bits(g["p"]), gc.bits(r["p"])) and np.array_equal(gc.bits(g["n"]), gc.bits(r["n"]))
+    srays = gc.rays_for(pb, instanced.nodes(), 20000, 43, shadow=True)
+    assert np.array_equal(instanced.intersect_p(srays), sc.intersect_p(srays))

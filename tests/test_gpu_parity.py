@@ -92,6 +92,32 @@ def test_gpu_matches_checker_on_a_larger_scene(pb, checker):
     assert abs(int(st.regular_rays) - int(ref_st.regular_rays)) <= ref_st.regular_rays // 1000 + 2
 
 
+def test_instanced_soup_matches_checker(pb, checker):
+    """A soup object instanced 4 x 4 times with random rotations (the generator of BASELINE.json configs[3] at a size the
+    CPU checker renders in a second): hits bit-identical, any-hits equal, image and ray counters as for every scene."""
+    hs = pb.HostScene.instanced_soup(2000, grid=4, xres=64, yres=36, spp=4)
+    sc = checker.scene(hs)
+    rays = gc.rays_for(pb, hs.nodes(), 20000, 51)
+    assert hs.intersect(rays).tobytes() == _without_b(sc.intersect(rays), hs.intersect(rays))
+    srays = gc.rays_for(pb, hs.nodes(), 20000, 52, shadow=True)
+    assert np.array_equal(hs.intersect_p(srays), sc.intersect_p(srays))
+    img, st = hs.render()
+    ref_img, _, ref_st = sc.render(n_threads=0)
+    frac, mean_rel = image_metrics(img, ref_img)
+    assert frac >= 0.999 and mean_rel <= 1e-4
+    assert st.camera_rays == ref_st.camera_rays == 64 * 36 * 4
+    assert abs(int(st.regular_rays) - int(ref_st.regular_rays)) <= ref_st.regular_rays // 1000 + 2
+    assert abs(int(st.shadow_rays) - int(ref_st.shadow_rays)) <= ref_st.shadow_rays // 1000 + 2
+    # traversal counters: both BVH levels count like the reference's STAT_COUNTERs would
+    dev = hs.device_scene()
+    film = np.zeros((36, 64, 4), np.float32)
+    cst = pb.Stats()
+    pb.check(pb.lib().pb2_render_path(dev, hs.camera, hs.film, hs.params_copy(flags=1), pb.ptr(film), C.byref(cst)))
+    if checker.kind == "port":
+        assert abs(int(cst.node_visits) - int(ref_st.node_visits)) <= ref_st.node_visits // 1000 + 10
+        assert abs(int(cst.prim_tests) - int(ref_st.prim_tests)) <= ref_st.prim_tests // 1000 + 10
+
+
 def _without_b(ref_hits, gpu_hits):
     """The checker's SurfaceInteraction has no barycentrics; take the GPU's so that every other byte is compared."""
     h = ref_hits.copy()
