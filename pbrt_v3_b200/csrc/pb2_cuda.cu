@@ -167,7 +167,8 @@ struct pb2_scene {
     unsigned long long *counters = nullptr;  // CTR_*
     int64_t nPrims = 0;
     int nLights = 0;
-    int bvhDepth = 0;  // maximum number of simultaneously pending far children = tree depth
+    int bvhDepth = 0;  // maximum number of simultaneously pending far children = tree depth (scene BVH)
+    int instDepth = 0; // the same for the deepest instanced object's BVH
     // wavefront pool (allocated on first render)
     void *wfCtx = nullptr;
     int *wfQueues = nullptr;
@@ -504,7 +505,11 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         traceDynStack = sdepth;
         traceTop = top;
     };
-    if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
+    // instanced scenes: the tuned 32-B-node kernel with the instance frame on its stack, as long as the
+    // two levels fit the 64-entry stack; PB2_TRACE=14 keeps them on the plain kernel (tests compare both)
+    const bool instancedTuned = instanced && variant != 14 && scene->bvhDepth + 3 + scene->instDepth <= 64;
+    if (instancedTuned) trace = k_wf_trace<8, 8, 2, 32, true, true, 6, true>;
+    else if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
     else if (wideNodes && variant == 0) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1>, 128, 16, false);
     else if (wideNodes && variant == 5) wideKernel(k_wf_trace_w<12, 8, 4, 16, 8>, 128, 16, false);
     else if (wideNodes && variant == 8) wideKernel(k_wf_trace_w<8, 8, 2, 4, 8>, 128, 4, false);   // tests: forces the local-memory stack spill
@@ -573,7 +578,7 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
             CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents], stream));
         }
         if (countTraversal) k_wf_trace_plain<true><<<blocks128, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
-        else if (instanced) k_wf_trace_plain<false><<<blocks128, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
+        else if (instanced && !instancedTuned) k_wf_trace_plain<false><<<blocks128, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
         else trace<<<persistentBlocks, traceBlock, traceSmem, stream>>>(scene->d, pool, WQ_TRACE0 + cur);
         if (timeTrace) {
             CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents + 1], stream));
@@ -736,6 +741,7 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
         }
         if (depth > 64) return setError(PB2_ERR_UNSUPPORTED, "BVH deeper than the reference's 64-entry traversal stack (bvh.cpp:671)");
         if (k == 0) s->bvhDepth = depth;
+        else s->instDepth = std::max(s->instDepth, depth);
     }
     for (int64_t j = 0; j < nBvhPrims; ++j)
         if (d->bvh_prims[j] < 0 || d->bvh_prims[j] >= d->n_prims) return setError(PB2_ERR_INVALID, "bvh_prims entry out of range");

@@ -187,7 +187,13 @@ __global__ void __launch_bounds__(128) k_wf_trace_plain(DScene sc, WfPool pool, 
 //     diverging into push and pop branches;
 //   * context words are read / written with streaming hints so nodes + leaf records stay in L2.
 // ---------------------------------------------------------------------------------------------
-template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, bool DEEP, bool SPHERES, int MINB>
+// INST: object instances (TransformedPrimitive).  An instance is a leaf primitive: the lane saves
+// (tMax, rest of the leaf) in a 3-entry frame on its stack, takes the ray to instance space
+// (Transform::operator()(Ray), transform.h:251-264) and walks the object's BVH with `instBase` as
+// the stack floor; when that walk ends it comes back through the leaf step (F_EXIT), restores the
+// world-space ray from its context and continues with the rest of the leaf - r.tMax = ray.tMax
+// (primitive.cpp:83) if something was hit inside, the saved tMax otherwise.
+template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, bool DEEP, bool SPHERES, int MINB, bool INST = false>
 __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, int traceQ) {
     __shared__ int sstack[SDEPTH][128];
     int lstack[DEEP ? 64 - SDEPTH : 1];
@@ -196,7 +202,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
     const int lane = tid & 31;
     const unsigned n = pool.counts[traceQ];
     enum { M_FETCH = 0, M_NODE = 1, M_LEAF = 2 };
-    enum { F_ANY = 1, F_FOUND = 2, F_EXHAUSTED = 4 };
+    enum { F_ANY = 1, F_FOUND = 2, F_EXHAUSTED = 4, F_EXIT = 8, F_HITIN = 16 };
+    int inst = -1, hitInst = -1, instBase = 0;   // INST only; instBase = 0 outside an instance
     int mode = M_FETCH;
     int c = -1;
     int flags = 0;
@@ -253,8 +260,13 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
                         leafFirst = second;
                         leafN = nPrims;
                         mode = M_LEAF;
-                    } else if (sp == 0) {
-                        mode = M_FETCH;
+                    } else if (sp == instBase) {
+                        if (INST && inst >= 0) {
+                            mode = M_LEAF;   // the object's BVH is exhausted: leave the instance in the leaf step
+                            flags |= F_EXIT;
+                            leafN = 0;
+                        } else
+                            mode = M_FETCH;
                     } else {
                         cur = top;
                         --sp;
@@ -263,12 +275,59 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
             }
         } else if (step == M_LEAF) {
             if (mode == M_LEAF) {
-                bool finished = false;
+                if (INST && (flags & F_EXIT)) {
+                    // back to world space (TransformedPrimitive::Intersect returns, primitive.cpp:82-86)
+                    flags &= ~F_EXIT;
+                    sp -= 3;
+                    float saved = __int_as_float(stackGet(sp));
+                    leafFirst = stackGet(sp + 1);
+                    leafN = stackGet(sp + 2);
+                    if (!(flags & F_HITIN)) tMax = saved;
+                    const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
+                    float4 ra = p[0], rb = p[1];
+                    rs = setupRay(mk3(ra.y, ra.z, ra.w), mk3(rb.x, rb.y, rb.z));
+                    inst = -1;
+                    instBase = 0;
+                }
+                bool finished = false, entered = false;
                 const bool any = (flags & F_ANY) != 0;
-                for (int i = 0; i < leafN; ++i) {
-                    const float4 *rec = &sc.leafPrims[3 * (size_t)(leafFirst + i)];
+                while (leafN > 0) {
+                    const int idx = leafFirst;
+                    ++leafFirst;
+                    --leafN;
+                    const float4 *rec = &sc.leafPrims[3 * (size_t)idx];
                     float4 a = ldg4(rec), b = ldg4(rec + 1), c4 = ldg4(rec + 2);
                     uint32_t pf = floatBits(b.w);
+                    if (INST && (pf & LEAF_INSTANCE)) {
+                        const int id = asInt(c4.w);
+                        const DInstance &in = sc.instances[id];
+                        const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
+                        float4 ra = p[0], rb = p[1];
+                        DRay ray;
+                        ray.o = mk3(ra.y, ra.z, ra.w);
+                        ray.d = mk3(rb.x, rb.y, rb.z);
+                        ray.tMax = rb.w;
+                        DRay r2 = xfRay(in.w2i, ray, tMax);
+                        stackPut(sp, __float_as_int(tMax));
+                        stackPut(sp + 1, leafFirst);
+                        stackPut(sp + 2, leafN);
+                        sp += 3;
+                        instBase = sp;
+                        inst = id;
+                        flags &= ~F_HITIN;
+                        rs = setupRay(r2.o, r2.d);
+                        tMax = r2.tMax;
+                        if (in.root >= 0) {
+                            cur = in.root;
+                            mode = M_NODE;
+                            leafN = 0;
+                            entered = true;
+                            break;
+                        }
+                        leafFirst = in.lone;   // one-primitive object: its record is the whole "leaf"
+                        leafN = 1;
+                        continue;
+                    }
                     if (SPHERES && (pf & LEAF_SPHERE)) {
                         const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
                         float4 ra = p[0], rb = p[1];
@@ -276,12 +335,17 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
                         ray.o = mk3(ra.y, ra.z, ra.w);
                         ray.d = mk3(rb.x, rb.y, rb.z);
                         ray.tMax = rb.w;
+                        if (INST && inst >= 0) ray = xfRay(sc.instances[inst].w2i, ray, tMax);
                         float t, phi;
                         if (sphereLeafTest(sc, asInt(c4.w), ray, tMax, &t, &phi)) {
                             flags |= F_FOUND;
                             if (any) { finished = true; break; }
                             tMax = t;
-                            __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(leafFirst + i), phi, 0.f, 0.f));
+                            if (INST) {
+                                hitInst = inst;
+                                if (inst >= 0) flags |= F_HITIN;
+                            }
+                            __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(idx), phi, 0.f, 0.f));
                         }
                         continue;
                     }
@@ -291,15 +355,24 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
                         if (pf & LEAF_DEGENERATE) continue;
                         flags |= F_FOUND;
                         tMax = t;
-                        __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(leafFirst + i), b0, b1, b2));
+                        if (INST) {
+                            hitInst = inst;
+                            if (inst >= 0) flags |= F_HITIN;
+                        }
+                        __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(idx), b0, b1, b2));
                     }
                 }
-                leafN = 0;
-                if (finished || sp == 0) mode = M_FETCH;
-                else {
-                    --sp;
-                    cur = stackGet(sp);
-                    mode = M_NODE;
+                if (!entered) {
+                    leafN = 0;
+                    if (finished) mode = M_FETCH;
+                    else if (sp == instBase) {
+                        if (INST && inst >= 0) flags |= F_EXIT;   // stays a leaf lane: the next leaf step leaves the instance
+                        else mode = M_FETCH;
+                    } else {
+                        --sp;
+                        cur = stackGet(sp);
+                        mode = M_NODE;
+                    }
                 }
             }
         } else {  // M_FETCH: flush finished rays, then take new ones
@@ -308,7 +381,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
             if (flush) {
                 WfCtx &cx = pool.ctx[c];
                 state = (flags & F_ANY) ? LS_SHADOW : __ldcs(&cx.ln.state);
-                __stcs(reinterpret_cast<float2 *>(&cx.tHit), make_float2(tMax, __int_as_float((flags & F_FOUND) ? 1 : 0)));
+                const int foundCode = (flags & F_FOUND) ? ((INST && !(flags & F_ANY) && hitInst >= 0) ? 2 + hitInst : 1) : 0;
+                __stcs(reinterpret_cast<float2 *>(&cx.tHit), make_float2(tMax, __int_as_float(foundCode)));
             }
             wfPush(pool.queue[WQ_SHADE], &pool.counts[WQ_SHADE], c, flush && state == LS_PATH);
             wfPush(pool.queue[WQ_LIGHT], &pool.counts[WQ_LIGHT], c, flush && state != LS_PATH);
@@ -335,6 +409,10 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
                         sp = 0;
                         leafN = 0;
                         mode = M_NODE;
+                        if (INST) {
+                            inst = hitInst = -1;
+                            instBase = 0;
+                        }
                     }
                 }
             }
