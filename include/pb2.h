@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 2   /* 2: pb2_scene_desc grew the object-instancing block at its end */
+#define PB2_ABI_VERSION 3   /* 2: object-instancing block at the end of pb2_scene_desc; 3: mirror / glass fields in pb2_material */
 
 typedef enum pb2_status {
     PB2_OK = 0,
@@ -53,7 +53,7 @@ typedef struct pb2_bvh_node {
 } pb2_bvh_node;
 
 enum { PB2_PRIM_TRIANGLE = 0, PB2_PRIM_SPHERE = 1, PB2_PRIM_INSTANCE = 2 };
-enum { PB2_MAT_NONE = 0, PB2_MAT_MATTE = 1, PB2_MAT_PLASTIC = 2 };
+enum { PB2_MAT_NONE = 0, PB2_MAT_MATTE = 1, PB2_MAT_PLASTIC = 2, PB2_MAT_MIRROR = 3, PB2_MAT_GLASS = 4 };
 enum { PB2_LIGHTDIST_UNIFORM = 0, PB2_LIGHTDIST_POWER = 1, PB2_LIGHTDIST_SPATIAL = 2 };
 
 /* One TriangleMesh (src/shapes/triangle.h:46-68).  Vertices are already in world space
@@ -86,6 +86,13 @@ typedef struct pb2_material {
     float roughness;
     int32_t remap_roughness;
     int32_t pad[2];
+    /* MirrorMaterial (src/materials/mirror.cpp:45-58): kr.  GlassMaterial (src/materials/glass.cpp:45-93)
+     * with uroughness == vroughness == 0: kr, kt, eta (the "index"/"eta" parameter); rough glass is refused. */
+    float kr[3];
+    float kt[3];
+    float eta;
+    float uroughness, vroughness;
+    int32_t pad2[3];
 } pb2_material;
 
 /* DiffuseAreaLight (src/lights/diffuse.h:49-79) attached to one primitive. */

@@ -55,6 +55,8 @@
 #include "lights/diffuse.h"
 #include "materials/matte.h"
 #include "materials/plastic.h"
+#include "materials/mirror.h"
+#include "materials/glass.h"
 #include "samplers/halton.h"
 #include "shapes/loopsubdiv.h"
 #include "shapes/sphere.h"
@@ -229,6 +231,16 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
             auto ks = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.ks));
             auto rough = std::make_shared<ConstantTexture<Float>>(pm.roughness);
             materials[i] = std::make_shared<PlasticMaterial>(kd, ks, rough, nullptr, pm.remap_roughness != 0);
+        } else if (pm.type == PB2_MAT_MIRROR) {
+            auto kr = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kr));
+            materials[i] = std::make_shared<MirrorMaterial>(kr, nullptr);
+        } else if (pm.type == PB2_MAT_GLASS) {
+            auto kr = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kr));
+            auto kt = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kt));
+            auto ur = std::make_shared<ConstantTexture<Float>>(pm.uroughness);
+            auto vr = std::make_shared<ConstantTexture<Float>>(pm.vroughness);
+            auto index = std::make_shared<ConstantTexture<Float>>(pm.eta);
+            materials[i] = std::make_shared<GlassMaterial>(kr, kt, ur, vr, index, nullptr, pm.remap_roughness != 0);
         }
     }
     // primitives + lights (lights indexed as in the description = Scene::lights order)

@@ -81,7 +81,7 @@ PB2_HD void startMisOrFinish(DLane &ln) {
 
 // The path ray has been traced: one iteration of the bounce loop up to (not including) the results
 // of the two direct-lighting rays.
-template <bool SPH>
+template <bool SPH, bool SPEC = true>
 PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &pp, DLane &ln, bool found, const DHit &hit,
                         float tMax) {
     DInteraction isect;
@@ -97,7 +97,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
         return;
     }
     DBsdf bsdf;
-    if (!makeBsdf(sc, isect, &bsdf)) {
+    if (!makeBsdf<SPEC>(sc, isect, &bsdf)) {
         ln.ray = spawnRay(isect, ln.ray.d);  // null BSDF: skip the surface, same bounce count
         return;
     }
@@ -141,7 +141,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
             }
             // BSDF-sampling half (integrator.cpp:162-213); area lights are not delta lights
             V3 wi;
-            V3 f = bsdfSampleF(bsdf, isect.wo, &wi, uScattering, &scatteringPdf);
+            V3 f = bsdfSampleF<SPEC>(bsdf, isect.wo, &wi, uScattering, &scatteringPdf);
             if (scatteringPdf != 0) f = f * absDot(wi, isect.ns);
             else f = mk3(0, 0, 0);
             if (!isBlack(f) && scatteringPdf > 0) {
@@ -166,11 +166,17 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
     {
         V3 wo = -ln.ray.d, wi;
         float pdf;
-        V3 f = bsdfSampleF(bsdf, wo, &wi, get2D(h, smp), &pdf);
+        int sampled = 0;
+        V3 f = bsdfSampleF<SPEC>(bsdf, wo, &wi, get2D(h, smp), &pdf, &sampled);
         if (!(isBlack(f) || pdf == 0.f)) {
             V3 s = f * absDot(wi, isect.ns);
             V3 beta = ln.beta * mk3(s.x / pdf, s.y / pdf, s.z / pdf);
-            ln.specularBounce = false;
+            ln.specularBounce = (sampled & BSDF_SAMPLED_SPECULAR) != 0;
+            if ((sampled & BSDF_SAMPLED_SPECULAR) && (sampled & BSDF_SAMPLED_TRANSMISSION)) {
+                // radiance scaling of refraction, tracked for Russian roulette only (path.cpp:142-149)
+                float eta = bsdf.eta;
+                ln.etaScale *= (dot(wo, isect.n) > 0) ? (eta * eta) : 1 / (eta * eta);
+            }
             DRay nr = spawnRay(isect, wi);
             bool survive = true;
             V3 rrBeta = beta * ln.etaScale;
@@ -226,10 +232,10 @@ PB2_HD void lightAdvance(const DScene &sc, DLane &ln, bool found, const DHit &hi
 
 // Advance a lane after its current ray was traced.  Returns true when the path ended in this call
 // (ln.L is then final and ln.state == LS_IDLE).
-template <bool SPH>
+template <bool SPH, bool SPEC = true>
 PB2_HD bool laneAdvance(const DScene &sc, const DHalton &h, const DPathParams &pp, DLane &ln, bool found, const DHit &hit,
                         float tMax) {
-    if (ln.state == LS_PATH) shadeVertex<SPH>(sc, h, pp, ln, found, hit, tMax);
+    if (ln.state == LS_PATH) shadeVertex<SPH, SPEC>(sc, h, pp, ln, found, hit, tMax);
     else lightAdvance<SPH>(sc, ln, found, hit, tMax);
     return ln.state == LS_IDLE;
 }

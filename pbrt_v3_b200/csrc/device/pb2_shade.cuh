@@ -236,7 +236,12 @@ struct DBsdf {
     int hasMicrofacet;
     V3 Ks;
     float alpha;           // TrowbridgeReitz alphax == alphay
+    // perfectly specular BxDF (not counted in nLobes, which is NumComponents(~BSDF_SPECULAR)):
+    int specKind;          // 0 none, 1 SpecularReflection + FresnelNoOp (mirror), 2 FresnelSpecular (smooth glass)
+    V3 specR, specT;
+    float eta;             // BSDF::eta (reflection.h:216): the glass index, 1 otherwise
 };
+enum { BSDF_SAMPLED_SPECULAR = 1, BSDF_SAMPLED_TRANSMISSION = 2 };
 
 PB2_HD V3 clampSpectrum(const float c[3]) {  // Spectrum::Clamp(0, Infinity), spectrum.h:126-132
     return mk3(clampf(c[0], 0.f, PB2_INFINITY), clampf(c[1], 0.f, PB2_INFINITY), clampf(c[2], 0.f, PB2_INFINITY));
@@ -251,6 +256,8 @@ PB2_HD float roughnessToAlpha(float roughness) {
 
 // Material::ComputeScatteringFunctions for matte (matte.cpp:45-62) and plastic (plastic.cpp:45-70).
 // Returns false when the primitive has no material (null BSDF: the path skips the surface).
+// SPEC = false compiles the specular materials away (scenes without mirror / glass get the leaner kernel).
+template <bool SPEC = true>
 PB2_HD bool makeBsdf(const DScene &sc, const DInteraction &it, DBsdf *bsdf) {
     int m = sc.primMaterial[it.prim];
     if (m < 0) return false;
@@ -267,6 +274,29 @@ PB2_HD bool makeBsdf(const DScene &sc, const DInteraction &it, DBsdf *bsdf) {
     bsdf->Ks = mk3(0, 0, 0);
     bsdf->A = bsdf->B = 0;
     bsdf->alpha = 0;
+    bsdf->specKind = 0;
+    bsdf->specR = bsdf->specT = mk3(0, 0, 0);
+    bsdf->eta = 1;
+    if (SPEC && mat.type == PB2_MAT_MIRROR) {
+        // mirror.cpp:45-58
+        V3 r = clampSpectrum(mat.kr);
+        if (!isBlack(r)) {
+            bsdf->specKind = 1;
+            bsdf->specR = r;
+        }
+        return true;
+    }
+    if (SPEC && mat.type == PB2_MAT_GLASS) {
+        // glass.cpp:45-68 with urough == vrough == 0 and allowMultipleLobes (path.cpp:106): one FresnelSpecular
+        V3 r = clampSpectrum(mat.kr), t = clampSpectrum(mat.kt);
+        bsdf->eta = mat.eta;
+        if (!(isBlack(r) && isBlack(t))) {
+            bsdf->specKind = 2;
+            bsdf->specR = r;
+            bsdf->specT = t;
+        }
+        return true;
+    }
     V3 kd = clampSpectrum(mat.kd);
     if (mat.type == PB2_MAT_MATTE) {
         float sig = clampf(mat.sigma, 0.f, 90.f);
@@ -478,8 +508,63 @@ PB2_HD float bsdfPdf(const DBsdf &b, V3 woW, V3 wiW) {
     return pdf / b.nLobes;
 }
 // BSDF::Sample_f (reflection.cpp:714-779).  Returns f; *pdf == 0 means no sample.
-PB2_HD V3 bsdfSampleF(const DBsdf &b, V3 woW, V3 *wiW, V2 u, float *pdf) {
+// Refract (reflection.h:97-109)
+PB2_HD bool refract(V3 wi, V3 n, float eta, V3 *wt) {
+    float cosThetaI = dot(n, wi);
+    float sin2ThetaI = pmax(0.f, 1 - cosThetaI * cosThetaI);
+    float sin2ThetaT = eta * eta * sin2ThetaI;
+    if (sin2ThetaT >= 1) return false;
+    float cosThetaT = sqrtf(1 - sin2ThetaT);
+    *wt = eta * (-wi) + (eta * cosThetaI - cosThetaT) * n;
+    return true;
+}
+
+// *sampledFlags (optional): BSDF_SAMPLED_* of the BxDF that was sampled.
+template <bool SPEC = true>
+PB2_HD V3 bsdfSampleF(const DBsdf &b, V3 woW, V3 *wiW, V2 u, float *pdf, int *sampledFlags = nullptr) {
     *pdf = 0;
+    if (sampledFlags) *sampledFlags = 0;
+    if (SPEC && b.specKind) {
+        // the BSDF holds exactly one BxDF, a specular one: matchingComps == 1, u is handed through
+        // (uRemapped[0] = min(u[0], OneMinusEpsilon)), no pdf averaging and no re-evaluation of f
+        // (reflection.cpp:725-775)
+        V3 wo = worldToLocal(b, woW), wi;
+        if (wo.z == 0) return mk3(0, 0, 0);
+        V3 f;
+        int flags = BSDF_SAMPLED_SPECULAR;
+        if (b.specKind == 1) {
+            // SpecularReflection::Sample_f with FresnelNoOp (reflection.cpp:136-143)
+            wi = mk3(-wo.x, -wo.y, wo.z);
+            *pdf = 1;
+            f = mk3(b.specR.x / absCosTheta(wi), b.specR.y / absCosTheta(wi), b.specR.z / absCosTheta(wi));
+        } else {
+            // FresnelSpecular::Sample_f (reflection.cpp:487-521), etaA = 1, etaB = eta, TransportMode::Radiance
+            float u0 = pmin(u.x, kOneMinusEpsilon);
+            float F = frDielectric(cosTheta(wo), 1.f, b.eta);
+            if (u0 < F) {
+                wi = mk3(-wo.x, -wo.y, wo.z);
+                *pdf = F;
+                V3 fr = F * b.specR;
+                f = mk3(fr.x / absCosTheta(wi), fr.y / absCosTheta(wi), fr.z / absCosTheta(wi));
+            } else {
+                bool entering = cosTheta(wo) > 0;
+                float etaI = entering ? 1.f : b.eta;
+                float etaT = entering ? b.eta : 1.f;
+                V3 nn = mk3(0, 0, 1);
+                if (dot(nn, wo) < 0) nn = -nn;  // Faceforward
+                if (!refract(wo, nn, etaI / etaT, &wi)) return mk3(0, 0, 0);
+                V3 ft = b.specT * (1 - F);
+                ft = ft * ((etaI * etaI) / (etaT * etaT));
+                flags |= BSDF_SAMPLED_TRANSMISSION;
+                *pdf = 1 - F;
+                f = mk3(ft.x / absCosTheta(wi), ft.y / absCosTheta(wi), ft.z / absCosTheta(wi));
+            }
+        }
+        if (*pdf == 0) return mk3(0, 0, 0);
+        *wiW = localToWorld(b, wi);
+        if (sampledFlags) *sampledFlags = flags;
+        return f;
+    }
     int matching = b.nLobes;
     if (matching == 0) return mk3(0, 0, 0);
     int comp = (int)floorf(u.x * matching);

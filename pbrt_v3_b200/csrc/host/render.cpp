@@ -34,6 +34,25 @@ pb2_material PlasticMaterial::Record() const {
     m.remap_roughness = remapRoughness ? 1 : 0;
     return m;
 }
+pb2_material MirrorMaterial::Record() const {
+    pb2_material m;
+    std::memset(&m, 0, sizeof(m));
+    m.type = PB2_MAT_MIRROR;
+    clampSpectrum(Kr, m.kr);
+    return m;
+}
+pb2_material GlassMaterial::Record() const {
+    pb2_material m;
+    std::memset(&m, 0, sizeof(m));
+    m.type = PB2_MAT_GLASS;
+    clampSpectrum(Kr, m.kr);
+    clampSpectrum(Kt, m.kt);
+    m.eta = index;
+    m.uroughness = uRoughness;
+    m.vroughness = vRoughness;
+    m.remap_roughness = remapRoughness ? 1 : 0;
+    return m;
+}
 static void rejectTextures(const TextureParams &mp, const char *what, std::initializer_list<const char *> names) {
     for (const char *n : names)
         if (mp.geomParams.FindTexture(n) != "" || mp.materialParams.FindTexture(n) != "")
@@ -45,6 +64,25 @@ MatteMaterial *CreateMatteMaterial(const TextureParams &mp) {
     Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(0.5f));
     Float sigma = mp.GetFloatTexture("sigma", 0.f);
     return new MatteMaterial(Kd, sigma);
+}
+// mirror.cpp:60-66
+MirrorMaterial *CreateMirrorMaterial(const TextureParams &mp) {
+    rejectTextures(mp, "mirror", {"Kr", "bumpmap"});
+    return new MirrorMaterial(mp.GetSpectrumTexture("Kr", Spectrum(0.9f)));
+}
+// glass.cpp:95-112
+GlassMaterial *CreateGlassMaterial(const TextureParams &mp) {
+    rejectTextures(mp, "glass", {"Kr", "Kt", "eta", "index", "uroughness", "vroughness", "bumpmap"});
+    Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f));
+    Spectrum Kt = mp.GetSpectrumTexture("Kt", Spectrum(1.f));
+    // "eta" wins over "index" when both are given (GetFloatTextureOrNull("eta") first)
+    Float eta = mp.GetFloatTexture("eta", mp.GetFloatTexture("index", 1.5f));
+    Float roughu = mp.GetFloatTexture("uroughness", 0.f);
+    Float roughv = mp.GetFloatTexture("vroughness", 0.f);
+    bool remap = mp.FindBool("remaproughness", true);
+    if (roughu != 0 || roughv != 0)
+        Error("glass: rough dielectrics (MicrofacetTransmission) are outside the GPU path's scope; rendering it smooth");
+    return new GlassMaterial(Kr, Kt, 0.f, 0.f, eta, remap);
 }
 PlasticMaterial *CreatePlasticMaterial(const TextureParams &mp) {
     rejectTextures(mp, "plastic", {"Kd", "Ks", "roughness", "bumpmap"});

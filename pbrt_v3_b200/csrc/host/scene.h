@@ -139,6 +139,24 @@ class PlasticMaterial : public Material {
     Float roughness;
     bool remapRoughness;
 };
+// mirror.h:49-66 / glass.h:49-77 with constant textures
+class MirrorMaterial : public Material {
+  public:
+    explicit MirrorMaterial(const Spectrum &Kr) : Kr(Kr) {}
+    pb2_material Record() const override;
+    Spectrum Kr;
+};
+class GlassMaterial : public Material {
+  public:
+    GlassMaterial(const Spectrum &Kr, const Spectrum &Kt, Float uRoughness, Float vRoughness, Float index, bool remapRoughness)
+        : Kr(Kr), Kt(Kt), uRoughness(uRoughness), vRoughness(vRoughness), index(index), remapRoughness(remapRoughness) {}
+    pb2_material Record() const override;
+    Spectrum Kr, Kt;
+    Float uRoughness, vRoughness, index;
+    bool remapRoughness;
+};
+MirrorMaterial *CreateMirrorMaterial(const TextureParams &mp);
+GlassMaterial *CreateGlassMaterial(const TextureParams &mp);
 MatteMaterial *CreateMatteMaterial(const TextureParams &mp);
 PlasticMaterial *CreatePlasticMaterial(const TextureParams &mp);
 

@@ -169,6 +169,7 @@ struct pb2_scene {
     int nLights = 0;
     int bvhDepth = 0;  // maximum number of simultaneously pending far children = tree depth (scene BVH)
     int instDepth = 0; // the same for the deepest instanced object's BVH
+    bool hasSpecular = false;  // a mirror / glass material exists: the shade kernel with the specular BxDFs is used
     // wavefront pool (allocated on first render)
     void *wfCtx = nullptr;
     int *wfQueues = nullptr;
@@ -525,7 +526,8 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     else trace = k_wf_trace<12, 8, 4, 32, false, false, 8>;   // also PB2_TRACE=7: the 32-B-node kernel on a triangle scene
     static const int shadeMinB = envInt("PB2_SHADE_MINB", 4);
     AdvanceKernel advLight = spheres ? k_wf_advance<false, true, 8> : k_wf_advance<false, false, 8>;
-    AdvanceKernel advShade = spheres ? k_wf_advance<true, true, 4>
+    AdvanceKernel advShade = scene->hasSpecular ? (spheres ? k_wf_advance<true, true, 4, true> : k_wf_advance<true, false, 4, true>)
+                             : spheres ? k_wf_advance<true, true, 4>
                              : shadeMinB == 3 ? k_wf_advance<true, false, 3>
                              : shadeMinB == 5 ? k_wf_advance<true, false, 5>
                              : shadeMinB == 6 ? k_wf_advance<true, false, 6>
@@ -682,13 +684,16 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
         return setError(PB2_ERR_INVALID, "scene has no primitives / BVH");
     if (d->n_prims > 0x7fffffffLL || d->n_nodes > 0x7fffffffLL) return setError(PB2_ERR_UNSUPPORTED, "more than 2^31 primitives/nodes");
     for (int i = 0; i < d->n_materials; ++i)
-        if (d->materials[i].type != PB2_MAT_NONE && d->materials[i].type != PB2_MAT_MATTE && d->materials[i].type != PB2_MAT_PLASTIC)
-            return setError(PB2_ERR_UNSUPPORTED, "material type outside the path's scope (matte, plastic)");
+        if (d->materials[i].type != PB2_MAT_NONE && d->materials[i].type != PB2_MAT_MATTE && d->materials[i].type != PB2_MAT_PLASTIC &&
+            d->materials[i].type != PB2_MAT_MIRROR && !(d->materials[i].type == PB2_MAT_GLASS && d->materials[i].uroughness == 0 && d->materials[i].vroughness == 0))
+            return setError(PB2_ERR_UNSUPPORTED, "material type outside the path's scope (matte, plastic, mirror, smooth glass)");
     struct Guard {
         pb2_scene *s;
         ~Guard() { if (s) pb2_scene_destroy(s); }
     } guard{new pb2_scene()};
     pb2_scene *s = guard.s;
+    for (int i = 0; i < d->n_materials; ++i)
+        if (d->materials[i].type == PB2_MAT_MIRROR || d->materials[i].type == PB2_MAT_GLASS) s->hasSpecular = true;
     DScene &sc = s->d;
     memset(&sc, 0, sizeof(sc));
     sc.nNodes = d->n_nodes;

@@ -644,7 +644,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
 // vertex is evaluated); SHADE = false: the light list (shadow / MIS rays: a few adds and the next
 // ray).  Two instantiations so that the light kernel is small and the warps of each stay converged.
 // ---------------------------------------------------------------------------------------------
-template <bool SHADE, bool SPH, int MINB>
+template <bool SHADE, bool SPH, int MINB, bool SPEC = false>
 __global__ void __launch_bounds__(128, MINB) k_wf_advance(DScene sc, DRenderParams rp, WfPool pool, int srcQ, int traceQ,
                                                                    int freeQ, float4 *film, unsigned long long *counters) {
     unsigned n = pool.counts[srcQ];
@@ -668,7 +668,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_advance(DScene sc, DRenderPara
             hit.inst = foundCode >= 2 ? foundCode - 2 : -1;
             bool found = foundCode != 0;
             float tHit = cx.tHit;
-            if (SHADE) shadeVertex<SPH>(sc, rp.halton, rp.path, ln, found, hit, tHit);
+            if (SHADE) shadeVertex<SPH, SPEC>(sc, rp.halton, rp.path, ln, found, hit, tHit);
             else lightAdvance<SPH>(sc, ln, found, hit, tHit);
             ended = ln.state == LS_IDLE;
             if (ended) addSample(rp, film, cx.pFilm, guardRadiance(ln.L));

@@ -12,7 +12,7 @@ from test_oracle import same_bvh
 
 def test_host_bvh_equals_reference_bvh(pb):
     """The host SAH builder reproduces BVHAccel's LinearBVHNode array and primitive order (src/accelerators/bvh.cpp:183-402)."""
-    for name in ("soup", "killeroo_like", "materials", "instances"):
+    for name in ("soup", "killeroo_like", "materials", "instances", "specular"):
         g = np.load(os.path.join(GOLDEN, name + ".npz"))
         hs = gc.soup_scene(pb) if name == "soup" else pb.HostScene.from_file(os.path.join(SCENES, name + ".pbrt"))
         assert same_bvh(hs.nodes(), g["bvh_nodes"]), name
@@ -110,7 +110,7 @@ def test_defaults_when_scene_file_is_silent(pb):
 
 def test_unsupported_plugins_are_reported_not_silently_replaced(pb):
     before = pb.lib().pb2h_error_count()
-    pb.HostScene.from_string('Sampler "halton"\nWorldBegin\nMaterial "glass"\nShape "sphere"\nWorldEnd\n')
+    pb.HostScene.from_string('Sampler "halton"\nWorldBegin\nMaterial "metal"\nShape "sphere"\nWorldEnd\n')
     assert pb.lib().pb2h_error_count() > before
 
 
@@ -163,3 +163,21 @@ def test_object_instancing_directives(pb):
     assert pb.lib().pb2h_error_count() == before + 1
     pb.HostScene.from_string('WorldBegin\nShape "sphere"\nObjectBegin "a"\nObjectBegin "b"\nObjectEnd\nObjectEnd\nWorldEnd\n')
     assert pb.lib().pb2h_error_count() > before + 1
+
+
+def test_mirror_and_glass_parameters(pb):
+    """CreateMirrorMaterial / CreateGlassMaterial defaults and parameter names (mirror.cpp:60-66, glass.cpp:95-112)."""
+    hs = pb.HostScene.from_file(os.path.join(SCENES, "specular.pbrt"))
+    d = hs.desc.contents
+    mats = [d.materials[i] for i in range(d.n_materials)]
+    mirrors = [m for m in mats if m.type == pb.PB2_MAT_MIRROR]
+    glasses = [m for m in mats if m.type == pb.PB2_MAT_GLASS]
+    assert len(mirrors) == 2 and len(glasses) == 2
+    assert np.allclose(tuple(mirrors[0].kr), (.9, .85, .8)) and np.allclose(tuple(mirrors[1].kr), (.9, .9, .9))   # default Kr 0.9
+    assert glasses[0].eta == np.float32(1.5) and tuple(glasses[0].kr) == (1, 1, 1) and tuple(glasses[0].kt) == (1, 1, 1)
+    assert glasses[1].eta == np.float32(1.33) and np.allclose(tuple(glasses[1].kt), (.8, .95, .85))
+    assert all(g.uroughness == 0 and g.vroughness == 0 for g in glasses)
+    # rough glass is reported, not silently rendered as something else
+    before = pb.lib().pb2h_error_count()
+    pb.HostScene.from_string('WorldBegin\nMaterial "glass" "float uroughness" 0.2\nShape "sphere"\nWorldEnd\n')
+    assert pb.lib().pb2h_error_count() > before
