@@ -88,6 +88,9 @@ class ClockSampler:
 
 def build_scene(args):
     import pbrt_v3_b200 as pb
+    if args.workload == "instanced":
+        # BASELINE.json configs[3]: one args.tris-triangle object instanced grid x grid times
+        return pb.HostScene.instanced_soup(args.tris, grid=args.grid, xres=args.xres, yres=args.yres, spp=args.spp, maxdepth=args.maxdepth)
     return pb.HostScene.soup(args.tris, seed=WORKLOAD["seed"], jitter=WORKLOAD["jitter"], xres=args.xres, yres=args.yres,
                              spp=args.spp, maxdepth=args.maxdepth)
 
@@ -104,13 +107,14 @@ def crop_params(hs, frac):
     return p, w * h
 
 
-def time_reference(hs, args, target_seconds, threads=0):
+def time_reference(hs, args, target_seconds, threads=0, scene=None):
     """Times the reference CPU path (oracle/_ref; the C++ port if _ref was not built) on a centred crop."""
     from oracle import pyoracle
     checker = pyoracle.reference() or pyoracle.port()
     if checker is None:
-        return None
-    scene = checker.scene(hs)
+        return None, None
+    if scene is None:
+        scene = checker.scene(hs)   # builds the reference's own BVH (seconds for 1 M triangles; outside the timing)
     spp = hs.params.contents.samples_per_pixel
     probe_params, probe_px = crop_params(hs, 64 * 32 / (args.xres * args.yres))
     _, secs, _ = scene.render(n_threads=threads, params=probe_params)
@@ -132,8 +136,11 @@ def run_reference_arm(args):
     hs = build_scene(args)
     vals = []
     info = None
+    scene = None
+    # every step is a bounded sample of the workload; the whole run stays within ~2.5 minutes of rendering
+    per_step = min(args.ref_seconds, 150.0 / max(1, args.warmup + args.steps))
     for i in range(args.warmup + args.steps):
-        info, _ = time_reference(hs, args, target_seconds=args.ref_seconds)
+        info, scene = time_reference(hs, args, target_seconds=per_step, scene=scene)
         if info is None:
             print(json.dumps({"impl": "reference", "unavailable": "neither oracle/_ref nor the oracle port is built"}))
             return 0
@@ -156,6 +163,13 @@ def run_reference_arm(args):
 
 
 def workload_config(args, parallelism):
+    if args.workload == "instanced":
+        return {"workload": "synthetic instanced triangles (SURVEY.md §8d C4): one %d-triangle soup object x %d instances, %dx%dx%dspp Halton, "
+                            "PathIntegrator maxdepth %d, matte Kd .6, 2-triangle area light"
+                            % (args.tris, args.grid * args.grid, args.xres, args.yres, args.spp, args.maxdepth),
+                "triangles": args.tris * args.grid * args.grid, "resolution": [args.xres, args.yres], "spp": args.spp,
+                "maxdepth": args.maxdepth, "parallelism": parallelism,
+                "l2_note": "inputs larger than L2: every step streams the 1 GiB path-context pool through the 126 MB L2; no explicit flush"}
     return {"workload": "synthetic %d random triangles (soup, SURVEY.md §8d C2), %dx%dx%dspp Halton, PathIntegrator maxdepth %d, "
                         "matte Kd .6, 2-triangle area light" % (args.tris, args.xres, args.yres, args.spp, args.maxdepth),
             "triangles": args.tris, "resolution": [args.xres, args.yres], "spp": args.spp, "maxdepth": args.maxdepth,
@@ -170,16 +184,23 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--tris", type=int, default=WORKLOAD["tris"])
+    ap.add_argument("--workload", default="soup", choices=["soup", "instanced"],
+                    help="soup = BASELINE.json configs[1], the headline (default); instanced = configs[3]'s generator")
+    ap.add_argument("--tris", type=int, default=None, help="triangles (soup: 1 000 000) / triangles of the instanced object (100 000)")
+    ap.add_argument("--grid", type=int, default=10, help="instanced: grid x grid instances")
     ap.add_argument("--xres", type=int, default=WORKLOAD["xres"])
     ap.add_argument("--yres", type=int, default=WORKLOAD["yres"])
-    ap.add_argument("--spp", type=int, default=WORKLOAD["spp"])
-    ap.add_argument("--maxdepth", type=int, default=WORKLOAD["maxdepth"])
+    ap.add_argument("--spp", type=int, default=None)
+    ap.add_argument("--maxdepth", type=int, default=None)
     ap.add_argument("--ref-seconds", type=float, default=15.0, help="CPU seconds per reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    default_workload = all(getattr(args, k) == WORKLOAD[k] for k in ("tris", "xres", "yres", "spp", "maxdepth"))
-    args.warmup = max(args.warmup, 0)
+    inst = args.workload == "instanced"
+    if args.tris is None: args.tris = 100000 if inst else WORKLOAD["tris"]
+    if args.spp is None: args.spp = 128 if inst else WORKLOAD["spp"]
+    if args.maxdepth is None: args.maxdepth = 5 if inst else WORKLOAD["maxdepth"]
+    default_workload = not inst and all(getattr(args, k) == WORKLOAD[k] for k in ("tris", "xres", "yres", "spp", "maxdepth"))
+    args.warmup = max(args.warmup, 3)   # timing rule: at least three untimed steps
 
     if args.impl == "reference":
         return run_reference_arm(args)
