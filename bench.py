@@ -319,7 +319,7 @@ def main():
                          "bytes_per_ray": alg_bytes / max(rays_frame, 1), "trace_ms_per_frame": trace_ms / args.steps,
                          "trace_share_of_step": (trace_ms / args.steps) / ms_per_step},
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # the CPU side-by-side is reported by the N = 1 run only
             try:
                 cb, _ = time_reference(hs, args, target_seconds=args.ref_seconds)
                 if cb:
