@@ -6,7 +6,7 @@
 //   wide       the same tree with the boxes moved up one level: one 64-B record per INTERIOR node,
 //              float4 q0 = (c0.min.xyz, c0.max.x), q1 = (c0.max.yz, c1.min.xy), q2 = (c1.min.z, c1.max.xyz),
 //              q3 = (ref0, ref1, meta, -) with c0 = the node's first child (index + 1), c1 = its second;
-//              ref = index of the child's wide record, or WIDE_LEAF | nPrims << 24 | primitivesOffset;
+//              ref = index of the child's wide record, or WIDE_LEAF | (nPrims - 1) << 27 | primitivesOffset;
 //              meta = the node's split axis (bits 0-1) | WIDE_SINGLE.  Record 0 is a pseudo node whose
 //              only child is the root.  One fetch tests both children's boxes, so the render kernel
 //              makes half the dependent memory round trips of the 32-B layout; every box is still
@@ -37,11 +37,13 @@ enum : uint32_t {
     LEAF_INSTANCE = 16u,      // record describes a TransformedPrimitive: c.w = instance number
 };
 enum : uint32_t {
-    WIDE_LEAF = 0x80000000u,  // child reference: bits 0-23 primitivesOffset, bits 24-30 nPrimitives
+    WIDE_LEAF = 0x80000000u,  // child reference: bits 0-26 primitivesOffset, bits 27-30 nPrimitives - 1
+    WIDE_LEAF_COUNT_SHIFT = 27,
+    WIDE_LEAF_OFFSET_MASK = (1u << 27) - 1,
     WIDE_SINGLE = 4u,         // meta: the record has only child 0 (the pseudo node above the root)
     WIDE_TOP = 0x40000000u,   // child reference inside wideTop: bits 0-23 index into wideTop
-    WIDE_MAX_PRIMS = 1u << 24,
-    WIDE_MAX_LEAF = 127u,
+    WIDE_MAX_PRIMS = 1u << 27,   // 134 M primitives (config 5 has 50 M)
+    WIDE_MAX_LEAF = 16u,         // primitives per leaf (the reference's default maxnodeprims is 4)
 };
 
 struct DLightDist {

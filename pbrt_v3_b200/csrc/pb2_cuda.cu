@@ -805,7 +805,7 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
             std::vector<WideRec> wide((size_t)nWide);
             auto childRef = [&](int64_t i) -> uint32_t {
                 const pb2_bvh_node &n = d->nodes[i];
-                return n.n_prims == 0 ? (uint32_t)wideOf[i] : (WIDE_LEAF | ((uint32_t)n.n_prims << 24) | (uint32_t)n.offset);
+                return n.n_prims == 0 ? (uint32_t)wideOf[i] : (WIDE_LEAF | ((uint32_t)(n.n_prims - 1) << WIDE_LEAF_COUNT_SHIFT) | (uint32_t)n.offset);
             };
             auto putBox = [&](float *dst, const pb2_bvh_node &n) {
                 dst[0] = n.bmin[0]; dst[1] = n.bmin[1]; dst[2] = n.bmin[2];

@@ -468,8 +468,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
     // continue with child reference `ref`
     auto enter = [&](int ref) {
         if (ref < 0) {
-            leafFirst = ref & 0xffffff;
-            leafN = (ref >> 24) & 0x7f;
+            leafFirst = ref & (int)WIDE_LEAF_OFFSET_MASK;
+            leafN = ((ref >> WIDE_LEAF_COUNT_SHIFT) & 0xf) + 1;
             mode = M_LEAF;
         } else {
             cur = ref;
@@ -549,8 +549,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
                         const int ref = pn ? rn : rf;
                         const bool have = pn | pf;
                         const bool isLeaf = have & (ref < 0);
-                        leafFirst = isLeaf ? (ref & 0xffffff) : leafFirst;
-                        leafN = isLeaf ? ((ref >> 24) & 0x7f) : leafN;
+                        leafFirst = isLeaf ? (ref & (int)WIDE_LEAF_OFFSET_MASK) : leafFirst;
+                        leafN = isLeaf ? (((ref >> WIDE_LEAF_COUNT_SHIFT) & 0xf) + 1) : leafN;
                         mode = isLeaf ? (int)M_LEAF : (int)M_NODE;
                         cur = (have & !isLeaf) ? ref : -1;
                     } else if (pn) {

@@ -92,6 +92,24 @@ def test_gpu_matches_checker_on_a_larger_scene(pb, checker):
     assert abs(int(st.regular_rays) - int(ref_st.regular_rays)) <= ref_st.regular_rays // 1000 + 2
 
 
+@pytest.mark.parametrize("maxprims,split", [(16, "sah"), (40, "equal"), (1, "middle")])
+def test_other_bvh_shapes_match_checker(pb, checker, maxprims, split):
+    """Leaves of up to 16 primitives still fit the two-child records, 40 do not (the 32-byte-node kernel takes over),
+    1 gives the deepest tree; every variant must trace and render like the checker's BVHAccel built the same way."""
+    text = open(os.path.join(SCENES, "killeroo_like.pbrt")).read().replace(
+        "WorldBegin", 'Accelerator "bvh" "string splitmethod" "%s" "integer maxnodeprims" [%d]\nWorldBegin' % (split, maxprims))
+    hs = pb.HostScene.from_string(text)
+    sm = {"sah": 0, "middle": 2, "equal": 3}[split]
+    sc = checker.scene(hs, max_prims_in_node=maxprims, split_method=sm)
+    rays = gc.rays_for(pb, hs.nodes(), 20000, 61)
+    assert hs.intersect(rays).tobytes() == _without_b(sc.intersect(rays), hs.intersect(rays))
+    img, st = hs.render()
+    ref_img, _, ref_st = sc.render(n_threads=0)
+    frac, mean_rel = image_metrics(img, ref_img)
+    assert frac >= 0.999 and mean_rel <= 1e-4
+    assert abs(int(st.regular_rays) - int(ref_st.regular_rays)) <= ref_st.regular_rays // 1000 + 2
+
+
 def test_instanced_soup_matches_checker(pb, checker):
     """A soup object instanced 4 x 4 times with random rotations (the generator of BASELINE.json configs[3] at a size the
     CPU checker renders in a second): hits bit-identical, any-hits equal, image and ray counters as for every scene."""
