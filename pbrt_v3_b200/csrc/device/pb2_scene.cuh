@@ -167,6 +167,52 @@ PB2_HD bool slabTestT(float minx, float miny, float minz, float maxx, float maxy
     return !miss1 & !miss2 & (tMin < rayTMax) & (tMax > 0);
 }
 
+// Both children of a two-child record at once.  On the device the subtractions, multiplications and
+// the far-plane scaling run as packed FP32x2 operations (FADD2 / FMUL2, sm_100: `__fadd2_rn`,
+// `__fmul2_rn`), lane 0 = child 0, lane 1 = child 1 - per component these are the IEEE operations of
+// slabTestT, so the verdicts and tMin values are bit-identical to two slabTestT calls.
+PB2_HD void slabTestPair(float4 q0, float4 q1, float4 q2, const DRaySetup &r, float rayTMax, bool *pass0, bool *pass1,
+                         float *tMin0, float *tMin1) {
+#if defined(__CUDA_ARCH__)
+    // child 0: min = (q0.x, q0.y, q0.z), max = (q0.w, q1.x, q1.y); child 1: min = (q1.z, q1.w, q2.x), max = (q2.y, q2.z, q2.w)
+    const float2 minX = make_float2(q0.x, q1.z), minY = make_float2(q0.y, q1.w), minZ = make_float2(q0.z, q2.x);
+    const float2 maxX = make_float2(q0.w, q2.y), maxY = make_float2(q1.x, q2.z), maxZ = make_float2(q1.y, q2.w);
+    const float2 nearX = r.neg0 ? maxX : minX, farX = r.neg0 ? minX : maxX;
+    const float2 nearY = r.neg1 ? maxY : minY, farY = r.neg1 ? minY : maxY;
+    const float2 nearZ = r.neg2 ? maxZ : minZ, farZ = r.neg2 ? minZ : maxZ;
+    const float2 nox = make_float2(-r.o.x, -r.o.x), noy = make_float2(-r.o.y, -r.o.y), noz = make_float2(-r.o.z, -r.o.z);
+    const float2 ix = make_float2(r.invDir.x, r.invDir.x), iy = make_float2(r.invDir.y, r.invDir.y), iz = make_float2(r.invDir.z, r.invDir.z);
+    const float2 sc2 = make_float2(kSlabScale, kSlabScale);
+    float2 tMin = __fmul2_rn(__fadd2_rn(nearX, nox), ix);
+    float2 tMax = __fmul2_rn(__fmul2_rn(__fadd2_rn(farX, nox), ix), sc2);
+    const float2 tyMin = __fmul2_rn(__fadd2_rn(nearY, noy), iy);
+    const float2 tyMax = __fmul2_rn(__fmul2_rn(__fadd2_rn(farY, noy), iy), sc2);
+    const float2 tzMin = __fmul2_rn(__fadd2_rn(nearZ, noz), iz);
+    const float2 tzMax = __fmul2_rn(__fmul2_rn(__fadd2_rn(farZ, noz), iz), sc2);
+    {
+        const bool miss1 = (tMin.x > tyMax.x) | (tyMin.x > tMax.x);
+        float a = (tyMin.x > tMin.x) ? tyMin.x : tMin.x, b = (tyMax.x < tMax.x) ? tyMax.x : tMax.x;
+        const bool miss2 = (a > tzMax.x) | (tzMin.x > b);
+        a = (tzMin.x > a) ? tzMin.x : a;
+        b = (tzMax.x < b) ? tzMax.x : b;
+        *tMin0 = a;
+        *pass0 = !miss1 & !miss2 & (a < rayTMax) & (b > 0);
+    }
+    {
+        const bool miss1 = (tMin.y > tyMax.y) | (tyMin.y > tMax.y);
+        float a = (tyMin.y > tMin.y) ? tyMin.y : tMin.y, b = (tyMax.y < tMax.y) ? tyMax.y : tMax.y;
+        const bool miss2 = (a > tzMax.y) | (tzMin.y > b);
+        a = (tzMin.y > a) ? tzMin.y : a;
+        b = (tzMax.y < b) ? tzMax.y : b;
+        *tMin1 = a;
+        *pass1 = !miss1 & !miss2 & (a < rayTMax) & (b > 0);
+    }
+#else
+    *pass0 = slabTestT(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, rayTMax, tMin0);
+    *pass1 = slabTestT(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, rayTMax, tMin1);
+#endif
+}
+
 PB2_HD bool slabTest(float4 n0, float4 n1, const DRaySetup &r, float rayTMax) {
     // n0 = (min.x, min.y, min.z, max.x), n1 = (max.y, max.z, offset, meta)
     float bx0 = r.neg0 ? n0.w : n0.x, bx1 = r.neg0 ? n0.x : n0.w;

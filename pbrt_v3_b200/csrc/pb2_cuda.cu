@@ -511,8 +511,9 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     const bool instancedTuned = instanced && variant != 14 && scene->bvhDepth + 3 + scene->instDepth <= 64;
     if (instancedTuned) trace = k_wf_trace<8, 8, 2, 32, true, true, 6, true>;
     else if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
-    else if (wideNodes && variant == 0) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1>, 128, 16, false);
+    else if (wideNodes && variant == 0) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1, 128, false, true>, 128, 16, false);
     else if (wideNodes && variant == 5) wideKernel(k_wf_trace_w<12, 8, 4, 16, 8>, 128, 16, false);
+    else if (wideNodes && variant == 15) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1>, 128, 16, false);   // scalar slab tests
     else if (wideNodes && variant == 8) wideKernel(k_wf_trace_w<8, 8, 2, 4, 8>, 128, 4, false);   // tests: forces the local-memory stack spill
     else if (wideNodes && variant == 9) wideKernel(k_wf_trace_w<8, 8, 3, 16, 1, 1, 1024, true>, 1024, 16, true);
     else if (wideNodes && variant == 10) wideKernel(k_wf_trace_w<8, 8, 3, 12, 1, 1, 1024, true>, 1024, 12, true);

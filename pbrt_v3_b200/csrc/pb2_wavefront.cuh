@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
 // copied into shared memory at kernel start and read from there: the kernel is bound by the number
 // of L1 tag look-ups (4 scattered 16-byte requests per record), not by bytes, and shared-memory
 // reads need none.  BLOCK = 1024 gives one resident block per SM, so that copy exists once per SM.
-template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, int TAIL = 0, int BLOCK = 128, bool TOP = false>
+template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, int TAIL = 0, int BLOCK = 128, bool TOP = false, bool PACKED = false>
 __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
     extern __shared__ int2 dynSmem[];
     int2 *sstack = dynSmem;                // [SDEPTH][BLOCK] of (child reference, tMin bits)
@@ -527,8 +527,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
                         q0 = ldg4(w); q1 = ldg4(w + 1); q2 = ldg4(w + 2); q3 = ldg4(w + 3);
                     }
                     float t0, t1;
-                    bool p0 = slabTestT(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, rs, tMax, &t0);
-                    bool p1 = slabTestT(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, rs, tMax, &t1);
+                    bool p0, p1;
+                    if (PACKED) slabTestPair(q0, q1, q2, rs, tMax, &p0, &p1, &t0, &t1);
+                    else {
+                        p0 = slabTestT(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, rs, tMax, &t0);
+                        p1 = slabTestT(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, rs, tMax, &t1);
+                    }
                     uint32_t meta = floatBits(q3.z);
                     if (meta & WIDE_SINGLE) p1 = false;
                     int axis = (int)(meta & 3u);
