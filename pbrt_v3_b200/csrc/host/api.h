@@ -15,39 +15,32 @@ struct Options {
     Float cropWindow[2][2] = {{0, 1}, {0, 1}};
 };
 
-void pbrtInit(const Options &opt);
+// -- life cycle (api.cpp:682-722)
+void pbrtInit(const Options &options);
 bool pbrtIsInitialized();
 void pbrtCleanup();
+
+// -- current transformation matrix (api.cpp:724-872).  Matrices arrive column-major, as in scene files.
 void pbrtIdentity();
-void pbrtTranslate(Float dx, Float dy, Float dz);
-void pbrtRotate(Float angle, Float ax, Float ay, Float az);
-void pbrtScale(Float sx, Float sy, Float sz);
-void pbrtLookAt(Float ex, Float ey, Float ez, Float lx, Float ly, Float lz, Float ux, Float uy, Float uz);
-void pbrtConcatTransform(Float transform[16]);
-void pbrtTransform(Float transform[16]);
-void pbrtCoordinateSystem(const std::string &);
-void pbrtCoordSysTransform(const std::string &);
-void pbrtPixelFilter(const std::string &name, const ParamSet &params);
-void pbrtFilm(const std::string &type, const ParamSet &params);
-void pbrtSampler(const std::string &name, const ParamSet &params);
-void pbrtAccelerator(const std::string &name, const ParamSet &params);
-void pbrtIntegrator(const std::string &name, const ParamSet &params);
-void pbrtCamera(const std::string &, const ParamSet &cameraParams);
-void pbrtWorldBegin();
-void pbrtAttributeBegin();
-void pbrtAttributeEnd();
-void pbrtTransformBegin();
-void pbrtTransformEnd();
-void pbrtMaterial(const std::string &name, const ParamSet &params);
-void pbrtMakeNamedMaterial(const std::string &name, const ParamSet &params);
-void pbrtNamedMaterial(const std::string &name);
-void pbrtAreaLightSource(const std::string &name, const ParamSet &params);
-void pbrtShape(const std::string &name, const ParamSet &params);
-void pbrtObjectBegin(const std::string &name);
-void pbrtObjectEnd();
-void pbrtObjectInstance(const std::string &name);
+void pbrtTranslate(Float tx, Float ty, Float tz);
+void pbrtRotate(Float degrees, Float axisX, Float axisY, Float axisZ);
+void pbrtScale(Float x, Float y, Float z);
+void pbrtLookAt(Float eyeX, Float eyeY, Float eyeZ, Float lookX, Float lookY, Float lookZ, Float upX, Float upY, Float upZ);
+void pbrtConcatTransform(Float columnMajor[16]);
+void pbrtTransform(Float columnMajor[16]);
+void pbrtCoordinateSystem(const std::string &coordSysName), pbrtCoordSysTransform(const std::string &coordSysName);
+
+// -- options block: the one-per-scene plugins (api.cpp:874-1010)
+typedef void PluginDirective(const std::string &pluginName, const ParamSet &pluginParams);
+PluginDirective pbrtPixelFilter, pbrtFilm, pbrtSampler, pbrtAccelerator, pbrtIntegrator, pbrtCamera;
+
+// -- world block: attribute / transform stacks, materials, lights, shapes, objects (api.cpp:1023-1588)
+void pbrtWorldBegin(), pbrtWorldEnd();
+void pbrtAttributeBegin(), pbrtAttributeEnd(), pbrtTransformBegin(), pbrtTransformEnd();
+PluginDirective pbrtMaterial, pbrtMakeNamedMaterial, pbrtAreaLightSource, pbrtShape;
+void pbrtNamedMaterial(const std::string &materialName);
+void pbrtObjectBegin(const std::string &objectName), pbrtObjectEnd(), pbrtObjectInstance(const std::string &objectName);
 void pbrtReverseOrientation();
-void pbrtWorldEnd();
 
 void pbrtParseFile(std::string filename);
 void pbrtParseString(std::string str);
