@@ -510,6 +510,7 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     // two levels fit the 64-entry stack; PB2_TRACE=14 keeps them on the plain kernel (tests compare both)
     const bool instancedTuned = instanced && variant != 14 && scene->bvhDepth + 3 + scene->instDepth <= 64;
     if (instancedTuned) trace = k_wf_trace<8, 8, 2, 32, true, true, 6, true>;
+    else if (spheres && wideNodes && variant != 7) wideKernel(k_wf_trace_w<8, 8, 3, 16, 6, 1, 128, false, true, true>, 128, 16, false);
     else if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
     else if (wideNodes && variant == 0) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1, 128, false, true>, 128, 16, false);
     else if (wideNodes && variant == 5) wideKernel(k_wf_trace_w<12, 8, 4, 16, 8>, 128, 16, false);

@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
 // copied into shared memory at kernel start and read from there: the kernel is bound by the number
 // of L1 tag look-ups (4 scattered 16-byte requests per record), not by bytes, and shared-memory
 // reads need none.  BLOCK = 1024 gives one resident block per SM, so that copy exists once per SM.
-template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, int TAIL = 0, int BLOCK = 128, bool TOP = false, bool PACKED = false>
+template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, int TAIL = 0, int BLOCK = 128, bool TOP = false, bool PACKED = false, bool SPHERES = false>
 __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
     extern __shared__ int2 dynSmem[];
     int2 *sstack = dynSmem;                // [SDEPTH][BLOCK] of (child reference, tMin bits)
@@ -579,6 +579,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
                     const float4 *rec = &sc.leafPrims[3 * (size_t)(leafFirst + i)];
                     float4 a = ldg4(rec), b = ldg4(rec + 1), c4 = ldg4(rec + 2);
                     uint32_t pf = floatBits(b.w);
+                    if (SPHERES && (pf & LEAF_SPHERE)) {
+                        const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
+                        float4 ra = p[0], rb = p[1];
+                        DRay ray;
+                        ray.o = mk3(ra.y, ra.z, ra.w);
+                        ray.d = mk3(rb.x, rb.y, rb.z);
+                        ray.tMax = rb.w;
+                        float t, phi;
+                        if (sphereLeafTest(sc, asInt(c4.w), ray, tMax, &t, &phi)) {
+                            flags |= F_FOUND;
+                            if (any) { finished = true; break; }
+                            tMax = t;
+                            __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(leafFirst + i), phi, 0.f, 0.f));
+                        }
+                        continue;
+                    }
                     float t, b0, b1, b2;
                     if (triangleTest(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c4.x, c4.y, c4.z), rs, tMax, &t, &b0, &b1, &b2)) {
                         if (any) { flags |= F_FOUND; finished = true; break; }
