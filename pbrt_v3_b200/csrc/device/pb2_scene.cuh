@@ -60,7 +60,7 @@ struct DInstance {
     int root;       // global index of the object BVH's root node, or -1
     int lone;       // root < 0: leaf record of the object's only primitive
     int identity;   // Transform::IsIdentity(): the interaction is then not transformed (primitive.cpp:85-86)
-    int pad;
+    int wroot;      // two-child records: the pseudo record whose only child is the object BVH's root, or -1
 };
 
 struct DScene {

@@ -509,7 +509,8 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     // instanced scenes: the tuned 32-B-node kernel with the instance frame on its stack, as long as the
     // two levels fit the 64-entry stack; PB2_TRACE=14 keeps them on the plain kernel (tests compare both)
     const bool instancedTuned = instanced && variant != 14 && scene->bvhDepth + 3 + scene->instDepth <= 64;
-    if (instancedTuned) trace = k_wf_trace<8, 8, 2, 32, true, true, 6, true>;
+    if (instancedTuned && wideNodes && variant != 7) wideKernel(k_wf_trace_w<8, 8, 3, 16, 6, 1, 128, false, true, true, true>, 128, 16, false);
+    else if (instancedTuned) trace = k_wf_trace<8, 8, 2, 32, true, true, 6, true>;
     else if (spheres && wideNodes && variant != 7) wideKernel(k_wf_trace_w<8, 8, 3, 16, 6, 1, 128, false, true, true>, 128, 16, false);
     else if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
     else if (wideNodes && variant == 0) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1, 128, false, true>, 128, 16, false);
@@ -770,7 +771,7 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
             memcpy(inst[i].i2w.m, pi.instance_to_world, sizeof(float) * 16);
             memcpy(inst[i].w2i.m, pi.world_to_instance, sizeof(float) * 16);
             inst[i].identity = memcmp(pi.instance_to_world, identity, sizeof(identity)) == 0;   // Transform::IsIdentity (transform.h:137-143)
-            inst[i].pad = 0;
+            inst[i].wroot = pi.bvh >= 0 ? pi.bvh : -1;   // the pseudo record above the object BVH's root (two-child records)
             if (pi.bvh >= 0) {
                 if (pi.bvh == 0 || pi.bvh >= (int)bvhs.size()) return setError(PB2_ERR_INVALID, "instance BVH out of range");
                 inst[i].root = (int)bvhs[pi.bvh].node_offset;
@@ -792,21 +793,24 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
     }
     sc.nodes = reinterpret_cast<const float4 *>(nodes);
     sc.wide = nullptr;
-    if (d->n_nodes > 0 && d->n_prims < (int64_t)WIDE_MAX_PRIMS && bvhs.size() == 1 && d->n_instances == 0) {
-        // two-child records (pb2_scene.cuh): interior nodes keep their depth-first order
+    if (d->n_nodes > 0 && d->n_prims < (int64_t)WIDE_MAX_PRIMS) {
+        // two-child records (pb2_scene.cuh): interior nodes keep their depth-first order; records
+        // 0 .. nBvh-1 are the pseudo nodes above the root of each BVH (scene BVH, then instanced objects)
+        const pb2_bvh_node *src = rebased.empty() ? d->nodes : rebased.data();   // indices global across BVHs
+        const int32_t nBvh = (int32_t)bvhs.size();
         std::vector<int32_t> wideOf((size_t)d->n_nodes, -1);
-        int32_t nWide = 1;
+        int32_t nWide = nBvh;
         bool fits = true;
         for (int64_t i = 0; i < d->n_nodes; ++i) {
-            if (d->nodes[i].n_prims == 0) wideOf[i] = nWide++;
-            else if (d->nodes[i].n_prims > WIDE_MAX_LEAF) fits = false;
+            if (src[i].n_prims == 0) wideOf[i] = nWide++;
+            else if (src[i].n_prims > WIDE_MAX_LEAF) fits = false;
         }
         if (fits) {
             struct WideRec { float b[12]; uint32_t ref0, ref1, meta, pad; };
             static_assert(sizeof(WideRec) == 64, "wide record is 64 bytes");
             std::vector<WideRec> wide((size_t)nWide);
             auto childRef = [&](int64_t i) -> uint32_t {
-                const pb2_bvh_node &n = d->nodes[i];
+                const pb2_bvh_node &n = src[i];
                 return n.n_prims == 0 ? (uint32_t)wideOf[i] : (WIDE_LEAF | ((uint32_t)(n.n_prims - 1) << WIDE_LEAF_COUNT_SHIFT) | (uint32_t)n.offset);
             };
             auto putBox = [&](float *dst, const pb2_bvh_node &n) {
@@ -814,16 +818,19 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
                 dst[3] = n.bmax[0]; dst[4] = n.bmax[1]; dst[5] = n.bmax[2];
             };
             memset(wide.data(), 0, wide.size() * sizeof(WideRec));
-            putBox(wide[0].b, d->nodes[0]);
-            putBox(wide[0].b + 6, d->nodes[0]);
-            wide[0].ref0 = wide[0].ref1 = childRef(0);
-            wide[0].meta = WIDE_SINGLE;
+            for (int32_t k = 0; k < nBvh; ++k) {
+                const int64_t root = bvhs[(size_t)k].node_offset;
+                putBox(wide[(size_t)k].b, src[root]);
+                putBox(wide[(size_t)k].b + 6, src[root]);
+                wide[(size_t)k].ref0 = wide[(size_t)k].ref1 = childRef(root);
+                wide[(size_t)k].meta = WIDE_SINGLE;
+            }
             for (int64_t i = 0; i < d->n_nodes; ++i) {
-                const pb2_bvh_node &n = d->nodes[i];
+                const pb2_bvh_node &n = src[i];
                 if (n.n_prims != 0) continue;
                 WideRec &w = wide[(size_t)wideOf[i]];
-                putBox(w.b, d->nodes[i + 1]);
-                putBox(w.b + 6, d->nodes[n.offset]);
+                putBox(w.b, src[i + 1]);
+                putBox(w.b + 6, src[n.offset]);
                 w.ref0 = childRef(i + 1);
                 w.ref1 = childRef(n.offset);
                 w.meta = (uint32_t)n.axis & 3u;

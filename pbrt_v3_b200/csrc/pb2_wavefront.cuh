@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
 // copied into shared memory at kernel start and read from there: the kernel is bound by the number
 // of L1 tag look-ups (4 scattered 16-byte requests per record), not by bytes, and shared-memory
 // reads need none.  BLOCK = 1024 gives one resident block per SM, so that copy exists once per SM.
-template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, int TAIL = 0, int BLOCK = 128, bool TOP = false, bool PACKED = false, bool SPHERES = false>
+template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, int TAIL = 0, int BLOCK = 128, bool TOP = false, bool PACKED = false, bool SPHERES = false, bool INST = false>
 __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
     extern __shared__ int2 dynSmem[];
     int2 *sstack = dynSmem;                // [SDEPTH][BLOCK] of (child reference, tMin bits)
@@ -454,7 +454,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
     const int lane = tid & 31;
     const unsigned n = pool.counts[traceQ];
     enum { M_FETCH = 0, M_NODE = 1, M_LEAF = 2 };
-    enum { F_ANY = 1, F_FOUND = 2, F_EXHAUSTED = 4 };
+    enum { F_ANY = 1, F_FOUND = 2, F_EXHAUSTED = 4, F_EXIT = 8, F_HITIN = 16 };
+    static_assert(!INST || TAIL, "the instance frame is only written for the straight-line tail");
+    // INST (object instances): as in k_wf_trace - an instance is a leaf primitive; the lane pushes a
+    // frame of two entries ((rest of the leaf), (tMax, -)), walks the object's records from the pseudo
+    // record above its root with `instBase` as stack floor, and leaves through the leaf step (F_EXIT).
+    int inst = -1, hitInst = -1, instBase = 0;
+    auto stGet = [&](int i) -> int2 { return i < SDEPTH ? sstack[i * BLOCK + tid] : lstack[i - SDEPTH]; };
+    auto stPut = [&](int i, int2 e) {
+        if (i < SDEPTH) sstack[i * BLOCK + tid] = e;
+        else lstack[i - SDEPTH] = e;
+    };
     int mode = M_FETCH;
     int c = -1;
     int flags = 0;
@@ -508,8 +518,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         if (mode == M_NODE && cur < 0) {
-                            if (sp == 0) mode = M_FETCH;
-                            else {
+                            if (sp == instBase) {
+                                if (INST && inst >= 0) {
+                                    mode = M_LEAF;   // the object is exhausted: leave the instance in the leaf step
+                                    flags |= F_EXIT;
+                                    leafN = 0;
+                                } else
+                                    mode = M_FETCH;
+                            } else {
                                 --sp;
                                 int2 e = sp < SDEPTH ? sstack[sp * BLOCK + tid] : lstack[sp - SDEPTH];
                                 if (__int_as_float(e.y) < tMax) enter(e.x);
@@ -573,12 +589,58 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
             }
         } else if (step == M_LEAF) {
             if (mode == M_LEAF) {
-                bool finished = false;
+                if (INST && (flags & F_EXIT)) {
+                    // back to world space (TransformedPrimitive::Intersect returns, primitive.cpp:82-86)
+                    flags &= ~F_EXIT;
+                    sp -= 2;
+                    const int2 rest = stGet(sp), saved = stGet(sp + 1);
+                    leafFirst = rest.x;
+                    leafN = rest.y;
+                    if (!(flags & F_HITIN)) tMax = __int_as_float(saved.x);
+                    const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
+                    float4 ra = p[0], rb = p[1];
+                    rs = setupRay(mk3(ra.y, ra.z, ra.w), mk3(rb.x, rb.y, rb.z));
+                    inst = -1;
+                    instBase = 0;
+                }
+                bool finished = false, entered = false;
                 const bool any = (flags & F_ANY) != 0;
-                for (int i = 0; i < leafN; ++i) {
-                    const float4 *rec = &sc.leafPrims[3 * (size_t)(leafFirst + i)];
+                while (leafN > 0) {
+                    const int idx = leafFirst;
+                    ++leafFirst;
+                    --leafN;
+                    const float4 *rec = &sc.leafPrims[3 * (size_t)idx];
                     float4 a = ldg4(rec), b = ldg4(rec + 1), c4 = ldg4(rec + 2);
                     uint32_t pf = floatBits(b.w);
+                    if (INST && (pf & LEAF_INSTANCE)) {
+                        const int id = asInt(c4.w);
+                        const DInstance &in = sc.instances[id];
+                        const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
+                        float4 ra = p[0], rb = p[1];
+                        DRay ray;
+                        ray.o = mk3(ra.y, ra.z, ra.w);
+                        ray.d = mk3(rb.x, rb.y, rb.z);
+                        ray.tMax = rb.w;
+                        DRay r2 = xfRay(in.w2i, ray, tMax);
+                        stPut(sp, make_int2(leafFirst, leafN));
+                        stPut(sp + 1, make_int2(__float_as_int(tMax), 0));
+                        sp += 2;
+                        instBase = sp;
+                        inst = id;
+                        flags &= ~F_HITIN;
+                        rs = setupRay(r2.o, r2.d);
+                        tMax = r2.tMax;
+                        if (in.wroot >= 0) {
+                            cur = in.wroot;
+                            mode = M_NODE;
+                            leafN = 0;
+                            entered = true;
+                            break;
+                        }
+                        leafFirst = in.lone;   // one-primitive object: its record is the whole "leaf"
+                        leafN = 1;
+                        continue;
+                    }
                     if (SPHERES && (pf & LEAF_SPHERE)) {
                         const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
                         float4 ra = p[0], rb = p[1];
@@ -586,12 +648,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
                         ray.o = mk3(ra.y, ra.z, ra.w);
                         ray.d = mk3(rb.x, rb.y, rb.z);
                         ray.tMax = rb.w;
+                        if (INST && inst >= 0) ray = xfRay(sc.instances[inst].w2i, ray, tMax);
                         float t, phi;
                         if (sphereLeafTest(sc, asInt(c4.w), ray, tMax, &t, &phi)) {
                             flags |= F_FOUND;
                             if (any) { finished = true; break; }
                             tMax = t;
-                            __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(leafFirst + i), phi, 0.f, 0.f));
+                            if (INST) {
+                                hitInst = inst;
+                                if (inst >= 0) flags |= F_HITIN;
+                            }
+                            __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(idx), phi, 0.f, 0.f));
                         }
                         continue;
                     }
@@ -601,16 +668,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
                         if (pf & LEAF_DEGENERATE) continue;
                         flags |= F_FOUND;
                         tMax = t;
-                        __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(leafFirst + i), b0, b1, b2));
+                        if (INST) {
+                            hitInst = inst;
+                            if (inst >= 0) flags |= F_HITIN;
+                        }
+                        __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(idx), b0, b1, b2));
                     }
                 }
-                leafN = 0;
-                if (finished) mode = M_FETCH;
-                else if (!TAIL) popNext();
-                else if (sp == 0) mode = M_FETCH;
-                else {
-                    mode = M_NODE;   // the next node visit pops
-                    cur = -1;
+                if (!entered) {
+                    leafN = 0;
+                    if (finished) mode = M_FETCH;
+                    else if (!TAIL) popNext();
+                    else if (sp == instBase) {
+                        if (INST && inst >= 0) flags |= F_EXIT;   // stays a leaf lane: the next leaf step leaves the instance
+                        else mode = M_FETCH;
+                    } else {
+                        mode = M_NODE;   // the next node visit pops
+                        cur = -1;
+                    }
                 }
             }
         } else {  // M_FETCH: flush finished rays, then take new ones
@@ -619,7 +694,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
             if (flush) {
                 WfCtx &cx = pool.ctx[c];
                 state = (flags & F_ANY) ? LS_SHADOW : __ldcs(&cx.ln.state);
-                __stcs(reinterpret_cast<float2 *>(&cx.tHit), make_float2(tMax, __int_as_float((flags & F_FOUND) ? 1 : 0)));
+                const int foundCode = (flags & F_FOUND) ? ((INST && !(flags & F_ANY) && hitInst >= 0) ? 2 + hitInst : 1) : 0;
+                __stcs(reinterpret_cast<float2 *>(&cx.tHit), make_float2(tMax, __int_as_float(foundCode)));
             }
             wfPush(pool.queue[WQ_SHADE], &pool.counts[WQ_SHADE], c, flush && state == LS_PATH);
             wfPush(pool.queue[WQ_LIGHT], &pool.counts[WQ_LIGHT], c, flush && state != LS_PATH);
@@ -643,6 +719,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
                         rs = setupRay(mk3(ra.y, ra.z, ra.w), mk3(rb.x, rb.y, rb.z));
                         tMax = rb.w;
                         cur = TOP ? (int)WIDE_TOP : 0;   // the pseudo node above the root
+                        if (INST) {
+                            inst = hitInst = -1;
+                            instBase = 0;
+                        }
                         sp = 0;
                         leafN = 0;
                         mode = M_NODE;
