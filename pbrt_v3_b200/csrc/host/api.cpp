@@ -9,6 +9,7 @@
 #include "api.h"
 
 #include <fstream>
+#include <chrono>
 #include <list>
 #include <sstream>
 
@@ -464,6 +465,8 @@ void pbrtWorldEnd() {
     }
     // MakeScene (api.cpp:1651-1660)
     std::shared_ptr<Primitive> accel;
+    const auto tBuild0 = std::chrono::steady_clock::now();
+    const size_t nScenePrims = ro.primitives.size();
     if (ro.AcceleratorName == "bvh")
         accel = CreateBVHAccelerator(std::move(ro.primitives), ro.AcceleratorParams);
     else {
@@ -471,6 +474,9 @@ void pbrtWorldEnd() {
         accel = std::make_shared<BVHAccel>(std::move(ro.primitives));
     }
     ro.AcceleratorParams.ReportUnused();
+    if (std::getenv("PB2_VERBOSE"))
+        std::fprintf(stderr, "pb2: BVH over %zu primitives built in %.2f s\n", nScenePrims,
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - tBuild0).count());
     setup->scene.reset(new Scene(accel, ro.lights));
     ro.primitives.clear();
     ro.lights.clear();
