@@ -5,6 +5,10 @@
 // SAH, leaf when cheaper and <= maxPrimsInNode, middle / equal-count alternatives.  The tree is
 // built directly into a flat pool of build records instead of arena-allocated pointer nodes, and
 // the primitive order is produced as an index permutation.
+#include <atomic>
+#include <chrono>
+#include <future>
+#include <thread>
 #include <unordered_map>
 
 #include "scene.h"
@@ -29,25 +33,29 @@ struct Builder {
     int maxPrimsInNode;
     BVHAccel::SplitMethod method;
 
-    int makeLeaf(int node, int start, int end, const Bounds3f &bounds) {
-        pool[node].firstPrimOffset = (int)ordered.size();
-        for (int i = start; i < end; ++i) ordered.push_back((int32_t)info[i].number);
+    // The build runs on several threads: sub-ranges of `info` are disjoint, build records come from a
+    // pre-sized pool through an atomic counter, and a subtree over n primitives owns a fixed range of
+    // n slots of the ordered list (orderedStart), so the result does not depend on the schedule.
+    std::atomic<int> nextNode{0};
+
+    int makeLeaf(int node, int start, int end, const Bounds3f &bounds, int orderedStart) {
+        pool[node].firstPrimOffset = orderedStart;
+        for (int i = start; i < end; ++i) ordered[orderedStart + (i - start)] = (int32_t)info[i].number;
         pool[node].nPrimitives = end - start;
         pool[node].bounds = bounds;
         return node;
     }
 
-    int build(int start, int end) {
-        int node = (int)pool.size();
-        pool.push_back(BuildNode());
+    int build(int start, int end, int orderedStart, int spawnLevels) {
+        int node = nextNode.fetch_add(1);
         Bounds3f bounds;
         for (int i = start; i < end; ++i) bounds = Union(bounds, info[i].bounds);
         int nPrims = end - start;
-        if (nPrims == 1) return makeLeaf(node, start, end, bounds);
+        if (nPrims == 1) return makeLeaf(node, start, end, bounds, orderedStart);
         Bounds3f cb;
         for (int i = start; i < end; ++i) cb = Union(cb, info[i].centroid);
         int dim = cb.MaximumExtent();
-        if (cb.pMax[dim] == cb.pMin[dim]) return makeLeaf(node, start, end, bounds);
+        if (cb.pMax[dim] == cb.pMin[dim]) return makeLeaf(node, start, end, bounds, orderedStart);
 
         int mid = (start + end) / 2;
         auto equalCounts = [&]() {
@@ -99,14 +107,23 @@ struct Builder {
                                                  [&](const PrimInfo &pi) { return bucketOf(pi) <= minBucket; });
                     mid = (int)(m - &info[0]);
                 } else
-                    return makeLeaf(node, start, end, bounds);
+                    return makeLeaf(node, start, end, bounds, orderedStart);
             }
         }
         // The reference passes both recursive calls as arguments of InitInterior (bvh.cpp:394-398);
         // its compiler (gcc, x86-64) evaluates them right to left, so the second child's primitives
         // are appended to the ordered list first.  Keep that order: it fixes primitivesOffset values.
-        int c1 = build(mid, end);
-        int c0 = build(start, mid);
+        // -> the second child's primitives come first in the ordered list: its range starts at
+        // orderedStart, the first child's right after it.
+        int c0, c1;
+        if (spawnLevels > 0 && nPrims > 65536) {
+            std::future<int> second = std::async(std::launch::async, [=] { return build(mid, end, orderedStart, spawnLevels - 1); });
+            c0 = build(start, mid, orderedStart + (end - mid), spawnLevels - 1);
+            c1 = second.get();
+        } else {
+            c1 = build(mid, end, orderedStart, 0);
+            c0 = build(start, mid, orderedStart + (end - mid), 0);
+        }
         pool[node].child[0] = c0;
         pool[node].child[1] = c1;
         pool[node].bounds = Union(pool[c0].bounds, pool[c1].bounds);
@@ -148,19 +165,31 @@ BVHAccel::BVHAccel(std::vector<std::shared_ptr<Primitive>> p, int maxPrims, Spli
     Builder b;
     b.maxPrimsInNode = maxPrimsInNode;
     b.method = splitMethod == SplitMethod::HLBVH ? SplitMethod::SAH : splitMethod;
+    auto clk = [] { return std::chrono::steady_clock::now(); };
+    auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto t0 = clk();
     b.info.resize(sceneOrderPrims.size());
     for (size_t i = 0; i < sceneOrderPrims.size(); ++i) {
         Bounds3f wb = sceneOrderPrims[i]->WorldBound();
         b.info[i] = PrimInfo{i, wb, .5f * wb.pMin + .5f * wb.pMax};
     }
-    b.pool.reserve(2 * sceneOrderPrims.size());
-    b.ordered.reserve(sceneOrderPrims.size());
-    int root = b.build(0, (int)sceneOrderPrims.size());
+    b.pool.resize(2 * sceneOrderPrims.size());
+    b.ordered.resize(sceneOrderPrims.size());
+    int spawnLevels = 0;
+    for (unsigned t = std::max(1u, std::thread::hardware_concurrency()); t > 1; t >>= 1) ++spawnLevels;
+    const auto t1 = clk();
+    int root = b.build(0, (int)sceneOrderPrims.size(), 0, spawnLevels + 2);
+    const auto t2 = clk();
+    b.pool.resize((size_t)b.nextNode.load());
     nodes.reserve(b.pool.size());
     b.flatten(root, nodes);
+    const auto t3 = clk();
     orderedPrimNumbers = std::move(b.ordered);
     primitives.reserve(orderedPrimNumbers.size());
     for (int32_t n : orderedPrimNumbers) primitives.push_back(sceneOrderPrims[n]);
+    if (std::getenv("PB2_VERBOSE") && sceneOrderPrims.size() > 100000)
+        std::fprintf(stderr, "pb2: BVHAccel: bounds %.2f s, recursive build %.2f s, flatten %.2f s, ordered primitives %.2f s\n",
+                     secs(t0, t1), secs(t1, t2), secs(t2, t3), secs(t3, clk()));
 }
 
 BVHAccel::~BVHAccel() {}
