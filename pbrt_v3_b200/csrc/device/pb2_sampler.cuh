@@ -178,7 +178,9 @@ PB2_HD V2 concentricSampleDisk(V2 u) {
         r = oy;
         theta = kPiOver2 - kPiOver4 * (ox / oy);
     }
-    return mk2(r * pcosf(theta), r * psinf(theta));
+    float st, ct;
+    psincosf(theta, &st, &ct);
+    return mk2(r * ct, r * st);
 }
 // sampling.h:159-163
 PB2_HD V3 cosineSampleHemisphere(V2 u) {
@@ -196,7 +198,9 @@ PB2_HD V3 uniformSampleSphere(V2 u) {
     float z = 1 - 2 * u.x;
     float r = sqrtf(pmax(0.f, 1.f - z * z));
     float phi = 2 * kPi * u.y;
-    return mk3(r * pcosf(phi), r * psinf(phi), z);
+    float sp, cp;
+    psincosf(phi, &sp, &cp);
+    return mk3(r * cp, r * sp, z);
 }
 // sampling.h:171-174 with nf = ng = 1
 PB2_HD float powerHeuristic(float fPdf, float gPdf) {

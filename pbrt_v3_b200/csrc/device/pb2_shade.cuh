@@ -396,8 +396,10 @@ PB2_HDN void trSample11(float cosThetaV, float U1, float U2, float *slope_x, flo
     if ((double)cosThetaV > .9999) {
         float r = (float)sqrt((double)(U1 / (1 - U1)));
         float phi = (float)(6.28318530718 * (double)U2);
-        *slope_x = (float)((double)r * cos((double)phi));
-        *slope_y = (float)((double)r * sin((double)phi));
+        double sPhi, cPhi;
+        sincos((double)phi, &sPhi, &cPhi);
+        *slope_x = (float)((double)r * cPhi);
+        *slope_y = (float)((double)r * sPhi);
         return;
     }
     float sinThetaV = sqrtf(pmax(0.f, 1.f - cosThetaV * cosThetaV));
@@ -673,7 +675,9 @@ PB2_HDN DLightSample sampleSphereLight(const DScene &sc, const pb2_light &l, con
         float sinAlpha = sqrtf(pmax(0.f, 1.f - cosAlpha * cosAlpha));
         float phi = u.y * 2 * kPi;
         // SphericalDirection(sinAlpha, cosAlpha, phi, -wcX, -wcY, -wc) (geometry.h:1461-1466)
-        V3 nWorld = sinAlpha * pcosf(phi) * (-wcX) + sinAlpha * psinf(phi) * (-wcY) + cosAlpha * (-wc);
+        float sinPhiS, cosPhiS;
+        psincosf(phi, &sinPhiS, &cosPhiS);
+        V3 nWorld = sinAlpha * cosPhiS * (-wcX) + sinAlpha * sinPhiS * (-wcY) + cosAlpha * (-wc);
         V3 pWorld = pCenter + s.radius * nWorld;
         ls.p = pWorld;
         ls.pError = kGamma5 * vabs(pWorld);
