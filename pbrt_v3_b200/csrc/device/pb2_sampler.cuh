@@ -93,14 +93,30 @@ PB2_HD float scrambledRadicalInverse32(uint32_t base, uint64_t magic, uint32_t a
     const float invBase = 1.f / (float)base;
     uint64_t reversedDigits = 0;
     float invBaseN = 1;
+    const uint32_t perm0 = perm[0];
+    // three digits per trip: their permutation look-ups are issued back to back before the first one is
+    // folded in, so the loop waits for one L1 round trip per three digits instead of one per digit
+    // (the accumulation order, and with it every value, is that of the one-digit loop)
     while (a) {
-        uint32_t next = divMagic(a, magic);
-        uint32_t digit = a - next * base;
-        reversedDigits = reversedDigits * base + (uint32_t)perm[digit];
+        const uint32_t n1 = divMagic(a, magic), d1 = a - n1 * base;
+        const uint32_t n2 = divMagic(n1, magic), d2 = n1 - n2 * base;
+        const uint32_t n3 = divMagic(n2, magic), d3 = n2 - n3 * base;
+        const uint32_t p1 = perm[d1];
+        const uint32_t p2 = perm[d2];   // d2 / d3 are digits of zero when the index has run out: harmless reads of perm[0]
+        const uint32_t p3 = perm[d3];
+        reversedDigits = reversedDigits * base + p1;
         invBaseN *= invBase;
-        a = next;
+        if (n1) {
+            reversedDigits = reversedDigits * base + p2;
+            invBaseN *= invBase;
+            if (n2) {
+                reversedDigits = reversedDigits * base + p3;
+                invBaseN *= invBase;
+            }
+        }
+        a = n1 ? (n2 ? n3 : 0u) : 0u;
     }
-    return pmin(invBaseN * ((float)reversedDigits + invBase * perm[0] / (1 - invBase)), kOneMinusEpsilon);
+    return pmin(invBaseN * ((float)reversedDigits + invBase * perm0 / (1 - invBase)), kOneMinusEpsilon);
 }
 
 // RadicalInverse(baseIndex, a), lowdiscrepancy.cpp:427-
