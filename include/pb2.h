@@ -53,7 +53,7 @@ typedef struct pb2_bvh_node {
 } pb2_bvh_node;
 
 enum { PB2_PRIM_TRIANGLE = 0, PB2_PRIM_SPHERE = 1, PB2_PRIM_INSTANCE = 2 };
-enum { PB2_MAT_NONE = 0, PB2_MAT_MATTE = 1, PB2_MAT_PLASTIC = 2, PB2_MAT_MIRROR = 3, PB2_MAT_GLASS = 4 };
+enum { PB2_MAT_NONE = 0, PB2_MAT_MATTE = 1, PB2_MAT_PLASTIC = 2, PB2_MAT_MIRROR = 3, PB2_MAT_GLASS = 4, PB2_MAT_SUBSTRATE = 5 };
 enum { PB2_LIGHTDIST_UNIFORM = 0, PB2_LIGHTDIST_POWER = 1, PB2_LIGHTDIST_SPATIAL = 2 };
 
 /* One TriangleMesh (src/shapes/triangle.h:46-68).  Vertices are already in world space
@@ -87,7 +87,8 @@ typedef struct pb2_material {
     int32_t remap_roughness;
     int32_t pad[2];
     /* MirrorMaterial (src/materials/mirror.cpp:45-58): kr.  GlassMaterial (src/materials/glass.cpp:45-93)
-     * with uroughness == vroughness == 0: kr, kt, eta (the "index"/"eta" parameter); rough glass is refused. */
+     * with uroughness == vroughness == 0: kr, kt, eta (the "index"/"eta" parameter); rough glass is refused.
+     * SubstrateMaterial (src/materials/substrate.cpp:45-65): kd, ks, uroughness, vroughness, remap_roughness. */
     float kr[3];
     float kt[3];
     float eta;

@@ -315,6 +315,7 @@ struct Spectrum {
     Spectrum(Float r, Float g, Float b) { c[0] = r; c[1] = g; c[2] = b; }
     Spectrum operator+(const Spectrum &s) const { return Spectrum(c[0] + s.c[0], c[1] + s.c[1], c[2] + s.c[2]); }
     Spectrum &operator+=(const Spectrum &s) { for (int i = 0; i < 3; ++i) c[i] += s.c[i]; return *this; }
+    Spectrum operator-(const Spectrum &s) const { return Spectrum(c[0] - s.c[0], c[1] - s.c[1], c[2] - s.c[2]); }
     Spectrum operator*(const Spectrum &s) const { return Spectrum(c[0] * s.c[0], c[1] * s.c[1], c[2] * s.c[2]); }
     Spectrum &operator*=(const Spectrum &s) { for (int i = 0; i < 3; ++i) c[i] *= s.c[i]; return *this; }
     Spectrum operator*(Float a) const { return Spectrum(c[0] * a, c[1] * a, c[2] * a); }

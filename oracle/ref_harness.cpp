@@ -57,6 +57,7 @@
 #include "materials/plastic.h"
 #include "materials/mirror.h"
 #include "materials/glass.h"
+#include "materials/substrate.h"
 #include "samplers/halton.h"
 #include "shapes/loopsubdiv.h"
 #include "shapes/sphere.h"
@@ -234,6 +235,11 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
         } else if (pm.type == PB2_MAT_MIRROR) {
             auto kr = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kr));
             materials[i] = std::make_shared<MirrorMaterial>(kr, nullptr);
+        } else if (pm.type == PB2_MAT_SUBSTRATE) {
+            auto ks = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.ks));
+            auto nu = std::make_shared<ConstantTexture<Float>>(pm.uroughness);
+            auto nv = std::make_shared<ConstantTexture<Float>>(pm.vroughness);
+            materials[i] = std::make_shared<SubstrateMaterial>(kd, ks, nu, nv, nullptr, pm.remap_roughness != 0);
         } else if (pm.type == PB2_MAT_GLASS) {
             auto kr = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kr));
             auto kt = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kt));

@@ -25,7 +25,7 @@ c_uint8_p = C.POINTER(C.c_uint8)
 
 PB2_OK, PB2_ERR_NO_DEVICE, PB2_ERR_CUDA, PB2_ERR_INVALID, PB2_ERR_UNSUPPORTED, PB2_ERR_NCCL = range(6)
 PB2_PRIM_TRIANGLE, PB2_PRIM_SPHERE, PB2_PRIM_INSTANCE = 0, 1, 2
-PB2_MAT_NONE, PB2_MAT_MATTE, PB2_MAT_PLASTIC, PB2_MAT_MIRROR, PB2_MAT_GLASS = 0, 1, 2, 3, 4
+PB2_MAT_NONE, PB2_MAT_MATTE, PB2_MAT_PLASTIC, PB2_MAT_MIRROR, PB2_MAT_GLASS, PB2_MAT_SUBSTRATE = 0, 1, 2, 3, 4, 5
 PB2_ABI_VERSION = 3   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
 PB2_LIGHTDIST_UNIFORM, PB2_LIGHTDIST_POWER, PB2_LIGHTDIST_SPATIAL = 0, 1, 2
 

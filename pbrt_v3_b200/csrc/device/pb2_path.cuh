@@ -129,8 +129,8 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
             DLightSample ls = sampleLight<SPH>(sc, light, lightRec, isect, uLight);
             float lightPdf = ls.pdf, scatteringPdf = 0;
             if (lightPdf > 0 && !isBlack(ls.Li)) {
-                V3 f = bsdfF(bsdf, isect.wo, ls.wi) * absDot(ls.wi, isect.ns);
-                scatteringPdf = bsdfPdf(bsdf, isect.wo, ls.wi);
+                V3 f = bsdfF<SPEC>(bsdf, isect.wo, ls.wi) * absDot(ls.wi, isect.ns);
+                scatteringPdf = bsdfPdf<SPEC>(bsdf, isect.wo, ls.wi);
                 if (!isBlack(f)) {
                     shadow = spawnRayTo(isect, ls.p, ls.pError, ls.n);
                     hasShadow = true;

@@ -240,6 +240,9 @@ struct DBsdf {
     int specKind;          // 0 none, 1 SpecularReflection + FresnelNoOp (mirror), 2 FresnelSpecular (smooth glass)
     V3 specR, specT;
     float eta;             // BSDF::eta (reflection.h:216): the glass index, 1 otherwise
+    // FresnelBlend (substrate): the one glossy lobe of the BSDF, Rd in R, Rs in Ks, anisotropic Trowbridge-Reitz
+    int blend;
+    float alphaX, alphaY;
 };
 enum { BSDF_SAMPLED_SPECULAR = 1, BSDF_SAMPLED_TRANSMISSION = 2 };
 
@@ -277,6 +280,26 @@ PB2_HD bool makeBsdf(const DScene &sc, const DInteraction &it, DBsdf *bsdf) {
     bsdf->specKind = 0;
     bsdf->specR = bsdf->specT = mk3(0, 0, 0);
     bsdf->eta = 1;
+    bsdf->blend = 0;
+    bsdf->alphaX = bsdf->alphaY = 0;
+    if (SPEC && mat.type == PB2_MAT_SUBSTRATE) {
+        // substrate.cpp:45-65
+        V3 d = clampSpectrum(mat.kd), sp = clampSpectrum(mat.ks);
+        if (!isBlack(d) || !isBlack(sp)) {
+            float roughu = mat.uroughness, roughv = mat.vroughness;
+            if (mat.remap_roughness) {
+                roughu = roughnessToAlpha(roughu);
+                roughv = roughnessToAlpha(roughv);
+            }
+            bsdf->R = d;
+            bsdf->Ks = sp;
+            bsdf->alphaX = pmax(0.001f, roughu);
+            bsdf->alphaY = pmax(0.001f, roughv);
+            bsdf->blend = 1;
+            bsdf->nLobes = 1;
+        }
+        return true;
+    }
     if (SPEC && mat.type == PB2_MAT_MIRROR) {
         // mirror.cpp:45-58
         V3 r = clampSpectrum(mat.kr);
@@ -443,6 +466,59 @@ PB2_HD V3 trSampleWh(float alpha, V3 wo, V2 u) {
     return wh;
 }
 
+// The same distribution with alphax != alphay (microfacet.cpp:155-184, 284-344), used by FresnelBlend
+PB2_HD float trD2(float ax, float ay, V3 wh) {
+    float t2 = tan2Theta(wh);
+    if (isinf(t2)) return 0.;
+    const float cos4Theta = cos2Theta(wh) * cos2Theta(wh);
+    float e = (cos2Phi(wh) / (ax * ax) + sin2Phi(wh) / (ay * ay)) * t2;
+    return 1 / (kPi * ax * ay * cos4Theta * (1 + e) * (1 + e));
+}
+PB2_HD float trLambda2(float ax, float ay, V3 w) {
+    float absTanTheta = fabsf(tanTheta(w));
+    if (isinf(absTanTheta)) return 0.;
+    float a = sqrtf(cos2Phi(w) * ax * ax + sin2Phi(w) * ay * ay);
+    float alpha2Tan2Theta = (a * absTanTheta) * (a * absTanTheta);
+    return (-1 + sqrtf(1.f + alpha2Tan2Theta)) / 2;
+}
+PB2_HD float trPdf2(float ax, float ay, V3 wo, V3 wh) {
+    return trD2(ax, ay, wh) * (1 / (1 + trLambda2(ax, ay, wo))) * absDot(wo, wh) / absCosTheta(wo);
+}
+PB2_HD V3 trSampleWh2(float ax, float ay, V3 wo, V2 u) {
+    bool flip = wo.z < 0;
+    V3 wi = flip ? -wo : wo;
+    V3 wiStretched = normalize(mk3(ax * wi.x, ay * wi.y, wi.z));
+    float slope_x, slope_y;
+    trSample11(cosTheta(wiStretched), u.x, u.y, &slope_x, &slope_y);
+    float tmp = cosPhi(wiStretched) * slope_x - sinPhi(wiStretched) * slope_y;
+    slope_y = sinPhi(wiStretched) * slope_x + cosPhi(wiStretched) * slope_y;
+    slope_x = tmp;
+    slope_x = ax * slope_x;
+    slope_y = ay * slope_y;
+    V3 wh = normalize(mk3(-slope_x, -slope_y, 1.f));
+    if (flip) wh = -wh;
+    return wh;
+}
+// FresnelBlend::f / Pdf (reflection.cpp:290-303, 480-485)
+PB2_HD float pow5f(float v) { return (v * v) * (v * v) * v; }
+PB2_HD V3 blendF(const DBsdf &b, V3 wo, V3 wi) {
+    V3 one = mk3(1, 1, 1);
+    V3 diffuse = (28.f / (23.f * kPi)) * b.R * (one - b.Ks) * (1 - pow5f(1 - .5f * absCosTheta(wi))) * (1 - pow5f(1 - .5f * absCosTheta(wo)));
+    V3 wh = wi + wo;
+    if (wh.x == 0 && wh.y == 0 && wh.z == 0) return mk3(0, 0, 0);
+    wh = normalize(wh);
+    float cosT = dot(wi, wh);
+    V3 schlick = b.Ks + pow5f(1 - cosT) * (one - b.Ks);
+    V3 specular = (trD2(b.alphaX, b.alphaY, wh) / (4 * absDot(wi, wh) * pmax(absCosTheta(wi), absCosTheta(wo)))) * schlick;
+    return diffuse + specular;
+}
+PB2_HD float blendPdf(const DBsdf &b, V3 wo, V3 wi) {
+    if (!sameHemisphere(wo, wi)) return 0;
+    V3 wh = normalize(wo + wi);
+    float pdf_wh = trPdf2(b.alphaX, b.alphaY, wo, wh);
+    return .5f * (absCosTheta(wi) * kInvPi + pdf_wh / (4 * dot(wo, wh)));
+}
+
 // individual BxDFs (local frame)
 PB2_HD V3 diffuseF(const DBsdf &b, V3 wo, V3 wi) {
     if (b.diffuseKind == 1) return b.R * kInvPi;
@@ -488,11 +564,13 @@ PB2_HD float microfacetPdf(const DBsdf &b, V3 wo, V3 wi) {
 
 // BSDF::f (reflection.cpp:680-693).  All lobes in scope are reflective and non-specular, so they
 // match both BSDF_ALL and BSDF_ALL & ~BSDF_SPECULAR.
+template <bool SPEC = true>
 PB2_HD V3 bsdfF(const DBsdf &b, V3 woW, V3 wiW) {
     V3 wi = worldToLocal(b, wiW), wo = worldToLocal(b, woW);
     if (wo.z == 0) return mk3(0, 0, 0);
     bool reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
     V3 f = mk3(0, 0, 0);
+    if (SPEC && b.blend) return reflect ? blendF(b, wo, wi) : f;
     if (reflect) {
         if (b.diffuseKind) f = f + diffuseF(b, wo, wi);
         if (b.hasMicrofacet) f = f + microfacetF(b, wo, wi);
@@ -500,10 +578,12 @@ PB2_HD V3 bsdfF(const DBsdf &b, V3 woW, V3 wiW) {
     return f;
 }
 // BSDF::Pdf (reflection.cpp:781-796)
+template <bool SPEC = true>
 PB2_HD float bsdfPdf(const DBsdf &b, V3 woW, V3 wiW) {
     if (b.nLobes == 0) return 0.f;
     V3 wo = worldToLocal(b, woW), wi = worldToLocal(b, wiW);
     if (wo.z == 0) return 0.;
+    if (SPEC && b.blend) return blendPdf(b, wo, wi);
     float pdf = 0.f;
     if (b.diffuseKind) pdf += diffusePdf(wo, wi);
     if (b.hasMicrofacet) pdf += microfacetPdf(b, wo, wi);
@@ -569,6 +649,28 @@ PB2_HD V3 bsdfSampleF(const DBsdf &b, V3 woW, V3 *wiW, V2 u, float *pdf, int *sa
     }
     int matching = b.nLobes;
     if (matching == 0) return mk3(0, 0, 0);
+    if (SPEC && b.blend) {
+        // one glossy BxDF: comp 0, uRemapped[0] = min(u[0], OneMinusEpsilon); FresnelBlend::Sample_f
+        // (reflection.cpp:460-478); f is then re-evaluated by the BSDF (reflection.cpp:767-775)
+        V3 wo = worldToLocal(b, woW), wi;
+        if (wo.z == 0) return mk3(0, 0, 0);
+        V2 uu = mk2(pmin(u.x, kOneMinusEpsilon), u.y);
+        if ((double)uu.x < .5) {
+            uu.x = pmin(2 * uu.x, kOneMinusEpsilon);
+            wi = cosineSampleHemisphere(uu);
+            if (wo.z < 0) wi.z *= -1;
+        } else {
+            uu.x = pmin(2 * (uu.x - .5f), kOneMinusEpsilon);
+            V3 wh = trSampleWh2(b.alphaX, b.alphaY, wo, uu);
+            wi = -wo + 2 * dot(wo, wh) * wh;  // Reflect
+            if (!sameHemisphere(wo, wi)) return mk3(0, 0, 0);
+        }
+        *pdf = blendPdf(b, wo, wi);
+        if (*pdf == 0) return mk3(0, 0, 0);
+        *wiW = localToWorld(b, wi);
+        bool reflect = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
+        return reflect ? blendF(b, wo, wi) : mk3(0, 0, 0);
+    }
     int comp = (int)floorf(u.x * matching);
     if (comp > matching - 1) comp = matching - 1;
     // lobe order: diffuse first, then microfacet (plastic.cpp:53-68)

@@ -53,6 +53,17 @@ pb2_material GlassMaterial::Record() const {
     m.remap_roughness = remapRoughness ? 1 : 0;
     return m;
 }
+pb2_material SubstrateMaterial::Record() const {
+    pb2_material m;
+    std::memset(&m, 0, sizeof(m));
+    m.type = PB2_MAT_SUBSTRATE;
+    clampSpectrum(Kd, m.kd);
+    clampSpectrum(Ks, m.ks);
+    m.uroughness = nu;
+    m.vroughness = nv;
+    m.remap_roughness = remapRoughness ? 1 : 0;
+    return m;
+}
 static void rejectTextures(const TextureParams &mp, const char *what, std::initializer_list<const char *> names) {
     for (const char *n : names)
         if (mp.geomParams.FindTexture(n) != "" || mp.materialParams.FindTexture(n) != "")
@@ -64,6 +75,16 @@ MatteMaterial *CreateMatteMaterial(const TextureParams &mp) {
     Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(0.5f));
     Float sigma = mp.GetFloatTexture("sigma", 0.f);
     return new MatteMaterial(Kd, sigma);
+}
+// substrate.cpp:67-81
+SubstrateMaterial *CreateSubstrateMaterial(const TextureParams &mp) {
+    rejectTextures(mp, "substrate", {"Kd", "Ks", "uroughness", "vroughness", "bumpmap"});
+    Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(.5f));
+    Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(.5f));
+    Float uroughness = mp.GetFloatTexture("uroughness", .1f);
+    Float vroughness = mp.GetFloatTexture("vroughness", .1f);
+    bool remap = mp.FindBool("remaproughness", true);
+    return new SubstrateMaterial(Kd, Ks, uroughness, vroughness, remap);
 }
 // mirror.cpp:60-66
 MirrorMaterial *CreateMirrorMaterial(const TextureParams &mp) {

@@ -155,6 +155,17 @@ class GlassMaterial : public Material {
     Float uRoughness, vRoughness, index;
     bool remapRoughness;
 };
+// substrate.h:49-72 with constant textures
+class SubstrateMaterial : public Material {
+  public:
+    SubstrateMaterial(const Spectrum &Kd, const Spectrum &Ks, Float nu, Float nv, bool remapRoughness)
+        : Kd(Kd), Ks(Ks), nu(nu), nv(nv), remapRoughness(remapRoughness) {}
+    pb2_material Record() const override;
+    Spectrum Kd, Ks;
+    Float nu, nv;
+    bool remapRoughness;
+};
+SubstrateMaterial *CreateSubstrateMaterial(const TextureParams &mp);
 MirrorMaterial *CreateMirrorMaterial(const TextureParams &mp);
 GlassMaterial *CreateGlassMaterial(const TextureParams &mp);
 MatteMaterial *CreateMatteMaterial(const TextureParams &mp);

@@ -12,7 +12,7 @@ from test_oracle import same_bvh
 
 def test_host_bvh_equals_reference_bvh(pb):
     """The host SAH builder reproduces BVHAccel's LinearBVHNode array and primitive order (src/accelerators/bvh.cpp:183-402)."""
-    for name in ("soup", "killeroo_like", "materials", "instances", "specular"):
+    for name in ("soup", "killeroo_like", "materials", "instances", "specular", "substrate"):
         g = np.load(os.path.join(GOLDEN, name + ".npz"))
         hs = gc.soup_scene(pb) if name == "soup" else pb.HostScene.from_file(os.path.join(SCENES, name + ".pbrt"))
         assert same_bvh(hs.nodes(), g["bvh_nodes"]), name
