@@ -970,8 +970,13 @@ struct DCamera {
 PB2_HD DRay generateCameraRay(const DCamera &cam, const DHalton &h, DSampler &smp, int px, int py, V2 *pFilmOut) {
     V2 uf = get2D(h, smp);
     V2 pFilm = mk2((float)px + uf.x, (float)py + uf.y);
-    get1D(h, smp);             // time
-    V2 uLens = get2D(h, smp);  // pLens
+    // CameraSample::time and pLens (sampler.cpp:46-52) take dimensions 2-4.  The sample values are pure
+    // functions of (index, dimension): what is not read is not computed - time never is (static scenes),
+    // pLens only with a finite aperture.
+    smp.dim += 1;
+    V2 uLens = mk2(0, 0);
+    if (cam.lensRadius > 0) uLens = get2D(h, smp);
+    else smp.dim += 2;
     *pFilmOut = pFilm;
     V3 pCamera = xfPoint(cam.rasterToCamera, mk3(pFilm.x, pFilm.y, 0));
     DRay ray;
