@@ -181,3 +181,15 @@ def test_mirror_and_glass_parameters(pb):
     before = pb.lib().pb2h_error_count()
     pb.HostScene.from_string('WorldBegin\nMaterial "glass" "float uroughness" 0.2\nShape "sphere"\nWorldEnd\n')
     assert pb.lib().pb2h_error_count() > before
+
+
+def test_threaded_bvh_build_is_the_sequential_tree(pb, port):
+    """Above 65 536 primitives the host builder hands subtrees to other threads; every subtree owns a fixed range of
+    the ordered-primitive list, so the LinearBVHNode array and the primitive order must still be the reference's
+    (the port builds sequentially, in the reference's order)."""
+    hs = pb.HostScene.soup(300000, seed=7, jitter=0.01, xres=16, yres=16, spp=1)
+    nodes, prims = port.scene(hs).bvh()
+    first_nodes, first_prims = hs.nodes(), hs.bvh_prims()
+    assert same_bvh(first_nodes, nodes) and np.array_equal(first_prims, prims)
+    again = pb.HostScene.soup(300000, seed=7, jitter=0.01, xres=16, yres=16, spp=1)   # replaces the parsed scene
+    assert again.nodes().tobytes() == first_nodes.tobytes() and np.array_equal(again.bvh_prims(), first_prims)
