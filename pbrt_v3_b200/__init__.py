@@ -203,8 +203,16 @@ def init(device=None):
 class HostScene:
     """A scene held by the C++ host front end (one at a time: it mirrors pbrt's global API state)."""
 
+    _generation = 0
+
     def __init__(self):
         self.L = lib()
+        HostScene._generation += 1
+        self._gen = HostScene._generation   # a later parse replaces the C++ side's scene: this object then refuses to be used
+
+    def _current(self):
+        if self._gen != HostScene._generation:
+            raise RuntimeError("this HostScene was replaced by a later HostScene (the host front end holds one scene at a time)")
 
     @classmethod
     def from_file(cls, path, outfile=None):
@@ -240,6 +248,7 @@ class HostScene:
     # flattened descriptions (host memory owned by the C++ side)
     @property
     def desc(self):
+        self._current()
         p = self.L.pb2h_scene_desc()
         if not p:
             raise RuntimeError("scene could not be flattened (see stderr)")
@@ -247,10 +256,12 @@ class HostScene:
 
     @property
     def camera(self):
+        self._current()
         return self.L.pb2h_camera()
 
     @property
     def film(self):
+        self._current()
         return self.L.pb2h_film()
 
     @property
