@@ -513,11 +513,13 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     else if (instancedTuned) trace = k_wf_trace<8, 8, 2, 32, true, true, 6, true>;
     else if (spheres && wideNodes && variant != 7) wideKernel(k_wf_trace_w<8, 8, 3, 16, 6, 1, 128, false, true, true>, 128, 16, false);
     else if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
-    else if (wideNodes && variant == 0) wideKernel(k_wf_trace_w<8, 8, 3, 16, 9, 1, 128, false, true>, 128, 16, false);   // 55 registers: 9 blocks / SM
+    else if (wideNodes && variant == 0) wideKernel(k_wf_trace_w<8, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);   // 56 registers: 9 blocks / SM
     else if (wideNodes && variant == 5) wideKernel(k_wf_trace_w<12, 8, 4, 16, 8>, 128, 16, false);
     else if (wideNodes && variant == 20) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1, 128, false, true>, 128, 16, false);
     else if (wideNodes && variant == 21) wideKernel(k_wf_trace_w<8, 8, 3, 16, 10, 1, 128, false, true>, 128, 16, false);
     else if (wideNodes && variant == 22) wideKernel(k_wf_trace_w<8, 8, 3, 12, 10, 1, 128, false, true>, 128, 12, false);
+    else if (wideNodes && variant == 23) wideKernel(k_wf_trace_w<8, 8, 3, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 24) wideKernel(k_wf_trace_w<8, 8, 3, 16, 9, 1, 128, false, true>, 128, 16, false);   // branchy two-attempt pop
     else if (wideNodes && variant == 15) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1>, 128, 16, false);   // scalar slab tests
     else if (wideNodes && variant == 8) wideKernel(k_wf_trace_w<8, 8, 2, 4, 8>, 128, 4, false);   // tests: forces the local-memory stack spill
     else if (wideNodes && variant == 9) wideKernel(k_wf_trace_w<8, 8, 3, 16, 1, 1, 1024, true>, 1024, 16, true);

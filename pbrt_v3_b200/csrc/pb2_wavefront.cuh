@@ -512,7 +512,31 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
         if (step == M_NODE) {
 #pragma unroll
             for (int sub = 0; sub < NSUB; ++sub) {
-                if (TAIL && mode == M_NODE && cur < 0) {
+                if (TAIL == 2) {
+                    // the same pop as below, once per visit, as straight-line code for the whole warp: nearly
+                    // every visit has SOME lane that must pop, and those few lanes used to run ~25
+                    // instructions alone while the rest of the warp waited
+                    const bool need = (mode == M_NODE) & (cur < 0);
+                    const bool empty = need & (sp == instBase);
+                    const bool pop = need & !empty;
+                    const int slot = pop ? sp - 1 : 0;
+                    const int2 e = slot < SDEPTH ? sstack[slot * BLOCK + tid] : lstack[slot - SDEPTH];
+                    sp = pop ? sp - 1 : sp;
+                    const bool take = pop & (__int_as_float(e.y) < tMax);
+                    const bool leafRef = take & (e.x < 0);
+                    leafFirst = leafRef ? (e.x & (int)WIDE_LEAF_OFFSET_MASK) : leafFirst;
+                    leafN = leafRef ? (((e.x >> WIDE_LEAF_COUNT_SHIFT) & 0xf) + 1) : leafN;
+                    cur = (take & !leafRef) ? e.x : cur;
+                    mode = leafRef ? (int)M_LEAF : mode;
+                    if (empty) {
+                        if (INST && inst >= 0) {
+                            mode = M_LEAF;
+                            flags |= F_EXIT;
+                            leafN = 0;
+                        } else
+                            mode = M_FETCH;
+                    }
+                } else if (TAIL && mode == M_NODE && cur < 0) {
                     // the last visit (or leaf) left nothing to descend into: take pending far children,
                     // at most two per visit (a culled one costs a load and a compare)
 #pragma unroll
