@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 3   /* 2: object-instancing block at the end of pb2_scene_desc; 3: mirror / glass fields in pb2_material */
+#define PB2_ABI_VERSION 4   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc */
 
 typedef enum pb2_status {
     PB2_OK = 0,
@@ -55,6 +55,7 @@ typedef struct pb2_bvh_node {
 enum { PB2_PRIM_TRIANGLE = 0, PB2_PRIM_SPHERE = 1, PB2_PRIM_INSTANCE = 2 };
 enum { PB2_MAT_NONE = 0, PB2_MAT_MATTE = 1, PB2_MAT_PLASTIC = 2, PB2_MAT_MIRROR = 3, PB2_MAT_GLASS = 4, PB2_MAT_SUBSTRATE = 5 };
 enum { PB2_LIGHTDIST_UNIFORM = 0, PB2_LIGHTDIST_POWER = 1, PB2_LIGHTDIST_SPATIAL = 2 };
+enum { PB2_FILTER_BOX = 0, PB2_FILTER_GAUSSIAN = 1, PB2_FILTER_MITCHELL = 2, PB2_FILTER_SINC = 3, PB2_FILTER_TRIANGLE = 4 };
 
 /* One TriangleMesh (src/shapes/triangle.h:46-68).  Vertices are already in world space
  * (src/shapes/triangle.cpp:73-74); normals already transformed (triangle.cpp:83). */
@@ -186,13 +187,18 @@ typedef struct pb2_camera {
     float dx_camera[3], dy_camera[3];
 } pb2_camera;
 
-/* Film (src/core/film.cpp:45-78) with a box filter (src/filters/box.cpp). */
+/* Film (src/core/film.cpp:45-78) and its reconstruction filter (src/filters/{box,gaussian,mitchell,sinc,triangle}.cpp). */
 typedef struct pb2_film_desc {
     int32_t full_resolution[2];
     int32_t cropped_pixel_bounds[4]; /* x0 y0 x1 y1 (Film::croppedPixelBounds) */
-    float filter_radius[2];          /* box filter only in this scope */
+    float filter_radius[2];          /* Filter::radius */
     float max_sample_luminance;
     float scale;
+    /* reconstruction filter (one of src/filters/); zero-initialised = box.  filter_param: gaussian {alpha, -},
+     * mitchell {B, C}, sinc {tau, -}.  The 16x16 weight table of Film (film.cpp:68-77) is computed inside. */
+    int32_t filter_type;             /* PB2_FILTER_* */
+    float filter_param[2];
+    int32_t pad;
 } pb2_film_desc;
 
 /* HaltonSampler (src/samplers/halton.cpp:65-131) + PathIntegrator parameters

@@ -51,6 +51,10 @@
 #include "core/scene.h"
 #include "core/stats.h"
 #include "filters/box.h"
+#include "filters/gaussian.h"
+#include "filters/mitchell.h"
+#include "filters/sinc.h"
+#include "filters/triangle.h"
 #include "integrators/path.h"
 #include "lights/diffuse.h"
 #include "materials/matte.h"
@@ -139,7 +143,15 @@ RenderObjects makeRenderObjects(const RefScene &rs, const pb2_camera *cam, const
                   Point2f((fd->cropped_pixel_bounds[2] - 0.5f) / res.x, (fd->cropped_pixel_bounds[3] - 0.5f) / res.y));
     crop.pMin.x = std::max(crop.pMin.x, 0.f);
     crop.pMin.y = std::max(crop.pMin.y, 0.f);
-    std::unique_ptr<Filter> filter(new BoxFilter(Vector2f(fd->filter_radius[0], fd->filter_radius[1])));
+    const Vector2f radius(fd->filter_radius[0], fd->filter_radius[1]);
+    std::unique_ptr<Filter> filter;
+    switch (fd->filter_type) {
+    case PB2_FILTER_GAUSSIAN: filter.reset(new GaussianFilter(radius, fd->filter_param[0])); break;
+    case PB2_FILTER_MITCHELL: filter.reset(new MitchellFilter(radius, fd->filter_param[0], fd->filter_param[1])); break;
+    case PB2_FILTER_SINC: filter.reset(new LanczosSincFilter(radius, fd->filter_param[0])); break;
+    case PB2_FILTER_TRIANGLE: filter.reset(new TriangleFilter(radius)); break;
+    default: filter.reset(new BoxFilter(radius)); break;
+    }
     ro.film = new Film(res, crop, std::move(filter), 35.f, "ref.pfm", fd->scale, fd->max_sample_luminance);
     CHECK_EQ(ro.film->croppedPixelBounds.pMin.x, fd->cropped_pixel_bounds[0]);
     CHECK_EQ(ro.film->croppedPixelBounds.pMin.y, fd->cropped_pixel_bounds[1]);

@@ -25,8 +25,9 @@ c_uint8_p = C.POINTER(C.c_uint8)
 
 PB2_OK, PB2_ERR_NO_DEVICE, PB2_ERR_CUDA, PB2_ERR_INVALID, PB2_ERR_UNSUPPORTED, PB2_ERR_NCCL = range(6)
 PB2_PRIM_TRIANGLE, PB2_PRIM_SPHERE, PB2_PRIM_INSTANCE = 0, 1, 2
+PB2_FILTER_BOX, PB2_FILTER_GAUSSIAN, PB2_FILTER_MITCHELL, PB2_FILTER_SINC, PB2_FILTER_TRIANGLE = 0, 1, 2, 3, 4
 PB2_MAT_NONE, PB2_MAT_MATTE, PB2_MAT_PLASTIC, PB2_MAT_MIRROR, PB2_MAT_GLASS, PB2_MAT_SUBSTRATE = 0, 1, 2, 3, 4, 5
-PB2_ABI_VERSION = 3   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
+PB2_ABI_VERSION = 4   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
 PB2_LIGHTDIST_UNIFORM, PB2_LIGHTDIST_POWER, PB2_LIGHTDIST_SPATIAL = 0, 1, 2
 
 
@@ -93,7 +94,8 @@ class Camera(C.Structure):
 
 class FilmDesc(C.Structure):
     _fields_ = [("full_resolution", C.c_int32 * 2), ("cropped_pixel_bounds", C.c_int32 * 4),
-                ("filter_radius", C.c_float * 2), ("max_sample_luminance", C.c_float), ("scale", C.c_float)]
+                ("filter_radius", C.c_float * 2), ("max_sample_luminance", C.c_float), ("scale", C.c_float),
+                ("filter_type", C.c_int32), ("filter_param", C.c_float * 2), ("pad", C.c_int32)]
 
 
 class PathParams(C.Structure):

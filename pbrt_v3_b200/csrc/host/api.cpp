@@ -434,10 +434,19 @@ void pbrtWorldEnd() {
     RenderOptions &ro = *renderOptions;
     // MakeCamera (api.cpp:1716-1727)
     std::unique_ptr<Filter> filter;
+    // MakeFilter (api.cpp:862-878)
     if (ro.FilterName == "box")
         filter.reset(CreateBoxFilter(ro.FilterParams));
+    else if (ro.FilterName == "gaussian")
+        filter.reset(CreateGaussianFilter(ro.FilterParams));
+    else if (ro.FilterName == "mitchell")
+        filter.reset(CreateMitchellFilter(ro.FilterParams));
+    else if (ro.FilterName == "sinc")
+        filter.reset(CreateSincFilter(ro.FilterParams));
+    else if (ro.FilterName == "triangle")
+        filter.reset(CreateTriangleFilter(ro.FilterParams));
     else {
-        Error("Filter \"%s\" is outside the GPU path's scope (box). Using \"box\" with default radius.", ro.FilterName.c_str());
+        Error("Filter \"%s\" unknown. Using \"box\" with default radius.", ro.FilterName.c_str());
         filter.reset(new BoxFilter(0.5f, 0.5f));
     }
     ro.FilterParams.ReportUnused();

@@ -137,6 +137,24 @@ BoxFilter *CreateBoxFilter(const ParamSet &ps) {
     Float yw = ps.FindOneFloat("ywidth", 0.5f);
     return new BoxFilter(xw, yw);
 }
+// gaussian.cpp:45-51, mitchell.cpp:45-52, sinc.cpp:45-50, triangle.cpp:46-51
+GaussianFilter *CreateGaussianFilter(const ParamSet &ps) {
+    Float xw = ps.FindOneFloat("xwidth", 2.f), yw = ps.FindOneFloat("ywidth", 2.f);
+    return new GaussianFilter(xw, yw, ps.FindOneFloat("alpha", 2.f));
+}
+MitchellFilter *CreateMitchellFilter(const ParamSet &ps) {
+    Float xw = ps.FindOneFloat("xwidth", 2.f), yw = ps.FindOneFloat("ywidth", 2.f);
+    Float B = ps.FindOneFloat("B", 1.f / 3.f), C = ps.FindOneFloat("C", 1.f / 3.f);
+    return new MitchellFilter(xw, yw, B, C);
+}
+LanczosSincFilter *CreateSincFilter(const ParamSet &ps) {
+    Float xw = ps.FindOneFloat("xwidth", 4.f), yw = ps.FindOneFloat("ywidth", 4.f);
+    return new LanczosSincFilter(xw, yw, ps.FindOneFloat("tau", 3.f));
+}
+TriangleFilter *CreateTriangleFilter(const ParamSet &ps) {
+    Float xw = ps.FindOneFloat("xwidth", 2.f), yw = ps.FindOneFloat("ywidth", 2.f);
+    return new TriangleFilter(xw, yw);
+}
 
 Film::Film(const Point2i &resolution, const Bounds2f &cropWindow, std::unique_ptr<Filter> filt, Float diagonal,
            const std::string &filename, Float scale, Float maxSampleLuminance)
@@ -252,6 +270,9 @@ pb2_film_desc Film::Desc() const {
     d.cropped_pixel_bounds[3] = croppedPixelBounds.pMax.y;
     d.filter_radius[0] = filter->radius[0];
     d.filter_radius[1] = filter->radius[1];
+    d.filter_type = filter->type;
+    d.filter_param[0] = filter->param[0];
+    d.filter_param[1] = filter->param[1];
     d.max_sample_luminance = maxSampleLuminance;
     d.scale = scale;
     return d;

@@ -300,17 +300,41 @@ std::shared_ptr<DeviceScene> GetDeviceScene(const BVHAccel &bvh, const std::vect
 pb2_scene *DeviceSceneHandle(const DeviceScene &);
 
 // ---------------------------------------------------------------- film / camera / sampler
+// filter.h:50-62 and src/filters/*.h: the host keeps radius and parameters; the 16x16 weight table of the
+// Film (film.cpp:68-77) is computed where it is used, inside the CUDA library.
 class Filter {
   public:
-    Filter(Float xr, Float yr) : radius{xr, yr} {}
+    Filter(Float xr, Float yr, int type = PB2_FILTER_BOX, Float p0 = 0, Float p1 = 0) : radius{xr, yr}, type(type), param{p0, p1} {}
     virtual ~Filter() {}
     Float radius[2];
+    const int type;        // PB2_FILTER_*
+    const Float param[2];  // gaussian: alpha; mitchell: B, C; sinc: tau
 };
 class BoxFilter : public Filter {
   public:
     BoxFilter(Float xr, Float yr) : Filter(xr, yr) {}
 };
+class GaussianFilter : public Filter {
+  public:
+    GaussianFilter(Float xr, Float yr, Float alpha) : Filter(xr, yr, PB2_FILTER_GAUSSIAN, alpha) {}
+};
+class MitchellFilter : public Filter {
+  public:
+    MitchellFilter(Float xr, Float yr, Float B, Float C) : Filter(xr, yr, PB2_FILTER_MITCHELL, B, C) {}
+};
+class LanczosSincFilter : public Filter {
+  public:
+    LanczosSincFilter(Float xr, Float yr, Float tau) : Filter(xr, yr, PB2_FILTER_SINC, tau) {}
+};
+class TriangleFilter : public Filter {
+  public:
+    TriangleFilter(Float xr, Float yr) : Filter(xr, yr, PB2_FILTER_TRIANGLE) {}
+};
 BoxFilter *CreateBoxFilter(const ParamSet &ps);
+GaussianFilter *CreateGaussianFilter(const ParamSet &ps);
+MitchellFilter *CreateMitchellFilter(const ParamSet &ps);
+LanczosSincFilter *CreateSincFilter(const ParamSet &ps);
+TriangleFilter *CreateTriangleFilter(const ParamSet &ps);
 
 class Film {
   public:

@@ -163,6 +163,7 @@ struct pb2_scene {
     DScene d;
     std::vector<void *> allocations;
     float *film = nullptr;  // cached device film for pb2_render_path
+    float *filterTable = nullptr;  // 16 x 16 filter weights of the frame being rendered (non-box filters)
     size_t filmFloats = 0;
     unsigned long long *counters = nullptr;  // CTR_*
     int64_t nPrims = 0;
@@ -302,6 +303,8 @@ struct DRenderParams {
     int pbx0, pby0, pbx1, pby1;  // PathIntegrator::pixelBounds
     int cx0, cy0, cx1, cy1;      // Film::croppedPixelBounds
     float filterRadiusX, filterRadiusY;
+    float invFilterRadiusX, invFilterRadiusY;
+    const float *filterTable;    // 16 x 16 weights of Film::filterTable, nullptr for the box filter (all ones)
     float maxSampleLuminance;
     int nTilesX, nTilesY;
     int tileRank, tileCount;
@@ -344,9 +347,37 @@ __device__ __forceinline__ bool decodeWork(const DRenderParams &rp, long long it
 // FilmTile::AddSample (film.h:121-161) with a box filter, accumulated straight into the merged film
 // (MergeFilmTile's sum, film.cpp:117-130).  For every tile the tile's pixel bounds contain the
 // support of each of its samples, so the clamp to the tile bounds is the clamp to the cropped bounds.
+// FilmTile::AddSample with a filter weight table (film.h:121-161); out of line so that the kernels
+// that call it do not carry its registers on their main path.
+__device__ __noinline__ void addSampleFiltered(const DRenderParams &rp, float4 *film, V2 pFilm, V3 L) {
+    float dx = pFilm.x - 0.5f, dy = pFilm.y - 0.5f;
+    int p0x = (int)ceilf(dx - rp.filterRadiusX), p0y = (int)ceilf(dy - rp.filterRadiusY);
+    int p1x = (int)floorf(dx + rp.filterRadiusX) + 1, p1y = (int)floorf(dy + rp.filterRadiusY) + 1;
+    p0x = max(p0x, rp.cx0);
+    p0y = max(p0y, rp.cy0);
+    p1x = min(p1x, rp.cx1);
+    p1y = min(p1y, rp.cy1);
+    int width = rp.cx1 - rp.cx0;
+    for (int yy = p0y; yy < p1y; ++yy) {
+        float fy = fabsf(((float)yy - dy) * rp.invFilterRadiusY * 16.f);
+        int ify = min((int)floorf(fy), 15);
+        for (int xx = p0x; xx < p1x; ++xx) {
+            float fx = fabsf(((float)xx - dx) * rp.invFilterRadiusX * 16.f);
+            int ifx = min((int)floorf(fx), 15);
+            float w = rp.filterTable[ify * 16 + ifx];
+            float4 *px = film + ((size_t)(yy - rp.cy0) * width + (xx - rp.cx0));
+            atomicAdd(px, make_float4(L.x * w, L.y * w, L.z * w, w));   // contribSum += L * sampleWeight(1) * w
+        }
+    }
+}
+
 __device__ __forceinline__ void addSample(const DRenderParams &rp, float4 *film, V2 pFilm, V3 L) {
     float y = luminance(L);
     if (y > rp.maxSampleLuminance) L = L * (rp.maxSampleLuminance / y);
+    if (rp.filterTable) {
+        addSampleFiltered(rp, film, pFilm, L);
+        return;
+    }
     float dx = pFilm.x - 0.5f, dy = pFilm.y - 0.5f;
     int p0x = (int)ceilf(dx - rp.filterRadiusX), p0y = (int)ceilf(dy - rp.filterRadiusY);
     int p1x = (int)floorf(dx + rp.filterRadiusX) + 1, p1y = (int)floorf(dy + rp.filterRadiusY) + 1;
@@ -418,6 +449,57 @@ static int requireDevice() {
     return PB2_OK;
 }
 
+// Film's filter weight table (film.cpp:68-77): filter->Evaluate at the centres of a 16 x 16 grid over
+// the positive quadrant of the filter's support.  Filter::Evaluate of src/filters/{gaussian,mitchell,sinc,
+// triangle}.{h,cpp}, evaluated on the host in float like the reference does.
+static bool computeFilterTable(const pb2_film_desc *f, float table[256]) {
+    const float rx = f->filter_radius[0], ry = f->filter_radius[1];
+    const float p0 = f->filter_param[0], p1 = f->filter_param[1];
+    auto eval = [&](float x, float y) -> float {
+        switch (f->filter_type) {
+        case PB2_FILTER_GAUSSIAN: {   // gaussian.h:50-66
+            const float alpha = p0, expX = std::exp(-alpha * rx * rx), expY = std::exp(-alpha * ry * ry);
+            auto g = [&](float d, float expv) { return std::max((float)0, float(std::exp(-alpha * d * d) - expv)); };
+            return g(x, expX) * g(y, expY);
+        }
+        case PB2_FILTER_MITCHELL: {   // mitchell.h:53-63
+            const float B = p0, C = p1;
+            auto m1 = [&](float v) {
+                v = std::abs(2 * v);
+                if (v > 1)
+                    return ((-B - 6 * C) * v * v * v + (6 * B + 30 * C) * v * v + (-12 * B - 48 * C) * v + (8 * B + 24 * C)) * (1.f / 6.f);
+                return ((12 - 9 * B - 6 * C) * v * v * v + (-18 + 12 * B + 6 * C) * v * v + (6 - 2 * B)) * (1.f / 6.f);
+            };
+            const float invRx = 1 / rx, invRy = 1 / ry;
+            return m1(x * invRx) * m1(y * invRy);
+        }
+        case PB2_FILTER_SINC: {       // sinc.h:53-63
+            const float tau = p0, Pi = 3.14159265358979323846f;
+            auto sinc = [&](float v) -> float {
+                v = std::abs(v);
+                if (v < 1e-5) return 1;
+                return std::sin(Pi * v) / (Pi * v);
+            };
+            auto ws = [&](float v, float radius) -> float {
+                v = std::abs(v);
+                if (v > radius) return 0;
+                float lanczos = sinc(v / tau);
+                return sinc(v) * lanczos;
+            };
+            return ws(x, rx) * ws(y, ry);
+        }
+        case PB2_FILTER_TRIANGLE:     // triangle.cpp:40-43
+            return std::max((float)0, rx - std::abs(x)) * std::max((float)0, ry - std::abs(y));
+        default:
+            return 1.f;               // box.cpp:40
+        }
+    };
+    int offset = 0;
+    for (int y = 0; y < 16; ++y)
+        for (int x = 0; x < 16; ++x, ++offset) table[offset] = eval((x + 0.5f) * rx / 16, (y + 0.5f) * ry / 16);
+    return f->filter_type != PB2_FILTER_BOX;
+}
+
 static DRenderParams makeRenderParams(const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp) {
     DRenderParams rp;
     memset(&rp, 0, sizeof(rp));
@@ -435,6 +517,9 @@ static DRenderParams makeRenderParams(const pb2_camera *cam, const pb2_film_desc
     rp.cx1 = film->cropped_pixel_bounds[2]; rp.cy1 = film->cropped_pixel_bounds[3];
     rp.filterRadiusX = film->filter_radius[0];
     rp.filterRadiusY = film->filter_radius[1];
+    rp.invFilterRadiusX = 1.f / film->filter_radius[0];   // Filter::invRadius (filter.h:55)
+    rp.invFilterRadiusY = 1.f / film->filter_radius[1];
+    rp.filterTable = nullptr;
     rp.maxSampleLuminance = film->max_sample_luminance;
     rp.nTilesX = (sb.x1 - sb.x0 + 15) / 16;
     rp.nTilesY = (sb.y1 - sb.y0 + 15) / 16;
@@ -455,6 +540,7 @@ static int validateRenderArgs(const pb2_scene *scene, const pb2_camera *cam, con
     if (film->cropped_pixel_bounds[2] < film->cropped_pixel_bounds[0] || film->cropped_pixel_bounds[3] < film->cropped_pixel_bounds[1])
         return setError(PB2_ERR_INVALID, "bad cropped pixel bounds");
     if (!(film->filter_radius[0] > 0) || !(film->filter_radius[1] > 0)) return setError(PB2_ERR_INVALID, "bad filter radius");
+    if (film->filter_type < PB2_FILTER_BOX || film->filter_type > PB2_FILTER_TRIANGLE) return setError(PB2_ERR_INVALID, "unknown filter type");
     return PB2_OK;
 }
 
@@ -674,6 +760,7 @@ int pb2_scene_destroy(pb2_scene *s) {
     if (!s) return PB2_OK;
     for (void *p : s->allocations) cudaFree(p);
     if (s->film) cudaFree(s->film);
+    if (s->filterTable) cudaFree(s->filterTable);
     if (s->wfCtx) cudaFree(s->wfCtx);
     if (s->wfQueues) cudaFree(s->wfQueues);
     if (s->wfCounts) cudaFree(s->wfCounts);
@@ -1033,6 +1120,15 @@ int pb2_render_path_device(pb2_scene *scene, const pb2_camera *cam, const pb2_fi
     if (!film_rgbw_device) return setError(PB2_ERR_INVALID, "null film pointer");
     cudaStream_t stream = (cudaStream_t)stream_;
     DRenderParams rp = makeRenderParams(cam, film, pp);
+    {
+        float table[256];
+        if (computeFilterTable(film, table)) {
+            if (!scene->filterTable) CUDA_TRY(cudaMalloc((void **)&scene->filterTable, sizeof(table)));
+            CUDA_TRY(cudaMemcpyAsync(scene->filterTable, table, sizeof(table), cudaMemcpyHostToDevice, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));   // `table` is on this stack frame
+            rp.filterTable = scene->filterTable;
+        }
+    }
     size_t nPixels = (size_t)(rp.cx1 - rp.cx0) * (size_t)(rp.cy1 - rp.cy0);
     if (clear) CUDA_TRY(cudaMemsetAsync(film_rgbw_device, 0, nPixels * 4 * sizeof(float), stream));
     CUDA_TRY(cudaMemsetAsync(scene->counters, 0, CTR_COUNT * sizeof(unsigned long long), stream));

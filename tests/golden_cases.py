@@ -48,3 +48,31 @@ def points_for(nodes, n, seed):
 
 def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+# Reconstruction filters (src/filters/): the PixelFilter line and the Film line of each case; geometry, lights and
+# materials are tests/scenes/materials.pbrt's.  Wider-than-a-pixel filters make neighbouring tiles overlap in the film,
+# so the order in which tiles are merged shows in the last bit: these cases are rendered by ONE thread on the CPU side.
+FILTER_CASES = {
+    "gaussian": ('PixelFilter "gaussian"', ""),
+    "mitchell": ('PixelFilter "mitchell"', ""),
+    "sinc": ('PixelFilter "sinc"', ""),
+    "triangle": ('PixelFilter "triangle"', ""),
+    "gaussian_aniso_crop": ('PixelFilter "gaussian" "float xwidth" [1.25] "float ywidth" [3] "float alpha" [1]',
+                            ' "float cropwindow" [.2 .9 .1 .7]'),
+    "mitchell_sharp": ('PixelFilter "mitchell" "float B" [0] "float C" [.5] "float xwidth" [2.5] "float ywidth" [1.5]', ""),
+    "sinc_narrow": ('PixelFilter "sinc" "float xwidth" [2] "float ywidth" [3] "float tau" [2]', ""),
+    "box_wide": ('PixelFilter "box" "float xwidth" [1.5] "float ywidth" [.75]', ""),
+}
+
+
+def filter_scene_text(scene_dir, case):
+    import os
+    import re
+    pixel_filter, film_extra = FILTER_CASES[case]
+    text = open(os.path.join(scene_dir, "materials.pbrt")).read()
+    text, n = re.subn(r'Film "image"[^\n]*', 'Film "image" "integer xresolution" [40] "integer yresolution" [28]' + film_extra, text)
+    assert n == 1
+    text, n = re.subn(r'"integer pixelsamples" \[8\]', '"integer pixelsamples" [4]', text)
+    assert n == 1
+    return text.replace("WorldBegin", pixel_filter + "\nWorldBegin", 1)

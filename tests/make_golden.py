@@ -43,6 +43,20 @@ def record_scene(ref, hs, name, n_rays=1500, n_samples=3000, n_points=400):
     print(name, "image mean", img.mean(), "rays", st.camera_rays, st.regular_rays, st.shadow_rays)
 
 
+def record_filters(ref):
+    """One image per reconstruction-filter case (tests/golden_cases.py FILTER_CASES), rendered by one thread."""
+    out = {}
+    for case in gc.FILTER_CASES:
+        hs = pb.HostScene.from_string(gc.filter_scene_text(os.path.join(ROOT, "tests", "scenes"), case))
+        img, _, st = ref.scene(hs).render(n_threads=1)
+        out["image_" + case] = img
+        out["rays_" + case] = np.array([st.camera_rays, st.regular_rays, st.shadow_rays], np.int64)
+        f = hs.film.contents
+        out["film_" + case] = np.array([f.filter_type, *f.filter_radius, *f.filter_param, *f.cropped_pixel_bounds], np.float64)
+        print("filter", case, "image mean", img.mean())
+    np.savez_compressed(os.path.join(OUT, "filters.npz"), **out)
+
+
 def main():
     ref = pyoracle.reference()
     if ref is None:
@@ -54,6 +68,7 @@ def main():
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "instances.pbrt")), "instances")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "specular.pbrt")), "specular")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "substrate.pbrt")), "substrate")
+    record_filters(ref)
     # low-discrepancy known answers (src/tests/sampling.cpp:15-74 checks the same functions against naive versions)
     a = np.concatenate([np.arange(0, 64), np.array([1023, 65535, 1234567, 2 ** 31 + 12345, 2 ** 40 + 7, 2 ** 62 + 99])]).astype(np.uint64)
     np.savez_compressed(os.path.join(OUT, "lowdiscrepancy.npz"), a=a,

@@ -193,3 +193,22 @@ def test_threaded_bvh_build_is_the_sequential_tree(pb, port):
     assert same_bvh(first_nodes, nodes) and np.array_equal(first_prims, prims)
     again = pb.HostScene.soup(300000, seed=7, jitter=0.01, xres=16, yres=16, spp=1)   # replaces the parsed scene
     assert again.nodes().tobytes() == first_nodes.tobytes() and np.array_equal(again.bvh_prims(), first_prims)
+
+
+def test_pixel_filter_directive_fills_the_film_description(pb):
+    """MakeFilter (api.cpp:862-878) + Create*Filter defaults (src/filters/*.cpp) as recorded from the reference's Film."""
+    g = np.load(os.path.join(GOLDEN, "filters.npz"))
+    want_types = {"gaussian": pb.PB2_FILTER_GAUSSIAN, "mitchell": pb.PB2_FILTER_MITCHELL, "sinc": pb.PB2_FILTER_SINC,
+                  "triangle": pb.PB2_FILTER_TRIANGLE, "box_wide": pb.PB2_FILTER_BOX}
+    for case in gc.FILTER_CASES:
+        hs = pb.HostScene.from_string(gc.filter_scene_text(SCENES, case))
+        f = hs.film.contents
+        got = np.array([f.filter_type, *f.filter_radius, *f.filter_param, *f.cropped_pixel_bounds], np.float64)
+        assert np.array_equal(got, g["film_" + case]), case
+        if case in want_types:
+            assert f.filter_type == want_types[case]
+    f = pb.HostScene.from_string(gc.filter_scene_text(SCENES, "sinc")).film.contents
+    assert list(f.filter_radius) == [4, 4] and f.filter_param[0] == 3
+    before = pb.lib().pb2h_error_count()
+    f = pb.HostScene.from_string('PixelFilter "lanczos9"\nWorldBegin\nWorldEnd\n').film.contents
+    assert pb.lib().pb2h_error_count() > before and f.filter_type == pb.PB2_FILTER_BOX

@@ -71,6 +71,24 @@ def test_port_matches_compiled_reference_live(pb, port, reference, name):
         assert a[k].tobytes() == b[k].tobytes(), k
 
 
+@pytest.mark.parametrize("case", sorted(gc.FILTER_CASES))
+def test_port_filters_match_reference_golden(pb, port, case):
+    """Reconstruction filters (src/filters/) through Film's 16x16 weight table (film.cpp:68-77, film.h:121-161)."""
+    g = np.load(os.path.join(GOLDEN, "filters.npz"))
+    hs = pb.HostScene.from_string(gc.filter_scene_text(SCENES, case))
+    img, _, st = port.scene(hs).render(n_threads=1)   # one thread: overlapping tiles merge in a fixed order
+    assert np.array_equal(gc.bits(img), gc.bits(g["image_" + case])), "image must be bit-identical to the reference's"
+    assert [st.camera_rays, st.regular_rays, st.shadow_rays] == [int(x) for x in g["rays_" + case]]
+
+
+def test_port_filters_match_compiled_reference_live(pb, port, reference):
+    for case in sorted(gc.FILTER_CASES):
+        hs = pb.HostScene.from_string(gc.filter_scene_text(SCENES, case))
+        a, _, _ = reference.scene(hs).render(n_threads=1)
+        b, _, _ = port.scene(hs).render(n_threads=1)
+        assert a.tobytes() == b.tobytes(), case
+
+
 def test_low_discrepancy_golden(port):
     g = np.load(os.path.join(GOLDEN, "lowdiscrepancy.npz"))
     for b in (0, 1, 2, 3, 10, 50, 127, 500, 999):

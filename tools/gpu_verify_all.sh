@@ -9,4 +9,5 @@ PROBE_TAG=c4 python tools/perf_probe_instanced.py 2>&1 | tail -1
 echo "== bench"; timeout 900 python bench.py 2>/dev/null | tail -1 > gpurun_out/bench_n1.json
 python -c "
 import json; d=json.load(open('gpurun_out/bench_n1.json')); print(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['trace_share_of_step'], d['gpu_launches'], d['clocks'], d['cpu_baseline']['value'])"
+[ -n "$SKIP_NCU" ] && exit 0
 echo "== ncu"; PROBE_SPP=4 PROBE_ITERS=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_wf_advance|k_wf_trace_w" --launch-skip 4 --launch-count 3 -o gpurun_out/final_kernels -f python tools/perf_probe.py > gpurun_out/ncu_final.log 2>&1; tail -1 gpurun_out/ncu_final.log
