@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 4   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc */
+#define PB2_ABI_VERSION 5   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc;
+                             * 5: uber / metal fields in pb2_material (128 bytes) */
 
 typedef enum pb2_status {
     PB2_OK = 0,
@@ -53,7 +54,8 @@ typedef struct pb2_bvh_node {
 } pb2_bvh_node;
 
 enum { PB2_PRIM_TRIANGLE = 0, PB2_PRIM_SPHERE = 1, PB2_PRIM_INSTANCE = 2 };
-enum { PB2_MAT_NONE = 0, PB2_MAT_MATTE = 1, PB2_MAT_PLASTIC = 2, PB2_MAT_MIRROR = 3, PB2_MAT_GLASS = 4, PB2_MAT_SUBSTRATE = 5 };
+enum { PB2_MAT_NONE = 0, PB2_MAT_MATTE = 1, PB2_MAT_PLASTIC = 2, PB2_MAT_MIRROR = 3, PB2_MAT_GLASS = 4, PB2_MAT_SUBSTRATE = 5, PB2_MAT_METAL = 6,
+       PB2_MAT_UBER = 7 };
 enum { PB2_LIGHTDIST_UNIFORM = 0, PB2_LIGHTDIST_POWER = 1, PB2_LIGHTDIST_SPATIAL = 2 };
 enum { PB2_FILTER_BOX = 0, PB2_FILTER_GAUSSIAN = 1, PB2_FILTER_MITCHELL = 2, PB2_FILTER_SINC = 3, PB2_FILTER_TRIANGLE = 4 };
 
@@ -94,7 +96,14 @@ typedef struct pb2_material {
     float kt[3];
     float eta;
     float uroughness, vroughness;
-    int32_t pad2[3];
+    /* UberMaterial (src/materials/uber.cpp:45-104): kd, ks, kr, kt, opacity, eta, remap_roughness and
+     * uroughness / vroughness already resolved ("uroughness" else "roughness"; "vroughness" else the u value).
+     * MetalMaterial (src/materials/metal.cpp:60-80): metal_eta, metal_k, remap_roughness and uroughness /
+     * vroughness resolved the same way (each falls back to "roughness"). */
+    float opacity[3];
+    float metal_eta[3];
+    float metal_k[3];
+    int32_t pad3[2];
 } pb2_material;
 
 /* DiffuseAreaLight (src/lights/diffuse.h:49-79) attached to one primitive. */

@@ -320,6 +320,8 @@ struct Spectrum {
     Spectrum &operator*=(const Spectrum &s) { for (int i = 0; i < 3; ++i) c[i] *= s.c[i]; return *this; }
     Spectrum operator*(Float a) const { return Spectrum(c[0] * a, c[1] * a, c[2] * a); }
     Spectrum operator/(Float a) const { return Spectrum(c[0] / a, c[1] / a, c[2] / a); }
+    Spectrum operator/(const Spectrum &s) const { return Spectrum(c[0] / s.c[0], c[1] / s.c[1], c[2] / s.c[2]); }
+    Spectrum operator-() const { return Spectrum(-c[0], -c[1], -c[2]); }
     Spectrum &operator/=(Float a) { for (int i = 0; i < 3; ++i) c[i] /= a; return *this; }
     bool IsBlack() const { return c[0] == 0. && c[1] == 0. && c[2] == 0.; }
     bool HasNaNs() const { return std::isnan(c[0]) || std::isnan(c[1]) || std::isnan(c[2]); }
@@ -330,6 +332,7 @@ struct Spectrum {
     }
 };
 inline Spectrum operator*(Float a, const Spectrum &s) { return s * a; }
+inline Spectrum Sqrt(const Spectrum &s) { return Spectrum(std::sqrt(s.c[0]), std::sqrt(s.c[1]), std::sqrt(s.c[2])); }  // spectrum.h:206-211
 inline void RGBToXYZ(const Float rgb[3], Float xyz[3]) {  // spectrum.h:62-66
     xyz[0] = 0.412453f * rgb[0] + 0.357580f * rgb[1] + 0.180423f * rgb[2];
     xyz[1] = 0.212671f * rgb[0] + 0.715160f * rgb[1] + 0.072169f * rgb[2];

@@ -83,6 +83,13 @@ class Oracle:
         self._f("camera_derived")(camera, film, ptr(r2c), ptr(dx), ptr(dy))
         return r2c, dx, dy
 
+    def copper_rgb(self):
+        """(eta, k) RGB of the metal material's default copper spectra (reference only)."""
+        eta = np.zeros(3, np.float32)
+        k = np.zeros(3, np.float32)
+        self._f("copper_rgb")(ptr(eta), ptr(k))
+        return eta, k
+
     def transform(self, kind, args):
         args = np.ascontiguousarray(args, np.float32)
         m = np.zeros(16, np.float32)

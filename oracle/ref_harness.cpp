@@ -62,6 +62,8 @@
 #include "materials/mirror.h"
 #include "materials/glass.h"
 #include "materials/substrate.h"
+#include "materials/metal.h"
+#include "materials/uber.h"
 #include "samplers/halton.h"
 #include "shapes/loopsubdiv.h"
 #include "shapes/sphere.h"
@@ -252,6 +254,17 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
             auto nu = std::make_shared<ConstantTexture<Float>>(pm.uroughness);
             auto nv = std::make_shared<ConstantTexture<Float>>(pm.vroughness);
             materials[i] = std::make_shared<SubstrateMaterial>(kd, ks, nu, nv, nullptr, pm.remap_roughness != 0);
+        } else if (pm.type == PB2_MAT_UBER) {
+            auto spec = [](const float *c) { return std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(c)); };
+            auto flt = [](float v) { return std::make_shared<ConstantTexture<Float>>(v); };
+            // the description carries the resolved u / v roughness (pb2.h); "roughness" itself is then never read
+            materials[i] = std::make_shared<UberMaterial>(kd, spec(pm.ks), spec(pm.kr), spec(pm.kt), flt(pm.uroughness), flt(pm.uroughness),
+                                                          flt(pm.vroughness), spec(pm.opacity), flt(pm.eta), nullptr, pm.remap_roughness != 0);
+        } else if (pm.type == PB2_MAT_METAL) {
+            auto spec = [](const float *c) { return std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(c)); };
+            auto flt = [](float v) { return std::make_shared<ConstantTexture<Float>>(v); };
+            materials[i] = std::make_shared<MetalMaterial>(spec(pm.metal_eta), spec(pm.metal_k), flt(pm.uroughness), flt(pm.uroughness),
+                                                           flt(pm.vroughness), nullptr, pm.remap_roughness != 0);
         } else if (pm.type == PB2_MAT_GLASS) {
             auto kr = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kr));
             auto kt = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kt));

@@ -26,8 +26,8 @@ c_uint8_p = C.POINTER(C.c_uint8)
 PB2_OK, PB2_ERR_NO_DEVICE, PB2_ERR_CUDA, PB2_ERR_INVALID, PB2_ERR_UNSUPPORTED, PB2_ERR_NCCL = range(6)
 PB2_PRIM_TRIANGLE, PB2_PRIM_SPHERE, PB2_PRIM_INSTANCE = 0, 1, 2
 PB2_FILTER_BOX, PB2_FILTER_GAUSSIAN, PB2_FILTER_MITCHELL, PB2_FILTER_SINC, PB2_FILTER_TRIANGLE = 0, 1, 2, 3, 4
-PB2_MAT_NONE, PB2_MAT_MATTE, PB2_MAT_PLASTIC, PB2_MAT_MIRROR, PB2_MAT_GLASS, PB2_MAT_SUBSTRATE = 0, 1, 2, 3, 4, 5
-PB2_ABI_VERSION = 4   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
+PB2_MAT_NONE, PB2_MAT_MATTE, PB2_MAT_PLASTIC, PB2_MAT_MIRROR, PB2_MAT_GLASS, PB2_MAT_SUBSTRATE, PB2_MAT_METAL, PB2_MAT_UBER = range(8)
+PB2_ABI_VERSION = 5   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
 PB2_LIGHTDIST_UNIFORM, PB2_LIGHTDIST_POWER, PB2_LIGHTDIST_SPATIAL = 0, 1, 2
 
 
@@ -53,7 +53,8 @@ class Material(C.Structure):
     _fields_ = [("type", C.c_int32), ("kd", C.c_float * 3), ("sigma", C.c_float), ("ks", C.c_float * 3),
                 ("roughness", C.c_float), ("remap_roughness", C.c_int32), ("pad", C.c_int32 * 2),
                 ("kr", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float), ("uroughness", C.c_float),
-                ("vroughness", C.c_float), ("pad2", C.c_int32 * 3)]
+                ("vroughness", C.c_float), ("opacity", C.c_float * 3), ("metal_eta", C.c_float * 3),
+                ("metal_k", C.c_float * 3), ("pad3", C.c_int32 * 2)]
 
 
 class Light(C.Structure):

@@ -141,7 +141,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
             }
             // BSDF-sampling half (integrator.cpp:162-213); area lights are not delta lights
             V3 wi;
-            V3 f = bsdfSampleF<SPEC>(bsdf, isect.wo, &wi, uScattering, &scatteringPdf);
+            V3 f = bsdfSampleF<SPEC>(bsdf, isect.wo, &wi, uScattering, &scatteringPdf, nullptr, true);
             if (scatteringPdf != 0) f = f * absDot(wi, isect.ns);
             else f = mk3(0, 0, 0);
             if (!isBlack(f) && scatteringPdf > 0) {

@@ -243,8 +243,17 @@ struct DBsdf {
     // FresnelBlend (substrate): the one glossy lobe of the BSDF, Rd in R, Rs in Ks, anisotropic Trowbridge-Reitz
     int blend;
     float alphaX, alphaY;
+    // BSDFs that are a LIST of BxDFs (uber.cpp:45-104, metal.cpp:60-80): bit i of `general` = lobe i is present,
+    // in the order the material adds them.  nLobes counts the non-specular ones (GEN_LAMBERT, GEN_MICROFACET).
+    int general;
+    int conductor;         // the microfacet lobe's Fresnel: FresnelConductor(1, condEta, condK) instead of FresnelDielectric(1, e)
+    V3 T0;                 // GEN_OPACITY: SpecularTransmission(T0, 1, 1)
+    V3 condEta, condK;
+    float e;               // the index the lobes' Fresnel terms use (BSDF::eta is 1 when GEN_OPACITY is present)
 };
 enum { BSDF_SAMPLED_SPECULAR = 1, BSDF_SAMPLED_TRANSMISSION = 2 };
+enum { GEN_OPACITY = 1, GEN_LAMBERT = 2, GEN_MICROFACET = 4, GEN_SPEC_REFLECTION = 8, GEN_SPEC_TRANSMISSION = 16,
+       GEN_NON_SPECULAR = GEN_LAMBERT | GEN_MICROFACET };
 
 PB2_HD V3 clampSpectrum(const float c[3]) {  // Spectrum::Clamp(0, Infinity), spectrum.h:126-132
     return mk3(clampf(c[0], 0.f, PB2_INFINITY), clampf(c[1], 0.f, PB2_INFINITY), clampf(c[2], 0.f, PB2_INFINITY));
@@ -282,6 +291,70 @@ PB2_HD bool makeBsdf(const DScene &sc, const DInteraction &it, DBsdf *bsdf) {
     bsdf->eta = 1;
     bsdf->blend = 0;
     bsdf->alphaX = bsdf->alphaY = 0;
+    bsdf->general = 0;
+    bsdf->conductor = 0;
+    bsdf->T0 = bsdf->condEta = bsdf->condK = mk3(0, 0, 0);
+    bsdf->e = 1;
+    if (SPEC && mat.type == PB2_MAT_METAL) {
+        // metal.cpp:60-80: one MicrofacetReflection(1, TrowbridgeReitz(uRough, vRough), FresnelConductor(1, eta, k))
+        float uRough = mat.uroughness, vRough = mat.vroughness;
+        if (mat.remap_roughness) {
+            uRough = roughnessToAlpha(uRough);
+            vRough = roughnessToAlpha(vRough);
+        }
+        bsdf->Ks = mk3(1, 1, 1);
+        bsdf->alphaX = pmax(0.001f, uRough);
+        bsdf->alphaY = pmax(0.001f, vRough);
+        bsdf->conductor = 1;
+        bsdf->condEta = mk3(mat.metal_eta[0], mat.metal_eta[1], mat.metal_eta[2]);
+        bsdf->condK = mk3(mat.metal_k[0], mat.metal_k[1], mat.metal_k[2]);
+        bsdf->general = GEN_MICROFACET;
+        bsdf->nLobes = 1;
+        return true;
+    }
+    if (SPEC && mat.type == PB2_MAT_UBER) {
+        // uber.cpp:45-104
+        const float e = mat.eta;
+        V3 op = clampSpectrum(mat.opacity);
+        V3 t = mk3(clampf(-op.x + 1.f, 0.f, PB2_INFINITY), clampf(-op.y + 1.f, 0.f, PB2_INFINITY), clampf(-op.z + 1.f, 0.f, PB2_INFINITY));
+        bsdf->e = e;
+        if (!isBlack(t)) {
+            bsdf->T0 = t;
+            bsdf->general |= GEN_OPACITY;
+        } else
+            bsdf->eta = e;
+        V3 kd = op * clampSpectrum(mat.kd);
+        if (!isBlack(kd)) {
+            bsdf->R = kd;
+            bsdf->diffuseKind = 1;
+            bsdf->general |= GEN_LAMBERT;
+            bsdf->nLobes++;
+        }
+        V3 ks = op * clampSpectrum(mat.ks);
+        if (!isBlack(ks)) {
+            float roughu = mat.uroughness, roughv = mat.vroughness;
+            if (mat.remap_roughness) {
+                roughu = roughnessToAlpha(roughu);
+                roughv = roughnessToAlpha(roughv);
+            }
+            bsdf->Ks = ks;
+            bsdf->alphaX = pmax(0.001f, roughu);
+            bsdf->alphaY = pmax(0.001f, roughv);
+            bsdf->general |= GEN_MICROFACET;
+            bsdf->nLobes++;
+        }
+        V3 kr = op * clampSpectrum(mat.kr);
+        if (!isBlack(kr)) {
+            bsdf->specR = kr;
+            bsdf->general |= GEN_SPEC_REFLECTION;
+        }
+        V3 kt = op * clampSpectrum(mat.kt);
+        if (!isBlack(kt)) {
+            bsdf->specT = kt;
+            bsdf->general |= GEN_SPEC_TRANSMISSION;
+        }
+        return true;
+    }
     if (SPEC && mat.type == PB2_MAT_SUBSTRATE) {
         // substrate.cpp:45-65
         V3 d = clampSpectrum(mat.kd), sp = clampSpectrum(mat.ks);
@@ -562,6 +635,63 @@ PB2_HD float microfacetPdf(const DBsdf &b, V3 wo, V3 wi) {
     return trPdf(b.alpha, wo, wh) / (4 * dot(wo, wh));
 }
 
+// FrConductor (reflection.cpp:71-95): the Spectrum arithmetic per channel, in the reference's order.
+PB2_HD float frConductor1(float cosThetaI, float cosThetaI2, float sinThetaI2, float etat, float k) {
+    float eta = etat / 1.f, etak = k / 1.f;   // etai == 1 (metal.cpp:75)
+    float eta2 = eta * eta, etak2 = etak * etak;
+    float t0 = eta2 - etak2 - sinThetaI2;
+    float a2plusb2 = sqrtf(t0 * t0 + 4 * eta2 * etak2);
+    float t1 = a2plusb2 + cosThetaI2;
+    float a = sqrtf(0.5f * (a2plusb2 + t0));
+    float t2 = (2 * cosThetaI) * a;
+    float Rs = (t1 - t2) / (t1 + t2);
+    float t3 = cosThetaI2 * a2plusb2 + sinThetaI2 * sinThetaI2;
+    float t4 = t2 * sinThetaI2;
+    float Rp = Rs * (t3 - t4) / (t3 + t4);
+    return 0.5f * (Rp + Rs);
+}
+PB2_HD V3 frConductor(float cosThetaI, V3 etat, V3 k) {
+    cosThetaI = clampf(cosThetaI, -1.f, 1.f);
+    float cosThetaI2 = cosThetaI * cosThetaI;
+    float sinThetaI2 = (float)(1. - (double)cosThetaI2);
+    return mk3(frConductor1(cosThetaI, cosThetaI2, sinThetaI2, etat.x, k.x), frConductor1(cosThetaI, cosThetaI2, sinThetaI2, etat.y, k.y),
+               frConductor1(cosThetaI, cosThetaI2, sinThetaI2, etat.z, k.z));
+}
+// MicrofacetReflection::f / Pdf (reflection.cpp:226-238, 425-429) over TrowbridgeReitz(alphaX, alphaY) with the
+// lobe's own Fresnel term
+PB2_HD V3 microfacetFGen(const DBsdf &b, V3 wo, V3 wi) {
+    float cosThetaO = absCosTheta(wo), cosThetaI = absCosTheta(wi);
+    V3 wh = wi + wo;
+    if (cosThetaI == 0 || cosThetaO == 0) return mk3(0, 0, 0);
+    if (wh.x == 0 && wh.y == 0 && wh.z == 0) return mk3(0, 0, 0);
+    wh = normalize(wh);
+    float c = dot(wi, faceforward(wh, mk3(0, 0, 1)));
+    V3 F;
+    if (b.conductor) F = frConductor(fabsf(c), b.condEta, b.condK);
+    else {
+        float Fd = frDielectric(c, 1.f, b.e);
+        F = mk3(Fd, Fd, Fd);
+    }
+    float G = 1 / (1 + trLambda2(b.alphaX, b.alphaY, wo) + trLambda2(b.alphaX, b.alphaY, wi));
+    V3 num = b.Ks * trD2(b.alphaX, b.alphaY, wh) * G * F;
+    float den = (4 * cosThetaI * cosThetaO);
+    return mk3(num.x / den, num.y / den, num.z / den);
+}
+PB2_HD float microfacetPdfGen(const DBsdf &b, V3 wo, V3 wi) {
+    if (!sameHemisphere(wo, wi)) return 0;
+    V3 wh = normalize(wo + wi);
+    return trPdf2(b.alphaX, b.alphaY, wo, wh) / (4 * dot(wo, wh));
+}
+// BSDF::f over the lobe list: the two non-specular lobes are reflective, the specular ones return 0
+PB2_HD V3 genF(const DBsdf &b, V3 wo, V3 wi, bool reflect) {
+    V3 f = mk3(0, 0, 0);
+    if (reflect) {
+        if (b.general & GEN_LAMBERT) f = f + b.R * kInvPi;
+        if (b.general & GEN_MICROFACET) f = f + microfacetFGen(b, wo, wi);
+    }
+    return f;
+}
+
 // BSDF::f (reflection.cpp:680-693).  All lobes in scope are reflective and non-specular, so they
 // match both BSDF_ALL and BSDF_ALL & ~BSDF_SPECULAR.
 template <bool SPEC = true>
@@ -571,6 +701,7 @@ PB2_HD V3 bsdfF(const DBsdf &b, V3 woW, V3 wiW) {
     bool reflect = dot(wiW, b.ng) * dot(woW, b.ng) > 0;
     V3 f = mk3(0, 0, 0);
     if (SPEC && b.blend) return reflect ? blendF(b, wo, wi) : f;
+    if (SPEC && b.general) return genF(b, wo, wi, reflect);
     if (reflect) {
         if (b.diffuseKind) f = f + diffuseF(b, wo, wi);
         if (b.hasMicrofacet) f = f + microfacetF(b, wo, wi);
@@ -584,6 +715,13 @@ PB2_HD float bsdfPdf(const DBsdf &b, V3 woW, V3 wiW) {
     V3 wo = worldToLocal(b, woW), wi = worldToLocal(b, wiW);
     if (wo.z == 0) return 0.;
     if (SPEC && b.blend) return blendPdf(b, wo, wi);
+    if (SPEC && b.general) {
+        // the callers ask with BSDF_ALL & ~BSDF_SPECULAR (integrator.cpp:134): matchingComps == nLobes
+        float pdf = 0.f;
+        if (b.general & GEN_LAMBERT) pdf += diffusePdf(wo, wi);
+        if (b.general & GEN_MICROFACET) pdf += microfacetPdfGen(b, wo, wi);
+        return pdf / b.nLobes;
+    }
     float pdf = 0.f;
     if (b.diffuseKind) pdf += diffusePdf(wo, wi);
     if (b.hasMicrofacet) pdf += microfacetPdf(b, wo, wi);
@@ -601,11 +739,87 @@ PB2_HD bool refract(V3 wi, V3 n, float eta, V3 *wt) {
     return true;
 }
 
+// BSDF::Sample_f (reflection.cpp:714-779) over a lobe list.  nonSpecularOnly: the `type` argument is
+// BSDF_ALL & ~BSDF_SPECULAR (EstimateDirect, integrator.cpp:165) instead of BSDF_ALL (path.cpp:133).
+PB2_HDN V3 genSampleF(const DBsdf &b, V3 woW, V3 *wiW, V2 u, float *pdf, int *sampledFlags, bool nonSpecularOnly) {
+    const int mask = nonSpecularOnly ? (b.general & GEN_NON_SPECULAR) : b.general;
+    int matching = 0;
+    for (int i = 0; i < 5; ++i) matching += (mask >> i) & 1;
+    if (matching == 0) return mk3(0, 0, 0);
+    int comp = (int)floorf(u.x * matching);
+    if (comp > matching - 1) comp = matching - 1;
+    int lobe = 0, count = comp;
+    for (int i = 0; i < 5; ++i)
+        if ((mask >> i) & 1) {
+            if (count-- == 0) {
+                lobe = 1 << i;
+                break;
+            }
+        }
+    V2 uRemapped = mk2(pmin(u.x * matching - comp, kOneMinusEpsilon), u.y);
+    V3 wo = worldToLocal(b, woW), wi = mk3(0, 0, 0);
+    if (wo.z == 0) return mk3(0, 0, 0);
+    V3 f = mk3(0, 0, 0);
+    int flags = 0;
+    if (lobe == GEN_LAMBERT) {
+        wi = cosineSampleHemisphere(uRemapped);   // BxDF::Sample_f (reflection.cpp:383-390)
+        if (wo.z < 0) wi.z *= -1;
+        *pdf = diffusePdf(wo, wi);
+    } else if (lobe == GEN_MICROFACET) {
+        // MicrofacetReflection::Sample_f (reflection.cpp:410-423)
+        V3 wh = trSampleWh2(b.alphaX, b.alphaY, wo, uRemapped);
+        if (dot(wo, wh) < 0) return mk3(0, 0, 0);
+        wi = -wo + 2 * dot(wo, wh) * wh;  // Reflect
+        if (!sameHemisphere(wo, wi)) return mk3(0, 0, 0);
+        *pdf = trPdf2(b.alphaX, b.alphaY, wo, wh) / (4 * dot(wo, wh));
+    } else if (lobe == GEN_SPEC_REFLECTION) {
+        // SpecularReflection::Sample_f with FresnelDielectric(1, e) (reflection.cpp:136-143)
+        wi = mk3(-wo.x, -wo.y, wo.z);
+        *pdf = 1;
+        float F = frDielectric(cosTheta(wi), 1.f, b.e);
+        V3 fr = mk3(F, F, F) * b.specR;
+        f = mk3(fr.x / absCosTheta(wi), fr.y / absCosTheta(wi), fr.z / absCosTheta(wi));
+        flags = BSDF_SAMPLED_SPECULAR;
+    } else {
+        // SpecularTransmission::Sample_f (reflection.cpp:151-166), TransportMode::Radiance
+        const float etaA = 1.f, etaB = (lobe == GEN_OPACITY) ? 1.f : b.e;
+        const V3 T = (lobe == GEN_OPACITY) ? b.T0 : b.specT;
+        bool entering = cosTheta(wo) > 0;
+        float etaI = entering ? etaA : etaB;
+        float etaT = entering ? etaB : etaA;
+        V3 nn = mk3(0, 0, 1);
+        if (dot(nn, wo) < 0) nn = -nn;  // Faceforward
+        if (!refract(wo, nn, etaI / etaT, &wi)) return mk3(0, 0, 0);
+        *pdf = 1;
+        float F = frDielectric(cosTheta(wi), etaA, etaB);
+        V3 ft = T * mk3(1.f - F, 1.f - F, 1.f - F);
+        ft = ft * ((etaI * etaI) / (etaT * etaT));
+        f = mk3(ft.x / absCosTheta(wi), ft.y / absCosTheta(wi), ft.z / absCosTheta(wi));
+        flags = BSDF_SAMPLED_SPECULAR | BSDF_SAMPLED_TRANSMISSION;
+    }
+    if (*pdf == 0) return mk3(0, 0, 0);
+    *wiW = localToWorld(b, wi);
+    const bool specular = (lobe & GEN_NON_SPECULAR) == 0;
+    if (!specular && matching > 1) {
+        // the other matching lobes' Pdf(); specular ones return 0 (reflection.cpp:758-761)
+        if (lobe != GEN_LAMBERT && (mask & GEN_LAMBERT)) *pdf += diffusePdf(wo, wi);
+        if (lobe != GEN_MICROFACET && (mask & GEN_MICROFACET)) *pdf += microfacetPdfGen(b, wo, wi);
+    }
+    if (matching > 1) *pdf /= matching;
+    if (!specular) {
+        bool reflect = dot(*wiW, b.ng) * dot(woW, b.ng) > 0;
+        f = genF(b, wo, wi, reflect);
+    }
+    if (sampledFlags) *sampledFlags = flags;
+    return f;
+}
+
 // *sampledFlags (optional): BSDF_SAMPLED_* of the BxDF that was sampled.
 template <bool SPEC = true>
-PB2_HD V3 bsdfSampleF(const DBsdf &b, V3 woW, V3 *wiW, V2 u, float *pdf, int *sampledFlags = nullptr) {
+PB2_HD V3 bsdfSampleF(const DBsdf &b, V3 woW, V3 *wiW, V2 u, float *pdf, int *sampledFlags = nullptr, bool nonSpecularOnly = false) {
     *pdf = 0;
     if (sampledFlags) *sampledFlags = 0;
+    if (SPEC && b.general) return genSampleF(b, woW, wiW, u, pdf, sampledFlags, nonSpecularOnly);
     if (SPEC && b.specKind) {
         // the BSDF holds exactly one BxDF, a specular one: matchingComps == 1, u is handed through
         // (uRemapped[0] = min(u[0], OneMinusEpsilon)), no pdf averaging and no re-evaluation of f

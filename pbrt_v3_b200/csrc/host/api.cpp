@@ -112,6 +112,10 @@ std::shared_ptr<Material> MakeMaterial(const std::string &name, const TexturePar
         material = CreatePlasticMaterial(mp);
     else if (name == "substrate")
         material = CreateSubstrateMaterial(mp);
+    else if (name == "uber")
+        material = CreateUberMaterial(mp);
+    else if (name == "metal")
+        material = CreateMetalMaterial(mp);
     else if (name == "mirror")
         material = CreateMirrorMaterial(mp);
     else if (name == "glass")
@@ -119,7 +123,7 @@ std::shared_ptr<Material> MakeMaterial(const std::string &name, const TexturePar
     else {
         // api.cpp:587-590 falls back to matte for unknown names; materials that exist in the
         // reference but not here are an error so the difference is visible.
-        Error("Material \"%s\" is outside the GPU path's scope (matte, plastic, substrate, mirror, glass). Using \"matte\".", name.c_str());
+        Error("Material \"%s\" is outside the GPU path's scope (matte, plastic, substrate, metal, uber, mirror, glass). Using \"matte\".", name.c_str());
         material = CreateMatteMaterial(mp);
     }
     mp.ReportUnused();

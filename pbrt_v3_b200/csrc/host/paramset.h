@@ -126,6 +126,17 @@ class TextureParams {
         }
         return geomParams.FindOneFloat(n, materialParams.FindOneFloat(n, def));
     }
+    // GetFloatTextureOrNull (paramset.cpp:703-732) for constant values: false when neither parameter list has it
+    bool GetFloatOrNull(const std::string &n, Float *value) const {
+        for (const ParamSet *ps : {&geomParams, &materialParams}) {
+            const ParamSet::Item *it = ps->Find(ParamSet::Type::Float, n);
+            if (it && !it->nums.empty()) {
+                *value = (Float)it->nums[0];
+                return true;
+            }
+        }
+        return false;
+    }
     bool FindBool(const std::string &n, bool d) const { return geomParams.FindOneBool(n, materialParams.FindOneBool(n, d)); }
     std::string FindString(const std::string &n, const std::string &d = "") const {
         return geomParams.FindOneString(n, materialParams.FindOneString(n, d));

@@ -64,6 +64,37 @@ pb2_material SubstrateMaterial::Record() const {
     m.remap_roughness = remapRoughness ? 1 : 0;
     return m;
 }
+pb2_material UberMaterial::Record() const {
+    pb2_material m;
+    std::memset(&m, 0, sizeof(m));
+    m.type = PB2_MAT_UBER;
+    // the device clamps like uber.cpp:54-55, 64, 70, 92, 98 do; the record carries the parameters as given
+    for (int c = 0; c < 3; ++c) {
+        m.kd[c] = Kd.c[c];
+        m.ks[c] = Ks.c[c];
+        m.kr[c] = Kr.c[c];
+        m.kt[c] = Kt.c[c];
+        m.opacity[c] = opacity.c[c];
+    }
+    m.eta = eta;
+    m.uroughness = roughnessu;
+    m.vroughness = roughnessv;
+    m.remap_roughness = remapRoughness ? 1 : 0;
+    return m;
+}
+pb2_material MetalMaterial::Record() const {
+    pb2_material m;
+    std::memset(&m, 0, sizeof(m));
+    m.type = PB2_MAT_METAL;
+    for (int c = 0; c < 3; ++c) {
+        m.metal_eta[c] = eta.c[c];
+        m.metal_k[c] = k.c[c];
+    }
+    m.uroughness = uRoughness;
+    m.vroughness = vRoughness;
+    m.remap_roughness = remapRoughness ? 1 : 0;
+    return m;
+}
 static void rejectTextures(const TextureParams &mp, const char *what, std::initializer_list<const char *> names) {
     for (const char *n : names)
         if (mp.geomParams.FindTexture(n) != "" || mp.materialParams.FindTexture(n) != "")
@@ -85,6 +116,39 @@ SubstrateMaterial *CreateSubstrateMaterial(const TextureParams &mp) {
     Float vroughness = mp.GetFloatTexture("vroughness", .1f);
     bool remap = mp.FindBool("remaproughness", true);
     return new SubstrateMaterial(Kd, Ks, uroughness, vroughness, remap);
+}
+// uber.cpp:106-131
+UberMaterial *CreateUberMaterial(const TextureParams &mp) {
+    rejectTextures(mp, "uber", {"Kd", "Ks", "Kr", "Kt", "roughness", "uroughness", "vroughness", "eta", "index", "opacity", "bumpmap"});
+    Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(0.25f));
+    Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(0.25f));
+    Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(0.f));
+    Spectrum Kt = mp.GetSpectrumTexture("Kt", Spectrum(0.f));
+    Float roughness = mp.GetFloatTexture("roughness", .1f);
+    Float roughu = roughness, roughv;
+    mp.GetFloatOrNull("uroughness", &roughu);
+    roughv = roughu;   // uber.cpp:77-80: "vroughness" falls back to the u value
+    mp.GetFloatOrNull("vroughness", &roughv);
+    Float eta;
+    if (!mp.GetFloatOrNull("eta", &eta)) eta = mp.GetFloatTexture("index", 1.5f);
+    Spectrum opacity = mp.GetSpectrumTexture("opacity", Spectrum(1.f));
+    bool remap = mp.FindBool("remaproughness", true);
+    return new UberMaterial(Kd, Ks, Kr, Kt, roughu, roughv, opacity, eta, remap);
+}
+// metal.cpp:120-140.  The defaults are copper's measured index and absorption converted to RGB by
+// Spectrum::FromSampled (metal.cpp:82-118, spectrum.h:438-466); the six numbers below are that conversion's result,
+// recorded from the compiled reference (tests/golden/metal_defaults.npz, tests/make_golden.py).
+MetalMaterial *CreateMetalMaterial(const TextureParams &mp) {
+    rejectTextures(mp, "metal", {"eta", "k", "roughness", "uroughness", "vroughness", "bumpmap"});
+    static const Spectrum copperN(0.19999069f, 0.92208463f, 1.09987593f), copperK(3.90463543f, 2.44763327f, 2.13765264f);
+    Spectrum eta = mp.GetSpectrumTexture("eta", copperN);
+    Spectrum k = mp.GetSpectrumTexture("k", copperK);
+    Float roughness = mp.GetFloatTexture("roughness", .01f);
+    Float uRough = roughness, vRough = roughness;   // metal.cpp:67-70: each falls back to "roughness"
+    mp.GetFloatOrNull("uroughness", &uRough);
+    mp.GetFloatOrNull("vroughness", &vRough);
+    bool remap = mp.FindBool("remaproughness", true);
+    return new MetalMaterial(eta, k, uRough, vRough, remap);
 }
 // mirror.cpp:60-66
 MirrorMaterial *CreateMirrorMaterial(const TextureParams &mp) {

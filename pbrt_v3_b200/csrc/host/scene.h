@@ -165,6 +165,29 @@ class SubstrateMaterial : public Material {
     Float nu, nv;
     bool remapRoughness;
 };
+// uber.h:49-85 / metal.h:49-76 with constant textures.  The "uroughness" / "vroughness" fall-backs of
+// ComputeScatteringFunctions (uber.cpp:71-80, metal.cpp:67-70) are resolved at creation.
+class UberMaterial : public Material {
+  public:
+    UberMaterial(const Spectrum &Kd, const Spectrum &Ks, const Spectrum &Kr, const Spectrum &Kt, Float roughnessu, Float roughnessv,
+                 const Spectrum &opacity, Float eta, bool remapRoughness)
+        : Kd(Kd), Ks(Ks), Kr(Kr), Kt(Kt), opacity(opacity), roughnessu(roughnessu), roughnessv(roughnessv), eta(eta), remapRoughness(remapRoughness) {}
+    pb2_material Record() const override;
+    Spectrum Kd, Ks, Kr, Kt, opacity;
+    Float roughnessu, roughnessv, eta;
+    bool remapRoughness;
+};
+class MetalMaterial : public Material {
+  public:
+    MetalMaterial(const Spectrum &eta, const Spectrum &k, Float uRoughness, Float vRoughness, bool remapRoughness)
+        : eta(eta), k(k), uRoughness(uRoughness), vRoughness(vRoughness), remapRoughness(remapRoughness) {}
+    pb2_material Record() const override;
+    Spectrum eta, k;
+    Float uRoughness, vRoughness;
+    bool remapRoughness;
+};
+UberMaterial *CreateUberMaterial(const TextureParams &mp);
+MetalMaterial *CreateMetalMaterial(const TextureParams &mp);
 SubstrateMaterial *CreateSubstrateMaterial(const TextureParams &mp);
 MirrorMaterial *CreateMirrorMaterial(const TextureParams &mp);
 GlassMaterial *CreateGlassMaterial(const TextureParams &mp);

@@ -780,15 +780,18 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
     if (d->n_prims > 0x7fffffffLL || d->n_nodes > 0x7fffffffLL) return setError(PB2_ERR_UNSUPPORTED, "more than 2^31 primitives/nodes");
     for (int i = 0; i < d->n_materials; ++i)
         if (d->materials[i].type != PB2_MAT_NONE && d->materials[i].type != PB2_MAT_MATTE && d->materials[i].type != PB2_MAT_PLASTIC &&
-            d->materials[i].type != PB2_MAT_MIRROR && d->materials[i].type != PB2_MAT_SUBSTRATE && !(d->materials[i].type == PB2_MAT_GLASS && d->materials[i].uroughness == 0 && d->materials[i].vroughness == 0))
-            return setError(PB2_ERR_UNSUPPORTED, "material type outside the path's scope (matte, plastic, substrate, mirror, smooth glass)");
+            d->materials[i].type != PB2_MAT_MIRROR && d->materials[i].type != PB2_MAT_SUBSTRATE && d->materials[i].type != PB2_MAT_METAL &&
+            d->materials[i].type != PB2_MAT_UBER && !(d->materials[i].type == PB2_MAT_GLASS && d->materials[i].uroughness == 0 && d->materials[i].vroughness == 0))
+            return setError(PB2_ERR_UNSUPPORTED, "material type outside the path's scope (matte, plastic, substrate, metal, uber, mirror, smooth glass)");
     struct Guard {
         pb2_scene *s;
         ~Guard() { if (s) pb2_scene_destroy(s); }
     } guard{new pb2_scene()};
     pb2_scene *s = guard.s;
     for (int i = 0; i < d->n_materials; ++i)
-        if (d->materials[i].type == PB2_MAT_MIRROR || d->materials[i].type == PB2_MAT_GLASS || d->materials[i].type == PB2_MAT_SUBSTRATE) s->hasSpecular = true;
+        if (d->materials[i].type == PB2_MAT_MIRROR || d->materials[i].type == PB2_MAT_GLASS || d->materials[i].type == PB2_MAT_SUBSTRATE ||
+            d->materials[i].type == PB2_MAT_METAL || d->materials[i].type == PB2_MAT_UBER)
+            s->hasSpecular = true;
     DScene &sc = s->d;
     memset(&sc, 0, sizeof(sc));
     sc.nNodes = d->n_nodes;

@@ -68,7 +68,12 @@ def main():
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "instances.pbrt")), "instances")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "specular.pbrt")), "specular")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "substrate.pbrt")), "substrate")
+    record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "metal.pbrt")), "metal")
+    record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "uber.pbrt")), "uber")
     record_filters(ref)
+    # the metal material's default eta / k: copper's measured spectra through Spectrum::FromSampled (metal.cpp:121-126)
+    eta, k = ref.copper_rgb()
+    np.savez_compressed(os.path.join(OUT, "metal_defaults.npz"), eta=eta, k=k)
     # low-discrepancy known answers (src/tests/sampling.cpp:15-74 checks the same functions against naive versions)
     a = np.concatenate([np.arange(0, 64), np.array([1023, 65535, 1234567, 2 ** 31 + 12345, 2 ** 40 + 7, 2 ** 62 + 99])]).astype(np.uint64)
     np.savez_compressed(os.path.join(OUT, "lowdiscrepancy.npz"), a=a,

@@ -110,7 +110,7 @@ def test_defaults_when_scene_file_is_silent(pb):
 
 def test_unsupported_plugins_are_reported_not_silently_replaced(pb):
     before = pb.lib().pb2h_error_count()
-    pb.HostScene.from_string('Sampler "halton"\nWorldBegin\nMaterial "metal"\nShape "sphere"\nWorldEnd\n')
+    pb.HostScene.from_string('Sampler "halton"\nWorldBegin\nMaterial "translucent"\nShape "sphere"\nWorldEnd\n')
     assert pb.lib().pb2h_error_count() > before
 
 
@@ -212,3 +212,36 @@ def test_pixel_filter_directive_fills_the_film_description(pb):
     before = pb.lib().pb2h_error_count()
     f = pb.HostScene.from_string('PixelFilter "lanczos9"\nWorldBegin\nWorldEnd\n').film.contents
     assert pb.lib().pb2h_error_count() > before and f.filter_type == pb.PB2_FILTER_BOX
+
+
+def test_uber_and_metal_parameters(pb):
+    """CreateUberMaterial / CreateMetalMaterial (uber.cpp:106-131, metal.cpp:120-140): defaults, the "eta"-over-"index"
+    rule, the roughness fall-backs of ComputeScatteringFunctions, and the copper defaults recorded from the reference."""
+    f32 = np.float32
+    hs = pb.HostScene.from_file(os.path.join(SCENES, "uber.pbrt"))
+    d = hs.desc.contents
+    ub = [d.materials[i] for i in range(d.n_materials) if d.materials[i].type == pb.PB2_MAT_UBER]
+    assert len(ub) == 5
+    dflt = ub[0]
+    assert tuple(dflt.kd) == (.25,) * 3 and tuple(dflt.ks) == (.25,) * 3 and tuple(dflt.kr) == (0,) * 3 and tuple(dflt.kt) == (0,) * 3
+    assert tuple(dflt.opacity) == (1,) * 3 and dflt.eta == f32(1.5) and dflt.uroughness == f32(.1) == dflt.vroughness and dflt.remap_roughness == 1
+    assert ub[1].eta == f32(1.33) and ub[1].uroughness == f32(.05) == ub[1].vroughness and np.allclose(tuple(ub[1].opacity), (.8, .7, .6))
+    assert ub[2].eta == f32(1.6)                                   # "eta" wins over "index"
+    assert ub[3].uroughness == f32(.3) and ub[3].vroughness == f32(.04) and ub[3].remap_roughness == 0
+    assert tuple(ub[4].opacity) == (0, 0, 0)
+    hs = pb.HostScene.from_string('WorldBegin\nMaterial "uber" "float roughness" .3 "float uroughness" .02\nShape "sphere"\nWorldEnd\n')
+    m = [hs.desc.contents.materials[i] for i in range(hs.desc.contents.n_materials) if hs.desc.contents.materials[i].type == pb.PB2_MAT_UBER][0]
+    assert m.uroughness == f32(.02) == m.vroughness                # uber: "vroughness" falls back to the u value (uber.cpp:77-80)
+    hs = pb.HostScene.from_file(os.path.join(SCENES, "metal.pbrt"))
+    d = hs.desc.contents
+    me = [d.materials[i] for i in range(d.n_materials) if d.materials[i].type == pb.PB2_MAT_METAL]
+    assert len(me) == 3
+    g = np.load(os.path.join(GOLDEN, "metal_defaults.npz"))
+    assert np.array_equal(gc.bits(np.array(tuple(me[0].metal_eta), f32)), gc.bits(g["eta"]))
+    assert np.array_equal(gc.bits(np.array(tuple(me[0].metal_k), f32)), gc.bits(g["k"]))
+    assert me[0].uroughness == f32(.01) == me[0].vroughness and me[0].remap_roughness == 1
+    assert me[1].uroughness == f32(.05) and me[1].vroughness == f32(.4)
+    assert me[2].uroughness == f32(.15) == me[2].vroughness and me[2].remap_roughness == 0
+    hs = pb.HostScene.from_string('WorldBegin\nMaterial "metal" "float roughness" .3 "float uroughness" .02\nShape "sphere"\nWorldEnd\n')
+    m = [hs.desc.contents.materials[i] for i in range(hs.desc.contents.n_materials) if hs.desc.contents.materials[i].type == pb.PB2_MAT_METAL][0]
+    assert m.uroughness == f32(.02) and m.vroughness == f32(.3)    # metal: each falls back to "roughness" (metal.cpp:67-70)
