@@ -28,8 +28,9 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 5   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc;
-                             * 5: uber / metal fields in pb2_material (128 bytes) */
+#define PB2_ABI_VERSION 6   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc;
+                             * 5: uber / metal fields in pb2_material (128 bytes); 6: point / spot / distant lights
+                             * (pb2_light.type, pb2_scene_desc.delta_lights) */
 
 typedef enum pb2_status {
     PB2_OK = 0,
@@ -106,14 +107,27 @@ typedef struct pb2_material {
     int32_t pad3[2];
 } pb2_material;
 
-/* DiffuseAreaLight (src/lights/diffuse.h:49-79) attached to one primitive. */
+/* One entry of Scene::lights, in the scene's order.  PB2_LIGHT_AREA: a DiffuseAreaLight (src/lights/diffuse.h:49-79)
+ * attached to one primitive.  The other types are the delta lights (src/lights/{point,spot,distant}.cpp): L holds
+ * I (point, spot) or L (distant), prim is -1, and delta_lights[same index] the geometry. */
+enum { PB2_LIGHT_AREA = 0, PB2_LIGHT_POINT = 1, PB2_LIGHT_SPOT = 2, PB2_LIGHT_DISTANT = 3 };
 typedef struct pb2_light {
     int32_t prim;       /* index into prim_type[]/prim_index[] */
     float L[3];         /* Lemit = L * scale */
     int32_t two_sided;
     float area;         /* Shape::Area() of that primitive (DiffuseAreaLight::area, diffuse.cpp:52) */
-    int32_t pad[2];
+    int32_t type;       /* PB2_LIGHT_* */
+    int32_t pad;
 } pb2_light;
+
+typedef struct pb2_delta_light {
+    float p[3];                 /* point, spot: pLight (point.h:52, spot.h:54); distant: wLight, normalised (distant.cpp:46) */
+    float cos_total_width;      /* spot (spot.cpp:49-50) */
+    float cos_falloff_start;
+    float world_radius;         /* distant: DistantLight::Preprocess (distant.h:55-57), from the scene bounds */
+    float world_to_light[9];    /* spot: upper-left 3x3 of WorldToLight, row-major (SpotLight::Falloff, spot.cpp:63-72) */
+    float pad;
+} pb2_delta_light;
 
 /* One BVHAccel of the scene: bvhs[0] is Scene::aggregate, bvhs[k > 0] the accelerator that
  * pbrtObjectInstance builds over the primitives of an instanced object (src/core/api.cpp:1565-1573).
@@ -180,6 +194,8 @@ typedef struct pb2_scene_desc {
     const pb2_instance *instances;
     const pb2_bvh *bvhs;
     int64_t n_bvh_prims;          /* length of bvh_prims when n_bvhs > 0 */
+    /* n_lights entries, read for lights[i].type != PB2_LIGHT_AREA; NULL when every light is an area light */
+    const pb2_delta_light *delta_lights;
 } pb2_scene_desc;
 
 /* PerspectiveCamera (src/cameras/perspective.cpp:45-67, 95-144). */

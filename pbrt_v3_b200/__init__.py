@@ -27,8 +27,9 @@ PB2_OK, PB2_ERR_NO_DEVICE, PB2_ERR_CUDA, PB2_ERR_INVALID, PB2_ERR_UNSUPPORTED, P
 PB2_PRIM_TRIANGLE, PB2_PRIM_SPHERE, PB2_PRIM_INSTANCE = 0, 1, 2
 PB2_FILTER_BOX, PB2_FILTER_GAUSSIAN, PB2_FILTER_MITCHELL, PB2_FILTER_SINC, PB2_FILTER_TRIANGLE = 0, 1, 2, 3, 4
 PB2_MAT_NONE, PB2_MAT_MATTE, PB2_MAT_PLASTIC, PB2_MAT_MIRROR, PB2_MAT_GLASS, PB2_MAT_SUBSTRATE, PB2_MAT_METAL, PB2_MAT_UBER = range(8)
-PB2_ABI_VERSION = 5   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
+PB2_ABI_VERSION = 6   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
 PB2_LIGHTDIST_UNIFORM, PB2_LIGHTDIST_POWER, PB2_LIGHTDIST_SPATIAL = 0, 1, 2
+PB2_LIGHT_AREA, PB2_LIGHT_POINT, PB2_LIGHT_SPOT, PB2_LIGHT_DISTANT = 0, 1, 2, 3
 
 
 class BvhNode(C.Structure):
@@ -59,7 +60,12 @@ class Material(C.Structure):
 
 class Light(C.Structure):
     _fields_ = [("prim", C.c_int32), ("L", C.c_float * 3), ("two_sided", C.c_int32), ("area", C.c_float),
-                ("pad", C.c_int32 * 2)]
+                ("type", C.c_int32), ("pad", C.c_int32)]
+
+
+class DeltaLight(C.Structure):
+    _fields_ = [("p", C.c_float * 3), ("cos_total_width", C.c_float), ("cos_falloff_start", C.c_float),
+                ("world_radius", C.c_float), ("world_to_light", C.c_float * 9), ("pad", C.c_float)]
 
 
 class Bvh(C.Structure):
@@ -83,7 +89,7 @@ class SceneDesc(C.Structure):
                 ("n_lights", C.c_int32), ("lights", C.POINTER(Light)),
                 ("light_strategy", C.c_int32), ("spatial_max_voxels", C.c_int32),
                 ("n_instances", C.c_int32), ("n_bvhs", C.c_int32), ("instances", C.POINTER(Instance)),
-                ("bvhs", C.POINTER(Bvh)), ("n_bvh_prims", C.c_int64)]
+                ("bvhs", C.POINTER(Bvh)), ("n_bvh_prims", C.c_int64), ("delta_lights", C.POINTER(DeltaLight))]
 
 
 class Camera(C.Structure):

@@ -126,7 +126,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
             V2 uLight = get2D(h, smp);
             V2 uScattering = get2D(h, smp);
             // EstimateDirect, light-sampling half (integrator.cpp:116-160)
-            DLightSample ls = sampleLight<SPH>(sc, light, lightRec, isect, uLight);
+            DLightSample ls = sampleLight<SPH>(sc, lightNum, light, lightRec, isect, uLight);
             float lightPdf = ls.pdf, scatteringPdf = 0;
             if (lightPdf > 0 && !isBlack(ls.Li)) {
                 V3 f = bsdfF<SPEC>(bsdf, isect.wo, ls.wi) * absDot(ls.wi, isect.ns);
@@ -134,16 +134,20 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
                 if (!isBlack(f)) {
                     shadow = spawnRayTo(isect, ls.p, ls.pError, ls.n);
                     hasShadow = true;
-                    float weight = powerHeuristic(lightPdf, scatteringPdf);
+                    // a delta light's sample is not weighted (integrator.cpp:150-151): f * Li / lightPdf
+                    float weight = ls.delta ? 1.f : powerHeuristic(lightPdf, scatteringPdf);
                     V3 fl = f * ls.Li * weight;
                     ln.ldLight = mk3(fl.x / lightPdf, fl.y / lightPdf, fl.z / lightPdf);
                 }
             }
-            // BSDF-sampling half (integrator.cpp:162-213); area lights are not delta lights
+            // BSDF-sampling half (integrator.cpp:162-213), skipped for delta lights
             V3 wi;
-            V3 f = bsdfSampleF<SPEC>(bsdf, isect.wo, &wi, uScattering, &scatteringPdf, nullptr, true);
-            if (scatteringPdf != 0) f = f * absDot(wi, isect.ns);
-            else f = mk3(0, 0, 0);
+            V3 f = mk3(0, 0, 0);
+            if (!ls.delta) {
+                f = bsdfSampleF<SPEC>(bsdf, isect.wo, &wi, uScattering, &scatteringPdf, nullptr, true);
+                if (scatteringPdf != 0) f = f * absDot(wi, isect.ns);
+                else f = mk3(0, 0, 0);
+            }
             if (!isBlack(f) && scatteringPdf > 0) {
                 lightPdf = lightPdfLi<SPH>(sc, light, lightRec, isect, wi);
                 if (lightPdf != 0) {

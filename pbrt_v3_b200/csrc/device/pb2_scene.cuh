@@ -79,6 +79,7 @@ struct DScene {
     const int32_t *primIndex, *primMaterial, *primLight;
     const pb2_material *materials;
     const pb2_light *lights;
+    const pb2_delta_light *deltaLights;   // parallel to lights, nullptr when every light is an area light
     int nLights;
     const DInstance *instances;   // nullptr: no object instancing in this scene
     int nInstances;

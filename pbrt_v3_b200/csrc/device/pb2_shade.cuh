@@ -253,7 +253,8 @@ struct DBsdf {
 };
 enum { BSDF_SAMPLED_SPECULAR = 1, BSDF_SAMPLED_TRANSMISSION = 2 };
 enum { GEN_OPACITY = 1, GEN_LAMBERT = 2, GEN_MICROFACET = 4, GEN_SPEC_REFLECTION = 8, GEN_SPEC_TRANSMISSION = 16,
-       GEN_NON_SPECULAR = GEN_LAMBERT | GEN_MICROFACET };
+       GEN_MICRO_TRANSMISSION = 32,   // MicrofacetTransmission(specT, TrowbridgeReitz(alphaX, alphaY), 1, e): rough glass
+       GEN_LOBES = 6, GEN_NON_SPECULAR = GEN_LAMBERT | GEN_MICROFACET | GEN_MICRO_TRANSMISSION };
 
 PB2_HD V3 clampSpectrum(const float c[3]) {  // Spectrum::Clamp(0, Infinity), spectrum.h:126-132
     return mk3(clampf(c[0], 0.f, PB2_INFINITY), clampf(c[1], 0.f, PB2_INFINITY), clampf(c[2], 0.f, PB2_INFINITY));
@@ -379,6 +380,31 @@ PB2_HD bool makeBsdf(const DScene &sc, const DInteraction &it, DBsdf *bsdf) {
         if (!isBlack(r)) {
             bsdf->specKind = 1;
             bsdf->specR = r;
+        }
+        return true;
+    }
+    if (SPEC && mat.type == PB2_MAT_GLASS && !(mat.uroughness == 0 && mat.vroughness == 0)) {
+        // glass.cpp:45-93, rough: MicrofacetReflection(R, distrib, FresnelDielectric(1, eta)) + MicrofacetTransmission(T, distrib, 1, eta)
+        V3 r = clampSpectrum(mat.kr), t = clampSpectrum(mat.kt);
+        bsdf->eta = mat.eta;
+        bsdf->e = mat.eta;
+        if (isBlack(r) && isBlack(t)) return true;
+        float urough = mat.uroughness, vrough = mat.vroughness;
+        if (mat.remap_roughness) {
+            urough = roughnessToAlpha(urough);
+            vrough = roughnessToAlpha(vrough);
+        }
+        bsdf->alphaX = pmax(0.001f, urough);
+        bsdf->alphaY = pmax(0.001f, vrough);
+        if (!isBlack(r)) {
+            bsdf->Ks = r;
+            bsdf->general |= GEN_MICROFACET;
+            bsdf->nLobes++;
+        }
+        if (!isBlack(t)) {
+            bsdf->specT = t;
+            bsdf->general |= GEN_MICRO_TRANSMISSION;
+            bsdf->nLobes++;
         }
         return true;
     }
@@ -682,13 +708,41 @@ PB2_HD float microfacetPdfGen(const DBsdf &b, V3 wo, V3 wi) {
     V3 wh = normalize(wo + wi);
     return trPdf2(b.alphaX, b.alphaY, wo, wh) / (4 * dot(wo, wh));
 }
-// BSDF::f over the lobe list: the two non-specular lobes are reflective, the specular ones return 0
+// MicrofacetTransmission::f / Pdf (reflection.cpp:246-270, 444-458), etaA = 1, etaB = e, TransportMode::Radiance
+PB2_HD V3 microTransF(const DBsdf &b, V3 wo, V3 wi) {
+    if (sameHemisphere(wo, wi)) return mk3(0, 0, 0);
+    float cosThetaO = cosTheta(wo), cosThetaI = cosTheta(wi);
+    if (cosThetaI == 0 || cosThetaO == 0) return mk3(0, 0, 0);
+    float eta = cosTheta(wo) > 0 ? (b.e / 1.f) : (1.f / b.e);
+    V3 wh = normalize(wo + wi * eta);
+    if (wh.z < 0) wh = -wh;
+    if (dot(wo, wh) * dot(wi, wh) > 0) return mk3(0, 0, 0);
+    float F = frDielectric(dot(wo, wh), 1.f, b.e);
+    float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+    float factor = 1 / eta;
+    float G = 1 / (1 + trLambda2(b.alphaX, b.alphaY, wo) + trLambda2(b.alphaX, b.alphaY, wi));
+    float v = fabsf(trD2(b.alphaX, b.alphaY, wh) * G * eta * eta * absDot(wi, wh) * absDot(wo, wh) * factor * factor /
+                    (cosThetaI * cosThetaO * sqrtDenom * sqrtDenom));
+    return mk3(1.f - F, 1.f - F, 1.f - F) * b.specT * v;
+}
+PB2_HD float microTransPdf(const DBsdf &b, V3 wo, V3 wi) {
+    if (sameHemisphere(wo, wi)) return 0;
+    float eta = cosTheta(wo) > 0 ? (b.e / 1.f) : (1.f / b.e);
+    V3 wh = normalize(wo + wi * eta);
+    if (dot(wo, wh) * dot(wi, wh) > 0) return 0;
+    float sqrtDenom = dot(wo, wh) + eta * dot(wi, wh);
+    float dwh_dwi = fabsf((eta * eta * dot(wi, wh)) / (sqrtDenom * sqrtDenom));
+    return trPdf2(b.alphaX, b.alphaY, wo, wh) * dwh_dwi;
+}
+// BSDF::f over the lobe list (reflection.cpp:680-693): reflective lobes when wi and wo are on the same side of the
+// geometric normal, transmissive ones otherwise; the specular lobes return 0
 PB2_HD V3 genF(const DBsdf &b, V3 wo, V3 wi, bool reflect) {
     V3 f = mk3(0, 0, 0);
     if (reflect) {
         if (b.general & GEN_LAMBERT) f = f + b.R * kInvPi;
         if (b.general & GEN_MICROFACET) f = f + microfacetFGen(b, wo, wi);
-    }
+    } else if (b.general & GEN_MICRO_TRANSMISSION)
+        f = f + microTransF(b, wo, wi);
     return f;
 }
 
@@ -720,6 +774,7 @@ PB2_HD float bsdfPdf(const DBsdf &b, V3 woW, V3 wiW) {
         float pdf = 0.f;
         if (b.general & GEN_LAMBERT) pdf += diffusePdf(wo, wi);
         if (b.general & GEN_MICROFACET) pdf += microfacetPdfGen(b, wo, wi);
+        if (b.general & GEN_MICRO_TRANSMISSION) pdf += microTransPdf(b, wo, wi);
         return pdf / b.nLobes;
     }
     float pdf = 0.f;
@@ -744,12 +799,12 @@ PB2_HD bool refract(V3 wi, V3 n, float eta, V3 *wt) {
 PB2_HDN V3 genSampleF(const DBsdf &b, V3 woW, V3 *wiW, V2 u, float *pdf, int *sampledFlags, bool nonSpecularOnly) {
     const int mask = nonSpecularOnly ? (b.general & GEN_NON_SPECULAR) : b.general;
     int matching = 0;
-    for (int i = 0; i < 5; ++i) matching += (mask >> i) & 1;
+    for (int i = 0; i < GEN_LOBES; ++i) matching += (mask >> i) & 1;
     if (matching == 0) return mk3(0, 0, 0);
     int comp = (int)floorf(u.x * matching);
     if (comp > matching - 1) comp = matching - 1;
     int lobe = 0, count = comp;
-    for (int i = 0; i < 5; ++i)
+    for (int i = 0; i < GEN_LOBES; ++i)
         if ((mask >> i) & 1) {
             if (count-- == 0) {
                 lobe = 1 << i;
@@ -772,6 +827,14 @@ PB2_HDN V3 genSampleF(const DBsdf &b, V3 woW, V3 *wiW, V2 u, float *pdf, int *sa
         wi = -wo + 2 * dot(wo, wh) * wh;  // Reflect
         if (!sameHemisphere(wo, wi)) return mk3(0, 0, 0);
         *pdf = trPdf2(b.alphaX, b.alphaY, wo, wh) / (4 * dot(wo, wh));
+    } else if (lobe == GEN_MICRO_TRANSMISSION) {
+        // MicrofacetTransmission::Sample_f (reflection.cpp:431-442)
+        V3 wh = trSampleWh2(b.alphaX, b.alphaY, wo, uRemapped);
+        if (dot(wo, wh) < 0) return mk3(0, 0, 0);
+        float eta = cosTheta(wo) > 0 ? (1.f / b.e) : (b.e / 1.f);
+        if (!refract(wo, wh, eta, &wi)) return mk3(0, 0, 0);
+        *pdf = microTransPdf(b, wo, wi);
+        flags = BSDF_SAMPLED_TRANSMISSION;
     } else if (lobe == GEN_SPEC_REFLECTION) {
         // SpecularReflection::Sample_f with FresnelDielectric(1, e) (reflection.cpp:136-143)
         wi = mk3(-wo.x, -wo.y, wo.z);
@@ -804,6 +867,7 @@ PB2_HDN V3 genSampleF(const DBsdf &b, V3 woW, V3 *wiW, V2 u, float *pdf, int *sa
         // the other matching lobes' Pdf(); specular ones return 0 (reflection.cpp:758-761)
         if (lobe != GEN_LAMBERT && (mask & GEN_LAMBERT)) *pdf += diffusePdf(wo, wi);
         if (lobe != GEN_MICROFACET && (mask & GEN_MICROFACET)) *pdf += microfacetPdfGen(b, wo, wi);
+        if (lobe != GEN_MICRO_TRANSMISSION && (mask & GEN_MICRO_TRANSMISSION)) *pdf += microTransPdf(b, wo, wi);
     }
     if (matching > 1) *pdf /= matching;
     if (!specular) {
@@ -931,6 +995,7 @@ struct DLightSample {
     V3 wi;
     V3 Li;
     float pdf;
+    bool delta;        // IsDeltaLight(light.flags) (light.h:57-60)
 };
 
 // Triangle::Area (triangle.cpp:574-580)
@@ -1079,11 +1144,54 @@ PB2_HD DLightSample sampleTriangleLight(const DScene &sc, const pb2_light &l, co
     return s;
 }
 
-// `rec` is the light's record out of DScene::lightRecs.
+// PointLight / SpotLight / DistantLight::Sample_Li (point.cpp:44-53, spot.cpp:52-72, distant.cpp:48-58).  The
+// VisibilityTester's second point carries no normal and no error bounds, so SpawnRayTo aims at it exactly.
+PB2_HDN DLightSample sampleDeltaLight(const pb2_light &l, const pb2_delta_light &dl, V3 refP) {
+    DLightSample s;
+    s.delta = true;
+    s.pError = s.n = mk3(0, 0, 0);
+    s.pdf = 1.f;
+    const V3 I = mk3(l.L[0], l.L[1], l.L[2]);
+    if (l.type == PB2_LIGHT_DISTANT) {
+        V3 wLight = mk3(dl.p[0], dl.p[1], dl.p[2]);
+        s.wi = wLight;
+        s.p = refP + wLight * (2 * dl.world_radius);
+        s.Li = I;
+        return s;
+    }
+    V3 pLight = mk3(dl.p[0], dl.p[1], dl.p[2]);
+    s.p = pLight;
+    s.wi = normalize(pLight - refP);
+    float d2 = lengthSquared(pLight - refP);
+    if (l.type == PB2_LIGHT_POINT) {
+        s.Li = mk3(I.x / d2, I.y / d2, I.z / d2);
+        return s;
+    }
+    // SpotLight::Falloff(-wi)
+    V3 w = -s.wi;
+    const float *m = dl.world_to_light;
+    V3 wl = normalize(mk3(m[0] * w.x + m[1] * w.y + m[2] * w.z, m[3] * w.x + m[4] * w.y + m[5] * w.z, m[6] * w.x + m[7] * w.y + m[8] * w.z));
+    float cosT = wl.z, falloff;
+    if (cosT < dl.cos_total_width) falloff = 0;
+    else if (cosT >= dl.cos_falloff_start) falloff = 1;
+    else {
+        float delta = (cosT - dl.cos_total_width) / (dl.cos_falloff_start - dl.cos_total_width);
+        falloff = (delta * delta) * (delta * delta);
+    }
+    V3 If = I * falloff;
+    s.Li = mk3(If.x / d2, If.y / d2, If.z / d2);
+    return s;
+}
+
+// `rec` is the light's record out of DScene::lightRecs, lightNum its index in Scene::lights.
 template <bool SPH = true>
-PB2_HD DLightSample sampleLight(const DScene &sc, const pb2_light &l, const TriRec &rec, const DInteraction &ref, V2 u) {
-    if (SPH && (rec.flags & LEAF_SPHERE)) return sampleSphereLight(sc, l, ref, u);
-    return sampleTriangleLight(sc, l, rec, ref.p, u);
+PB2_HD DLightSample sampleLight(const DScene &sc, int lightNum, const pb2_light &l, const TriRec &rec, const DInteraction &ref, V2 u) {
+    if (sc.deltaLights && l.type != PB2_LIGHT_AREA) return sampleDeltaLight(l, sc.deltaLights[lightNum], ref.p);
+    DLightSample s;
+    if (SPH && (rec.flags & LEAF_SPHERE)) s = sampleSphereLight(sc, l, ref, u);
+    else s = sampleTriangleLight(sc, l, rec, ref.p, u);
+    s.delta = false;
+    return s;
 }
 
 // DiffuseAreaLight::Pdf_Li -> Shape::Pdf(ref, wi) (shape.cpp:78-95): re-intersect the light's own
@@ -1150,7 +1258,7 @@ PB2_HD void computeVoxelDistribution(const DScene &sc, const DHalton &h, const D
         intr.prim = -1;
         V2 u = mk2(radicalInverse(h, 3, i), radicalInverse(h, 4, i));
         for (int j = 0; j < n; ++j) {
-            DLightSample ls = sampleLight(sc, sc.lights[j], loadTriRec(sc.lightRecs, (size_t)j), intr, u);
+            DLightSample ls = sampleLight(sc, j, sc.lights[j], loadTriRec(sc.lightRecs, (size_t)j), intr, u);
             if (ls.pdf > 0) rec[j] += luminance(ls.Li) / ls.pdf;
         }
     }

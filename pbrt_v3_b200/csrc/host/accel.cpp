@@ -236,16 +236,51 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
     std::unordered_map<const Material *, int> materialIds;
     std::unordered_map<const AreaLight *, int> lightIds;
     // Scene::lights order is the order of creation in the scene file (api.cpp:1413-1416)
-    for (size_t i = 0; i < lights.size(); ++i) {
-        const AreaLight *al = dynamic_cast<const AreaLight *>(lights[i].get());
-        if (!al) {
-            Error("Only diffuse area lights are inside the GPU path's scope (SURVEY.md §2 rows 14-15)");
-            return nullptr;
-        }
-        lightIds[al] = (int)i;
-    }
     fs->lights.resize(lights.size());
     std::vector<char> lightSeen(lights.size(), 0);
+    for (size_t i = 0; i < lights.size(); ++i) {
+        if (const AreaLight *al = dynamic_cast<const AreaLight *>(lights[i].get())) {
+            lightIds[al] = (int)i;
+            continue;
+        }
+        // delta lights: no primitive, geometry in the parallel record
+        if (fs->deltaLights.empty()) {
+            fs->deltaLights.resize(lights.size());
+            std::memset(fs->deltaLights.data(), 0, fs->deltaLights.size() * sizeof(pb2_delta_light));
+        }
+        pb2_light rec;
+        std::memset(&rec, 0, sizeof(rec));
+        rec.prim = -1;
+        pb2_delta_light &dl = fs->deltaLights[i];
+        if (const PointLight *pl = dynamic_cast<const PointLight *>(lights[i].get())) {
+            rec.type = PB2_LIGHT_POINT;
+            for (int c = 0; c < 3; ++c) rec.L[c] = pl->I.c[c];
+            dl.p[0] = pl->pLight.x; dl.p[1] = pl->pLight.y; dl.p[2] = pl->pLight.z;
+        } else if (const SpotLight *sl = dynamic_cast<const SpotLight *>(lights[i].get())) {
+            rec.type = PB2_LIGHT_SPOT;
+            for (int c = 0; c < 3; ++c) rec.L[c] = sl->I.c[c];
+            dl.p[0] = sl->pLight.x; dl.p[1] = sl->pLight.y; dl.p[2] = sl->pLight.z;
+            dl.cos_total_width = sl->cosTotalWidth;
+            dl.cos_falloff_start = sl->cosFalloffStart;
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) dl.world_to_light[3 * r + c] = sl->WorldToLight.GetMatrix().m[r][c];
+        } else if (const DistantLight *dd = dynamic_cast<const DistantLight *>(lights[i].get())) {
+            rec.type = PB2_LIGHT_DISTANT;
+            for (int c = 0; c < 3; ++c) rec.L[c] = dd->L.c[c];
+            dl.p[0] = dd->wLight.x; dl.p[1] = dd->wLight.y; dl.p[2] = dd->wLight.z;
+            // DistantLight::Preprocess (distant.h:55-57): Bounds3::BoundingSphere of Scene::WorldBound (geometry.h:769-772)
+            Bounds3f wb = bvh.WorldBound();
+            Point3f center = (wb.pMin + wb.pMax) / 2;
+            bool inside = center.x >= wb.pMin.x && center.x <= wb.pMax.x && center.y >= wb.pMin.y && center.y <= wb.pMax.y &&
+                          center.z >= wb.pMin.z && center.z <= wb.pMax.z;
+            dl.world_radius = inside ? Distance(center, wb.pMax) : 0;
+        } else {
+            Error("Light type outside the GPU path's scope (diffuse area, point, spot, distant; SURVEY.md §2 rows 14-15)");
+            return nullptr;
+        }
+        fs->lights[i] = rec;
+        lightSeen[i] = 1;
+    }
     bool anyN = false, anyUV = false, anyS = false;
 
     // Primitive numbering: the scene-level primitives in scene order (GeometricPrimitives and
@@ -465,6 +500,7 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
     d.materials = fs->materials.data();
     d.n_lights = (int32_t)fs->lights.size();
     d.lights = fs->lights.data();
+    d.delta_lights = fs->deltaLights.empty() ? nullptr : fs->deltaLights.data();
     // lightdistrib.cpp:48-66: a single light always gets the uniform distribution
     if (lightStrategy == "uniform" || lights.size() == 1) d.light_strategy = PB2_LIGHTDIST_UNIFORM;
     else if (lightStrategy == "power") d.light_strategy = PB2_LIGHTDIST_POWER;

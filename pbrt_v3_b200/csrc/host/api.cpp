@@ -336,6 +336,23 @@ void pbrtNamedMaterial(const std::string &name) {
     }
     graphicsState.currentMaterial = it->second;
 }
+// api.cpp:1302-1316 with MakeLight (api.cpp:727-754) for the delta lights in scope
+void pbrtLightSource(const std::string &name, const ParamSet &params) {
+    if (!verifyWorld("LightSource")) return;
+    std::shared_ptr<Light> lt;
+    if (name == "point")
+        lt = CreatePointLight(curTransform, params);
+    else if (name == "spot")
+        lt = CreateSpotLight(curTransform, params);
+    else if (name == "distant")
+        lt = CreateDistantLight(curTransform, params);
+    else if (name == "goniometric" || name == "projection" || name == "infinite" || name == "exinfinite")
+        Error("LightSource \"%s\" is outside the GPU path's scope (point, spot, distant and diffuse area lights); skipped", name.c_str());
+    else
+        Error("LightSource: light type \"%s\" unknown.", name.c_str());
+    params.ReportUnused();
+    if (lt) renderOptions->lights.push_back(lt);
+}
 void pbrtAreaLightSource(const std::string &name, const ParamSet &params) {
     if (!verifyWorld("AreaLightSource")) return;
     graphicsState.areaLight = name;
@@ -779,7 +796,8 @@ struct Parser {
             else if (tok == "ObjectBegin") pbrtObjectBegin(requireString());
             else if (tok == "ObjectEnd") pbrtObjectEnd();
             else if (tok == "ObjectInstance") pbrtObjectInstance(requireString());
-            else if (tok == "LightSource" || tok == "Texture" || tok == "MakeNamedMedium" || tok == "MediumInterface") {
+            else if (tok == "LightSource") basic(pbrtLightSource);
+            else if (tok == "Texture" || tok == "MakeNamedMedium" || tok == "MediumInterface") {
                 // directives of the reference that lead outside this path (SURVEY.md §2 rows 15,33,42; §8 a19)
                 Error("%s:%d: directive \"%s\" is outside the GPU path's scope; skipped", cur().filename.c_str(), cur().line, tok.c_str());
                 std::string n;

@@ -37,7 +37,7 @@ PluginDirective pbrtPixelFilter, pbrtFilm, pbrtSampler, pbrtAccelerator, pbrtInt
 // -- world block: attribute / transform stacks, materials, lights, shapes, objects (api.cpp:1023-1588)
 void pbrtWorldBegin(), pbrtWorldEnd();
 void pbrtAttributeBegin(), pbrtAttributeEnd(), pbrtTransformBegin(), pbrtTransformEnd();
-PluginDirective pbrtMaterial, pbrtMakeNamedMaterial, pbrtAreaLightSource, pbrtShape;
+PluginDirective pbrtMaterial, pbrtMakeNamedMaterial, pbrtLightSource, pbrtAreaLightSource, pbrtShape;
 void pbrtNamedMaterial(const std::string &materialName);
 void pbrtObjectBegin(const std::string &objectName), pbrtObjectEnd(), pbrtObjectInstance(const std::string &objectName);
 void pbrtReverseOrientation();

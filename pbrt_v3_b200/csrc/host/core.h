@@ -97,6 +97,14 @@ inline Vector3f Cross(const Vector3f &v1, const Vector3f &v2) {
                     (Float)((v1x * v2y) - (v1y * v2x)));
 }
 inline Vector3f Normalize(const Vector3f &v) { return v / v.Length(); }
+// geometry.h:1020-1028
+inline void CoordinateSystem(const Vector3f &v1, Vector3f *v2, Vector3f *v3) {
+    if (std::abs(v1.x) > std::abs(v1.y))
+        *v2 = Vector3f(-v1.z, 0, v1.x) / std::sqrt(v1.x * v1.x + v1.z * v1.z);
+    else
+        *v2 = Vector3f(0, v1.z, -v1.y) / std::sqrt(v1.y * v1.y + v1.z * v1.z);
+    *v3 = Cross(v1, *v2);
+}
 inline Float Distance(const Point3f &a, const Point3f &b) { return (a - b).Length(); }
 
 struct Bounds3f {

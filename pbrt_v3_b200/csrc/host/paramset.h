@@ -74,6 +74,11 @@ class ParamSet {
         if (it && it->nums.size() == 3) return Spectrum((Float)it->nums[0], (Float)it->nums[1], (Float)it->nums[2]);
         return d;
     }
+    Point3f FindOnePoint3f(const std::string &n, const Point3f &d) const {
+        const Item *it = Find(Type::Point3, n);
+        if (it && it->nums.size() == 3) return Point3f((Float)it->nums[0], (Float)it->nums[1], (Float)it->nums[2]);
+        return d;
+    }
     std::string FindTexture(const std::string &n) const {
         const Item *it = Find(Type::Texture, n);
         return (it && it->strs.size() == 1) ? it->strs[0] : std::string();

@@ -95,6 +95,44 @@ pb2_material MetalMaterial::Record() const {
     m.remap_roughness = remapRoughness ? 1 : 0;
     return m;
 }
+// point.cpp:84-92, spot.cpp:103-125, distant.cpp:92-100
+std::shared_ptr<PointLight> CreatePointLight(const Transform &light2world, const ParamSet &paramSet) {
+    Spectrum I = paramSet.FindOneSpectrum("I", Spectrum(1.0));
+    Spectrum sc = paramSet.FindOneSpectrum("scale", Spectrum(1.0));
+    Point3f P = paramSet.FindOnePoint3f("from", Point3f(0, 0, 0));
+    Transform l2w = Translate(Vector3f(P.x, P.y, P.z)) * light2world;
+    return std::make_shared<PointLight>(l2w, I * sc);
+}
+std::shared_ptr<SpotLight> CreateSpotLight(const Transform &l2w, const ParamSet &paramSet) {
+    Spectrum I = paramSet.FindOneSpectrum("I", Spectrum(1.0));
+    Spectrum sc = paramSet.FindOneSpectrum("scale", Spectrum(1.0));
+    Float coneangle = paramSet.FindOneFloat("coneangle", 30.);
+    Float conedelta = paramSet.FindOneFloat("conedeltaangle", 5.);
+    Point3f from = paramSet.FindOnePoint3f("from", Point3f(0, 0, 0));
+    Point3f to = paramSet.FindOnePoint3f("to", Point3f(0, 0, 1));
+    Vector3f dir = Normalize(to - from);
+    Vector3f du, dv;
+    CoordinateSystem(dir, &du, &dv);
+    Matrix4x4 rows;
+    const Vector3f axes[3] = {du, dv, dir};
+    for (int r = 0; r < 3; ++r) {
+        rows.m[r][0] = axes[r].x;
+        rows.m[r][1] = axes[r].y;
+        rows.m[r][2] = axes[r].z;
+        rows.m[r][3] = 0;
+    }
+    Transform dirToZ(rows);
+    Transform light2world = l2w * Translate(Vector3f(from.x, from.y, from.z)) * Inverse(dirToZ);
+    return std::make_shared<SpotLight>(light2world, I * sc, coneangle, coneangle - conedelta);
+}
+std::shared_ptr<DistantLight> CreateDistantLight(const Transform &light2world, const ParamSet &paramSet) {
+    Spectrum L = paramSet.FindOneSpectrum("L", Spectrum(1.0));
+    Spectrum sc = paramSet.FindOneSpectrum("scale", Spectrum(1.0));
+    Point3f from = paramSet.FindOnePoint3f("from", Point3f(0, 0, 0));
+    Point3f to = paramSet.FindOnePoint3f("to", Point3f(0, 0, 1));
+    Vector3f dir = from - to;
+    return std::make_shared<DistantLight>(light2world, L * sc, dir);
+}
 static void rejectTextures(const TextureParams &mp, const char *what, std::initializer_list<const char *> names) {
     for (const char *n : names)
         if (mp.geomParams.FindTexture(n) != "" || mp.materialParams.FindTexture(n) != "")
@@ -165,9 +203,7 @@ GlassMaterial *CreateGlassMaterial(const TextureParams &mp) {
     Float roughu = mp.GetFloatTexture("uroughness", 0.f);
     Float roughv = mp.GetFloatTexture("vroughness", 0.f);
     bool remap = mp.FindBool("remaproughness", true);
-    if (roughu != 0 || roughv != 0)
-        Error("glass: rough dielectrics (MicrofacetTransmission) are outside the GPU path's scope; rendering it smooth");
-    return new GlassMaterial(Kr, Kt, 0.f, 0.f, eta, remap);
+    return new GlassMaterial(Kr, Kt, roughu, roughv, eta, remap);
 }
 PlasticMaterial *CreatePlasticMaterial(const TextureParams &mp) {
     rejectTextures(mp, "plastic", {"Kd", "Ks", "roughness", "bumpmap"});

@@ -199,6 +199,33 @@ class Light {
     virtual ~Light() {}
 };
 class AreaLight : public Light {};
+// point.h:49-71, spot.h:49-76, distant.h:49-72: the delta lights, as the parameters their Sample_Li reads
+class PointLight : public Light {
+  public:
+    PointLight(const Transform &LightToWorld, const Spectrum &I) : pLight(LightToWorld(Point3f(0, 0, 0))), I(I) {}
+    const Point3f pLight;
+    const Spectrum I;
+};
+class SpotLight : public Light {
+  public:
+    SpotLight(const Transform &LightToWorld, const Spectrum &I, Float totalWidth, Float falloffStart)
+        : pLight(LightToWorld(Point3f(0, 0, 0))), I(I), WorldToLight(Inverse(LightToWorld)),
+          cosTotalWidth(std::cos(Radians(totalWidth))), cosFalloffStart(std::cos(Radians(falloffStart))) {}
+    const Point3f pLight;
+    const Spectrum I;
+    const Transform WorldToLight;
+    const Float cosTotalWidth, cosFalloffStart;
+};
+class DistantLight : public Light {
+  public:
+    DistantLight(const Transform &LightToWorld, const Spectrum &L, const Vector3f &w)
+        : L(L), wLight(Normalize(LightToWorld.ApplyVector(w))) {}
+    const Spectrum L;
+    const Vector3f wLight;
+};
+std::shared_ptr<PointLight> CreatePointLight(const Transform &light2world, const ParamSet &paramSet);
+std::shared_ptr<SpotLight> CreateSpotLight(const Transform &light2world, const ParamSet &paramSet);
+std::shared_ptr<DistantLight> CreateDistantLight(const Transform &light2world, const ParamSet &paramSet);
 class DiffuseAreaLight : public AreaLight {
   public:
     DiffuseAreaLight(const Transform &LightToWorld, const Spectrum &Lemit, int nSamples,
@@ -307,6 +334,7 @@ struct FlatScene {
     std::vector<int32_t> primIndex, primMaterial, primLight;
     std::vector<pb2_material> materials;
     std::vector<pb2_light> lights;
+    std::vector<pb2_delta_light> deltaLights;   // empty when every light is an area light
     // object instancing: every BVH's nodes / ordered primitive numbers concatenated (scene BVH first)
     std::vector<pb2_bvh_node> nodes;
     std::vector<int32_t> bvhPrims;

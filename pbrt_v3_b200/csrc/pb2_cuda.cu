@@ -779,10 +779,8 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
         return setError(PB2_ERR_INVALID, "scene has no primitives / BVH");
     if (d->n_prims > 0x7fffffffLL || d->n_nodes > 0x7fffffffLL) return setError(PB2_ERR_UNSUPPORTED, "more than 2^31 primitives/nodes");
     for (int i = 0; i < d->n_materials; ++i)
-        if (d->materials[i].type != PB2_MAT_NONE && d->materials[i].type != PB2_MAT_MATTE && d->materials[i].type != PB2_MAT_PLASTIC &&
-            d->materials[i].type != PB2_MAT_MIRROR && d->materials[i].type != PB2_MAT_SUBSTRATE && d->materials[i].type != PB2_MAT_METAL &&
-            d->materials[i].type != PB2_MAT_UBER && !(d->materials[i].type == PB2_MAT_GLASS && d->materials[i].uroughness == 0 && d->materials[i].vroughness == 0))
-            return setError(PB2_ERR_UNSUPPORTED, "material type outside the path's scope (matte, plastic, substrate, metal, uber, mirror, smooth glass)");
+        if (d->materials[i].type < PB2_MAT_NONE || d->materials[i].type > PB2_MAT_UBER)
+            return setError(PB2_ERR_UNSUPPORTED, "material type outside the path's scope (matte, plastic, substrate, metal, uber, mirror, glass)");
     struct Guard {
         pb2_scene *s;
         ~Guard() { if (s) pb2_scene_destroy(s); }
@@ -973,6 +971,12 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
     if ((rc = upload(s, d->prim_light, (size_t)d->n_prims, &sc.primLight))) return rc;
     if ((rc = upload(s, d->materials, (size_t)d->n_materials, &sc.materials))) return rc;
     if ((rc = upload(s, d->lights, (size_t)d->n_lights, &sc.lights))) return rc;
+    sc.deltaLights = nullptr;
+    for (int i = 0; i < d->n_lights; ++i) {
+        if (d->lights[i].type < PB2_LIGHT_AREA || d->lights[i].type > PB2_LIGHT_DISTANT) return setError(PB2_ERR_INVALID, "unknown light type");
+        if (d->lights[i].type != PB2_LIGHT_AREA && !d->delta_lights) return setError(PB2_ERR_INVALID, "a delta light without delta_lights");
+    }
+    if (d->delta_lights && d->n_lights > 0 && (rc = upload(s, d->delta_lights, (size_t)d->n_lights, &sc.deltaLights))) return rc;
     for (int m = 0; m < d->n_meshes; ++m) {
         if (d->meshes[m].has_n && !d->N) return setError(PB2_ERR_INVALID, "mesh has_n but N is null");
         if (d->meshes[m].has_uv && !d->UV) return setError(PB2_ERR_INVALID, "mesh has_uv but UV is null");
@@ -995,6 +999,10 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
         // the same record for every area light's shape, in light order
         std::vector<int32_t> lightPrims(d->n_lights);
         for (int i = 0; i < d->n_lights; ++i) {
+            if (d->lights[i].type != PB2_LIGHT_AREA) {
+                lightPrims[i] = 0;   // delta lights have no shape; the record is never read
+                continue;
+            }
             if (d->lights[i].prim < 0 || d->lights[i].prim >= d->n_prims) return setError(PB2_ERR_INVALID, "light primitive out of range");
             lightPrims[i] = d->lights[i].prim;
         }
@@ -1024,9 +1032,19 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
             else {
                 // DiffuseAreaLight::Power (diffuse.cpp:64-66): (twoSided ? 2 : 1) * Lemit * area * Pi, then y()
                 const pb2_light &l = d->lights[i];
+                const float Pi = 3.14159265358979323846f;
                 float s2 = l.two_sided ? 2.f : 1.f;
                 float p[3];
-                for (int c = 0; c < 3; ++c) p[c] = ((s2 * l.L[c]) * l.area) * 3.14159265358979323846f;
+                for (int c = 0; c < 3; ++c) {
+                    if (l.type == PB2_LIGHT_POINT)          // point.cpp:54: 4 * Pi * I
+                        p[c] = l.L[c] * (4 * Pi);
+                    else if (l.type == PB2_LIGHT_SPOT)      // spot.cpp:74-76: I * 2 * Pi * (1 - .5f * (cosFalloffStart + cosTotalWidth))
+                        p[c] = ((l.L[c] * 2) * Pi) * (1 - .5f * (d->delta_lights[i].cos_falloff_start + d->delta_lights[i].cos_total_width));
+                    else if (l.type == PB2_LIGHT_DISTANT)   // distant.cpp:61-63: L * Pi * worldRadius * worldRadius
+                        p[c] = ((l.L[c] * Pi) * d->delta_lights[i].world_radius) * d->delta_lights[i].world_radius;
+                    else
+                        p[c] = ((s2 * l.L[c]) * l.area) * Pi;
+                }
                 rec[i] = 0.212671f * p[0] + 0.715160f * p[1] + 0.072169f * p[2];
             }
         }

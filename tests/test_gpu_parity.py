@@ -21,7 +21,7 @@ from test_oracle import load_scene, tessellated_sphere_scene
 
 pytestmark = pytest.mark.gpu
 
-SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber"]
+SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass"]
 
 
 def li_ok(got, want):

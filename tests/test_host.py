@@ -177,10 +177,10 @@ def test_mirror_and_glass_parameters(pb):
     assert glasses[0].eta == np.float32(1.5) and tuple(glasses[0].kr) == (1, 1, 1) and tuple(glasses[0].kt) == (1, 1, 1)
     assert glasses[1].eta == np.float32(1.33) and np.allclose(tuple(glasses[1].kt), (.8, .95, .85))
     assert all(g.uroughness == 0 and g.vroughness == 0 for g in glasses)
-    # rough glass is reported, not silently rendered as something else
-    before = pb.lib().pb2h_error_count()
-    pb.HostScene.from_string('WorldBegin\nMaterial "glass" "float uroughness" 0.2\nShape "sphere"\nWorldEnd\n')
-    assert pb.lib().pb2h_error_count() > before
+    hs = pb.HostScene.from_string('WorldBegin\nMaterial "glass" "float uroughness" 0.2\nShape "sphere"\nWorldEnd\n')
+    d = hs.desc.contents
+    rough = [d.materials[i] for i in range(d.n_materials) if d.materials[i].type == pb.PB2_MAT_GLASS][0]
+    assert rough.uroughness == np.float32(.2) and rough.vroughness == 0 and rough.remap_roughness == 1
 
 
 def test_threaded_bvh_build_is_the_sequential_tree(pb, port):

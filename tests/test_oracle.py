@@ -11,7 +11,7 @@ import pytest
 import golden_cases as gc
 from conftest import GOLDEN, SCENES
 
-SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber"]
+SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass"]
 
 
 def load_scene(pb, name):
