@@ -121,9 +121,10 @@ typedef struct pb2_light {
 } pb2_light;
 
 typedef struct pb2_delta_light {
-    float p[3];                 /* point, spot: pLight (point.h:52, spot.h:54); distant: wLight, normalised (distant.cpp:46) */
-    float cos_total_width;      /* spot (spot.cpp:49-50) */
-    float cos_falloff_start;
+    float p[3];                 /* point, spot: pLight (point.h:52, spot.h:54); distant: LightToWorld(from - to), NOT normalised
+                                 * (the constructor argument of distant.cpp:43-46; the library normalises it as the constructor does) */
+    float total_width_deg;      /* spot: the constructor's totalWidth / falloffStart in degrees (spot.cpp:43-50); the library takes */
+    float falloff_start_deg;    /*       their cosines as the constructor does */
     float world_radius;         /* distant: DistantLight::Preprocess (distant.h:55-57), from the scene bounds */
     float world_to_light[9];    /* spot: upper-left 3x3 of WorldToLight, row-major (SpotLight::Falloff, spot.cpp:63-72) */
     float pad;

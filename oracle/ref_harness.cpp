@@ -57,6 +57,9 @@
 #include "filters/triangle.h"
 #include "integrators/path.h"
 #include "lights/diffuse.h"
+#include "lights/distant.h"
+#include "lights/point.h"
+#include "lights/spot.h"
 #include "materials/matte.h"
 #include "materials/plastic.h"
 #include "materials/mirror.h"
@@ -329,6 +332,24 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
         rs->bvh = std::make_shared<BVHAccel>(top, maxPrims, sm);
     } else
         rs->bvh = std::make_shared<BVHAccel>(rs->prims, maxPrims, sm);
+    // delta lights, built through the reference's own constructors.  The description carries what the constructors
+    // derive from LightToWorld (pLight; the 3x3 of WorldToLight; LightToWorld(from - to)), so LightToWorld is rebuilt as
+    // a translation to pLight whose inverse holds the recorded WorldToLight rows (Falloff only transforms a vector).
+    for (int i = 0; i < d->n_lights; ++i) {
+        const pb2_light &pl = d->lights[i];
+        if (pl.type == PB2_LIGHT_AREA) continue;
+        const pb2_delta_light &dl = d->delta_lights[i];
+        Spectrum I = Spectrum::FromRGB(pl.L);
+        if (pl.type == PB2_LIGHT_POINT)
+            rs->lights[i] = std::make_shared<PointLight>(Translate(Vector3f(dl.p[0], dl.p[1], dl.p[2])), MediumInterface(), I);
+        else if (pl.type == PB2_LIGHT_SPOT) {
+            Matrix4x4 m = Translate(Vector3f(dl.p[0], dl.p[1], dl.p[2])).GetMatrix(), mInv;
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) mInv.m[r][c] = dl.world_to_light[3 * r + c];
+            rs->lights[i] = std::make_shared<SpotLight>(Transform(m, mInv), MediumInterface(), I, dl.total_width_deg, dl.falloff_start_deg);
+        } else
+            rs->lights[i] = std::make_shared<DistantLight>(Transform(), I, Vector3f(dl.p[0], dl.p[1], dl.p[2]));
+    }
     rs->scene.reset(new Scene(rs->bvh, rs->lights));
     return rs.release();
 }

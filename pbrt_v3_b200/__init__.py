@@ -64,7 +64,7 @@ class Light(C.Structure):
 
 
 class DeltaLight(C.Structure):
-    _fields_ = [("p", C.c_float * 3), ("cos_total_width", C.c_float), ("cos_falloff_start", C.c_float),
+    _fields_ = [("p", C.c_float * 3), ("total_width_deg", C.c_float), ("falloff_start_deg", C.c_float),
                 ("world_radius", C.c_float), ("world_to_light", C.c_float * 9), ("pad", C.c_float)]
 
 

@@ -63,6 +63,15 @@ struct DInstance {
     int wroot;      // two-child records: the pseudo record whose only child is the object BVH's root, or -1
 };
 
+// A delta light as its constructor leaves it (point.h:52, spot.cpp:43-50, distant.cpp:43-46), derived from pb2_delta_light at upload
+struct DDeltaLight {
+    float p[3];                 // pLight, or the normalised wLight of a distant light
+    float cosTotalWidth, cosFalloffStart;
+    float worldRadius;
+    float worldToLight[9];
+    float pad;
+};
+
 struct DScene {
     const float4 *nodes;
     const float4 *wide;       // two-child nodes (below), nullptr when the scene exceeds their limits
@@ -79,7 +88,7 @@ struct DScene {
     const int32_t *primIndex, *primMaterial, *primLight;
     const pb2_material *materials;
     const pb2_light *lights;
-    const pb2_delta_light *deltaLights;   // parallel to lights, nullptr when every light is an area light
+    const DDeltaLight *deltaLights;       // parallel to lights, nullptr when every light is an area light
     int nLights;
     const DInstance *instances;   // nullptr: no object instancing in this scene
     int nInstances;

@@ -1146,7 +1146,7 @@ PB2_HD DLightSample sampleTriangleLight(const DScene &sc, const pb2_light &l, co
 
 // PointLight / SpotLight / DistantLight::Sample_Li (point.cpp:44-53, spot.cpp:52-72, distant.cpp:48-58).  The
 // VisibilityTester's second point carries no normal and no error bounds, so SpawnRayTo aims at it exactly.
-PB2_HDN DLightSample sampleDeltaLight(const pb2_light &l, const pb2_delta_light &dl, V3 refP) {
+PB2_HDN DLightSample sampleDeltaLight(const pb2_light &l, const DDeltaLight &dl, V3 refP) {
     DLightSample s;
     s.delta = true;
     s.pError = s.n = mk3(0, 0, 0);
@@ -1155,7 +1155,7 @@ PB2_HDN DLightSample sampleDeltaLight(const pb2_light &l, const pb2_delta_light 
     if (l.type == PB2_LIGHT_DISTANT) {
         V3 wLight = mk3(dl.p[0], dl.p[1], dl.p[2]);
         s.wi = wLight;
-        s.p = refP + wLight * (2 * dl.world_radius);
+        s.p = refP + wLight * (2 * dl.worldRadius);
         s.Li = I;
         return s;
     }
@@ -1169,13 +1169,13 @@ PB2_HDN DLightSample sampleDeltaLight(const pb2_light &l, const pb2_delta_light 
     }
     // SpotLight::Falloff(-wi)
     V3 w = -s.wi;
-    const float *m = dl.world_to_light;
+    const float *m = dl.worldToLight;
     V3 wl = normalize(mk3(m[0] * w.x + m[1] * w.y + m[2] * w.z, m[3] * w.x + m[4] * w.y + m[5] * w.z, m[6] * w.x + m[7] * w.y + m[8] * w.z));
     float cosT = wl.z, falloff;
-    if (cosT < dl.cos_total_width) falloff = 0;
-    else if (cosT >= dl.cos_falloff_start) falloff = 1;
+    if (cosT < dl.cosTotalWidth) falloff = 0;
+    else if (cosT >= dl.cosFalloffStart) falloff = 1;
     else {
-        float delta = (cosT - dl.cos_total_width) / (dl.cos_falloff_start - dl.cos_total_width);
+        float delta = (cosT - dl.cosTotalWidth) / (dl.cosFalloffStart - dl.cosTotalWidth);
         falloff = (delta * delta) * (delta * delta);
     }
     V3 If = I * falloff;

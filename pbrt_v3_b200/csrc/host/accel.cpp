@@ -260,14 +260,14 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
             rec.type = PB2_LIGHT_SPOT;
             for (int c = 0; c < 3; ++c) rec.L[c] = sl->I.c[c];
             dl.p[0] = sl->pLight.x; dl.p[1] = sl->pLight.y; dl.p[2] = sl->pLight.z;
-            dl.cos_total_width = sl->cosTotalWidth;
-            dl.cos_falloff_start = sl->cosFalloffStart;
+            dl.total_width_deg = sl->totalWidth;
+            dl.falloff_start_deg = sl->falloffStart;
             for (int r = 0; r < 3; ++r)
                 for (int c = 0; c < 3; ++c) dl.world_to_light[3 * r + c] = sl->WorldToLight.GetMatrix().m[r][c];
         } else if (const DistantLight *dd = dynamic_cast<const DistantLight *>(lights[i].get())) {
             rec.type = PB2_LIGHT_DISTANT;
             for (int c = 0; c < 3; ++c) rec.L[c] = dd->L.c[c];
-            dl.p[0] = dd->wLight.x; dl.p[1] = dd->wLight.y; dl.p[2] = dd->wLight.z;
+            dl.p[0] = dd->wWorld.x; dl.p[1] = dd->wWorld.y; dl.p[2] = dd->wWorld.z;
             // DistantLight::Preprocess (distant.h:55-57): Bounds3::BoundingSphere of Scene::WorldBound (geometry.h:769-772)
             Bounds3f wb = bvh.WorldBound();
             Point3f center = (wb.pMin + wb.pMax) / 2;

@@ -209,18 +209,20 @@ class PointLight : public Light {
 class SpotLight : public Light {
   public:
     SpotLight(const Transform &LightToWorld, const Spectrum &I, Float totalWidth, Float falloffStart)
-        : pLight(LightToWorld(Point3f(0, 0, 0))), I(I), WorldToLight(Inverse(LightToWorld)),
-          cosTotalWidth(std::cos(Radians(totalWidth))), cosFalloffStart(std::cos(Radians(falloffStart))) {}
+        : pLight(LightToWorld(Point3f(0, 0, 0))), I(I), WorldToLight(Inverse(LightToWorld)), totalWidth(totalWidth),
+          falloffStart(falloffStart), cosTotalWidth(std::cos(Radians(totalWidth))), cosFalloffStart(std::cos(Radians(falloffStart))) {}
     const Point3f pLight;
     const Spectrum I;
     const Transform WorldToLight;
+    const Float totalWidth, falloffStart;   // degrees, as given to the constructor
     const Float cosTotalWidth, cosFalloffStart;
 };
 class DistantLight : public Light {
   public:
     DistantLight(const Transform &LightToWorld, const Spectrum &L, const Vector3f &w)
-        : L(L), wLight(Normalize(LightToWorld.ApplyVector(w))) {}
+        : L(L), wWorld(LightToWorld.ApplyVector(w)), wLight(Normalize(wWorld)) {}
     const Spectrum L;
+    const Vector3f wWorld;   // LightToWorld(w) before normalisation
     const Vector3f wLight;
 };
 std::shared_ptr<PointLight> CreatePointLight(const Transform &light2world, const ParamSet &paramSet);

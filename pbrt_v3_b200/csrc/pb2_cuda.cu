@@ -976,7 +976,24 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
         if (d->lights[i].type < PB2_LIGHT_AREA || d->lights[i].type > PB2_LIGHT_DISTANT) return setError(PB2_ERR_INVALID, "unknown light type");
         if (d->lights[i].type != PB2_LIGHT_AREA && !d->delta_lights) return setError(PB2_ERR_INVALID, "a delta light without delta_lights");
     }
-    if (d->delta_lights && d->n_lights > 0 && (rc = upload(s, d->delta_lights, (size_t)d->n_lights, &sc.deltaLights))) return rc;
+    std::vector<DDeltaLight> deltaLights;
+    if (d->delta_lights && d->n_lights > 0) {
+        deltaLights.resize(d->n_lights);
+        memset(deltaLights.data(), 0, deltaLights.size() * sizeof(DDeltaLight));
+        for (int i = 0; i < d->n_lights; ++i) {
+            const pb2_delta_light &in = d->delta_lights[i];
+            DDeltaLight &o = deltaLights[i];
+            V3 p = mk3(in.p[0], in.p[1], in.p[2]);
+            if (d->lights[i].type == PB2_LIGHT_DISTANT) p = normalize(p);   // distant.cpp:46
+            o.p[0] = p.x; o.p[1] = p.y; o.p[2] = p.z;
+            const float radPerDeg = 3.14159265358979323846f / 180;           // Radians() (pbrt.h:353), then std::cos(float) (spot.cpp:49-50)
+            o.cosTotalWidth = std::cos(radPerDeg * in.total_width_deg);
+            o.cosFalloffStart = std::cos(radPerDeg * in.falloff_start_deg);
+            o.worldRadius = in.world_radius;
+            for (int k = 0; k < 9; ++k) o.worldToLight[k] = in.world_to_light[k];
+        }
+        if ((rc = upload(s, deltaLights.data(), deltaLights.size(), &sc.deltaLights))) return rc;
+    }
     for (int m = 0; m < d->n_meshes; ++m) {
         if (d->meshes[m].has_n && !d->N) return setError(PB2_ERR_INVALID, "mesh has_n but N is null");
         if (d->meshes[m].has_uv && !d->UV) return setError(PB2_ERR_INVALID, "mesh has_uv but UV is null");
@@ -1039,9 +1056,9 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
                     if (l.type == PB2_LIGHT_POINT)          // point.cpp:54: 4 * Pi * I
                         p[c] = l.L[c] * (4 * Pi);
                     else if (l.type == PB2_LIGHT_SPOT)      // spot.cpp:74-76: I * 2 * Pi * (1 - .5f * (cosFalloffStart + cosTotalWidth))
-                        p[c] = ((l.L[c] * 2) * Pi) * (1 - .5f * (d->delta_lights[i].cos_falloff_start + d->delta_lights[i].cos_total_width));
+                        p[c] = ((l.L[c] * 2) * Pi) * (1 - .5f * (deltaLights[i].cosFalloffStart + deltaLights[i].cosTotalWidth));
                     else if (l.type == PB2_LIGHT_DISTANT)   // distant.cpp:61-63: L * Pi * worldRadius * worldRadius
-                        p[c] = ((l.L[c] * Pi) * d->delta_lights[i].world_radius) * d->delta_lights[i].world_radius;
+                        p[c] = ((l.L[c] * Pi) * deltaLights[i].worldRadius) * deltaLights[i].worldRadius;
                     else
                         p[c] = ((s2 * l.L[c]) * l.area) * Pi;
                 }

@@ -21,7 +21,7 @@ from test_oracle import load_scene, tessellated_sphere_scene
 
 pytestmark = pytest.mark.gpu
 
-SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass"]
+SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass", "lights"]
 
 
 def li_ok(got, want):
@@ -119,6 +119,26 @@ def test_gpu_matches_checker_on_a_larger_scene(pb, checker):
     assert frac >= 0.999 and mean_rel <= 1e-4
     assert st.camera_rays == ref_st.camera_rays == 96 * 54 * 8
     assert abs(int(st.regular_rays) - int(ref_st.regular_rays)) <= ref_st.regular_rays // 1000 + 2
+
+
+@pytest.mark.parametrize("strategy", ["spatial", "uniform"])
+def test_delta_lights_under_other_light_sampling_strategies(pb, checker, strategy):
+    """The golden case `lights` uses "power"; the spatial distribution calls every light's Sample_Li from voxel sample
+    points (lightdistrib.cpp:232-300) and must come out bit-identical, delta lights included."""
+    text = open(os.path.join(SCENES, "lights.pbrt")).read().replace('"string lightsamplestrategy" "power"', '"string lightsamplestrategy" "%s"' % strategy)
+    hs = pb.HostScene.from_string(text)
+    sc = checker.scene(hs)
+    pts = gc.points_for(hs.nodes(), 400, 15)
+    assert np.array_equal(gc.bits(hs.light_distribution(pts)), gc.bits(sc.light_distribution(pts)))
+    pix, sn = gc.sample_ids(64, 48, 8, 3000, 13)
+    li, pfilm = hs.li_samples(pix, sn)
+    ref_li, ref_pfilm = sc.li_samples(pix, sn)
+    assert np.array_equal(gc.bits(pfilm), gc.bits(ref_pfilm)) and li_ok(li, ref_li) >= 0.999
+    img, st = hs.render()
+    ref_img, _, ref_st = sc.render(n_threads=0)
+    frac, mean_rel = image_metrics(img, ref_img)
+    assert frac >= 0.999 and mean_rel <= 1e-4
+    assert abs(int(st.shadow_rays) - int(ref_st.shadow_rays)) <= ref_st.shadow_rays // 1000 + 2
 
 
 @pytest.mark.parametrize("maxprims,split", [(16, "sah"), (40, "equal"), (1, "middle")])

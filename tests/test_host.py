@@ -245,3 +245,35 @@ def test_uber_and_metal_parameters(pb):
     hs = pb.HostScene.from_string('WorldBegin\nMaterial "metal" "float roughness" .3 "float uroughness" .02\nShape "sphere"\nWorldEnd\n')
     m = [hs.desc.contents.materials[i] for i in range(hs.desc.contents.n_materials) if hs.desc.contents.materials[i].type == pb.PB2_MAT_METAL][0]
     assert m.uroughness == f32(.02) and m.vroughness == f32(.3)    # metal: each falls back to "roughness" (metal.cpp:67-70)
+
+
+def test_light_source_directives(pb):
+    """pbrtLightSource (api.cpp:1302-1316) + CreatePointLight / CreateSpotLight / CreateDistantLight (point.cpp:84-92,
+    spot.cpp:103-125, distant.cpp:92-100): Scene::lights keeps file order with the area lights, "from" / "to" / "scale"
+    and the CTM are applied as the reference does."""
+    f32 = np.float32
+    hs = pb.HostScene.from_file(os.path.join(SCENES, "lights.pbrt"))
+    d = hs.desc.contents
+    assert [d.lights[i].type for i in range(d.n_lights)] == [pb.PB2_LIGHT_POINT, pb.PB2_LIGHT_AREA, pb.PB2_LIGHT_AREA, pb.PB2_LIGHT_SPOT,
+                                                            pb.PB2_LIGHT_DISTANT, pb.PB2_LIGHT_DISTANT]
+    assert all(d.lights[i].prim == -1 for i in (0, 3, 4, 5)) and d.lights[1].prim >= 0
+    assert tuple(d.delta_lights[0].p) == (f32(-2.2), f32(-1.5), f32(2.5)) and tuple(d.lights[0].L) == (9, 7, 5)
+    spot = d.delta_lights[3]
+    assert np.allclose(tuple(d.lights[3].L), (20, 24, 21)) and spot.total_width_deg == 28 and spot.falloff_start_deg == 19   # coneangle - conedeltaangle
+    w2l = np.array(tuple(spot.world_to_light), np.float64).reshape(3, 3)
+    assert np.allclose(w2l @ w2l.T, np.eye(3), atol=1e-6)          # rotations only on this light's CTM
+    # the spot looks from "from" to "to" (both under the CTM): WorldToLight maps that direction to +z
+    ang = np.radians(20)
+    rot = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1]])
+    frm, to = rot @ (np.array([0, -2.5, 3.2]) + [.3, 0, 0]), rot @ (np.array([.4, .2, 0]) + [.3, 0, 0])
+    assert np.allclose(tuple(spot.p), frm, atol=1e-5)
+    dirw = (to - frm) / np.linalg.norm(to - frm)
+    assert np.allclose(w2l @ dirw, (0, 0, 1), atol=1e-5)
+    assert tuple(d.delta_lights[4].p) == (1, -2, 4)                # from - to, not normalised
+    assert np.allclose(tuple(d.delta_lights[5].p), (-.2, -.1, 2)) and np.allclose(tuple(d.lights[5].L), (.15, .2, .3))   # defaults: L 1, from 0; Scale 1 1 2
+    nodes = hs.nodes()
+    c = (nodes["bmin"][0].astype(f32) + nodes["bmax"][0].astype(f32)) / f32(2)
+    assert abs(d.delta_lights[4].world_radius - np.linalg.norm(c - nodes["bmax"][0])) < 1e-5
+    before = pb.lib().pb2h_error_count()
+    hs = pb.HostScene.from_string('WorldBegin\nLightSource "infinite"\nShape "sphere"\nWorldEnd\n')
+    assert pb.lib().pb2h_error_count() > before and hs.desc.contents.n_lights == 0

@@ -11,7 +11,7 @@ import pytest
 import golden_cases as gc
 from conftest import GOLDEN, SCENES
 
-SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass"]
+SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass", "lights"]
 
 
 def load_scene(pb, name):
@@ -79,6 +79,15 @@ def test_port_filters_match_reference_golden(pb, port, case):
     img, _, st = port.scene(hs).render(n_threads=1)   # one thread: overlapping tiles merge in a fixed order
     assert np.array_equal(gc.bits(img), gc.bits(g["image_" + case])), "image must be bit-identical to the reference's"
     assert [st.camera_rays, st.regular_rays, st.shadow_rays] == [int(x) for x in g["rays_" + case]]
+
+
+@pytest.mark.parametrize("strategy", ["spatial", "uniform"])
+def test_port_delta_lights_other_strategies_live(pb, port, reference, strategy):
+    text = open(os.path.join(SCENES, "lights.pbrt")).read().replace('"string lightsamplestrategy" "power"', '"string lightsamplestrategy" "%s"' % strategy)
+    hs = pb.HostScene.from_string(text)
+    a, b = recompute(pb, reference, hs), recompute(pb, port, hs)
+    for k in ("light_distribution", "li", "image", "rays"):
+        assert a[k].tobytes() == b[k].tobytes(), k
 
 
 def test_port_filters_match_compiled_reference_live(pb, port, reference):
