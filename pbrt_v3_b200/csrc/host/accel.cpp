@@ -7,6 +7,7 @@
 // the primitive order is produced as an index permutation.
 #include <atomic>
 #include <chrono>
+#include <functional>
 #include <future>
 #include <thread>
 #include <unordered_map>
@@ -132,6 +133,151 @@ struct Builder {
         return node;
     }
 
+    // ---- HLBVH (bvh.cpp:404-638): Morton-ordered treelets below, a SAH tree over the treelet roots above.
+    struct MortonPrim { int32_t primitiveIndex; uint32_t mortonCode; };
+    static uint32_t leftShift3(uint32_t x) {   // bvh.cpp:106-130
+        if (x == (1 << 10)) --x;
+        x = (x | (x << 16)) & 0x30000ff;
+        x = (x | (x << 8)) & 0x300f00f;
+        x = (x | (x << 4)) & 0x30c30c3;
+        x = (x | (x << 2)) & 0x9249249;
+        return x;
+    }
+    // emitLBVH (bvh.cpp:472-539).  `first` is the position of mp[0] in the sorted list: the reference hands out the
+    // ordered-primitive slots through an atomic counter as leaves are created; run by one thread that is the sorted
+    // order itself, which is what every schedule produces here.
+    int emitLBVH(const MortonPrim *mp, int first, int nPrimitives, int bitIndex) {
+        if (bitIndex == -1 || nPrimitives < maxPrimsInNode) {
+            int node = nextNode.fetch_add(1);
+            Bounds3f bounds;
+            for (int i = 0; i < nPrimitives; ++i) {
+                ordered[first + i] = mp[i].primitiveIndex;
+                bounds = Union(bounds, info[mp[i].primitiveIndex].bounds);
+            }
+            pool[node].firstPrimOffset = first;
+            pool[node].nPrimitives = nPrimitives;
+            pool[node].bounds = bounds;
+            return node;
+        }
+        uint32_t mask = 1u << bitIndex;
+        if ((mp[0].mortonCode & mask) == (mp[nPrimitives - 1].mortonCode & mask)) return emitLBVH(mp, first, nPrimitives, bitIndex - 1);
+        int searchStart = 0, searchEnd = nPrimitives - 1;
+        while (searchStart + 1 != searchEnd) {
+            int mid = (searchStart + searchEnd) / 2;
+            if ((mp[searchStart].mortonCode & mask) == (mp[mid].mortonCode & mask)) searchStart = mid;
+            else searchEnd = mid;
+        }
+        int splitOffset = searchEnd;
+        int node = nextNode.fetch_add(1);
+        int c0 = emitLBVH(mp, first, splitOffset, bitIndex - 1);
+        int c1 = emitLBVH(mp + splitOffset, first + splitOffset, nPrimitives - splitOffset, bitIndex - 1);
+        pool[node].child[0] = c0;
+        pool[node].child[1] = c1;
+        pool[node].bounds = Union(pool[c0].bounds, pool[c1].bounds);
+        pool[node].splitAxis = bitIndex % 3;
+        pool[node].nPrimitives = 0;
+        return node;
+    }
+    // buildUpperSAH (bvh.cpp:541-638)
+    int buildUpperSAH(std::vector<int> &roots, int start, int end) {
+        int nNodes = end - start;
+        if (nNodes == 1) return roots[start];
+        int node = nextNode.fetch_add(1);
+        Bounds3f bounds;
+        for (int i = start; i < end; ++i) bounds = Union(bounds, pool[roots[i]].bounds);
+        Bounds3f centroidBounds;
+        for (int i = start; i < end; ++i) {
+            Point3f centroid = (pool[roots[i]].bounds.pMin + pool[roots[i]].bounds.pMax) * 0.5f;
+            centroidBounds = Union(centroidBounds, centroid);
+        }
+        int dim = centroidBounds.MaximumExtent();
+        constexpr int nBuckets = 12;
+        struct Bucket { int count = 0; Bounds3f bounds; } buckets[nBuckets];
+        const Float cmin = centroidBounds.pMin[dim], cmax = centroidBounds.pMax[dim];
+        auto bucketOf = [&](int r) {
+            Float centroid = (pool[r].bounds.pMin[dim] + pool[r].bounds.pMax[dim]) * 0.5f;
+            int b = nBuckets * ((centroid - cmin) / (cmax - cmin));
+            if (b == nBuckets) b = nBuckets - 1;
+            return b;
+        };
+        for (int i = start; i < end; ++i) {
+            int b = bucketOf(roots[i]);
+            buckets[b].count++;
+            buckets[b].bounds = Union(buckets[b].bounds, pool[roots[i]].bounds);
+        }
+        Float cost[nBuckets - 1];
+        for (int i = 0; i < nBuckets - 1; ++i) {
+            Bounds3f b0, b1;
+            int count0 = 0, count1 = 0;
+            for (int j = 0; j <= i; ++j) { b0 = Union(b0, buckets[j].bounds); count0 += buckets[j].count; }
+            for (int j = i + 1; j < nBuckets; ++j) { b1 = Union(b1, buckets[j].bounds); count1 += buckets[j].count; }
+            cost[i] = .125f + (count0 * b0.SurfaceArea() + count1 * b1.SurfaceArea()) / bounds.SurfaceArea();
+        }
+        Float minCost = cost[0];
+        int minCostSplitBucket = 0;
+        for (int i = 1; i < nBuckets - 1; ++i)
+            if (cost[i] < minCost) { minCost = cost[i]; minCostSplitBucket = i; }
+        int *pmid = std::partition(&roots[start], &roots[end - 1] + 1, [&](int r) { return bucketOf(r) <= minCostSplitBucket; });
+        int mid = (int)(pmid - &roots[0]);
+        int c0 = buildUpperSAH(roots, start, mid);
+        int c1 = buildUpperSAH(roots, mid, end);
+        pool[node].child[0] = c0;
+        pool[node].child[1] = c1;
+        pool[node].bounds = Union(pool[c0].bounds, pool[c1].bounds);
+        pool[node].splitAxis = dim;
+        pool[node].nPrimitives = 0;
+        return node;
+    }
+    int buildHLBVH() {
+        Bounds3f bounds;
+        for (const PrimInfo &pi : info) bounds = Union(bounds, pi.centroid);
+        const int n = (int)info.size();
+        std::vector<MortonPrim> mortonPrims(n);
+        const unsigned nThreads = std::max(1u, std::thread::hardware_concurrency());
+        auto parallelFor = [&](int count, const std::function<void(int)> &fn) {
+            if (count < 4096 || nThreads == 1) {
+                for (int i = 0; i < count; ++i) fn(i);
+                return;
+            }
+            std::atomic<int> next{0};
+            std::vector<std::thread> workers;
+            for (unsigned t = 0; t < nThreads; ++t)
+                workers.emplace_back([&] {
+                    for (;;) {
+                        int b = next.fetch_add(1024);
+                        if (b >= count) return;
+                        for (int i = b; i < std::min(count, b + 1024); ++i) fn(i);
+                    }
+                });
+            for (auto &w : workers) w.join();
+        };
+        parallelFor(n, [&](int i) {
+            constexpr int mortonScale = 1 << 10;
+            mortonPrims[i].primitiveIndex = (int32_t)info[i].number;
+            Vector3f o = bounds.Offset(info[i].centroid) * mortonScale;
+            mortonPrims[i].mortonCode = (leftShift3((uint32_t)o.z) << 2) | (leftShift3((uint32_t)o.y) << 1) | leftShift3((uint32_t)o.x);
+        });
+        // RadixSort (bvh.cpp:139-180) is a least-significant-digit sort over all 30 bits: a stable sort by the code
+        std::stable_sort(mortonPrims.begin(), mortonPrims.end(), [](const MortonPrim &a, const MortonPrim &b) { return a.mortonCode < b.mortonCode; });
+        struct Treelet { int start, nPrimitives, root; };
+        std::vector<Treelet> treelets;
+        for (int start = 0, end = 1; end <= n; ++end) {
+            const uint32_t mask = 0x3ffc0000;
+            if (end == n || ((mortonPrims[start].mortonCode & mask) != (mortonPrims[end].mortonCode & mask))) {
+                treelets.push_back({start, end - start, -1});
+                start = end;
+            }
+        }
+        parallelFor((int)treelets.size(), [&](int i) {
+            Treelet &tr = treelets[i];
+            tr.root = emitLBVH(&mortonPrims[tr.start], tr.start, tr.nPrimitives, 29 - 12);
+        });
+        std::vector<int> roots;
+        roots.reserve(treelets.size());
+        for (const Treelet &tr : treelets) roots.push_back(tr.root);
+        return buildUpperSAH(roots, 0, (int)roots.size());
+    }
+
     int flatten(int bn, std::vector<pb2_bvh_node> &out) {
         int my = (int)out.size();
         out.push_back(pb2_bvh_node());
@@ -159,12 +305,9 @@ struct Builder {
 BVHAccel::BVHAccel(std::vector<std::shared_ptr<Primitive>> p, int maxPrims, SplitMethod sm)
     : sceneOrderPrims(std::move(p)), maxPrimsInNode(std::min(255, maxPrims)), splitMethod(sm) {
     if (sceneOrderPrims.empty()) return;
-    if (splitMethod == SplitMethod::HLBVH) {
-        Warning("BVH split method \"hlbvh\" is built with \"sah\" here (SURVEY.md §8f.3)");
-    }
     Builder b;
     b.maxPrimsInNode = maxPrimsInNode;
-    b.method = splitMethod == SplitMethod::HLBVH ? SplitMethod::SAH : splitMethod;
+    b.method = splitMethod;
     auto clk = [] { return std::chrono::steady_clock::now(); };
     auto secs = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
     const auto t0 = clk();
@@ -178,7 +321,7 @@ BVHAccel::BVHAccel(std::vector<std::shared_ptr<Primitive>> p, int maxPrims, Spli
     int spawnLevels = 0;
     for (unsigned t = std::max(1u, std::thread::hardware_concurrency()); t > 1; t >>= 1) ++spawnLevels;
     const auto t1 = clk();
-    int root = b.build(0, (int)sceneOrderPrims.size(), 0, spawnLevels + 2);
+    int root = splitMethod == SplitMethod::HLBVH ? b.buildHLBVH() : b.build(0, (int)sceneOrderPrims.size(), 0, spawnLevels + 2);
     const auto t2 = clk();
     b.pool.resize((size_t)b.nextNode.load());
     nodes.reserve(b.pool.size());

@@ -76,3 +76,20 @@ def filter_scene_text(scene_dir, case):
     text, n = re.subn(r'"integer pixelsamples" \[8\]', '"integer pixelsamples" [4]', text)
     assert n == 1
     return text.replace("WorldBegin", pixel_filter + "\nWorldBegin", 1)
+
+
+def with_accelerator(text, split, maxprims):
+    return text.replace("WorldBegin", 'Accelerator "bvh" "string splitmethod" "%s" "integer maxnodeprims" [%d]\nWorldBegin' % (split, maxprims), 1)
+
+
+def random_mesh_scene_text(n_tris, seed):
+    """A scene file with one trianglemesh of n_tris small random triangles inside the unit cube (for BVH-build tests)."""
+    rng = np.random.RandomState(seed)
+    c = rng.rand(n_tris, 1, 3).astype(np.float32)
+    P = (c + 0.03 * (rng.rand(n_tris, 3, 3).astype(np.float32) - 0.5)).reshape(-1, 3)
+    idx = np.arange(3 * n_tris)
+    return ('LookAt .5 -2 .5  .5 .5 .5  0 0 1\nCamera "perspective" "float fov" 40\nSampler "halton" "integer pixelsamples" 1\n'
+            'Film "image" "integer xresolution" 16 "integer yresolution" 16\nWorldBegin\n'
+            'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [5 5 5]\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 2 1 0 2 0 1 2]\nAttributeEnd\n'
+            'Shape "trianglemesh" "integer indices" [%s] "point P" [%s]\nWorldEnd\n'
+            % (" ".join(map(str, idx)), " ".join("%.9g" % v for v in P.ravel())))

@@ -57,6 +57,23 @@ def record_filters(ref):
     np.savez_compressed(os.path.join(OUT, "filters.npz"), **out)
 
 
+def record_hlbvh(ref):
+    """BVHAccel's linear nodes and primitive order with splitmethod "hlbvh" (bvh.cpp:404-638).  The reference hands out the
+    ordered-primitive slots of the treelets through an atomic counter, so the order is only reproducible with one
+    worker thread: ref_li_samples switches the reference to one thread before the scenes are built."""
+    warm = gc.soup_scene(pb)
+    ref.scene(warm).li_samples(np.zeros((1, 2), np.int32), np.zeros(1, np.int64))
+    out = {}
+    cases = [("killeroo_like", open(os.path.join(ROOT, "tests", "scenes", "killeroo_like.pbrt")).read(), mp) for mp in (4, 1, 16)]
+    cases.append(("random20k", gc.random_mesh_scene_text(20000, 5), 4))
+    for name, text, mp in cases:
+        hs = pb.HostScene.from_string(gc.with_accelerator(text, "hlbvh", mp))
+        nodes, prims = ref.scene(hs, max_prims_in_node=mp, split_method=1).bvh()
+        out["nodes_%s_%d" % (name, mp)], out["prims_%s_%d" % (name, mp)] = nodes, prims
+        print("hlbvh", name, mp, len(nodes), "nodes")
+    np.savez_compressed(os.path.join(OUT, "hlbvh.npz"), **out)
+
+
 def main():
     ref = pyoracle.reference()
     if ref is None:
@@ -73,6 +90,7 @@ def main():
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "roughglass.pbrt")), "roughglass")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "lights.pbrt")), "lights")
     record_filters(ref)
+    record_hlbvh(ref)
     # the metal material's default eta / k: copper's measured spectra through Spectrum::FromSampled (metal.cpp:121-126)
     eta, k = ref.copper_rgb()
     np.savez_compressed(os.path.join(OUT, "metal_defaults.npz"), eta=eta, k=k)

@@ -141,6 +141,21 @@ def test_delta_lights_under_other_light_sampling_strategies(pb, checker, strateg
     assert abs(int(st.shadow_rays) - int(ref_st.shadow_rays)) <= ref_st.shadow_rays // 1000 + 2
 
 
+def test_hlbvh_tree_traces_and_renders_like_the_sah_tree(pb):
+    """A different BVH over the same primitives changes the traversal, not the answers: closest hits and the image of
+    the golden case killeroo_like (recorded with the default SAH tree) must come out of the HLBVH tree as well."""
+    g = np.load(os.path.join(GOLDEN, "killeroo_like.npz"))
+    rays = gc.rays_for(pb, load_scene(pb, "killeroo_like").nodes(), 1500, 11)    # the rays the golden hits were recorded for
+    hs = pb.HostScene.from_string(gc.with_accelerator(open(os.path.join(SCENES, "killeroo_like.pbrt")).read(), "hlbvh", 4))
+    hits = hs.intersect(rays)
+    same = hits["prim"] == g["hits"]["prim"]
+    assert same.mean() >= 0.999                      # ties on shared edges may go to the neighbouring triangle
+    assert np.array_equal(gc.bits(hits["t"][same]), gc.bits(g["hits"]["t"][same]))
+    img, st = hs.render()
+    frac, mean_rel = image_metrics(img, g["image"])
+    assert frac >= 0.999 and mean_rel <= 1e-4, (frac, mean_rel)
+
+
 @pytest.mark.parametrize("maxprims,split", [(16, "sah"), (40, "equal"), (1, "middle")])
 def test_other_bvh_shapes_match_checker(pb, checker, maxprims, split):
     """Leaves of up to 16 primitives still fit the two-child records, 40 do not (the 32-byte-node kernel takes over),

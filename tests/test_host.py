@@ -277,3 +277,14 @@ def test_light_source_directives(pb):
     before = pb.lib().pb2h_error_count()
     hs = pb.HostScene.from_string('WorldBegin\nLightSource "infinite"\nShape "sphere"\nWorldEnd\n')
     assert pb.lib().pb2h_error_count() > before and hs.desc.contents.n_lights == 0
+
+
+@pytest.mark.parametrize("name,maxprims", [("killeroo_like", 4), ("killeroo_like", 1), ("killeroo_like", 16), ("random20k", 4)])
+def test_hlbvh_build_equals_reference(pb, name, maxprims):
+    """splitmethod "hlbvh": Morton codes, the stable 30-bit sort, treelets on the top 12 bits, emitLBVH and the SAH tree
+    over the treelet roots (bvh.cpp:404-638) give the reference's node array byte for byte and its primitive order."""
+    g = np.load(os.path.join(GOLDEN, "hlbvh.npz"))
+    text = gc.random_mesh_scene_text(20000, 5) if name == "random20k" else open(os.path.join(SCENES, name + ".pbrt")).read()
+    hs = pb.HostScene.from_string(gc.with_accelerator(text, "hlbvh", maxprims))
+    assert same_bvh(hs.nodes(), g["nodes_%s_%d" % (name, maxprims)])
+    assert np.array_equal(hs.bvh_prims(0), g["prims_%s_%d" % (name, maxprims)])
