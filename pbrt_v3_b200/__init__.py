@@ -180,6 +180,7 @@ def lib():
     L.pb2h_resolve_film.argtypes = [vp, vp]
     L.pb2h_device_scene.restype = vp
     L.pb2h_write_pfm.argtypes = [C.c_char_p, vp, C.c_int, C.c_int]
+    L.pb2h_write_image.argtypes = [C.c_char_p, vp] + [C.c_int] * 6
     L.pb2h_loop_subdivide.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, vp]
     L.pb2h_set_light_strategy.argtypes = [C.c_int]
     _lib = L

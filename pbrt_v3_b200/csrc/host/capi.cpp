@@ -284,6 +284,10 @@ pb2_scene *pb2h_device_scene(void) {
 }
 
 int pb2h_write_pfm(const char *path, const float *rgb, int w, int h) { return WriteImagePFM(path, rgb, w, h) ? 0 : 1; }
+// WriteImage (imageio.cpp:81-122): EXR / PFM / PNG / TGA by extension; the window arguments only matter for EXR
+int pb2h_write_image(const char *path, const float *rgb, int w, int h, int total_w, int total_h, int x_offset, int y_offset) {
+    return WriteImage(path, rgb, w, h, total_w, total_h, x_offset, y_offset) ? 0 : 1;
+}
 
 // Loop subdivision of a control mesh (tests compare with the reference's CreateLoopSubdiv).
 // Call once with out pointers NULL to get the sizes, then again with buffers.

@@ -343,20 +343,187 @@ bool ReadImagePFM(const std::string &filename, std::vector<Float> *rgb, int *wid
     return ok;
 }
 
+// ---------------------------------------------------------------- image writers (src/core/imageio.cpp:81-122)
+// The reference hands EXR to OpenEXR (RgbaOutputFile, half RGB), PNG to lodepng and TGA to libtarga.  These
+// writers produce the same pixel values in the same formats with the simplest legal encoding of each container:
+// scan-line EXR without compression, PNG with stored deflate blocks, type-2 TGA.
+namespace {
+// float -> IEEE half, round to nearest even (what OpenEXR's half(float) does), overflow to infinity
+uint16_t floatToHalf(float f) {
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    uint32_t sign = (x >> 16) & 0x8000u;
+    int32_t exp = (int32_t)((x >> 23) & 0xff) - 127 + 15;
+    uint32_t man = x & 0x7fffffu;
+    if (((x >> 23) & 0xff) == 0xff) return (uint16_t)(sign | 0x7c00u | (man ? 0x200u : 0));   // inf / nan
+    if (exp >= 31) return (uint16_t)(sign | 0x7c00u);
+    if (exp <= 0) {
+        if (exp < -10) return (uint16_t)sign;              // rounds to zero
+        man |= 0x800000u;                                  // denormal half: shift the implicit one in
+        int shift = 14 - exp;
+        uint32_t h = man >> shift, rem = man & ((1u << shift) - 1), half = 1u << (shift - 1);
+        if (rem > half || (rem == half && (h & 1))) ++h;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((uint32_t)exp << 10) | (man >> 13), rem = man & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) ++h;   // may carry into the exponent, up to infinity: still right
+    return (uint16_t)(sign | h);
+}
+struct ByteSink {
+    std::vector<uint8_t> b;
+    void u8(uint8_t v) { b.push_back(v); }
+    void le16(uint16_t v) { u8(v & 0xff); u8(v >> 8); }
+    void le32(uint32_t v) { for (int i = 0; i < 4; ++i) u8((v >> (8 * i)) & 0xff); }
+    void le64(uint64_t v) { for (int i = 0; i < 8; ++i) u8((v >> (8 * i)) & 0xff); }
+    void be32(uint32_t v) { for (int i = 3; i >= 0; --i) u8((v >> (8 * i)) & 0xff); }
+    void str(const char *s) { while (*s) u8((uint8_t)*s++); u8(0); }
+    void raw(const void *p, size_t n) { const uint8_t *q = (const uint8_t *)p; b.insert(b.end(), q, q + n); }
+};
+bool writeAll(const std::string &filename, const std::vector<uint8_t> &bytes) {
+    FILE *fp = std::fopen(filename.c_str(), "wb");
+    if (!fp) {
+        Error("Unable to open output file \"%s\"", filename.c_str());
+        return false;
+    }
+    bool ok = std::fwrite(bytes.data(), 1, bytes.size(), fp) == bytes.size();
+    std::fclose(fp);
+    return ok;
+}
+// 8-bit formats: gamma (pbrt.h:293-296), then TO_BYTE of imageio.cpp:100
+inline Float GammaCorrect(Float value) {
+    if (value <= 0.0031308f) return 12.92f * value;
+    return 1.055f * std::pow(value, (Float)(1.f / 2.4f)) - 0.055f;
+}
+std::vector<uint8_t> toRGB8(const Float *rgb, int w, int h) {
+    std::vector<uint8_t> out((size_t)3 * w * h);
+    for (size_t i = 0; i < out.size(); ++i) {
+        Float v = 255.f * GammaCorrect(rgb[i]) + 0.5f;
+        out[i] = (uint8_t)(v < 0.f ? 0.f : (v > 255.f ? 255.f : v));
+    }
+    return out;
+}
+uint32_t crc32(const uint8_t *p, size_t n, uint32_t crc = 0) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        init = true;
+    }
+    crc = ~crc;
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    return ~crc;
+}
+}  // namespace
+
+// imageio.cpp:164-190: RGB half channels, display window = the full resolution, data window = the cropped pixels
+bool WriteImageEXR(const std::string &filename, const Float *rgb, int xRes, int yRes, int totalXRes, int totalYRes, int xOffset, int yOffset) {
+    ByteSink o;
+    o.le32(20000630);   // magic
+    o.le32(2);          // version 2, single-part scan-line file
+    auto attr = [&](const char *name, const char *type, uint32_t size) { o.str(name); o.str(type); o.le32(size); };
+    attr("channels", "chlist", 3 * 18 + 1);
+    for (const char *ch : {"B", "G", "R"}) {   // alphabetical, as the format requires
+        o.str(ch);
+        o.le32(1);      // HALF
+        o.u8(0); o.u8(0); o.u8(0); o.u8(0);   // pLinear + reserved
+        o.le32(1); o.le32(1);                 // sampling
+    }
+    o.u8(0);
+    attr("compression", "compression", 1); o.u8(0);   // NO_COMPRESSION
+    attr("dataWindow", "box2i", 16);
+    o.le32(xOffset); o.le32(yOffset); o.le32(xOffset + xRes - 1); o.le32(yOffset + yRes - 1);
+    attr("displayWindow", "box2i", 16);
+    o.le32(0); o.le32(0); o.le32(totalXRes - 1); o.le32(totalYRes - 1);
+    attr("lineOrder", "lineOrder", 1); o.u8(0);       // INCREASING_Y
+    float one = 1.f, zero = 0.f;
+    attr("pixelAspectRatio", "float", 4); o.raw(&one, 4);
+    attr("screenWindowCenter", "v2f", 8); o.raw(&zero, 4); o.raw(&zero, 4);
+    attr("screenWindowWidth", "float", 4); o.raw(&one, 4);
+    o.u8(0);            // end of header
+    const uint64_t lineBytes = (uint64_t)xRes * 3 * 2, tableStart = o.b.size();
+    for (int y = 0; y < yRes; ++y) o.le64(tableStart + 8ull * yRes + (uint64_t)y * (8 + lineBytes));
+    std::vector<uint16_t> line((size_t)xRes * 3);
+    for (int y = 0; y < yRes; ++y) {
+        o.le32(yOffset + y);
+        o.le32((uint32_t)lineBytes);
+        for (int c = 0; c < 3; ++c)            // B, G, R planes of this scan line
+            for (int x = 0; x < xRes; ++x) line[(size_t)c * xRes + x] = floatToHalf(rgb[3 * ((size_t)y * xRes + x) + (2 - c)]);
+        for (uint16_t v : line) o.le16(v);
+    }
+    return writeAll(filename, o.b);
+}
+// imageio.cpp:93-117 (lodepng_encode24_file): 8-bit RGB, no interlace; zlib stream of stored blocks
+bool WriteImagePNG(const std::string &filename, const Float *rgb, int w, int h) {
+    std::vector<uint8_t> px = toRGB8(rgb, w, h), rawData;
+    rawData.reserve((size_t)h * (3 * w + 1));
+    for (int y = 0; y < h; ++y) {
+        rawData.push_back(0);   // filter type None
+        rawData.insert(rawData.end(), px.begin() + (size_t)y * 3 * w, px.begin() + (size_t)(y + 1) * 3 * w);
+    }
+    ByteSink z;
+    z.u8(0x78); z.u8(0x01);
+    size_t pos = 0;
+    do {
+        size_t n = std::min<size_t>(65535, rawData.size() - pos);
+        z.u8(pos + n == rawData.size() ? 1 : 0);
+        z.le16((uint16_t)n); z.le16((uint16_t)~n);
+        z.raw(rawData.data() + pos, n);
+        pos += n;
+    } while (pos < rawData.size());
+    uint32_t a = 1, b = 0;   // Adler-32
+    for (uint8_t v : rawData) { a = (a + v) % 65521; b = (b + a) % 65521; }
+    z.be32((b << 16) | a);
+    ByteSink o;
+    const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    o.raw(sig, 8);
+    auto chunk = [&](const char *type, const std::vector<uint8_t> &data) {
+        o.be32((uint32_t)data.size());
+        size_t start = o.b.size();
+        o.raw(type, 4);
+        o.raw(data.data(), data.size());
+        o.be32(crc32(&o.b[start], o.b.size() - start));
+    };
+    ByteSink ihdr;
+    ihdr.be32(w); ihdr.be32(h); ihdr.u8(8); ihdr.u8(2); ihdr.u8(0); ihdr.u8(0); ihdr.u8(0);
+    chunk("IHDR", ihdr.b);
+    chunk("IDAT", z.b);
+    chunk("IEND", {});
+    return writeAll(filename, o.b);
+}
+// imageio.cpp:193-214 + targa.cpp:494-541: uncompressed 24-bit BGR, rows top to bottom
+bool WriteImageTGA(const std::string &filename, const Float *rgb, int w, int h) {
+    std::vector<uint8_t> px = toRGB8(rgb, w, h);
+    ByteSink o;
+    o.u8(0); o.u8(0); o.u8(2);                  // no id, no colour map, true-colour
+    for (int i = 0; i < 5; ++i) o.u8(0);        // colour map specification
+    o.le16(0); o.le16(0); o.le16((uint16_t)w); o.le16((uint16_t)h);
+    o.u8(24); o.u8(0x20);                       // TGA_T_TO_B_BIT
+    for (size_t i = 0; i < (size_t)w * h; ++i) { o.u8(px[3 * i + 2]); o.u8(px[3 * i + 1]); o.u8(px[3 * i]); }
+    return writeAll(filename, o.b);
+}
+
+// WriteImage (imageio.cpp:81-122): the container follows the file name's extension
+bool WriteImage(const std::string &name, const Float *rgb, int xRes, int yRes, int totalXRes, int totalYRes, int xOffset, int yOffset) {
+    size_t dot = name.rfind('.');
+    std::string ext = dot == std::string::npos ? "" : name.substr(dot);
+    for (char &c : ext) c = (char)std::tolower((unsigned char)c);
+    if (ext == ".exr") return WriteImageEXR(name, rgb, xRes, yRes, totalXRes, totalYRes, xOffset, yOffset);
+    if (ext == ".pfm") return WriteImagePFM(name, rgb, xRes, yRes);
+    if (ext == ".png") return WriteImagePNG(name, rgb, xRes, yRes);
+    if (ext == ".tga") return WriteImageTGA(name, rgb, xRes, yRes);
+    Error("Can't determine image file type from suffix of filename \"%s\"", name.c_str());
+    return false;
+}
+
 void Film::WriteImage(Float splatScale) {
     std::vector<Float> rgb = ResolveRGB();
     int w = croppedPixelBounds.pMax.x - croppedPixelBounds.pMin.x;
     int h = croppedPixelBounds.pMax.y - croppedPixelBounds.pMin.y;
-    std::string out = filename;
-    size_t dot = out.rfind('.');
-    std::string ext = dot == std::string::npos ? "" : out.substr(dot);
-    if (ext != ".pfm") {
-        // EXR/PNG/TGA encoders are file-format code outside the path; the
-        // float32 PFM carries strictly more precision than the reference's half-float EXR.
-        out = (dot == std::string::npos ? out : out.substr(0, dot)) + ".pfm";
-        Warning("Image format \"%s\" is not written by this build; writing float32 PFM \"%s\" instead", ext.c_str(), out.c_str());
-    }
-    WriteImagePFM(out, rgb.data(), w, h);
+    pbrt::WriteImage(filename, rgb.data(), w, h, fullResolution.x, fullResolution.y, croppedPixelBounds.pMin.x, croppedPixelBounds.pMin.y);
 }
 
 pb2_film_desc Film::Desc() const {

@@ -413,6 +413,7 @@ class Film {
 };
 Film *CreateFilm(const ParamSet &params, std::unique_ptr<Filter> filter);
 bool WriteImagePFM(const std::string &filename, const Float *rgb, int width, int height);
+bool WriteImage(const std::string &name, const Float *rgb, int xRes, int yRes, int totalXRes, int totalYRes, int xOffset, int yOffset);
 bool ReadImagePFM(const std::string &filename, std::vector<Float> *rgb, int *width, int *height);
 
 class Camera {

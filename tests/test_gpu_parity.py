@@ -326,6 +326,16 @@ def test_reference_shaped_api_and_cli(pb, tmp_path):
     assert data.startswith(b"PF\n48 32\n-1.000000\n")
     cli = np.frombuffer(data[len(b"PF\n48 32\n-1.000000\n"):], "<f4").reshape(32, 48, 3)[::-1]
     assert np.allclose(cli, img, rtol=1e-5, atol=1e-6)
+    # the reference's default container: half-float EXR (imageio.cpp:164-190), read back by hand
+    import struct
+    out = tmp_path / "out.exr"
+    res = subprocess.run([exe, "--outfile", str(out), os.path.join(SCENES, "materials.pbrt")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout
+    data = open(out, "rb").read()
+    assert struct.unpack_from("<I", data, 0)[0] == 20000630
+    body = np.frombuffer(data[-32 * (8 + 48 * 6):], np.uint8).reshape(32, 8 + 48 * 6)[:, 8:].copy().view(np.float16).reshape(32, 3, 48)
+    exr = body[:, ::-1, :].transpose(0, 2, 1).astype(np.float32)
+    assert np.allclose(exr, img, rtol=2e-3, atol=1e-4)      # half precision: 11 significant bits
 
 
 def test_single_shape_intersect_goes_to_the_device(pb):

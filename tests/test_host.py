@@ -288,3 +288,89 @@ def test_hlbvh_build_equals_reference(pb, name, maxprims):
     hs = pb.HostScene.from_string(gc.with_accelerator(text, "hlbvh", maxprims))
     assert same_bvh(hs.nodes(), g["nodes_%s_%d" % (name, maxprims)])
     assert np.array_equal(hs.bvh_prims(0), g["prims_%s_%d" % (name, maxprims)])
+
+
+def _to_byte(rgb):
+    f32 = np.float32
+    v = rgb.astype(f32)
+    g = np.where(v <= f32(0.0031308), f32(12.92) * v, f32(1.055) * np.power(np.maximum(v, 0), f32(1 / 2.4), dtype=f32) - f32(0.055)).astype(f32)
+    return np.clip(f32(255) * g + f32(0.5), 0, 255).astype(np.uint8)
+
+
+def test_image_writers_exr_png_tga(pb, tmp_path):
+    """WriteImage (imageio.cpp:81-122): the container follows the extension.  EXR: half RGB, data window = the cropped
+    pixels inside the display window; PNG / TGA: gamma-corrected bytes (TO_BYTE, imageio.cpp:100).  Decoded here by
+    hand-written readers of the three containers."""
+    import struct
+    import zlib
+    rng = np.random.RandomState(3)
+    w, h = 7, 5
+    rgb = (rng.rand(h, w, 3) ** 3 * 4).astype(np.float32)
+    rgb[0, 0] = (0, 1e-9, 6.1e-5)          # zero, flush-to-zero, half denormal range
+    rgb[0, 1] = (65504, 65520, 1e9)         # largest half, the tie that rounds to infinity, overflow
+    rgb[0, 2] = (1 + 2 ** -11, 1 + 3 * 2 ** -11, 0.0031308)   # ties to even in both directions
+    L = pb.lib()
+    path = str(tmp_path / "out.exr").encode()
+    assert L.pb2h_write_image(path, pb.ptr(rgb), w, h, 20, 10, 3, 2) == 0
+    b = open(path, "rb").read()
+    assert struct.unpack_from("<II", b, 0) == (20000630, 2)
+    pos, attrs = 8, {}
+    while b[pos] != 0:
+        name_end = b.index(b"\0", pos)
+        type_end = b.index(b"\0", name_end + 1)
+        size = struct.unpack_from("<I", b, type_end + 1)[0]
+        attrs[b[pos:name_end].decode()] = (b[name_end + 1:type_end].decode(), b[type_end + 5:type_end + 5 + size])
+        pos = type_end + 5 + size
+    pos += 1
+    assert attrs["compression"] == ("compression", b"\0") and attrs["lineOrder"][1] == b"\0"
+    assert struct.unpack("<4i", attrs["dataWindow"][1]) == (3, 2, 3 + w - 1, 2 + h - 1)
+    assert struct.unpack("<4i", attrs["displayWindow"][1]) == (0, 0, 19, 9)
+    chl = attrs["channels"][1]
+    assert [chl[i * 18:i * 18 + 1] for i in range(3)] == [b"B", b"G", b"R"] and all(struct.unpack_from("<i", chl, i * 18 + 2)[0] == 1 for i in range(3))
+    offsets = struct.unpack_from("<%dQ" % h, b, pos)
+    got = np.zeros((h, w, 3), np.float16)
+    for y, off in enumerate(offsets):
+        yy, nbytes = struct.unpack_from("<ii", b, off)
+        assert yy == 2 + y and nbytes == w * 6
+        planes = np.frombuffer(b, np.float16, 3 * w, off + 8).reshape(3, w)
+        got[y] = planes[::-1].T              # B, G, R planes -> rgb
+    assert offsets[-1] + 8 + w * 6 == len(b)
+    with np.errstate(over="ignore"):
+        want = rgb.astype(np.float16)        # IEEE round-to-nearest-even, overflow to inf: what half(float) does
+    assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
+    assert np.isinf(got[0, 1, 1]) and got[0, 1, 0] == 65504 and got[0, 0, 1] == 0 and got[0, 0, 2] != 0
+
+    img = np.clip(rgb, 0, 2)
+    path = str(tmp_path / "out.png").encode()
+    assert L.pb2h_write_image(path, pb.ptr(img), w, h, w, h, 0, 0) == 0
+    b = open(path, "rb").read()
+    assert b[:8] == bytes([0x89, 80, 78, 71, 13, 10, 26, 10])
+    pos, chunks = 8, []
+    while pos < len(b):
+        n, typ = struct.unpack_from(">I4s", b, pos)
+        data = b[pos + 8:pos + 8 + n]
+        assert struct.unpack_from(">I", b, pos + 8 + n)[0] == zlib.crc32(typ + data)
+        chunks.append((typ, data))
+        pos += 12 + n
+    assert [c[0] for c in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+    assert struct.unpack(">IIBBBBB", chunks[0][1]) == (w, h, 8, 2, 0, 0, 0)
+    raw = np.frombuffer(zlib.decompress(chunks[1][1]), np.uint8).reshape(h, 1 + 3 * w)
+    assert (raw[:, 0] == 0).all()
+    px = raw[:, 1:].reshape(h, w, 3).astype(int)
+    assert np.abs(px - _to_byte(img).astype(int)).max() <= 1 and (px == _to_byte(img)).mean() > 0.95   # powf vs numpy's pow at .5 boundaries
+
+    path = str(tmp_path / "out.tga").encode()
+    assert L.pb2h_write_image(path, pb.ptr(img), w, h, w, h, 0, 0) == 0
+    b = open(path, "rb").read()
+    assert b[:3] == bytes([0, 0, 2]) and struct.unpack_from("<HHHHBB", b, 8) == (0, 0, w, h, 24, 0x20) and len(b) == 18 + 3 * w * h
+    bgr = np.frombuffer(b, np.uint8, 3 * w * h, 18).reshape(h, w, 3)
+    assert np.array_equal(bgr[..., ::-1], px)
+    # a big image crosses the 65535-byte stored-block limit of deflate
+    big = rng.rand(120, 300, 3).astype(np.float32)
+    path = str(tmp_path / "big.png").encode()
+    assert L.pb2h_write_image(path, pb.ptr(big), 300, 120, 300, 120, 0, 0) == 0
+    b = open(path, "rb").read()
+    n = struct.unpack_from(">I", b, 33)[0]
+    raw = np.frombuffer(zlib.decompress(b[41:41 + n]), np.uint8).reshape(120, 901)
+    assert np.abs(raw[:, 1:].reshape(120, 300, 3).astype(int) - _to_byte(big).astype(int)).max() <= 1
+    assert L.pb2h_write_image(str(tmp_path / "out.bmp").encode(), pb.ptr(img), w, h, w, h, 0, 0) != 0
