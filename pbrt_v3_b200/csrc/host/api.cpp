@@ -18,6 +18,7 @@ namespace pbrt {
 std::string g_sceneDirectory;
 std::string g_imageFileOverride;
 Float g_cropWindow[2][2] = {{0, 1}, {0, 1}};
+bool g_quickRender = false;
 
 namespace {
 
@@ -181,6 +182,7 @@ std::vector<std::shared_ptr<Shape>> MakeShapes(const std::string &name, const Tr
 void pbrtInit(const Options &opt) {
     g_imageFileOverride = opt.imageFile;
     std::memcpy(g_cropWindow, opt.cropWindow, sizeof(g_cropWindow));
+    g_quickRender = opt.quickRender;
     if (apiState != APIState::Uninitialized) Error("pbrtInit() has already been called.");
     apiState = APIState::OptionsBlock;
     renderOptions.reset(new RenderOptions);

@@ -10,6 +10,7 @@ namespace pbrt {
 
 struct Options {
     int nThreads = 0;  // accepted for CLI compatibility; the GPU path does not use host threads
+    bool quickRender = false;  // --quick (pbrt.cpp:116-117): quarter resolution, one sample per pixel
     bool quiet = false;
     std::string imageFile;
     Float cropWindow[2][2] = {{0, 1}, {0, 1}};

@@ -39,8 +39,13 @@ int pb2h_parse_file(const char *path, const char *outfile) {
     return pbrtLastSetup() && pbrtLastSetup()->integrator ? 0 : 1;
 }
 
+// The command line's --quick for the next pb2h_parse_* calls (Options::quickRender)
+static bool g_nextQuick = false;
+void pb2h_set_quick_render(int on) { g_nextQuick = on != 0; }
+
 int pb2h_parse_string(const char *text) {
     Options opt;
+    opt.quickRender = g_nextQuick;
     g_flat.reset();
     if (pbrtIsInitialized()) pbrtCleanup();
     pbrtInit(opt);

@@ -14,7 +14,8 @@ static void usage(const char *msg = nullptr) {
                  "  --cropwindow <x0,x1,y0,y1>  Specify an image crop window.\n"
                  "  --help               Print this help text.\n"
                  "  --nthreads <num>     Accepted for compatibility (rendering runs on the GPU).\n"
-                 "  --outfile <filename> Write the final image to the given filename (float32 PFM).\n"
+                 "  --outfile <filename> Write the final image to the given filename (.exr, .pfm, .png, .tga).\n"
+                 "  --quick              Automatically reduce a number of quality settings to render more quickly.\n"
                  "  --quiet              Suppress all text output other than error messages.\n");
     std::exit(msg ? 1 : 0);
 }
@@ -40,8 +41,18 @@ int main(int argc, char *argv[]) {
             options.cropWindow[0][1] = (Float)std::atof(argv[++i]);
             options.cropWindow[1][0] = (Float)std::atof(argv[++i]);
             options.cropWindow[1][1] = (Float)std::atof(argv[++i]);
+        } else if (a == "--quick" || a == "-quick") {
+            options.quickRender = true;
         } else if (a == "--quiet" || a == "-quiet") {
             options.quiet = true;
+        } else if (a == "--logtostderr" || a == "-logtostderr" || a == "--verbose" || a == "-verbose" || a == "--v" || a == "-v") {
+            // logging switches of the reference's glog front end (pbrt.cpp:118-139): nothing to configure here
+        } else if (a == "--minloglevel" || a == "-minloglevel" || a == "--logdir" || a == "-logdir") {
+            if (i + 1 == argc) usage(("missing value after " + a + " argument").c_str());
+            ++i;
+        } else if (a.compare(0, 14, "--minloglevel=") == 0 || a.compare(0, 9, "--logdir=") == 0 || a.compare(0, 4, "--v=") == 0) {
+        } else if (a == "--cat" || a == "-cat" || a == "--toply" || a == "-toply") {
+            usage((a + ": scene re-printing is not part of this build").c_str());
         } else if (a == "--help" || a == "-help" || a == "-h") {
             usage();
         } else if (a.size() > 1 && a[0] == '-') {

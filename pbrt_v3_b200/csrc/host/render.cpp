@@ -547,6 +547,7 @@ pb2_film_desc Film::Desc() const {
 
 extern std::string g_imageFileOverride;  // api.cpp (--outfile)
 extern Float g_cropWindow[2][2];
+extern bool g_quickRender;             // --quick
 Film *CreateFilm(const ParamSet &params, std::unique_ptr<Filter> filter) {
     std::string filename;
     if (g_imageFileOverride != "") {
@@ -559,6 +560,8 @@ Film *CreateFilm(const ParamSet &params, std::unique_ptr<Filter> filter) {
         filename = params.FindOneString("filename", "pbrt.exr");
     int xres = params.FindOneInt("xresolution", 1280);
     int yres = params.FindOneInt("yresolution", 720);
+    if (g_quickRender) xres = std::max(1, xres / 4);   // film.cpp:228-229
+    if (g_quickRender) yres = std::max(1, yres / 4);
     Bounds2f crop;
     bool haveCrop = false;
     std::vector<Float> cr = params.FindFloats(ParamSet::Type::Float, "cropwindow", &haveCrop);
@@ -642,6 +645,7 @@ PerspectiveCamera *CreatePerspectiveCamera(const ParamSet &params, const Transfo
 // ---------------------------------------------------------------- sampler / integrator factories
 HaltonSampler *CreateHaltonSampler(const ParamSet &params, const Bounds2i &sampleBounds) {
     int nsamp = params.FindOneInt("pixelsamples", 16);
+    if (g_quickRender) nsamp = 1;                      // halton.cpp:136
     bool sampleAtCenter = params.FindOneBool("samplepixelcenter", false);
     return new HaltonSampler(nsamp, sampleBounds, sampleAtCenter);
 }

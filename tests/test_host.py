@@ -374,3 +374,16 @@ def test_image_writers_exr_png_tga(pb, tmp_path):
     raw = np.frombuffer(zlib.decompress(b[41:41 + n]), np.uint8).reshape(120, 901)
     assert np.abs(raw[:, 1:].reshape(120, 300, 3).astype(int) - _to_byte(big).astype(int)).max() <= 1
     assert L.pb2h_write_image(str(tmp_path / "out.bmp").encode(), pb.ptr(img), w, h, w, h, 0, 0) != 0
+
+
+def test_quick_render_option(pb):
+    """--quick (pbrt.cpp:116-117): Film divides the resolution by 4 (film.cpp:228-229), Halton takes one sample (halton.cpp:136)."""
+    text = open(os.path.join(SCENES, "materials.pbrt")).read()
+    pb.lib().pb2h_set_quick_render(1)
+    try:
+        hs = pb.HostScene.from_string(text)
+        assert tuple(hs.film.contents.full_resolution) == (12, 8) and hs.params.contents.samples_per_pixel == 1
+    finally:
+        pb.lib().pb2h_set_quick_render(0)
+    hs = pb.HostScene.from_string(text)
+    assert tuple(hs.film.contents.full_resolution) == (48, 32) and hs.params.contents.samples_per_pixel == 8
