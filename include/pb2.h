@@ -336,6 +336,25 @@ int pb2_halton_samples(const pb2_film_desc *film, const pb2_path_params *params,
  * for each point writes n_lights func values followed by n_lights+1 cdf values. HOST pointers. */
 int pb2_light_distribution(pb2_scene *scene, const float *points_xyz, int64_t n, float *out);
 
+/* The lower half of BVHAccel::HLBVHBuild on the device (src/accelerators/bvh.cpp:404-470): Morton codes of the primitive
+ * centroids over the centroid bounds (bvh.cpp:408-423), the stable sort by the 30-bit code (RadixSort, bvh.cpp:139-180),
+ * and one LBVH treelet per distinct top-12-bit prefix (bvh.cpp:428-466, emitLBVH 472-539).  The caller finishes with
+ * buildUpperSAH over the treelet roots (bvh.cpp:541-638) and flattens.
+ *   prim_bounds      n x 6 floats, (pMin, pMax) of each primitive's world bound, in primitive order
+ *   pool             2n records; treelet t's nodes occupy pool[2*start_t ...], children are pool indices
+ *   ordered_prims    n primitive numbers in sorted (= BVHAccel::primitives) order; a leaf's first_prim_offset indexes it
+ *   treelet_roots    up to 4096 pool indices in sorted order, *n_treelets of them
+ * HOST pointers; blocking.  The result equals the host build (and the reference run by one thread) bit for bit. */
+typedef struct pb2_build_node {
+    float bmin[3], bmax[3];
+    int32_t child[2];          /* -1, -1 for a leaf */
+    int32_t split_axis;
+    int32_t first_prim_offset;
+    int32_t n_primitives;      /* 0 for an interior node */
+} pb2_build_node;
+int pb2_hlbvh_treelets(const float *prim_bounds, int64_t n, int32_t max_prims_in_node, pb2_build_node *pool,
+                       int32_t *ordered_prims, int32_t *treelet_roots, int32_t *n_treelets, double *device_ms);
+
 #ifdef __cplusplus
 }
 #endif

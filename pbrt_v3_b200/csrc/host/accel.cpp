@@ -228,6 +228,30 @@ struct Builder {
         pool[node].nPrimitives = 0;
         return node;
     }
+    // The same lower half on the GPU (pb2_hlbvh_treelets, include/pb2.h): Morton codes, sort and treelets come back as
+    // this builder's own records; only the small SAH tree over the treelet roots is built here.
+    int buildHLBVHOnDevice(double *deviceMs) {
+        static_assert(sizeof(BuildNode) == sizeof(pb2_build_node), "BuildNode is the ABI's pb2_build_node");
+        const int n = (int)info.size();
+        std::vector<float> primBounds((size_t)n * 6);
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k) {
+                primBounds[6 * (size_t)i + k] = info[i].bounds.pMin[k];
+                primBounds[6 * (size_t)i + 3 + k] = info[i].bounds.pMax[k];
+            }
+        std::vector<int32_t> roots32(4096);
+        int32_t nTreelets = 0;
+        if (!EnsureDevice()) return -1;
+        pool.resize((size_t)2 * n + 4096);
+        if (pb2_hlbvh_treelets(primBounds.data(), n, maxPrimsInNode, reinterpret_cast<pb2_build_node *>(pool.data()), ordered.data(),
+                               roots32.data(), &nTreelets, deviceMs) != PB2_OK) {
+            Error("Device BVH build failed: %s", pb2_last_error());
+            return -1;
+        }
+        nextNode.store(2 * n);
+        std::vector<int> roots(roots32.begin(), roots32.begin() + nTreelets);
+        return buildUpperSAH(roots, 0, (int)roots.size());
+    }
     int buildHLBVH() {
         Bounds3f bounds;
         for (const PrimInfo &pi : info) bounds = Union(bounds, pi.centroid);
@@ -302,8 +326,8 @@ struct Builder {
 };
 }  // namespace
 
-BVHAccel::BVHAccel(std::vector<std::shared_ptr<Primitive>> p, int maxPrims, SplitMethod sm)
-    : sceneOrderPrims(std::move(p)), maxPrimsInNode(std::min(255, maxPrims)), splitMethod(sm) {
+BVHAccel::BVHAccel(std::vector<std::shared_ptr<Primitive>> p, int maxPrims, SplitMethod sm, bool deviceBuild)
+    : sceneOrderPrims(std::move(p)), maxPrimsInNode(std::min(255, maxPrims)), splitMethod(sm), deviceBuild(deviceBuild) {
     if (sceneOrderPrims.empty()) return;
     Builder b;
     b.maxPrimsInNode = maxPrimsInNode;
@@ -321,7 +345,16 @@ BVHAccel::BVHAccel(std::vector<std::shared_ptr<Primitive>> p, int maxPrims, Spli
     int spawnLevels = 0;
     for (unsigned t = std::max(1u, std::thread::hardware_concurrency()); t > 1; t >>= 1) ++spawnLevels;
     const auto t1 = clk();
-    int root = splitMethod == SplitMethod::HLBVH ? b.buildHLBVH() : b.build(0, (int)sceneOrderPrims.size(), 0, spawnLevels + 2);
+    int root = -1;
+    double deviceMs = 0;
+    if (splitMethod == SplitMethod::HLBVH && deviceBuild) root = b.buildHLBVHOnDevice(&deviceMs);
+    else if (splitMethod == SplitMethod::HLBVH) root = b.buildHLBVH();
+    else root = b.build(0, (int)sceneOrderPrims.size(), 0, spawnLevels + 2);
+    if (root < 0) {   // the device build reported an error: leave an empty accelerator, like a scene without primitives
+        sceneOrderPrims.clear();
+        return;
+    }
+    lastBuildDeviceMs = deviceMs;
     const auto t2 = clk();
     b.pool.resize((size_t)b.nextNode.load());
     nodes.reserve(b.pool.size());
@@ -357,7 +390,15 @@ std::shared_ptr<BVHAccel> CreateBVHAccelerator(std::vector<std::shared_ptr<Primi
         sm = BVHAccel::SplitMethod::SAH;
     }
     int maxPrimsInNode = ps.FindOneInt("maxnodeprims", 4);
-    return std::make_shared<BVHAccel>(std::move(prims), maxPrimsInNode, sm);
+    // Not a parameter of the reference: "bool devicebuild" (or PB2_DEVICE_BVH=1) asks for the HLBVH treelets to be
+    // built by the CUDA library instead of the host threads; the tree is the same either way.
+    const char *env = std::getenv("PB2_DEVICE_BVH");
+    bool deviceBuild = ps.FindOneBool("devicebuild", env && env[0] == '1');
+    if (deviceBuild && sm != BVHAccel::SplitMethod::HLBVH) {
+        Warning("\"devicebuild\" applies to splitmethod \"hlbvh\" only; building on the host");
+        deviceBuild = false;
+    }
+    return std::make_shared<BVHAccel>(std::move(prims), maxPrimsInNode, sm, deviceBuild);
 }
 
 const AreaLight *Aggregate::GetAreaLight() const {

@@ -681,7 +681,7 @@ struct DeviceScene {
 };
 pb2_scene *DeviceSceneHandle(const DeviceScene &d) { return d.handle; }
 
-static bool ensureDevice() {
+bool EnsureDevice() {
     static std::once_flag once;
     static int status = PB2_OK;
     std::call_once(once, [] {
@@ -696,7 +696,7 @@ static bool ensureDevice() {
 std::shared_ptr<DeviceScene> GetDeviceScene(const BVHAccel &bvh, const std::vector<std::shared_ptr<Light>> &lights,
                                             const std::string &lightStrategy) {
     if (bvh.device) return bvh.device;
-    if (!ensureDevice()) return nullptr;
+    if (!EnsureDevice()) return nullptr;
     auto ds = std::make_shared<DeviceScene>();
     ds->flat = FlattenScene(bvh, lights, lightStrategy);
     if (!ds->flat) return nullptr;

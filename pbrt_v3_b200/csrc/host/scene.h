@@ -294,7 +294,7 @@ class BVHAccel : public Aggregate {
   public:
     enum class SplitMethod { SAH, HLBVH, Middle, EqualCounts };
     BVHAccel(std::vector<std::shared_ptr<Primitive>> p, int maxPrimsInNode = 1,
-             SplitMethod splitMethod = SplitMethod::SAH);
+             SplitMethod splitMethod = SplitMethod::SAH, bool deviceBuild = false);
     ~BVHAccel();
     Bounds3f WorldBound() const override;
     bool Intersect(const Ray &ray, SurfaceInteraction *isect) const override;
@@ -307,6 +307,8 @@ class BVHAccel : public Aggregate {
     std::vector<int32_t> orderedPrimNumbers;                    // primitives[j] == sceneOrderPrims[orderedPrimNumbers[j]]
     const int maxPrimsInNode;
     const SplitMethod splitMethod;
+    const bool deviceBuild;           // HLBVH treelets built by pb2_hlbvh_treelets
+    double lastBuildDeviceMs = 0;     // its device time
     mutable std::shared_ptr<DeviceScene> device;  // lazily created by Intersect/IntersectP/Render
 };
 std::shared_ptr<BVHAccel> CreateBVHAccelerator(std::vector<std::shared_ptr<Primitive>> prims, const ParamSet &ps);
@@ -348,6 +350,7 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
                                         const std::string &lightStrategy);
 // Creates (once) the device copy of a BVHAccel-rooted scene; returns nullptr and reports through
 // Error() when the CUDA library refuses (no device, unsupported feature).
+bool EnsureDevice();   // pb2_init once per process (PB2_DEVICE / LOCAL_RANK pick the GPU); false + Error() without one
 std::shared_ptr<DeviceScene> GetDeviceScene(const BVHAccel &bvh, const std::vector<std::shared_ptr<Light>> &lights,
                                             const std::string &lightStrategy);
 pb2_scene *DeviceSceneHandle(const DeviceScene &);

@@ -11,6 +11,7 @@
 // Compile flags that matter for parity: -fmad=false (the reference has no FMA contraction),
 // default IEEE division and square root, no fast-math.
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
 #include <cstddef>
@@ -1326,3 +1327,220 @@ int pb2_light_distribution(pb2_scene *scene, const float *points_xyz, int64_t n,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- HLBVH treelets on the device (bvh.cpp:404-539)
+namespace {
+__device__ __forceinline__ unsigned hlbvhLeftShift3(unsigned x) {   // bvh.cpp:106-130
+    if (x == (1u << 10)) --x;
+    x = (x | (x << 16)) & 0x30000ffu;
+    x = (x | (x << 8)) & 0x300f00fu;
+    x = (x | (x << 4)) & 0x30c30c3u;
+    x = (x | (x << 2)) & 0x9249249u;
+    return x;
+}
+// order-preserving map float <-> unsigned for atomicMin / atomicMax on floats
+__device__ __forceinline__ unsigned floatOrdered(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float orderedFloat(unsigned u) {
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+// BVHPrimitiveInfo::centroid (bvh.cpp:57-58) and the bounds of all centroids (bvh.cpp:409-411): min / max are exact,
+// so a block reduction followed by six atomics gives the sequential Union's result
+__global__ void k_hlbvh_centroid_bounds(const float *bounds, int n, unsigned *box /* min xyz, max xyz, ordered */) {
+    float lo[3] = {PB2_INFINITY, PB2_INFINITY, PB2_INFINITY}, hi[3] = {-PB2_INFINITY, -PB2_INFINITY, -PB2_INFINITY};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        for (int k = 0; k < 3; ++k) {
+            float c = .5f * bounds[6 * (size_t)i + k] + .5f * bounds[6 * (size_t)i + 3 + k];
+            lo[k] = fminf(lo[k], c);
+            hi[k] = fmaxf(hi[k], c);
+        }
+    for (int k = 0; k < 3; ++k) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&box[k], floatOrdered(lo[k]));
+            atomicMax(&box[3 + k], floatOrdered(hi[k]));
+        }
+    }
+}
+// bvh.cpp:414-423: mortonCode = EncodeMorton3(bounds.Offset(centroid) * 1024)
+__global__ void k_hlbvh_morton(const float *bounds, int n, const unsigned *box, unsigned *codes, int *index) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned v[3];
+    for (int k = 0; k < 3; ++k) {
+        float c = .5f * bounds[6 * (size_t)i + k] + .5f * bounds[6 * (size_t)i + 3 + k];
+        float lo = orderedFloat(box[k]), hi = orderedFloat(box[3 + k]);
+        float o = c - lo;                       // Bounds3::Offset (geometry.h:756-763)
+        if (hi > lo) o /= hi - lo;
+        v[k] = (unsigned)(o * 1024.f);
+    }
+    codes[i] = (hlbvhLeftShift3(v[2]) << 2) | (hlbvhLeftShift3(v[1]) << 1) | hlbvhLeftShift3(v[0]);
+    index[i] = i;
+}
+// bvh.cpp:431-448: a treelet starts where the top 12 bits change; at most 4096 of them, one slot per prefix
+__global__ void k_hlbvh_treelet_starts(const unsigned *codes, int n, int *start /* 4096, preset to -1 */) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned mask = 0x3ffc0000u;
+    if (i == 0 || (codes[i] & mask) != (codes[i - 1] & mask)) start[(codes[i] & mask) >> 18] = i;
+}
+// emitLBVH (bvh.cpp:472-539), one thread per treelet, the recursion unrolled over an explicit stack.  Nodes are
+// numbered in the reference's allocation order (a node before its subtrees, the first subtree before the second)
+// inside the treelet's 2 * nPrimitives slots; interior bounds are filled bottom-up afterwards.
+__global__ void k_hlbvh_emit(const float *bounds, const unsigned *codes, const int *sorted, const int2 *treelets /* start, count */,
+                             int nTreelets, int maxPrimsInNode, pb2_build_node *pool, int *roots) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nTreelets) return;
+    const int first = treelets[t].x, count = treelets[t].y;
+    const unsigned *mp = codes + first;
+    pb2_build_node *nodes = pool + 2 * (size_t)first;
+    const int base = 2 * first;
+    int next = 0;
+    struct Item { int lo, n, bit, parent, side; };
+    Item stack[40];
+    int sp = 0;
+    stack[sp++] = Item{0, count, 29 - 12, -1, 0};
+    while (sp > 0) {
+        Item it = stack[--sp];
+        // levels without a split are passed through (bvh.cpp:496-501); the leaf test precedes them at every level
+        bool leaf = false;
+        for (;;) {
+            if (it.bit == -1 || it.n < maxPrimsInNode) {
+                leaf = true;
+                break;
+            }
+            unsigned mask = 1u << it.bit;
+            if ((mp[it.lo] & mask) != (mp[it.lo + it.n - 1] & mask)) break;
+            --it.bit;
+        }
+        int me = next++;
+        if (it.parent >= 0) nodes[it.parent].child[it.side] = base + me;
+        pb2_build_node &nd = nodes[me];
+        if (leaf) {
+            float lo[3] = {PB2_INFINITY, PB2_INFINITY, PB2_INFINITY}, hi[3] = {-PB2_INFINITY, -PB2_INFINITY, -PB2_INFINITY};
+            for (int i = 0; i < it.n; ++i) {
+                const float *b = bounds + 6 * (size_t)sorted[first + it.lo + i];
+                for (int k = 0; k < 3; ++k) {
+                    lo[k] = fminf(lo[k], b[k]);
+                    hi[k] = fmaxf(hi[k], b[3 + k]);
+                }
+            }
+            for (int k = 0; k < 3; ++k) { nd.bmin[k] = lo[k]; nd.bmax[k] = hi[k]; }
+            nd.child[0] = nd.child[1] = -1;
+            nd.split_axis = 0;
+            nd.first_prim_offset = first + it.lo;
+            nd.n_primitives = it.n;
+            continue;
+        }
+        unsigned mask = 1u << it.bit;
+        int searchStart = 0, searchEnd = it.n - 1;   // bvh.cpp:503-517
+        while (searchStart + 1 != searchEnd) {
+            int mid = (searchStart + searchEnd) / 2;
+            if ((mp[it.lo + searchStart] & mask) == (mp[it.lo + mid] & mask)) searchStart = mid;
+            else searchEnd = mid;
+        }
+        int splitOffset = searchEnd;
+        nd.child[0] = nd.child[1] = -1;
+        nd.split_axis = it.bit % 3;
+        nd.first_prim_offset = 0;
+        nd.n_primitives = 0;
+        // the first subtree is emitted first: push the second one below it
+        stack[sp++] = Item{it.lo + splitOffset, it.n - splitOffset, it.bit - 1, me, 1};
+        stack[sp++] = Item{it.lo, splitOffset, it.bit - 1, me, 0};
+    }
+    for (int i = next - 1; i >= 0; --i) {   // children carry larger numbers than their parent
+        pb2_build_node &nd = nodes[i];
+        if (nd.n_primitives > 0) continue;
+        const pb2_build_node &a = pool[nd.child[0]], &b = pool[nd.child[1]];
+        for (int k = 0; k < 3; ++k) {
+            nd.bmin[k] = fminf(a.bmin[k], b.bmin[k]);
+            nd.bmax[k] = fmaxf(a.bmax[k], b.bmax[k]);
+        }
+    }
+    roots[t] = base;
+}
+}  // namespace
+
+extern "C" int pb2_hlbvh_treelets(const float *prim_bounds, int64_t n, int32_t max_prims_in_node, pb2_build_node *pool,
+                                  int32_t *ordered_prims, int32_t *treelet_roots, int32_t *n_treelets, double *device_ms) {
+    int rc = requireDevice();
+    if (rc) return rc;
+    if (!prim_bounds || !pool || !ordered_prims || !treelet_roots || !n_treelets) return setError(PB2_ERR_INVALID, "null argument");
+    if (n <= 0 || n >= (int64_t)1 << 30) return setError(PB2_ERR_INVALID, "primitive count out of range");
+    const int N = (int)n;
+    float *dBounds = nullptr;
+    unsigned *dBox = nullptr, *dCodes = nullptr, *dCodesSorted = nullptr;
+    int *dIndex = nullptr, *dSorted = nullptr, *dStart = nullptr, *dRoots = nullptr;
+    int2 *dTreelets = nullptr;
+    pb2_build_node *dPool = nullptr;
+    void *dTemp = nullptr;
+    size_t tempBytes = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::vector<int> start(4096);
+    std::vector<int2> treelets;
+    cudaError_t e = cudaSuccess;
+    auto step = [&](cudaError_t r) { if (e == cudaSuccess) e = r; return e == cudaSuccess; };
+    step(cudaMalloc((void **)&dBounds, (size_t)N * 6 * sizeof(float)));
+    step(cudaMalloc((void **)&dBox, 6 * sizeof(unsigned)));
+    step(cudaMalloc((void **)&dCodes, (size_t)N * sizeof(unsigned)));
+    step(cudaMalloc((void **)&dCodesSorted, (size_t)N * sizeof(unsigned)));
+    step(cudaMalloc((void **)&dIndex, (size_t)N * sizeof(int)));
+    step(cudaMalloc((void **)&dSorted, (size_t)N * sizeof(int)));
+    step(cudaMalloc((void **)&dStart, 4096 * sizeof(int)));
+    step(cudaMalloc((void **)&dRoots, 4096 * sizeof(int)));
+    step(cudaMalloc((void **)&dTreelets, 4096 * sizeof(int2)));
+    step(cudaMalloc((void **)&dPool, (size_t)2 * N * sizeof(pb2_build_node)));
+    if (e == cudaSuccess) step(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, dCodes, dCodesSorted, dIndex, dSorted, N, 0, 30));
+    step(cudaMalloc(&dTemp, tempBytes ? tempBytes : 1));
+    step(cudaEventCreate(&e0));
+    step(cudaEventCreate(&e1));
+    step(cudaMemcpy(dBounds, prim_bounds, (size_t)N * 6 * sizeof(float), cudaMemcpyHostToDevice));
+    if (e == cudaSuccess) {
+        const unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+        step(cudaMemcpy(dBox, init, sizeof(init), cudaMemcpyHostToDevice));
+        step(cudaMemset(dStart, 0xff, 4096 * sizeof(int)));
+        step(cudaEventRecord(e0));
+        const int threads = 256, blocks = (N + threads - 1) / threads;
+        k_hlbvh_centroid_bounds<<<std::min(blocks, 148 * 8), threads>>>(dBounds, N, dBox);
+        k_hlbvh_morton<<<blocks, threads>>>(dBounds, N, dBox, dCodes, dIndex);
+        // the reference's LSD radix sort over all 30 bits is a stable sort by the code; so is this one
+        step(cub::DeviceRadixSort::SortPairs(dTemp, tempBytes, dCodes, dCodesSorted, dIndex, dSorted, N, 0, 30));
+        k_hlbvh_treelet_starts<<<blocks, threads>>>(dCodesSorted, N, dStart);
+        step(cudaGetLastError());
+        step(cudaMemcpy(start.data(), dStart, 4096 * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    if (e == cudaSuccess) {
+        for (int v = 0; v < 4096; ++v)
+            if (start[v] >= 0) treelets.push_back(make_int2(start[v], 0));
+        for (size_t i = 0; i < treelets.size(); ++i) treelets[i].y = (i + 1 < treelets.size() ? treelets[i + 1].x : N) - treelets[i].x;
+        step(cudaMemcpy(dTreelets, treelets.data(), treelets.size() * sizeof(int2), cudaMemcpyHostToDevice));
+        k_hlbvh_emit<<<((int)treelets.size() + 31) / 32, 32>>>(dBounds, dCodesSorted, dSorted, dTreelets, (int)treelets.size(), max_prims_in_node, dPool, dRoots);
+        step(cudaGetLastError());
+        step(cudaEventRecord(e1));
+        step(cudaMemcpy(pool, dPool, (size_t)2 * N * sizeof(pb2_build_node), cudaMemcpyDeviceToHost));
+        step(cudaMemcpy(ordered_prims, dSorted, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost));
+        step(cudaMemcpy(treelet_roots, dRoots, treelets.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        float ms = 0;
+        if (e == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && device_ms) *device_ms = ms;
+        *n_treelets = (int32_t)treelets.size();
+    }
+    for (void *p : {(void *)dBounds, (void *)dBox, (void *)dCodes, (void *)dCodesSorted, (void *)dIndex, (void *)dSorted, (void *)dStart,
+                    (void *)dRoots, (void *)dTreelets, (void *)dPool, dTemp})
+        cudaFree(p);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (e != cudaSuccess) return setError(PB2_ERR_CUDA, std::string("pb2_hlbvh_treelets: ") + cudaGetErrorString(e));
+    return PB2_OK;
+}

@@ -78,8 +78,9 @@ def filter_scene_text(scene_dir, case):
     return text.replace("WorldBegin", pixel_filter + "\nWorldBegin", 1)
 
 
-def with_accelerator(text, split, maxprims):
-    return text.replace("WorldBegin", 'Accelerator "bvh" "string splitmethod" "%s" "integer maxnodeprims" [%d]\nWorldBegin' % (split, maxprims), 1)
+def with_accelerator(text, split, maxprims, device_build=False):
+    extra = ' "bool devicebuild" "true"' if device_build else ""
+    return text.replace("WorldBegin", 'Accelerator "bvh" "string splitmethod" "%s" "integer maxnodeprims" [%d]%s\nWorldBegin' % (split, maxprims, extra), 1)
 
 
 def random_mesh_scene_text(n_tris, seed):

@@ -17,7 +17,7 @@ import pytest
 
 import golden_cases as gc
 from conftest import GOLDEN, SCENES
-from test_oracle import load_scene, tessellated_sphere_scene
+from test_oracle import load_scene, same_bvh, tessellated_sphere_scene
 
 pytestmark = pytest.mark.gpu
 
@@ -139,6 +139,28 @@ def test_delta_lights_under_other_light_sampling_strategies(pb, checker, strateg
     frac, mean_rel = image_metrics(img, ref_img)
     assert frac >= 0.999 and mean_rel <= 1e-4
     assert abs(int(st.shadow_rays) - int(ref_st.shadow_rays)) <= ref_st.shadow_rays // 1000 + 2
+
+
+@pytest.mark.parametrize("name,maxprims", [("killeroo_like", 4), ("killeroo_like", 1), ("killeroo_like", 16), ("random20k", 4)])
+def test_device_hlbvh_build_equals_reference(pb, name, maxprims):
+    """pb2_hlbvh_treelets: Morton codes, the sort and the treelets built by CUDA kernels, the SAH top on the host, give the
+    reference's node array and primitive order (the fixtures tests/test_host.py checks the host build against)."""
+    g = np.load(os.path.join(GOLDEN, "hlbvh.npz"))
+    text = gc.random_mesh_scene_text(20000, 5) if name == "random20k" else open(os.path.join(SCENES, name + ".pbrt")).read()
+    hs = pb.HostScene.from_string(gc.with_accelerator(text, "hlbvh", maxprims, device_build=True))
+    assert same_bvh(hs.nodes(), g["nodes_%s_%d" % (name, maxprims)])
+    assert np.array_equal(hs.bvh_prims(0), g["prims_%s_%d" % (name, maxprims)])
+
+
+def test_device_hlbvh_build_equals_host_build_on_a_larger_mesh(pb):
+    text = gc.random_mesh_scene_text(200000, 9)
+    hs = pb.HostScene.from_string(gc.with_accelerator(text, "hlbvh", 4))
+    nodes, prims = hs.nodes().copy(), hs.bvh_prims(0).copy()
+    hs = pb.HostScene.from_string(gc.with_accelerator(text, "hlbvh", 4, device_build=True))
+    assert len(nodes) > 100000 and same_bvh(hs.nodes(), nodes) and np.array_equal(hs.bvh_prims(0), prims)
+    rays = gc.rays_for(pb, nodes, 2000, 3)
+    hits = hs.intersect(rays)
+    assert (hits["prim"] >= 0).sum() > 100
 
 
 def test_hlbvh_tree_traces_and_renders_like_the_sah_tree(pb):
