@@ -38,6 +38,8 @@ struct GraphicsState {
     ParamSet areaLightParams;
     std::string areaLight;
     bool reverseOrientation = false;
+    // floatTextures / spectrumTextures (api.cpp:160-165), constant-valued ones only; copied with the graphics state
+    ConstantTextures textures;
 };
 
 struct RenderOptions {
@@ -150,11 +152,11 @@ std::shared_ptr<Material> materialForShape(const ParamSet &shapeParams) {
     if (!graphicsState.currentMaterial) {
         // default material: matte Kd 0.5 (api.cpp:207-210)
         static ParamSet empty;
-        TextureParams mp(shapeParams, empty);
+        TextureParams mp(shapeParams, empty, &graphicsState.textures);
         return MakeMaterial("matte", mp);
     }
     if (shapeMaySetMaterialParameters(shapeParams)) {
-        TextureParams mp(shapeParams, graphicsState.currentMaterial->params);
+        TextureParams mp(shapeParams, graphicsState.currentMaterial->params, &graphicsState.textures);
         return MakeMaterial(graphicsState.currentMaterial->name, mp);
     }
     return graphicsState.currentMaterial->material;
@@ -303,7 +305,7 @@ void pbrtTransformEnd() {
 void pbrtMaterial(const std::string &name, const ParamSet &params) {
     if (!verifyWorld("Material")) return;
     static ParamSet empty;
-    TextureParams mp(empty, params);
+    TextureParams mp(empty, params, &graphicsState.textures);
     auto mi = std::make_shared<MaterialInstance>();
     mi->name = name;
     mi->params = params;
@@ -313,7 +315,7 @@ void pbrtMaterial(const std::string &name, const ParamSet &params) {
 void pbrtMakeNamedMaterial(const std::string &name, const ParamSet &params) {
     if (!verifyWorld("MakeNamedMaterial")) return;
     static ParamSet empty;
-    TextureParams mp(empty, params);
+    TextureParams mp(empty, params, &graphicsState.textures);
     std::string matName = mp.FindString("type");
     if (matName == "") {
         Error("No parameter string \"type\" found in MakeNamedMaterial");
@@ -337,6 +339,57 @@ void pbrtNamedMaterial(const std::string &name) {
         return;
     }
     graphicsState.currentMaterial = it->second;
+}
+// pbrtTexture (api.cpp:1189-1245) for the texture classes whose value is the same everywhere: "constant" (constant.cpp),
+// "scale" (scale.cpp:40-52: tex1 * tex2) and "mix" (mix.cpp:40-54: (1 - amount) * tex1 + amount * tex2) of constants.
+void pbrtTexture(const std::string &name, const std::string &type, const std::string &texname, const ParamSet &params) {
+    if (!verifyWorld("Texture")) return;
+    TextureParams tp(params, params, &graphicsState.textures);
+    const bool isFloat = type == "float", isSpectrum = type == "color" || type == "spectrum";
+    if (!isFloat && !isSpectrum) {
+        Error("Texture type \"%s\" unknown.", type.c_str());
+        return;
+    }
+    auto varying = [&](std::initializer_list<const char *> names) {
+        for (const char *n : names)
+            if (tp.IsVaryingTexture(n)) return true;
+        return false;
+    };
+    bool ok = false;
+    Float fv = 0;
+    Spectrum sv;
+    if (texname == "constant") {
+        ok = true;
+        if (isFloat) fv = params.FindOneFloat("value", 1.f);     // constant.cpp:40-48: plain values, not texture names
+        else sv = params.FindOneSpectrum("value", Spectrum(1.f));
+    } else if (texname == "scale" && !varying({"tex1", "tex2"})) {
+        ok = true;
+        if (isFloat) fv = tp.GetFloatTexture("tex1", 1.f) * tp.GetFloatTexture("tex2", 1.f);
+        else sv = tp.GetSpectrumTexture("tex1", Spectrum(1.f)) * tp.GetSpectrumTexture("tex2", Spectrum(1.f));
+    } else if (texname == "mix" && !varying({"tex1", "tex2", "amount"})) {
+        ok = true;
+        Float amt = tp.GetFloatTexture("amount", 0.5f);
+        if (isFloat) fv = (1 - amt) * tp.GetFloatTexture("tex1", 0.f) + amt * tp.GetFloatTexture("tex2", 1.f);
+        else {
+            Spectrum t1 = tp.GetSpectrumTexture("tex1", Spectrum(0.f)), t2 = tp.GetSpectrumTexture("tex2", Spectrum(1.f));
+            for (int c = 0; c < 3; ++c) sv.c[c] = (1 - amt) * t1.c[c] + amt * t2.c[c];
+        }
+    }
+    if (!ok) {
+        Error("Texture \"%s\" of class \"%s\" varies over the surface: outside the GPU path's scope (SURVEY.md §2 row 33); "
+              "parameters that name it keep their defaults", name.c_str(), texname.c_str());
+        return;
+    }
+    params.ReportUnused();
+    auto &floats = graphicsState.textures.floats;
+    auto &spectra = graphicsState.textures.spectra;
+    if (isFloat) {
+        if (floats.count(name)) Warning("Texture \"%s\" being redefined", name.c_str());
+        floats[name] = fv;
+    } else {
+        if (spectra.count(name)) Warning("Texture \"%s\" being redefined", name.c_str());
+        spectra[name] = sv;
+    }
 }
 // api.cpp:1302-1316 with MakeLight (api.cpp:727-754) for the delta lights in scope
 void pbrtLightSource(const std::string &name, const ParamSet &params) {
@@ -799,13 +852,16 @@ struct Parser {
             else if (tok == "ObjectEnd") pbrtObjectEnd();
             else if (tok == "ObjectInstance") pbrtObjectInstance(requireString());
             else if (tok == "LightSource") basic(pbrtLightSource);
-            else if (tok == "Texture" || tok == "MakeNamedMedium" || tok == "MediumInterface") {
+            else if (tok == "Texture") {
+                std::string name = requireString(), type = requireString(), texname = requireString();
+                pbrtTexture(name, type, texname, parseParams());
+            }
+            else if (tok == "MakeNamedMedium" || tok == "MediumInterface") {
                 // directives of the reference that lead outside this path (SURVEY.md §2 rows 15,33,42; §8 a19)
                 Error("%s:%d: directive \"%s\" is outside the GPU path's scope; skipped", cur().filename.c_str(), cur().line, tok.c_str());
                 std::string n;
                 if (tok != "MediumInterface") {
                     requireString();
-                    if (tok == "Texture") { requireString(); requireString(); }
                     parseParams();
                 } else {
                     requireString();

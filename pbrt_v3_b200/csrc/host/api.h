@@ -40,6 +40,7 @@ void pbrtWorldBegin(), pbrtWorldEnd();
 void pbrtAttributeBegin(), pbrtAttributeEnd(), pbrtTransformBegin(), pbrtTransformEnd();
 PluginDirective pbrtMaterial, pbrtMakeNamedMaterial, pbrtLightSource, pbrtAreaLightSource, pbrtShape;
 void pbrtNamedMaterial(const std::string &materialName);
+void pbrtTexture(const std::string &name, const std::string &type, const std::string &texname, const ParamSet &params);
 void pbrtObjectBegin(const std::string &objectName), pbrtObjectEnd(), pbrtObjectInstance(const std::string &objectName);
 void pbrtReverseOrientation();
 

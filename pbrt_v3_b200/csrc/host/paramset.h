@@ -111,12 +111,36 @@ class ParamSet {
 
 // TextureParams (src/core/paramset.h:142-190) restricted to constant textures: a material
 // parameter is looked up in the shape's parameters first, then in the material's.
+// Named textures whose value does not vary over a surface: "constant", and "scale" / "mix" of such (src/textures/
+// constant.h, scale.h, mix.h).  They are the Texture directives that stay inside this path; a material parameter that
+// names one is simply that value.
+struct ConstantTextures {
+    std::map<std::string, Float> floats;
+    std::map<std::string, Spectrum> spectra;
+};
 class TextureParams {
   public:
-    TextureParams(const ParamSet &geom, const ParamSet &mat) : geomParams(geom), materialParams(mat) {}
+    TextureParams(const ParamSet &geom, const ParamSet &mat, const ConstantTextures *tex = nullptr)
+        : geomParams(geom), materialParams(mat), textures(tex) {}
+    // the texture a parameter names (the shape's list first, paramset.cpp:649-655), or ""
+    std::string NamedTexture(const std::string &n) const {
+        std::string name = geomParams.FindTexture(n);
+        return name == "" ? materialParams.FindTexture(n) : name;
+    }
+    // true when the parameter names a texture that is not one of the constant ones (image maps, procedurals, unknown names)
+    bool IsVaryingTexture(const std::string &n) const {
+        std::string name = NamedTexture(n);
+        if (name == "") return false;
+        return !(textures && (textures->floats.count(name) || textures->spectra.count(name)));
+    }
     Spectrum GetSpectrumTexture(const std::string &n, const Spectrum &def, bool *isTexture = nullptr) const {
         if (isTexture) *isTexture = false;
-        if (geomParams.FindTexture(n) != "" || materialParams.FindTexture(n) != "") {
+        std::string name = NamedTexture(n);
+        if (name != "") {
+            if (textures) {
+                auto it = textures->spectra.find(name);
+                if (it != textures->spectra.end()) return it->second;
+            }
             if (isTexture) *isTexture = true;
             return def;
         }
@@ -125,7 +149,12 @@ class TextureParams {
     }
     Float GetFloatTexture(const std::string &n, Float def, bool *isTexture = nullptr) const {
         if (isTexture) *isTexture = false;
-        if (geomParams.FindTexture(n) != "" || materialParams.FindTexture(n) != "") {
+        std::string name = NamedTexture(n);
+        if (name != "") {
+            if (textures) {
+                auto it = textures->floats.find(name);
+                if (it != textures->floats.end()) return it->second;
+            }
             if (isTexture) *isTexture = true;
             return def;
         }
@@ -133,6 +162,15 @@ class TextureParams {
     }
     // GetFloatTextureOrNull (paramset.cpp:703-732) for constant values: false when neither parameter list has it
     bool GetFloatOrNull(const std::string &n, Float *value) const {
+        std::string name = NamedTexture(n);
+        if (name != "") {
+            auto it = textures ? textures->floats.find(name) : std::map<std::string, Float>::const_iterator();
+            if (textures && it != textures->floats.end()) {
+                *value = it->second;
+                return true;
+            }
+            return false;   // a varying texture: reported by the material's factory
+        }
         for (const ParamSet *ps : {&geomParams, &materialParams}) {
             const ParamSet::Item *it = ps->Find(ParamSet::Type::Float, n);
             if (it && !it->nums.empty()) {
@@ -148,6 +186,7 @@ class TextureParams {
     }
     void ReportUnused() const { materialParams.ReportUnused(); }
     const ParamSet &geomParams, &materialParams;
+    const ConstantTextures *textures;
 };
 
 }  // namespace pbrt

@@ -135,7 +135,7 @@ std::shared_ptr<DistantLight> CreateDistantLight(const Transform &light2world, c
 }
 static void rejectTextures(const TextureParams &mp, const char *what, std::initializer_list<const char *> names) {
     for (const char *n : names)
-        if (mp.geomParams.FindTexture(n) != "" || mp.materialParams.FindTexture(n) != "")
+        if (mp.IsVaryingTexture(n))
             Error("%s: textured parameter \"%s\" is outside the GPU path's scope (constant textures only, SURVEY.md §2 row 33); "
                   "using the default value", what, n);
 }

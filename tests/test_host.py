@@ -387,3 +387,43 @@ def test_quick_render_option(pb):
         pb.lib().pb2h_set_quick_render(0)
     hs = pb.HostScene.from_string(text)
     assert tuple(hs.film.contents.full_resolution) == (48, 32) and hs.params.contents.samples_per_pixel == 8
+
+
+def test_constant_valued_texture_directives(pb):
+    """Texture "..." "constant" / "scale" / "mix" of constants (pbrtTexture api.cpp:1189-1245, constant.cpp, scale.cpp,
+    mix.cpp) resolve to the value a material parameter naming them gets; textures that vary over the surface are reported."""
+    f32 = np.float32
+    text = """WorldBegin
+Texture "base" "spectrum" "constant" "rgb value" [.2 .4 .6]
+Texture "rough" "float" "constant" "float value" .25
+Texture "dim" "color" "scale" "texture tex1" "base" "rgb tex2" [.5 .5 2]
+Texture "blend" "spectrum" "mix" "texture tex1" "base" "rgb tex2" [1 1 1] "float amount" .25
+Texture "r2" "float" "mix" "texture tex1" "rough" "float tex2" 1 "texture amount" "rough"
+AttributeBegin
+  Texture "base" "spectrum" "constant" "rgb value" [9 9 9]
+AttributeEnd
+Material "plastic" "texture Kd" "dim" "texture Ks" "blend" "texture roughness" "r2"
+Shape "sphere"
+Material "matte" "texture Kd" "base"
+Shape "sphere" "float radius" 2
+Material "uber" "texture uroughness" "rough"
+Shape "sphere" "float radius" 3
+WorldEnd
+"""
+    before = pb.lib().pb2h_error_count()
+    hs = pb.HostScene.from_string(text)
+    assert pb.lib().pb2h_error_count() == before
+    d = hs.desc.contents
+    mats = [d.materials[i] for i in range(d.n_materials)]
+    plastic = [m for m in mats if m.type == pb.PB2_MAT_PLASTIC][0]
+    assert tuple(plastic.kd) == (f32(.2) * f32(.5), f32(.4) * f32(.5), f32(.6) * f32(2))
+    amt = f32(.25)
+    assert tuple(plastic.ks) == tuple((f32(1) - amt) * f32(v) + amt * f32(1) for v in (.2, .4, .6))
+    assert plastic.roughness == (f32(1) - amt) * amt + amt * f32(1)
+    matte = [m for m in mats if m.type == pb.PB2_MAT_MATTE and tuple(m.kd) != (.5, .5, .5)][0]
+    assert tuple(matte.kd) == (f32(.2), f32(.4), f32(.6))          # the redefinition inside the attribute block is gone again
+    uber = [m for m in mats if m.type == pb.PB2_MAT_UBER][0]
+    assert uber.uroughness == f32(.25) == uber.vroughness
+    hs = pb.HostScene.from_string('WorldBegin\nTexture "img" "spectrum" "imagemap" "string filename" "x.png"\n'
+                                  'Material "matte" "texture Kd" "img"\nShape "sphere"\nWorldEnd\n')
+    assert pb.lib().pb2h_error_count() >= before + 2                 # the directive and the parameter that names it
