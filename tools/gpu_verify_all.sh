@@ -6,6 +6,7 @@ for s in lights uber; do echo "== $s vs oracle"; python tools/gpu_check.py tests
 echo "== smoke"; python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 echo "== probes"; for i in 1 2; do PROBE_SPP=16 PROBE_TAG=c2_$i python tools/perf_probe.py 2>&1 | grep probe | tail -1; done
 PROBE_TAG=c4 python tools/perf_probe_instanced.py 2>&1 | tail -1
+python tools/hlbvh_probe.py 1000000 10000000 2>&1 | grep "hlbvh probe"
 echo "== bench"; timeout 900 python bench.py 2>/dev/null | tail -1 > gpurun_out/bench_n1.json
 python -c "
 import json; d=json.load(open('gpurun_out/bench_n1.json')); print(d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['frac'], d['roofline']['trace_share_of_step'], d['gpu_launches'], d['clocks'], d['cpu_baseline']['value'])"
