@@ -94,3 +94,26 @@ def random_mesh_scene_text(n_tris, seed):
             'AttributeBegin\nAreaLightSource "diffuse" "rgb L" [5 5 5]\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 2 1 0 2 0 1 2]\nAttributeEnd\n'
             'Shape "trianglemesh" "integer indices" [%s] "point P" [%s]\nWorldEnd\n'
             % (" ".join(map(str, idx)), " ".join("%.9g" % v for v in P.ravel())))
+
+
+# The reference's own end-to-end tests of this path (src/tests/analytic_scenes.cpp:68-248, 270-296, 54-66): furnace scenes
+# inside a unit sphere seen by a perspective camera at its centre, PathIntegrator depth 8, Halton 256 spp, 10 x 10 film;
+# the average pixel value must be 1 within 0.02.
+ANALYTIC_SCENES = {
+    "one_point_light": 'LightSource "point" "rgb I" [3.14159265358979 3.14159265358979 3.14159265358979]\n'
+                       'Material "matte" "rgb Kd" [.5 .5 .5]\n',
+    "four_point_lights": 'LightSource "point" "rgb I" [.785398163397448 .785398163397448 .785398163397448]\n' * 4
+                         + 'Material "matte" "rgb Kd" [.5 .5 .5]\n',
+    "emissive_sphere": 'Material "matte" "rgb Kd" [.5 .5 .5]\nAreaLightSource "diffuse" "rgb L" [.5 .5 .5]\n',
+    "uber_kd_kr": 'LightSource "point" "rgb I" [9.42477796076938 9.42477796076938 9.42477796076938]\n'
+                  'Material "uber" "rgb Kd" [.25 .25 .25] "rgb Ks" [0 0 0] "rgb Kr" [.5 .5 .5] "rgb Kt" [0 0 0] "float roughness" 0 '
+                  '"rgb opacity" [1 1 1] "float index" 1 "bool remaproughness" "false"\n',
+}
+ANALYTIC_EXPECTED, ANALYTIC_DELTA = 1.0, 0.02
+
+
+def analytic_scene_text(case):
+    return ('Camera "perspective" "float fov" 45 "float screenwindow" [-1 1 -1 1]\n'
+            'Film "image" "integer xresolution" 10 "integer yresolution" 10 "float diagonal" 1\n'
+            'Sampler "halton" "integer pixelsamples" 256\nIntegrator "path" "integer maxdepth" 8\nWorldBegin\n'
+            + ANALYTIC_SCENES[case] + 'ReverseOrientation\nShape "sphere" "float radius" 1\nWorldEnd\n')

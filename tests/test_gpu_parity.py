@@ -34,6 +34,19 @@ def image_metrics(got, want):
     return float((rel.max(axis=2) <= 0.01).mean()), float(rel.mean())
 
 
+@pytest.mark.parametrize("case", sorted(gc.ANALYTIC_SCENES))
+def test_reference_analytic_scenes_on_gpu(pb, checker, case):
+    """The reference's own end-to-end tests of the path (src/tests/analytic_scenes.cpp, Path / perspective / Halton 256):
+    the furnace scenes must average to radiance 1 within 0.02 - and match the CPU checker like every other scene."""
+    hs = pb.HostScene.from_string(gc.analytic_scene_text(case))
+    img, st = hs.render()
+    assert abs(float(img.mean()) - gc.ANALYTIC_EXPECTED) <= gc.ANALYTIC_DELTA, float(img.mean())
+    ref_img, _, ref_st = checker.scene(hs).render(n_threads=0)
+    frac, mean_rel = image_metrics(img, ref_img)
+    assert frac >= 0.99 and mean_rel <= 1e-4, (frac, mean_rel)
+    assert st.camera_rays == ref_st.camera_rays == 25600
+
+
 @pytest.mark.parametrize("case", sorted(gc.FILTER_CASES))
 def test_gpu_filters_match_reference_golden(pb, case):
     """Film::AddSample through the filter weight table on the device against the reference's image.  The device adds

@@ -98,6 +98,15 @@ def test_port_filters_match_compiled_reference_live(pb, port, reference):
         assert a.tobytes() == b.tobytes(), case
 
 
+@pytest.mark.parametrize("case", sorted(gc.ANALYTIC_SCENES))
+def test_reference_analytic_scenes(pb, port, case):
+    """The reference's RenderTest.RadianceMatches for Path / perspective / Halton (analytic_scenes.cpp): radiance 1 +- 0.02."""
+    hs = pb.HostScene.from_string(gc.analytic_scene_text(case))
+    img, _, _ = port.scene(hs).render(n_threads=0)
+    assert img.shape == (10, 10, 3)
+    assert abs(float(img.mean()) - gc.ANALYTIC_EXPECTED) <= gc.ANALYTIC_DELTA, float(img.mean())
+
+
 def test_low_discrepancy_golden(port):
     g = np.load(os.path.join(GOLDEN, "lowdiscrepancy.npz"))
     for b in (0, 1, 2, 3, 10, 50, 127, 500, 999):
