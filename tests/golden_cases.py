@@ -117,3 +117,54 @@ def analytic_scene_text(case):
             'Film "image" "integer xresolution" 10 "integer yresolution" 10 "float diagonal" 1\n'
             'Sampler "halton" "integer pixelsamples" 256\nIntegrator "path" "integer maxdepth" 8\nWorldBegin\n'
             + ANALYTIC_SCENES[case] + 'ReverseOrientation\nShape "sphere" "float radius" 1\nWorldEnd\n')
+
+
+def sphere_reintersect_case(pb, i, partial):
+    """One case of FullSphere.Reintersect / PartialSphere.Reintersect (src/tests/shapes.cpp:427-497): a sphere whose radius
+    spans eight decades, rays from far-away origins (coordinates up to 1e8) into its bounding box.  Returns (scene text, rays)."""
+    rng = np.random.RandomState(1000 + i)
+
+    def pexp(e=8):   # shapes.cpp:18-25: +- 10^[-e, e]
+        return (1 if rng.rand() < .5 else -1) * 10.0 ** rng.uniform(-e, e)
+    radius = abs(pexp(4))
+    zmin, zmax, phimax = -radius, radius, 360.0
+    if partial:
+        if rng.rand() >= .5:
+            zmin = rng.uniform(-radius, radius)
+        if rng.rand() >= .5:
+            zmax = rng.uniform(-radius, radius)
+        if rng.rand() >= .5:
+            phimax = rng.rand() * 360
+    text = ('Camera "perspective"\nFilm "image" "integer xresolution" [4] "integer yresolution" [4]\nWorldBegin\n'
+            'Shape "sphere" "float radius" %.9g "float zmin" %.9g "float zmax" %.9g "float phimax" %.9g\nWorldEnd\n' % (radius, zmin, zmax, phimax))
+    n = 400
+    rays = np.zeros(n, pb.RAY_DTYPE)
+    rays["o"] = np.array([[pexp() for _ in range(3)] for _ in range(n)], np.float32)
+    lo, hi = np.float32(min(zmin, zmax)), np.float32(max(zmin, zmax))
+    box_lo, box_hi = np.array([-radius, -radius, lo], np.float32), np.array([radius, radius, hi], np.float32)
+    target = (box_lo + rng.rand(n, 3).astype(np.float32) * (box_hi - box_lo)).astype(np.float32)
+    d = target - rays["o"]
+    norm = rng.rand(n) < .5
+    d[norm] /= np.linalg.norm(d[norm], axis=1, keepdims=True)
+    rays["d"] = d
+    rays["t_max"] = np.inf
+    return text, rays, rng
+
+
+def spawned_rays(pb, hits, rng):
+    """Interaction::SpawnRay (interaction.h:64-67, OffsetRayOrigin geometry.h:1440-1454) in a random direction on the
+    normal's side of every hit."""
+    n = len(hits)
+    w = rng.normal(size=(n, 3)).astype(np.float32)
+    w /= np.linalg.norm(w, axis=1, keepdims=True)
+    nrm, p, pe = hits["n"], hits["p"], hits["p_error"]
+    w[(w * nrm).sum(axis=1) < 0] *= -1                     # Faceforward(w, isect.n)
+    d = (np.abs(nrm) * pe).sum(axis=1, keepdims=True)
+    off = (d * nrm).astype(np.float32)
+    po = (p + off).astype(np.float32)
+    up, dn = off > 0, off < 0
+    po[up] = np.nextafter(po[up], np.float32(np.inf))
+    po[dn] = np.nextafter(po[dn], np.float32(-np.inf))
+    rays = np.zeros(n, pb.RAY_DTYPE)
+    rays["o"], rays["d"], rays["t_max"] = po, w, np.inf
+    return rays

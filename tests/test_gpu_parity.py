@@ -292,6 +292,27 @@ def test_stack_spill_of_the_two_child_kernel():
     assert out.returncode == 0 and "spill ok" in out.stdout, out.stdout + out.stderr
 
 
+@pytest.mark.parametrize("partial", [False, True])
+def test_sphere_spawned_rays_do_not_reintersect_on_gpu(pb, port, partial):
+    """FullSphere.Reintersect / PartialSphere.Reintersect (src/tests/shapes.cpp:427-497) through pb2_intersect / pb2_intersect_p,
+    and the hits themselves against the CPU checker."""
+    found = 0
+    for i in range(12):
+        text, rays, rng = gc.sphere_reintersect_case(pb, i, partial)
+        hs = pb.HostScene.from_string(text)
+        h = hs.intersect(rays)
+        want = port.scene(hs).intersect(rays)
+        assert np.array_equal(h["prim"], want["prim"]) and np.array_equal(gc.bits(h["t"]), gc.bits(want["t"]))
+        assert np.array_equal(gc.bits(h["p"]), gc.bits(want["p"])) and np.array_equal(gc.bits(h["p_error"]), gc.bits(want["p_error"]))
+        h = h[h["prim"] >= 0]
+        found += len(h)
+        if len(h) == 0:
+            continue
+        out = gc.spawned_rays(pb, h, rng)
+        assert (hs.intersect(out)["prim"] == -1).all() and not hs.intersect_p(out).any()
+    assert found > 300
+
+
 def test_watertight_on_gpu(pb):
     hs, verts = tessellated_sphere_scene(pb)
     rng = np.random.RandomState(1)

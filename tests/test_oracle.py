@@ -242,6 +242,28 @@ def test_spawned_rays_do_not_reintersect(pb, port):
         assert (sc.intersect(rays2[ok])["prim"] == -1).all()
 
 
+@pytest.mark.parametrize("partial", [False, True])
+def test_sphere_spawned_rays_do_not_reintersect(pb, port, partial):
+    """FullSphere.Reintersect / PartialSphere.Reintersect / ParialSphere.Normal (src/tests/shapes.cpp:427-497)."""
+    found = 0
+    for i in range(40):
+        text, rays, rng = gc.sphere_reintersect_case(pb, i, partial)
+        hs = pb.HostScene.from_string(text)
+        sc = port.scene(hs)
+        h = sc.intersect(rays)
+        h = h[h["prim"] >= 0]
+        found += len(h)
+        if len(h) == 0:
+            continue
+        # the normal is radial (ParialSphere.Normal)
+        pn = h["p"] / np.linalg.norm(h["p"], axis=1, keepdims=True)
+        nn = h["n"] / np.linalg.norm(h["n"], axis=1, keepdims=True)
+        assert np.allclose((pn * nn).sum(axis=1), 1, atol=1e-5)
+        out = gc.spawned_rays(pb, h, rng)
+        assert (sc.intersect(out)["prim"] == -1).all() and not sc.intersect_p(out).any()
+    assert found > 1000
+
+
 def test_empty_and_degenerate_inputs(pb, port):
     hs = gc.soup_scene(pb)
     sc = port.scene(hs)
