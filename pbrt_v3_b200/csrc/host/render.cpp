@@ -403,18 +403,19 @@ std::vector<uint8_t> toRGB8(const Float *rgb, int w, int h) {
     return out;
 }
 uint32_t crc32(const uint8_t *p, size_t n, uint32_t crc = 0) {
-    static uint32_t table[256];
-    static bool init = false;
-    if (!init) {
-        for (uint32_t i = 0; i < 256; ++i) {
-            uint32_t c = i;
-            for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1;
-            table[i] = c;
+    struct Table {
+        uint32_t v[256];
+        Table() {
+            for (uint32_t i = 0; i < 256; ++i) {
+                uint32_t c = i;
+                for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xedb88320u ^ (c >> 1) : c >> 1;
+                v[i] = c;
+            }
         }
-        init = true;
-    }
+    };
+    static const Table table;   // initialised once, thread-safe
     crc = ~crc;
-    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    for (size_t i = 0; i < n; ++i) crc = table.v[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
     return ~crc;
 }
 }  // namespace
