@@ -79,6 +79,10 @@ int pb2h_synth_soup(int64_t n_tris, uint64_t seed, float jitter, int xres, int y
     film.AddInt("yresolution", {yres});
     film.AddString("filename", "soup.pfm");
     pbrtFilm("image", film);
+    if (const char *pf = std::getenv("PB2_SOUP_FILTER")) {   // developer switch: the same workload under another reconstruction filter
+        ParamSet none;
+        pbrtPixelFilter(pf, none);
+    }
     ParamSet samp;
     samp.AddInt("pixelsamples", {spp});
     pbrtSampler("halton", samp);
