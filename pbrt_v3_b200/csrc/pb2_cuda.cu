@@ -7,6 +7,8 @@
 //   k_wf_gen / k_wf_trace* / k_wf_advance<>   the wavefront renderer (pb2_wavefront.cuh):
 //                             SamplerIntegrator::Render + PathIntegrator::Li + FilmTile::AddSample
 //   k_li_samples, k_halton_samples, k_light_distribution   parity / debug entry points
+//   k_hlbvh_centroid_bounds / k_hlbvh_morton / k_hlbvh_treelet_starts / k_hlbvh_emit   the O(n) stages of
+//                             BVHAccel::HLBVHBuild behind pb2_hlbvh_treelets (with cub's radix sort between them)
 //
 // Compile flags that matter for parity: -fmad=false (the reference has no FMA contraction),
 // default IEEE division and square root, no fast-math.
