@@ -365,6 +365,13 @@ def test_tile_partition_sums_to_the_full_film(pb):
         assert rays == st.camera_rays == 80 * 45 * 4
         assert np.allclose(sum(parts), full, rtol=1e-5, atol=1e-5)
         assert np.array_equal(sum(p[..., 3] for p in parts), full[..., 3])
+    # a filter wider than a pixel: samples of one rank's tiles reach into pixels of the other ranks' tiles, so the sum of
+    # the per-rank films (the NCCL reduce) is what merges them, as Film::MergeFilmTile merges overlapping tiles
+    hs = pb.HostScene.from_string(gc.filter_scene_text(SCENES, "gaussian").replace('"integer xresolution" [40]', '"integer xresolution" [72]'))
+    full, st = hs.render_rgbw()
+    parts = [hs.render_rgbw(hs.params_copy(tile_rank=r, tile_count=3))[0] for r in range(3)]
+    assert np.allclose(sum(parts), full, rtol=1e-4, atol=1e-5)
+    assert sum(int((p[..., 3] > 0).sum()) for p in parts) > int((full[..., 3] > 0).sum())   # the per-rank supports overlap
 
 
 def test_reference_shaped_api_and_cli(pb, tmp_path):
