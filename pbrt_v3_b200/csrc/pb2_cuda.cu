@@ -602,13 +602,31 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     else if (instancedTuned) trace = k_wf_trace<8, 8, 2, 32, true, true, 6, true>;
     else if (spheres && wideNodes && variant != 7) wideKernel(k_wf_trace_w<8, 8, 3, 16, 6, 1, 128, false, true, true>, 128, 16, false);
     else if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
-    else if (wideNodes && variant == 0) wideKernel(k_wf_trace_w<8, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);   // 56 registers: 9 blocks / SM
+    // LEAF_T = 1: a warp turns to its leaves as soon as one lane holds one (sweep 16 / 12 / 8 / 6 / 4 / 3 / 2 / 1 at
+    // 16 spp: 192.8 / 199.3 / 202.9 / 203.6 / 204.4 / 204.7 / 205.2 / 205.9 Msamples/s); 56 registers, 9 blocks / SM
+    else if (wideNodes && variant == 0) wideKernel(k_wf_trace_w<1, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
     else if (wideNodes && variant == 5) wideKernel(k_wf_trace_w<12, 8, 4, 16, 8>, 128, 16, false);
     else if (wideNodes && variant == 20) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1, 128, false, true>, 128, 16, false);
     else if (wideNodes && variant == 21) wideKernel(k_wf_trace_w<8, 8, 3, 16, 10, 1, 128, false, true>, 128, 16, false);
     else if (wideNodes && variant == 22) wideKernel(k_wf_trace_w<8, 8, 3, 12, 10, 1, 128, false, true>, 128, 12, false);
     else if (wideNodes && variant == 23) wideKernel(k_wf_trace_w<8, 8, 3, 16, 9, 2, 128, false, true>, 128, 16, false);
     else if (wideNodes && variant == 24) wideKernel(k_wf_trace_w<8, 8, 3, 16, 9, 1, 128, false, true>, 128, 16, false);   // branchy two-attempt pop
+    // threshold / unroll sweep around the default <8, 8, 4, 16, 9, 2> (kept for A/B probes)
+    else if (wideNodes && variant == 30) wideKernel(k_wf_trace_w<8, 8, 5, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 31) wideKernel(k_wf_trace_w<8, 8, 6, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 32) wideKernel(k_wf_trace_w<4, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 33) wideKernel(k_wf_trace_w<12, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 34) wideKernel(k_wf_trace_w<8, 4, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 35) wideKernel(k_wf_trace_w<8, 12, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 36) wideKernel(k_wf_trace_w<8, 8, 4, 16, 8, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 37) wideKernel(k_wf_trace_w<16, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 38) wideKernel(k_wf_trace_w<8, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);   // the previous default
+    else if (wideNodes && variant == 39) wideKernel(k_wf_trace_w<2, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 40) wideKernel(k_wf_trace_w<3, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 41) wideKernel(k_wf_trace_w<6, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 42) wideKernel(k_wf_trace_w<4, 8, 3, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 43) wideKernel(k_wf_trace_w<4, 10, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
+    else if (wideNodes && variant == 44) wideKernel(k_wf_trace_w<4, 6, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
     else if (wideNodes && variant == 15) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1>, 128, 16, false);   // scalar slab tests
     else if (wideNodes && variant == 8) wideKernel(k_wf_trace_w<8, 8, 2, 4, 8>, 128, 4, false);   // tests: forces the local-memory stack spill
     else if (wideNodes && variant == 9) wideKernel(k_wf_trace_w<8, 8, 3, 16, 1, 1, 1024, true>, 1024, 16, true);
