@@ -598,7 +598,11 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     // instanced scenes: the tuned 32-B-node kernel with the instance frame on its stack, as long as the
     // two levels fit the 64-entry stack; PB2_TRACE=14 keeps them on the plain kernel (tests compare both)
     const bool instancedTuned = instanced && variant != 14 && scene->bvhDepth + 3 + scene->instDepth <= 64;
-    if (instancedTuned && wideNodes && variant != 7) wideKernel(k_wf_trace_w<8, 8, 3, 16, 6, 1, 128, false, true, true, true>, 128, 16, false);
+    if (instancedTuned && wideNodes && variant == 50) wideKernel(k_wf_trace_w<1, 8, 3, 16, 6, 1, 128, false, true, true, true>, 128, 16, false);   // probes
+    else if (instancedTuned && wideNodes && variant == 51) wideKernel(k_wf_trace_w<1, 8, 4, 16, 6, 2, 128, false, true, true, true>, 128, 16, false);
+    else if (!instancedTuned && spheres && wideNodes && variant == 50) wideKernel(k_wf_trace_w<1, 8, 3, 16, 6, 1, 128, false, true, true>, 128, 16, false);
+    else if (!instancedTuned && spheres && wideNodes && variant == 51) wideKernel(k_wf_trace_w<1, 8, 4, 16, 6, 2, 128, false, true, true>, 128, 16, false);
+    else if (instancedTuned && wideNodes && variant != 7) wideKernel(k_wf_trace_w<8, 8, 3, 16, 6, 1, 128, false, true, true, true>, 128, 16, false);
     else if (instancedTuned) trace = k_wf_trace<8, 8, 2, 32, true, true, 6, true>;
     else if (spheres && wideNodes && variant != 7) wideKernel(k_wf_trace_w<8, 8, 3, 16, 6, 1, 128, false, true, true>, 128, 16, false);
     else if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
