@@ -107,6 +107,16 @@ def test_reference_analytic_scenes(pb, port, case):
     assert abs(float(img.mean()) - gc.ANALYTIC_EXPECTED) <= gc.ANALYTIC_DELTA, float(img.mean())
 
 
+@pytest.mark.parametrize("name,maxprims", [("killeroo_like", 4), ("killeroo_like", 1), ("killeroo_like", 16), ("random20k", 4)])
+def test_port_hlbvh_matches_reference_golden(pb, port, name, maxprims):
+    """BVHAccel with splitmethod "hlbvh" (bvh.cpp:404-638): node array and primitive order of the compiled reference."""
+    g = np.load(os.path.join(GOLDEN, "hlbvh.npz"))
+    text = gc.random_mesh_scene_text(20000, 5) if name == "random20k" else open(os.path.join(SCENES, name + ".pbrt")).read()
+    hs = pb.HostScene.from_string(gc.with_accelerator(text, "hlbvh", maxprims))
+    nodes, prims = port.scene(hs, max_prims_in_node=maxprims, split_method=1).bvh()
+    assert same_bvh(nodes, g["nodes_%s_%d" % (name, maxprims)]) and np.array_equal(prims, g["prims_%s_%d" % (name, maxprims)])
+
+
 def test_low_discrepancy_golden(port):
     g = np.load(os.path.join(GOLDEN, "lowdiscrepancy.npz"))
     for b in (0, 1, 2, 3, 10, 50, 127, 500, 999):
