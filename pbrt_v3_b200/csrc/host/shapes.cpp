@@ -424,8 +424,15 @@ int plyTypeSize(const std::string &t) {
     if (t == "double" || t == "float64") return 8;
     return 0;
 }
-double plyReadBinary(const unsigned char *&ptr, const std::string &t) {
+double plyReadBinary(const unsigned char *&src, const std::string &t, bool bigEndian) {
     double v = 0;
+    unsigned char swapped[8];
+    const unsigned char *ptr = src;
+    const int size = plyTypeSize(t);
+    if (bigEndian && size > 1) {
+        for (int i = 0; i < size; ++i) swapped[i] = src[size - 1 - i];
+        ptr = swapped;
+    }
     if (t == "char" || t == "int8") v = *(const int8_t *)ptr;
     else if (t == "uchar" || t == "uint8") v = *(const uint8_t *)ptr;
     else if (t == "short" || t == "int16") { int16_t x; std::memcpy(&x, ptr, 2); v = x; }
@@ -434,7 +441,7 @@ double plyReadBinary(const unsigned char *&ptr, const std::string &t) {
     else if (t == "uint" || t == "uint32") { uint32_t x; std::memcpy(&x, ptr, 4); v = x; }
     else if (t == "float" || t == "float32") { float x; std::memcpy(&x, ptr, 4); v = x; }
     else if (t == "double" || t == "float64") { double x; std::memcpy(&x, ptr, 8); v = x; }
-    ptr += plyTypeSize(t);
+    src += size;
     return v;
 }
 }  // namespace
@@ -472,7 +479,7 @@ bool ReadPLY(const std::string &filename, std::vector<Point3f> *P, std::vector<N
         Error("\"%s\" is not a PLY file", filename.c_str());
         return false;
     }
-    bool ascii = false;
+    bool ascii = false, bigEndian = false;
     struct Element { std::string name; long count; std::vector<PlyProp> props; };
     std::vector<Element> elems;
     while (pos < data.size()) {
@@ -482,6 +489,7 @@ bool ReadPLY(const std::string &filename, std::vector<Point3f> *P, std::vector<N
         if (std::sscanf(line.c_str(), "format %63s", a) == 1) {
             std::string fmt(a);
             if (fmt == "ascii") ascii = true;
+            else if (fmt == "binary_big_endian") bigEndian = true;
             else if (fmt != "binary_little_endian") {
                 Error("PLY format \"%s\" not supported", a);
                 return false;
@@ -523,20 +531,20 @@ bool ReadPLY(const std::string &filename, std::vector<Point3f> *P, std::vector<N
             for (size_t k = 0; k < e.props.size(); ++k) {
                 const PlyProp &pr = e.props[k];
                 if (pr.countType.empty()) {
-                    vals[k] = ascii ? nextAscii() : plyReadBinary(ptr, pr.type);
+                    vals[k] = ascii ? nextAscii() : plyReadBinary(ptr, pr.type, bigEndian);
                 } else {
-                    int cnt = (int)(ascii ? nextAscii() : plyReadBinary(ptr, pr.countType));
+                    int cnt = (int)(ascii ? nextAscii() : plyReadBinary(ptr, pr.countType, bigEndian));
                     std::vector<int> lst(cnt);
-                    for (int j = 0; j < cnt; ++j) lst[j] = (int)(ascii ? nextAscii() : plyReadBinary(ptr, pr.type));
+                    for (int j = 0; j < cnt; ++j) lst[j] = (int)(ascii ? nextAscii() : plyReadBinary(ptr, pr.type, bigEndian));
                     if (isFace && (pr.name == "vertex_indices" || pr.name == "vertex_index")) {
                         // plymesh.cpp:123-156: triangles as-is, quads split (0,1,2) (2,3,0)... via a fan
                         if (cnt == 3) {
                             indices->insert(indices->end(), {lst[0], lst[1], lst[2]});
                         } else if (cnt == 4) {
                             indices->insert(indices->end(), {lst[0], lst[1], lst[2], lst[3], lst[0], lst[2]});
-                        } else if (cnt > 4) {
-                            Error("plymesh: only triangles and quads are supported");
-                            return false;
+                        } else {
+                            // plymesh.cpp:112-116
+                            Warning("plymesh: Ignoring face with %i vertices (only triangles and quads are supported!)", cnt);
                         }
                     }
                 }

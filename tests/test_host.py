@@ -427,3 +427,47 @@ WorldEnd
     hs = pb.HostScene.from_string('WorldBegin\nTexture "img" "spectrum" "imagemap" "string filename" "x.png"\n'
                                   'Material "matte" "texture Kd" "img"\nShape "sphere"\nWorldEnd\n')
     assert pb.lib().pb2h_error_count() >= before + 2                 # the directive and the parameter that names it
+
+
+def test_plymesh_reader(pb, tmp_path):
+    """Shape "plymesh" (src/shapes/plymesh.cpp): ASCII, binary little- and big-endian files with normals and uv give the
+    same mesh as the equivalent "trianglemesh"; a quad becomes (0,1,2),(3,0,2) (plymesh.cpp:137-145), a pentagon is skipped
+    with a warning (plymesh.cpp:112-116)."""
+    import struct
+    rng = np.random.RandomState(4)
+    P = rng.rand(6, 3).astype(np.float32)
+    N = rng.normal(size=(6, 3)).astype(np.float32)
+    UV = rng.rand(6, 2).astype(np.float32)
+    faces = [[0, 1, 2], [2, 3, 4, 5], [0, 1, 2, 3, 4], [5, 1, 3]]
+    want_idx = [0, 1, 2, 2, 3, 4, 5, 2, 4, 5, 1, 3]
+    header = ("ply\nformat %s 1.0\ncomment test\nelement vertex 6\nproperty float x\nproperty float y\nproperty float z\n"
+              "property float nx\nproperty float ny\nproperty float nz\nproperty float u\nproperty float v\n"
+              "element face 4\nproperty list uchar int vertex_indices\nend_header\n")
+    files = {}
+    body = "".join(" ".join("%.9g" % x for x in np.concatenate([P[i], N[i], UV[i]])) + "\n" for i in range(6))
+    body += "".join("%d %s\n" % (len(f), " ".join(map(str, f))) for f in faces)
+    files["ascii"] = (header % "ascii" + body).encode()
+    for fmt, e in (("binary_little_endian", "<"), ("binary_big_endian", ">")):
+        b = b"".join(struct.pack(e + "8f", *np.concatenate([P[i], N[i], UV[i]])) for i in range(6))
+        b += b"".join(struct.pack(e + "B%di" % len(f), len(f), *f) for f in faces)
+        files[fmt] = (header % fmt).encode() + b
+    scene = ('Camera "perspective"\nFilm "image" "integer xresolution" [4] "integer yresolution" [4]\nWorldBegin\nTranslate .1 .2 .3\n%s\nWorldEnd\n')
+    tri = 'Shape "trianglemesh" "integer indices" [%s] "point P" [%s] "normal N" [%s] "float uv" [%s]' % (
+        " ".join(map(str, want_idx)), " ".join("%.9g" % x for x in P.ravel()), " ".join("%.9g" % x for x in N.ravel()),
+        " ".join("%.9g" % x for x in UV.ravel()))
+    hs = pb.HostScene.from_string(scene % tri)
+    d = hs.desc.contents
+
+    def arrays(d):
+        nv = d.n_vertices
+        return (np.ctypeslib.as_array(d.P, shape=(nv, 3)).copy(), np.ctypeslib.as_array(d.N, shape=(nv, 3)).copy(),
+                np.ctypeslib.as_array(d.UV, shape=(nv, 2)).copy(), np.ctypeslib.as_array(d.tri_index, shape=(d.n_tris * 3,)).copy())
+    want = arrays(d)
+    assert d.n_tris == 4
+    for fmt, data in files.items():
+        path = tmp_path / (fmt + ".ply")
+        path.write_bytes(data)
+        hs = pb.HostScene.from_string(scene % ('Shape "plymesh" "string filename" "%s"' % path))
+        got = arrays(hs.desc.contents)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), fmt
