@@ -471,3 +471,91 @@ def test_plymesh_reader(pb, tmp_path):
         got = arrays(hs.desc.contents)
         for a, b in zip(got, want):
             assert np.array_equal(a, b), fmt
+
+
+def _mesh_world_points(hs):
+    d = hs.desc.contents
+    return np.ctypeslib.as_array(d.P, shape=(d.n_vertices, 3)).copy()
+
+
+def test_include_named_materials_and_coordinate_systems(pb, tmp_path):
+    """Include (parser.cpp:1013-1024, relative to the including file), MakeNamedMaterial / NamedMaterial (api.cpp:1247-1300),
+    CoordinateSystem / CoordSysTransform (api.cpp:842-868), Transform / ConcatTransform (column-major, api.cpp:796-840)."""
+    f32 = np.float32
+    inc = tmp_path / "geometry.pbrt"
+    inc.write_text('NamedMaterial "shiny"\nShape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]\n')
+    main = tmp_path / "main.pbrt"
+    main.write_text("""Camera "perspective"
+Film "image" "integer xresolution" [4] "integer yresolution" [4]
+WorldBegin
+MakeNamedMaterial "shiny" "string type" "plastic" "rgb Kd" [.1 .2 .3] "float roughness" .07
+MakeNamedMaterial "dull" "string type" "matte" "rgb Kd" [.9 .8 .7]
+Translate 1 2 3
+CoordinateSystem "shifted"
+AttributeBegin
+  Scale 2 2 2
+  Include "geometry.pbrt"
+AttributeEnd
+AttributeBegin
+  Identity
+  Transform [0 1 0 0  -1 0 0 0  0 0 1 0  5 6 7 1]
+  ConcatTransform [1 0 0 0  0 1 0 0  0 0 1 0  0 0 10 1]
+  NamedMaterial "dull"
+  Shape "trianglemesh" "integer indices" [0 1 2] "point P" [1 0 0 0 1 0 0 0 1]
+AttributeEnd
+TransformBegin
+  Identity
+  CoordSysTransform "shifted"
+  NamedMaterial "nosuch"
+  Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0]
+TransformEnd
+WorldEnd
+""")
+    before = pb.lib().pb2h_error_count()
+    hs = pb.HostScene.from_file(str(main))
+    assert pb.lib().pb2h_error_count() == before + 1          # only the unknown named material (api.cpp:1290-1293)
+    P = _mesh_world_points(hs)
+    # mesh 1: Translate(1,2,3) * Scale(2)
+    assert np.array_equal(P[0:3], np.array([[1, 2, 3], [3, 2, 3], [1, 4, 3]], f32))
+    # mesh 2: column-major matrix = rotation by 90 degrees about z then translation (5,6,7); ConcatTransform adds z + 10 first
+    assert np.array_equal(P[3:6], np.array([[5, 7, 17], [4, 6, 17], [5, 6, 18]], f32))
+    # mesh 3: the named coordinate system is the CTM at the time it was named
+    assert np.array_equal(P[6:9], np.array([[1, 2, 3], [2, 2, 3], [1, 3, 3]], f32))
+    d = hs.desc.contents
+    pm = np.ctypeslib.as_array(d.prim_material, shape=(d.n_prims,))
+    kinds = [(d.materials[m].type, tuple(np.float32(x) for x in d.materials[m].kd)) for m in pm]
+    assert kinds[0] == (pb.PB2_MAT_PLASTIC, (f32(.1), f32(.2), f32(.3))) and kinds[1] == (pb.PB2_MAT_MATTE, (f32(.9), f32(.8), f32(.7)))
+    # an unknown NamedMaterial leaves the current material in place: at world level that is the default matte (api.cpp:207-210)
+    assert kinds[2] == (pb.PB2_MAT_MATTE, (f32(.5), f32(.5), f32(.5)))
+
+
+def test_camera_film_sampler_and_integrator_parameters(pb):
+    """CreatePerspectiveCamera (perspective.cpp:246-290), CreateFilm (film.cpp:213-252), CreateHaltonSampler (halton.cpp:133-140),
+    CreatePathIntegrator (path.cpp:190-213): every parameter reaches the ABI structs with the reference's defaults and rules."""
+    f32 = np.float32
+
+    def parse(camera="", film="", sampler="", integrator=""):
+        return pb.HostScene.from_string('Camera "perspective" %s\nFilm "image" "integer xresolution" [30] "integer yresolution" [20] %s\n'
+                                        'Sampler "halton" %s\nIntegrator "path" %s\nWorldBegin\nShape "sphere"\nWorldEnd\n' % (camera, film, sampler, integrator))
+    hs = parse()
+    cam, film, pp = hs.camera.contents, hs.film.contents, hs.params.contents
+    assert tuple(cam.screen_window) == (-1.5, 1.5, -1, 1) and cam.fov == 90 and cam.lens_radius == 0 and cam.focal_distance == f32(1e6)
+    assert (cam.shutter_open, cam.shutter_close) == (0, 1)
+    assert tuple(film.cropped_pixel_bounds) == (0, 0, 30, 20) and film.scale == 1 and np.isinf(film.max_sample_luminance)
+    assert pp.samples_per_pixel == 16 and pp.sample_at_pixel_center == 0 and pp.max_depth == 5 and pp.rr_threshold == 1
+    assert tuple(pp.pixel_bounds) == (0, 0, 30, 20)
+    hs = parse(camera='"float frameaspectratio" .5 "float halffov" 20 "float lensradius" .1 "float focaldistance" 3 "float shutteropen" .8 "float shutterclose" .2')
+    cam = hs.camera.contents
+    assert tuple(cam.screen_window) == (-1, 1, -2, 2) and cam.fov == 40 and cam.lens_radius == f32(.1) and cam.focal_distance == 3
+    assert (cam.shutter_open, cam.shutter_close) == (f32(.2), f32(.8))           # swapped with a warning (perspective.cpp:253-257)
+    hs = parse(camera='"float screenwindow" [-2 1 -.5 .25] "float fov" 30')
+    assert tuple(hs.camera.contents.screen_window) == (-2, 1, f32(-.5), f32(.25))
+    hs = parse(film='"float cropwindow" [.1 .5 .25 .75] "float scale" 2.5 "float maxsampleluminance" 10',
+               sampler='"integer pixelsamples" 3 "bool samplepixelcenter" "true"',
+               integrator='"integer maxdepth" 9 "float rrthreshold" .25 "integer pixelbounds" [2 9 1 12]')
+    film, pp = hs.film.contents, hs.params.contents
+    assert tuple(film.cropped_pixel_bounds) == (3, 5, 15, 15)                     # ceil(res * crop) (film.cpp:55-60)
+    assert film.scale == 2.5 and film.max_sample_luminance == 10
+    assert pp.samples_per_pixel == 3 and pp.sample_at_pixel_center == 1 and pp.max_depth == 9 and pp.rr_threshold == f32(.25)
+    # pixelbounds is given as x0 x1 y0 y1 and intersected with the camera's sample bounds (path.cpp:195-207)
+    assert tuple(pp.pixel_bounds) == (3, 5, 9, 12)

@@ -11,7 +11,7 @@ import pytest
 import golden_cases as gc
 from conftest import GOLDEN, SCENES
 
-SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass", "lights"]
+SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass", "lights", "params"]
 
 
 def load_scene(pb, name):
