@@ -21,7 +21,7 @@ from test_oracle import load_scene, same_bvh, tessellated_sphere_scene
 
 pytestmark = pytest.mark.gpu
 
-SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass", "lights"]
+SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass", "lights", "params"]
 
 
 def li_ok(got, want):
@@ -418,10 +418,3 @@ def test_single_shape_intersect_goes_to_the_device(pb):
     h = hs.intersect(rays)
     assert h["prim"][0] == 0 and h["prim"][1] == -1 and h["t"][0] == 1.0
     assert np.allclose(h["b"][0], (0.5, 0.25, 0.25)) and np.allclose(h["p"][0], (0.25, 0.25, 0))
-
-
-# Fixtures added after the round's last run on GPU hardware: the same checks, reported but not yet allowed to fail the suite.
-@pytest.mark.xfail(reason="fixture added after the last hardware run of round 1; promote to SCENE_CASES once seen green", strict=False)
-@pytest.mark.parametrize("name", ["params"])
-def test_gpu_matches_reference_golden_new_fixtures(pb, name):
-    check_scene_against_golden(pb, name)
