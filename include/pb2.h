@@ -90,8 +90,9 @@ typedef struct pb2_material {
     float roughness;
     int32_t remap_roughness;
     int32_t pad[2];
-    /* MirrorMaterial (src/materials/mirror.cpp:45-58): kr.  GlassMaterial (src/materials/glass.cpp:45-93)
-     * with uroughness == vroughness == 0: kr, kt, eta (the "index"/"eta" parameter); rough glass is refused.
+    /* MirrorMaterial (src/materials/mirror.cpp:45-58): kr.  GlassMaterial (src/materials/glass.cpp:45-93): kr, kt, eta
+     * (the "index"/"eta" parameter), uroughness, vroughness, remap_roughness; both roughnesses zero = one FresnelSpecular,
+     * otherwise the MicrofacetReflection + MicrofacetTransmission pair.
      * SubstrateMaterial (src/materials/substrate.cpp:45-65): kd, ks, uroughness, vroughness, remap_roughness. */
     float kr[3];
     float kt[3];
