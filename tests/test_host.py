@@ -559,3 +559,23 @@ def test_camera_film_sampler_and_integrator_parameters(pb):
     assert pp.samples_per_pixel == 3 and pp.sample_at_pixel_center == 1 and pp.max_depth == 9 and pp.rr_threshold == f32(.25)
     # pixelbounds is given as x0 x1 y0 y1 and intersected with the camera's sample bounds (path.cpp:195-207)
     assert tuple(pp.pixel_bounds) == (3, 5, 9, 12)
+
+
+@pytest.mark.parametrize("header,world,renders", [
+    ('Sampler "sobol" "integer pixelsamples" 4', '', False), ('Camera "orthographic"', '', False), ('Integrator "bdpt"', '', False),
+    ('Accelerator "kdtree"', 'Shape "sphere"', True), ('PixelFilter "lanczos"', 'Shape "sphere"', True),
+    ('', 'Shape "cylinder"', True), ('', 'LightSource "goniometric"\nShape "sphere"', True),
+    ('', 'MakeNamedMedium "fog" "string type" "homogeneous"\nShape "sphere"', True), ('', 'ActiveTransform StartTime\nShape "sphere"', True)])
+def test_plugins_outside_the_scope_are_reported(pb, header, world, renders):
+    """Every plugin name or directive of the reference that this path does not implement produces an Error() - never a
+    silent substitute.  Without a sampler, camera or integrator there is nothing to render (api.cpp:1662-1714 returns no
+    integrator either); the others continue with the reported fallback or without the skipped directive."""
+    before = pb.lib().pb2h_error_count()
+    text = "%s\nWorldBegin\n%s\nWorldEnd\n" % (header, world)
+    if renders:
+        hs = pb.HostScene.from_string(text)
+        assert hs.params.contents.samples_per_pixel == 16
+    else:
+        with pytest.raises(RuntimeError):
+            pb.HostScene.from_string(text)
+    assert pb.lib().pb2h_error_count() > before
