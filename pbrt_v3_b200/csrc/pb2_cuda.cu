@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "device/pb2_path.cuh"
+#include "device/pb2_wide4.cuh"
 #include "host/core.h"  // pbrt::RNG for the Halton permutation table
 #include "pb2.h"
 
@@ -1351,6 +1352,86 @@ int pb2_light_distribution(pb2_scene *scene, const float *points_xyz, int64_t n,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- four-child records: host-side check (pb2_wide4.cuh)
+// Not part of the ABI: replays BVHAccel::Intersect's traversal (bvh.cpp:662-700) over the 32-byte nodes and the traversal
+// of the four-child records over the same tree, with the slab test the kernels use, and returns the sequence of primitive
+// numbers each of them tests.  A primitive is stood in for by its bounding box (prim_bounds: n x 6, by primitive number; a
+// box hit shrinks tMax to its entry distance), which is all the traversal order depends on.  Runs on the host.
+extern "C" int pb2_debug_wide4_sequences(const pb2_bvh_node *nodes, int64_t n_nodes, const int32_t *bvh_prims, const float *prim_bounds,
+                                         const float *rays_od, int64_t n_rays, int32_t max_len, int32_t *seq_binary,
+                                         int32_t *seq_wide4, int32_t *len_binary, int32_t *len_wide4) {
+    if (!nodes || n_nodes <= 0 || !bvh_prims || !prim_bounds || !rays_od) return PB2_ERR_INVALID;
+    const std::vector<float4> recs = buildWide4Records(nodes, n_nodes);
+    for (int64_t i = 0; i < n_rays; ++i) {
+        const float *rd = rays_od + 6 * i;
+        const DRaySetup r = setupRay(mk3(rd[0], rd[1], rd[2]), mk3(rd[3], rd[4], rd[5]));
+        auto leafTests = [&](int32_t first, int32_t count, float *tMax, int32_t *seq, int32_t *len) {
+            for (int32_t j = first; j < first + count; ++j) {
+                const int32_t prim = bvh_prims[j];
+                if (*len < max_len) seq[*len] = prim;
+                ++*len;
+                const float *b = prim_bounds + 6 * (size_t)prim;
+                float t;
+                if (slabTestT(b[0], b[1], b[2], b[3], b[4], b[5], r, *tMax, &t) && t > 0) *tMax = t;
+            }
+        };
+        {   // the reference's loop over the linear nodes
+            float tMax = PB2_INFINITY;
+            int32_t *seq = seq_binary + (size_t)i * max_len, len = 0, stack[64], sp = 0, cur = 0;
+            for (;;) {
+                const pb2_bvh_node &n = nodes[cur];
+                float t;
+                if (slabTestT(n.bmin[0], n.bmin[1], n.bmin[2], n.bmax[0], n.bmax[1], n.bmax[2], r, tMax, &t)) {
+                    if (n.n_prims > 0) {
+                        leafTests(n.offset, n.n_prims, &tMax, seq, &len);
+                        if (sp == 0) break;
+                        cur = stack[--sp];
+                    } else {
+                        const int neg = n.axis == 0 ? r.neg0 : (n.axis == 1 ? r.neg1 : r.neg2);
+                        if (neg) { stack[sp++] = cur + 1; cur = n.offset; }
+                        else { stack[sp++] = n.offset; cur = cur + 1; }
+                    }
+                } else {
+                    if (sp == 0) break;
+                    cur = stack[--sp];
+                }
+            }
+            len_binary[i] = len;
+        }
+        {   // four-child records
+            float tMax = PB2_INFINITY;
+            int32_t *seq = seq_wide4 + (size_t)i * max_len, len = 0, sp = 0;
+            struct Entry { uint32_t ref; float tMin; } stack[3 * 64];
+            float t;
+            const pb2_bvh_node &root = nodes[0];
+            bool have = slabTestT(root.bmin[0], root.bmin[1], root.bmin[2], root.bmax[0], root.bmax[1], root.bmax[2], r, tMax, &t);
+            uint32_t cur = 0;   // record of the root
+            while (have) {
+                if (cur & WIDE_LEAF) {
+                    leafTests((int32_t)(cur & WIDE_LEAF_OFFSET_MASK), (int32_t)((cur >> WIDE_LEAF_COUNT_SHIFT) & 0xf) + 1, &tMax, seq, &len);
+                    have = false;
+                } else {
+                    uint32_t refs[4];
+                    float tMins[4];
+                    const int n = wide4Visit(&recs[8 * (size_t)cur], r, tMax, refs, tMins);
+                    for (int k = n - 1; k >= 1; --k) stack[sp++] = Entry{refs[k], tMins[k]};
+                    have = n > 0;
+                    if (have) cur = refs[0];
+                }
+                while (!have && sp > 0) {
+                    const Entry e = stack[--sp];
+                    if (e.tMin < tMax) {   // the deferred child's box against the tMax of this moment
+                        cur = e.ref;
+                        have = true;
+                    }
+                }
+            }
+            len_wide4[i] = len;
+        }
+    }
+    return PB2_OK;
+}
 
 // ---------------------------------------------------------------- HLBVH treelets on the device (bvh.cpp:404-539)
 namespace {

@@ -579,3 +579,37 @@ def test_plugins_outside_the_scope_are_reported(pb, header, world, renders):
         with pytest.raises(RuntimeError):
             pb.HostScene.from_string(text)
     assert pb.lib().pb2h_error_count() > before
+
+
+def test_wide4_records_keep_the_reference_order(pb):
+    """Groundwork for the next trace kernel (pbrt_v3_b200/csrc/device/pb2_wide4.cuh): the binary BVH collapsed into four-child
+    records and traversed near-first per collapsed level tests the same primitives in the same order as BVHAccel::Intersect's
+    loop (bvh.cpp:662-700).  Host-only check with the kernels' slab test; primitives are stood in for by their boxes."""
+    import ctypes as C
+    L = pb.lib()
+    fn = L.pb2_debug_wide4_sequences
+    fn.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32] + [C.c_void_p] * 4
+    fn.restype = C.c_int
+    for maker in (lambda: pb.HostScene.soup(4000, seed=11, jitter=0.25, xres=16, yres=16, spp=1),
+                  lambda: pb.HostScene.from_string(gc.with_accelerator(gc.random_mesh_scene_text(3000, 3), "sah", 1)),
+                  lambda: pb.HostScene.from_string(gc.with_accelerator(gc.random_mesh_scene_text(5, 3), "sah", 16))):
+        hs = maker()
+        d = hs.desc.contents
+        nodes, prims = np.ascontiguousarray(hs.nodes()), np.ascontiguousarray(hs.bvh_prims(0))
+        P = np.ctypeslib.as_array(d.P, shape=(d.n_vertices, 3))
+        idx = np.ctypeslib.as_array(d.tri_index, shape=(d.n_tris, 3))
+        tri = P[idx][np.ctypeslib.as_array(d.prim_index, shape=(d.n_prims,))]
+        bounds = np.ascontiguousarray(np.concatenate([tri.min(axis=1), tri.max(axis=1)], 1), np.float32)
+        n = 3000
+        rays = gc.rays_for(pb, nodes, n, 2)
+        rng = np.random.RandomState(3)
+        target = tri[rng.randint(0, len(tri), n)].mean(axis=1)
+        aimed = (target - rays["o"]).astype(np.float32)
+        od = np.ascontiguousarray(np.concatenate([rays["o"], np.where((np.arange(n) < n // 20)[:, None], rays["d"], aimed)], 1), np.float32)
+        max_len = 512
+        sb, sw = np.zeros((n, max_len), np.int32), np.zeros((n, max_len), np.int32)
+        lb, lw = np.zeros(n, np.int32), np.zeros(n, np.int32)
+        assert fn(pb.ptr(nodes), len(nodes), pb.ptr(prims), pb.ptr(bounds), pb.ptr(od), n, max_len, pb.ptr(sb), pb.ptr(sw), pb.ptr(lb), pb.ptr(lw)) == 0
+        assert np.array_equal(lb, lw) and lb.max() <= max_len
+        assert np.array_equal(sb, sw)
+        assert lb.sum() > n // 2                  # leaves were reached (several per ray on the dense soup)
