@@ -28,9 +28,9 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 6   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc;
+#define PB2_ABI_VERSION 7   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc;
                              * 5: uber / metal fields in pb2_material (128 bytes); 6: point / spot / distant lights
-                             * (pb2_light.type, pb2_scene_desc.delta_lights) */
+                             * (pb2_light.type, pb2_scene_desc.delta_lights); 7: pb2_trace_wavefront, kernel-selector flags */
 
 typedef enum pb2_status {
     PB2_OK = 0,
@@ -250,6 +250,12 @@ typedef struct pb2_path_params {
 /* Trace with the kernel that reads the 32-byte LinearBVHNode array directly instead of the derived
  * two-child records (same results; kept selectable so both kernels stay under test). */
 #define PB2_FLAG_LINEAR_NODES 2
+/* Trace with the kernel over the two-child records instead of the default four-child records (same results). */
+#define PB2_FLAG_WIDE2 4
+/* Trace with the one-thread-per-ray kernel (BVHAccel::Intersect as written) instead of the persistent-warp kernels. */
+#define PB2_FLAG_PLAIN_TRACE 8
+/* Give the record kernels 4 instead of 16 shared-memory stack entries per lane (tests: exercises the spill path). */
+#define PB2_FLAG_SMALL_STACK 16
 
 typedef struct pb2_ray {
     float o[3];
@@ -319,6 +325,23 @@ int pb2_render_path(pb2_scene *scene, const pb2_camera *camera, const pb2_film_d
 int pb2_render_path_device(pb2_scene *scene, const pb2_camera *camera, const pb2_film_desc *film,
                            const pb2_path_params *params, float *film_rgbw_device, int clear,
                            void *stream, pb2_stats *stats);
+
+/* The traversal kernel of the RENDER path over a batch of rays (parity / debug entry point).  pb2_intersect[_p] run
+ * BVHAccel::Intersect[P] one thread per ray as the reference writes it; the renderer traces with persistent-warp
+ * kernels over derived node records (`flags`: the PB2_FLAG_* kernel selectors of pb2_path_params.flags).  This call puts
+ * the rays into path contexts exactly as the renderer does, launches the kernel the renderer would launch for this scene
+ * and these flags, and returns the raw records it leaves in the contexts.  any_hit[i] != 0 (may be NULL): ray i is
+ * traced as a shadow ray (Scene::IntersectP, early exit), otherwise as a path ray (Scene::Intersect).  HOST pointers. */
+typedef struct pb2_wf_hit {
+    int32_t found;   /* 0 = miss, 1 = hit, 2 + i = hit inside instance i (path rays) */
+    int32_t leaf;    /* position of the hit primitive in BVHAccel::primitives order (path rays), -1 = none */
+    int32_t prim;    /* its scene-order primitive number, -1 = miss / shadow ray */
+    float t;         /* ray.tMax after the traversal */
+    float b[3];      /* barycentrics of the closest hit (sphere: phi, 0, 0) */
+    int32_t listed;  /* 1 = the kernel queued the context for shading, 2 = for the light step (exactly one of them) */
+} pb2_wf_hit;
+int pb2_trace_wavefront(pb2_scene *scene, const pb2_ray *rays, const uint8_t *any_hit, int64_t n, int32_t flags,
+                        pb2_wf_hit *out);
 
 /* PathIntegrator::Li for explicit (pixel, sample number) pairs, after the NaN/negative/infinite
  * guard of integrator.cpp:294-315: out_rgb gets 3 floats per sample, out_pfilm 2 floats

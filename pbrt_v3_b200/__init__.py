@@ -27,7 +27,7 @@ PB2_OK, PB2_ERR_NO_DEVICE, PB2_ERR_CUDA, PB2_ERR_INVALID, PB2_ERR_UNSUPPORTED, P
 PB2_PRIM_TRIANGLE, PB2_PRIM_SPHERE, PB2_PRIM_INSTANCE = 0, 1, 2
 PB2_FILTER_BOX, PB2_FILTER_GAUSSIAN, PB2_FILTER_MITCHELL, PB2_FILTER_SINC, PB2_FILTER_TRIANGLE = 0, 1, 2, 3, 4
 PB2_MAT_NONE, PB2_MAT_MATTE, PB2_MAT_PLASTIC, PB2_MAT_MIRROR, PB2_MAT_GLASS, PB2_MAT_SUBSTRATE, PB2_MAT_METAL, PB2_MAT_UBER = range(8)
-PB2_ABI_VERSION = 6   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
+PB2_ABI_VERSION = 7   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
 PB2_LIGHTDIST_UNIFORM, PB2_LIGHTDIST_POWER, PB2_LIGHTDIST_SPATIAL = 0, 1, 2
 PB2_LIGHT_AREA, PB2_LIGHT_POINT, PB2_LIGHT_SPOT, PB2_LIGHT_DISTANT = 0, 1, 2, 3
 
@@ -121,6 +121,11 @@ class Hit(C.Structure):
                 ("uv", C.c_float * 2)]
 
 
+class WfHit(C.Structure):
+    _fields_ = [("found", C.c_int32), ("leaf", C.c_int32), ("prim", C.c_int32), ("t", C.c_float), ("b", C.c_float * 3),
+                ("listed", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("camera_rays", C.c_uint64), ("regular_rays", C.c_uint64), ("shadow_rays", C.c_uint64),
                 ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64), ("kernel_launches", C.c_uint64),
@@ -131,8 +136,12 @@ RAY_DTYPE = np.dtype([("o", np.float32, 3), ("d", np.float32, 3), ("t_max", np.f
 HIT_DTYPE = np.dtype([("prim", np.int32), ("t", np.float32), ("b", np.float32, 3), ("p", np.float32, 3),
                       ("p_error", np.float32, 3), ("n", np.float32, 3), ("ns", np.float32, 3),
                       ("dpdu", np.float32, 3), ("uv", np.float32, 2)])
+WFHIT_DTYPE = np.dtype([("found", np.int32), ("leaf", np.int32), ("prim", np.int32), ("t", np.float32), ("b", np.float32, 3),
+                        ("listed", np.int32)])
+PB2_FLAG_COUNT_TRAVERSAL, PB2_FLAG_LINEAR_NODES, PB2_FLAG_WIDE2, PB2_FLAG_PLAIN_TRACE, PB2_FLAG_SMALL_STACK = 1, 2, 4, 8, 16
 NODE_DTYPE = np.dtype([("bmin", np.float32, 3), ("bmax", np.float32, 3), ("offset", np.int32),
                        ("n_prims", np.uint16), ("axis", np.uint8), ("pad", np.uint8)])
+assert WFHIT_DTYPE.itemsize == C.sizeof(WfHit)
 assert RAY_DTYPE.itemsize == C.sizeof(Ray) and HIT_DTYPE.itemsize == C.sizeof(Hit) and NODE_DTYPE.itemsize == 32
 
 
@@ -160,6 +169,7 @@ def lib():
     L.pb2_scene_destroy.argtypes = [vp]
     L.pb2_intersect.argtypes = [vp, vp, C.c_int64, vp]
     L.pb2_intersect_p.argtypes = [vp, vp, C.c_int64, vp]
+    L.pb2_trace_wavefront.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
     L.pb2_render_path.argtypes = [vp, C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), vp, C.POINTER(Stats)]
     L.pb2_render_path_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), vp,
                                          C.c_int, vp, C.POINTER(Stats)]
@@ -360,6 +370,16 @@ class HostScene:
         occ = np.zeros(len(rays), np.uint8)
         check(self.L.pb2_intersect_p(dev, ptr(rays), len(rays), ptr(occ)))
         return occ
+
+    def trace_wavefront(self, rays, any_hit=None, flags=0):
+        """The render path's traversal kernel over a ray batch (pb2_trace_wavefront): raw (found, leaf, prim, t, b) records."""
+        dev = self.device_scene()
+        rays = np.ascontiguousarray(rays, RAY_DTYPE)
+        out = np.zeros(len(rays), WFHIT_DTYPE)
+        if any_hit is not None:
+            any_hit = np.ascontiguousarray(any_hit, np.uint8)
+        check(self.L.pb2_trace_wavefront(dev, ptr(rays), ptr(any_hit), len(rays), flags, ptr(out)))
+        return out
 
     def li_samples(self, pixel_xy, sample_num, params=None):
         dev = self.device_scene()

@@ -11,6 +11,8 @@
 //              only child is the root.  One fetch tests both children's boxes, so the render kernel
 //              makes half the dependent memory round trips of the 32-B layout; every box is still
 //              tested exactly once per ray, with the verdict the reference reaches (see k_wf_trace_w).
+//   wide4      two levels of the tree per record: one 128-B record per interior node of every second level with the
+//              boxes of its four grandchildren (device/pb2_wide4.cuh) - what the default trace kernel walks.
 //   leafPrims  one 48-B record per primitive IN BVH ORDER (= BVHAccel::primitives order):
 //              float4 a = (p0.xyz, primNumber), b = (p1.xyz, flags),
 //              c = (p2.xyz, area-light number or -1 | sphereIndex for a sphere);
@@ -41,7 +43,6 @@ enum : uint32_t {
     WIDE_LEAF_COUNT_SHIFT = 27,
     WIDE_LEAF_OFFSET_MASK = (1u << 27) - 1,
     WIDE_SINGLE = 4u,         // meta: the record has only child 0 (the pseudo node above the root)
-    WIDE_TOP = 0x40000000u,   // child reference inside wideTop: bits 0-23 index into wideTop
     WIDE_MAX_PRIMS = 1u << 27,   // 134 M primitives (config 5 has 50 M)
     WIDE_MAX_LEAF = 16u,         // primitives per leaf (the reference's default maxnodeprims is 4)
 };
@@ -61,6 +62,7 @@ struct DInstance {
     int lone;       // root < 0: leaf record of the object's only primitive
     int identity;   // Transform::IsIdentity(): the interaction is then not transformed (primitive.cpp:85-86)
     int wroot;      // two-child records: the pseudo record whose only child is the object BVH's root, or -1
+    int wroot4;     // four-child records: the record of the object BVH's root
 };
 
 // A delta light as its constructor leaves it (point.h:52, spot.cpp:43-50, distant.cpp:43-46), derived from pb2_delta_light at upload
@@ -75,8 +77,7 @@ struct DDeltaLight {
 struct DScene {
     const float4 *nodes;
     const float4 *wide;       // two-child nodes (below), nullptr when the scene exceeds their limits
-    const float4 *wideTop;    // the first nTop of them in breadth-first order, child references into this table
-    int nTop;                 //   carry WIDE_TOP; a trace kernel may keep the table in shared memory
+    const float4 *wide4;      // four-child records (pb2_wide4.cuh), nullptr under the same condition
     const float4 *leafPrims;
     const float4 *lightRecs;
     int64_t nNodes, nPrims, nTris;

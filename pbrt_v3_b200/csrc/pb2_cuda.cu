@@ -429,6 +429,47 @@ __global__ void k_li_samples(DScene sc, DRenderParams rp, const int32_t *pixelXY
     }
 }
 
+// pb2_trace_wavefront: rays -> path contexts of the wavefront pool (state + ray, what the trace kernels read) ...
+__global__ void k_wf_debug_fill(WfPool pool, const pb2_ray *rays, const uint8_t *anyHit, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        for (int q = 0; q < WQ_COUNT; ++q) pool.counts[q] = 0;
+        pool.counts[WQ_TRACE0] = (unsigned)n;
+    }
+    if (i >= n) return;
+    WfCtx &cx = pool.ctx[i];
+    cx.ln.state = (anyHit && anyHit[i]) ? LS_SHADOW : LS_PATH;
+    cx.ln.ray.o = mk3(rays[i].o[0], rays[i].o[1], rays[i].o[2]);
+    cx.ln.ray.d = mk3(rays[i].d[0], rays[i].d[1], rays[i].d[2]);
+    cx.ln.ray.tMax = rays[i].t_max;
+    cx.hit = make_float4(__int_as_float(-1), 0.f, 0.f, 0.f);
+    cx.tHit = 0.f;
+    cx.found = -1;
+    pool.queue[WQ_TRACE0][i] = i;
+}
+// ... and the records the trace kernel left in them -> pb2_wf_hit
+__global__ void k_wf_debug_read(DScene sc, WfPool pool, int n, pb2_wf_hit *out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const WfCtx &cx = pool.ctx[i];
+    pb2_wf_hit h;
+    h.found = cx.found;
+    h.t = cx.tHit;
+    h.leaf = __float_as_int(cx.hit.x);
+    h.b[0] = cx.hit.y; h.b[1] = cx.hit.z; h.b[2] = cx.hit.w;
+    h.prim = (cx.found > 0 && h.leaf >= 0) ? asInt(ldg4(&sc.leafPrims[3 * (size_t)h.leaf]).w) : -1;
+    h.listed = 0;
+    out[i] = h;
+}
+__global__ void k_wf_debug_lists(WfPool pool, pb2_wf_hit *out) {
+    // which list the kernel appended each context to: 1 = shade list (path rays), 2 = light list (shadow rays)
+    unsigned ns = pool.counts[WQ_SHADE], nl = pool.counts[WQ_LIGHT];
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < ns + nl; i += gridDim.x * blockDim.x) {
+        int c = i < ns ? pool.queue[WQ_SHADE][i] : pool.queue[WQ_LIGHT][i - ns];
+        atomicAdd(&out[c].listed, i < ns ? 1 : 2);
+    }
+}
+
 __global__ void k_halton_samples(DHalton h, const int32_t *pixelXY, const int64_t *sampleNum, const int32_t *dim, int64_t n,
                                  float *out) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -551,15 +592,81 @@ static int validateRenderArgs(const pb2_scene *scene, const pb2_camera *cam, con
 typedef void (*TraceKernel)(DScene, WfPool, int);
 typedef void (*AdvanceKernel)(DScene, DRenderParams, WfPool, int, int, int, float4 *, unsigned long long *);
 
-// Host driver of the wavefront rounds (see pb2_wavefront.cuh).
-static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *film, cudaStream_t stream, int flags,
-                           bool timeTrace, unsigned long long *launches, double *traceMs) {
-    const bool countTraversal = (flags & PB2_FLAG_COUNT_TRAVERSAL) != 0;
-    const bool wideNodes = scene->d.wide != nullptr && !(flags & PB2_FLAG_LINEAR_NODES);
-    // 4 M contexts (1 GiB) measured best on 1920x1080: 1 M -> 160, 2 M -> 174, 4 M -> 180 Msamples/s
-    static const int maxCapacity = envInt("PB2_POOL", 1 << 22);
-    long long want = std::min<long long>(maxCapacity, std::max<long long>(rp.nWorkItems, 1024));
-    int capacity = (int)((want + 255) / 256 * 256);
+// Which traversal kernel a scene is traced with (pb2_wavefront.cuh), and its launch shape.
+//   default                   k_wf_trace_w<4>: persistent warps over the four-child records
+//   PB2_FLAG_WIDE2            k_wf_trace_w<2>: the same over the two-child records
+//   PB2_FLAG_LINEAR_NODES     k_wf_trace: the same over the reference's 32-B LinearBVHNode array; also the fallback for
+//                             scenes beyond the record limits (2^27 primitives, 16 per leaf)
+//   PB2_FLAG_PLAIN_TRACE /    k_wf_trace_plain: one thread per ray, BVHAccel::Intersect as written (the counting form
+//   PB2_FLAG_COUNT_TRAVERSAL  also returns node / primitive counters)
+//   PB2_FLAG_SMALL_STACK      4 instead of 16 shared-memory stack entries per lane (tests: forces the local-memory spill)
+struct TraceLaunch {
+    TraceKernel fn = nullptr;
+    int block = 128;
+    size_t smem = 0;
+    int grid = 0;          // persistent kernels: SMs x resident blocks; 0 = one thread per list entry (plain kernels)
+    const char *name = "";
+};
+
+static int selectTraceKernel(const pb2_scene *scene, int flags, TraceLaunch *out) {
+    TraceLaunch t;
+    const bool spheres = scene->d.spheres != nullptr;
+    const bool instanced = scene->d.instances != nullptr;
+    const bool records = scene->d.wide4 != nullptr && !(flags & PB2_FLAG_LINEAR_NODES);
+    const bool small = (flags & PB2_FLAG_SMALL_STACK) != 0;
+    int sdepth = 0;
+    // the two levels of an instanced scene must fit the 64-entry stack of the 32-B-node kernel
+    const bool linearFits = !instanced || scene->bvhDepth + 3 + scene->instDepth <= 64;
+    if (flags & PB2_FLAG_COUNT_TRAVERSAL) { t.fn = k_wf_trace_plain<true>; t.name = "k_wf_trace_plain<count>"; }
+    else if ((flags & PB2_FLAG_PLAIN_TRACE) || (!records && !linearFits)) { t.fn = k_wf_trace_plain<false>; t.name = "k_wf_trace_plain"; }
+    else if (records && !(flags & PB2_FLAG_WIDE2)) {
+        t.name = "k_wf_trace_w<4>";
+        sdepth = small ? 4 : 16;
+        if (instanced) t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 5, true, true> : k_wf_trace_w<4, 1, 8, 4, 16, 5, true, true>;
+        else if (spheres) t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 5, true> : k_wf_trace_w<4, 1, 8, 4, 16, 5, true>;
+        else t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 7> : k_wf_trace_w<4, 1, 8, 4, 16, 7>;
+    } else if (records) {
+        // LEAF_T = 1: a warp turns to its leaves as soon as one lane holds one (sweep 16 / 12 / 8 / 6 / 4 / 3 / 2 / 1 at
+        // 16 spp: 192.8 / 199.3 / 202.9 / 203.6 / 204.4 / 204.7 / 205.2 / 205.9 Msamples/s); 56 registers, 9 blocks / SM
+        t.name = "k_wf_trace_w<2>";
+        sdepth = small ? 4 : 16;
+        if (instanced) t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 6, true, true> : k_wf_trace_w<2, 1, 8, 4, 16, 6, true, true>;
+        else if (spheres) t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 6, true> : k_wf_trace_w<2, 1, 8, 4, 16, 6, true>;
+        else t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 9> : k_wf_trace_w<2, 1, 8, 4, 16, 9>;
+    } else {
+        t.name = "k_wf_trace";
+        if (instanced) t.fn = k_wf_trace<8, 8, 2, 32, true, true, 6, true>;
+        else if (spheres) t.fn = k_wf_trace<8, 8, 2, 32, true, true, 6>;
+        else if (scene->bvhDepth > 32) t.fn = k_wf_trace<12, 8, 4, 32, true, false, 8>;
+        else t.fn = k_wf_trace<12, 8, 4, 32, false, false, 8>;
+    }
+    if (t.name[10] == 'p') {   // k_wf_trace_plain: one thread per list entry, no stack in shared memory
+        *out = t;
+        return PB2_OK;
+    }
+    // the record kernels take their stack as dynamic shared memory
+    if (sdepth > 0) {
+        t.smem = (size_t)sdepth * t.block * sizeof(int2);
+        CUDA_TRY(cudaFuncSetAttribute(t.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+    }
+    int blocksPerSM = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, t.fn, t.block, t.smem));
+    // ask for exactly the shared-memory carve-out the resident blocks need; the rest stays L1
+    cudaFuncAttributes fa;
+    CUDA_TRY(cudaFuncGetAttributes(&fa, t.fn));
+    size_t need = (size_t)blocksPerSM * (fa.sharedSizeBytes + t.smem + 1024);
+    int pct = (int)std::min<size_t>(100, (need * 100 + 233471) / 233472);
+    CUDA_TRY(cudaFuncSetAttribute(t.fn, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    static const int verbose = envInt("PB2_VERBOSE", 0);
+    if (verbose)
+        fprintf(stderr, "pb2: trace kernel %s: %d regs, %zu B smem, %d blocks/SM, carve-out %d %%, BVH depth %d\n", t.name, fa.numRegs,
+                fa.sharedSizeBytes + t.smem, blocksPerSM, pct, scene->bvhDepth);
+    t.grid = g_numSMs * std::max(1, blocksPerSM);
+    *out = t;
+    return PB2_OK;
+}
+
+static int ensurePool(pb2_scene *scene, int capacity) {
     if (scene->wfCapacity < capacity) {
         if (scene->wfCtx) cudaFree(scene->wfCtx);
         if (scene->wfQueues) cudaFree(scene->wfQueues);
@@ -568,111 +675,40 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         scene->wfCapacity = 0;
         CUDA_TRY(cudaMalloc(&scene->wfCtx, (size_t)capacity * sizeof(WfCtx)));
         CUDA_TRY(cudaMalloc((void **)&scene->wfQueues, (size_t)capacity * 6 * sizeof(int)));
-        if (!scene->wfCounts) CUDA_TRY(cudaMalloc((void **)&scene->wfCounts, WQ_COUNT * sizeof(unsigned)));
-        if (!scene->wfHostCounts) CUDA_TRY(cudaMallocHost((void **)&scene->wfHostCounts, (WQ_COUNT + 2) * sizeof(unsigned long long)));
         scene->wfCapacity = capacity;
     }
+    if (!scene->wfCounts) CUDA_TRY(cudaMalloc((void **)&scene->wfCounts, WQ_COUNT * sizeof(unsigned)));
+    if (!scene->wfHostCounts) CUDA_TRY(cudaMallocHost((void **)&scene->wfHostCounts, (WQ_COUNT + 2) * sizeof(unsigned long long)));
+    return PB2_OK;
+}
+
+static WfPool poolOf(const pb2_scene *scene, int capacity) {
     WfPool pool;
     pool.capacity = capacity;
     pool.ctx = (WfCtx *)scene->wfCtx;
     for (int q = 0; q < 6; ++q) pool.queue[q] = scene->wfQueues + (size_t)q * scene->wfCapacity;
     pool.counts = scene->wfCounts;
+    pool.ctr = scene->counters;
+    return pool;
+}
 
-    // kernel selection: triangle scenes take the two-child-record kernel (any BVH depth); scenes with
-    // spheres, or beyond the record limits, the 32-B-node kernel (shared-memory stack of 32, local
-    // spill beyond).  PB2_TRACE selects tuning variants for experiments.
+// Host driver of the wavefront rounds (see pb2_wavefront.cuh).
+static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *film, cudaStream_t stream, int flags,
+                           bool timeTrace, unsigned long long *launches, double *traceMs) {
+    // 4 M contexts (1 GiB) measured best on 1920x1080: 1 M -> 160, 2 M -> 174, 4 M -> 180 Msamples/s
+    static const int maxCapacity = envInt("PB2_POOL", 1 << 22);
+    long long want = std::min<long long>(maxCapacity, std::max<long long>(rp.nWorkItems, 1024));
+    int capacity = (int)((want + 255) / 256 * 256);
+    int rc = ensurePool(scene, capacity);
+    if (rc) return rc;
+    WfPool pool = poolOf(scene, capacity);
+    TraceLaunch trace;
+    if ((rc = selectTraceKernel(scene, flags, &trace))) return rc;
     const bool spheres = scene->d.spheres != nullptr;
-    // scenes with object instances (TransformedPrimitive, two BVH levels) are traced by the plain
-    // one-thread-per-ray kernel for now; the tuned kernels know triangles and spheres only
-    const bool instanced = scene->d.instances != nullptr;
-    static const int variant = envInt("PB2_TRACE", 0);
-    TraceKernel trace;
-    int traceBlock = 128, traceDynStack = 0;
-    bool traceTop = false;
-    size_t traceSmem = 0;
-    auto wideKernel = [&](TraceKernel k, int block, int sdepth, bool top) {
-        trace = k;
-        traceBlock = block;
-        traceDynStack = sdepth;
-        traceTop = top;
-    };
-    // instanced scenes: the tuned 32-B-node kernel with the instance frame on its stack, as long as the
-    // two levels fit the 64-entry stack; PB2_TRACE=14 keeps them on the plain kernel (tests compare both)
-    const bool instancedTuned = instanced && variant != 14 && scene->bvhDepth + 3 + scene->instDepth <= 64;
-    if (instancedTuned && wideNodes && variant == 50) wideKernel(k_wf_trace_w<1, 8, 3, 16, 6, 1, 128, false, true, true, true>, 128, 16, false);   // probes
-    else if (instancedTuned && wideNodes && variant == 51) wideKernel(k_wf_trace_w<1, 8, 4, 16, 6, 2, 128, false, true, true, true>, 128, 16, false);
-    else if (!instancedTuned && spheres && wideNodes && variant == 50) wideKernel(k_wf_trace_w<1, 8, 3, 16, 6, 1, 128, false, true, true>, 128, 16, false);
-    else if (!instancedTuned && spheres && wideNodes && variant == 51) wideKernel(k_wf_trace_w<1, 8, 4, 16, 6, 2, 128, false, true, true>, 128, 16, false);
-    else if (instancedTuned && wideNodes && variant != 7) wideKernel(k_wf_trace_w<8, 8, 3, 16, 6, 1, 128, false, true, true, true>, 128, 16, false);
-    else if (instancedTuned) trace = k_wf_trace<8, 8, 2, 32, true, true, 6, true>;
-    else if (spheres && wideNodes && variant != 7) wideKernel(k_wf_trace_w<8, 8, 3, 16, 6, 1, 128, false, true, true>, 128, 16, false);
-    else if (spheres) trace = k_wf_trace<8, 8, 2, 32, true, true, 6>;
-    // LEAF_T = 1: a warp turns to its leaves as soon as one lane holds one (sweep 16 / 12 / 8 / 6 / 4 / 3 / 2 / 1 at
-    // 16 spp: 192.8 / 199.3 / 202.9 / 203.6 / 204.4 / 204.7 / 205.2 / 205.9 Msamples/s); 56 registers, 9 blocks / SM
-    else if (wideNodes && variant == 0) wideKernel(k_wf_trace_w<1, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 5) wideKernel(k_wf_trace_w<12, 8, 4, 16, 8>, 128, 16, false);
-    else if (wideNodes && variant == 20) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 21) wideKernel(k_wf_trace_w<8, 8, 3, 16, 10, 1, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 22) wideKernel(k_wf_trace_w<8, 8, 3, 12, 10, 1, 128, false, true>, 128, 12, false);
-    else if (wideNodes && variant == 23) wideKernel(k_wf_trace_w<8, 8, 3, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 24) wideKernel(k_wf_trace_w<8, 8, 3, 16, 9, 1, 128, false, true>, 128, 16, false);   // branchy two-attempt pop
-    // threshold / unroll sweep around the default <8, 8, 4, 16, 9, 2> (kept for A/B probes)
-    else if (wideNodes && variant == 30) wideKernel(k_wf_trace_w<8, 8, 5, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 31) wideKernel(k_wf_trace_w<8, 8, 6, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 32) wideKernel(k_wf_trace_w<4, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 33) wideKernel(k_wf_trace_w<12, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 34) wideKernel(k_wf_trace_w<8, 4, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 35) wideKernel(k_wf_trace_w<8, 12, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 36) wideKernel(k_wf_trace_w<8, 8, 4, 16, 8, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 37) wideKernel(k_wf_trace_w<16, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 38) wideKernel(k_wf_trace_w<8, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);   // the previous default
-    else if (wideNodes && variant == 39) wideKernel(k_wf_trace_w<2, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 40) wideKernel(k_wf_trace_w<3, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 41) wideKernel(k_wf_trace_w<6, 8, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 42) wideKernel(k_wf_trace_w<4, 8, 3, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 43) wideKernel(k_wf_trace_w<4, 10, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 44) wideKernel(k_wf_trace_w<4, 6, 4, 16, 9, 2, 128, false, true>, 128, 16, false);
-    else if (wideNodes && variant == 15) wideKernel(k_wf_trace_w<8, 8, 3, 16, 8, 1>, 128, 16, false);   // scalar slab tests
-    else if (wideNodes && variant == 8) wideKernel(k_wf_trace_w<8, 8, 2, 4, 8>, 128, 4, false);   // tests: forces the local-memory stack spill
-    else if (wideNodes && variant == 9) wideKernel(k_wf_trace_w<8, 8, 3, 16, 1, 1, 1024, true>, 1024, 16, true);
-    else if (wideNodes && variant == 10) wideKernel(k_wf_trace_w<8, 8, 3, 12, 1, 1, 1024, true>, 1024, 12, true);
-    else if (wideNodes && variant == 11) wideKernel(k_wf_trace_w<8, 8, 3, 16, 1, 1, 1024, false>, 1024, 16, false);
-    else if (wideNodes && variant == 12) wideKernel(k_wf_trace_w<8, 8, 3, 16, 2, 1, 512, true>, 512, 16, true);
-    else if (scene->bvhDepth > 32) trace = k_wf_trace<12, 8, 4, 32, true, false, 8>;
-    else if (variant == 1) trace = k_wf_trace<12, 8, 8, 32, false, false, 8>;
-    else if (variant == 2) trace = k_wf_trace<16, 8, 4, 32, false, false, 8>;
-    else if (variant == 3) trace = k_wf_trace<12, 8, 4, 32, false, false, 10>;
-    else if (variant == 4) trace = k_wf_trace<12, 12, 6, 32, false, false, 8>;
-    else trace = k_wf_trace<12, 8, 4, 32, false, false, 8>;   // also PB2_TRACE=7: the 32-B-node kernel on a triangle scene
-    static const int shadeMinB = envInt("PB2_SHADE_MINB", 4);
     AdvanceKernel advLight = spheres ? k_wf_advance<false, true, 8> : k_wf_advance<false, false, 8>;
     AdvanceKernel advShade = scene->hasSpecular ? (spheres ? k_wf_advance<true, true, 4, true> : k_wf_advance<true, false, 4, true>)
                              : spheres ? k_wf_advance<true, true, 4>
-                             : shadeMinB == 3 ? k_wf_advance<true, false, 3>
-                             : shadeMinB == 5 ? k_wf_advance<true, false, 5>
-                             : shadeMinB == 6 ? k_wf_advance<true, false, 6>
-                             : shadeMinB == 8 ? k_wf_advance<true, false, 8>
-                                              : k_wf_advance<true, false, 4>;
-    // the two-child kernels take their stack (and the optional top-of-tree table) as dynamic shared memory
-    if (traceDynStack > 0) {
-        traceSmem = (size_t)traceDynStack * traceBlock * sizeof(int2) + (traceTop ? (size_t)scene->d.nTop * 64 : 0);
-        CUDA_TRY(cudaFuncSetAttribute(trace, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceSmem));
-    }
-    int traceBlocksPerSM = 1;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&traceBlocksPerSM, trace, traceBlock, traceSmem));
-    {
-        // ask for exactly the shared-memory carve-out the resident blocks need; the rest stays L1
-        cudaFuncAttributes fa;
-        CUDA_TRY(cudaFuncGetAttributes(&fa, trace));
-        size_t need = (size_t)traceBlocksPerSM * (fa.sharedSizeBytes + traceSmem + 1024);
-        int pct = (int)std::min<size_t>(100, (need * 100 + 233471) / 233472);
-        CUDA_TRY(cudaFuncSetAttribute(trace, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
-        static const int verbose = envInt("PB2_VERBOSE", 0);
-        if (verbose)
-            fprintf(stderr, "pb2: trace kernel %d regs, %zu B smem, %d blocks/SM, carve-out %d %%, BVH depth %d, wide %d\n", fa.numRegs,
-                    fa.sharedSizeBytes, traceBlocksPerSM, pct, scene->bvhDepth, scene->d.wide ? 1 : 0);
-    }
-    const int persistentBlocks = g_numSMs * std::max(1, traceBlocksPerSM);
+                                       : k_wf_advance<true, false, 4>;
     const int blocks256 = std::min((capacity + 255) / 256, g_numSMs * 16);
     const int blocks128 = std::min((capacity + 127) / 128, g_numSMs * 32);
 
@@ -699,9 +735,7 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
             }
             CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents], stream));
         }
-        if (countTraversal) k_wf_trace_plain<true><<<blocks128, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
-        else if (instanced && !instancedTuned) k_wf_trace_plain<false><<<blocks128, 128, 0, stream>>>(scene->d, pool, WQ_TRACE0 + cur, scene->counters);
-        else trace<<<persistentBlocks, traceBlock, traceSmem, stream>>>(scene->d, pool, WQ_TRACE0 + cur);
+        trace.fn<<<trace.grid ? trace.grid : blocks128, trace.block, trace.smem, stream>>>(scene->d, pool, WQ_TRACE0 + cur);
         if (timeTrace) {
             CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents + 1], stream));
             nEvents += 2;
@@ -882,8 +916,8 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
     if ((rc = upload(s, rebased.empty() ? d->nodes : rebased.data(), (size_t)d->n_nodes, &nodes))) return rc;
     sc.instances = nullptr;
     sc.nInstances = d->n_instances;
+    std::vector<DInstance> inst((size_t)std::max(0, d->n_instances));   // uploaded below, once the record numbers are known
     if (d->n_instances > 0) {
-        std::vector<DInstance> inst((size_t)d->n_instances);
         const float identity[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
         for (int i = 0; i < d->n_instances; ++i) {
             const pb2_instance &pi = d->instances[i];
@@ -891,6 +925,7 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
             memcpy(inst[i].w2i.m, pi.world_to_instance, sizeof(float) * 16);
             inst[i].identity = memcmp(pi.instance_to_world, identity, sizeof(identity)) == 0;   // Transform::IsIdentity (transform.h:137-143)
             inst[i].wroot = pi.bvh >= 0 ? pi.bvh : -1;   // the pseudo record above the object BVH's root (two-child records)
+            inst[i].wroot4 = -1;
             if (pi.bvh >= 0) {
                 if (pi.bvh == 0 || pi.bvh >= (int)bvhs.size()) return setError(PB2_ERR_INVALID, "instance BVH out of range");
                 inst[i].root = (int)bvhs[pi.bvh].node_offset;
@@ -906,12 +941,10 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
             for (int64_t j = 0; j < bvhs[k].n_prims; ++j)
                 if (d->prim_type[d->bvh_prims[bvhs[k].prim_offset + j]] == PB2_PRIM_INSTANCE)
                     return setError(PB2_ERR_INVALID, "instance inside an object BVH (api.cpp:1554-1557 forbids it)");
-        const DInstance *dInst;
-        if ((rc = upload(s, inst.data(), inst.size(), &dInst))) return rc;
-        sc.instances = dInst;
     }
     sc.nodes = reinterpret_cast<const float4 *>(nodes);
     sc.wide = nullptr;
+    sc.wide4 = nullptr;
     if (d->n_nodes > 0 && d->n_prims < (int64_t)WIDE_MAX_PRIMS) {
         // two-child records (pb2_scene.cuh): interior nodes keep their depth-first order; records
         // 0 .. nBvh-1 are the pseudo nodes above the root of each BVH (scene BVH, then instanced objects)
@@ -957,31 +990,22 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
             const WideRec *dWide;
             if ((rc = upload(s, wide.data(), wide.size(), &dWide))) return rc;
             sc.wide = reinterpret_cast<const float4 *>(dWide);
-            // the top of the tree in breadth-first order (any prefix of that order is closed under "parent of")
-            static const int topMax = std::max(1, std::min(envInt("PB2_TOP", 1024), 3072));
-            std::vector<int32_t> bfs{0};
-            std::vector<int32_t> topOf((size_t)nWide, -1);
-            topOf[0] = 0;
-            for (size_t qi = 0; qi < bfs.size() && (int)bfs.size() < topMax; ++qi) {
-                const WideRec &w = wide[(size_t)bfs[qi]];
-                const uint32_t refs[2] = {w.ref0, w.ref1};
-                for (int k = 0; k < ((w.meta & WIDE_SINGLE) ? 1 : 2); ++k)
-                    if (!(refs[k] & WIDE_LEAF) && (int)bfs.size() < topMax && topOf[refs[k]] < 0) {
-                        topOf[refs[k]] = (int32_t)bfs.size();
-                        bfs.push_back((int32_t)refs[k]);
-                    }
-            }
-            std::vector<WideRec> top(bfs.size());
-            for (size_t i = 0; i < bfs.size(); ++i) {
-                top[i] = wide[(size_t)bfs[i]];
-                if (!(top[i].ref0 & WIDE_LEAF) && topOf[top[i].ref0] >= 0) top[i].ref0 = WIDE_TOP | (uint32_t)topOf[top[i].ref0];
-                if (!(top[i].ref1 & WIDE_LEAF) && topOf[top[i].ref1] >= 0) top[i].ref1 = WIDE_TOP | (uint32_t)topOf[top[i].ref1];
-            }
-            const WideRec *dTop;
-            if ((rc = upload(s, top.data(), top.size(), &dTop))) return rc;
-            sc.wideTop = reinterpret_cast<const float4 *>(dTop);
-            sc.nTop = (int)top.size();
+            // four-child records (device/pb2_wide4.cuh): every BVH's root gets a record of its own
+            std::vector<int64_t> roots(bvhs.size());
+            for (size_t k = 0; k < bvhs.size(); ++k) roots[k] = bvhs[k].node_offset;
+            std::vector<int32_t> rootRecord(bvhs.size(), 0);
+            const std::vector<float4> wide4 = buildWide4Records(src, roots.data(), roots.size(), rootRecord.data());
+            const float4 *dWide4;
+            if ((rc = upload(s, wide4.data(), wide4.size(), &dWide4))) return rc;
+            sc.wide4 = dWide4;
+            for (int i = 0; i < d->n_instances; ++i)
+                inst[(size_t)i].wroot4 = d->instances[i].bvh >= 0 ? rootRecord[(size_t)d->instances[i].bvh] : -1;
         }
+    }
+    if (d->n_instances > 0) {
+        const DInstance *dInst;
+        if ((rc = upload(s, inst.data(), inst.size(), &dInst))) return rc;
+        sc.instances = dInst;
     }
     if ((rc = upload(s, d->P, 3 * (size_t)d->n_vertices, &sc.P))) return rc;
     if ((rc = upload(s, d->N, d->N ? 3 * (size_t)d->n_vertices : 0, &sc.N))) return rc;
@@ -1176,6 +1200,41 @@ int pb2_intersect_p(pb2_scene *scene, const pb2_ray *rays, int64_t n, uint8_t *o
     return PB2_OK;
 }
 
+int pb2_trace_wavefront(pb2_scene *scene, const pb2_ray *rays, const uint8_t *any_hit, int64_t n, int32_t flags, pb2_wf_hit *out) {
+    int rc = requireDevice();
+    if (rc) return rc;
+    if (!scene || (n > 0 && (!rays || !out))) return setError(PB2_ERR_INVALID, "null argument");
+    if (n <= 0) return PB2_OK;
+    if (n > (1 << 24)) return setError(PB2_ERR_INVALID, "at most 2^24 rays per call");
+    const int N = (int)n;
+    if ((rc = ensurePool(scene, (N + 255) / 256 * 256))) return rc;
+    WfPool pool = poolOf(scene, scene->wfCapacity);
+    TraceLaunch trace;
+    if ((rc = selectTraceKernel(scene, flags, &trace))) return rc;
+    pb2_ray *dRays = nullptr;
+    uint8_t *dAny = nullptr;
+    pb2_wf_hit *dOut = nullptr;
+    cudaError_t e = cudaMalloc((void **)&dRays, n * sizeof(pb2_ray));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dOut, n * sizeof(pb2_wf_hit));
+    if (e == cudaSuccess && any_hit) e = cudaMalloc((void **)&dAny, n);
+    if (e == cudaSuccess) e = cudaMemcpy(dRays, rays, n * sizeof(pb2_ray), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && any_hit) e = cudaMemcpy(dAny, any_hit, n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const int blocks = (N + 127) / 128;
+        k_wf_debug_fill<<<blocks, 128>>>(pool, dRays, dAny, N);
+        trace.fn<<<trace.grid ? trace.grid : blocks, trace.block, trace.smem>>>(scene->d, pool, WQ_TRACE0);
+        k_wf_debug_read<<<blocks, 128>>>(scene->d, pool, N, dOut);
+        k_wf_debug_lists<<<std::min(blocks, g_numSMs * 8), 128>>>(pool, dOut);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dOut, n * sizeof(pb2_wf_hit), cudaMemcpyDeviceToHost);
+    cudaFree(dRays);
+    cudaFree(dAny);
+    cudaFree(dOut);
+    if (e != cudaSuccess) return setError(PB2_ERR_CUDA, std::string("pb2_trace_wavefront: ") + cudaGetErrorString(e));
+    return PB2_OK;
+}
+
 int pb2_render_path_device(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp,
                            float *film_rgbw_device, int clear, void *stream_, pb2_stats *stats) {
     int rc = requireDevice();
@@ -1362,7 +1421,9 @@ extern "C" int pb2_debug_wide4_sequences(const pb2_bvh_node *nodes, int64_t n_no
                                          const float *rays_od, int64_t n_rays, int32_t max_len, int32_t *seq_binary,
                                          int32_t *seq_wide4, int32_t *len_binary, int32_t *len_wide4) {
     if (!nodes || n_nodes <= 0 || !bvh_prims || !prim_bounds || !rays_od) return PB2_ERR_INVALID;
-    const std::vector<float4> recs = buildWide4Records(nodes, n_nodes);
+    const int64_t root0 = 0;
+    int32_t rootRecord = 0;
+    const std::vector<float4> recs = buildWide4Records(nodes, &root0, 1, &rootRecord);
     for (int64_t i = 0; i < n_rays; ++i) {
         const float *rd = rays_od + 6 * i;
         const DRaySetup r = setupRay(mk3(rd[0], rd[1], rd[2]), mk3(rd[3], rd[4], rd[5]));
@@ -1399,25 +1460,30 @@ extern "C" int pb2_debug_wide4_sequences(const pb2_bvh_node *nodes, int64_t n_no
             }
             len_binary[i] = len;
         }
-        {   // four-child records
+        {   // four-child records, walked as k_wf_trace_w<4> walks them (the root's own box is not tested: see pb2_wide4.cuh)
             float tMax = PB2_INFINITY;
             int32_t *seq = seq_wide4 + (size_t)i * max_len, len = 0, sp = 0;
             struct Entry { uint32_t ref; float tMin; } stack[3 * 64];
-            float t;
-            const pb2_bvh_node &root = nodes[0];
-            bool have = slabTestT(root.bmin[0], root.bmin[1], root.bmin[2], root.bmax[0], root.bmax[1], root.bmax[2], r, tMax, &t);
-            uint32_t cur = 0;   // record of the root
+            bool have = true;
+            uint32_t cur = (uint32_t)rootRecord;
             while (have) {
                 if (cur & WIDE_LEAF) {
                     leafTests((int32_t)(cur & WIDE_LEAF_OFFSET_MASK), (int32_t)((cur >> WIDE_LEAF_COUNT_SHIFT) & 0xf) + 1, &tMax, seq, &len);
                     have = false;
                 } else {
+                    const float4 *w = &recs[8 * (size_t)cur];
+                    uint32_t meta;
+                    memcpy(&meta, &w[7].x, 4);
+                    const Wide4Visit v = wide4Visit(w[0], w[1], w[2], w[3], w[4], w[5], w[6], meta, r, tMax);
                     uint32_t refs[4];
-                    float tMins[4];
-                    const int n = wide4Visit(&recs[8 * (size_t)cur], r, tMax, refs, tMins);
-                    for (int k = n - 1; k >= 1; --k) stack[sp++] = Entry{refs[k], tMins[k]};
-                    have = n > 0;
-                    if (have) cur = refs[0];
+                    memcpy(refs, &w[6], sizeof(refs));
+                    have = v.nPass > 0;
+                    for (int k = 0; k < 4; ++k) {
+                        if (!v.pass[k]) continue;
+                        if (v.after[k] == v.nPass - 1) cur = refs[k];
+                        else stack[sp + v.after[k]] = Entry{refs[k], v.tMin[k]};
+                    }
+                    if (v.nPass > 1) sp += v.nPass - 1;
                 }
                 while (!have && sp > 0) {
                     const Entry e = stack[--sp];

@@ -41,6 +41,7 @@ struct WfPool {
     WfCtx *ctx;
     int *queue[6];            // WQ_TRACE0..WQ_FREE1, capacity entries each
     unsigned *counts;         // WQ_COUNT counters
+    unsigned long long *ctr;  // the scene's CTR_* counters (ray / traversal statistics)
 };
 
 // warp-aggregated append of one index per participating lane
@@ -119,7 +120,8 @@ __global__ void __launch_bounds__(256) k_wf_gen(DRenderParams rp, WfPool pool, i
 // (COUNT) and as the simplest statement of what the tuned kernels below compute.
 // ---------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_wf_trace_plain(DScene sc, WfPool pool, int traceQ, unsigned long long *counters) {
+__global__ void __launch_bounds__(128) k_wf_trace_plain(DScene sc, WfPool pool, int traceQ) {
+    unsigned long long *counters = pool.ctr;
     unsigned n = pool.counts[traceQ];
     unsigned stride = gridDim.x * blockDim.x;
     DCounters ctr;
@@ -435,27 +437,28 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
 // dependent fetch per interior node it descends into instead of one per node it touches
 // (82 -> ~41 on the bench scene), and the two slab tests of a step are independent instructions.
 // ---------------------------------------------------------------------------------------------
-// TOP: the first sc.nTop records in breadth-first order (the levels every ray walks through) are
-// copied into shared memory at kernel start and read from there: the kernel is bound by the number
-// of L1 tag look-ups (4 scattered 16-byte requests per record), not by bytes, and shared-memory
-// reads need none.  BLOCK = 1024 gives one resident block per SM, so that copy exists once per SM.
-template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, int TAIL = 0, int BLOCK = 128, bool TOP = false, bool PACKED = false, bool SPHERES = false, bool INST = false>
-__global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
+// Template parameters: LEAF_T / FETCH_T = lanes that must wait before the warp runs a leaf / fetch step,
+// NSUB = node visits per scheduling round, SDEPTH = stack entries kept in shared memory (deeper ones
+// spill to local memory), MINB = resident blocks per SM asked of the compiler.
+// WIDTH = 2: the two-child records (DScene::wide); WIDTH = 4: the four-child records (DScene::wide4,
+// device/pb2_wide4.cuh) - two levels of the reference's tree per fetch: a visit tests the four
+// grandchildren's boxes, continues with the first entered one in the reference's visiting order and
+// defers the others (up to three stack entries, the next one to visit on top).
+template <int WIDTH, int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, bool SPHERES = false, bool INST = false>
+__global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
+    static_assert(WIDTH == 2 || WIDTH == 4, "two- or four-child records");
+    constexpr int BLOCK = 128;
     extern __shared__ int2 dynSmem[];
     int2 *sstack = dynSmem;                // [SDEPTH][BLOCK] of (child reference, tMin bits)
-    float4 *stop = reinterpret_cast<float4 *>(dynSmem + SDEPTH * BLOCK);   // [4 * sc.nTop]
-    int2 lstack[64 - SDEPTH];              // entries beyond SDEPTH (rare: only passing far children are pushed)
+    // entries beyond SDEPTH (rare: only passing far children are pushed).  Worst case: one entry per level of the
+    // reference's <= 64-level stack for WIDTH 2, three per two levels for WIDTH 4, plus the instance frame
+    int2 lstack[(WIDTH == 4 ? 100 : 66) - SDEPTH];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x;
-    if (TOP) {
-        for (int i = tid; i < 4 * sc.nTop; i += BLOCK) stop[i] = sc.wideTop[i];
-        __syncthreads();
-    }
     const int lane = tid & 31;
     const unsigned n = pool.counts[traceQ];
     enum { M_FETCH = 0, M_NODE = 1, M_LEAF = 2 };
     enum { F_ANY = 1, F_FOUND = 2, F_EXHAUSTED = 4, F_EXIT = 8, F_HITIN = 16 };
-    static_assert(!INST || TAIL, "the instance frame is only written for the straight-line tail");
     // INST (object instances): as in k_wf_trace - an instance is a leaf primitive; the lane pushes a
     // frame of two entries ((rest of the leaf), (tMax, -)), walks the object's records from the pseudo
     // record above its root with `instBase` as stack floor, and leaves through the leaf step (F_EXIT).
@@ -475,29 +478,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
     rs.Sx = rs.Sy = rs.Sz = 0;
     float tMax = 0;
     int cur = 0, sp = 0, leafFirst = 0, leafN = 0;
-    // continue with child reference `ref`
-    auto enter = [&](int ref) {
-        if (ref < 0) {
-            leafFirst = ref & (int)WIDE_LEAF_OFFSET_MASK;
-            leafN = ((ref >> WIDE_LEAF_COUNT_SHIFT) & 0xf) + 1;
-            mode = M_LEAF;
-        } else {
-            cur = ref;
-            mode = M_NODE;
-        }
-    };
-    // pop far children until one still passes `tMin < tMax`; the ray is finished when none is left
-    auto popNext = [&]() {
-        mode = M_FETCH;
-        while (sp > 0) {
-            --sp;
-            int2 e = sp < SDEPTH ? sstack[sp * BLOCK + tid] : lstack[sp - SDEPTH];
-            if (__int_as_float(e.y) < tMax) {
-                enter(e.x);
-                break;
-            }
-        }
-    };
     while (true) {
         unsigned mNode = __ballot_sync(FULL, mode == M_NODE);
         unsigned mLeaf = __ballot_sync(FULL, mode == M_LEAF);
@@ -512,10 +492,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
         if (step == M_NODE) {
 #pragma unroll
             for (int sub = 0; sub < NSUB; ++sub) {
-                if (TAIL == 2) {
-                    // the same pop as below, once per visit, as straight-line code for the whole warp: nearly
-                    // every visit has SOME lane that must pop, and those few lanes used to run ~25
-                    // instructions alone while the rest of the warp waited
+                {
+                    // A lane whose last visit (or leaf) left nothing to descend into (cur < 0) takes its next
+                    // pending far child.  Straight-line predicated code for the whole warp: nearly every visit
+                    // has SOME lane that must pop, and those few lanes would otherwise run ~25 instructions
+                    // alone while the rest of the warp waited.  A popped entry whose tMin no longer beats
+                    // tMax is dropped (the reference's box test at the pop, bvh.cpp:694-697); the next visit
+                    // pops again.
                     const bool need = (mode == M_NODE) & (cur < 0);
                     const bool empty = need & (sp == instBase);
                     const bool pop = need & !empty;
@@ -530,49 +513,48 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
                     mode = leafRef ? (int)M_LEAF : mode;
                     if (empty) {
                         if (INST && inst >= 0) {
-                            mode = M_LEAF;
+                            mode = M_LEAF;   // the object is exhausted: leave the instance in the leaf step
                             flags |= F_EXIT;
                             leafN = 0;
                         } else
                             mode = M_FETCH;
                     }
-                } else if (TAIL && mode == M_NODE && cur < 0) {
-                    // the last visit (or leaf) left nothing to descend into: take pending far children,
-                    // at most two per visit (a culled one costs a load and a compare)
+                }
+                if (WIDTH == 4) {
+                    if (mode == M_NODE && cur >= 0) {
+                        const float4 *w = &sc.wide4[8 * (size_t)cur];
+                        const float4 q0 = ldg4(w), q1 = ldg4(w + 1), q2 = ldg4(w + 2), q3 = ldg4(w + 3), q4 = ldg4(w + 4), q5 = ldg4(w + 5),
+                                     q6 = ldg4(w + 6);
+                        const uint32_t meta = __ldg(reinterpret_cast<const unsigned *>(w + 7));
+                        const Wide4Visit v = wide4Visit(q0, q1, q2, q3, q4, q5, q6, meta, rs, tMax);
+                        const int refs[4] = {asInt(q6.x), asInt(q6.y), asInt(q6.z), asInt(q6.w)};
+                        const int last = v.nPass - 1;
+                        int ref = -1;
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) {
-                        if (mode == M_NODE && cur < 0) {
-                            if (sp == instBase) {
-                                if (INST && inst >= 0) {
-                                    mode = M_LEAF;   // the object is exhausted: leave the instance in the leaf step
-                                    flags |= F_EXIT;
-                                    leafN = 0;
-                                } else
-                                    mode = M_FETCH;
-                            } else {
-                                --sp;
-                                int2 e = sp < SDEPTH ? sstack[sp * BLOCK + tid] : lstack[sp - SDEPTH];
-                                if (__int_as_float(e.y) < tMax) enter(e.x);
+                        for (int k = 0; k < 4; ++k) {
+                            const bool first = v.pass[k] & (v.after[k] == last);
+                            ref = first ? refs[k] : ref;
+                            if (v.pass[k] & !first) {   // deferred: stack position sp + after puts the next one to visit on top
+                                const int slot = sp + v.after[k];
+                                const int2 e = make_int2(refs[k], __float_as_int(v.tMin[k]));
+                                if (slot < SDEPTH) sstack[slot * BLOCK + tid] = e;
+                                else lstack[slot - SDEPTH] = e;
                             }
                         }
+                        sp += last > 0 ? last : 0;
+                        const bool have = v.nPass > 0;
+                        const bool isLeaf = have & (ref < 0);
+                        leafFirst = isLeaf ? (ref & (int)WIDE_LEAF_OFFSET_MASK) : leafFirst;
+                        leafN = isLeaf ? (((ref >> WIDE_LEAF_COUNT_SHIFT) & 0xf) + 1) : leafN;
+                        mode = isLeaf ? (int)M_LEAF : (int)M_NODE;
+                        cur = (have & !isLeaf) ? ref : -1;
                     }
-                }
-                if (mode == M_NODE && (!TAIL || cur >= 0)) {
-                    float4 q0, q1, q2, q3;
-                    if (TOP && (cur & (int)WIDE_TOP)) {
-                        const float4 *w = &stop[4 * (cur & 0xffffff)];
-                        q0 = w[0]; q1 = w[1]; q2 = w[2]; q3 = w[3];
-                    } else {
-                        const float4 *w = &sc.wide[4 * (size_t)cur];
-                        q0 = ldg4(w); q1 = ldg4(w + 1); q2 = ldg4(w + 2); q3 = ldg4(w + 3);
-                    }
+                } else if (mode == M_NODE && cur >= 0) {
+                    const float4 *w = &sc.wide[4 * (size_t)cur];
+                    const float4 q0 = ldg4(w), q1 = ldg4(w + 1), q2 = ldg4(w + 2), q3 = ldg4(w + 3);
                     float t0, t1;
                     bool p0, p1;
-                    if (PACKED) slabTestPair(q0, q1, q2, rs, tMax, &p0, &p1, &t0, &t1);
-                    else {
-                        p0 = slabTestT(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, rs, tMax, &t0);
-                        p1 = slabTestT(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, rs, tMax, &t1);
-                    }
+                    slabTestPair(q0, q1, q2, rs, tMax, &p0, &p1, &t0, &t1);
                     uint32_t meta = floatBits(q3.z);
                     if (meta & WIDE_SINGLE) p1 = false;
                     int axis = (int)(meta & 3u);
@@ -581,34 +563,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
                     bool pn = isNeg ? p1 : p0, pf = isNeg ? p0 : p1;
                     int rn = isNeg ? ref1 : ref0, rf = isNeg ? ref0 : ref1;
                     float tf = isNeg ? t0 : t1;
-                    if (TAIL) {
-                        // straight-line tail: push the far child if both pass, continue with whichever
-                        // passed, otherwise leave the pop to the next visit
-                        if (pn & pf) {
-                            int2 e = make_int2(rf, __float_as_int(tf));
-                            if (sp < SDEPTH) sstack[sp * BLOCK + tid] = e;
-                            else lstack[sp - SDEPTH] = e;
-                            ++sp;
-                        }
-                        const int ref = pn ? rn : rf;
-                        const bool have = pn | pf;
-                        const bool isLeaf = have & (ref < 0);
-                        leafFirst = isLeaf ? (ref & (int)WIDE_LEAF_OFFSET_MASK) : leafFirst;
-                        leafN = isLeaf ? (((ref >> WIDE_LEAF_COUNT_SHIFT) & 0xf) + 1) : leafN;
-                        mode = isLeaf ? (int)M_LEAF : (int)M_NODE;
-                        cur = (have & !isLeaf) ? ref : -1;
-                    } else if (pn) {
-                        if (pf) {
-                            int2 e = make_int2(rf, __float_as_int(tf));
-                            if (sp < SDEPTH) sstack[sp * BLOCK + tid] = e;
-                            else lstack[sp - SDEPTH] = e;
-                            ++sp;
-                        }
-                        enter(rn);
-                    } else if (pf)
-                        enter(rf);
-                    else
-                        popNext();
+                    // straight-line tail: push the far child if both pass, continue with whichever
+                    // passed, otherwise leave the pop to the next visit
+                    if (pn & pf) {
+                        int2 e = make_int2(rf, __float_as_int(tf));
+                        if (sp < SDEPTH) sstack[sp * BLOCK + tid] = e;
+                        else lstack[sp - SDEPTH] = e;
+                        ++sp;
+                    }
+                    const int ref = pn ? rn : rf;
+                    const bool have = pn | pf;
+                    const bool isLeaf = have & (ref < 0);
+                    leafFirst = isLeaf ? (ref & (int)WIDE_LEAF_OFFSET_MASK) : leafFirst;
+                    leafN = isLeaf ? (((ref >> WIDE_LEAF_COUNT_SHIFT) & 0xf) + 1) : leafN;
+                    mode = isLeaf ? (int)M_LEAF : (int)M_NODE;
+                    cur = (have & !isLeaf) ? ref : -1;
                 }
             }
         } else if (step == M_LEAF) {
@@ -655,7 +624,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
                         rs = setupRay(r2.o, r2.d);
                         tMax = r2.tMax;
                         if (in.wroot >= 0) {
-                            cur = in.wroot;
+                            cur = WIDTH == 4 ? in.wroot4 : in.wroot;
                             mode = M_NODE;
                             leafN = 0;
                             entered = true;
@@ -702,7 +671,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
                 if (!entered) {
                     leafN = 0;
                     if (finished) mode = M_FETCH;
-                    else if (!TAIL) popNext();
                     else if (sp == instBase) {
                         if (INST && inst >= 0) flags |= F_EXIT;   // stays a leaf lane: the next leaf step leaves the instance
                         else mode = M_FETCH;
@@ -742,7 +710,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_wf_trace_w(DScene sc, WfPool po
                         flags = (__float_as_int(ra.x) == LS_SHADOW) ? F_ANY : 0;
                         rs = setupRay(mk3(ra.y, ra.z, ra.w), mk3(rb.x, rb.y, rb.z));
                         tMax = rb.w;
-                        cur = TOP ? (int)WIDE_TOP : 0;   // the pseudo node above the root
+                        cur = 0;   // WIDTH 2: the pseudo node above the root; WIDTH 4: the root's record
                         if (INST) {
                             inst = hitInst = -1;
                             instBase = 0;

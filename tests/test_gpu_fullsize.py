@@ -79,6 +79,48 @@ def test_per_sample_parity_on_the_full_size_scene(pb, big, port):
     assert np.array_equal(gc.bits(g["p"]), gc.bits(r["p"])) and np.array_equal(gc.bits(g["n"]), gc.bits(r["n"]))
 
 
+def test_wavefront_trace_records_at_full_size(pb, big, port):
+    """The benchmarked kernel on the benchmarked scene: k_wf_trace_w<4> (and the other variants) over 200 000 path rays
+    and 200 000 shadow rays of the 1 M-triangle soup leave (found, primitive, t, b0, b1, b2) bit-identical to
+    pb2_intersect / pb2_intersect_p, which the test above pins to the CPU checker on this very scene."""
+    from test_gpu_parity import check_wavefront_records
+    nodes = big.nodes()
+    rays, srays = gc.rays_for(pb, nodes, 200000, 33), gc.rays_for(pb, nodes, 200000, 34, shadow=True)
+    hits, occ = big.intersect(rays), big.intersect_p(srays)
+    assert 0.2 < (hits["prim"] >= 0).mean() and 0.05 < occ.mean() < 0.95
+    sc = port.scene(big)
+    sub = slice(0, 20000)
+    ref = sc.intersect(rays[sub])
+    assert np.array_equal(hits["prim"][sub], ref["prim"]) and np.array_equal(gc.bits(hits["t"][sub]), gc.bits(ref["t"]))
+    assert np.array_equal(occ[sub], sc.intersect_p(srays[sub]))
+    check_wavefront_records(pb, big, rays, srays, hits, occ)
+
+
+CROPS = [(256, 128), (1408, 208), (832, 496), (320, 880), (1600, 864)]   # x0, y0 of 128 x 72 windows spread over the frame
+
+
+def test_wavefront_image_parity_on_crops_of_the_full_size_frame(pb, checker):
+    """BASELINE.json configs[1] exactly (1 M triangles, 1920x1080, 64 spp, maxdepth 8) through the wavefront renderer,
+    compared pixel by pixel with the CPU checker (the compiled reference where present) on five 128 x 72 crop windows
+    (PathIntegrator "pixelbounds") spread over the frame; image tolerances of DESIGN.md section 4."""
+    hs = pb.HostScene.soup(TRIS, xres=XRES, yres=YRES, spp=64, maxdepth=8)
+    sc = checker.scene(hs)
+    for x0, y0 in CROPS:
+        p = hs.params_copy()
+        p.pixel_bounds[0], p.pixel_bounds[1], p.pixel_bounds[2], p.pixel_bounds[3] = x0, y0, x0 + 128, y0 + 72
+        rgbw, st = hs.render_rgbw(p)
+        assert st.camera_rays == 128 * 72 * 64
+        got = hs.resolve(rgbw)[y0:y0 + 72, x0:x0 + 128]
+        ref_img, _, ref_st = sc.render(n_threads=0, params=p)
+        want = ref_img[y0:y0 + 72, x0:x0 + 128]
+        assert rgbw[..., 3].sum() == rgbw[y0:y0 + 72, x0:x0 + 128, 3].sum()   # nothing lands outside the window
+        rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-3)
+        assert (rel.max(axis=2) <= 0.01).mean() >= 0.999 and rel.mean() <= 1e-4, ((x0, y0), float(rel.mean()))
+        assert abs(float(got.mean()) - float(want.mean())) <= 1e-4 * float(want.mean())
+        assert abs(int(st.regular_rays) - int(ref_st.regular_rays)) <= ref_st.regular_rays // 1000 + 2
+        assert abs(int(st.shadow_rays) - int(ref_st.shadow_rays)) <= ref_st.shadow_rays // 1000 + 2
+
+
 # ---------------------------------------------------------------- BASELINE.json configs[3]: 10 M instanced triangles
 @pytest.fixture(scope="module")
 def instanced(pb):

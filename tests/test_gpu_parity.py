@@ -262,38 +262,74 @@ def test_traversal_counters_equal_the_reference_order(pb, port):
     film2, st2 = hs.render_rgbw()
     assert np.allclose(film, film2, rtol=1e-5, atol=1e-5)
     assert st2.regular_rays == st.regular_rays and st2.shadow_rays == st.shadow_rays
-    # ... and so does the tuned kernel over the 32-byte LinearBVHNode array (PB2_FLAG_LINEAR_NODES)
-    film3 = np.zeros((27, 48, 4), np.float32)
-    st3 = pb.Stats()
-    pb.check(pb.lib().pb2_render_path(dev, hs.camera, hs.film, hs.params_copy(flags=2), pb.ptr(film3), C.byref(st3)))
-    assert np.allclose(film, film3, rtol=1e-5, atol=1e-5)
-    assert st3.regular_rays == st.regular_rays and st3.shadow_rays == st.shadow_rays
+    # ... and so do the other kernels (two-child records, the 32-byte LinearBVHNode array, the small-stack builds)
+    for kname, flags in wf_kernels(pb).items():
+        film3 = np.zeros((27, 48, 4), np.float32)
+        st3 = pb.Stats()
+        pb.check(pb.lib().pb2_render_path(dev, hs.camera, hs.film, hs.params_copy(flags=flags), pb.ptr(film3), C.byref(st3)))
+        assert np.allclose(film, film3, rtol=1e-5, atol=1e-5), kname
+        assert st3.regular_rays == st.regular_rays and st3.shadow_rays == st.shadow_rays, kname
 
 
-def test_stack_spill_of_the_two_child_kernel():
-    """PB2_TRACE=8 builds the two-child-record kernel with a 4-entry shared-memory stack, so nearly every ray
-    uses the local-memory spill; the film must equal the 32-byte-node kernel's (own process: the variant is read once)."""
-    import os
-    import subprocess
-    import sys
-    code = (
-        "import ctypes as C, numpy as np, pbrt_v3_b200 as pb\n"
-        "pb.init()\n"
-        "hs = pb.HostScene.soup(20000, xres=64, yres=36, spp=4)\n"
-        "dev = hs.device_scene()\n"
-        "films = []\n"
-        "for flags in (0, 2):\n"
-        "    film = np.zeros((36, 64, 4), np.float32); st = pb.Stats()\n"
-        "    pb.check(pb.lib().pb2_render_path(dev, hs.camera, hs.film, hs.params_copy(flags=flags), pb.ptr(film), C.byref(st)))\n"
-        "    films.append(film)\n"
-        "assert films[0][..., 3].sum() > 0\n"
-        "assert np.allclose(films[0], films[1], rtol=1e-5, atol=1e-5), float(np.abs(films[0] - films[1]).max())\n"
-        "print('spill ok')\n"
-    )
-    env = dict(os.environ, PB2_TRACE="8")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and "spill ok" in out.stdout, out.stdout + out.stderr
+def wf_kernels(pb):
+    """Every traversal kernel of the render path (selected by pb2_path_params.flags)."""
+    return {"wide4": 0, "wide2": pb.PB2_FLAG_WIDE2, "linear": pb.PB2_FLAG_LINEAR_NODES, "plain": pb.PB2_FLAG_PLAIN_TRACE,
+            "wide4_spill": pb.PB2_FLAG_SMALL_STACK, "wide2_spill": pb.PB2_FLAG_SMALL_STACK | pb.PB2_FLAG_WIDE2}
+
+
+def check_wavefront_records(pb, hs, rays, srays, want_hits, want_occluded):
+    """pb2_trace_wavefront (the persistent-warp kernels the renderer launches) against Scene::Intersect / IntersectP
+    results: found flag, primitive, t and the barycentrics BIT FOR BIT, for every kernel variant, with the two ray
+    classes alone and mixed inside the same warps."""
+    hit = want_hits["prim"] >= 0
+    mixed = np.concatenate([rays, srays])
+    cls = np.concatenate([np.zeros(len(rays), np.uint8), np.ones(len(srays), np.uint8)])
+    perm = np.random.RandomState(5).permutation(len(mixed))
+    for kname, flags in wf_kernels(pb).items():
+        for batch in ("split", "mixed"):
+            if batch == "split":
+                r = hs.trace_wavefront(rays, flags=flags)
+                q = hs.trace_wavefront(srays, any_hit=np.ones(len(srays), np.uint8), flags=flags)
+            else:
+                m = hs.trace_wavefront(mixed[perm], any_hit=cls[perm], flags=flags)
+                back = np.empty_like(m)
+                back[perm] = m
+                r, q = back[: len(rays)], back[len(rays):]
+            assert np.array_equal(r["found"] > 0, hit), kname
+            assert np.array_equal(r["prim"], want_hits["prim"]), kname
+            assert np.array_equal(gc.bits(r["t"]), gc.bits(want_hits["t"])), kname
+            assert np.array_equal(gc.bits(r["b"][hit]), gc.bits(want_hits["b"][hit])), kname
+            assert (r["listed"] == 1).all() and (q["listed"] == 2).all(), kname
+            assert np.array_equal(q["found"] > 0, want_occluded != 0), kname
+
+
+@pytest.mark.parametrize("name", SCENE_CASES)
+def test_wavefront_trace_kernels_write_the_reference_hit_records(pb, name):
+    """The kernels that are BENCHMARKED (k_wf_trace_w<4>, <2>, k_wf_trace) leave the reference's closest hit in the path
+    contexts: same rays as the golden hit test, compared with the golden prim / t recorded from the compiled reference
+    and with every bit of pb2_intersect's (t, b0, b1, b2), which that test pins to the reference."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    hs = load_scene(pb, name)
+    nodes = hs.nodes()
+    rays, srays = gc.rays_for(pb, nodes, 1500, 11), gc.rays_for(pb, nodes, 1500, 12, shadow=True)
+    hits = hs.intersect(rays)
+    assert np.array_equal(hits["prim"], g["hits"]["prim"]) and np.array_equal(gc.bits(hits["t"]), gc.bits(g["hits"]["t"]))
+    check_wavefront_records(pb, hs, rays, srays, hits, g["occluded"])
+
+
+def test_wavefront_trace_kernels_on_instances_and_deep_stacks(pb, checker):
+    """Instanced soup (two BVH levels, the instance frame on the kernel's stack) and a BVH with one primitive per leaf
+    (deepest stacks): hit records of every kernel variant against the CPU checker's Scene::Intersect."""
+    deep = open(os.path.join(SCENES, "killeroo_like.pbrt")).read().replace(
+        "WorldBegin", 'Accelerator "bvh" "string splitmethod" "middle" "integer maxnodeprims" [1]\nWorldBegin')
+    for hs, kw in ((pb.HostScene.instanced_soup(2000, grid=4, xres=64, yres=36, spp=4), {}),
+                   (pb.HostScene.from_string(deep), dict(max_prims_in_node=1, split_method=2))):
+        sc = checker.scene(hs, **kw)
+        rays, srays = gc.rays_for(pb, hs.nodes(), 20000, 61), gc.rays_for(pb, hs.nodes(), 20000, 62, shadow=True)
+        want = sc.intersect(rays)
+        got = hs.intersect(rays)
+        assert np.array_equal(got["prim"], want["prim"]) and np.array_equal(gc.bits(got["t"]), gc.bits(want["t"]))
+        check_wavefront_records(pb, hs, rays, srays, got, sc.intersect_p(srays))
 
 
 @pytest.mark.parametrize("partial", [False, True])
