@@ -18,13 +18,21 @@ One JSON line is printed by rank 0:
   roofline     the BVH traversal kernel (k_wf_trace_w): algorithmic bytes (32 B x node visits + 36 B x
                primitive tests, counted on the device in the reference's traversal order) / its summed
                launch time, against MEASURED_PEAKS.json's HBM copy bandwidth
-  cpu_baseline the reference's own CPU implementation (oracle/_ref, all host cores) on a bounded
-               sample of the same workload (centred crop at full spp)
+  cpu_baseline the reference's own CPU implementation (oracle/_ref, every host thread this process may
+               use) on a bounded sample of the same workload: the first k of the spp Halton samples of EVERY
+               pixel of the frame (k chosen so that the sample takes --ref-seconds), so both arms trace the
+               same mix of rays (rays_per_sample is printed by both)
+
+Workloads (BASELINE.json configs): soup = configs[1] (default; --tris 10000000 / 50000000 for the scenes
+beyond L2), killeroo = configs[2] (scenes/killeroo-simple.pbrt at 1920x1080x256, staged by
+__graft_entry__.build() into baseline/_scenes/), instanced = configs[3].
 """
 import argparse
 import ctypes as C
 import json
+import math
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -86,47 +94,79 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+SCENES_DIR = os.path.join(ROOT, "baseline", "_scenes")   # staged by __graft_entry__.build(); git-ignored, travels with gpurun
+
+
 def build_scene(args):
     import pbrt_v3_b200 as pb
     if args.workload == "instanced":
         # BASELINE.json configs[3]: one args.tris-triangle object instanced grid x grid times
         return pb.HostScene.instanced_soup(args.tris, grid=args.grid, xres=args.xres, yres=args.yres, spp=args.spp, maxdepth=args.maxdepth)
-    return pb.HostScene.soup(args.tris, seed=WORKLOAD["seed"], jitter=WORKLOAD["jitter"], xres=args.xres, yres=args.yres,
+    if args.workload == "killeroo":
+        # BASELINE.json configs[2]: the reference's own scenes/killeroo-simple.pbrt, only film size and sample count changed
+        src = os.path.join(SCENES_DIR, "killeroo-simple.pbrt")
+        if not os.path.exists(src):
+            raise SystemExit("bench.py --workload killeroo: %s is missing (run __graft_entry__.build() where /root/reference exists)" % src)
+        text = open(src).read()
+        text, n1 = re.subn(r'"integer xresolution" \[\d+\] "integer yresolution" \[\d+\]',
+                           '"integer xresolution" [%d] "integer yresolution" [%d]' % (args.xres, args.yres), text, count=1)
+        text, n2 = re.subn(r'"integer pixelsamples" \[\d+\]', '"integer pixelsamples" [%d]' % args.spp, text, count=1)
+        text, n3 = re.subn(r'Integrator "path"', 'Integrator "path" "integer maxdepth" [%d]' % args.maxdepth, text, count=1)
+        assert n1 == 1 and n2 == 1 and n3 == 1
+        dst = os.path.join(SCENES_DIR, "killeroo-%dx%dx%d.pbrt" % (args.xres, args.yres, args.spp))   # next to geometry/ (Include is relative)
+        if int(os.environ.get("RANK", "0")) == 0 or not os.path.exists(dst):
+            tmp = dst + ".%d.tmp" % os.getpid()
+            open(tmp, "w").write(text)
+            os.replace(tmp, dst)
+        return pb.HostScene.from_file(dst)
+    return pb.HostScene.soup(args.tris, seed=args.seed, jitter=args.jitter, xres=args.xres, yres=args.yres,
                              spp=args.spp, maxdepth=args.maxdepth)
 
 
-def crop_params(hs, frac):
-    """PathIntegrator pixelbounds = centred crop holding `frac` of the pixels (full spp)."""
-    import math
-    xres, yres = hs.film.contents.full_resolution[0], hs.film.contents.full_resolution[1]
-    s = math.sqrt(min(1.0, max(frac, 1e-6)))
-    w, h = max(16, int(xres * s) // 16 * 16), max(16, int(yres * s) // 16 * 16)
-    x0, y0 = (xres - w) // 2 // 16 * 16, (yres - h) // 2 // 16 * 16
-    p = hs.params_copy()
-    p.pixel_bounds[0], p.pixel_bounds[1], p.pixel_bounds[2], p.pixel_bounds[3] = x0, y0, x0 + w, y0 + h
-    return p, w * h
+def host_threads():
+    """Threads this process may really use: CPU affinity, capped by the cgroup CPU quota (not os.cpu_count())."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]            # cgroup v2
+        if quota != "max":
+            n = min(n, max(1, int(math.ceil(int(quota) / int(period)))))
+    except Exception:
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())             # cgroup v1
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0 and period > 0:
+                n = min(n, max(1, int(math.ceil(quota / period))))
+        except Exception:
+            pass
+    return max(1, n)
 
 
 def time_reference(hs, args, target_seconds, threads=0, scene=None):
-    """Times the reference CPU path (oracle/_ref; the C++ port if _ref was not built) on a centred crop."""
+    """Times the reference CPU path (oracle/_ref: the reference's own SamplerIntegrator::Render + PathIntegrator; the
+    C++ port if _ref was not built) on a bounded sample of the workload: samples 0 .. k-1 of every pixel of the frame.
+    A HaltonSampler's sample i of a pixel does not depend on the total count, so this is a subset of the very samples
+    the full render takes, spread uniformly over the frame; the sample's rays per camera sample are printed."""
     from oracle import pyoracle
     checker = pyoracle.reference() or pyoracle.port()
     if checker is None:
         return None, None
+    if threads <= 0:
+        threads = host_threads()
     if scene is None:
         scene = checker.scene(hs)   # builds the reference's own BVH (seconds for 1 M triangles; outside the timing)
     spp = hs.params.contents.samples_per_pixel
-    probe_params, probe_px = crop_params(hs, 64 * 32 / (args.xres * args.yres))
-    _, secs, _ = scene.render(n_threads=threads, params=probe_params)
-    rate = probe_px * spp / max(secs, 1e-6)
-    frac = min(1.0, rate * target_seconds / (args.xres * args.yres * spp))
-    params, px = crop_params(hs, frac)
-    _, secs, st = scene.render(n_threads=threads, params=params)
-    nsamp = px * spp
-    return {"value": nsamp / secs / 1e6, "unit": "Msamples/s", "cores": threads if threads > 0 else (os.cpu_count() or 1),
-            "kind": checker.kind, "seconds": secs, "mrays_per_s": (st.regular_rays + st.shadow_rays) / secs / 1e6,
-            "sample": "centred %d-pixel crop of the %dx%d frame at the full %d spp (%d camera samples), all host threads"
-                      % (px, args.xres, args.yres, spp, nsamp)}, scene
+    pixels = args.xres * args.yres
+    _, secs, _ = scene.render(n_threads=threads, params=hs.params_copy(samples_per_pixel=1))
+    rate = pixels / max(secs, 1e-6)
+    k = int(max(1, min(spp, rate * target_seconds // pixels)))
+    _, secs, st = scene.render(n_threads=threads, params=hs.params_copy(samples_per_pixel=k))
+    nsamp = pixels * k
+    rays = int(st.regular_rays + st.shadow_rays)
+    return {"value": nsamp / secs / 1e6, "unit": "Msamples/s", "cores": threads, "host_cpus": os.cpu_count(),
+            "kind": checker.kind, "seconds": secs, "mrays_per_s": rays / secs / 1e6, "rays_per_sample": rays / nsamp,
+            "sample": "samples 0..%d of the %d Halton samples of every pixel of the %dx%d frame (%d camera samples), %d host threads; "
+                      "scene generated and flattened by this repo's host front end, rendered by the reference's SamplerIntegrator::Render"
+                      % (k - 1, spp, args.xres, args.yres, nsamp, threads)}, scene
 
 
 def run_reference_arm(args):
@@ -150,32 +190,42 @@ def run_reference_arm(args):
     best = dict(vals[-1])
     best["value"] = sum(v["value"] * v["seconds"] for v in vals) / sum(v["seconds"] for v in vals)
     best["mrays_per_s"] = sum(v["mrays_per_s"] * v["seconds"] for v in vals) / sum(v["seconds"] for v in vals)
+    best["rays_per_sample"] = sum(v["rays_per_sample"] * v["seconds"] for v in vals) / sum(v["seconds"] for v in vals)
     ms = 1e3 * sum(v["seconds"] for v in vals) / len(vals)
     line = {"metric": "Msamples/sec", "value": best["value"], "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": workload_config(args, "cpu"),
-            "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample", "rays_per_sample")},
             "e2e": {"value": best["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "mrays_per_s": best["mrays_per_s"], "gpu_launches": 0}
+            "mrays_per_s": best["mrays_per_s"], "rays_per_sample": best["rays_per_sample"], "gpu_launches": 0}
     print(json.dumps(line))
     return 0
 
 
 def workload_config(args, parallelism):
+    common = {"resolution": [args.xres, args.yres], "spp": args.spp, "maxdepth": args.maxdepth, "parallelism": parallelism}
     if args.workload == "instanced":
-        return {"workload": "synthetic instanced triangles (SURVEY.md §8d C4): one %d-triangle soup object x %d instances, %dx%dx%dspp Halton, "
-                            "PathIntegrator maxdepth %d, matte Kd .6, 2-triangle area light"
-                            % (args.tris, args.grid * args.grid, args.xres, args.yres, args.spp, args.maxdepth),
-                "triangles": args.tris * args.grid * args.grid, "resolution": [args.xres, args.yres], "spp": args.spp,
-                "maxdepth": args.maxdepth, "parallelism": parallelism,
-                "l2_note": "inputs larger than L2: every step streams the 1 GiB path-context pool through the 126 MB L2; no explicit flush"}
-    return {"workload": "synthetic %d random triangles (soup, SURVEY.md §8d C2), %dx%dx%dspp Halton, PathIntegrator maxdepth %d, "
-                        "matte Kd .6, 2-triangle area light" % (args.tris, args.xres, args.yres, args.spp, args.maxdepth),
-            "triangles": args.tris, "resolution": [args.xres, args.yres], "spp": args.spp, "maxdepth": args.maxdepth,
-            "parallelism": parallelism,
-            "l2_note": "inputs larger than L2: every step streams the 1 GiB path-context pool and the 33 MB film through the 126 MB L2 "
-                       "next to the scene (BVH records 61 MB + leaf records 48 MB); no explicit flush"}
+        return dict(common, workload="synthetic instanced triangles (SURVEY.md §8d C4): one %d-triangle soup object x %d instances, "
+                                     "%dx%dx%dspp Halton, PathIntegrator maxdepth %d, matte Kd .6, 2-triangle area light"
+                                     % (args.tris, args.grid * args.grid, args.xres, args.yres, args.spp, args.maxdepth),
+                    triangles=args.tris * args.grid * args.grid,
+                    l2_note="inputs larger than L2: every step streams the 1 GiB path-context pool through the 126 MB L2; no explicit flush")
+    if args.workload == "killeroo":
+        return dict(common, workload="scenes/killeroo-simple.pbrt of the reference (SURVEY.md §8d C3): 66 533 primitives (two loop-subdivided "
+                                     "killeroos with normals, plastic; sphere area light), %dx%dx%dspp Halton, PathIntegrator maxdepth %d"
+                                     % (args.xres, args.yres, args.spp, args.maxdepth),
+                    triangles=66532,
+                    l2_note="inputs larger than L2: every step streams the 1 GiB path-context pool and the film through the 126 MB L2; "
+                            "the scene itself (a few MB) is L2-resident; no explicit flush")
+    scene_mb = args.tris * (61 + 48) / 1e6
+    return dict(common, workload="synthetic %d random triangles (soup, SURVEY.md §8d C2%s), %dx%dx%dspp Halton, PathIntegrator maxdepth %d, "
+                                 "matte Kd .6, 2-triangle area light"
+                                 % (args.tris, "" if args.tris == WORKLOAD["tris"] else " generator at another size", args.xres, args.yres, args.spp,
+                                    args.maxdepth),
+                triangles=args.tris,
+                l2_note="inputs larger than L2: every step streams the 1 GiB path-context pool and the film through the 126 MB L2 "
+                        "next to the scene (node records + leaf records = %.0f MB); no explicit flush" % scene_mb)
 
 
 def main():
@@ -184,9 +234,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="soup", choices=["soup", "instanced"],
-                    help="soup = BASELINE.json configs[1], the headline (default); instanced = configs[3]'s generator")
+    ap.add_argument("--workload", default="soup", choices=["soup", "instanced", "killeroo"],
+                    help="soup = BASELINE.json configs[1], the headline (default; --tris for the 10 M / 50 M variants); "
+                         "killeroo = configs[2]; instanced = configs[3]'s generator")
     ap.add_argument("--tris", type=int, default=None, help="triangles (soup: 1 000 000) / triangles of the instanced object (100 000)")
+    ap.add_argument("--seed", type=int, default=WORKLOAD["seed"])
+    ap.add_argument("--jitter", type=float, default=None, help="soup: half edge of a triangle's vertex cube (0.02; SURVEY's 50 M scene: 0.005)")
     ap.add_argument("--grid", type=int, default=10, help="instanced: grid x grid instances")
     ap.add_argument("--xres", type=int, default=WORKLOAD["xres"])
     ap.add_argument("--yres", type=int, default=WORKLOAD["yres"])
@@ -195,11 +248,12 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=15.0, help="CPU seconds per reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    inst = args.workload == "instanced"
+    inst, kill = args.workload == "instanced", args.workload == "killeroo"
     if args.tris is None: args.tris = 100000 if inst else WORKLOAD["tris"]
-    if args.spp is None: args.spp = 128 if inst else WORKLOAD["spp"]
-    if args.maxdepth is None: args.maxdepth = 5 if inst else WORKLOAD["maxdepth"]
-    default_workload = not inst and all(getattr(args, k) == WORKLOAD[k] for k in ("tris", "xres", "yres", "spp", "maxdepth"))
+    if args.spp is None: args.spp = 128 if inst else 256 if kill else WORKLOAD["spp"]
+    if args.maxdepth is None: args.maxdepth = 5 if (inst or kill) else WORKLOAD["maxdepth"]
+    if args.jitter is None: args.jitter = WORKLOAD["jitter"]
+    default_workload = args.workload == "soup" and all(getattr(args, k) == WORKLOAD[k] for k in ("tris", "xres", "yres", "spp", "maxdepth"))
     args.warmup = max(args.warmup, 3)   # timing rule: at least three untimed steps
 
     if args.impl == "reference":
@@ -323,7 +377,7 @@ def main():
             try:
                 cb, _ = time_reference(hs, args, target_seconds=args.ref_seconds)
                 if cb:
-                    line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                    line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "host_cpus", "kind", "sample", "rays_per_sample")}
                     line["cpu_baseline"]["mrays_per_s"] = cb["mrays_per_s"]
             except Exception as e:  # the baseline is reporting only; never lose the GPU line
                 line["cpu_baseline"] = {"error": repr(e)}

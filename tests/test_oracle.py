@@ -284,3 +284,26 @@ def test_empty_and_degenerate_inputs(pb, port):
     rays["t_max"] = [np.inf, np.inf, 0.0]
     h = sc.intersect(rays)
     assert h["prim"][0] >= 0 and h["prim"][1] == -1 and h["prim"][2] == -1
+
+
+def test_killeroo_simple_fingerprint_of_the_surveyed_reference(pb, reference, tmp_path):
+    """`pbrt --outfile k8.pfm scenes/killeroo-simple.pbrt` of the reference binary gives md5
+    5424ce0f17db0c040e0f988ebcfe4b4d with 16 870 506 regular + 6 157 124 shadow ray tests.  The same file parsed by
+    THIS repo's host front end (parser, loop subdivision, transforms, SAH BVH builder), rendered by oracle/_ref (the
+    reference's own sources behind ref_harness.cpp) and written by our PFM writer must give those bytes: one test pins
+    the harness, the parser, the subdivision and the builder to the surveyed binary."""
+    import hashlib
+    from conftest import ROOT
+    scene = os.path.join(ROOT, "baseline", "_scenes", "killeroo-simple.pbrt")
+    if not os.path.exists(scene):
+        pytest.skip("baseline/_scenes/killeroo-simple.pbrt not staged (no /root/reference at build time)")
+    hs = pb.HostScene.from_file(scene)
+    d = hs.desc.contents
+    assert d.n_prims == 66533 and d.n_nodes == 59188 + 59189
+    img, _, st = reference.scene(hs).render(n_threads=0)
+    assert img.shape == (700, 700, 3)
+    assert (int(st.camera_rays), int(st.regular_rays), int(st.shadow_rays)) == (3920000, 16870506, 6157124)
+    out = str(tmp_path / "k8.pfm")
+    img = np.ascontiguousarray(img, np.float32)
+    assert pb.lib().pb2h_write_pfm(out.encode(), pb.ptr(img), 700, 700) == 0
+    assert hashlib.md5(open(out, "rb").read()).hexdigest() == "5424ce0f17db0c040e0f988ebcfe4b4d"
