@@ -9,7 +9,9 @@ PathIntegrator::Li for every pixel sample of BASELINE.json's configs[1] — synt
 triangles, 1920x1080, 64 spp (Halton), maxdepth 8, 1 B200 per rank.  The scene (BVH, triangles,
 materials, lights, light-distribution tables, Halton tables) is resident in HBM before the timed
 region; with N ranks the film's 16x16 tiles are dealt round-robin to the ranks, every rank renders
-its tiles into its own film and one NCCL reduce(sum) to rank 0 merges them.
+its tiles into its own film and one ncclReduce(sum) to rank 0 merges them - partition
+and reduce happen INSIDE pb2_render_path[_device] (pb2_dist_init; torch.distributed only launches the
+ranks, carries the NCCL id and takes the max over ranks of the timings).
 
 One JSON line is printed by rank 0:
   value        whole-job Msamples/s from the device-timed steps (inputs resident, film left on device)
@@ -273,19 +275,23 @@ def main():
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
     pb.init(local_rank)
     L = pb.lib()
+    if world > 1:
+        # the library's own NCCL communicator (pb2_dist_init): torch.distributed only carries rank 0's unique id to the others
+        from pbrt_v3_b200 import multigpu
+        multigpu.dist_init_from_torch()
 
     hs = build_scene(args)
     dev = hs.device_scene()  # BVH + triangles + tables resident in HBM from here on
     h, w = hs.film_shape()
     film = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")
-    params = hs.params_copy(tile_rank=rank, tile_count=world)
+    # tile_count = 0: the render call is a collective - every rank renders the tiles t with t % world == rank and the
+    # library sums the per-rank films onto rank 0 with one ncclReduce on the same stream (the distributed MergeFilmTile)
+    params = hs.params_copy(tile_rank=0, tile_count=0)
     stream = torch.cuda.current_stream().cuda_stream
     n_samples = w * h * args.spp
 
     def step(stats=None):
         pb.check(L.pb2_render_path_device(dev, hs.camera, hs.film, params, C.c_void_p(film.data_ptr()), 1, C.c_void_p(stream), stats))
-        if world > 1:
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
 
     def sync():
         if world > 1:
@@ -294,7 +300,7 @@ def main():
 
     # algorithmic bytes of one frame: one untimed frame with the counting traversal kernel
     st = pb.Stats()
-    count_params = hs.params_copy(tile_rank=rank, tile_count=world, flags=1)
+    count_params = hs.params_copy(tile_rank=0, tile_count=0, flags=1)
     pb.check(L.pb2_render_path_device(dev, hs.camera, hs.film, count_params, C.c_void_p(film.data_ptr()), 1, C.c_void_p(stream), C.byref(st)))
     node_visits, prim_tests = int(st.node_visits), int(st.prim_tests)
     rays_frame = int(st.regular_rays + st.shadow_rays)
@@ -328,21 +334,22 @@ def main():
     ms_per_step = ms_total / args.steps
     value = n_samples / ms_per_step / 1e3
 
-    # end to end through the host-buffer ABI call (rank-local tiles; N>1: plus the NCCL reduce and the D2H of rank 0)
-    host_film = np.zeros((h, w, 4), np.float32)
+    # end to end through the host-buffer ABI call pb2_render_path, at every N: structs in, this rank's tiles rendered, the
+    # NCCL reduce inside the call, and the merged film copied into rank 0's page-locked host buffer inside the call
+    host_ptr = C.c_void_p()
+    pb.check(L.pb2_host_alloc(h * w * 16, C.byref(host_ptr)))
+    host_film = np.ctypeslib.as_array(C.cast(host_ptr, C.POINTER(C.c_float)), shape=(h, w, 4))
     e2e_ms = []
     for i in range(2 + args.steps):
         sync()
         t0 = time.perf_counter()
-        if world == 1:
-            pb.check(L.pb2_render_path(dev, hs.camera, hs.film, params, pb.ptr(host_film), None))
-        else:
-            step()
-            if rank == 0:
-                host_film = film.cpu().numpy()
+        pb.check(L.pb2_render_path(dev, hs.camera, hs.film, params, host_ptr if rank == 0 else None, None))
         sync()
         if i >= 2:
             e2e_ms.append((time.perf_counter() - t0) * 1e3)
+    if rank == 0:
+        wsum = float(host_film[..., 3].sum())
+        assert n_samples <= wsum <= 1.02 * n_samples, "the merged film must hold every camera sample (weight sum %r)" % wsum
     e2e_t = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -384,6 +391,7 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        L.pb2_dist_shutdown()
         dist.destroy_process_group()
     return 0
 

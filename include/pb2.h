@@ -22,15 +22,17 @@
 #ifndef PB2_H
 #define PB2_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 7   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc;
+#define PB2_ABI_VERSION 8   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc;
                              * 5: uber / metal fields in pb2_material (128 bytes); 6: point / spot / distant lights
-                             * (pb2_light.type, pb2_scene_desc.delta_lights); 7: pb2_trace_wavefront, kernel-selector flags */
+                             * (pb2_light.type, pb2_scene_desc.delta_lights); 7: pb2_trace_wavefront, kernel-selector flags;
+                             * 8: pb2_dist_* (NCCL film reduce inside the render calls), pb2_host_alloc */
 
 typedef enum pb2_status {
     PB2_OK = 0,
@@ -38,7 +40,7 @@ typedef enum pb2_status {
     PB2_ERR_CUDA = 2,        /* a CUDA runtime call failed */
     PB2_ERR_INVALID = 3,     /* bad argument / inconsistent scene description */
     PB2_ERR_UNSUPPORTED = 4, /* feature of the reference outside this path's scope */
-    PB2_ERR_NCCL = 5
+    PB2_ERR_NCCL = 5         /* libnccl could not be loaded, or an NCCL call failed */
 } pb2_status;
 
 /* ---- scene description (host memory, flattened by the host-side Scene) ------------------- */
@@ -250,12 +252,15 @@ typedef struct pb2_path_params {
 /* Trace with the kernel that reads the 32-byte LinearBVHNode array directly instead of the derived
  * two-child records (same results; kept selectable so both kernels stay under test). */
 #define PB2_FLAG_LINEAR_NODES 2
-/* Trace with the kernel over the two-child records instead of the default four-child records (same results). */
-#define PB2_FLAG_WIDE2 4
+/* Trace with the kernel over the four-child records (two tree levels per fetch) instead of the default two-child
+ * records (same results; measured slightly slower, kept selectable and under test). */
+#define PB2_FLAG_WIDE4 4
 /* Trace with the one-thread-per-ray kernel (BVHAccel::Intersect as written) instead of the persistent-warp kernels. */
 #define PB2_FLAG_PLAIN_TRACE 8
 /* Give the record kernels 4 instead of 16 shared-memory stack entries per lane (tests: exercises the spill path). */
 #define PB2_FLAG_SMALL_STACK 16
+/* Fetch node records with 16-byte instead of 32-byte loads per lane (same results). */
+#define PB2_FLAG_LD128 32
 
 typedef struct pb2_ray {
     float o[3];
@@ -299,6 +304,35 @@ const char *pb2_last_error(void);
 int pb2_init(int device_id);
 int pb2_shutdown(void);
 
+/* Multi-GPU: one process per GPU; the film's 16x16 sample tiles are dealt round-robin to the ranks,
+ * the scene is replicated, and the distributed Film::MergeFilmTile (src/core/film.cpp:117-130) is ONE ncclReduce(sum) of
+ * the W x H x 4 floats to rank 0, issued by pb2_render_path[_device] itself.  NCCL (libnccl.so.2) is loaded at run time.
+ *   pb2_dist_unique_id   rank 0: a fresh communicator id (PB2_DIST_ID_BYTES bytes) to hand to every rank (any transport:
+ *                        bench.py broadcasts it over torch.distributed, pb2_pbrt passes it through the environment)
+ *   pb2_dist_init        collective over all ranks, after pb2_init: joins the communicator on this process's device
+ * After that a render call whose params.tile_count is 0 is a COLLECTIVE: every rank renders its own tiles, rank 0
+ * receives the merged film (the other ranks' film_rgbw may be NULL and is left untouched).  tile_count >= 1 keeps its
+ * meaning of an explicit, unreduced partition.  Without pb2_dist_init (or with world 1) nothing changes. */
+#define PB2_DIST_ID_BYTES 128
+int pb2_dist_unique_id(void *id);
+int pb2_dist_init(int rank, int world, const void *id);
+int pb2_dist_info(int *rank, int *world);
+int pb2_dist_shutdown(void);
+
+/* The work partition of the render kernels, evaluated on the host (no device needed; the kernels run the same function):
+ * for work items first .. first + n - 1 of the partition (params->tile_rank, params->tile_count) writes (pixel x, pixel y,
+ * sample number) per item, or (-1, -1, -1) for an item that falls outside the sample bounds / pixelbounds and is skipped;
+ * *n_items receives the number of work items of that partition.  Items are ordered tile by tile (the reference's 16 x 16
+ * tiles, src/core/integrator.cpp:235-240; tile t belongs to rank t % tile_count), then by sample number, then along a
+ * Morton curve inside the tile.  Used by the multi-process tests; `out` may be NULL to query the count. */
+int pb2_work_items(const pb2_film_desc *film, const pb2_path_params *params, int64_t first, int64_t n, int32_t *out,
+                   int64_t *n_items);
+
+/* Page-locked host memory for film buffers: pb2_render_path copies the film back at the full PCIe rate into such a
+ * buffer (cudaMemcpy into pageable memory is staged by the driver). */
+int pb2_host_alloc(size_t bytes, void **out);
+int pb2_host_free(void *p);
+
 /* Uploads a flattened Scene (src/core/scene.h:50-80).  Builds the spatial light-distribution
  * tables (src/core/lightdistrib.cpp:232-300) on the device. */
 int pb2_scene_create(const pb2_scene_desc *desc, pb2_scene **out);
@@ -321,7 +355,10 @@ int pb2_render_path(pb2_scene *scene, const pb2_camera *camera, const pb2_film_d
 /* Same computation with the film left resident in device memory (used by bench.py's device-timed
  * `value` and by the multi-GPU reduce).  film_rgbw_device is a DEVICE pointer to
  * 4*width*height floats, zeroed by the call when `clear` is non-zero.  `stream` is a cudaStream_t
- * (0 = default stream). Does not synchronise unless stats != NULL. */
+ * (0 = default stream).  The call BLOCKS: the host reads the wavefront's counters every few rounds to detect the
+ * end of the frame (work enqueued after the last of those reads may still be running on `stream` at return unless
+ * stats != NULL).  A pb2_scene carries the scratch of ONE render at a time (path-context pool, queues, counters):
+ * concurrent render calls on the same scene from different threads or streams are not supported. */
 int pb2_render_path_device(pb2_scene *scene, const pb2_camera *camera, const pb2_film_desc *film,
                            const pb2_path_params *params, float *film_rgbw_device, int clear,
                            void *stream, pb2_stats *stats);

@@ -27,7 +27,7 @@ PB2_OK, PB2_ERR_NO_DEVICE, PB2_ERR_CUDA, PB2_ERR_INVALID, PB2_ERR_UNSUPPORTED, P
 PB2_PRIM_TRIANGLE, PB2_PRIM_SPHERE, PB2_PRIM_INSTANCE = 0, 1, 2
 PB2_FILTER_BOX, PB2_FILTER_GAUSSIAN, PB2_FILTER_MITCHELL, PB2_FILTER_SINC, PB2_FILTER_TRIANGLE = 0, 1, 2, 3, 4
 PB2_MAT_NONE, PB2_MAT_MATTE, PB2_MAT_PLASTIC, PB2_MAT_MIRROR, PB2_MAT_GLASS, PB2_MAT_SUBSTRATE, PB2_MAT_METAL, PB2_MAT_UBER = range(8)
-PB2_ABI_VERSION = 7   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
+PB2_ABI_VERSION = 8   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
 PB2_LIGHTDIST_UNIFORM, PB2_LIGHTDIST_POWER, PB2_LIGHTDIST_SPATIAL = 0, 1, 2
 PB2_LIGHT_AREA, PB2_LIGHT_POINT, PB2_LIGHT_SPOT, PB2_LIGHT_DISTANT = 0, 1, 2, 3
 
@@ -138,7 +138,7 @@ HIT_DTYPE = np.dtype([("prim", np.int32), ("t", np.float32), ("b", np.float32, 3
                       ("dpdu", np.float32, 3), ("uv", np.float32, 2)])
 WFHIT_DTYPE = np.dtype([("found", np.int32), ("leaf", np.int32), ("prim", np.int32), ("t", np.float32), ("b", np.float32, 3),
                         ("listed", np.int32)])
-PB2_FLAG_COUNT_TRAVERSAL, PB2_FLAG_LINEAR_NODES, PB2_FLAG_WIDE2, PB2_FLAG_PLAIN_TRACE, PB2_FLAG_SMALL_STACK = 1, 2, 4, 8, 16
+PB2_FLAG_COUNT_TRAVERSAL, PB2_FLAG_LINEAR_NODES, PB2_FLAG_WIDE4, PB2_FLAG_PLAIN_TRACE, PB2_FLAG_SMALL_STACK, PB2_FLAG_LD128 = 1, 2, 4, 8, 16, 32
 NODE_DTYPE = np.dtype([("bmin", np.float32, 3), ("bmax", np.float32, 3), ("offset", np.int32),
                        ("n_prims", np.uint16), ("axis", np.uint8), ("pad", np.uint8)])
 assert WFHIT_DTYPE.itemsize == C.sizeof(WfHit)
@@ -170,6 +170,12 @@ def lib():
     L.pb2_intersect.argtypes = [vp, vp, C.c_int64, vp]
     L.pb2_intersect_p.argtypes = [vp, vp, C.c_int64, vp]
     L.pb2_trace_wavefront.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
+    L.pb2_work_items.argtypes = [C.POINTER(FilmDesc), C.POINTER(PathParams), C.c_int64, C.c_int64, vp, C.POINTER(C.c_int64)]
+    L.pb2_dist_unique_id.argtypes = [vp]
+    L.pb2_dist_init.argtypes = [C.c_int, C.c_int, vp]
+    L.pb2_dist_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.pb2_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.pb2_host_free.argtypes = [vp]
     L.pb2_render_path.argtypes = [vp, C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), vp, C.POINTER(Stats)]
     L.pb2_render_path_device.argtypes = [vp, C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), vp,
                                          C.c_int, vp, C.POINTER(Stats)]

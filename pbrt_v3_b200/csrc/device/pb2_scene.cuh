@@ -122,6 +122,7 @@ struct DRaySetup {
     int neg0, neg1, neg2;
     int kx, ky, kz;
     float Sx, Sy, Sz;
+    int slow;   // origin or 1 / d not finite: slab tests may meet NaNs (0 * inf) and must take the reference's exact compare sequence
 };
 
 PB2_HD float permuted(V3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
@@ -144,6 +145,9 @@ PB2_HD DRaySetup setupRay(V3 o, V3 d) {
     s.Sx = -dx / dz;
     s.Sy = -dy / dz;
     s.Sz = 1.f / dz;
+    // |x| < inf is false for NaN and infinities alike
+    s.slow = !((fabsf(s.invDir.x) < PB2_INFINITY) & (fabsf(s.invDir.y) < PB2_INFINITY) & (fabsf(s.invDir.z) < PB2_INFINITY) &
+               (fabsf(o.x) < PB2_INFINITY) & (fabsf(o.y) < PB2_INFINITY) & (fabsf(o.z) < PB2_INFINITY));
     return s;
 }
 
@@ -221,6 +225,41 @@ PB2_HD void slabTestPair(float4 q0, float4 q1, float4 q2, const DRaySetup &r, fl
 #else
     *pass0 = slabTestT(q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, r, rayTMax, tMin0);
     *pass1 = slabTestT(q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, r, rayTMax, tMin1);
+#endif
+}
+
+// The same verdicts with min / max instructions, for rays whose origin and 1 / d are finite (DRaySetup::slow == 0).
+// Without NaNs the reference's compare-and-assign steps ARE maxima and minima: tMin = max(tx0, ty0, tz0), tMax =
+// min(tx1, ty1, tz1) (values equal up to the sign of a zero, which no comparison sees), and its two early returns reject
+// exactly the boxes where some entry parameter exceeds ANOTHER axis' exit parameter.  `tMin <= tMax` also compares the
+// two parameters of the same axis; they can only be out of order when the exit parameter is negative (the far-plane
+// scaling by 1 + 2 gamma(3) moves it away from zero), and then the reference's final `tMax > 0` rejects the box as well.
+// FMNMX3 takes three operands: a box costs 5 instructions after the multiplications instead of ~16.
+PB2_HD void slabTestPairFast(float4 q0, float4 q1, float4 q2, const DRaySetup &r, float rayTMax, bool *pass0, bool *pass1,
+                             float *tMin0, float *tMin1) {
+#if defined(__CUDA_ARCH__)
+    const float2 minX = make_float2(q0.x, q1.z), minY = make_float2(q0.y, q1.w), minZ = make_float2(q0.z, q2.x);
+    const float2 maxX = make_float2(q0.w, q2.y), maxY = make_float2(q1.x, q2.z), maxZ = make_float2(q1.y, q2.w);
+    const float2 nearX = r.neg0 ? maxX : minX, farX = r.neg0 ? minX : maxX;
+    const float2 nearY = r.neg1 ? maxY : minY, farY = r.neg1 ? minY : maxY;
+    const float2 nearZ = r.neg2 ? maxZ : minZ, farZ = r.neg2 ? minZ : maxZ;
+    const float2 nox = make_float2(-r.o.x, -r.o.x), noy = make_float2(-r.o.y, -r.o.y), noz = make_float2(-r.o.z, -r.o.z);
+    const float2 ix = make_float2(r.invDir.x, r.invDir.x), iy = make_float2(r.invDir.y, r.invDir.y), iz = make_float2(r.invDir.z, r.invDir.z);
+    const float2 sc2 = make_float2(kSlabScale, kSlabScale);
+    const float2 tMin = __fmul2_rn(__fadd2_rn(nearX, nox), ix);
+    const float2 tMax = __fmul2_rn(__fmul2_rn(__fadd2_rn(farX, nox), ix), sc2);
+    const float2 tyMin = __fmul2_rn(__fadd2_rn(nearY, noy), iy);
+    const float2 tyMax = __fmul2_rn(__fmul2_rn(__fadd2_rn(farY, noy), iy), sc2);
+    const float2 tzMin = __fmul2_rn(__fadd2_rn(nearZ, noz), iz);
+    const float2 tzMax = __fmul2_rn(__fmul2_rn(__fadd2_rn(farZ, noz), iz), sc2);
+    const float lo0 = fmaxf(fmaxf(tMin.x, tyMin.x), tzMin.x), hi0 = fminf(fminf(tMax.x, tyMax.x), tzMax.x);
+    const float lo1 = fmaxf(fmaxf(tMin.y, tyMin.y), tzMin.y), hi1 = fminf(fminf(tMax.y, tyMax.y), tzMax.y);
+    *tMin0 = lo0;
+    *tMin1 = lo1;
+    *pass0 = (lo0 <= hi0) & (lo0 < rayTMax) & (hi0 > 0);
+    *pass1 = (lo1 <= hi1) & (lo1 < rayTMax) & (hi1 > 0);
+#else
+    slabTestPair(q0, q1, q2, r, rayTMax, pass0, pass1, tMin0, tMin1);
 #endif
 }
 
@@ -313,6 +352,18 @@ PB2_HD float4 ldg4(const float4 *p) {
 #endif
 }
 PB2_HD int asInt(float f) { return (int)floatBits(f); }
+// 32 bytes per lane in one request (LDG.E.256, sm_100): a node record is fetched with half as many L1 wavefronts as
+// with 16-byte loads - each lane of a warp reads another record, and the L1 data pipe serves such a scattered request
+// one lane per cycle whatever its width (ncu: l1tex__data_pipe_lsu_wavefronts at 88 % of peak with 16-byte loads).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void ldg256(const float4 *p, float4 &a, float4 &b) {
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
+#else
+inline void ldg256(const float4 *p, float4 &a, float4 &b) { a = p[0]; b = p[1]; }
+#endif
 
 struct SphereHit;  // pb2_sphere.cuh
 PB2_HDN bool sphereLeafTest(const DScene &sc, int sphereIndex, const DRay &ray, float rayTMax, float *tHit, float *phi);

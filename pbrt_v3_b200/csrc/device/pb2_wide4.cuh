@@ -155,6 +155,35 @@ PB2_HD void slabTestPair4(float4 a, float4 b, float4 c, const DRaySetup &r, floa
 #endif
 }
 
+// slabTestPairFast (pb2_scene.cuh) for two slots of a four-child record: rays with finite origin and 1 / d only.
+PB2_HD void slabTestPair4Fast(float4 a, float4 b, float4 c, const DRaySetup &r, float rayTMax, bool *pass0, bool *pass1, float *tMin0,
+                              float *tMin1) {
+#if defined(__CUDA_ARCH__)
+    const float2 minX = make_float2(a.x, a.y), minY = make_float2(a.z, a.w), minZ = make_float2(b.x, b.y);
+    const float2 maxX = make_float2(b.z, b.w), maxY = make_float2(c.x, c.y), maxZ = make_float2(c.z, c.w);
+    const float2 nearX = r.neg0 ? maxX : minX, farX = r.neg0 ? minX : maxX;
+    const float2 nearY = r.neg1 ? maxY : minY, farY = r.neg1 ? minY : maxY;
+    const float2 nearZ = r.neg2 ? maxZ : minZ, farZ = r.neg2 ? minZ : maxZ;
+    const float2 nox = make_float2(-r.o.x, -r.o.x), noy = make_float2(-r.o.y, -r.o.y), noz = make_float2(-r.o.z, -r.o.z);
+    const float2 ix = make_float2(r.invDir.x, r.invDir.x), iy = make_float2(r.invDir.y, r.invDir.y), iz = make_float2(r.invDir.z, r.invDir.z);
+    const float2 sc2 = make_float2(kSlabScale, kSlabScale);
+    const float2 tMin = __fmul2_rn(__fadd2_rn(nearX, nox), ix);
+    const float2 tMax = __fmul2_rn(__fmul2_rn(__fadd2_rn(farX, nox), ix), sc2);
+    const float2 tyMin = __fmul2_rn(__fadd2_rn(nearY, noy), iy);
+    const float2 tyMax = __fmul2_rn(__fmul2_rn(__fadd2_rn(farY, noy), iy), sc2);
+    const float2 tzMin = __fmul2_rn(__fadd2_rn(nearZ, noz), iz);
+    const float2 tzMax = __fmul2_rn(__fmul2_rn(__fadd2_rn(farZ, noz), iz), sc2);
+    const float lo0 = fmaxf(fmaxf(tMin.x, tyMin.x), tzMin.x), hi0 = fminf(fminf(tMax.x, tyMax.x), tzMax.x);
+    const float lo1 = fmaxf(fmaxf(tMin.y, tyMin.y), tzMin.y), hi1 = fminf(fminf(tMax.y, tyMax.y), tzMax.y);
+    *tMin0 = lo0;
+    *tMin1 = lo1;
+    *pass0 = (lo0 <= hi0) & (lo0 < rayTMax) & (hi0 > 0);
+    *pass1 = (lo1 <= hi1) & (lo1 < rayTMax) & (hi1 > 0);
+#else
+    slabTestPair4(a, b, c, r, rayTMax, pass0, pass1, tMin0, tMin1);
+#endif
+}
+
 // One visit of a four-child record: which slots' boxes the ray enters (pass, tMin) and, for each entered slot, how many
 // entered slots the reference's order visits AFTER it (`after`).  The slot with after == nPass - 1 is the one to continue
 // with; every other entered slot goes on the stack at position sp + after[slot], which puts the next one to visit on top.
@@ -167,11 +196,17 @@ struct Wide4Visit {
     int after[4];
     int nPass;
 };
+template <bool FAST = false>
 PB2_HD Wide4Visit wide4Visit(float4 q0, float4 q1, float4 q2, float4 q3, float4 q4, float4 q5, float4 q6, uint32_t meta, const DRaySetup &r,
                              float tMax) {
     Wide4Visit v;
-    slabTestPair4(q0, q1, q2, r, tMax, &v.pass[0], &v.pass[1], &v.tMin[0], &v.tMin[1]);
-    slabTestPair4(q3, q4, q5, r, tMax, &v.pass[2], &v.pass[3], &v.tMin[2], &v.tMin[3]);
+    if (FAST) {
+        slabTestPair4Fast(q0, q1, q2, r, tMax, &v.pass[0], &v.pass[1], &v.tMin[0], &v.tMin[1]);
+        slabTestPair4Fast(q3, q4, q5, r, tMax, &v.pass[2], &v.pass[3], &v.tMin[2], &v.tMin[3]);
+    } else {
+        slabTestPair4(q0, q1, q2, r, tMax, &v.pass[0], &v.pass[1], &v.tMin[0], &v.tMin[1]);
+        slabTestPair4(q3, q4, q5, r, tMax, &v.pass[2], &v.pass[3], &v.tMin[2], &v.tMin[3]);
+    }
     // an empty slot's box is (+inf, -inf), which no ray enters; the explicit test keeps NaNs of 0 * inf out of the verdict
     v.pass[1] &= floatBits(q6.y) != WIDE4_EMPTY;
     v.pass[3] &= floatBits(q6.w) != WIDE4_EMPTY;

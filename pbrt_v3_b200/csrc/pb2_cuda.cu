@@ -14,8 +14,11 @@
 // default IEEE division and square root, no fast-math.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: libnccl is loaded at run time by pb2_dist_init (no link-time dependency)
 
 #include <algorithm>
+#include <chrono>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -48,6 +51,51 @@ static int setError(int code, const std::string &msg) {
 static bool g_initialised = false;
 static int g_device = -1;
 static int g_numSMs = 0;
+
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU: one process per GPU, the film reduce over NCCL.  The communicator spans the processes
+// that called pb2_dist_init with the same unique id; rank r renders the tiles t with t % world == r and
+// Film::MergeFilmTile across GPUs is one ncclReduce(sum) of the W x H x 4 floats to rank 0.
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*GetVersion)(int *) = nullptr;
+};
+static NcclApi g_nccl;
+static struct {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+} g_dist;
+
+static int loadNccl() {
+    if (g_nccl.handle) return PB2_OK;
+    // a libnccl.so.2 that is already mapped into the process (torch's bundled copy under torchrun) is found by its soname
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return setError(PB2_ERR_NCCL, std::string("libnccl.so.2 could not be loaded: ") + dlerror());
+    NcclApi a;
+    a.handle = h;
+    a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+    a.Reduce = (decltype(a.Reduce))dlsym(h, "ncclReduce");
+    a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+    a.GetVersion = (decltype(a.GetVersion))dlsym(h, "ncclGetVersion");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.Reduce || !a.GetErrorString)
+        return setError(PB2_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
+    g_nccl = a;
+    return PB2_OK;
+}
+#define NCCL_TRY(expr)                                                                                        \
+    do {                                                                                                      \
+        ncclResult_t _r = (expr);                                                                             \
+        if (_r != ncclSuccess) return setError(PB2_ERR_NCCL, std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); \
+    } while (0)
 
 static int envInt(const char *name, int def) {
     const char *v = std::getenv(name);
@@ -319,7 +367,7 @@ struct DRenderParams {
 
 enum { CTR_WORK = 0, CTR_CAMERA = 1, CTR_REGULAR = 2, CTR_SHADOW = 3, CTR_NODES = 4, CTR_PRIMS = 5, CTR_COUNT = 8 };
 
-__device__ __forceinline__ int compact1by1(unsigned x) {
+PB2_HD int compact1by1(unsigned x) {
     x &= 0x55555555u;
     x = (x ^ (x >> 1)) & 0x33333333u;
     x = (x ^ (x >> 2)) & 0x0f0f0f0fu;
@@ -331,7 +379,7 @@ __device__ __forceinline__ int compact1by1(unsigned x) {
 // integrator.cpp:235-240), then by sample number, then in Morton order inside the tile, so 32
 // consecutive items are one sample number of an 8x4 pixel block: coherent camera rays for a warp.
 // Tile t belongs to this call when t % tileCount == tileRank (multi-GPU partition).
-__device__ __forceinline__ bool decodeWork(const DRenderParams &rp, long long item, int *px, int *py, int *sample) {
+PB2_HD bool decodeWork(const DRenderParams &rp, long long item, int *px, int *py, int *sample) {
     long long perTile = 256LL * rp.spp;
     long long owned = item / perTile;
     int r = (int)(item - owned * perTile);
@@ -593,13 +641,17 @@ typedef void (*TraceKernel)(DScene, WfPool, int);
 typedef void (*AdvanceKernel)(DScene, DRenderParams, WfPool, int, int, int, float4 *, unsigned long long *);
 
 // Which traversal kernel a scene is traced with (pb2_wavefront.cuh), and its launch shape.
-//   default                   k_wf_trace_w<4>: persistent warps over the four-child records
-//   PB2_FLAG_WIDE2            k_wf_trace_w<2>: the same over the two-child records
+//   default                   k_wf_trace_w<2>: persistent warps over the two-child records, 32-byte loads
+//   PB2_FLAG_WIDE4            k_wf_trace_w<4>: the same over the four-child records (two tree levels per fetch)
+//   PB2_FLAG_LD128            either of them with 16-byte instead of 32-byte loads
 //   PB2_FLAG_LINEAR_NODES     k_wf_trace: the same over the reference's 32-B LinearBVHNode array; also the fallback for
 //                             scenes beyond the record limits (2^27 primitives, 16 per leaf)
 //   PB2_FLAG_PLAIN_TRACE /    k_wf_trace_plain: one thread per ray, BVHAccel::Intersect as written (the counting form
 //   PB2_FLAG_COUNT_TRAVERSAL  also returns node / primitive counters)
 //   PB2_FLAG_SMALL_STACK      4 instead of 16 shared-memory stack entries per lane (tests: forces the local-memory spill)
+// Measured (1920x1080x16, 1 M soup / instanced / killeroo-like, Msamples/s): two-child 207.4 / 173.4 / 187.3, four-child
+// 204.8 / 163.9 / 181.9 - the four-child visit needs as many instructions per box as the two-child one (ordering and up
+// to three deferred entries), so halving the dependent fetches buys nothing; 32-byte loads: +4 % on both.
 struct TraceLaunch {
     TraceKernel fn = nullptr;
     int block = 128;
@@ -614,25 +666,34 @@ static int selectTraceKernel(const pb2_scene *scene, int flags, TraceLaunch *out
     const bool instanced = scene->d.instances != nullptr;
     const bool records = scene->d.wide4 != nullptr && !(flags & PB2_FLAG_LINEAR_NODES);
     const bool small = (flags & PB2_FLAG_SMALL_STACK) != 0;
-    int sdepth = 0;
     // the two levels of an instanced scene must fit the 64-entry stack of the 32-B-node kernel
     const bool linearFits = !instanced || scene->bvhDepth + 3 + scene->instDepth <= 64;
     if (flags & PB2_FLAG_COUNT_TRAVERSAL) { t.fn = k_wf_trace_plain<true>; t.name = "k_wf_trace_plain<count>"; }
     else if ((flags & PB2_FLAG_PLAIN_TRACE) || (!records && !linearFits)) { t.fn = k_wf_trace_plain<false>; t.name = "k_wf_trace_plain"; }
-    else if (records && !(flags & PB2_FLAG_WIDE2)) {
+    else if (records && (flags & PB2_FLAG_WIDE4)) {
         t.name = "k_wf_trace_w<4>";
-        sdepth = small ? 4 : 16;
-        if (instanced) t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 5, true, true> : k_wf_trace_w<4, 1, 8, 4, 16, 5, true, true>;
-        else if (spheres) t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 5, true> : k_wf_trace_w<4, 1, 8, 4, 16, 5, true>;
-        else t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 7> : k_wf_trace_w<4, 1, 8, 4, 16, 7>;
+        if (flags & PB2_FLAG_LD128) {
+            if (instanced) t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 5, true, true> : k_wf_trace_w<4, 1, 8, 4, 16, 5, true, true>;
+            else if (spheres) t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 5, true> : k_wf_trace_w<4, 1, 8, 4, 16, 5, true>;
+            else t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 7> : k_wf_trace_w<4, 1, 8, 4, 16, 7>;
+        } else {
+            if (instanced) t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 5, true, true, true> : k_wf_trace_w<4, 1, 8, 4, 16, 5, true, true, true>;
+            else if (spheres) t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 5, true, false, true> : k_wf_trace_w<4, 1, 8, 4, 16, 5, true, false, true>;
+            else t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 7, false, false, true> : k_wf_trace_w<4, 1, 8, 4, 16, 7, false, false, true>;
+        }
     } else if (records) {
         // LEAF_T = 1: a warp turns to its leaves as soon as one lane holds one (sweep 16 / 12 / 8 / 6 / 4 / 3 / 2 / 1 at
         // 16 spp: 192.8 / 199.3 / 202.9 / 203.6 / 204.4 / 204.7 / 205.2 / 205.9 Msamples/s); 56 registers, 9 blocks / SM
         t.name = "k_wf_trace_w<2>";
-        sdepth = small ? 4 : 16;
-        if (instanced) t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 6, true, true> : k_wf_trace_w<2, 1, 8, 4, 16, 6, true, true>;
-        else if (spheres) t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 6, true> : k_wf_trace_w<2, 1, 8, 4, 16, 6, true>;
-        else t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 9> : k_wf_trace_w<2, 1, 8, 4, 16, 9>;
+        if (flags & PB2_FLAG_LD128) {
+            if (instanced) t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 6, true, true> : k_wf_trace_w<2, 1, 8, 4, 16, 6, true, true>;
+            else if (spheres) t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 6, true> : k_wf_trace_w<2, 1, 8, 4, 16, 6, true>;
+            else t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 9> : k_wf_trace_w<2, 1, 8, 4, 16, 9>;
+        } else {
+            if (instanced) t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 6, true, true, true> : k_wf_trace_w<2, 1, 8, 4, 16, 6, true, true, true>;
+            else if (spheres) t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 6, true, false, true> : k_wf_trace_w<2, 1, 8, 4, 16, 6, true, false, true>;
+            else t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 9, false, false, true> : k_wf_trace_w<2, 1, 8, 4, 16, 9, false, false, true>;
+        }
     } else {
         t.name = "k_wf_trace";
         if (instanced) t.fn = k_wf_trace<8, 8, 2, 32, true, true, 6, true>;
@@ -643,11 +704,6 @@ static int selectTraceKernel(const pb2_scene *scene, int flags, TraceLaunch *out
     if (t.name[10] == 'p') {   // k_wf_trace_plain: one thread per list entry, no stack in shared memory
         *out = t;
         return PB2_OK;
-    }
-    // the record kernels take their stack as dynamic shared memory
-    if (sdepth > 0) {
-        t.smem = (size_t)sdepth * t.block * sizeof(int2);
-        CUDA_TRY(cudaFuncSetAttribute(t.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
     }
     int blocksPerSM = 1;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, t.fn, t.block, t.smem));
@@ -709,6 +765,13 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     AdvanceKernel advShade = scene->hasSpecular ? (spheres ? k_wf_advance<true, true, 4, true> : k_wf_advance<true, false, 4, true>)
                              : spheres ? k_wf_advance<true, true, 4>
                                        : k_wf_advance<true, false, 4>;
+    typedef void (*FinishKernel)(DScene, DRenderParams, WfPool, int, unsigned, float4 *);
+    FinishKernel finish = scene->hasSpecular ? (spheres ? k_wf_finish<true, true> : k_wf_finish<false, true>)
+                                             : (spheres ? k_wf_finish<true, false> : k_wf_finish<false, false>);
+    // the frame's last paths are walked to their end by one thread each once this few are left (k_wf_finish)
+    static const int finishPerSM = envInt("PB2_FINISH", 256);
+    const unsigned finishThreshold = (flags & PB2_FLAG_COUNT_TRAVERSAL) ? 0u : (unsigned)(g_numSMs * std::max(0, finishPerSM));
+    const int finishBlocks = std::max(1, (int)((finishThreshold + 127) / 128));
     const int blocks256 = std::min((capacity + 255) / 256, g_numSMs * 16);
     const int blocks128 = std::min((capacity + 127) / 128, g_numSMs * 32);
 
@@ -742,8 +805,9 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         }
         advLight<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
         advShade<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_SHADE, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
-        k_wf_reset<<<1, 32, 0, stream>>>(pool, WQ_FREE0 + cur, WQ_TRACE0 + cur);
-        nLaunch += 5;
+        if (finishThreshold) finish<<<finishBlocks, 128, 0, stream>>>(scene->d, rp, pool, WQ_TRACE0 + next, finishThreshold, film);
+        k_wf_reset<<<1, 32, 0, stream>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur, WQ_TRACE0 + next, finishThreshold);
+        nLaunch += finishThreshold ? 6 : 5;
         cur = next;
         // The host looks at the counters only every `syncEvery` rounds; rounds enqueued after the frame
         // has drained find empty lists and cost a few microseconds each.
@@ -813,6 +877,79 @@ int pb2_shutdown(void) {
     g_halton.primes = g_halton.primeSums = nullptr;
     g_halton.perms = nullptr;
     g_initialised = false;
+    return PB2_OK;
+}
+
+int pb2_work_items(const pb2_film_desc *film, const pb2_path_params *pp, int64_t first, int64_t n, int32_t *out, int64_t *n_items) {
+    if (!film || !pp) return setError(PB2_ERR_INVALID, "null argument");
+    if (pp->samples_per_pixel <= 0 || pp->tile_count < 0 || pp->tile_rank < 0 || (pp->tile_count > 0 && pp->tile_rank >= pp->tile_count))
+        return setError(PB2_ERR_INVALID, "bad samples_per_pixel / tile_rank / tile_count");
+    pb2_camera cam;
+    memset(&cam, 0, sizeof(cam));
+    const DRenderParams rp = makeRenderParams(&cam, film, pp);   // the partition does not depend on the camera
+    if (n_items) *n_items = rp.nWorkItems;
+    for (int64_t i = 0; i < n && out; ++i) {
+        int px = -1, py = -1, sample = -1;
+        const bool inside = first + i >= 0 && first + i < rp.nWorkItems && decodeWork(rp, first + i, &px, &py, &sample);
+        out[3 * i] = inside ? px : -1;
+        out[3 * i + 1] = inside ? py : -1;
+        out[3 * i + 2] = inside ? sample : -1;
+    }
+    return PB2_OK;
+}
+
+int pb2_dist_unique_id(void *id128) {
+    if (!id128) return setError(PB2_ERR_INVALID, "null argument");
+    int rc = loadNccl();
+    if (rc) return rc;
+    static_assert(sizeof(ncclUniqueId) == PB2_DIST_ID_BYTES, "ncclUniqueId is 128 bytes");
+    ncclUniqueId id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return PB2_OK;
+}
+
+int pb2_dist_init(int rank, int world, const void *id128) {
+    int rc = requireDevice();
+    if (rc) return rc;
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !id128)) return setError(PB2_ERR_INVALID, "bad rank / world / id");
+    if (g_dist.comm) return setError(PB2_ERR_INVALID, "pb2_dist_init: a communicator already exists (call pb2_dist_shutdown first)");
+    g_dist.rank = rank;
+    g_dist.world = world;
+    if (world == 1) return PB2_OK;
+    if ((rc = loadNccl())) return rc;
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof(id));
+    CUDA_TRY(cudaSetDevice(g_device));
+    NCCL_TRY(g_nccl.CommInitRank(&g_dist.comm, world, id, rank));
+    return PB2_OK;
+}
+
+int pb2_dist_info(int *rank, int *world) {
+    if (rank) *rank = g_dist.rank;
+    if (world) *world = g_dist.world;
+    return PB2_OK;
+}
+
+int pb2_dist_shutdown(void) {
+    if (g_dist.comm) g_nccl.CommDestroy(g_dist.comm);
+    g_dist.comm = nullptr;
+    g_dist.rank = 0;
+    g_dist.world = 1;
+    return PB2_OK;
+}
+
+int pb2_host_alloc(size_t bytes, void **out) {
+    if (!out) return setError(PB2_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int rc = requireDevice();
+    if (rc) return rc;
+    CUDA_TRY(cudaMallocHost(out, std::max<size_t>(bytes, 1)));
+    return PB2_OK;
+}
+
+int pb2_host_free(void *p) {
+    if (p) cudaFreeHost(p);
     return PB2_OK;
 }
 
@@ -1242,6 +1379,15 @@ int pb2_render_path_device(pb2_scene *scene, const pb2_camera *cam, const pb2_fi
     if ((rc = validateRenderArgs(scene, cam, film, pp))) return rc;
     if (!film_rgbw_device) return setError(PB2_ERR_INVALID, "null film pointer");
     cudaStream_t stream = (cudaStream_t)stream_;
+    // tile_count == 0: the partition of the communicator (every rank renders its tiles, the films are summed on rank 0);
+    // a caller that sets tile_count >= 1 partitions by hand and gets exactly the tiles it asked for, unreduced
+    const bool distributed = pp->tile_count == 0 && g_dist.world > 1;
+    pb2_path_params ppLocal = *pp;
+    if (distributed) {
+        ppLocal.tile_rank = g_dist.rank;
+        ppLocal.tile_count = g_dist.world;
+        pp = &ppLocal;
+    }
     DRenderParams rp = makeRenderParams(cam, film, pp);
     {
         float table[256];
@@ -1265,8 +1411,14 @@ int pb2_render_path_device(pb2_scene *scene, const pb2_camera *cam, const pb2_fi
     double traceMs = 0;
     if (rp.nWorkItems > 0) {
         rc = renderWavefront(scene, rp, (float4 *)film_rgbw_device, stream, pp->flags, stats != nullptr, &launches, &traceMs);
-        if (rc) return rc;
+        if (rc) {
+            if (e0) cudaEventDestroy(e0);
+            if (e1) cudaEventDestroy(e1);
+            return rc;
+        }
     }
+    if (distributed)   // the distributed Film::MergeFilmTile (film.cpp:117-130): in place, the sum lands in rank 0's film
+        NCCL_TRY(g_nccl.Reduce(film_rgbw_device, film_rgbw_device, nPixels * 4, ncclFloat, ncclSum, 0, g_dist.comm, stream));
     if (stats) {
         CUDA_TRY(cudaEventRecord(e1, stream));
         CUDA_TRY(cudaEventSynchronize(e1));
@@ -1295,7 +1447,7 @@ int pb2_render_path(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc
     int rc = requireDevice();
     if (rc) return rc;
     if ((rc = validateRenderArgs(scene, cam, film, pp))) return rc;
-    if (!film_rgbw) return setError(PB2_ERR_INVALID, "null film pointer");
+    if (!film_rgbw && !(pp->tile_count == 0 && g_dist.world > 1 && g_dist.rank != 0)) return setError(PB2_ERR_INVALID, "null film pointer");
     size_t nFloats = 4 * (size_t)(film->cropped_pixel_bounds[2] - film->cropped_pixel_bounds[0]) *
                      (size_t)(film->cropped_pixel_bounds[3] - film->cropped_pixel_bounds[1]);
     if (nFloats == 0) return PB2_OK;
@@ -1310,18 +1462,15 @@ int pb2_render_path(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc
     memset(&local, 0, sizeof(local));
     rc = pb2_render_path_device(scene, cam, film, pp, scene->film, 1, nullptr, stats ? &local : nullptr);
     if (rc) return rc;
-    cudaEvent_t e0, e1;
-    CUDA_TRY(cudaEventCreate(&e0));
-    CUDA_TRY(cudaEventCreate(&e1));
-    CUDA_TRY(cudaEventRecord(e0));
-    CUDA_TRY(cudaMemcpy(film_rgbw, scene->film, nFloats * sizeof(float), cudaMemcpyDeviceToHost));
-    CUDA_TRY(cudaEventRecord(e1));
-    CUDA_TRY(cudaEventSynchronize(e1));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    local.d2h_ms = ms;
+    const bool receives = !(pp->tile_count == 0 && g_dist.world > 1 && g_dist.rank != 0);   // the merged film lands on rank 0
+    if (receives) {
+        // full PCIe rate when film_rgbw is page-locked (pb2_host_alloc); staged by the driver otherwise
+        auto t0 = std::chrono::steady_clock::now();
+        CUDA_TRY(cudaMemcpyAsync(film_rgbw, scene->film, nFloats * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
+        CUDA_TRY(cudaStreamSynchronize(nullptr));
+        local.d2h_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    } else
+        CUDA_TRY(cudaStreamSynchronize(nullptr));
     if (stats) *stats = local;
     return PB2_OK;
 }

@@ -444,12 +444,11 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
 // device/pb2_wide4.cuh) - two levels of the reference's tree per fetch: a visit tests the four
 // grandchildren's boxes, continues with the first entered one in the reference's visiting order and
 // defers the others (up to three stack entries, the next one to visit on top).
-template <int WIDTH, int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, bool SPHERES = false, bool INST = false>
+template <int WIDTH, int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, bool SPHERES = false, bool INST = false, bool LD256 = false>
 __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
     static_assert(WIDTH == 2 || WIDTH == 4, "two- or four-child records");
     constexpr int BLOCK = 128;
-    extern __shared__ int2 dynSmem[];
-    int2 *sstack = dynSmem;                // [SDEPTH][BLOCK] of (child reference, tMin bits)
+    __shared__ int2 sstack[SDEPTH * BLOCK];   // [SDEPTH][BLOCK] of (child reference, tMin bits)
     // entries beyond SDEPTH (rare: only passing far children are pushed).  Worst case: one entry per level of the
     // reference's <= 64-level stack for WIDTH 2, three per two levels for WIDTH 4, plus the instance frame
     int2 lstack[(WIDTH == 4 ? 100 : 66) - SDEPTH];
@@ -476,6 +475,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
     rs.neg0 = rs.neg1 = rs.neg2 = 0;
     rs.kx = rs.ky = rs.kz = 0;
     rs.Sx = rs.Sy = rs.Sz = 0;
+    rs.slow = 0;
     float tMax = 0;
     int cur = 0, sp = 0, leafFirst = 0, leafN = 0;
     while (true) {
@@ -490,6 +490,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
         else break;
 
         if (step == M_NODE) {
+            // min / max slab tests unless some lane's ray has a non-finite origin or 1 / d (see slabTestPairFast)
+            const bool warpSlow = __any_sync(FULL, rs.slow != 0);
 #pragma unroll
             for (int sub = 0; sub < NSUB; ++sub) {
                 {
@@ -523,10 +525,20 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                 if (WIDTH == 4) {
                     if (mode == M_NODE && cur >= 0) {
                         const float4 *w = &sc.wide4[8 * (size_t)cur];
-                        const float4 q0 = ldg4(w), q1 = ldg4(w + 1), q2 = ldg4(w + 2), q3 = ldg4(w + 3), q4 = ldg4(w + 4), q5 = ldg4(w + 5),
-                                     q6 = ldg4(w + 6);
-                        const uint32_t meta = __ldg(reinterpret_cast<const unsigned *>(w + 7));
-                        const Wide4Visit v = wide4Visit(q0, q1, q2, q3, q4, q5, q6, meta, rs, tMax);
+                        float4 q0, q1, q2, q3, q4, q5, q6, q7;
+                        if (LD256) {
+                            ldg256(w, q0, q1);
+                            ldg256(w + 2, q2, q3);
+                            ldg256(w + 4, q4, q5);
+                            ldg256(w + 6, q6, q7);
+                        } else {
+                            q0 = ldg4(w); q1 = ldg4(w + 1); q2 = ldg4(w + 2); q3 = ldg4(w + 3); q4 = ldg4(w + 4); q5 = ldg4(w + 5);
+                            q6 = ldg4(w + 6);
+                            q7.x = __uint_as_float(__ldg(reinterpret_cast<const unsigned *>(w + 7)));
+                        }
+                        const uint32_t meta = floatBits(q7.x);
+                        const Wide4Visit v = warpSlow ? wide4Visit<false>(q0, q1, q2, q3, q4, q5, q6, meta, rs, tMax)
+                                                      : wide4Visit<true>(q0, q1, q2, q3, q4, q5, q6, meta, rs, tMax);
                         const int refs[4] = {asInt(q6.x), asInt(q6.y), asInt(q6.z), asInt(q6.w)};
                         const int last = v.nPass - 1;
                         int ref = -1;
@@ -534,12 +546,13 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                         for (int k = 0; k < 4; ++k) {
                             const bool first = v.pass[k] & (v.after[k] == last);
                             ref = first ? refs[k] : ref;
-                            if (v.pass[k] & !first) {   // deferred: stack position sp + after puts the next one to visit on top
-                                const int slot = sp + v.after[k];
-                                const int2 e = make_int2(refs[k], __float_as_int(v.tMin[k]));
-                                if (slot < SDEPTH) sstack[slot * BLOCK + tid] = e;
-                                else lstack[slot - SDEPTH] = e;
-                            }
+                            // deferred: stack position sp + after puts the next one to visit on top.  One predicated
+                            // shared-memory store; the local-memory spill is a branch that is almost never taken
+                            const bool deferred = v.pass[k] & !first;
+                            const int slot = sp + v.after[k];
+                            const int2 e = make_int2(refs[k], __float_as_int(v.tMin[k]));
+                            if (deferred & (slot < SDEPTH)) sstack[slot * BLOCK + tid] = e;
+                            if (deferred & (slot >= SDEPTH)) lstack[slot - SDEPTH] = e;
                         }
                         sp += last > 0 ? last : 0;
                         const bool have = v.nPass > 0;
@@ -551,28 +564,33 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                     }
                 } else if (mode == M_NODE && cur >= 0) {
                     const float4 *w = &sc.wide[4 * (size_t)cur];
-                    const float4 q0 = ldg4(w), q1 = ldg4(w + 1), q2 = ldg4(w + 2), q3 = ldg4(w + 3);
+                    float4 q0, q1, q2, q3;
+                    if (LD256) {
+                        ldg256(w, q0, q1);
+                        ldg256(w + 2, q2, q3);
+                    } else {
+                        q0 = ldg4(w); q1 = ldg4(w + 1); q2 = ldg4(w + 2); q3 = ldg4(w + 3);
+                    }
                     float t0, t1;
                     bool p0, p1;
-                    slabTestPair(q0, q1, q2, rs, tMax, &p0, &p1, &t0, &t1);
-                    uint32_t meta = floatBits(q3.z);
+                    if (warpSlow) slabTestPair(q0, q1, q2, rs, tMax, &p0, &p1, &t0, &t1);
+                    else slabTestPairFast(q0, q1, q2, rs, tMax, &p0, &p1, &t0, &t1);
+                    const uint32_t meta = floatBits(q3.z);
                     if (meta & WIDE_SINGLE) p1 = false;
-                    int axis = (int)(meta & 3u);
-                    int isNeg = axis == 0 ? rs.neg0 : (axis == 1 ? rs.neg1 : rs.neg2);
-                    int ref0 = asInt(q3.x), ref1 = asInt(q3.y);
-                    bool pn = isNeg ? p1 : p0, pf = isNeg ? p0 : p1;
-                    int rn = isNeg ? ref1 : ref0, rf = isNeg ? ref0 : ref1;
-                    float tf = isNeg ? t0 : t1;
-                    // straight-line tail: push the far child if both pass, continue with whichever
-                    // passed, otherwise leave the pop to the next visit
-                    if (pn & pf) {
-                        int2 e = make_int2(rf, __float_as_int(tf));
-                        if (sp < SDEPTH) sstack[sp * BLOCK + tid] = e;
-                        else lstack[sp - SDEPTH] = e;
-                        ++sp;
+                    const int axis = (int)(meta & 3u);
+                    const bool isNeg = (axis == 0 ? rs.neg0 : (axis == 1 ? rs.neg1 : rs.neg2)) != 0;
+                    const int ref0 = asInt(q3.x), ref1 = asInt(q3.y);
+                    // straight-line tail: push the far child if both pass, continue with the near one (or with
+                    // the only one that passed); with none, the pop is left to the next visit
+                    const bool both = p0 & p1;
+                    {
+                        const int2 e = make_int2(isNeg ? ref0 : ref1, __float_as_int(isNeg ? t0 : t1));
+                        if (both & (sp < SDEPTH)) sstack[sp * BLOCK + tid] = e;
+                        if (both & (sp >= SDEPTH)) lstack[sp - SDEPTH] = e;
+                        sp += both ? 1 : 0;
                     }
-                    const int ref = pn ? rn : rf;
-                    const bool have = pn | pf;
+                    const int ref = (both ? isNeg : !p0) ? ref1 : ref0;
+                    const bool have = p0 | p1;
                     const bool isLeaf = have & (ref < 0);
                     leafFirst = isLeaf ? (ref & (int)WIDE_LEAF_OFFSET_MASK) : leafFirst;
                     leafN = isLeaf ? (((ref >> WIDE_LEAF_COUNT_SHIFT) & 0xf) + 1) : leafN;
@@ -773,15 +791,52 @@ __global__ void __launch_bounds__(128, MINB) k_wf_advance(DScene sc, DRenderPara
     wfCountRays(counters, regular, shadow);
 }
 
+// ---------------------------------------------------------------------------------------------
+// End of a frame.  Once the work counter has run out the pool is no longer refilled and the number of paths in
+// flight decays round by round: ~25 more rounds, each a handful of launches over a few thousand rays that cannot
+// fill the machine (measured round 1: a fixed ~7.8 ms per frame whatever the GPU count - 10 % of a frame at 8 GPUs).
+// k_wf_finish runs after the shade step of every round and does nothing until (a) no work item is left and (b) at
+// most `threshold` contexts are still in flight; then every thread takes ONE of them and walks it to the end of its
+// path with the per-lane state machine (traceLane + laneAdvance, the code of k_li_samples / pb2_li_samples), deposits
+// the sample, and the frame is over.  Same functions, same order of operations per path as the wavefront kernels.
+// k_wf_reset (below) empties the list under the same condition.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool wfFinishNow(const DRenderParams &rp, const WfPool &pool, int traceQ, unsigned threshold) {
+    const unsigned n = pool.counts[traceQ];
+    return n > 0 && n <= threshold && (long long)pool.ctr[CTR_WORK] >= rp.nWorkItems;
+}
+
+template <bool SPH, bool SPEC>
+__global__ void __launch_bounds__(128) k_wf_finish(DScene sc, DRenderParams rp, WfPool pool, int traceQ, unsigned threshold, float4 *film) {
+    if (!wfFinishNow(rp, pool, traceQ, threshold)) return;
+    const unsigned n = pool.counts[traceQ];
+    unsigned regular = 0, shadow = 0;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        WfCtx &cx = pool.ctx[pool.queue[traceQ][i]];
+        DLane &ln = cx.ln;
+        while (ln.state != LS_IDLE) {
+            DHit hit;
+            float tMax;
+            const bool found = traceLane(sc, ln, &tMax, &hit, nullptr);
+            laneAdvance<SPH, SPEC>(sc, rp.halton, rp.path, ln, found, hit, tMax);
+            if (ln.state == LS_SHADOW) shadow++;        // the next ray is a Scene::IntersectP call
+            else if (ln.state != LS_IDLE) regular++;    // ... a Scene::Intersect call
+        }
+        addSample(rp, film, cx.pFilm, guardRadiance(ln.L));
+    }
+    wfCountRays(pool.ctr, regular, shadow);
+}
+
 __global__ void k_wf_init(WfPool pool) {
     unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < (unsigned)pool.capacity) pool.queue[WQ_FREE0][i] = (int)i;
     if (i < WQ_COUNT) pool.counts[i] = (i == WQ_FREE0) ? (unsigned)pool.capacity : 0u;
 }
 
-// end of a round: the lists consumed in it are emptied
-__global__ void k_wf_reset(WfPool pool, int a, int b) {
+// end of a round: the lists consumed in it are emptied (and the next trace list, if k_wf_finish has just run it dry)
+__global__ void k_wf_reset(DRenderParams rp, WfPool pool, int a, int b, int traceNext, unsigned threshold) {
     if (threadIdx.x == 0) {
+        if (wfFinishNow(rp, pool, traceNext, threshold)) pool.counts[traceNext] = 0;
         pool.counts[WQ_CURSOR] = 0;
         pool.counts[WQ_SHADE] = 0;
         pool.counts[WQ_LIGHT] = 0;

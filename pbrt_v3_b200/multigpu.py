@@ -1,35 +1,48 @@
-"""Multi-GPU partition of the film (one process per GPU).
+"""Multi-GPU launch helpers (one process per GPU).
 
-The sample tiles of SamplerIntegrator::Render (16x16 pixels, src/core/integrator.cpp:235-240) are dealt
-round-robin to the ranks: tile t (row-major over the sample bounds) belongs to rank t % world.  The BVH and
-every other scene table are replicated; each rank renders its tiles into its own zero-initialised film and
-one reduce(sum) over the W*H*4 floats merges them on rank 0 — the distributed form of Film::MergeFilmTile
-(src/core/film.cpp:117-130).  With the box filter a sample touches a neighbouring tile's pixel only when it
-falls exactly on a pixel boundary, which is why the merge is a sum and not a gather.
+The partition of the film and the reduce of the per-rank films live in the library: pb2_render_path[_device] with
+``tile_count == 0`` renders this rank's 16x16 tiles (tile t belongs to rank t % world) and sums the films onto rank 0
+with one ncclReduce (include/pb2.h, pb2_dist_*).  What is left for Python is the rendezvous: handing rank 0's NCCL
+unique id to the other ranks over the process group torchrun has already set up.
 """
+import ctypes as C
+
 import numpy as np
 
-TILE = 16
+from . import PathParams, check, lib, ptr
+
+PB2_DIST_ID_BYTES = 128
 
 
-def tile_owner_map(sample_bounds, world):
-    """owner[y, x] = rank that renders sample-space pixel (x, y); sample_bounds = (x0, y0, x1, y1)."""
-    x0, y0, x1, y1 = sample_bounds
-    nx = (x1 - x0 + TILE - 1) // TILE
-    ys, xs = np.mgrid[y0:y1, x0:x1]
-    tile = ((ys - y0) // TILE) * nx + (xs - x0) // TILE
-    return (tile % world).astype(np.int32)
-
-
-def owned_tile_count(sample_bounds, rank, world):
-    x0, y0, x1, y1 = sample_bounds
-    n = ((x1 - x0 + TILE - 1) // TILE) * ((y1 - y0 + TILE - 1) // TILE)
-    return (n - rank + world - 1) // world if n > rank else 0
-
-
-def reduce_film(film, dst=0):
-    """Sum the per-rank films onto rank `dst` (torch.distributed; NCCL over NVLink on the GPU box, gloo in CPU tests)."""
+def dist_init_from_torch():
+    """pb2_dist_init over torch.distributed's default process group (call after pb2_init / pbrt_v3_b200.init).
+    Returns (rank, world); a no-op returning (0, 1) when no process group is initialised."""
+    import torch
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.reduce(film, dst=dst, op=dist.ReduceOp.SUM)
-    return film
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0, 1
+    L = lib()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    uid = np.zeros(PB2_DIST_ID_BYTES, np.uint8)
+    if rank == 0:
+        check(L.pb2_dist_unique_id(ptr(uid)))
+    device = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.from_numpy(uid).to(device)
+    dist.broadcast(t, src=0)
+    uid = np.ascontiguousarray(t.cpu().numpy())
+    check(L.pb2_dist_init(rank, world, ptr(uid)))
+    return rank, world
+
+
+def work_items(film, params, tile_rank=0, tile_count=1):
+    """(pixel x, pixel y, sample number) of every work item of one rank's partition, as the render kernels enumerate them
+    (pb2_work_items: the kernels' own decode function compiled for the host); skipped items are dropped."""
+    L = lib()
+    p = PathParams()
+    C.memmove(C.byref(p), params if isinstance(params, C._Pointer) else C.byref(params), C.sizeof(PathParams))
+    p.tile_rank, p.tile_count = tile_rank, tile_count
+    n = C.c_int64()
+    check(L.pb2_work_items(film, C.byref(p), 0, 0, None, C.byref(n)))
+    out = np.zeros((n.value, 3), np.int32)
+    check(L.pb2_work_items(film, C.byref(p), 0, n.value, ptr(out), None))
+    return out[out[:, 0] >= 0]

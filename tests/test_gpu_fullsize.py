@@ -80,7 +80,7 @@ def test_per_sample_parity_on_the_full_size_scene(pb, big, port):
 
 
 def test_wavefront_trace_records_at_full_size(pb, big, port):
-    """The benchmarked kernel on the benchmarked scene: k_wf_trace_w<4> (and the other variants) over 200 000 path rays
+    """The benchmarked kernel on the benchmarked scene: k_wf_trace_w<2> (and the other variants) over 200 000 path rays
     and 200 000 shadow rays of the 1 M-triangle soup leave (found, primitive, t, b0, b1, b2) bit-identical to
     pb2_intersect / pb2_intersect_p, which the test above pins to the CPU checker on this very scene."""
     from test_gpu_parity import check_wavefront_records
@@ -113,7 +113,9 @@ def test_wavefront_image_parity_on_crops_of_the_full_size_frame(pb, checker):
         got = hs.resolve(rgbw)[y0:y0 + 72, x0:x0 + 128]
         ref_img, _, ref_st = sc.render(n_threads=0, params=p)
         want = ref_img[y0:y0 + 72, x0:x0 + 128]
-        assert rgbw[..., 3].sum() == rgbw[y0:y0 + 72, x0:x0 + 128, 3].sum()   # nothing lands outside the window
+        # a sample exactly on a pixel boundary also weighs in the neighbouring pixel (film.h:128-131), window border included
+        outside = rgbw[..., 3].sum() - rgbw[y0:y0 + 72, x0:x0 + 128, 3].sum()
+        assert 0 <= outside <= 64 and (rgbw[y0:y0 + 72, x0:x0 + 128, 3] >= 64).all()
         rel = np.abs(got - want) / np.maximum(np.abs(want), 1e-3)
         assert (rel.max(axis=2) <= 0.01).mean() >= 0.999 and rel.mean() <= 1e-4, ((x0, y0), float(rel.mean()))
         assert abs(float(got.mean()) - float(want.mean())) <= 1e-4 * float(want.mean())

@@ -273,8 +273,9 @@ def test_traversal_counters_equal_the_reference_order(pb, port):
 
 def wf_kernels(pb):
     """Every traversal kernel of the render path (selected by pb2_path_params.flags)."""
-    return {"wide4": 0, "wide2": pb.PB2_FLAG_WIDE2, "linear": pb.PB2_FLAG_LINEAR_NODES, "plain": pb.PB2_FLAG_PLAIN_TRACE,
-            "wide4_spill": pb.PB2_FLAG_SMALL_STACK, "wide2_spill": pb.PB2_FLAG_SMALL_STACK | pb.PB2_FLAG_WIDE2}
+    return {"wide2": 0, "wide4": pb.PB2_FLAG_WIDE4, "linear": pb.PB2_FLAG_LINEAR_NODES, "plain": pb.PB2_FLAG_PLAIN_TRACE,
+            "wide2_spill": pb.PB2_FLAG_SMALL_STACK, "wide4_spill": pb.PB2_FLAG_SMALL_STACK | pb.PB2_FLAG_WIDE4,
+            "wide2_ld128": pb.PB2_FLAG_LD128, "wide4_ld128": pb.PB2_FLAG_LD128 | pb.PB2_FLAG_WIDE4}
 
 
 def check_wavefront_records(pb, hs, rays, srays, want_hits, want_occluded):
@@ -305,7 +306,7 @@ def check_wavefront_records(pb, hs, rays, srays, want_hits, want_occluded):
 
 @pytest.mark.parametrize("name", SCENE_CASES)
 def test_wavefront_trace_kernels_write_the_reference_hit_records(pb, name):
-    """The kernels that are BENCHMARKED (k_wf_trace_w<4>, <2>, k_wf_trace) leave the reference's closest hit in the path
+    """The kernels that are BENCHMARKED (k_wf_trace_w<2>, <4>, k_wf_trace) leave the reference's closest hit in the path
     contexts: same rays as the golden hit test, compared with the golden prim / t recorded from the compiled reference
     and with every bit of pb2_intersect's (t, b0, b1, b2), which that test pins to the reference."""
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -322,8 +323,9 @@ def test_wavefront_trace_kernels_on_instances_and_deep_stacks(pb, checker):
     (deepest stacks): hit records of every kernel variant against the CPU checker's Scene::Intersect."""
     deep = open(os.path.join(SCENES, "killeroo_like.pbrt")).read().replace(
         "WorldBegin", 'Accelerator "bvh" "string splitmethod" "middle" "integer maxnodeprims" [1]\nWorldBegin')
-    for hs, kw in ((pb.HostScene.instanced_soup(2000, grid=4, xres=64, yres=36, spp=4), {}),
-                   (pb.HostScene.from_string(deep), dict(max_prims_in_node=1, split_method=2))):
+    for make, kw in ((lambda: pb.HostScene.instanced_soup(2000, grid=4, xres=64, yres=36, spp=4), {}),
+                     (lambda: pb.HostScene.from_string(deep), dict(max_prims_in_node=1, split_method=2))):
+        hs = make()   # the host front end holds one scene at a time
         sc = checker.scene(hs, **kw)
         rays, srays = gc.rays_for(pb, hs.nodes(), 20000, 61), gc.rays_for(pb, hs.nodes(), 20000, 62, shadow=True)
         want = sc.intersect(rays)
