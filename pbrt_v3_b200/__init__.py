@@ -199,6 +199,7 @@ def lib():
     L.pb2h_write_image.argtypes = [C.c_char_p, vp] + [C.c_int] * 6
     L.pb2h_loop_subdivide.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, vp]
     L.pb2h_set_light_strategy.argtypes = [C.c_int]
+    L.pb2h_scene_intersect.argtypes = [vp, vp, vp]
     _lib = L
     return L
 

@@ -18,7 +18,9 @@
 
 namespace pb2 {
 
-enum { LS_IDLE = 0, LS_PATH = 1, LS_SHADOW = 2, LS_MIS = 3 };
+// LS_DEFER: only ever seen between shadeVertex and its caller - the vertex fell into a voxel whose light distribution is
+// not built yet (lazy SpatialLightDistribution); nothing of the lane was touched, the caller shades it again later.
+enum { LS_IDLE = 0, LS_PATH = 1, LS_SHADOW = 2, LS_MIS = 3, LS_DEFER = 4 };
 
 struct DLane {
     int state;
@@ -81,12 +83,24 @@ PB2_HD void startMisOrFinish(DLane &ln) {
 
 // The path ray has been traced: one iteration of the bounce loop up to (not including) the results
 // of the two direct-lighting rays.
-template <bool SPH, bool SPEC = true>
+// LAZY = false compiles the deferral of the lazy light distribution out (the bench scene's shade kernel sits exactly at
+// its 128-register budget)
+template <bool SPH, bool SPEC = true, bool LAZY = true>
 PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &pp, DLane &ln, bool found, const DHit &hit,
                         float tMax) {
     DInteraction isect;
     int li = -1;
     if (found) isect = hitInteraction<SPH>(sc, hit, ln.ray, tMax, &li);
+    const float *lazyDistrib = nullptr;
+    if (LAZY && sc.lightDist.slots && found && ln.bounces < pp.maxDepth) {
+        // lazy light distribution: look the voxel up before anything of the lane changes, so that a miss can hand the
+        // vertex back untouched (the record is a pure function of the voxel: when it is built does not matter)
+        lazyDistrib = lightDistLookup(sc.lightDist, isect.p);
+        if (!lazyDistrib) {
+            ln.state = LS_DEFER;
+            return;
+        }
+    }
     if (ln.bounces == 0 || ln.specularBounce) {
         if (found) {
             if (li >= 0) ln.L = ln.L + ln.beta * lightL(sc.lights[li], isect.n, -ln.ray.d);
@@ -101,7 +115,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
         ln.ray = spawnRay(isect, ln.ray.d);  // null BSDF: skip the surface, same bounce count
         return;
     }
-    const float *distrib = lightDistLookup(sc.lightDist, isect.p);
+    const float *distrib = (LAZY && lazyDistrib) ? lazyDistrib : lightDistLookup(sc.lightDist, isect.p);
     // The lane lives in HBM and is updated in place, the sampler's dimension counter included (a
     // register copy of ln.smp across this function was measured: -12 %, the 128-register budget is full).
     DSampler &smp = ln.smp;

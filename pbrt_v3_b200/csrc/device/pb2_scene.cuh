@@ -51,9 +51,19 @@ struct DLightDist {
     int strategy;             // PB2_LIGHTDIST_*
     int nVoxels[3];
     V3 boundsMin, boundsMax;  // Scene::WorldBound()
-    const float *table;       // uniform/power: one record; spatial: one record per voxel
+    const float *table;       // uniform/power: one record; spatial: one record per voxel (eager) / per touched voxel (lazy)
     int stride;               // floats per record: nLights func, nLights+1 cdf, 1 funcInt
+    // Lazy spatial distribution (scenes with so many lights that a record for every voxel would not fit: every emissive
+    // triangle is a light).  Like the reference's hash table (lightdistrib.cpp:141-230) a voxel's distribution is computed
+    // when a path vertex first falls into it - here without waiting inside a kernel: the lookup of a missing voxel puts it
+    // on a request list and returns null, the vertex is deferred, k_lightdist_build computes the requested records
+    // between two kernels of the round, and the deferred vertices are shaded again.
+    int *slots;               // nullptr = eager.  Per voxel: LD_ABSENT, LD_REQUESTED, or the record's index in `table`
+    int *requests;            // voxels asked for since the last build (each voxel is asked for at most once)
+    int *counters;            // [0] number of requests, [1] records allocated, [2] set when the pool overflowed
+    int poolRecords;          // capacity of `table` in records
 };
+enum { LD_ABSENT = -1, LD_REQUESTED = -2 };
 
 // TransformedPrimitive with a static transform (pb2_instance).
 struct DInstance {

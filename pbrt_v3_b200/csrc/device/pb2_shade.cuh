@@ -1228,27 +1228,43 @@ PB2_HD const float *lightDistLookup(const DLightDist &ld, V3 p) {
         pi[i] = iv < 0 ? 0 : (iv > ld.nVoxels[i] - 1 ? ld.nVoxels[i] - 1 : iv);
     }
     int64_t voxel = ((int64_t)pi[0] * ld.nVoxels[1] + pi[1]) * ld.nVoxels[2] + pi[2];
-    return ld.table + voxel * ld.stride;
+    if (!ld.slots) return ld.table + voxel * ld.stride;
+#if defined(__CUDA_ARCH__)
+    int s = ld.slots[voxel];
+    if (s >= 0) return ld.table + (size_t)s * ld.stride;
+    if (s == LD_ABSENT && atomicCAS(&ld.slots[voxel], (int)LD_ABSENT, (int)LD_REQUESTED) == LD_ABSENT)
+        ld.requests[atomicAdd(&ld.counters[0], 1)] = (int)voxel;
+#endif
+    return nullptr;   // not built yet: the caller defers the vertex
 }
 
 // SpatialLightDistribution::ComputeDistribution (lightdistrib.cpp:232-300) for one voxel, written
-// into rec = [func(n) | cdf(n+1) | funcInt] (Distribution1D ctor, sampling.h:57-70).
-PB2_HD void computeVoxelDistribution(const DScene &sc, const DHalton &h, const DLightDist &ld, int px, int py, int pz,
-                                     float *rec) {
-    int n = sc.nLights;
+// into rec = [func(n) | cdf(n+1) | funcInt] (Distribution1D ctor, sampling.h:57-70).  Three pieces, so that the
+// eager builder (one thread per voxel) and the lazy one (one block per voxel, one thread per light) share every line
+// of arithmetic: the voxel's bounds, the contribution of ONE light summed over the 128 Halton points in their order,
+// and the floor + cdf over all lights in their order.
+struct DVoxelBounds { V3 vMin, vMax; };
+PB2_HD DVoxelBounds voxelBounds(const DLightDist &ld, int px, int py, int pz) {
     V3 p0 = mk3((float)px / (float)ld.nVoxels[0], (float)py / (float)ld.nVoxels[1], (float)pz / (float)ld.nVoxels[2]);
     V3 p1 = mk3((float)(px + 1) / (float)ld.nVoxels[0], (float)(py + 1) / (float)ld.nVoxels[1], (float)(pz + 1) / (float)ld.nVoxels[2]);
     // Bounds3f(WorldBound().Lerp(p0), WorldBound().Lerp(p1)): the two-point ctor takes min/max
     V3 a = mk3(lerpf(p0.x, ld.boundsMin.x, ld.boundsMax.x), lerpf(p0.y, ld.boundsMin.y, ld.boundsMax.y), lerpf(p0.z, ld.boundsMin.z, ld.boundsMax.z));
     V3 b = mk3(lerpf(p1.x, ld.boundsMin.x, ld.boundsMax.x), lerpf(p1.y, ld.boundsMin.y, ld.boundsMax.y), lerpf(p1.z, ld.boundsMin.z, ld.boundsMax.z));
-    V3 vMin = mk3(pmin(a.x, b.x), pmin(a.y, b.y), pmin(a.z, b.z));
-    V3 vMax = mk3(pmax(a.x, b.x), pmax(a.y, b.y), pmax(a.z, b.z));
-    for (int j = 0; j < n; ++j) rec[j] = 0;
-    const int nSamples = 128;
-    for (int i = 0; i < nSamples; ++i) {
+    DVoxelBounds vb;
+    vb.vMin = mk3(pmin(a.x, b.x), pmin(a.y, b.y), pmin(a.z, b.z));
+    vb.vMax = mk3(pmax(a.x, b.x), pmax(a.y, b.y), pmax(a.z, b.z));
+    return vb;
+}
+constexpr int kVoxelSamples = 128;
+// light j's importance for the voxel: sum over the sample points of Li.y() / pdf, visibility ignored (lightdistrib.cpp:255-276)
+PB2_HD float voxelLightContribution(const DScene &sc, const DHalton &h, const DVoxelBounds &vb, int j) {
+    const pb2_light light = sc.lights[j];
+    const TriRec rec = loadTriRec(sc.lightRecs, (size_t)j);
+    float contrib = 0;
+    for (int i = 0; i < kVoxelSamples; ++i) {
         V3 t = mk3(radicalInverse(h, 0, i), radicalInverse(h, 1, i), radicalInverse(h, 2, i));
         DInteraction intr;
-        intr.p = mk3(lerpf(t.x, vMin.x, vMax.x), lerpf(t.y, vMin.y, vMax.y), lerpf(t.z, vMin.z, vMax.z));
+        intr.p = mk3(lerpf(t.x, vb.vMin.x, vb.vMax.x), lerpf(t.y, vb.vMin.y, vb.vMax.y), lerpf(t.z, vb.vMin.z, vb.vMax.z));
         intr.pError = mk3(0, 0, 0);
         intr.n = mk3(0, 0, 0);
         intr.wo = mk3(1, 0, 0);
@@ -1257,17 +1273,18 @@ PB2_HD void computeVoxelDistribution(const DScene &sc, const DHalton &h, const D
         intr.uv = mk2(0, 0);
         intr.prim = -1;
         V2 u = mk2(radicalInverse(h, 3, i), radicalInverse(h, 4, i));
-        for (int j = 0; j < n; ++j) {
-            DLightSample ls = sampleLight(sc, j, sc.lights[j], loadTriRec(sc.lightRecs, (size_t)j), intr, u);
-            if (ls.pdf > 0) rec[j] += luminance(ls.Li) / ls.pdf;
-        }
+        DLightSample ls = sampleLight(sc, j, light, rec, intr, u);
+        if (ls.pdf > 0) contrib += luminance(ls.Li) / ls.pdf;
     }
+    return contrib;
+}
+// rec[0 .. n) holds the contributions: floor them (lightdistrib.cpp:278-294) and build the Distribution1D
+PB2_HD void finishVoxelDistribution(int n, float *rec) {
     float sumContrib = 0;
     for (int j = 0; j < n; ++j) sumContrib += rec[j];
-    float avgContrib = sumContrib / (nSamples * n);
+    float avgContrib = sumContrib / (kVoxelSamples * n);
     float minContrib = (avgContrib > 0) ? (float)(.001 * (double)avgContrib) : 1;
     for (int j = 0; j < n; ++j) rec[j] = pmax(rec[j], minContrib);
-    // Distribution1D
     float *cdf = rec + n;
     cdf[0] = 0;
     for (int i = 1; i < n + 1; ++i) cdf[i] = cdf[i - 1] + rec[i - 1] / n;
@@ -1278,6 +1295,12 @@ PB2_HD void computeVoxelDistribution(const DScene &sc, const DHalton &h, const D
         for (int i = 1; i < n + 1; ++i) cdf[i] /= funcInt;
     }
     rec[2 * n + 1] = funcInt;
+}
+PB2_HD void computeVoxelDistribution(const DScene &sc, const DHalton &h, const DLightDist &ld, int px, int py, int pz,
+                                     float *rec) {
+    const DVoxelBounds vb = voxelBounds(ld, px, py, pz);
+    for (int j = 0; j < sc.nLights; ++j) rec[j] = voxelLightContribution(sc, h, vb, j);
+    finishVoxelDistribution(sc.nLights, rec);
 }
 
 // ---------------------------------------------------------------- camera

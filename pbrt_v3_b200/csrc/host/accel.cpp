@@ -544,6 +544,9 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
             // leaves the light out of Scene::lights; the primitive would still emit when seen directly.  That
             // unsampled emission is not carried to the device.
             Warning("Emission of an area light inside an instanced object is ignored on the GPU path");
+        } else if (gp->areaLight && lights.empty()) {
+            // an aggregate asked to intersect on its own (BVHAccel::Intersect before / without Render) is flattened
+            // without lights: geometry only, emission is not part of that query
         } else if (gp->areaLight) {
             auto it = lightIds.find(gp->areaLight.get());
             if (it == lightIds.end()) {

@@ -292,6 +292,18 @@ pb2_scene *pb2h_device_scene(void) {
     return ds ? DeviceSceneHandle(*ds) : nullptr;
 }
 
+// Scene::Intersect through the host classes (scene.cpp:45-49 -> BVHAccel::Intersect -> the device), as a caller of the
+// reference's API would issue it before or without Integrator::Render.  Returns 1 on a hit and fills t.
+int pb2h_scene_intersect(const float *o, const float *d, float *t_hit) {
+    RenderSetup *s = pbrtLastSetup();
+    if (!s || !s->scene) return -1;
+    Ray ray(Point3f(o[0], o[1], o[2]), Vector3f(d[0], d[1], d[2]));
+    SurfaceInteraction isect;
+    if (!s->scene->Intersect(ray, &isect)) return 0;
+    if (t_hit) *t_hit = ray.tMax;
+    return 1;
+}
+
 int pb2h_write_pfm(const char *path, const float *rgb, int w, int h) { return WriteImagePFM(path, rgb, w, h) ? 0 : 1; }
 // WriteImage (imageio.cpp:81-122): EXR / PFM / PNG / TGA by extension; the window arguments only matter for EXR
 int pb2h_write_image(const char *path, const float *rgb, int w, int h, int total_w, int total_h, int x_offset, int y_offset) {

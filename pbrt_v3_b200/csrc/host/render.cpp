@@ -676,6 +676,8 @@ PathIntegrator *CreatePathIntegrator(const ParamSet &params, std::shared_ptr<Sam
 struct DeviceScene {
     pb2_scene *handle = nullptr;
     std::unique_ptr<FlatScene> flat;
+    std::vector<const Light *> lightKey;   // what the scene was flattened with (cache key of GetDeviceScene)
+    std::string strategyKey;
     ~DeviceScene() {
         if (handle) pb2_scene_destroy(handle);
     }
@@ -694,11 +696,18 @@ bool EnsureDevice() {
     return status == PB2_OK;
 }
 
+// The device copy is cached on the aggregate under the lights and the light-sampling strategy it was flattened with:
+// a Render after a stand-alone BVHAccel::Intersect (which flattens without lights), or a second Render with another
+// lightsamplestrategy, gets a scene of its own instead of the stale tables.
 std::shared_ptr<DeviceScene> GetDeviceScene(const BVHAccel &bvh, const std::vector<std::shared_ptr<Light>> &lights,
                                             const std::string &lightStrategy) {
-    if (bvh.device) return bvh.device;
+    std::vector<const Light *> key;
+    for (const auto &l : lights) key.push_back(l.get());
+    if (bvh.device && bvh.device->lightKey == key && bvh.device->strategyKey == lightStrategy) return bvh.device;
     if (!EnsureDevice()) return nullptr;
     auto ds = std::make_shared<DeviceScene>();
+    ds->lightKey = key;
+    ds->strategyKey = lightStrategy;
     ds->flat = FlattenScene(bvh, lights, lightStrategy);
     if (!ds->flat) return nullptr;
     if (pb2_scene_create(&ds->flat->desc, &ds->handle) != PB2_OK) {
@@ -724,7 +733,7 @@ static void fillInteraction(const pb2_hit &h, const FlatScene &flat, const Ray &
 bool BVHAccel::Intersect(const Ray &ray, SurfaceInteraction *isect) const {
     if (nodes.empty()) return false;
     std::vector<std::shared_ptr<Light>> noLights;
-    std::shared_ptr<DeviceScene> ds = device ? device : GetDeviceScene(*this, noLights, "uniform");
+    std::shared_ptr<DeviceScene> ds = device ? device : GetDeviceScene(*this, noLights, "uniform");   // any cached copy answers a geometric query
     if (!ds) return false;
     pb2_ray r = {{ray.o.x, ray.o.y, ray.o.z}, {ray.d.x, ray.d.y, ray.d.z}, ray.tMax};
     pb2_hit h;
@@ -741,7 +750,7 @@ bool BVHAccel::Intersect(const Ray &ray, SurfaceInteraction *isect) const {
 bool BVHAccel::IntersectP(const Ray &ray) const {
     if (nodes.empty()) return false;
     std::vector<std::shared_ptr<Light>> noLights;
-    std::shared_ptr<DeviceScene> ds = device ? device : GetDeviceScene(*this, noLights, "uniform");
+    std::shared_ptr<DeviceScene> ds = device ? device : GetDeviceScene(*this, noLights, "uniform");   // any cached copy answers a geometric query
     if (!ds) return false;
     pb2_ray r = {{ray.o.x, ray.o.y, ray.o.z}, {ray.d.x, ray.d.y, ray.d.z}, ray.tMax};
     uint8_t occ = 0;

@@ -223,6 +223,8 @@ struct pb2_scene {
     int bvhDepth = 0;  // maximum number of simultaneously pending far children = tree depth (scene BVH)
     int instDepth = 0; // the same for the deepest instanced object's BVH
     bool hasSpecular = false;  // a mirror / glass material exists: the shade kernel with the specular BxDFs is used
+    bool lazyLightDist = false;   // spatial light distribution built on demand (DLightDist::slots)
+    int *ldHostCounters = nullptr;   // pinned copy of DLightDist::counters
     // wavefront pool (allocated on first render)
     void *wfCtx = nullptr;
     int *wfQueues = nullptr;
@@ -450,7 +452,7 @@ __device__ __forceinline__ void addSample(const DRenderParams &rp, float4 *film,
 
 // PathIntegrator::Li for explicit (pixel, sample) pairs: the same lane functions, one thread per sample.
 __global__ void k_li_samples(DScene sc, DRenderParams rp, const int32_t *pixelXY, const int64_t *sampleNum, int64_t n,
-                             float *outRGB, float *outPFilm) {
+                             float *outRGB, float *outPFilm, int *deferred) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     int px = pixelXY[2 * i], py = pixelXY[2 * i + 1];
@@ -466,6 +468,10 @@ __global__ void k_li_samples(DScene sc, DRenderParams rp, const int32_t *pixelXY
         float tMax;
         bool found = traceLane(sc, ln, &tMax, &hit, nullptr);
         laneAdvance<true>(sc, rp.halton, rp.path, ln, found, hit, tMax);
+        if (ln.state == LS_DEFER) {   // lazy light distribution: the voxel has been requested; the host builds it and runs the sample again
+            atomicAdd(deferred, 1);
+            return;
+        }
     }
     V3 L = guardRadiance(ln.L);
     outRGB[3 * i] = L.x;
@@ -530,6 +536,7 @@ __global__ void k_light_distribution(DScene sc, const float *points, int64_t n, 
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float *rec = lightDistLookup(sc.lightDist, mk3(points[3 * i], points[3 * i + 1], points[3 * i + 2]));
+    if (!rec) return;   // lazy: requested; the host builds the record and launches again
     int stride = 2 * sc.nLights + 1;
     for (int k = 0; k < stride; ++k) out[i * stride + k] = rec[k];
 }
@@ -537,6 +544,34 @@ __global__ void k_light_distribution(DScene sc, const float *points, int64_t n, 
 // ---------------------------------------------------------------------------------------------
 // host side of the ABI
 // ---------------------------------------------------------------------------------------------
+static DHalton haltonTablesOnly() {   // what radicalInverse() needs: the tables, no film geometry
+    DHalton h;
+    memset(&h, 0, sizeof(h));
+    h.primes = g_halton.primes;
+    h.primeSums = g_halton.primeSums;
+    h.perms = g_halton.perms;
+    h.dimRecs = g_halton.dimRecs;
+    return h;
+}
+
+// Lazy light distribution: build the records requested so far (no host synchronisation: the kernel reads the count).
+static void launchLightDistBuild(const pb2_scene *scene, cudaStream_t stream) {
+    k_lightdist_build<<<g_numSMs * 4, 128, 0, stream>>>(scene->d, haltonTablesOnly());
+    k_lightdist_done<<<1, 32, 0, stream>>>(scene->d);
+}
+static int lightDistOverflowed(pb2_scene *scene, cudaStream_t stream, bool *overflowed) {
+    *overflowed = false;
+    if (!scene->lazyLightDist) return PB2_OK;
+    CUDA_TRY(cudaMemcpyAsync(scene->ldHostCounters, scene->d.lightDist.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    *overflowed = scene->ldHostCounters[2] != 0;
+    return PB2_OK;
+}
+static int lightDistOverflowError() {
+    return setError(PB2_ERR_UNSUPPORTED, "the on-demand pool of spatial light distributions is exhausted (very many lights x very many voxels touched): "
+                                         "raise PB2_LIGHTDIST_POOL_MB or use lightsamplestrategy \"power\" / \"uniform\"");
+}
+
 static int requireDevice() {
     if (!g_initialised) return setError(PB2_ERR_NO_DEVICE, "pb2_init() has not succeeded: no CUDA device is bound (there is no CPU fallback)");
     return PB2_OK;
@@ -628,6 +663,11 @@ static DRenderParams makeRenderParams(const pb2_camera *cam, const pb2_film_desc
 static int validateRenderArgs(const pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp) {
     if (!scene || !cam || !film || !pp) return setError(PB2_ERR_INVALID, "null argument");
     if (pp->samples_per_pixel <= 0 || pp->max_depth < 0) return setError(PB2_ERR_INVALID, "bad samples_per_pixel / max_depth");
+    // a path vertex consumes up to 8 sampler dimensions after the camera sample's 5; the reference aborts with
+    // "HaltonSampler can only sample 1000 dimensions" (lowdiscrepancy.cpp:2506 via halton.cpp:112) when a path gets there -
+    // here the tables end at the same place, so a maxdepth that could reach it is refused up front
+    if (5 + 8 * ((long long)pp->max_depth + 1) > kMaxHaltonDims)
+        return setError(PB2_ERR_UNSUPPORTED, "maxdepth above 123: HaltonSampler can only sample 1000 dimensions");
     if (pp->tile_count < 0 || pp->tile_rank < 0 || (pp->tile_count > 0 && pp->tile_rank >= pp->tile_count))
         return setError(PB2_ERR_INVALID, "bad tile_rank / tile_count");
     if (film->cropped_pixel_bounds[2] < film->cropped_pixel_bounds[0] || film->cropped_pixel_bounds[3] < film->cropped_pixel_bounds[1])
@@ -730,7 +770,7 @@ static int ensurePool(pb2_scene *scene, int capacity) {
         scene->wfQueues = nullptr;
         scene->wfCapacity = 0;
         CUDA_TRY(cudaMalloc(&scene->wfCtx, (size_t)capacity * sizeof(WfCtx)));
-        CUDA_TRY(cudaMalloc((void **)&scene->wfQueues, (size_t)capacity * 6 * sizeof(int)));
+        CUDA_TRY(cudaMalloc((void **)&scene->wfQueues, (size_t)capacity * WQ_COUNT * sizeof(int)));
         scene->wfCapacity = capacity;
     }
     if (!scene->wfCounts) CUDA_TRY(cudaMalloc((void **)&scene->wfCounts, WQ_COUNT * sizeof(unsigned)));
@@ -742,7 +782,7 @@ static WfPool poolOf(const pb2_scene *scene, int capacity) {
     WfPool pool;
     pool.capacity = capacity;
     pool.ctx = (WfCtx *)scene->wfCtx;
-    for (int q = 0; q < 6; ++q) pool.queue[q] = scene->wfQueues + (size_t)q * scene->wfCapacity;
+    for (int q = 0; q < WQ_COUNT; ++q) pool.queue[q] = scene->wfQueues + (size_t)q * scene->wfCapacity;
     pool.counts = scene->wfCounts;
     pool.ctr = scene->counters;
     return pool;
@@ -765,12 +805,17 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     AdvanceKernel advShade = scene->hasSpecular ? (spheres ? k_wf_advance<true, true, 4, true> : k_wf_advance<true, false, 4, true>)
                              : spheres ? k_wf_advance<true, true, 4>
                                        : k_wf_advance<true, false, 4>;
+    if (scene->lazyLightDist)   // the shade kernels that can hand a vertex back (DLightDist::slots)
+        advShade = scene->hasSpecular ? (spheres ? k_wf_advance<true, true, 4, true, true> : k_wf_advance<true, false, 4, true, true>)
+                   : spheres ? k_wf_advance<true, true, 4, false, true>
+                             : k_wf_advance<true, false, 4, false, true>;
     typedef void (*FinishKernel)(DScene, DRenderParams, WfPool, int, unsigned, float4 *);
     FinishKernel finish = scene->hasSpecular ? (spheres ? k_wf_finish<true, true> : k_wf_finish<false, true>)
                                              : (spheres ? k_wf_finish<true, false> : k_wf_finish<false, false>);
     // the frame's last paths are walked to their end by one thread each once this few are left (k_wf_finish)
     static const int finishPerSM = envInt("PB2_FINISH", 256);
-    const unsigned finishThreshold = (flags & PB2_FLAG_COUNT_TRAVERSAL) ? 0u : (unsigned)(g_numSMs * std::max(0, finishPerSM));
+    const bool lazyLights = scene->lazyLightDist;   // k_wf_finish cannot defer a vertex: the rounds run to the end instead
+    const unsigned finishThreshold = ((flags & PB2_FLAG_COUNT_TRAVERSAL) || lazyLights) ? 0u : (unsigned)(g_numSMs * std::max(0, finishPerSM));
     const int finishBlocks = std::max(1, (int)((finishThreshold + 127) / 128));
     const int blocks256 = std::min((capacity + 255) / 256, g_numSMs * 16);
     const int blocks128 = std::min((capacity + 127) / 128, g_numSMs * 32);
@@ -805,6 +850,12 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         }
         advLight<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
         advShade<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_SHADE, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
+        if (lazyLights) {
+            // vertices that fell into voxels without a light distribution yet were put aside: build those records, shade again
+            launchLightDistBuild(scene, stream);
+            advShade<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_RETRY, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
+            nLaunch += 3;
+        }
         if (finishThreshold) finish<<<finishBlocks, 128, 0, stream>>>(scene->d, rp, pool, WQ_TRACE0 + next, finishThreshold, film);
         k_wf_reset<<<1, 32, 0, stream>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur, WQ_TRACE0 + next, finishThreshold);
         nLaunch += finishThreshold ? 6 : 5;
@@ -815,6 +866,9 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         CUDA_TRY(cudaMemcpyAsync((void *)scene->wfHostCounts, pool.counts, WQ_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaMemcpyAsync(hWork, &scene->counters[CTR_WORK], sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
+        bool overflowed = false;
+        if ((rc = lightDistOverflowed(scene, stream, &overflowed))) return rc;
+        if (overflowed) return lightDistOverflowError();
         unsigned traceNext = hc[WQ_TRACE0 + cur], freeNext = hc[WQ_FREE0 + cur];
         bool workLeft = (long long)*hWork < rp.nWorkItems;
         if (traceNext == 0 && !(workLeft && freeNext > 0)) break;
@@ -962,6 +1016,7 @@ int pb2_scene_destroy(pb2_scene *s) {
     if (s->wfQueues) cudaFree(s->wfQueues);
     if (s->wfCounts) cudaFree(s->wfCounts);
     if (s->wfHostCounts) cudaFreeHost(s->wfHostCounts);
+    if (s->ldHostCounters) cudaFreeHost(s->ldHostCounters);
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     delete s;
     return PB2_OK;
@@ -1271,20 +1326,35 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
         int maxVoxels = d->spatial_max_voxels > 0 ? d->spatial_max_voxels : 64;
         for (int i = 0; i < 3; ++i) ld.nVoxels[i] = std::max(1, int(std::round(diag[i] / bmax * maxVoxels)));
         size_t nVox = (size_t)ld.nVoxels[0] * ld.nVoxels[1] * ld.nVoxels[2];
-        if (nVox * ld.stride * sizeof(float) > (size_t)8 << 30)
-            return setError(PB2_ERR_UNSUPPORTED, "spatial light distribution table would exceed 8 GiB (too many lights); use lightsamplestrategy \"uniform\" or \"power\"");
-        float *table;
-        if ((rc = allocate(s, nVox * ld.stride, &table))) return rc;
-        ld.table = table;
-        DHalton h;
-        memset(&h, 0, sizeof(h));
-        h.primes = g_halton.primes;
-        h.primeSums = g_halton.primeSums;
-        h.perms = g_halton.perms;
-        h.dimRecs = g_halton.dimRecs;
-        int threads = 128;
-        k_spatial_light_dist<<<(unsigned)((nVox + threads - 1) / threads), threads>>>(sc, h, table);
-        CUDA_TRY(cudaGetLastError());
+        const size_t recordBytes = (size_t)ld.stride * sizeof(float);
+        // One record per voxel up front when that is small (a few lights: 6 MB for the bench scene); otherwise - every
+        // emissive triangle is a light, a mesh of them makes records of kilobytes - records only for the voxels that path
+        // vertices fall into, built on demand into a bounded pool (the reference's lazily filled hash table,
+        // lightdistrib.cpp:141-230).  PB2_LIGHTDIST_LAZY=1 forces the lazy form (tests).
+        const size_t eagerLimit = (size_t)std::max(1, envInt("PB2_LIGHTDIST_EAGER_MB", 256)) << 20;
+        const bool lazy = envInt("PB2_LIGHTDIST_LAZY", 0) != 0 || nVox * recordBytes > eagerLimit;
+        if (!lazy) {
+            float *table;
+            if ((rc = allocate(s, nVox * ld.stride, &table))) return rc;
+            ld.table = table;
+            int threads = 128;
+            k_spatial_light_dist<<<(unsigned)((nVox + threads - 1) / threads), threads>>>(sc, haltonTablesOnly(), table);
+            CUDA_TRY(cudaGetLastError());
+        } else {
+            const size_t poolLimit = (size_t)std::max(1, envInt("PB2_LIGHTDIST_POOL_MB", 2048)) << 20;
+            const size_t records = std::max<size_t>(1, std::min(nVox, poolLimit / recordBytes));
+            float *table;
+            if ((rc = allocate(s, records * ld.stride, &table))) return rc;
+            ld.table = table;
+            ld.poolRecords = (int)records;
+            if ((rc = allocate(s, nVox, &ld.slots))) return rc;
+            if ((rc = allocate(s, nVox, &ld.requests))) return rc;
+            if ((rc = allocate(s, (size_t)4, &ld.counters))) return rc;
+            CUDA_TRY(cudaMemset(ld.slots, 0xff, nVox * sizeof(int)));   // LD_ABSENT
+            CUDA_TRY(cudaMemset(ld.counters, 0, 4 * sizeof(int)));
+            CUDA_TRY(cudaMallocHost((void **)&s->ldHostCounters, 4 * sizeof(int)));
+            s->lazyLightDist = true;
+        }
     }
     if ((rc = allocate(s, (size_t)CTR_COUNT, &s->counters))) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
@@ -1492,10 +1562,27 @@ int pb2_li_samples(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc 
     if (e == cudaSuccess) e = cudaMalloc((void **)&dPF, n * 2 * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(dXY, pixel_xy, n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(dS, sample_num, n * sizeof(int64_t), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        k_li_samples<<<(unsigned)((n + 63) / 64), 64>>>(scene->d, rp, dXY, dS, n, dRGB, dPF);
-        e = cudaGetLastError();
+    int *dDeferred = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dDeferred, sizeof(int));
+    for (int pass = 0; e == cudaSuccess; ++pass) {
+        // lazy light distribution: a sample that meets a voxel without a record stops; the records are built and ALL samples
+        // run again (a pure function of pixel and sample number), until none stops - at most one pass per path vertex
+        int deferred = 0;
+        e = cudaMemset(dDeferred, 0, sizeof(int));
+        if (e == cudaSuccess) {
+            k_li_samples<<<(unsigned)((n + 63) / 64), 64>>>(scene->d, rp, dXY, dS, n, dRGB, dPF, dDeferred);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(&deferred, dDeferred, sizeof(int), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess || deferred == 0) break;
+        launchLightDistBuild(scene, nullptr);
+        bool overflowed = false;
+        if (lightDistOverflowed(scene, nullptr, &overflowed) != PB2_OK || overflowed || pass > 4096) {
+            cudaFree(dXY); cudaFree(dS); cudaFree(dRGB); cudaFree(dPF); cudaFree(dDeferred);
+            return overflowed ? lightDistOverflowError() : setError(PB2_ERR_CUDA, "pb2_li_samples: light distribution build failed");
+        }
     }
+    cudaFree(dDeferred);
     if (e == cudaSuccess) e = cudaMemcpy(out_rgb, dRGB, n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && out_pfilm) e = cudaMemcpy(out_pfilm, dPF, n * 2 * sizeof(float), cudaMemcpyDeviceToHost);
     cudaFree(dXY);
@@ -1548,9 +1635,18 @@ int pb2_light_distribution(pb2_scene *scene, const float *points_xyz, int64_t n,
     cudaError_t e = cudaMalloc((void **)&dP, n * 3 * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void **)&dOut, n * stride * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(dP, points_xyz, n * 3 * sizeof(float), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
+    for (int pass = 0; pass < (scene->lazyLightDist ? 2 : 1) && e == cudaSuccess; ++pass) {
         k_light_distribution<<<(unsigned)((n + 127) / 128), 128>>>(scene->d, dP, n, dOut);
         e = cudaGetLastError();
+        if (scene->lazyLightDist && pass == 0 && e == cudaSuccess) {   // first pass requested the missing voxels
+            launchLightDistBuild(scene, nullptr);
+            bool overflowed = false;
+            if (lightDistOverflowed(scene, nullptr, &overflowed) != PB2_OK || overflowed) {
+                cudaFree(dP);
+                cudaFree(dOut);
+                return lightDistOverflowError();
+            }
+        }
     }
     if (e == cudaSuccess) e = cudaMemcpy(out, dOut, n * stride * sizeof(float), cudaMemcpyDeviceToHost);
     cudaFree(dP);

@@ -34,12 +34,13 @@ static_assert(offsetof(WfCtx, ln) == 0 && offsetof(DLane, state) == 0 && offseto
               "the trace kernels read the first 32 bytes of a context as {state, o, d, tMax}");
 static_assert(offsetof(WfCtx, tHit) % 8 == 0 && offsetof(WfCtx, found) == offsetof(WfCtx, tHit) + 4, "tHit/found are stored as one float2");
 
-enum { WQ_TRACE0 = 0, WQ_TRACE1 = 1, WQ_SHADE = 2, WQ_LIGHT = 3, WQ_FREE0 = 4, WQ_FREE1 = 5, WQ_CURSOR = 6, WQ_COUNT = 8 };
+// WQ_RETRY: path vertices deferred by the shade step (lazy light distribution), shaded again after k_lightdist_build
+enum { WQ_TRACE0 = 0, WQ_TRACE1 = 1, WQ_SHADE = 2, WQ_LIGHT = 3, WQ_FREE0 = 4, WQ_FREE1 = 5, WQ_CURSOR = 6, WQ_RETRY = 7, WQ_COUNT = 8 };
 
 struct WfPool {
     int capacity;
     WfCtx *ctx;
-    int *queue[6];            // WQ_TRACE0..WQ_FREE1, capacity entries each
+    int *queue[WQ_COUNT];     // capacity entries each; WQ_CURSOR is a counter only, WQ_RETRY exists for lazy scenes only
     unsigned *counts;         // WQ_COUNT counters
     unsigned long long *ctr;  // the scene's CTR_* counters (ray / traversal statistics)
 };
@@ -754,7 +755,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
 // vertex is evaluated); SHADE = false: the light list (shadow / MIS rays: a few adds and the next
 // ray).  Two instantiations so that the light kernel is small and the warps of each stay converged.
 // ---------------------------------------------------------------------------------------------
-template <bool SHADE, bool SPH, int MINB, bool SPEC = false>
+template <bool SHADE, bool SPH, int MINB, bool SPEC = false, bool LAZY = false>
 __global__ void __launch_bounds__(128, MINB) k_wf_advance(DScene sc, DRenderParams rp, WfPool pool, int srcQ, int traceQ,
                                                                    int freeQ, float4 *film, unsigned long long *counters) {
     unsigned n = pool.counts[srcQ];
@@ -764,7 +765,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_advance(DScene sc, DRenderPara
         unsigned i = base + threadIdx.x;
         bool have = i < n;
         int c = have ? pool.queue[srcQ][i] : 0;
-        bool ended = false;
+        bool ended = false, deferred = false;
         if (have) {
             WfCtx &cx = pool.ctx[c];
             DLane &ln = cx.ln;  // updated in place: each kernel touches only the fields its state needs
@@ -778,14 +779,20 @@ __global__ void __launch_bounds__(128, MINB) k_wf_advance(DScene sc, DRenderPara
             hit.inst = foundCode >= 2 ? foundCode - 2 : -1;
             bool found = foundCode != 0;
             float tHit = cx.tHit;
-            if (SHADE) shadeVertex<SPH, SPEC>(sc, rp.halton, rp.path, ln, found, hit, tHit);
+            if (SHADE) shadeVertex<SPH, SPEC, LAZY>(sc, rp.halton, rp.path, ln, found, hit, tHit);
             else lightAdvance<SPH>(sc, ln, found, hit, tHit);
-            ended = ln.state == LS_IDLE;
-            if (ended) addSample(rp, film, cx.pFilm, guardRadiance(ln.L));
-            else if (ln.state == LS_SHADOW) shadow++;   // Scene::IntersectP call (scene.cpp:51-55)
-            else regular++;                             // Scene::Intersect call (scene.cpp:45-49)
+            if (SHADE && LAZY && ln.state == LS_DEFER) {
+                ln.state = LS_PATH;   // untouched: shaded again from the retry list once its voxel's record exists
+                deferred = true;
+            } else {
+                ended = ln.state == LS_IDLE;
+                if (ended) addSample(rp, film, cx.pFilm, guardRadiance(ln.L));
+                else if (ln.state == LS_SHADOW) shadow++;   // Scene::IntersectP call (scene.cpp:51-55)
+                else regular++;                             // Scene::Intersect call (scene.cpp:45-49)
+            }
         }
-        wfPush(pool.queue[traceQ], &pool.counts[traceQ], c, have && !ended);
+        if (SHADE && LAZY) wfPush(pool.queue[WQ_RETRY], &pool.counts[WQ_RETRY], c, deferred);
+        wfPush(pool.queue[traceQ], &pool.counts[traceQ], c, have && !ended && !deferred);
         wfPush(pool.queue[freeQ], &pool.counts[freeQ], c, have && ended);
     }
     wfCountRays(counters, regular, shadow);
@@ -819,12 +826,54 @@ __global__ void __launch_bounds__(128) k_wf_finish(DScene sc, DRenderParams rp, 
             float tMax;
             const bool found = traceLane(sc, ln, &tMax, &hit, nullptr);
             laneAdvance<SPH, SPEC>(sc, rp.halton, rp.path, ln, found, hit, tMax);
+            if (ln.state == LS_DEFER) break;            // (never: this kernel is not launched for lazily lit scenes)
             if (ln.state == LS_SHADOW) shadow++;        // the next ray is a Scene::IntersectP call
             else if (ln.state != LS_IDLE) regular++;    // ... a Scene::Intersect call
         }
         addSample(rp, film, cx.pFilm, guardRadiance(ln.L));
     }
     wfCountRays(pool.ctr, regular, shadow);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Lazy SpatialLightDistribution: the records of the voxels requested since the last build (lightDistLookup), one block
+// per voxel.  Thread t owns lights t, t + 128, ...: a light's contribution is a sum over the 128 sample points in their
+// order, so any assignment of lights to threads gives the eager builder's (and the reference's) bits; thread 0 then runs
+// the sequential floor + cdf and publishes the record's index in the voxel's slot.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_lightdist_build(DScene sc, DHalton h) {
+    const DLightDist &ld = sc.lightDist;
+    const int nReq = ld.counters[0];
+    __shared__ int sRecord;
+    for (int r = blockIdx.x; r < nReq; r += gridDim.x) {
+        const int voxel = ld.requests[r];
+        if (threadIdx.x == 0) {
+            int k = atomicAdd(&ld.counters[1], 1);
+            if (k >= ld.poolRecords) {
+                ld.counters[2] = 1;   // pool exhausted: the host fails the render loudly
+                k = -1;
+            }
+            sRecord = k;
+        }
+        __syncthreads();
+        const int k = sRecord;
+        if (k >= 0) {
+            float *rec = const_cast<float *>(ld.table) + (size_t)k * ld.stride;
+            const int pz = voxel % ld.nVoxels[2], py = (voxel / ld.nVoxels[2]) % ld.nVoxels[1], px = voxel / (ld.nVoxels[2] * ld.nVoxels[1]);
+            const DVoxelBounds vb = voxelBounds(ld, px, py, pz);
+            for (int j = threadIdx.x; j < sc.nLights; j += blockDim.x) rec[j] = voxelLightContribution(sc, h, vb, j);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                finishVoxelDistribution(sc.nLights, rec);
+                __threadfence();
+                ld.slots[voxel] = k;
+            }
+        }
+        __syncthreads();
+    }
+}
+__global__ void k_lightdist_done(DScene sc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) sc.lightDist.counters[0] = 0;
 }
 
 __global__ void k_wf_init(WfPool pool) {
@@ -836,6 +885,7 @@ __global__ void k_wf_init(WfPool pool) {
 // end of a round: the lists consumed in it are emptied (and the next trace list, if k_wf_finish has just run it dry)
 __global__ void k_wf_reset(DRenderParams rp, WfPool pool, int a, int b, int traceNext, unsigned threshold) {
     if (threadIdx.x == 0) {
+        pool.counts[WQ_RETRY] = 0;
         if (wfFinishNow(rp, pool, traceNext, threshold)) pool.counts[traceNext] = 0;
         pool.counts[WQ_CURSOR] = 0;
         pool.counts[WQ_SHADE] = 0;

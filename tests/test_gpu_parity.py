@@ -456,3 +456,105 @@ def test_single_shape_intersect_goes_to_the_device(pb):
     h = hs.intersect(rays)
     assert h["prim"][0] == 0 and h["prim"][1] == -1 and h["t"][0] == 1.0
     assert np.allclose(h["b"][0], (0.5, 0.25, 0.25)) and np.allclose(h["p"][0], (0.25, 0.25, 0))
+
+
+def emissive_mesh_scene(n_side, res=(48, 32), spp=4):
+    """A grid of 2 * n_side^2 emissive triangles (each one a DiffuseAreaLight, api.cpp:1394-1400) over a matte floor and a
+    plastic box: 'spatial' light sampling with thousands of lights."""
+    pts, idx = [], []
+    for j in range(n_side + 1):
+        for i in range(n_side + 1):
+            pts += [-1 + 2 * i / n_side, -1 + 2 * j / n_side, 1.6 + 0.1 * np.sin(3.0 * i / n_side) * np.cos(2.0 * j / n_side)]
+    for j in range(n_side):
+        for i in range(n_side):
+            a = j * (n_side + 1) + i
+            idx += [a, a + n_side + 1, a + 1, a + 1, a + n_side + 1, a + n_side + 2]
+    fmt = lambda v: " ".join("%.6g" % x for x in v)
+    return """
+LookAt 0 -4 1.2  0 0 .5  0 0 1
+Camera "perspective" "float fov" [40]
+Film "image" "integer xresolution" [%d] "integer yresolution" [%d] "string filename" "emissive.pfm"
+Sampler "halton" "integer pixelsamples" [%d]
+Integrator "path" "integer maxdepth" [4]
+WorldBegin
+AttributeBegin
+  AreaLightSource "diffuse" "rgb L" [6 5 4]
+  Shape "trianglemesh" "point P" [%s] "integer indices" [%s]
+AttributeEnd
+Material "matte" "rgb Kd" [.6 .6 .6]
+Shape "trianglemesh" "point P" [-3 -3 0 3 -3 0 3 3 0 -3 3 0] "integer indices" [0 1 2 0 2 3]
+Material "plastic" "rgb Kd" [.3 .5 .3] "rgb Ks" [.4 .4 .4] "float roughness" [.1]
+Shape "trianglemesh" "point P" [-.5 -.5 0 .5 -.5 0 .5 .5 0 -.5 .5 0 -.5 -.5 .8 .5 -.5 .8 .5 .5 .8 -.5 .5 .8]
+  "integer indices" [0 1 5 0 5 4 1 2 6 1 6 5 2 3 7 2 7 6 3 0 4 3 4 7 4 5 6 4 6 7]
+WorldEnd
+""" % (res[0], res[1], spp, fmt(pts), " ".join(str(i) for i in idx))
+
+
+@pytest.mark.parametrize("name", ["soup", "materials", "lights_spatial"])
+def test_lazy_light_distribution_equals_the_eager_one(pb, name, monkeypatch):
+    """PB2_LIGHTDIST_LAZY=1: voxel records are built on demand (requested by the first vertex that falls into the voxel,
+    built between two kernels, the vertex shaded again).  Everything that depends on them must come out as with the eager
+    table: the distributions themselves bit for bit, per-sample Li, the film and the ray counters."""
+    def make():
+        if name == "lights_spatial":
+            return pb.HostScene.from_string(open(os.path.join(SCENES, "lights.pbrt")).read().replace('"power"', '"spatial"'))
+        return load_scene(pb, name)
+    results = []
+    for lazy in ("0", "1"):
+        monkeypatch.setenv("PB2_LIGHTDIST_LAZY", lazy)
+        hs = make()
+        nodes = hs.nodes()
+        xres, yres = hs.film.contents.full_resolution[0], hs.film.contents.full_resolution[1]
+        spp = hs.params.contents.samples_per_pixel
+        pix, sn = gc.sample_ids(xres, yres, spp, 3000, 13)
+        results.append((hs.light_distribution(gc.points_for(nodes, 400, 15)), hs.li_samples(pix, sn)[0]) + hs.render_rgbw())
+    (d0, l0, f0, s0), (d1, l1, f1, s1) = results
+    assert np.array_equal(gc.bits(d0), gc.bits(d1))
+    assert np.array_equal(gc.bits(l0), gc.bits(l1))
+    assert np.array_equal(f0[..., 3], f1[..., 3]) and np.allclose(f0, f1, rtol=1e-5, atol=1e-5)
+    assert (s0.camera_rays, s0.regular_rays, s0.shadow_rays) == (s1.camera_rays, s1.regular_rays, s1.shadow_rays)
+
+
+def test_emissive_mesh_with_thousands_of_lights(pb, checker):
+    """Every emissive triangle is a light (2 x 40 x 40 = 3200 here).  A spatial-distribution record is 25 KB then: the table
+    for all 64^3 voxels would take 6 GB and 10^11 light samples; built on demand only the voxels path vertices fall into
+    exist - as in the reference, whose results this must match."""
+    hs = pb.HostScene.from_string(emissive_mesh_scene(40))
+    assert hs.desc.contents.n_lights == 3200
+    sc = checker.scene(hs)
+    nodes = hs.nodes()
+    pts = gc.points_for(nodes, 60, 15)
+    assert np.array_equal(gc.bits(hs.light_distribution(pts)), gc.bits(sc.light_distribution(pts)))
+    pix, sn = gc.sample_ids(48, 32, 4, 1500, 13)
+    li, _ = hs.li_samples(pix, sn)
+    ref_li, _ = sc.li_samples(pix, sn)
+    assert li_ok(li, ref_li) >= 0.999
+    img, st = hs.render()
+    ref_img, _, ref_st = sc.render(n_threads=0)
+    frac, mean_rel = image_metrics(img, ref_img)
+    assert frac >= 0.999 and mean_rel <= 1e-4, (frac, mean_rel)
+    assert st.camera_rays == ref_st.camera_rays
+    assert abs(int(st.regular_rays) - int(ref_st.regular_rays)) <= ref_st.regular_rays // 1000 + 2
+
+
+def test_render_after_a_standalone_intersect_sees_the_lights(pb):
+    """Scene::Intersect before Render flattens the aggregate without lights; Render must not reuse that copy (a scene lit
+    by delta lights only would come out black, one with area lights would fail to flatten)."""
+    for name in ("lights", "materials"):
+        first, _ = pb.HostScene.from_file(os.path.join(SCENES, name + ".pbrt")).render()
+        hs = pb.HostScene.from_file(os.path.join(SCENES, name + ".pbrt"))
+        o, d, t = np.array([0, 0, 5], np.float32), np.array([0, 0, -1], np.float32), np.zeros(1, np.float32)
+        nodes = hs.nodes()
+        o[:] = 0.5 * (nodes["bmin"][0] + nodes["bmax"][0]) + np.float32([0, 0, 2 * (nodes["bmax"][0][2] - nodes["bmin"][0][2])])
+        assert hs.L.pb2h_scene_intersect(pb.ptr(o), pb.ptr(d), pb.ptr(t)) in (0, 1)
+        img, st = hs.render()
+        assert img.mean() > 0 and np.allclose(img, first, rtol=1e-5, atol=1e-6)
+
+
+def test_maxdepth_beyond_the_halton_tables_is_refused(pb):
+    hs = gc.soup_scene(pb)
+    dev = hs.device_scene()
+    out = np.zeros(hs.film_shape() + (4,), np.float32)
+    rc = hs.L.pb2_render_path(dev, hs.camera, hs.film, hs.params_copy(max_depth=124), pb.ptr(out), None)
+    assert rc == pb.PB2_ERR_UNSUPPORTED and b"1000 dimensions" in hs.L.pb2_last_error()
+    pb.check(hs.L.pb2_render_path(dev, hs.camera, hs.film, hs.params_copy(max_depth=123), pb.ptr(out), None))
