@@ -302,6 +302,14 @@ const char *pb2_last_error(void);
 /* Binds the calling process to one CUDA device (one process per GPU).  Replaces the reference's
  * ParallelInit() (src/core/parallel.cpp:301-336) as "bring up the execution resource". */
 int pb2_init(int device_id);
+/* Binds the calling process to a GROUP of local devices (n = 0: every visible device); device_ids[0] is the primary one.
+ * pb2_scene_create then keeps one copy of the scene per device, and a render call whose params.tile_count is 0 deals the
+ * film's 16x16 tiles round-robin to the devices (one host thread each) and adds the per-device films on the primary device,
+ * which reads the others' memory over NVLink peer access - Film::MergeFilmTile (src/core/film.cpp:117-130) across GPUs
+ * without leaving the process.  This is what the pb2_pbrt command line uses; one process per GPU + pb2_dist_init (below)
+ * is the other way to use several GPUs, and the two do not combine. */
+int pb2_init_devices(int n_devices, const int *device_ids);
+int pb2_device_count(void);   /* devices bound by pb2_init / pb2_init_devices (0 before) */
 int pb2_shutdown(void);
 
 /* Multi-GPU: one process per GPU; the film's 16x16 sample tiles are dealt round-robin to the ranks,

@@ -171,6 +171,7 @@ def lib():
     L.pb2_intersect_p.argtypes = [vp, vp, C.c_int64, vp]
     L.pb2_trace_wavefront.argtypes = [vp, vp, vp, C.c_int64, C.c_int32, vp]
     L.pb2_work_items.argtypes = [C.POINTER(FilmDesc), C.POINTER(PathParams), C.c_int64, C.c_int64, vp, C.POINTER(C.c_int64)]
+    L.pb2_init_devices.argtypes = [C.c_int, C.POINTER(C.c_int)]
     L.pb2_dist_unique_id.argtypes = [vp]
     L.pb2_dist_init.argtypes = [C.c_int, C.c_int, vp]
     L.pb2_dist_info.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]

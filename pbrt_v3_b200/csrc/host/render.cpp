@@ -688,9 +688,13 @@ bool EnsureDevice() {
     static std::once_flag once;
     static int status = PB2_OK;
     std::call_once(once, [] {
+        // a process that has bound its device(s) already keeps them (tests, bench.py: one process per GPU); PB2_DEVICE /
+        // LOCAL_RANK name one device; otherwise - the pb2_pbrt command line - every visible GPU renders (film tiles dealt to
+        // the devices, films merged on the first one)
+        if (pb2_device_count() > 0) return;
         const char *dev = std::getenv("PB2_DEVICE");
         if (!dev) dev = std::getenv("LOCAL_RANK");
-        status = pb2_init(dev ? std::atoi(dev) : 0);
+        status = dev ? pb2_init(std::atoi(dev)) : pb2_init_devices(0, nullptr);
     });
     if (status != PB2_OK) Error("pb2_init failed: %s (there is no CPU fallback for the path-tracing hot path)", pb2_last_error());
     return status == PB2_OK;

@@ -488,7 +488,9 @@ class PathIntegrator : public SamplerIntegrator {
     const std::string &LightSampleStrategy() const { return lightSampleStrategy; }
     pb2_stats lastStats{};
     bool writeImage = true;
-    int tileRank = 0, tileCount = 1;
+    // 0 = the library's own partition: all of the film on one device, or the film's tiles dealt to the bound device group /
+    // the ranks of the communicator (include/pb2.h: pb2_init_devices, pb2_dist_init) with the films merged on the first
+    int tileRank = 0, tileCount = 0;
   private:
     const int maxDepth;
     const Float rrThreshold;

@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "device/pb2_path.cuh"
@@ -48,9 +49,25 @@ static int setError(int code, const std::string &msg) {
             return setError(PB2_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));           \
     } while (0)
 
+// Devices bound by pb2_init / pb2_init_devices.  g_devs[0] is the primary one (every single-device entry point, the root of
+// a multi-device render); a render over several local devices runs one host thread per device, each with t_dev set to its
+// entry, so that the code below - written for "the current device" - needs no device argument.
+struct DeviceState {
+    int id = -1;
+    int numSMs = 0;
+    int32_t *primes = nullptr, *primeSums = nullptr;   // Halton tables in this device's memory
+    uint16_t *perms = nullptr;
+    ulonglong2 *dimRecs = nullptr;
+    bool peerOfPrimary = false;   // the primary device can read this one's memory directly (NVLink / PCIe peer access)
+};
+static std::vector<DeviceState> g_devs;
+static thread_local int t_dev = 0;
 static bool g_initialised = false;
-static int g_device = -1;
-static int g_numSMs = 0;
+static DeviceState &cur() {
+    static DeviceState none;   // before pb2_init: null tables (host-only entry points such as pb2_work_items never read them)
+    return (size_t)t_dev < g_devs.size() ? g_devs[(size_t)t_dev] : none;
+}
+#define g_numSMs (cur().numSMs)
 
 // ---------------------------------------------------------------------------------------------
 // Multi-GPU: one process per GPU, the film reduce over NCCL.  The communicator spans the processes
@@ -105,10 +122,7 @@ static int envInt(const char *name, int def) {
 // ---------------------------------------------------------------------------------------------
 // Halton tables (lowdiscrepancy.cpp:40,124,2490-2504; halton.cpp:65-93)
 // ---------------------------------------------------------------------------------------------
-struct HaltonTables {
-    int32_t *primes = nullptr, *primeSums = nullptr;
-    uint16_t *perms = nullptr;
-    ulonglong2 *dimRecs = nullptr;   // per dimension: {ceil(2^64 / prime), prime | primeSum << 32}
+struct HaltonTables {   // host copies; the device copies live in DeviceState (dimRecs: per dimension {ceil(2^64 / prime), prime | primeSum << 32})
     std::vector<int32_t> hPrimes, hPrimeSums;
     std::vector<ulonglong2> hDimRecs;
     std::vector<uint16_t> hPerms;
@@ -201,10 +215,10 @@ static DHalton makeHalton(const pb2_film_desc *film, const pb2_path_params *pp) 
     h.multInverse[1] = (int)multiplicativeInverse(h.baseScales[0], h.baseScales[1]);
     h.sampleAtPixelCenter = pp->sample_at_pixel_center;
     h.samplesPerPixel = pp->samples_per_pixel;
-    h.perms = g_halton.perms;
-    h.primes = g_halton.primes;
-    h.primeSums = g_halton.primeSums;
-    h.dimRecs = g_halton.dimRecs;
+    h.perms = cur().perms;
+    h.primes = cur().primes;
+    h.primeSums = cur().primeSums;
+    h.dimRecs = cur().dimRecs;
     return h;
 }
 
@@ -223,6 +237,8 @@ struct pb2_scene {
     int bvhDepth = 0;  // maximum number of simultaneously pending far children = tree depth (scene BVH)
     int instDepth = 0; // the same for the deepest instanced object's BVH
     bool hasSpecular = false;  // a mirror / glass material exists: the shade kernel with the specular BxDFs is used
+    int devIndex = 0;             // entry of g_devs this copy lives on
+    std::vector<pb2_scene *> replicas;   // primary only: the copies on g_devs[1..] (pb2_init_devices with several devices)
     bool lazyLightDist = false;   // spatial light distribution built on demand (DLightDist::slots)
     int *ldHostCounters = nullptr;   // pinned copy of DLightDist::counters
     // wavefront pool (allocated on first render)
@@ -547,10 +563,10 @@ __global__ void k_light_distribution(DScene sc, const float *points, int64_t n, 
 static DHalton haltonTablesOnly() {   // what radicalInverse() needs: the tables, no film geometry
     DHalton h;
     memset(&h, 0, sizeof(h));
-    h.primes = g_halton.primes;
-    h.primeSums = g_halton.primeSums;
-    h.perms = g_halton.perms;
-    h.dimRecs = g_halton.dimRecs;
+    h.primes = cur().primes;
+    h.primeSums = cur().primeSums;
+    h.perms = cur().perms;
+    h.dimRecs = cur().dimRecs;
     return h;
 }
 
@@ -890,7 +906,19 @@ extern "C" {
 int pb2_abi_version(void) { return PB2_ABI_VERSION; }
 const char *pb2_last_error(void) { return g_lastError.c_str(); }
 
-int pb2_init(int device_id) {
+static void freeDeviceTables() {
+    for (DeviceState &d : g_devs) {
+        cudaSetDevice(d.id);
+        cudaFree(d.primes);
+        cudaFree(d.primeSums);
+        cudaFree(d.perms);
+        cudaFree(d.dimRecs);
+    }
+    g_devs.clear();
+    g_initialised = false;
+}
+
+int pb2_init_devices(int n, const int *device_ids) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -899,38 +927,69 @@ int pb2_init(int device_id) {
                                                (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
                                                "); the path-tracing hot path has no CPU fallback");
     }
-    if (device_id < 0 || device_id >= count) return setError(PB2_ERR_INVALID, "device id out of range");
-    if (g_initialised && g_device == device_id) return PB2_OK;
-    CUDA_TRY(cudaSetDevice(device_id));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device_id));
-    if (prop.major < 10)
-        return setError(PB2_ERR_NO_DEVICE, std::string("device \"") + prop.name + "\" is not sm_100-class; this library is built for sm_100a only");
-    g_numSMs = prop.multiProcessorCount;
+    std::vector<int> ids;
+    if (n <= 0) for (int i = 0; i < count; ++i) ids.push_back(i);   // every visible device
+    else {
+        if (!device_ids) return setError(PB2_ERR_INVALID, "null device list");
+        ids.assign(device_ids, device_ids + n);
+    }
+    for (size_t i = 0; i < ids.size(); ++i) {
+        if (ids[i] < 0 || ids[i] >= count) return setError(PB2_ERR_INVALID, "device id out of range");
+        for (size_t j = 0; j < i; ++j)
+            if (ids[j] == ids[i]) return setError(PB2_ERR_INVALID, "device listed twice");
+    }
+    if (g_initialised && g_devs.size() == ids.size()) {
+        bool same = true;
+        for (size_t i = 0; i < ids.size(); ++i) same &= g_devs[i].id == ids[i];
+        if (same) return PB2_OK;
+    }
+    if (g_dist.comm) return setError(PB2_ERR_INVALID, "pb2_init: shut the communicator down (pb2_dist_shutdown) before rebinding devices");
+    freeDeviceTables();
     buildHaltonHostTables();
-    CUDA_TRY(cudaMalloc((void **)&g_halton.primes, g_halton.hPrimes.size() * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc((void **)&g_halton.primeSums, g_halton.hPrimeSums.size() * sizeof(int32_t)));
-    CUDA_TRY(cudaMalloc((void **)&g_halton.perms, g_halton.hPerms.size() * sizeof(uint16_t)));
-    CUDA_TRY(cudaMalloc((void **)&g_halton.dimRecs, g_halton.hDimRecs.size() * sizeof(ulonglong2)));
-    CUDA_TRY(cudaMemcpy(g_halton.dimRecs, g_halton.hDimRecs.data(), g_halton.hDimRecs.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(g_halton.primes, g_halton.hPrimes.data(), g_halton.hPrimes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(g_halton.primeSums, g_halton.hPrimeSums.data(), g_halton.hPrimeSums.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(g_halton.perms, g_halton.hPerms.data(), g_halton.hPerms.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    g_device = device_id;
+    t_dev = 0;
+    for (int id : ids) {
+        CUDA_TRY(cudaSetDevice(id));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, id));
+        if (prop.major < 10) {
+            freeDeviceTables();
+            return setError(PB2_ERR_NO_DEVICE, std::string("device \"") + prop.name + "\" is not sm_100-class; this library is built for sm_100a only");
+        }
+        g_devs.emplace_back();
+        DeviceState &d = g_devs.back();
+        d.id = id;
+        d.numSMs = prop.multiProcessorCount;
+        CUDA_TRY(cudaMalloc((void **)&d.primes, g_halton.hPrimes.size() * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc((void **)&d.primeSums, g_halton.hPrimeSums.size() * sizeof(int32_t)));
+        CUDA_TRY(cudaMalloc((void **)&d.perms, g_halton.hPerms.size() * sizeof(uint16_t)));
+        CUDA_TRY(cudaMalloc((void **)&d.dimRecs, g_halton.hDimRecs.size() * sizeof(ulonglong2)));
+        CUDA_TRY(cudaMemcpy(d.dimRecs, g_halton.hDimRecs.data(), g_halton.hDimRecs.size() * sizeof(ulonglong2), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.primes, g_halton.hPrimes.data(), g_halton.hPrimes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.primeSums, g_halton.hPrimeSums.data(), g_halton.hPrimeSums.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.perms, g_halton.hPerms.data(), g_halton.hPerms.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    // the film merge of a multi-device render reads the other devices' films from the primary one over NVLink
+    CUDA_TRY(cudaSetDevice(g_devs[0].id));
+    for (size_t i = 1; i < g_devs.size(); ++i) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, g_devs[0].id, g_devs[i].id) == cudaSuccess && can) {
+            cudaError_t pe = cudaDeviceEnablePeerAccess(g_devs[i].id, 0);
+            g_devs[i].peerOfPrimary = pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled;
+        }
+        cudaGetLastError();
+    }
     g_initialised = true;
     return PB2_OK;
 }
 
+int pb2_init(int device_id) { return pb2_init_devices(1, &device_id); }
+
+int pb2_device_count(void) { return g_initialised ? (int)g_devs.size() : 0; }
+
 int pb2_shutdown(void) {
     if (!g_initialised) return PB2_OK;
-    cudaFree(g_halton.primes);
-    cudaFree(g_halton.primeSums);
-    cudaFree(g_halton.perms);
-    cudaFree(g_halton.dimRecs);
-    g_halton.dimRecs = nullptr;
-    g_halton.primes = g_halton.primeSums = nullptr;
-    g_halton.perms = nullptr;
-    g_initialised = false;
+    pb2_dist_shutdown();
+    freeDeviceTables();
     return PB2_OK;
 }
 
@@ -974,7 +1033,8 @@ int pb2_dist_init(int rank, int world, const void *id128) {
     if ((rc = loadNccl())) return rc;
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
-    CUDA_TRY(cudaSetDevice(g_device));
+    if (g_devs.size() != 1) return setError(PB2_ERR_INVALID, "pb2_dist_init: one device per process (pb2_init), not a local device group");
+    CUDA_TRY(cudaSetDevice(g_devs[0].id));
     NCCL_TRY(g_nccl.CommInitRank(&g_dist.comm, world, id, rank));
     return PB2_OK;
 }
@@ -1009,6 +1069,9 @@ int pb2_host_free(void *p) {
 
 int pb2_scene_destroy(pb2_scene *s) {
     if (!s) return PB2_OK;
+    for (pb2_scene *r : s->replicas) pb2_scene_destroy(r);
+    s->replicas.clear();
+    if (g_initialised && (size_t)s->devIndex < g_devs.size()) cudaSetDevice(g_devs[(size_t)s->devIndex].id);
     for (void *p : s->allocations) cudaFree(p);
     if (s->film) cudaFree(s->film);
     if (s->filterTable) cudaFree(s->filterTable);
@@ -1019,14 +1082,44 @@ int pb2_scene_destroy(pb2_scene *s) {
     if (s->ldHostCounters) cudaFreeHost(s->ldHostCounters);
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     delete s;
+    if (g_initialised) cudaSetDevice(g_devs[0].id);
     return PB2_OK;
 }
 
+static int createSceneOnCurrentDevice(const pb2_scene_desc *d, pb2_scene **out);
+
+// One copy of the scene per bound device (the BVH and every table are replicated); the handle is the
+// primary device's copy, which owns the others.
 int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
     if (!d || !out) return setError(PB2_ERR_INVALID, "null argument");
     *out = nullptr;
     int rc = requireDevice();
     if (rc) return rc;
+    t_dev = 0;
+    CUDA_TRY(cudaSetDevice(g_devs[0].id));
+    pb2_scene *primary = nullptr;
+    if ((rc = createSceneOnCurrentDevice(d, &primary))) return rc;
+    for (size_t i = 1; i < g_devs.size() && rc == PB2_OK; ++i) {
+        t_dev = (int)i;
+        pb2_scene *rep = nullptr;
+        if (cudaSetDevice(g_devs[i].id) != cudaSuccess) rc = setError(PB2_ERR_CUDA, "cudaSetDevice failed");
+        else if ((rc = createSceneOnCurrentDevice(d, &rep)) == PB2_OK) {
+            rep->devIndex = (int)i;
+            primary->replicas.push_back(rep);
+        }
+    }
+    t_dev = 0;
+    cudaSetDevice(g_devs[0].id);
+    if (rc) {
+        pb2_scene_destroy(primary);
+        return rc;
+    }
+    *out = primary;
+    return PB2_OK;
+}
+
+static int createSceneOnCurrentDevice(const pb2_scene_desc *d, pb2_scene **out) {
+    int rc = PB2_OK;
     if (d->n_prims <= 0 || d->n_nodes <= 0 || !d->nodes || !d->bvh_prims || !d->prim_type || !d->prim_index)
         return setError(PB2_ERR_INVALID, "scene has no primitives / BVH");
     if (d->n_prims > 0x7fffffffLL || d->n_nodes > 0x7fffffffLL) return setError(PB2_ERR_UNSUPPORTED, "more than 2^31 primitives/nodes");
@@ -1038,6 +1131,7 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
         ~Guard() { if (s) pb2_scene_destroy(s); }
     } guard{new pb2_scene()};
     pb2_scene *s = guard.s;
+    s->devIndex = t_dev;
     for (int i = 0; i < d->n_materials; ++i)
         if (d->materials[i].type == PB2_MAT_MIRROR || d->materials[i].type == PB2_MAT_GLASS || d->materials[i].type == PB2_MAT_SUBSTRATE ||
             d->materials[i].type == PB2_MAT_METAL || d->materials[i].type == PB2_MAT_UBER)
@@ -1442,12 +1536,124 @@ int pb2_trace_wavefront(pb2_scene *scene, const pb2_ray *rays, const uint8_t *an
     return PB2_OK;
 }
 
+// film[i] += sum over the peers' films: the Film::MergeFilmTile of a multi-device render, run on the primary device, which
+// reads the other devices' memory directly (peer access over NVLink): 33 MB per peer at 1080p
+__global__ void k_film_sum_peers(float4 *film, const float4 *p0, const float4 *p1, const float4 *p2, const float4 *p3, const float4 *p4,
+                                 const float4 *p5, const float4 *p6, int nPeers, size_t nPixels) {
+    const float4 *peers[7] = {p0, p1, p2, p3, p4, p5, p6};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nPixels; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = film[i];
+        for (int k = 0; k < nPeers; ++k) {
+            const float4 b = peers[k][i];
+            a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        }
+        film[i] = a;
+    }
+}
+
+static int ensureFilm(pb2_scene *scene, size_t nFloats) {
+    if (scene->filmFloats < nFloats) {
+        if (scene->film) cudaFree(scene->film);
+        scene->film = nullptr;
+        scene->filmFloats = 0;
+        CUDA_TRY(cudaMalloc((void **)&scene->film, nFloats * sizeof(float)));
+        scene->filmFloats = nFloats;
+    }
+    return PB2_OK;
+}
+
+static int renderPathDeviceOne(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp,
+                               float *film_rgbw_device, int clear, void *stream_, pb2_stats *stats);
+
+// A render over the local device group (pb2_init_devices with n > 1, params.tile_count == 0): one host thread per device
+// renders the tiles t with t % n == its index into its own copy of the scene and its own film; the primary device then adds
+// the other films to its own.
+static int renderPathDeviceGroup(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp,
+                                 float *film_rgbw_device, int clear, cudaStream_t stream, pb2_stats *stats) {
+    const int n = (int)g_devs.size();
+    if (n > 8) return setError(PB2_ERR_UNSUPPORTED, "at most 8 local devices");
+    if ((int)scene->replicas.size() != n - 1) return setError(PB2_ERR_INVALID, "the scene was created before pb2_init_devices bound this device group");
+    const size_t nPixels = (size_t)(film->cropped_pixel_bounds[2] - film->cropped_pixel_bounds[0]) *
+                           (size_t)(film->cropped_pixel_bounds[3] - film->cropped_pixel_bounds[1]);
+    std::vector<int> rcs((size_t)n, PB2_OK);
+    std::vector<std::string> errs((size_t)n);
+    std::vector<pb2_stats> sts((size_t)n);
+    std::vector<std::thread> workers;
+    CUDA_TRY(cudaStreamSynchronize(stream));   // the caller's earlier work on the film
+    for (int i = 0; i < n; ++i)
+        workers.emplace_back([&, i] {
+            t_dev = i;
+            pb2_scene *rep = i == 0 ? scene : scene->replicas[(size_t)i - 1];
+            int rc = cudaSetDevice(g_devs[(size_t)i].id) == cudaSuccess ? PB2_OK : setError(PB2_ERR_CUDA, "cudaSetDevice failed");
+            float *target = film_rgbw_device;
+            if (rc == PB2_OK && i > 0) {
+                rc = ensureFilm(rep, nPixels * 4);
+                target = rep->film;
+            }
+            pb2_path_params p = *pp;
+            p.tile_rank = i;
+            p.tile_count = n;
+            memset(&sts[(size_t)i], 0, sizeof(pb2_stats));
+            if (rc == PB2_OK) rc = renderPathDeviceOne(rep, cam, film, &p, target, i == 0 ? clear : 1, nullptr, &sts[(size_t)i]);
+            if (rc == PB2_OK && cudaDeviceSynchronize() != cudaSuccess) rc = setError(PB2_ERR_CUDA, "device synchronisation failed after the render");
+            rcs[(size_t)i] = rc;
+            errs[(size_t)i] = g_lastError;
+        });
+    for (std::thread &w : workers) w.join();
+    t_dev = 0;
+    CUDA_TRY(cudaSetDevice(g_devs[0].id));
+    for (int i = 0; i < n; ++i)
+        if (rcs[(size_t)i]) return setError(rcs[(size_t)i], "device " + std::to_string(g_devs[(size_t)i].id) + ": " + errs[(size_t)i]);
+    // merge
+    const float4 *peers[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<float *> staged;
+    for (int i = 1; i < n; ++i) {
+        pb2_scene *rep = scene->replicas[(size_t)i - 1];
+        if (g_devs[(size_t)i].peerOfPrimary) peers[i - 1] = reinterpret_cast<const float4 *>(rep->film);
+        else {   // no peer access between the two devices: stage the film through a copy
+            float *tmp = nullptr;
+            CUDA_TRY(cudaMalloc((void **)&tmp, nPixels * 16));
+            staged.push_back(tmp);
+            CUDA_TRY(cudaMemcpyPeerAsync(tmp, g_devs[0].id, rep->film, g_devs[(size_t)i].id, nPixels * 16, stream));
+            peers[i - 1] = reinterpret_cast<const float4 *>(tmp);
+        }
+    }
+    const int blocks = (int)std::min<size_t>((nPixels + 255) / 256, (size_t)g_numSMs * 8);
+    k_film_sum_peers<<<blocks, 256, 0, stream>>>(reinterpret_cast<float4 *>(film_rgbw_device), peers[0], peers[1], peers[2], peers[3], peers[4],
+                                                 peers[5], peers[6], n - 1, nPixels);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    for (float *t : staged) cudaFree(t);
+    if (stats) {
+        memset(stats, 0, sizeof(*stats));
+        for (const pb2_stats &st : sts) {
+            stats->camera_rays += st.camera_rays;
+            stats->regular_rays += st.regular_rays;
+            stats->shadow_rays += st.shadow_rays;
+            stats->node_visits += st.node_visits;
+            stats->prim_tests += st.prim_tests;
+            stats->kernel_launches += st.kernel_launches;
+            stats->render_ms = std::max(stats->render_ms, st.render_ms);   // the devices run concurrently
+            stats->trace_ms = std::max(stats->trace_ms, st.trace_ms);
+        }
+        stats->kernel_launches += 1;
+    }
+    return PB2_OK;
+}
+
 int pb2_render_path_device(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp,
                            float *film_rgbw_device, int clear, void *stream_, pb2_stats *stats) {
     int rc = requireDevice();
     if (rc) return rc;
     if ((rc = validateRenderArgs(scene, cam, film, pp))) return rc;
     if (!film_rgbw_device) return setError(PB2_ERR_INVALID, "null film pointer");
+    if (pp->tile_count == 0 && g_devs.size() > 1) return renderPathDeviceGroup(scene, cam, film, pp, film_rgbw_device, clear, (cudaStream_t)stream_, stats);
+    return renderPathDeviceOne(scene, cam, film, pp, film_rgbw_device, clear, stream_, stats);
+}
+
+static int renderPathDeviceOne(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp,
+                               float *film_rgbw_device, int clear, void *stream_, pb2_stats *stats) {
+    int rc = PB2_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     // tile_count == 0: the partition of the communicator (every rank renders its tiles, the films are summed on rank 0);
     // a caller that sets tile_count >= 1 partitions by hand and gets exactly the tiles it asked for, unreduced
@@ -1521,13 +1727,7 @@ int pb2_render_path(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc
     size_t nFloats = 4 * (size_t)(film->cropped_pixel_bounds[2] - film->cropped_pixel_bounds[0]) *
                      (size_t)(film->cropped_pixel_bounds[3] - film->cropped_pixel_bounds[1]);
     if (nFloats == 0) return PB2_OK;
-    if (scene->filmFloats < nFloats) {
-        if (scene->film) cudaFree(scene->film);
-        scene->film = nullptr;
-        scene->filmFloats = 0;
-        CUDA_TRY(cudaMalloc((void **)&scene->film, nFloats * sizeof(float)));
-        scene->filmFloats = nFloats;
-    }
+    if ((rc = ensureFilm(scene, nFloats))) return rc;
     pb2_stats local;
     memset(&local, 0, sizeof(local));
     rc = pb2_render_path_device(scene, cam, film, pp, scene->film, 1, nullptr, stats ? &local : nullptr);

@@ -70,3 +70,37 @@ def test_two_processes_render_and_reduce_inside_the_library(tmp_path):
            "--master-port", str(port), str(script), ROOT]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=ROOT)
     assert res.returncode == 0 and res.stdout.count(" ok") == 2, res.stdout[-4000:]
+
+
+GROUP_WORKER = r'''
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import pbrt_v3_b200 as pb
+L = pb.lib()
+pb.check(L.pb2_init_devices(0, None))            # every visible device, one process
+n = L.pb2_device_count()
+assert n >= 2, n
+for make in (lambda: pb.HostScene.soup(20000, xres=100, yres=70, spp=4),
+             lambda: pb.HostScene.instanced_soup(2000, grid=4, xres=64, yres=36, spp=4),
+             lambda: pb.HostScene.from_file(os.path.join(sys.argv[1], "tests", "scenes", "killeroo_like.pbrt"))):
+    hs = make()
+    group, sg = hs.render_rgbw(hs.params_copy(tile_rank=0, tile_count=0))      # tiles dealt to the devices, films merged on the first
+    alone, sa = hs.render_rgbw(hs.params_copy(tile_rank=0, tile_count=1))      # the primary device alone
+    assert (sg.camera_rays, sg.regular_rays, sg.shadow_rays) == (sa.camera_rays, sa.regular_rays, sa.shadow_rays)
+    assert np.array_equal(group[..., 3], alone[..., 3]) and np.allclose(group, alone, rtol=1e-4, atol=1e-4)
+    img, st = hs.render()                                                     # Integrator::Render of the host classes: the group as well
+    assert st.camera_rays == sa.camera_rays and np.allclose(img, hs.resolve(alone), rtol=1e-4, atol=1e-5)
+print("group of", n, "ok")
+'''
+
+
+def test_one_process_renders_on_every_visible_device(tmp_path):
+    """pb2_init_devices: scene replicas, one host thread per device, the film merge on the primary device over peer access."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    script = tmp_path / "group.py"
+    script.write_text(GROUP_WORKER)
+    res = subprocess.run([sys.executable, str(script), ROOT], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, cwd=ROOT)
+    assert res.returncode == 0 and " ok" in res.stdout, res.stdout[-4000:]
