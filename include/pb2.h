@@ -261,6 +261,9 @@ typedef struct pb2_path_params {
 #define PB2_FLAG_SMALL_STACK 16
 /* Fetch node records with 16-byte instead of 32-byte loads per lane (same results). */
 #define PB2_FLAG_LD128 32
+/* Experiment kept for the record: stage leaf records into shared memory with TMA bulk copies
+ * (cp.async.bulk / UBLKCP + mbarrier) before the triangle tests; triangle scenes, two-child kernel.  Same results, slower. */
+#define PB2_FLAG_LEAF_TMA 64
 
 typedef struct pb2_ray {
     float o[3];

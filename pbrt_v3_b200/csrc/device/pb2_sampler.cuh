@@ -31,7 +31,34 @@ struct DHalton {
 #else
     const void *dimRecs;
 #endif
+    // digit tables of the scrambled radical inverse (scrambledRadicalInverseTab below); null = digit loop
+    const struct HaltonDimTab *dimTabs;   // one record per dimension
+    const uint16_t *digitTab;             // per dimension: nat[B] followed by full[B]
 };
+
+// The scrambled radical inverse several digits at a time.  For base b let B = b^m be the largest power <= 8192.  Of an
+// index a = (top B + mid) B + lo the digit loop of ScrambledRadicalInverseSpecialized (lowdiscrepancy.cpp:405-424) first
+// consumes the m digits of lo, then those of mid, then what is left; its state is the integer reversedDigits and the count n
+// of digits seen (invBaseN is invBase multiplied n times in float: a function of n alone).  Two tables per dimension give
+// the state after a block of digits at once:
+//   full[x] = the m permuted digits of x reversed (leading zeros included: the loop does run over them when more follows)
+//   nat[x]  = the permuted digits of x reversed as far as the loop goes when NOTHING follows (it stops at the last non-zero
+//             digit), with that digit count in bits 13-15
+// and reversedDigits = full[lo] b^n' + nat[mid] (n' digits in mid) is plain integer arithmetic: the same integer, the same
+// n, hence the same float as the loop's, for one multiply-high and two or three look-ups instead of ~12 instructions and a
+// dependent L1 round trip per digit.  Built on the host by the loop itself (buildHaltonHostTables, pb2_cuda.cu).
+struct HaltonDimTab {
+    uint64_t magicB;      // ceil(2^64 / B)
+    uint32_t B;           // b^m
+    uint32_t m;
+    uint32_t tabOffset;   // into DHalton::digitTab
+    uint32_t pow[6];      // b^0 .. b^5 (m <= 5)
+    float invPow[16];     // invBase multiplied n times, n = 0 .. 15 (a 32-bit index has at most 14 digits in base 5)
+    float tail;           // invBase * perm[0] / (1 - invBase): the permuted zero digits beyond the last one
+    uint32_t pad[4];
+};
+static_assert(sizeof(HaltonDimTab) == 128, "one 128-byte record per dimension");
+constexpr uint32_t kHaltonTabMax = 8192;
 
 PB2_HD uint64_t reverseBits64(uint64_t n) {
 #if defined(__CUDA_ARCH__)
@@ -119,6 +146,40 @@ PB2_HD float scrambledRadicalInverse32(uint32_t base, uint64_t magic, uint32_t a
     return pmin(invBaseN * ((float)reversedDigits + invBase * perm0 / (1 - invBase)), kOneMinusEpsilon);
 }
 
+// ScrambledRadicalInverse of an index below 2^32 through the digit tables (see HaltonDimTab).
+PB2_HD float scrambledRadicalInverseTab(const HaltonDimTab &t, const uint16_t *digitTab, uint32_t base, uint64_t magicBase, uint32_t a,
+                                        const uint16_t *perm) {
+    const uint16_t *nat = digitTab + t.tabOffset, *full = nat + t.B;
+    const uint32_t q1 = divMagic(a, t.magicB), lo = a - q1 * t.B;
+    uint64_t reversedDigits;
+    uint32_t n;
+    if (q1 == 0) {
+        const uint32_t e = nat[lo];
+        reversedDigits = e & 0x1fffu;
+        n = e >> 13;
+    } else {
+        const uint32_t q2 = divMagic(q1, t.magicB), mid = q1 - q2 * t.B;
+        const uint32_t f = full[lo];
+        if (q2 == 0) {
+            const uint32_t e = nat[mid], nh = e >> 13;
+            reversedDigits = (uint64_t)f * t.pow[nh] + (e & 0x1fffu);
+            n = t.m + nh;
+        } else {
+            // an index of more than 2 m digits: the rest one digit at a time, as the loop would
+            reversedDigits = (uint64_t)f * t.B + full[mid];
+            n = 2 * t.m;
+            uint32_t rest = q2;
+            while (rest) {
+                const uint32_t next = divMagic(rest, magicBase), digit = rest - next * base;
+                reversedDigits = reversedDigits * base + perm[digit];
+                ++n;
+                rest = next;
+            }
+        }
+    }
+    return pmin(t.invPow[n] * ((float)reversedDigits + t.tail), kOneMinusEpsilon);
+}
+
 // RadicalInverse(baseIndex, a), lowdiscrepancy.cpp:427-
 PB2_HD float radicalInverse(const DHalton &h, int baseIndex, uint64_t a) {
     if (baseIndex == 0) return (float)((double)reverseBits64(a) * 0x1p-64);
@@ -162,7 +223,10 @@ PB2_HD float haltonSample(const DHalton &h, int64_t index, int dim) {
     if (dim == 1) return radicalInverseBase(3u, (uint64_t)(index / h.baseScales[1]), nullptr);
 #if defined(__CUDA_ARCH__)
     const ulonglong2 rec = __ldg(&h.dimRecs[dim]);   // {magic, prime | primeSum << 32}: one 16-B load per dimension
-    if (((uint64_t)index >> 32) == 0) return scrambledRadicalInverse32((uint32_t)rec.y, rec.x, (uint32_t)index, h.perms + (uint32_t)(rec.y >> 32));
+    if (((uint64_t)index >> 32) == 0) {
+        if (h.dimTabs) return scrambledRadicalInverseTab(h.dimTabs[dim], h.digitTab, (uint32_t)rec.y, rec.x, (uint32_t)index, h.perms + (uint32_t)(rec.y >> 32));
+        return scrambledRadicalInverse32((uint32_t)rec.y, rec.x, (uint32_t)index, h.perms + (uint32_t)(rec.y >> 32));
+    }
     return radicalInverseBase((uint32_t)rec.y, (uint64_t)index, h.perms + (uint32_t)(rec.y >> 32), rec.x);
 #else
     return radicalInverseBase((uint32_t)h.primes[dim], (uint64_t)index, h.perms + h.primeSums[dim]);

@@ -58,6 +58,8 @@ struct DeviceState {
     int32_t *primes = nullptr, *primeSums = nullptr;   // Halton tables in this device's memory
     uint16_t *perms = nullptr;
     ulonglong2 *dimRecs = nullptr;
+    HaltonDimTab *dimTabs = nullptr;
+    uint16_t *digitTab = nullptr;
     bool peerOfPrimary = false;   // the primary device can read this one's memory directly (NVLink / PCIe peer access)
 };
 static std::vector<DeviceState> g_devs;
@@ -124,6 +126,8 @@ static int envInt(const char *name, int def) {
 // ---------------------------------------------------------------------------------------------
 struct HaltonTables {   // host copies; the device copies live in DeviceState (dimRecs: per dimension {ceil(2^64 / prime), prime | primeSum << 32})
     std::vector<int32_t> hPrimes, hPrimeSums;
+    std::vector<HaltonDimTab> hDimTabs;   // digit tables of the scrambled radical inverse (pb2_sampler.cuh)
+    std::vector<uint16_t> hDigitTab;
     std::vector<ulonglong2> hDimRecs;
     std::vector<uint16_t> hPerms;
 };
@@ -165,6 +169,53 @@ static void buildHaltonHostTables() {
         uint64_t d = (uint64_t)primes[i];
         uint64_t magic = ~0ull / d + 1;   // d is never a power of two above 2, and base 2 does not use it
         g_halton.hDimRecs[i] = make_ulonglong2(magic, (uint64_t)(uint32_t)primes[i] | ((uint64_t)(uint32_t)g_halton.hPrimeSums[i] << 32));
+    }
+    // digit tables: the digit loop of ScrambledRadicalInverseSpecialized (lowdiscrepancy.cpp:405-424) run once per table
+    // entry, over exactly m digits (full) and until the value is used up (nat)
+    g_halton.hDimTabs.resize(kMaxHaltonDims);
+    for (int i = 0; i < kMaxHaltonDims; ++i) {
+        HaltonDimTab &t = g_halton.hDimTabs[i];
+        memset(&t, 0, sizeof(t));
+        const uint32_t base = (uint32_t)primes[i];
+        const uint16_t *perm = g_halton.hPerms.data() + g_halton.hPrimeSums[i];
+        uint32_t B = base, m = 1;
+        while ((uint64_t)B * base <= kHaltonTabMax && m < 5) {   // n must fit the 3 bits above the 13 of the reversed digits
+            B *= base;
+            ++m;
+        }
+        t.B = B;
+        t.m = m;
+        t.magicB = ~0ull / B + 1;
+        t.tabOffset = (uint32_t)g_halton.hDigitTab.size();
+        uint32_t p = 1;
+        for (int k = 0; k < 6; ++k) {
+            t.pow[k] = p;
+            p = (uint64_t)p * base > 0xffffffffull ? 0u : p * base;
+        }
+        const float invBase = 1.f / (float)base;
+        float invBaseN = 1;
+        for (int k = 0; k < 16; ++k) {
+            t.invPow[k] = invBaseN;
+            invBaseN *= invBase;
+        }
+        t.tail = invBase * perm[0] / (1 - invBase);
+        g_halton.hDigitTab.resize(g_halton.hDigitTab.size() + 2 * (size_t)B);
+        uint16_t *nat = g_halton.hDigitTab.data() + t.tabOffset, *full = nat + B;
+        for (uint32_t x = 0; x < B; ++x) {
+            uint32_t a = x, rev = 0, n = 0, revFull = 0;
+            for (uint32_t k = 0; k < m; ++k) {
+                const uint32_t next = a / base, digit = a - next * base;
+                revFull = revFull * base + perm[digit];
+                if (a) {
+                    rev = revFull;
+                    n = k + 1;
+                }
+                a = next;
+            }
+            // (rev: the state when the loop stops at the last non-zero digit = revFull as of that digit)
+            nat[x] = (uint16_t)(rev | (n << 13));
+            full[x] = (uint16_t)revFull;
+        }
     }
 }
 
@@ -219,6 +270,8 @@ static DHalton makeHalton(const pb2_film_desc *film, const pb2_path_params *pp) 
     h.primes = cur().primes;
     h.primeSums = cur().primeSums;
     h.dimRecs = cur().dimRecs;
+    h.dimTabs = envInt("PB2_HALTON_TAB", 0) ? cur().dimTabs : nullptr;   // digit tables: opt-in until measured
+    h.digitTab = cur().digitTab;
     return h;
 }
 
@@ -567,6 +620,8 @@ static DHalton haltonTablesOnly() {   // what radicalInverse() needs: the tables
     h.primeSums = cur().primeSums;
     h.perms = cur().perms;
     h.dimRecs = cur().dimRecs;
+    h.dimTabs = cur().dimTabs;
+    h.digitTab = cur().digitTab;
     return h;
 }
 
@@ -748,6 +803,7 @@ static int selectTraceKernel(const pb2_scene *scene, int flags, TraceLaunch *out
         } else {
             if (instanced) t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 6, true, true, true> : k_wf_trace_w<2, 1, 8, 4, 16, 6, true, true, true>;
             else if (spheres) t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 6, true, false, true> : k_wf_trace_w<2, 1, 8, 4, 16, 6, true, false, true>;
+            else if (flags & PB2_FLAG_LEAF_TMA) t.fn = k_wf_trace_w<2, 1, 8, 4, 16, 5, false, false, true, true>;
             else t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 9, false, false, true> : k_wf_trace_w<2, 1, 8, 4, 16, 9, false, false, true>;
         }
     } else {
@@ -848,7 +904,7 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     unsigned long long *hWork = reinterpret_cast<unsigned long long *>(scene->wfHostCounts + WQ_COUNT);
     for (long long round = 0;; ++round) {
         int next = 1 - cur;
-        k_wf_gen<<<blocks256, 256, 0, stream>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur, scene->counters);
+        k_wf_gen<<<blocks256, 256, 0, stream>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur);
         if (timeTrace) {
             if (scene->traceEvents.size() < nEvents + 2) {
                 cudaEvent_t e0, e1;
@@ -913,6 +969,8 @@ static void freeDeviceTables() {
         cudaFree(d.primeSums);
         cudaFree(d.perms);
         cudaFree(d.dimRecs);
+        cudaFree(d.dimTabs);
+        cudaFree(d.digitTab);
     }
     g_devs.clear();
     g_initialised = false;
@@ -967,6 +1025,10 @@ int pb2_init_devices(int n, const int *device_ids) {
         CUDA_TRY(cudaMemcpy(d.primes, g_halton.hPrimes.data(), g_halton.hPrimes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(d.primeSums, g_halton.hPrimeSums.data(), g_halton.hPrimeSums.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
         CUDA_TRY(cudaMemcpy(d.perms, g_halton.hPerms.data(), g_halton.hPerms.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMalloc((void **)&d.dimTabs, g_halton.hDimTabs.size() * sizeof(HaltonDimTab)));
+        CUDA_TRY(cudaMalloc((void **)&d.digitTab, g_halton.hDigitTab.size() * sizeof(uint16_t)));
+        CUDA_TRY(cudaMemcpy(d.dimTabs, g_halton.hDimTabs.data(), g_halton.hDimTabs.size() * sizeof(HaltonDimTab), cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(d.digitTab, g_halton.hDigitTab.data(), g_halton.hDigitTab.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
     }
     // the film merge of a multi-device render reads the other devices' films from the primary one over NVLink
     CUDA_TRY(cudaSetDevice(g_devs[0].id));
@@ -990,6 +1052,22 @@ int pb2_shutdown(void) {
     if (!g_initialised) return PB2_OK;
     pb2_dist_shutdown();
     freeDeviceTables();
+    return PB2_OK;
+}
+
+// Host-side check of the digit tables (tests, no device): ScrambledRadicalInverse of index[i] in dimension dim[i] by the
+// digit loop (out_loop) and through the tables (out_tab); the two must agree bit for bit.
+int pb2_debug_radical_inverse_tables(const uint32_t *index, const int32_t *dim, int64_t n, float *out_loop, float *out_tab) {
+    if (!index || !dim || !out_loop || !out_tab) return setError(PB2_ERR_INVALID, "null argument");
+    buildHaltonHostTables();
+    for (int64_t i = 0; i < n; ++i) {
+        if (dim[i] < 2 || dim[i] >= kMaxHaltonDims) return setError(PB2_ERR_INVALID, "dimension out of range");
+        const uint32_t base = (uint32_t)g_halton.hPrimes[dim[i]];
+        const uint16_t *perm = g_halton.hPerms.data() + g_halton.hPrimeSums[dim[i]];
+        const uint64_t magic = g_halton.hDimRecs[dim[i]].x;
+        out_loop[i] = scrambledRadicalInverse32(base, magic, index[i], perm);
+        out_tab[i] = scrambledRadicalInverseTab(g_halton.hDimTabs[dim[i]], g_halton.hDigitTab.data(), base, magic, index[i], perm);
+    }
     return PB2_OK;
 }
 

@@ -68,50 +68,62 @@ __device__ __forceinline__ void wfCountRays(unsigned long long *counters, unsign
     }
 }
 
-__global__ void __launch_bounds__(256) k_wf_gen(DRenderParams rp, WfPool pool, int freeQ, int traceQ, unsigned long long *counters) {
-    unsigned n = pool.counts[freeQ];
+// A context takes the next work item (pixel, sample number) and starts its camera ray: GetCameraSample + GenerateRay
+// (Halton dims 0-4, perspective camera).  Warp-collective: all 32 lanes call it, `want` says which of them take part; work
+// items that map outside the sample bounds / pixel bounds are skipped (integrator.cpp:274), so a lane may draw several.
+// Returns false for a lane that did not want a sample or found the work counter exhausted (its context retires).
+__device__ __forceinline__ bool wfStartSample(const DRenderParams &rp, const WfPool &pool, int c, bool want, unsigned *cameraRays) {
+    bool started = false;
+    while (__any_sync(0xffffffffu, want && !started)) {
+        const bool draw = want && !started;
+        const unsigned mask = __ballot_sync(0xffffffffu, draw);
+        const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+        unsigned long long w0 = 0;
+        if (lane == leader) w0 = atomicAdd(&pool.ctr[CTR_WORK], (unsigned long long)__popc(mask));
+        w0 = __shfl_sync(0xffffffffu, w0, leader);
+        if (draw) {
+            const long long item = (long long)w0 + __popc(mask & ((1u << lane) - 1u));
+            if (item >= rp.nWorkItems) {
+                want = false;  // no work left
+            } else {
+                int px, py, sample;
+                if (decodeWork(rp, item, &px, &py, &sample)) {
+                    WfCtx &cx = pool.ctx[c];
+                    DSampler smp;
+                    smp.index = haltonIndex(rp.halton, px, py, sample);
+                    smp.dim = 0;
+                    V2 pFilm;
+                    DRay ray = generateCameraRay(rp.cam, rp.halton, smp, px, py, &pFilm);
+                    laneStartPath(cx.ln, ray, smp);
+                    cx.pFilm = pFilm;
+                    ++*cameraRays;
+                    started = true;
+                }
+            }
+        }
+    }
+    return started;
+}
+
+// Contexts on the free list take their next sample.  (Letting a context whose path has ended take its next sample right
+// inside k_wf_advance - no free list, no separate launch - was measured: 225 -> 205 Msamples/s at 16 spp on the 1 M soup,
+// 187 -> 159 on the killeroo-like scene: the few lanes of a warp that end a path run this code alone inside the
+// register-heavy, low-occupancy shade kernel.)
+__global__ void __launch_bounds__(256) k_wf_gen(DRenderParams rp, WfPool pool, int freeQ, int traceQ) {
+    const unsigned n = pool.counts[freeQ];
     unsigned stride = gridDim.x * blockDim.x;
     unsigned cameraRays = 0;
     for (unsigned base = blockIdx.x * blockDim.x; base < n; base += stride) {
         unsigned i = base + threadIdx.x;
-        bool have = i < n;
-        int c = have ? pool.queue[freeQ][i] : -1;
-        bool started = false;
-        // draw work items until one maps to a pixel inside the sample bounds / pixel bounds
-        while (__any_sync(0xffffffffu, have && !started)) {
-            bool want = have && !started;
-            unsigned mask = __ballot_sync(0xffffffffu, want);
-            int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
-            unsigned long long w0 = 0;
-            if (lane == leader) w0 = atomicAdd(&counters[CTR_WORK], (unsigned long long)__popc(mask));
-            w0 = __shfl_sync(0xffffffffu, w0, leader);
-            if (want) {
-                long long item = (long long)w0 + __popc(mask & ((1u << lane) - 1u));
-                if (item >= rp.nWorkItems) {
-                    have = false;  // no work left: the context retires
-                } else {
-                    int px, py, sample;
-                    if (decodeWork(rp, item, &px, &py, &sample)) {
-                        WfCtx &cx = pool.ctx[c];
-                        DSampler smp;
-                        smp.index = haltonIndex(rp.halton, px, py, sample);
-                        smp.dim = 0;
-                        V2 pFilm;
-                        DRay ray = generateCameraRay(rp.cam, rp.halton, smp, px, py, &pFilm);
-                        laneStartPath(cx.ln, ray, smp);
-                        cx.pFilm = pFilm;
-                        cameraRays++;
-                        started = true;
-                    }
-                }
-            }
-        }
+        const bool have = i < n;
+        const int c = have ? pool.queue[freeQ][i] : -1;
+        const bool started = wfStartSample(rp, pool, c, have, &cameraRays);
         wfPush(pool.queue[traceQ], &pool.counts[traceQ], c, started);
     }
     for (int o = 16; o > 0; o >>= 1) cameraRays += __shfl_down_sync(0xffffffffu, cameraRays, o);
     if ((threadIdx.x & 31) == 0 && cameraRays) {
-        atomicAdd(&counters[CTR_CAMERA], (unsigned long long)cameraRays);
-        atomicAdd(&counters[CTR_REGULAR], (unsigned long long)cameraRays);  // every camera ray is a Scene::Intersect call
+        atomicAdd(&pool.ctr[CTR_CAMERA], (unsigned long long)cameraRays);
+        atomicAdd(&pool.ctr[CTR_REGULAR], (unsigned long long)cameraRays);  // every camera ray is a Scene::Intersect call
     }
 }
 
@@ -445,9 +457,26 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
 // device/pb2_wide4.cuh) - two levels of the reference's tree per fetch: a visit tests the four
 // grandchildren's boxes, continues with the first entered one in the reference's visiting order and
 // defers the others (up to three stack entries, the next one to visit on top).
-template <int WIDTH, int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, bool SPHERES = false, bool INST = false, bool LD256 = false>
+// LEAFTMA (experiment, PB2_FLAG_LEAF_TMA; measured and NOT adopted): the leaf records of the lanes that
+// take a leaf step are staged into shared memory by the TMA unit - one cp.async.bulk (UBLKCP) of up to four 48-byte records
+// per lane, completion counted by one mbarrier per warp - and the triangle tests read them from there.
+template <int WIDTH, int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, bool SPHERES = false, bool INST = false, bool LD256 = false,
+          bool LEAFTMA = false>
 __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
     static_assert(WIDTH == 2 || WIDTH == 4, "two- or four-child records");
+    static_assert(!LEAFTMA || (!SPHERES && !INST), "the staging experiment covers triangle scenes");
+    constexpr int STAGED = 4;   // records staged per lane and leaf step (the reference's default maxnodeprims)
+    __shared__ alignas(16) float4 sleaf[LEAFTMA ? 128 * 3 * STAGED : 1];
+    __shared__ alignas(8) unsigned long long sbar[LEAFTMA ? 4 : 1];
+    unsigned barPhase = 0;
+    if (LEAFTMA) {
+        if ((threadIdx.x & 31) == 0) {
+            const unsigned bar = (unsigned)__cvta_generic_to_shared(&sbar[threadIdx.x >> 5]);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     constexpr int BLOCK = 128;
     __shared__ int2 sstack[SDEPTH * BLOCK];   // [SDEPTH][BLOCK] of (child reference, tMin bits)
     // entries beyond SDEPTH (rare: only passing far children are pushed).  Worst case: one entry per level of the
@@ -600,6 +629,31 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                 }
             }
         } else if (step == M_LEAF) {
+            int stagedN = 0;
+            if (LEAFTMA) {
+                // every lane of the warp takes part in the barrier protocol; lanes with a leaf issue one bulk copy each
+                const unsigned bar = (unsigned)__cvta_generic_to_shared(&sbar[tid >> 5]);
+                stagedN = (mode == M_LEAF) ? min(leafN, STAGED) : 0;
+                unsigned bytes = (unsigned)stagedN * 48u;
+                for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(FULL, bytes, o);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slots were read by ordinary loads in the last leaf step
+                if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                __syncwarp();
+                if (stagedN > 0) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(&sleaf[tid * STAGED * 3]);
+                    const float4 *src = &sc.leafPrims[3 * (size_t)leafFirst];
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                                 "r"((unsigned)stagedN * 48u), "r"(bar)
+                                 : "memory");
+                }
+                unsigned done = 0;
+                while (!done)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(done)
+                                 : "r"(bar), "r"(barPhase)
+                                 : "memory");
+                barPhase ^= 1u;
+            }
             if (mode == M_LEAF) {
                 if (INST && (flags & F_EXIT)) {
                     // back to world space (TransformedPrimitive::Intersect returns, primitive.cpp:82-86)
@@ -617,12 +671,20 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                 }
                 bool finished = false, entered = false;
                 const bool any = (flags & F_ANY) != 0;
+                int staged = 0;
                 while (leafN > 0) {
                     const int idx = leafFirst;
                     ++leafFirst;
                     --leafN;
                     const float4 *rec = &sc.leafPrims[3 * (size_t)idx];
-                    float4 a = ldg4(rec), b = ldg4(rec + 1), c4 = ldg4(rec + 2);
+                    float4 a, b, c4;
+                    if (LEAFTMA && staged < stagedN) {
+                        const float4 *sl = &sleaf[(tid * STAGED + staged) * 3];
+                        a = sl[0]; b = sl[1]; c4 = sl[2];
+                        ++staged;
+                    } else {
+                        a = ldg4(rec); b = ldg4(rec + 1); c4 = ldg4(rec + 2);
+                    }
                     uint32_t pf = floatBits(b.w);
                     if (INST && (pf & LEAF_INSTANCE)) {
                         const int id = asInt(c4.w);

@@ -1,5 +1,6 @@
 """Host-side C++ front end (parser, pbrt API state machine, transforms, loop subdivision, SAH BVH build, film)
 against golden vectors recorded from the reference and against the oracle port.  CPU only."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -613,3 +614,24 @@ def test_wide4_records_keep_the_reference_order(pb):
         assert np.array_equal(lb, lw) and lb.max() <= max_len
         assert np.array_equal(sb, sw)
         assert lb.sum() > n // 2                  # leaves were reached (several per ray on the dense soup)
+
+
+def test_radical_inverse_digit_tables_equal_the_digit_loop(pb):
+    """The shade kernels evaluate ScrambledRadicalInverse (lowdiscrepancy.cpp:405-424) through per-dimension digit tables
+    (pb2_sampler.cuh: several digits per look-up).  The host build of the same function must give the digit loop's bits for
+    every dimension and any 32-bit index: random indices, the sample indices a render uses, block boundaries of the tables."""
+    L = pb.lib()
+    rng = np.random.RandomState(1)
+    idx = np.concatenate([rng.randint(0, 2 ** 32, 300000, dtype=np.uint64), rng.randint(0, 3000000, 200000, dtype=np.uint64),
+                          np.arange(100000, dtype=np.uint64)]).astype(np.uint32)
+    dim = rng.randint(2, 1000, len(idx)).astype(np.int32)
+    dim[: len(idx) // 2] = rng.randint(2, 40, len(idx) // 2)
+    for d in (2, 3, 4, 5, 10, 25, 30, 100, 999):
+        edge = np.array([0, 1, 2, 3124, 3125, 3126, 8191, 8192, 2 ** 31, 2 ** 32 - 1, 9765624, 9765625, 9765626], np.uint32)
+        idx = np.concatenate([idx, edge])
+        dim = np.concatenate([dim, np.full(len(edge), d, np.int32)])
+    a, b = np.zeros(len(idx), np.float32), np.zeros(len(idx), np.float32)
+    L.pb2_debug_radical_inverse_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    assert L.pb2_debug_radical_inverse_tables(pb.ptr(idx), pb.ptr(dim), len(idx), pb.ptr(a), pb.ptr(b)) == 0
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert 0 <= a.min() and a.max() < 1
