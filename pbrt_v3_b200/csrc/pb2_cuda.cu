@@ -270,7 +270,9 @@ static DHalton makeHalton(const pb2_film_desc *film, const pb2_path_params *pp) 
     h.primes = cur().primes;
     h.primeSums = cur().primeSums;
     h.dimRecs = cur().dimRecs;
-    h.dimTabs = envInt("PB2_HALTON_TAB", 0) ? cur().dimTabs : nullptr;   // digit tables: opt-in until measured
+    // digit tables (pb2_sampler.cuh): +7.8 % on the shading-bound killeroo-like scene, +0.8 % on the 1 M soup, bit-identical
+    // values; PB2_HALTON_LOOP=1 selects the digit loop (A/B)
+    h.dimTabs = envInt("PB2_HALTON_LOOP", 0) ? nullptr : cur().dimTabs;
     h.digitTab = cur().digitTab;
     return h;
 }
@@ -804,6 +806,8 @@ static int selectTraceKernel(const pb2_scene *scene, int flags, TraceLaunch *out
             if (instanced) t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 6, true, true, true> : k_wf_trace_w<2, 1, 8, 4, 16, 6, true, true, true>;
             else if (spheres) t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 6, true, false, true> : k_wf_trace_w<2, 1, 8, 4, 16, 6, true, false, true>;
             else if (flags & PB2_FLAG_LEAF_TMA) t.fn = k_wf_trace_w<2, 1, 8, 4, 16, 5, false, false, true, true>;
+            // (round-2 sweep around these parameters with the min/max slab tests and 32-byte loads in place - LEAF_T 2 / 4, NSUB 3 / 6,
+            // FETCH_T 12, 10 resident blocks: 221.6 ... 223.2 against 224.0 Msamples/s at 16 spp; the scheduling constants are flat)
             else t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 9, false, false, true> : k_wf_trace_w<2, 1, 8, 4, 16, 9, false, false, true>;
         }
     } else {
@@ -873,6 +877,7 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     TraceLaunch trace;
     if ((rc = selectTraceKernel(scene, flags, &trace))) return rc;
     const bool spheres = scene->d.spheres != nullptr;
+    // (12 / 16 resident blocks for the light step - 40 / 32 registers with small spills - measured: 222.5 / 220.9 against 224.0)
     AdvanceKernel advLight = spheres ? k_wf_advance<false, true, 8> : k_wf_advance<false, false, 8>;
     AdvanceKernel advShade = scene->hasSpecular ? (spheres ? k_wf_advance<true, true, 4, true> : k_wf_advance<true, false, 4, true>)
                              : spheres ? k_wf_advance<true, true, 4>
