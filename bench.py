@@ -45,7 +45,9 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = dict(tris=1000000, seed=1234, jitter=0.02, xres=1920, yres=1080, spp=64, maxdepth=8)
 # DRAM bytes of one full-pool k_wf_trace_w launch on this workload, from the committed `ncu --set full` capture
-NCU_TRACE_DRAM_BYTES_PER_LAUNCH = 938578432 + 161948416
+# (profiles/r02_w2_ld256_1m_ncu_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum)
+NCU_TRACE_DRAM_BYTES_PER_LAUNCH = 1069858000 + 176269568
+NCU_TRACE_ALGORITHMIC_BYTES_OF_THAT_LAUNCH = 4194304 * 2820   # 4.19 M rays x 2820 B
 HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md
 
 
@@ -374,8 +376,13 @@ def main():
             "roofline": {"kernel": "k_wf_trace_w (BVH traversal + ray/triangle tests)", "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
                          "traffic": NCU_TRACE_DRAM_BYTES_PER_LAUNCH if default_workload else None,
-                         "traffic_source": "profiles/r01_trace_w_ncu_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum of one "
-                                           "full-pool launch (4.19 M rays, 11.8 GB algorithmic): the 124 MB of nodes + leaf records live in L2",
+                         "traffic_source": "profiles/r02_w2_ld256_1m_ncu_summary.txt: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                           "full-pool launch (4.19 M rays, 11.8 GB algorithmic): the 110 MB of records + leaf records live in L2",
+                         "basis": "NOMINAL: `achieved` divides the reference traversal's algorithmic bytes (SURVEY.md 8d: 32 B x node visits + 36 B x "
+                                  "primitive tests, counted on the device) by the kernel's time, as the contract defines it; the kernel's measured "
+                                  "DRAM traffic is ~10 % of that (L2 hit rate 82-85 %, also on the 10 M-triangle scene), its limiters are the L1 "
+                                  "data pipe (68 % of peak) and instruction issue (70 %), not HBM",
+                         "dram_bytes_over_algorithmic_bytes": (NCU_TRACE_DRAM_BYTES_PER_LAUNCH / NCU_TRACE_ALGORITHMIC_BYTES_OF_THAT_LAUNCH) if default_workload else None,
                          "algorithmic_bytes_per_frame": alg_bytes, "node_visits": node_visits, "prim_tests": prim_tests,
                          "bytes_per_ray": alg_bytes / max(rays_frame, 1), "trace_ms_per_frame": trace_ms / args.steps,
                          "trace_share_of_step": (trace_ms / args.steps) / ms_per_step},

@@ -303,6 +303,8 @@ struct pb2_scene {
     unsigned *wfHostCounts = nullptr;  // pinned
     int wfCapacity = 0;
     std::vector<cudaEvent_t> traceEvents;
+    cudaStream_t stream2 = nullptr;          // second pipeline of the wavefront (renderWavefront)
+    cudaEvent_t forkEvent = nullptr, joinEvent = nullptr;
 };
 
 template <typename T>
@@ -838,6 +840,7 @@ static int selectTraceKernel(const pb2_scene *scene, int flags, TraceLaunch *out
     return PB2_OK;
 }
 
+enum { kMaxPipes = 2 };
 static int ensurePool(pb2_scene *scene, int capacity) {
     if (scene->wfCapacity < capacity) {
         if (scene->wfCtx) cudaFree(scene->wfCtx);
@@ -849,17 +852,19 @@ static int ensurePool(pb2_scene *scene, int capacity) {
         CUDA_TRY(cudaMalloc((void **)&scene->wfQueues, (size_t)capacity * WQ_COUNT * sizeof(int)));
         scene->wfCapacity = capacity;
     }
-    if (!scene->wfCounts) CUDA_TRY(cudaMalloc((void **)&scene->wfCounts, WQ_COUNT * sizeof(unsigned)));
-    if (!scene->wfHostCounts) CUDA_TRY(cudaMallocHost((void **)&scene->wfHostCounts, (WQ_COUNT + 2) * sizeof(unsigned long long)));
+    if (!scene->wfCounts) CUDA_TRY(cudaMalloc((void **)&scene->wfCounts, kMaxPipes * WQ_COUNT * sizeof(unsigned)));
+    if (!scene->wfHostCounts) CUDA_TRY(cudaMallocHost((void **)&scene->wfHostCounts, (kMaxPipes * WQ_COUNT + 2) * sizeof(unsigned long long)));
     return PB2_OK;
 }
 
-static WfPool poolOf(const pb2_scene *scene, int capacity) {
+// Pipeline `pipe` of `nPipes`: an equal slice of the context pool with queues and counters of its own.
+static WfPool poolOf(const pb2_scene *scene, int capacity, int pipe = 0, int nPipes = 1) {
     WfPool pool;
-    pool.capacity = capacity;
-    pool.ctx = (WfCtx *)scene->wfCtx;
-    for (int q = 0; q < WQ_COUNT; ++q) pool.queue[q] = scene->wfQueues + (size_t)q * scene->wfCapacity;
-    pool.counts = scene->wfCounts;
+    const int cap = capacity / nPipes;
+    pool.capacity = cap;
+    pool.ctx = (WfCtx *)scene->wfCtx + (size_t)pipe * cap;
+    for (int q = 0; q < WQ_COUNT; ++q) pool.queue[q] = scene->wfQueues + ((size_t)pipe * WQ_COUNT + q) * cap;
+    pool.counts = scene->wfCounts + (size_t)pipe * WQ_COUNT;
     pool.ctr = scene->counters;
     return pool;
 }
@@ -873,7 +878,6 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     int capacity = (int)((want + 255) / 256 * 256);
     int rc = ensurePool(scene, capacity);
     if (rc) return rc;
-    WfPool pool = poolOf(scene, capacity);
     TraceLaunch trace;
     if ((rc = selectTraceKernel(scene, flags, &trace))) return rc;
     const bool spheres = scene->d.spheres != nullptr;
@@ -894,62 +898,93 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     const bool lazyLights = scene->lazyLightDist;   // k_wf_finish cannot defer a vertex: the rounds run to the end instead
     const unsigned finishThreshold = ((flags & PB2_FLAG_COUNT_TRAVERSAL) || lazyLights) ? 0u : (unsigned)(g_numSMs * std::max(0, finishPerSM));
     const int finishBlocks = std::max(1, (int)((finishThreshold + 127) / 128));
-    const int blocks256 = std::min((capacity + 255) / 256, g_numSMs * 16);
-    const int blocks128 = std::min((capacity + 127) / 128, g_numSMs * 32);
-
     static const int syncEvery = std::max(1, envInt("PB2_SYNC_EVERY", 8));
     // (A persisting-L2 access-policy window over the node array was measured and lost 3.5 %: the 126 MB
     // L2 already holds nodes + leaf records, and carving a persisting partition only shrinks what the
     // path contexts get.)
-    k_wf_init<<<(capacity + 255) / 256, 256, 0, stream>>>(pool);
-    unsigned long long nLaunch = 1;
+    // Two pipelines, each with half of the contexts and its own lists, on two streams: the kernels of one fill the SMs
+    // that the other leaves idle at the end of every launch (a persistent trace launch ends with ~0.2 ms in which the last
+    // long rays finish while most warps have exited; 136 launches per frame).  Both draw samples from the one work counter.
+    // PB2_PIPES=1: one pipeline.  Lazily lit scenes share one request list: one pipeline.
+    static const int pipesWanted = std::min((int)kMaxPipes, std::max(1, envInt("PB2_PIPES", 2)));
+    const int nPipes = (lazyLights || capacity < 65536) ? 1 : pipesWanted;
+    cudaStream_t streams[kMaxPipes] = {stream, stream};
+    if (nPipes > 1) {
+        if (!scene->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&scene->stream2, cudaStreamNonBlocking));
+        if (!scene->forkEvent) CUDA_TRY(cudaEventCreateWithFlags(&scene->forkEvent, cudaEventDisableTiming));
+        if (!scene->joinEvent) CUDA_TRY(cudaEventCreateWithFlags(&scene->joinEvent, cudaEventDisableTiming));
+        streams[1] = scene->stream2;
+        CUDA_TRY(cudaEventRecord(scene->forkEvent, stream));            // the film clear / counter reset of the caller's stream
+        CUDA_TRY(cudaStreamWaitEvent(scene->stream2, scene->forkEvent, 0));
+    }
+    WfPool pools[kMaxPipes];
+    for (int p = 0; p < nPipes; ++p) pools[p] = poolOf(scene, capacity / nPipes * nPipes, p, nPipes);
+    const int capP = pools[0].capacity;
+    const int blocks256 = std::min((capP + 255) / 256, g_numSMs * 16);
+    const int blocks128 = std::min((capP + 127) / 128, g_numSMs * 32);
+    for (int p = 0; p < nPipes; ++p) k_wf_init<<<(capP + 255) / 256, 256, 0, streams[p]>>>(pools[p]);
+    unsigned long long nLaunch = nPipes;
     size_t nEvents = 0;
     int cur = 0;
     volatile unsigned *hc = scene->wfHostCounts;
-    unsigned long long *hWork = reinterpret_cast<unsigned long long *>(scene->wfHostCounts + WQ_COUNT);
+    unsigned long long *hWork = reinterpret_cast<unsigned long long *>(scene->wfHostCounts + kMaxPipes * WQ_COUNT);
     for (long long round = 0;; ++round) {
         int next = 1 - cur;
-        k_wf_gen<<<blocks256, 256, 0, stream>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur);
-        if (timeTrace) {
-            if (scene->traceEvents.size() < nEvents + 2) {
-                cudaEvent_t e0, e1;
-                CUDA_TRY(cudaEventCreate(&e0));
-                CUDA_TRY(cudaEventCreate(&e1));
-                scene->traceEvents.push_back(e0);
-                scene->traceEvents.push_back(e1);
+        for (int p = 0; p < nPipes; ++p) {
+            const WfPool &pool = pools[p];
+            cudaStream_t st = streams[p];
+            k_wf_gen<<<blocks256, 256, 0, st>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur);
+            if (timeTrace) {
+                if (scene->traceEvents.size() < nEvents + 2) {
+                    cudaEvent_t e0, e1;
+                    CUDA_TRY(cudaEventCreate(&e0));
+                    CUDA_TRY(cudaEventCreate(&e1));
+                    scene->traceEvents.push_back(e0);
+                    scene->traceEvents.push_back(e1);
+                }
+                CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents], st));
             }
-            CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents], stream));
+            trace.fn<<<trace.grid ? trace.grid : blocks128, trace.block, trace.smem, st>>>(scene->d, pool, WQ_TRACE0 + cur);
+            if (timeTrace) {
+                CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents + 1], st));
+                nEvents += 2;
+            }
+            advLight<<<blocks128, 128, 0, st>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
+            advShade<<<blocks128, 128, 0, st>>>(scene->d, rp, pool, WQ_SHADE, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
+            if (lazyLights) {
+                // vertices that fell into voxels without a light distribution yet were put aside: build those records, shade again
+                launchLightDistBuild(scene, st);
+                advShade<<<blocks128, 128, 0, st>>>(scene->d, rp, pool, WQ_RETRY, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
+                nLaunch += 3;
+            }
+            if (finishThreshold) finish<<<finishBlocks, 128, 0, st>>>(scene->d, rp, pool, WQ_TRACE0 + next, finishThreshold, film);
+            k_wf_reset<<<1, 32, 0, st>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur, WQ_TRACE0 + next, finishThreshold);
+            nLaunch += finishThreshold ? 6 : 5;
         }
-        trace.fn<<<trace.grid ? trace.grid : blocks128, trace.block, trace.smem, stream>>>(scene->d, pool, WQ_TRACE0 + cur);
-        if (timeTrace) {
-            CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents + 1], stream));
-            nEvents += 2;
-        }
-        advLight<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
-        advShade<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_SHADE, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
-        if (lazyLights) {
-            // vertices that fell into voxels without a light distribution yet were put aside: build those records, shade again
-            launchLightDistBuild(scene, stream);
-            advShade<<<blocks128, 128, 0, stream>>>(scene->d, rp, pool, WQ_RETRY, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
-            nLaunch += 3;
-        }
-        if (finishThreshold) finish<<<finishBlocks, 128, 0, stream>>>(scene->d, rp, pool, WQ_TRACE0 + next, finishThreshold, film);
-        k_wf_reset<<<1, 32, 0, stream>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur, WQ_TRACE0 + next, finishThreshold);
-        nLaunch += finishThreshold ? 6 : 5;
         cur = next;
         // The host looks at the counters only every `syncEvery` rounds; rounds enqueued after the frame
         // has drained find empty lists and cost a few microseconds each.
         if ((round + 1) % syncEvery != 0) continue;
-        CUDA_TRY(cudaMemcpyAsync((void *)scene->wfHostCounts, pool.counts, WQ_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, stream));
+        for (int p = 0; p < nPipes; ++p)
+            CUDA_TRY(cudaMemcpyAsync((void *)(scene->wfHostCounts + p * WQ_COUNT), pools[p].counts, WQ_COUNT * sizeof(unsigned), cudaMemcpyDeviceToHost, streams[p]));
+        for (int p = 1; p < nPipes; ++p) CUDA_TRY(cudaStreamSynchronize(streams[p]));
         CUDA_TRY(cudaMemcpyAsync(hWork, &scene->counters[CTR_WORK], sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
         bool overflowed = false;
         if ((rc = lightDistOverflowed(scene, stream, &overflowed))) return rc;
         if (overflowed) return lightDistOverflowError();
-        unsigned traceNext = hc[WQ_TRACE0 + cur], freeNext = hc[WQ_FREE0 + cur];
-        bool workLeft = (long long)*hWork < rp.nWorkItems;
-        if (traceNext == 0 && !(workLeft && freeNext > 0)) break;
+        const bool workLeft = (long long)*hWork < rp.nWorkItems;
+        bool done = true;
+        for (int p = 0; p < nPipes; ++p) {
+            const unsigned traceNext = hc[p * WQ_COUNT + WQ_TRACE0 + cur], freeNext = hc[p * WQ_COUNT + WQ_FREE0 + cur];
+            if (!(traceNext == 0 && !(workLeft && freeNext > 0))) done = false;
+        }
+        if (done) break;
         if (round > 100000000LL) return setError(PB2_ERR_CUDA, "wavefront did not terminate");
+    }
+    if (nPipes > 1) {   // what follows on the caller's stream (film reduce, copies) comes after both pipelines
+        CUDA_TRY(cudaEventRecord(scene->joinEvent, scene->stream2));
+        CUDA_TRY(cudaStreamWaitEvent(stream, scene->joinEvent, 0));
     }
     CUDA_TRY(cudaGetLastError());
     *launches = nLaunch;
@@ -959,6 +994,7 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         CUDA_TRY(cudaEventElapsedTime(&ms, scene->traceEvents[e], scene->traceEvents[e + 1]));
         *traceMs += ms;
     }
+    if (nPipes > 1) *traceMs /= nPipes;   // the pipelines' launches overlap in time: their mean is the per-frame figure
     return PB2_OK;
 }
 
@@ -1164,6 +1200,9 @@ int pb2_scene_destroy(pb2_scene *s) {
     if (s->wfHostCounts) cudaFreeHost(s->wfHostCounts);
     if (s->ldHostCounters) cudaFreeHost(s->ldHostCounters);
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
+    if (s->stream2) cudaStreamDestroy(s->stream2);
+    if (s->forkEvent) cudaEventDestroy(s->forkEvent);
+    if (s->joinEvent) cudaEventDestroy(s->joinEvent);
     delete s;
     if (g_initialised) cudaSetDevice(g_devs[0].id);
     return PB2_OK;
