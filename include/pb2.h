@@ -264,6 +264,9 @@ typedef struct pb2_path_params {
 /* Experiment kept for the record: stage leaf records into shared memory with TMA bulk copies
  * (cp.async.bulk / UBLKCP + mbarrier) before the triangle tests; triangle scenes, two-child kernel.  Same results, slower. */
 #define PB2_FLAG_LEAF_TMA 64
+/* Trace triangle scenes with the kernel that keeps a pool of 64 rays per warp in shared memory and picks, for every step,
+ * the rays that are in the phase being run (k_wf_trace_pool).  Same results. */
+#define PB2_FLAG_POOL 128
 
 typedef struct pb2_ray {
     float o[3];

@@ -138,7 +138,7 @@ HIT_DTYPE = np.dtype([("prim", np.int32), ("t", np.float32), ("b", np.float32, 3
                       ("dpdu", np.float32, 3), ("uv", np.float32, 2)])
 WFHIT_DTYPE = np.dtype([("found", np.int32), ("leaf", np.int32), ("prim", np.int32), ("t", np.float32), ("b", np.float32, 3),
                         ("listed", np.int32)])
-PB2_FLAG_COUNT_TRAVERSAL, PB2_FLAG_LINEAR_NODES, PB2_FLAG_WIDE4, PB2_FLAG_PLAIN_TRACE, PB2_FLAG_SMALL_STACK, PB2_FLAG_LD128, PB2_FLAG_LEAF_TMA = 1, 2, 4, 8, 16, 32, 64
+PB2_FLAG_COUNT_TRAVERSAL, PB2_FLAG_LINEAR_NODES, PB2_FLAG_WIDE4, PB2_FLAG_PLAIN_TRACE, PB2_FLAG_SMALL_STACK, PB2_FLAG_LD128, PB2_FLAG_LEAF_TMA, PB2_FLAG_POOL = 1, 2, 4, 8, 16, 32, 64, 128
 NODE_DTYPE = np.dtype([("bmin", np.float32, 3), ("bmax", np.float32, 3), ("offset", np.int32),
                        ("n_prims", np.uint16), ("axis", np.uint8), ("pad", np.uint8)])
 assert WFHIT_DTYPE.itemsize == C.sizeof(WfHit)

@@ -303,6 +303,7 @@ struct pb2_scene {
     unsigned *wfHostCounts = nullptr;  // pinned
     int wfCapacity = 0;
     std::vector<cudaEvent_t> traceEvents;
+    int2 *wfSpill = nullptr;                 // k_wf_trace_pool: stack entries beyond its shared-memory depth
     cudaStream_t stream2 = nullptr;          // second pipeline of the wavefront (renderWavefront)
     cudaEvent_t forkEvent = nullptr, joinEvent = nullptr;
 };
@@ -785,7 +786,12 @@ static int selectTraceKernel(const pb2_scene *scene, int flags, TraceLaunch *out
     const bool linearFits = !instanced || scene->bvhDepth + 3 + scene->instDepth <= 64;
     if (flags & PB2_FLAG_COUNT_TRAVERSAL) { t.fn = k_wf_trace_plain<true>; t.name = "k_wf_trace_plain<count>"; }
     else if ((flags & PB2_FLAG_PLAIN_TRACE) || (!records && !linearFits)) { t.fn = k_wf_trace_plain<false>; t.name = "k_wf_trace_plain"; }
-    else if (records && (flags & PB2_FLAG_WIDE4)) {
+    else if (records && (flags & PB2_FLAG_POOL) && !spheres && !instanced) {
+        t.name = "k_wf_trace_pool";
+        t.fn = k_wf_trace_pool<4, 5>;
+        t.smem = 4 * sizeof(PoolWarp);
+        CUDA_TRY(cudaFuncSetAttribute(t.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
+    } else if (records && (flags & PB2_FLAG_WIDE4)) {
         t.name = "k_wf_trace_w<4>";
         if (flags & PB2_FLAG_LD128) {
             if (instanced) t.fn = small ? k_wf_trace_w<4, 1, 8, 4, 4, 5, true, true> : k_wf_trace_w<4, 1, 8, 4, 16, 5, true, true>;
@@ -835,7 +841,7 @@ static int selectTraceKernel(const pb2_scene *scene, int flags, TraceLaunch *out
     if (verbose)
         fprintf(stderr, "pb2: trace kernel %s: %d regs, %zu B smem, %d blocks/SM, carve-out %d %%, BVH depth %d\n", t.name, fa.numRegs,
                 fa.sharedSizeBytes + t.smem, blocksPerSM, pct, scene->bvhDepth);
-    t.grid = g_numSMs * std::max(1, blocksPerSM);
+    t.grid = g_numSMs * std::max(1, std::min(blocksPerSM, 8));
     *out = t;
     return PB2_OK;
 }
@@ -853,6 +859,8 @@ static int ensurePool(pb2_scene *scene, int capacity) {
         scene->wfCapacity = capacity;
     }
     if (!scene->wfCounts) CUDA_TRY(cudaMalloc((void **)&scene->wfCounts, kMaxPipes * WQ_COUNT * sizeof(unsigned)));
+    if (!scene->wfSpill)   // per pipeline: up to 8 resident blocks per SM x 4 warps x PL_R slots x PL_SPILL entries
+        CUDA_TRY(cudaMalloc((void **)&scene->wfSpill, (size_t)kMaxPipes * g_numSMs * 8 * 4 * PL_R * PL_SPILL * sizeof(int2)));
     if (!scene->wfHostCounts) CUDA_TRY(cudaMallocHost((void **)&scene->wfHostCounts, (kMaxPipes * WQ_COUNT + 2) * sizeof(unsigned long long)));
     return PB2_OK;
 }
@@ -866,6 +874,7 @@ static WfPool poolOf(const pb2_scene *scene, int capacity, int pipe = 0, int nPi
     for (int q = 0; q < WQ_COUNT; ++q) pool.queue[q] = scene->wfQueues + ((size_t)pipe * WQ_COUNT + q) * cap;
     pool.counts = scene->wfCounts + (size_t)pipe * WQ_COUNT;
     pool.ctr = scene->counters;
+    pool.spill = scene->wfSpill + (size_t)pipe * g_numSMs * 8 * 4 * PL_R * PL_SPILL;
     return pool;
 }
 
@@ -1200,6 +1209,7 @@ int pb2_scene_destroy(pb2_scene *s) {
     if (s->wfHostCounts) cudaFreeHost(s->wfHostCounts);
     if (s->ldHostCounters) cudaFreeHost(s->ldHostCounters);
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
+    if (s->wfSpill) cudaFree(s->wfSpill);
     if (s->stream2) cudaStreamDestroy(s->stream2);
     if (s->forkEvent) cudaEventDestroy(s->forkEvent);
     if (s->joinEvent) cudaEventDestroy(s->joinEvent);

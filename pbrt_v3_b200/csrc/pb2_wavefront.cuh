@@ -43,6 +43,7 @@ struct WfPool {
     int *queue[WQ_COUNT];     // capacity entries each; WQ_CURSOR is a counter only, WQ_RETRY exists for lazy scenes only
     unsigned *counts;         // WQ_COUNT counters
     unsigned long long *ctr;  // the scene's CTR_* counters (ray / traversal statistics)
+    int2 *spill;              // k_wf_trace_pool: stack entries beyond its shared-memory depth, [warp][slot][PL_SPILL]
 };
 
 // warp-aggregated append of one index per participating lane
@@ -803,6 +804,224 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                 }
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Trace kernel with a per-warp POOL of rays (triangle scenes, two-child records; PB2_FLAG_POOL).  k_wf_trace_w binds a ray
+// to a lane for its whole life, so a step runs with the lanes that happen to be in that phase: ~21 of 32 in node steps, ~6 in
+// leaf steps.  Here a warp owns R = 64 rays whose state lives in shared memory (structure of arrays, one column per ray: ray
+// constants, tMax, current record, stack pointer, leaf range, flags; the stack of pending far children next to it), and every
+// step the warp picks up to 32 rays THAT ARE IN THE PHASE BEING RUN, loads their state, runs the step in registers and stores
+// what changed.  Per ray the traversal is the one of k_wf_trace_w, operation for operation (same records, same order, same
+// pops against the tMax of the moment): only which lane executes a step of which ray differs.
+// Slot flags: bit 0 any-hit, 1 found, 2-4 direction signs, 5-6 / 7-8 / 9-10 kx ky kz, 11 slow (non-finite), 12-13 phase.
+// ---------------------------------------------------------------------------------------------
+enum { PL_EMPTY = 0, PL_NODE = 1, PL_LEAF = 2, PL_DONE = 3, PL_R = 64, PL_SD = 12, PL_SPILL = 52 };
+struct PoolWarp {   // one warp's slice of shared memory
+    float f[10][PL_R];        // ox oy oz ix iy iz tMax Sx Sy Sz
+    int i[6][PL_R];           // cur, sp, ctx, flags, leafFirst, leafN
+    int2 stk[PL_SD][PL_R];    // (child reference, tMin bits); deeper entries go to WfPool::spill
+    int list[PL_R];           // slots chosen for the step, in rank order
+};
+
+template <int NSUB, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_wf_trace_pool(DScene sc, WfPool pool, int traceQ) {
+    extern __shared__ PoolWarp poolSmem[];
+    PoolWarp &pw = poolSmem[threadIdx.x >> 5];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned ltMask = (1u << lane) - 1u;
+    const unsigned n = pool.counts[traceQ];
+    int2 *spill = pool.spill + ((size_t)(blockIdx.x * 4 + (threadIdx.x >> 5)) * PL_R) * PL_SPILL;   // [slot][PL_SPILL]
+    pw.i[3][lane] = 0;
+    pw.i[3][lane + 32] = 0;
+    __syncwarp();
+    bool exhausted = false;
+    // stack access of slot s
+    auto stGet = [&](int s, int d) -> int2 { return d < PL_SD ? pw.stk[d][s] : spill[(size_t)s * PL_SPILL + (d - PL_SD)]; };
+    auto stPut = [&](int s, int d, int2 e) {
+        if (d < PL_SD) pw.stk[d][s] = e;
+        else spill[(size_t)s * PL_SPILL + (d - PL_SD)] = e;
+    };
+    while (true) {
+        // ---- census of the 64 slots
+        const int fl0 = pw.i[3][lane], fl1 = pw.i[3][lane + 32];
+        const int m0 = (fl0 >> 12) & 3, m1 = (fl1 >> 12) & 3;
+        const unsigned bN0 = __ballot_sync(FULL, m0 == PL_NODE), bN1 = __ballot_sync(FULL, m1 == PL_NODE);
+        const unsigned bL0 = __ballot_sync(FULL, m0 == PL_LEAF), bL1 = __ballot_sync(FULL, m1 == PL_LEAF);
+        const unsigned bD0 = __ballot_sync(FULL, m0 == PL_DONE), bD1 = __ballot_sync(FULL, m1 == PL_DONE);
+        const int nN = __popc(bN0) + __popc(bN1), nL = __popc(bL0) + __popc(bL1), nD = __popc(bD0) + __popc(bD1);
+        const int nE = PL_R - nN - nL - nD;
+        int phase;
+        if (nD + (exhausted ? 0 : nE) >= 24 || (nN == 0 && nL == 0 && (nD > 0 || (!exhausted && nE > 0)))) phase = PL_DONE;   // flush + fill
+        else if (nL >= 24 || (nL > 0 && nN == 0)) phase = PL_LEAF;
+        else if (nN > 0) phase = PL_NODE;
+        else break;   // nothing in flight, nothing to flush, the list is exhausted
+
+        if (phase == PL_DONE) {
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int s = lane + 32 * h;
+                const int fl = pw.i[3][s];
+                const int mode = (fl >> 12) & 3;
+                const bool flush = mode == PL_DONE;
+                int c = flush ? pw.i[2][s] : -1;
+                int state = LS_IDLE;
+                if (flush) {
+                    WfCtx &cx = pool.ctx[c];
+                    state = (fl & 1) ? LS_SHADOW : __ldcs(&cx.ln.state);
+                    __stcs(reinterpret_cast<float2 *>(&cx.tHit), make_float2(pw.f[6][s], __int_as_float((fl & 2) ? 1 : 0)));
+                }
+                wfPush(pool.queue[WQ_SHADE], &pool.counts[WQ_SHADE], c, flush && state == LS_PATH);
+                wfPush(pool.queue[WQ_LIGHT], &pool.counts[WQ_LIGHT], c, flush && state != LS_PATH);
+                bool want = (flush || mode == PL_EMPTY) && !exhausted;
+                const unsigned wantMask = __ballot_sync(FULL, want);
+                int newFlags = 0;   // PL_EMPTY
+                if (wantMask) {
+                    const int leader = __ffs(wantMask) - 1;
+                    unsigned base = 0;
+                    if (lane == leader) base = atomicAdd(&pool.counts[WQ_CURSOR], (unsigned)__popc(wantMask));
+                    base = __shfl_sync(FULL, base, leader);
+                    const unsigned idx = base + __popc(wantMask & ltMask);
+                    if (want && idx < n) {
+                        c = pool.queue[traceQ][idx];
+                        const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
+                        const float4 ra = __ldcs(p), rb = __ldcs(p + 1);
+                        const DRaySetup rs = setupRay(mk3(ra.y, ra.z, ra.w), mk3(rb.x, rb.y, rb.z));
+                        pw.f[0][s] = rs.o.x; pw.f[1][s] = rs.o.y; pw.f[2][s] = rs.o.z;
+                        pw.f[3][s] = rs.invDir.x; pw.f[4][s] = rs.invDir.y; pw.f[5][s] = rs.invDir.z;
+                        pw.f[6][s] = rb.w;
+                        pw.f[7][s] = rs.Sx; pw.f[8][s] = rs.Sy; pw.f[9][s] = rs.Sz;
+                        pw.i[0][s] = 0;   // the pseudo node above the root
+                        pw.i[1][s] = 0;
+                        pw.i[2][s] = c;
+                        newFlags = ((__float_as_int(ra.x) == LS_SHADOW) ? 1 : 0) | (rs.neg0 << 2) | (rs.neg1 << 3) | (rs.neg2 << 4) | (rs.kx << 5) |
+                                   (rs.ky << 7) | (rs.kz << 9) | (rs.slow << 11) | (PL_NODE << 12);
+                    }
+                    if (__any_sync(FULL, want && idx >= n)) exhausted = true;
+                }
+                if (flush || want) pw.i[3][s] = newFlags;
+            }
+            __syncwarp();
+            continue;
+        }
+
+        // ---- hand the slots of the chosen phase to the lanes: slot `lane` first, then slot `lane + 32`, in rank order
+        const unsigned b0 = phase == PL_NODE ? bN0 : bL0, b1 = phase == PL_NODE ? bN1 : bL1;
+        const int c0 = __popc(b0);
+        if (b0 & (1u << lane)) pw.list[__popc(b0 & ltMask)] = lane;
+        if (b1 & (1u << lane)) pw.list[c0 + __popc(b1 & ltMask)] = lane + 32;
+        __syncwarp();
+        const int nSel = min(c0 + __popc(b1), 32);
+        const bool active = lane < nSel;
+        const int s = active ? pw.list[lane] : 0;
+        __syncwarp();
+
+        if (phase == PL_NODE) {
+            DRaySetup rs;
+            rs.o = mk3(pw.f[0][s], pw.f[1][s], pw.f[2][s]);
+            rs.invDir = mk3(pw.f[3][s], pw.f[4][s], pw.f[5][s]);
+            float tMax = pw.f[6][s];
+            int cur = pw.i[0][s], sp = pw.i[1][s];
+            int fl = pw.i[3][s];
+            rs.neg0 = (fl >> 2) & 1; rs.neg1 = (fl >> 3) & 1; rs.neg2 = (fl >> 4) & 1;
+            rs.kx = rs.ky = rs.kz = 0;
+            rs.Sx = rs.Sy = rs.Sz = 0;
+            rs.slow = (fl >> 11) & 1;
+            int mode = active ? (int)PL_NODE : (int)PL_EMPTY;   // lanes without a slot idle through the step
+            int leafFirst = 0, leafN = 0;
+            const bool warpSlow = __any_sync(FULL, active && rs.slow != 0);
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+                {
+                    // take the next pending far child when the last visit left nothing to descend into (cur < 0)
+                    const bool need = (mode == PL_NODE) & (cur < 0);
+                    const bool empty = need & (sp == 0);
+                    const bool pop = need & !empty;
+                    int2 e = make_int2(0, 0);
+                    if (pop) e = stGet(s, sp - 1);
+                    sp = pop ? sp - 1 : sp;
+                    const bool take = pop & (__int_as_float(e.y) < tMax);
+                    const bool leafRef = take & (e.x < 0);
+                    leafFirst = leafRef ? (e.x & (int)WIDE_LEAF_OFFSET_MASK) : leafFirst;
+                    leafN = leafRef ? (((e.x >> WIDE_LEAF_COUNT_SHIFT) & 0xf) + 1) : leafN;
+                    cur = (take & !leafRef) ? e.x : cur;
+                    mode = leafRef ? (int)PL_LEAF : mode;
+                    if (empty) mode = PL_DONE;
+                }
+                if (mode == PL_NODE && cur >= 0) {
+                    const float4 *w = &sc.wide[4 * (size_t)cur];
+                    float4 q0, q1, q2, q3;
+                    ldg256(w, q0, q1);
+                    ldg256(w + 2, q2, q3);
+                    float t0, t1;
+                    bool p0, p1;
+                    if (warpSlow) slabTestPair(q0, q1, q2, rs, tMax, &p0, &p1, &t0, &t1);
+                    else slabTestPairFast(q0, q1, q2, rs, tMax, &p0, &p1, &t0, &t1);
+                    const uint32_t meta = floatBits(q3.z);
+                    if (meta & WIDE_SINGLE) p1 = false;
+                    const int axis = (int)(meta & 3u);
+                    const bool isNeg = (axis == 0 ? rs.neg0 : (axis == 1 ? rs.neg1 : rs.neg2)) != 0;
+                    const int ref0 = asInt(q3.x), ref1 = asInt(q3.y);
+                    const bool both = p0 & p1;
+                    if (both) stPut(s, sp, make_int2(isNeg ? ref0 : ref1, __float_as_int(isNeg ? t0 : t1)));
+                    sp += both ? 1 : 0;
+                    const int ref = (both ? isNeg : !p0) ? ref1 : ref0;
+                    const bool have = p0 | p1;
+                    const bool isLeaf = have & (ref < 0);
+                    leafFirst = isLeaf ? (ref & (int)WIDE_LEAF_OFFSET_MASK) : leafFirst;
+                    leafN = isLeaf ? (((ref >> WIDE_LEAF_COUNT_SHIFT) & 0xf) + 1) : leafN;
+                    mode = isLeaf ? (int)PL_LEAF : (int)PL_NODE;
+                    cur = (have & !isLeaf) ? ref : -1;
+                }
+            }
+            if (active) {
+                pw.i[0][s] = cur;
+                pw.i[1][s] = sp;
+                pw.i[3][s] = (fl & 0xfff) | (mode << 12);
+                pw.i[4][s] = leafFirst;
+                pw.i[5][s] = leafN;
+            }
+        } else {   // PL_LEAF: every primitive of the leaf, in order (GeometricPrimitive::Intersect[P] + Triangle)
+            if (active) {
+                DRaySetup rs;
+                rs.o = mk3(pw.f[0][s], pw.f[1][s], pw.f[2][s]);
+                rs.invDir = mk3(0, 0, 0);
+                float tMax = pw.f[6][s];
+                rs.Sx = pw.f[7][s]; rs.Sy = pw.f[8][s]; rs.Sz = pw.f[9][s];
+                int fl = pw.i[3][s];
+                rs.neg0 = rs.neg1 = rs.neg2 = 0;
+                rs.kx = (fl >> 5) & 3; rs.ky = (fl >> 7) & 3; rs.kz = (fl >> 9) & 3;
+                rs.slow = 0;
+                const int c = pw.i[2][s];
+                int leafFirst = pw.i[4][s], leafN = pw.i[5][s];
+                const bool any = (fl & 1) != 0;
+                bool finished = false;
+                while (leafN > 0) {
+                    const int idx = leafFirst;
+                    ++leafFirst;
+                    --leafN;
+                    const float4 *rec = &sc.leafPrims[3 * (size_t)idx];
+                    const float4 a = ldg4(rec), b = ldg4(rec + 1), c4 = ldg4(rec + 2);
+                    const uint32_t pf = floatBits(b.w);
+                    float t, b0, b1, b2;
+                    if (triangleTest(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c4.x, c4.y, c4.z), rs, tMax, &t, &b0, &b1, &b2)) {
+                        if (any) { fl |= 2; finished = true; break; }
+                        if (pf & LEAF_DEGENERATE) continue;
+                        fl |= 2;
+                        tMax = t;
+                        __stcs(reinterpret_cast<float4 *>(&pool.ctx[c].hit), make_float4(__int_as_float(idx), b0, b1, b2));
+                    }
+                }
+                const int sp = pw.i[1][s];
+                const int mode = (finished || sp == 0) ? (int)PL_DONE : (int)PL_NODE;
+                pw.f[6][s] = tMax;
+                pw.i[0][s] = -1;   // the next node step pops
+                pw.i[3][s] = (fl & 0xfff) | (mode << 12);
+            }
+        }
+        __syncwarp();
     }
 }
 

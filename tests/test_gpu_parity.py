@@ -276,7 +276,7 @@ def wf_kernels(pb):
     return {"wide2": 0, "wide4": pb.PB2_FLAG_WIDE4, "linear": pb.PB2_FLAG_LINEAR_NODES, "plain": pb.PB2_FLAG_PLAIN_TRACE,
             "wide2_spill": pb.PB2_FLAG_SMALL_STACK, "wide4_spill": pb.PB2_FLAG_SMALL_STACK | pb.PB2_FLAG_WIDE4,
             "wide2_ld128": pb.PB2_FLAG_LD128, "wide4_ld128": pb.PB2_FLAG_LD128 | pb.PB2_FLAG_WIDE4,
-            "wide2_leaf_tma": pb.PB2_FLAG_LEAF_TMA}
+            "wide2_leaf_tma": pb.PB2_FLAG_LEAF_TMA, "ray_pool": pb.PB2_FLAG_POOL}
 
 
 def check_wavefront_records(pb, hs, rays, srays, want_hits, want_occluded):
