@@ -385,7 +385,11 @@ def main():
                          "dram_bytes_over_algorithmic_bytes": (NCU_TRACE_DRAM_BYTES_PER_LAUNCH / NCU_TRACE_ALGORITHMIC_BYTES_OF_THAT_LAUNCH) if default_workload else None,
                          "algorithmic_bytes_per_frame": alg_bytes, "node_visits": node_visits, "prim_tests": prim_tests,
                          "bytes_per_ray": alg_bytes / max(rays_frame, 1), "trace_ms_per_frame": trace_ms / args.steps,
-                         "trace_share_of_step": (trace_ms / args.steps) / ms_per_step},
+                         "trace_share_of_step": (trace_ms / args.steps) / ms_per_step,
+                         "concurrency_note": "the renderer runs two wavefront pipelines on two streams: a trace launch shares the GPU with the other "
+                                             "pipeline's kernels, so the summed launch durations (trace_ms_per_frame) can exceed the kernel's share of "
+                                             "the step and `achieved` is the per-launch figure under that sharing (PB2_PIPES=1: 0.75 on this workload)",
+                         "frac_of_step": (alg_bytes / world) / (ms_per_step / 1e3) / 1e9 / peak},
         }
         if not args.no_cpu_baseline and world == 1:   # the CPU side-by-side is reported by the N = 1 run only
             try:

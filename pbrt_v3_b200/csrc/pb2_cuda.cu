@@ -303,9 +303,11 @@ struct pb2_scene {
     unsigned *wfHostCounts = nullptr;  // pinned
     int wfCapacity = 0;
     std::vector<cudaEvent_t> traceEvents;
+    int pipesChosen = 0;                     // wavefront pipelines for this scene, chosen after its first frame (0 = not yet)
+    cudaEvent_t frameEvents[2] = {nullptr, nullptr};
     int2 *wfSpill = nullptr;                 // k_wf_trace_pool: stack entries beyond its shared-memory depth
-    cudaStream_t stream2 = nullptr;          // second pipeline of the wavefront (renderWavefront)
-    cudaEvent_t forkEvent = nullptr, joinEvent = nullptr;
+    cudaStream_t pipeStreams[4] = {nullptr, nullptr, nullptr, nullptr};   // streams of the wavefront pipelines 1.. (renderWavefront)
+    cudaEvent_t forkEvent = nullptr, joinEvents[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 template <typename T>
@@ -753,6 +755,7 @@ static int validateRenderArgs(const pb2_scene *scene, const pb2_camera *cam, con
     return PB2_OK;
 }
 
+enum { kMaxPipes = 4 };   // wavefront pipelines (renderWavefront)
 typedef void (*TraceKernel)(DScene, WfPool, int);
 typedef void (*AdvanceKernel)(DScene, DRenderParams, WfPool, int, int, int, float4 *, unsigned long long *);
 
@@ -776,7 +779,7 @@ struct TraceLaunch {
     const char *name = "";
 };
 
-static int selectTraceKernel(const pb2_scene *scene, int flags, TraceLaunch *out) {
+static int selectTraceKernel(pb2_scene *scene, int flags, TraceLaunch *out) {
     TraceLaunch t;
     const bool spheres = scene->d.spheres != nullptr;
     const bool instanced = scene->d.instances != nullptr;
@@ -788,8 +791,13 @@ static int selectTraceKernel(const pb2_scene *scene, int flags, TraceLaunch *out
     else if ((flags & PB2_FLAG_PLAIN_TRACE) || (!records && !linearFits)) { t.fn = k_wf_trace_plain<false>; t.name = "k_wf_trace_plain"; }
     else if (records && (flags & PB2_FLAG_POOL) && !spheres && !instanced) {
         t.name = "k_wf_trace_pool";
-        t.fn = k_wf_trace_pool<4, 5>;
-        t.smem = 4 * sizeof(PoolWarp);
+        if (!scene->wfSpill)   // per pipeline: up to 8 resident blocks per SM x 4 warps x PL_R slots x PL_SPILL entries
+            CUDA_TRY(cudaMalloc((void **)&scene->wfSpill, (size_t)kMaxPipes * g_numSMs * 8 * 4 * PL_R * PL_SPILL * sizeof(int2)));
+        // 48 rays per warp, 8 stack entries per ray in shared memory: 25 KB per block, 8 resident blocks per SM.  Sweep (1 M soup,
+        // 16 spp, one pipeline; k_wf_trace_w: 219.3 Msamples/s): 64 rays / 12 entries / 5 blocks 194.6; NSUB 2: 190.8; leaf steps
+        // from 16 ready rays: 192.9; NSUB 1: 178.9; this one 203.6; 40 rays: 202.2; 64 rays / 8 entries / 6 blocks: 196.3
+        t.fn = k_wf_trace_pool<4, 8, 16, 12, 48, 8>;
+        t.smem = 4 * sizeof(PoolWarp<48, 8>);
         CUDA_TRY(cudaFuncSetAttribute(t.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t.smem));
     } else if (records && (flags & PB2_FLAG_WIDE4)) {
         t.name = "k_wf_trace_w<4>";
@@ -846,7 +854,6 @@ static int selectTraceKernel(const pb2_scene *scene, int flags, TraceLaunch *out
     return PB2_OK;
 }
 
-enum { kMaxPipes = 2 };
 static int ensurePool(pb2_scene *scene, int capacity) {
     if (scene->wfCapacity < capacity) {
         if (scene->wfCtx) cudaFree(scene->wfCtx);
@@ -859,8 +866,6 @@ static int ensurePool(pb2_scene *scene, int capacity) {
         scene->wfCapacity = capacity;
     }
     if (!scene->wfCounts) CUDA_TRY(cudaMalloc((void **)&scene->wfCounts, kMaxPipes * WQ_COUNT * sizeof(unsigned)));
-    if (!scene->wfSpill)   // per pipeline: up to 8 resident blocks per SM x 4 warps x PL_R slots x PL_SPILL entries
-        CUDA_TRY(cudaMalloc((void **)&scene->wfSpill, (size_t)kMaxPipes * g_numSMs * 8 * 4 * PL_R * PL_SPILL * sizeof(int2)));
     if (!scene->wfHostCounts) CUDA_TRY(cudaMallocHost((void **)&scene->wfHostCounts, (kMaxPipes * WQ_COUNT + 2) * sizeof(unsigned long long)));
     return PB2_OK;
 }
@@ -874,13 +879,14 @@ static WfPool poolOf(const pb2_scene *scene, int capacity, int pipe = 0, int nPi
     for (int q = 0; q < WQ_COUNT; ++q) pool.queue[q] = scene->wfQueues + ((size_t)pipe * WQ_COUNT + q) * cap;
     pool.counts = scene->wfCounts + (size_t)pipe * WQ_COUNT;
     pool.ctr = scene->counters;
-    pool.spill = scene->wfSpill + (size_t)pipe * g_numSMs * 8 * 4 * PL_R * PL_SPILL;
+    pool.spill = scene->wfSpill ? scene->wfSpill + (size_t)pipe * g_numSMs * 8 * 4 * PL_R * PL_SPILL : nullptr;
     return pool;
 }
 
 // Host driver of the wavefront rounds (see pb2_wavefront.cuh).
 static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *film, cudaStream_t stream, int flags,
                            bool timeTrace, unsigned long long *launches, double *traceMs) {
+    const bool lazyLights = scene->lazyLightDist;   // k_wf_finish cannot defer a vertex: the rounds run to the end instead
     // 4 M contexts (1 GiB) measured best on 1920x1080: 1 M -> 160, 2 M -> 174, 4 M -> 180 Msamples/s
     static const int maxCapacity = envInt("PB2_POOL", 1 << 22);
     long long want = std::min<long long>(maxCapacity, std::max<long long>(rp.nWorkItems, 1024));
@@ -904,7 +910,6 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
                                              : (spheres ? k_wf_finish<true, false> : k_wf_finish<false, false>);
     // the frame's last paths are walked to their end by one thread each once this few are left (k_wf_finish)
     static const int finishPerSM = envInt("PB2_FINISH", 256);
-    const bool lazyLights = scene->lazyLightDist;   // k_wf_finish cannot defer a vertex: the rounds run to the end instead
     const unsigned finishThreshold = ((flags & PB2_FLAG_COUNT_TRAVERSAL) || lazyLights) ? 0u : (unsigned)(g_numSMs * std::max(0, finishPerSM));
     const int finishBlocks = std::max(1, (int)((finishThreshold + 127) / 128));
     static const int syncEvery = std::max(1, envInt("PB2_SYNC_EVERY", 8));
@@ -915,16 +920,30 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     // that the other leaves idle at the end of every launch (a persistent trace launch ends with ~0.2 ms in which the last
     // long rays finish while most warps have exited; 136 launches per frame).  Both draw samples from the one work counter.
     // PB2_PIPES=1: one pipeline.  Lazily lit scenes share one request list: one pipeline.
-    static const int pipesWanted = std::min((int)kMaxPipes, std::max(1, envInt("PB2_PIPES", 2)));
+    // How many: a traversal-bound scene (1 M soup: trace 80 % of the kernel time) is best with two - 219 / 229 / 222 / 216
+    // Msamples/s with 1 / 2 / 3 / 4 pipelines - a shading-bound one (killeroo-like: trace 22 %) with four: 195 / 221 / 249 / 261.
+    // The first frame of a scene runs with two and measures the trace kernel's share of the frame; later frames use four
+    // when that share is small.  PB2_PIPES fixes the number.
+    static const int pipesEnv = envInt("PB2_PIPES", 0);
+    const bool calibrate = pipesEnv <= 0 && scene->pipesChosen == 0 && !lazyLights && capacity >= 65536 && rp.nWorkItems >= 4 * (long long)capacity;
+    if (calibrate) timeTrace = true;
+    const int pipesWanted = std::min((int)kMaxPipes, pipesEnv > 0 ? pipesEnv : (scene->pipesChosen > 0 ? scene->pipesChosen : 2));
     const int nPipes = (lazyLights || capacity < 65536) ? 1 : pipesWanted;
-    cudaStream_t streams[kMaxPipes] = {stream, stream};
+    if (calibrate) {
+        for (int k = 0; k < 2; ++k)
+            if (!scene->frameEvents[k]) CUDA_TRY(cudaEventCreate(&scene->frameEvents[k]));
+        CUDA_TRY(cudaEventRecord(scene->frameEvents[0], stream));
+    }
+    cudaStream_t streams[kMaxPipes] = {stream, stream, stream, stream};
     if (nPipes > 1) {
-        if (!scene->stream2) CUDA_TRY(cudaStreamCreateWithFlags(&scene->stream2, cudaStreamNonBlocking));
         if (!scene->forkEvent) CUDA_TRY(cudaEventCreateWithFlags(&scene->forkEvent, cudaEventDisableTiming));
-        if (!scene->joinEvent) CUDA_TRY(cudaEventCreateWithFlags(&scene->joinEvent, cudaEventDisableTiming));
-        streams[1] = scene->stream2;
         CUDA_TRY(cudaEventRecord(scene->forkEvent, stream));            // the film clear / counter reset of the caller's stream
-        CUDA_TRY(cudaStreamWaitEvent(scene->stream2, scene->forkEvent, 0));
+        for (int p = 1; p < nPipes; ++p) {
+            if (!scene->pipeStreams[p]) CUDA_TRY(cudaStreamCreateWithFlags(&scene->pipeStreams[p], cudaStreamNonBlocking));
+            if (!scene->joinEvents[p]) CUDA_TRY(cudaEventCreateWithFlags(&scene->joinEvents[p], cudaEventDisableTiming));
+            streams[p] = scene->pipeStreams[p];
+            CUDA_TRY(cudaStreamWaitEvent(streams[p], scene->forkEvent, 0));
+        }
     }
     WfPool pools[kMaxPipes];
     for (int p = 0; p < nPipes; ++p) pools[p] = poolOf(scene, capacity / nPipes * nPipes, p, nPipes);
@@ -992,8 +1011,10 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         if (round > 100000000LL) return setError(PB2_ERR_CUDA, "wavefront did not terminate");
     }
     if (nPipes > 1) {   // what follows on the caller's stream (film reduce, copies) comes after both pipelines
-        CUDA_TRY(cudaEventRecord(scene->joinEvent, scene->stream2));
-        CUDA_TRY(cudaStreamWaitEvent(stream, scene->joinEvent, 0));
+        for (int p = 1; p < nPipes; ++p) {
+            CUDA_TRY(cudaEventRecord(scene->joinEvents[p], streams[p]));
+            CUDA_TRY(cudaStreamWaitEvent(stream, scene->joinEvents[p], 0));
+        }
     }
     CUDA_TRY(cudaGetLastError());
     *launches = nLaunch;
@@ -1003,7 +1024,20 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         CUDA_TRY(cudaEventElapsedTime(&ms, scene->traceEvents[e], scene->traceEvents[e + 1]));
         *traceMs += ms;
     }
-    if (nPipes > 1) *traceMs /= nPipes;   // the pipelines' launches overlap in time: their mean is the per-frame figure
+    // (with two pipelines this is the sum of launch durations of kernels that each shared the GPU with the other pipeline's
+    // kernels: algorithmic bytes / this time is the per-launch figure the roofline contract asks for, a conservative one)
+    if (calibrate) {
+        CUDA_TRY(cudaEventRecord(scene->frameEvents[1], stream));
+        CUDA_TRY(cudaEventSynchronize(scene->frameEvents[1]));
+        float frameMs = 0;
+        CUDA_TRY(cudaEventElapsedTime(&frameMs, scene->frameEvents[0], scene->frameEvents[1]));
+        // mean over the two pipelines of (summed duration of its trace launches) / frame: 0.41 on the 1 M soup, 0.42 on the
+        // instanced scene (two pipelines are best), 0.25 on the killeroo-like scene (four are)
+        const double share = frameMs > 0 ? *traceMs / nPipes / frameMs : 1;
+        scene->pipesChosen = share < 0.33 ? 4 : 2;
+        static const int verbose = envInt("PB2_VERBOSE", 0);
+        if (verbose) fprintf(stderr, "pb2: trace share of the first frame %.2f -> %d wavefront pipelines\n", share, scene->pipesChosen);
+    }
     return PB2_OK;
 }
 
@@ -1210,9 +1244,13 @@ int pb2_scene_destroy(pb2_scene *s) {
     if (s->ldHostCounters) cudaFreeHost(s->ldHostCounters);
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->wfSpill) cudaFree(s->wfSpill);
-    if (s->stream2) cudaStreamDestroy(s->stream2);
+    for (int p = 0; p < 4; ++p) {
+        if (s->pipeStreams[p]) cudaStreamDestroy(s->pipeStreams[p]);
+        if (s->joinEvents[p]) cudaEventDestroy(s->joinEvents[p]);
+    }
     if (s->forkEvent) cudaEventDestroy(s->forkEvent);
-    if (s->joinEvent) cudaEventDestroy(s->joinEvent);
+    for (int k = 0; k < 2; ++k)
+        if (s->frameEvents[k]) cudaEventDestroy(s->frameEvents[k]);
     delete s;
     if (g_initialised) cudaSetDevice(g_devs[0].id);
     return PB2_OK;
@@ -1641,9 +1679,9 @@ int pb2_trace_wavefront(pb2_scene *scene, const pb2_ray *rays, const uint8_t *an
     if (n > (1 << 24)) return setError(PB2_ERR_INVALID, "at most 2^24 rays per call");
     const int N = (int)n;
     if ((rc = ensurePool(scene, (N + 255) / 256 * 256))) return rc;
-    WfPool pool = poolOf(scene, scene->wfCapacity);
     TraceLaunch trace;
     if ((rc = selectTraceKernel(scene, flags, &trace))) return rc;
+    WfPool pool = poolOf(scene, scene->wfCapacity);
     pb2_ray *dRays = nullptr;
     uint8_t *dAny = nullptr;
     pb2_wf_hit *dOut = nullptr;

@@ -817,25 +817,28 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
 // pops against the tMax of the moment): only which lane executes a step of which ray differs.
 // Slot flags: bit 0 any-hit, 1 found, 2-4 direction signs, 5-6 / 7-8 / 9-10 kx ky kz, 11 slow (non-finite), 12-13 phase.
 // ---------------------------------------------------------------------------------------------
-enum { PL_EMPTY = 0, PL_NODE = 1, PL_LEAF = 2, PL_DONE = 3, PL_R = 64, PL_SD = 12, PL_SPILL = 52 };
+enum { PL_EMPTY = 0, PL_NODE = 1, PL_LEAF = 2, PL_DONE = 3, PL_R = 64, PL_SPILL = 64 };   // PL_R: the most slots a warp can have
+template <int R, int SD>
 struct PoolWarp {   // one warp's slice of shared memory
-    float f[10][PL_R];        // ox oy oz ix iy iz tMax Sx Sy Sz
-    int i[6][PL_R];           // cur, sp, ctx, flags, leafFirst, leafN
-    int2 stk[PL_SD][PL_R];    // (child reference, tMin bits); deeper entries go to WfPool::spill
-    int list[PL_R];           // slots chosen for the step, in rank order
+    float f[10][R];        // ox oy oz ix iy iz tMax Sx Sy Sz
+    int i[6][R];           // cur, sp, ctx, flags, leafFirst, leafN
+    int2 stk[SD][R];       // (child reference, tMin bits); deeper entries go to WfPool::spill
+    int list[R];           // slots chosen for the step, in rank order
 };
 
-template <int NSUB, int MINB>
+template <int NSUB, int MINB, int LEAF_T = 24, int FILL_T = 24, int R = 64, int PL_SD = 12>
 __global__ void __launch_bounds__(128, MINB) k_wf_trace_pool(DScene sc, WfPool pool, int traceQ) {
-    extern __shared__ PoolWarp poolSmem[];
-    PoolWarp &pw = poolSmem[threadIdx.x >> 5];
+    static_assert(R > 32 && R <= PL_R, "a warp owns 33 .. 64 slots");
+    extern __shared__ unsigned char poolSmemRaw[];
+    PoolWarp<R, PL_SD> &pw = reinterpret_cast<PoolWarp<R, PL_SD> *>(poolSmemRaw)[threadIdx.x >> 5];
+    const bool second = (threadIdx.x & 31) + 32 < R;   // this lane also looks after slot lane + 32
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned ltMask = (1u << lane) - 1u;
     const unsigned n = pool.counts[traceQ];
     int2 *spill = pool.spill + ((size_t)(blockIdx.x * 4 + (threadIdx.x >> 5)) * PL_R) * PL_SPILL;   // [slot][PL_SPILL]
     pw.i[3][lane] = 0;
-    pw.i[3][lane + 32] = 0;
+    if (second) pw.i[3][lane + 32] = 0;
     __syncwarp();
     bool exhausted = false;
     // stack access of slot s
@@ -846,24 +849,25 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_pool(DScene sc, WfPool p
     };
     while (true) {
         // ---- census of the 64 slots
-        const int fl0 = pw.i[3][lane], fl1 = pw.i[3][lane + 32];
-        const int m0 = (fl0 >> 12) & 3, m1 = (fl1 >> 12) & 3;
+        const int fl0 = pw.i[3][lane], fl1 = second ? pw.i[3][lane + 32] : -1;
+        const int m0 = (fl0 >> 12) & 3, m1 = second ? ((fl1 >> 12) & 3) : -1;   // -1: no such slot
         const unsigned bN0 = __ballot_sync(FULL, m0 == PL_NODE), bN1 = __ballot_sync(FULL, m1 == PL_NODE);
         const unsigned bL0 = __ballot_sync(FULL, m0 == PL_LEAF), bL1 = __ballot_sync(FULL, m1 == PL_LEAF);
         const unsigned bD0 = __ballot_sync(FULL, m0 == PL_DONE), bD1 = __ballot_sync(FULL, m1 == PL_DONE);
         const int nN = __popc(bN0) + __popc(bN1), nL = __popc(bL0) + __popc(bL1), nD = __popc(bD0) + __popc(bD1);
-        const int nE = PL_R - nN - nL - nD;
+        const int nE = R - nN - nL - nD;
         int phase;
-        if (nD + (exhausted ? 0 : nE) >= 24 || (nN == 0 && nL == 0 && (nD > 0 || (!exhausted && nE > 0)))) phase = PL_DONE;   // flush + fill
-        else if (nL >= 24 || (nL > 0 && nN == 0)) phase = PL_LEAF;
+        if (nD + (exhausted ? 0 : nE) >= FILL_T || (nN == 0 && nL == 0 && (nD > 0 || (!exhausted && nE > 0)))) phase = PL_DONE;   // flush + fill
+        else if (nL >= LEAF_T || (nL > 0 && nN == 0)) phase = PL_LEAF;
         else if (nN > 0) phase = PL_NODE;
         else break;   // nothing in flight, nothing to flush, the list is exhausted
 
         if (phase == PL_DONE) {
 #pragma unroll 1
             for (int h = 0; h < 2; ++h) {
-                const int s = lane + 32 * h;
-                const int fl = pw.i[3][s];
+                const bool exists = h == 0 || second;
+                const int s = exists ? lane + 32 * h : lane;
+                const int fl = exists ? pw.i[3][s] : (PL_NODE << 12);   // a lane without a second slot just takes part in the votes
                 const int mode = (fl >> 12) & 3;
                 const bool flush = mode == PL_DONE;
                 int c = flush ? pw.i[2][s] : -1;
