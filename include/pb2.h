@@ -29,10 +29,11 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 8   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc;
+#define PB2_ABI_VERSION 9   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc;
                              * 5: uber / metal fields in pb2_material (128 bytes); 6: point / spot / distant lights
                              * (pb2_light.type, pb2_scene_desc.delta_lights); 7: pb2_trace_wavefront, kernel-selector flags;
-                             * 8: pb2_dist_* (NCCL film reduce inside the render calls), pb2_host_alloc */
+                             * 8: pb2_dist_* (NCCL film reduce inside the render calls), pb2_host_alloc;
+                             * 9: PB2_LIGHT_INFINITE, pb2_delta_light.light_to_world (112 bytes) */
 
 typedef enum pb2_status {
     PB2_OK = 0,
@@ -112,8 +113,11 @@ typedef struct pb2_material {
 
 /* One entry of Scene::lights, in the scene's order.  PB2_LIGHT_AREA: a DiffuseAreaLight (src/lights/diffuse.h:49-79)
  * attached to one primitive.  The other types are the delta lights (src/lights/{point,spot,distant}.cpp): L holds
- * I (point, spot) or L (distant), prim is -1, and delta_lights[same index] the geometry. */
-enum { PB2_LIGHT_AREA = 0, PB2_LIGHT_POINT = 1, PB2_LIGHT_SPOT = 2, PB2_LIGHT_DISTANT = 3 };
+ * I (point, spot) or L (distant), prim is -1, and delta_lights[same index] the geometry.  PB2_LIGHT_INFINITE: an
+ * InfiniteAreaLight (src/lights/infinite.cpp) WITHOUT a texture map - constant radiance L = "L" * "scale" from every direction;
+ * prim is -1, delta_lights[same index] carries its two 3x3 matrices and world_radius (Preprocess, infinite.h:61-63).  Rays
+ * that leave the scene see it (path.cpp:96-98).  Environment maps ("mapname") need image readers and are out of scope. */
+enum { PB2_LIGHT_AREA = 0, PB2_LIGHT_POINT = 1, PB2_LIGHT_SPOT = 2, PB2_LIGHT_DISTANT = 3, PB2_LIGHT_INFINITE = 4 };
 typedef struct pb2_light {
     int32_t prim;       /* index into prim_type[]/prim_index[] */
     float L[3];         /* Lemit = L * scale */
@@ -129,8 +133,11 @@ typedef struct pb2_delta_light {
     float total_width_deg;      /* spot: the constructor's totalWidth / falloffStart in degrees (spot.cpp:43-50); the library takes */
     float falloff_start_deg;    /*       their cosines as the constructor does */
     float world_radius;         /* distant: DistantLight::Preprocess (distant.h:55-57), from the scene bounds */
-    float world_to_light[9];    /* spot: upper-left 3x3 of WorldToLight, row-major (SpotLight::Falloff, spot.cpp:63-72) */
+    float world_to_light[9];    /* spot, infinite: upper-left 3x3 of WorldToLight, row-major (SpotLight::Falloff, spot.cpp:63-72;
+                                 * InfiniteAreaLight::Le / Pdf_Li, infinite.cpp:90-94, 124-132) */
     float pad;
+    float light_to_world[9];    /* infinite: upper-left 3x3 of LightToWorld (InfiniteAreaLight::Sample_Li, infinite.cpp:96-122) */
+    float pad2[3];
 } pb2_delta_light;
 
 /* One BVHAccel of the scene: bvhs[0] is Scene::aggregate, bvhs[k > 0] the accelerator that

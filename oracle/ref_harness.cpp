@@ -58,6 +58,7 @@
 #include "integrators/path.h"
 #include "lights/diffuse.h"
 #include "lights/distant.h"
+#include "lights/infinite.h"
 #include "lights/point.h"
 #include "lights/spot.h"
 #include "materials/matte.h"
@@ -84,6 +85,8 @@ Loc *parserLoc = nullptr;
 static std::mutex g_imageMutex;
 static std::vector<Float> g_lastImage;
 static Bounds2i g_lastBounds;
+// (imageio.cpp is not compiled: an InfiniteAreaLight is only ever built without a map here)
+std::unique_ptr<RGBSpectrum[]> ReadImage(const std::string &, Point2i *) { return nullptr; }
 void WriteImage(const std::string &, const Float *rgb, const Bounds2i &outputBounds, const Point2i &) {
     std::lock_guard<std::mutex> lock(g_imageMutex);
     g_lastBounds = outputBounds;
@@ -347,6 +350,17 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
             for (int r = 0; r < 3; ++r)
                 for (int c = 0; c < 3; ++c) mInv.m[r][c] = dl.world_to_light[3 * r + c];
             rs->lights[i] = std::make_shared<SpotLight>(Transform(m, mInv), MediumInterface(), I, dl.total_width_deg, dl.falloff_start_deg);
+        } else if (pl.type == PB2_LIGHT_INFINITE) {
+            // the reference's own InfiniteAreaLight without a texture map; Le / Sample_Li / Pdf_Li only transform vectors.
+            // Its constructor runs a ParallelFor (infinite.cpp:71-81): the thread pool must exist (parallel.cpp:186)
+            setThreads(0);
+            Matrix4x4 m, mInv;
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    m.m[r][c] = dl.light_to_world[3 * r + c];
+                    mInv.m[r][c] = dl.world_to_light[3 * r + c];
+                }
+            rs->lights[i] = std::make_shared<InfiniteAreaLight>(Transform(m, mInv), I, 1, "");
         } else
             rs->lights[i] = std::make_shared<DistantLight>(Transform(), I, Vector3f(dl.p[0], dl.p[1], dl.p[2]));
     }

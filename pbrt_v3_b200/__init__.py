@@ -27,9 +27,9 @@ PB2_OK, PB2_ERR_NO_DEVICE, PB2_ERR_CUDA, PB2_ERR_INVALID, PB2_ERR_UNSUPPORTED, P
 PB2_PRIM_TRIANGLE, PB2_PRIM_SPHERE, PB2_PRIM_INSTANCE = 0, 1, 2
 PB2_FILTER_BOX, PB2_FILTER_GAUSSIAN, PB2_FILTER_MITCHELL, PB2_FILTER_SINC, PB2_FILTER_TRIANGLE = 0, 1, 2, 3, 4
 PB2_MAT_NONE, PB2_MAT_MATTE, PB2_MAT_PLASTIC, PB2_MAT_MIRROR, PB2_MAT_GLASS, PB2_MAT_SUBSTRATE, PB2_MAT_METAL, PB2_MAT_UBER = range(8)
-PB2_ABI_VERSION = 8   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
+PB2_ABI_VERSION = 9   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
 PB2_LIGHTDIST_UNIFORM, PB2_LIGHTDIST_POWER, PB2_LIGHTDIST_SPATIAL = 0, 1, 2
-PB2_LIGHT_AREA, PB2_LIGHT_POINT, PB2_LIGHT_SPOT, PB2_LIGHT_DISTANT = 0, 1, 2, 3
+PB2_LIGHT_AREA, PB2_LIGHT_POINT, PB2_LIGHT_SPOT, PB2_LIGHT_DISTANT, PB2_LIGHT_INFINITE = 0, 1, 2, 3, 4
 
 
 class BvhNode(C.Structure):
@@ -65,7 +65,8 @@ class Light(C.Structure):
 
 class DeltaLight(C.Structure):
     _fields_ = [("p", C.c_float * 3), ("total_width_deg", C.c_float), ("falloff_start_deg", C.c_float),
-                ("world_radius", C.c_float), ("world_to_light", C.c_float * 9), ("pad", C.c_float)]
+                ("world_radius", C.c_float), ("world_to_light", C.c_float * 9), ("pad", C.c_float),
+                ("light_to_world", C.c_float * 9), ("pad2", C.c_float * 3)]
 
 
 class Bvh(C.Structure):

@@ -104,6 +104,10 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
     if (ln.bounces == 0 || ln.specularBounce) {
         if (found) {
             if (li >= 0) ln.L = ln.L + ln.beta * lightL(sc.lights[li], isect.n, -ln.ray.d);
+        } else {
+            // the ray escaped: every infinite light is seen directly (path.cpp:96-98)
+            for (int k = 0; k < sc.nInfinite; ++k)
+                ln.L = ln.L + ln.beta * infiniteLe(sc.lights[sc.infinite[k]], sc.deltaLights[sc.infinite[k]], ln.ray.d);
         }
     }
     if (!found || ln.bounces >= pp.maxDepth) {
@@ -163,12 +167,15 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
                 else f = mk3(0, 0, 0);
             }
             if (!isBlack(f) && scatteringPdf > 0) {
-                lightPdf = lightPdfLi<SPH>(sc, light, lightRec, isect, wi);
+                lightPdf = lightPdfLi<SPH>(sc, light, lightRec, isect, wi, lightNum);
                 if (lightPdf != 0) {
                     float weight = powerHeuristic(scatteringPdf, lightPdf);
                     // Li is the light's Lemit when the MIS ray reaches its emitting side (checked after
-                    // the trace); f * Li * Tr(=1) * weight / scatteringPdf
-                    V3 fl = f * mk3(light.L[0], light.L[1], light.L[2]) * weight;
+                    // the trace); f * Li * Tr(=1) * weight / scatteringPdf.  An infinite light is seen when the ray
+                    // escapes instead (integrator.cpp:209-211): its Le along wi is known here already.
+                    V3 Lmis = mk3(light.L[0], light.L[1], light.L[2]);
+                    if (sc.deltaLights && light.type == PB2_LIGHT_INFINITE) Lmis = infiniteLe(light, sc.deltaLights[lightNum], wi);
+                    V3 fl = f * Lmis * weight;
                     ln.misTerm = mk3(fl.x / scatteringPdf, fl.y / scatteringPdf, fl.z / scatteringPdf);
                     DRay mr = spawnRay(isect, wi);
                     ln.misO = mr.o;
@@ -229,7 +236,10 @@ PB2_HD void lightAdvance(const DScene &sc, DLane &ln, bool found, const DHit &hi
         if (!found) ln.ldSum = ln.ldSum + ln.ldLight;  // VisibilityTester::Unoccluded
         startMisOrFinish(ln);
     } else {
-        if (found) {
+        if (!found) {
+            // the MIS ray escaped: Li = light.Le(ray), which is zero for every light but an infinite one (integrator.cpp:209-211)
+            if (sc.deltaLights && sc.lights[ln.lightNum].type == PB2_LIGHT_INFINITE) ln.ldSum = ln.ldSum + ln.misTerm;
+        } else if (!(sc.deltaLights && sc.lights[ln.lightNum].type == PB2_LIGHT_INFINITE)) {
             // the hit primitive's light number rides in its leaf record (spheres: via primLight)
             float4 b = ldg4(&sc.leafPrims[3 * (size_t)hit.leaf + 1]), c = ldg4(&sc.leafPrims[3 * (size_t)hit.leaf + 2]);
             int hitLight = asInt(c.w);

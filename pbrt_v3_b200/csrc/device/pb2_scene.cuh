@@ -82,6 +82,12 @@ struct DDeltaLight {
     float worldRadius;
     float worldToLight[9];
     float pad;
+    // InfiniteAreaLight with constant radiance (infinite.cpp:43-83 without a texture map): its 1 x 1 radiance map is
+    // pb2_light::L; the sampling distribution over the 2 x 2 image the constructor derives from it, as three
+    // Distribution1D records [func(2) | cdf(3) | funcInt]: row v = 0, row v = 1, the marginal over the rows
+    float lightToWorld[9];
+    float dist[18];
+    float pad2;
 };
 
 struct DScene {
@@ -101,6 +107,8 @@ struct DScene {
     const pb2_light *lights;
     const DDeltaLight *deltaLights;       // parallel to lights, nullptr when every light is an area light
     int nLights;
+    int nInfinite;            // Scene::infiniteLights (scene.h:66): entries of `lights` that escaped rays see
+    int infinite[4];
     const DInstance *instances;   // nullptr: no object instancing in this scene
     int nInstances;
     DLightDist lightDist;

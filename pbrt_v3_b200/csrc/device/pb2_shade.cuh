@@ -1183,9 +1183,95 @@ PB2_HDN DLightSample sampleDeltaLight(const pb2_light &l, const DDeltaLight &dl,
     return s;
 }
 
+// ---------------------------------------------------------------- InfiniteAreaLight with constant radiance
+// MIPMap<RGBSpectrum>::Lookup(st, width = 0) on the light's 1 x 1 map: Levels() - 1 + Log2(1e-8) < 0, i.e.
+// MIPMap::triangle(0, st) (mipmap.h:245-274) - a bilinear blend of four copies of the one texel under ImageWrap::Repeat,
+// whose weights sum to one only up to rounding, so the blend is evaluated as written there.
+PB2_HD V3 infiniteLookup(const pb2_light &l, V2 st) {
+    const V3 T = mk3(l.L[0], l.L[1], l.L[2]);
+    const float s = st.x * 1 - 0.5f, t = st.y * 1 - 0.5f;
+    const float s0 = floorf(s), t0 = floorf(t);
+    const float ds = s - (float)(int)s0, dt = t - (float)(int)t0;
+    return ((1 - ds) * (1 - dt)) * T + ((1 - ds) * dt) * T + (ds * (1 - dt)) * T + (ds * dt) * T;
+}
+// Distribution1D::SampleContinuous (sampling.h:73-89) over a record [func(n) | cdf(n+1) | funcInt]
+PB2_HD float sampleContinuous1D(const float *rec, int n, float u, float *pdf, int *off) {
+    const float *func = rec, *cdf = rec + n;
+    const float funcInt = rec[2 * n + 1];
+    int first = 0, len = n + 1;   // FindInterval(size = n + 1, cdf[i] <= u), pbrt.h:403-415
+    while (len > 0) {
+        int half = len >> 1, middle = first + half;
+        if (cdf[middle] <= u) {
+            first = middle + 1;
+            len -= half + 1;
+        } else
+            len = half;
+    }
+    int offset = first - 1;
+    offset = offset < 0 ? 0 : (offset > n - 1 ? n - 1 : offset);   // Clamp(first - 1, 0, size - 2)
+    *off = offset;
+    float du = u - cdf[offset];
+    if ((cdf[offset + 1] - cdf[offset]) > 0) du /= (cdf[offset + 1] - cdf[offset]);
+    *pdf = (funcInt > 0) ? func[offset] / funcInt : 0;
+    return (offset + du) / n;
+}
+// InfiniteAreaLight::Le (infinite.cpp:90-94): SphericalPhi / SphericalTheta of the direction in light space (geometry.h:1456-1465)
+PB2_HDN V3 infiniteLe(const pb2_light &l, const DDeltaLight &dl, V3 d) {
+    const float *m = dl.worldToLight;
+    const V3 w = normalize(mk3(m[0] * d.x + m[1] * d.y + m[2] * d.z, m[3] * d.x + m[4] * d.y + m[5] * d.z, m[6] * d.x + m[7] * d.y + m[8] * d.z));
+    float phi = patan2f(w.y, w.x);
+    if (phi < 0) phi = phi + 2 * kPi;
+    const float theta = pacosf(clampf(w.z, -1.f, 1.f));
+    return infiniteLookup(l, mk2(phi * (0.5f * kInvPi), theta * kInvPi));
+}
+// InfiniteAreaLight::Sample_Li (infinite.cpp:96-122); the VisibilityTester's far point has neither normal nor error bounds
+PB2_HDN DLightSample sampleInfiniteLight(const pb2_light &l, const DDeltaLight &dl, V3 refP, V2 u) {
+    DLightSample s;
+    s.delta = false;
+    s.pError = s.n = mk3(0, 0, 0);
+    s.p = refP;
+    s.wi = mk3(0, 0, 1);
+    s.pdf = 0;
+    s.Li = mk3(0, 0, 0);
+    // Distribution2D::SampleContinuous (sampling.h:117-125): the row from the marginal with u[1], then inside the row with u[0]
+    float pdf1, pdf0;
+    int v, uo;
+    const float d1 = sampleContinuous1D(dl.dist + 12, 2, u.y, &pdf1, &v);
+    const float d0 = sampleContinuous1D(dl.dist + 6 * v, 2, u.x, &pdf0, &uo);
+    const float mapPdf = pdf0 * pdf1;
+    if (mapPdf == 0) return s;
+    const float theta = d1 * kPi, phi = d0 * 2 * kPi;
+    const float cosTheta = pcosf(theta), sinTheta = psinf(theta);
+    const float sinPhi = psinf(phi), cosPhi = pcosf(phi);
+    const V3 vl = mk3(sinTheta * cosPhi, sinTheta * sinPhi, cosTheta);
+    const float *m = dl.lightToWorld;
+    s.wi = mk3(m[0] * vl.x + m[1] * vl.y + m[2] * vl.z, m[3] * vl.x + m[4] * vl.y + m[5] * vl.z, m[6] * vl.x + m[7] * vl.y + m[8] * vl.z);
+    s.pdf = mapPdf / (2 * kPi * kPi * sinTheta);
+    if (sinTheta == 0) s.pdf = 0;
+    s.p = refP + s.wi * (2 * dl.worldRadius);
+    s.Li = infiniteLookup(l, mk2(d0, d1));
+    return s;
+}
+// InfiniteAreaLight::Pdf_Li (infinite.cpp:124-132), Distribution2D::Pdf (sampling.h:126-132)
+PB2_HDN float infinitePdfLi(const DDeltaLight &dl, V3 w) {
+    const float *m = dl.worldToLight;
+    const V3 wi = mk3(m[0] * w.x + m[1] * w.y + m[2] * w.z, m[3] * w.x + m[4] * w.y + m[5] * w.z, m[6] * w.x + m[7] * w.y + m[8] * w.z);
+    const float theta = pacosf(clampf(wi.z, -1.f, 1.f));
+    float phi = patan2f(wi.y, wi.x);
+    if (phi < 0) phi = phi + 2 * kPi;
+    const float sinTheta = psinf(theta);
+    if (sinTheta == 0) return 0;
+    const float px = phi * (0.5f * kInvPi), py = theta * kInvPi;
+    int iu = (int)(px * 2), iv = (int)(py * 2);
+    iu = iu < 0 ? 0 : (iu > 1 ? 1 : iu);
+    iv = iv < 0 ? 0 : (iv > 1 ? 1 : iv);
+    return (dl.dist[6 * iv + iu] / dl.dist[12 + 5]) / (2 * kPi * kPi * sinTheta);
+}
+
 // `rec` is the light's record out of DScene::lightRecs, lightNum its index in Scene::lights.
 template <bool SPH = true>
 PB2_HD DLightSample sampleLight(const DScene &sc, int lightNum, const pb2_light &l, const TriRec &rec, const DInteraction &ref, V2 u) {
+    if (sc.deltaLights && l.type == PB2_LIGHT_INFINITE) return sampleInfiniteLight(l, sc.deltaLights[lightNum], ref.p, u);
     if (sc.deltaLights && l.type != PB2_LIGHT_AREA) return sampleDeltaLight(l, sc.deltaLights[lightNum], ref.p);
     DLightSample s;
     if (SPH && (rec.flags & LEAF_SPHERE)) s = sampleSphereLight(sc, l, ref, u);
@@ -1197,7 +1283,8 @@ PB2_HD DLightSample sampleLight(const DScene &sc, int lightNum, const pb2_light 
 // DiffuseAreaLight::Pdf_Li -> Shape::Pdf(ref, wi) (shape.cpp:78-95): re-intersect the light's own
 // shape with the spawned ray and convert the area density to solid angle.
 template <bool SPH = true>
-PB2_HD float lightPdfLi(const DScene &sc, const pb2_light &l, const TriRec &rec, const DInteraction &ref, V3 wi) {
+PB2_HD float lightPdfLi(const DScene &sc, const pb2_light &l, const TriRec &rec, const DInteraction &ref, V3 wi, int lightNum = -1) {
+    if (sc.deltaLights && l.type == PB2_LIGHT_INFINITE) return infinitePdfLi(sc.deltaLights[lightNum], wi);
     if (SPH && (rec.flags & LEAF_SPHERE)) return sphereLightPdf(sc, l, ref, wi);
     DRay ray = spawnRay(ref, wi);
     const TriVerts t = rec.tv;

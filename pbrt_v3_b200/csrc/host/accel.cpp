@@ -458,8 +458,22 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
             bool inside = center.x >= wb.pMin.x && center.x <= wb.pMax.x && center.y >= wb.pMin.y && center.y <= wb.pMax.y &&
                           center.z >= wb.pMin.z && center.z <= wb.pMax.z;
             dl.world_radius = inside ? Distance(center, wb.pMax) : 0;
+        } else if (const InfiniteAreaLight *il = dynamic_cast<const InfiniteAreaLight *>(lights[i].get())) {
+            rec.type = PB2_LIGHT_INFINITE;
+            for (int c = 0; c < 3; ++c) rec.L[c] = il->L.c[c];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) {
+                    dl.world_to_light[3 * r + c] = il->WorldToLight.GetMatrix().m[r][c];
+                    dl.light_to_world[3 * r + c] = il->LightToWorld.GetMatrix().m[r][c];
+                }
+            // InfiniteAreaLight::Preprocess (infinite.h:61-63): the bounding sphere of Scene::WorldBound, as for DistantLight
+            Bounds3f wb = bvh.WorldBound();
+            Point3f center = (wb.pMin + wb.pMax) / 2;
+            bool inside = center.x >= wb.pMin.x && center.x <= wb.pMax.x && center.y >= wb.pMin.y && center.y <= wb.pMax.y &&
+                          center.z >= wb.pMin.z && center.z <= wb.pMax.z;
+            dl.world_radius = inside ? Distance(center, wb.pMax) : 0;
         } else {
-            Error("Light type outside the GPU path's scope (diffuse area, point, spot, distant; SURVEY.md §2 rows 14-15)");
+            Error("Light type outside the GPU path's scope (diffuse area, point, spot, distant, infinite; SURVEY.md §2 rows 14-15)");
             return nullptr;
         }
         fs->lights[i] = rec;

@@ -401,8 +401,10 @@ void pbrtLightSource(const std::string &name, const ParamSet &params) {
         lt = CreateSpotLight(curTransform, params);
     else if (name == "distant")
         lt = CreateDistantLight(curTransform, params);
-    else if (name == "goniometric" || name == "projection" || name == "infinite" || name == "exinfinite")
-        Error("LightSource \"%s\" is outside the GPU path's scope (point, spot, distant and diffuse area lights); skipped", name.c_str());
+    else if (name == "infinite" || name == "exinfinite")
+        lt = CreateInfiniteLight(curTransform, params);
+    else if (name == "goniometric" || name == "projection")
+        Error("LightSource \"%s\" is outside the GPU path's scope (point, spot, distant, infinite and diffuse area lights); skipped", name.c_str());
     else
         Error("LightSource: light type \"%s\" unknown.", name.c_str());
     params.ReportUnused();

@@ -133,6 +133,19 @@ std::shared_ptr<DistantLight> CreateDistantLight(const Transform &light2world, c
     Vector3f dir = from - to;
     return std::make_shared<DistantLight>(light2world, L * sc, dir);
 }
+// CreateInfiniteLight (infinite.cpp:177-188).  "mapname" would need the image readers (imageio.cpp ReadImage) and the
+// MIP-map pyramid, which are outside the path's scope: reported, and the light is created without the map like the
+// reference does when the file cannot be read.
+std::shared_ptr<InfiniteAreaLight> CreateInfiniteLight(const Transform &light2world, const ParamSet &paramSet) {
+    Spectrum L = paramSet.FindOneSpectrum("L", Spectrum(1.0));
+    Spectrum sc = paramSet.FindOneSpectrum("scale", Spectrum(1.0));
+    std::string texmap = paramSet.FindOneString("mapname", "");
+    paramSet.FindOneInt("samples", paramSet.FindOneInt("nsamples", 1));
+    if (texmap != "")
+        Error("LightSource \"infinite\": environment map \"%s\" is outside the GPU path's scope (constant radiance only); using \"L\" alone",
+              texmap.c_str());
+    return std::make_shared<InfiniteAreaLight>(light2world, L * sc);
+}
 static void rejectTextures(const TextureParams &mp, const char *what, std::initializer_list<const char *> names) {
     for (const char *n : names)
         if (mp.IsVaryingTexture(n))

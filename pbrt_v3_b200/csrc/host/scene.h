@@ -225,6 +225,14 @@ class DistantLight : public Light {
     const Vector3f wWorld;   // LightToWorld(w) before normalisation
     const Vector3f wLight;
 };
+// infinite.h:49-83 without a texture map: constant radiance from every direction
+class InfiniteAreaLight : public Light {
+  public:
+    InfiniteAreaLight(const Transform &LightToWorld, const Spectrum &L) : LightToWorld(LightToWorld), WorldToLight(Inverse(LightToWorld)), L(L) {}
+    const Transform LightToWorld, WorldToLight;
+    const Spectrum L;
+};
+std::shared_ptr<InfiniteAreaLight> CreateInfiniteLight(const Transform &light2world, const ParamSet &paramSet);
 std::shared_ptr<PointLight> CreatePointLight(const Transform &light2world, const ParamSet &paramSet);
 std::shared_ptr<SpotLight> CreateSpotLight(const Transform &light2world, const ParamSet &paramSet);
 std::shared_ptr<DistantLight> CreateDistantLight(const Transform &light2world, const ParamSet &paramSet);

@@ -1479,7 +1479,7 @@ static int createSceneOnCurrentDevice(const pb2_scene_desc *d, pb2_scene **out) 
     if ((rc = upload(s, d->lights, (size_t)d->n_lights, &sc.lights))) return rc;
     sc.deltaLights = nullptr;
     for (int i = 0; i < d->n_lights; ++i) {
-        if (d->lights[i].type < PB2_LIGHT_AREA || d->lights[i].type > PB2_LIGHT_DISTANT) return setError(PB2_ERR_INVALID, "unknown light type");
+        if (d->lights[i].type < PB2_LIGHT_AREA || d->lights[i].type > PB2_LIGHT_INFINITE) return setError(PB2_ERR_INVALID, "unknown light type");
         if (d->lights[i].type != PB2_LIGHT_AREA && !d->delta_lights) return setError(PB2_ERR_INVALID, "a delta light without delta_lights");
     }
     std::vector<DDeltaLight> deltaLights;
@@ -1497,6 +1497,45 @@ static int createSceneOnCurrentDevice(const pb2_scene_desc *d, pb2_scene **out) 
             o.cosFalloffStart = std::cos(radPerDeg * in.falloff_start_deg);
             o.worldRadius = in.world_radius;
             for (int k = 0; k < 9; ++k) o.worldToLight[k] = in.world_to_light[k];
+            for (int k = 0; k < 9; ++k) o.lightToWorld[k] = in.light_to_world[k];
+            if (d->lights[i].type == PB2_LIGHT_INFINITE) {
+                if (sc.nInfinite >= 4) return setError(PB2_ERR_UNSUPPORTED, "more than four infinite lights");
+                sc.infinite[sc.nInfinite++] = i;
+                // The sampling distribution of the constructor (infinite.cpp:61-82) for the 1 x 1 map: a 2 x 2 image of
+                // Lmap->Lookup((u + .5) / 2, (v + .5) / 2, width .25).y() * sin(Pi (v + .5) / 2); the look-up is
+                // MIPMap::triangle(0, st) (level = log2(.25) < 0), evaluated in float as written (mipmap.h:264-274)
+                const pb2_light &pl = d->lights[i];
+                float img[4];
+                for (int v = 0; v < 2; ++v) {
+                    const float vp = (v + .5f) / (float)2;
+                    const float sinTheta = std::sin(3.14159265358979323846f * (v + .5f) / 2);
+                    for (int u = 0; u < 2; ++u) {
+                        const float up = (u + .5f) / (float)2;
+                        const float s_ = up * 1 - 0.5f, t_ = vp * 1 - 0.5f;
+                        const int s0 = (int)std::floor(s_), t0 = (int)std::floor(t_);
+                        const float ds = s_ - s0, dt = t_ - t0;
+                        float rgb[3];
+                        for (int c = 0; c < 3; ++c)
+                            rgb[c] = ((1 - ds) * (1 - dt)) * pl.L[c] + ((1 - ds) * dt) * pl.L[c] + (ds * (1 - dt)) * pl.L[c] + (ds * dt) * pl.L[c];
+                        img[u + v * 2] = 0.212671f * rgb[0] + 0.715160f * rgb[1] + 0.072169f * rgb[2];   // RGBSpectrum::y()
+                        img[u + v * 2] *= sinTheta;
+                    }
+                }
+                auto dist1D = [](const float *f, int n, float *rec) {   // Distribution1D ctor (sampling.h:57-70)
+                    for (int k = 0; k < n; ++k) rec[k] = f[k];
+                    float *cdf = rec + n;
+                    cdf[0] = 0;
+                    for (int k = 1; k < n + 1; ++k) cdf[k] = cdf[k - 1] + f[k - 1] / n;
+                    const float funcInt = cdf[n];
+                    if (funcInt == 0) for (int k = 1; k < n + 1; ++k) cdf[k] = float(k) / float(n);
+                    else for (int k = 1; k < n + 1; ++k) cdf[k] /= funcInt;
+                    rec[2 * n + 1] = funcInt;
+                };
+                dist1D(img, 2, o.dist);
+                dist1D(img + 2, 2, o.dist + 6);
+                const float marginal[2] = {o.dist[5], o.dist[6 + 5]};
+                dist1D(marginal, 2, o.dist + 12);
+            }
         }
         if ((rc = upload(s, deltaLights.data(), deltaLights.size(), &sc.deltaLights))) return rc;
     }
@@ -1565,6 +1604,8 @@ static int createSceneOnCurrentDevice(const pb2_scene_desc *d, pb2_scene **out) 
                         p[c] = ((l.L[c] * 2) * Pi) * (1 - .5f * (deltaLights[i].cosFalloffStart + deltaLights[i].cosTotalWidth));
                     else if (l.type == PB2_LIGHT_DISTANT)   // distant.cpp:61-63: L * Pi * worldRadius * worldRadius
                         p[c] = ((l.L[c] * Pi) * deltaLights[i].worldRadius) * deltaLights[i].worldRadius;
+                    else if (l.type == PB2_LIGHT_INFINITE)  // infinite.cpp:84-88: Pi * r * r * Lookup((.5, .5), .5) = the texel itself
+                        p[c] = ((Pi * deltaLights[i].worldRadius) * deltaLights[i].worldRadius) * l.L[c];
                     else
                         p[c] = ((s2 * l.L[c]) * l.area) * Pi;
                 }

@@ -21,7 +21,8 @@ from test_oracle import load_scene, same_bvh, tessellated_sphere_scene
 
 pytestmark = pytest.mark.gpu
 
-SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass", "lights", "params"]
+SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass", "lights", "params",
+               "envlight"]
 
 
 def li_ok(got, want):

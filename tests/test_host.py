@@ -276,7 +276,7 @@ def test_light_source_directives(pb):
     c = (nodes["bmin"][0].astype(f32) + nodes["bmax"][0].astype(f32)) / f32(2)
     assert abs(d.delta_lights[4].world_radius - np.linalg.norm(c - nodes["bmax"][0])) < 1e-5
     before = pb.lib().pb2h_error_count()
-    hs = pb.HostScene.from_string('WorldBegin\nLightSource "infinite"\nShape "sphere"\nWorldEnd\n')
+    hs = pb.HostScene.from_string('WorldBegin\nLightSource "goniometric"\nShape "sphere"\nWorldEnd\n')
     assert pb.lib().pb2h_error_count() > before and hs.desc.contents.n_lights == 0
 
 
@@ -635,3 +635,21 @@ def test_radical_inverse_digit_tables_equal_the_digit_loop(pb):
     assert L.pb2_debug_radical_inverse_tables(pb.ptr(idx), pb.ptr(dim), len(idx), pb.ptr(a), pb.ptr(b)) == 0
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert 0 <= a.min() and a.max() < 1
+
+
+def test_infinite_light_is_flattened_with_its_transform(pb):
+    """LightSource "infinite" (constant radiance; src/lights/infinite.cpp:177-188 for the parameters): first in Scene::lights,
+    L * scale, both 3x3 matrices of the CTM, the world radius of Preprocess; an environment map is reported, not silently used."""
+    hs = pb.HostScene.from_file(os.path.join(SCENES, "envlight.pbrt"))
+    d = hs.desc.contents
+    assert d.n_lights == 3 and [d.lights[i].type for i in range(3)] == [pb.PB2_LIGHT_INFINITE, pb.PB2_LIGHT_AREA, pb.PB2_LIGHT_AREA]
+    assert np.allclose(list(d.lights[0].L), [.45 * 1.2, .6, .9 * .8]) and d.lights[0].prim == -1
+    dl = d.delta_lights[0]
+    l2w, w2l = np.array(dl.light_to_world).reshape(3, 3), np.array(dl.world_to_light).reshape(3, 3)
+    assert np.allclose(l2w @ w2l, np.eye(3), atol=1e-6) and not np.allclose(l2w, np.eye(3))
+    nodes = hs.nodes()
+    assert np.isclose(dl.world_radius, 0.5 * np.linalg.norm(nodes["bmax"][0] - nodes["bmin"][0]), rtol=1e-6)
+    text = open(os.path.join(SCENES, "envlight.pbrt")).read().replace('"rgb L" [.45 .6 .9]', '"rgb L" [.45 .6 .9] "string mapname" "sky.exr"')
+    before = pb.lib().pb2h_error_count()
+    hs2 = pb.HostScene.from_string(text)
+    assert pb.lib().pb2h_error_count() == before + 1 and hs2.desc.contents.lights[0].type == pb.PB2_LIGHT_INFINITE
