@@ -29,11 +29,12 @@
 extern "C" {
 #endif
 
-#define PB2_ABI_VERSION 9   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc;
+#define PB2_ABI_VERSION 10   /* 2: instancing block in pb2_scene_desc; 3: mirror / glass fields in pb2_material; 4: filter type in pb2_film_desc;
                              * 5: uber / metal fields in pb2_material (128 bytes); 6: point / spot / distant lights
                              * (pb2_light.type, pb2_scene_desc.delta_lights); 7: pb2_trace_wavefront, kernel-selector flags;
                              * 8: pb2_dist_* (NCCL film reduce inside the render calls), pb2_host_alloc;
-                             * 9: PB2_LIGHT_INFINITE, pb2_delta_light.light_to_world (112 bytes) */
+                             * 9: PB2_LIGHT_INFINITE, pb2_delta_light.light_to_world (112 bytes);
+                             * 10: image textures (pb2_texture, pb2_material.tex, pb2_mesh.alpha_tex / shadow_alpha_tex) */
 
 typedef enum pb2_status {
     PB2_OK = 0,
@@ -71,8 +72,35 @@ typedef struct pb2_mesh {
     int32_t has_n, has_uv, has_s;
     int32_t reverse_orientation;
     int32_t transform_swaps_handedness;
+    /* TriangleMesh::alphaMask / shadowAlphaMask (triangle.h:61, triangle.cpp:333-338, 531-569): 0 = none, else 1 + index
+     * into pb2_scene_desc.textures of a one-channel texture; a hit where it evaluates to exactly 0 is no hit
+     * (alpha_tex: Intersect and IntersectP; shadow_alpha_tex: IntersectP only). */
+    int32_t alpha_tex, shadow_alpha_tex;
     int32_t pad;
 } pb2_mesh;
+
+/* An ImageTexture (src/textures/imagemap.h:72-128) with a UVMapping2D (src/core/texture.cpp:93-99), described by what its
+ * constructor hands to MIPMap (src/core/mipmap.h:112-119): the texels AFTER ReadImage, the flip in y (imagemap.cpp:77-84) and
+ * convertIn (scale, inverse gamma, luminance for one-channel textures; imagemap.h:97-106).  The library resamples to a power
+ * of two and builds the pyramid as the MIPMap constructor does (mipmap.h:121-203) and filters as MIPMap::Lookup does
+ * (trilinear: mipmap.h:227-245; EWA: mipmap.h:263-350).  Texture differentials come from the camera ray's differentials
+ * (perspective.cpp:117-144, scaled by 1/sqrt(spp), integrator.cpp:273-274) through SurfaceInteraction::ComputeDifferentials
+ * (interaction.cpp:101-147); rays after the first bounce carry none (path.cpp:130-131), as in the reference. */
+enum { PB2_WRAP_REPEAT = 0, PB2_WRAP_BLACK = 1, PB2_WRAP_CLAMP = 2 };
+typedef struct pb2_texture {
+    int32_t channels;        /* 1: ImageTexture<Float, Float>; 3: ImageTexture<RGBSpectrum, Spectrum> */
+    int32_t width, height;   /* resolution of texels[] (any size; not yet a power of two) */
+    int32_t wrap;            /* PB2_WRAP_* ("wrap") */
+    int32_t do_trilinear;    /* "trilinear" */
+    float max_anisotropy;    /* "maxanisotropy" */
+    float su, sv, du, dv;    /* UVMapping2D: "uscale" "vscale" "udelta" "vdelta" */
+    int32_t pad[2];
+    const float *texels;     /* channels * width * height, row 0 is t = 0 */
+} pb2_texture;
+
+/* slots of pb2_material.tex: which parameter a texture replaces */
+enum { PB2_TEX_KD = 0, PB2_TEX_KS = 1, PB2_TEX_KR = 2, PB2_TEX_KT = 3, PB2_TEX_OPACITY = 4, PB2_TEX_SIGMA = 5, PB2_TEX_ROUGHNESS = 6,
+       PB2_TEX_UROUGHNESS = 7, PB2_TEX_VROUGHNESS = 8, PB2_TEX_ETA = 9, PB2_TEX_METAL_ETA = 10, PB2_TEX_METAL_K = 11, PB2_TEX_SLOTS = 12 };
 
 /* Sphere (src/shapes/sphere.h:47-77). Matrices are row-major 4x4 (Matrix4x4::m). */
 typedef struct pb2_sphere {
@@ -109,6 +137,11 @@ typedef struct pb2_material {
     float metal_eta[3];
     float metal_k[3];
     int32_t pad3[2];
+    /* tex[PB2_TEX_*]: 0 = the constant above, else 1 + index into pb2_scene_desc.textures of the texture that is evaluated
+     * at every shaded point instead (Kd->Evaluate(*si) etc., matte.cpp:53-54); spectrum parameters take three-channel
+     * textures, float parameters one-channel ones.  The u / v roughness slots hold what the material's fall-back rules
+     * resolve to ("uroughness" else "roughness", uber.cpp:82-85). */
+    int32_t tex[12];
 } pb2_material;
 
 /* One entry of Scene::lights, in the scene's order.  PB2_LIGHT_AREA: a DiffuseAreaLight (src/lights/diffuse.h:49-79)
@@ -207,6 +240,10 @@ typedef struct pb2_scene_desc {
     int64_t n_bvh_prims;          /* length of bvh_prims when n_bvhs > 0 */
     /* n_lights entries, read for lights[i].type != PB2_LIGHT_AREA; NULL when every light is an area light */
     const pb2_delta_light *delta_lights;
+    /* image textures named by pb2_material.tex and pb2_mesh.alpha_tex (NULL / 0: a scene of constant textures) */
+    int32_t n_textures;
+    int32_t pad_textures;
+    const pb2_texture *textures;
 } pb2_scene_desc;
 
 /* PerspectiveCamera (src/cameras/perspective.cpp:45-67, 95-144). */
@@ -417,6 +454,16 @@ int pb2_halton_samples(const pb2_film_desc *film, const pb2_path_params *params,
 /* Distribution1D of SpatialLightDistribution::Lookup(p) (src/core/lightdistrib.cpp:141-230):
  * for each point writes n_lights func values followed by n_lights+1 cdf values. HOST pointers. */
 int pb2_light_distribution(pb2_scene *scene, const float *points_xyz, int64_t n, float *out);
+
+/* The MIP pyramid the library builds for one texture (the MIPMap constructor, src/core/mipmap.h:112-203: Lanczos
+ * resampling to a power of two, then box-filtered levels).  Host code only - no device needed.  *n_levels, *w and *h
+ * (resolution of `level`) are always written; `out` (channels * w * h floats, row-major) may be NULL.  Parity/debug. */
+int pb2_texture_pyramid(const pb2_texture *texture, int32_t level, int32_t *n_levels, int32_t *w, int32_t *h, float *out);
+
+/* MIPMap::Lookup(st, dst0, dst1) (mipmap.h:260-287: trilinear or EWA as the texture says) for a batch, evaluated on the
+ * device with the code the shade kernel uses.  st: 2 floats per look-up, dst: 4 (dst0.x dst0.y dst1.x dst1.y), out: 3
+ * (one-channel textures repeat their value).  The UVMapping2D parameters of the texture are NOT applied.  HOST pointers. */
+int pb2_texture_lookup(const pb2_texture *texture, int64_t n, const float *st, const float *dst, float *out);
 
 /* The lower half of BVHAccel::HLBVHBuild on the device (src/accelerators/bvh.cpp:404-470): Morton codes of the primitive
  * centroids over the centroid bounds (bvh.cpp:408-423), the stable sort by the 30-bit code (RadixSort, bvh.cpp:139-180),

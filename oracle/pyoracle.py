@@ -83,6 +83,24 @@ class Oracle:
         self._f("camera_derived")(camera, film, ptr(r2c), ptr(dx), ptr(dy))
         return r2c, dx, dy
 
+    def texture_pyramid(self, texture):
+        """MIPMap::pyramid of the reference for one pb2_texture: list of (h, w, channels) arrays (reference only)."""
+        import pbrt_v3_b200 as pb
+        fn = self._f("texture_pyramid")
+        fn.argtypes = [C.POINTER(pb.Texture), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]
+        return pb.texture_pyramid(texture, fn)
+
+    def texture_lookup(self, texture, st, dst):
+        """MIPMap::Lookup(st, dst0, dst1) of the reference for a batch (reference only)."""
+        import pbrt_v3_b200 as pb
+        st = np.ascontiguousarray(st, np.float32)
+        dst = np.ascontiguousarray(dst, np.float32)
+        out = np.zeros((len(st), 3), np.float32)
+        fn = self._f("texture_lookup")
+        fn.argtypes = [C.POINTER(pb.Texture), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        fn(C.byref(texture), len(st), ptr(st), ptr(dst), ptr(out))
+        return out
+
     def copper_rgb(self):
         """(eta, k) RGB of the metal material's default copper spectra (reference only)."""
         eta = np.zeros(3, np.float32)

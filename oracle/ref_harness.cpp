@@ -73,6 +73,8 @@
 #include "shapes/sphere.h"
 #include "shapes/triangle.h"
 #include "textures/constant.h"
+#include "mipmap.h"
+#include "texture.h"
 #undef private
 #undef protected
 
@@ -199,15 +201,110 @@ uint64_t parseStat(const std::string &text, const char *label) {
 
 }  // namespace
 
+// One pb2_texture as a reference texture: the reference's own MIPMap (pyramid construction, trilinear / EWA look-up) behind
+// the reference's UVMapping2D, evaluated the way ImageTexture::Evaluate does (imagemap.h:83-89).  ImageTexture itself is
+// not used because its constructor reads a file (ReadImage: imageio.cpp needs OpenEXR and is not compiled here); the
+// description already holds what ImageTexture::GetTexture would hand to the MIPMap constructor.
+template <typename Tmem, typename Tret>
+class DescImageTexture : public Texture<Tret> {
+  public:
+    explicit DescImageTexture(const pb2_texture &t) : mapping(new UVMapping2D(t.su, t.sv, t.du, t.dv)) {
+        std::vector<Tmem> texels((size_t)t.width * t.height);
+        for (size_t i = 0; i < texels.size(); ++i) texels[i] = load(t.texels + i * t.channels);
+        const ImageWrap wrap = t.wrap == PB2_WRAP_BLACK ? ImageWrap::Black : t.wrap == PB2_WRAP_CLAMP ? ImageWrap::Clamp : ImageWrap::Repeat;
+        mipmap.reset(new MIPMap<Tmem>(Point2i(t.width, t.height), texels.data(), t.do_trilinear != 0, t.max_anisotropy, wrap));
+    }
+    Tret Evaluate(const SurfaceInteraction &si) const override {
+        Vector2f dstdx, dstdy;
+        Point2f st = mapping->Map(si, &dstdx, &dstdy);
+        return convertOut(mipmap->Lookup(st, dstdx, dstdy));
+    }
+
+  private:
+    static Float load(const float *p) { return *p; }
+    static Float convertOut(Float v) { return v; }
+    static Spectrum convertOut(const RGBSpectrum &from) {   // imagemap.h:107-111
+        Float rgb[3];
+        from.ToRGB(rgb);
+        return Spectrum::FromRGB(rgb);
+    }
+    std::unique_ptr<TextureMapping2D> mapping;
+    std::unique_ptr<MIPMap<Tmem>> mipmap;
+};
+template <>
+DescImageTexture<RGBSpectrum, Spectrum>::DescImageTexture(const pb2_texture &t) : mapping(new UVMapping2D(t.su, t.sv, t.du, t.dv)) {
+    std::vector<RGBSpectrum> texels((size_t)t.width * t.height);
+    for (size_t i = 0; i < texels.size(); ++i) texels[i] = RGBSpectrum::FromRGB(t.texels + 3 * i);
+    const ImageWrap wrap = t.wrap == PB2_WRAP_BLACK ? ImageWrap::Black : t.wrap == PB2_WRAP_CLAMP ? ImageWrap::Clamp : ImageWrap::Repeat;
+    mipmap.reset(new MIPMap<RGBSpectrum>(Point2i(t.width, t.height), texels.data(), t.do_trilinear != 0, t.max_anisotropy, wrap));
+}
+
 extern "C" {
 
 const char *ref_kind(void) { return "reference"; }
+
+// MIPMap<T>::pyramid[level] of the reference for one texture description (row-major, channels floats per texel)
+int ref_texture_pyramid(const pb2_texture *t, int level, int *n_levels, int *w, int *h, float *out) {
+    setThreads(0);
+    const ImageWrap wrap = t->wrap == PB2_WRAP_BLACK ? ImageWrap::Black : t->wrap == PB2_WRAP_CLAMP ? ImageWrap::Clamp : ImageWrap::Repeat;
+    const size_t n = (size_t)t->width * t->height;
+    if (t->channels == 1) {
+        MIPMap<Float> mm(Point2i(t->width, t->height), t->texels, t->do_trilinear != 0, t->max_anisotropy, wrap);
+        *n_levels = mm.Levels();
+        if (level < 0 || level >= mm.Levels()) return 1;
+        *w = mm.pyramid[level]->uSize();
+        *h = mm.pyramid[level]->vSize();
+        if (out)
+            for (int y = 0; y < *h; ++y)
+                for (int x = 0; x < *w; ++x) out[(size_t)y * *w + x] = (*mm.pyramid[level])(x, y);
+    } else {
+        std::vector<RGBSpectrum> texels(n);
+        for (size_t i = 0; i < n; ++i) texels[i] = RGBSpectrum::FromRGB(t->texels + 3 * i);
+        MIPMap<RGBSpectrum> mm(Point2i(t->width, t->height), texels.data(), t->do_trilinear != 0, t->max_anisotropy, wrap);
+        *n_levels = mm.Levels();
+        if (level < 0 || level >= mm.Levels()) return 1;
+        *w = mm.pyramid[level]->uSize();
+        *h = mm.pyramid[level]->vSize();
+        if (out)
+            for (int y = 0; y < *h; ++y)
+                for (int x = 0; x < *w; ++x) (*mm.pyramid[level])(x, y).ToRGB(out + 3 * ((size_t)y * *w + x));
+    }
+    return 0;
+}
+// MIPMap<T>::Lookup(st, dst0, dst1) of the reference for a batch (st: 2 floats, dst: 4, out: 3 per look-up)
+int ref_texture_lookup(const pb2_texture *t, int64_t n, const float *st, const float *dst, float *out) {
+    setThreads(0);
+    const ImageWrap wrap = t->wrap == PB2_WRAP_BLACK ? ImageWrap::Black : t->wrap == PB2_WRAP_CLAMP ? ImageWrap::Clamp : ImageWrap::Repeat;
+    const size_t nt = (size_t)t->width * t->height;
+    if (t->channels == 1) {
+        MIPMap<Float> mm(Point2i(t->width, t->height), t->texels, t->do_trilinear != 0, t->max_anisotropy, wrap);
+        for (int64_t i = 0; i < n; ++i) {
+            Float v = mm.Lookup(Point2f(st[2 * i], st[2 * i + 1]), Vector2f(dst[4 * i], dst[4 * i + 1]), Vector2f(dst[4 * i + 2], dst[4 * i + 3]));
+            out[3 * i] = out[3 * i + 1] = out[3 * i + 2] = v;
+        }
+    } else {
+        std::vector<RGBSpectrum> texels(nt);
+        for (size_t i = 0; i < nt; ++i) texels[i] = RGBSpectrum::FromRGB(t->texels + 3 * i);
+        MIPMap<RGBSpectrum> mm(Point2i(t->width, t->height), texels.data(), t->do_trilinear != 0, t->max_anisotropy, wrap);
+        for (int64_t i = 0; i < n; ++i)
+            mm.Lookup(Point2f(st[2 * i], st[2 * i + 1]), Vector2f(dst[4 * i], dst[4 * i + 1]), Vector2f(dst[4 * i + 2], dst[4 * i + 3])).ToRGB(out + 3 * i);
+    }
+    return 0;
+}
 
 void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split_method) {
     std::unique_ptr<RefScene> rs(new RefScene);
     rs->transforms.emplace_back(new Transform());
     const Transform *identity = rs->transforms.back().get();
     rs->lightStrategy = d->light_strategy;
+    // image textures (the MIPMap constructor runs ParallelFors: the thread pool must exist, parallel.cpp:186)
+    std::vector<std::shared_ptr<Texture<Float>>> floatTex(d->n_textures);
+    std::vector<std::shared_ptr<Texture<Spectrum>>> specTex(d->n_textures);
+    if (d->n_textures > 0) setThreads(0);
+    for (int i = 0; i < d->n_textures; ++i) {
+        if (d->textures[i].channels == 1) floatTex[i] = std::make_shared<DescImageTexture<Float, Float>>(d->textures[i]);
+        else specTex[i] = std::make_shared<DescImageTexture<RGBSpectrum, Spectrum>>(d->textures[i]);
+    }
 
     // shapes
     std::vector<std::vector<std::shared_ptr<Shape>>> meshShapes(d->n_meshes);
@@ -222,7 +319,8 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
         // Vertices/normals in the description are already in world space, so the mesh is rebuilt
         // under the identity transform (which maps every finite float to itself).
         meshShapes[m] = CreateTriangleMesh(identity, identity, pm.reverse_orientation != 0, pm.n_tris, local.data(),
-                                           pm.n_vertices, P, S, N, UV, nullptr, nullptr, nullptr);
+                                           pm.n_vertices, P, S, N, UV, pm.alpha_tex ? floatTex[pm.alpha_tex - 1] : nullptr,
+                                           pm.shadow_alpha_tex ? floatTex[pm.shadow_alpha_tex - 1] : nullptr, nullptr);
         for (auto &s : meshShapes[m])
             const_cast<bool &>(s->transformSwapsHandedness) = pm.transform_swaps_handedness != 0;
     }
@@ -240,44 +338,43 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
         const_cast<bool &>(sp->transformSwapsHandedness) = ps.transform_swaps_handedness != 0;
         sphereShapes[s] = sp;
     }
-    // materials
+    // materials: every parameter is the constant of the record, or the image texture its slot names
     std::vector<std::shared_ptr<Material>> materials(d->n_materials);
     for (int i = 0; i < d->n_materials; ++i) {
         const pb2_material &pm = d->materials[i];
-        auto kd = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kd));
+        auto spec = [&](int slot, const float *c) -> std::shared_ptr<Texture<Spectrum>> {
+            if (pm.tex[slot]) return specTex[pm.tex[slot] - 1];
+            return std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(c));
+        };
+        auto flt = [&](int slot, float v) -> std::shared_ptr<Texture<Float>> {
+            if (pm.tex[slot]) return floatTex[pm.tex[slot] - 1];
+            return std::make_shared<ConstantTexture<Float>>(v);
+        };
+        auto kd = spec(PB2_TEX_KD, pm.kd);
         if (pm.type == PB2_MAT_MATTE) {
-            auto sigma = std::make_shared<ConstantTexture<Float>>(pm.sigma);
-            materials[i] = std::make_shared<MatteMaterial>(kd, sigma, nullptr);
+            materials[i] = std::make_shared<MatteMaterial>(kd, flt(PB2_TEX_SIGMA, pm.sigma), nullptr);
         } else if (pm.type == PB2_MAT_PLASTIC) {
-            auto ks = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.ks));
-            auto rough = std::make_shared<ConstantTexture<Float>>(pm.roughness);
-            materials[i] = std::make_shared<PlasticMaterial>(kd, ks, rough, nullptr, pm.remap_roughness != 0);
+            materials[i] = std::make_shared<PlasticMaterial>(kd, spec(PB2_TEX_KS, pm.ks), flt(PB2_TEX_ROUGHNESS, pm.roughness), nullptr,
+                                                             pm.remap_roughness != 0);
         } else if (pm.type == PB2_MAT_MIRROR) {
-            auto kr = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kr));
-            materials[i] = std::make_shared<MirrorMaterial>(kr, nullptr);
+            materials[i] = std::make_shared<MirrorMaterial>(spec(PB2_TEX_KR, pm.kr), nullptr);
         } else if (pm.type == PB2_MAT_SUBSTRATE) {
-            auto ks = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.ks));
-            auto nu = std::make_shared<ConstantTexture<Float>>(pm.uroughness);
-            auto nv = std::make_shared<ConstantTexture<Float>>(pm.vroughness);
-            materials[i] = std::make_shared<SubstrateMaterial>(kd, ks, nu, nv, nullptr, pm.remap_roughness != 0);
+            materials[i] = std::make_shared<SubstrateMaterial>(kd, spec(PB2_TEX_KS, pm.ks), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
+                                                               flt(PB2_TEX_VROUGHNESS, pm.vroughness), nullptr, pm.remap_roughness != 0);
         } else if (pm.type == PB2_MAT_UBER) {
-            auto spec = [](const float *c) { return std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(c)); };
-            auto flt = [](float v) { return std::make_shared<ConstantTexture<Float>>(v); };
             // the description carries the resolved u / v roughness (pb2.h); "roughness" itself is then never read
-            materials[i] = std::make_shared<UberMaterial>(kd, spec(pm.ks), spec(pm.kr), spec(pm.kt), flt(pm.uroughness), flt(pm.uroughness),
-                                                          flt(pm.vroughness), spec(pm.opacity), flt(pm.eta), nullptr, pm.remap_roughness != 0);
+            materials[i] = std::make_shared<UberMaterial>(kd, spec(PB2_TEX_KS, pm.ks), spec(PB2_TEX_KR, pm.kr), spec(PB2_TEX_KT, pm.kt),
+                                                          flt(PB2_TEX_UROUGHNESS, pm.uroughness), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
+                                                          flt(PB2_TEX_VROUGHNESS, pm.vroughness), spec(PB2_TEX_OPACITY, pm.opacity),
+                                                          flt(PB2_TEX_ETA, pm.eta), nullptr, pm.remap_roughness != 0);
         } else if (pm.type == PB2_MAT_METAL) {
-            auto spec = [](const float *c) { return std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(c)); };
-            auto flt = [](float v) { return std::make_shared<ConstantTexture<Float>>(v); };
-            materials[i] = std::make_shared<MetalMaterial>(spec(pm.metal_eta), spec(pm.metal_k), flt(pm.uroughness), flt(pm.uroughness),
-                                                           flt(pm.vroughness), nullptr, pm.remap_roughness != 0);
+            materials[i] = std::make_shared<MetalMaterial>(spec(PB2_TEX_METAL_ETA, pm.metal_eta), spec(PB2_TEX_METAL_K, pm.metal_k),
+                                                           flt(PB2_TEX_UROUGHNESS, pm.uroughness), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
+                                                           flt(PB2_TEX_VROUGHNESS, pm.vroughness), nullptr, pm.remap_roughness != 0);
         } else if (pm.type == PB2_MAT_GLASS) {
-            auto kr = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kr));
-            auto kt = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pm.kt));
-            auto ur = std::make_shared<ConstantTexture<Float>>(pm.uroughness);
-            auto vr = std::make_shared<ConstantTexture<Float>>(pm.vroughness);
-            auto index = std::make_shared<ConstantTexture<Float>>(pm.eta);
-            materials[i] = std::make_shared<GlassMaterial>(kr, kt, ur, vr, index, nullptr, pm.remap_roughness != 0);
+            materials[i] = std::make_shared<GlassMaterial>(spec(PB2_TEX_KR, pm.kr), spec(PB2_TEX_KT, pm.kt), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
+                                                           flt(PB2_TEX_VROUGHNESS, pm.vroughness), flt(PB2_TEX_ETA, pm.eta), nullptr,
+                                                           pm.remap_roughness != 0);
         }
     }
     // primitives + lights (lights indexed as in the description = Scene::lights order)

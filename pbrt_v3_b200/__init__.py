@@ -27,7 +27,7 @@ PB2_OK, PB2_ERR_NO_DEVICE, PB2_ERR_CUDA, PB2_ERR_INVALID, PB2_ERR_UNSUPPORTED, P
 PB2_PRIM_TRIANGLE, PB2_PRIM_SPHERE, PB2_PRIM_INSTANCE = 0, 1, 2
 PB2_FILTER_BOX, PB2_FILTER_GAUSSIAN, PB2_FILTER_MITCHELL, PB2_FILTER_SINC, PB2_FILTER_TRIANGLE = 0, 1, 2, 3, 4
 PB2_MAT_NONE, PB2_MAT_MATTE, PB2_MAT_PLASTIC, PB2_MAT_MIRROR, PB2_MAT_GLASS, PB2_MAT_SUBSTRATE, PB2_MAT_METAL, PB2_MAT_UBER = range(8)
-PB2_ABI_VERSION = 9   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
+PB2_ABI_VERSION = 10   # include/pb2.h (tests/test_abi.py checks that header, this mirror and the library agree)
 PB2_LIGHTDIST_UNIFORM, PB2_LIGHTDIST_POWER, PB2_LIGHTDIST_SPATIAL = 0, 1, 2
 PB2_LIGHT_AREA, PB2_LIGHT_POINT, PB2_LIGHT_SPOT, PB2_LIGHT_DISTANT, PB2_LIGHT_INFINITE = 0, 1, 2, 3, 4
 
@@ -40,7 +40,8 @@ class BvhNode(C.Structure):
 class Mesh(C.Structure):
     _fields_ = [("first_tri", C.c_int32), ("n_tris", C.c_int32), ("first_vertex", C.c_int32),
                 ("n_vertices", C.c_int32), ("has_n", C.c_int32), ("has_uv", C.c_int32), ("has_s", C.c_int32),
-                ("reverse_orientation", C.c_int32), ("transform_swaps_handedness", C.c_int32), ("pad", C.c_int32)]
+                ("reverse_orientation", C.c_int32), ("transform_swaps_handedness", C.c_int32),
+                ("alpha_tex", C.c_int32), ("shadow_alpha_tex", C.c_int32), ("pad", C.c_int32)]
 
 
 class Sphere(C.Structure):
@@ -55,7 +56,18 @@ class Material(C.Structure):
                 ("roughness", C.c_float), ("remap_roughness", C.c_int32), ("pad", C.c_int32 * 2),
                 ("kr", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float), ("uroughness", C.c_float),
                 ("vroughness", C.c_float), ("opacity", C.c_float * 3), ("metal_eta", C.c_float * 3),
-                ("metal_k", C.c_float * 3), ("pad3", C.c_int32 * 2)]
+                ("metal_k", C.c_float * 3), ("pad3", C.c_int32 * 2), ("tex", C.c_int32 * 12)]
+
+
+PB2_WRAP_REPEAT, PB2_WRAP_BLACK, PB2_WRAP_CLAMP = 0, 1, 2
+(PB2_TEX_KD, PB2_TEX_KS, PB2_TEX_KR, PB2_TEX_KT, PB2_TEX_OPACITY, PB2_TEX_SIGMA, PB2_TEX_ROUGHNESS, PB2_TEX_UROUGHNESS,
+ PB2_TEX_VROUGHNESS, PB2_TEX_ETA, PB2_TEX_METAL_ETA, PB2_TEX_METAL_K) = range(12)
+
+
+class Texture(C.Structure):
+    _fields_ = [("channels", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("wrap", C.c_int32),
+                ("do_trilinear", C.c_int32), ("max_anisotropy", C.c_float), ("su", C.c_float), ("sv", C.c_float),
+                ("du", C.c_float), ("dv", C.c_float), ("pad", C.c_int32 * 2), ("texels", c_float_p)]
 
 
 class Light(C.Structure):
@@ -90,7 +102,8 @@ class SceneDesc(C.Structure):
                 ("n_lights", C.c_int32), ("lights", C.POINTER(Light)),
                 ("light_strategy", C.c_int32), ("spatial_max_voxels", C.c_int32),
                 ("n_instances", C.c_int32), ("n_bvhs", C.c_int32), ("instances", C.POINTER(Instance)),
-                ("bvhs", C.POINTER(Bvh)), ("n_bvh_prims", C.c_int64), ("delta_lights", C.POINTER(DeltaLight))]
+                ("bvhs", C.POINTER(Bvh)), ("n_bvh_prims", C.c_int64), ("delta_lights", C.POINTER(DeltaLight)),
+                ("n_textures", C.c_int32), ("pad_textures", C.c_int32), ("textures", C.POINTER(Texture))]
 
 
 class Camera(C.Structure):
@@ -184,6 +197,8 @@ def lib():
     L.pb2_li_samples.argtypes = [vp, C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), vp, vp, C.c_int64, vp, vp]
     L.pb2_halton_samples.argtypes = [C.POINTER(FilmDesc), C.POINTER(PathParams), vp, vp, vp, C.c_int64, vp]
     L.pb2_light_distribution.argtypes = [vp, vp, C.c_int64, vp]
+    L.pb2_texture_pyramid.argtypes = [C.POINTER(Texture), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
+    L.pb2_texture_lookup.argtypes = [C.POINTER(Texture), C.c_int64, vp, vp, vp]
     L.pb2h_parse_file.argtypes = [C.c_char_p, C.c_char_p]
     L.pb2h_parse_string.argtypes = [C.c_char_p]
     L.pb2h_synth_soup.argtypes = [C.c_int64, C.c_uint64, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
@@ -227,6 +242,31 @@ def init(device=None):
         return
     check(lib().pb2_init(device))
     _initialised_device = device
+
+
+def texture_pyramid(texture, fn=None):
+    """The levels of the MIP pyramid the library builds for one pb2_texture (host code, no device): list of (h, w, channels)
+    arrays, finest first.  fn: the entry point (default pb2_texture_pyramid; the oracle passes its own)."""
+    fn = fn or lib().pb2_texture_pyramid
+    nl, w, h = C.c_int32(), C.c_int32(), C.c_int32()
+    check(fn(C.byref(texture), 0, C.byref(nl), C.byref(w), C.byref(h), None))
+    levels = []
+    for lv in range(nl.value):
+        check(fn(C.byref(texture), lv, C.byref(nl), C.byref(w), C.byref(h), None))
+        a = np.zeros((h.value, w.value, texture.channels), np.float32)
+        check(fn(C.byref(texture), lv, C.byref(nl), C.byref(w), C.byref(h), ptr(a)))
+        levels.append(a)
+    return levels
+
+
+def texture_lookup(texture, st, dst):
+    """MIPMap::Lookup(st, dst0, dst1) on the device for a batch: st (n, 2), dst (n, 4) -> (n, 3)."""
+    init()
+    st = np.ascontiguousarray(st, np.float32)
+    dst = np.ascontiguousarray(dst, np.float32)
+    out = np.zeros((len(st), 3), np.float32)
+    check(lib().pb2_texture_lookup(C.byref(texture), len(st), ptr(st), ptr(dst), ptr(out)))
+    return out
 
 
 class HostScene:
@@ -389,6 +429,11 @@ class HostScene:
             any_hit = np.ascontiguousarray(any_hit, np.uint8)
         check(self.L.pb2_trace_wavefront(dev, ptr(rays), ptr(any_hit), len(rays), flags, ptr(out)))
         return out
+
+    def textures(self):
+        """The scene description's image textures (ctypes pb2_texture records; valid while this scene is the current one)."""
+        d = self.desc.contents
+        return [d.textures[i] for i in range(d.n_textures)]
 
     def li_samples(self, pixel_xy, sample_num, params=None):
         dev = self.device_scene()

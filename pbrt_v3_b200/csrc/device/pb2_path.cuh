@@ -30,6 +30,7 @@ struct DLane {
     DSampler smp;
     int bounces;
     bool specularBounce;
+    bool camRay;         // the ray to shade next is the camera ray itself: the only one with differentials (path.cpp:130-131)
     float etaScale;
     // pending at the current vertex
     bool doNEE, hasMis, hasNext;
@@ -49,6 +50,7 @@ PB2_HD void laneStartPath(DLane &ln, const DRay &ray, const DSampler &smp) {
     ln.smp = smp;
     ln.bounces = 0;
     ln.specularBounce = false;
+    ln.camRay = true;
     ln.etaScale = 1;
     ln.doNEE = ln.hasMis = ln.hasNext = false;
 }
@@ -85,12 +87,35 @@ PB2_HD void startMisOrFinish(DLane &ln) {
 // of the two direct-lighting rays.
 // LAZY = false compiles the deferral of the lazy light distribution out (the bench scene's shade kernel sits exactly at
 // its 128-register budget)
-template <bool SPH, bool SPEC = true, bool LAZY = true>
+// TEX = true evaluates image textures; tc then carries what the camera ray's differentials are rebuilt from.
+struct DTexCtx {
+    const DCamera *cam;
+    V2 pFilm;           // of this camera sample
+    float diffScale;    // 1 / sqrt(samples per pixel)
+};
+
+template <bool SPH, bool SPEC = true, bool LAZY = true, bool TEX = false>
 PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &pp, DLane &ln, bool found, const DHit &hit,
-                        float tMax) {
+                        float tMax, const DTexCtx *tc = nullptr) {
     DInteraction isect;
     int li = -1;
-    if (found) isect = hitInteraction<SPH>(sc, hit, ln.ray, tMax, &li);
+    DTexGeom tg;
+    DUvDiff uvDiff;
+    uvDiff.dudx = uvDiff.dvdx = uvDiff.dudy = uvDiff.dvdy = 0;
+    if (found) isect = hitInteraction<SPH>(sc, hit, ln.ray, tMax, &li, (TEX && tc) ? &tg : nullptr);
+    if (TEX && tc && sc.textures) {
+        if (found && ln.camRay) {
+            // the camera ray's differentials are a pure function of the camera sample: rebuilt here, not carried in the lane
+            V2 uLens = mk2(0, 0);
+            if (tc->cam->lensRadius > 0) {
+                DSampler ls = ln.smp;
+                ls.dim = 3;   // CameraSample::pLens (sampler.cpp:46-52)
+                uLens = get2D(h, ls);
+            }
+            const DRayDiff rd = cameraRayDifferentials(*tc->cam, tc->pFilm, uLens, tc->diffScale, ln.ray.o, ln.ray.d);
+            uvDiff = computeUvDifferentials(isect.p, isect.n, tg.dpdu, tg.dpdv, rd);
+        }
+    }
     const float *lazyDistrib = nullptr;
     if (LAZY && sc.lightDist.slots && found && ln.bounces < pp.maxDepth) {
         // lazy light distribution: look the voxel up before anything of the lane changes, so that a miss can hand the
@@ -114,8 +139,9 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
         ln.state = LS_IDLE;
         return;
     }
+    if (TEX) ln.camRay = false;   // every ray spawned from here on is a plain Ray
     DBsdf bsdf;
-    if (!makeBsdf<SPEC>(sc, isect, &bsdf)) {
+    if (!makeBsdf<SPEC, TEX>(sc, isect, &bsdf, TEX ? &uvDiff : nullptr)) {
         ln.ray = spawnRay(isect, ln.ray.d);  // null BSDF: skip the surface, same bounce count
         return;
     }
@@ -260,10 +286,10 @@ PB2_HD void lightAdvance(const DScene &sc, DLane &ln, bool found, const DHit &hi
 
 // Advance a lane after its current ray was traced.  Returns true when the path ended in this call
 // (ln.L is then final and ln.state == LS_IDLE).
-template <bool SPH, bool SPEC = true>
+template <bool SPH, bool SPEC = true, bool TEX = false>
 PB2_HD bool laneAdvance(const DScene &sc, const DHalton &h, const DPathParams &pp, DLane &ln, bool found, const DHit &hit,
-                        float tMax) {
-    if (ln.state == LS_PATH) shadeVertex<SPH, SPEC>(sc, h, pp, ln, found, hit, tMax);
+                        float tMax, const DTexCtx *tc = nullptr) {
+    if (ln.state == LS_PATH) shadeVertex<SPH, SPEC, true, TEX>(sc, h, pp, ln, found, hit, tMax, tc);
     else lightAdvance<SPH>(sc, ln, found, hit, tMax);
     return ln.state == LS_IDLE;
 }

@@ -28,6 +28,7 @@
 
 #include "pb2.h"
 #include "pb2_math.cuh"
+#include "pb2_texture.cuh"
 
 namespace pb2 {
 
@@ -37,6 +38,7 @@ enum : uint32_t {
     LEAF_FLIP = 4u,           // reverseOrientation ^ transformSwapsHandedness of the triangle's mesh
     LEAF_ATTR = 8u,           // the mesh has per-vertex N, S or UV: shading must go through the index buffer
     LEAF_INSTANCE = 16u,      // record describes a TransformedPrimitive: c.w = instance number
+    LEAF_ALPHA = 32u,         // the triangle's mesh has an alpha or shadow-alpha texture (triangle.cpp:333-338, 531-569)
 };
 enum : uint32_t {
     WIDE_LEAF = 0x80000000u,  // child reference: bits 0-26 primitivesOffset, bits 27-30 nPrimitives - 1
@@ -112,6 +114,10 @@ struct DScene {
     const DInstance *instances;   // nullptr: no object instancing in this scene
     int nInstances;
     DLightDist lightDist;
+    const DTexture *textures;     // image textures (pb2_texture.cuh); nullptr: a scene of constant textures
+    const float *texels;          // [0, 128): MIPMap::weightLut, then the pyramids
+    int nTextures;
+    int hasAlpha;                 // some mesh carries an alpha or shadow-alpha texture
 };
 
 struct DRay {
@@ -405,6 +411,26 @@ PB2_HD DRay xfRay(const M44 &t, const DRay &r, float tMax) {
     return out;
 }
 
+// The alpha test of Triangle::Intersect (triangle.cpp:333-338) and IntersectP (triangle.cpp:531-569) for a hit at
+// barycentrics (b0, b1, b2) of scene primitive `prim`: true when the hit does not count.  The look-up has no differentials
+// (isectLocal is built without any), so both MIPMap filters reduce to the bilinear one at the finest level.
+PB2_HDN bool alphaRejects(const DScene &sc, int prim, float b0, float b1, float b2, bool anyHit) {
+    const int tri = sc.primIndex[prim];
+    const pb2_mesh &mesh = sc.meshes[sc.triMesh[tri]];
+    if (!mesh.alpha_tex && !(anyHit && mesh.shadow_alpha_tex)) return false;
+    V2 uv0 = mk2(0, 0), uv1 = mk2(1, 0), uv2 = mk2(1, 1);   // Triangle::GetUVs (triangle.h:98-108)
+    if (mesh.has_uv) {
+        const int64_t v0 = sc.triIndex[3 * (int64_t)tri], v1 = sc.triIndex[3 * (int64_t)tri + 1], v2 = sc.triIndex[3 * (int64_t)tri + 2];
+        uv0 = mk2(sc.UV[2 * v0], sc.UV[2 * v0 + 1]);
+        uv1 = mk2(sc.UV[2 * v1], sc.UV[2 * v1 + 1]);
+        uv2 = mk2(sc.UV[2 * v2], sc.UV[2 * v2 + 1]);
+    }
+    const V2 uvHit = mk2(b0 * uv0.x + b1 * uv1.x + b2 * uv2.x, b0 * uv0.y + b1 * uv1.y + b2 * uv2.y);
+    if (mesh.alpha_tex && texEvaluateNoDiff(sc.textures[mesh.alpha_tex - 1], sc.texels, uvHit).x == 0) return true;
+    if (anyHit && mesh.shadow_alpha_tex && texEvaluateNoDiff(sc.textures[mesh.shadow_alpha_tex - 1], sc.texels, uvHit).x == 0) return true;
+    return false;
+}
+
 template <int LEVEL>
 PB2_HD bool traverseLevel(const DScene &sc, int root, const DRay &ray, const DRaySetup &rs, const bool ANY, float *tMaxInOut,
                           DHit *hit, DCounters *ctr, int instId);
@@ -445,6 +471,7 @@ PB2_HD bool testLeafRecord(const DScene &sc, int recIndex, const DRay &ray, cons
     }
     float t, b0, b1, b2;
     if (!triangleTest(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), rs, *tMax, &t, &b0, &b1, &b2)) return false;
+    if ((flags & LEAF_ALPHA) && alphaRejects(sc, asInt(a.w), b0, b1, b2, ANY)) return false;
     if (ANY) return true;
     if (flags & LEAF_DEGENERATE) return false;
     *tMax = t;

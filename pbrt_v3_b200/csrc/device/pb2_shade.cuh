@@ -34,6 +34,9 @@ struct DInteraction {   // the part of (Surface)Interaction that Li and Estimate
     int prim;           // scene-order primitive number
 };
 
+// What SurfaceInteraction::ComputeDifferentials reads besides p and n: the (geometric) dpdu, dpdv of the hit
+struct DTexGeom { V3 dpdu, dpdv; };
+
 struct TriVerts { V3 p0, p1, p2; };
 
 PB2_HD V3 ld3(const float *a, int64_t i) { return mk3(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
@@ -105,7 +108,7 @@ PB2_HD TriRec loadTriRec(const float4 *recs, size_t i) {
     return r;
 }
 
-PB2_HD DInteraction triangleInteraction(const DScene &sc, const TriRec &rec, float b0, float b1, float b2, V3 rayD) {
+PB2_HD DInteraction triangleInteraction(const DScene &sc, const TriRec &rec, float b0, float b1, float b2, V3 rayD, DTexGeom *tg = nullptr) {
     DInteraction it;
     const int prim = rec.prim;
     const TriVerts tv = rec.tv;   // bitwise the vertices the index buffer leads to
@@ -123,6 +126,10 @@ PB2_HD DInteraction triangleInteraction(const DScene &sc, const TriRec &rec, flo
     triUVs(sc, tri, mesh, uv);
     V3 dpdu, dpdv;
     triPartials(tv.p0, tv.p1, tv.p2, uv, &dpdu, &dpdv);
+    if (tg) {
+        tg->dpdu = dpdu;
+        tg->dpdv = dpdv;
+    }
     float xAbsSum = (fabsf(b0 * tv.p0.x) + fabsf(b1 * tv.p1.x) + fabsf(b2 * tv.p2.x));
     float yAbsSum = (fabsf(b0 * tv.p0.y) + fabsf(b1 * tv.p1.y) + fabsf(b2 * tv.p2.y));
     float zAbsSum = (fabsf(b0 * tv.p0.z) + fabsf(b1 * tv.p1.z) + fabsf(b2 * tv.p2.z));
@@ -179,7 +186,7 @@ namespace pb2 {
 // interaction is built there and then taken to world space as TransformedPrimitive::Intersect does
 // with Transform::operator()(const SurfaceInteraction &) (primitive.cpp:85-86, transform.cpp:262-297).
 template <bool SPH = true>
-PB2_HD DInteraction hitInteraction(const DScene &sc, const DHit &hit, const DRay &ray, float tHit, int *light = nullptr) {
+PB2_HD DInteraction hitInteraction(const DScene &sc, const DHit &hit, const DRay &ray, float tHit, int *light = nullptr, DTexGeom *tg = nullptr) {
     TriRec rec = loadTriRec(sc.leafPrims, (size_t)hit.leaf);
     const DInstance *inst = nullptr;
     DRay r = ray;
@@ -190,10 +197,10 @@ PB2_HD DInteraction hitInteraction(const DScene &sc, const DHit &hit, const DRay
     DInteraction it;
     if (SPH && (rec.flags & LEAF_SPHERE)) {
         if (light) *light = sc.primLight[rec.prim];
-        it = sphereInteraction(sc, rec.prim, r, tHit, hit.b0);
+        it = sphereInteraction(sc, rec.prim, r, tHit, hit.b0, tg);
     } else {
         if (light) *light = rec.light;
-        it = triangleInteraction(sc, rec, hit.b0, hit.b1, hit.b2, r.d);
+        it = triangleInteraction(sc, rec, hit.b0, hit.b1, hit.b2, r.d, tg);
     }
     if (inst && !inst->identity) {
         V3 pError;
@@ -204,6 +211,10 @@ PB2_HD DInteraction hitInteraction(const DScene &sc, const DHit &hit, const DRay
         it.ns = normalize(xfNormalInv(inst->w2i, it.ns));
         it.dpdus = xfVector(inst->i2w, it.dpdus);
         it.ns = faceforward(it.ns, it.n);
+        if (tg) {
+            tg->dpdu = xfVector(inst->i2w, tg->dpdu);
+            tg->dpdv = xfVector(inst->i2w, tg->dpdv);
+        }
     }
     return it;
 }
@@ -270,12 +281,44 @@ PB2_HD float roughnessToAlpha(float roughness) {
 // Material::ComputeScatteringFunctions for matte (matte.cpp:45-62) and plastic (plastic.cpp:45-70).
 // Returns false when the primitive has no material (null BSDF: the path skips the surface).
 // SPEC = false compiles the specular materials away (scenes without mirror / glass get the leaner kernel).
-template <bool SPEC = true>
-PB2_HD bool makeBsdf(const DScene &sc, const DInteraction &it, DBsdf *bsdf) {
+// The textured parameters of a material at one shaded point: every slot of pb2_material::tex that names a texture is
+// evaluated (Texture::Evaluate(*si), e.g. matte.cpp:53-54) and written over the constant.
+PB2_HDN void applyTextures(const DScene &sc, V2 uv, const DUvDiff &d, pb2_material *mat) {
+    for (int k = 0; k < PB2_TEX_SLOTS; ++k) {
+        const int id = mat->tex[k];
+        if (!id) continue;
+        const V3 v = texEvaluate(sc.textures[id - 1], sc.texels, uv, d);
+        float *dst3 = nullptr;
+        switch (k) {
+        case PB2_TEX_KD: dst3 = mat->kd; break;
+        case PB2_TEX_KS: dst3 = mat->ks; break;
+        case PB2_TEX_KR: dst3 = mat->kr; break;
+        case PB2_TEX_KT: dst3 = mat->kt; break;
+        case PB2_TEX_OPACITY: dst3 = mat->opacity; break;
+        case PB2_TEX_METAL_ETA: dst3 = mat->metal_eta; break;
+        case PB2_TEX_METAL_K: dst3 = mat->metal_k; break;
+        case PB2_TEX_SIGMA: mat->sigma = v.x; break;
+        case PB2_TEX_ROUGHNESS: mat->roughness = v.x; break;
+        case PB2_TEX_UROUGHNESS: mat->uroughness = v.x; break;
+        case PB2_TEX_VROUGHNESS: mat->vroughness = v.x; break;
+        case PB2_TEX_ETA: mat->eta = v.x; break;
+        }
+        if (dst3) {
+            dst3[0] = v.x;
+            dst3[1] = v.y;
+            dst3[2] = v.z;
+        }
+    }
+}
+
+// TEX = true: image textures are evaluated (uvDiff: the point's (u, v) differentials); false compiles them away.
+template <bool SPEC = true, bool TEX = false>
+PB2_HD bool makeBsdf(const DScene &sc, const DInteraction &it, DBsdf *bsdf, const DUvDiff *uvDiff = nullptr) {
     int m = sc.primMaterial[it.prim];
     if (m < 0) return false;
-    const pb2_material mat = sc.materials[m];
+    pb2_material mat = sc.materials[m];
     if (mat.type == PB2_MAT_NONE) return false;
+    if (TEX && sc.textures && uvDiff) applyTextures(sc, it.uv, *uvDiff, &mat);
     bsdf->ns = it.ns;
     bsdf->ng = it.n;
     bsdf->ss = normalize(it.dpdus);
@@ -1394,7 +1437,87 @@ PB2_HD void computeVoxelDistribution(const DScene &sc, const DHalton &h, const D
 struct DCamera {
     M44 rasterToCamera, cameraToWorld;
     float lensRadius, focalDistance;
+    V3 dxCamera, dyCamera;    // ProjectiveCamera: the camera-space step of one pixel in x / y (perspective.cpp:59-62)
 };
+
+// A camera ray's differentials (world space).
+struct DRayDiff { V3 rxo, rxd, ryo, ryd; };
+
+// The offset rays PerspectiveCamera::GenerateRayDifferential adds to a camera ray (perspective.cpp:117-144), taken to world
+// space (Transform::operator()(RayDifferential), transform.h:266-275: the auxiliary origins are NOT moved along the ray as
+// the main one is) and scaled as SamplerIntegrator::Render does (integrator.cpp:273-274, geometry.h:908-913).
+// (o, d): the main ray in world space as it was traced; uLens: the lens sample of this camera sample.
+PB2_HD DRayDiff cameraRayDifferentials(const DCamera &cam, V2 pFilm, V2 uLens, float scale, V3 o, V3 d) {
+    V3 pCamera = xfPoint(cam.rasterToCamera, mk3(pFilm.x, pFilm.y, 0));
+    V3 rxo = mk3(0, 0, 0), ryo = mk3(0, 0, 0), rxd, ryd;
+    if (cam.lensRadius > 0) {
+        V2 dsk = concentricSampleDisk(uLens);
+        V2 pLens = mk2(cam.lensRadius * dsk.x, cam.lensRadius * dsk.y);
+        V3 dx = normalize(pCamera + cam.dxCamera);
+        float ft = cam.focalDistance / dx.z;
+        V3 pFocus = mk3(0, 0, 0) + (ft * dx);
+        rxo = mk3(pLens.x, pLens.y, 0);
+        rxd = normalize(pFocus - rxo);
+        V3 dy = normalize(pCamera + cam.dyCamera);
+        ft = cam.focalDistance / dy.z;
+        pFocus = mk3(0, 0, 0) + (ft * dy);
+        ryo = mk3(pLens.x, pLens.y, 0);
+        ryd = normalize(pFocus - ryo);
+    } else {
+        rxd = normalize(pCamera + cam.dxCamera);
+        ryd = normalize(pCamera + cam.dyCamera);
+    }
+    DRayDiff r;
+    r.rxo = xfPoint(cam.cameraToWorld, rxo);
+    r.ryo = xfPoint(cam.cameraToWorld, ryo);
+    r.rxd = xfVector(cam.cameraToWorld, rxd);
+    r.ryd = xfVector(cam.cameraToWorld, ryd);
+    r.rxo = o + (r.rxo - o) * scale;
+    r.ryo = o + (r.ryo - o) * scale;
+    r.rxd = d + (r.rxd - d) * scale;
+    r.ryd = d + (r.ryd - d) * scale;
+    return r;
+}
+
+// SurfaceInteraction::ComputeDifferentials (interaction.cpp:101-147): the (u, v) footprint of the pixel at a hit
+PB2_HD DUvDiff computeUvDifferentials(V3 p, V3 n, V3 dpdu, V3 dpdv, const DRayDiff &rd) {
+    DUvDiff z;
+    z.dudx = z.dvdx = z.dudy = z.dvdy = 0;
+    float dd = dot(n, p);
+    float tx = -(dot(n, rd.rxo) - dd) / dot(n, rd.rxd);
+    if (isinf(tx) || tx != tx) return z;
+    V3 px = rd.rxo + tx * rd.rxd;
+    float ty = -(dot(n, rd.ryo) - dd) / dot(n, rd.ryd);
+    if (isinf(ty) || ty != ty) return z;
+    V3 py = rd.ryo + ty * rd.ryd;
+    int d0, d1;
+    if (fabsf(n.x) > fabsf(n.y) && fabsf(n.x) > fabsf(n.z)) {
+        d0 = 1;
+        d1 = 2;
+    } else if (fabsf(n.y) > fabsf(n.z)) {
+        d0 = 0;
+        d1 = 2;
+    } else {
+        d0 = 0;
+        d1 = 1;
+    }
+    const float A00 = comp(dpdu, d0), A01 = comp(dpdv, d0), A10 = comp(dpdu, d1), A11 = comp(dpdv, d1);
+    const float Bx0 = comp(px, d0) - comp(p, d0), Bx1 = comp(px, d1) - comp(p, d1);
+    const float By0 = comp(py, d0) - comp(p, d0), By1 = comp(py, d1) - comp(p, d1);
+    // SolveLinearSystem2x2 (transform.cpp:41-49)
+    float det = A00 * A11 - A01 * A10;
+    if (!(fabsf(det) < 1e-10f)) {
+        DUvDiff r = z;
+        r.dudx = (A11 * Bx0 - A01 * Bx1) / det;
+        r.dvdx = (A00 * Bx1 - A10 * Bx0) / det;
+        if (r.dudx != r.dudx || r.dvdx != r.dvdx) r.dudx = r.dvdx = 0;
+        r.dudy = (A11 * By0 - A01 * By1) / det;
+        r.dvdy = (A00 * By1 - A10 * By0) / det;
+        if (r.dudy != r.dudy || r.dvdy != r.dvdy) r.dudy = r.dvdy = 0;
+        return r;
+    }
+    return z;
+}
 
 // Sampler::GetCameraSample (sampler.cpp:46-52) + PerspectiveCamera::GenerateRayDifferential
 // (perspective.cpp:95-144) + Transform::operator()(Ray) (transform.h:251-264).  Differentials are

@@ -180,7 +180,7 @@ PB2_HDN bool sphereLeafTest(const DScene &sc, int sphereIndex, const DRay &ray, 
 // SurfaceInteraction of a sphere hit (sphere.cpp:105-155) mapped to world space
 // (transform.cpp:262-297).  The hit is recomputed from the ray with the tMax the traversal saw just
 // before accepting it: any tMax >= tHit accepts the same root, so +inf is used.
-PB2_HDN DInteraction sphereInteraction(const DScene &sc, int prim, const DRay &ray, float tHit, float) {
+PB2_HDN DInteraction sphereInteraction(const DScene &sc, int prim, const DRay &ray, float tHit, float, DTexGeom *tg = nullptr) {
     (void)tHit;
     DInteraction it;
     const pb2_sphere s = sc.spheres[sc.primIndex[prim]];
@@ -209,6 +209,10 @@ PB2_HDN DInteraction sphereInteraction(const DScene &sc, int prim, const DRay &r
     it.wo = normalize(xfVector(o2w, normalize(-h.oRayD)));
     it.uv = mk2(u, v);
     it.dpdus = xfVector(o2w, dpdu);
+    if (tg) {
+        tg->dpdu = it.dpdus;
+        tg->dpdv = xfVector(o2w, dpdv);
+    }
     it.ns = normalize(xfNormalInv(w2o, nsObj));
     it.ns = faceforward(it.ns, it.n);
     it.prim = prim;

@@ -418,6 +418,17 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
     std::unique_ptr<FlatScene> fs(new FlatScene());
     std::unordered_map<const TriangleMesh *, int> meshIds;
     std::unordered_map<const Material *, int> materialIds;
+    // image textures in order of first use; 0 = none, else 1 + index (pb2_material::tex, pb2_mesh::alpha_tex)
+    std::unordered_map<const ImageTexture *, int> textureIds;
+    auto textureId = [&](const std::shared_ptr<ImageTexture> &t) -> int32_t {
+        if (!t) return 0;
+        auto it = textureIds.find(t.get());
+        if (it != textureIds.end()) return it->second;
+        fs->textureObjects.push_back(t);
+        const int id = (int)fs->textureObjects.size();
+        textureIds[t.get()] = id;
+        return id;
+    };
     std::unordered_map<const AreaLight *, int> lightIds;
     // Scene::lights order is the order of creation in the scene file (api.cpp:1413-1416)
     fs->lights.resize(lights.size());
@@ -545,7 +556,9 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
             auto it = materialIds.find(gp->material.get());
             if (it == materialIds.end()) {
                 mid = (int)fs->materials.size();
-                fs->materials.push_back(gp->material->Record());
+                pb2_material rec = gp->material->Record();
+                for (int k = 0; k < PB2_TEX_SLOTS; ++k) rec.tex[k] = textureId(gp->material->tex[k]);
+                fs->materials.push_back(rec);
                 materialIds[gp->material.get()] = mid;
             } else
                 mid = it->second;
@@ -598,6 +611,8 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
                 m.has_s = !mesh->s.empty();
                 m.reverse_orientation = tri->reverseOrientation;
                 m.transform_swaps_handedness = tri->transformSwapsHandedness;
+                m.alpha_tex = textureId(mesh->alphaMask);
+                m.shadow_alpha_tex = textureId(mesh->shadowAlphaMask);
                 anyN |= m.has_n != 0; anyUV |= m.has_uv != 0; anyS |= m.has_s != 0;
                 for (int v = 0; v < mesh->nVertices; ++v) {
                     fs->P.insert(fs->P.end(), {mesh->p[v].x, mesh->p[v].y, mesh->p[v].z});
@@ -699,6 +714,21 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
     }
     d.n_materials = (int32_t)fs->materials.size();
     d.materials = fs->materials.data();
+    for (const std::shared_ptr<ImageTexture> &t : fs->textureObjects) {
+        pb2_texture pt;
+        std::memset(&pt, 0, sizeof(pt));
+        pt.channels = t->channels;
+        pt.width = t->width;
+        pt.height = t->height;
+        pt.wrap = t->wrap;
+        pt.do_trilinear = t->trilinear ? 1 : 0;
+        pt.max_anisotropy = t->maxAniso;
+        pt.su = t->su; pt.sv = t->sv; pt.du = t->du; pt.dv = t->dv;
+        pt.texels = t->texels.data();
+        fs->textures.push_back(pt);
+    }
+    d.n_textures = (int32_t)fs->textures.size();
+    d.textures = fs->textures.empty() ? nullptr : fs->textures.data();
     d.n_lights = (int32_t)fs->lights.size();
     d.lights = fs->lights.data();
     d.delta_lights = fs->deltaLights.empty() ? nullptr : fs->deltaLights.data();

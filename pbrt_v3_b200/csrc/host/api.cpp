@@ -175,6 +175,27 @@ std::vector<std::shared_ptr<Shape>> MakeShapes(const std::string &name, const Tr
         shapes = CreateLoopSubdiv(o2w, w2o, reverseOrientation, ps);
     else
         Error("Shape \"%s\" is outside the GPU path's scope (sphere, trianglemesh, plymesh, loopsubdiv).", name.c_str());
+    if ((name == "trianglemesh" || name == "plymesh") && !shapes.empty()) {
+        // the "alpha" / "shadowalpha" masks of a mesh (triangle.cpp:717-740, plymesh.cpp:349-372): a float texture by name,
+        // or the constant 0 (a mesh that is never hit)
+        auto mask = [&](const char *pn) -> std::shared_ptr<ImageTexture> {
+            const std::string texName = ps.FindTexture(pn);
+            if (texName != "") {
+                const ConstantTextures &tx = graphicsState.textures;
+                auto it = tx.floatImages.find(texName);
+                if (it != tx.floatImages.end()) return it->second;
+                auto ic = tx.floats.find(texName);
+                if (ic != tx.floats.end()) return ConstantFloatImage(ic->second);
+                Error("Couldn't find float texture \"%s\" for \"%s\" parameter", texName.c_str(), pn);
+                return nullptr;
+            }
+            if (ps.FindOneFloat(pn, 1.f) == 0.f) return ConstantFloatImage(0.f);
+            return nullptr;
+        };
+        TriangleMesh *mesh = static_cast<Triangle *>(shapes[0].get())->mesh.get();
+        mesh->alphaMask = mask("alpha");
+        mesh->shadowAlphaMask = mask("shadowalpha");
+    }
     return shapes;
 }
 
@@ -355,6 +376,26 @@ void pbrtTexture(const std::string &name, const std::string &type, const std::st
             if (tp.IsVaryingTexture(n)) return true;
         return false;
     };
+    auto &floats = graphicsState.textures.floats;
+    auto &spectra = graphicsState.textures.spectra;
+    auto &floatImages = graphicsState.textures.floatImages;
+    auto &spectrumImages = graphicsState.textures.spectrumImages;
+    if (texname == "imagemap") {
+        // CreateImageFloatTexture / CreateImageSpectrumTexture (imagemap.cpp:113-197); a later definition of the name
+        // replaces an earlier one of either kind (api.cpp:1216-1243)
+        std::shared_ptr<ImageTexture> tex = CreateImageTexture(tp, isSpectrum);
+        params.ReportUnused();
+        if ((isFloat ? floats.count(name) + floatImages.count(name) : spectra.count(name) + spectrumImages.count(name)) != 0)
+            Warning("Texture \"%s\" being redefined", name.c_str());
+        if (isFloat) {
+            floats.erase(name);
+            floatImages[name] = tex;
+        } else {
+            spectra.erase(name);
+            spectrumImages[name] = tex;
+        }
+        return;
+    }
     bool ok = false;
     Float fv = 0;
     Spectrum sv;
@@ -376,18 +417,18 @@ void pbrtTexture(const std::string &name, const std::string &type, const std::st
         }
     }
     if (!ok) {
-        Error("Texture \"%s\" of class \"%s\" varies over the surface: outside the GPU path's scope (SURVEY.md §2 row 33); "
+        Error("Texture \"%s\" of class \"%s\" is outside the GPU path's scope (constant textures and \"imagemap\", SURVEY.md §8 f.2); "
               "parameters that name it keep their defaults", name.c_str(), texname.c_str());
         return;
     }
     params.ReportUnused();
-    auto &floats = graphicsState.textures.floats;
-    auto &spectra = graphicsState.textures.spectra;
     if (isFloat) {
-        if (floats.count(name)) Warning("Texture \"%s\" being redefined", name.c_str());
+        if (floats.count(name) || floatImages.count(name)) Warning("Texture \"%s\" being redefined", name.c_str());
+        floatImages.erase(name);
         floats[name] = fv;
     } else {
-        if (spectra.count(name)) Warning("Texture \"%s\" being redefined", name.c_str());
+        if (spectra.count(name) || spectrumImages.count(name)) Warning("Texture \"%s\" being redefined", name.c_str());
+        spectrumImages.erase(name);
         spectra[name] = sv;
     }
 }

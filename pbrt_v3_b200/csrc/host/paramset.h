@@ -5,6 +5,7 @@
 #define PB2_HOST_PARAMSET_H
 
 #include <map>
+#include <memory>
 #include "core.h"
 
 namespace pbrt {
@@ -114,9 +115,22 @@ class ParamSet {
 // Named textures whose value does not vary over a surface: "constant", and "scale" / "mix" of such (src/textures/
 // constant.h, scale.h, mix.h).  They are the Texture directives that stay inside this path; a material parameter that
 // names one is simply that value.
+// An "imagemap" texture (imagemap.h:72-128) with a "uv" mapping: what the MIPMap constructor receives plus the mapping
+// and filter parameters - one pb2_texture of the scene description.
+struct ImageTexture {
+    int channels = 3;                 // 1: float texture, 3: spectrum texture
+    int width = 0, height = 0;
+    std::vector<float> texels;        // channels * width * height, row 0 is t = 0, after scale / gamma / luminance
+    int wrap = 0;                     // PB2_WRAP_*
+    bool trilinear = false;
+    Float maxAniso = 8.f;
+    Float su = 1, sv = 1, du = 0, dv = 0;
+};
 struct ConstantTextures {
     std::map<std::string, Float> floats;
     std::map<std::string, Spectrum> spectra;
+    // the named textures that do vary: image maps
+    std::map<std::string, std::shared_ptr<ImageTexture>> floatImages, spectrumImages;
 };
 class TextureParams {
   public:
@@ -133,6 +147,19 @@ class TextureParams {
         if (name == "") return false;
         return !(textures && (textures->floats.count(name) || textures->spectra.count(name)));
     }
+    // the image texture a parameter names (float or spectrum ones as asked), or null
+    std::shared_ptr<ImageTexture> GetImageTexture(const std::string &n, bool spectrum) const {
+        std::string name = NamedTexture(n);
+        if (name == "" || !textures) return nullptr;
+        const auto &m = spectrum ? textures->spectrumImages : textures->floatImages;
+        auto it = m.find(name);
+        return it == m.end() ? nullptr : it->second;
+    }
+    // true when the parameter names a texture that is neither constant nor an image map of the right kind
+    bool IsUnsupportedTexture(const std::string &n, bool spectrum) const {
+        return IsVaryingTexture(n) && !GetImageTexture(n, spectrum);
+    }
+    Float FindFloat(const std::string &n, Float d) const { return geomParams.FindOneFloat(n, materialParams.FindOneFloat(n, d)); }
     Spectrum GetSpectrumTexture(const std::string &n, const Spectrum &def, bool *isTexture = nullptr) const {
         if (isTexture) *isTexture = false;
         std::string name = NamedTexture(n);

@@ -146,85 +146,133 @@ std::shared_ptr<InfiniteAreaLight> CreateInfiniteLight(const Transform &light2wo
               texmap.c_str());
     return std::make_shared<InfiniteAreaLight>(light2world, L * sc);
 }
-static void rejectTextures(const TextureParams &mp, const char *what, std::initializer_list<const char *> names) {
-    for (const char *n : names)
-        if (mp.IsVaryingTexture(n))
-            Error("%s: textured parameter \"%s\" is outside the GPU path's scope (constant textures only, SURVEY.md §2 row 33); "
-                  "using the default value", what, n);
+// Textured parameters.  A parameter that names an image texture ("imagemap") of the right kind is attached to the
+// material's slot (Material::tex -> pb2_material::tex); one that names anything else that varies (procedural textures,
+// unknown names, a float texture where a spectrum is expected) is reported and keeps its default.  "bumpmap" is always
+// outside the path's scope.
+struct TexParam {
+    const char *name;
+    int slot;          // PB2_TEX_*
+    bool spectrum;
+};
+static void attachTextures(Material *m, const TextureParams &mp, const char *what, std::initializer_list<TexParam> params) {
+    for (const TexParam &tp : params) {
+        if (auto t = mp.GetImageTexture(tp.name, tp.spectrum)) m->tex[tp.slot] = t;
+        else if (mp.IsVaryingTexture(tp.name))
+            Error("%s: the texture named by \"%s\" is outside the GPU path's scope (constant and \"imagemap\" textures with a "
+                  "\"uv\" mapping, SURVEY.md §8 f.2); using the default value", what, tp.name);
+    }
+    if (mp.NamedTexture("bumpmap") != "") Error("%s: bump mapping is outside the GPU path's scope; \"bumpmap\" ignored", what);
+}
+// A float parameter that may be absent, a constant or an image texture (GetFloatTextureOrNull, paramset.cpp:703-732)
+struct FloatParam {
+    bool present = false;
+    std::shared_ptr<ImageTexture> tex;
+    Float value = 0;
+};
+static FloatParam floatParam(const TextureParams &mp, const char *name) {
+    FloatParam r;
+    r.tex = mp.GetImageTexture(name, false);
+    if (r.tex) r.present = true;
+    else r.present = mp.GetFloatOrNull(name, &r.value);
+    return r;
 }
 MatteMaterial *CreateMatteMaterial(const TextureParams &mp) {
-    rejectTextures(mp, "matte", {"Kd", "sigma", "bumpmap"});
     Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(0.5f));
     Float sigma = mp.GetFloatTexture("sigma", 0.f);
-    return new MatteMaterial(Kd, sigma);
+    auto *m = new MatteMaterial(Kd, sigma);
+    attachTextures(m, mp, "matte", {{"Kd", PB2_TEX_KD, true}, {"sigma", PB2_TEX_SIGMA, false}});
+    return m;
 }
 // substrate.cpp:67-81
 SubstrateMaterial *CreateSubstrateMaterial(const TextureParams &mp) {
-    rejectTextures(mp, "substrate", {"Kd", "Ks", "uroughness", "vroughness", "bumpmap"});
     Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(.5f));
     Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(.5f));
     Float uroughness = mp.GetFloatTexture("uroughness", .1f);
     Float vroughness = mp.GetFloatTexture("vroughness", .1f);
     bool remap = mp.FindBool("remaproughness", true);
-    return new SubstrateMaterial(Kd, Ks, uroughness, vroughness, remap);
+    auto *m = new SubstrateMaterial(Kd, Ks, uroughness, vroughness, remap);
+    attachTextures(m, mp, "substrate", {{"Kd", PB2_TEX_KD, true}, {"Ks", PB2_TEX_KS, true}, {"uroughness", PB2_TEX_UROUGHNESS, false},
+                                        {"vroughness", PB2_TEX_VROUGHNESS, false}});
+    return m;
 }
 // uber.cpp:106-131
 UberMaterial *CreateUberMaterial(const TextureParams &mp) {
-    rejectTextures(mp, "uber", {"Kd", "Ks", "Kr", "Kt", "roughness", "uroughness", "vroughness", "eta", "index", "opacity", "bumpmap"});
     Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(0.25f));
     Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(0.25f));
     Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(0.f));
     Spectrum Kt = mp.GetSpectrumTexture("Kt", Spectrum(0.f));
     Float roughness = mp.GetFloatTexture("roughness", .1f);
-    Float roughu = roughness, roughv;
-    mp.GetFloatOrNull("uroughness", &roughu);
-    roughv = roughu;   // uber.cpp:77-80: "vroughness" falls back to the u value
-    mp.GetFloatOrNull("vroughness", &roughv);
-    Float eta;
-    if (!mp.GetFloatOrNull("eta", &eta)) eta = mp.GetFloatTexture("index", 1.5f);
+    // uber.cpp:71-80: roughu = "uroughness" if given, else "roughness"; roughv = "vroughness" if given, else roughu
+    const FloatParam pu = floatParam(mp, "uroughness"), pv = floatParam(mp, "vroughness");
+    Float roughu = pu.present ? pu.value : roughness;
+    std::shared_ptr<ImageTexture> texU = pu.present ? pu.tex : mp.GetImageTexture("roughness", false);
+    Float roughv = pv.present ? pv.value : roughu;
+    std::shared_ptr<ImageTexture> texV = pv.present ? pv.tex : texU;
+    const FloatParam pe = floatParam(mp, "eta");
+    Float eta = pe.present ? pe.value : mp.GetFloatTexture("index", 1.5f);
     Spectrum opacity = mp.GetSpectrumTexture("opacity", Spectrum(1.f));
     bool remap = mp.FindBool("remaproughness", true);
-    return new UberMaterial(Kd, Ks, Kr, Kt, roughu, roughv, opacity, eta, remap);
+    auto *m = new UberMaterial(Kd, Ks, Kr, Kt, roughu, roughv, opacity, eta, remap);
+    attachTextures(m, mp, "uber", {{"Kd", PB2_TEX_KD, true}, {"Ks", PB2_TEX_KS, true}, {"Kr", PB2_TEX_KR, true}, {"Kt", PB2_TEX_KT, true},
+                                   {"opacity", PB2_TEX_OPACITY, true}, {"roughness", PB2_TEX_ROUGHNESS, false},
+                                   {"uroughness", PB2_TEX_UROUGHNESS, false}, {"vroughness", PB2_TEX_VROUGHNESS, false},
+                                   {pe.present ? "eta" : "index", PB2_TEX_ETA, false}});
+    m->tex[PB2_TEX_ROUGHNESS] = nullptr;   // resolved into the u / v slots
+    m->tex[PB2_TEX_UROUGHNESS] = texU;
+    m->tex[PB2_TEX_VROUGHNESS] = texV;
+    return m;
 }
 // metal.cpp:120-140.  The defaults are copper's measured index and absorption converted to RGB by
 // Spectrum::FromSampled (metal.cpp:82-118, spectrum.h:438-466); the six numbers below are that conversion's result,
 // recorded from the compiled reference (tests/golden/metal_defaults.npz, tests/make_golden.py).
 MetalMaterial *CreateMetalMaterial(const TextureParams &mp) {
-    rejectTextures(mp, "metal", {"eta", "k", "roughness", "uroughness", "vroughness", "bumpmap"});
     static const Spectrum copperN(0.19999069f, 0.92208463f, 1.09987593f), copperK(3.90463543f, 2.44763327f, 2.13765264f);
     Spectrum eta = mp.GetSpectrumTexture("eta", copperN);
     Spectrum k = mp.GetSpectrumTexture("k", copperK);
     Float roughness = mp.GetFloatTexture("roughness", .01f);
-    Float uRough = roughness, vRough = roughness;   // metal.cpp:67-70: each falls back to "roughness"
-    mp.GetFloatOrNull("uroughness", &uRough);
-    mp.GetFloatOrNull("vroughness", &vRough);
+    // metal.cpp:67-70: each of the two falls back to "roughness"
+    const FloatParam pu = floatParam(mp, "uroughness"), pv = floatParam(mp, "vroughness");
+    const std::shared_ptr<ImageTexture> texR = mp.GetImageTexture("roughness", false);
+    Float uRough = pu.present ? pu.value : roughness, vRough = pv.present ? pv.value : roughness;
     bool remap = mp.FindBool("remaproughness", true);
-    return new MetalMaterial(eta, k, uRough, vRough, remap);
+    auto *m = new MetalMaterial(eta, k, uRough, vRough, remap);
+    attachTextures(m, mp, "metal", {{"eta", PB2_TEX_METAL_ETA, true}, {"k", PB2_TEX_METAL_K, true}, {"roughness", PB2_TEX_ROUGHNESS, false},
+                                    {"uroughness", PB2_TEX_UROUGHNESS, false}, {"vroughness", PB2_TEX_VROUGHNESS, false}});
+    m->tex[PB2_TEX_ROUGHNESS] = nullptr;
+    m->tex[PB2_TEX_UROUGHNESS] = pu.present ? pu.tex : texR;
+    m->tex[PB2_TEX_VROUGHNESS] = pv.present ? pv.tex : texR;
+    return m;
 }
 // mirror.cpp:60-66
 MirrorMaterial *CreateMirrorMaterial(const TextureParams &mp) {
-    rejectTextures(mp, "mirror", {"Kr", "bumpmap"});
-    return new MirrorMaterial(mp.GetSpectrumTexture("Kr", Spectrum(0.9f)));
+    auto *m = new MirrorMaterial(mp.GetSpectrumTexture("Kr", Spectrum(0.9f)));
+    attachTextures(m, mp, "mirror", {{"Kr", PB2_TEX_KR, true}});
+    return m;
 }
 // glass.cpp:95-112
 GlassMaterial *CreateGlassMaterial(const TextureParams &mp) {
-    rejectTextures(mp, "glass", {"Kr", "Kt", "eta", "index", "uroughness", "vroughness", "bumpmap"});
     Spectrum Kr = mp.GetSpectrumTexture("Kr", Spectrum(1.f));
     Spectrum Kt = mp.GetSpectrumTexture("Kt", Spectrum(1.f));
     // "eta" wins over "index" when both are given (GetFloatTextureOrNull("eta") first)
-    Float eta = mp.GetFloatTexture("eta", mp.GetFloatTexture("index", 1.5f));
+    const FloatParam pe = floatParam(mp, "eta");
+    Float eta = pe.present ? pe.value : mp.GetFloatTexture("index", 1.5f);
     Float roughu = mp.GetFloatTexture("uroughness", 0.f);
     Float roughv = mp.GetFloatTexture("vroughness", 0.f);
     bool remap = mp.FindBool("remaproughness", true);
-    return new GlassMaterial(Kr, Kt, roughu, roughv, eta, remap);
+    auto *m = new GlassMaterial(Kr, Kt, roughu, roughv, eta, remap);
+    attachTextures(m, mp, "glass", {{"Kr", PB2_TEX_KR, true}, {"Kt", PB2_TEX_KT, true}, {"uroughness", PB2_TEX_UROUGHNESS, false},
+                                    {"vroughness", PB2_TEX_VROUGHNESS, false}, {pe.present ? "eta" : "index", PB2_TEX_ETA, false}});
+    return m;
 }
 PlasticMaterial *CreatePlasticMaterial(const TextureParams &mp) {
-    rejectTextures(mp, "plastic", {"Kd", "Ks", "roughness", "bumpmap"});
     Spectrum Kd = mp.GetSpectrumTexture("Kd", Spectrum(0.25f));
     Spectrum Ks = mp.GetSpectrumTexture("Ks", Spectrum(0.25f));
     Float roughness = mp.GetFloatTexture("roughness", .1f);
     bool remap = mp.FindBool("remaproughness", true);
-    return new PlasticMaterial(Kd, Ks, roughness, remap);
+    auto *m = new PlasticMaterial(Kd, Ks, roughness, remap);
+    attachTextures(m, mp, "plastic", {{"Kd", PB2_TEX_KD, true}, {"Ks", PB2_TEX_KS, true}, {"roughness", PB2_TEX_ROUGHNESS, false}});
+    return m;
 }
 
 DiffuseAreaLight::DiffuseAreaLight(const Transform &LightToWorld, const Spectrum &Lemit, int nSamples,

@@ -74,6 +74,7 @@ struct TriangleMesh {
     std::vector<Normal3f> n;  // empty if absent
     std::vector<Vector3f> s;
     std::vector<Point2f> uv;
+    std::shared_ptr<ImageTexture> alphaMask, shadowAlphaMask;   // triangle.h:61: one-channel textures, or null
 };
 
 class Triangle : public Shape {
@@ -122,7 +123,12 @@ class Material {
   public:
     virtual ~Material() {}
     virtual pb2_material Record() const = 0;  // constant-texture parameters for the device BSDF
+    // image textures that replace constants of the record (PB2_TEX_* slots); null = the constant
+    std::shared_ptr<ImageTexture> tex[PB2_TEX_SLOTS];
 };
+bool ReadImage(const std::string &name, std::vector<float> *rgb, int *w, int *h);   // RGB per pixel, row 0 at the top
+std::shared_ptr<ImageTexture> CreateImageTexture(const TextureParams &tp, bool spectrum);
+std::shared_ptr<ImageTexture> ConstantFloatImage(Float v);
 class MatteMaterial : public Material {
   public:
     MatteMaterial(const Spectrum &Kd, Float sigma) : Kd(Kd), sigma(sigma) {}
@@ -353,6 +359,8 @@ struct FlatScene {
     std::vector<pb2_bvh> bvhs;
     std::vector<pb2_instance> instances;
     std::vector<const Primitive *> primObjects;   // primitive number -> object (GeometricPrimitive or TransformedPrimitive)
+    std::vector<pb2_texture> textures;            // image textures named by materials / meshes (1-based there)
+    std::vector<std::shared_ptr<ImageTexture>> textureObjects;   // keeps the texel arrays alive
 };
 std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<std::shared_ptr<Light>> &lights,
                                         const std::string &lightStrategy);

@@ -111,9 +111,6 @@ std::vector<std::shared_ptr<Shape>> CreateTriangleMeshShape(const Transform *o2w
             Error("trianglemesh has out of-bounds vertex index %d (%d \"P\" values were given", vi[i], npi);
             return {};
         }
-    if (params.FindTexture("alpha") != "" || params.FindTexture("shadowalpha") != "" ||
-        params.FindOneFloat("alpha", 1.f) == 0.f || params.FindOneFloat("shadowalpha", 1.f) == 0.f)
-        Error("alpha-masked triangle meshes are outside the GPU path's scope (SURVEY.md §8f.2); ignoring the mask");
     params.FindInts("faceIndices");
     return CreateTriangleMesh(o2w, w2o, reverseOrientation, (int)vi.size() / 3, vi.data(), npi, P.data(),
                               haveS ? S.data() : nullptr, haveN ? N.data() : nullptr,
@@ -593,8 +590,6 @@ std::vector<std::shared_ptr<Shape>> CreatePLYMesh(const Transform *o2w, const Tr
         Error("PLY file \"%s\" is invalid! No face/vertex elements found!", filename.c_str());
         return {};
     }
-    if (params.FindTexture("alpha") != "" || params.FindTexture("shadowalpha") != "")
-        Error("alpha-masked meshes are outside the GPU path's scope; ignoring the mask");
     return CreateTriangleMesh(o2w, w2o, reverseOrientation, (int)idx.size() / 3, idx.data(), (int)P.size(), P.data(),
                               nullptr, N.empty() ? nullptr : N.data(), UV.empty() ? nullptr : UV.data());
 }

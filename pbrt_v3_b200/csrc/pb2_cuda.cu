@@ -354,6 +354,7 @@ __global__ void k_build_leaf_records(DScene sc, const int32_t *prims, int64_t n,
         if (!triPartials(t.p0, t.p1, t.p2, uv, &dpdu, &dpdv)) flags |= LEAF_DEGENERATE;
         if ((mesh.reverse_orientation != 0) ^ (mesh.transform_swaps_handedness != 0)) flags |= LEAF_FLIP;
         if (mesh.has_n || mesh.has_s || mesh.has_uv) flags |= LEAF_ATTR;
+        if (mesh.alpha_tex || mesh.shadow_alpha_tex) flags |= LEAF_ALPHA;
         a = make_float4(t.p0.x, t.p0.y, t.p0.z, __int_as_float(prim));
         b = make_float4(t.p1.x, t.p1.y, t.p1.z, __uint_as_float(flags));
         c = make_float4(t.p2.x, t.p2.y, t.p2.z, __int_as_float(sc.primLight[prim]));
@@ -441,6 +442,7 @@ struct DRenderParams {
     long long nOwnedTiles;
     long long nWorkItems;        // nOwnedTiles * 256 * spp
     int spp;
+    float diffScale;             // 1 / sqrt(spp): RayDifferential::ScaleDifferentials in SamplerIntegrator::Render (integrator.cpp:273-274)
 };
 
 enum { CTR_WORK = 0, CTR_CAMERA = 1, CTR_REGULAR = 2, CTR_SHADOW = 3, CTR_NODES = 4, CTR_PRIMS = 5, CTR_COUNT = 8 };
@@ -543,7 +545,11 @@ __global__ void k_li_samples(DScene sc, DRenderParams rp, const int32_t *pixelXY
         DHit hit;
         float tMax;
         bool found = traceLane(sc, ln, &tMax, &hit, nullptr);
-        laneAdvance<true>(sc, rp.halton, rp.path, ln, found, hit, tMax);
+        DTexCtx tc;
+        tc.cam = &rp.cam;
+        tc.pFilm = pFilm;
+        tc.diffScale = rp.diffScale;
+        laneAdvance<true, true, true>(sc, rp.halton, rp.path, ln, found, hit, tMax, &tc);
         if (ln.state == LS_DEFER) {   // lazy light distribution: the voxel has been requested; the host builds it and runs the sample again
             atomicAdd(deferred, 1);
             return;
@@ -713,6 +719,9 @@ static DRenderParams makeRenderParams(const pb2_camera *cam, const pb2_film_desc
     memcpy(rp.cam.cameraToWorld.m, cam->camera_to_world, sizeof(float) * 16);
     rp.cam.lensRadius = cam->lens_radius;
     rp.cam.focalDistance = cam->focal_distance;
+    rp.cam.dxCamera = mk3(cam->dx_camera[0], cam->dx_camera[1], cam->dx_camera[2]);
+    rp.cam.dyCamera = mk3(cam->dy_camera[0], cam->dy_camera[1], cam->dy_camera[2]);
+    rp.diffScale = 1 / std::sqrt((float)pp->samples_per_pixel);
     rp.halton = makeHalton(film, pp);
     rp.path.maxDepth = pp->max_depth;
     rp.path.rrThreshold = pp->rr_threshold;
@@ -789,7 +798,17 @@ static int selectTraceKernel(pb2_scene *scene, int flags, TraceLaunch *out) {
     const bool linearFits = !instanced || scene->bvhDepth + 3 + scene->instDepth <= 64;
     if (flags & PB2_FLAG_COUNT_TRAVERSAL) { t.fn = k_wf_trace_plain<true>; t.name = "k_wf_trace_plain<count>"; }
     else if ((flags & PB2_FLAG_PLAIN_TRACE) || (!records && !linearFits)) { t.fn = k_wf_trace_plain<false>; t.name = "k_wf_trace_plain"; }
-    else if (records && (flags & PB2_FLAG_POOL) && !spheres && !instanced) {
+    else if (scene->d.hasAlpha) {
+        // alpha-masked meshes: the default two-child kernel with the alpha test compiled in (the selector flags of the
+        // experiments are not honoured for such scenes); without records, the one-thread-per-ray traversal
+        if (!records) { t.fn = k_wf_trace_plain<false>; t.name = "k_wf_trace_plain"; }
+        else {
+            t.name = "k_wf_trace_w<2,alpha>";
+            if (instanced) t.fn = k_wf_trace_w<2, 1, 8, 4, 16, 6, true, true, true, false, true>;
+            else if (spheres) t.fn = k_wf_trace_w<2, 1, 8, 4, 16, 6, true, false, true, false, true>;
+            else t.fn = k_wf_trace_w<2, 1, 8, 4, 16, 6, false, false, true, false, true>;
+        }
+    } else if (records && (flags & PB2_FLAG_POOL) && !spheres && !instanced) {
         t.name = "k_wf_trace_pool";
         if (!scene->wfSpill)   // per pipeline: up to 8 resident blocks per SM x 4 warps x PL_R slots x PL_SPILL entries
             CUDA_TRY(cudaMalloc((void **)&scene->wfSpill, (size_t)kMaxPipes * g_numSMs * 8 * 4 * PL_R * PL_SPILL * sizeof(int2)));
@@ -905,12 +924,17 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         advShade = scene->hasSpecular ? (spheres ? k_wf_advance<true, true, 4, true, true> : k_wf_advance<true, false, 4, true, true>)
                    : spheres ? k_wf_advance<true, true, 4, false, true>
                              : k_wf_advance<true, false, 4, false, true>;
+    // image textures: the one shade kernel that evaluates them (spheres, specular materials and the lazy light distribution
+    // compiled in; 3 resident blocks, its register budget is not the bench scene's)
+    const bool textured = scene->d.nTextures > 0;
+    if (textured) advShade = k_wf_advance<true, true, 3, true, true, true>;
     typedef void (*FinishKernel)(DScene, DRenderParams, WfPool, int, unsigned, float4 *);
     FinishKernel finish = scene->hasSpecular ? (spheres ? k_wf_finish<true, true> : k_wf_finish<false, true>)
                                              : (spheres ? k_wf_finish<true, false> : k_wf_finish<false, false>);
     // the frame's last paths are walked to their end by one thread each once this few are left (k_wf_finish)
     static const int finishPerSM = envInt("PB2_FINISH", 256);
-    const unsigned finishThreshold = ((flags & PB2_FLAG_COUNT_TRAVERSAL) || lazyLights) ? 0u : (unsigned)(g_numSMs * std::max(0, finishPerSM));
+    // (textured scenes: the tail kernel's lane functions are the untextured instantiation, so the rounds run to the end)
+    const unsigned finishThreshold = ((flags & PB2_FLAG_COUNT_TRAVERSAL) || lazyLights || textured) ? 0u : (unsigned)(g_numSMs * std::max(0, finishPerSM));
     const int finishBlocks = std::max(1, (int)((finishThreshold + 127) / 128));
     static const int syncEvery = std::max(1, envInt("PB2_SYNC_EVERY", 8));
     // (A persisting-L2 access-policy window over the node array was measured and lost 3.5 %: the 126 MB
@@ -1288,6 +1312,207 @@ int pb2_scene_create(const pb2_scene_desc *d, pb2_scene **out) {
     return PB2_OK;
 }
 
+// ---- image textures: the MIPMap constructor (src/core/mipmap.h:112-203) on the host --------------------------------------
+// Lanczos (src/core/texture.cpp:254-262) with the default tau = 2
+static float texLanczos(float x) {
+    const float tau = 2;
+    x = std::abs(x);
+    if (x < 1e-5f) return 1;
+    if (x > 1.f) return 0;
+    x *= 3.14159265358979323846f;
+    float sv = std::sin(x * tau) / (x * tau);
+    float lanczos = std::sin(x) / x;
+    return sv * lanczos;
+}
+struct TexResampleWeight {
+    int firstTexel;
+    float weight[4];
+};
+// MIPMap::resampleWeights (mipmap.h:75-94)
+static std::vector<TexResampleWeight> texResampleWeights(int oldRes, int newRes) {
+    std::vector<TexResampleWeight> wt((size_t)newRes);
+    const float filterwidth = 2.f;
+    for (int i = 0; i < newRes; ++i) {
+        float center = (i + .5f) * oldRes / newRes;
+        wt[i].firstTexel = (int)std::floor((center - filterwidth) + 0.5f);
+        for (int j = 0; j < 4; ++j) {
+            float pos = wt[i].firstTexel + j + .5f;
+            wt[i].weight[j] = texLanczos((pos - center) / filterwidth);
+        }
+        float invSumWts = 1 / (wt[i].weight[0] + wt[i].weight[1] + wt[i].weight[2] + wt[i].weight[3]);
+        for (int j = 0; j < 4; ++j) wt[i].weight[j] *= invSumWts;
+    }
+    return wt;
+}
+static int texWrapIndex(int i, int n, int wrap) {   // the index a wrap mode turns i into, or -1 (black)
+    if (wrap == PB2_WRAP_REPEAT) return texMod(i, n);
+    if (wrap == PB2_WRAP_CLAMP) return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+    return (i >= 0 && i < n) ? i : -1;
+}
+// Appends the levels of one texture to `pool` (finest first) and fills its DTexture.
+static int buildTexturePyramid(const pb2_texture &in, std::vector<float> &pool, DTexture *out) {
+    if ((in.channels != 1 && in.channels != 3) || in.width <= 0 || in.height <= 0 || !in.texels)
+        return setError(PB2_ERR_INVALID, "texture: channels must be 1 or 3, the resolution positive, texels not null");
+    if (in.wrap < PB2_WRAP_REPEAT || in.wrap > PB2_WRAP_CLAMP) return setError(PB2_ERR_INVALID, "texture: unknown wrap mode");
+    if (in.width > 32768 || in.height > 32768) return setError(PB2_ERR_UNSUPPORTED, "texture larger than 32768 in one direction");
+    const int C = in.channels;
+    int rw = in.width, rh = in.height;
+    std::vector<float> level0;
+    auto isPow2 = [](int v) { return v && !(v & (v - 1)); };
+    auto roundUpPow2 = [](int v) { int p = 1; while (p < v) p <<= 1; return p; };
+    if (!isPow2(rw) || !isPow2(rh)) {
+        // resample to a power of two: first in s, then in t (mipmap.h:128-176)
+        const int pw = roundUpPow2(rw), ph = roundUpPow2(rh);
+        std::vector<float> img((size_t)pw * ph * C, 0.f);
+        std::vector<TexResampleWeight> sW = texResampleWeights(rw, pw);
+        for (int t = 0; t < rh; ++t)
+            for (int sx = 0; sx < pw; ++sx)
+                for (int c = 0; c < C; ++c) {
+                    float v = 0.f;
+                    for (int j = 0; j < 4; ++j) {
+                        int origS = texWrapIndex(sW[sx].firstTexel + j, rw, in.wrap);
+                        if (origS >= 0 && origS < rw) v += sW[sx].weight[j] * in.texels[((size_t)t * rw + origS) * C + c];
+                    }
+                    img[((size_t)t * pw + sx) * C + c] = v;
+                }
+        std::vector<TexResampleWeight> tW = texResampleWeights(rh, ph);
+        std::vector<float> work((size_t)ph);
+        for (int sx = 0; sx < pw; ++sx)
+            for (int c = 0; c < C; ++c) {
+                for (int t = 0; t < ph; ++t) {
+                    float v = 0.f;
+                    for (int j = 0; j < 4; ++j) {
+                        int offset = texWrapIndex(tW[t].firstTexel + j, rh, in.wrap);
+                        if (offset >= 0 && offset < rh) v += tW[t].weight[j] * img[((size_t)offset * pw + sx) * C + c];
+                    }
+                    work[t] = v;
+                }
+                for (int t = 0; t < ph; ++t) img[((size_t)t * pw + sx) * C + c] = work[t] < 0.f ? 0.f : work[t];   // clamp(v, 0, Infinity)
+            }
+        level0.swap(img);
+        rw = pw;
+        rh = ph;
+    } else
+        level0.assign(in.texels, in.texels + (size_t)rw * rh * C);
+    int nLevels = 1;
+    for (int m = std::max(rw, rh); m > 1; m >>= 1) ++nLevels;   // 1 + Log2Int(max)
+    memset(out, 0, sizeof(*out));
+    out->channels = C;
+    out->nLevels = nLevels;
+    out->w = rw;
+    out->h = rh;
+    out->wrap = in.wrap;
+    out->doTrilinear = in.do_trilinear != 0;
+    out->maxAniso = in.max_anisotropy;
+    out->su = in.su; out->sv = in.sv; out->du = in.du; out->dv = in.dv;
+    out->levelOfs[0] = (long long)pool.size();
+    pool.insert(pool.end(), level0.begin(), level0.end());
+    int pw = rw, ph = rh;
+    for (int i = 1; i < nLevels; ++i) {
+        // each coarser level: the mean of four texels of the finer one, fetched through the wrap mode (mipmap.h:186-194)
+        const int sRes = std::max(1, pw / 2), tRes = std::max(1, ph / 2);
+        const size_t prev = (size_t)out->levelOfs[i - 1];
+        out->levelOfs[i] = (long long)pool.size();
+        pool.resize(pool.size() + (size_t)sRes * tRes * C);
+        float *dst = pool.data() + out->levelOfs[i];
+        const float *src = pool.data() + prev;
+        auto texel = [&](int sx, int t, int c) -> float {
+            sx = texWrapIndex(sx, pw, in.wrap);
+            t = texWrapIndex(t, ph, in.wrap);
+            if (sx < 0 || t < 0) return 0.f;
+            return src[((size_t)t * pw + sx) * C + c];
+        };
+        for (int t = 0; t < tRes; ++t)
+            for (int sx = 0; sx < sRes; ++sx)
+                for (int c = 0; c < C; ++c)
+                    dst[((size_t)t * sRes + sx) * C + c] =
+                        .25f * (texel(2 * sx, 2 * t, c) + texel(2 * sx + 1, 2 * t, c) + texel(2 * sx, 2 * t + 1, c) + texel(2 * sx + 1, 2 * t + 1, c));
+        pw = sRes;
+        ph = tRes;
+    }
+    return PB2_OK;
+}
+
+static void texWeightLut(std::vector<float> &pool);
+static int uploadTextures(pb2_scene *s, const pb2_scene_desc *d) {
+    DScene &sc = s->d;
+    if (d->n_textures <= 0) return PB2_OK;
+    if (!d->textures) return setError(PB2_ERR_INVALID, "n_textures > 0 but textures is null");
+    std::vector<float> pool;
+    texWeightLut(pool);
+    std::vector<DTexture> tex((size_t)d->n_textures);
+    for (int i = 0; i < d->n_textures; ++i) {
+        int rc = buildTexturePyramid(d->textures[i], pool, &tex[i]);
+        if (rc) return rc;
+    }
+    int rc;
+    if ((rc = upload(s, tex.data(), tex.size(), &sc.textures))) return rc;
+    if ((rc = upload(s, pool.data(), pool.size(), &sc.texels))) return rc;
+    sc.nTextures = d->n_textures;
+    return PB2_OK;
+}
+
+static void texWeightLut(std::vector<float> &pool) {   // MIPMap::weightLut (mipmap.h:196-202)
+    pool.assign((size_t)TEX_LUT_SIZE, 0.f);
+    for (int i = 0; i < TEX_LUT_SIZE; ++i) {
+        float alpha = 2;
+        float r2 = float(i) / float(TEX_LUT_SIZE - 1);
+        pool[i] = std::exp(-alpha * r2) - std::exp(-alpha);
+    }
+}
+
+extern "C" int pb2_texture_pyramid(const pb2_texture *texture, int32_t level, int32_t *n_levels, int32_t *w, int32_t *h, float *out) {
+    if (!texture || !n_levels || !w || !h) return setError(PB2_ERR_INVALID, "null argument");
+    std::vector<float> pool;
+    DTexture t;
+    int rc = buildTexturePyramid(*texture, pool, &t);
+    if (rc) return rc;
+    if (level < 0 || level >= t.nLevels) return setError(PB2_ERR_INVALID, "texture level out of range");
+    *n_levels = t.nLevels;
+    *w = std::max(1, t.w >> level);
+    *h = std::max(1, t.h >> level);
+    if (out) memcpy(out, pool.data() + t.levelOfs[level], (size_t)*w * *h * t.channels * sizeof(float));
+    return PB2_OK;
+}
+
+__global__ void k_texture_lookup(DTexture tx, const float *pool, int64_t n, const float *st, const float *dst, float *out) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    V3 v = texLookup(tx, pool, mk2(st[2 * i], st[2 * i + 1]), mk2(dst[4 * i], dst[4 * i + 1]), mk2(dst[4 * i + 2], dst[4 * i + 3]));
+    out[3 * i] = v.x;
+    out[3 * i + 1] = v.y;
+    out[3 * i + 2] = v.z;
+}
+
+extern "C" int pb2_texture_lookup(const pb2_texture *texture, int64_t n, const float *st, const float *dst, float *out) {
+    if (!g_initialised) return setError(PB2_ERR_NO_DEVICE, "pb2_init was not called or failed (no CUDA device: this library has no CPU fallback)");
+    if (!texture || n < 0 || (n > 0 && (!st || !dst || !out))) return setError(PB2_ERR_INVALID, "null argument");
+    std::vector<float> pool;
+    texWeightLut(pool);
+    DTexture t;
+    int rc = buildTexturePyramid(*texture, pool, &t);
+    if (rc || n == 0) return rc;
+    float *dPool = nullptr, *dSt = nullptr, *dDst = nullptr, *dOut = nullptr;
+    cudaError_t e = cudaMalloc((void **)&dPool, pool.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dSt, (size_t)n * 2 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dDst, (size_t)n * 4 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&dOut, (size_t)n * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(dPool, pool.data(), pool.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dSt, st, (size_t)n * 2 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dDst, dst, (size_t)n * 4 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_texture_lookup<<<(unsigned)((n + 127) / 128), 128>>>(t, dPool, n, dSt, dDst, dOut);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, dOut, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(dPool);
+    cudaFree(dSt);
+    cudaFree(dDst);
+    cudaFree(dOut);
+    if (e != cudaSuccess) return setError(PB2_ERR_CUDA, cudaGetErrorString(e));
+    return PB2_OK;
+}
+
 static int createSceneOnCurrentDevice(const pb2_scene_desc *d, pb2_scene **out) {
     int rc = PB2_OK;
     if (d->n_prims <= 0 || d->n_nodes <= 0 || !d->nodes || !d->bvh_prims || !d->prim_type || !d->prim_index)
@@ -1296,6 +1521,25 @@ static int createSceneOnCurrentDevice(const pb2_scene_desc *d, pb2_scene **out) 
     for (int i = 0; i < d->n_materials; ++i)
         if (d->materials[i].type < PB2_MAT_NONE || d->materials[i].type > PB2_MAT_UBER)
             return setError(PB2_ERR_UNSUPPORTED, "material type outside the path's scope (matte, plastic, substrate, metal, uber, mirror, glass)");
+    // texture references: in range, one channel for float parameters and alpha masks, three for spectra
+    for (int i = 0; i < d->n_materials; ++i)
+        for (int k = 0; k < PB2_TEX_SLOTS; ++k) {
+            const int id = d->materials[i].tex[k];
+            if (!id) continue;
+            if (id < 0 || id > d->n_textures || !d->textures) return setError(PB2_ERR_INVALID, "material texture index out of range");
+            const bool spectrum = k == PB2_TEX_KD || k == PB2_TEX_KS || k == PB2_TEX_KR || k == PB2_TEX_KT || k == PB2_TEX_OPACITY ||
+                                  k == PB2_TEX_METAL_ETA || k == PB2_TEX_METAL_K;
+            if (d->textures[id - 1].channels != (spectrum ? 3 : 1))
+                return setError(PB2_ERR_INVALID, "material texture has the wrong number of channels for its parameter");
+        }
+    bool hasAlpha = false;
+    for (int i = 0; i < d->n_meshes; ++i)
+        for (int id : {d->meshes[i].alpha_tex, d->meshes[i].shadow_alpha_tex}) {
+            if (!id) continue;
+            if (id < 0 || id > d->n_textures || !d->textures || d->textures[id - 1].channels != 1)
+                return setError(PB2_ERR_INVALID, "mesh alpha texture: index out of range or not a one-channel texture");
+            hasAlpha = true;
+        }
     struct Guard {
         pb2_scene *s;
         ~Guard() { if (s) pb2_scene_destroy(s); }
@@ -1476,6 +1720,8 @@ static int createSceneOnCurrentDevice(const pb2_scene_desc *d, pb2_scene **out) 
     if ((rc = upload(s, d->prim_material, (size_t)d->n_prims, &sc.primMaterial))) return rc;
     if ((rc = upload(s, d->prim_light, (size_t)d->n_prims, &sc.primLight))) return rc;
     if ((rc = upload(s, d->materials, (size_t)d->n_materials, &sc.materials))) return rc;
+    if ((rc = uploadTextures(s, d))) return rc;
+    sc.hasAlpha = hasAlpha ? 1 : 0;
     if ((rc = upload(s, d->lights, (size_t)d->n_lights, &sc.lights))) return rc;
     sc.deltaLights = nullptr;
     for (int i = 0; i < d->n_lights; ++i) {

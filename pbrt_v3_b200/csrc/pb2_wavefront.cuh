@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
 // take a leaf step are staged into shared memory by the TMA unit - one cp.async.bulk (UBLKCP) of up to four 48-byte records
 // per lane, completion counted by one mbarrier per warp - and the triangle tests read them from there.
 template <int WIDTH, int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, bool SPHERES = false, bool INST = false, bool LD256 = false,
-          bool LEAFTMA = false>
+          bool LEAFTMA = false, bool ALPHA = false>
 __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
     static_assert(WIDTH == 2 || WIDTH == 4, "two- or four-child records");
     static_assert(!LEAFTMA || (!SPHERES && !INST), "the staging experiment covers triangle scenes");
@@ -739,6 +739,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                     }
                     float t, b0, b1, b2;
                     if (triangleTest(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c4.x, c4.y, c4.z), rs, tMax, &t, &b0, &b1, &b2)) {
+                        // alpha-masked meshes (ALPHA instantiations only): a hit on a texel of value 0 is no hit
+                        if (ALPHA && (pf & LEAF_ALPHA) && alphaRejects(sc, asInt(a.w), b0, b1, b2, any)) continue;
                         if (any) { flags |= F_FOUND; finished = true; break; }
                         if (pf & LEAF_DEGENERATE) continue;
                         flags |= F_FOUND;
@@ -1040,7 +1042,9 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_pool(DScene sc, WfPool p
 // vertex is evaluated); SHADE = false: the light list (shadow / MIS rays: a few adds and the next
 // ray).  Two instantiations so that the light kernel is small and the warps of each stay converged.
 // ---------------------------------------------------------------------------------------------
-template <bool SHADE, bool SPH, int MINB, bool SPEC = false, bool LAZY = false>
+// TEX = true: the shade step of a scene with image textures (the camera ray's differentials are rebuilt from the
+// context's pFilm); one instantiation, with everything else compiled in.
+template <bool SHADE, bool SPH, int MINB, bool SPEC = false, bool LAZY = false, bool TEX = false>
 __global__ void __launch_bounds__(128, MINB) k_wf_advance(DScene sc, DRenderParams rp, WfPool pool, int srcQ, int traceQ,
                                                                    int freeQ, float4 *film, unsigned long long *counters) {
     unsigned n = pool.counts[srcQ];
@@ -1064,7 +1068,13 @@ __global__ void __launch_bounds__(128, MINB) k_wf_advance(DScene sc, DRenderPara
             hit.inst = foundCode >= 2 ? foundCode - 2 : -1;
             bool found = foundCode != 0;
             float tHit = cx.tHit;
-            if (SHADE) shadeVertex<SPH, SPEC, LAZY>(sc, rp.halton, rp.path, ln, found, hit, tHit);
+            if (SHADE && TEX) {
+                DTexCtx tc;
+                tc.cam = &rp.cam;
+                tc.pFilm = cx.pFilm;
+                tc.diffScale = rp.diffScale;
+                shadeVertex<SPH, SPEC, LAZY, true>(sc, rp.halton, rp.path, ln, found, hit, tHit, &tc);
+            } else if (SHADE) shadeVertex<SPH, SPEC, LAZY>(sc, rp.halton, rp.path, ln, found, hit, tHit);
             else lightAdvance<SPH>(sc, ln, found, hit, tHit);
             if (SHADE && LAZY && ln.state == LS_DEFER) {
                 ln.state = LS_PATH;   // untouched: shaded again from the retry list once its voxel's record exists

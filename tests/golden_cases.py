@@ -168,3 +168,27 @@ def spawned_rays(pb, hits, rng):
     rays = np.zeros(n, pb.RAY_DTYPE)
     rays["o"], rays["d"], rays["t_max"] = po, w, np.inf
     return rays
+
+
+def texture_lookup_inputs(n, seed):
+    """(st, dst) batches for MIPMap::Lookup: footprints from none at all to several times the whole image, isotropic
+    and up to 60 : 1 anisotropic (beyond every maxanisotropy in use), one derivative zero, st outside [0, 1] for the wrap modes."""
+    rs = np.random.RandomState(seed)
+    st = rs.uniform(-0.6, 1.6, (n, 2)).astype(np.float32)
+    kind = rs.randint(0, 7, n)
+    size = np.exp(rs.uniform(np.log(1e-4), np.log(3.0), n))
+    ang = rs.uniform(0, 2 * np.pi, n)
+    ratio = np.exp(rs.uniform(0, np.log(60.0), n))
+    d0 = np.stack([np.cos(ang), np.sin(ang)], 1) * size[:, None]
+    ang1 = ang + np.where(kind == 5, rs.uniform(0, np.pi, n), np.pi / 2)   # kind 5: not orthogonal
+    d1 = np.stack([np.cos(ang1), np.sin(ang1)], 1) * (size / ratio)[:, None]
+    d1[kind == 1] = d0[kind == 1][:, ::-1] * [1, -1]    # isotropic
+    d0[kind == 0] = 0                                  # no differentials at all
+    d1[kind == 0] = 0
+    d1[kind == 2] = 0                                  # one derivative zero
+    swap = kind == 3                                   # the second one is the longer
+    d0[swap], d1[swap] = d1[swap].copy(), d0[swap].copy()
+    exact = kind == 6                                  # footprints of exactly 2^-k texture widths
+    d0[exact] = np.stack([2.0 ** -rs.randint(0, 8, exact.sum()), np.zeros(exact.sum())], 1)
+    d1[exact] = d0[exact][:, ::-1]
+    return st, np.concatenate([d0, d1], 1).astype(np.float32)

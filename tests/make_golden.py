@@ -83,6 +83,22 @@ def record_hlbvh(ref):
     np.savez_compressed(os.path.join(OUT, "hlbvh.npz"), **out)
 
 
+def record_textures(ref):
+    """MIPMap::Lookup of the reference for every image texture of tests/scenes/textured.pbrt (EWA and trilinear, the three
+    wrap modes, resampled and power-of-two pyramids, one- and three-channel) over tests/golden_cases.py's footprints,
+    and a checksum of every pyramid level."""
+    hs = pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "textured.pbrt"))
+    out = {}
+    for i, t in enumerate(hs.textures()):
+        st, dst = gc.texture_lookup_inputs(3000, 100 + i)
+        out["lookup_%d" % i] = ref.texture_lookup(t, st, dst)
+        levels = ref.texture_pyramid(t)
+        out["levels_%d" % i] = np.array([[lv.shape[1], lv.shape[0]] for lv in levels], np.int32)
+        out["pyramid_%d" % i] = np.concatenate([lv.ravel() for lv in levels])
+    np.savez_compressed(os.path.join(OUT, "textures.npz"), **out)
+    print("textures:", len(hs.textures()), "textures recorded")
+
+
 def main():
     ref = pyoracle.reference()
     if ref is None:
@@ -100,6 +116,9 @@ def main():
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "lights.pbrt")), "lights")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "params.pbrt")), "params")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "envlight.pbrt")), "envlight")
+    record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "textured.pbrt")), "textured")
+    record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "textured_lens.pbrt")), "textured_lens")
+    record_textures(ref)
     record_filters(ref)
     record_hlbvh(ref)
     # the metal material's default eta / k: copper's measured spectra through Spectrum::FromSampled (metal.cpp:121-126)

@@ -22,7 +22,7 @@ from test_oracle import load_scene, same_bvh, tessellated_sphere_scene
 pytestmark = pytest.mark.gpu
 
 SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass", "lights", "params",
-               "envlight"]
+               "envlight", "textured", "textured_lens"]
 
 
 def li_ok(got, want):
@@ -560,3 +560,34 @@ def test_maxdepth_beyond_the_halton_tables_is_refused(pb):
     rc = hs.L.pb2_render_path(dev, hs.camera, hs.film, hs.params_copy(max_depth=124), pb.ptr(out), None)
     assert rc == pb.PB2_ERR_UNSUPPORTED and b"1000 dimensions" in hs.L.pb2_last_error()
     pb.check(hs.L.pb2_render_path(dev, hs.camera, hs.film, hs.params_copy(max_depth=123), pb.ptr(out), None))
+
+
+def test_texture_lookups_match_the_reference_mipmap(pb):
+    """MIPMap::Lookup on the device (EWA and trilinear filtering, three wrap modes, resampled pyramids) against look-ups
+    recorded from the compiled reference, for every texture of tests/scenes/textured.pbrt.  The arithmetic is the
+    reference's operation for operation; the level of detail goes through log(), where the device's logf and glibc's may
+    differ in the last bit: nearly every look-up must be bit-identical, all of them within 2e-6 (relative to the value 1)."""
+    g = np.load(os.path.join(GOLDEN, "textures.npz"))
+    hs = load_scene(pb, "textured")
+    textures = hs.textures()
+    assert len(textures) == 10
+    for i, t in enumerate(textures):
+        st, dst = gc.texture_lookup_inputs(3000, 100 + i)
+        got = pb.texture_lookup(t, st, dst)
+        want = g["lookup_%d" % i]
+        same = (gc.bits(got) == gc.bits(want)).all(axis=1).mean()
+        err = np.abs(got - want).max() / max(1.0, float(np.abs(want).max()))
+        assert same >= 0.995 and err <= 2e-6, (i, same, err)
+
+
+def test_alpha_masked_meshes_through_every_render_kernel(pb):
+    """The alpha test (triangle.cpp:333-338, 531-569) inside the tuned trace kernel and inside the one-thread-per-ray
+    traversal give the same film: the cut-out scene rendered with the default kernel selection and with
+    PB2_FLAG_PLAIN_TRACE / PB2_FLAG_LINEAR_NODES (both end in the plain traversal for such scenes)."""
+    hs = load_scene(pb, "textured")
+    base, st0 = hs.render_rgbw(hs.params_copy(flags=0))
+    for flags in (pb.PB2_FLAG_PLAIN_TRACE, pb.PB2_FLAG_LINEAR_NODES):
+        film, st = hs.render_rgbw(hs.params_copy(flags=flags))
+        assert np.array_equal(film[..., 3], base[..., 3])
+        assert np.allclose(film, base, rtol=1e-4, atol=1e-5)
+        assert st.regular_rays == st0.regular_rays and st.shadow_rays == st0.shadow_rays

@@ -425,9 +425,89 @@ WorldEnd
     assert tuple(matte.kd) == (f32(.2), f32(.4), f32(.6))          # the redefinition inside the attribute block is gone again
     uber = [m for m in mats if m.type == pb.PB2_MAT_UBER][0]
     assert uber.uroughness == f32(.25) == uber.vroughness
-    hs = pb.HostScene.from_string('WorldBegin\nTexture "img" "spectrum" "imagemap" "string filename" "x.png"\n'
+    hs = pb.HostScene.from_string('WorldBegin\nTexture "img" "spectrum" "checkerboard"\n'
                                   'Material "matte" "texture Kd" "img"\nShape "sphere"\nWorldEnd\n')
     assert pb.lib().pb2h_error_count() >= before + 2                 # the directive and the parameter that names it
+
+
+def test_image_texture_directives(pb, tmp_path):
+    """Texture "..." "imagemap" (imagemap.cpp:113-197): the readers (PFM, PNG with every scanline filter, run-length TGA), the
+    flip in y, scale / inverse gamma / luminance (imagemap.h:97-106), the mapping and filter parameters, the slots of the
+    materials that name the textures (with the u / v roughness fall-backs), alpha / shadowalpha masks, and the errors."""
+    import ctypes as C
+    f32 = np.float32
+    tex = os.path.join(SCENES, "textures")
+    dec = np.load(os.path.join(tex, "decoded_8bit.npz"))
+    text = """WorldBegin
+Texture "png" "spectrum" "imagemap" "string filename" "%(t)s/tiles_20x12.png" "float scale" 2 "float maxanisotropy" 4 "string wrap" "clamp"
+Texture "png-linear" "spectrum" "imagemap" "string filename" "%(t)s/tiles_20x12.png" "bool gamma" "false" "float uscale" 3 "float vdelta" .5
+Texture "tga" "color" "imagemap" "string filename" "%(t)s/tiles_24x10.tga" "bool gamma" "false" "bool trilinear" "true" "string wrap" "black"
+Texture "tga-y" "float" "imagemap" "string filename" "%(t)s/tiles_24x10.tga"
+Texture "holes" "float" "imagemap" "string filename" "%(t)s/holes_16x16.pfm"
+Texture "missing" "float" "imagemap" "string filename" "%(t)s/nothing.pfm"
+Texture "zero" "float" "constant" "float value" 0
+Material "plastic" "texture Kd" "png" "texture Ks" "tga" "texture roughness" "tga-y"
+Shape "sphere"
+Material "uber" "texture Kd" "png-linear" "texture roughness" "tga-y" "texture vroughness" "holes" "texture index" "missing"
+Shape "sphere" "float radius" 2
+Material "metal" "texture roughness" "holes" "float uroughness" .3
+Shape "sphere" "float radius" 3
+Material "matte"
+Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 0 1 0 0 0 1 0] "texture alpha" "holes" "texture shadowalpha" "tga-y"
+Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 1 1 0 1 0 1 1] "texture alpha" "zero"
+Shape "trianglemesh" "integer indices" [0 1 2] "point P" [0 0 2 1 0 2 0 1 2] "float shadowalpha" 0
+WorldEnd
+""" % {"t": tex}
+    before = pb.lib().pb2h_error_count()
+    hs = pb.HostScene.from_string(text)
+    assert pb.lib().pb2h_error_count() == before + 1          # nothing.pfm cannot be read (a grey 1 x 1 texture replaces it)
+    d = hs.desc.contents
+    T = {}
+    mats = {d.materials[i].type: d.materials[i] for i in range(d.n_materials)}
+
+    def texels(t):
+        return np.ctypeslib.as_array(t.texels, shape=(t.height, t.width, t.channels))
+
+    def igc(v):   # InverseGammaCorrect in float (pbrt.h:298-301)
+        v = np.asarray(v, f32)
+        return np.where(v <= f32(0.04045), v * f32(1) / f32(12.92), np.power((v + f32(0.055)) * f32(1) / f32(1.055), f32(2.4)).astype(f32))
+
+    plastic, uber, metal = mats[pb.PB2_MAT_PLASTIC], mats[pb.PB2_MAT_UBER], mats[pb.PB2_MAT_METAL]
+    png = d.textures[plastic.tex[pb.PB2_TEX_KD] - 1]
+    assert (png.channels, png.width, png.height, png.wrap, png.do_trilinear, png.max_anisotropy) == (3, 20, 12, pb.PB2_WRAP_CLAMP, 0, 4.0)
+    want = f32(2) * igc(dec["png"][::-1].astype(f32) / f32(255))            # row 0 of the texels is the image's LAST row
+    assert np.allclose(texels(png), want, rtol=2e-6, atol=0)                 # (powf may differ from numpy's in the last bit)
+    lin = d.textures[uber.tex[pb.PB2_TEX_KD] - 1]
+    assert np.array_equal(texels(lin), dec["png"][::-1].astype(f32) / f32(255))
+    assert (lin.su, lin.sv, lin.du, lin.dv, lin.wrap) == (3.0, 1.0, 0.0, 0.5, pb.PB2_WRAP_REPEAT)
+    tga = d.textures[plastic.tex[pb.PB2_TEX_KS] - 1]
+    assert (tga.channels, tga.width, tga.height, tga.wrap, tga.do_trilinear) == (3, 24, 10, pb.PB2_WRAP_BLACK, 1)
+    assert np.array_equal(texels(tga), dec["tga"][::-1].astype(f32) / f32(255))
+    tga_y = d.textures[plastic.tex[pb.PB2_TEX_ROUGHNESS] - 1]
+    c = dec["tga"][::-1].astype(f32) / f32(255)
+    y = f32(0.212671) * c[..., 0] + f32(0.715160) * c[..., 1] + f32(0.072169) * c[..., 2]
+    assert tga_y.channels == 1 and np.allclose(texels(tga_y)[..., 0], igc(y), rtol=2e-6, atol=0)   # .tga: gamma defaults to true
+    # uber.cpp:71-80: u <- "roughness" (no "uroughness" given), v <- "vroughness"; "index" names the unreadable file
+    assert uber.tex[pb.PB2_TEX_UROUGHNESS] == plastic.tex[pb.PB2_TEX_ROUGHNESS] and uber.tex[pb.PB2_TEX_ROUGHNESS] == 0
+    holes = d.textures[uber.tex[pb.PB2_TEX_VROUGHNESS] - 1]
+    assert (holes.channels, holes.width, holes.height) == (1, 16, 16) and set(np.unique(texels(holes))) == {0.0, 1.0}
+    grey = d.textures[uber.tex[pb.PB2_TEX_ETA] - 1]
+    assert (grey.channels, grey.width, grey.height) == (1, 1, 1) and texels(grey).ravel()[0] == f32(0.212671) * f32(.5) + f32(0.715160) * f32(.5) + f32(0.072169) * f32(.5)
+    # metal.cpp:67-70: "uroughness" is a constant, v falls back to the "roughness" texture
+    assert metal.tex[pb.PB2_TEX_UROUGHNESS] == 0 and metal.uroughness == f32(.3) and metal.tex[pb.PB2_TEX_VROUGHNESS] == uber.tex[pb.PB2_TEX_VROUGHNESS]
+    meshes = [d.meshes[i] for i in range(d.n_meshes)]
+    assert meshes[0].alpha_tex == uber.tex[pb.PB2_TEX_VROUGHNESS] and meshes[0].shadow_alpha_tex == plastic.tex[pb.PB2_TEX_ROUGHNESS]
+    zero = d.textures[meshes[1].alpha_tex - 1]
+    assert meshes[1].shadow_alpha_tex == 0 and (zero.width, zero.height) == (1, 1) and texels(zero).ravel()[0] == 0
+    assert meshes[2].alpha_tex == 0 and texels(d.textures[meshes[2].shadow_alpha_tex - 1]).ravel()[0] == 0
+    # outside the scope: other mappings, bump maps, a float texture where a spectrum is expected
+    for bad in ('Texture "t" "spectrum" "imagemap" "string filename" "%s/holes_16x16.pfm" "string mapping" "spherical"\nMaterial "matte" "texture Kd" "t"' % tex,
+                'Texture "t" "float" "imagemap" "string filename" "%s/holes_16x16.pfm"\nMaterial "matte" "texture bumpmap" "t"' % tex,
+                'Texture "t" "float" "imagemap" "string filename" "%s/holes_16x16.pfm"\nMaterial "matte" "texture Kd" "t"' % tex,
+                'Texture "t" "spectrum" "imagemap" "string filename" "%s/tiles.exr"\nMaterial "matte" "texture Kd" "t"' % tex):
+        before = pb.lib().pb2h_error_count()
+        pb.HostScene.from_string('WorldBegin\n%s\nShape "sphere"\nWorldEnd\n' % bad)
+        assert pb.lib().pb2h_error_count() > before, bad
 
 
 def test_plymesh_reader(pb, tmp_path):

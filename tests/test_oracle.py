@@ -307,3 +307,35 @@ def test_killeroo_simple_fingerprint_of_the_surveyed_reference(pb, reference, tm
     img = np.ascontiguousarray(img, np.float32)
     assert pb.lib().pb2h_write_pfm(out.encode(), pb.ptr(img), 700, 700) == 0
     assert hashlib.md5(open(out, "rb").read()).hexdigest() == "5424ce0f17db0c040e0f988ebcfe4b4d"
+
+
+def test_library_texture_pyramids_are_the_reference_mipmaps(pb):
+    """The MIP pyramid the library builds on the host (Lanczos resampling of the 37x23 / 20x12 / 24x10 images to a power of
+    two, the clamp, the box-filtered levels under each wrap mode) against MIPMap::pyramid recorded from the compiled
+    reference: every texel of every level BIT FOR BIT, for every texture of tests/scenes/textured.pbrt."""
+    g = np.load(os.path.join(GOLDEN, "textures.npz"))
+    hs = load_scene(pb, "textured")
+    textures = hs.textures()
+    assert len(textures) == 10
+    resampled = 0
+    for i, t in enumerate(textures):
+        levels = pb.texture_pyramid(t)
+        assert np.array_equal(np.array([[lv.shape[1], lv.shape[0]] for lv in levels], np.int32), g["levels_%d" % i])
+        assert np.array_equal(gc.bits(np.concatenate([lv.ravel() for lv in levels])), gc.bits(g["pyramid_%d" % i])), i
+        resampled += (levels[0].shape[1], levels[0].shape[0]) != (t.width, t.height)
+        assert levels[-1].shape[:2] == (1, 1)
+    assert resampled >= 4
+
+
+def test_library_texture_pyramids_match_reference_live(pb, reference):
+    """... and against the reference live, on random images of awkward sizes (1 x N, N x 1, primes, already a power of two)."""
+    import ctypes as C
+    rs = np.random.RandomState(9)
+    for (w, h, ch, wrap) in [(1, 1, 1, 0), (1, 7, 3, 0), (5, 1, 1, 2), (13, 31, 3, 1), (16, 4, 1, 0), (33, 64, 3, 2), (100, 3, 1, 1)]:
+        texels = rs.uniform(0, 2, (h, w, ch)).astype(np.float32)
+        t = pb.Texture(channels=ch, width=w, height=h, wrap=wrap, do_trilinear=0, max_anisotropy=8.0, su=1, sv=1, du=0, dv=0,
+                       texels=texels.ctypes.data_as(C.POINTER(C.c_float)))
+        a, b = pb.texture_pyramid(t), reference.texture_pyramid(t)
+        assert len(a) == len(b)
+        for la, lb in zip(a, b):
+            assert la.shape == lb.shape and np.array_equal(gc.bits(la), gc.bits(lb)), (w, h, ch, wrap)
