@@ -34,7 +34,7 @@ extern "C" {
                              * (pb2_light.type, pb2_scene_desc.delta_lights); 7: pb2_trace_wavefront, kernel-selector flags;
                              * 8: pb2_dist_* (NCCL film reduce inside the render calls), pb2_host_alloc;
                              * 9: PB2_LIGHT_INFINITE, pb2_delta_light.light_to_world (112 bytes);
-                             * 10: image textures (pb2_texture, pb2_material.tex, pb2_mesh.alpha_tex / shadow_alpha_tex) */
+                             * 10: image textures (pb2_texture, pb2_material.tex, pb2_mesh.alpha_tex / shadow_alpha_tex), pb2_path_params.sampler */
 
 typedef enum pb2_status {
     PB2_OK = 0,
@@ -286,8 +286,14 @@ typedef struct pb2_path_params {
      * tiles t of SamplerIntegrator::Render (integrator.cpp:235-240) with t % tile_count == tile_rank */
     int32_t tile_rank, tile_count;
     int32_t flags;            /* PB2_FLAG_* */
-    int32_t pad;
+    int32_t sampler;          /* PB2_SAMPLER_*; zero-initialised = the HaltonSampler */
 } pb2_path_params;
+
+/* The two GlobalSamplers of the reference.  PB2_SAMPLER_SOBOL: SobolSampler (src/samplers/sobol.cpp:41-60,
+ * src/core/lowdiscrepancy.h:229-274): samples_per_pixel must already be the power of two its constructor rounds up to
+ * (sobol.h:52); sample_at_pixel_center does not exist there and is ignored.  The generator matrices come from
+ * pbrt_v3_b200/lib/sobol_matrices32.bin next to the library (tools/make_sobol_tables.py, run by build()). */
+enum { PB2_SAMPLER_HALTON = 0, PB2_SAMPLER_SOBOL = 1 };
 
 /* Count LinearBVHNode fetches and primitive tests (pb2_stats.node_visits / prim_tests) with the
  * one-thread-per-ray traversal kernel instead of the tuned one: the device analogue of the
@@ -451,6 +457,13 @@ int pb2_halton_samples(const pb2_film_desc *film, const pb2_path_params *params,
                        const int32_t *pixel_xy, const int64_t *sample_num, const int32_t *dim,
                        int64_t n, float *out);
 
+/* SobolSampler::SampleDimension(GetIndexForSample(sample_num), dim) for a batch, evaluated on the HOST by the same source
+ * functions the kernels compile (sobolIntervalToIndex, sobolSampleFloat; device/pb2_sampler.cuh) - no device needed; with
+ * tables != NULL also the two SobolIntervalToIndex tables derived for this film's resolution (2 x 52 entries:
+ * VdCSobolMatrices[m - 1], VdCSobolMatricesInv[m - 1], zero-padded).  Parity/debug entry point. */
+int pb2_sobol_samples_host(const pb2_film_desc *film, const pb2_path_params *params, const int32_t *pixel_xy,
+                           const int64_t *sample_num, const int32_t *dim, int64_t n, float *out, uint64_t *tables);
+
 /* Distribution1D of SpatialLightDistribution::Lookup(p) (src/core/lightdistrib.cpp:141-230):
  * for each point writes n_lights func values followed by n_lights+1 cdf values. HOST pointers. */
 int pb2_light_distribution(pb2_scene *scene, const float *points_xyz, int64_t n, float *out);
@@ -483,6 +496,16 @@ typedef struct pb2_build_node {
 } pb2_build_node;
 int pb2_hlbvh_treelets(const float *prim_bounds, int64_t n, int32_t max_prims_in_node, pb2_build_node *pool,
                        int32_t *ordered_prims, int32_t *treelet_roots, int32_t *n_treelets, double *device_ms);
+
+/* All of BVHAccel::HLBVHBuild and flattenBVHTree on the device (bvh.cpp:404-658): the stages above, then buildUpperSAH over
+ * the treelet roots (bvh.cpp:541-638; one thread - at most 4096 leaves, each split partitions the range the next ones work
+ * on - with libstdc++'s std::partition order) and the depth-first LinearBVHNode layout (bvh.cpp:640-658; a treelet's nodes
+ * are numbered depth-first when they are emitted, so each lands as one block).  Only the finished array crosses the bus:
+ *   nodes            room for 2n LinearBVHNodes; *n_nodes of them are written
+ *   ordered_prims    n primitive numbers in BVHAccel::primitives order
+ * HOST pointers; blocking.  Bit for bit the nodes the host build (and the reference run by one thread) produces. */
+int pb2_hlbvh_build(const float *prim_bounds, int64_t n, int32_t max_prims_in_node, pb2_bvh_node *nodes, int64_t *n_nodes,
+                    int32_t *ordered_prims, double *device_ms);
 
 #ifdef __cplusplus
 }

@@ -55,7 +55,8 @@ class Oracle:
         sample_num = np.ascontiguousarray(sample_num, np.int64)
         dim = np.ascontiguousarray(dim, np.int32)
         out = np.zeros(len(dim), np.float32)
-        self._f("halton_samples")(film, params, ptr(pixel_xy), ptr(sample_num), ptr(dim), len(dim), ptr(out))
+        if self._f("halton_samples")(film, params, ptr(pixel_xy), ptr(sample_num), ptr(dim), len(dim), ptr(out)):
+            raise RuntimeError("the %s oracle does not restate this sampler" % self.kind)
         return out
 
     def radical_inverse(self, base_index, a, scrambled=False):
@@ -100,6 +101,16 @@ class Oracle:
         fn.argtypes = [C.POINTER(pb.Texture), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
         fn(C.byref(texture), len(st), ptr(st), ptr(dst), ptr(out))
         return out
+
+    def sobol_tables(self, m):
+        """The reference's VdCSobolMatrices[m - 1] / VdCSobolMatricesInv[m - 1] (104 entries) and SobolMatrices32 (reference only)."""
+        tab = np.zeros(104, np.uint64)
+        mats = np.zeros((1024, 52), np.uint32)
+        fn = self._f("sobol_tables")
+        fn.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+        if fn(m, ptr(tab), ptr(mats)):
+            raise ValueError("resolution 2^%d outside the reference's tables" % m)
+        return tab, mats
 
     def copper_rgb(self):
         """(eta, k) RGB of the metal material's default copper spectra (reference only)."""
@@ -158,8 +169,10 @@ class OracleScene:
         out = np.zeros((h, w, 3), np.float32)
         secs = C.c_double()
         st = Stats()
-        self.o._f("render")(self.h, self.hs.camera, self.hs.film, params if params is not None else self.hs.params,
-                            n_threads, ptr(out), C.byref(secs), C.byref(st))
+        rc = self.o._f("render")(self.h, self.hs.camera, self.hs.film, params if params is not None else self.hs.params,
+                                 n_threads, ptr(out), C.byref(secs), C.byref(st))
+        if rc:
+            raise RuntimeError("the %s oracle does not cover this frame (sampler outside its restatement)" % self.o.kind)
         return out, secs.value, st
 
     def li_samples(self, pixel_xy, sample_num, params=None):
@@ -168,8 +181,9 @@ class OracleScene:
         n = len(sample_num)
         rgb = np.zeros((n, 3), np.float32)
         pfilm = np.zeros((n, 2), np.float32)
-        self.o._f("li_samples")(self.h, self.hs.camera, self.hs.film, params if params is not None else self.hs.params,
-                                ptr(pixel_xy), ptr(sample_num), n, ptr(rgb), ptr(pfilm))
+        if self.o._f("li_samples")(self.h, self.hs.camera, self.hs.film, params if params is not None else self.hs.params,
+                                   ptr(pixel_xy), ptr(sample_num), n, ptr(rgb), ptr(pfilm)):
+            raise RuntimeError("the %s oracle does not cover this frame (sampler outside its restatement)" % self.o.kind)
         return rgb, pfilm
 
     def light_distribution(self, points):

@@ -69,6 +69,7 @@
 #include "materials/metal.h"
 #include "materials/uber.h"
 #include "samplers/halton.h"
+#include "samplers/sobol.h"
 #include "shapes/loopsubdiv.h"
 #include "shapes/sphere.h"
 #include "shapes/triangle.h"
@@ -172,7 +173,8 @@ RenderObjects makeRenderObjects(const RefScene &rs, const pb2_camera *cam, const
     Bounds2f screen(Point2f(cam->screen_window[0], cam->screen_window[2]), Point2f(cam->screen_window[1], cam->screen_window[3]));
     ro.camera.reset(new PerspectiveCamera(ac2w, screen, cam->shutter_open, cam->shutter_close, cam->lens_radius,
                                           cam->focal_distance, cam->fov, ro.film, nullptr));
-    ro.sampler.reset(new HaltonSampler(pp->samples_per_pixel, ro.film->GetSampleBounds(), pp->sample_at_pixel_center != 0));
+    if (pp->sampler == PB2_SAMPLER_SOBOL) ro.sampler.reset(new SobolSampler(pp->samples_per_pixel, ro.film->GetSampleBounds()));
+    else ro.sampler.reset(new HaltonSampler(pp->samples_per_pixel, ro.film->GetSampleBounds(), pp->sample_at_pixel_center != 0));
     Bounds2i pb(Point2i(pp->pixel_bounds[0], pp->pixel_bounds[1]), Point2i(pp->pixel_bounds[2], pp->pixel_bounds[3]));
     ro.integrator.reset(new PathIntegrator(pp->max_depth, ro.camera, ro.sampler, pb, pp->rr_threshold,
                                            strategyName(rs.lightStrategy)));
@@ -611,12 +613,32 @@ int ref_halton_samples(const pb2_film_desc *fd, const pb2_path_params *pp, const
                         (int)std::floor(fd->cropped_pixel_bounds[1] + 0.5f - fd->filter_radius[1])),
                 Point2i((int)std::ceil(fd->cropped_pixel_bounds[2] - 0.5f + fd->filter_radius[0]),
                         (int)std::ceil(fd->cropped_pixel_bounds[3] - 0.5f + fd->filter_radius[1])));
+    if (pp->sampler == PB2_SAMPLER_SOBOL) {
+        SobolSampler ss(pp->samples_per_pixel, sb);
+        for (int64_t i = 0; i < n; ++i) {
+            ss.StartPixel(Point2i(pixel_xy[2 * i], pixel_xy[2 * i + 1]));
+            out[i] = ss.SampleDimension(ss.GetIndexForSample(sample_num[i]), dim[i]);
+        }
+        return 0;
+    }
     HaltonSampler hs(pp->samples_per_pixel, sb, pp->sample_at_pixel_center != 0);
     for (int64_t i = 0; i < n; ++i) {
         hs.StartPixel(Point2i(pixel_xy[2 * i], pixel_xy[2 * i + 1]));
         int64_t index = hs.GetIndexForSample(sample_num[i]);
         out[i] = hs.SampleDimension(index, dim[i]);
     }
+    return 0;
+}
+
+// The reference's own tables behind SobolIntervalToIndex for resolution 2^m (sobolmatrices.cpp): 52 entries of
+// VdCSobolMatrices[m - 1], then 52 of VdCSobolMatricesInv[m - 1]; and SobolMatrices32 (1024 x 52) when asked for.
+int ref_sobol_tables(int m, uint64_t *out104, uint32_t *matrices32) {
+    if (m < 1 || m > 25) return 1;
+    for (int c = 0; c < SobolMatrixSize; ++c) {
+        out104[c] = VdCSobolMatrices[m - 1][c];
+        out104[SobolMatrixSize + c] = VdCSobolMatricesInv[m - 1][c];
+    }
+    if (matrices32) std::memcpy(matrices32, SobolMatrices32, sizeof(uint32_t) * NumSobolDimensions * SobolMatrixSize);
     return 0;
 }
 

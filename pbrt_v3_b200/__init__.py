@@ -60,6 +60,7 @@ class Material(C.Structure):
 
 
 PB2_WRAP_REPEAT, PB2_WRAP_BLACK, PB2_WRAP_CLAMP = 0, 1, 2
+PB2_SAMPLER_HALTON, PB2_SAMPLER_SOBOL = 0, 1
 (PB2_TEX_KD, PB2_TEX_KS, PB2_TEX_KR, PB2_TEX_KT, PB2_TEX_OPACITY, PB2_TEX_SIGMA, PB2_TEX_ROUGHNESS, PB2_TEX_UROUGHNESS,
  PB2_TEX_VROUGHNESS, PB2_TEX_ETA, PB2_TEX_METAL_ETA, PB2_TEX_METAL_K) = range(12)
 
@@ -122,7 +123,7 @@ class FilmDesc(C.Structure):
 class PathParams(C.Structure):
     _fields_ = [("samples_per_pixel", C.c_int32), ("sample_at_pixel_center", C.c_int32), ("max_depth", C.c_int32),
                 ("rr_threshold", C.c_float), ("pixel_bounds", C.c_int32 * 4), ("tile_rank", C.c_int32),
-                ("tile_count", C.c_int32), ("flags", C.c_int32), ("pad", C.c_int32)]
+                ("tile_count", C.c_int32), ("flags", C.c_int32), ("sampler", C.c_int32)]
 
 
 class Ray(C.Structure):
@@ -197,6 +198,7 @@ def lib():
     L.pb2_li_samples.argtypes = [vp, C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), vp, vp, C.c_int64, vp, vp]
     L.pb2_halton_samples.argtypes = [C.POINTER(FilmDesc), C.POINTER(PathParams), vp, vp, vp, C.c_int64, vp]
     L.pb2_light_distribution.argtypes = [vp, vp, C.c_int64, vp]
+    L.pb2_sobol_samples_host.argtypes = [C.POINTER(FilmDesc), C.POINTER(PathParams), vp, vp, vp, C.c_int64, vp, vp]
     L.pb2_texture_pyramid.argtypes = [C.POINTER(Texture), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     L.pb2_texture_lookup.argtypes = [C.POINTER(Texture), C.c_int64, vp, vp, vp]
     L.pb2h_parse_file.argtypes = [C.c_char_p, C.c_char_p]
@@ -242,6 +244,17 @@ def init(device=None):
         return
     check(lib().pb2_init(device))
     _initialised_device = device
+
+
+def sobol_samples_host(film, params, pixel_xy, sample_num, dim, tables=False):
+    """SobolSampler sample values computed on the host by the kernels' own source functions (pb2_sobol_samples_host)."""
+    pixel_xy = np.ascontiguousarray(pixel_xy, np.int32)
+    sample_num = np.ascontiguousarray(sample_num, np.int64)
+    dim = np.ascontiguousarray(dim, np.int32)
+    out = np.zeros(len(dim), np.float32)
+    tab = np.zeros(104, np.uint64)
+    check(lib().pb2_sobol_samples_host(film, params, ptr(pixel_xy), ptr(sample_num), ptr(dim), len(dim), ptr(out), ptr(tab)))
+    return (out, tab) if tables else out
 
 
 def texture_pyramid(texture, fn=None):

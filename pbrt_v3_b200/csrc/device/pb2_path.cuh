@@ -87,7 +87,8 @@ PB2_HD void startMisOrFinish(DLane &ln) {
 // of the two direct-lighting rays.
 // LAZY = false compiles the deferral of the lazy light distribution out (the bench scene's shade kernel sits exactly at
 // its 128-register budget)
-// TEX = true evaluates image textures; tc then carries what the camera ray's differentials are rebuilt from.
+// TEX = true is the GENERAL instantiation: it evaluates image textures (tc then carries what the camera ray's differentials
+// are rebuilt from) and draws from the SobolSampler when the frame uses it (sampleDimension<true>).
 struct DTexCtx {
     const DCamera *cam;
     V2 pFilm;           // of this camera sample
@@ -110,7 +111,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
             if (tc->cam->lensRadius > 0) {
                 DSampler ls = ln.smp;
                 ls.dim = 3;   // CameraSample::pLens (sampler.cpp:46-52)
-                uLens = get2D(h, ls);
+                uLens = get2D<TEX>(h, ls);
             }
             const DRayDiff rd = cameraRayDifferentials(*tc->cam, tc->pFilm, uLens, tc->diffScale, ln.ray.o, ln.ray.d);
             uvDiff = computeUvDifferentials(isect.p, isect.n, tg.dpdu, tg.dpdv, rd);
@@ -161,14 +162,14 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
     if (ln.doNEE && sc.nLights > 0) {
         // UniformSampleOneLight (integrator.cpp:85-106)
         float lightPickPdf;
-        int lightNum = sampleDiscrete(distrib, sc.nLights, get1D(h, smp), &lightPickPdf);
+        int lightNum = sampleDiscrete(distrib, sc.nLights, get1D<TEX>(h, smp), &lightPickPdf);
         if (lightPickPdf != 0) {
             ln.pick = lightPickPdf;
             ln.lightNum = lightNum;
             const pb2_light light = sc.lights[lightNum];
             const TriRec lightRec = loadTriRec(sc.lightRecs, (size_t)lightNum);
-            V2 uLight = get2D(h, smp);
-            V2 uScattering = get2D(h, smp);
+            V2 uLight = get2D<TEX>(h, smp);
+            V2 uScattering = get2D<TEX>(h, smp);
             // EstimateDirect, light-sampling half (integrator.cpp:116-160)
             DLightSample ls = sampleLight<SPH>(sc, lightNum, light, lightRec, isect, uLight);
             float lightPdf = ls.pdf, scatteringPdf = 0;
@@ -218,7 +219,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
         V3 wo = -ln.ray.d, wi;
         float pdf;
         int sampled = 0;
-        V3 f = bsdfSampleF<SPEC>(bsdf, wo, &wi, get2D(h, smp), &pdf, &sampled);
+        V3 f = bsdfSampleF<SPEC>(bsdf, wo, &wi, get2D<TEX>(h, smp), &pdf, &sampled);
         if (!(isBlack(f) || pdf == 0.f)) {
             V3 s = f * absDot(wi, isect.ns);
             V3 beta = ln.beta * mk3(s.x / pdf, s.y / pdf, s.z / pdf);
@@ -233,7 +234,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
             V3 rrBeta = beta * ln.etaScale;
             if (maxComponentValue(rrBeta) < pp.rrThreshold && ln.bounces > 3) {
                 float q = pmax(.05f, 1 - maxComponentValue(rrBeta));
-                if (get1D(h, smp) < q) survive = false;
+                if (get1D<TEX>(h, smp) < q) survive = false;
                 else {
                     float d = 1 - q;
                     beta = mk3(beta.x / d, beta.y / d, beta.z / d);

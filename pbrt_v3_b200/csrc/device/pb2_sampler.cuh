@@ -34,7 +34,15 @@ struct DHalton {
     // digit tables of the scrambled radical inverse (scrambledRadicalInverseTab below); null = digit loop
     const struct HaltonDimTab *dimTabs;   // one record per dimension
     const uint16_t *digitTab;             // per dimension: nat[B] followed by full[B]
+    // SobolSampler instead (pb2_path_params::sampler == PB2_SAMPLER_SOBOL): non-null.  Read only by the <GENERAL = true>
+    // instantiations of the sampling functions below, so the Halton-only kernels carry none of it.
+    const uint32_t *sobol;                // SobolMatrices32: 1024 dimensions x 52 columns
+    const uint64_t *sobolVdc;             // for this resolution 2^m: VdCSobolMatrices[m - 1] (52 - 2m entries, zero-padded to 52),
+                                          // then VdCSobolMatricesInv[m - 1] (2m entries)
+    int sobolLog2Res, sobolRes;           // SobolSampler::log2Resolution / resolution (sobol.h:53-57)
+    int sbx0, sby0;                       // sampleBounds.pMin
 };
+enum { kSobolDims = 1024, kSobolMatrixSize = 52 };
 
 // The scrambled radical inverse several digits at a time.  For base b let B = b^m be the largest power <= 8192.  Of an
 // index a = (top B + mid) B + lo the digit loop of ScrambledRadicalInverseSpecialized (lowdiscrepancy.cpp:405-424) first
@@ -233,15 +241,62 @@ PB2_HD float haltonSample(const DHalton &h, int64_t index, int dim) {
 #endif
 }
 
+// SobolIntervalToIndex (lowdiscrepancy.h:229-249): the index of sample `frame` of pixel p (relative to the sample bounds)
+PB2_HD uint64_t sobolIntervalToIndex(const DHalton &h, uint64_t frame, int px, int py) {
+    const uint32_t m = (uint32_t)h.sobolLog2Res;
+    if (m == 0) return 0;
+    const uint32_t m2 = m << 1;
+    uint64_t index = frame << m2;
+    uint64_t delta = 0;
+    for (int c = 0; frame; frame >>= 1, ++c)
+        if (frame & 1) delta ^= h.sobolVdc[c];
+    uint64_t b = (((uint64_t)((uint32_t)px) << m) | ((uint32_t)py)) ^ delta;
+    for (int c = 0; b; b >>= 1, ++c)
+        if (b & 1) index ^= h.sobolVdc[kSobolMatrixSize + c];
+    return index;
+}
+// SobolSampleFloat (lowdiscrepancy.h:259-274), scramble = 0
+PB2_HD float sobolSampleFloat(const DHalton &h, int64_t a, int dimension) {
+    uint32_t v = 0;
+    for (int i = dimension * kSobolMatrixSize; a != 0; a >>= 1, i++)
+        if (a & 1) v ^= h.sobol[i];
+    float f = v * 0x1p-32f;
+    return f < kOneMinusEpsilon ? f : kOneMinusEpsilon;
+}
+// SobolSampler::SampleDimension (sobol.cpp:46-59) for the two pixel dimensions: the sample's offset inside its pixel
+PB2_HD float sobolPixelSample(const DHalton &h, int64_t index, int dim, int pixelCoord) {
+    float sv = sobolSampleFloat(h, index, dim);
+    sv = sv * h.sobolRes + (dim == 0 ? h.sbx0 : h.sby0);
+    return clampf(sv - pixelCoord, 0.f, kOneMinusEpsilon);
+}
+
+// The value of dimension `dim` of sample `index`: HaltonSampler::SampleDimension, or (GENERAL instantiations, when the frame
+// uses the SobolSampler) SobolSampler::SampleDimension for dim >= 2 - its two pixel dimensions need the pixel and go through
+// sobolPixelSample at the one place they are drawn (generateCameraRay).
+template <bool GENERAL>
+PB2_HD float sampleDimension(const DHalton &h, int64_t index, int dim) {
+    if (GENERAL && h.sobol) return sobolSampleFloat(h, index, dim);
+    return haltonSample(h, index, dim);
+}
+
+// GlobalSampler::GetIndexForSample: HaltonSampler's (halton.cpp:96-116) or SobolSampler's (sobol.cpp:41-44)
+template <bool GENERAL>
+PB2_HD int64_t sampleIndex(const DHalton &h, int px, int py, int64_t sampleNum) {
+    if (GENERAL && h.sobol) return (int64_t)sobolIntervalToIndex(h, (uint64_t)sampleNum, px - h.sbx0, py - h.sby0);
+    return haltonIndex(h, px, py, sampleNum);
+}
+
 // The GlobalSampler's dimension counter (sampler.cpp:178-195; PathIntegrator requests no sample
 // arrays, so arrayStartDim == arrayEndDim and no dimension is ever skipped).
 struct DSampler {
     int64_t index;
     int dim;
 };
-PB2_HD float get1D(const DHalton &h, DSampler &s) { return haltonSample(h, s.index, s.dim++); }
+template <bool GENERAL = false>
+PB2_HD float get1D(const DHalton &h, DSampler &s) { return sampleDimension<GENERAL>(h, s.index, s.dim++); }
+template <bool GENERAL = false>
 PB2_HD V2 get2D(const DHalton &h, DSampler &s) {
-    V2 p = mk2(haltonSample(h, s.index, s.dim), haltonSample(h, s.index, s.dim + 1));
+    V2 p = mk2(sampleDimension<GENERAL>(h, s.index, s.dim), sampleDimension<GENERAL>(h, s.index, s.dim + 1));
     s.dim += 2;
     return p;
 }

@@ -1522,15 +1522,21 @@ PB2_HD DUvDiff computeUvDifferentials(V3 p, V3 n, V3 dpdu, V3 dpdv, const DRayDi
 // Sampler::GetCameraSample (sampler.cpp:46-52) + PerspectiveCamera::GenerateRayDifferential
 // (perspective.cpp:95-144) + Transform::operator()(Ray) (transform.h:251-264).  Differentials are
 // not carried: nothing on this path reads them (constant textures only).
+template <bool GENERAL = false>
 PB2_HD DRay generateCameraRay(const DCamera &cam, const DHalton &h, DSampler &smp, int px, int py, V2 *pFilmOut) {
-    V2 uf = get2D(h, smp);
+    V2 uf;
+    if (GENERAL && h.sobol) {
+        uf = mk2(sobolPixelSample(h, smp.index, 0, px), sobolPixelSample(h, smp.index, 1, py));
+        smp.dim += 2;
+    } else
+        uf = get2D(h, smp);
     V2 pFilm = mk2((float)px + uf.x, (float)py + uf.y);
     // CameraSample::time and pLens (sampler.cpp:46-52) take dimensions 2-4.  The sample values are pure
     // functions of (index, dimension): what is not read is not computed - time never is (static scenes),
     // pLens only with a finite aperture.
     smp.dim += 1;
     V2 uLens = mk2(0, 0);
-    if (cam.lensRadius > 0) uLens = get2D(h, smp);
+    if (cam.lensRadius > 0) uLens = get2D<GENERAL>(h, smp);
     else smp.dim += 2;
     *pFilmOut = pFilm;
     V3 pCamera = xfPoint(cam.rasterToCamera, mk3(pFilm.x, pFilm.y, 0));

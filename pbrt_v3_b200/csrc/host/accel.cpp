@@ -228,8 +228,29 @@ struct Builder {
         pool[node].nPrimitives = 0;
         return node;
     }
-    // The same lower half on the GPU (pb2_hlbvh_treelets, include/pb2.h): Morton codes, sort and treelets come back as
-    // this builder's own records; only the small SAH tree over the treelet roots is built here.
+    // The whole HLBVH build on the GPU (pb2_hlbvh_build, include/pb2.h): Morton codes, sort, treelets, the SAH tree over
+    // their roots and the depth-first layout; the finished LinearBVHNode array and the primitive order come back.
+    bool buildHLBVHAllOnDevice(std::vector<pb2_bvh_node> *nodes, double *deviceMs) {
+        const int n = (int)info.size();
+        std::vector<float> primBounds((size_t)n * 6);
+        for (int i = 0; i < n; ++i)
+            for (int k = 0; k < 3; ++k) {
+                primBounds[6 * (size_t)i + k] = info[i].bounds.pMin[k];
+                primBounds[6 * (size_t)i + 3 + k] = info[i].bounds.pMax[k];
+            }
+        if (!EnsureDevice()) return false;
+        nodes->resize((size_t)2 * n);
+        int64_t nNodes = 0;
+        if (pb2_hlbvh_build(primBounds.data(), n, maxPrimsInNode, nodes->data(), &nNodes, ordered.data(), deviceMs) != PB2_OK) {
+            Error("Device BVH build failed: %s", pb2_last_error());
+            nodes->clear();
+            return false;
+        }
+        nodes->resize((size_t)nNodes);
+        return true;
+    }
+    // Only the lower half on the GPU (pb2_hlbvh_treelets; PB2_DEVICE_BVH_UPPER=host): Morton codes, sort and treelets come
+    // back as this builder's own records, the small SAH tree over the treelet roots and the flatten run here.
     int buildHLBVHOnDevice(double *deviceMs) {
         static_assert(sizeof(BuildNode) == sizeof(pb2_build_node), "BuildNode is the ABI's pb2_build_node");
         const int n = (int)info.size();
@@ -347,6 +368,20 @@ BVHAccel::BVHAccel(std::vector<std::shared_ptr<Primitive>> p, int maxPrims, Spli
     const auto t1 = clk();
     int root = -1;
     double deviceMs = 0;
+    const char *upperEnv = std::getenv("PB2_DEVICE_BVH_UPPER");
+    const bool upperOnHost = upperEnv && std::string(upperEnv) == "host";
+    if (splitMethod == SplitMethod::HLBVH && deviceBuild && !upperOnHost) {
+        // everything on the device: nothing left to flatten here
+        if (!b.buildHLBVHAllOnDevice(&nodes, &deviceMs)) {
+            sceneOrderPrims.clear();
+            return;
+        }
+        lastBuildDeviceMs = deviceMs;
+        orderedPrimNumbers = std::move(b.ordered);
+        primitives.reserve(orderedPrimNumbers.size());
+        for (int32_t n : orderedPrimNumbers) primitives.push_back(sceneOrderPrims[n]);
+        return;
+    }
     if (splitMethod == SplitMethod::HLBVH && deviceBuild) root = b.buildHLBVHOnDevice(&deviceMs);
     else if (splitMethod == SplitMethod::HLBVH) root = b.buildHLBVH();
     else root = b.build(0, (int)sceneOrderPrims.size(), 0, spawnLevels + 2);

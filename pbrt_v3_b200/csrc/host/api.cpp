@@ -579,10 +579,12 @@ void pbrtWorldEnd() {
     ro.CameraParams.ReportUnused();
     // MakeIntegrator (api.cpp:1662-1714)
     if (setup->camera) {
-        if (ro.SamplerName != "halton")
-            Error("Sampler \"%s\" is outside the GPU path's scope (halton).", ro.SamplerName.c_str());
-        else
+        if (ro.SamplerName == "halton")
             setup->sampler.reset(CreateHaltonSampler(ro.SamplerParams, setup->film->GetSampleBounds()));
+        else if (ro.SamplerName == "sobol")
+            setup->sampler.reset(CreateSobolSampler(ro.SamplerParams, setup->film->GetSampleBounds()));
+        else
+            Error("Sampler \"%s\" is outside the GPU path's scope (halton, sobol).", ro.SamplerName.c_str());
         ro.SamplerParams.ReportUnused();
         if (setup->sampler) {
             if (ro.IntegratorName != "path")

@@ -712,6 +712,22 @@ HaltonSampler *CreateHaltonSampler(const ParamSet &params, const Bounds2i &sampl
     return new HaltonSampler(nsamp, sampleBounds, sampleAtCenter);
 }
 
+static int64_t roundUpPow2(int64_t v) {
+    int64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+SobolSampler::SobolSampler(int64_t nsamp, const Bounds2i &sampleBounds) : Sampler(roundUpPow2(nsamp)), sampleBounds(sampleBounds) {
+    if (samplesPerPixel != nsamp)
+        Warning("Non power-of-two sample count rounded up to %lld for SobolSampler.", (long long)samplesPerPixel);
+}
+// sobol.cpp:65-70
+SobolSampler *CreateSobolSampler(const ParamSet &params, const Bounds2i &sampleBounds) {
+    int nsamp = params.FindOneInt("pixelsamples", 16);
+    if (g_quickRender) nsamp = 1;
+    return new SobolSampler(nsamp, sampleBounds);
+}
+
 PathIntegrator *CreatePathIntegrator(const ParamSet &params, std::shared_ptr<Sampler> sampler,
                                      std::shared_ptr<const Camera> camera) {
     int maxDepth = params.FindOneInt("maxdepth", 5);
@@ -892,6 +908,7 @@ pb2_path_params PathIntegrator::Params() const {
     p.pixel_bounds[2] = pixelBounds.pMax.x; p.pixel_bounds[3] = pixelBounds.pMax.y;
     p.tile_rank = tileRank;
     p.tile_count = tileCount;
+    p.sampler = dynamic_cast<const SobolSampler *>(sampler.get()) ? PB2_SAMPLER_SOBOL : PB2_SAMPLER_HALTON;
     return p;
 }
 
@@ -902,8 +919,8 @@ void PathIntegrator::Render(const Scene &scene) {
         Error("PathIntegrator::Render: the GPU path needs Accelerator \"bvh\" (kd-tree is out of scope, SURVEY.md §2 row 41)");
         return;
     }
-    if (!dynamic_cast<const HaltonSampler *>(sampler.get())) {
-        Error("PathIntegrator::Render: only Sampler \"halton\" is inside the GPU path's scope (SURVEY.md §2 rows 19-20)");
+    if (!dynamic_cast<const HaltonSampler *>(sampler.get()) && !dynamic_cast<const SobolSampler *>(sampler.get())) {
+        Error("PathIntegrator::Render: only the GlobalSamplers \"halton\" and \"sobol\" are inside the GPU path's scope (SURVEY.md §2 rows 19-20)");
         return;
     }
     if (bvh->nodes.empty()) {

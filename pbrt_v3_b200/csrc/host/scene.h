@@ -471,6 +471,13 @@ class HaltonSampler : public Sampler {
     bool sampleAtPixelCenter;
 };
 HaltonSampler *CreateHaltonSampler(const ParamSet &params, const Bounds2i &sampleBounds);
+// sobol.h:47-77: the sample count is rounded up to a power of two
+class SobolSampler : public Sampler {
+  public:
+    SobolSampler(int64_t nsamp, const Bounds2i &sampleBounds);
+    Bounds2i sampleBounds;
+};
+SobolSampler *CreateSobolSampler(const ParamSet &params, const Bounds2i &sampleBounds);
 
 // ---------------------------------------------------------------- integrators
 class Integrator {

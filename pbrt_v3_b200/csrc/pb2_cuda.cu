@@ -18,6 +18,7 @@
 #include <nccl.h>   // types and prototypes only: libnccl is loaded at run time by pb2_dist_init (no link-time dependency)
 
 #include <algorithm>
+#include <mutex>
 #include <chrono>
 #include <cstddef>
 #include <cstdio>
@@ -60,6 +61,8 @@ struct DeviceState {
     ulonglong2 *dimRecs = nullptr;
     HaltonDimTab *dimTabs = nullptr;
     uint16_t *digitTab = nullptr;
+    uint32_t *sobol = nullptr;        // SobolMatrices32 (uploaded on the first frame that uses the SobolSampler)
+    uint64_t *sobolVdc = nullptr;     // the two SobolIntervalToIndex tables of the frame being rendered (104 entries)
     bool peerOfPrimary = false;   // the primary device can read this one's memory directly (NVLink / PCIe peer access)
 };
 static std::vector<DeviceState> g_devs;
@@ -274,7 +277,113 @@ static DHalton makeHalton(const pb2_film_desc *film, const pb2_path_params *pp) 
     // values; PB2_HALTON_LOOP=1 selects the digit loop (A/B)
     h.dimTabs = envInt("PB2_HALTON_LOOP", 0) ? nullptr : cur().dimTabs;
     h.digitTab = cur().digitTab;
+    h.sobol = nullptr;
+    h.sobolVdc = nullptr;
+    h.sobolLog2Res = h.sobolRes = 0;
+    h.sbx0 = sb.x0;
+    h.sby0 = sb.y0;
     return h;
+}
+
+// ---- SobolSampler (src/samplers/sobol.{h,cpp}) ---------------------------------------------------------------------------
+// The generator matrices (1024 dimensions x 52 columns of 32-bit fractions) are read once from sobol_matrices32.bin next to
+// this library (tools/make_sobol_tables.py).  The two tables SobolIntervalToIndex needs (the reference's VdCSobolMatrices /
+// VdCSobolMatricesInv, sobolmatrices.cpp) follow from dimensions 0 and 1 and are derived here for the frame's resolution
+// 2^m: the pixel a sample falls into is the upper m bits of its first two dimensions, i.e. a GF(2)-linear map A of the
+// index bits; column (2m + c) of A is the pixel offset that bit c of the sample number ("frame") adds - VdCSobolMatrices[m-1][c]
+// - and the inverse of A's first 2m columns turns a pixel back into the low index bits - VdCSobolMatricesInv[m-1][c] is the
+// c-th column of that inverse.
+static std::vector<uint32_t> g_sobolMatrices;
+static std::mutex g_sobolMutex;
+static int loadSobolMatrices() {
+    std::lock_guard<std::mutex> lock(g_sobolMutex);
+    if (!g_sobolMatrices.empty()) return PB2_OK;
+    Dl_info info;
+    std::string dir = ".";
+    if (dladdr((void *)&loadSobolMatrices, &info) && info.dli_fname) {
+        dir = info.dli_fname;
+        size_t slash = dir.find_last_of('/');
+        dir = slash == std::string::npos ? "." : dir.substr(0, slash);
+    }
+    const std::string path = dir + "/sobol_matrices32.bin";
+    FILE *f = fopen(path.c_str(), "rb");
+    std::vector<uint32_t> m((size_t)kSobolDims * kSobolMatrixSize);
+    if (!f || fread(m.data(), sizeof(uint32_t), m.size(), f) != m.size()) {
+        if (f) fclose(f);
+        return setError(PB2_ERR_UNSUPPORTED, "SobolSampler: cannot read " + path + " (run tools/make_sobol_tables.py or __graft_entry__.build())");
+    }
+    fclose(f);
+    // dimension 0 must be the van der Corput sequence and dimension 1 start with the all-ones row: a cheap sanity check of the file
+    for (int k = 0; k < 32; ++k)
+        if (m[k] != (0x80000000u >> k) || !(m[kSobolMatrixSize + k] & 0x80000000u))
+            return setError(PB2_ERR_INVALID, "SobolSampler: " + path + " does not hold Sobol' generator matrices");
+    g_sobolMatrices.swap(m);
+    return PB2_OK;
+}
+// (px << m | py) offset that index bit k adds, for resolution 2^m (m <= 26: the columns' upper 32 bits are enough)
+static uint64_t sobolPixelColumn(int k, int m) {
+    const uint64_t c0 = g_sobolMatrices[k], c1 = g_sobolMatrices[kSobolMatrixSize + k];
+    return ((c0 >> (32 - m)) << m) | (c1 >> (32 - m));
+}
+static void sobolIntervalTables(int m, uint64_t out[2 * kSobolMatrixSize]) {
+    memset(out, 0, 2 * kSobolMatrixSize * sizeof(uint64_t));
+    if (m <= 0) return;
+    const int n = 2 * m;
+    for (int c = 0; c + n < kSobolMatrixSize; ++c) out[c] = sobolPixelColumn(n + c, m);
+    // invert the n x n matrix whose column k is sobolPixelColumn(k, m): Gauss-Jordan on rows {A row | identity row}
+    std::vector<uint64_t> a((size_t)n, 0), id((size_t)n);
+    for (int r = 0; r < n; ++r) {
+        for (int k = 0; k < n; ++k)
+            if ((sobolPixelColumn(k, m) >> r) & 1) a[r] |= 1ull << k;
+        id[r] = 1ull << r;
+    }
+    for (int k = 0, rr = 0; k < n; ++k, ++rr) {
+        int p = rr;
+        while (p < n && !((a[p] >> k) & 1)) ++p;   // (always found: the first two Sobol' dimensions form a (0, 2)-sequence)
+        if (p == n) return;
+        std::swap(a[rr], a[p]);
+        std::swap(id[rr], id[p]);
+        for (int r = 0; r < n; ++r)
+            if (r != rr && ((a[r] >> k) & 1)) {
+                a[r] ^= a[rr];
+                id[r] ^= id[rr];
+            }
+    }
+    // now a[k] == 1 << k: index bit k = parity(id[k] & pixel bits); column c of the inverse collects the k with bit c set
+    for (int c = 0; c < n; ++c) {
+        uint64_t v = 0;
+        for (int k = 0; k < n; ++k)
+            if ((id[k] >> c) & 1) v |= 1ull << k;
+        out[kSobolMatrixSize + c] = v;
+    }
+}
+// Completes a DHalton for a frame that uses the SobolSampler, on the current device.
+static int attachSobol(DHalton *h, const pb2_film_desc *film) {
+    int rc = loadSobolMatrices();
+    if (rc) return rc;
+    DeviceState &dev = cur();
+    if (!dev.sobol) {
+        CUDA_TRY(cudaMalloc((void **)&dev.sobol, g_sobolMatrices.size() * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpy(dev.sobol, g_sobolMatrices.data(), g_sobolMatrices.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    if (!dev.sobolVdc) CUDA_TRY(cudaMalloc((void **)&dev.sobolVdc, 2 * kSobolMatrixSize * sizeof(uint64_t)));
+    // SobolSampler's constructor (sobol.h:52-57): resolution = RoundUpPow2(max extent of the sample bounds)
+    SampleBounds sb = filmSampleBounds(film);
+    int extent = std::max(sb.x1 - sb.x0, sb.y1 - sb.y0), res = 1, log2Res = 0;
+    while (res < extent) {
+        res <<= 1;
+        ++log2Res;
+    }
+    if (log2Res > 26) return setError(PB2_ERR_UNSUPPORTED, "SobolSampler: sample bounds beyond 2^26 pixels in one direction");
+    uint64_t tables[2 * kSobolMatrixSize];
+    sobolIntervalTables(log2Res, tables);
+    CUDA_TRY(cudaMemcpy(dev.sobolVdc, tables, sizeof(tables), cudaMemcpyHostToDevice));
+    h->sobol = dev.sobol;
+    h->sobolVdc = dev.sobolVdc;
+    h->sobolLog2Res = log2Res;
+    h->sobolRes = res;
+    h->sampleAtPixelCenter = 0;
+    return PB2_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -535,10 +644,10 @@ __global__ void k_li_samples(DScene sc, DRenderParams rp, const int32_t *pixelXY
     if (i >= n) return;
     int px = pixelXY[2 * i], py = pixelXY[2 * i + 1];
     DSampler smp;
-    smp.index = haltonIndex(rp.halton, px, py, sampleNum[i]);
+    smp.index = sampleIndex<true>(rp.halton, px, py, sampleNum[i]);
     smp.dim = 0;
     V2 pFilm;
-    DRay ray = generateCameraRay(rp.cam, rp.halton, smp, px, py, &pFilm);
+    DRay ray = generateCameraRay<true>(rp.cam, rp.halton, smp, px, py, &pFilm);
     DLane ln;
     laneStartPath(ln, ray, smp);
     while (ln.state != LS_IDLE) {
@@ -610,8 +719,11 @@ __global__ void k_halton_samples(DHalton h, const int32_t *pixelXY, const int64_
                                  float *out) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int64_t index = haltonIndex(h, pixelXY[2 * i], pixelXY[2 * i + 1], sampleNum[i]);
-    out[i] = haltonSample(h, index, dim[i]);
+    const int px = pixelXY[2 * i], py = pixelXY[2 * i + 1];
+    int64_t index = sampleIndex<true>(h, px, py, sampleNum[i]);
+    // (SobolSampler::SampleDimension turns its two pixel dimensions into the offset inside the current pixel)
+    if (h.sobol && dim[i] < 2) out[i] = sobolPixelSample(h, index, dim[i], dim[i] == 0 ? px : py);
+    else out[i] = sampleDimension<true>(h, index, dim[i]);
 }
 
 __global__ void k_light_distribution(DScene sc, const float *points, int64_t n, float *out) {
@@ -757,6 +869,9 @@ static int validateRenderArgs(const pb2_scene *scene, const pb2_camera *cam, con
         return setError(PB2_ERR_UNSUPPORTED, "maxdepth above 123: HaltonSampler can only sample 1000 dimensions");
     if (pp->tile_count < 0 || pp->tile_rank < 0 || (pp->tile_count > 0 && pp->tile_rank >= pp->tile_count))
         return setError(PB2_ERR_INVALID, "bad tile_rank / tile_count");
+    if (pp->sampler != PB2_SAMPLER_HALTON && pp->sampler != PB2_SAMPLER_SOBOL) return setError(PB2_ERR_INVALID, "unknown sampler");
+    if (pp->sampler == PB2_SAMPLER_SOBOL && (pp->samples_per_pixel & (pp->samples_per_pixel - 1)))
+        return setError(PB2_ERR_INVALID, "SobolSampler: samples_per_pixel must be the power of two its constructor rounds up to (sobol.h:52)");
     if (film->cropped_pixel_bounds[2] < film->cropped_pixel_bounds[0] || film->cropped_pixel_bounds[3] < film->cropped_pixel_bounds[1])
         return setError(PB2_ERR_INVALID, "bad cropped pixel bounds");
     if (!(film->filter_radius[0] > 0) || !(film->filter_radius[1] > 0)) return setError(PB2_ERR_INVALID, "bad filter radius");
@@ -926,7 +1041,9 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
                              : k_wf_advance<true, false, 4, false, true>;
     // image textures: the one shade kernel that evaluates them (spheres, specular materials and the lazy light distribution
     // compiled in; 3 resident blocks, its register budget is not the bench scene's)
-    const bool textured = scene->d.nTextures > 0;
+    // ... and the one that draws from the SobolSampler: the same general instantiation
+    const bool sobol = rp.halton.sobol != nullptr;
+    const bool textured = scene->d.nTextures > 0 || sobol;
     if (textured) advShade = k_wf_advance<true, true, 3, true, true, true>;
     typedef void (*FinishKernel)(DScene, DRenderParams, WfPool, int, unsigned, float4 *);
     FinishKernel finish = scene->hasSpecular ? (spheres ? k_wf_finish<true, true> : k_wf_finish<false, true>)
@@ -985,7 +1102,8 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         for (int p = 0; p < nPipes; ++p) {
             const WfPool &pool = pools[p];
             cudaStream_t st = streams[p];
-            k_wf_gen<<<blocks256, 256, 0, st>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur);
+            if (sobol) k_wf_gen<true><<<blocks256, 256, 0, st>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur);
+            else k_wf_gen<false><<<blocks256, 256, 0, st>>>(rp, pool, WQ_FREE0 + cur, WQ_TRACE0 + cur);
             if (timeTrace) {
                 if (scene->traceEvents.size() < nEvents + 2) {
                     cudaEvent_t e0, e1;
@@ -1079,6 +1197,8 @@ static void freeDeviceTables() {
         cudaFree(d.dimRecs);
         cudaFree(d.dimTabs);
         cudaFree(d.digitTab);
+        cudaFree(d.sobol);
+        cudaFree(d.sobolVdc);
     }
     g_devs.clear();
     g_initialised = false;
@@ -2122,6 +2242,7 @@ static int renderPathDeviceOne(pb2_scene *scene, const pb2_camera *cam, const pb
         pp = &ppLocal;
     }
     DRenderParams rp = makeRenderParams(cam, film, pp);
+    if (pp->sampler == PB2_SAMPLER_SOBOL && (rc = attachSobol(&rp.halton, film))) return rc;
     {
         float table[256];
         if (computeFilterTable(film, table)) {
@@ -2210,6 +2331,7 @@ int pb2_li_samples(pb2_scene *scene, const pb2_camera *cam, const pb2_film_desc 
     if (n <= 0) return PB2_OK;
     if (!pixel_xy || !sample_num || !out_rgb) return setError(PB2_ERR_INVALID, "null argument");
     DRenderParams rp = makeRenderParams(cam, film, pp);
+    if (pp->sampler == PB2_SAMPLER_SOBOL && (rc = attachSobol(&rp.halton, film))) return rc;
     int32_t *dXY = nullptr;
     int64_t *dS = nullptr;
     float *dRGB = nullptr, *dPF = nullptr;
@@ -2259,6 +2381,7 @@ int pb2_halton_samples(const pb2_film_desc *film, const pb2_path_params *pp, con
     for (int64_t i = 0; i < n; ++i)
         if (dim[i] < 0 || dim[i] >= kMaxHaltonDims) return setError(PB2_ERR_INVALID, "HaltonSampler can only sample 1000 dimensions");
     DHalton h = makeHalton(film, pp);
+    if (pp->sampler == PB2_SAMPLER_SOBOL && (rc = attachSobol(&h, film))) return rc;
     int32_t *dXY = nullptr, *dDim = nullptr;
     int64_t *dS = nullptr;
     float *dOut = nullptr;
@@ -2279,6 +2402,38 @@ int pb2_halton_samples(const pb2_film_desc *film, const pb2_path_params *pp, con
     cudaFree(dDim);
     cudaFree(dOut);
     if (e != cudaSuccess) return setError(PB2_ERR_CUDA, std::string("pb2_halton_samples: ") + cudaGetErrorString(e));
+    return PB2_OK;
+}
+
+int pb2_sobol_samples_host(const pb2_film_desc *film, const pb2_path_params *pp, const int32_t *pixel_xy, const int64_t *sample_num,
+                           const int32_t *dim, int64_t n, float *out, uint64_t *tablesOut) {
+    if (!film || !pp || (n > 0 && (!pixel_xy || !sample_num || !dim || !out))) return setError(PB2_ERR_INVALID, "null argument");
+    int rc = loadSobolMatrices();
+    if (rc) return rc;
+    DHalton h;
+    memset(&h, 0, sizeof(h));
+    SampleBounds sb = filmSampleBounds(film);
+    int extent = std::max(sb.x1 - sb.x0, sb.y1 - sb.y0), res = 1, log2Res = 0;
+    while (res < extent) {
+        res <<= 1;
+        ++log2Res;
+    }
+    if (log2Res > 26) return setError(PB2_ERR_UNSUPPORTED, "SobolSampler: sample bounds beyond 2^26 pixels in one direction");
+    uint64_t tables[2 * kSobolMatrixSize];
+    sobolIntervalTables(log2Res, tables);
+    if (tablesOut) memcpy(tablesOut, tables, sizeof(tables));
+    h.sobol = g_sobolMatrices.data();
+    h.sobolVdc = tables;
+    h.sobolLog2Res = log2Res;
+    h.sobolRes = res;
+    h.sbx0 = sb.x0;
+    h.sby0 = sb.y0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (dim[i] < 0 || dim[i] >= kSobolDims) return setError(PB2_ERR_INVALID, "SobolSampler can only sample up to 1024 dimensions");
+        const int px = pixel_xy[2 * i], py = pixel_xy[2 * i + 1];
+        const int64_t index = sampleIndex<true>(h, px, py, sample_num[i]);
+        out[i] = dim[i] < 2 ? sobolPixelSample(h, index, dim[i], dim[i] == 0 ? px : py) : sampleDimension<true>(h, index, dim[i]);
+    }
     return PB2_OK;
 }
 
@@ -2473,7 +2628,7 @@ __global__ void k_hlbvh_treelet_starts(const unsigned *codes, int n, int *start 
 // numbered in the reference's allocation order (a node before its subtrees, the first subtree before the second)
 // inside the treelet's 2 * nPrimitives slots; interior bounds are filled bottom-up afterwards.
 __global__ void k_hlbvh_emit(const float *bounds, const unsigned *codes, const int *sorted, const int2 *treelets /* start, count */,
-                             int nTreelets, int maxPrimsInNode, pb2_build_node *pool, int *roots) {
+                             int nTreelets, int maxPrimsInNode, pb2_build_node *pool, int *roots, int *treeletNodes = nullptr) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nTreelets) return;
     const int first = treelets[t].x, count = treelets[t].y;
@@ -2543,14 +2698,212 @@ __global__ void k_hlbvh_emit(const float *bounds, const unsigned *codes, const i
         }
     }
     roots[t] = base;
+    if (treeletNodes) treeletNodes[t] = next;
+}
+
+// ---- the upper half of HLBVHBuild on the device: buildUpperSAH (bvh.cpp:541-638) and flattenBVHTree (bvh.cpp:640-658) ----
+// Working set of k_hlbvh_upper (at most 4096 treelets, hence at most 4095 nodes above them).
+struct HlbvhUpper {
+    int *order;            // the treelets as buildUpperSAH permutes them (std::partition)
+    float *box;            // 6 floats per treelet: the bounds of its root
+    int4 *stack;           // pending ranges {start, end, parent, side}
+    pb2_build_node *nodes; // the nodes above the treelets, a parent before its children, the first subtree before the second;
+                           // child >= 0: another of these nodes, child < 0: treelet -(child + 1)
+    int *size, *offset;    // per upper node: nodes in its subtree, its place in the linear array
+    int *treeletBase;      // per treelet: where its first node lands in the linear array
+    int *counts;           // [0] upper nodes, [1] total nodes
+};
+// One thread: the SAH tree over the treelet roots is small (<= 4096 leaves) and sequential by nature (every split partitions
+// the range the next ones work on).  The arithmetic is buildUpperSAH's, operation for operation, including libstdc++'s
+// bidirectional std::partition (the order it leaves the elements in decides the tree).  Because a parent is numbered before
+// its children and the first subtree is finished before the second starts, the numbering is the depth-first order
+// flattenBVHTree walks: subtree sizes follow from one backward pass, offsets from one forward pass.
+__global__ void k_hlbvh_upper(const pb2_build_node *pool, const int *roots, const int *treeletNodes, int nTreelets, HlbvhUpper w,
+                              pb2_bvh_node *linear) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    for (int t = 0; t < nTreelets; ++t) {
+        w.order[t] = t;
+        const pb2_build_node &r = pool[roots[t]];
+        for (int k = 0; k < 3; ++k) {
+            w.box[6 * t + k] = r.bmin[k];
+            w.box[6 * t + 3 + k] = r.bmax[k];
+        }
+    }
+    int nUpper = 0, sp = 0;
+    if (nTreelets == 1) w.treeletBase[0] = 0;
+    else w.stack[sp++] = make_int4(0, nTreelets, -1, 0);
+    constexpr int nBuckets = 12;
+    while (sp > 0) {
+        const int4 f = w.stack[--sp];
+        const int start = f.x, end = f.y;
+        if (end - start == 1) {
+            w.nodes[f.z].child[f.w] = -(w.order[start] + 1);
+            continue;
+        }
+        const int u = nUpper++;
+        if (f.z >= 0) w.nodes[f.z].child[f.w] = u;
+        float bmin[3] = {PB2_INFINITY, PB2_INFINITY, PB2_INFINITY}, bmax[3] = {-PB2_INFINITY, -PB2_INFINITY, -PB2_INFINITY};
+        float cmin[3] = {PB2_INFINITY, PB2_INFINITY, PB2_INFINITY}, cmax[3] = {-PB2_INFINITY, -PB2_INFINITY, -PB2_INFINITY};
+        for (int i = start; i < end; ++i) {
+            const float *b = w.box + 6 * w.order[i];
+            for (int k = 0; k < 3; ++k) {
+                bmin[k] = fminf(bmin[k], b[k]);
+                bmax[k] = fmaxf(bmax[k], b[3 + k]);
+                const float c = (b[k] + b[3 + k]) * 0.5f;
+                cmin[k] = fminf(cmin[k], c);
+                cmax[k] = fmaxf(cmax[k], c);
+            }
+        }
+        // Bounds3::MaximumExtent (geometry.h:733-741)
+        const float dx = cmax[0] - cmin[0], dy = cmax[1] - cmin[1], dz = cmax[2] - cmin[2];
+        const int dim = (dx > dy && dx > dz) ? 0 : (dy > dz ? 1 : 2);
+        int count[nBuckets];
+        float lo[nBuckets][3], hi[nBuckets][3];
+        for (int b = 0; b < nBuckets; ++b) {
+            count[b] = 0;
+            for (int k = 0; k < 3; ++k) {
+                lo[b][k] = PB2_INFINITY;
+                hi[b][k] = -PB2_INFINITY;
+            }
+        }
+        const float c0 = cmin[dim], c1 = cmax[dim];
+        auto bucketOf = [&](int t) {
+            const float centroid = (w.box[6 * t + dim] + w.box[6 * t + 3 + dim]) * 0.5f;
+            int b = (int)(nBuckets * ((centroid - c0) / (c1 - c0)));
+            if (b == nBuckets) b = nBuckets - 1;
+            return b;
+        };
+        for (int i = start; i < end; ++i) {
+            const int t = w.order[i], b = bucketOf(t);
+            count[b]++;
+            for (int k = 0; k < 3; ++k) {
+                lo[b][k] = fminf(lo[b][k], w.box[6 * t + k]);
+                hi[b][k] = fmaxf(hi[b][k], w.box[6 * t + 3 + k]);
+            }
+        }
+        auto area = [](const float *mn, const float *mx) {   // Bounds3::SurfaceArea (geometry.h:723-726)
+            const float ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
+            return 2 * (ex * ey + ex * ez + ey * ez);
+        };
+        float minCost = 0;
+        int minCostSplitBucket = 0;
+        for (int i = 0; i < nBuckets - 1; ++i) {
+            float l0[3] = {PB2_INFINITY, PB2_INFINITY, PB2_INFINITY}, h0[3] = {-PB2_INFINITY, -PB2_INFINITY, -PB2_INFINITY};
+            float l1[3] = {PB2_INFINITY, PB2_INFINITY, PB2_INFINITY}, h1[3] = {-PB2_INFINITY, -PB2_INFINITY, -PB2_INFINITY};
+            int count0 = 0, count1 = 0;
+            for (int j = 0; j <= i; ++j) {
+                for (int k = 0; k < 3; ++k) {
+                    l0[k] = fminf(l0[k], lo[j][k]);
+                    h0[k] = fmaxf(h0[k], hi[j][k]);
+                }
+                count0 += count[j];
+            }
+            for (int j = i + 1; j < nBuckets; ++j) {
+                for (int k = 0; k < 3; ++k) {
+                    l1[k] = fminf(l1[k], lo[j][k]);
+                    h1[k] = fmaxf(h1[k], hi[j][k]);
+                }
+                count1 += count[j];
+            }
+            const float cost = .125f + (count0 * area(l0, h0) + count1 * area(l1, h1)) / area(bmin, bmax);
+            if (i == 0 || cost < minCost) {
+                minCost = cost;
+                minCostSplitBucket = i;
+            }
+        }
+        // std::partition for bidirectional iterators as libstdc++ writes it (bits/stl_algo.h __partition): the order of
+        // the two halves it leaves behind is part of the result
+        int first = start, last = end;
+        for (;;) {
+            for (;;) {
+                if (first == last) break;
+                if (bucketOf(w.order[first]) <= minCostSplitBucket) ++first;
+                else break;
+            }
+            if (first == last) break;
+            --last;
+            for (;;) {
+                if (first == last) break;
+                if (!(bucketOf(w.order[last]) <= minCostSplitBucket)) --last;
+                else break;
+            }
+            if (first == last) break;
+            const int tmp = w.order[first];
+            w.order[first] = w.order[last];
+            w.order[last] = tmp;
+            ++first;
+        }
+        const int mid = first;
+        pb2_build_node &nd = w.nodes[u];
+        for (int k = 0; k < 3; ++k) {
+            nd.bmin[k] = bmin[k];   // == Union of the two children's bounds (min / max are exact)
+            nd.bmax[k] = bmax[k];
+        }
+        nd.split_axis = dim;
+        nd.n_primitives = 0;
+        nd.first_prim_offset = 0;
+        w.stack[sp++] = make_int4(mid, end, u, 1);
+        w.stack[sp++] = make_int4(start, mid, u, 0);   // the first subtree is built (and numbered) first
+    }
+    auto sizeOf = [&](int child) { return child >= 0 ? w.size[child] : treeletNodes[-(child + 1)]; };
+    for (int u = nUpper - 1; u >= 0; --u) w.size[u] = 1 + sizeOf(w.nodes[u].child[0]) + sizeOf(w.nodes[u].child[1]);
+    if (nUpper > 0) w.offset[0] = 0;
+    for (int u = 0; u < nUpper; ++u) {
+        const int a = w.nodes[u].child[0], b = w.nodes[u].child[1];
+        const int offA = w.offset[u] + 1, offB = offA + sizeOf(a);
+        if (a >= 0) w.offset[a] = offA;
+        else w.treeletBase[-(a + 1)] = offA;
+        if (b >= 0) w.offset[b] = offB;
+        else w.treeletBase[-(b + 1)] = offB;
+        pb2_bvh_node out;
+        for (int k = 0; k < 3; ++k) {
+            out.bmin[k] = w.nodes[u].bmin[k];
+            out.bmax[k] = w.nodes[u].bmax[k];
+        }
+        out.offset = offB;    // secondChildOffset
+        out.n_prims = 0;
+        out.axis = (uint8_t)w.nodes[u].split_axis;
+        out.pad = 0;
+        linear[w.offset[u]] = out;
+    }
+    w.counts[0] = nUpper;
+    w.counts[1] = nUpper > 0 ? w.size[0] : treeletNodes[0];
+}
+// flattenBVHTree for the treelets: emitLBVH numbered each treelet's nodes in depth-first order already, so a treelet lands
+// in the linear array as one block and only the child references change base.  One block per treelet.
+__global__ void k_hlbvh_flatten(const pb2_build_node *pool, const int2 *treelets, const int *treeletNodes, const int *treeletBase,
+                                int nTreelets, pb2_bvh_node *linear) {
+    for (int t = blockIdx.x; t < nTreelets; t += gridDim.x) {
+        const int poolBase = 2 * treelets[t].x, n = treeletNodes[t], linBase = treeletBase[t];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const pb2_build_node &nd = pool[poolBase + i];
+            pb2_bvh_node out;
+            for (int k = 0; k < 3; ++k) {
+                out.bmin[k] = nd.bmin[k];
+                out.bmax[k] = nd.bmax[k];
+            }
+            if (nd.n_primitives > 0) {
+                out.offset = nd.first_prim_offset;
+                out.n_prims = (uint16_t)nd.n_primitives;
+                out.axis = 0;
+            } else {
+                out.offset = linBase + (nd.child[1] - poolBase);
+                out.n_prims = 0;
+                out.axis = (uint8_t)nd.split_axis;
+            }
+            out.pad = 0;
+            linear[linBase + i] = out;
+        }
+    }
 }
 }  // namespace
 
-extern "C" int pb2_hlbvh_treelets(const float *prim_bounds, int64_t n, int32_t max_prims_in_node, pb2_build_node *pool,
-                                  int32_t *ordered_prims, int32_t *treelet_roots, int32_t *n_treelets, double *device_ms) {
+// Both HLBVH entry points.  nodes == nullptr: pb2_hlbvh_treelets (the treelets come back as build nodes, the caller builds
+// the tree above them); otherwise pb2_hlbvh_build (everything on the device, the finished LinearBVHNode array comes back).
+static int hlbvhOnDevice(const float *prim_bounds, int64_t n, int32_t max_prims_in_node, pb2_build_node *pool, int32_t *ordered_prims,
+                         int32_t *treelet_roots, int32_t *n_treelets, pb2_bvh_node *nodes, int64_t *n_nodes, double *device_ms) {
     int rc = requireDevice();
     if (rc) return rc;
-    if (!prim_bounds || !pool || !ordered_prims || !treelet_roots || !n_treelets) return setError(PB2_ERR_INVALID, "null argument");
     if (n <= 0 || n >= (int64_t)1 << 30) return setError(PB2_ERR_INVALID, "primitive count out of range");
     const int N = (int)n;
     float *dBounds = nullptr;
@@ -2558,6 +2911,10 @@ extern "C" int pb2_hlbvh_treelets(const float *prim_bounds, int64_t n, int32_t m
     int *dIndex = nullptr, *dSorted = nullptr, *dStart = nullptr, *dRoots = nullptr;
     int2 *dTreelets = nullptr;
     pb2_build_node *dPool = nullptr;
+    int *dTreeletNodes = nullptr;
+    pb2_bvh_node *dLinear = nullptr;
+    HlbvhUpper up;
+    memset(&up, 0, sizeof(up));
     void *dTemp = nullptr;
     size_t tempBytes = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -2575,6 +2932,18 @@ extern "C" int pb2_hlbvh_treelets(const float *prim_bounds, int64_t n, int32_t m
     step(cudaMalloc((void **)&dRoots, 4096 * sizeof(int)));
     step(cudaMalloc((void **)&dTreelets, 4096 * sizeof(int2)));
     step(cudaMalloc((void **)&dPool, (size_t)2 * N * sizeof(pb2_build_node)));
+    step(cudaMalloc((void **)&dTreeletNodes, 4096 * sizeof(int)));
+    if (nodes) {
+        step(cudaMalloc((void **)&dLinear, ((size_t)2 * N + 4096) * sizeof(pb2_bvh_node)));
+        step(cudaMalloc((void **)&up.order, 4096 * sizeof(int)));
+        step(cudaMalloc((void **)&up.box, 4096 * 6 * sizeof(float)));
+        step(cudaMalloc((void **)&up.stack, 8192 * sizeof(int4)));
+        step(cudaMalloc((void **)&up.nodes, 4096 * sizeof(pb2_build_node)));
+        step(cudaMalloc((void **)&up.size, 4096 * sizeof(int)));
+        step(cudaMalloc((void **)&up.offset, 4096 * sizeof(int)));
+        step(cudaMalloc((void **)&up.treeletBase, 4096 * sizeof(int)));
+        step(cudaMalloc((void **)&up.counts, 2 * sizeof(int)));
+    }
     if (e == cudaSuccess) step(cub::DeviceRadixSort::SortPairs(nullptr, tempBytes, dCodes, dCodesSorted, dIndex, dSorted, N, 0, 30));
     step(cudaMalloc(&dTemp, tempBytes ? tempBytes : 1));
     step(cudaEventCreate(&e0));
@@ -2599,21 +2968,51 @@ extern "C" int pb2_hlbvh_treelets(const float *prim_bounds, int64_t n, int32_t m
             if (start[v] >= 0) treelets.push_back(make_int2(start[v], 0));
         for (size_t i = 0; i < treelets.size(); ++i) treelets[i].y = (i + 1 < treelets.size() ? treelets[i + 1].x : N) - treelets[i].x;
         step(cudaMemcpy(dTreelets, treelets.data(), treelets.size() * sizeof(int2), cudaMemcpyHostToDevice));
-        k_hlbvh_emit<<<((int)treelets.size() + 31) / 32, 32>>>(dBounds, dCodesSorted, dSorted, dTreelets, (int)treelets.size(), max_prims_in_node, dPool, dRoots);
+        const int nT = (int)treelets.size();
+        k_hlbvh_emit<<<(nT + 31) / 32, 32>>>(dBounds, dCodesSorted, dSorted, dTreelets, nT, max_prims_in_node, dPool, dRoots, dTreeletNodes);
         step(cudaGetLastError());
+        if (nodes && e == cudaSuccess) {
+            // the SAH tree over the treelet roots and the depth-first layout, without leaving the device
+            k_hlbvh_upper<<<1, 32>>>(dPool, dRoots, dTreeletNodes, nT, up, dLinear);
+            k_hlbvh_flatten<<<std::min(nT, 148 * 8), 128>>>(dPool, dTreelets, dTreeletNodes, up.treeletBase, nT, dLinear);
+            step(cudaGetLastError());
+        }
         step(cudaEventRecord(e1));
-        step(cudaMemcpy(pool, dPool, (size_t)2 * N * sizeof(pb2_build_node), cudaMemcpyDeviceToHost));
+        if (nodes) {
+            int counts[2] = {0, 0};
+            step(cudaMemcpy(counts, up.counts, sizeof(counts), cudaMemcpyDeviceToHost));
+            if (e == cudaSuccess) {
+                *n_nodes = counts[1];
+                step(cudaMemcpy(nodes, dLinear, (size_t)counts[1] * sizeof(pb2_bvh_node), cudaMemcpyDeviceToHost));
+            }
+        } else {
+            step(cudaMemcpy(pool, dPool, (size_t)2 * N * sizeof(pb2_build_node), cudaMemcpyDeviceToHost));
+            step(cudaMemcpy(treelet_roots, dRoots, treelets.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        }
         step(cudaMemcpy(ordered_prims, dSorted, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost));
-        step(cudaMemcpy(treelet_roots, dRoots, treelets.size() * sizeof(int), cudaMemcpyDeviceToHost));
         float ms = 0;
         if (e == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && device_ms) *device_ms = ms;
-        *n_treelets = (int32_t)treelets.size();
+        if (n_treelets) *n_treelets = (int32_t)treelets.size();
     }
     for (void *p : {(void *)dBounds, (void *)dBox, (void *)dCodes, (void *)dCodesSorted, (void *)dIndex, (void *)dSorted, (void *)dStart,
-                    (void *)dRoots, (void *)dTreelets, (void *)dPool, dTemp})
+                    (void *)dRoots, (void *)dTreelets, (void *)dPool, dTemp, (void *)dTreeletNodes, (void *)dLinear, (void *)up.order,
+                    (void *)up.box, (void *)up.stack, (void *)up.nodes, (void *)up.size, (void *)up.offset, (void *)up.treeletBase,
+                    (void *)up.counts})
         cudaFree(p);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    if (e != cudaSuccess) return setError(PB2_ERR_CUDA, std::string("pb2_hlbvh_treelets: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) return setError(PB2_ERR_CUDA, std::string("HLBVH build on the device: ") + cudaGetErrorString(e));
     return PB2_OK;
+}
+
+extern "C" int pb2_hlbvh_treelets(const float *prim_bounds, int64_t n, int32_t max_prims_in_node, pb2_build_node *pool,
+                                  int32_t *ordered_prims, int32_t *treelet_roots, int32_t *n_treelets, double *device_ms) {
+    if (!prim_bounds || !pool || !ordered_prims || !treelet_roots || !n_treelets) return setError(PB2_ERR_INVALID, "null argument");
+    return hlbvhOnDevice(prim_bounds, n, max_prims_in_node, pool, ordered_prims, treelet_roots, n_treelets, nullptr, nullptr, device_ms);
+}
+
+extern "C" int pb2_hlbvh_build(const float *prim_bounds, int64_t n, int32_t max_prims_in_node, pb2_bvh_node *nodes, int64_t *n_nodes,
+                               int32_t *ordered_prims, double *device_ms) {
+    if (!prim_bounds || !nodes || !n_nodes || !ordered_prims) return setError(PB2_ERR_INVALID, "null argument");
+    return hlbvhOnDevice(prim_bounds, n, max_prims_in_node, nullptr, ordered_prims, nullptr, nullptr, nodes, n_nodes, device_ms);
 }

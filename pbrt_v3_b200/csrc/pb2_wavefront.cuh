@@ -73,6 +73,7 @@ __device__ __forceinline__ void wfCountRays(unsigned long long *counters, unsign
 // (Halton dims 0-4, perspective camera).  Warp-collective: all 32 lanes call it, `want` says which of them take part; work
 // items that map outside the sample bounds / pixel bounds are skipped (integrator.cpp:274), so a lane may draw several.
 // Returns false for a lane that did not want a sample or found the work counter exhausted (its context retires).
+template <bool GENERAL>
 __device__ __forceinline__ bool wfStartSample(const DRenderParams &rp, const WfPool &pool, int c, bool want, unsigned *cameraRays) {
     bool started = false;
     while (__any_sync(0xffffffffu, want && !started)) {
@@ -91,10 +92,10 @@ __device__ __forceinline__ bool wfStartSample(const DRenderParams &rp, const WfP
                 if (decodeWork(rp, item, &px, &py, &sample)) {
                     WfCtx &cx = pool.ctx[c];
                     DSampler smp;
-                    smp.index = haltonIndex(rp.halton, px, py, sample);
+                    smp.index = sampleIndex<GENERAL>(rp.halton, px, py, sample);
                     smp.dim = 0;
                     V2 pFilm;
-                    DRay ray = generateCameraRay(rp.cam, rp.halton, smp, px, py, &pFilm);
+                    DRay ray = generateCameraRay<GENERAL>(rp.cam, rp.halton, smp, px, py, &pFilm);
                     laneStartPath(cx.ln, ray, smp);
                     cx.pFilm = pFilm;
                     ++*cameraRays;
@@ -110,6 +111,8 @@ __device__ __forceinline__ bool wfStartSample(const DRenderParams &rp, const WfP
 // inside k_wf_advance - no free list, no separate launch - was measured: 225 -> 205 Msamples/s at 16 spp on the 1 M soup,
 // 187 -> 159 on the killeroo-like scene: the few lanes of a warp that end a path run this code alone inside the
 // register-heavy, low-occupancy shade kernel.)
+// GENERAL = true: the instantiation that can also draw from the SobolSampler (frames that use it).
+template <bool GENERAL>
 __global__ void __launch_bounds__(256) k_wf_gen(DRenderParams rp, WfPool pool, int freeQ, int traceQ) {
     const unsigned n = pool.counts[freeQ];
     unsigned stride = gridDim.x * blockDim.x;
@@ -118,7 +121,7 @@ __global__ void __launch_bounds__(256) k_wf_gen(DRenderParams rp, WfPool pool, i
         unsigned i = base + threadIdx.x;
         const bool have = i < n;
         const int c = have ? pool.queue[freeQ][i] : -1;
-        const bool started = wfStartSample(rp, pool, c, have, &cameraRays);
+        const bool started = wfStartSample<GENERAL>(rp, pool, c, have, &cameraRays);
         wfPush(pool.queue[traceQ], &pool.counts[traceQ], c, started);
     }
     for (int o = 16; o > 0; o >>= 1) cameraRays += __shfl_down_sync(0xffffffffu, cameraRays, o);

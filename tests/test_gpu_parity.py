@@ -22,7 +22,7 @@ from test_oracle import load_scene, same_bvh, tessellated_sphere_scene
 pytestmark = pytest.mark.gpu
 
 SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass", "lights", "params",
-               "envlight", "textured", "textured_lens"]
+               "envlight", "textured", "textured_lens", "sobol"]
 
 
 def li_ok(got, want):
@@ -160,14 +160,17 @@ def test_delta_lights_under_other_light_sampling_strategies(pb, checker, strateg
 
 
 @pytest.mark.parametrize("name,maxprims", [("killeroo_like", 4), ("killeroo_like", 1), ("killeroo_like", 16), ("random20k", 4)])
-def test_device_hlbvh_build_equals_reference(pb, name, maxprims):
-    """pb2_hlbvh_treelets: Morton codes, the sort and the treelets built by CUDA kernels, the SAH top on the host, give the
-    reference's node array and primitive order (the fixtures tests/test_host.py checks the host build against)."""
+def test_device_hlbvh_build_equals_reference(pb, name, maxprims, monkeypatch):
+    """pb2_hlbvh_build: Morton codes, the sort, the treelets, the SAH tree over the treelet roots and the depth-first layout,
+    all by CUDA kernels, give the reference's LinearBVHNode array and primitive order (the fixtures tests/test_host.py checks
+    the host build against) - and so does pb2_hlbvh_treelets with the upper tree and the flatten on the host."""
     g = np.load(os.path.join(GOLDEN, "hlbvh.npz"))
     text = gc.random_mesh_scene_text(20000, 5) if name == "random20k" else open(os.path.join(SCENES, name + ".pbrt")).read()
-    hs = pb.HostScene.from_string(gc.with_accelerator(text, "hlbvh", maxprims, device_build=True))
-    assert same_bvh(hs.nodes(), g["nodes_%s_%d" % (name, maxprims)])
-    assert np.array_equal(hs.bvh_prims(0), g["prims_%s_%d" % (name, maxprims)])
+    for upper in ("device", "host"):
+        monkeypatch.setenv("PB2_DEVICE_BVH_UPPER", upper)
+        hs = pb.HostScene.from_string(gc.with_accelerator(text, "hlbvh", maxprims, device_build=True))
+        assert same_bvh(hs.nodes(), g["nodes_%s_%d" % (name, maxprims)]), upper
+        assert np.array_equal(hs.bvh_prims(0), g["prims_%s_%d" % (name, maxprims)]), upper
 
 
 def test_device_hlbvh_build_equals_host_build_on_a_larger_mesh(pb):

@@ -642,8 +642,20 @@ def test_camera_film_sampler_and_integrator_parameters(pb):
     assert tuple(pp.pixel_bounds) == (3, 5, 9, 12)
 
 
+def test_sobol_sampler_directive(pb):
+    """Sampler "sobol" (sobol.cpp:65-70, sobol.h:51-57): the sample count is rounded up to a power of two (with a warning),
+    "samplepixelcenter" does not exist for it."""
+    hs = pb.HostScene.from_string('Sampler "sobol" "integer pixelsamples" 5\nWorldBegin\nShape "sphere"\nWorldEnd\n')
+    pp = hs.params.contents
+    assert pp.sampler == pb.PB2_SAMPLER_SOBOL and pp.samples_per_pixel == 8 and pp.sample_at_pixel_center == 0
+    hs = pb.HostScene.from_string('Sampler "sobol"\nWorldBegin\nShape "sphere"\nWorldEnd\n')
+    assert hs.params.contents.samples_per_pixel == 16 and hs.params.contents.sampler == pb.PB2_SAMPLER_SOBOL
+    hs = pb.HostScene.from_string('WorldBegin\nShape "sphere"\nWorldEnd\n')
+    assert hs.params.contents.sampler == pb.PB2_SAMPLER_HALTON
+
+
 @pytest.mark.parametrize("header,world,renders", [
-    ('Sampler "sobol" "integer pixelsamples" 4', '', False), ('Camera "orthographic"', '', False), ('Integrator "bdpt"', '', False),
+    ('Sampler "02sequence" "integer pixelsamples" 4', '', False), ('Camera "orthographic"', '', False), ('Integrator "bdpt"', '', False),
     ('Accelerator "kdtree"', 'Shape "sphere"', True), ('PixelFilter "lanczos"', 'Shape "sphere"', True),
     ('', 'Shape "cylinder"', True), ('', 'LightSource "goniometric"\nShape "sphere"', True),
     ('', 'MakeNamedMedium "fog" "string type" "homogeneous"\nShape "sphere"', True), ('', 'ActiveTransform StartTime\nShape "sphere"', True)])

@@ -339,3 +339,37 @@ def test_library_texture_pyramids_match_reference_live(pb, reference):
         assert len(a) == len(b)
         for la, lb in zip(a, b):
             assert la.shape == lb.shape and np.array_equal(gc.bits(la), gc.bits(lb)), (w, h, ch, wrap)
+
+
+def test_sobol_sampler_matches_reference_golden(pb):
+    """SobolSampler::SampleDimension(GetIndexForSample(k), dim) - index from pixel and sample number (SobolIntervalToIndex), the
+    two pixel dimensions remapped into the pixel, 198 more dimensions - computed on the host by the functions the kernels
+    compile, from generator matrices that tools/make_sobol_tables.py derives from the Joe-Kuo direction numbers: BIT FOR BIT
+    the values recorded from the compiled reference (tests/golden/sobol.npz)."""
+    g = np.load(os.path.join(GOLDEN, "sobol.npz"))
+    hs = load_scene(pb, "sobol")
+    assert hs.params.contents.sampler == pb.PB2_SAMPLER_SOBOL and hs.params.contents.samples_per_pixel == 8
+    hpix, hsn, hdim = gc.sample_ids(80, 50, 8, 4000, 14, max_dim=200)
+    got = pb.sobol_samples_host(hs.film, hs.params, hpix, hsn, hdim)
+    assert np.array_equal(gc.bits(got), gc.bits(g["halton"]))
+    assert (hdim < 2).sum() > 10 and (got[hdim < 2] < 1).all()
+
+
+def test_sobol_tables_are_the_reference_tables(pb, reference):
+    """The generator matrices (from scipy's copy of the Joe-Kuo direction numbers) equal the reference's SobolMatrices32, and
+    the two SobolIntervalToIndex tables the library derives from dimensions 0 and 1 by inverting a matrix over GF(2) equal
+    VdCSobolMatrices / VdCSobolMatricesInv for every resolution from 2 to 2^25 pixels."""
+    import ctypes as C
+    mats = np.fromfile(os.path.join(os.path.dirname(pb.__file__), "lib", "sobol_matrices32.bin"), "<u4").reshape(1024, 52)
+    _, ref_mats = reference.sobol_tables(1)
+    assert np.array_equal(mats, ref_mats)
+    film = pb.FilmDesc()
+    film.filter_radius[0] = film.filter_radius[1] = 0.5
+    pp = pb.PathParams(samples_per_pixel=1, sampler=pb.PB2_SAMPLER_SOBOL)
+    for m in range(1, 26):
+        res = 1 << m
+        film.full_resolution[0], film.full_resolution[1] = res, 1
+        film.cropped_pixel_bounds[0], film.cropped_pixel_bounds[1], film.cropped_pixel_bounds[2], film.cropped_pixel_bounds[3] = 0, 0, res, 1
+        _, tab = pb.sobol_samples_host(C.byref(film), C.byref(pp), np.zeros((1, 2), np.int32), np.zeros(1, np.int64), np.zeros(1, np.int32), tables=True)
+        want, _ = reference.sobol_tables(m)
+        assert np.array_equal(tab, want), m
