@@ -83,6 +83,11 @@ int pb2h_synth_soup(int64_t n_tris, uint64_t seed, float jitter, int xres, int y
         ParamSet none;
         pbrtPixelFilter(pf, none);
     }
+    if (const char *sm = std::getenv("PB2_SOUP_SPLIT")) {    // developer switch: the same workload over another BVH ("hlbvh")
+        ParamSet acc;
+        acc.AddString("splitmethod", sm);
+        pbrtAccelerator("bvh", acc);
+    }
     ParamSet samp;
     samp.AddInt("pixelsamples", {spp});
     pbrtSampler("halton", samp);
