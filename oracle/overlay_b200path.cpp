@@ -257,8 +257,9 @@ void B200PathIntegrator::Render(const Scene &scene) {
     const PerspectiveCamera *pc = dynamic_cast<const PerspectiveCamera *>(camera.get());
     const HaltonSampler *hs = dynamic_cast<const HaltonSampler *>(sampler.get());
     Film *film = camera->film;
-    if (!pc || !hs) {
-        error = "the path binds PerspectiveCamera and HaltonSampler";
+    const SobolSampler *ss = dynamic_cast<const SobolSampler *>(sampler.get());
+    if (!pc || (!hs && !ss)) {
+        error = "the path binds PerspectiveCamera and the two GlobalSamplers (HaltonSampler, SobolSampler)";
         return;
     }
     pb2_camera cam;
@@ -299,7 +300,8 @@ void B200PathIntegrator::Render(const Scene &scene) {
     pb2_path_params pp;
     std::memset(&pp, 0, sizeof(pp));
     pp.samples_per_pixel = (int32_t)sampler->samplesPerPixel;
-    pp.sample_at_pixel_center = hs->sampleAtPixelCenter ? 1 : 0;
+    pp.sample_at_pixel_center = (hs && hs->sampleAtPixelCenter) ? 1 : 0;
+    pp.sampler = ss ? PB2_SAMPLER_SOBOL : PB2_SAMPLER_HALTON;
     pp.max_depth = maxDepth;
     pp.rr_threshold = rrThreshold;
     pp.pixel_bounds[0] = pixelBounds.pMin.x;

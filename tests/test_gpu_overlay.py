@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 OVERLAY = os.path.join(ROOT, "oracle", "_ref", "libb200_overlay.so")
 
 
-@pytest.mark.parametrize("name", ["soup", "killeroo_like", "materials_matte_plastic"])
+@pytest.mark.parametrize("name", ["soup", "soup_sobol", "killeroo_like", "materials_matte_plastic"])
 def test_reference_scene_through_the_b200_integrator(pb, name):
     if not os.path.exists(OVERLAY):
         pytest.skip("oracle/_ref/libb200_overlay.so not built (no /root/reference at build time)")
@@ -28,7 +28,7 @@ def test_reference_scene_through_the_b200_integrator(pb, name):
     L.ref_scene_destroy.argtypes = [vp]
     L.ref_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), C.c_int, vp, C.POINTER(C.c_double), C.POINTER(Stats)]
     L.ref_render_b200.argtypes = [vp, C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), vp, C.POINTER(Stats), C.c_char_p, C.c_int]
-    if name == "soup":
+    if name in ("soup", "soup_sobol"):
         hs = pb.HostScene.soup(5000, xres=64, yres=36, spp=4)
     elif name == "killeroo_like":
         hs = pb.HostScene.from_file(os.path.join(SCENES, "killeroo_like.pbrt"))
@@ -37,14 +37,16 @@ def test_reference_scene_through_the_b200_integrator(pb, name):
         hs = pb.HostScene.from_string(text)
     ref = L.ref_scene_create(hs.desc, 4, 0)     # the reference's own objects, its own BVHAccel
     assert ref
+    # soup_sobol: the reference's SobolSampler in the Scene's integrator, which the binding maps to PB2_SAMPLER_SOBOL
+    params = C.byref(hs.params_copy(sampler=pb.PB2_SAMPLER_SOBOL)) if name == "soup_sobol" else hs.params
     h, w = hs.film_shape()
     want = np.zeros((h, w, 3), np.float32)
     secs, st = C.c_double(), Stats()
-    L.ref_render(ref, hs.camera, hs.film, hs.params, 0, pb.ptr(want), C.byref(secs), C.byref(st))
+    L.ref_render(ref, hs.camera, hs.film, params, 0, pb.ptr(want), C.byref(secs), C.byref(st))
     got = np.zeros((h, w, 3), np.float32)
     st2 = Stats()
     err = C.create_string_buffer(512)
-    rc = L.ref_render_b200(ref, hs.camera, hs.film, hs.params, pb.ptr(got), C.byref(st2), err, 512)
+    rc = L.ref_render_b200(ref, hs.camera, hs.film, params, pb.ptr(got), C.byref(st2), err, 512)
     L.ref_scene_destroy(ref)
     if rc != 0 and name == "materials_matte_plastic" and b"matte and plastic" in err.value:
         pytest.skip("scene uses materials this overlay does not bind")
