@@ -147,9 +147,10 @@ typedef struct pb2_material {
 /* One entry of Scene::lights, in the scene's order.  PB2_LIGHT_AREA: a DiffuseAreaLight (src/lights/diffuse.h:49-79)
  * attached to one primitive.  The other types are the delta lights (src/lights/{point,spot,distant}.cpp): L holds
  * I (point, spot) or L (distant), prim is -1, and delta_lights[same index] the geometry.  PB2_LIGHT_INFINITE: an
- * InfiniteAreaLight (src/lights/infinite.cpp) WITHOUT a texture map - constant radiance L = "L" * "scale" from every direction;
+ * InfiniteAreaLight (src/lights/infinite.cpp): constant radiance L = "L" * "scale" from every direction, or an environment map
+ * (pb2_delta_light.env_tex);
  * prim is -1, delta_lights[same index] carries its two 3x3 matrices and world_radius (Preprocess, infinite.h:61-63).  Rays
- * that leave the scene see it (path.cpp:96-98).  Environment maps ("mapname") need image readers and are out of scope. */
+ * that leave the scene see it (path.cpp:96-98). */
 enum { PB2_LIGHT_AREA = 0, PB2_LIGHT_POINT = 1, PB2_LIGHT_SPOT = 2, PB2_LIGHT_DISTANT = 3, PB2_LIGHT_INFINITE = 4 };
 typedef struct pb2_light {
     int32_t prim;       /* index into prim_type[]/prim_index[] */
@@ -170,7 +171,11 @@ typedef struct pb2_delta_light {
                                  * InfiniteAreaLight::Le / Pdf_Li, infinite.cpp:90-94, 124-132) */
     float pad;
     float light_to_world[9];    /* infinite: upper-left 3x3 of LightToWorld (InfiniteAreaLight::Sample_Li, infinite.cpp:96-122) */
-    float pad2[3];
+    int32_t env_tex;            /* infinite: 0 = constant radiance pb2_light.L; else 1 + index into pb2_scene_desc.textures of the
+                                 * environment map - a three-channel texture holding ReadImage(mapname) * L (infinite.cpp:50-57;
+                                 * NOT flipped in y, wrap repeat), pb2_light.L is then ignored.  The library builds Lmap's pyramid
+                                 * and the Distribution2D over the 2w x 2h luminance * sin(theta) image (infinite.cpp:61-82) */
+    float pad2[2];
 } pb2_delta_light;
 
 /* One BVHAccel of the scene: bvhs[0] is Scene::aggregate, bvhs[k > 0] the accelerator that
@@ -472,6 +477,12 @@ int pb2_light_distribution(pb2_scene *scene, const float *points_xyz, int64_t n,
  * resampling to a power of two, then box-filtered levels).  Host code only - no device needed.  *n_levels, *w and *h
  * (resolution of `level`) are always written; `out` (channels * w * h floats, row-major) may be NULL.  Parity/debug. */
 int pb2_texture_pyramid(const pb2_texture *texture, int32_t level, int32_t *n_levels, int32_t *w, int32_t *h, float *out);
+
+/* The sampling distribution the library derives for an InfiniteAreaLight whose environment map is `texture` (infinite.cpp:64-82:
+ * the Distribution2D over the 2w x 2h image of luminance * sin(theta)).  Host code only.  *nu = 2w, *nv = 2h (w, h: the map's
+ * resolution after MIPMap's power-of-two resampling) are always written; `out` (may be NULL) receives nv rows of
+ * [func(nu) | cdf(nu + 1) | funcInt] followed by the marginal [func(nv) | cdf(nv + 1) | funcInt].  Parity/debug. */
+int pb2_env_distribution(const pb2_texture *texture, int32_t *nu, int32_t *nv, float *out);
 
 /* MIPMap::Lookup(st, dst0, dst1) (mipmap.h:260-287: trilinear or EWA as the texture says) for a batch, evaluated on the
  * device with the code the shade kernel uses.  st: 2 floats per look-up, dst: 4 (dst0.x dst0.y dst1.x dst1.y), out: 3

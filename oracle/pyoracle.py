@@ -112,6 +112,14 @@ class Oracle:
             raise ValueError("resolution 2^%d outside the reference's tables" % m)
         return tab, mats
 
+    def env_distribution(self, texture):
+        """InfiniteAreaLight::distribution for an environment map given as a pb2_texture: (nu, nv, table) in the layout of
+        pb2_env_distribution (reference only)."""
+        import pbrt_v3_b200 as pb
+        fn = self._f("env_distribution")
+        fn.argtypes = [C.POINTER(pb.Texture), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]
+        return pb.env_distribution(texture, fn)
+
     def copper_rgb(self):
         """(eta, k) RGB of the metal material's default copper spectra (reference only)."""
         eta = np.zeros(3, np.float32)

@@ -88,8 +88,23 @@ Loc *parserLoc = nullptr;
 static std::mutex g_imageMutex;
 static std::vector<Float> g_lastImage;
 static Bounds2i g_lastBounds;
-// (imageio.cpp is not compiled: an InfiniteAreaLight is only ever built without a map here)
-std::unique_ptr<RGBSpectrum[]> ReadImage(const std::string &, Point2i *) { return nullptr; }
+// imageio.cpp is not compiled (it needs OpenEXR).  ReadImage serves images that ref_scene_create registered under a name
+// of its own: the environment map of an InfiniteAreaLight travels in the scene description (pb2_delta_light::env_tex) as
+// the texels ReadImage(mapname) * L, and the reference's constructor reads them back through this function.
+static std::mutex g_registryMutex;
+struct RegisteredImage { int w, h; std::vector<float> rgb; };
+static std::map<std::string, RegisteredImage> g_imageRegistry;
+std::unique_ptr<RGBSpectrum[]> ReadImage(const std::string &name, Point2i *resolution) {
+    std::lock_guard<std::mutex> lock(g_registryMutex);
+    auto it = g_imageRegistry.find(name);
+    if (it == g_imageRegistry.end()) return nullptr;
+    const RegisteredImage &im = it->second;
+    resolution->x = im.w;
+    resolution->y = im.h;
+    std::unique_ptr<RGBSpectrum[]> out(new RGBSpectrum[(size_t)im.w * im.h]);
+    for (size_t i = 0; i < (size_t)im.w * im.h; ++i) out[i] = RGBSpectrum::FromRGB(&im.rgb[3 * i]);
+    return out;
+}
 void WriteImage(const std::string &, const Float *rgb, const Bounds2i &outputBounds, const Point2i &) {
     std::lock_guard<std::mutex> lock(g_imageMutex);
     g_lastBounds = outputBounds;
@@ -273,6 +288,39 @@ int ref_texture_pyramid(const pb2_texture *t, int level, int *n_levels, int *w, 
     }
     return 0;
 }
+// InfiniteAreaLight::distribution of the reference for an environment map given as a texture description, in the layout of
+// pb2_env_distribution: nv rows of [func | cdf | funcInt], then the marginal
+int ref_env_distribution(const pb2_texture *t, int *nu, int *nv, float *out) {
+    setThreads(0);
+    const std::string name = "pb2env:probe";
+    {
+        std::lock_guard<std::mutex> lock(g_registryMutex);
+        RegisteredImage &im = g_imageRegistry[name];
+        im.w = t->width;
+        im.h = t->height;
+        im.rgb.assign(t->texels, t->texels + (size_t)3 * t->width * t->height);
+    }
+    InfiniteAreaLight light(Transform(), Spectrum(1.f), 1, name);
+    {
+        std::lock_guard<std::mutex> lock(g_registryMutex);
+        g_imageRegistry.erase(name);
+    }
+    const Distribution2D &d2 = *light.distribution;
+    *nu = d2.pConditionalV[0]->Count();
+    *nv = d2.pMarginal->Count();
+    if (!out) return 0;
+    auto put = [&](const Distribution1D &d, float *dst) {
+        const int n = d.Count();
+        for (int i = 0; i < n; ++i) dst[i] = d.func[i];
+        for (int i = 0; i <= n; ++i) dst[n + i] = d.cdf[i];
+        dst[2 * n + 1] = d.funcInt;
+    };
+    const size_t stride = 2 * (size_t)*nu + 2;
+    for (int v = 0; v < *nv; ++v) put(*d2.pConditionalV[v], out + (size_t)v * stride);
+    put(*d2.pMarginal, out + (size_t)*nv * stride);
+    return 0;
+}
+
 // MIPMap<T>::Lookup(st, dst0, dst1) of the reference for a batch (st: 2 floats, dst: 4, out: 3 per look-up)
 int ref_texture_lookup(const pb2_texture *t, int64_t n, const float *st, const float *dst, float *out) {
     setThreads(0);
@@ -459,7 +507,24 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
                     m.m[r][c] = dl.light_to_world[3 * r + c];
                     mInv.m[r][c] = dl.world_to_light[3 * r + c];
                 }
-            rs->lights[i] = std::make_shared<InfiniteAreaLight>(Transform(m, mInv), I, 1, "");
+            std::string mapName;
+            Spectrum Linf = I;
+            if (dl.env_tex) {
+                // the description's texels are already ReadImage(mapname) * L: the constructor multiplies them by L = 1
+                const pb2_texture &pt = d->textures[dl.env_tex - 1];
+                mapName = "pb2env:" + std::to_string((long long)(size_t)rs.get()) + ":" + std::to_string(i);
+                std::lock_guard<std::mutex> lock(g_registryMutex);
+                RegisteredImage &im = g_imageRegistry[mapName];
+                im.w = pt.width;
+                im.h = pt.height;
+                im.rgb.assign(pt.texels, pt.texels + (size_t)3 * pt.width * pt.height);
+                Linf = Spectrum(1.f);
+            }
+            rs->lights[i] = std::make_shared<InfiniteAreaLight>(Transform(m, mInv), Linf, 1, mapName);
+            if (dl.env_tex) {
+                std::lock_guard<std::mutex> lock(g_registryMutex);
+                g_imageRegistry.erase(mapName);
+            }
         } else
             rs->lights[i] = std::make_shared<DistantLight>(Transform(), I, Vector3f(dl.p[0], dl.p[1], dl.p[2]));
     }

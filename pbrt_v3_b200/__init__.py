@@ -79,7 +79,7 @@ class Light(C.Structure):
 class DeltaLight(C.Structure):
     _fields_ = [("p", C.c_float * 3), ("total_width_deg", C.c_float), ("falloff_start_deg", C.c_float),
                 ("world_radius", C.c_float), ("world_to_light", C.c_float * 9), ("pad", C.c_float),
-                ("light_to_world", C.c_float * 9), ("pad2", C.c_float * 3)]
+                ("light_to_world", C.c_float * 9), ("env_tex", C.c_int32), ("pad2", C.c_float * 2)]
 
 
 class Bvh(C.Structure):
@@ -201,6 +201,7 @@ def lib():
     L.pb2_sobol_samples_host.argtypes = [C.POINTER(FilmDesc), C.POINTER(PathParams), vp, vp, vp, C.c_int64, vp, vp]
     L.pb2_texture_pyramid.argtypes = [C.POINTER(Texture), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     L.pb2_texture_lookup.argtypes = [C.POINTER(Texture), C.c_int64, vp, vp, vp]
+    L.pb2_env_distribution.argtypes = [C.POINTER(Texture), C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     L.pb2h_parse_file.argtypes = [C.c_char_p, C.c_char_p]
     L.pb2h_parse_string.argtypes = [C.c_char_p]
     L.pb2h_synth_soup.argtypes = [C.c_int64, C.c_uint64, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
@@ -216,6 +217,7 @@ def lib():
     L.pb2h_device_scene.restype = vp
     L.pb2h_write_pfm.argtypes = [C.c_char_p, vp, C.c_int, C.c_int]
     L.pb2h_write_image.argtypes = [C.c_char_p, vp] + [C.c_int] * 6
+    L.pb2h_read_image.argtypes = [C.c_char_p, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.pb2h_loop_subdivide.argtypes = [C.c_int, C.c_int, vp, C.c_int, vp, C.POINTER(C.c_int), C.POINTER(C.c_int), vp, vp, vp]
     L.pb2h_set_light_strategy.argtypes = [C.c_int]
     L.pb2h_scene_intersect.argtypes = [vp, vp, vp]
@@ -270,6 +272,26 @@ def texture_pyramid(texture, fn=None):
         check(fn(C.byref(texture), lv, C.byref(nl), C.byref(w), C.byref(h), ptr(a)))
         levels.append(a)
     return levels
+
+
+def env_distribution(texture, fn=None):
+    """The Distribution2D the library derives for an InfiniteAreaLight with this environment map (host code): (nu, nv, table)."""
+    fn = fn or lib().pb2_env_distribution
+    nu, nv = C.c_int32(), C.c_int32()
+    check(fn(C.byref(texture), C.byref(nu), C.byref(nv), None))
+    table = np.zeros(nv.value * (2 * nu.value + 2) + 2 * nv.value + 2, np.float32)
+    check(fn(C.byref(texture), C.byref(nu), C.byref(nv), ptr(table)))
+    return nu.value, nv.value, table
+
+
+def read_image(path):
+    """The host front end's ReadImage (PFM / PNG / TGA / OpenEXR): (h, w, 3) float32, row 0 at the top."""
+    w, h = C.c_int(), C.c_int()
+    if lib().pb2h_read_image(path.encode(), None, C.byref(w), C.byref(h)) != 0:
+        raise RuntimeError("cannot read %s" % path)
+    out = np.zeros((h.value, w.value, 3), np.float32)
+    lib().pb2h_read_image(path.encode(), ptr(out), C.byref(w), C.byref(h))
+    return out
 
 
 def texture_lookup(texture, st, dst):

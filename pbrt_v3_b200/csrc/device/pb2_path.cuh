@@ -133,7 +133,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
         } else {
             // the ray escaped: every infinite light is seen directly (path.cpp:96-98)
             for (int k = 0; k < sc.nInfinite; ++k)
-                ln.L = ln.L + ln.beta * infiniteLe(sc.lights[sc.infinite[k]], sc.deltaLights[sc.infinite[k]], ln.ray.d);
+                ln.L = ln.L + ln.beta * infiniteLe(sc, sc.lights[sc.infinite[k]], sc.deltaLights[sc.infinite[k]], ln.ray.d);
         }
     }
     if (!found || ln.bounces >= pp.maxDepth) {
@@ -201,7 +201,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
                     // the trace); f * Li * Tr(=1) * weight / scatteringPdf.  An infinite light is seen when the ray
                     // escapes instead (integrator.cpp:209-211): its Le along wi is known here already.
                     V3 Lmis = mk3(light.L[0], light.L[1], light.L[2]);
-                    if (sc.deltaLights && light.type == PB2_LIGHT_INFINITE) Lmis = infiniteLe(light, sc.deltaLights[lightNum], wi);
+                    if (sc.deltaLights && light.type == PB2_LIGHT_INFINITE) Lmis = infiniteLe(sc, light, sc.deltaLights[lightNum], wi);
                     V3 fl = f * Lmis * weight;
                     ln.misTerm = mk3(fl.x / scatteringPdf, fl.y / scatteringPdf, fl.z / scatteringPdf);
                     DRay mr = spawnRay(isect, wi);

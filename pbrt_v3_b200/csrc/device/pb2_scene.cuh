@@ -90,6 +90,13 @@ struct DDeltaLight {
     float lightToWorld[9];
     float dist[18];
     float pad2;
+    // ... with an environment map (pb2_delta_light::env_tex): Lmap is texture envTex - 1 of the scene's texture pool, the
+    // Distribution2D over its 2w x 2h image is envDist: envNv rows of [func(envNu) | cdf(envNu + 1) | funcInt], then the
+    // marginal [func(envNv) | cdf(envNv + 1) | funcInt] over the rows' integrals
+    const float *envDist;
+    int envNu, envNv;
+    int envTex;
+    int pad3;
 };
 
 struct DScene {

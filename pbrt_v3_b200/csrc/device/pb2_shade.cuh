@@ -1259,16 +1259,22 @@ PB2_HD float sampleContinuous1D(const float *rec, int n, float u, float *pdf, in
     return (offset + du) / n;
 }
 // InfiniteAreaLight::Le (infinite.cpp:90-94): SphericalPhi / SphericalTheta of the direction in light space (geometry.h:1456-1465)
-PB2_HDN V3 infiniteLe(const pb2_light &l, const DDeltaLight &dl, V3 d) {
+// Lmap->Lookup(st) of a light with an environment map: MIPMap::Lookup(st, width = 0) is the bilinear look-up at the finest
+// level (mipmap.h:227-235: level = Levels - 1 + log2(1e-8) < 0), wrap mode repeat
+PB2_HD V3 envLookup(const DScene &sc, const pb2_light &l, const DDeltaLight &dl, V2 st) {
+    if (dl.envTex) return texTriangle(sc.textures[dl.envTex - 1], sc.texels, 0, st);
+    return infiniteLookup(l, st);
+}
+PB2_HDN V3 infiniteLe(const DScene &sc, const pb2_light &l, const DDeltaLight &dl, V3 d) {
     const float *m = dl.worldToLight;
     const V3 w = normalize(mk3(m[0] * d.x + m[1] * d.y + m[2] * d.z, m[3] * d.x + m[4] * d.y + m[5] * d.z, m[6] * d.x + m[7] * d.y + m[8] * d.z));
     float phi = patan2f(w.y, w.x);
     if (phi < 0) phi = phi + 2 * kPi;
     const float theta = pacosf(clampf(w.z, -1.f, 1.f));
-    return infiniteLookup(l, mk2(phi * (0.5f * kInvPi), theta * kInvPi));
+    return envLookup(sc, l, dl, mk2(phi * (0.5f * kInvPi), theta * kInvPi));
 }
 // InfiniteAreaLight::Sample_Li (infinite.cpp:96-122); the VisibilityTester's far point has neither normal nor error bounds
-PB2_HDN DLightSample sampleInfiniteLight(const pb2_light &l, const DDeltaLight &dl, V3 refP, V2 u) {
+PB2_HDN DLightSample sampleInfiniteLight(const DScene &sc, const pb2_light &l, const DDeltaLight &dl, V3 refP, V2 u) {
     DLightSample s;
     s.delta = false;
     s.pError = s.n = mk3(0, 0, 0);
@@ -1279,8 +1285,15 @@ PB2_HDN DLightSample sampleInfiniteLight(const pb2_light &l, const DDeltaLight &
     // Distribution2D::SampleContinuous (sampling.h:117-125): the row from the marginal with u[1], then inside the row with u[0]
     float pdf1, pdf0;
     int v, uo;
-    const float d1 = sampleContinuous1D(dl.dist + 12, 2, u.y, &pdf1, &v);
-    const float d0 = sampleContinuous1D(dl.dist + 6 * v, 2, u.x, &pdf0, &uo);
+    float d0, d1;
+    if (dl.envTex) {
+        const int nu = dl.envNu, nv = dl.envNv;
+        d1 = sampleContinuous1D(dl.envDist + (size_t)nv * (2 * nu + 2), nv, u.y, &pdf1, &v);
+        d0 = sampleContinuous1D(dl.envDist + (size_t)v * (2 * nu + 2), nu, u.x, &pdf0, &uo);
+    } else {
+        d1 = sampleContinuous1D(dl.dist + 12, 2, u.y, &pdf1, &v);
+        d0 = sampleContinuous1D(dl.dist + 6 * v, 2, u.x, &pdf0, &uo);
+    }
     const float mapPdf = pdf0 * pdf1;
     if (mapPdf == 0) return s;
     const float theta = d1 * kPi, phi = d0 * 2 * kPi;
@@ -1292,7 +1305,7 @@ PB2_HDN DLightSample sampleInfiniteLight(const pb2_light &l, const DDeltaLight &
     s.pdf = mapPdf / (2 * kPi * kPi * sinTheta);
     if (sinTheta == 0) s.pdf = 0;
     s.p = refP + s.wi * (2 * dl.worldRadius);
-    s.Li = infiniteLookup(l, mk2(d0, d1));
+    s.Li = envLookup(sc, l, dl, mk2(d0, d1));
     return s;
 }
 // InfiniteAreaLight::Pdf_Li (infinite.cpp:124-132), Distribution2D::Pdf (sampling.h:126-132)
@@ -1305,6 +1318,14 @@ PB2_HDN float infinitePdfLi(const DDeltaLight &dl, V3 w) {
     const float sinTheta = psinf(theta);
     if (sinTheta == 0) return 0;
     const float px = phi * (0.5f * kInvPi), py = theta * kInvPi;
+    if (dl.envTex) {
+        const int nu = dl.envNu, nv = dl.envNv;
+        int iu = (int)(px * nu), iv = (int)(py * nv);
+        iu = iu < 0 ? 0 : (iu > nu - 1 ? nu - 1 : iu);
+        iv = iv < 0 ? 0 : (iv > nv - 1 ? nv - 1 : iv);
+        const float marginalInt = dl.envDist[(size_t)nv * (2 * nu + 2) + 2 * nv + 1];
+        return (dl.envDist[(size_t)iv * (2 * nu + 2) + iu] / marginalInt) / (2 * kPi * kPi * sinTheta);
+    }
     int iu = (int)(px * 2), iv = (int)(py * 2);
     iu = iu < 0 ? 0 : (iu > 1 ? 1 : iu);
     iv = iv < 0 ? 0 : (iv > 1 ? 1 : iv);
@@ -1314,7 +1335,7 @@ PB2_HDN float infinitePdfLi(const DDeltaLight &dl, V3 w) {
 // `rec` is the light's record out of DScene::lightRecs, lightNum its index in Scene::lights.
 template <bool SPH = true>
 PB2_HD DLightSample sampleLight(const DScene &sc, int lightNum, const pb2_light &l, const TriRec &rec, const DInteraction &ref, V2 u) {
-    if (sc.deltaLights && l.type == PB2_LIGHT_INFINITE) return sampleInfiniteLight(l, sc.deltaLights[lightNum], ref.p, u);
+    if (sc.deltaLights && l.type == PB2_LIGHT_INFINITE) return sampleInfiniteLight(sc, l, sc.deltaLights[lightNum], ref.p, u);
     if (sc.deltaLights && l.type != PB2_LIGHT_AREA) return sampleDeltaLight(l, sc.deltaLights[lightNum], ref.p);
     DLightSample s;
     if (SPH && (rec.flags & LEAF_SPHERE)) s = sampleSphereLight(sc, l, ref, u);

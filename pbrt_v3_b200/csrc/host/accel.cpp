@@ -453,6 +453,10 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
     std::unique_ptr<FlatScene> fs(new FlatScene());
     std::unordered_map<const TriangleMesh *, int> meshIds;
     std::unordered_map<const Material *, int> materialIds;
+    std::unordered_map<const AreaLight *, int> lightIds;
+    // Scene::lights order is the order of creation in the scene file (api.cpp:1413-1416)
+    fs->lights.resize(lights.size());
+    std::vector<char> lightSeen(lights.size(), 0);
     // image textures in order of first use; 0 = none, else 1 + index (pb2_material::tex, pb2_mesh::alpha_tex)
     std::unordered_map<const ImageTexture *, int> textureIds;
     auto textureId = [&](const std::shared_ptr<ImageTexture> &t) -> int32_t {
@@ -464,10 +468,6 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
         textureIds[t.get()] = id;
         return id;
     };
-    std::unordered_map<const AreaLight *, int> lightIds;
-    // Scene::lights order is the order of creation in the scene file (api.cpp:1413-1416)
-    fs->lights.resize(lights.size());
-    std::vector<char> lightSeen(lights.size(), 0);
     for (size_t i = 0; i < lights.size(); ++i) {
         if (const AreaLight *al = dynamic_cast<const AreaLight *>(lights[i].get())) {
             lightIds[al] = (int)i;
@@ -507,6 +507,7 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
         } else if (const InfiniteAreaLight *il = dynamic_cast<const InfiniteAreaLight *>(lights[i].get())) {
             rec.type = PB2_LIGHT_INFINITE;
             for (int c = 0; c < 3; ++c) rec.L[c] = il->L.c[c];
+            dl.env_tex = textureId(il->envMap);
             for (int r = 0; r < 3; ++r)
                 for (int c = 0; c < 3; ++c) {
                     dl.world_to_light[3 * r + c] = il->WorldToLight.GetMatrix().m[r][c];

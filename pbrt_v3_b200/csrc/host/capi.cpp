@@ -311,6 +311,14 @@ int pb2h_scene_intersect(const float *o, const float *d, float *t_hit) {
 
 int pb2h_write_pfm(const char *path, const float *rgb, int w, int h) { return WriteImagePFM(path, rgb, w, h) ? 0 : 1; }
 // WriteImage (imageio.cpp:81-122): EXR / PFM / PNG / TGA by extension; the window arguments only matter for EXR
+// ReadImage (imageio.cpp:60-79): PFM / PNG / TGA / OpenEXR by extension; rgb (3 floats per pixel, row 0 at the top) may be
+// NULL to ask for the resolution only
+int pb2h_read_image(const char *path, float *rgb, int *w, int *h) {
+    std::vector<float> data;
+    if (!ReadImage(path, &data, w, h)) return 1;
+    if (rgb) std::memcpy(rgb, data.data(), data.size() * sizeof(float));
+    return 0;
+}
 int pb2h_write_image(const char *path, const float *rgb, int w, int h, int total_w, int total_h, int x_offset, int y_offset) {
     return WriteImage(path, rgb, w, h, total_w, total_h, x_offset, y_offset) ? 0 : 1;
 }

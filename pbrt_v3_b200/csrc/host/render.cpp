@@ -133,18 +133,31 @@ std::shared_ptr<DistantLight> CreateDistantLight(const Transform &light2world, c
     Vector3f dir = from - to;
     return std::make_shared<DistantLight>(light2world, L * sc, dir);
 }
-// CreateInfiniteLight (infinite.cpp:177-188).  "mapname" would need the image readers (imageio.cpp ReadImage) and the
-// MIP-map pyramid, which are outside the path's scope: reported, and the light is created without the map like the
-// reference does when the file cannot be read.
+// CreateInfiniteLight (infinite.cpp:177-188).  "mapname": the image (PFM, PNG, TGA; texture.cpp ReadImage) times L becomes
+// the light's radiance map; a file that cannot be read leaves the constant light, as in the reference (infinite.cpp:58-62).
+extern std::string g_sceneDirectory;
 std::shared_ptr<InfiniteAreaLight> CreateInfiniteLight(const Transform &light2world, const ParamSet &paramSet) {
     Spectrum L = paramSet.FindOneSpectrum("L", Spectrum(1.0));
     Spectrum sc = paramSet.FindOneSpectrum("scale", Spectrum(1.0));
     std::string texmap = paramSet.FindOneString("mapname", "");
     paramSet.FindOneInt("samples", paramSet.FindOneInt("nsamples", 1));
-    if (texmap != "")
-        Error("LightSource \"infinite\": environment map \"%s\" is outside the GPU path's scope (constant radiance only); using \"L\" alone",
-              texmap.c_str());
-    return std::make_shared<InfiniteAreaLight>(light2world, L * sc);
+    L = L * sc;
+    std::shared_ptr<ImageTexture> envMap;
+    if (texmap != "") {
+        std::string path = texmap;
+        if (path[0] != '/' && !g_sceneDirectory.empty()) path = g_sceneDirectory + "/" + path;
+        std::vector<float> rgb;
+        int w = 0, h = 0;
+        if (ReadImage(path, &rgb, &w, &h)) {
+            envMap = std::make_shared<ImageTexture>();
+            envMap->channels = 3;
+            envMap->width = w;
+            envMap->height = h;
+            envMap->texels.resize(rgb.size());
+            for (size_t i = 0; i < rgb.size(); ++i) envMap->texels[i] = rgb[i] * L.c[i % 3];   // texels[i] *= L (infinite.cpp:56)
+        }
+    }
+    return std::make_shared<InfiniteAreaLight>(light2world, L, envMap);
 }
 // Textured parameters.  A parameter that names an image texture ("imagemap") of the right kind is attached to the
 // material's slot (Material::tex -> pb2_material::tex); one that names anything else that varies (procedural textures,

@@ -234,9 +234,12 @@ class DistantLight : public Light {
 // infinite.h:49-83 without a texture map: constant radiance from every direction
 class InfiniteAreaLight : public Light {
   public:
-    InfiniteAreaLight(const Transform &LightToWorld, const Spectrum &L) : LightToWorld(LightToWorld), WorldToLight(Inverse(LightToWorld)), L(L) {}
+    InfiniteAreaLight(const Transform &LightToWorld, const Spectrum &L, std::shared_ptr<ImageTexture> envMap = nullptr)
+        : LightToWorld(LightToWorld), WorldToLight(Inverse(LightToWorld)), L(L), envMap(std::move(envMap)) {}
     const Transform LightToWorld, WorldToLight;
     const Spectrum L;
+    // "mapname": the texels ReadImage returned, times L (infinite.cpp:50-57), as the constructor hands them to Lmap; null = constant
+    const std::shared_ptr<ImageTexture> envMap;
 };
 std::shared_ptr<InfiniteAreaLight> CreateInfiniteLight(const Transform &light2world, const ParamSet &paramSet);
 std::shared_ptr<PointLight> CreatePointLight(const Transform &light2world, const ParamSet &paramSet);

@@ -5,7 +5,7 @@
 //   ImageTexture::GetTexture (flip in y, convertIn)             src/textures/imagemap.cpp:50-107, imagemap.h:97-106
 //   CreateImageFloatTexture / CreateImageSpectrumTexture        src/textures/imagemap.cpp:113-197
 // The MIP pyramid and the filtering live in the CUDA library (pb2_texture, include/pb2.h); what is built here is the texel
-// array the MIPMap constructor receives.  OpenEXR input needs the PIZ / ZIP wavelet codecs and is reported as an error.
+// array the MIPMap constructor receives.
 #include <zlib.h>
 
 #include <cmath>
@@ -237,6 +237,164 @@ static bool readPNG(const std::string &name, std::vector<float> *rgb, int *w, in
     return true;
 }
 
+// ---- OpenEXR: single-part scan-line files, half / float / uint channels R, G, B (or a lone Y), compression NONE, RLE, ZIPS
+// and ZIP (what imgtool / pbrt's WriteImageEXR produce); PIZ and the lossy codecs, tiled, deep and multi-part files are refused.
+// ReadImageEXR (imageio.cpp:125-151) reads the data window through an RgbaInputFile: the same pixels.
+static float halfToFloat(uint16_t h) {
+    const uint32_t sign = (uint32_t)(h >> 15) << 31, exp = (h >> 10) & 31, man = h & 1023;
+    uint32_t bits;
+    if (exp == 0) {
+        if (man == 0) bits = sign;
+        else {   // subnormal half: normalise
+            int e = -1;
+            uint32_t m = man;
+            do {
+                ++e;
+                m <<= 1;
+            } while (!(m & 1024));
+            bits = sign | ((uint32_t)(127 - 15 - e) << 23) | ((m & 1023) << 13);
+        }
+    } else if (exp == 31) bits = sign | 0x7f800000u | (man << 13);
+    else bits = sign | ((exp + 127 - 15) << 23) | (man << 13);
+    float f;
+    memcpy(&f, &bits, 4);
+    return f;
+}
+static bool readEXR(const std::string &name, std::vector<float> *rgb, int *w, int *h, std::string *why) {
+    std::vector<uint8_t> b;
+    if (!readFile(name, &b) || b.size() < 8) { *why = "cannot open"; return false; }
+    auto i32 = [&](size_t p) { int32_t v; memcpy(&v, &b[p], 4); return v; };
+    if ((uint32_t)i32(0) != 20000630u) { *why = "not an OpenEXR file"; return false; }
+    const uint32_t version = (uint32_t)i32(4);
+    if ((version & 0xff) != 2 || (version & (0x200 | 0x800 | 0x1000))) { *why = "tiled, deep or multi-part file"; return false; }
+    size_t pos = 8;
+    struct Channel { std::string name; int type, xs, ys; };
+    std::vector<Channel> channels;
+    int compression = -1, dw[4] = {0, 0, -1, -1};
+    auto cstr = [&](std::string *out) {
+        out->clear();
+        while (pos < b.size() && b[pos]) out->push_back((char)b[pos++]);
+        if (pos >= b.size()) return false;
+        ++pos;
+        return true;
+    };
+    for (;;) {
+        std::string an, at;
+        if (!cstr(&an)) { *why = "truncated header"; return false; }
+        if (an.empty()) break;
+        if (!cstr(&at) || pos + 4 > b.size()) { *why = "truncated header"; return false; }
+        const int size = i32(pos);
+        pos += 4;
+        if (size < 0 || pos + (size_t)size > b.size()) { *why = "truncated header"; return false; }
+        if (an == "channels") {
+            size_t p = pos;
+            while (p < pos + size && b[p]) {
+                Channel c;
+                while (b[p]) c.name.push_back((char)b[p++]);
+                ++p;
+                c.type = i32(p);
+                c.xs = i32(p + 8);
+                c.ys = i32(p + 12);
+                p += 16;
+                channels.push_back(c);
+            }
+        } else if (an == "compression") compression = b[pos];
+        else if (an == "dataWindow")
+            for (int k = 0; k < 4; ++k) dw[k] = i32(pos + 4 * k);
+        pos += (size_t)size;
+    }
+    *w = dw[2] - dw[0] + 1;
+    *h = dw[3] - dw[1] + 1;
+    if (*w <= 0 || *h <= 0 || channels.empty()) { *why = "no data window / channels"; return false; }
+    if (compression < 0 || compression > 3) { *why = "compression other than NONE / RLE / ZIPS / ZIP (e.g. PIZ)"; return false; }
+    size_t lineBytes = 0;
+    std::vector<size_t> chOffset(channels.size());
+    int src[3] = {-1, -1, -1};
+    for (size_t c = 0; c < channels.size(); ++c) {
+        if (channels[c].xs != 1 || channels[c].ys != 1) { *why = "sub-sampled channels"; return false; }
+        if (channels[c].type < 0 || channels[c].type > 2) { *why = "unknown pixel type"; return false; }
+        chOffset[c] = lineBytes;
+        lineBytes += (size_t)*w * (channels[c].type == 1 ? 2 : 4);
+        if (channels[c].name == "R") src[0] = (int)c;
+        if (channels[c].name == "G") src[1] = (int)c;
+        if (channels[c].name == "B") src[2] = (int)c;
+    }
+    if (src[0] < 0 && src[1] < 0 && src[2] < 0)
+        for (size_t c = 0; c < channels.size(); ++c)
+            if (channels[c].name == "Y") src[0] = src[1] = src[2] = (int)c;
+    if (src[0] < 0 && src[1] < 0 && src[2] < 0) { *why = "no R, G, B or Y channel"; return false; }
+    const int linesPerBlock = compression == 3 ? 16 : 1;
+    const int nBlocks = (*h + linesPerBlock - 1) / linesPerBlock;
+    if (pos + (size_t)nBlocks * 8 > b.size()) { *why = "truncated offset table"; return false; }
+    rgb->assign((size_t)3 * *w * *h, 0.f);
+    std::vector<uint8_t> raw, tmp;
+    for (int blk = 0; blk < nBlocks; ++blk) {
+        uint64_t off;
+        memcpy(&off, &b[pos + (size_t)blk * 8], 8);
+        if (off + 8 > b.size()) { *why = "bad chunk offset"; return false; }
+        const int y0 = i32(off) - dw[1], dataSize = i32(off + 4);
+        const int lines = std::min(linesPerBlock, *h - y0);
+        if (y0 < 0 || lines <= 0 || dataSize < 0 || off + 8 + (size_t)dataSize > b.size()) { *why = "bad chunk"; return false; }
+        const size_t rawSize = lineBytes * lines;
+        raw.resize(rawSize);
+        const uint8_t *data = &b[off + 8];
+        if ((size_t)dataSize >= rawSize || compression == 0) {   // stored as is (a block that did not shrink is not compressed)
+            if ((size_t)dataSize < rawSize) { *why = "short block"; return false; }
+            memcpy(raw.data(), data, rawSize);
+        } else {
+            tmp.resize(rawSize);
+            if (compression == 1) {   // run-length: count < 0 -> -count literal bytes, else count + 1 copies of the next byte
+                size_t o = 0, p = 0;
+                while (p < (size_t)dataSize && o < rawSize) {
+                    const int count = (int8_t)data[p++];
+                    if (count < 0) {
+                        const size_t n = (size_t)(-count);
+                        if (p + n > (size_t)dataSize || o + n > rawSize) { *why = "bad RLE block"; return false; }
+                        memcpy(&tmp[o], &data[p], n);
+                        p += n;
+                        o += n;
+                    } else {
+                        const size_t n = (size_t)count + 1;
+                        if (p >= (size_t)dataSize || o + n > rawSize) { *why = "bad RLE block"; return false; }
+                        memset(&tmp[o], data[p++], n);
+                        o += n;
+                    }
+                }
+                if (o != rawSize) { *why = "bad RLE block"; return false; }
+            } else {
+                uLongf n = (uLongf)rawSize;
+                if (uncompress(tmp.data(), &n, data, (uLong)dataSize) != Z_OK || n != rawSize) { *why = "bad ZIP block"; return false; }
+            }
+            // undo the byte-delta predictor, then the split into even and odd bytes
+            for (size_t i = 1; i < rawSize; ++i) tmp[i] = (uint8_t)(tmp[i - 1] + tmp[i] - 128);
+            const size_t half = (rawSize + 1) / 2;
+            for (size_t i = 0; i < rawSize; ++i) raw[i] = (i & 1) ? tmp[half + i / 2] : tmp[i / 2];
+        }
+        for (int l = 0; l < lines; ++l)
+            for (int c = 0; c < 3; ++c) {
+                if (src[c] < 0) continue;
+                const Channel &ch = channels[(size_t)src[c]];
+                const uint8_t *line = raw.data() + (size_t)l * lineBytes + chOffset[(size_t)src[c]];
+                float *dst = rgb->data() + 3 * (size_t)(y0 + l) * *w + c;
+                for (int x = 0; x < *w; ++x) {
+                    float v;
+                    if (ch.type == 1) {
+                        uint16_t hv;
+                        memcpy(&hv, line + 2 * (size_t)x, 2);
+                        v = halfToFloat(hv);
+                    } else if (ch.type == 2) memcpy(&v, line + 4 * (size_t)x, 4);
+                    else {
+                        uint32_t u;
+                        memcpy(&u, line + 4 * (size_t)x, 4);
+                        v = (float)u;
+                    }
+                    dst[3 * (size_t)x] = v;
+                }
+            }
+    }
+    return true;
+}
+
 // ReadImage (imageio.cpp:60-79): RGB per pixel, row 0 at the top
 bool ReadImage(const std::string &name, std::vector<float> *rgb, int *w, int *h) {
     bool ok = false;
@@ -244,8 +402,12 @@ bool ReadImage(const std::string &name, std::vector<float> *rgb, int *w, int *h)
     else if (hasExtension(name, ".tga")) ok = readTGA(name, rgb, w, h);
     else if (hasExtension(name, ".png")) ok = readPNG(name, rgb, w, h);
     else if (hasExtension(name, ".exr")) {
-        Error("Unable to load \"%s\": OpenEXR input is outside the GPU path's scope (PFM, PNG and TGA are read)", name.c_str());
-        return false;
+        std::string why;
+        ok = readEXR(name, rgb, w, h, &why);
+        if (!ok) {
+            Error("Unable to read OpenEXR file \"%s\": %s (scan-line files with NONE / RLE / ZIPS / ZIP compression are read)", name.c_str(), why.c_str());
+            return false;
+        }
     } else {
         Error("Unable to load image stored in format \"%s\" for filename \"%s\".",
               strrchr(name.c_str(), '.') ? (strrchr(name.c_str(), '.') + 1) : "(unknown)", name.c_str());

@@ -1554,13 +1554,20 @@ static int buildTexturePyramid(const pb2_texture &in, std::vector<float> &pool, 
 }
 
 static void texWeightLut(std::vector<float> &pool);
-static int uploadTextures(pb2_scene *s, const pb2_scene_desc *d) {
+// The pyramids as they are uploaded, kept on the host while the scene is being created (an infinite light with an
+// environment map derives its sampling distribution from them).
+struct HostTextures {
+    std::vector<float> pool;
+    std::vector<DTexture> tex;
+};
+static int uploadTextures(pb2_scene *s, const pb2_scene_desc *d, HostTextures *host) {
     DScene &sc = s->d;
     if (d->n_textures <= 0) return PB2_OK;
     if (!d->textures) return setError(PB2_ERR_INVALID, "n_textures > 0 but textures is null");
-    std::vector<float> pool;
+    std::vector<float> &pool = host->pool;
     texWeightLut(pool);
-    std::vector<DTexture> tex((size_t)d->n_textures);
+    std::vector<DTexture> &tex = host->tex;
+    tex.resize((size_t)d->n_textures);
     for (int i = 0; i < d->n_textures; ++i) {
         int rc = buildTexturePyramid(d->textures[i], pool, &tex[i]);
         if (rc) return rc;
@@ -1630,6 +1637,49 @@ extern "C" int pb2_texture_lookup(const pb2_texture *texture, int64_t n, const f
     cudaFree(dDst);
     cudaFree(dOut);
     if (e != cudaSuccess) return setError(PB2_ERR_CUDA, cudaGetErrorString(e));
+    return PB2_OK;
+}
+
+// The Distribution2D of an InfiniteAreaLight over its environment map (infinite.cpp:64-82, sampling.cpp:52-62) as one table:
+// 2h rows of [func(2w) | cdf(2w + 1) | funcInt], then the marginal [func(2h) | cdf(2h + 1) | funcInt].
+static int buildEnvDistribution(const DTexture &tx, const float *pool, std::vector<float> *out) {
+    const int width = 2 * tx.w, height = 2 * tx.h;
+    if ((size_t)width * height > ((size_t)1 << 27)) return setError(PB2_ERR_UNSUPPORTED, "environment map too large for its sampling table");
+    const size_t rowStride = 2 * (size_t)width + 2;
+    std::vector<float> &table = *out;
+    table.assign((size_t)height * rowStride + 2 * (size_t)height + 2, 0.f);
+    const float fwidth = 0.5f / std::min(width, height);
+    for (int v = 0; v < height; ++v) {
+        const float vp = (v + .5f) / (float)height;
+        const float sinTheta = std::sin(3.14159265358979323846f * (v + .5f) / height);
+        float *row = table.data() + (size_t)v * rowStride;
+        for (int u = 0; u < width; ++u) {
+            const float up = (u + .5f) / (float)width;
+            const V3 c = texLookupWidth(tx, pool, mk2(up, vp), fwidth);
+            row[u] = 0.212671f * c.x + 0.715160f * c.y + 0.072169f * c.z;   // RGBSpectrum::y()
+            row[u] *= sinTheta;
+        }
+        finishVoxelDistribution(width, row);   // Distribution1D's constructor over [func | cdf | funcInt] (sampling.h:57-70)
+    }
+    float *marginal = table.data() + (size_t)height * rowStride;
+    for (int v = 0; v < height; ++v) marginal[v] = table[(size_t)v * rowStride + 2 * (size_t)width + 1];
+    finishVoxelDistribution(height, marginal);
+    return PB2_OK;
+}
+
+extern "C" int pb2_env_distribution(const pb2_texture *texture, int32_t *nu, int32_t *nv, float *out) {
+    if (!texture || !nu || !nv) return setError(PB2_ERR_INVALID, "null argument");
+    std::vector<float> pool;
+    texWeightLut(pool);
+    DTexture t;
+    int rc = buildTexturePyramid(*texture, pool, &t);
+    if (rc) return rc;
+    *nu = 2 * t.w;
+    *nv = 2 * t.h;
+    if (!out) return PB2_OK;
+    std::vector<float> table;
+    if ((rc = buildEnvDistribution(t, pool.data(), &table))) return rc;
+    memcpy(out, table.data(), table.size() * sizeof(float));
     return PB2_OK;
 }
 
@@ -1840,7 +1890,8 @@ static int createSceneOnCurrentDevice(const pb2_scene_desc *d, pb2_scene **out) 
     if ((rc = upload(s, d->prim_material, (size_t)d->n_prims, &sc.primMaterial))) return rc;
     if ((rc = upload(s, d->prim_light, (size_t)d->n_prims, &sc.primLight))) return rc;
     if ((rc = upload(s, d->materials, (size_t)d->n_materials, &sc.materials))) return rc;
-    if ((rc = uploadTextures(s, d))) return rc;
+    HostTextures hostTextures;
+    if ((rc = uploadTextures(s, d, &hostTextures))) return rc;
     sc.hasAlpha = hasAlpha ? 1 : 0;
     if ((rc = upload(s, d->lights, (size_t)d->n_lights, &sc.lights))) return rc;
     sc.deltaLights = nullptr;
@@ -1864,7 +1915,34 @@ static int createSceneOnCurrentDevice(const pb2_scene_desc *d, pb2_scene **out) 
             o.worldRadius = in.world_radius;
             for (int k = 0; k < 9; ++k) o.worldToLight[k] = in.world_to_light[k];
             for (int k = 0; k < 9; ++k) o.lightToWorld[k] = in.light_to_world[k];
-            if (d->lights[i].type == PB2_LIGHT_INFINITE) {
+            if (d->lights[i].type == PB2_LIGHT_INFINITE && in.env_tex) {
+                // Environment map.  Lmap = MIPMap<RGBSpectrum>(resolution, texels) with the default filter parameters
+                // (infinite.cpp:62): texture env_tex - 1 of the pool.  The sampling distribution (infinite.cpp:64-82): a
+                // 2w x 2h image of Lmap->Lookup((u + .5) / width, (v + .5) / height, fwidth).y() * sin(theta), trilinear
+                // look-ups evaluated here on the host by the functions the kernels use, then one Distribution1D per row
+                // and the marginal over the rows' integrals (Distribution2D, sampling.cpp:52-62).
+                if (sc.nInfinite >= 4) return setError(PB2_ERR_UNSUPPORTED, "more than four infinite lights");
+                sc.infinite[sc.nInfinite++] = i;
+                if (in.env_tex < 0 || in.env_tex > d->n_textures || d->textures[in.env_tex - 1].channels != 3)
+                    return setError(PB2_ERR_INVALID, "infinite light: env_tex out of range or not a three-channel texture");
+                const pb2_texture &pt = d->textures[in.env_tex - 1];
+                if (pt.wrap != PB2_WRAP_REPEAT || pt.do_trilinear || pt.max_anisotropy != 8.f)
+                    return setError(PB2_ERR_INVALID, "infinite light: the environment map must carry MIPMap's default parameters (repeat, EWA, 8)");
+                const DTexture &tx = hostTextures.tex[(size_t)in.env_tex - 1];
+                const float *pool = hostTextures.pool.data();
+                const int width = 2 * tx.w, height = 2 * tx.h;
+                std::vector<float> table;
+                if ((rc = buildEnvDistribution(tx, pool, &table))) return rc;
+                const float *dTable = nullptr;
+                if ((rc = upload(s, table.data(), table.size(), &dTable))) return rc;
+                o.envDist = dTable;
+                o.envNu = width;
+                o.envNv = height;
+                o.envTex = in.env_tex;
+                // InfiniteAreaLight::Power's radiance (infinite.cpp:84-88), kept in dist[0..2] for the power light distribution
+                const V3 pw = texLookupWidth(tx, pool, mk2(.5f, .5f), .5f);
+                o.dist[0] = pw.x; o.dist[1] = pw.y; o.dist[2] = pw.z;
+            } else if (d->lights[i].type == PB2_LIGHT_INFINITE) {
                 if (sc.nInfinite >= 4) return setError(PB2_ERR_UNSUPPORTED, "more than four infinite lights");
                 sc.infinite[sc.nInfinite++] = i;
                 // The sampling distribution of the constructor (infinite.cpp:61-82) for the 1 x 1 map: a 2 x 2 image of
@@ -1970,8 +2048,8 @@ static int createSceneOnCurrentDevice(const pb2_scene_desc *d, pb2_scene **out) 
                         p[c] = ((l.L[c] * 2) * Pi) * (1 - .5f * (deltaLights[i].cosFalloffStart + deltaLights[i].cosTotalWidth));
                     else if (l.type == PB2_LIGHT_DISTANT)   // distant.cpp:61-63: L * Pi * worldRadius * worldRadius
                         p[c] = ((l.L[c] * Pi) * deltaLights[i].worldRadius) * deltaLights[i].worldRadius;
-                    else if (l.type == PB2_LIGHT_INFINITE)  // infinite.cpp:84-88: Pi * r * r * Lookup((.5, .5), .5) = the texel itself
-                        p[c] = ((Pi * deltaLights[i].worldRadius) * deltaLights[i].worldRadius) * l.L[c];
+                    else if (l.type == PB2_LIGHT_INFINITE)  // infinite.cpp:84-88: Pi * r * r * Lookup((.5, .5), .5) (constant: the texel itself)
+                        p[c] = ((Pi * deltaLights[i].worldRadius) * deltaLights[i].worldRadius) * (deltaLights[i].envTex ? deltaLights[i].dist[c] : l.L[c]);
                     else
                         p[c] = ((s2 * l.L[c]) * l.area) * Pi;
                 }

@@ -99,6 +99,16 @@ def record_textures(ref):
     print("textures:", len(hs.textures()), "textures recorded")
 
 
+def record_env_distribution(ref):
+    """InfiniteAreaLight::distribution of the reference for the environment map of tests/scenes/envmap.pbrt."""
+    hs = pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "envmap.pbrt"))
+    d = hs.desc.contents
+    env = [d.delta_lights[i].env_tex for i in range(d.n_lights) if d.lights[i].type == pb.PB2_LIGHT_INFINITE][0]
+    nu, nv, table = ref.env_distribution(d.textures[env - 1])
+    np.savez_compressed(os.path.join(OUT, "env_distribution.npz"), nu=nu, nv=nv, table=table)
+    print("env distribution", nu, nv)
+
+
 def main():
     ref = pyoracle.reference()
     if ref is None:
@@ -119,6 +129,8 @@ def main():
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "textured.pbrt")), "textured")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "textured_lens.pbrt")), "textured_lens")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "sobol.pbrt")), "sobol")
+    record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "envmap.pbrt")), "envmap")
+    record_env_distribution(ref)
     record_textures(ref)
     record_filters(ref)
     record_hlbvh(ref)

@@ -90,6 +90,44 @@ def write_tga(path, rgb8, rle=True):
         f.write(body)
 
 
+def write_exr(path, img, compression="zip"):
+    """Scan-line OpenEXR, half B / G / R channels (stored alphabetically), ZIP (16 lines per block), ZIPS (1) or NONE."""
+    img = np.asarray(img, np.float16)
+    h, w, _ = img.shape
+    comp = {"none": 0, "zips": 2, "zip": 3}[compression]
+    lines_per_block = 16 if comp == 3 else 1
+
+    def attr(name, typ, data):
+        return name.encode() + b"\0" + typ.encode() + b"\0" + struct.pack("<i", len(data)) + data
+
+    chlist = b"".join(c + b"\0" + struct.pack("<iB3xii", 1, 0, 1, 1) for c in (b"B", b"G", b"R")) + b"\0"
+    box = struct.pack("<4i", 0, 0, w - 1, h - 1)
+    header = (struct.pack("<II", 20000630, 2) + attr("channels", "chlist", chlist) + attr("compression", "compression", bytes([comp]))
+              + attr("dataWindow", "box2i", box) + attr("displayWindow", "box2i", box) + attr("lineOrder", "lineOrder", b"\0")
+              + attr("pixelAspectRatio", "float", struct.pack("<f", 1.0)) + attr("screenWindowCenter", "v2f", struct.pack("<2f", 0, 0))
+              + attr("screenWindowWidth", "float", struct.pack("<f", 1.0)) + b"\0")
+    chunks = []
+    for y0 in range(0, h, lines_per_block):
+        raw = b"".join(img[y, :, c].astype("<f2").tobytes() for y in range(y0, min(h, y0 + lines_per_block)) for c in (2, 1, 0))
+        data = raw
+        if comp:
+            a = np.frombuffer(raw, np.uint8)
+            t = np.concatenate([a[0::2], a[1::2]]).astype(np.int32)      # even bytes first, then odd bytes
+            d = t.copy()
+            d[1:] = (t[1:] - t[:-1] + 128 + 256) % 256                   # byte deltas
+            z = zlib.compress(d.astype(np.uint8).tobytes(), 9)
+            if len(z) < len(raw):
+                data = z
+        chunks.append(struct.pack("<ii", y0, len(data)) + data)
+    offset = len(header) + 8 * len(chunks)
+    table = b""
+    for c in chunks:
+        table += struct.pack("<Q", offset)
+        offset += len(c)
+    with open(path, "wb") as f:
+        f.write(header + table + b"".join(chunks))
+
+
 def pattern(w, h, seed):
     """coloured tiles with a smooth gradient on top: detail at the texel scale and below"""
     rs = np.random.RandomState(seed)
@@ -116,7 +154,12 @@ def main():
     rgb8b = (pattern(24, 10, 5) * 255 + 0.5).astype(np.uint8)
     rgb8b[2:5, 3:15] = rgb8b[2, 3]   # some runs for the run-length packets
     write_tga(os.path.join(OUT, "tiles_24x10.tga"), rgb8b)
-    np.savez_compressed(os.path.join(OUT, "decoded_8bit.npz"), png=rgb8, tga=rgb8b)
+    hdr = (pattern(24, 18, 6) * np.float32(3.0)).astype(np.float16)      # 18 lines: a full ZIP block of 16 and a short one
+    hdr[3, 5] = [1000.0, 0.001, 0.0]
+    write_exr(os.path.join(OUT, "tiles_24x18_zip.exr"), hdr, "zip")
+    write_exr(os.path.join(OUT, "tiles_24x18_zips.exr"), hdr, "zips")
+    write_exr(os.path.join(OUT, "tiles_24x18_none.exr"), hdr, "none")
+    np.savez_compressed(os.path.join(OUT, "decoded_8bit.npz"), png=rgb8, tga=rgb8b, exr=hdr.astype(np.float32))
 
 
 if __name__ == "__main__":

@@ -744,4 +744,57 @@ def test_infinite_light_is_flattened_with_its_transform(pb):
     text = open(os.path.join(SCENES, "envlight.pbrt")).read().replace('"rgb L" [.45 .6 .9]', '"rgb L" [.45 .6 .9] "string mapname" "sky.exr"')
     before = pb.lib().pb2h_error_count()
     hs2 = pb.HostScene.from_string(text)
-    assert pb.lib().pb2h_error_count() == before + 1 and hs2.desc.contents.lights[0].type == pb.PB2_LIGHT_INFINITE
+    # an unreadable map (OpenEXR input is outside the scope) is reported and leaves the constant light (infinite.cpp:58-62)
+    assert pb.lib().pb2h_error_count() >= before + 1 and hs2.desc.contents.lights[0].type == pb.PB2_LIGHT_INFINITE
+    assert hs2.desc.contents.delta_lights[0].env_tex == 0 and hs2.desc.contents.n_textures == 0
+
+
+def test_infinite_light_environment_map_is_flattened(pb):
+    """LightSource "infinite" "string mapname": the texels are ReadImage(mapname) * (L * scale), NOT flipped in y (infinite.cpp:50-57),
+    as one three-channel texture with MIPMap's default parameters, named by pb2_delta_light.env_tex."""
+    import struct
+    hs = pb.HostScene.from_file(os.path.join(SCENES, "envmap.pbrt"))
+    d = hs.desc.contents
+    assert d.lights[0].type == pb.PB2_LIGHT_INFINITE and d.delta_lights[0].env_tex == 1 and d.n_textures == 1
+    t = d.textures[0]
+    assert (t.channels, t.width, t.height, t.wrap, t.do_trilinear, t.max_anisotropy) == (3, 40, 20, pb.PB2_WRAP_REPEAT, 0, 8.0)
+    raw = open(os.path.join(SCENES, "textures", "sky_40x20.pfm"), "rb").read()
+    body = np.frombuffer(raw[-40 * 20 * 12:], "<f4").reshape(20, 40, 3)[::-1]    # PFM stores the bottom row first
+    L = np.float32([.5, .6, .7]) * np.float32([1.2, 1, .9])
+    got = np.ctypeslib.as_array(t.texels, shape=(20, 40, 3))
+    assert np.array_equal(got, body * L)
+
+
+def test_openexr_reader(pb, tmp_path):
+    """ReadImage for OpenEXR scan-line files (imageio.cpp:125-151 reads them through OpenEXR's RgbaInputFile): half channels
+    stored B, G, R; ZIP blocks of 16 lines (the last one short) with the byte-delta predictor and the even / odd byte split,
+    blocks stored raw when they do not shrink, and uncompressed files - the committed files of tests/scenes/make_textures.py,
+    the container this library writes itself, and (where the reference's bundled OpenEXR sources are present) OpenEXR's own
+    test images, which hold one picture under every codec."""
+    tex = os.path.join(SCENES, "textures")
+    want = np.load(os.path.join(tex, "decoded_8bit.npz"))["exr"]
+    for kind in ("zip", "zips", "none"):
+        got = pb.read_image(os.path.join(tex, "tiles_24x18_%s.exr" % kind))
+        assert got.shape == (18, 24, 3) and np.array_equal(got, want), kind
+    assert want[3, 5, 0] == 1000.0 and 0 < want[3, 5, 1] < 0.0011          # values beyond 8 bits, a subnormal-range half
+    # the writer of Film::WriteImage (half, uncompressed) and this reader are inverse to each other on half values
+    out = str(tmp_path / "roundtrip.exr")
+    assert pb.lib().pb2h_write_image(out.encode(), pb.ptr(np.ascontiguousarray(want)), 24, 18, 24, 18, 0, 0) == 0
+    assert np.array_equal(pb.read_image(out), want)
+    # as a texture: the directive reads it like any other container (no gamma for .exr)
+    hs = pb.HostScene.from_string('WorldBegin\nTexture "t" "spectrum" "imagemap" "string filename" "%s/tiles_24x18_zip.exr"\n'
+                                  'Material "matte" "texture Kd" "t"\nShape "sphere"\nWorldEnd\n' % tex)
+    t = hs.desc.contents.textures[0]
+    assert np.array_equal(np.ctypeslib.as_array(t.texels, shape=(18, 24, 3)), want[::-1])
+    ilm = "/root/reference/src/ext/openexr/OpenEXR/IlmImfTest"
+    if os.path.exists(os.path.join(ilm, "comp_none.exr")):
+        base = pb.read_image(os.path.join(ilm, "comp_none.exr"))
+        assert base.shape == (675, 587, 3) and np.isfinite(base).all()
+        for codec in ("rle", "zips", "zip"):
+            assert np.array_equal(pb.read_image(os.path.join(ilm, "comp_%s.exr" % codec)).view(np.uint32), base.view(np.uint32)), codec
+    # the wavelet codec is reported, not misread
+    before = pb.lib().pb2h_error_count()
+    if os.path.exists(os.path.join(ilm, "comp_piz.exr")):
+        with pytest.raises(RuntimeError):
+            pb.read_image(os.path.join(ilm, "comp_piz.exr"))
+        assert pb.lib().pb2h_error_count() > before

@@ -373,3 +373,17 @@ def test_sobol_tables_are_the_reference_tables(pb, reference):
         _, tab = pb.sobol_samples_host(C.byref(film), C.byref(pp), np.zeros((1, 2), np.int32), np.zeros(1, np.int64), np.zeros(1, np.int32), tables=True)
         want, _ = reference.sobol_tables(m)
         assert np.array_equal(tab, want), m
+
+
+def test_environment_map_distribution_is_the_reference_distribution(pb):
+    """An InfiniteAreaLight's sampling distribution over its environment map - the map's pyramid (40 x 20 resampled to 64 x 32),
+    128 x 64 trilinear look-ups, luminance, sin(theta), one Distribution1D per row and the marginal - computed by the library
+    on the host: BIT FOR BIT InfiniteAreaLight::distribution recorded from the compiled reference."""
+    g = np.load(os.path.join(GOLDEN, "env_distribution.npz"))
+    hs = load_scene(pb, "envmap")
+    d = hs.desc.contents
+    env = [d.delta_lights[i].env_tex for i in range(d.n_lights) if d.lights[i].type == pb.PB2_LIGHT_INFINITE]
+    assert len(env) == 1 and env[0] >= 1
+    nu, nv, table = pb.env_distribution(d.textures[env[0] - 1])
+    assert (nu, nv) == (int(g["nu"]), int(g["nv"])) == (128, 64)
+    assert np.array_equal(gc.bits(table), gc.bits(g["table"]))
