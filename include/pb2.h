@@ -100,7 +100,10 @@ typedef struct pb2_texture {
 
 /* slots of pb2_material.tex: which parameter a texture replaces */
 enum { PB2_TEX_KD = 0, PB2_TEX_KS = 1, PB2_TEX_KR = 2, PB2_TEX_KT = 3, PB2_TEX_OPACITY = 4, PB2_TEX_SIGMA = 5, PB2_TEX_ROUGHNESS = 6,
-       PB2_TEX_UROUGHNESS = 7, PB2_TEX_VROUGHNESS = 8, PB2_TEX_ETA = 9, PB2_TEX_METAL_ETA = 10, PB2_TEX_METAL_K = 11, PB2_TEX_SLOTS = 12 };
+       PB2_TEX_UROUGHNESS = 7, PB2_TEX_VROUGHNESS = 8, PB2_TEX_ETA = 9, PB2_TEX_METAL_ETA = 10, PB2_TEX_METAL_K = 11,
+       /* the "bumpmap" displacement (a one-channel texture): Material::Bump (src/core/material.cpp:45-82) perturbs the shading
+        * geometry before the material's other textures are evaluated */
+       PB2_TEX_BUMP = 12, PB2_TEX_SLOTS = 13 };
 
 /* Sphere (src/shapes/sphere.h:47-77). Matrices are row-major 4x4 (Matrix4x4::m). */
 typedef struct pb2_sphere {
@@ -141,7 +144,7 @@ typedef struct pb2_material {
      * at every shaded point instead (Kd->Evaluate(*si) etc., matte.cpp:53-54); spectrum parameters take three-channel
      * textures, float parameters one-channel ones.  The u / v roughness slots hold what the material's fall-back rules
      * resolve to ("uroughness" else "roughness", uber.cpp:82-85). */
-    int32_t tex[12];
+    int32_t tex[16];            /* PB2_TEX_SLOTS of them are used */
 } pb2_material;
 
 /* One entry of Scene::lights, in the scene's order.  PB2_LIGHT_AREA: a DiffuseAreaLight (src/lights/diffuse.h:49-79)
@@ -322,6 +325,10 @@ enum { PB2_SAMPLER_HALTON = 0, PB2_SAMPLER_SOBOL = 1 };
 /* Trace triangle scenes with the kernel that keeps a pool of 64 rays per warp in shared memory and picks, for every step,
  * the rays that are in the phase being run (k_wf_trace_pool).  Same results. */
 #define PB2_FLAG_POOL 128
+/* Experiment kept for the record: the default trace kernels with the light step inside - when a shadow
+ * or MIS ray ends, its lane adds the term, starts the vertex's next ray (MIS ray, continuation of the path) and traces it in
+ * the same launch, so that a bounce takes one round instead of up to three.  Same results, fewer launches, slower. */
+#define PB2_FLAG_CHAIN 256
 
 typedef struct pb2_ray {
     float o[3];

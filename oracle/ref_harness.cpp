@@ -401,29 +401,30 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
             return std::make_shared<ConstantTexture<Float>>(v);
         };
         auto kd = spec(PB2_TEX_KD, pm.kd);
+        std::shared_ptr<Texture<Float>> bump = pm.tex[PB2_TEX_BUMP] ? floatTex[pm.tex[PB2_TEX_BUMP] - 1] : nullptr;
         if (pm.type == PB2_MAT_MATTE) {
-            materials[i] = std::make_shared<MatteMaterial>(kd, flt(PB2_TEX_SIGMA, pm.sigma), nullptr);
+            materials[i] = std::make_shared<MatteMaterial>(kd, flt(PB2_TEX_SIGMA, pm.sigma), bump);
         } else if (pm.type == PB2_MAT_PLASTIC) {
-            materials[i] = std::make_shared<PlasticMaterial>(kd, spec(PB2_TEX_KS, pm.ks), flt(PB2_TEX_ROUGHNESS, pm.roughness), nullptr,
+            materials[i] = std::make_shared<PlasticMaterial>(kd, spec(PB2_TEX_KS, pm.ks), flt(PB2_TEX_ROUGHNESS, pm.roughness), bump,
                                                              pm.remap_roughness != 0);
         } else if (pm.type == PB2_MAT_MIRROR) {
-            materials[i] = std::make_shared<MirrorMaterial>(spec(PB2_TEX_KR, pm.kr), nullptr);
+            materials[i] = std::make_shared<MirrorMaterial>(spec(PB2_TEX_KR, pm.kr), bump);
         } else if (pm.type == PB2_MAT_SUBSTRATE) {
             materials[i] = std::make_shared<SubstrateMaterial>(kd, spec(PB2_TEX_KS, pm.ks), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
-                                                               flt(PB2_TEX_VROUGHNESS, pm.vroughness), nullptr, pm.remap_roughness != 0);
+                                                               flt(PB2_TEX_VROUGHNESS, pm.vroughness), bump, pm.remap_roughness != 0);
         } else if (pm.type == PB2_MAT_UBER) {
             // the description carries the resolved u / v roughness (pb2.h); "roughness" itself is then never read
             materials[i] = std::make_shared<UberMaterial>(kd, spec(PB2_TEX_KS, pm.ks), spec(PB2_TEX_KR, pm.kr), spec(PB2_TEX_KT, pm.kt),
                                                           flt(PB2_TEX_UROUGHNESS, pm.uroughness), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
                                                           flt(PB2_TEX_VROUGHNESS, pm.vroughness), spec(PB2_TEX_OPACITY, pm.opacity),
-                                                          flt(PB2_TEX_ETA, pm.eta), nullptr, pm.remap_roughness != 0);
+                                                          flt(PB2_TEX_ETA, pm.eta), bump, pm.remap_roughness != 0);
         } else if (pm.type == PB2_MAT_METAL) {
             materials[i] = std::make_shared<MetalMaterial>(spec(PB2_TEX_METAL_ETA, pm.metal_eta), spec(PB2_TEX_METAL_K, pm.metal_k),
                                                            flt(PB2_TEX_UROUGHNESS, pm.uroughness), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
-                                                           flt(PB2_TEX_VROUGHNESS, pm.vroughness), nullptr, pm.remap_roughness != 0);
+                                                           flt(PB2_TEX_VROUGHNESS, pm.vroughness), bump, pm.remap_roughness != 0);
         } else if (pm.type == PB2_MAT_GLASS) {
             materials[i] = std::make_shared<GlassMaterial>(spec(PB2_TEX_KR, pm.kr), spec(PB2_TEX_KT, pm.kt), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
-                                                           flt(PB2_TEX_VROUGHNESS, pm.vroughness), flt(PB2_TEX_ETA, pm.eta), nullptr,
+                                                           flt(PB2_TEX_VROUGHNESS, pm.vroughness), flt(PB2_TEX_ETA, pm.eta), bump,
                                                            pm.remap_roughness != 0);
         }
     }

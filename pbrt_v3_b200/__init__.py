@@ -56,13 +56,13 @@ class Material(C.Structure):
                 ("roughness", C.c_float), ("remap_roughness", C.c_int32), ("pad", C.c_int32 * 2),
                 ("kr", C.c_float * 3), ("kt", C.c_float * 3), ("eta", C.c_float), ("uroughness", C.c_float),
                 ("vroughness", C.c_float), ("opacity", C.c_float * 3), ("metal_eta", C.c_float * 3),
-                ("metal_k", C.c_float * 3), ("pad3", C.c_int32 * 2), ("tex", C.c_int32 * 12)]
+                ("metal_k", C.c_float * 3), ("pad3", C.c_int32 * 2), ("tex", C.c_int32 * 16)]
 
 
 PB2_WRAP_REPEAT, PB2_WRAP_BLACK, PB2_WRAP_CLAMP = 0, 1, 2
 PB2_SAMPLER_HALTON, PB2_SAMPLER_SOBOL = 0, 1
 (PB2_TEX_KD, PB2_TEX_KS, PB2_TEX_KR, PB2_TEX_KT, PB2_TEX_OPACITY, PB2_TEX_SIGMA, PB2_TEX_ROUGHNESS, PB2_TEX_UROUGHNESS,
- PB2_TEX_VROUGHNESS, PB2_TEX_ETA, PB2_TEX_METAL_ETA, PB2_TEX_METAL_K) = range(12)
+ PB2_TEX_VROUGHNESS, PB2_TEX_ETA, PB2_TEX_METAL_ETA, PB2_TEX_METAL_K, PB2_TEX_BUMP) = range(13)
 
 
 class Texture(C.Structure):
@@ -154,6 +154,7 @@ HIT_DTYPE = np.dtype([("prim", np.int32), ("t", np.float32), ("b", np.float32, 3
 WFHIT_DTYPE = np.dtype([("found", np.int32), ("leaf", np.int32), ("prim", np.int32), ("t", np.float32), ("b", np.float32, 3),
                         ("listed", np.int32)])
 PB2_FLAG_COUNT_TRAVERSAL, PB2_FLAG_LINEAR_NODES, PB2_FLAG_WIDE4, PB2_FLAG_PLAIN_TRACE, PB2_FLAG_SMALL_STACK, PB2_FLAG_LD128, PB2_FLAG_LEAF_TMA, PB2_FLAG_POOL = 1, 2, 4, 8, 16, 32, 64, 128
+PB2_FLAG_CHAIN = 256
 NODE_DTYPE = np.dtype([("bmin", np.float32, 3), ("bmax", np.float32, 3), ("offset", np.int32),
                        ("n_prims", np.uint16), ("axis", np.uint8), ("pad", np.uint8)])
 assert WFHIT_DTYPE.itemsize == C.sizeof(WfHit)

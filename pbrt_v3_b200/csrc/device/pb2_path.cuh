@@ -116,6 +116,12 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
             const DRayDiff rd = cameraRayDifferentials(*tc->cam, tc->pFilm, uLens, tc->diffScale, ln.ray.o, ln.ray.d);
             uvDiff = computeUvDifferentials(isect.p, isect.n, tg.dpdu, tg.dpdv, rd);
         }
+        if (found && ln.bounces < pp.maxDepth) {
+            // the material's bump map (e.g. matte.cpp:50: before its other textures are evaluated)
+            const int m = sc.primMaterial[isect.prim];
+            const int bump = m >= 0 ? sc.materials[m].tex[PB2_TEX_BUMP] : 0;
+            if (bump) bumpShading(sc, sc.textures[bump - 1], tg, uvDiff, &isect);
+        }
     }
     const float *lazyDistrib = nullptr;
     if (LAZY && sc.lightDist.slots && found && ln.bounces < pp.maxDepth) {

@@ -35,7 +35,8 @@ struct DInteraction {   // the part of (Surface)Interaction that Li and Estimate
 };
 
 // What SurfaceInteraction::ComputeDifferentials reads besides p and n: the (geometric) dpdu, dpdv of the hit
-struct DTexGeom { V3 dpdu, dpdv; };
+// ... and what Material::Bump reads: the shading dpdv, dndu, dndv (shading.dpdu is DInteraction::dpdus)
+struct DTexGeom { V3 dpdu, dpdv, dpdvs, dndus, dndvs; };
 
 struct TriVerts { V3 p0, p1, p2; };
 
@@ -129,6 +130,8 @@ PB2_HD DInteraction triangleInteraction(const DScene &sc, const TriRec &rec, flo
     if (tg) {
         tg->dpdu = dpdu;
         tg->dpdv = dpdv;
+        tg->dpdvs = dpdv;   // without per-vertex N / S the shading geometry is the geometric one, dndu = dndv = 0
+        tg->dndus = tg->dndvs = mk3(0, 0, 0);
     }
     float xAbsSum = (fabsf(b0 * tv.p0.x) + fabsf(b1 * tv.p1.x) + fabsf(b2 * tv.p2.x));
     float yAbsSum = (fabsf(b0 * tv.p0.y) + fabsf(b1 * tv.p1.y) + fabsf(b2 * tv.p2.y));
@@ -169,6 +172,26 @@ PB2_HD DInteraction triangleInteraction(const DScene &sc, const TriRec &rec, flo
         it.ns = normalize(cross(ss, ts));
         it.n = faceforward(it.n, it.ns);
         it.dpdus = ss;
+        if (tg) {
+            tg->dpdvs = ts;
+            if (mesh.has_n) {
+                // dndu, dndv of the interpolated normal (triangle.cpp:383-413)
+                const float duv02x = uv[0].x - uv[2].x, duv02y = uv[0].y - uv[2].y;
+                const float duv12x = uv[1].x - uv[2].x, duv12y = uv[1].y - uv[2].y;
+                const V3 n0 = ld3(sc.N, v0), n1 = ld3(sc.N, v1), n2 = ld3(sc.N, v2);
+                const V3 dn1 = n0 - n2, dn2 = n1 - n2;
+                const float determinant = duv02x * duv12y - duv02y * duv12x;
+                if ((double)fabsf(determinant) < 1e-8) {
+                    const V3 dn = cross(n2 - n0, n1 - n0);
+                    if (lengthSquared(dn) == 0) tg->dndus = tg->dndvs = mk3(0, 0, 0);
+                    else coordinateSystem(dn, &tg->dndus, &tg->dndvs);
+                } else {
+                    const float invDet = 1 / determinant;
+                    tg->dndus = (duv12y * dn1 - duv02y * dn2) * invDet;
+                    tg->dndvs = (-duv12x * dn1 + duv02x * dn2) * invDet;
+                }
+            }
+        }
     }
     return it;
 }
@@ -214,6 +237,9 @@ PB2_HD DInteraction hitInteraction(const DScene &sc, const DHit &hit, const DRay
         if (tg) {
             tg->dpdu = xfVector(inst->i2w, tg->dpdu);
             tg->dpdv = xfVector(inst->i2w, tg->dpdv);
+            tg->dpdvs = xfVector(inst->i2w, tg->dpdvs);
+            tg->dndus = xfNormalInv(inst->w2i, tg->dndus);
+            tg->dndvs = xfNormalInv(inst->w2i, tg->dndvs);
         }
     }
     return it;
@@ -309,6 +335,24 @@ PB2_HDN void applyTextures(const DScene &sc, V2 uv, const DUvDiff &d, pb2_materi
             dst3[2] = v.z;
         }
     }
+}
+
+// Material::Bump (material.cpp:45-82): the displacement texture evaluated at (u, v), (u + du, v) and (u, v + dv) tilts the
+// shading frame.  Only what an ImageTexture with a UVMapping2D reads is shifted (uv; the look-ups share the point's
+// differentials); the new shading normal is flipped to the side of the geometric one (SetShadingGeometry with
+// orientationIsAuthoritative = false).
+PB2_HDN void bumpShading(const DScene &sc, const DTexture &tx, const DTexGeom &tg, const DUvDiff &d, DInteraction *it) {
+    float du = .5f * (fabsf(d.dudx) + fabsf(d.dudy));
+    if (du == 0) du = .0005f;
+    const float uDisplace = texEvaluate(tx, sc.texels, mk2(it->uv.x + du, it->uv.y + 0.f), d).x;
+    float dv = .5f * (fabsf(d.dvdx) + fabsf(d.dvdy));
+    if (dv == 0) dv = .0005f;
+    const float vDisplace = texEvaluate(tx, sc.texels, mk2(it->uv.x + 0.f, it->uv.y + dv), d).x;
+    const float displace = texEvaluate(tx, sc.texels, it->uv, d).x;
+    const V3 dpdu = it->dpdus + ((uDisplace - displace) / du) * it->ns + displace * tg.dndus;
+    const V3 dpdv = tg.dpdvs + ((vDisplace - displace) / dv) * it->ns + displace * tg.dndvs;
+    it->ns = faceforward(normalize(cross(dpdu, dpdv)), it->n);
+    it->dpdus = dpdu;
 }
 
 // TEX = true: image textures are evaluated (uvDiff: the point's (u, v) differentials); false compiles them away.

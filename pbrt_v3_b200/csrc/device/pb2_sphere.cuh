@@ -211,7 +211,19 @@ PB2_HDN DInteraction sphereInteraction(const DScene &sc, int prim, const DRay &r
     it.dpdus = xfVector(o2w, dpdu);
     if (tg) {
         tg->dpdu = it.dpdus;
-        tg->dpdv = xfVector(o2w, dpdv);
+        tg->dpdv = tg->dpdvs = xfVector(o2w, dpdv);
+        // dndu, dndv from the fundamental forms (sphere.cpp:122-143), taken to world space as normals
+        const V3 d2Pduu = (-s.phi_max * s.phi_max) * mk3(pHit.x, pHit.y, 0);
+        const V3 d2Pduv = (((s.theta_max - s.theta_min) * pHit.z) * s.phi_max) * mk3(-sinPhiV, cosPhiV, 0.f);
+        const V3 d2Pdvv = (-(s.theta_max - s.theta_min) * (s.theta_max - s.theta_min)) * mk3(pHit.x, pHit.y, pHit.z);
+        const float E = dot(dpdu, dpdu), F = dot(dpdu, dpdv), G = dot(dpdv, dpdv);
+        const V3 Nn = normalize(cross(dpdu, dpdv));
+        const float e = dot(Nn, d2Pduu), f = dot(Nn, d2Pduv), g = dot(Nn, d2Pdvv);
+        const float invEGF2 = 1 / (E * G - F * F);
+        const V3 dndu = ((f * F - e * G) * invEGF2) * dpdu + ((e * F - f * E) * invEGF2) * dpdv;
+        const V3 dndv = ((g * F - f * G) * invEGF2) * dpdu + ((f * F - g * E) * invEGF2) * dpdv;
+        tg->dndus = xfNormalInv(w2o, dndu);
+        tg->dndvs = xfNormalInv(w2o, dndv);
     }
     it.ns = normalize(xfNormalInv(w2o, nsObj));
     it.ns = faceforward(it.ns, it.n);

@@ -161,8 +161,7 @@ std::shared_ptr<InfiniteAreaLight> CreateInfiniteLight(const Transform &light2wo
 }
 // Textured parameters.  A parameter that names an image texture ("imagemap") of the right kind is attached to the
 // material's slot (Material::tex -> pb2_material::tex); one that names anything else that varies (procedural textures,
-// unknown names, a float texture where a spectrum is expected) is reported and keeps its default.  "bumpmap" is always
-// outside the path's scope.
+// unknown names, a float texture where a spectrum is expected) is reported and keeps its default.
 struct TexParam {
     const char *name;
     int slot;          // PB2_TEX_*
@@ -175,7 +174,12 @@ static void attachTextures(Material *m, const TextureParams &mp, const char *wha
             Error("%s: the texture named by \"%s\" is outside the GPU path's scope (constant and \"imagemap\" textures with a "
                   "\"uv\" mapping, SURVEY.md §8 f.2); using the default value", what, tp.name);
     }
-    if (mp.NamedTexture("bumpmap") != "") Error("%s: bump mapping is outside the GPU path's scope; \"bumpmap\" ignored", what);
+    // "bumpmap" (GetFloatTextureOrNull("bumpmap"), e.g. matte.cpp:70-71): an image texture, or a constant one as a 1 x 1 image
+    Float bumpValue;
+    if (auto t = mp.GetImageTexture("bumpmap", false)) m->tex[PB2_TEX_BUMP] = t;
+    else if (mp.GetFloatOrNull("bumpmap", &bumpValue)) m->tex[PB2_TEX_BUMP] = ConstantFloatImage(bumpValue);
+    else if (mp.NamedTexture("bumpmap") != "")
+        Error("%s: the texture named by \"bumpmap\" is outside the GPU path's scope (constant and \"imagemap\" textures); ignored", what);
 }
 // A float parameter that may be absent, a constant or an image texture (GetFloatTextureOrNull, paramset.cpp:703-732)
 struct FloatParam {

@@ -415,6 +415,7 @@ struct pb2_scene {
     int pipesChosen = 0;                     // wavefront pipelines for this scene, chosen after its first frame (0 = not yet)
     cudaEvent_t frameEvents[2] = {nullptr, nullptr};
     int2 *wfSpill = nullptr;                 // k_wf_trace_pool: stack entries beyond its shared-memory depth
+    void *chainBuf = nullptr;                // device copies of {DScene, DRenderParams} for the CHAIN trace kernels
     cudaStream_t pipeStreams[4] = {nullptr, nullptr, nullptr, nullptr};   // streams of the wavefront pipelines 1.. (renderWavefront)
     cudaEvent_t forkEvent = nullptr, joinEvents[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -880,7 +881,7 @@ static int validateRenderArgs(const pb2_scene *scene, const pb2_camera *cam, con
 }
 
 enum { kMaxPipes = 4 };   // wavefront pipelines (renderWavefront)
-typedef void (*TraceKernel)(DScene, WfPool, int);
+typedef void (*TraceKernel)(DScene, WfPool, int, WfChain);
 typedef void (*AdvanceKernel)(DScene, DRenderParams, WfPool, int, int, int, float4 *, unsigned long long *);
 
 // Which traversal kernel a scene is traced with (pb2_wavefront.cuh), and its launch shape.
@@ -900,11 +901,14 @@ struct TraceLaunch {
     int block = 128;
     size_t smem = 0;
     int grid = 0;          // persistent kernels: SMs x resident blocks; 0 = one thread per list entry (plain kernels)
+    bool chain = false;    // the kernel advances shadow / MIS rays itself (no k_wf_advance<light> launch)
     const char *name = "";
 };
 
-static int selectTraceKernel(pb2_scene *scene, int flags, TraceLaunch *out) {
+// allowChain: the caller is a render (the contexts are whole paths); pb2_trace_wavefront's contexts are bare rays.
+static int selectTraceKernel(pb2_scene *scene, int flags, TraceLaunch *out, bool allowChain = false) {
     TraceLaunch t;
+    const bool wantChain = allowChain && (flags & PB2_FLAG_CHAIN) != 0;
     const bool spheres = scene->d.spheres != nullptr;
     const bool instanced = scene->d.instances != nullptr;
     const bool records = scene->d.wide4 != nullptr && !(flags & PB2_FLAG_LINEAR_NODES);
@@ -959,6 +963,15 @@ static int selectTraceKernel(pb2_scene *scene, int flags, TraceLaunch *out) {
             // (round-2 sweep around these parameters with the min/max slab tests and 32-byte loads in place - LEAF_T 2 / 4, NSUB 3 / 6,
             // FETCH_T 12, 10 resident blocks: 221.6 ... 223.2 against 224.0 Msamples/s at 16 spp; the scheduling constants are flat)
             else t.fn = small ? k_wf_trace_w<2, 1, 8, 4, 4, 9, false, false, true> : k_wf_trace_w<2, 1, 8, 4, 16, 9, false, false, true>;
+            // (experiment, PB2_FLAG_CHAIN; measured and NOT adopted) the default kernels with the light step
+            // inside: shadow ray -> MIS ray -> continuation follow each other in the lane, one round per bounce
+            if (wantChain && !small && !(flags & PB2_FLAG_LEAF_TMA)) {
+                t.chain = true;
+                t.name = "k_wf_trace_w<2,chain>";
+                if (instanced) t.fn = k_wf_trace_w<2, 1, 8, 4, 16, 6, true, true, true, false, false, true>;
+                else if (spheres) t.fn = k_wf_trace_w<2, 1, 8, 4, 16, 6, true, false, true, false, false, true>;
+                else t.fn = k_wf_trace_w<2, 1, 8, 4, 16, 9, false, false, true, false, false, true>;
+            }
         }
     } else {
         t.name = "k_wf_trace";
@@ -1028,7 +1041,18 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     int rc = ensurePool(scene, capacity);
     if (rc) return rc;
     TraceLaunch trace;
-    if ((rc = selectTraceKernel(scene, flags, &trace))) return rc;
+    if ((rc = selectTraceKernel(scene, flags, &trace, true))) return rc;
+    WfChain chain;
+    memset(&chain, 0, sizeof(chain));
+    if (trace.chain) {
+        // the scene and this frame's parameters as objects in device memory for wfChainLight
+        if (!scene->chainBuf) CUDA_TRY(cudaMalloc(&scene->chainBuf, sizeof(DScene) + sizeof(DRenderParams)));
+        CUDA_TRY(cudaMemcpyAsync(scene->chainBuf, &scene->d, sizeof(DScene), cudaMemcpyHostToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync((char *)scene->chainBuf + sizeof(DScene), &rp, sizeof(DRenderParams), cudaMemcpyHostToDevice, stream));
+        chain.sc = reinterpret_cast<const DScene *>(scene->chainBuf);
+        chain.rp = reinterpret_cast<const DRenderParams *>((char *)scene->chainBuf + sizeof(DScene));
+        chain.film = film;
+    }
     const bool spheres = scene->d.spheres != nullptr;
     // (12 / 16 resident blocks for the light step - 40 / 32 registers with small spills - measured: 222.5 / 220.9 against 224.0)
     AdvanceKernel advLight = spheres ? k_wf_advance<false, true, 8> : k_wf_advance<false, false, 8>;
@@ -1114,12 +1138,14 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
                 }
                 CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents], st));
             }
-            trace.fn<<<trace.grid ? trace.grid : blocks128, trace.block, trace.smem, st>>>(scene->d, pool, WQ_TRACE0 + cur);
+            chain.freeQ = WQ_FREE0 + next;
+            trace.fn<<<trace.grid ? trace.grid : blocks128, trace.block, trace.smem, st>>>(scene->d, pool, WQ_TRACE0 + cur, chain);
             if (timeTrace) {
                 CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents + 1], st));
                 nEvents += 2;
             }
-            advLight<<<blocks128, 128, 0, st>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
+            if (!trace.chain) advLight<<<blocks128, 128, 0, st>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
+            else --nLaunch;
             advShade<<<blocks128, 128, 0, st>>>(scene->d, rp, pool, WQ_SHADE, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
             if (lazyLights) {
                 // vertices that fell into voxels without a light distribution yet were put aside: build those records, shade again
@@ -1388,6 +1414,7 @@ int pb2_scene_destroy(pb2_scene *s) {
     if (s->ldHostCounters) cudaFreeHost(s->ldHostCounters);
     for (cudaEvent_t e : s->traceEvents) cudaEventDestroy(e);
     if (s->wfSpill) cudaFree(s->wfSpill);
+    if (s->chainBuf) cudaFree(s->chainBuf);
     for (int p = 0; p < 4; ++p) {
         if (s->pipeStreams[p]) cudaStreamDestroy(s->pipeStreams[p]);
         if (s->joinEvents[p]) cudaEventDestroy(s->joinEvents[p]);
@@ -2178,7 +2205,9 @@ int pb2_trace_wavefront(pb2_scene *scene, const pb2_ray *rays, const uint8_t *an
     if (e == cudaSuccess) {
         const int blocks = (N + 127) / 128;
         k_wf_debug_fill<<<blocks, 128>>>(pool, dRays, dAny, N);
-        trace.fn<<<trace.grid ? trace.grid : blocks, trace.block, trace.smem>>>(scene->d, pool, WQ_TRACE0);
+        WfChain noChain;
+        memset(&noChain, 0, sizeof(noChain));
+        trace.fn<<<trace.grid ? trace.grid : blocks, trace.block, trace.smem>>>(scene->d, pool, WQ_TRACE0, noChain);
         k_wf_debug_read<<<blocks, 128>>>(scene->d, pool, N, dOut);
         k_wf_debug_lists<<<std::min(blocks, g_numSMs * 8), 128>>>(pool, dOut);
         e = cudaGetLastError();

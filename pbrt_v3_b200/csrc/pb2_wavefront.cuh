@@ -69,6 +69,32 @@ __device__ __forceinline__ void wfCountRays(unsigned long long *counters, unsign
     }
 }
 
+// What a CHAIN instantiation of the trace kernel needs to advance a context itself when a shadow or MIS ray ends (the work of
+// k_wf_advance<light>): the scene and the frame's parameters as objects in device memory, the film, the list of freed contexts.
+struct WfChain {
+    const DScene *sc;
+    const DRenderParams *rp;
+    float4 *film;
+    int freeQ;
+    int pad;
+};
+
+// The light step for ONE context, inside the trace kernel: lightAdvance (shadow ray: add the light sample if unoccluded;
+// MIS ray: add the BSDF sample if it reached the light), then the vertex's next ray - the MIS ray, or the continuation of
+// the path - or the end of the path (the sample goes to the film).  Returns the lane's new state.  Out of line: the
+// traversal loop must not carry its registers.
+template <bool SPH>
+__device__ __noinline__ int wfChainLight(const WfChain &ch, WfCtx *cx, bool found) {
+    DLane &ln = cx->ln;
+    DHit hit;
+    hit.leaf = __float_as_int(cx->hit.x);   // (meaningful for a MIS ray that hit something: the kernel stored it there)
+    hit.b0 = hit.b1 = hit.b2 = 0;
+    hit.inst = -1;
+    lightAdvance<SPH>(*ch.sc, ln, found, hit, 0.f);
+    if (ln.state == LS_IDLE) addSample(*ch.rp, ch.film, cx->pFilm, guardRadiance(ln.L));
+    return ln.state;
+}
+
 // A context takes the next work item (pixel, sample number) and starts its camera ray: GetCameraSample + GenerateRay
 // (Halton dims 0-4, perspective camera).  Warp-collective: all 32 lanes call it, `want` says which of them take part; work
 // items that map outside the sample bounds / pixel bounds are skipped (integrator.cpp:274), so a lane may draw several.
@@ -137,7 +163,7 @@ __global__ void __launch_bounds__(256) k_wf_gen(DRenderParams rp, WfPool pool, i
 // (COUNT) and as the simplest statement of what the tuned kernels below compute.
 // ---------------------------------------------------------------------------------------------
 template <bool COUNT>
-__global__ void __launch_bounds__(128) k_wf_trace_plain(DScene sc, WfPool pool, int traceQ) {
+__global__ void __launch_bounds__(128) k_wf_trace_plain(DScene sc, WfPool pool, int traceQ, WfChain) {
     unsigned long long *counters = pool.ctr;
     unsigned n = pool.counts[traceQ];
     unsigned stride = gridDim.x * blockDim.x;
@@ -213,7 +239,7 @@ __global__ void __launch_bounds__(128) k_wf_trace_plain(DScene sc, WfPool pool, 
 // world-space ray from its context and continues with the rest of the leaf - r.tMax = ray.tMax
 // (primitive.cpp:83) if something was hit inside, the saved tMax otherwise.
 template <int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, bool DEEP, bool SPHERES, int MINB, bool INST = false>
-__global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, int traceQ) {
+__global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, int traceQ, WfChain) {
     __shared__ int sstack[SDEPTH][128];
     int lstack[DEEP ? 64 - SDEPTH : 1];
     const unsigned FULL = 0xffffffffu;
@@ -465,8 +491,8 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace(DScene sc, WfPool pool, 
 // take a leaf step are staged into shared memory by the TMA unit - one cp.async.bulk (UBLKCP) of up to four 48-byte records
 // per lane, completion counted by one mbarrier per warp - and the triangle tests read them from there.
 template <int WIDTH, int LEAF_T, int FETCH_T, int NSUB, int SDEPTH, int MINB, bool SPHERES = false, bool INST = false, bool LD256 = false,
-          bool LEAFTMA = false, bool ALPHA = false>
-__global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ) {
+          bool LEAFTMA = false, bool ALPHA = false, bool CHAIN = false>
+__global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool, int traceQ, WfChain chain) {
     static_assert(WIDTH == 2 || WIDTH == 4, "two- or four-child records");
     static_assert(!LEAFTMA || (!SPHERES && !INST), "the staging experiment covers triangle scenes");
     constexpr int STAGED = 4;   // records staged per lane and leaf step (the reference's default maxnodeprims)
@@ -483,6 +509,11 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
     }
     constexpr int BLOCK = 128;
     __shared__ int2 sstack[SDEPTH * BLOCK];   // [SDEPTH][BLOCK] of (child reference, tMin bits)
+    __shared__ unsigned sCount[2];            // CHAIN: Scene::Intersect / IntersectP calls started in this block (regular, shadow)
+    if (CHAIN) {
+        if (threadIdx.x < 2) sCount[threadIdx.x] = 0;
+        __syncthreads();
+    }
     // entries beyond SDEPTH (rare: only passing far children are pushed).  Worst case: one entry per level of the
     // reference's <= 64-level stack for WIDTH 2, three per two levels for WIDTH 4, plus the instance frame
     int2 lstack[(WIDTH == 4 ? 100 : 66) - SDEPTH];
@@ -777,8 +808,39 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
                 __stcs(reinterpret_cast<float2 *>(&cx.tHit), make_float2(tMax, __int_as_float(foundCode)));
             }
             wfPush(pool.queue[WQ_SHADE], &pool.counts[WQ_SHADE], c, flush && state == LS_PATH);
-            wfPush(pool.queue[WQ_LIGHT], &pool.counts[WQ_LIGHT], c, flush && state != LS_PATH);
-            if (flush) c = -1;
+            bool again = false;   // CHAIN: the context goes on with its next ray in this lane
+            if (CHAIN) {
+                // a shadow or MIS ray ended: the light step right here, and the vertex's next ray (MIS ray, or the path's
+                // continuation) in this lane, in this launch - one round per bounce instead of up to three
+                int next = LS_PATH;
+                if (flush && state != LS_PATH) {
+                    next = wfChainLight<SPHERES>(chain, &pool.ctx[c], (flags & F_FOUND) != 0);
+                    again = next != LS_IDLE;
+                }
+                const unsigned mShadow = __ballot_sync(FULL, again && next == LS_SHADOW), mRegular = __ballot_sync(FULL, again && next != LS_SHADOW);
+                if (lane == 0) {
+                    if (mShadow) atomicAdd(&sCount[1], (unsigned)__popc(mShadow));
+                    if (mRegular) atomicAdd(&sCount[0], (unsigned)__popc(mRegular));
+                }
+                wfPush(pool.queue[chain.freeQ], &pool.counts[chain.freeQ], c, flush && state != LS_PATH && !again);
+            } else
+                wfPush(pool.queue[WQ_LIGHT], &pool.counts[WQ_LIGHT], c, flush && state != LS_PATH);
+            if (again) {
+                const float4 *p = reinterpret_cast<const float4 *>(&pool.ctx[c]);
+                const float4 ra = p[0], rb = p[1];
+                flags = (__float_as_int(ra.x) == LS_SHADOW) ? F_ANY : 0;
+                rs = setupRay(mk3(ra.y, ra.z, ra.w), mk3(rb.x, rb.y, rb.z));
+                tMax = rb.w;
+                cur = 0;
+                if (INST) {
+                    inst = hitInst = -1;
+                    instBase = 0;
+                }
+                sp = 0;
+                leafN = 0;
+                mode = M_NODE;
+            } else if (flush)
+                c = -1;
             bool want = mode == M_FETCH && !(flags & F_EXHAUSTED);
             unsigned wantMask = __ballot_sync(FULL, want);
             if (wantMask) {
@@ -810,6 +872,13 @@ __global__ void __launch_bounds__(128, MINB) k_wf_trace_w(DScene sc, WfPool pool
             }
         }
     }
+    if (CHAIN) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (sCount[0]) atomicAdd(&pool.ctr[CTR_REGULAR], (unsigned long long)sCount[0]);
+            if (sCount[1]) atomicAdd(&pool.ctr[CTR_SHADOW], (unsigned long long)sCount[1]);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -832,7 +901,7 @@ struct PoolWarp {   // one warp's slice of shared memory
 };
 
 template <int NSUB, int MINB, int LEAF_T = 24, int FILL_T = 24, int R = 64, int PL_SD = 12>
-__global__ void __launch_bounds__(128, MINB) k_wf_trace_pool(DScene sc, WfPool pool, int traceQ) {
+__global__ void __launch_bounds__(128, MINB) k_wf_trace_pool(DScene sc, WfPool pool, int traceQ, WfChain) {
     static_assert(R > 32 && R <= PL_R, "a warp owns 33 .. 64 slots");
     extern __shared__ unsigned char poolSmemRaw[];
     PoolWarp<R, PL_SD> &pw = reinterpret_cast<PoolWarp<R, PL_SD> *>(poolSmemRaw)[threadIdx.x >> 5];

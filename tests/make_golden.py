@@ -130,6 +130,7 @@ def main():
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "textured_lens.pbrt")), "textured_lens")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "sobol.pbrt")), "sobol")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "envmap.pbrt")), "envmap")
+    record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "bumpmap.pbrt")), "bumpmap")
     record_env_distribution(ref)
     record_textures(ref)
     record_filters(ref)

@@ -149,6 +149,9 @@ def main():
     write_pfm(os.path.join(OUT, "stripes_16x16.pfm"), stripes)
     rs = np.random.RandomState(3)
     write_pfm(os.path.join(OUT, "rough_8x8.pfm"), rs.uniform(0.02, 0.35, (8, 8)).astype(np.float32))
+    # a smooth height field for bump mapping (periodic, so that the repeat wrap has no seam)
+    yy, xx = np.mgrid[0:32, 0:32] * (2 * np.pi / 32)
+    write_pfm(os.path.join(OUT, "bumps_32x32.pfm"), (0.5 + 0.25 * np.sin(3 * xx) * np.cos(2 * yy) + 0.2 * np.sin(xx + 4 * yy)).astype(np.float32))
     rgb8 = (pattern(20, 12, 4) * 255 + 0.5).astype(np.uint8)
     write_png(os.path.join(OUT, "tiles_20x12.png"), rgb8)
     rgb8b = (pattern(24, 10, 5) * 255 + 0.5).astype(np.uint8)

@@ -22,7 +22,7 @@ from test_oracle import load_scene, same_bvh, tessellated_sphere_scene
 pytestmark = pytest.mark.gpu
 
 SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass", "lights", "params",
-               "envlight", "textured", "textured_lens", "sobol", "envmap"]
+               "envlight", "textured", "textured_lens", "sobol", "envmap", "bumpmap"]
 
 
 def li_ok(got, want):
@@ -594,3 +594,16 @@ def test_alpha_masked_meshes_through_every_render_kernel(pb):
         assert np.array_equal(film[..., 3], base[..., 3])
         assert np.allclose(film, base, rtol=1e-4, atol=1e-5)
         assert st.regular_rays == st0.regular_rays and st.shadow_rays == st0.shadow_rays
+
+
+@pytest.mark.parametrize("name", ["soup", "materials", "instances", "specular", "lights"])
+def test_chained_light_step_renders_the_same_film(pb, name):
+    """PB2_FLAG_CHAIN (the light step inside the trace kernel: shadow ray, MIS ray and continuation follow each other in one
+    launch) changes the schedule, not the arithmetic of a path: same ray counts, same film up to the order of the atomic adds."""
+    hs = load_scene(pb, name)
+    base, st0 = hs.render_rgbw(hs.params_copy(flags=0))
+    film, st = hs.render_rgbw(hs.params_copy(flags=pb.PB2_FLAG_CHAIN))
+    assert np.array_equal(film[..., 3], base[..., 3])
+    assert np.allclose(film, base, rtol=1e-4, atol=1e-5)
+    assert (st.camera_rays, st.regular_rays, st.shadow_rays) == (st0.camera_rays, st0.regular_rays, st0.shadow_rays)
+    assert st.kernel_launches < st0.kernel_launches

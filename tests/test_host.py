@@ -500,9 +500,8 @@ WorldEnd
     zero = d.textures[meshes[1].alpha_tex - 1]
     assert meshes[1].shadow_alpha_tex == 0 and (zero.width, zero.height) == (1, 1) and texels(zero).ravel()[0] == 0
     assert meshes[2].alpha_tex == 0 and texels(d.textures[meshes[2].shadow_alpha_tex - 1]).ravel()[0] == 0
-    # outside the scope: other mappings, bump maps, a float texture where a spectrum is expected
+    # outside the scope: other mappings, a float texture where a spectrum is expected, an unreadable container
     for bad in ('Texture "t" "spectrum" "imagemap" "string filename" "%s/holes_16x16.pfm" "string mapping" "spherical"\nMaterial "matte" "texture Kd" "t"' % tex,
-                'Texture "t" "float" "imagemap" "string filename" "%s/holes_16x16.pfm"\nMaterial "matte" "texture bumpmap" "t"' % tex,
                 'Texture "t" "float" "imagemap" "string filename" "%s/holes_16x16.pfm"\nMaterial "matte" "texture Kd" "t"' % tex,
                 'Texture "t" "spectrum" "imagemap" "string filename" "%s/tiles.exr"\nMaterial "matte" "texture Kd" "t"' % tex):
         before = pb.lib().pb2h_error_count()
@@ -763,6 +762,28 @@ def test_infinite_light_environment_map_is_flattened(pb):
     L = np.float32([.5, .6, .7]) * np.float32([1.2, 1, .9])
     got = np.ctypeslib.as_array(t.texels, shape=(20, 40, 3))
     assert np.array_equal(got, body * L)
+
+
+def test_bumpmap_parameter(pb):
+    """"bumpmap" (GetFloatTextureOrNull, e.g. matte.cpp:70-71) on every material: an image texture goes into the record's
+    PB2_TEX_BUMP slot, a constant (plain float or constant texture) becomes a 1 x 1 image, a spectrum texture is refused."""
+    tex = os.path.join(SCENES, "textures")
+    hs = pb.HostScene.from_file(os.path.join(SCENES, "bumpmap.pbrt"))
+    d = hs.desc.contents
+    mats = [d.materials[i] for i in range(d.n_materials)]
+    bumped = [m for m in mats if m.tex[pb.PB2_TEX_BUMP]]
+    assert sorted(m.type for m in bumped) == sorted([pb.PB2_MAT_PLASTIC, pb.PB2_MAT_MATTE, pb.PB2_MAT_PLASTIC, pb.PB2_MAT_MIRROR, pb.PB2_MAT_GLASS,
+                                                     pb.PB2_MAT_MATTE, pb.PB2_MAT_UBER])
+    const = [m for m in bumped if m.type == pb.PB2_MAT_MATTE and not m.tex[pb.PB2_TEX_KD]][0]
+    t = d.textures[const.tex[pb.PB2_TEX_BUMP] - 1]
+    assert (t.channels, t.width, t.height) == (1, 1, 1) and t.texels[0] == np.float32(0.15)
+    for i in range(d.n_textures):
+        if d.textures[i].width == 32:
+            assert d.textures[i].channels == 1
+    before = pb.lib().pb2h_error_count()
+    pb.HostScene.from_string('WorldBegin\nTexture "t" "spectrum" "imagemap" "string filename" "%s/tiles_37x23.pfm"\n'
+                             'Material "matte" "texture bumpmap" "t"\nShape "sphere"\nWorldEnd\n' % tex)
+    assert pb.lib().pb2h_error_count() > before
 
 
 def test_openexr_reader(pb, tmp_path):

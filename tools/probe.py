@@ -28,7 +28,7 @@ else:
 hs.device_scene()
 print("probe %s %s: scene ready in %.1f s" % (kind, what, time.time() - t0), flush=True)
 n = 1920 * 1080 * spp
-names = {0: "wide2 ld256", 32: "wide2 ld128", 4: "wide4 ld256", 36: "wide4 ld128", 64: "wide2 ld256 + TMA-staged leaves", 128: "ray pool", 2: "linear", 8: "plain"}
+names = {0: "wide2 ld256", 32: "wide2 ld128", 4: "wide4 ld256", 36: "wide4 ld128", 64: "wide2 ld256 + TMA-staged leaves", 128: "ray pool", 256: "light step chained into the trace kernel", 2: "linear", 8: "plain"}
 for flags in flag_list:
     best = None
     for _ in range(iters):

@@ -23,7 +23,7 @@ sys.path.insert(0, "tests")
 import test_gpu_parity as tgp  # noqa: E402
 
 makers.append(("emissive_mesh_lazy_lightdist", lambda: pb.HostScene.from_string(tgp.emissive_mesh_scene(12, res=(32, 20), spp=2))))
-for _n in ("textured", "textured_lens", "sobol", "envlight", "envmap"):   # image textures + alpha masks, the SobolSampler, the infinite light
+for _n in ("textured", "textured_lens", "sobol", "envlight", "envmap", "bumpmap"):   # image textures + alpha masks, the SobolSampler, the infinite light
     makers.append((_n, lambda _n=_n: pb.HostScene.from_file(os.path.join("tests", "scenes", _n + ".pbrt"))))
 for name, make in makers:
     hs = make()   # the host front end keeps ONE parsed scene: build, use, then build the next
@@ -33,7 +33,7 @@ for name, make in makers:
     # every trace-kernel selection of round 2 (four-child records, 16-byte loads, small stacks, TMA-staged leaves, ray pool,
     # one thread per ray) through a render and through pb2_trace_wavefront
     for flags in (pb.PB2_FLAG_WIDE4, pb.PB2_FLAG_LD128, pb.PB2_FLAG_SMALL_STACK, pb.PB2_FLAG_SMALL_STACK | pb.PB2_FLAG_WIDE4,
-                  pb.PB2_FLAG_LEAF_TMA, pb.PB2_FLAG_POOL, pb.PB2_FLAG_PLAIN_TRACE):
+                  pb.PB2_FLAG_LEAF_TMA, pb.PB2_FLAG_POOL, pb.PB2_FLAG_PLAIN_TRACE, pb.PB2_FLAG_CHAIN):
         hs.render_rgbw(hs.params_copy(flags=flags))
         wr = np.zeros(300, pb.RAY_DTYPE)
         wr["o"] = (0, -3, 1)
