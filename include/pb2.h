@@ -94,9 +94,17 @@ typedef struct pb2_texture {
     int32_t do_trilinear;    /* "trilinear" */
     float max_anisotropy;    /* "maxanisotropy" */
     float su, sv, du, dv;    /* UVMapping2D: "uscale" "vscale" "udelta" "vdelta" */
-    int32_t pad[2];
-    const float *texels;     /* channels * width * height, row 0 is t = 0 */
+    int32_t kind;            /* PB2_TEXKIND_*; zero-initialised = an image */
+    int32_t pad;
+    const float *texels;     /* PB2_TEXKIND_IMAGE: channels * width * height, row 0 is t = 0; NULL otherwise */
+    /* the combinators over other textures of the array (1 + index, each smaller than the texture's own index, at most three
+     * levels deep): PB2_TEXKIND_SCALE = child[0] * child[1] (ScaleTexture, src/textures/scale.h:50-64), PB2_TEXKIND_MIX =
+     * (1 - a) * child[0] + a * child[1] with a = the one-channel texture child[2] (MixTexture, src/textures/mix.h:50-66);
+     * children have the texture's own channel count.  PB2_TEXKIND_CONSTANT = value[0 .. channels) (ConstantTexture). */
+    int32_t child[3];
+    float value[3];
 } pb2_texture;
+enum { PB2_TEXKIND_IMAGE = 0, PB2_TEXKIND_CONSTANT = 1, PB2_TEXKIND_SCALE = 2, PB2_TEXKIND_MIX = 3 };
 
 /* slots of pb2_material.tex: which parameter a texture replaces */
 enum { PB2_TEX_KD = 0, PB2_TEX_KS = 1, PB2_TEX_KR = 2, PB2_TEX_KT = 3, PB2_TEX_OPACITY = 4, PB2_TEX_SIGMA = 5, PB2_TEX_ROUGHNESS = 6,

@@ -74,6 +74,8 @@
 #include "shapes/sphere.h"
 #include "shapes/triangle.h"
 #include "textures/constant.h"
+#include "textures/mix.h"
+#include "textures/scale.h"
 #include "mipmap.h"
 #include "texture.h"
 #undef private
@@ -352,8 +354,19 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
     std::vector<std::shared_ptr<Texture<Spectrum>>> specTex(d->n_textures);
     if (d->n_textures > 0) setThreads(0);
     for (int i = 0; i < d->n_textures; ++i) {
-        if (d->textures[i].channels == 1) floatTex[i] = std::make_shared<DescImageTexture<Float, Float>>(d->textures[i]);
-        else specTex[i] = std::make_shared<DescImageTexture<RGBSpectrum, Spectrum>>(d->textures[i]);
+        const pb2_texture &pt = d->textures[i];
+        const bool one = pt.channels == 1;
+        if (pt.kind == PB2_TEXKIND_CONSTANT) {
+            if (one) floatTex[i] = std::make_shared<ConstantTexture<Float>>(pt.value[0]);
+            else specTex[i] = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pt.value));
+        } else if (pt.kind == PB2_TEXKIND_SCALE) {   // the reference's own ScaleTexture / MixTexture over the children
+            if (one) floatTex[i] = std::make_shared<ScaleTexture<Float, Float>>(floatTex[pt.child[0] - 1], floatTex[pt.child[1] - 1]);
+            else specTex[i] = std::make_shared<ScaleTexture<Spectrum, Spectrum>>(specTex[pt.child[0] - 1], specTex[pt.child[1] - 1]);
+        } else if (pt.kind == PB2_TEXKIND_MIX) {
+            if (one) floatTex[i] = std::make_shared<MixTexture<Float>>(floatTex[pt.child[0] - 1], floatTex[pt.child[1] - 1], floatTex[pt.child[2] - 1]);
+            else specTex[i] = std::make_shared<MixTexture<Spectrum>>(specTex[pt.child[0] - 1], specTex[pt.child[1] - 1], floatTex[pt.child[2] - 1]);
+        } else if (one) floatTex[i] = std::make_shared<DescImageTexture<Float, Float>>(pt);
+        else specTex[i] = std::make_shared<DescImageTexture<RGBSpectrum, Spectrum>>(pt);
     }
 
     // shapes

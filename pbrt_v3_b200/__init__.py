@@ -68,7 +68,11 @@ PB2_SAMPLER_HALTON, PB2_SAMPLER_SOBOL = 0, 1
 class Texture(C.Structure):
     _fields_ = [("channels", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("wrap", C.c_int32),
                 ("do_trilinear", C.c_int32), ("max_anisotropy", C.c_float), ("su", C.c_float), ("sv", C.c_float),
-                ("du", C.c_float), ("dv", C.c_float), ("pad", C.c_int32 * 2), ("texels", c_float_p)]
+                ("du", C.c_float), ("dv", C.c_float), ("kind", C.c_int32), ("pad", C.c_int32), ("texels", c_float_p),
+                ("child", C.c_int32 * 3), ("value", C.c_float * 3)]
+
+
+PB2_TEXKIND_IMAGE, PB2_TEXKIND_CONSTANT, PB2_TEXKIND_SCALE, PB2_TEXKIND_MIX = 0, 1, 2, 3
 
 
 class Light(C.Structure):

@@ -120,7 +120,7 @@ PB2_HD void shadeVertex(const DScene &sc, const DHalton &h, const DPathParams &p
             // the material's bump map (e.g. matte.cpp:50: before its other textures are evaluated)
             const int m = sc.primMaterial[isect.prim];
             const int bump = m >= 0 ? sc.materials[m].tex[PB2_TEX_BUMP] : 0;
-            if (bump) bumpShading(sc, sc.textures[bump - 1], tg, uvDiff, &isect);
+            if (bump) bumpShading(sc, bump - 1, tg, uvDiff, &isect);
         }
     }
     const float *lazyDistrib = nullptr;

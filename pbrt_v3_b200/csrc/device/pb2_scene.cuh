@@ -433,8 +433,10 @@ PB2_HDN bool alphaRejects(const DScene &sc, int prim, float b0, float b1, float 
         uv2 = mk2(sc.UV[2 * v2], sc.UV[2 * v2 + 1]);
     }
     const V2 uvHit = mk2(b0 * uv0.x + b1 * uv1.x + b2 * uv2.x, b0 * uv0.y + b1 * uv1.y + b2 * uv2.y);
-    if (mesh.alpha_tex && texEvaluateNoDiff(sc.textures[mesh.alpha_tex - 1], sc.texels, uvHit).x == 0) return true;
-    if (anyHit && mesh.shadow_alpha_tex && texEvaluateNoDiff(sc.textures[mesh.shadow_alpha_tex - 1], sc.texels, uvHit).x == 0) return true;
+    DUvDiff none;   // (zero footprint: both MIPMap filters reduce to the bilinear look-up at the finest level)
+    none.dudx = none.dvdx = none.dudy = none.dvdy = 0;
+    if (mesh.alpha_tex && texEvaluateNode(sc.textures, sc.texels, mesh.alpha_tex - 1, uvHit, none).x == 0) return true;
+    if (anyHit && mesh.shadow_alpha_tex && texEvaluateNode(sc.textures, sc.texels, mesh.shadow_alpha_tex - 1, uvHit, none).x == 0) return true;
     return false;
 }
 

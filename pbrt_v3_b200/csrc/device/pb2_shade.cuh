@@ -313,7 +313,7 @@ PB2_HDN void applyTextures(const DScene &sc, V2 uv, const DUvDiff &d, pb2_materi
     for (int k = 0; k < PB2_TEX_SLOTS; ++k) {
         const int id = mat->tex[k];
         if (!id) continue;
-        const V3 v = texEvaluate(sc.textures[id - 1], sc.texels, uv, d);
+        const V3 v = texEvaluateNode(sc.textures, sc.texels, id - 1, uv, d);
         float *dst3 = nullptr;
         switch (k) {
         case PB2_TEX_KD: dst3 = mat->kd; break;
@@ -341,14 +341,14 @@ PB2_HDN void applyTextures(const DScene &sc, V2 uv, const DUvDiff &d, pb2_materi
 // shading frame.  Only what an ImageTexture with a UVMapping2D reads is shifted (uv; the look-ups share the point's
 // differentials); the new shading normal is flipped to the side of the geometric one (SetShadingGeometry with
 // orientationIsAuthoritative = false).
-PB2_HDN void bumpShading(const DScene &sc, const DTexture &tx, const DTexGeom &tg, const DUvDiff &d, DInteraction *it) {
+PB2_HDN void bumpShading(const DScene &sc, int tex, const DTexGeom &tg, const DUvDiff &d, DInteraction *it) {
     float du = .5f * (fabsf(d.dudx) + fabsf(d.dudy));
     if (du == 0) du = .0005f;
-    const float uDisplace = texEvaluate(tx, sc.texels, mk2(it->uv.x + du, it->uv.y + 0.f), d).x;
+    const float uDisplace = texEvaluateNode(sc.textures, sc.texels, tex, mk2(it->uv.x + du, it->uv.y + 0.f), d).x;
     float dv = .5f * (fabsf(d.dvdx) + fabsf(d.dvdy));
     if (dv == 0) dv = .0005f;
-    const float vDisplace = texEvaluate(tx, sc.texels, mk2(it->uv.x + 0.f, it->uv.y + dv), d).x;
-    const float displace = texEvaluate(tx, sc.texels, it->uv, d).x;
+    const float vDisplace = texEvaluateNode(sc.textures, sc.texels, tex, mk2(it->uv.x + 0.f, it->uv.y + dv), d).x;
+    const float displace = texEvaluateNode(sc.textures, sc.texels, tex, it->uv, d).x;
     const V3 dpdu = it->dpdus + ((uDisplace - displace) / du) * it->ns + displace * tg.dndus;
     const V3 dpdv = tg.dpdvs + ((vDisplace - displace) / dv) * it->ns + displace * tg.dndvs;
     it->ns = faceforward(normalize(cross(dpdu, dpdv)), it->n);

@@ -23,8 +23,11 @@ struct DTexture {
     int wrap, doTrilinear;
     float maxAniso;
     float su, sv, du, dv;
-    int pad;
+    int kind;                 // PB2_TEXKIND_*: an image (the fields above), a constant, or a combinator over other textures
     long long levelOfs[TEX_MAX_LEVELS];   // float index of each level in the pool
+    int child[3];             // 1 + index into the texture array (SCALE: two factors; MIX: two operands and the amount)
+    float value[3];           // CONSTANT
+    int pad2[2];
 };
 
 // pbrt's Mod (pbrt.h:291-296): the remainder is never negative
@@ -150,6 +153,35 @@ PB2_HD V3 texEvaluate(const DTexture &tx, const float *pool, V2 uv, const DUvDif
     V2 dstdx = mk2(tx.su * d.dudx, tx.sv * d.dvdx), dstdy = mk2(tx.su * d.dudy, tx.sv * d.dvdy);
     V2 st = mk2(tx.su * uv.x + tx.du, tx.sv * uv.y + tx.dv);
     return texLookup(tx, pool, st, dstdx, dstdy);
+}
+
+// Texture::Evaluate for any node of the scene's texture array: an image, a constant, ScaleTexture (scale.h:56-58) or
+// MixTexture (mix.h:57-61).  The library checks at upload that children precede their parents and that no chain is deeper
+// than TEX_MAX_DEPTH, so the recursion unrolls at compile time.
+enum { TEX_MAX_DEPTH = 3 };
+template <int DEPTH>
+struct TexEval {
+    static PB2_HD V3 node(const DTexture *textures, const float *pool, int id, V2 uv, const DUvDiff &d) {
+        const DTexture &tx = textures[id];
+        if (tx.kind == PB2_TEXKIND_IMAGE) return texEvaluate(tx, pool, uv, d);
+        if (tx.kind == PB2_TEXKIND_CONSTANT) return mk3(tx.value[0], tx.value[1], tx.value[2]);
+        const V3 a = TexEval<DEPTH - 1>::node(textures, pool, tx.child[0] - 1, uv, d);
+        const V3 b = TexEval<DEPTH - 1>::node(textures, pool, tx.child[1] - 1, uv, d);
+        if (tx.kind == PB2_TEXKIND_SCALE) return a * b;
+        const float amt = TexEval<DEPTH - 1>::node(textures, pool, tx.child[2] - 1, uv, d).x;
+        return (1 - amt) * a + amt * b;
+    }
+};
+template <>
+struct TexEval<0> {
+    static PB2_HD V3 node(const DTexture *textures, const float *pool, int id, V2 uv, const DUvDiff &d) {
+        const DTexture &tx = textures[id];
+        if (tx.kind == PB2_TEXKIND_CONSTANT) return mk3(tx.value[0], tx.value[1], tx.value[2]);
+        return texEvaluate(tx, pool, uv, d);
+    }
+};
+PB2_HD V3 texEvaluateNode(const DTexture *textures, const float *pool, int id, V2 uv, const DUvDiff &d) {
+    return TexEval<TEX_MAX_DEPTH>::node(textures, pool, id, uv, d);
 }
 
 // ... at a point without differentials (the alpha test inside Triangle::Intersect, triangle.cpp:333-338): both filters

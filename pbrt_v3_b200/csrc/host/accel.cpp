@@ -459,10 +459,11 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
     std::vector<char> lightSeen(lights.size(), 0);
     // image textures in order of first use; 0 = none, else 1 + index (pb2_material::tex, pb2_mesh::alpha_tex)
     std::unordered_map<const ImageTexture *, int> textureIds;
-    auto textureId = [&](const std::shared_ptr<ImageTexture> &t) -> int32_t {
+    std::function<int32_t(const std::shared_ptr<ImageTexture> &)> textureId = [&](const std::shared_ptr<ImageTexture> &t) -> int32_t {
         if (!t) return 0;
         auto it = textureIds.find(t.get());
         if (it != textureIds.end()) return it->second;
+        for (const auto &c : t->child) textureId(c);   // children before their parent (pb2_texture::child)
         fs->textureObjects.push_back(t);
         const int id = (int)fs->textureObjects.size();
         textureIds[t.get()] = id;
@@ -760,7 +761,12 @@ std::unique_ptr<FlatScene> FlattenScene(const BVHAccel &bvh, const std::vector<s
         pt.do_trilinear = t->trilinear ? 1 : 0;
         pt.max_anisotropy = t->maxAniso;
         pt.su = t->su; pt.sv = t->sv; pt.du = t->du; pt.dv = t->dv;
-        pt.texels = t->texels.data();
+        pt.texels = t->kind == PB2_TEXKIND_IMAGE ? t->texels.data() : nullptr;
+        pt.kind = t->kind;
+        for (int c = 0; c < 3; ++c) {
+            pt.child[c] = t->child[c] ? textureIds[t->child[c].get()] : 0;
+            pt.value[c] = t->value[c];
+        }
         fs->textures.push_back(pt);
     }
     d.n_textures = (int32_t)fs->textures.size();

@@ -396,6 +396,44 @@ void pbrtTexture(const std::string &name, const std::string &type, const std::st
         }
         return;
     }
+    // "scale" / "mix" with an operand that varies (an image map, or a combinator of one): a node over the operands
+    // (CreateScale*Texture scale.cpp:40-52, CreateMix*Texture mix.cpp:40-54); constants among them become constant nodes
+    if ((texname == "scale" || texname == "mix") &&
+        (tp.GetImageTexture("tex1", isSpectrum) || tp.GetImageTexture("tex2", isSpectrum) || (texname == "mix" && tp.GetImageTexture("amount", false)))) {
+        auto operand = [&](const char *pn, bool spectrum, Float def) -> std::shared_ptr<ImageTexture> {
+            if (auto t = tp.GetImageTexture(pn, spectrum)) return t;
+            auto c = std::make_shared<ImageTexture>();
+            c->kind = PB2_TEXKIND_CONSTANT;
+            c->channels = spectrum ? 3 : 1;
+            if (spectrum) {
+                Spectrum v = tp.GetSpectrumTexture(pn, Spectrum(def));
+                for (int k = 0; k < 3; ++k) c->value[k] = v.c[k];
+            } else
+                c->value[0] = tp.GetFloatTexture(pn, def);
+            return c;
+        };
+        auto node = std::make_shared<ImageTexture>();
+        node->channels = isSpectrum ? 3 : 1;
+        if (texname == "scale") {
+            node->kind = PB2_TEXKIND_SCALE;
+            node->child[0] = operand("tex1", isSpectrum, 1.f);
+            node->child[1] = operand("tex2", isSpectrum, 1.f);
+        } else {
+            node->kind = PB2_TEXKIND_MIX;
+            node->child[0] = operand("tex1", isSpectrum, 0.f);
+            node->child[1] = operand("tex2", isSpectrum, 1.f);
+            node->child[2] = operand("amount", false, 0.5f);
+        }
+        params.ReportUnused();
+        if (isFloat) {
+            floats.erase(name);
+            floatImages[name] = node;
+        } else {
+            spectra.erase(name);
+            spectrumImages[name] = node;
+        }
+        return;
+    }
     bool ok = false;
     Float fv = 0;
     Spectrum sv;

@@ -125,6 +125,11 @@ struct ImageTexture {
     bool trilinear = false;
     Float maxAniso = 8.f;
     Float su = 1, sv = 1, du = 0, dv = 0;
+    // A node that is not an image (PB2_TEXKIND_*): a constant, or ScaleTexture / MixTexture over other nodes (scale.h, mix.h).
+    // Combinators of constants alone are folded at the directive; these exist when an operand varies.
+    int kind = 0;
+    std::shared_ptr<ImageTexture> child[3];   // SCALE: tex1, tex2; MIX: tex1, tex2, amount
+    Float value[3] = {0, 0, 0};
 };
 struct ConstantTextures {
     std::map<std::string, Float> floats;

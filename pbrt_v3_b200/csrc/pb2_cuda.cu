@@ -1498,6 +1498,7 @@ static int texWrapIndex(int i, int n, int wrap) {   // the index a wrap mode tur
 }
 // Appends the levels of one texture to `pool` (finest first) and fills its DTexture.
 static int buildTexturePyramid(const pb2_texture &in, std::vector<float> &pool, DTexture *out) {
+    if (in.kind != PB2_TEXKIND_IMAGE) return setError(PB2_ERR_INVALID, "texture: not an image (a constant or a combinator has no pyramid)");
     if ((in.channels != 1 && in.channels != 3) || in.width <= 0 || in.height <= 0 || !in.texels)
         return setError(PB2_ERR_INVALID, "texture: channels must be 1 or 3, the resolution positive, texels not null");
     if (in.wrap < PB2_WRAP_REPEAT || in.wrap > PB2_WRAP_CLAMP) return setError(PB2_ERR_INVALID, "texture: unknown wrap mode");
@@ -1595,9 +1596,33 @@ static int uploadTextures(pb2_scene *s, const pb2_scene_desc *d, HostTextures *h
     texWeightLut(pool);
     std::vector<DTexture> &tex = host->tex;
     tex.resize((size_t)d->n_textures);
+    std::vector<int> depth((size_t)d->n_textures, 0);
     for (int i = 0; i < d->n_textures; ++i) {
-        int rc = buildTexturePyramid(d->textures[i], pool, &tex[i]);
-        if (rc) return rc;
+        const pb2_texture &in = d->textures[i];
+        if (in.kind == PB2_TEXKIND_IMAGE) {
+            int rc = buildTexturePyramid(in, pool, &tex[i]);
+            if (rc) return rc;
+            continue;
+        }
+        // a constant or a combinator (scale.h, mix.h): children must come before it, agree in channels, stay TEX_MAX_DEPTH deep
+        DTexture &t = tex[i];
+        memset(&t, 0, sizeof(t));
+        if (in.channels != 1 && in.channels != 3) return setError(PB2_ERR_INVALID, "texture: channels must be 1 or 3");
+        t.channels = in.channels;
+        t.kind = in.kind;
+        for (int c = 0; c < 3; ++c) t.value[c] = in.value[in.channels == 3 ? c : 0];
+        if (in.kind == PB2_TEXKIND_CONSTANT) continue;
+        if (in.kind != PB2_TEXKIND_SCALE && in.kind != PB2_TEXKIND_MIX) return setError(PB2_ERR_INVALID, "texture: unknown kind");
+        const int nChildren = in.kind == PB2_TEXKIND_MIX ? 3 : 2;
+        for (int c = 0; c < nChildren; ++c) {
+            const int id = in.child[c];
+            if (id < 1 || id > i) return setError(PB2_ERR_INVALID, "texture combinator: a child must precede its parent in the texture array");
+            const int want = (in.kind == PB2_TEXKIND_MIX && c == 2) ? 1 : in.channels;
+            if (d->textures[id - 1].channels != want) return setError(PB2_ERR_INVALID, "texture combinator: child with the wrong number of channels");
+            t.child[c] = id;
+            depth[i] = std::max(depth[i], depth[(size_t)id - 1] + 1);
+        }
+        if (depth[i] > TEX_MAX_DEPTH) return setError(PB2_ERR_UNSUPPORTED, "texture combinators nested more than three levels deep");
     }
     int rc;
     if ((rc = upload(s, tex.data(), tex.size(), &sc.textures))) return rc;
@@ -1953,6 +1978,7 @@ static int createSceneOnCurrentDevice(const pb2_scene_desc *d, pb2_scene **out) 
                 if (in.env_tex < 0 || in.env_tex > d->n_textures || d->textures[in.env_tex - 1].channels != 3)
                     return setError(PB2_ERR_INVALID, "infinite light: env_tex out of range or not a three-channel texture");
                 const pb2_texture &pt = d->textures[in.env_tex - 1];
+                if (pt.kind != PB2_TEXKIND_IMAGE) return setError(PB2_ERR_INVALID, "infinite light: the environment map must be an image");
                 if (pt.wrap != PB2_WRAP_REPEAT || pt.do_trilinear || pt.max_anisotropy != 8.f)
                     return setError(PB2_ERR_INVALID, "infinite light: the environment map must carry MIPMap's default parameters (repeat, EWA, 8)");
                 const DTexture &tx = hostTextures.tex[(size_t)in.env_tex - 1];

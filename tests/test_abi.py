@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(pb):
 def test_struct_layouts_match_header(pb):
     """ctypes mirrors of the ABI structs have the sizes the C compiler gives them (checked through the host helpers)."""
     assert C.sizeof(pb.BvhNode) == 32 and C.sizeof(pb.Ray) == 28 and C.sizeof(pb.Hit) == 88
-    assert C.sizeof(pb.Material) == 192 and C.sizeof(pb.Instance) == 144 and C.sizeof(pb.Bvh) == 32 and C.sizeof(pb.Light) == 32 and C.sizeof(pb.Mesh) == 48 and C.sizeof(pb.Texture) == 56
+    assert C.sizeof(pb.Material) == 192 and C.sizeof(pb.Instance) == 144 and C.sizeof(pb.Bvh) == 32 and C.sizeof(pb.Light) == 32 and C.sizeof(pb.Mesh) == 48 and C.sizeof(pb.Texture) == 80
     assert C.sizeof(pb.PathParams) == 48 and C.sizeof(pb.FilmDesc) == 56
     hs = pb.HostScene.soup(10, xres=16, yres=16, spp=1)
     d = hs.desc.contents

@@ -786,6 +786,29 @@ def test_bumpmap_parameter(pb):
     assert pb.lib().pb2h_error_count() > before
 
 
+def test_texture_combinators(pb):
+    """Texture "scale" / "mix" with an operand that varies (scale.cpp:40-52, mix.cpp:40-54): nodes of the description's texture
+    array whose children precede them; constant operands become constant nodes; combinators of constants alone stay folded."""
+    hs = pb.HostScene.from_file(os.path.join(SCENES, "texcombine.pbrt"))
+    d = hs.desc.contents
+    tex = [d.textures[i] for i in range(d.n_textures)]
+    kinds = [t.kind for t in tex]
+    assert kinds.count(pb.PB2_TEXKIND_SCALE) == 3 and kinds.count(pb.PB2_TEXKIND_MIX) == 3
+    for i, t in enumerate(tex):
+        if t.kind in (pb.PB2_TEXKIND_SCALE, pb.PB2_TEXKIND_MIX):
+            n = 3 if t.kind == pb.PB2_TEXKIND_MIX else 2
+            assert all(1 <= t.child[c] <= i for c in range(n)) and not t.texels
+            assert all(tex[t.child[c] - 1].channels == t.channels for c in range(2))
+            if n == 3:
+                assert tex[t.child[2] - 1].channels == 1
+    washed = [t for t in tex if t.kind == pb.PB2_TEXKIND_MIX and tex[t.child[0] - 1].kind == pb.PB2_TEXKIND_SCALE][0]   # two levels
+    assert tuple(np.float32(v) for v in tex[washed.child[1] - 1].value) == (np.float32(.8),) * 3 and tex[washed.child[2] - 1].value[0] == np.float32(.3)
+    # constants alone: folded into the material record, no texture nodes
+    hs = pb.HostScene.from_string('WorldBegin\nTexture "a" "spectrum" "scale" "rgb tex1" [.5 .5 .5] "rgb tex2" [.5 1 2]\n'
+                                  'Material "matte" "texture Kd" "a"\nShape "sphere"\nWorldEnd\n')
+    assert hs.desc.contents.n_textures == 0 and tuple(hs.desc.contents.materials[0].kd) == (.25, .5, 1.0)
+
+
 def test_openexr_reader(pb, tmp_path):
     """ReadImage for OpenEXR scan-line files (imageio.cpp:125-151 reads them through OpenEXR's RgbaInputFile): half channels
     stored B, G, R; ZIP blocks of 16 lines (the last one short) with the byte-delta predictor and the even / odd byte split,
