@@ -237,8 +237,8 @@ static bool readPNG(const std::string &name, std::vector<float> *rgb, int *w, in
     return true;
 }
 
-// ---- OpenEXR: single-part scan-line files, half / float / uint channels R, G, B (or a lone Y), compression NONE, RLE, ZIPS
-// and ZIP (what imgtool / pbrt's WriteImageEXR produce); PIZ and the lossy codecs, tiled, deep and multi-part files are refused.
+// ---- OpenEXR: single-part scan-line files, half / float / uint channels R, G, B (or a lone Y), compression NONE, RLE, ZIPS,
+// ZIP (what imgtool / pbrt's WriteImageEXR produce) and PIZ; the lossy codecs, tiled, deep and multi-part files are refused.
 // ReadImageEXR (imageio.cpp:125-151) reads the data window through an RgbaInputFile: the same pixels.
 static float halfToFloat(uint16_t h) {
     const uint32_t sign = (uint32_t)(h >> 15) << 31, exp = (h >> 10) & 31, man = h & 1023;
@@ -260,6 +260,158 @@ static float halfToFloat(uint16_t h) {
     memcpy(&f, &bits, 4);
     return f;
 }
+// ---- the PIZ codec of OpenEXR (what most other tools write): a block's 16-bit words go through a value look-up table
+// (only the values that occur are numbered), a 2D Haar-like wavelet per channel and a canonical Huffman code with a
+// run-length symbol.  Decoder written from the format: range table, code lengths (6 bits each, zero runs escaped), codes
+// assigned per length in symbol order, bits most significant first.
+namespace {
+struct PizBits {   // most-significant-bit-first reader
+    const uint8_t *p, *end;
+    uint64_t acc = 0;
+    int n = 0;
+    bool ok = true;
+    uint64_t get(int bits) {
+        while (n < bits) {
+            if (p >= end) {
+                ok = false;
+                return 0;
+            }
+            acc = (acc << 8) | *p++;
+            n += 8;
+        }
+        n -= bits;
+        return (acc >> n) & ((bits == 64) ? ~0ull : ((1ull << bits) - 1));
+    }
+};
+// one inverse wavelet step on a pair: 14-bit data (plain integer average / difference) or full 16-bit data (modulo form)
+inline void pizUnpair(bool w14, uint16_t l, uint16_t hgh, uint16_t *a, uint16_t *b) {
+    if (w14) {
+        const int ls = (int16_t)l, hi = (int16_t)hgh;
+        const int ai = ls + (hi & 1) + (hi >> 1);
+        *a = (uint16_t)(int16_t)ai;
+        *b = (uint16_t)(int16_t)(ai - hi);
+    } else {
+        const int m = l, d = hgh;
+        const int bb = (m - (d >> 1)) & 0xffff;
+        *b = (uint16_t)bb;
+        *a = (uint16_t)((d + bb - 0x8000) & 0xffff);
+    }
+}
+// inverse 2D wavelet of an nx x ny array with strides ox / oy, coarsest level first
+void pizWaveletDecode(uint16_t *in, int nx, int ox, int ny, int oy, uint16_t maxValue) {
+    const bool w14 = maxValue < (1 << 14);
+    const int n = nx > ny ? ny : nx;
+    int p = 1;
+    while (p <= n) p <<= 1;
+    p >>= 1;
+    int p2 = p;
+    p >>= 1;
+    while (p >= 1) {
+        const int oy1 = oy * p, oy2 = oy * p2, ox1 = ox * p, ox2 = ox * p2;
+        int y = 0;
+        for (; y <= ny - p2; y += p2) {
+            uint16_t *row = in + (size_t)oy * y;
+            int x = 0;
+            for (; x <= nx - p2; x += p2) {
+                uint16_t *px = row + (size_t)ox * x, *p01 = px + ox1, *p10 = px + oy1, *p11 = p10 + ox1;
+                uint16_t i00, i01, i10, i11;
+                pizUnpair(w14, *px, *p10, &i00, &i10);
+                pizUnpair(w14, *p01, *p11, &i01, &i11);
+                pizUnpair(w14, i00, i01, px, p01);
+                pizUnpair(w14, i10, i11, p10, p11);
+            }
+            if (nx & p) {   // an odd column at this level: one vertical pair
+                uint16_t *px = row + (size_t)ox * x, *p10 = px + oy1, i00;
+                pizUnpair(w14, *px, *p10, &i00, p10);
+                *px = i00;
+            }
+        }
+        if (ny & p) {       // an odd row: horizontal pairs
+            uint16_t *row = in + (size_t)oy * y;
+            for (int x = 0; x <= nx - p2; x += p2) {
+                uint16_t *px = row + (size_t)ox * x, *p01 = px + ox1, i00;
+                pizUnpair(w14, *px, *p01, &i00, p01);
+                *px = i00;
+            }
+        }
+        (void)oy2;
+        (void)ox2;
+        p2 = p;
+        p >>= 1;
+    }
+}
+// Huffman: `data` = {first symbol, last symbol (= the run-length symbol), table length, bit count, reserved}, the packed
+// code lengths, the bit stream; nOut 16-bit words come out
+bool pizHuffmanDecode(const uint8_t *data, size_t size, uint16_t *out, size_t nOut) {
+    if (size < 20) return nOut == 0;
+    auto u32 = [&](size_t o) { uint32_t v; memcpy(&v, data + o, 4); return v; };
+    const uint32_t im = u32(0), iM = u32(4), nBits = u32(12);
+    const int kSymbols = (1 << 16) + 1;
+    if (im >= (uint32_t)kSymbols || iM >= (uint32_t)kSymbols || im > iM) return false;
+    std::vector<uint8_t> length((size_t)kSymbols, 0);
+    PizBits tb{data + 20, data + size};
+    for (uint32_t sym = im; sym <= iM; ++sym) {
+        const int l = (int)tb.get(6);
+        if (!tb.ok) return false;
+        if (l == 63 || l >= 59) {   // a run of zero lengths: 63 -> 8 more bits + 6, 59..62 -> l - 59 + 2
+            int run = l == 63 ? (int)tb.get(8) + 6 : l - 59 + 2;
+            if (!tb.ok || sym + run > iM + 1) return false;
+            sym += run - 1;
+        } else
+            length[sym] = (uint8_t)l;
+    }
+    // canonical codes: the numerically lowest code of each length, from the longest length down; then in symbol order
+    uint64_t count[59] = {0}, first[59] = {0};
+    for (int i = 0; i < kSymbols; ++i) count[length[i]]++;
+    uint64_t c = 0;
+    for (int l = 58; l > 0; --l) {
+        first[l] = c;
+        c = (c + count[l]) >> 1;
+    }
+    std::vector<uint32_t> offset(60, 0), sorted;
+    sorted.reserve(iM - im + 1);
+    for (int l = 1; l <= 58; ++l) {
+        offset[l] = (uint32_t)sorted.size();
+        if (count[l])
+            for (uint32_t sym = im; sym <= iM; ++sym)
+                if (length[sym] == l) sorted.push_back(sym);
+    }
+    // (the loop above is O(58 * symbols) only for lengths in use: a few dozen passes over at most 65537 entries)
+    const uint8_t *bits = tb.n >= 8 ? tb.p - tb.n / 8 : tb.p;   // the bit stream starts at the next whole byte after the table
+    PizBits in{bits, data + size};
+    size_t o = 0;
+    uint64_t used = 0;
+    while (used < nBits) {
+        uint64_t code = 0;
+        int l = 0;
+        uint32_t sym = 0;
+        for (;;) {
+            if (used >= nBits || l >= 58) return false;
+            code = (code << 1) | in.get(1);
+            if (!in.ok) return false;
+            ++used;
+            ++l;
+            if (count[l] && code >= first[l] && code - first[l] < count[l]) {
+                sym = sorted[offset[l] + (uint32_t)(code - first[l])];
+                break;
+            }
+        }
+        if (sym == iM) {   // run length: repeat the last word
+            if (used + 8 > nBits || o == 0) return false;
+            size_t run = (size_t)in.get(8);
+            used += 8;
+            if (!in.ok || o + run > nOut) return false;
+            const uint16_t v = out[o - 1];
+            while (run--) out[o++] = v;
+        } else {
+            if (o >= nOut) return false;
+            out[o++] = (uint16_t)sym;
+        }
+    }
+    return o == nOut;
+}
+}  // namespace
+
 static bool readEXR(const std::string &name, std::vector<float> *rgb, int *w, int *h, std::string *why) {
     std::vector<uint8_t> b;
     if (!readFile(name, &b) || b.size() < 8) { *why = "cannot open"; return false; }
@@ -306,7 +458,7 @@ static bool readEXR(const std::string &name, std::vector<float> *rgb, int *w, in
     *w = dw[2] - dw[0] + 1;
     *h = dw[3] - dw[1] + 1;
     if (*w <= 0 || *h <= 0 || channels.empty()) { *why = "no data window / channels"; return false; }
-    if (compression < 0 || compression > 3) { *why = "compression other than NONE / RLE / ZIPS / ZIP (e.g. PIZ)"; return false; }
+    if (compression < 0 || compression > 4) { *why = "compression other than NONE / RLE / ZIPS / ZIP / PIZ (a lossy codec)"; return false; }
     size_t lineBytes = 0;
     std::vector<size_t> chOffset(channels.size());
     int src[3] = {-1, -1, -1};
@@ -323,7 +475,7 @@ static bool readEXR(const std::string &name, std::vector<float> *rgb, int *w, in
         for (size_t c = 0; c < channels.size(); ++c)
             if (channels[c].name == "Y") src[0] = src[1] = src[2] = (int)c;
     if (src[0] < 0 && src[1] < 0 && src[2] < 0) { *why = "no R, G, B or Y channel"; return false; }
-    const int linesPerBlock = compression == 3 ? 16 : 1;
+    const int linesPerBlock = compression == 3 ? 16 : (compression == 4 ? 32 : 1);
     const int nBlocks = (*h + linesPerBlock - 1) / linesPerBlock;
     if (pos + (size_t)nBlocks * 8 > b.size()) { *why = "truncated offset table"; return false; }
     rgb->assign((size_t)3 * *w * *h, 0.f);
@@ -341,6 +493,52 @@ static bool readEXR(const std::string &name, std::vector<float> *rgb, int *w, in
         if ((size_t)dataSize >= rawSize || compression == 0) {   // stored as is (a block that did not shrink is not compressed)
             if ((size_t)dataSize < rawSize) { *why = "short block"; return false; }
             memcpy(raw.data(), data, rawSize);
+        } else if (compression == 4) {
+            // PIZ: [min, max non-zero byte of the value bitmap][that part of the bitmap][Huffman length][Huffman data]; the
+            // decoded words are the block channel by channel (each channel: its rows), wavelet-transformed per channel
+            if (dataSize < 4) { *why = "bad PIZ block"; return false; }
+            uint16_t minNZ, maxNZ;
+            memcpy(&minNZ, data, 2);
+            memcpy(&maxNZ, data + 2, 2);
+            size_t p = 4;
+            std::vector<uint8_t> bitmap(8192, 0);
+            if (maxNZ >= 8192) { *why = "bad PIZ block"; return false; }
+            if (minNZ <= maxNZ) {
+                const size_t nb = (size_t)maxNZ - minNZ + 1;
+                if (p + nb > (size_t)dataSize) { *why = "bad PIZ block"; return false; }
+                memcpy(bitmap.data() + minNZ, data + p, nb);
+                p += nb;
+            }
+            std::vector<uint16_t> lut(65536, 0);
+            int k = 0;
+            for (int i = 0; i < 65536; ++i)
+                if (i == 0 || (bitmap[i >> 3] & (1 << (i & 7)))) lut[k++] = (uint16_t)i;
+            const uint16_t maxValue = (uint16_t)(k - 1);
+            if (p + 4 > (size_t)dataSize) { *why = "bad PIZ block"; return false; }
+            int32_t hufLen;
+            memcpy(&hufLen, data + p, 4);
+            p += 4;
+            if (hufLen < 0 || p + (size_t)hufLen > (size_t)dataSize) { *why = "bad PIZ block"; return false; }
+            const size_t nWords = rawSize / 2;
+            std::vector<uint16_t> words(nWords);
+            if (!pizHuffmanDecode(data + p, (size_t)hufLen, words.data(), nWords)) { *why = "bad PIZ block (Huffman)"; return false; }
+            size_t start = 0;
+            std::vector<size_t> chStart(channels.size());
+            for (size_t c = 0; c < channels.size(); ++c) {
+                const int size = channels[c].type == 1 ? 1 : 2;   // 16-bit words per sample
+                chStart[c] = start;
+                for (int j = 0; j < size; ++j) pizWaveletDecode(words.data() + start + j, *w, size, lines, *w * size, maxValue);
+                start += (size_t)*w * lines * size;
+            }
+            for (size_t i = 0; i < nWords; ++i) words[i] = lut[words[i]];
+            // back to scan lines: for every line, every channel's samples
+            uint8_t *dstp = raw.data();
+            for (int l = 0; l < lines; ++l)
+                for (size_t c = 0; c < channels.size(); ++c) {
+                    const size_t n = (size_t)*w * (channels[c].type == 1 ? 1 : 2);
+                    memcpy(dstp, words.data() + chStart[c] + (size_t)l * n, n * 2);
+                    dstp += n * 2;
+                }
         } else {
             tmp.resize(rawSize);
             if (compression == 1) {   // run-length: count < 0 -> -count literal bytes, else count + 1 copies of the next byte
@@ -405,7 +603,7 @@ bool ReadImage(const std::string &name, std::vector<float> *rgb, int *w, int *h)
         std::string why;
         ok = readEXR(name, rgb, w, h, &why);
         if (!ok) {
-            Error("Unable to read OpenEXR file \"%s\": %s (scan-line files with NONE / RLE / ZIPS / ZIP compression are read)", name.c_str(), why.c_str());
+            Error("Unable to read OpenEXR file \"%s\": %s (scan-line files with NONE / RLE / ZIPS / ZIP / PIZ compression are read)", name.c_str(), why.c_str());
             return false;
         }
     } else {

@@ -812,7 +812,7 @@ def test_texture_combinators(pb):
 def test_openexr_reader(pb, tmp_path):
     """ReadImage for OpenEXR scan-line files (imageio.cpp:125-151 reads them through OpenEXR's RgbaInputFile): half channels
     stored B, G, R; ZIP blocks of 16 lines (the last one short) with the byte-delta predictor and the even / odd byte split,
-    blocks stored raw when they do not shrink, and uncompressed files - the committed files of tests/scenes/make_textures.py,
+    blocks stored raw when they do not shrink, uncompressed files, and the PIZ codec - the committed files of tests/scenes/make_textures.py,
     the container this library writes itself, and (where the reference's bundled OpenEXR sources are present) OpenEXR's own
     test images, which hold one picture under every codec."""
     tex = os.path.join(SCENES, "textures")
@@ -834,11 +834,12 @@ def test_openexr_reader(pb, tmp_path):
     if os.path.exists(os.path.join(ilm, "comp_none.exr")):
         base = pb.read_image(os.path.join(ilm, "comp_none.exr"))
         assert base.shape == (675, 587, 3) and np.isfinite(base).all()
-        for codec in ("rle", "zips", "zip"):
+        for codec in ("rle", "zips", "zip", "piz"):      # piz: value table + wavelet + Huffman with run lengths
             assert np.array_equal(pb.read_image(os.path.join(ilm, "comp_%s.exr" % codec)).view(np.uint32), base.view(np.uint32)), codec
-    # the wavelet codec is reported, not misread
-    before = pb.lib().pb2h_error_count()
-    if os.path.exists(os.path.join(ilm, "comp_piz.exr")):
+        up, down = (pb.read_image(os.path.join(ilm, "lineOrder_%s.exr" % o)) for o in ("increasing", "decreasing"))   # PIZ, 119 lines
+        assert up.shape == (119, 237, 3) and np.array_equal(up.view(np.uint32), down.view(np.uint32))
+        # the lossy codecs are reported, not misread
+        before = pb.lib().pb2h_error_count()
         with pytest.raises(RuntimeError):
-            pb.read_image(os.path.join(ilm, "comp_piz.exr"))
+            pb.read_image(os.path.join(ilm, "comp_b44.exr"))
         assert pb.lib().pb2h_error_count() > before
