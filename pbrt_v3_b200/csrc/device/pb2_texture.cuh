@@ -155,6 +155,9 @@ PB2_HD V3 texEvaluate(const DTexture &tx, const float *pool, V2 uv, const DUvDif
     return texLookup(tx, pool, st, dstdx, dstdy);
 }
 
+// (out of line: the combinator recursion below would otherwise inline the whole filter once per node position)
+PB2_HDN V3 texEvaluateImage(const DTexture &tx, const float *pool, V2 uv, const DUvDiff &d) { return texEvaluate(tx, pool, uv, d); }
+
 // Texture::Evaluate for any node of the scene's texture array: an image, a constant, ScaleTexture (scale.h:56-58) or
 // MixTexture (mix.h:57-61).  The library checks at upload that children precede their parents and that no chain is deeper
 // than TEX_MAX_DEPTH, so the recursion unrolls at compile time.
@@ -163,7 +166,7 @@ template <int DEPTH>
 struct TexEval {
     static PB2_HD V3 node(const DTexture *textures, const float *pool, int id, V2 uv, const DUvDiff &d) {
         const DTexture &tx = textures[id];
-        if (tx.kind == PB2_TEXKIND_IMAGE) return texEvaluate(tx, pool, uv, d);
+        if (tx.kind == PB2_TEXKIND_IMAGE) return texEvaluateImage(tx, pool, uv, d);
         if (tx.kind == PB2_TEXKIND_CONSTANT) return mk3(tx.value[0], tx.value[1], tx.value[2]);
         const V3 a = TexEval<DEPTH - 1>::node(textures, pool, tx.child[0] - 1, uv, d);
         const V3 b = TexEval<DEPTH - 1>::node(textures, pool, tx.child[1] - 1, uv, d);
@@ -177,7 +180,7 @@ struct TexEval<0> {
     static PB2_HD V3 node(const DTexture *textures, const float *pool, int id, V2 uv, const DUvDiff &d) {
         const DTexture &tx = textures[id];
         if (tx.kind == PB2_TEXKIND_CONSTANT) return mk3(tx.value[0], tx.value[1], tx.value[2]);
-        return texEvaluate(tx, pool, uv, d);
+        return texEvaluateImage(tx, pool, uv, d);
     }
 };
 PB2_HD V3 texEvaluateNode(const DTexture *textures, const float *pool, int id, V2 uv, const DUvDiff &d) {
