@@ -1042,9 +1042,22 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     if (rc) return rc;
     TraceLaunch trace;
     if ((rc = selectTraceKernel(scene, flags, &trace, true))) return rc;
+    // Once the work counter has run out the pool only decays: ~25 more rounds of ever fewer rays, each a handful of launches
+    // whose cost is latency, not work.  For those rounds the CHAIN form of the trace kernel (the light step inside: one round
+    // per bounce instead of three; slower under load, PB2_FLAG_CHAIN) is the better one: it halves what is left of the tail.
+    // PB2_DRAIN_CHAIN=0: off.
+    TraceLaunch drainTrace;
+    static const int drainChain = envInt("PB2_DRAIN_CHAIN", 1);
+    bool haveDrain = false;
+    if (drainChain && !trace.chain && !(flags & (PB2_FLAG_COUNT_TRAVERSAL | PB2_FLAG_PLAIN_TRACE | PB2_FLAG_LINEAR_NODES | PB2_FLAG_WIDE4 |
+                                                  PB2_FLAG_SMALL_STACK | PB2_FLAG_LD128 | PB2_FLAG_LEAF_TMA | PB2_FLAG_POOL))) {
+        if ((rc = selectTraceKernel(scene, flags | PB2_FLAG_CHAIN, &drainTrace, true))) return rc;
+        haveDrain = drainTrace.chain;
+    }
+    bool draining = false;
     WfChain chain;
     memset(&chain, 0, sizeof(chain));
-    if (trace.chain) {
+    if (trace.chain || haveDrain) {
         // the scene and this frame's parameters as objects in device memory for wfChainLight
         if (!scene->chainBuf) CUDA_TRY(cudaMalloc(&scene->chainBuf, sizeof(DScene) + sizeof(DRenderParams)));
         CUDA_TRY(cudaMemcpyAsync(scene->chainBuf, &scene->d, sizeof(DScene), cudaMemcpyHostToDevice, stream));
@@ -1139,12 +1152,13 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
                 CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents], st));
             }
             chain.freeQ = WQ_FREE0 + next;
-            trace.fn<<<trace.grid ? trace.grid : blocks128, trace.block, trace.smem, st>>>(scene->d, pool, WQ_TRACE0 + cur, chain);
+            const TraceLaunch &tl = draining ? drainTrace : trace;
+            tl.fn<<<tl.grid ? tl.grid : blocks128, tl.block, tl.smem, st>>>(scene->d, pool, WQ_TRACE0 + cur, chain);
             if (timeTrace) {
                 CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents + 1], st));
                 nEvents += 2;
             }
-            if (!trace.chain) advLight<<<blocks128, 128, 0, st>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
+            if (!tl.chain) advLight<<<blocks128, 128, 0, st>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
             else --nLaunch;
             advShade<<<blocks128, 128, 0, st>>>(scene->d, rp, pool, WQ_SHADE, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
             if (lazyLights) {
@@ -1170,6 +1184,7 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         if ((rc = lightDistOverflowed(scene, stream, &overflowed))) return rc;
         if (overflowed) return lightDistOverflowError();
         const bool workLeft = (long long)*hWork < rp.nWorkItems;
+        if (!workLeft && haveDrain) draining = true;   // (the lists of the rounds so far are consumed: the switch is between rounds)
         bool done = true;
         for (int p = 0; p < nPipes; ++p) {
             const unsigned traceNext = hc[p * WQ_COUNT + WQ_TRACE0 + cur], freeNext = hc[p * WQ_COUNT + WQ_FREE0 + cur];
