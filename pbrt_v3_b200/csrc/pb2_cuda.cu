@@ -412,7 +412,8 @@ struct pb2_scene {
     unsigned *wfHostCounts = nullptr;  // pinned
     int wfCapacity = 0;
     std::vector<cudaEvent_t> traceEvents;
-    int pipesChosen = 0;                     // wavefront pipelines for this scene, chosen after its first frame (0 = not yet)
+    int pipesChosen = 0;                     // wavefront pipelines for this scene, chosen from its second frame (0 = not yet)
+    int framesRendered = 0;
     cudaEvent_t frameEvents[2] = {nullptr, nullptr};
     int2 *wfSpill = nullptr;                 // k_wf_trace_pool: stack entries beyond its shared-memory depth
     void *chainBuf = nullptr;                // device copies of {DScene, DRenderParams} for the CHAIN trace kernels
@@ -1042,22 +1043,9 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     if (rc) return rc;
     TraceLaunch trace;
     if ((rc = selectTraceKernel(scene, flags, &trace, true))) return rc;
-    // Once the work counter has run out the pool only decays: ~25 more rounds of ever fewer rays, each a handful of launches
-    // whose cost is latency, not work.  For those rounds the CHAIN form of the trace kernel (the light step inside: one round
-    // per bounce instead of three; slower under load, PB2_FLAG_CHAIN) is the better one: it halves what is left of the tail.
-    // PB2_DRAIN_CHAIN=0: off.
-    TraceLaunch drainTrace;
-    static const int drainChain = envInt("PB2_DRAIN_CHAIN", 1);
-    bool haveDrain = false;
-    if (drainChain && !trace.chain && !(flags & (PB2_FLAG_COUNT_TRAVERSAL | PB2_FLAG_PLAIN_TRACE | PB2_FLAG_LINEAR_NODES | PB2_FLAG_WIDE4 |
-                                                  PB2_FLAG_SMALL_STACK | PB2_FLAG_LD128 | PB2_FLAG_LEAF_TMA | PB2_FLAG_POOL))) {
-        if ((rc = selectTraceKernel(scene, flags | PB2_FLAG_CHAIN, &drainTrace, true))) return rc;
-        haveDrain = drainTrace.chain;
-    }
-    bool draining = false;
     WfChain chain;
     memset(&chain, 0, sizeof(chain));
-    if (trace.chain || haveDrain) {
+    if (trace.chain) {
         // the scene and this frame's parameters as objects in device memory for wfChainLight
         if (!scene->chainBuf) CUDA_TRY(cudaMalloc(&scene->chainBuf, sizeof(DScene) + sizeof(DRenderParams)));
         CUDA_TRY(cudaMemcpyAsync(scene->chainBuf, &scene->d, sizeof(DScene), cudaMemcpyHostToDevice, stream));
@@ -1103,7 +1091,11 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     // The first frame of a scene runs with two and measures the trace kernel's share of the frame; later frames use four
     // when that share is small.  PB2_PIPES fixes the number.
     static const int pipesEnv = envInt("PB2_PIPES", 0);
-    const bool calibrate = pipesEnv <= 0 && scene->pipesChosen == 0 && !lazyLights && capacity >= 65536 && rp.nWorkItems >= 4 * (long long)capacity;
+    // (not on a scene's very first frame: that one also pays for loading the kernels it is the first to launch, which
+    // inflates the frame time the share is taken of - a box with a slow host was seen to choose four pipelines for the soup)
+    const bool calibrate = pipesEnv <= 0 && scene->pipesChosen == 0 && scene->framesRendered >= 1 && !lazyLights && capacity >= 65536 &&
+                           rp.nWorkItems >= 4 * (long long)capacity;
+    scene->framesRendered++;
     if (calibrate) timeTrace = true;
     const int pipesWanted = std::min((int)kMaxPipes, pipesEnv > 0 ? pipesEnv : (scene->pipesChosen > 0 ? scene->pipesChosen : 2));
     const int nPipes = (lazyLights || capacity < 65536) ? 1 : pipesWanted;
@@ -1152,13 +1144,12 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
                 CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents], st));
             }
             chain.freeQ = WQ_FREE0 + next;
-            const TraceLaunch &tl = draining ? drainTrace : trace;
-            tl.fn<<<tl.grid ? tl.grid : blocks128, tl.block, tl.smem, st>>>(scene->d, pool, WQ_TRACE0 + cur, chain);
+            trace.fn<<<trace.grid ? trace.grid : blocks128, trace.block, trace.smem, st>>>(scene->d, pool, WQ_TRACE0 + cur, chain);
             if (timeTrace) {
                 CUDA_TRY(cudaEventRecord(scene->traceEvents[nEvents + 1], st));
                 nEvents += 2;
             }
-            if (!tl.chain) advLight<<<blocks128, 128, 0, st>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
+            if (!trace.chain) advLight<<<blocks128, 128, 0, st>>>(scene->d, rp, pool, WQ_LIGHT, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
             else --nLaunch;
             advShade<<<blocks128, 128, 0, st>>>(scene->d, rp, pool, WQ_SHADE, WQ_TRACE0 + next, WQ_FREE0 + next, film, scene->counters);
             if (lazyLights) {
@@ -1184,7 +1175,6 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         if ((rc = lightDistOverflowed(scene, stream, &overflowed))) return rc;
         if (overflowed) return lightDistOverflowError();
         const bool workLeft = (long long)*hWork < rp.nWorkItems;
-        if (!workLeft && haveDrain) draining = true;   // (the lists of the rounds so far are consumed: the switch is between rounds)
         bool done = true;
         for (int p = 0; p < nPipes; ++p) {
             const unsigned traceNext = hc[p * WQ_COUNT + WQ_TRACE0 + cur], freeNext = hc[p * WQ_COUNT + WQ_FREE0 + cur];
