@@ -1088,7 +1088,7 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
     // PB2_PIPES=1: one pipeline.  Lazily lit scenes share one request list: one pipeline.
     // How many: a traversal-bound scene (1 M soup: trace 80 % of the kernel time) is best with two - 219 / 229 / 222 / 216
     // Msamples/s with 1 / 2 / 3 / 4 pipelines - a shading-bound one (killeroo-like: trace 22 %) with four: 195 / 221 / 249 / 261.
-    // The first frame of a scene runs with two and measures the trace kernel's share of the frame; later frames use four
+    // The first two frames of a scene run with two, the second one measures the trace kernel's share of the frame; later frames use four
     // when that share is small.  PB2_PIPES fixes the number.
     static const int pipesEnv = envInt("PB2_PIPES", 0);
     // (not on a scene's very first frame: that one also pays for loading the kernels it is the first to launch, which
@@ -1209,7 +1209,7 @@ static int renderWavefront(pb2_scene *scene, const DRenderParams &rp, float4 *fi
         const double share = frameMs > 0 ? *traceMs / nPipes / frameMs : 1;
         scene->pipesChosen = share < 0.33 ? 4 : 2;
         static const int verbose = envInt("PB2_VERBOSE", 0);
-        if (verbose) fprintf(stderr, "pb2: trace share of the first frame %.2f -> %d wavefront pipelines\n", share, scene->pipesChosen);
+        if (verbose) fprintf(stderr, "pb2: trace share of the calibration frame %.2f -> %d wavefront pipelines\n", share, scene->pipesChosen);
     }
     return PB2_OK;
 }
