@@ -104,7 +104,11 @@ typedef struct pb2_texture {
     int32_t child[3];
     float value[3];
 } pb2_texture;
-enum { PB2_TEXKIND_IMAGE = 0, PB2_TEXKIND_CONSTANT = 1, PB2_TEXKIND_SCALE = 2, PB2_TEXKIND_MIX = 3 };
+/* PB2_TEXKIND_CHECKERBOARD: Checkerboard2DTexture (src/textures/checkerboard.h:52-107) over child[0] / child[1] with the
+ * UVMapping2D in su .. dv; value[0] = 0: "aamode" "none", 1: "closedform".  PB2_TEXKIND_UV: UVTexture (src/textures/uv.h:48-63),
+ * three channels, the mapping in su .. dv. */
+enum { PB2_TEXKIND_IMAGE = 0, PB2_TEXKIND_CONSTANT = 1, PB2_TEXKIND_SCALE = 2, PB2_TEXKIND_MIX = 3, PB2_TEXKIND_CHECKERBOARD = 4,
+       PB2_TEXKIND_UV = 5 };
 
 /* slots of pb2_material.tex: which parameter a texture replaces */
 enum { PB2_TEX_KD = 0, PB2_TEX_KS = 1, PB2_TEX_KR = 2, PB2_TEX_KT = 3, PB2_TEX_OPACITY = 4, PB2_TEX_SIGMA = 5, PB2_TEX_ROUGHNESS = 6,
@@ -492,6 +496,12 @@ int pb2_light_distribution(pb2_scene *scene, const float *points_xyz, int64_t n,
  * resampling to a power of two, then box-filtered levels).  Host code only - no device needed.  *n_levels, *w and *h
  * (resolution of `level`) are always written; `out` (channels * w * h floats, row-major) may be NULL.  Parity/debug. */
 int pb2_texture_pyramid(const pb2_texture *texture, int32_t level, int32_t *n_levels, int32_t *w, int32_t *h, float *out);
+
+/* Texture::Evaluate(si) for texture `id` (0-based) of a texture array - any kind: image, constant, scale, mix, checkerboard,
+ * uv - at n points given by their (u, v) (2 floats each) and (dudx, dvdx, dudy, dvdy) (4 floats each), evaluated on the HOST by
+ * the functions the kernels compile.  out: 3 floats per point (one-channel textures repeat their value).  Parity/debug. */
+int pb2_texture_eval_host(const pb2_texture *textures, int32_t n_textures, int32_t id, int64_t n, const float *uv, const float *duv,
+                          float *out);
 
 /* The sampling distribution the library derives for an InfiniteAreaLight whose environment map is `texture` (infinite.cpp:64-82:
  * the Distribution2D over the 2w x 2h image of luminance * sin(theta)).  Host code only.  *nu = 2w, *nv = 2h (w, h: the map's

@@ -112,6 +112,13 @@ class Oracle:
             raise ValueError("resolution 2^%d outside the reference's tables" % m)
         return tab, mats
 
+    def texture_evaluate(self, textures, n_textures, tex_id, uv, duv):
+        """Texture::Evaluate of the reference's own texture objects built from a description's texture array (reference only)."""
+        import pbrt_v3_b200 as pb
+        fn = self._f("texture_evaluate")
+        fn.argtypes = [C.POINTER(pb.Texture), C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        return pb.texture_eval_host(textures, n_textures, tex_id, uv, duv, fn)
+
     def env_distribution(self, texture):
         """InfiniteAreaLight::distribution for an environment map given as a pb2_texture: (nu, nv, table) in the layout of
         pb2_env_distribution (reference only)."""

@@ -73,7 +73,9 @@
 #include "shapes/loopsubdiv.h"
 #include "shapes/sphere.h"
 #include "shapes/triangle.h"
+#include "textures/checkerboard.h"
 #include "textures/constant.h"
+#include "textures/uv.h"
 #include "textures/mix.h"
 #include "textures/scale.h"
 #include "mipmap.h"
@@ -258,6 +260,38 @@ DescImageTexture<RGBSpectrum, Spectrum>::DescImageTexture(const pb2_texture &t) 
     mipmap.reset(new MIPMap<RGBSpectrum>(Point2i(t.width, t.height), texels.data(), t.do_trilinear != 0, t.max_anisotropy, wrap));
 }
 
+// The reference's texture objects for a description's texture array (images through the reference's MIPMap, the other kinds
+// as the reference's own ConstantTexture / ScaleTexture / MixTexture / Checkerboard2DTexture / UVTexture)
+static void buildRefTextures(const pb2_scene_desc *d, std::vector<std::shared_ptr<Texture<Float>>> &floatTex,
+                             std::vector<std::shared_ptr<Texture<Spectrum>>> &specTex) {
+    // image textures (the MIPMap constructor runs ParallelFors: the thread pool must exist, parallel.cpp:186)
+    floatTex.assign(d->n_textures, nullptr);
+    specTex.assign(d->n_textures, nullptr);
+    if (d->n_textures > 0) setThreads(0);
+    for (int i = 0; i < d->n_textures; ++i) {
+        const pb2_texture &pt = d->textures[i];
+        const bool one = pt.channels == 1;
+        if (pt.kind == PB2_TEXKIND_CONSTANT) {
+            if (one) floatTex[i] = std::make_shared<ConstantTexture<Float>>(pt.value[0]);
+            else specTex[i] = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pt.value));
+        } else if (pt.kind == PB2_TEXKIND_SCALE) {   // the reference's own ScaleTexture / MixTexture over the children
+            if (one) floatTex[i] = std::make_shared<ScaleTexture<Float, Float>>(floatTex[pt.child[0] - 1], floatTex[pt.child[1] - 1]);
+            else specTex[i] = std::make_shared<ScaleTexture<Spectrum, Spectrum>>(specTex[pt.child[0] - 1], specTex[pt.child[1] - 1]);
+        } else if (pt.kind == PB2_TEXKIND_MIX) {
+            if (one) floatTex[i] = std::make_shared<MixTexture<Float>>(floatTex[pt.child[0] - 1], floatTex[pt.child[1] - 1], floatTex[pt.child[2] - 1]);
+            else specTex[i] = std::make_shared<MixTexture<Spectrum>>(specTex[pt.child[0] - 1], specTex[pt.child[1] - 1], floatTex[pt.child[2] - 1]);
+        } else if (pt.kind == PB2_TEXKIND_CHECKERBOARD) {
+            const AAMethod aa = pt.value[0] == 0 ? AAMethod::None : AAMethod::ClosedForm;
+            std::unique_ptr<TextureMapping2D> map(new UVMapping2D(pt.su, pt.sv, pt.du, pt.dv));
+            if (one) floatTex[i] = std::make_shared<Checkerboard2DTexture<Float>>(std::move(map), floatTex[pt.child[0] - 1], floatTex[pt.child[1] - 1], aa);
+            else specTex[i] = std::make_shared<Checkerboard2DTexture<Spectrum>>(std::move(map), specTex[pt.child[0] - 1], specTex[pt.child[1] - 1], aa);
+        } else if (pt.kind == PB2_TEXKIND_UV) {
+            specTex[i] = std::make_shared<UVTexture>(std::unique_ptr<TextureMapping2D>(new UVMapping2D(pt.su, pt.sv, pt.du, pt.dv)));
+        } else if (one) floatTex[i] = std::make_shared<DescImageTexture<Float, Float>>(pt);
+        else specTex[i] = std::make_shared<DescImageTexture<RGBSpectrum, Spectrum>>(pt);
+    }
+
+}
 extern "C" {
 
 const char *ref_kind(void) { return "reference"; }
@@ -344,31 +378,36 @@ int ref_texture_lookup(const pb2_texture *t, int64_t n, const float *st, const f
     return 0;
 }
 
+// Texture::Evaluate of the reference for texture `id` at points given by (u, v) and (dudx, dvdx, dudy, dvdy)
+int ref_texture_evaluate(const pb2_texture *textures, int n_textures, int id, int64_t n, const float *uv, const float *duv, float *out) {
+    pb2_scene_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.n_textures = n_textures;
+    d.textures = textures;
+    std::vector<std::shared_ptr<Texture<Float>>> floatTex;
+    std::vector<std::shared_ptr<Texture<Spectrum>>> specTex;
+    buildRefTextures(&d, floatTex, specTex);
+    for (int64_t i = 0; i < n; ++i) {
+        SurfaceInteraction si;
+        si.uv = Point2f(uv[2 * i], uv[2 * i + 1]);
+        si.dudx = duv[4 * i];
+        si.dvdx = duv[4 * i + 1];
+        si.dudy = duv[4 * i + 2];
+        si.dvdy = duv[4 * i + 3];
+        if (textures[id].channels == 1) out[3 * i] = out[3 * i + 1] = out[3 * i + 2] = floatTex[id]->Evaluate(si);
+        else specTex[id]->Evaluate(si).ToRGB(out + 3 * i);
+    }
+    return 0;
+}
+
 void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split_method) {
     std::unique_ptr<RefScene> rs(new RefScene);
     rs->transforms.emplace_back(new Transform());
     const Transform *identity = rs->transforms.back().get();
     rs->lightStrategy = d->light_strategy;
-    // image textures (the MIPMap constructor runs ParallelFors: the thread pool must exist, parallel.cpp:186)
-    std::vector<std::shared_ptr<Texture<Float>>> floatTex(d->n_textures);
-    std::vector<std::shared_ptr<Texture<Spectrum>>> specTex(d->n_textures);
-    if (d->n_textures > 0) setThreads(0);
-    for (int i = 0; i < d->n_textures; ++i) {
-        const pb2_texture &pt = d->textures[i];
-        const bool one = pt.channels == 1;
-        if (pt.kind == PB2_TEXKIND_CONSTANT) {
-            if (one) floatTex[i] = std::make_shared<ConstantTexture<Float>>(pt.value[0]);
-            else specTex[i] = std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(pt.value));
-        } else if (pt.kind == PB2_TEXKIND_SCALE) {   // the reference's own ScaleTexture / MixTexture over the children
-            if (one) floatTex[i] = std::make_shared<ScaleTexture<Float, Float>>(floatTex[pt.child[0] - 1], floatTex[pt.child[1] - 1]);
-            else specTex[i] = std::make_shared<ScaleTexture<Spectrum, Spectrum>>(specTex[pt.child[0] - 1], specTex[pt.child[1] - 1]);
-        } else if (pt.kind == PB2_TEXKIND_MIX) {
-            if (one) floatTex[i] = std::make_shared<MixTexture<Float>>(floatTex[pt.child[0] - 1], floatTex[pt.child[1] - 1], floatTex[pt.child[2] - 1]);
-            else specTex[i] = std::make_shared<MixTexture<Spectrum>>(specTex[pt.child[0] - 1], specTex[pt.child[1] - 1], floatTex[pt.child[2] - 1]);
-        } else if (one) floatTex[i] = std::make_shared<DescImageTexture<Float, Float>>(pt);
-        else specTex[i] = std::make_shared<DescImageTexture<RGBSpectrum, Spectrum>>(pt);
-    }
-
+    std::vector<std::shared_ptr<Texture<Float>>> floatTex;
+    std::vector<std::shared_ptr<Texture<Spectrum>>> specTex;
+    buildRefTextures(d, floatTex, specTex);
     // shapes
     std::vector<std::vector<std::shared_ptr<Shape>>> meshShapes(d->n_meshes);
     for (int m = 0; m < d->n_meshes; ++m) {

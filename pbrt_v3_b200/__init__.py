@@ -72,7 +72,7 @@ class Texture(C.Structure):
                 ("child", C.c_int32 * 3), ("value", C.c_float * 3)]
 
 
-PB2_TEXKIND_IMAGE, PB2_TEXKIND_CONSTANT, PB2_TEXKIND_SCALE, PB2_TEXKIND_MIX = 0, 1, 2, 3
+PB2_TEXKIND_IMAGE, PB2_TEXKIND_CONSTANT, PB2_TEXKIND_SCALE, PB2_TEXKIND_MIX, PB2_TEXKIND_CHECKERBOARD, PB2_TEXKIND_UV = 0, 1, 2, 3, 4, 5
 
 
 class Light(C.Structure):
@@ -207,6 +207,7 @@ def lib():
     L.pb2_texture_pyramid.argtypes = [C.POINTER(Texture), C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     L.pb2_texture_lookup.argtypes = [C.POINTER(Texture), C.c_int64, vp, vp, vp]
     L.pb2_env_distribution.argtypes = [C.POINTER(Texture), C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
+    L.pb2_texture_eval_host.argtypes = [C.POINTER(Texture), C.c_int32, C.c_int32, C.c_int64, vp, vp, vp]
     L.pb2h_parse_file.argtypes = [C.c_char_p, C.c_char_p]
     L.pb2h_parse_string.argtypes = [C.c_char_p]
     L.pb2h_synth_soup.argtypes = [C.c_int64, C.c_uint64, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]
@@ -277,6 +278,17 @@ def texture_pyramid(texture, fn=None):
         check(fn(C.byref(texture), lv, C.byref(nl), C.byref(w), C.byref(h), ptr(a)))
         levels.append(a)
     return levels
+
+
+def texture_eval_host(textures, n_textures, tex_id, uv, duv, fn=None):
+    """Texture::Evaluate of texture tex_id (0-based) of a description's texture array at points (u, v) with differentials
+    (dudx, dvdx, dudy, dvdy), on the host by the kernels' own functions (or, with fn, by the oracle): (n, 3)."""
+    fn = fn or lib().pb2_texture_eval_host
+    uv = np.ascontiguousarray(uv, np.float32)
+    duv = np.ascontiguousarray(duv, np.float32)
+    out = np.zeros((len(uv), 3), np.float32)
+    check(fn(textures, n_textures, tex_id, len(uv), ptr(uv), ptr(duv), ptr(out)))
+    return out
 
 
 def env_distribution(texture, fn=None):

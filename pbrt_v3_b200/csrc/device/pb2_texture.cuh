@@ -162,15 +162,43 @@ PB2_HDN V3 texEvaluateImage(const DTexture &tx, const float *pool, V2 uv, const 
 // MixTexture (mix.h:57-61).  The library checks at upload that children precede their parents and that no chain is deeper
 // than TEX_MAX_DEPTH, so the recursion unrolls at compile time.
 enum { TEX_MAX_DEPTH = 3 };
+// UVTexture::Evaluate (uv.h:53-59): the fractional parts of (s, t) as red and green
+PB2_HD V3 texUv(const DTexture &tx, V2 uv) {
+    const float s = tx.su * uv.x + tx.du, t = tx.sv * uv.y + tx.dv;
+    return mk3(s - floorf(s), t - floorf(t), 0.f);
+}
+// Checkerboard2DTexture::Evaluate (checkerboard.h:63-101): how much of tex2 the point sees - 0 or 1 for a point sample, the
+// box-filtered fraction in closed form when the footprint straddles a check
+PB2_HD float texCheckerWeight(const DTexture &tx, V2 uv, const DUvDiff &d) {
+    const float s = tx.su * uv.x + tx.du, t = tx.sv * uv.y + tx.dv;
+    const float point = (((int)floorf(s) + (int)floorf(t)) % 2 == 0) ? 0.f : 1.f;
+    if (tx.value[0] == 0) return point;   // "aamode" "none"
+    const float ds = pmax(fabsf(tx.su * d.dudx), fabsf(tx.su * d.dudy)), dt = pmax(fabsf(tx.sv * d.dvdx), fabsf(tx.sv * d.dvdy));
+    const float s0 = s - ds, s1 = s + ds, t0 = t - dt, t1 = t + dt;
+    if (floorf(s0) == floorf(s1) && floorf(t0) == floorf(t1)) return point;
+    auto bumpInt = [](float x) { return (int)floorf(x / 2) + 2 * pmax(x / 2 - (int)floorf(x / 2) - 0.5f, 0.f); };
+    const float sint = (bumpInt(s1) - bumpInt(s0)) / (2 * ds);
+    const float tint = (bumpInt(t1) - bumpInt(t0)) / (2 * dt);
+    float area2 = sint + tint - 2 * sint * tint;
+    if (ds > 1 || dt > 1) area2 = .5f;
+    return area2;
+}
 template <int DEPTH>
 struct TexEval {
     static PB2_HD V3 node(const DTexture *textures, const float *pool, int id, V2 uv, const DUvDiff &d) {
         const DTexture &tx = textures[id];
         if (tx.kind == PB2_TEXKIND_IMAGE) return texEvaluateImage(tx, pool, uv, d);
         if (tx.kind == PB2_TEXKIND_CONSTANT) return mk3(tx.value[0], tx.value[1], tx.value[2]);
+        if (tx.kind == PB2_TEXKIND_UV) return texUv(tx, uv);
         const V3 a = TexEval<DEPTH - 1>::node(textures, pool, tx.child[0] - 1, uv, d);
         const V3 b = TexEval<DEPTH - 1>::node(textures, pool, tx.child[1] - 1, uv, d);
         if (tx.kind == PB2_TEXKIND_SCALE) return a * b;
+        if (tx.kind == PB2_TEXKIND_CHECKERBOARD) {
+            const float area2 = texCheckerWeight(tx, uv, d);
+            if (area2 == 0) return a;          // (the reference evaluates only the texture of the check it is in)
+            if (area2 == 1) return b;
+            return (1 - area2) * a + area2 * b;
+        }
         const float amt = TexEval<DEPTH - 1>::node(textures, pool, tx.child[2] - 1, uv, d).x;
         return (1 - amt) * a + amt * b;
     }
@@ -180,18 +208,12 @@ struct TexEval<0> {
     static PB2_HD V3 node(const DTexture *textures, const float *pool, int id, V2 uv, const DUvDiff &d) {
         const DTexture &tx = textures[id];
         if (tx.kind == PB2_TEXKIND_CONSTANT) return mk3(tx.value[0], tx.value[1], tx.value[2]);
+        if (tx.kind == PB2_TEXKIND_UV) return texUv(tx, uv);
         return texEvaluateImage(tx, pool, uv, d);
     }
 };
 PB2_HD V3 texEvaluateNode(const DTexture *textures, const float *pool, int id, V2 uv, const DUvDiff &d) {
     return TexEval<TEX_MAX_DEPTH>::node(textures, pool, id, uv, d);
-}
-
-// ... at a point without differentials (the alpha test inside Triangle::Intersect, triangle.cpp:333-338): both filters
-// end in the bilinear look-up at the finest level
-PB2_HD V3 texEvaluateNoDiff(const DTexture &tx, const float *pool, V2 uv) {
-    V2 st = mk2(tx.su * uv.x + tx.du, tx.sv * uv.y + tx.dv);
-    return texTriangle(tx, pool, 0, st);
 }
 
 }  // namespace pb2

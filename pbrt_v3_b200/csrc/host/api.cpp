@@ -396,6 +396,62 @@ void pbrtTexture(const std::string &name, const std::string &type, const std::st
         }
         return;
     }
+    // "checkerboard" (2D, "uv" mapping; checkerboard.cpp:41-87) and "uv" (uv.cpp): always nodes
+    if (texname == "checkerboard" || texname == "uv") {
+        auto node = std::make_shared<ImageTexture>();
+        node->channels = isSpectrum ? 3 : 1;
+        bool ok = true;
+        std::string mapping = tp.FindString("mapping", "uv");
+        if (mapping != "uv") {
+            Error("2D texture mapping \"%s\" is outside the GPU path's scope (\"uv\" only); using \"uv\"", mapping.c_str());
+        }
+        node->su = tp.FindFloat("uscale", 1.);
+        node->sv = tp.FindFloat("vscale", 1.);
+        node->du = tp.FindFloat("udelta", 0.);
+        node->dv = tp.FindFloat("vdelta", 0.);
+        if (texname == "uv") {
+            node->kind = PB2_TEXKIND_UV;
+            if (isFloat) {   // CreateUVFloatTexture returns nullptr (uv.cpp:40-43)
+                Error("Texture \"%s\": \"uv\" is a spectrum texture", name.c_str());
+                ok = false;
+            }
+        } else {
+            const int dim = params.FindOneInt("dimension", 2);
+            if (dim != 2) {
+                Error("Texture \"%s\": the %d-dimensional checkerboard is outside the GPU path's scope (2D only)", name.c_str(), dim);
+                ok = false;
+            }
+            auto operand = [&](const char *pn, Float def) -> std::shared_ptr<ImageTexture> {
+                if (auto t = tp.GetImageTexture(pn, isSpectrum)) return t;
+                auto c = std::make_shared<ImageTexture>();
+                c->kind = PB2_TEXKIND_CONSTANT;
+                c->channels = isSpectrum ? 3 : 1;
+                if (isSpectrum) {
+                    Spectrum v = tp.GetSpectrumTexture(pn, Spectrum(def));
+                    for (int k = 0; k < 3; ++k) c->value[k] = v.c[k];
+                } else
+                    c->value[0] = tp.GetFloatTexture(pn, def);
+                return c;
+            };
+            node->kind = PB2_TEXKIND_CHECKERBOARD;
+            node->child[0] = operand("tex1", 1.f);
+            node->child[1] = operand("tex2", 0.f);
+            std::string aa = tp.FindString("aamode", "closedform");
+            if (aa != "none" && aa != "closedform")
+                Warning("Antialiasing mode \"%s\" not understood by Checkerboard2DTexture; using \"closedform\"", aa.c_str());
+            node->value[0] = aa == "none" ? 0.f : 1.f;
+        }
+        params.ReportUnused();
+        if (!ok) return;
+        if (isFloat) {
+            floats.erase(name);
+            floatImages[name] = node;
+        } else {
+            spectra.erase(name);
+            spectrumImages[name] = node;
+        }
+        return;
+    }
     // "scale" / "mix" with an operand that varies (an image map, or a combinator of one): a node over the operands
     // (CreateScale*Texture scale.cpp:40-52, CreateMix*Texture mix.cpp:40-54); constants among them become constant nodes
     if ((texname == "scale" || texname == "mix") &&

@@ -1593,9 +1593,19 @@ struct HostTextures {
     std::vector<float> pool;
     std::vector<DTexture> tex;
 };
+static int buildHostTextures(const pb2_scene_desc *d, HostTextures *host);
 static int uploadTextures(pb2_scene *s, const pb2_scene_desc *d, HostTextures *host) {
     DScene &sc = s->d;
     if (d->n_textures <= 0) return PB2_OK;
+    int rc = buildHostTextures(d, host);
+    if (rc) return rc;
+    if ((rc = upload(s, host->tex.data(), host->tex.size(), &sc.textures))) return rc;
+    if ((rc = upload(s, host->pool.data(), host->pool.size(), &sc.texels))) return rc;
+    sc.nTextures = d->n_textures;
+    return PB2_OK;
+}
+// The pyramids of the image textures and the records of all textures, in host memory
+static int buildHostTextures(const pb2_scene_desc *d, HostTextures *host) {
     if (!d->textures) return setError(PB2_ERR_INVALID, "n_textures > 0 but textures is null");
     std::vector<float> &pool = host->pool;
     texWeightLut(pool);
@@ -1617,7 +1627,13 @@ static int uploadTextures(pb2_scene *s, const pb2_scene_desc *d, HostTextures *h
         t.kind = in.kind;
         for (int c = 0; c < 3; ++c) t.value[c] = in.value[in.channels == 3 ? c : 0];
         if (in.kind == PB2_TEXKIND_CONSTANT) continue;
-        if (in.kind != PB2_TEXKIND_SCALE && in.kind != PB2_TEXKIND_MIX) return setError(PB2_ERR_INVALID, "texture: unknown kind");
+        t.su = in.su; t.sv = in.sv; t.du = in.du; t.dv = in.dv;   // the UVMapping2D of a checkerboard / uv texture
+        if (in.kind == PB2_TEXKIND_UV) {
+            if (in.channels != 3) return setError(PB2_ERR_INVALID, "texture: a uv texture has three channels");
+            continue;
+        }
+        if (in.kind == PB2_TEXKIND_CHECKERBOARD) t.value[0] = in.value[0];   // the antialiasing mode, not a colour
+        else if (in.kind != PB2_TEXKIND_SCALE && in.kind != PB2_TEXKIND_MIX) return setError(PB2_ERR_INVALID, "texture: unknown kind");
         const int nChildren = in.kind == PB2_TEXKIND_MIX ? 3 : 2;
         for (int c = 0; c < nChildren; ++c) {
             const int id = in.child[c];
@@ -1629,10 +1645,32 @@ static int uploadTextures(pb2_scene *s, const pb2_scene_desc *d, HostTextures *h
         }
         if (depth[i] > TEX_MAX_DEPTH) return setError(PB2_ERR_UNSUPPORTED, "texture combinators nested more than three levels deep");
     }
-    int rc;
-    if ((rc = upload(s, tex.data(), tex.size(), &sc.textures))) return rc;
-    if ((rc = upload(s, pool.data(), pool.size(), &sc.texels))) return rc;
-    sc.nTextures = d->n_textures;
+    return PB2_OK;
+}
+
+// Texture::Evaluate for texture `id` of a texture array at n points given by (u, v) and (dudx, dvdx, dudy, dvdy), evaluated on
+// the HOST by the functions the kernels compile (texEvaluateNode): parity / debug entry point, no device needed.
+extern "C" int pb2_texture_eval_host(const pb2_texture *textures, int32_t n_textures, int32_t id, int64_t n, const float *uv,
+                                     const float *duv, float *out) {
+    if (!textures || n_textures <= 0 || id < 0 || id >= n_textures || (n > 0 && (!uv || !duv || !out))) return setError(PB2_ERR_INVALID, "bad argument");
+    pb2_scene_desc d;
+    memset(&d, 0, sizeof(d));
+    d.n_textures = n_textures;
+    d.textures = textures;
+    HostTextures host;
+    int rc = buildHostTextures(&d, &host);
+    if (rc) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+        DUvDiff dd;
+        dd.dudx = duv[4 * i];
+        dd.dvdx = duv[4 * i + 1];
+        dd.dudy = duv[4 * i + 2];
+        dd.dvdy = duv[4 * i + 3];
+        const V3 v = texEvaluateNode(host.tex.data(), host.pool.data(), id, mk2(uv[2 * i], uv[2 * i + 1]), dd);
+        out[3 * i] = v.x;
+        out[3 * i + 1] = v.y;
+        out[3 * i + 2] = v.z;
+    }
     return PB2_OK;
 }
 

@@ -192,3 +192,16 @@ def texture_lookup_inputs(n, seed):
     d0[exact] = np.stack([2.0 ** -rs.randint(0, 8, exact.sum()), np.zeros(exact.sum())], 1)
     d1[exact] = d0[exact][:, ::-1]
     return st, np.concatenate([d0, d1], 1).astype(np.float32)
+
+
+TEXTURE_EVAL_SCENES = ("textured", "texcombine", "checker")
+
+
+def texture_eval_inputs(n, seed):
+    """(u, v) in [-1, 3]^2 and (dudx, dvdx, dudy, dvdy) from 1e-4 to 0.7, every fifth point without differentials."""
+    rs = np.random.RandomState(seed)
+    uv = rs.uniform(-1, 3, (n, 2)).astype(np.float32)
+    mag = np.exp(rs.uniform(np.log(1e-4), np.log(.7), (n, 1)))
+    duv = (rs.normal(size=(n, 4)) * mag).astype(np.float32)
+    duv[::5] = 0
+    return uv, duv

@@ -99,6 +99,21 @@ def record_textures(ref):
     print("textures:", len(hs.textures()), "textures recorded")
 
 
+def record_texture_evaluations(ref):
+    """Texture::Evaluate of the reference's own texture objects (ImageTexture's filter behind a UVMapping2D, ConstantTexture,
+    ScaleTexture, MixTexture, Checkerboard2DTexture, UVTexture) for every texture of the textured golden scenes, at the points
+    and differentials of tests/golden_cases.py."""
+    out = {}
+    for scene in gc.TEXTURE_EVAL_SCENES:
+        hs = pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", scene + ".pbrt"))
+        d = hs.desc.contents
+        uv, duv = gc.texture_eval_inputs(2000, 7)
+        for t in range(d.n_textures):
+            out["%s_%d" % (scene, t)] = ref.texture_evaluate(d.textures, d.n_textures, t, uv, duv)
+    np.savez_compressed(os.path.join(OUT, "texture_evaluations.npz"), **out)
+    print("texture evaluations:", len(out), "textures")
+
+
 def record_env_distribution(ref):
     """InfiniteAreaLight::distribution of the reference for the environment map of tests/scenes/envmap.pbrt."""
     hs = pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "envmap.pbrt"))
@@ -132,6 +147,8 @@ def main():
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "envmap.pbrt")), "envmap")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "bumpmap.pbrt")), "bumpmap")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "texcombine.pbrt")), "texcombine")
+    record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "checker.pbrt")), "checker")
+    record_texture_evaluations(ref)
     record_env_distribution(ref)
     record_textures(ref)
     record_filters(ref)

@@ -22,7 +22,7 @@ from test_oracle import load_scene, same_bvh, tessellated_sphere_scene
 pytestmark = pytest.mark.gpu
 
 SCENE_CASES = ["soup", "killeroo_like", "materials", "instances", "specular", "substrate", "metal", "uber", "roughglass", "lights", "params",
-               "envlight", "textured", "textured_lens", "sobol", "envmap", "bumpmap", "texcombine"]
+               "envlight", "textured", "textured_lens", "sobol", "envmap", "bumpmap", "texcombine", "checker"]
 
 
 def li_ok(got, want):

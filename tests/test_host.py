@@ -425,7 +425,7 @@ WorldEnd
     assert tuple(matte.kd) == (f32(.2), f32(.4), f32(.6))          # the redefinition inside the attribute block is gone again
     uber = [m for m in mats if m.type == pb.PB2_MAT_UBER][0]
     assert uber.uroughness == f32(.25) == uber.vroughness
-    hs = pb.HostScene.from_string('WorldBegin\nTexture "img" "spectrum" "checkerboard"\n'
+    hs = pb.HostScene.from_string('WorldBegin\nTexture "img" "spectrum" "dots"\n'
                                   'Material "matte" "texture Kd" "img"\nShape "sphere"\nWorldEnd\n')
     assert pb.lib().pb2h_error_count() >= before + 2                 # the directive and the parameter that names it
 

@@ -387,3 +387,23 @@ def test_environment_map_distribution_is_the_reference_distribution(pb):
     nu, nv, table = pb.env_distribution(d.textures[env[0] - 1])
     assert (nu, nv) == (int(g["nu"]), int(g["nv"])) == (128, 64)
     assert np.array_equal(gc.bits(table), gc.bits(g["table"]))
+
+
+@pytest.mark.parametrize("scene", gc.TEXTURE_EVAL_SCENES)
+def test_texture_nodes_evaluate_like_the_reference_textures(pb, scene):
+    """Texture::Evaluate(si) for every texture of the textured golden scenes - image maps (EWA and trilinear) behind their uv
+    mappings with the point's differentials, constants, scale, mix (nested), checkerboards (point-sampled and box-filtered in
+    closed form) and uv textures - computed on the host by the functions the kernels compile: BIT FOR BIT what the reference's
+    own texture objects return (tests/golden/texture_evaluations.npz)."""
+    g = np.load(os.path.join(GOLDEN, "texture_evaluations.npz"))
+    hs = load_scene(pb, scene)
+    d = hs.desc.contents
+    uv, duv = gc.texture_eval_inputs(2000, 7)
+    kinds = set()
+    for t in range(d.n_textures):
+        got = pb.texture_eval_host(d.textures, d.n_textures, t, uv, duv)
+        want = g["%s_%d" % (scene, t)]
+        assert np.array_equal(gc.bits(got), gc.bits(want)) or np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(gc.bits(got[~np.isnan(got)]), gc.bits(want[~np.isnan(want)])), (scene, t)
+        kinds.add(d.textures[t].kind)
+    if scene == "checker":
+        assert {pb.PB2_TEXKIND_CHECKERBOARD, pb.PB2_TEXKIND_UV, pb.PB2_TEXKIND_MIX, pb.PB2_TEXKIND_IMAGE, pb.PB2_TEXKIND_CONSTANT} <= kinds

@@ -23,7 +23,7 @@ sys.path.insert(0, "tests")
 import test_gpu_parity as tgp  # noqa: E402
 
 makers.append(("emissive_mesh_lazy_lightdist", lambda: pb.HostScene.from_string(tgp.emissive_mesh_scene(12, res=(32, 20), spp=2))))
-for _n in ("textured", "textured_lens", "sobol", "envlight", "envmap", "bumpmap", "texcombine"):   # image textures + alpha masks, the SobolSampler, the infinite light
+for _n in ("textured", "textured_lens", "sobol", "envlight", "envmap", "bumpmap", "texcombine", "checker"):   # image textures + alpha masks, the SobolSampler, the infinite light
     makers.append((_n, lambda _n=_n: pb.HostScene.from_file(os.path.join("tests", "scenes", _n + ".pbrt"))))
 for name, make in makers:
     hs = make()   # the host front end keeps ONE parsed scene: build, use, then build the next
