@@ -503,6 +503,17 @@ int pb2_texture_pyramid(const pb2_texture *texture, int32_t level, int32_t *n_le
 int pb2_texture_eval_host(const pb2_texture *textures, int32_t n_textures, int32_t id, int64_t n, const float *uv, const float *duv,
                           float *out);
 
+/* The two functions behind texture filtering footprints, evaluated on the HOST by the source the kernels compile.  Parity/debug.
+ * pb2_camera_differentials_host: the offset rays PerspectiveCamera::GenerateRayDifferential adds to a camera ray
+ * (perspective.cpp:117-144), in world space and scaled by 1 / sqrt(samples_per_pixel) (integrator.cpp:273-274).  Per sample in:
+ * p_film (2), u_lens (2: CameraSample::pLens), the main ray's world o (3) and d (3) as traced = 10 floats; out: rxOrigin,
+ * rxDirection, ryOrigin, ryDirection = 12 floats.
+ * pb2_uv_differentials_host: SurfaceInteraction::ComputeDifferentials (interaction.cpp:101-147).  Per point in: p, n, dpdu,
+ * dpdv (12 floats) and the four offset-ray vectors (12 floats) = 24 floats; out: dudx, dvdx, dudy, dvdy. */
+int pb2_camera_differentials_host(const pb2_camera *camera, const pb2_film_desc *film, const pb2_path_params *params, int64_t n,
+                                  const float *in, float *out);
+int pb2_uv_differentials_host(int64_t n, const float *in, float *out);
+
 /* The sampling distribution the library derives for an InfiniteAreaLight whose environment map is `texture` (infinite.cpp:64-82:
  * the Distribution2D over the 2w x 2h image of luminance * sin(theta)).  Host code only.  *nu = 2w, *nv = 2h (w, h: the map's
  * resolution after MIPMap's power-of-two resampling) are always written; `out` (may be NULL) receives nv rows of

@@ -201,6 +201,18 @@ class OracleScene:
             raise RuntimeError("the %s oracle does not cover this frame (sampler outside its restatement)" % self.o.kind)
         return rgb, pfilm
 
+    def camera_differentials(self, pixel_xy, sample_num, params=None):
+        """Camera rays with their differentials, the first hit and its (u, v) differentials as the reference computes them:
+        (n, 39) records (layout in oracle/ref_harness.cpp, ref_camera_differentials; reference only)."""
+        pixel_xy = np.ascontiguousarray(pixel_xy, np.int32)
+        sample_num = np.ascontiguousarray(sample_num, np.int64)
+        out = np.zeros((len(sample_num), 39), np.float32)
+        fn = self.o._f("camera_differentials")
+        fn.argtypes = [C.c_void_p, C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        fn(self.h, self.hs.camera, self.hs.film, params if params is not None else self.hs.params, ptr(pixel_xy), ptr(sample_num),
+           len(sample_num), ptr(out))
+        return out
+
     def light_distribution(self, points):
         points = np.ascontiguousarray(points, np.float32)
         out = np.zeros((len(points), 2 * self.n_lights + 1), np.float32)

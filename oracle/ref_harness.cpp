@@ -724,6 +724,41 @@ int ref_li_samples(void *h, const pb2_camera *cam, const pb2_film_desc *fd, cons
     return 0;
 }
 
+// The camera ray of each (pixel, sample) with its differentials as SamplerIntegrator::Render hands it to Li, the first
+// intersection and what SurfaceInteraction::ComputeDifferentials derives there.  39 floats per sample:
+// pFilm(2) pLens(2) o(3) d(3) rxOrigin(3) rxDirection(3) ryOrigin(3) ryDirection(3) hit(1) p(3) n(3) dpdu(3) dpdv(3) dudx dvdx dudy dvdy
+int ref_camera_differentials(void *h, const pb2_camera *cam, const pb2_film_desc *fd, const pb2_path_params *pp,
+                             const int32_t *pixel_xy, const int64_t *sample_num, int64_t n, float *out) {
+    RefScene *rs = static_cast<RefScene *>(h);
+    setThreads(1);
+    RenderObjects ro = makeRenderObjects(*rs, cam, fd, pp);
+    std::unique_ptr<Sampler> sampler = ro.sampler->Clone(0);
+    for (int64_t i = 0; i < n; ++i) {
+        float *o = out + 39 * i;
+        std::memset(o, 0, 39 * sizeof(float));
+        Point2i pixel(pixel_xy[2 * i], pixel_xy[2 * i + 1]);
+        sampler->StartPixel(pixel);
+        sampler->SetSampleNumber(sample_num[i]);
+        CameraSample cs = sampler->GetCameraSample(pixel);
+        RayDifferential ray;
+        ro.camera->GenerateRayDifferential(cs, &ray);
+        ray.ScaleDifferentials(1 / std::sqrt((Float)sampler->samplesPerPixel));
+        o[0] = cs.pFilm.x; o[1] = cs.pFilm.y; o[2] = cs.pLens.x; o[3] = cs.pLens.y;
+        const Float v[18] = {ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z, ray.rxOrigin.x, ray.rxOrigin.y, ray.rxOrigin.z,
+                             ray.rxDirection.x, ray.rxDirection.y, ray.rxDirection.z, ray.ryOrigin.x, ray.ryOrigin.y, ray.ryOrigin.z,
+                             ray.ryDirection.x, ray.ryDirection.y, ray.ryDirection.z};
+        for (int k = 0; k < 18; ++k) o[4 + k] = v[k];
+        SurfaceInteraction isect;
+        if (!rs->scene->Intersect(ray, &isect)) continue;
+        isect.ComputeDifferentials(ray);
+        o[22] = 1;
+        const Float w[16] = {isect.p.x, isect.p.y, isect.p.z, isect.n.x, isect.n.y, isect.n.z, isect.dpdu.x, isect.dpdu.y, isect.dpdu.z,
+                             isect.dpdv.x, isect.dpdv.y, isect.dpdv.z, isect.dudx, isect.dvdx, isect.dudy, isect.dvdy};
+        for (int k = 0; k < 16; ++k) o[23 + k] = w[k];
+    }
+    return 0;
+}
+
 int ref_halton_samples(const pb2_film_desc *fd, const pb2_path_params *pp, const int32_t *pixel_xy,
                        const int64_t *sample_num, const int32_t *dim, int64_t n, float *out) {
     // sample bounds as Film::GetSampleBounds() computes them (film.cpp:80-86)

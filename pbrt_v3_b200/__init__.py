@@ -208,6 +208,8 @@ def lib():
     L.pb2_texture_lookup.argtypes = [C.POINTER(Texture), C.c_int64, vp, vp, vp]
     L.pb2_env_distribution.argtypes = [C.POINTER(Texture), C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     L.pb2_texture_eval_host.argtypes = [C.POINTER(Texture), C.c_int32, C.c_int32, C.c_int64, vp, vp, vp]
+    L.pb2_camera_differentials_host.argtypes = [C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), C.c_int64, vp, vp]
+    L.pb2_uv_differentials_host.argtypes = [C.c_int64, vp, vp]
     L.pb2h_parse_file.argtypes = [C.c_char_p, C.c_char_p]
     L.pb2h_parse_string.argtypes = [C.c_char_p]
     L.pb2h_synth_soup.argtypes = [C.c_int64, C.c_uint64, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_char_p]

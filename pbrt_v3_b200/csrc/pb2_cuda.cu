@@ -2613,6 +2613,47 @@ int pb2_sobol_samples_host(const pb2_film_desc *film, const pb2_path_params *pp,
     return PB2_OK;
 }
 
+int pb2_camera_differentials_host(const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp, int64_t n, const float *in,
+                                  float *out) {
+    if (!cam || !film || !pp || pp->samples_per_pixel <= 0 || (n > 0 && (!in || !out))) return setError(PB2_ERR_INVALID, "bad argument");
+    DCamera c;
+    memcpy(c.rasterToCamera.m, cam->raster_to_camera, sizeof(float) * 16);
+    memcpy(c.cameraToWorld.m, cam->camera_to_world, sizeof(float) * 16);
+    c.lensRadius = cam->lens_radius;
+    c.focalDistance = cam->focal_distance;
+    c.dxCamera = mk3(cam->dx_camera[0], cam->dx_camera[1], cam->dx_camera[2]);
+    c.dyCamera = mk3(cam->dy_camera[0], cam->dy_camera[1], cam->dy_camera[2]);
+    const float scale = 1 / std::sqrt((float)pp->samples_per_pixel);
+    for (int64_t i = 0; i < n; ++i) {
+        const float *q = in + 10 * i;
+        const DRayDiff rd = cameraRayDifferentials(c, mk2(q[0], q[1]), mk2(q[2], q[3]), scale, mk3(q[4], q[5], q[6]), mk3(q[7], q[8], q[9]));
+        float *o = out + 12 * i;
+        o[0] = rd.rxo.x; o[1] = rd.rxo.y; o[2] = rd.rxo.z;
+        o[3] = rd.rxd.x; o[4] = rd.rxd.y; o[5] = rd.rxd.z;
+        o[6] = rd.ryo.x; o[7] = rd.ryo.y; o[8] = rd.ryo.z;
+        o[9] = rd.ryd.x; o[10] = rd.ryd.y; o[11] = rd.ryd.z;
+    }
+    return PB2_OK;
+}
+
+int pb2_uv_differentials_host(int64_t n, const float *in, float *out) {
+    if (n > 0 && (!in || !out)) return setError(PB2_ERR_INVALID, "null argument");
+    for (int64_t i = 0; i < n; ++i) {
+        const float *q = in + 24 * i;
+        DRayDiff rd;
+        rd.rxo = mk3(q[12], q[13], q[14]);
+        rd.rxd = mk3(q[15], q[16], q[17]);
+        rd.ryo = mk3(q[18], q[19], q[20]);
+        rd.ryd = mk3(q[21], q[22], q[23]);
+        const DUvDiff d = computeUvDifferentials(mk3(q[0], q[1], q[2]), mk3(q[3], q[4], q[5]), mk3(q[6], q[7], q[8]), mk3(q[9], q[10], q[11]), rd);
+        out[4 * i] = d.dudx;
+        out[4 * i + 1] = d.dvdx;
+        out[4 * i + 2] = d.dudy;
+        out[4 * i + 3] = d.dvdy;
+    }
+    return PB2_OK;
+}
+
 int pb2_light_distribution(pb2_scene *scene, const float *points_xyz, int64_t n, float *out) {
     int rc = requireDevice();
     if (rc) return rc;

@@ -205,3 +205,5 @@ def texture_eval_inputs(n, seed):
     duv = (rs.normal(size=(n, 4)) * mag).astype(np.float32)
     duv[::5] = 0
     return uv, duv
+
+DIFFERENTIAL_SCENES = ("textured", "textured_lens", "bumpmap", "instances")

@@ -114,6 +114,19 @@ def record_texture_evaluations(ref):
     print("texture evaluations:", len(out), "textures")
 
 
+def record_differentials(ref):
+    """Camera rays with their differentials, first hits and the (u, v) differentials there, from the reference
+    (GenerateRayDifferential + ScaleDifferentials, Scene::Intersect, SurfaceInteraction::ComputeDifferentials)."""
+    out = {}
+    for scene in gc.DIFFERENTIAL_SCENES:
+        hs = pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", scene + ".pbrt"))
+        f = hs.film.contents
+        pix, sn = gc.sample_ids(f.full_resolution[0], f.full_resolution[1], hs.params.contents.samples_per_pixel, 3000, 13)
+        out[scene] = ref.scene(hs).camera_differentials(pix, sn)
+    np.savez_compressed(os.path.join(OUT, "differentials.npz"), **out)
+    print("differentials:", {k: int((v[:, 22] > 0).sum()) for k, v in out.items()})
+
+
 def record_env_distribution(ref):
     """InfiniteAreaLight::distribution of the reference for the environment map of tests/scenes/envmap.pbrt."""
     hs = pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "envmap.pbrt"))
@@ -149,6 +162,7 @@ def main():
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "texcombine.pbrt")), "texcombine")
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "checker.pbrt")), "checker")
     record_texture_evaluations(ref)
+    record_differentials(ref)
     record_env_distribution(ref)
     record_textures(ref)
     record_filters(ref)

@@ -407,3 +407,27 @@ def test_texture_nodes_evaluate_like_the_reference_textures(pb, scene):
         kinds.add(d.textures[t].kind)
     if scene == "checker":
         assert {pb.PB2_TEXKIND_CHECKERBOARD, pb.PB2_TEXKIND_UV, pb.PB2_TEXKIND_MIX, pb.PB2_TEXKIND_IMAGE, pb.PB2_TEXKIND_CONSTANT} <= kinds
+
+
+@pytest.mark.parametrize("scene", gc.DIFFERENTIAL_SCENES)
+def test_ray_differentials_match_the_reference(pb, scene):
+    """The footprint of a pixel on a surface: the camera ray's offset rays (perspective.cpp:117-144 - pinhole and thin lens -
+    taken to world space and scaled by 1 / sqrt(spp)) and SurfaceInteraction::ComputeDifferentials (interaction.cpp:101-147) at
+    the first hit (triangles, spheres, instanced objects), computed on the host by the two functions the shade kernel compiles:
+    BIT FOR BIT the reference's values (tests/golden/differentials.npz: 3000 camera samples per scene)."""
+    rec = np.load(os.path.join(GOLDEN, "differentials.npz"))[scene]
+    hs = load_scene(pb, scene)
+    L = pb.lib()
+    inp = np.ascontiguousarray(rec[:, 0:10])          # pFilm, pLens, o, d
+    out = np.zeros((len(rec), 12), np.float32)
+    assert L.pb2_camera_differentials_host(hs.camera, hs.film, hs.params, len(rec), pb.ptr(inp), pb.ptr(out)) == 0
+    assert np.array_equal(gc.bits(out), gc.bits(np.ascontiguousarray(rec[:, 10:22])))
+    hit = rec[:, 22] > 0
+    assert hit.sum() > 2000
+    inp2 = np.ascontiguousarray(np.concatenate([rec[hit, 23:35], rec[hit, 10:22]], 1))   # p, n, dpdu, dpdv; the offset rays
+    duv = np.zeros((int(hit.sum()), 4), np.float32)
+    assert L.pb2_uv_differentials_host(int(hit.sum()), pb.ptr(inp2), pb.ptr(duv)) == 0
+    want = np.ascontiguousarray(rec[hit, 35:39])
+    assert np.array_equal(gc.bits(duv), gc.bits(want)) and (np.abs(want) > 0).mean() > 0.9
+    if scene == "textured_lens":
+        assert hs.camera.contents.lens_radius > 0 and not np.array_equal(rec[:, 4:7], rec[:, 10:13])   # the offset rays start on the lens
