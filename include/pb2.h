@@ -503,6 +503,13 @@ int pb2_texture_pyramid(const pb2_texture *texture, int32_t level, int32_t *n_le
 int pb2_texture_eval_host(const pb2_texture *textures, int32_t n_textures, int32_t id, int64_t n, const float *uv, const float *duv,
                           float *out);
 
+/* The BSDF of one material record at given shading frames, evaluated on the HOST by the source the shade kernel compiles
+ * (makeBsdf, bsdfF, bsdfPdf, bsdfSampleF; device/pb2_shade.cuh).  Parity/debug.  Per sample in: n (3), shading n (3), shading
+ * dpdu (3), wo (3), wi (3), u (2) = 17 floats.  out, 19 floats: f(wo, wi) and Pdf(wo, wi) over the non-specular lobes as
+ * EstimateDirect asks for them (integrator.cpp:127-130); Sample_f over the non-specular lobes (wi, f, pdf: integrator.cpp:166-169);
+ * Sample_f over all lobes as the path continues (wi, f, pdf, flags: path.cpp:130-131; flags = BSDF_SAMPLED_* of pb2_shade.cuh). */
+int pb2_bsdf_eval_host(const pb2_material *material, int64_t n, const float *in, float *out);
+
 /* The two functions behind texture filtering footprints, evaluated on the HOST by the source the kernels compile.  Parity/debug.
  * pb2_camera_differentials_host: the offset rays PerspectiveCamera::GenerateRayDifferential adds to a camera ray
  * (perspective.cpp:117-144), in world space and scaled by 1 / sqrt(samples_per_pixel) (integrator.cpp:273-274).  Per sample in:

@@ -112,6 +112,14 @@ class Oracle:
             raise ValueError("resolution 2^%d outside the reference's tables" % m)
         return tab, mats
 
+    def bsdf_eval(self, material, frames):
+        """The reference's own BSDF (Material::ComputeScatteringFunctions, BSDF::f / Pdf / Sample_f) for a material record at
+        given shading frames (reference only; layout as pb2_bsdf_eval_host)."""
+        import pbrt_v3_b200 as pb
+        fn = self._f("bsdf_eval")
+        fn.argtypes = [C.POINTER(pb.Material), C.c_int64, C.c_void_p, C.c_void_p]
+        return pb.bsdf_eval_host(material, frames, fn)
+
     def texture_evaluate(self, textures, n_textures, tex_id, uv, duv):
         """Texture::Evaluate of the reference's own texture objects built from a description's texture array (reference only)."""
         import pbrt_v3_b200 as pb

@@ -292,6 +292,46 @@ static void buildRefTextures(const pb2_scene_desc *d, std::vector<std::shared_pt
     }
 
 }
+// The reference's Material object for one record: every parameter is the record's constant, or the texture its slot names
+static std::shared_ptr<Material> makeRefMaterial(const pb2_material &pm, const std::vector<std::shared_ptr<Texture<Float>>> &floatTex,
+                                                 const std::vector<std::shared_ptr<Texture<Spectrum>>> &specTex) {
+    auto spec = [&](int slot, const float *c) -> std::shared_ptr<Texture<Spectrum>> {
+        if (pm.tex[slot]) return specTex[pm.tex[slot] - 1];
+        return std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(c));
+    };
+    auto flt = [&](int slot, float v) -> std::shared_ptr<Texture<Float>> {
+        if (pm.tex[slot]) return floatTex[pm.tex[slot] - 1];
+        return std::make_shared<ConstantTexture<Float>>(v);
+    };
+    auto kd = spec(PB2_TEX_KD, pm.kd);
+    std::shared_ptr<Texture<Float>> bump = pm.tex[PB2_TEX_BUMP] ? floatTex[pm.tex[PB2_TEX_BUMP] - 1] : nullptr;
+    if (pm.type == PB2_MAT_MATTE) {
+        return std::make_shared<MatteMaterial>(kd, flt(PB2_TEX_SIGMA, pm.sigma), bump);
+    } else if (pm.type == PB2_MAT_PLASTIC) {
+        return std::make_shared<PlasticMaterial>(kd, spec(PB2_TEX_KS, pm.ks), flt(PB2_TEX_ROUGHNESS, pm.roughness), bump,
+                                                         pm.remap_roughness != 0);
+    } else if (pm.type == PB2_MAT_MIRROR) {
+        return std::make_shared<MirrorMaterial>(spec(PB2_TEX_KR, pm.kr), bump);
+    } else if (pm.type == PB2_MAT_SUBSTRATE) {
+        return std::make_shared<SubstrateMaterial>(kd, spec(PB2_TEX_KS, pm.ks), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
+                                                           flt(PB2_TEX_VROUGHNESS, pm.vroughness), bump, pm.remap_roughness != 0);
+    } else if (pm.type == PB2_MAT_UBER) {
+        // the description carries the resolved u / v roughness (pb2.h); "roughness" itself is then never read
+        return std::make_shared<UberMaterial>(kd, spec(PB2_TEX_KS, pm.ks), spec(PB2_TEX_KR, pm.kr), spec(PB2_TEX_KT, pm.kt),
+                                                      flt(PB2_TEX_UROUGHNESS, pm.uroughness), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
+                                                      flt(PB2_TEX_VROUGHNESS, pm.vroughness), spec(PB2_TEX_OPACITY, pm.opacity),
+                                                      flt(PB2_TEX_ETA, pm.eta), bump, pm.remap_roughness != 0);
+    } else if (pm.type == PB2_MAT_METAL) {
+        return std::make_shared<MetalMaterial>(spec(PB2_TEX_METAL_ETA, pm.metal_eta), spec(PB2_TEX_METAL_K, pm.metal_k),
+                                                       flt(PB2_TEX_UROUGHNESS, pm.uroughness), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
+                                                       flt(PB2_TEX_VROUGHNESS, pm.vroughness), bump, pm.remap_roughness != 0);
+    } else if (pm.type == PB2_MAT_GLASS) {
+        return std::make_shared<GlassMaterial>(spec(PB2_TEX_KR, pm.kr), spec(PB2_TEX_KT, pm.kt), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
+                                                       flt(PB2_TEX_VROUGHNESS, pm.vroughness), flt(PB2_TEX_ETA, pm.eta), bump,
+                                                       pm.remap_roughness != 0);
+    }
+    return nullptr;
+}
 extern "C" {
 
 const char *ref_kind(void) { return "reference"; }
@@ -400,6 +440,57 @@ int ref_texture_evaluate(const pb2_texture *textures, int n_textures, int id, in
     return 0;
 }
 
+// The reference's BSDF for one material record at given shading frames (Material::ComputeScatteringFunctions with
+// allowMultipleLobes = true, path.cpp:106), evaluated the way EstimateDirect and the path's continuation do.  Layout of
+// in / out: pb2_bsdf_eval_host (include/pb2.h).
+int ref_bsdf_eval(const pb2_material *pm, int64_t n, const float *in, float *out) {
+    std::vector<std::shared_ptr<Texture<Float>>> floatTex;
+    std::vector<std::shared_ptr<Texture<Spectrum>>> specTex;
+    std::shared_ptr<Material> material = makeRefMaterial(*pm, floatTex, specTex);
+    MemoryArena arena;
+    const BxDFType nonSpecular = BxDFType(BSDF_ALL & ~BSDF_SPECULAR);
+    for (int64_t i = 0; i < n; ++i) {
+        const float *q = in + 17 * i;
+        float *o = out + 19 * i;
+        for (int k = 0; k < 19; ++k) o[k] = 0;
+        if (!material) continue;
+        SurfaceInteraction si;
+        si.n = Normal3f(q[0], q[1], q[2]);
+        si.shading.n = Normal3f(q[3], q[4], q[5]);
+        si.dpdu = si.shading.dpdu = Vector3f(q[6], q[7], q[8]);
+        const Vector3f wo(q[9], q[10], q[11]), wi(q[12], q[13], q[14]);
+        si.wo = wo;
+        const Point2f u(q[15], q[16]);
+        material->ComputeScatteringFunctions(&si, arena, TransportMode::Radiance, true);
+        if (!si.bsdf) continue;
+        Float rgb[3];
+        if (si.bsdf->NumComponents(nonSpecular) > 0) {
+            si.bsdf->f(wo, wi, nonSpecular).ToRGB(rgb);
+            o[0] = rgb[0]; o[1] = rgb[1]; o[2] = rgb[2];
+            o[3] = si.bsdf->Pdf(wo, wi, nonSpecular);
+            Vector3f wiS;
+            Float pdfS = 0;
+            BxDFType sampled;
+            Spectrum fS = si.bsdf->Sample_f(wo, &wiS, u, &pdfS, nonSpecular, &sampled);
+            if (pdfS != 0) { o[4] = wiS.x; o[5] = wiS.y; o[6] = wiS.z; }
+            fS.ToRGB(rgb);
+            o[7] = rgb[0]; o[8] = rgb[1]; o[9] = rgb[2];
+            o[10] = pdfS;
+        }
+        Vector3f wiC;
+        Float pdfC = 0;
+        BxDFType flags = BxDFType(0);
+        Spectrum fC = si.bsdf->Sample_f(wo, &wiC, u, &pdfC, BSDF_ALL, &flags);
+        if (pdfC != 0) { o[11] = wiC.x; o[12] = wiC.y; o[13] = wiC.z; }
+        fC.ToRGB(rgb);
+        o[14] = rgb[0]; o[15] = rgb[1]; o[16] = rgb[2];
+        o[17] = pdfC;
+        o[18] = (Float)(((flags & BSDF_SPECULAR) ? 1 : 0) | ((flags & BSDF_TRANSMISSION) ? 2 : 0));
+        arena.Reset();
+    }
+    return 0;
+}
+
 void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split_method) {
     std::unique_ptr<RefScene> rs(new RefScene);
     rs->transforms.emplace_back(new Transform());
@@ -440,46 +531,9 @@ void *ref_scene_create(const pb2_scene_desc *d, int max_prims_in_node, int split
         const_cast<bool &>(sp->transformSwapsHandedness) = ps.transform_swaps_handedness != 0;
         sphereShapes[s] = sp;
     }
-    // materials: every parameter is the constant of the record, or the image texture its slot names
+    // materials
     std::vector<std::shared_ptr<Material>> materials(d->n_materials);
-    for (int i = 0; i < d->n_materials; ++i) {
-        const pb2_material &pm = d->materials[i];
-        auto spec = [&](int slot, const float *c) -> std::shared_ptr<Texture<Spectrum>> {
-            if (pm.tex[slot]) return specTex[pm.tex[slot] - 1];
-            return std::make_shared<ConstantTexture<Spectrum>>(Spectrum::FromRGB(c));
-        };
-        auto flt = [&](int slot, float v) -> std::shared_ptr<Texture<Float>> {
-            if (pm.tex[slot]) return floatTex[pm.tex[slot] - 1];
-            return std::make_shared<ConstantTexture<Float>>(v);
-        };
-        auto kd = spec(PB2_TEX_KD, pm.kd);
-        std::shared_ptr<Texture<Float>> bump = pm.tex[PB2_TEX_BUMP] ? floatTex[pm.tex[PB2_TEX_BUMP] - 1] : nullptr;
-        if (pm.type == PB2_MAT_MATTE) {
-            materials[i] = std::make_shared<MatteMaterial>(kd, flt(PB2_TEX_SIGMA, pm.sigma), bump);
-        } else if (pm.type == PB2_MAT_PLASTIC) {
-            materials[i] = std::make_shared<PlasticMaterial>(kd, spec(PB2_TEX_KS, pm.ks), flt(PB2_TEX_ROUGHNESS, pm.roughness), bump,
-                                                             pm.remap_roughness != 0);
-        } else if (pm.type == PB2_MAT_MIRROR) {
-            materials[i] = std::make_shared<MirrorMaterial>(spec(PB2_TEX_KR, pm.kr), bump);
-        } else if (pm.type == PB2_MAT_SUBSTRATE) {
-            materials[i] = std::make_shared<SubstrateMaterial>(kd, spec(PB2_TEX_KS, pm.ks), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
-                                                               flt(PB2_TEX_VROUGHNESS, pm.vroughness), bump, pm.remap_roughness != 0);
-        } else if (pm.type == PB2_MAT_UBER) {
-            // the description carries the resolved u / v roughness (pb2.h); "roughness" itself is then never read
-            materials[i] = std::make_shared<UberMaterial>(kd, spec(PB2_TEX_KS, pm.ks), spec(PB2_TEX_KR, pm.kr), spec(PB2_TEX_KT, pm.kt),
-                                                          flt(PB2_TEX_UROUGHNESS, pm.uroughness), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
-                                                          flt(PB2_TEX_VROUGHNESS, pm.vroughness), spec(PB2_TEX_OPACITY, pm.opacity),
-                                                          flt(PB2_TEX_ETA, pm.eta), bump, pm.remap_roughness != 0);
-        } else if (pm.type == PB2_MAT_METAL) {
-            materials[i] = std::make_shared<MetalMaterial>(spec(PB2_TEX_METAL_ETA, pm.metal_eta), spec(PB2_TEX_METAL_K, pm.metal_k),
-                                                           flt(PB2_TEX_UROUGHNESS, pm.uroughness), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
-                                                           flt(PB2_TEX_VROUGHNESS, pm.vroughness), bump, pm.remap_roughness != 0);
-        } else if (pm.type == PB2_MAT_GLASS) {
-            materials[i] = std::make_shared<GlassMaterial>(spec(PB2_TEX_KR, pm.kr), spec(PB2_TEX_KT, pm.kt), flt(PB2_TEX_UROUGHNESS, pm.uroughness),
-                                                           flt(PB2_TEX_VROUGHNESS, pm.vroughness), flt(PB2_TEX_ETA, pm.eta), bump,
-                                                           pm.remap_roughness != 0);
-        }
-    }
+    for (int i = 0; i < d->n_materials; ++i) materials[i] = makeRefMaterial(d->materials[i], floatTex, specTex);
     // primitives + lights (lights indexed as in the description = Scene::lights order)
     rs->lights.resize(d->n_lights);
     rs->prims.resize(d->n_prims);

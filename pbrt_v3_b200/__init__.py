@@ -208,6 +208,7 @@ def lib():
     L.pb2_texture_lookup.argtypes = [C.POINTER(Texture), C.c_int64, vp, vp, vp]
     L.pb2_env_distribution.argtypes = [C.POINTER(Texture), C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     L.pb2_texture_eval_host.argtypes = [C.POINTER(Texture), C.c_int32, C.c_int32, C.c_int64, vp, vp, vp]
+    L.pb2_bsdf_eval_host.argtypes = [C.POINTER(Material), C.c_int64, vp, vp]
     L.pb2_camera_differentials_host.argtypes = [C.POINTER(Camera), C.POINTER(FilmDesc), C.POINTER(PathParams), C.c_int64, vp, vp]
     L.pb2_uv_differentials_host.argtypes = [C.c_int64, vp, vp]
     L.pb2h_parse_file.argtypes = [C.c_char_p, C.c_char_p]
@@ -280,6 +281,17 @@ def texture_pyramid(texture, fn=None):
         check(fn(C.byref(texture), lv, C.byref(nl), C.byref(w), C.byref(h), ptr(a)))
         levels.append(a)
     return levels
+
+
+def bsdf_eval_host(material, frames, fn=None):
+    """The BSDF of one pb2_material record at n shading frames (n, 17): n, ns, dpdu, wo, wi, u -> (n, 19): f, pdf, the non-specular
+    sample (wi, f, pdf), the continuation sample (wi, f, pdf, flags); on the host by the shade kernel's own functions (or, with
+    fn, by the oracle).  Layout: include/pb2.h, pb2_bsdf_eval_host."""
+    fn = fn or lib().pb2_bsdf_eval_host
+    frames = np.ascontiguousarray(frames, np.float32)
+    out = np.zeros((len(frames), 19), np.float32)
+    check(fn(C.byref(material), len(frames), ptr(frames), ptr(out)))
+    return out
 
 
 def texture_eval_host(textures, n_textures, tex_id, uv, duv, fn=None):

@@ -2613,6 +2613,50 @@ int pb2_sobol_samples_host(const pb2_film_desc *film, const pb2_path_params *pp,
     return PB2_OK;
 }
 
+int pb2_bsdf_eval_host(const pb2_material *material, int64_t n, const float *in, float *out) {
+    if (!material || (n > 0 && (!in || !out))) return setError(PB2_ERR_INVALID, "null argument");
+    DScene sc;
+    memset(&sc, 0, sizeof(sc));
+    const int32_t primMaterial = 0;
+    sc.primMaterial = &primMaterial;
+    sc.materials = material;
+    for (int64_t i = 0; i < n; ++i) {
+        const float *q = in + 17 * i;
+        float *o = out + 19 * i;
+        for (int k = 0; k < 19; ++k) o[k] = 0;
+        DInteraction it;
+        memset(&it, 0, sizeof(it));
+        it.n = mk3(q[0], q[1], q[2]);
+        it.ns = mk3(q[3], q[4], q[5]);
+        it.dpdus = mk3(q[6], q[7], q[8]);
+        const V3 wo = mk3(q[9], q[10], q[11]), wi = mk3(q[12], q[13], q[14]);
+        it.wo = wo;
+        it.prim = 0;
+        DBsdf bsdf;
+        if (!makeBsdf<true>(sc, it, &bsdf)) continue;
+        if (bsdf.nLobes > 0) {   // (EstimateDirect is only entered with non-specular lobes: path.cpp:119-126)
+            const V3 f = bsdfF<true>(bsdf, wo, wi);
+            o[0] = f.x; o[1] = f.y; o[2] = f.z;
+            o[3] = bsdfPdf<true>(bsdf, wo, wi);
+            V3 wiS;
+            float pdfS;
+            const V3 fS = bsdfSampleF<true>(bsdf, wo, &wiS, mk2(q[15], q[16]), &pdfS, nullptr, true);
+            if (pdfS != 0) { o[4] = wiS.x; o[5] = wiS.y; o[6] = wiS.z; }
+            o[7] = fS.x; o[8] = fS.y; o[9] = fS.z;
+            o[10] = pdfS;
+        }
+        V3 wiC;
+        float pdfC;
+        int flags = 0;
+        const V3 fC = bsdfSampleF<true>(bsdf, wo, &wiC, mk2(q[15], q[16]), &pdfC, &flags);
+        if (pdfC != 0) { o[11] = wiC.x; o[12] = wiC.y; o[13] = wiC.z; }
+        o[14] = fC.x; o[15] = fC.y; o[16] = fC.z;
+        o[17] = pdfC;
+        o[18] = (float)flags;
+    }
+    return PB2_OK;
+}
+
 int pb2_camera_differentials_host(const pb2_camera *cam, const pb2_film_desc *film, const pb2_path_params *pp, int64_t n, const float *in,
                                   float *out) {
     if (!cam || !film || !pp || pp->samples_per_pixel <= 0 || (n > 0 && (!in || !out))) return setError(PB2_ERR_INVALID, "bad argument");

@@ -207,3 +207,23 @@ def texture_eval_inputs(n, seed):
     return uv, duv
 
 DIFFERENTIAL_SCENES = ("textured", "textured_lens", "bumpmap", "instances")
+
+
+BSDF_SCENES = ("materials", "specular", "substrate", "metal", "uber", "roughglass")
+
+
+def bsdf_frames(n, seed):
+    """Random shading frames for BSDF evaluation: geometric normal, a shading normal near it (a third of them equal), a shading
+    dpdu (a quarter of them not perpendicular to ns), wo and wi anywhere on the sphere, a 2D sample."""
+    rs = np.random.RandomState(seed)
+
+    def unit(v):
+        return v / np.linalg.norm(v, axis=1, keepdims=True)
+    nrm = unit(rs.normal(size=(n, 3)))
+    ns = unit(nrm + 0.3 * rs.normal(size=(n, 3)))
+    ns[::3] = nrm[::3]
+    t = rs.normal(size=(n, 3))
+    dpdu = (t - ns * (t * ns).sum(1, keepdims=True)) * rs.uniform(.2, 3, (n, 1))
+    dpdu[::4] += 0.2 * ns[::4]
+    wo, wi = unit(rs.normal(size=(n, 3))), unit(rs.normal(size=(n, 3)))
+    return np.ascontiguousarray(np.concatenate([nrm, ns, dpdu, wo, wi, rs.uniform(0, 1, (n, 2))], 1), np.float32)

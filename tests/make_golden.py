@@ -127,6 +127,18 @@ def record_differentials(ref):
     print("differentials:", {k: int((v[:, 22] > 0).sum()) for k, v in out.items()})
 
 
+def record_bsdfs(ref):
+    """BSDF::f / Pdf / Sample_f of the reference for every material record of the material golden scenes at random frames."""
+    out = {}
+    for scene in gc.BSDF_SCENES:
+        hs = pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", scene + ".pbrt"))
+        d = hs.desc.contents
+        for m in range(d.n_materials):
+            out["%s_%d" % (scene, m)] = ref.bsdf_eval(d.materials[m], gc.bsdf_frames(1500, 17 + m))
+    np.savez_compressed(os.path.join(OUT, "bsdf.npz"), **out)
+    print("bsdf:", len(out), "materials")
+
+
 def record_env_distribution(ref):
     """InfiniteAreaLight::distribution of the reference for the environment map of tests/scenes/envmap.pbrt."""
     hs = pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "envmap.pbrt"))
@@ -163,6 +175,7 @@ def main():
     record_scene(ref, pb.HostScene.from_file(os.path.join(ROOT, "tests", "scenes", "checker.pbrt")), "checker")
     record_texture_evaluations(ref)
     record_differentials(ref)
+    record_bsdfs(ref)
     record_env_distribution(ref)
     record_textures(ref)
     record_filters(ref)

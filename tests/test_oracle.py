@@ -431,3 +431,25 @@ def test_ray_differentials_match_the_reference(pb, scene):
     assert np.array_equal(gc.bits(duv), gc.bits(want)) and (np.abs(want) > 0).mean() > 0.9
     if scene == "textured_lens":
         assert hs.camera.contents.lens_radius > 0 and not np.array_equal(rec[:, 4:7], rec[:, 10:13])   # the offset rays start on the lens
+
+
+@pytest.mark.parametrize("scene", gc.BSDF_SCENES)
+def test_shade_kernel_bsdf_functions_match_the_reference_bsdf(pb, scene):
+    """The functions the shade kernel compiles - makeBsdf (matte with and without sigma, plastic, substrate, metal, uber with
+    opacity / Kr / Kt, mirror, smooth and rough glass), bsdfF, bsdfPdf, bsdfSampleF - evaluated on the host for every material
+    record of a scene at 1500 random shading frames: f and Pdf over the non-specular lobes, the non-specular Sample_f of
+    EstimateDirect and the all-lobes Sample_f of the path's continuation (direction, value, pdf, sampled flags) are BIT FOR BIT
+    what the reference's Material::ComputeScatteringFunctions + BSDF return (tests/golden/bsdf.npz)."""
+    g = np.load(os.path.join(GOLDEN, "bsdf.npz"))
+    hs = load_scene(pb, scene)
+    d = hs.desc.contents
+    types = set()
+    for m in range(d.n_materials):
+        got = pb.bsdf_eval_host(d.materials[m], gc.bsdf_frames(1500, 17 + m))
+        want = g["%s_%d" % (scene, m)]
+        same = gc.bits(got) == gc.bits(want)
+        same[:, 18] |= want[:, 17] == 0          # the sampled flags mean something only when a direction was sampled
+        assert same.all(), (scene, m, d.materials[m].type, np.where(~same.all(0))[0])
+        assert (want[:, 17] != 0).mean() > 0.3   # (half of the frames see the surface from below the shading hemisphere or so)
+        types.add(d.materials[m].type)
+    assert pb.PB2_MAT_MATTE in types
